@@ -1,0 +1,103 @@
+"""Pin the model oracle to fixtures produced by executing the reference's own code
+(tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import graph_oracle as go
+from oracle import model_oracle as mo
+
+
+def _sd(z, prefix):
+    return {k[len(prefix):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(prefix)}
+
+
+@pytest.mark.parametrize("case", ["m8", "m16b"])
+def test_pq_decode(case, golden_dir):
+    z = np.load(os.path.join(golden_dir, f"pq_{case}.npz"))
+    x = mo.pq_decode(z["codes"], z["cen"], z["A"], z["b"])
+    np.testing.assert_allclose(x, z["x_numpy"], rtol=0, atol=1e-6)   # tolerance of pq_wrapper.py:235-239
+    np.testing.assert_allclose(x, z["x_torch"], rtol=0, atol=1e-5)
+    raw = mo.pq_decode(z["codes"], z["cen"])
+    assert (raw == z["x_nopre"]).all()                                # pure gather: bit-exact
+    idx = mo.pq_decode_indices(z["codes"])
+    assert (z["cen"].reshape(-1, z["cen"].shape[2])[idx].reshape(raw.shape) == raw).all()
+
+
+@pytest.mark.parametrize("case", ["untied", "tied"])
+def test_adaptive_softmax(case, golden_dir):
+    z = np.load(os.path.join(golden_dir, f"adaptive_{case}.npz"))
+    w = mo.adaptive_weights(_sd(z, "sd."))
+    cutoff = z["cutoff"].tolist()
+    x, t = torch.from_numpy(z["x"]), torch.from_numpy(z["target"])
+    lp = mo.adaptive_target_logprob(w, cutoff, x, t)
+    np.testing.assert_allclose(lp.numpy(), z["lp_target_mode_at_target"].reshape(-1), rtol=1e-5, atol=1e-5)
+    full = mo.adaptive_full_logprob(w, cutoff, x)
+    np.testing.assert_allclose(full.numpy(), z["lp_full"][0], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(torch.logsumexp(full, 1).numpy(), 0, atol=1e-4)
+
+
+@pytest.mark.parametrize("case", ["ip_t1", "l2_t001"])
+def test_knn_prob(case, golden_dir):
+    z = np.load(os.path.join(golden_dir, f"knn_{case}.npz"))
+    p, rec = mo.knn_target_prob(torch.from_numpy(z["dists"]), torch.from_numpy(z["ids"]),
+                                torch.from_numpy(z["vals"]), torch.from_numpy(z["targets"]),
+                                float(z["temp"]), str(z["metric"]))
+    np.testing.assert_allclose(p.numpy(), z["p_target"], rtol=1e-5, atol=1e-7)
+    assert (rec.numpy() == z["recall"]).all()
+    full = mo.knn_full_prob(torch.from_numpy(z["dists"]), torch.from_numpy(z["ids"]), torch.from_numpy(z["vals"]),
+                            int(z["V"]), float(z["temp"]), str(z["metric"]))
+    np.testing.assert_allclose(full.numpy(), z["p_full"], rtol=1e-5, atol=1e-7)
+
+
+def test_scorer_knn_mix(golden_dir):
+    z = np.load(os.path.join(golden_dir, "scorer_b1_knn.npz"))
+    w = mo.adaptive_weights(_sd(z, "sd."))
+    x, t = torch.from_numpy(z["feats"]), torch.from_numpy(z["target"])
+    lm = mo.adaptive_target_logprob(w, z["cutoff"].tolist(), x, t)
+    s0 = int(z["start_indices"][0, 0])
+    np.testing.assert_allclose(lm.numpy()[s0:], z["lm_pos_0"], rtol=1e-5, atol=1e-5)
+    p, rec = mo.knn_target_prob(torch.from_numpy(z["dists"]), torch.from_numpy(z["ids"]),
+                                torch.from_numpy(z["vals"]), t.reshape(-1), float(z["temp"]))
+    mix = mo.combine_knn_and_vocab_probs(p, lm, float(z["lmbda"]))
+    np.testing.assert_allclose(mix.numpy()[s0:], z["knn_pos_0"], rtol=1e-5, atol=1e-5)
+    assert (rec.numpy()[s0:] == z["knn_recall_0"]).all()
+
+
+def test_scorer_lm_b2_start_indices(golden_dir):
+    z = np.load(os.path.join(golden_dir, "scorer_b2_lm.npz"))
+    w = mo.adaptive_weights(_sd(z, "sd."))
+    x, t = torch.from_numpy(z["feats"]), torch.from_numpy(z["target"])
+    lm = mo.adaptive_target_logprob(w, z["cutoff"].tolist(), x, t).view(t.shape)
+    for i in range(t.shape[0]):
+        s = int(z["start_indices"][i, 0])
+        np.testing.assert_allclose(lm[i, s:].numpy(), z[f"lm_pos_{i}"], rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("case", ["l2_c1", "l3_c2"])
+def test_hgt_matches_reference_layer_code(case, golden_dir):
+    z = np.load(os.path.join(golden_dir, f"hgt_{case}.npz"))
+    g = go.build_batch(z["nbr"], z["offsets"], int(z["n_d"]), int(z["cl"]), int(z["cr"]))
+    sd = _sd(z, "sd.")
+    out = mo.hgt_forward(sd, torch.from_numpy(z["h_tgt"]), torch.from_numpy(z["h_ntgt"]), g,
+                         int(z["H"]), int(z["n_layers"]))
+    np.testing.assert_allclose(out["tgt"].numpy(), z["out_tgt"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(out["ntgt"].numpy(), z["out_ntgt"], rtol=1e-5, atol=2e-6)
+    B, L = z["nbr"].shape[:2]
+    out2 = mo.hgt_forward_csr(sd, torch.from_numpy(z["h_tgt"]), torch.from_numpy(z["h_ntgt"]), g, (B, L),
+                              int(z["H"]), int(z["n_layers"]))
+    np.testing.assert_allclose(out2["tgt"].numpy(), z["out_tgt"], rtol=1e-5, atol=2e-6)
+
+
+def test_zero_in_degree_tgt_gets_half_intra(golden_dir):
+    """DGL semantics restated: a tgt with no valid neighbour still averages over
+    two edge types, i.e. receives intra/2."""
+    z = np.load(os.path.join(golden_dir, "hgt_l2_c1.npz"))
+    assert (z["nbr"][0, 1] == -1).all()
+
+
+def test_perplexity():
+    nll2, ppl = mo.perplexity(-10.0 * np.log(2), 10)
+    assert abs(nll2 - 1.0) < 1e-12 and abs(ppl - 2.0) < 1e-12
