@@ -1,0 +1,89 @@
+"""ctypes binding of libgnnlm_sm100.so (include/gnnlm_sm100.h).  No fallback: if the library is
+missing or a call fails, raise."""
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgnnlm_sm100.so")
+
+F32, BF16, F16 = 0, 1, 2
+MATH_FP32_SIMT, MATH_TF32X3, MATH_TF32, MATH_BF16 = 0, 1, 2, 3
+MATH_NAMES = {"fp32": MATH_FP32_SIMT, "tf32x3": MATH_TF32X3, "tf32": MATH_TF32, "bf16": MATH_BF16}
+
+_p, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+
+# name -> (restype, argtypes): must list every symbol include/gnnlm_sm100.h declares
+SIGNATURES = {
+    "gnnlm_version": (_i32, []),
+    "gnnlm_last_error": (C.c_char_p, []),
+    "gnnlm_has_tcgen05": (_i32, []),
+    "gnnlm_graph_workspace_bytes": (_i64, [_i64]),
+    "gnnlm_graph_count": (_i32, [_p, _p, _i64, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _i64, _p]),
+    "gnnlm_graph_fill": (_i32, [_p, _p, _i64, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "gnnlm_graph_tt_num_edges": (_i64, [_i64, _i64, _i64]),
+    "gnnlm_graph_tt_csr": (_i32, [_i64, _i64, _i64, _p, _p, _p]),
+    "gnnlm_pq_gather_decode": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _i32, _p, _p, _p]),
+    "gnnlm_split_tf32": (_i32, [_p, _p, _p, _i64, _p]),
+    "gnnlm_linear": (_i32, [_p, _i32, _i64, _p, _p, _i64, _p, _p, _i64, _p, _i32, _i64, _i64, _p, _i64, _i64, _i32, _p]),
+    "gnnlm_lse_num_tiles": (_i64, [_i64, _i32]),
+    "gnnlm_linear_lse": (_i32, [_p, _i32, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _p]),
+    "gnnlm_lse_finish": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _p]),
+    "gnnlm_gather_rows": (_i32, [_p, _i64, _p, _p, _i64, _i64, _p, _i64, _i32, _p]),
+    "gnnlm_layernorm": (_i32, [_p, _i64, _p, _p, _f32, _p, _i32, _i64, _i64, _p, _i64, _p]),
+    "gnnlm_convert": (_i32, [_p, _i32, _p, _i32, _i64, _p]),
+    "gnnlm_hgt_edge_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _i64, _p, _i32, _i32, _p, _i64, _f32, _i32, _p]),
+    "gnnlm_hgt_causal_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _i64, _i64, _i64, _i32, _i32, _p, _i64, _f32, _i32, _p]),
+    "gnnlm_adapt_target": (_i32, [_p, _i64, _p, _i32, _p, _p, _p, _p, _p]),
+    "gnnlm_knn_mix_nll": (_i32, [_p, _p, _f32, _p, _p, _i64, _p, _i32, _i64, _p, _f32, _f32, _f32, _p, _p, _p, _p, _p, _i64, _p]),
+    "gnnlm_knn_full_prob": (_i32, [_p, _p, _i64, _p, _i32, _i64, _f32, _f32, _p, _i64, _i64, _p]),
+}
+
+_lib = None
+launches = 0          # number of C-ABI compute calls issued (bench.py reports kernel launches from this)
+
+
+class GnnlmError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library; raises if it is absent (there is no CPU fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise GnnlmError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                         "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the header and the library disagree
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "device tensor required"
+    return t.data_ptr()
+
+
+def dtype_code(dt):
+    return {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16}[dt]
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    global launches
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise GnnlmError(f"{name} failed ({rc}): {lib.gnnlm_last_error().decode()}")
+    launches += 1
+    return rc

@@ -1,0 +1,120 @@
+// Shared helpers for libgnnlm_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gnnlm_sm100.h"
+
+namespace gnnlm {
+
+void set_error(const char* fmt, ...);
+
+#define GNNLM_CHECK_ARG(cond, code, ...) \
+  do {                                   \
+    if (!(cond)) {                       \
+      gnnlm::set_error(__VA_ARGS__);     \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+// Launch check without synchronising: reports configuration errors only.
+#define GNNLM_LAUNCH_CHECK(name)                                              \
+  do {                                                                        \
+    cudaError_t e__ = cudaGetLastError();                                     \
+    if (e__ != cudaSuccess) {                                                 \
+      gnnlm::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
+      return (int32_t)e__;                                                    \
+    }                                                                         \
+  } while (0)
+
+#define GNNLM_CUDA(call)                                                        \
+  do {                                                                          \
+    cudaError_t e__ = (call);                                                   \
+    if (e__ != cudaSuccess) {                                                   \
+      gnnlm::set_error("%s failed: %s", #call, cudaGetErrorString(e__));        \
+      return (int32_t)e__;                                                      \
+    }                                                                           \
+  } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ int64_t live_rows(int64_t cap, const int32_t* dev) {
+  if (dev == nullptr) return cap;
+  int64_t n = (int64_t)__ldg(dev);
+  return n < cap ? n : cap;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- typed row access: load C contiguous elements starting at p (C in {1,2,4,8,16,32}) as fp32 ----
+template <int C>
+__device__ __forceinline__ void load_f32(const float* __restrict__ p, float (&r)[C]) {
+  if constexpr (C % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+      r[4 * i] = t.x; r[4 * i + 1] = t.y; r[4 * i + 2] = t.z; r[4 * i + 3] = t.w;
+    }
+  } else if constexpr (C == 2) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p));
+    r[0] = t.x; r[1] = t.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < C; ++i) r[i] = __ldg(p + i);
+  }
+}
+template <int C>
+__device__ __forceinline__ void load_bf16(const __nv_bfloat16* __restrict__ p, float (&r)[C]) {
+  if constexpr (C % 8 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 8; ++i) {
+      uint4 t = __ldg(reinterpret_cast<const uint4*>(p) + i);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(h[j]);
+        r[8 * i + 2 * j] = f.x; r[8 * i + 2 * j + 1] = f.y;
+      }
+    }
+  } else if constexpr (C == 4) {
+    uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+    float2 a = __bfloat1622float2(h[0]), b = __bfloat1622float2(h[1]);
+    r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y;
+  } else {
+#pragma unroll
+    for (int i = 0; i < C; ++i) r[i] = __bfloat162float(p[i]);
+  }
+}
+template <typename T, int C>
+__device__ __forceinline__ void load_row(const T* __restrict__ p, float (&r)[C]) {
+  if constexpr (sizeof(T) == 4) load_f32<C>(reinterpret_cast<const float*>(p), r);
+  else load_bf16<C>(reinterpret_cast<const __nv_bfloat16*>(p), r);
+}
+template <int C>
+__device__ __forceinline__ void store_f32(float* __restrict__ p, const float (&r)[C]) {
+  if constexpr (C % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i)
+      reinterpret_cast<float4*>(p)[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+  } else if constexpr (C == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(r[0], r[1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < C; ++i) p[i] = r[i];
+  }
+}
+
+}  // namespace gnnlm

@@ -1,0 +1,252 @@
+// HGT edge attention: per-edge-type Q.K' score, segmented softmax by destination, weighted V' sum,
+// cross-edge-type mean -- one warp per destination, shuffle reductions, no atomics.
+//
+// Replaces, per canonical edge type, the DGL sequence of HGTLayer.forward
+// (reference: fairseq/models/hgt.py:350-358,383-386): apply_edges(fn.v_dot_u('q','k','t')) (SDDMM),
+// `* relation_pri / sqrt_dk`, dgl.ops.edge_softmax(norm_by='dst'), and
+// multi_update_all({etype: (u_mul_e, sum)}, cross_reducer='mean').  The relation transforms
+// (:347-348) and the pri/sqrt(d_k) factor are folded into the K'/V' projection weights by the host
+// module, so `k`/`v` here are already K', V'.
+//
+// DGL semantics restated (DGL itself is absent): softmax is per destination and per
+// head, max-subtracted; a destination without in-edges receives 0 from that edge type; the
+// cross-type mean divides by the number of edge types targeting the node type regardless of degree
+// (out_scale = 1/n_etypes, accumulate chains the edge types).
+//
+// Layout: q [n_dst, d], k/v [n_src, d] row-major, d = H*d_k.  A warp owns one destination; lane l
+// owns the C = d/32 contiguous features [l*C, (l+1)*C), all inside head l / (32/H).  Scores are
+// reduced over the 32/H lanes of a head with xor-shuffles; softmax is online (running max / sum),
+// so each K'/V' row is read exactly once per in-edge and nothing intermediate ([E,H] scores, [E,H,d_k]
+// messages) is written.  Algorithmic HBM bytes per layer and edge type:
+// N_src*2*d*s + N_dst*d*s (q) + N_dst*d*4 (out) + E*4 + (N_dst+1)*4.
+#include "common.cuh"
+
+namespace gnnlm {
+
+constexpr int EA_THREADS = 256;
+
+template <typename T, int C, int UNROLL>
+__device__ __forceinline__ void attend_range(const float (&q)[C], const T* __restrict__ k, int64_t ldk,
+                                             const T* __restrict__ v, int64_t ldv, const int32_t* __restrict__ indices,
+                                             int64_t e_begin, int64_t e_end, int lane, int group, float& m_run,
+                                             float& l_run, float (&acc)[C]) {
+  int64_t e = e_begin;
+  for (; e + UNROLL <= e_end; e += UNROLL) {
+    float kk[UNROLL][C], vv[UNROLL][C];
+    float s[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t src = indices ? (int64_t)__ldg(indices + e + u) : (e + u);
+      load_row<T, C>(k + src * ldk + lane * C, kk[u]);
+      load_row<T, C>(v + src * ldv + lane * C, vv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      float p = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) p = fmaf(q[c], kk[u][c], p);
+      for (int o = group >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      s[u] = p;
+    }
+    float mx = m_run;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) mx = fmaxf(mx, s[u]);
+    const float corr = __expf(m_run - mx);          // m_run == -inf on first use -> 0
+    l_run *= corr;
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] *= corr;
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const float w = __expf(s[u] - mx);
+      l_run += w;
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = fmaf(w, vv[u][c], acc[c]);
+    }
+    m_run = mx;
+  }
+  for (; e < e_end; ++e) {
+    float kk[C], vv[C];
+    const int64_t src = indices ? (int64_t)__ldg(indices + e) : e;
+    load_row<T, C>(k + src * ldk + lane * C, kk);
+    load_row<T, C>(v + src * ldv + lane * C, vv);
+    float p = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) p = fmaf(q[c], kk[c], p);
+    for (int o = group >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    const float mx = fmaxf(m_run, p);
+    const float corr = __expf(m_run - mx);
+    const float w = __expf(p - mx);
+    l_run = l_run * corr + w;
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = fmaf(w, vv[c], acc[c] * corr);
+    m_run = mx;
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void write_out(float* __restrict__ o, const float (&acc)[C], float l_run, float out_scale,
+                                          int accumulate) {
+  const float inv = l_run > 0.f ? out_scale / l_run : 0.f;     // zero in-degree -> 0 (fn.sum semantics)
+  float r[C];
+  if (accumulate) {
+    load_f32<C>(o, r);
+#pragma unroll
+    for (int c = 0; c < C; ++c) r[c] = fmaf(acc[c], inv, r[c]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < C; ++c) r[c] = acc[c] * inv;
+  }
+  store_f32<C>(o, r);
+}
+
+// CSR edge attention.  UNROLL edges in flight per warp.
+template <typename T, int C, int UNROLL>
+__global__ void __launch_bounds__(EA_THREADS) edge_attn_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k,
+                                                               int64_t ldk, const T* __restrict__ v, int64_t ldv,
+                                                               const int32_t* __restrict__ indptr,
+                                                               const int32_t* __restrict__ indices,
+                                                               const int32_t* __restrict__ dst_ids, int64_t n_dst_cap,
+                                                               const int32_t* __restrict__ n_dst_dev, int group,
+                                                               float* __restrict__ out, int64_t ldo, float out_scale,
+                                                               int accumulate) {
+  const int64_t n_dst = live_rows(n_dst_cap, n_dst_dev);
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_dst; i += warps) {
+    const int64_t row = dst_ids ? (int64_t)__ldg(dst_ids + i) : i;
+    const int64_t e0 = __ldg(indptr + row), e1 = __ldg(indptr + row + 1);
+    float qr[C], acc[C];
+    load_row<T, C>(q + i * ldq + lane * C, qr);
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    attend_range<T, C, UNROLL>(qr, k, ldk, v, ldv, indices, e0, e1, lane, group, m_run, l_run, acc);
+    write_out<C>(out + i * ldo + lane * C, acc, l_run, out_scale, accumulate);
+  }
+}
+
+// Implicit causal attention inside blocks of L tokens: destination g = b*L + t attends to sources
+// b*L + [max(0, t-ctx+1), t].  v1: warp per destination (K'/V' rows come from L2: a 3072-token block is
+// 2 x 12.6 MB in fp32).
+template <typename T, int C, int UNROLL>
+__global__ void __launch_bounds__(EA_THREADS) causal_attn_kernel(const T* __restrict__ q, int64_t ldq,
+                                                                 const T* __restrict__ k, int64_t ldk,
+                                                                 const T* __restrict__ v, int64_t ldv, int64_t B,
+                                                                 int64_t L, int64_t ctx, int group, float* __restrict__ out,
+                                                                 int64_t ldo, float out_scale, int accumulate) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = B * L;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += warps) {
+    // longest rows first so the tail of the grid is made of short rows
+    const int64_t g = n - 1 - w;
+    const int64_t b = g / L, t = g % L;
+    const int64_t lo = (ctx > 0 && t + 1 > ctx) ? t + 1 - ctx : 0;
+    float qr[C], acc[C];
+    load_row<T, C>(q + g * ldq + lane * C, qr);
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    attend_range<T, C, UNROLL>(qr, k, ldk, v, ldv, nullptr, b * L + lo, b * L + t + 1, lane, group, m_run, l_run, acc);
+    write_out<C>(out + g * ldo + lane * C, acc, l_run, out_scale, accumulate);
+  }
+}
+
+template <typename T, int C>
+static int32_t launch_edge(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                           const int32_t* indptr, const int32_t* indices, const int32_t* dst_ids, int64_t n_dst_cap,
+                           const int32_t* n_dst_dev, int group, float* out, int64_t ldo, float out_scale, int accumulate,
+                           cudaStream_t st) {
+  constexpr int UNROLL = C >= 32 ? 2 : 4;
+  const int64_t warps_per_block = EA_THREADS / 32;
+  int64_t blocks = ceil_div(n_dst_cap, warps_per_block);
+  const int64_t max_blocks = 148 * 8 * 4;
+  if (blocks > max_blocks) blocks = max_blocks;
+  edge_attn_kernel<T, C, UNROLL><<<(unsigned)blocks, EA_THREADS, 0, st>>>(
+      (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, group, out,
+      ldo, out_scale, accumulate);
+  GNNLM_LAUNCH_CHECK("gnnlm_hgt_edge_attn");
+  return 0;
+}
+
+template <typename T, int C>
+static int32_t launch_causal(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t B,
+                             int64_t L, int64_t ctx, int group, float* out, int64_t ldo, float out_scale, int accumulate,
+                             cudaStream_t st) {
+  constexpr int UNROLL = C >= 32 ? 2 : 4;
+  int64_t blocks = ceil_div(B * L, EA_THREADS / 32);
+  causal_attn_kernel<T, C, UNROLL><<<(unsigned)blocks, EA_THREADS, 0, st>>>((const T*)q, ldq, (const T*)k, ldk,
+                                                                            (const T*)v, ldv, B, L, ctx, group, out, ldo,
+                                                                            out_scale, accumulate);
+  GNNLM_LAUNCH_CHECK("gnnlm_hgt_causal_attn");
+  return 0;
+}
+
+static int32_t check_shape(const char* who, int32_t H, int32_t d_k, int32_t dtype, int64_t ldq, int64_t ldk, int64_t ldv,
+                           int64_t ldo, int* C_out, int* group_out) {
+  GNNLM_CHECK_ARG(dtype == GNNLM_F32 || dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED, "%s: dtype must be F32 or BF16", who);
+  GNNLM_CHECK_ARG(H > 0 && H <= 32 && (H & (H - 1)) == 0, GNNLM_E_UNSUPPORTED, "%s: H must be a power of two <= 32 (H=%d)", who, H);
+  const int64_t d = (int64_t)H * d_k;
+  GNNLM_CHECK_ARG(d % 32 == 0, GNNLM_E_UNSUPPORTED, "%s: H*d_k must be a multiple of 32 (d=%lld)", who, (long long)d);
+  const int C = (int)(d / 32);
+  GNNLM_CHECK_ARG(C == 1 || C == 2 || C == 4 || C == 8 || C == 16 || C == 32, GNNLM_E_UNSUPPORTED,
+                  "%s: d/32 must be in {1,2,4,8,16,32} (d=%lld)", who, (long long)d);
+  GNNLM_CHECK_ARG(ldq % C == 0 && ldk % C == 0 && ldv % C == 0 && ldo % C == 0, GNNLM_E_SHAPE,
+                  "%s: leading dimensions must be multiples of d/32", who);
+  *C_out = C;
+  *group_out = 32 / H;
+  return 0;
+}
+
+#define DISPATCH_C(FN, T, ...)                   \
+  switch (C) {                                   \
+    case 1: return FN<T, 1>(__VA_ARGS__);        \
+    case 2: return FN<T, 2>(__VA_ARGS__);        \
+    case 4: return FN<T, 4>(__VA_ARGS__);        \
+    case 8: return FN<T, 8>(__VA_ARGS__);        \
+    case 16: return FN<T, 16>(__VA_ARGS__);      \
+    default: return FN<T, 32>(__VA_ARGS__);      \
+  }
+
+}  // namespace gnnlm
+
+using namespace gnnlm;
+
+extern "C" int32_t gnnlm_hgt_edge_attn(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                       int32_t dtype, const int32_t* indptr, const int32_t* indices,
+                                       const int32_t* dst_ids, int64_t n_dst_cap, const int32_t* n_dst_dev, int32_t H,
+                                       int32_t d_k, float* out, int64_t ldo, float out_scale, int32_t accumulate,
+                                       gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(q && k && v && indptr && out, GNNLM_E_ARG, "gnnlm_hgt_edge_attn: null pointer");
+  int C, group;
+  int32_t rc = check_shape("gnnlm_hgt_edge_attn", H, d_k, dtype, ldq, ldk, ldv, ldo, &C, &group);
+  if (rc) return rc;
+  if (n_dst_cap == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == GNNLM_F32) {
+    DISPATCH_C(launch_edge, float, q, ldq, k, ldk, v, ldv, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, group, out, ldo,
+               out_scale, accumulate, st)
+  } else {
+    DISPATCH_C(launch_edge, __nv_bfloat16, q, ldq, k, ldk, v, ldv, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, group,
+               out, ldo, out_scale, accumulate, st)
+  }
+}
+
+extern "C" int32_t gnnlm_hgt_causal_attn(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                                         int64_t ldv, int32_t dtype, int64_t B, int64_t L, int64_t intra_ctx, int32_t H,
+                                         int32_t d_k, float* out, int64_t ldo, float out_scale, int32_t accumulate,
+                                         gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(q && k && v && out, GNNLM_E_ARG, "gnnlm_hgt_causal_attn: null pointer");
+  GNNLM_CHECK_ARG(B >= 0 && L > 0, GNNLM_E_SHAPE, "gnnlm_hgt_causal_attn: bad sizes");
+  int C, group;
+  int32_t rc = check_shape("gnnlm_hgt_causal_attn", H, d_k, dtype, ldq, ldk, ldv, ldo, &C, &group);
+  if (rc) return rc;
+  if (B == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == GNNLM_F32) {
+    DISPATCH_C(launch_causal, float, q, ldq, k, ldk, v, ldv, B, L, intra_ctx, group, out, ldo, out_scale, accumulate, st)
+  } else {
+    DISPATCH_C(launch_causal, __nv_bfloat16, q, ldq, k, ldk, v, ldv, B, L, intra_ctx, group, out, ldo, out_scale,
+               accumulate, st)
+  }
+}

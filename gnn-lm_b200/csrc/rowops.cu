@@ -1,0 +1,208 @@
+// Row utilities between stages: row gather, LayerNorm, dtype conversion, tf32 hi/lo weight split.
+// Reference call sites: nn.LayerNorm of HGTLayer.forward (fairseq/models/hgt.py:404-405),
+// `precompute_feats[offsets].astype(np.float32)` (fairseq/data/token_block_dataset.py:327-329).
+// All are HBM-bound streaming kernels: vectorised 16 B accesses, one warp per row.
+#include "common.cuh"
+
+namespace gnnlm {
+
+template <typename V>
+__global__ void __launch_bounds__(256) gather_rows_kernel(const V* __restrict__ src, int64_t ld_src,
+                                                          const int32_t* __restrict__ ids, V* __restrict__ dst,
+                                                          int64_t ld_dst, int64_t n_cap, const int32_t* __restrict__ n_dev,
+                                                          int64_t d_vec) {
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const int64_t r = __ldg(ids + i);
+    const V* s = src + r * ld_src;
+    V* o = dst + i * ld_dst;
+    for (int64_t j = lane; j < d_vec; j += 32) o[j] = __ldg(s + j);
+  }
+}
+
+// one warp per row, two passes over registers-resident data when d <= 32*MAXV*4, else re-read
+template <typename OutT>
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t ldx,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, OutT* __restrict__ y, int64_t ldy, int64_t n_cap,
+                                                        const int32_t* __restrict__ n_dev, int64_t d) {
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const float* xr = x + i * ldx;
+    float s = 0.f;
+    for (int64_t j = lane; j < d; j += 32) s += xr[j];
+    const float mean = warp_sum(s) / (float)d;
+    float vs = 0.f;
+    for (int64_t j = lane; j < d; j += 32) {
+      float t = xr[j] - mean;
+      vs = fmaf(t, t, vs);
+    }
+    const float rstd = rsqrtf(warp_sum(vs) / (float)d + eps);
+    for (int64_t j = lane; j < d; j += 32) {
+      float v = (xr[j] - mean) * rstd * __ldg(gamma + j) + __ldg(beta + j);
+      if constexpr (sizeof(OutT) == 4) y[i * ldy + j] = v;
+      else y[i * ldy + j] = __float2bfloat16(v);
+    }
+  }
+}
+
+// vectorised variant: d % 128 == 0, row held in registers (d <= 4096)
+template <typename OutT, int NV>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, int64_t ldx,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps,
+                                                            OutT* __restrict__ y, int64_t ldy, int64_t n_cap,
+                                                            const int32_t* __restrict__ n_dev) {
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int lane = threadIdx.x & 31;
+  constexpr int d = NV * 128;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + i * ldx);
+    float4 r[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      r[j] = xr[lane + 32 * j];
+      s += r[j].x + r[j].y + r[j].z + r[j].w;
+    }
+    const float mean = warp_sum(s) * (1.f / d);
+    float vs = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      r[j].x -= mean; r[j].y -= mean; r[j].z -= mean; r[j].w -= mean;
+      vs += r[j].x * r[j].x + r[j].y * r[j].y + r[j].z * r[j].z + r[j].w * r[j].w;
+    }
+    const float rstd = rsqrtf(warp_sum(vs) * (1.f / d) + eps);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * j);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
+      float4 o = make_float4(r[j].x * rstd * g.x + b.x, r[j].y * rstd * g.y + b.y, r[j].z * rstd * g.z + b.z,
+                             r[j].w * rstd * g.w + b.w);
+      if constexpr (sizeof(OutT) == 4) {
+        reinterpret_cast<float4*>(y + i * ldy)[lane + 32 * j] = o;
+      } else {
+        __nv_bfloat162 a = __floats2bfloat162_rn(o.x, o.y), c = __floats2bfloat162_rn(o.z, o.w);
+        uint2 u;
+        u.x = *reinterpret_cast<uint32_t*>(&a);
+        u.y = *reinterpret_cast<uint32_t*>(&c);
+        reinterpret_cast<uint2*>(y + i * ldy)[lane + 32 * j] = u;
+      }
+    }
+  }
+}
+
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) convert_kernel(const S* __restrict__ src, D* __restrict__ dst, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v;
+    if constexpr (sizeof(S) == 4) v = src[i];
+    else v = (float)src[i];
+    if constexpr (sizeof(D) == 4) dst[i] = v;
+    else dst[i] = (D)v;
+  }
+}
+
+__global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi,
+                                                         float* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = w[i];
+    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);   // keep 10 explicit mantissa bits
+    hi[i] = h;
+    lo[i] = x - h;                                                        // exact in fp32
+  }
+}
+
+static inline unsigned grid_for(int64_t n, int per_block) {
+  int64_t b = ceil_div(n, per_block);
+  const int64_t cap = 148 * 32;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace gnnlm
+
+using namespace gnnlm;
+
+extern "C" int32_t gnnlm_gather_rows(const void* src, int64_t ld_src, const int32_t* ids, void* dst, int64_t ld_dst,
+                                     int64_t n_cap, const int32_t* n_dev, int64_t d, int32_t dtype, gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(src && ids && dst, GNNLM_E_ARG, "gnnlm_gather_rows: null pointer");
+  const int64_t es = dtype == GNNLM_F32 ? 4 : 2;
+  GNNLM_CHECK_ARG(dtype == GNNLM_F32 || dtype == GNNLM_BF16 || dtype == GNNLM_F16, GNNLM_E_UNSUPPORTED, "gnnlm_gather_rows: dtype");
+  if (n_cap == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t row_bytes = d * es;
+  const unsigned g = grid_for(n_cap, 8);
+  if (row_bytes % 16 == 0 && (ld_src * es) % 16 == 0 && (ld_dst * es) % 16 == 0 && (uintptr_t)src % 16 == 0 &&
+      (uintptr_t)dst % 16 == 0) {
+    gather_rows_kernel<uint4><<<g, 256, 0, st>>>((const uint4*)src, ld_src * es / 16, ids, (uint4*)dst, ld_dst * es / 16,
+                                                n_cap, n_dev, row_bytes / 16);
+  } else if (es == 4) {
+    gather_rows_kernel<uint32_t><<<g, 256, 0, st>>>((const uint32_t*)src, ld_src, ids, (uint32_t*)dst, ld_dst, n_cap, n_dev, d);
+  } else {
+    gather_rows_kernel<uint16_t><<<g, 256, 0, st>>>((const uint16_t*)src, ld_src, ids, (uint16_t*)dst, ld_dst, n_cap, n_dev, d);
+  }
+  GNNLM_LAUNCH_CHECK("gnnlm_gather_rows");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y,
+                                   int32_t out_dtype, int64_t ldy, int64_t n_cap, const int32_t* n_dev, int64_t d,
+                                   gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(x && gamma && beta && y, GNNLM_E_ARG, "gnnlm_layernorm: null pointer");
+  GNNLM_CHECK_ARG(out_dtype == GNNLM_F32 || out_dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED, "gnnlm_layernorm: out dtype");
+  GNNLM_CHECK_ARG(d > 0, GNNLM_E_SHAPE, "gnnlm_layernorm: d");
+  if (n_cap == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g = grid_for(n_cap, 8);
+  const bool vec = d % 128 == 0 && d <= 1024 && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)x % 16 == 0 &&
+                   (uintptr_t)y % 16 == 0 && (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0;
+#define LN_VEC(NV)                                                                                                      \
+  if (out_dtype == GNNLM_F32)                                                                                           \
+    layernorm_vec_kernel<float, NV><<<g, 256, 0, st>>>(x, ldx, gamma, beta, eps, (float*)y, ldy, n_cap, n_dev);          \
+  else                                                                                                                  \
+    layernorm_vec_kernel<__nv_bfloat16, NV><<<g, 256, 0, st>>>(x, ldx, gamma, beta, eps, (__nv_bfloat16*)y, ldy, n_cap, n_dev);
+  if (vec && d == 1024) { LN_VEC(8) }
+  else if (vec && d == 512) { LN_VEC(4) }
+  else if (vec && d == 256) { LN_VEC(2) }
+  else if (vec && d == 128) { LN_VEC(1) }
+  else if (out_dtype == GNNLM_F32)
+    layernorm_kernel<float><<<g, 256, 0, st>>>(x, ldx, gamma, beta, eps, (float*)y, ldy, n_cap, n_dev, d);
+  else
+    layernorm_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(x, ldx, gamma, beta, eps, (__nv_bfloat16*)y, ldy, n_cap, n_dev, d);
+#undef LN_VEC
+  GNNLM_LAUNCH_CHECK("gnnlm_layernorm");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n,
+                                 gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(src && dst, GNNLM_E_ARG, "gnnlm_convert: null pointer");
+  if (n == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g = grid_for(n, 1024);
+  if (src_dtype == GNNLM_F16 && dst_dtype == GNNLM_F32) convert_kernel<__half, float><<<g, 256, 0, st>>>((const __half*)src, (float*)dst, n);
+  else if (src_dtype == GNNLM_F16 && dst_dtype == GNNLM_BF16) convert_kernel<__half, __nv_bfloat16><<<g, 256, 0, st>>>((const __half*)src, (__nv_bfloat16*)dst, n);
+  else if (src_dtype == GNNLM_F32 && dst_dtype == GNNLM_BF16) convert_kernel<float, __nv_bfloat16><<<g, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else if (src_dtype == GNNLM_BF16 && dst_dtype == GNNLM_F32) convert_kernel<__nv_bfloat16, float><<<g, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else if (src_dtype == GNNLM_F32 && dst_dtype == GNNLM_F16) convert_kernel<float, __half><<<g, 256, 0, st>>>((const float*)src, (__half*)dst, n);
+  else if (src_dtype == GNNLM_F32 && dst_dtype == GNNLM_F32) convert_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, n);
+  else {
+    set_error("gnnlm_convert: unsupported conversion %d -> %d", src_dtype, dst_dtype);
+    return GNNLM_E_UNSUPPORTED;
+  }
+  GNNLM_LAUNCH_CHECK("gnnlm_convert");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(w && w_hi && w_lo, GNNLM_E_ARG, "gnnlm_split_tf32: null pointer");
+  if (n == 0) return 0;
+  split_tf32_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(w, w_hi, w_lo, n);
+  GNNLM_LAUNCH_CHECK("gnnlm_split_tf32");
+  return 0;
+}

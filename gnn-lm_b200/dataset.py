@@ -1,0 +1,154 @@
+"""Block dataset + batch assembly -- host-side mirror of the reference's data path for the graph LM:
+
+  GraphTokenBlockDataset   fairseq/data/token_block_dataset.py:172-333 (block slicing :246-285,
+                           source/target shift :304-319, neighbour-id gather :309, features :327-329)
+  GraphMonolingualDataset  fairseq/data/monolingual_dataset.py:209-266 (collater, no shuffling)
+  on-disk layout           knn/path_utils.py:13-41, fairseq/tasks/language_modeling.py:265-303
+
+What changes: the reference builds a DGL graph per block in Python inside DataLoader workers and
+ships codes/edges over PCIe; here __getitem__ only slices the *inputs* of graph assembly (neighbour
+ids, fp16 features, tokens -- contiguous slices in `none` break mode) and the graph is assembled on
+the device from the HBM-resident datastore (`DeviceDatastore`) by graph_build.cu / pq_decode.cu.
+Only `--sample-break-mode none` (the wiki103 / enwik8 scripts) is implemented; `eos` mode
+(one_billion scripts) is a ragged variant left for a later round."""
+import json
+import os
+from typing import List, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from .graph import TokenGraph, build_token_graph
+
+
+# ---- knn/path_utils.py:13-41
+def feature_path(data_dir, mode): return os.path.join(data_dir, f"{mode}_dstore", "keys.npy")
+def value_path(data_dir, mode): return os.path.join(data_dir, f"{mode}_dstore", "vals.npy")
+def dstore_path(data_dir, subset): return os.path.join(data_dir, f"{subset}_dstore")
+def quantized_feature_path(data_dir, mode): return os.path.join(data_dir, f"{mode}_dstore", "quantized-keys.npy")
+def neighbor_path(data_dir, mode, k=32): return os.path.join(data_dir, f"{mode}_dstore", f"neighbors.mmap.{k}")
+
+
+class DeviceDatastore:
+    """The quantised datastore replicated in one GPU's HBM: codes [N_d, M] uint8
+    (train_dstore/quantized-keys.npy) and values [N_d] int16/int32 (train_dstore/vals.npy)."""
+
+    def __init__(self, codes: torch.Tensor, vals: torch.Tensor):
+        assert codes.dtype == torch.uint8 and codes.dim() == 2
+        self.codes = codes.contiguous()
+        self.vals = vals.reshape(-1).contiguous()
+        assert self.vals.dtype in (torch.int16, torch.int32) and self.vals.numel() == codes.shape[0]
+        self.size = codes.shape[0]
+
+    @classmethod
+    def from_dir(cls, data_dir: str, vocab_size: int, device) -> "DeviceDatastore":
+        info = json.load(open(os.path.join(dstore_path(data_dir, "train"), "info.json")))
+        n = info["dstore_size"]
+        vdt = np.int16 if info.get("dstore_fp16") and vocab_size < 2 ** 15 else np.int32   # language_modeling.py:272
+        vals = np.memmap(value_path(data_dir, "train"), dtype=vdt, mode="r", shape=(n, 1))
+        codes = np.load(quantized_feature_path(data_dir, "train"), mmap_mode="r")
+        return cls(torch.from_numpy(np.ascontiguousarray(codes)).to(device),
+                   torch.from_numpy(np.ascontiguousarray(vals)).to(device))
+
+
+class GraphTokenBlockDataset:
+    """token_block_dataset.py:172-333 for break_mode='none' over a flat token stream."""
+
+    def __init__(self, tokens: np.ndarray, block_size: int, pad: int, eos: int, neighbor_offsets: np.ndarray,
+                 n_datastore: int, neighbor_context: Union[int, Tuple[int, int]] = 1,
+                 precompute_feats: Optional[np.ndarray] = None, invalid_neighbor_context: int = 0,
+                 context_window: int = 0, intra_context: int = 0, knn_dists: Optional[np.ndarray] = None,
+                 knn_ids: Optional[np.ndarray] = None, break_mode: str = "none", deprecated: bool = False):
+        if break_mode not in (None, "none"):
+            raise NotImplementedError("only --sample-break-mode none")
+        if deprecated:
+            raise NotImplementedError("--deprecated (dedup) graph build is a 'next' row (SURVEY.md 8f-4)")
+        self.tokens = tokens
+        self.block_size, self.pad, self.eos = block_size, pad, eos
+        self.neighbor_offsets = neighbor_offsets
+        self.n_datastore = n_datastore
+        if isinstance(neighbor_context, int):                           # :232-236
+            self.left_neighbor_context = self.right_neighbor_context = neighbor_context
+        else:
+            self.left_neighbor_context, self.right_neighbor_context = neighbor_context
+        self.precompute_feats = precompute_feats
+        self.invalid_neighbor_context = invalid_neighbor_context
+        self.context_window = context_window
+        self.max_intra_context = intra_context
+        self.knn_dists, self.knn_ids = knn_dists, knn_ids
+        n = len(tokens)
+        self.slice_indices = [(s, min(s + block_size, n)) for s in range(0, n, block_size)]   # token_block_utils_fast.pyx:22-35
+        self.sizes = np.array([e - s for s, e in self.slice_indices])
+
+    def __len__(self):
+        return len(self.slice_indices)
+
+    def __getitem__(self, index):
+        s, e = self.slice_indices[index]
+        cs = s if (self.context_window == 0 or index == 0) else max(0, s - self.context_window)    # :246-285
+        item = torch.from_numpy(np.asarray(self.tokens[cs:e]).astype(np.int64))
+        if cs == 0:                                                                                 # :310-319
+            source = torch.cat([item.new_tensor([self.eos]), item[:-1]])
+        else:
+            source = torch.from_numpy(np.asarray(self.tokens[cs - 1:e - 1]).astype(np.int64))
+        out = {"id": index, "source": source, "target": item, "offsets": (cs, e), "start_idx": s - cs,
+               "nbr": torch.from_numpy(np.ascontiguousarray(self.neighbor_offsets[cs:e]))}
+        if self.precompute_feats is not None:
+            out["feats"] = torch.from_numpy(np.ascontiguousarray(self.precompute_feats[cs:e]))
+        if self.knn_ids is not None:
+            out["knn_dists"] = torch.from_numpy(np.ascontiguousarray(self.knn_dists[cs:e]))
+            out["knn_ids"] = torch.from_numpy(np.ascontiguousarray(self.knn_ids[cs:e]))
+        return out
+
+    def collater(self, samples: List[dict]) -> dict:
+        """monolingual_dataset.py:13-53,237-262 for equal-length blocks (the reference's own
+        `x.view(bsz, tgt_len, -1)` assumes this, transformer.py:975 'todo: fix padding cases');
+        a ragged last block must be its own batch."""
+        if not samples:
+            return {}
+        Ls = {len(s["target"]) for s in samples}
+        assert len(Ls) == 1, "batch blocks of equal length only (SURVEY.md Q6)"
+        pin = lambda t: t.pin_memory() if torch.cuda.is_available() else t
+        st = lambda key: pin(torch.stack([s[key] for s in samples]))
+        batch = {
+            "id": torch.LongTensor([s["id"] for s in samples]),
+            "nsentences": len(samples),
+            "ntokens": sum(len(s["source"]) for s in samples),
+            "net_input": {"src_tokens": st("source"),
+                          "src_lengths": torch.LongTensor([s["source"].numel() for s in samples])},
+            "target": st("target"),
+            "start_indices": torch.LongTensor([[s["start_idx"]] for s in samples]),
+            "nbr": st("nbr"),
+            "positions": pin(torch.stack([torch.arange(s["offsets"][0], s["offsets"][1]) for s in samples])),
+        }
+        for k in ("feats", "knn_dists", "knn_ids"):
+            if k in samples[0]:
+                batch[k] = st(k)
+        return batch
+
+    def ordered_indices(self):
+        return np.arange(len(self))                                       # monolingual_dataset.py:264-266
+
+
+def move_to_cuda(batch: dict, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, device="cuda") -> dict:
+    """utils.move_to_cuda (fairseq/utils.py:43-67) + on-device graph assembly.  Returns the fairseq
+    `sample` dict with net_input.graph = TokenGraph."""
+    nb = lambda t: t.to(device, non_blocking=True)
+    nbr = nb(batch["nbr"])
+    pos = nb(batch["positions"])
+    g = build_token_graph(nbr, dstore.size, dataset.left_neighbor_context, dataset.right_neighbor_context,
+                          tgt_pos=pos if dataset.invalid_neighbor_context > 0 else None,
+                          invalid_ctx=dataset.invalid_neighbor_context, intra_ctx=dataset.max_intra_context)
+    g.codes_table = dstore.codes
+    g.labels_table = dstore.vals
+    if "feats" in batch:
+        feats = nb(batch["feats"])
+        g.nodes["tgt"].data["h"] = feats.view(-1, feats.shape[-1])
+    sample = {"id": batch["id"], "nsentences": batch["nsentences"], "ntokens": batch["ntokens"],
+              "net_input": {"src_tokens": nb(batch["net_input"]["src_tokens"]), "src_lengths": batch["net_input"]["src_lengths"],
+                            "graph": g},
+              "target": nb(batch["target"]), "start_indices": batch["start_indices"], "positions": pos}
+    if "knn_ids" in batch:
+        sample["knn_dists"] = nb(batch["knn_dists"]).view(-1, batch["knn_dists"].shape[-1])
+        sample["knn_ids"] = nb(batch["knn_ids"]).view(-1, batch["knn_ids"].shape[-1])
+    return sample

@@ -1,0 +1,252 @@
+"""Heterogeneous Graph Transformer over the kNN token graph -- host-side mirror of the reference's
+fairseq/models/hgt.py (HGTLayer :22-79,299-420; HGT :459-513) with identical constructor arguments,
+parameter names and state_dict keys, executing on libgnnlm_sm100.so kernels only.
+
+B200-first restructuring (results identical up to fp rounding, see tests/test_gpu_parity.py):
+  * the per-relation d_k x d_k transforms (hgt.py:347-348) and the relation_pri / sqrt(d_k) score
+    scale (:355) are folded into the K/V projection weights once per checkpoint, and the
+    projections that share an input are concatenated, so one GEMM emits Q | K' | V' directly;
+  * score, segmented softmax, weighted sum and the cross-edge-type mean are one fused kernel per
+    edge type (no [E,H] / [E,H,d_k] intermediates);
+  * tgt-intra-tgt is executed as implicit causal attention (no 4.7M-edge COO);
+  * ntgt nodes only ever receive messages from ntgt nodes, so the ntgt side of all layers is run
+    first and only the compact centre-node features each tgt layer needs are kept; in the
+    decoder's tgt-only mode the last layer skips the ntgt side and the one before computes centre
+    rows only (dead-work elimination).
+"""
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from .graph import TokenGraph
+
+
+def _fold(W: torch.Tensor, b: torch.Tensor, R: torch.Tensor, scale: Optional[torch.Tensor]):
+    """K' = (h W^T + b) @ blockdiag(R)  ==  h W'^T + b'   (fp64 fold, returned as fp32)."""
+    H, dk, _ = R.shape
+    d_in = W.shape[1]
+    W3 = W.detach().double().view(H, dk, d_in)
+    Rd = R.detach().double()
+    Wf = torch.einsum("ijk,ijd->ikd", Rd, W3)
+    bf = torch.einsum("ij,ijk->ik", b.detach().double().view(H, dk), Rd)
+    if scale is not None:
+        Wf = Wf * scale.double()[:, None, None]
+        bf = bf * scale.double()[:, None]
+    return Wf.reshape(H * dk, d_in).float(), bf.reshape(H * dk).float()
+
+
+class _Weight:
+    """A prepared [N,K] weight in the layout/precision the selected GEMM math wants."""
+
+    def __init__(self, W: torch.Tensor, b: Optional[torch.Tensor], math_mode: int):
+        W = W.contiguous().float()
+        self.b = None if b is None else b.contiguous().float()
+        self.lo = None
+        if math_mode == L.MATH_TF32X3:
+            self.W, self.lo = ops.split_tf32(W)
+        elif math_mode == L.MATH_BF16:
+            self.W = ops.convert(W, torch.bfloat16)
+        else:
+            self.W = W
+
+    def rows(self, a: int, b_: int) -> "_Weight":
+        v = object.__new__(_Weight)
+        v.W = self.W[a:b_]
+        v.lo = None if self.lo is None else self.lo[a:b_]
+        v.b = None if self.b is None else self.b[a:b_]
+        return v
+
+
+def _lin(x, w: _Weight, math_mode, **kw):
+    return ops.linear(x, w.W, w.b, W_lo=w.lo, math=math_mode, **kw)
+
+
+class HGTLayer(nn.Module):
+    """Same parameters as the reference layer (hgt.py:27-79)."""
+
+    def __init__(self, in_dim: int, out_dim: int, ntype2idx: Dict[str, int], etype2idx: Dict[str, int], n_heads: int,
+                 dropout=0.2, use_norm=True, two_stream=False, attn_drop=0.2):
+        super().__init__()
+        if two_stream:
+            raise NotImplementedError("two_stream is hard-wired False in the reference decoder (transformer.py:931)")
+        self.in_dim, self.out_dim = in_dim, out_dim
+        self.ntype2idx, self.etype2idx = ntype2idx, etype2idx
+        self.num_types, self.num_relations = len(ntype2idx), len(etype2idx)
+        self.n_heads = n_heads
+        assert out_dim % n_heads == 0
+        self.d_k = out_dim // n_heads
+        self.sqrt_dk = math.sqrt(self.d_k)
+        self.use_norm = use_norm
+        self.two_stream = two_stream
+        self.k_linears, self.q_linears = nn.ModuleList(), nn.ModuleList()
+        self.v_linears, self.a_linears = nn.ModuleList(), nn.ModuleList()
+        self.norms = nn.ModuleList()
+        for _ in range(self.num_types):
+            self.k_linears.append(nn.Linear(in_dim, out_dim))
+            self.q_linears.append(nn.Linear(in_dim, out_dim))
+            self.v_linears.append(nn.Linear(in_dim, out_dim))
+            self.a_linears.append(nn.Linear(out_dim, out_dim))
+            if use_norm:
+                self.norms.append(nn.LayerNorm(out_dim))
+        self.relation_pri = nn.Parameter(torch.ones(self.num_relations, n_heads))
+        self.relation_att = nn.Parameter(torch.Tensor(self.num_relations, n_heads, self.d_k, self.d_k))
+        self.relation_msg = nn.Parameter(torch.Tensor(self.num_relations, n_heads, self.d_k, self.d_k))
+        self.skip = nn.Parameter(torch.ones(self.num_types))      # unused by the reference forward (:399)
+        self.drop = nn.Dropout(dropout)
+        self.attn_drop = nn.Dropout(attn_drop)
+        nn.init.xavier_uniform_(self.relation_att)
+        nn.init.xavier_uniform_(self.relation_msg)
+        self._prep = None
+        self._prep_key = None
+
+    # ------------------------------------------------------------------ weight preparation
+    def prepare(self, math_mode: int):
+        key = (math_mode, self.relation_pri.device, tuple(int(p._version) for p in self.parameters()))
+        if self._prep is not None and self._prep_key == key:
+            return self._prep
+        if not self.use_norm:
+            raise NotImplementedError("use_norm=False is never used by the reference decoder")
+        t, n = self.ntype2idx["tgt"], self.ntype2idx["ntgt"]
+        intra, inter = self.etype2idx["intra"], self.etype2idx["inter"]
+        d = self.out_dim
+        pri = self.relation_pri.detach()
+
+        def kv(tau, rel):
+            Wk, bk = _fold(self.k_linears[tau].weight, self.k_linears[tau].bias, self.relation_att[rel],
+                           pri[rel] / self.sqrt_dk)
+            Wv, bv = _fold(self.v_linears[tau].weight, self.v_linears[tau].bias, self.relation_msg[rel], None)
+            return Wk, bk, Wv, bv
+
+        def qkv(tau):
+            Wk, bk, Wv, bv = kv(tau, intra)
+            W = torch.cat([self.q_linears[tau].weight.detach().float(), Wk, Wv], 0)
+            b = torch.cat([self.q_linears[tau].bias.detach().float(), bk, bv], 0)
+            return _Weight(W, b, math_mode)
+
+        Wk, bk, Wv, bv = kv(n, inter)
+        P = {
+            "tgt_qkv": qkv(t), "ntgt_qkv": qkv(n),
+            "ntgt_kv_inter": _Weight(torch.cat([Wk, Wv], 0), torch.cat([bk, bv], 0), math_mode),
+            "a": {tau: _Weight(self.a_linears[tau].weight.detach(), self.a_linears[tau].bias.detach(), math_mode)
+                  for tau in (t, n)},
+            "ln": {tau: (self.norms[tau].weight.detach().float().contiguous(),
+                         self.norms[tau].bias.detach().float().contiguous(), self.norms[tau].eps) for tau in (t, n)},
+            "math": math_mode, "d": d, "t": t, "n": n,
+        }
+        self._prep, self._prep_key = P, key
+        return P
+
+    # ------------------------------------------------------------------ building blocks
+    def _out(self, P, tau, t_agg, h_in, n_dev):
+        o = _lin(t_agg, P["a"][tau], P["math"], residual=h_in, m_dev=n_dev)              # hgt.py:401-403
+        g, b, eps = P["ln"][tau]
+        return ops.layernorm(o, g, b, eps, out=o, n_dev=n_dev)                            # :405
+
+    def ntgt_full(self, P, G: TokenGraph, h_n, n_dev):
+        """All ntgt nodes: Q|K'|V' -> chain attention -> A-linear + residual + LN."""
+        d, H = P["d"], self.n_heads
+        qkv = _lin(h_n, P["ntgt_qkv"], P["math"], m_dev=n_dev)
+        t_agg = torch.empty((h_n.shape[0], d), device=h_n.device, dtype=torch.float32)
+        ops.edge_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.nn_indptr, G.nn_indices, H, t_agg, n_dst_dev=n_dev)
+        return self._out(P, P["n"], t_agg, h_n, n_dev)
+
+    def ntgt_centre(self, P, G: TokenGraph, h_n, n_dev, hc, c_dev):
+        """Centre nodes only (compact rows): K'|V' for every node, Q / A-linear / LN for centres."""
+        d, H = P["d"], self.n_heads
+        kv = _lin(h_n, P["ntgt_qkv"].rows(d, 3 * d), P["math"], m_dev=n_dev)
+        qc = _lin(hc, P["ntgt_qkv"].rows(0, d), P["math"], m_dev=c_dev)
+        t_agg = torch.empty((hc.shape[0], d), device=h_n.device, dtype=torch.float32)
+        ops.edge_attn(qc, kv[:, :d], kv[:, d:], G.nn_indptr, G.nn_indices, H, t_agg, dst_ids=G.inter_indices,
+                      n_dst_dev=c_dev)
+        return self._out(P, P["n"], t_agg, hc, c_dev)
+
+    def tgt(self, P, G: TokenGraph, h_t, hc, c_dev):
+        """tgt nodes: mean of (centre ntgt -> tgt) attention and causal tgt -> tgt attention."""
+        d, H = P["d"], self.n_heads
+        qkv = _lin(h_t, P["tgt_qkv"], P["math"])
+        kvi = _lin(hc, P["ntgt_kv_inter"], P["math"], m_dev=c_dev)
+        t_agg = torch.empty((h_t.shape[0], d), device=h_t.device, dtype=torch.float32)
+        # inter edges in compact centre numbering are the contiguous ranges of inter_indptr
+        ops.edge_attn(qkv[:, :d], kvi[:, :d], kvi[:, d:], G.inter_indptr, None, H, t_agg, out_scale=0.5)
+        ops.causal_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5,
+                        accumulate=True)
+        return self._out(P, P["t"], t_agg, h_t, None)
+
+    def forward(self, G: TokenGraph, h: Dict[str, torch.Tensor], etypes=None, incremental_state=None,
+                math_mode: int = L.MATH_FP32_SIMT) -> Dict[str, torch.Tensor]:
+        """Full layer, every node of both types (hgt.py:299-420)."""
+        assert incremental_state is None, "only support lm (transformer.py:1028)"
+        P = self.prepare(math_mode)
+        n_valid = G.counts()[1]
+        hc = ops.gather_rows(h["ntgt"], G.inter_indices, n_cap=n_valid)
+        new_t = self.tgt(P, G, h["tgt"], hc, None)
+        new_n = self.ntgt_full(P, G, h["ntgt"], None)
+        return {"tgt": new_t, "ntgt": new_n}
+
+
+class HGT(nn.Module):
+    """Same constructor / keys as the reference (hgt.py:459-492)."""
+
+    def __init__(self, ntype2idx, etype2idx, in_dim, hidden_dim, out_dim, n_layers, n_heads, use_norm=True,
+                 dropout=0.0, two_stream=False, attn_drop=0.0):
+        super().__init__()
+        if in_dim != hidden_dim or hidden_dim != out_dim:
+            raise NotImplementedError("adapt_ws / out projections (hgt.py:482-492) are unused by every reference "
+                                      "config (decoder_gcn_dim == decoder_embed_dim)")
+        self.ntype2idx, self.etype2idx = ntype2idx, etype2idx
+        self.in_dim, self.hidden_dim, self.out_dim, self.n_layers = in_dim, hidden_dim, out_dim, n_layers
+        self.adapt_ws = nn.ModuleList()
+        self.gcs = nn.ModuleList(HGTLayer(hidden_dim, hidden_dim, ntype2idx, etype2idx, n_heads, use_norm=use_norm,
+                                          dropout=dropout, two_stream=two_stream, attn_drop=attn_drop)
+                                 for _ in range(n_layers))
+        self.math_mode = L.MATH_FP32_SIMT
+
+    def set_math(self, mode):
+        self.math_mode = L.MATH_NAMES[mode] if isinstance(mode, str) else int(mode)
+        return self
+
+    def forward(self, G: TokenGraph, features: Dict[str, torch.Tensor] = None, etypes=None, incremental_state=None):
+        """Reference-shaped call (hgt.py:494-513): returns features of every node of both types."""
+        h = {}
+        for ntype in ("tgt", "ntgt"):
+            x = None if not features else features.get(ntype)
+            if x is None:
+                x = G.nodes[ntype].data["h"]
+            h[ntype] = x.float().contiguous()
+        for layer in self.gcs:
+            h = layer(G, h, etypes=etypes, incremental_state=incremental_state, math_mode=self.math_mode)
+        return h
+
+    @torch.no_grad()
+    def forward_tgt(self, G: TokenGraph, h_tgt: torch.Tensor, h_ntgt: Optional[torch.Tensor],
+                    hc0: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """tgt features only (what the decoder consumes, transformer.py:1053), capacity-sized ntgt
+        arrays + device-side row counts: no host synchronisation anywhere.
+
+        h_ntgt [node_cap, d] decoded features of every ntgt node (may be None when n_layers == 1 and
+        hc0, the decoded centre rows [T*k, d], is given)."""
+        n_dev, c_dev = G.n_ntgt_dev, G.n_valid_dev
+        NL = self.n_layers
+        mode = self.math_mode
+        prep = [layer.prepare(mode) for layer in self.gcs]
+        # ---- ntgt side: compact centre features entering each layer
+        hc: List[torch.Tensor] = []
+        if hc0 is None:
+            hc0 = ops.gather_rows(h_ntgt, G.inter_indices, n_dev=c_dev)
+        hc.append(hc0)
+        h_n = h_ntgt
+        for l in range(NL - 1):
+            if l < NL - 2:
+                h_n = self.gcs[l].ntgt_full(prep[l], G, h_n, n_dev)
+                hc.append(ops.gather_rows(h_n, G.inter_indices, n_dev=c_dev))
+            else:
+                hc.append(self.gcs[l].ntgt_centre(prep[l], G, h_n, n_dev, hc[l], c_dev))
+        # ---- tgt side
+        h_t = h_tgt.float().contiguous()
+        for l in range(NL):
+            h_t = self.gcs[l].tgt(prep[l], G, h_t, hc[l], c_dev)
+        return h_t

@@ -1,0 +1,337 @@
+"""`transformer_lm` with `--graph_layer N > 0`: host-side mirror of the reference model surface on the
+evaluation hot path.
+
+  TransformerLanguageModel          fairseq/models/transformer_lm.py:27-188 (flags :122-139)
+  TokenGraphTransformerDecoder      fairseq/models/transformer.py:910-1085
+  AdaptiveSoftmax                   fairseq/modules/adaptive_softmax.py:50-206
+
+Same constructor arguments (an argparse-style `args`), same method names and the same state_dict
+keys for everything on the path (decoder.hgt_decoder.*, decoder.tgt_quantizer.*,
+decoder.adaptive_softmax.* / decoder.embed_out).  The 16-layer base transformer is out of scope: the
+target configs run with --use-precompute-feat, which bypasses it (transformer.py:974-976); its keys
+(decoder.layers.*, decoder.embed_tokens.*) are accepted and ignored by load_reference_state_dict().
+All arithmetic goes through libgnnlm_sm100.so.
+"""
+import math
+from argparse import Namespace
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from .graph import ETYPES, TokenGraph
+from .hgt import HGT, _Weight
+from .pq_codec import TorchPQCodec
+
+
+class _W(nn.Module):
+    """A bare `weight` holder so that state_dict keys match the reference module tree."""
+
+    def __init__(self, *shape):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(*shape))
+        nn.init.xavier_uniform_(self.weight)
+
+
+class _TiedHead(nn.Module):
+    """TiedHeadModule (adaptive_softmax.py:24-47): keys word_proj.weight, class_proj.weight."""
+
+    def __init__(self, n_words, d, n_classes):
+        super().__init__()
+        self.word_proj = _W(n_words, d)
+        self.class_proj = _W(n_classes, d)
+        self.register_buffer("_float_tensor", torch.FloatTensor(1))
+
+
+class AdaptiveSoftmax(nn.Module):
+    """Efficient softmax approximation (adaptive_softmax.py:50-115), evaluated at the target only.
+
+    `tied=True` reproduces the key layout of --tie-adaptive-weights/--tie-adaptive-proj checkpoints
+    (wiki103): head.word_proj / head.class_proj, tail.i.0.weight stored [d, dim_i]."""
+
+    def __init__(self, vocab_size: int, input_dim: int, cutoff: List[int], dropout: float = 0.0, factor: float = 4.0,
+                 tied: bool = False):
+        super().__init__()
+        cutoff = list(cutoff)
+        if vocab_size > cutoff[-1]:
+            cutoff = cutoff + [vocab_size]
+        else:
+            assert vocab_size == cutoff[-1], "cannot specify cutoff larger than vocab size"
+        self.vocab_size, self.cutoff, self.input_dim, self.factor, self.tied = vocab_size, cutoff, input_dim, factor, tied
+        n_tail = len(cutoff) - 1
+        if tied:
+            self.head = _TiedHead(cutoff[0], input_dim, n_tail)
+        else:
+            self.head = _W(cutoff[0] + n_tail, input_dim)
+        self.tail = nn.ModuleList()
+        for i in range(n_tail):
+            dim = int(input_dim // factor ** (i + 1))
+            proj = _W(input_dim, dim) if tied else _W(dim, input_dim)
+            self.tail.append(nn.Sequential(proj, nn.Dropout(dropout), _W(cutoff[i + 1] - cutoff[i], dim)))
+        self.register_buffer("version", torch.LongTensor([1]))
+        self._prep, self._prep_key = None, None
+
+    def prepare(self, math_mode):
+        key = (math_mode, self.version.device, tuple(int(p._version) for p in self.parameters()))
+        if self._prep is not None and self._prep_key == key:
+            return self._prep
+        if self.tied:
+            head = torch.cat([self.head.word_proj.weight.detach(), self.head.class_proj.weight.detach()], 0)
+        else:
+            head = self.head.weight.detach()
+        P = {"head": _Weight(head, None, math_mode), "proj": [], "out": []}
+        for seq in self.tail:
+            p = seq[0].weight.detach()
+            P["proj"].append(_Weight(p.t() if self.tied else p, None, math_mode))
+            P["out"].append(_Weight(seq[2].weight.detach(), None, math_mode))
+        self._prep, self._prep_key = P, key
+        return P
+
+    @torch.no_grad()
+    def target_log_prob(self, x: torch.Tensor, target: torch.Tensor, math_mode: int = L.MATH_FP32_SIMT) -> torch.Tensor:
+        """log p(target) per row: the only entries of get_log_prob's [T, V] tensor that the scorer reads
+        (adaptive_softmax.py:170-206 + sequence_scorer.py:48-53), computed without materialising it."""
+        x = x.reshape(-1, x.shape[-1])
+        target = target.reshape(-1).contiguous()
+        P = self.prepare(math_mode)
+        head_pick, tail_rows, tail_pick, tail_count = ops.adapt_target(target, self.cutoff)
+        lp = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
+        pm, ps, pk, nt = ops.linear_lse(x, P["head"].W, head_pick, W_lo=P["head"].lo, math=math_mode)
+        ops.lse_finish(pm, ps, pk, nt, lp)
+        for i in range(len(self.tail)):
+            cnt = tail_count[i:i + 1]
+            xi = ops.gather_rows(x, tail_rows[i], n_dev=cnt)
+            hi = ops.linear(xi, P["proj"][i].W, None, W_lo=P["proj"][i].lo, m_dev=cnt, math=math_mode)
+            pm, ps, pk, nt = ops.linear_lse(hi, P["out"][i].W, tail_pick[i], W_lo=P["out"][i].lo, m_dev=cnt, math=math_mode)
+            ops.lse_finish(pm, ps, pk, nt, lp, row_map=tail_rows[i], accumulate=True, m_dev=cnt)
+        return lp
+
+    @torch.no_grad()
+    def get_log_prob(self, input: torch.Tensor, target: Optional[torch.Tensor], math_mode: int = L.MATH_FP32_SIMT):
+        """API-compatibility path: the full [bsz, len, V] tensor of adaptive_softmax.py:170-206 with
+        every column populated (the reference's target=None behaviour; with a target the reference
+        leaves non-target tail columns at 0, which nobody reads).  GEMMs run on the library; the
+        row normalisation uses torch.log_softmax -- do not use on the hot path (it is the tensor this
+        project exists to avoid)."""
+        bsz, length, dim = input.shape
+        x = input.reshape(-1, dim).contiguous()
+        P = self.prepare(math_mode)
+        c0 = self.cutoff[0]
+        head = torch.log_softmax(ops.linear(x, P["head"].W, None, W_lo=P["head"].lo, math=math_mode), dim=1)
+        cols = [head[:, :c0]]
+        for i in range(len(self.tail)):
+            hi = ops.linear(x, P["proj"][i].W, None, W_lo=P["proj"][i].lo, math=math_mode)
+            ti = ops.linear(hi, P["out"][i].W, None, W_lo=P["out"][i].lo, math=math_mode)
+            cols.append(torch.log_softmax(ti, dim=1) + head[:, c0 + i, None])
+        return torch.cat(cols, 1).view(bsz, length, -1)
+
+
+def _get(args, name, default=None):
+    return getattr(args, name, default)
+
+
+class TokenGraphTransformerDecoder(nn.Module):
+    """transformer.py:910-1085.  `dictionary` only needs __len__ and eos()."""
+
+    def __init__(self, args, dictionary, embed_tokens=None, no_encoder_attn=True, quantizer: Optional[TorchPQCodec] = None):
+        super().__init__()
+        self.args = args
+        d = args.decoder_embed_dim
+        self.embed_dim = d
+        self.hgt_etypes = list(ETYPES)
+        self.hgt_decoder = HGT(ntype2idx={"tgt": 0, "ntgt": 1}, etype2idx={"intra": 0, "inter": 1}, in_dim=d,
+                               hidden_dim=_get(args, "decoder_gcn_dim", d), out_dim=d, n_layers=args.graph_layer,
+                               n_heads=args.decoder_attention_heads, dropout=_get(args, "dropout", 0.0), two_stream=False,
+                               attn_drop=_get(args, "attention_dropout", 0.0))
+        self.num_classes = len(dictionary)
+        self.eos_idx = dictionary.eos() if hasattr(dictionary, "eos") else 2
+        if quantizer is not None:
+            self.tgt_quantizer = quantizer
+        elif _get(args, "quantizer_path"):
+            import faiss  # reference behaviour (transformer.py:936-937); absent here -> pass `quantizer`
+            self.tgt_quantizer = TorchPQCodec(index=faiss.read_index(args.quantizer_path))
+        else:
+            self.tgt_quantizer = None
+        self.short_cut = _get(args, "short_cut", False)
+        self.orig_prob_ratio = _get(args, "orig_prob_ratio", 0.0)
+        cut = _get(args, "adaptive_softmax_cutoff")
+        if cut is not None:
+            if isinstance(cut, str):
+                cut = [int(c) for c in cut.split(",")]
+            self.adaptive_softmax = AdaptiveSoftmax(self.num_classes, d, cut, dropout=0.0,
+                                                    factor=_get(args, "adaptive_softmax_factor", 4),
+                                                    tied=bool(_get(args, "tie_adaptive_weights", False)))
+            self.embed_out = None
+        else:
+            self.adaptive_softmax = None
+            self.embed_out = nn.Parameter(torch.empty(self.num_classes, d))       # transformer.py:650-655
+            nn.init.normal_(self.embed_out, mean=0, std=d ** -0.5)
+        self.math_mode = L.MATH_FP32_SIMT
+        self._out_prep, self._out_key = None, None
+
+    def set_math(self, mode):
+        self.math_mode = L.MATH_NAMES[mode] if isinstance(mode, str) else int(mode)
+        self.hgt_decoder.set_math(self.math_mode)
+        return self
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, prev_output_tokens, encoder_out=None, incremental_state=None, features_only=False,
+                alignment_layer=None, alignment_heads=None, src_lengths=None, return_all_hiddens=False,
+                graph: TokenGraph = None):
+        bsz, tgt_len = prev_output_tokens.shape
+        if "h" not in graph.nodes["tgt"].data:
+            raise NotImplementedError("the base transformer is out of scope: evaluate with --use-precompute-feat "
+                                      "(transformer.py:974-976)")
+        x = graph.nodes["tgt"].data["h"]
+        if x.dtype != torch.float32:
+            x = ops.convert(x, torch.float32)                         # token_block_dataset.py:328
+        x = x.view(bsz, tgt_len, -1)
+        extra = {"inner_states": [x.transpose(0, 1)]}
+        orig_x = x if self.orig_prob_ratio > 0 else None
+        if not self.short_cut:
+            x = self.extract_graph_features(x, prev_output_tokens, graph, encoder_out, incremental_state)
+        extra["gcn_feat"] = x.transpose(0, 1)
+        if self.orig_prob_ratio > 0:
+            if self.adaptive_softmax is None:
+                raise NotImplementedError("orig_prob_ratio without adaptive softmax (transformer.py:1002) is unused")
+            extra["orig_x"] = orig_x
+            extra["orig_ratio"] = self.orig_prob_ratio
+        return x, extra      # adaptive softmax: output_layer is the identity (transformer.py:843-852)
+
+    def extract_graph_features(self, tgt_features, prev_output_tokens, graph: TokenGraph, encoder_out=None,
+                               incremental_state=None):
+        bsz, seq_len, h = tgt_features.shape
+        assert encoder_out is None and incremental_state is None, "only support lm"
+        h_tgt = tgt_features.reshape(-1, self.embed_dim)
+        nd = graph.nodes["ntgt"].data
+        mode = self.math_mode
+        NL = self.hgt_decoder.n_layers
+        if "h" in nd and nd["h"].dtype != torch.uint8:               # caller supplied decoded features
+            h_n = nd["h"].float()
+            out = self.hgt_decoder.forward_tgt(graph, h_tgt, h_n)
+        elif "h" in nd:                                               # explicit uint8 code rows (reference layout)
+            h_n = self.tgt_quantizer.decode(nd["h"], math_mode=mode)
+            out = self.hgt_decoder.forward_tgt(graph, h_tgt, h_n)
+        else:                                                         # fused gather from the HBM-resident datastore
+            codes = graph.codes_table
+            if NL == 1:   # only centre nodes are ever read
+                hc0 = self.tgt_quantizer.gather_decode(codes, graph.ntgt_row, row_ids=graph.inter_indices,
+                                                       n_dev=graph.n_valid_dev, math_mode=mode)
+                out = self.hgt_decoder.forward_tgt(graph, h_tgt, None, hc0=hc0)
+            else:
+                h_n = self.tgt_quantizer.gather_decode(codes, graph.ntgt_row, n_cap=graph.node_cap,
+                                                       n_dev=graph.n_ntgt_dev, math_mode=mode)
+                out = self.hgt_decoder.forward_tgt(graph, h_tgt, h_n)
+        return out.view(bsz, seq_len, -1)
+
+    # ------------------------------------------------------------------ probabilities
+    def _plain_out(self):
+        key = (self.math_mode, self.embed_out.device, int(self.embed_out._version))
+        if self._out_prep is None or self._out_key != key:
+            self._out_prep, self._out_key = _Weight(self.embed_out.detach(), None, self.math_mode), key
+        return self._out_prep
+
+    @torch.no_grad()
+    def target_log_probs(self, net_output, target: torch.Tensor) -> torch.Tensor:
+        """Fused fast path: per-token log p(target) [bsz, len], orig/GNN mixing included
+        (transformer.py:1064-1085 evaluated at the target column)."""
+        x, extra = net_output
+        mode = self.math_mode
+        if self.adaptive_softmax is not None:
+            lp = self.adaptive_softmax.target_log_prob(x, target, mode)
+            if "orig_x" in extra:
+                lo = self.adaptive_softmax.target_log_prob(extra["orig_x"], target, mode)
+                lp, _, _ = ops.knn_mix_nll(lp, orig_lp=lo, orig_ratio=self.orig_prob_ratio)
+        else:
+            w = self._plain_out()
+            pm, ps, pk, nt = ops.linear_lse(x.reshape(-1, x.shape[-1]), w.W, target.reshape(-1).to(torch.int32),
+                                            W_lo=w.lo, math=mode)
+            lp = torch.empty(pk.shape[0], device=pk.device, dtype=torch.float32)
+            ops.lse_finish(pm, ps, pk, nt, lp)
+        return lp.view(target.shape)
+
+    @torch.no_grad()
+    def get_normalized_probs(self, net_output, log_probs, sample):
+        """API-compatibility path returning [bsz, len, V] (transformer.py:1064-1085)."""
+        x, extra = net_output
+        if self.adaptive_softmax is not None:
+            target = sample["target"] if sample is not None else None
+            out = self.adaptive_softmax.get_log_prob(x, target, self.math_mode)
+            if "orig_x" in extra:
+                o = self.adaptive_softmax.get_log_prob(extra["orig_x"], target, self.math_mode)
+                a = self.orig_prob_ratio
+                out = torch.logsumexp(torch.stack([o + math.log(a), out + math.log(1 - a)]), 0)
+        else:
+            w = self._plain_out()
+            logits = ops.linear(x.reshape(-1, x.shape[-1]).contiguous(), w.W, None, W_lo=w.lo, math=self.math_mode)
+            out = torch.log_softmax(logits, dim=-1).view(x.shape[0], x.shape[1], -1)
+        return out if log_probs else out.exp_()
+
+    def max_positions(self):
+        return _get(self.args, "max_target_positions", 1 << 30)
+
+
+class TransformerLanguageModel(nn.Module):
+    """`transformer_lm` (transformer_lm.py:27); with graph_layer > 0 the decoder is the graph decoder
+    (:178-182)."""
+
+    def __init__(self, decoder: TokenGraphTransformerDecoder):
+        super().__init__()
+        self.decoder = decoder
+
+    @classmethod
+    def build_model(cls, args, task=None, dictionary=None, quantizer=None):
+        dictionary = dictionary if dictionary is not None else task.source_dictionary
+        if _get(args, "graph_layer", 0) <= 0:
+            raise NotImplementedError("only the --graph_layer > 0 decoder is on the hot path")
+        dec = TokenGraphTransformerDecoder(args, dictionary, None, no_encoder_attn=True, quantizer=quantizer)
+        return cls(dec)
+
+    def forward(self, src_tokens, **kwargs):
+        kwargs.pop("src_lengths", None)
+        return self.decoder(src_tokens, **kwargs)
+
+    def get_normalized_probs(self, net_output, log_probs, sample=None):
+        return self.decoder.get_normalized_probs(net_output, log_probs, sample)
+
+    def max_positions(self):
+        return self.decoder.max_positions()
+
+    def make_generation_fast_(self, **kwargs):
+        return self
+
+    def set_math(self, mode):
+        self.decoder.set_math(mode)
+        return self
+
+    def load_reference_state_dict(self, state_dict: Dict[str, torch.Tensor]):
+        """Strict for every key on the hot path; the bypassed base transformer's keys are ignored."""
+        own = self.state_dict()
+        skip_prefix = ("decoder.layers.", "decoder.embed_tokens.", "decoder.embed_positions.", "decoder.layer_norm.",
+                       "decoder.project_", "decoder.version", "decoder.xl_bias")
+        picked, ignored = {}, []
+        for k, v in state_dict.items():
+            if k in own:
+                picked[k] = v
+            elif k.startswith(skip_prefix):
+                ignored.append(k)
+            else:
+                raise KeyError(f"unexpected key on the hot path: {k}")
+        missing = [k for k in own if k not in picked]
+        if missing:
+            raise KeyError(f"missing keys: {missing[:8]}{'...' if len(missing) > 8 else ''}")
+        self.load_state_dict(picked, strict=True)
+        return ignored
+
+
+def default_args(**kw) -> Namespace:
+    """argparse-style args with the reference flag names (transformer_lm.py:122-139, :206-263)."""
+    a = dict(decoder_embed_dim=512, decoder_attention_heads=8, graph_layer=3, decoder_gcn_dim=None, quantizer_path="",
+             short_cut=False, orig_prob_ratio=0.0, adaptive_softmax_cutoff=None, adaptive_softmax_factor=4,
+             tie_adaptive_weights=False, dropout=0.0, attention_dropout=0.0, max_target_positions=1 << 30)
+    a.update(kw)
+    if a["decoder_gcn_dim"] is None:
+        a["decoder_gcn_dim"] = a["decoder_embed_dim"]
+    return Namespace(**a)

@@ -1,0 +1,170 @@
+"""Thin torch-tensor wrappers over the C ABI (include/gnnlm_sm100.h).
+
+torch is plumbing here: it owns device memory and the current stream; every computation below is
+a call into libgnnlm_sm100.so.  No function in this file has a CPU or torch-op fallback.
+"""
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+_I32 = torch.int32
+
+
+def _dev_count(t: Optional[torch.Tensor]):
+    return L.ptr(t)
+
+
+def linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, *, W_lo: Optional[torch.Tensor] = None,
+           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_dtype=None,
+           m_dev: Optional[torch.Tensor] = None, math: int = L.MATH_FP32_SIMT) -> torch.Tensor:
+    """C = A @ W^T + bias (+ residual).  A [M,K] (row stride arbitrary), W [N,K]."""
+    assert A.dim() == 2 and W.dim() == 2 and A.stride(1) == 1 and W.stride(1) == 1
+    M, K = A.shape
+    N = W.shape[0]
+    assert W.shape[1] == K, (A.shape, W.shape)
+    if out is None:
+        out = torch.empty((M, N), device=A.device, dtype=out_dtype or torch.float32)
+    assert out.stride(1) == 1 and out.shape == (M, N)
+    if residual is not None:
+        assert residual.dtype == torch.float32 and residual.stride(1) == 1
+    L.call("gnnlm_linear", L.ptr(A), L.dtype_code(A.dtype), A.stride(0), L.ptr(W), L.ptr(W_lo), W.stride(0),
+           L.ptr(bias), L.ptr(residual), residual.stride(0) if residual is not None else 0, L.ptr(out),
+           L.dtype_code(out.dtype), out.stride(0), M, _dev_count(m_dev), N, K, math, L.stream_ptr())
+    return out
+
+
+def linear_lse(A, W, pick, *, W_lo=None, m_dev=None, math=L.MATH_FP32_SIMT):
+    """Row log-sum-exp partials + picked column of A @ W^T without materialising it."""
+    M, K = A.shape
+    N = W.shape[0]
+    nt = L.load().gnnlm_lse_num_tiles(N, math)
+    pmax = torch.empty((M, nt), device=A.device, dtype=torch.float32)
+    psum = torch.empty((M, nt), device=A.device, dtype=torch.float32)
+    picked = torch.zeros((M,), device=A.device, dtype=torch.float32)
+    L.call("gnnlm_linear_lse", L.ptr(A), L.dtype_code(A.dtype), A.stride(0), L.ptr(W), L.ptr(W_lo), W.stride(0),
+           L.ptr(pick), L.ptr(pmax), L.ptr(psum), L.ptr(picked), M, _dev_count(m_dev), N, K, math, L.stream_ptr())
+    return pmax, psum, picked, nt
+
+
+def lse_finish(pmax, psum, picked, nt, out, *, row_map=None, accumulate=False, m_dev=None):
+    L.call("gnnlm_lse_finish", L.ptr(pmax), L.ptr(psum), L.ptr(picked), nt, L.ptr(row_map), L.ptr(out),
+           int(accumulate), pmax.shape[0], _dev_count(m_dev), L.stream_ptr())
+    return out
+
+
+def gather_rows(src, ids, n_cap=None, n_dev=None, out=None):
+    n = ids.shape[0] if n_cap is None else n_cap
+    d = src.shape[1]
+    if out is None:
+        out = torch.empty((n, d), device=src.device, dtype=src.dtype)
+    L.call("gnnlm_gather_rows", L.ptr(src), src.stride(0), L.ptr(ids), L.ptr(out), out.stride(0), n,
+           _dev_count(n_dev), d, L.dtype_code(src.dtype), L.stream_ptr())
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None, out_dtype=None, n_dev=None):
+    n, d = x.shape
+    if out is None:
+        out = torch.empty((n, d), device=x.device, dtype=out_dtype or torch.float32)
+    L.call("gnnlm_layernorm", L.ptr(x), x.stride(0), L.ptr(gamma), L.ptr(beta), float(eps), L.ptr(out),
+           L.dtype_code(out.dtype), out.stride(0), n, _dev_count(n_dev), d, L.stream_ptr())
+    return out
+
+
+def convert(src, dst_dtype):
+    src = src.contiguous()
+    out = torch.empty_like(src, dtype=dst_dtype)
+    L.call("gnnlm_convert", L.ptr(src), L.dtype_code(src.dtype), L.ptr(out), L.dtype_code(dst_dtype), src.numel(),
+           L.stream_ptr())
+    return out
+
+
+def split_tf32(w):
+    w = w.contiguous()
+    hi, lo = torch.empty_like(w), torch.empty_like(w)
+    L.call("gnnlm_split_tf32", L.ptr(w), L.ptr(hi), L.ptr(lo), w.numel(), L.stream_ptr())
+    return hi, lo
+
+
+def edge_attn(q, k, v, indptr, indices, H, out, *, dst_ids=None, n_dst=None, n_dst_dev=None, out_scale=1.0,
+              accumulate=False):
+    d = q.shape[1]
+    n = q.shape[0] if n_dst is None else n_dst
+    assert q.dtype == k.dtype == v.dtype and out.dtype == torch.float32
+    L.call("gnnlm_hgt_edge_attn", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0),
+           L.dtype_code(q.dtype), L.ptr(indptr), L.ptr(indices), L.ptr(dst_ids), n, _dev_count(n_dst_dev), H, d // H,
+           L.ptr(out), out.stride(0), float(out_scale), int(accumulate), L.stream_ptr())
+    return out
+
+
+def causal_attn(q, k, v, B, Lb, intra_ctx, H, out, *, out_scale=1.0, accumulate=False):
+    d = q.shape[1]
+    L.call("gnnlm_hgt_causal_attn", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0),
+           L.dtype_code(q.dtype), B, Lb, intra_ctx, H, d // H, L.ptr(out), out.stride(0), float(out_scale),
+           int(accumulate), L.stream_ptr())
+    return out
+
+
+def pq_gather_decode(codes, centroids, rows, *, bias=None, row_ids=None, n_cap=None, n_dev=None, out_dtype=torch.float32,
+                     labels_table=None, want_codes=False, decode=True):
+    n_d, M = codes.shape
+    dsub = centroids.shape[2]
+    n = (row_ids.shape[0] if row_ids is not None else rows.shape[0]) if n_cap is None else n_cap
+    dev = codes.device
+    out = torch.empty((n, M * dsub), device=dev, dtype=out_dtype) if decode else None
+    labels = torch.empty((n,), device=dev, dtype=torch.int64) if labels_table is not None else None
+    codes_out = torch.empty((n, M), device=dev, dtype=torch.uint8) if want_codes else None
+    lb = 0
+    if labels_table is not None:
+        lb = {torch.int16: 2, torch.int32: 4}[labels_table.dtype]
+    L.call("gnnlm_pq_gather_decode", L.ptr(codes), n_d, M, L.ptr(centroids), dsub,
+           L.ptr(bias) if bias is not None and bias.numel() else None, L.ptr(rows), L.ptr(row_ids), n, _dev_count(n_dev),
+           L.ptr(out), L.dtype_code(out_dtype), M * dsub, L.ptr(labels_table), lb, L.ptr(labels), L.ptr(codes_out),
+           L.stream_ptr())
+    return out, labels, codes_out
+
+
+def adapt_target(target, cutoff):
+    """target [T] int64 (device), cutoff: python list ending with vocab size."""
+    T = target.numel()
+    nt = len(cutoff) - 1
+    dev = target.device
+    head_pick = torch.empty((T,), device=dev, dtype=_I32)
+    tail_rows = torch.empty((max(nt, 1), T), device=dev, dtype=_I32)
+    tail_pick = torch.empty((max(nt, 1), T), device=dev, dtype=_I32)
+    tail_count = torch.zeros((max(nt, 1),), device=dev, dtype=_I32)
+    import ctypes as C
+    arr = (C.c_int64 * len(cutoff))(*cutoff)
+    L.call("gnnlm_adapt_target", L.ptr(target), T, C.cast(arr, C.c_void_p), len(cutoff), L.ptr(head_pick),
+           L.ptr(tail_rows), L.ptr(tail_pick), L.ptr(tail_count), L.stream_ptr())
+    return head_pick, tail_rows, tail_pick, tail_count
+
+
+def knn_mix_nll(lm_lp, *, target=None, dists=None, ids=None, vals=None, n_datastore=0, sim_sign=1.0, temperature=1.0,
+                lmbda=0.0, orig_lp=None, orig_ratio=0.0, weight=None, nll_acc=None, want_knn=False):
+    T = lm_lp.numel()
+    dev = lm_lp.device
+    out_lp = torch.empty((T,), device=dev, dtype=torch.float32)
+    use_knn = dists is not None and lmbda > 0
+    knn_p = torch.empty((T,), device=dev, dtype=torch.float32) if (use_knn and want_knn) else None
+    recall = torch.empty((T,), device=dev, dtype=_I32) if (use_knn and want_knn) else None
+    vb = 0
+    if use_knn:
+        vb = {torch.int16: 2, torch.int32: 4}[vals.dtype]
+        assert dists.dtype == torch.float32 and ids.dtype == torch.int64 and dists.is_contiguous() and ids.is_contiguous()
+    L.call("gnnlm_knn_mix_nll", L.ptr(lm_lp), L.ptr(orig_lp), float(orig_ratio), L.ptr(dists) if use_knn else None,
+           L.ptr(ids) if use_knn else None, dists.shape[1] if use_knn else 0, L.ptr(vals) if use_knn else None, vb,
+           n_datastore, L.ptr(target), float(sim_sign), float(temperature), float(lmbda), L.ptr(weight),
+           L.ptr(out_lp), L.ptr(knn_p), L.ptr(recall), L.ptr(nll_acc), T, L.stream_ptr())
+    return out_lp, knn_p, recall
+
+
+def knn_full_prob(dists, ids, vals, vocab, n_datastore, sim_sign=1.0, temperature=1.0):
+    T, k = dists.shape
+    probs = torch.empty((T, vocab), device=dists.device, dtype=torch.float32)
+    vb = {torch.int16: 2, torch.int32: 4}[vals.dtype]
+    L.call("gnnlm_knn_full_prob", L.ptr(dists), L.ptr(ids), k, L.ptr(vals), vb, n_datastore, float(sim_sign),
+           float(temperature), L.ptr(probs), vocab, T, L.stream_ptr())
+    return probs

@@ -1,0 +1,91 @@
+"""Product-quantisation codec -- host-side mirror of knn/pq_wrapper.py:87-203 (TorchPQCodec) with
+the same buffer names (`A`, `b`, `centroids_torch`, `norm2_centroids_torch`, `sdc_table_torch`;
+fairseq_cli/convert_ckpt.py:40-45 injects exactly these under decoder.tgt_quantizer.*), so the codec
+loads from the checkpoint and faiss is not needed at evaluation time.
+
+decode() runs on libgnnlm_sm100.so: TMA-staged codebook gather (pq_decode.cu) + the OPQ inverse
+rotation as a GEMM with W = A^T."""
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+
+
+class TorchPQCodec(nn.Module):
+    def __init__(self, centroids=None, A=None, b=None, index=None, metric: str = "ip"):
+        """centroids [M, 256, dsub]; optional OPQ pre-transform (A [d_out, d_in], b [d_out] or empty).
+        `index` (a faiss IndexPreTransform / IndexPQ) is accepted for signature parity when faiss is
+        importable; the arrays are extracted exactly as pq_wrapper.py:20-37 does."""
+        super().__init__()
+        if index is not None:
+            centroids, A, b = _arrays_from_faiss(index)
+        centroids = torch.as_tensor(np.asarray(centroids), dtype=torch.float32)
+        assert centroids.dim() == 3 and centroids.shape[1] == 256, "8-bit PQ expected (pq_wrapper.py:36)"
+        self.metric = metric
+        self.pre_torch = A is not None
+        if self.pre_torch:
+            self.register_buffer("A", torch.as_tensor(np.asarray(A), dtype=torch.float32))
+            self.register_buffer("b", torch.as_tensor(np.asarray(b if b is not None else np.zeros(0)), dtype=torch.float32))
+        self.register_buffer("centroids_torch", centroids)
+        self.register_buffer("norm2_centroids_torch", (centroids ** 2).sum(2))
+        if metric == "l2":
+            sdc = -torch.sqrt(((centroids.unsqueeze(2) - centroids.unsqueeze(1)) ** 2).sum(3))
+        else:
+            sdc = torch.matmul(centroids, centroids.transpose(1, 2))
+        self.register_buffer("sdc_table_torch", sdc)
+        self._rot = None
+        self._rot_key = None
+
+    @property
+    def M(self):
+        return self.centroids_torch.shape[0]
+
+    @property
+    def dsub(self):
+        return self.centroids_torch.shape[2]
+
+    def _rotation(self, math_mode):
+        """W = A^T so that x @ A == linear(x, W) (pq_wrapper.py:202)."""
+        from .hgt import _Weight
+        key = (math_mode, self.A.device, int(self.A._version))
+        if self._rot is None or self._rot_key != key:
+            self._rot, self._rot_key = _Weight(self.A.t().contiguous(), None, math_mode), key
+        return self._rot
+
+    @torch.no_grad()
+    def gather_decode(self, codes_table: torch.Tensor, rows: torch.Tensor, *, row_ids: Optional[torch.Tensor] = None,
+                      n_cap: Optional[int] = None, n_dev: Optional[torch.Tensor] = None,
+                      math_mode: int = L.MATH_FP32_SIMT) -> torch.Tensor:
+        """Fused `quant_neighbor_feats[rows]` + decode: codes_table [N_d, M] uint8 in HBM."""
+        b = self.b if self.pre_torch and self.b.numel() > 0 else None
+        x, _, _ = ops.pq_gather_decode(codes_table, self.centroids_torch, rows, bias=b, row_ids=row_ids, n_cap=n_cap,
+                                       n_dev=n_dev)
+        if self.pre_torch:
+            w = self._rotation(math_mode)
+            x = ops.linear(x, w.W, None, W_lo=w.lo, m_dev=n_dev, math=math_mode)
+        return x
+
+    @torch.no_grad()
+    def decode(self, codes: torch.Tensor, math_mode: int = L.MATH_FP32_SIMT) -> torch.Tensor:
+        """codes [n, M] uint8 -> [n, M*dsub] (pq_wrapper.py:169-203)."""
+        n, MM = codes.shape
+        assert MM == self.M, f"input codes have {MM} subspace, but quantizer have {self.M} subspace"
+        rows = torch.arange(n, device=codes.device, dtype=torch.int64)
+        return self.gather_decode(codes.contiguous(), rows, math_mode=math_mode)
+
+
+def _arrays_from_faiss(index):
+    import faiss  # noqa: only when the caller really has a faiss index
+    A = b = None
+    if isinstance(index, faiss.IndexPreTransform):
+        vt = faiss.downcast_VectorTransform(index.chain.at(0))
+        b = faiss.vector_to_array(vt.b)
+        A = faiss.vector_to_array(vt.A).reshape(vt.d_out, vt.d_in)
+        index = faiss.downcast_index(index.index)
+    pq = index.pq
+    cen = faiss.vector_to_array(pq.centroids).reshape(pq.M, pq.ksub, pq.dsub)
+    return cen, A, b

@@ -1,0 +1,145 @@
+"""Seeded synthetic problems of the shapes BASELINE.json names: random-init weights
+initialised like the reference modules, uniform tokens / codes / neighbour ids, N(0,1) features.
+Used by bench.py, __graft_entry__.smoke() and the tests.  No oracle imports here."""
+from argparse import Namespace
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import ops
+from .dataset import DeviceDatastore
+from .graph import build_token_graph
+from .knn_model import KNNModel
+from .model import TransformerLanguageModel, default_args
+from .pq_codec import TorchPQCodec
+from .sequence_scorer import SequenceScorer
+
+CONFIGS = {
+    # BASELINE.json configs[0]: tiny, CPU-runnable
+    "c1": dict(d=512, H=8, V=10000, cutoff=[2000, 6000], tied=False, B=2, L=256, k=8, c=1, M=64, NL=1, n_d=1 << 20,
+               k_nn=64, lmbda=0.25, temp=1.0),
+    # configs[1]: enwik8 shape (char vocab, plain softmax)
+    "c2": dict(d=512, H=8, V=204, cutoff=None, tied=False, B=1, L=512, k=32, c=1, M=64, NL=3, n_d=1 << 24,
+               k_nn=1024, lmbda=0.25, temp=1.0),
+    # configs[2]: wiki103 shape (the headline metric's config)
+    "c3": dict(d=1024, H=8, V=267744, cutoff=[20000, 60000], tied=True, B=1, L=3072, k=32, c=1, M=128, NL=3,
+               n_d=103227021, k_nn=1024, lmbda=0.25, temp=1.0),
+    # a small wiki103-like problem for tests (adaptive, tied, 3 layers)
+    "c3mini": dict(d=1024, H=8, V=30000, cutoff=[4000, 12000], tied=True, B=1, L=192, k=8, c=1, M=128, NL=3,
+                   n_d=1 << 18, k_nn=128, lmbda=0.25, temp=1.0),
+}
+
+
+class Dictionary:
+    def __init__(self, n):
+        self.n = n
+
+    def __len__(self):
+        return self.n
+
+    def pad(self):
+        return 1
+
+    def eos(self):
+        return 2
+
+
+def make_model(cfg: dict, seed: int = 1) -> TransformerLanguageModel:
+    """Random-init model on the CPU, `torch.manual_seed(seed)` like the scripts' --seed 1."""
+    torch.manual_seed(seed)
+    c = SimpleNamespace(**cfg)
+    rng = np.random.RandomState(seed)
+    dsub = c.d // c.M
+    cen = rng.randn(c.M, 256, dsub).astype(np.float32)
+    A = np.linalg.qr(rng.randn(c.d, c.d))[0].astype(np.float32)
+    codec = TorchPQCodec(centroids=cen, A=A, b=np.zeros(0, np.float32))
+    args = default_args(decoder_embed_dim=c.d, decoder_attention_heads=c.H, graph_layer=c.NL,
+                        adaptive_softmax_cutoff=c.cutoff, tie_adaptive_weights=c.tied)
+    model = TransformerLanguageModel.build_model(args, dictionary=Dictionary(c.V), quantizer=codec)
+    with torch.no_grad():   # make biases / pri / LN affine non-trivial so that parity exercises them
+        for n_, p in model.named_parameters():
+            if p.dim() == 1 or n_.endswith("relation_pri"):
+                p.add_(0.05 * torch.randn_like(p))
+    return model.eval()
+
+
+def make_data(cfg: dict, seed: int = 0, n_d: int = None, device="cpu", stress: bool = True) -> dict:
+    """One batch of inputs.  Large tables (codes, vals) are generated directly on `device`."""
+    c = SimpleNamespace(**cfg)
+    n_d = n_d or c.n_d
+    g = torch.Generator(device=device).manual_seed(seed)
+    T = c.B * c.L
+    codes = torch.randint(0, 256, (n_d, c.M), generator=g, device=device, dtype=torch.uint8)
+    vals = torch.randint(4, c.V, (n_d,), generator=g, device=device, dtype=torch.int32)
+    nbr = torch.randint(c.c, n_d - c.c, (c.B, c.L, c.k), generator=g, device=device, dtype=torch.int64)
+    if stress:   # 1% missing, 0.1% within c of either boundary
+        r = torch.rand((c.B, c.L, c.k), generator=g, device=device)
+        nbr[r < 0.01] = -1
+        edge = (r >= 0.01) & (r < 0.011)
+        nbr[edge] = torch.where(torch.rand(int(edge.sum()), generator=g, device=device) < 0.5, 0, n_d - 1)
+    feats = torch.randn((T, c.d), generator=g, device=device).half()
+    target = torch.randint(4, c.V, (c.B, c.L), generator=g, device=device, dtype=torch.int64)
+    dists = torch.randn((T, c.k_nn), generator=g, device=device)
+    ids = torch.randint(0, n_d, (T, c.k_nn), generator=g, device=device, dtype=torch.int64)
+    ids[torch.rand((T, c.k_nn), generator=g, device=device) < 0.002] = -1
+    # make a share of the retrieved values hit the target, as a real datastore would
+    hit = torch.rand((T,), generator=g, device=device) < 0.5
+    j = torch.randint(0, c.k_nn, (T,), generator=g, device=device)
+    rows = ids[torch.arange(T, device=device), j]
+    ok = hit & (rows >= 0)
+    flat_t = target.reshape(-1).clone()
+    flat_t[ok] = vals[rows[ok]].long()
+    target = flat_t.view(c.B, c.L)
+    return dict(codes=codes, vals=vals, nbr=nbr, feats=feats, target=target, knn_dists=dists, knn_ids=ids, n_d=n_d,
+                positions=torch.arange(T, device=device).view(c.B, c.L))
+
+
+def to_device(data: dict, device) -> dict:
+    return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in data.items()}
+
+
+class Runner:
+    """The call a user makes per batch, on device-resident tables: graph assembly -> PQ decode -> HGT ->
+    log-probs -> kNN mix -> NLL accumulation.  `step(host_batch)` is the e2e variant (pinned host
+    inputs, H2D inside)."""
+
+    def __init__(self, cfg: dict, model: TransformerLanguageModel, data: dict, device, math: str = "fp32"):
+        self.cfg, self.c, self.device = cfg, SimpleNamespace(**cfg), device
+        self.model = model.to(device).set_math(math)
+        self.dstore = DeviceDatastore(data["codes"].to(device), data["vals"].to(device))
+        self.knn = KNNModel(self.dstore.vals, vocab_size=self.c.V, metric_type="do_not_recomp_ip", k=self.c.k_nn)
+        self.args = Namespace(lmbda=self.c.lmbda, knn_keytype=None)
+        self.scorer = SequenceScorer(Dictionary(self.c.V), args=self.args)
+        self.acc = torch.zeros(2, dtype=torch.float64, device=device)
+
+    def sample_from(self, nbr, feats, target, dists, ids):
+        c = self.c
+        g = build_token_graph(nbr, self.dstore.size, c.c, c.c)
+        g.codes_table = self.dstore.codes
+        g.nodes["tgt"].data["h"] = feats.view(-1, feats.shape[-1])
+        self.knn.set_search_results(dists, ids)
+        return {"net_input": {"src_tokens": target, "graph": g}, "target": target, "ntokens": target.numel()}
+
+    def step_resident(self, dev_batch: dict, want_knn=False):
+        s = self.sample_from(dev_batch["nbr"], dev_batch["feats"], dev_batch["target"], dev_batch["knn_dists"],
+                             dev_batch["knn_ids"])
+        return self.scorer.score_tokens(self.model, s, self.knn, self.c.temp, nll_acc=self.acc, want_knn=want_knn)
+
+    def step_host(self, host_batch: dict):
+        """host_batch: pinned CPU tensors.  Copies in, scores, reads the scalar result back."""
+        nb = lambda k: host_batch[k].to(self.device, non_blocking=True)
+        s = self.sample_from(nb("nbr"), nb("feats"), nb("target"), nb("knn_dists"), nb("knn_ids"))
+        self.scorer.score_tokens(self.model, s, self.knn, self.c.temp, nll_acc=self.acc)
+        return self.acc.cpu()     # D2H read of the step's result (16 B), synchronises
+
+
+def run_gpu(cfg, model, data, device, math="fp32") -> dict:
+    r = Runner(cfg, model, data, device, math)
+    d = to_device({k: data[k] for k in ("nbr", "feats", "target", "knn_dists", "knn_ids")}, device)
+    lp, p, rec, dec_out = r.step_resident(d, want_knn=True)
+    s, n = r.acc.tolist()
+    nll2 = -s / n / np.log(2)
+    return {"logprob": lp.reshape(-1).cpu().numpy(), "knn_prob": p.cpu().numpy(), "recall": rec.cpu().numpy(),
+            "score_sum": s, "count": int(n), "ppl": float(2 ** nll2), "nll": -s / n,
+            "gcn_feat": dec_out[0].reshape(-1, dec_out[0].shape[-1]).cpu().numpy()}

@@ -1,0 +1,222 @@
+/*
+ * libgnnlm_sm100.so -- C ABI of the B200-native GNN-LM evaluation hot path.
+ *
+ * The reference (ShannonAI/GNN-LM) has no FFI: its boundary is fairseq's Python plugin API and its
+ * hot-path arithmetic lives in DGL / ATen / cuBLAS calls made from Python.  This header is the
+ * boundary a maintainer binds with ctypes; every entry point cites the
+ * reference call it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - extern "C", POD arguments only: device pointers, int64 sizes, int32 enums, cudaStream_t last.
+ *   - Every function returns int32: 0 = ok, >0 = cudaError_t, <0 = argument/shape error
+ *     (GNNLM_E_*).  gnnlm_last_error() returns a thread-local message for the last failure.
+ *   - No allocation, no ownership transfer, no hidden synchronisation: the caller owns every buffer
+ *     (workspaces are sized by the *_workspace_bytes queries) and every launch goes to `stream`.
+ *   - Row counts that are only known on the device after graph assembly (number of ntgt nodes,
+ *     number of valid neighbours, rows per adaptive-softmax cluster) are passed twice: a host-side
+ *     capacity `*_cap` used to size grids, and an optional device pointer `*_dev` (int32) holding
+ *     the true count; kernels process min(cap, *dev) rows.  Pass NULL when the host count is exact.
+ *   - All matrices are row-major with an explicit leading dimension in ELEMENTS.
+ */
+#ifndef GNNLM_SM100_H
+#define GNNLM_SM100_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* gnnlm_stream_t; /* == cudaStream_t */
+
+/* element types */
+#define GNNLM_F32 0
+#define GNNLM_BF16 1
+#define GNNLM_F16 2
+
+/* argument errors */
+#define GNNLM_E_ARG (-1)
+#define GNNLM_E_SHAPE (-2)
+#define GNNLM_E_UNSUPPORTED (-3)
+#define GNNLM_E_WORKSPACE (-4)
+
+/* GEMM arithmetic modes (gnnlm_linear*, `math` argument) */
+#define GNNLM_MATH_FP32_SIMT 0  /* fp32 FMA on CUDA cores: strict-parity / validation mode      */
+#define GNNLM_MATH_TF32X3 1     /* tcgen05 kind::tf32, 3-pass split (hi*hi + hi*lo + lo*hi)      */
+#define GNNLM_MATH_TF32 2       /* tcgen05 kind::tf32, single pass                              */
+#define GNNLM_MATH_BF16 3       /* tcgen05 kind::f16 with bf16 operands, fp32 accumulate        */
+
+int32_t gnnlm_version(void);
+const char* gnnlm_last_error(void);
+/* 1 when the library was built with the tcgen05/TMA GEMM and the device is sm_100. */
+int32_t gnnlm_has_tcgen05(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Graph assembly -- replaces GraphTokenBlockDataset.new_build_graph
+ *     (fairseq/data/token_block_dataset.py:338-412), build_ntgt_edges (:545-584),
+ *     auto_regressive_edges (:586-594) and dgl.batch (fairseq/data/monolingual_dataset.py:261).
+ *
+ *  nbr      [T, k] int64  neighbour datastore rows per target token, -1 = missing
+ *                         (= neighbor_offsets[offsets], token_block_dataset.py:309)
+ *  tgt_pos  [T]    int64  stream position of each target token (`offsets`); only read when
+ *                         invalid_ctx > 0 (token_block_dataset.py:361), may be NULL otherwise
+ *  Node numbering is the reference's: tgt id = b*L + t; ntgt ids in creation order (tgt-major,
+ *  neighbour-rank-major, centre, then left context ascending, then right context ascending).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Pass 1: per (token, neighbour) cluster sizes and their exclusive scans.
+ *  node_base  [T*k + 1] int32  first ntgt id of each cluster; node_base[T*k]  = n_ntgt
+ *  valid_base [T*k + 1] int32  #valid clusters before;        valid_base[T*k] = n_valid
+ *  workspace: gnnlm_graph_workspace_bytes(T*k) bytes. */
+int64_t gnnlm_graph_workspace_bytes(int64_t n_clusters);
+int32_t gnnlm_graph_count(const int64_t* nbr, const int64_t* tgt_pos, int64_t T, int64_t k,
+                          int64_t n_datastore, int32_t left_ctx, int32_t right_ctx, int64_t invalid_ctx,
+                          int32_t* node_base, int32_t* valid_base, void* workspace, int64_t workspace_bytes,
+                          gnnlm_stream_t stream);
+
+/* Pass 2: node tables and the canonical CSRs (COO in reference insertion order, stable-sorted by
+ * destination).  Capacity of the per-node outputs is node_cap = T*k*(1+left_ctx+right_ctx).
+ *  ntgt_row     [node_cap]   int64  datastore row of every ntgt node
+ *  ntgt_owner   [node_cap]   int32  tgt id whose neighbour produced the node        (nullable)
+ *  ntgt_dist    [node_cap]   int32  |sorted position - centre position| in cluster  (nullable)
+ *  nn_indptr    [node_cap+1] int32, nn_indices [3*node_cap] int32   ('ntgt','intra','ntgt')
+ *  inter_indptr [T+1] int32,        inter_indices [T*k] int32       ('ntgt','inter','tgt'); the
+ *               indices are exactly the centre-node ids in creation order. */
+int32_t gnnlm_graph_fill(const int64_t* nbr, const int64_t* tgt_pos, int64_t T, int64_t k,
+                         int64_t n_datastore, int32_t left_ctx, int32_t right_ctx, int64_t invalid_ctx,
+                         const int32_t* node_base, const int32_t* valid_base, int64_t* ntgt_row,
+                         int32_t* ntgt_owner, int32_t* ntgt_dist, int32_t* nn_indptr, int32_t* nn_indices,
+                         int32_t* inter_indptr, int32_t* inter_indices, gnnlm_stream_t stream);
+
+/* ('tgt','intra','tgt') CSR, materialised only for parity checks (the attention kernel treats it as
+ * implicit causal).  n_edges = B * sum_v min(v+1, intra_ctx or inf).  indptr [B*L+1], indices [E]. */
+int64_t gnnlm_graph_tt_num_edges(int64_t B, int64_t L, int64_t intra_ctx);
+int32_t gnnlm_graph_tt_csr(int64_t B, int64_t L, int64_t intra_ctx, int32_t* indptr, int32_t* indices,
+                           gnnlm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Datastore gather + PQ decode -- replaces `quant_neighbor_feats[offset]` /
+ *     `neighbor_tokens[offset]` (token_block_dataset.py:369-371,392-394) and the centroid gather of
+ *     TorchPQCodec.decode (knn/pq_wrapper.py:169-196).  `x -= b` (:200-201) is fused when bias != NULL;
+ *     the OPQ rotation `x @ A` (:202) is a gnnlm_linear call with W = A^T.
+ *
+ *  codes      [n_datastore, M] uint8 (quantized-keys.npy), centroids [M, 256, dsub] fp32
+ *  rows       [n_cap] int64 datastore rows (ntgt_row), optionally indirected through
+ *             row_ids [n_cap] int32 (process rows[row_ids[i]]; e.g. centre nodes only)
+ *  out        [n_cap, M*dsub] out_dtype, leading dimension ld_out
+ *  labels_table [n_datastore] int16/int32 (vals.npy; label_bytes = 2|4) -> labels_out [n_cap] int64
+ *             (nullable pair; `ntgt.labels`, token_block_dataset.py:410)
+ *  codes_out  [n_cap, M] uint8 gathered code rows (nullable; `ntgt.h`, :408-409) */
+int32_t gnnlm_pq_gather_decode(const uint8_t* codes, int64_t n_datastore, int32_t M, const float* centroids,
+                               int32_t dsub, const float* bias, const int64_t* rows, const int32_t* row_ids,
+                               int64_t n_cap, const int32_t* n_dev, void* out, int32_t out_dtype,
+                               int64_t ld_out, const void* labels_table, int32_t label_bytes,
+                               int64_t* labels_out, uint8_t* codes_out, gnnlm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) Dense projections -- replace the nn.Linear / einsum calls of HGTLayer.forward
+ *     (fairseq/models/hgt.py:320-322,347-348,401), the OPQ rotation (knn/pq_wrapper.py:202) and the
+ *     adaptive-softmax projections (fairseq/modules/adaptive_softmax.py:184,197,202).
+ *
+ *  C[m, n] = sum_k A[m, k] * W[n, k] + bias[n] (+ residual[m, n])          (nn.Linear layout)
+ *  A [M, K] a_dtype lda; W [N, K] (same dtype as A) ldw; bias fp32 [N] nullable; residual fp32
+ *  [M, N] ldr nullable; C c_dtype ldc.  For GNNLM_MATH_TF32X3, W_lo is the low half of the split
+ *  (W - tf32(W)), prepared once by gnnlm_split_tf32; NULL otherwise. */
+int32_t gnnlm_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, gnnlm_stream_t stream);
+int32_t gnnlm_linear(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, int64_t ldw,
+                     const float* bias, const float* residual, int64_t ldr, void* C, int32_t c_dtype,
+                     int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, int64_t K, int32_t math,
+                     gnnlm_stream_t stream);
+
+/* Same contraction, but instead of storing C the epilogue keeps, per row and per column tile,
+ * (max, sum exp(x - max)) and the single column `pick[m]` -- the [rows, vocab] tensor of
+ * AdaptiveSoftmax.get_log_prob (adaptive_softmax.py:184-203) is never written.
+ *  pick [M] int32 column to extract per row (-1: none); part_max / part_sum [M, n_tiles] fp32 with
+ *  n_tiles = gnnlm_lse_num_tiles(N, math); picked [M] fp32. */
+int64_t gnnlm_lse_num_tiles(int64_t N, int32_t math);
+int32_t gnnlm_linear_lse(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo,
+                         int64_t ldw, const int32_t* pick, float* part_max, float* part_sum, float* picked,
+                         int64_t M, const int32_t* m_dev, int64_t N, int64_t K, int32_t math,
+                         gnnlm_stream_t stream);
+/* out[row_map ? row_map[m] : m] (+)= picked[m] - logsumexp_m   (log-softmax at the picked column). */
+int32_t gnnlm_lse_finish(const float* part_max, const float* part_sum, const float* picked, int64_t n_tiles,
+                         const int32_t* row_map, float* out, int32_t accumulate, int64_t M,
+                         const int32_t* m_dev, gnnlm_stream_t stream);
+
+/* Row utilities used between stages. */
+/* dst[i, :] = src[ids[i], :]  (n x d elements of `dtype`) */
+int32_t gnnlm_gather_rows(const void* src, int64_t ld_src, const int32_t* ids, void* dst, int64_t ld_dst,
+                          int64_t n_cap, const int32_t* n_dev, int64_t d, int32_t dtype, gnnlm_stream_t stream);
+/* y = LayerNorm(x) * gamma + beta over the last dim (hgt.py:404-405; eps as nn.LayerNorm, 1e-5).
+ * x fp32 [n, d]; y out_dtype. In-place allowed when out_dtype == F32. */
+int32_t gnnlm_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y,
+                        int32_t out_dtype, int64_t ldy, int64_t n_cap, const int32_t* n_dev, int64_t d,
+                        gnnlm_stream_t stream);
+/* Convert fp16/fp32 rows (keys.npy slices, token_block_dataset.py:327-329) to fp32/bf16. */
+int32_t gnnlm_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n,
+                      gnnlm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (4) HGT edge attention -- replaces, per edge type, apply_edges(fn.v_dot_u) (hgt.py:354), the
+ *     relation_pri / sqrt(d_k) scaling (:355; folded into K' by the caller), dgl.ops.edge_softmax
+ *     (:356), and multi_update_all(u_mul_e, sum, cross_reducer='mean') (:383-386).
+ *     One warp per destination: shuffle reductions, online segmented softmax, no atomics.
+ *
+ *  out[dst] (+)= out_scale * sum_{e -> dst} softmax_dst(<q[dst,h,:], k[src_e,h,:]>)_e * v[src_e,h,:]
+ *  q [n_dst, H*d_k] ldq; k, v [n_src, H*d_k] ldk, ldv; dtype F32 or BF16 for q/k/v; out fp32 ldo.
+ *  CSR by destination: indptr [n_rows+1], indices [E] (NULL indices => source id = edge id, i.e.
+ *  contiguous ranges); dst_ids [n_dst] nullable: the CSR row (node id) of the i-th processed
+ *  destination (q and out rows are then compact, i = 0..n_dst).  Zero in-degree => contributes 0. */
+int32_t gnnlm_hgt_edge_attn(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                            int32_t dtype, const int32_t* indptr, const int32_t* indices,
+                            const int32_t* dst_ids, int64_t n_dst_cap, const int32_t* n_dst_dev, int32_t H,
+                            int32_t d_k, float* out, int64_t ldo, float out_scale, int32_t accumulate,
+                            gnnlm_stream_t stream);
+
+/* ('tgt','intra','tgt') as implicit causal attention inside each of B blocks of L tokens
+ * (edges u -> v for u <= v, v - u < intra_ctx when intra_ctx > 0; token_block_dataset.py:586-594). */
+int32_t gnnlm_hgt_causal_attn(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v,
+                              int64_t ldv, int32_t dtype, int64_t B, int64_t L, int64_t intra_ctx, int32_t H,
+                              int32_t d_k, float* out, int64_t ldo, float out_scale, int32_t accumulate,
+                              gnnlm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (5) Adaptive-softmax bookkeeping + kNN-LM interpolation + NLL -- replaces adapt_target
+ *     (adaptive_softmax.py:122-145), KNNModel.get_knn_prob minus the faiss search
+ *     (knn/knn_model.py:187-217), combine_knn_and_vocab_probs (fairseq/sequence_scorer.py:55-68),
+ *     combinetow_probs (fairseq/models/transformer.py:1055-1062) and the score accumulation of
+ *     fairseq_cli/eval_lm.py:273-274.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* cutoff [n_cut] int64 on the HOST (n_cut = 1 + #tails, last = vocab). For every token:
+ *  head_pick [T] = target if target < cutoff[0] else cutoff[0] + cluster;
+ *  for tail i: rows_i = tokens whose target is in [cutoff[i], cutoff[i+1]) in ascending order,
+ *  tail_rows [(n_cut-1), T] int32, tail_pick [(n_cut-1), T] int32 (= target - cutoff[i]),
+ *  tail_count [n_cut-1] int32.  Order inside a cluster is ascending token id (deterministic). */
+int32_t gnnlm_adapt_target(const int64_t* target, int64_t T, const int64_t* cutoff_host, int32_t n_cut,
+                           int32_t* head_pick, int32_t* tail_rows, int32_t* tail_pick, int32_t* tail_count,
+                           gnnlm_stream_t stream);
+
+/* Per token: p_knn = sum_j softmax(sims/T)_j [vals[ids_j] == target] with ids == -1 masked
+ * (sims = dists * sim_sign: +1 do_not_recomp_ip, -1 do_not_recomp_l2); recall = #matches;
+ * lp = logsumexp(lm_lp + ln(1-lambda), ln(p_knn + 1e-10) + ln(lambda)).  lambda == 0 or dists == NULL
+ * => lp = lm_lp.  Optional orig-LM mixing first: lm_lp = logsumexp(orig_lp + ln(a), lm_lp + ln(1-a)).
+ * Accumulates sum(lp * weight) and sum(weight) into nll_acc[0..1] (fp64, device) when non-NULL;
+ * weight [T] fp32 nullable (1 everywhere; 0 masks pad / context-window tokens).
+ *  vals: int16/int32 table (val_bytes = 2|4). */
+int32_t gnnlm_knn_mix_nll(const float* lm_lp, const float* orig_lp, float orig_ratio, const float* dists,
+                          const int64_t* ids, int64_t k_nn, const void* vals, int32_t val_bytes,
+                          int64_t n_datastore, const int64_t* target, float sim_sign, float temperature,
+                          float lambda, const float* weight, float* out_lp, float* out_knn_prob,
+                          int32_t* out_recall, double* nll_acc, int64_t T, gnnlm_stream_t stream);
+
+/* Full-vocabulary kNN distribution (knn_model.py:202-208): probs [T, V] fp32, zero-filled by the
+ * callee, += softmax weights at vals[ids]; kept for API parity with get_knn_prob(targets=None). */
+int32_t gnnlm_knn_full_prob(const float* dists, const int64_t* ids, int64_t k_nn, const void* vals,
+                            int32_t val_bytes, int64_t n_datastore, float sim_sign, float temperature,
+                            float* probs, int64_t V, int64_t T, gnnlm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNLM_SM100_H */
