@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- eval tokens/s of the GNN-LM hot path (graph assembly + PQ gather/decode -> HGT ->
+adaptive-softmax log-probs -> kNN-LM mix -> NLL) on synthetic data of the Wiki103 shape
+(BASELINE.json configs[2]: d=1024, H=8, V=267,744, cutoffs 20000/60000, L=3072, k=32, c=1, M=128, 3 HGT
+layers, k_nn=1024), one process per GPU.
+
+  python bench.py [--gpus N --steps K --warmup W] [--config c3] [--math tf32x3|fp32|tf32|bf16]
+  python bench.py --impl reference ...      # the CPU restatement of the reference path (oracle/) on host cores
+
+A "step" is one pass of the hot path over one batch (B blocks x L tokens).  `value` is measured with all
+inputs resident in HBM; `e2e` goes through the same public call with pinned HOST inputs (H2D inside the
+timed region, 16 B result read back per step).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=8)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--config", default="c3")
+    p.add_argument("--math", default="auto")
+    p.add_argument("--n-datastore", type=int, default=0, help="override datastore rows (default: the config's)")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-tokens", type=int, default=384, help="tokens in the CPU-baseline sample block")
+    return p.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU legs
+def cpu_sample(cfg_name, n_tokens, n_d=1 << 22):
+    """Bounded sample of the same workload for the CPU oracle: one block of n_tokens tokens with the
+    config's d / V / k / c / M / layers / k_nn and a 2^22-row datastore (the CPU cost per token does not
+    depend on the datastore size)."""
+    from tests.synth import make_problem
+    from gnnlm_b200 import synth
+    cfg = dict(synth.CONFIGS[cfg_name])
+    cfg.update(B=1, L=n_tokens, n_d=min(cfg["n_d"], n_d))
+    model = synth.make_model(cfg)
+    data = synth.make_data(cfg, seed=0, device="cpu")
+    return cfg, model, data
+
+
+def time_oracle(prob, steps, warmup):
+    from tests.synth import run_oracle
+    torch.set_num_threads(os.cpu_count())
+    for _ in range(warmup):
+        run_oracle(prob)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        out = run_oracle(prob)
+        ts.append(time.perf_counter() - t0)
+    return float(np.mean(ts)), out
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation cannot run here (needs dgl + faiss;
+    DESIGN.md), so this times the oracle port of it on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg, model, data = cpu_sample(args.config, args.cpu_tokens)
+    sec, out = time_oracle((cfg, model, data), max(1, args.steps), max(0, min(args.warmup, 1)))
+    tps = cfg["L"] / sec
+    sample = (f"1 block of {cfg['L']} tokens per step at the {args.config} shape (d={cfg['d']}, V={cfg['V']}, k={cfg['k']}, "
+              f"c={cfg['c']}, M={cfg['M']}, {cfg['NL']} HGT layers, k_nn={cfg['k_nn']}), datastore 2^22 rows, fp32, "
+              f"torch CPU {torch.get_num_threads()} threads")
+    line = {"impl": "reference", "metric": "eval tokens/s (HGT+kNN-LM fwd)", "value": tps, "unit": "tokens/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.config)},
+            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_name(cfg_name):
+    from gnnlm_b200 import synth
+    c = synth.CONFIGS[cfg_name]
+    return (f"{cfg_name}: wiki103-shape GNN+kNN eval" if cfg_name == "c3" else f"{cfg_name}") + \
+        f" d={c['d']} H={c['H']} V={c['V']} B={c['B']}xL={c['L']} k={c['k']} c={c['c']} M={c['M']} layers={c['NL']} k_nn={c['k_nn']}"
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from gnnlm_b200 import _lib as L
+    from gnnlm_b200 import synth
+    lib = L.load()
+    math = args.math
+    if math == "auto":
+        math = "tf32x3" if lib.gnnlm_has_tcgen05() else "fp32"
+    cfg = dict(synth.CONFIGS[args.config])
+    if args.n_datastore:
+        cfg["n_d"] = args.n_datastore
+    T = cfg["B"] * cfg["L"]
+
+    model = synth.make_model(cfg)
+    tables = synth.make_tables(cfg, seed=rank, device=dev)          # replicated datastore, per-rank stream
+    NB = 4                                                          # distinct resident batches, rotated
+    dev_batches = [synth.make_batch(cfg, tables, seed=1000 * rank + i, device=dev) for i in range(NB)]
+    host_batches = [{k: v.cpu().pin_memory() for k, v in b.items() if k != "positions"} for b in dev_batches]
+    runner = synth.Runner(cfg, model, tables, dev, math)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    resident = lambda i: runner.step_resident(dev_batches[i % NB])
+    host = lambda i: runner.step_host(host_batches[i % NB])
+
+    for i in range(max(3, args.warmup)):
+        resident(i)
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = L.launches
+    ms = timed(resident, args.steps)
+    launches = L.launches - l0
+    clk = clocks.stop()
+    for i in range(2):
+        host(i)
+    ms_e2e = timed(host, args.steps)
+
+    # the path's only collective: {sum log p, n_tokens}
+    acc = runner.acc.clone()
+    if dist is not None:
+        dist.all_reduce(acc)
+    score_sum, count = acc.tolist()
+
+    # ---- per-kernel pass (CUDA events around every C-ABI launch, same workload, separately timed region)
+    L.TIMING = []
+    for i in range(args.steps):
+        resident(i)
+    torch.cuda.synchronize(dev)
+    per = {}
+    for name, tag, a, b in L.TIMING:
+        key = name.replace("gnnlm_", "") + (f":{tag}" if tag else "")
+        d = per.setdefault(key, [0.0, 0])
+        d[0] += a.elapsed_time(b)
+        d[1] += 1
+    L.TIMING = None
+    step_ms_instr = sum(v[0] for v in per.values()) / args.steps
+    kernels = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / args.steps,
+                   "share": v[0] / args.steps / step_ms_instr} for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])}
+
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+
+    # edge-aggregation roofline (the metric's kernel): ntgt-intra-ntgt attention over all nodes.
+    # algorithmic bytes: K',V' rows once + Q + out + CSR
+    g = synth.build_token_graph(dev_batches[0]["nbr"], tables["n_d"], cfg["c"], cfg["c"])
+    n_ntgt, n_valid = g.counts()
+    d, s = cfg["d"], 4
+    roof = None
+    for key in ("hgt_edge_attn:nn_full", "hgt_edge_attn:nn_centre", "hgt_edge_attn:inter"):
+        if key in kernels:
+            if key.endswith("nn_full"):
+                E = 3 * n_ntgt - 2 * n_valid
+                alg = n_ntgt * 2 * d * s + n_ntgt * d * s + n_ntgt * d * 4 + E * 4 + (n_ntgt + 1) * 4
+            elif key.endswith("nn_centre"):
+                E = 3 * n_valid
+                alg = n_ntgt * 2 * d * s + n_valid * d * s + n_valid * d * 4 + E * 4 + 2 * n_valid * 4
+            else:
+                alg = n_valid * 2 * d * s + T * d * s + T * d * 4 + (T + 1) * 4
+            ach = alg / (kernels[key]["ms_per_launch"] * 1e-3) / 1e9
+            roof = {"kernel": key, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": hbm_src,
+                    "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "algorithmic_bytes": alg,
+                    "ms_per_launch": kernels[key]["ms_per_launch"], "share_of_step": kernels[key]["share"]}
+            break
+    # dominant dense kernel: the Q|K'|V' projection of all ntgt nodes
+    gemm_roof = None
+    gk = f"linear:linear[{3 * d}x{d}]"
+    if gk in kernels:
+        # launched for ntgt (n_ntgt rows) and tgt (T rows) -- take the per-step totals
+        flops = 2.0 * (n_ntgt * (cfg["NL"] > 2) + T) * 3 * d * d
+        tot_ms = kernels[gk]["ms_per_launch"] * kernels[gk]["launches_per_step"]
+        passes = {"tf32x3": 3, "fp32": 1, "tf32": 1, "bf16": 1}[math]
+        gemm_roof = {"kernel": gk, "bound": "tensor", "achieved": flops / (tot_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+                     "peak": tf_peak, "peak_note": "measured cuBLAS bf16 sustained; tf32 dense is half of it, "
+                                                   "3-pass split another third", "passes": passes}
+
+    tokens_all = world * args.steps * T
+    line = {
+        "metric": "eval tokens/s (HGT+kNN-LM fwd)", "value": tokens_all / (ms * 1e-3), "unit": "tokens/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core split)",
+                                                           "tf32": "tf32", "bf16": "bf16"}[math],
+        "data": "synthetic", "impl": "ours",
+        "config": {"workload": workload_name(args.config), "math": math, "n_datastore": tables["n_d"],
+                   "parallelism": f"dp{world} (contiguous block shards, replicated datastore, one 16 B all-reduce)",
+                   "l2_policy": "inputs larger than L2 (datastore + activations are GBs); 4 distinct batches rotated",
+                   "n_ntgt": n_ntgt, "n_valid_neighbours": n_valid},
+        "e2e": {"value": tokens_all / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host_batches[0].values())),
+                "d2h_bytes_per_step": 16},
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_gemm": gemm_roof,
+        "kernels": kernels, "score_sum": score_sum, "count": count,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        ccfg, cmodel, cdata = cpu_sample(args.config, args.cpu_tokens)
+        sec, _ = time_oracle((ccfg, cmodel, cdata), 1, 0)
+        line["cpu_baseline"] = {
+            "value": ccfg["L"] / sec, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"CPU oracle (torch fp32, {torch.get_num_threads()} threads), 1 block of {ccfg['L']} tokens at the "
+                      f"{args.config} shape, datastore 2^22 rows, {sec:.1f} s"}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -41,7 +41,9 @@ SIGNATURES = {
 }
 
 _lib = None
-launches = 0          # number of C-ABI compute calls issued (bench.py reports kernel launches from this)
+launches = 0          # number of CUDA kernels launched through the C ABI (bench.py's gpu_launches)
+KERNELS_PER_CALL = {"gnnlm_graph_count": 3, "gnnlm_knn_full_prob": 2}   # everything else launches exactly one
+TIMING = None         # when a list: (name, tag, start_event, end_event) per call (bench.py per-kernel pass)
 
 
 class GnnlmError(RuntimeError):
@@ -79,11 +81,17 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name, *args):
+def call(name, *args, tag=None):
     global launches
     lib = load()
+    if TIMING is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise GnnlmError(f"{name} failed ({rc}): {lib.gnnlm_last_error().decode()}")
-    launches += 1
+    if TIMING is not None:
+        e1.record()
+        TIMING.append((name, tag, e0, e1))
+    launches += KERNELS_PER_CALL.get(name, 1)
     return rc

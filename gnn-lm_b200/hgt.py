@@ -151,7 +151,8 @@ class HGTLayer(nn.Module):
         d, H = P["d"], self.n_heads
         qkv = _lin(h_n, P["ntgt_qkv"], P["math"], m_dev=n_dev)
         t_agg = torch.empty((h_n.shape[0], d), device=h_n.device, dtype=torch.float32)
-        ops.edge_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.nn_indptr, G.nn_indices, H, t_agg, n_dst_dev=n_dev)
+        ops.edge_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.nn_indptr, G.nn_indices, H, t_agg, n_dst_dev=n_dev,
+                      tag="nn_full")
         return self._out(P, P["n"], t_agg, h_n, n_dev)
 
     def ntgt_centre(self, P, G: TokenGraph, h_n, n_dev, hc, c_dev):
@@ -161,7 +162,7 @@ class HGTLayer(nn.Module):
         qc = _lin(hc, P["ntgt_qkv"].rows(0, d), P["math"], m_dev=c_dev)
         t_agg = torch.empty((hc.shape[0], d), device=h_n.device, dtype=torch.float32)
         ops.edge_attn(qc, kv[:, :d], kv[:, d:], G.nn_indptr, G.nn_indices, H, t_agg, dst_ids=G.inter_indices,
-                      n_dst_dev=c_dev)
+                      n_dst_dev=c_dev, tag="nn_centre")
         return self._out(P, P["n"], t_agg, hc, c_dev)
 
     def tgt(self, P, G: TokenGraph, h_t, hc, c_dev):
@@ -171,7 +172,7 @@ class HGTLayer(nn.Module):
         kvi = _lin(hc, P["ntgt_kv_inter"], P["math"], m_dev=c_dev)
         t_agg = torch.empty((h_t.shape[0], d), device=h_t.device, dtype=torch.float32)
         # inter edges in compact centre numbering are the contiguous ranges of inter_indptr
-        ops.edge_attn(qkv[:, :d], kvi[:, :d], kvi[:, d:], G.inter_indptr, None, H, t_agg, out_scale=0.5)
+        ops.edge_attn(qkv[:, :d], kvi[:, :d], kvi[:, d:], G.inter_indptr, None, H, t_agg, out_scale=0.5, tag="inter")
         ops.causal_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5,
                         accumulate=True)
         return self._out(P, P["t"], t_agg, h_t, None)

@@ -18,7 +18,7 @@ def _dev_count(t: Optional[torch.Tensor]):
 
 def linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, *, W_lo: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_dtype=None,
-           m_dev: Optional[torch.Tensor] = None, math: int = L.MATH_FP32_SIMT) -> torch.Tensor:
+           m_dev: Optional[torch.Tensor] = None, math: int = L.MATH_FP32_SIMT, tag=None) -> torch.Tensor:
     """C = A @ W^T + bias (+ residual).  A [M,K] (row stride arbitrary), W [N,K]."""
     assert A.dim() == 2 and W.dim() == 2 and A.stride(1) == 1 and W.stride(1) == 1
     M, K = A.shape
@@ -31,7 +31,8 @@ def linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None
         assert residual.dtype == torch.float32 and residual.stride(1) == 1
     L.call("gnnlm_linear", L.ptr(A), L.dtype_code(A.dtype), A.stride(0), L.ptr(W), L.ptr(W_lo), W.stride(0),
            L.ptr(bias), L.ptr(residual), residual.stride(0) if residual is not None else 0, L.ptr(out),
-           L.dtype_code(out.dtype), out.stride(0), M, _dev_count(m_dev), N, K, math, L.stream_ptr())
+           L.dtype_code(out.dtype), out.stride(0), M, _dev_count(m_dev), N, K, math, L.stream_ptr(),
+           tag=tag or f"linear[{N}x{K}]")
     return out
 
 
@@ -89,13 +90,13 @@ def split_tf32(w):
 
 
 def edge_attn(q, k, v, indptr, indices, H, out, *, dst_ids=None, n_dst=None, n_dst_dev=None, out_scale=1.0,
-              accumulate=False):
+              accumulate=False, tag=None):
     d = q.shape[1]
     n = q.shape[0] if n_dst is None else n_dst
     assert q.dtype == k.dtype == v.dtype and out.dtype == torch.float32
     L.call("gnnlm_hgt_edge_attn", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0),
            L.dtype_code(q.dtype), L.ptr(indptr), L.ptr(indices), L.ptr(dst_ids), n, _dev_count(n_dst_dev), H, d // H,
-           L.ptr(out), out.stride(0), float(out_scale), int(accumulate), L.stream_ptr())
+           L.ptr(out), out.stride(0), float(out_scale), int(accumulate), L.stream_ptr(), tag=tag)
     return out
 
 

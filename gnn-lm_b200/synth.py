@@ -64,14 +64,22 @@ def make_model(cfg: dict, seed: int = 1) -> TransformerLanguageModel:
     return model.eval()
 
 
-def make_data(cfg: dict, seed: int = 0, n_d: int = None, device="cpu", stress: bool = True) -> dict:
-    """One batch of inputs.  Large tables (codes, vals) are generated directly on `device`."""
+def make_tables(cfg: dict, seed: int = 0, n_d: int = None, device="cpu") -> dict:
+    """The datastore tables (quantized-keys.npy / vals.npy stand-ins), generated directly on `device`."""
     c = SimpleNamespace(**cfg)
     n_d = n_d or c.n_d
     g = torch.Generator(device=device).manual_seed(seed)
-    T = c.B * c.L
     codes = torch.randint(0, 256, (n_d, c.M), generator=g, device=device, dtype=torch.uint8)
     vals = torch.randint(4, c.V, (n_d,), generator=g, device=device, dtype=torch.int32)
+    return dict(codes=codes, vals=vals, n_d=n_d)
+
+
+def make_batch(cfg: dict, tables: dict, seed: int = 0, device="cpu", stress: bool = True) -> dict:
+    """One batch of per-token inputs: neighbour ids, fp16 features, targets, kNN-LM search results."""
+    c = SimpleNamespace(**cfg)
+    n_d, vals = tables["n_d"], tables["vals"]
+    g = torch.Generator(device=device).manual_seed(seed + 12345)
+    T = c.B * c.L
     nbr = torch.randint(c.c, n_d - c.c, (c.B, c.L, c.k), generator=g, device=device, dtype=torch.int64)
     if stress:   # 1% missing, 0.1% within c of either boundary (SURVEY.md 8d)
         r = torch.rand((c.B, c.L, c.k), generator=g, device=device)
@@ -89,10 +97,17 @@ def make_data(cfg: dict, seed: int = 0, n_d: int = None, device="cpu", stress: b
     rows = ids[torch.arange(T, device=device), j]
     ok = hit & (rows >= 0)
     flat_t = target.reshape(-1).clone()
-    flat_t[ok] = vals[rows[ok]].long()
+    flat_t[ok] = vals[rows[ok].to(vals.device)].long().to(device)
     target = flat_t.view(c.B, c.L)
-    return dict(codes=codes, vals=vals, nbr=nbr, feats=feats, target=target, knn_dists=dists, knn_ids=ids, n_d=n_d,
+    return dict(nbr=nbr, feats=feats, target=target, knn_dists=dists, knn_ids=ids,
                 positions=torch.arange(T, device=device).view(c.B, c.L))
+
+
+def make_data(cfg: dict, seed: int = 0, n_d: int = None, device="cpu", stress: bool = True) -> dict:
+    tables = make_tables(cfg, seed, n_d, device)
+    out = dict(tables)
+    out.update(make_batch(cfg, tables, seed, device, stress))
+    return out
 
 
 def to_device(data: dict, device) -> dict:
