@@ -1,16 +1,503 @@
-// placeholder until the tcgen05 kernel lands (next commit): reports "unsupported" loudly.
+// tcgen05 / TMEM / TMA GEMM for sm_100a: C[m,n] = sum_k A[m,k] * W[n,k] (+bias, +residual), or the
+// fused row log-sum-exp + column-pick epilogue.  Both operands K-major (nn.Linear layout).
+//
+// Replaces the cuBLAS calls behind nn.Linear / einsum / `x @ A` on the reference hot path
+// (fairseq/models/hgt.py:320-322,347-348,401; knn/pq_wrapper.py:202;
+// fairseq/modules/adaptive_softmax.py:184,197,202).
+//
+// Structure (persistent, warp-specialised, one CTA per SM, static round-robin tile schedule):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of a 128 x 128B A tile and a 256 x 128B W
+//               tile (SWIZZLE_128B) per k-block into a multi-stage smem ring, mbarrier expect_tx.
+//   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1 (M=128, N=256, K=8 tf32 / 16 bf16)
+//               with smem descriptors; accumulators live in TMEM (2 x 256 columns, double buffered so the
+//               epilogue of tile i overlaps the MMAs of tile i+1); tcgen05.commit frees smem stages and
+//               publishes accumulators.
+//   warp 2      TMEM allocator (512 columns).
+//   warps 4-7   epilogue: tcgen05.ld 32x32b.x32 -> registers -> bias / residual -> global, or the
+//               online (max, sum-exp, pick) reduction -- a thread owns one output row, so the LSE needs
+//               no cross-thread traffic.
+//   warps 8-11  (3xTF32 only) operand splitter: rewrites the fp32 A tile in smem as hi = A & ~0x1fff
+//               (what kind::tf32 consumes) and writes lo = A - hi to a second tile; W is pre-split on
+//               the host side once per checkpoint.  D += A_hi*W_lo + A_lo*W_hi + A_hi*W_hi recovers
+//               ~2^-21 relative accuracy from three tf32 passes ("fp32 mode" of the north star).
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace gnnlm {
-int32_t gemm_tc_supported() { return 0; }
-int64_t gemm_tc_lse_tile_n() { return 128; }
-int32_t gemm_tc_store(const void*, int32_t, int64_t, const void*, const void*, int64_t, const float*, const float*, int64_t,
-                      void*, int32_t, int64_t, int64_t, const int32_t*, int64_t, int64_t, int32_t, cudaStream_t) {
-  set_error("tcgen05 GEMM not built");
-  return GNNLM_E_UNSUPPORTED;
+
+namespace tc {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_N = 256;
+constexpr int ROW_BYTES = 128;                       // one SWIZZLE_128B row == one k-block
+constexpr int A_TILE = BLOCK_M * ROW_BYTES;          // 16 KB
+constexpr int B_TILE = BLOCK_N * ROW_BYTES;          // 32 KB
+constexpr int TMEM_COLS = 512;
+constexpr int EPI_WARP0 = 4, CONV_WARP0 = 8;
+
+enum Mode { X3 = 0, TF32 = 1, BF16 = 2 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-int32_t gemm_tc_lse(const void*, int32_t, int64_t, const void*, const void*, int64_t, const int32_t*, float*, float*, float*,
-                    int64_t, const int32_t*, int64_t, int64_t, int32_t, cudaStream_t) {
-  set_error("tcgen05 GEMM not built");
-  return GNNLM_E_UNSUPPORTED;
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (spin > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major, SWIZZLE_128B smem operand descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 = 1 [16,30) | SBO>>4 = 64 (8 rows x 128 B) [32,46) | version 1 [46,48) | layout 2 [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int KIND_TF32>
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (KIND_TF32) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct EpiStore {
+  const float* bias;
+  const float* residual;
+  int64_t ldr;
+  void* C;
+  int64_t ldc;
+  int c_bf16;
+};
+struct EpiLse {
+  const int32_t* pick;
+  float* part_max;
+  float* part_sum;
+  float* picked;
+  int64_t n_tiles;
+};
+
+template <int MODE, bool LSE>
+__global__ void __launch_bounds__(MODE == X3 ? 384 : 256, 1)
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ CUtensorMap map_blo, int64_t M_cap, const int32_t* __restrict__ m_dev, int64_t N,
+                   int64_t K, EpiStore es, EpiLse el) {
+  constexpr int ELEM = MODE == BF16 ? 2 : 4;
+  constexpr int BLOCK_K = ROW_BYTES / ELEM;                 // 32 tf32 / 64 bf16
+  constexpr int UMMA_K = 32 / ELEM;                         // 8 tf32 / 16 bf16
+  constexpr int STAGE_BYTES = MODE == X3 ? 2 * (A_TILE + B_TILE) : (A_TILE + B_TILE);
+  constexpr int STAGES = MODE == X3 ? 2 : 4;
+  constexpr uint32_t TX_BYTES = MODE == X3 ? A_TILE + 2 * B_TILE : A_TILE + B_TILE;
+  // instruction descriptor (cute InstrDescriptor): c=F32 [4,6) | a,b format [7,10),[10,13) | N>>3 [17,23) | M>>4 [24,29)
+  constexpr uint32_t FMT = MODE == BF16 ? 1u : 2u;
+  constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                             ((uint32_t)(BLOCK_M >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], conv_bar[STAGES], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t M = live_rows(M_cap, m_dev);
+  const int64_t n_m = (M + BLOCK_M - 1) / BLOCK_M, n_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int64_t total = n_m * n_n;
+  const int n_kb = (int)((K + BLOCK_K - 1) / BLOCK_K);
+
+  auto sA = [&](int s) { return smem + (size_t)s * STAGE_BYTES; };
+  auto sB = [&](int s) { return smem + (size_t)s * STAGE_BYTES + A_TILE; };
+  auto sAlo = [&](int s) { return smem + (size_t)s * STAGE_BYTES + A_TILE + B_TILE; };
+  auto sBlo = [&](int s) { return smem + (size_t)s * STAGE_BYTES + 2 * A_TILE + B_TILE; };
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    if (MODE == X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&conv_bar[s], 4);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int m0 = (int)((tile / n_n) * BLOCK_M), n0 = (int)((tile % n_n) * BLOCK_N);
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], TX_BYTES);
+          tma_load_2d(sA(stage), &map_a, kb * BLOCK_K, m0, &full_bar[stage]);
+          tma_load_2d(sB(stage), &map_b, kb * BLOCK_K, n0, &full_bar[stage]);
+          if (MODE == X3) tma_load_2d(sBlo(stage), &map_blo, kb * BLOCK_K, n0, &full_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int64_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int acc = (int)(it & 1);
+        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BLOCK_N;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(MODE == X3 ? &conv_bar[stage] : &full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_desc(smem_u32(sA(stage))), db = make_desc(smem_u32(sB(stage)));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * ELEM) >> 4);     // advance inside the 128 B swizzle row
+            if (MODE == X3) {
+              const uint64_t dal = make_desc(smem_u32(sAlo(stage))), dbl = make_desc(smem_u32(sBlo(stage)));
+              umma<1>(d_tmem, da + koff, dbl + koff, IDESC, (kb | k) > 0 ? 1u : 0u);
+              umma<1>(d_tmem, dal + koff, db + koff, IDESC, 1u);
+              umma<1>(d_tmem, da + koff, db + koff, IDESC, 1u);
+            } else {
+              umma<MODE != BF16>(d_tmem, da + koff, db + koff, IDESC, (kb | k) > 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(&empty_bar[stage]);              // smem stage reusable once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(&tmem_full[acc]);                  // accumulator complete
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int acc = (int)(it & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      const int64_t m_blk = tile / n_n, n_blk = tile % n_n;
+      const int64_t m = m_blk * BLOCK_M + q * 32 + lane;
+      const int64_t n_base = n_blk * BLOCK_N;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      float run_max = -INFINITY, run_sum = 0.f;
+      const int32_t want = (LSE && m < M && el.pick) ? __ldg(el.pick + m) : -1;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        if (n_base + c >= N) break;                  // warp-uniform
+        float v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+        const int64_t n0 = n_base + c;
+        if constexpr (!LSE) {
+          if (m < M) {
+            if (es.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < N) v[j] += __ldg(es.bias + n0 + j);
+            }
+            const bool full = n0 + 32 <= N;
+            if (es.residual) {
+              const float* r = es.residual + m * es.ldr + n0;
+              if (full && (es.ldr & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 t = __ldg(reinterpret_cast<const float4*>(r) + j);
+                  v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n0 + j < N) v[j] += __ldg(r + j);
+              }
+            }
+            if (!es.c_bf16) {
+              float* o = reinterpret_cast<float*>(es.C) + m * es.ldc + n0;
+              if (full && (es.ldc & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n0 + j < N) o[j] = v[j];
+              }
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(es.C) + m * es.ldc + n0;
+              if (full && (es.ldc & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  uint4 u;
+                  __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                  __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                  u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+                  u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+                  reinterpret_cast<uint4*>(o)[j] = u;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n0 + j < N) o[j] = __float2bfloat16(v[j]);
+              }
+            }
+          }
+        } else {
+          float mx = run_max;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < N) {
+              mx = fmaxf(mx, v[j]);
+              if (n0 + j == want) el.picked[m] = v[j];
+            }
+          float s = run_sum * __expf(run_max - mx);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < N) s += __expf(v[j] - mx);
+          run_max = mx;
+          run_sum = s;
+        }
+      }
+      if constexpr (LSE) {
+        if (m < M) {
+          el.part_max[m * el.n_tiles + n_blk] = run_max;
+          el.part_sum[m * el.n_tiles + n_blk] = run_sum;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+  } else if (MODE == X3 && warp >= CONV_WARP0) {
+    // ===================== operand splitter (3xTF32) =====================
+    const int ct = threadIdx.x - CONV_WARP0 * 32;     // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        float4* a = reinterpret_cast<float4*>(sA(stage));
+        float4* lo = reinterpret_cast<float4*>(sAlo(stage));
+#pragma unroll
+        for (int i = 0; i < A_TILE / 16 / 128; ++i) {
+          const int idx = ct + i * 128;
+          float4 x = a[idx], h;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          a[idx] = h;
+          lo[idx] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to UMMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static int device_is_sm100() {
+  static int cached = -1;
+  if (cached < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+      cudaGetLastError();
+      cached = 0;
+    } else {
+      cached = major == 10;
+    }
+  }
+  return cached;
+}
+
+static int make_map(CUtensorMap* map, const void* base, int bf16, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  const int elem = bf16 ? 2 : 4;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * elem};
+  cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / elem), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_fn()(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                           const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return (int)r;
+}
+
+template <int MODE, bool LSE>
+static int32_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mblo, int64_t M, const int32_t* m_dev,
+                      int64_t N, int64_t K, const EpiStore& es, const EpiLse& el, cudaStream_t st) {
+  constexpr int STAGE_BYTES = MODE == X3 ? 2 * (A_TILE + B_TILE) : (A_TILE + B_TILE);
+  constexpr int STAGES = MODE == X3 ? 2 : 4;
+  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GNNLM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    GNNLM_CUDA(cudaGetDevice(&dev));
+    GNNLM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int64_t tiles = ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
+  const unsigned grid = (unsigned)(tiles < n_sm ? tiles : n_sm);
+  gemm_tc_kernel<MODE, LSE><<<grid, MODE == X3 ? 384 : 256, smem, st>>>(ma, mb, mblo, M, m_dev, N, K, es, el);
+  GNNLM_LAUNCH_CHECK("gemm_tcgen05");
+  return 0;
+}
+
+}  // namespace tc
+
+int32_t gemm_tc_supported() { return tc::encode_fn() != nullptr && tc::device_is_sm100(); }
+int64_t gemm_tc_lse_tile_n() { return tc::BLOCK_N; }
+
+static int32_t tc_prepare(const char* who, const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo,
+                          int64_t ldw, int64_t M, int64_t N, int64_t K, int32_t math, CUtensorMap* ma, CUtensorMap* mb,
+                          CUtensorMap* mblo) {
+  GNNLM_CHECK_ARG(gemm_tc_supported(), GNNLM_E_UNSUPPORTED, "%s: tcgen05 path needs an sm_100 device and driver TMA support", who);
+  const int bf16 = math == GNNLM_MATH_BF16;
+  const int elem = bf16 ? 2 : 4;
+  GNNLM_CHECK_ARG((lda * elem) % 16 == 0 && (ldw * elem) % 16 == 0 && (uintptr_t)A % 16 == 0 && (uintptr_t)W % 16 == 0,
+                  GNNLM_E_SHAPE, "%s: TMA needs 16 B aligned bases and row strides (lda=%lld ldw=%lld)", who, (long long)lda,
+                  (long long)ldw);
+  GNNLM_CHECK_ARG(math != GNNLM_MATH_TF32X3 || (W_lo && (uintptr_t)W_lo % 16 == 0), GNNLM_E_ARG,
+                  "%s: MATH_TF32X3 needs W_lo (gnnlm_split_tf32)", who);
+  int r = tc::make_map(ma, A, bf16, M, K, lda, tc::BLOCK_M);
+  if (!r) r = tc::make_map(mb, W, bf16, N, K, ldw, tc::BLOCK_N);
+  if (!r) r = tc::make_map(mblo, math == GNNLM_MATH_TF32X3 ? W_lo : W, bf16, N, K, ldw, tc::BLOCK_N);
+  GNNLM_CHECK_ARG(r == 0, GNNLM_E_ARG, "%s: cuTensorMapEncodeTiled failed (%d)", who, r);
+  return 0;
+}
+
+int32_t gemm_tc_store(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, int64_t ldw,
+                      const float* bias, const float* residual, int64_t ldr, void* C, int32_t c_dtype, int64_t ldc,
+                      int64_t M, const int32_t* m_dev, int64_t N, int64_t K, int32_t math, cudaStream_t st) {
+  if (M == 0) return 0;
+  CUtensorMap ma, mb, mblo;
+  int32_t rc = tc_prepare("gnnlm_linear", A, a_dtype, lda, W, W_lo, ldw, M, N, K, math, &ma, &mb, &mblo);
+  if (rc) return rc;
+  tc::EpiStore es{bias, residual, ldr, C, ldc, c_dtype == GNNLM_BF16};
+  tc::EpiLse el{};
+  if (math == GNNLM_MATH_TF32X3) return tc::launch<tc::X3, false>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
+  if (math == GNNLM_MATH_TF32) return tc::launch<tc::TF32, false>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
+  return tc::launch<tc::BF16, false>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
+}
+
+int32_t gemm_tc_lse(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, int64_t ldw,
+                    const int32_t* pick, float* part_max, float* part_sum, float* picked, int64_t M,
+                    const int32_t* m_dev, int64_t N, int64_t K, int32_t math, cudaStream_t st) {
+  if (M == 0) return 0;
+  CUtensorMap ma, mb, mblo;
+  int32_t rc = tc_prepare("gnnlm_linear_lse", A, a_dtype, lda, W, W_lo, ldw, M, N, K, math, &ma, &mb, &mblo);
+  if (rc) return rc;
+  tc::EpiStore es{};
+  tc::EpiLse el{pick, part_max, part_sum, picked, ceil_div(N, tc::BLOCK_N)};
+  if (math == GNNLM_MATH_TF32X3) return tc::launch<tc::X3, true>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
+  if (math == GNNLM_MATH_TF32) return tc::launch<tc::TF32, true>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
+  return tc::launch<tc::BF16, true>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
+}
+
 }  // namespace gnnlm
