@@ -152,6 +152,197 @@ __global__ void __launch_bounds__(EA_THREADS) causal_attn_kernel(const T* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Tiled ("flash") form of the implicit causal attention for fp32 and d_k in {64, 128}: one CTA owns a
+// 64-query tile of one head, streams 32-key K'/V' tiles through shared memory, keeps the running
+// (max, sum) per query row and the 64 x d_k output tile in registers.  K'/V' of a 3072-token block are
+// re-read L/64 times from L2 instead of L times (warp-per-destination form above), and all arithmetic
+// is fp32 FMA (exact-parity modes).  Thread layout keeps every shared-memory request to one wavefront:
+// a warp covers 8 query-row groups x 4 column groups, rows padded by 16 B.
+constexpr int FA_BQ = 64, FA_BK = 32, FA_THREADS = 256;
+
+template <int DK>
+__global__ void __launch_bounds__(FA_THREADS, 2)
+    causal_flash_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
+                        const float* __restrict__ v, int64_t ldv, int64_t L, int64_t ctx, float* __restrict__ out,
+                        int64_t ldo, float out_scale, int accumulate) {
+  constexpr int LD = DK + 4;                 // padded row (floats)
+  constexpr int LDP = FA_BK + 4;
+  constexpr int OC = DK / 16;                // output columns per thread (8 for d_k=128)
+  extern __shared__ __align__(16) float fsm[];
+  float* Qs = fsm;                           // [64][LD]
+  float* Ks = Qs + FA_BQ * LD;               // [32][LD]
+  float* Vs = Ks + FA_BK * LD;               // [32][LD]
+  float* Ps = Vs + FA_BK * LD;               // [64][LDP]
+  float* alpha_s = Ps + FA_BQ * LDP;         // [64]
+
+  const int n_qt = (int)((L + FA_BQ - 1) / FA_BQ);
+  const int qt = n_qt - 1 - (int)blockIdx.x;               // longest tiles first
+  const int h = blockIdx.y;
+  const int64_t b = blockIdx.z;
+  const int64_t row0 = b * L;                              // first token of this block
+  const int q0 = qt * FA_BQ;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int ty = (w & 1) * 8 + (lane >> 2);                // 0..15
+  const int tx = (w >> 1) * 4 + (lane & 3);                // 0..15
+  const int64_t col0 = (int64_t)h * DK;
+
+  // Q tile -> smem (rows beyond L are zero)
+  for (int i = tid; i < FA_BQ * (DK / 4); i += FA_THREADS) {
+    const int r = i / (DK / 4), c4 = i % (DK / 4);
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < L) t = __ldg(reinterpret_cast<const float4*>(q + (row0 + q0 + r) * ldq + col0) + c4);
+    *reinterpret_cast<float4*>(Qs + r * LD + c4 * 4) = t;
+  }
+  float o[4][OC];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int c = 0; c < OC; ++c) o[i][c] = 0.f;
+  // softmax bookkeeping: thread (tid/4) owns row tid/4 together with 3 neighbours (8 columns each)
+  const int srow = tid >> 2, spart = tid & 3;
+  float m_run = -INFINITY, l_run = 0.f;
+
+  const int q_hi = min(q0 + FA_BQ, (int)L) - 1;            // last query of the tile
+  int kt_lo = 0;
+  if (ctx > 0) {
+    const int64_t first_key = (int64_t)q0 + 1 - ctx;       // earliest key any query of the tile may see
+    if (first_key > 0) kt_lo = (int)(first_key / FA_BK);
+  }
+  const int kt_hi = q_hi / FA_BK;                          // inclusive
+  for (int kt = kt_lo; kt <= kt_hi; ++kt) {
+    const int k0 = kt * FA_BK;
+    __syncthreads();                                       // previous tile's P.V done (and Q visible on first pass)
+    for (int i = tid; i < FA_BK * (DK / 4); i += FA_THREADS) {
+      const int r = i / (DK / 4), c4 = i % (DK / 4);
+      float4 tk = make_float4(0.f, 0.f, 0.f, 0.f), tv = tk;
+      if (k0 + r < L) {
+        tk = __ldg(reinterpret_cast<const float4*>(k + (row0 + k0 + r) * ldk + col0) + c4);
+        tv = __ldg(reinterpret_cast<const float4*>(v + (row0 + k0 + r) * ldv + col0) + c4);
+      }
+      *reinterpret_cast<float4*>(Ks + r * LD + c4 * 4) = tk;
+      *reinterpret_cast<float4*>(Vs + r * LD + c4 * 4) = tv;
+    }
+    __syncthreads();
+    // ---- S = Q K^T: thread -> rows ty*4+i, key columns tx*2+j
+    float s[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i][0] = s[i][1] = 0.f;
+#pragma unroll 8
+    for (int d4 = 0; d4 < DK / 4; ++d4) {
+      float4 a[4], bb[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(Qs + (ty * 4 + i) * LD + d4 * 4);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) bb[j] = *reinterpret_cast<const float4*>(Ks + (tx * 2 + j) * LD + d4 * 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          s[i][j] = fmaf(a[i].x, bb[j].x, s[i][j]);
+          s[i][j] = fmaf(a[i].y, bb[j].y, s[i][j]);
+          s[i][j] = fmaf(a[i].z, bb[j].z, s[i][j]);
+          s[i][j] = fmaf(a[i].w, bb[j].w, s[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int qi = q0 + ty * 4 + i, kj = k0 + tx * 2 + j;
+        const bool ok = kj <= qi && kj < L && (ctx <= 0 || qi - kj < ctx);
+        Ps[(ty * 4 + i) * LDP + tx * 2 + j] = ok ? s[i][j] : -INFINITY;
+      }
+    __syncthreads();
+    // ---- online softmax over the 32 new columns of each row
+    {
+      float* pr = Ps + srow * LDP + spart * 8;
+      float4 x0 = *reinterpret_cast<float4*>(pr), x1 = *reinterpret_cast<float4*>(pr + 4);
+      float mx = fmaxf(fmaxf(fmaxf(x0.x, x0.y), fmaxf(x0.z, x0.w)), fmaxf(fmaxf(x1.x, x1.y), fmaxf(x1.z, x1.w)));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_new = fmaxf(m_run, mx);
+      const float base = m_new == -INFINITY ? 0.f : m_new;            // fully masked so far -> all p = 0
+      x0.x = __expf(x0.x - base); x0.y = __expf(x0.y - base); x0.z = __expf(x0.z - base); x0.w = __expf(x0.w - base);
+      x1.x = __expf(x1.x - base); x1.y = __expf(x1.y - base); x1.z = __expf(x1.z - base); x1.w = __expf(x1.w - base);
+      *reinterpret_cast<float4*>(pr) = x0;
+      *reinterpret_cast<float4*>(pr + 4) = x1;
+      float sum = (x0.x + x0.y) + (x0.z + x0.w) + (x1.x + x1.y) + (x1.z + x1.w);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float al = m_run == -INFINITY ? 0.f : __expf(m_run - base);
+      l_run = l_run * al + sum;
+      m_run = m_new;
+      if (spart == 0) alpha_s[srow] = al;
+    }
+    __syncthreads();
+    // ---- O = O * alpha + P V: thread -> rows ty*4+i, dims tx*OC..
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float al = alpha_s[ty * 4 + i];
+#pragma unroll
+      for (int c = 0; c < OC; ++c) o[i][c] *= al;
+    }
+#pragma unroll 2
+    for (int j4 = 0; j4 < FA_BK / 4; ++j4) {
+      float4 p[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) p[i] = *reinterpret_cast<const float4*>(Ps + (ty * 4 + i) * LDP + j4 * 4);
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        float vv[OC];
+#pragma unroll
+        for (int c4 = 0; c4 < OC / 4; ++c4) {
+          const float4 t = *reinterpret_cast<const float4*>(Vs + (j4 * 4 + jj) * LD + tx * OC + c4 * 4);
+          vv[c4 * 4] = t.x; vv[c4 * 4 + 1] = t.y; vv[c4 * 4 + 2] = t.z; vv[c4 * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float pij = jj == 0 ? p[i].x : (jj == 1 ? p[i].y : (jj == 2 ? p[i].z : p[i].w));
+#pragma unroll
+          for (int c = 0; c < OC; ++c) o[i][c] = fmaf(pij, vv[c], o[i][c]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (spart == 0) alpha_s[srow] = l_run;                   // reuse as the row-sum table
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int qi = q0 + ty * 4 + i;
+    if (qi >= L) continue;
+    const float l = alpha_s[ty * 4 + i];
+    const float inv = l > 0.f ? out_scale / l : 0.f;
+    float* dst = out + (row0 + qi) * ldo + col0 + tx * OC;
+#pragma unroll
+    for (int c4 = 0; c4 < OC / 4; ++c4) {
+      float4 r = make_float4(o[i][c4 * 4] * inv, o[i][c4 * 4 + 1] * inv, o[i][c4 * 4 + 2] * inv, o[i][c4 * 4 + 3] * inv);
+      if (accumulate) {
+        const float4 old = *reinterpret_cast<const float4*>(dst + c4 * 4);
+        r.x += old.x; r.y += old.y; r.z += old.z; r.w += old.w;
+      }
+      *reinterpret_cast<float4*>(dst + c4 * 4) = r;
+    }
+  }
+}
+
+template <int DK>
+static int32_t launch_flash(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, int64_t B,
+                            int64_t L, int64_t ctx, int H, float* out, int64_t ldo, float out_scale, int accumulate,
+                            cudaStream_t st) {
+  const size_t smem = sizeof(float) * ((size_t)(FA_BQ + 2 * FA_BK) * (DK + 4) + (size_t)FA_BQ * (FA_BK + 4) + FA_BQ);
+  static bool attr = false;
+  if (!attr) {
+    GNNLM_CUDA(cudaFuncSetAttribute(causal_flash_kernel<DK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid((unsigned)ceil_div(L, FA_BQ), (unsigned)H, (unsigned)B);
+  causal_flash_kernel<DK><<<grid, FA_THREADS, smem, st>>>(q, ldq, k, ldk, v, ldv, L, ctx, out, ldo, out_scale, accumulate);
+  GNNLM_LAUNCH_CHECK("gnnlm_hgt_causal_attn(flash)");
+  return 0;
+}
+
 template <typename T, int C>
 static int32_t launch_edge(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                            const int32_t* indptr, const int32_t* indices, const int32_t* dst_ids, int64_t n_dst_cap,
@@ -243,6 +434,15 @@ extern "C" int32_t gnnlm_hgt_causal_attn(const void* q, int64_t ldq, const void*
   if (rc) return rc;
   if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool al16 = ((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
+                    ((uintptr_t)out % 16 == 0) && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0;
+  if (dtype == GNNLM_F32 && al16 && L >= 64 && B <= 65535 && (d_k == 128 || d_k == 64)) {
+    if (d_k == 128)
+      return launch_flash<128>((const float*)q, ldq, (const float*)k, ldk, (const float*)v, ldv, B, L, intra_ctx, H, out,
+                               ldo, out_scale, accumulate, st);
+    return launch_flash<64>((const float*)q, ldq, (const float*)k, ldk, (const float*)v, ldv, B, L, intra_ctx, H, out, ldo,
+                            out_scale, accumulate, st);
+  }
   if (dtype == GNNLM_F32) {
     DISPATCH_C(launch_causal, float, q, ldq, k, ldk, v, ldv, B, L, intra_ctx, group, out, ldo, out_scale, accumulate, st)
   } else {

@@ -221,20 +221,25 @@ def test_hgt_vs_oracle(d, H, L, k, c, NL, dev):
     np.testing.assert_allclose(full["tgt"].cpu().double().numpy(), ref["tgt"].numpy(), rtol=1e-4, atol=1e-4)
 
 
-def test_causal_attn_with_intra_context(dev):
+@pytest.mark.parametrize("B,L,H,d,ctx", [(2, 37, 4, 128, 5), (2, 200, 8, 1024, 0), (1, 333, 8, 512, 70), (1, 64, 2, 256, 0),
+                                         (3, 129, 8, 1024, 33)])
+def test_causal_attn_with_intra_context(B, L, H, d, ctx, dev):
+    """warp-per-destination form (L < 64 / other d_k) and the tiled flash form (d_k in {64,128})."""
     from gnnlm_b200 import ops
     torch.manual_seed(3)
-    B, L, H, d, ctx = 2, 37, 4, 128, 5
     q, k, v = torch.randn(B * L, d), torch.randn(B * L, d), torch.randn(B * L, d)
     out = torch.zeros(B * L, d, device=dev)
-    ops.causal_attn(q.to(dev), k.to(dev), v.to(dev), B, L, ctx, H, out)
+    out.fill_(1.0)
+    ops.causal_attn(q.to(dev), k.to(dev), v.to(dev), B, L, ctx, H, out, out_scale=0.5, accumulate=True)
+    out = (out - 1.0) * 2.0
     qh, kh, vh = (t.view(B, L, H, d // H).permute(0, 2, 1, 3).double() for t in (q, k, v))
     s = qh @ kh.transpose(-1, -2)
     i = torch.arange(L)
-    mask = (i[None, :] <= i[:, None]) & (i[:, None] - i[None, :] < ctx)
+    mask = (i[None, :] <= i[:, None]) & ((i[:, None] - i[None, :] < ctx) if ctx else True)
     s = s.masked_fill(~mask, -float("inf"))
     ref = (torch.softmax(s, -1) @ vh).permute(0, 2, 1, 3).reshape(B * L, d)
-    np.testing.assert_allclose(out.cpu().double().numpy(), ref.numpy(), rtol=1e-4, atol=1e-5)
+    # unnormalised N(0,1) q,k give |scores| up to ~40: fp32 dot-product rounding ~1e-5 on the logits
+    np.testing.assert_allclose(out.cpu().double().numpy(), ref.numpy(), rtol=1e-4, atol=5e-5)
 
 
 # ------------------------------------------------------------------------------------------ log-probs / kNN
