@@ -241,7 +241,8 @@ def main():
     n_ntgt, n_valid = g.counts()
     d, s = cfg["d"], 4
     roof = None
-    for key in ("hgt_edge_attn:nn_full", "hgt_edge_attn:nn_centre", "hgt_edge_attn:inter"):
+    for key in ("hgt_cluster_attn:nn_full", "hgt_edge_attn:nn_full", "hgt_cluster_attn:nn_centre", "hgt_edge_attn:nn_centre",
+                "hgt_edge_attn:inter"):
         if key in kernels:
             if key.endswith("nn_full"):
                 E = 3 * n_ntgt - 2 * n_valid
@@ -256,6 +257,20 @@ def main():
                     "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "algorithmic_bytes": alg,
                     "ms_per_launch": kernels[key]["ms_per_launch"], "share_of_step": kernels[key]["share"]}
             break
+    def _edge_bytes(key):
+        if key.endswith("nn_full"):
+            return n_ntgt * 2 * d * s + n_ntgt * d * s + n_ntgt * d * 4 + (3 * n_ntgt - 2 * n_valid) * 4 + (n_ntgt + 1) * 4
+        if key.endswith("nn_centre"):
+            return n_ntgt * 2 * d * s + n_valid * d * s + n_valid * d * 4 + 3 * n_valid * 4 + 2 * n_valid * 4
+        return n_valid * 2 * d * s + T * d * s + T * d * 4 + (T + 1) * 4
+    edge_all = {key: {"GB/s": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9,
+                      "frac": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
+                for key, kv in kernels.items() if key.startswith(("hgt_cluster_attn", "hgt_edge_attn"))}
+    pq_key = "pq_gather_decode"
+    if pq_key in kernels:
+        pq_bytes = n_ntgt * (cfg["M"] + 8 + d * 4)
+        edge_all[pq_key] = {"GB/s": pq_bytes / (kernels[pq_key]["ms_per_launch"] * 1e-3) / 1e9,
+                            "frac": pq_bytes / (kernels[pq_key]["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
     # dominant dense kernel: the Q|K'|V' projection of all ntgt nodes
     gemm_roof = None
     gk = f"linear:linear[{3 * d}x{d}]"
@@ -282,7 +297,7 @@ def main():
         "e2e": {"value": tokens_all / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host_batches[0].values())),
                 "d2h_bytes_per_step": 16},
-        "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_gemm": gemm_roof,
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_gemm": gemm_roof, "hbm_kernels": edge_all,
         "kernels": kernels, "score_sum": score_sum, "count": count,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -1,0 +1,167 @@
+// ntgt-intra-ntgt attention without the CSR indirection (gnnlm_hgt_cluster_attn).
+//
+// Same arithmetic as gnnlm_hgt_edge_attn over (nn_indptr, nn_indices) -- i.e. the DGL sequence of
+// HGTLayer.forward (reference: fairseq/models/hgt.py:350-358,383-386) for the ('ntgt','intra','ntgt')
+// edge type -- but driven by the structure graph assembly already knows: every valid
+// (token, neighbour) pair owns a cluster of w contiguous node ids whose intra edges are a chain with
+// self loops (build_ntgt_edges(context=1, bidirect=True), fairseq/data/token_block_dataset.py:395-400).
+//
+// Why a second kernel: the CSR form is latency-bound (indptr -> indices -> rows is three dependent
+// round trips per destination, and each K'/V' row is fetched by three destinations).  Here one warp owns
+// one (cluster, feature slice): one round trip for (node_base, cluster_nl), then the 3w row segments of
+// Q / K' / V' are all in flight together and each is read exactly once -- HBM traffic equals the
+// algorithmic bytes of SURVEY.md 8(d): N*(2+1)*d*s read + N*d*4 written.
+#include "common.cuh"
+
+namespace gnnlm {
+
+constexpr int CA_THREADS = 256;
+
+__device__ __forceinline__ int ca_pos_to_id(int q, int nl) { return q == nl ? 0 : (q < nl ? q + 1 : q); }
+
+template <int C>
+__device__ __forceinline__ float group_dot(const float (&a)[C], const float (&b)[C], int group) {
+  float p = 0.f;
+#pragma unroll
+  for (int c = 0; c < C; ++c) p = fmaf(a[c], b[c], p);
+  for (int o = group >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+  return p;
+}
+
+template <typename T, int C, int WMAX>
+__global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k,
+                                                                  int64_t ldk, const T* __restrict__ v, int64_t ldv,
+                                                                  const int32_t* __restrict__ node_base,
+                                                                  const int32_t* __restrict__ valid_base,
+                                                                  const int32_t* __restrict__ cluster_nl, int64_t n_clusters,
+                                                                  int centre_only, int group, int n_slices,
+                                                                  float* __restrict__ out, int64_t ldo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_items = n_clusters * n_slices;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n_items; it += warps) {
+    const int64_t c = it / n_slices;
+    const int col = ((int)(it % n_slices) * 32 + lane) * C;
+    const int base = __ldg(node_base + c);
+    const int w = __ldg(node_base + c + 1) - base;
+    if (w <= 0) continue;                                    // invalid neighbour: no cluster
+    const int nl = __ldg(cluster_nl + c);
+    if (!centre_only) {
+      float qq[WMAX][C], kk[WMAX][C], vv[WMAX][C];
+#pragma unroll
+      for (int p = 0; p < WMAX; ++p) {
+        if (p < w) {
+          const int64_t id = base + ca_pos_to_id(p, nl);
+          load_row<T, C>(q + id * ldq + col, qq[p]);
+          load_row<T, C>(k + id * ldk + col, kk[p]);
+          load_row<T, C>(v + id * ldv + col, vv[p]);
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < WMAX; ++p) {
+        if (p < w) {
+          const float s1 = group_dot<C>(qq[p], kk[p], group);
+          float s0 = -INFINITY, s2 = -INFINITY;
+          if (p > 0) s0 = group_dot<C>(qq[p], kk[p > 0 ? p - 1 : 0], group);
+          if (p + 1 < WMAX && p + 1 < w) s2 = group_dot<C>(qq[p], kk[p + 1 < WMAX ? p + 1 : p], group);
+          const float mx = fmaxf(s1, fmaxf(s0, s2));
+          const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx), e2 = __expf(s2 - mx);
+          const float inv = 1.f / (e0 + e1 + e2);
+          float r[C];
+#pragma unroll
+          for (int cc = 0; cc < C; ++cc) {
+            float a = e1 * vv[p][cc];
+            if (p > 0) a = fmaf(e0, vv[p > 0 ? p - 1 : 0][cc], a);
+            if (p + 1 < WMAX && p + 1 < w) a = fmaf(e2, vv[p + 1 < WMAX ? p + 1 : p][cc], a);
+            r[cc] = a * inv;
+          }
+          store_f32<C>(out + (int64_t)(base + ca_pos_to_id(p, nl)) * ldo + col, r);
+        }
+      }
+    } else {
+      // centre node (sorted position nl) attends to positions nl-1, nl, nl+1
+      const int64_t ci = __ldg(valid_base + c);             // compact row of q / out
+      float qq[C], kk[3][C], vv[3][C];
+      load_row<T, C>(q + ci * ldq + col, qq);
+      const bool has_l = nl > 0, has_r = nl + 1 < w;
+      const int64_t idl = base + (has_l ? ca_pos_to_id(nl - 1, nl) : 0), idr = base + (has_r ? ca_pos_to_id(nl + 1, nl) : 0);
+      load_row<T, C>(k + (int64_t)base * ldk + col, kk[1]);
+      load_row<T, C>(v + (int64_t)base * ldv + col, vv[1]);
+      if (has_l) { load_row<T, C>(k + idl * ldk + col, kk[0]); load_row<T, C>(v + idl * ldv + col, vv[0]); }
+      if (has_r) { load_row<T, C>(k + idr * ldk + col, kk[2]); load_row<T, C>(v + idr * ldv + col, vv[2]); }
+      const float s1 = group_dot<C>(qq, kk[1], group);
+      float s0 = -INFINITY, s2 = -INFINITY;
+      if (has_l) s0 = group_dot<C>(qq, kk[0], group);
+      if (has_r) s2 = group_dot<C>(qq, kk[2], group);
+      const float mx = fmaxf(s1, fmaxf(s0, s2));
+      const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx), e2 = __expf(s2 - mx);
+      const float inv = 1.f / (e0 + e1 + e2);
+      float r[C];
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) {
+        float a = e1 * vv[1][cc];
+        if (has_l) a = fmaf(e0, vv[0][cc], a);
+        if (has_r) a = fmaf(e2, vv[2][cc], a);
+        r[cc] = a * inv;
+      }
+      store_f32<C>(out + ci * ldo + col, r);
+    }
+  }
+}
+
+template <typename T, int C, int WMAX>
+static int32_t launch_cluster(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                              const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl,
+                              int64_t n_clusters, int centre_only, int group, int n_slices, float* out, int64_t ldo,
+                              cudaStream_t st) {
+  int64_t blocks = ceil_div(n_clusters * n_slices, CA_THREADS / 32);
+  const int64_t max_blocks = 148 * 8 * 8;
+  if (blocks > max_blocks) blocks = max_blocks;
+  cluster_attn_kernel<T, C, WMAX><<<(unsigned)blocks, CA_THREADS, 0, st>>>(
+      (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, group,
+      n_slices, out, ldo);
+  GNNLM_LAUNCH_CHECK("gnnlm_hgt_cluster_attn");
+  return 0;
+}
+
+template <typename T, int C>
+static int32_t dispatch_w(int wmax, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                          const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl, int64_t n_clusters,
+                          int centre_only, int group, int n_slices, float* out, int64_t ldo, cudaStream_t st) {
+  if (wmax <= 1) return launch_cluster<T, C, 1>(q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, group, n_slices, out, ldo, st);
+  if (wmax <= 3) return launch_cluster<T, C, 3>(q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, group, n_slices, out, ldo, st);
+  if (wmax <= 5) return launch_cluster<T, C, 5>(q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, group, n_slices, out, ldo, st);
+  return launch_cluster<T, C, 7>(q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, group, n_slices, out, ldo, st);
+}
+
+}  // namespace gnnlm
+
+using namespace gnnlm;
+
+extern "C" int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                          int32_t dtype, const int32_t* node_base, const int32_t* valid_base,
+                                          const int32_t* cluster_nl, int64_t n_clusters, int32_t max_cluster,
+                                          int32_t centre_only, int32_t H, int32_t d_k, float* out, int64_t ldo,
+                                          gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(q && k && v && node_base && cluster_nl && out, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn: null pointer");
+  GNNLM_CHECK_ARG(!centre_only || valid_base, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn: centre_only needs valid_base");
+  GNNLM_CHECK_ARG(dtype == GNNLM_F32 || dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED, "gnnlm_hgt_cluster_attn: dtype");
+  GNNLM_CHECK_ARG(max_cluster >= 1 && max_cluster <= 7, GNNLM_E_UNSUPPORTED,
+                  "gnnlm_hgt_cluster_attn: cluster size %d > 7 (use gnnlm_hgt_edge_attn)", max_cluster);
+  GNNLM_CHECK_ARG(H > 0 && H <= 32 && (H & (H - 1)) == 0, GNNLM_E_UNSUPPORTED, "gnnlm_hgt_cluster_attn: H must be a power of two <= 32");
+  const int64_t d = (int64_t)H * d_k;
+  const int Cs = dtype == GNNLM_F32 ? 4 : 8;                 // 16 B per lane per row
+  // a warp covers 32*Cs features; a head (d_k features) must live inside one warp and heads may not straddle warps
+  GNNLM_CHECK_ARG(d % (32 * Cs) == 0 && d_k % Cs == 0 && d_k / Cs <= 32 && 32 % (d_k / Cs) == 0, GNNLM_E_UNSUPPORTED,
+                  "gnnlm_hgt_cluster_attn: unsupported (H=%d, d_k=%d) -- use gnnlm_hgt_edge_attn", H, d_k);
+  GNNLM_CHECK_ARG(ldq % Cs == 0 && ldk % Cs == 0 && ldv % Cs == 0 && ldo % 4 == 0, GNNLM_E_SHAPE,
+                  "gnnlm_hgt_cluster_attn: leading dimensions must keep 16 B alignment");
+  if (n_clusters == 0) return 0;
+  const int group = d_k / Cs, n_slices = (int)(d / (32 * Cs));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == GNNLM_F32)
+    return dispatch_w<float, 4>(max_cluster, q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only,
+                                group, n_slices, out, ldo, st);
+  return dispatch_w<__nv_bfloat16, 8>(max_cluster, q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters,
+                                      centre_only, group, n_slices, out, ldo, st);
+}

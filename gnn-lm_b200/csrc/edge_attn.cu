@@ -28,57 +28,50 @@ constexpr int EA_THREADS = 256;
 template <typename T, int C, int UNROLL>
 __device__ __forceinline__ void attend_range(const float (&q)[C], const T* __restrict__ k, int64_t ldk,
                                              const T* __restrict__ v, int64_t ldv, const int32_t* __restrict__ indices,
-                                             int64_t e_begin, int64_t e_end, int lane, int group, float& m_run,
+                                             int64_t e_begin, int64_t e_end, int col, int group, float& m_run,
                                              float& l_run, float (&acc)[C]) {
-  int64_t e = e_begin;
-  for (; e + UNROLL <= e_end; e += UNROLL) {
+  // UNROLL in-edges in flight per pass, predicated (a chain node has <= 3 in-edges: one pass, one
+  // round of memory latency).  `col` = first feature owned by this lane.
+  for (int64_t e = e_begin; e < e_end; e += UNROLL) {
     float kk[UNROLL][C], vv[UNROLL][C];
     float s[UNROLL];
+    int64_t src[UNROLL];
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const int64_t src = indices ? (int64_t)__ldg(indices + e + u) : (e + u);
-      load_row<T, C>(k + src * ldk + lane * C, kk[u]);
-      load_row<T, C>(v + src * ldv + lane * C, vv[u]);
+      const bool ok = e + u < e_end;
+      src[u] = ok ? (indices ? (int64_t)__ldg(indices + e + u) : (e + u)) : -1;
     }
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      if (src[u] >= 0) {
+        load_row<T, C>(k + src[u] * ldk + col, kk[u]);
+        load_row<T, C>(v + src[u] * ldv + col, vv[u]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) kk[u][c] = vv[u][c] = 0.f;
+      }
+    }
+    float mx = m_run;
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
       float p = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) p = fmaf(q[c], kk[u][c], p);
       for (int o = group >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-      s[u] = p;
+      s[u] = src[u] >= 0 ? p : -INFINITY;
+      mx = fmaxf(mx, s[u]);
     }
-    float mx = m_run;
-#pragma unroll
-    for (int u = 0; u < UNROLL; ++u) mx = fmaxf(mx, s[u]);
     const float corr = __expf(m_run - mx);          // m_run == -inf on first use -> 0
     l_run *= corr;
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] *= corr;
 #pragma unroll
     for (int u = 0; u < UNROLL; ++u) {
-      const float w = __expf(s[u] - mx);
+      const float w = __expf(s[u] - mx);            // -inf -> 0 for the predicated-off slots
       l_run += w;
 #pragma unroll
       for (int c = 0; c < C; ++c) acc[c] = fmaf(w, vv[u][c], acc[c]);
     }
-    m_run = mx;
-  }
-  for (; e < e_end; ++e) {
-    float kk[C], vv[C];
-    const int64_t src = indices ? (int64_t)__ldg(indices + e) : e;
-    load_row<T, C>(k + src * ldk + lane * C, kk);
-    load_row<T, C>(v + src * ldv + lane * C, vv);
-    float p = 0.f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) p = fmaf(q[c], kk[c], p);
-    for (int o = group >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-    const float mx = fmaxf(m_run, p);
-    const float corr = __expf(m_run - mx);
-    const float w = __expf(p - mx);
-    l_run = l_run * corr + w;
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = fmaf(w, vv[c], acc[c] * corr);
     m_run = mx;
   }
 }
@@ -99,29 +92,33 @@ __device__ __forceinline__ void write_out(float* __restrict__ o, const float (&a
   store_f32<C>(o, r);
 }
 
-// CSR edge attention.  UNROLL edges in flight per warp.
+// CSR edge attention.  Work item = (destination, feature slice of 32*C floats): a warp reads 128*C
+// contiguous bytes of each Q / K' / V' row, so registers stay small (many warps resident, several rows in
+// flight per warp) and every row segment is one coalesced request.  `group` = lanes per head.
 template <typename T, int C, int UNROLL>
 __global__ void __launch_bounds__(EA_THREADS) edge_attn_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k,
                                                                int64_t ldk, const T* __restrict__ v, int64_t ldv,
                                                                const int32_t* __restrict__ indptr,
                                                                const int32_t* __restrict__ indices,
                                                                const int32_t* __restrict__ dst_ids, int64_t n_dst_cap,
-                                                               const int32_t* __restrict__ n_dst_dev, int group,
+                                                               const int32_t* __restrict__ n_dst_dev, int group, int n_slices,
                                                                float* __restrict__ out, int64_t ldo, float out_scale,
                                                                int accumulate) {
-  const int64_t n_dst = live_rows(n_dst_cap, n_dst_dev);
+  const int64_t n_items = live_rows(n_dst_cap, n_dst_dev) * n_slices;
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_dst; i += warps) {
+  for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n_items; it += warps) {
+    const int64_t i = it / n_slices;
+    const int col = ((int)(it % n_slices) * 32 + lane) * C;
     const int64_t row = dst_ids ? (int64_t)__ldg(dst_ids + i) : i;
     const int64_t e0 = __ldg(indptr + row), e1 = __ldg(indptr + row + 1);
     float qr[C], acc[C];
-    load_row<T, C>(q + i * ldq + lane * C, qr);
+    load_row<T, C>(q + i * ldq + col, qr);
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
-    attend_range<T, C, UNROLL>(qr, k, ldk, v, ldv, indices, e0, e1, lane, group, m_run, l_run, acc);
-    write_out<C>(out + i * ldo + lane * C, acc, l_run, out_scale, accumulate);
+    attend_range<T, C, UNROLL>(qr, k, ldk, v, ldv, indices, e0, e1, col, group, m_run, l_run, acc);
+    write_out<C>(out + i * ldo + col, acc, l_run, out_scale, accumulate);
   }
 }
 
@@ -147,7 +144,7 @@ __global__ void __launch_bounds__(EA_THREADS) causal_attn_kernel(const T* __rest
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
-    attend_range<T, C, UNROLL>(qr, k, ldk, v, ldv, nullptr, b * L + lo, b * L + t + 1, lane, group, m_run, l_run, acc);
+    attend_range<T, C, UNROLL>(qr, k, ldk, v, ldv, nullptr, b * L + lo, b * L + t + 1, lane * C, group, m_run, l_run, acc);
     write_out<C>(out + g * ldo + lane * C, acc, l_run, out_scale, accumulate);
   }
 }
@@ -346,16 +343,16 @@ static int32_t launch_flash(const float* q, int64_t ldq, const float* k, int64_t
 template <typename T, int C>
 static int32_t launch_edge(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                            const int32_t* indptr, const int32_t* indices, const int32_t* dst_ids, int64_t n_dst_cap,
-                           const int32_t* n_dst_dev, int group, float* out, int64_t ldo, float out_scale, int accumulate,
-                           cudaStream_t st) {
-  constexpr int UNROLL = C >= 32 ? 2 : 4;
-  const int64_t warps_per_block = EA_THREADS / 32;
-  int64_t blocks = ceil_div(n_dst_cap, warps_per_block);
-  const int64_t max_blocks = 148 * 8 * 4;
+                           const int32_t* n_dst_dev, int group, int n_slices, float* out, int64_t ldo, float out_scale,
+                           int accumulate, cudaStream_t st) {
+  constexpr int UNROLL = 4;
+  const int64_t items = n_dst_cap * n_slices;
+  int64_t blocks = ceil_div(items, EA_THREADS / 32);
+  const int64_t max_blocks = 148 * 8 * 8;
   if (blocks > max_blocks) blocks = max_blocks;
   edge_attn_kernel<T, C, UNROLL><<<(unsigned)blocks, EA_THREADS, 0, st>>>(
-      (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, group, out,
-      ldo, out_scale, accumulate);
+      (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, group, n_slices,
+      out, ldo, out_scale, accumulate);
   GNNLM_LAUNCH_CHECK("gnnlm_hgt_edge_attn");
   return 0;
 }
@@ -414,12 +411,20 @@ extern "C" int32_t gnnlm_hgt_edge_attn(const void* q, int64_t ldq, const void* k
   if (rc) return rc;
   if (n_dst_cap == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  // feature slicing: lanes own Cs floats; a warp covers 32*Cs features; heads must not straddle lanes
+  int n_slices = 1;
+  const int Cs = dtype == GNNLM_F32 ? 4 : 8;                   // 16 B per lane per row
+  if (C > Cs && d_k % Cs == 0 && d_k / Cs <= 32 && 32 % (d_k / Cs) == 0) {   // a head must live inside one warp
+    n_slices = C / Cs;
+    group = d_k / Cs;                                          // lanes per head inside a slice
+    C = Cs;
+  }
   if (dtype == GNNLM_F32) {
-    DISPATCH_C(launch_edge, float, q, ldq, k, ldk, v, ldv, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, group, out, ldo,
-               out_scale, accumulate, st)
+    DISPATCH_C(launch_edge, float, q, ldq, k, ldk, v, ldv, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, group, n_slices,
+               out, ldo, out_scale, accumulate, st)
   } else {
     DISPATCH_C(launch_edge, __nv_bfloat16, q, ldq, k, ldk, v, ldv, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, group,
-               out, ldo, out_scale, accumulate, st)
+               n_slices, out, ldo, out_scale, accumulate, st)
   }
 }
 

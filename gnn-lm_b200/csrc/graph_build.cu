@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(256) graph_fill_kernel(const int64_t* __restri
                                                          int32_t* __restrict__ ntgt_dist, int32_t* __restrict__ nn_indptr,
                                                          int32_t* __restrict__ nn_indices,
                                                          int32_t* __restrict__ inter_indptr,
-                                                         int32_t* __restrict__ inter_indices) {
+                                                         int32_t* __restrict__ inter_indices,
+                                                         int32_t* __restrict__ cluster_nl) {
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n) return;
   const int64_t t = idx / k;
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(256) graph_fill_kernel(const int64_t* __restri
   const int64_t o = __ldg(nbr + idx);
   const int64_t pos = tgt_pos ? __ldg(tgt_pos + t) : 0;
   const ClusterShape s = cluster_shape(o, pos, n_datastore, left_ctx, right_ctx, invalid_ctx);
+  if (cluster_nl) cluster_nl[idx] = s.valid ? s.nl : -1;
   if (!s.valid) return;
   if (inter_indices) inter_indices[vb] = base;                 // centre node is created first (:367-374)
   const int nl = s.nl, nr = s.nr, w = 1 + nl + nr;
@@ -273,7 +275,8 @@ extern "C" int32_t gnnlm_graph_fill(const int64_t* nbr, const int64_t* tgt_pos, 
                                     int64_t n_datastore, int32_t left_ctx, int32_t right_ctx, int64_t invalid_ctx,
                                     const int32_t* node_base, const int32_t* valid_base, int64_t* ntgt_row,
                                     int32_t* ntgt_owner, int32_t* ntgt_dist, int32_t* nn_indptr, int32_t* nn_indices,
-                                    int32_t* inter_indptr, int32_t* inter_indices, gnnlm_stream_t stream) {
+                                    int32_t* inter_indptr, int32_t* inter_indices, int32_t* cluster_nl,
+                                    gnnlm_stream_t stream) {
   GNNLM_CHECK_ARG(nbr && node_base && valid_base, GNNLM_E_ARG, "gnnlm_graph_fill: null pointer");
   GNNLM_CHECK_ARG(!nn_indices || nn_indptr, GNNLM_E_ARG, "gnnlm_graph_fill: nn_indices needs nn_indptr");
   GNNLM_CHECK_ARG(invalid_ctx <= 0 || tgt_pos, GNNLM_E_ARG, "gnnlm_graph_fill: tgt_pos required when invalid_ctx > 0");
@@ -287,7 +290,7 @@ extern "C" int32_t gnnlm_graph_fill(const int64_t* nbr, const int64_t* tgt_pos, 
   graph_fill_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(nbr, tgt_pos, n, k, n_datastore, left_ctx, right_ctx,
                                                                  invalid_ctx, node_base, valid_base, ntgt_row,
                                                                  ntgt_owner, ntgt_dist, nn_indptr, nn_indices,
-                                                                 inter_indptr, inter_indices);
+                                                                 inter_indptr, inter_indices, cluster_nl);
   GNNLM_LAUNCH_CHECK("gnnlm_graph_fill");
   return 0;
 }

@@ -107,22 +107,24 @@ __global__ void __launch_bounds__(PQ_THREADS, 1)
   const int64_t node_end = min(n, node0 + nodes_per_cta);
   const float4* cb4 = reinterpret_cast<const float4*>(cb);
 
-  // 2 nodes in flight per warp per iteration to overlap the dependent (row -> code -> centroid) chain
-  for (int64_t i = node0 + warp * 2; i < node_end; i += (PQ_THREADS / 32) * 2) {
-    int64_t r[2];
-    uint32_t c[2];
+  // PQ_INFLIGHT nodes in flight per warp per iteration to overlap the dependent (row -> code -> centroid)
+  // chain: the kernel is latency-bound otherwise
+  constexpr int PQ_INFLIGHT = 8;
+  for (int64_t i = node0 + warp * PQ_INFLIGHT; i < node_end; i += (PQ_THREADS / 32) * PQ_INFLIGHT) {
+    int64_t r[PQ_INFLIGHT];
+    uint32_t c[PQ_INFLIGHT];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < PQ_INFLIGHT; ++u) {
       int64_t node = i + u;
       bool ok = node < node_end;
       int64_t nid = ok ? (row_ids ? (int64_t)__ldg(row_ids + node) : node) : 0;
       r[u] = ok ? __ldg(rows + nid) : -1;
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < PQ_INFLIGHT; ++u)
       c[u] = (r[u] >= 0 && active) ? (uint32_t)__ldg(codes + (size_t)r[u] * M + m0 + sub) : 0u;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < PQ_INFLIGHT; ++u) {
       if (r[u] >= 0 && active) {
         float4 v = cb4[((size_t)sub * 256 + c[u]) * f4_per_sub + part];
         v.x -= bsub.x; v.y -= bsub.y; v.z -= bsub.z; v.w -= bsub.w;

@@ -40,6 +40,7 @@ class TokenGraph:
         self.ntgt_row = self.ntgt_owner = self.ntgt_dist = None
         self.nn_indptr = self.nn_indices = self.inter_indptr = self.inter_indices = None
         self.tt_indptr = self.tt_indices = None
+        self.cluster_nl = None
         self._counts_host = None
 
     # ---- device-side counts (no host sync needed by the kernels) ----
@@ -113,7 +114,8 @@ def build_token_graph(nbr: torch.Tensor, n_datastore: int, left_ctx: int, right_
     g.nn_indices = torch.empty(3 * cap, **i32)
     g.inter_indptr = torch.empty(g.T + 1, **i32)
     g.inter_indices = torch.empty(n, **i32)
+    g.cluster_nl = torch.empty(n, **i32)
     L.call("gnnlm_graph_fill", L.ptr(nbr), L.ptr(tgt_pos), g.T, k, n_datastore, left_ctx, right_ctx, invalid_ctx,
            L.ptr(g.node_base), L.ptr(g.valid_base), L.ptr(g.ntgt_row), L.ptr(g.ntgt_owner), L.ptr(g.ntgt_dist),
-           L.ptr(g.nn_indptr), L.ptr(g.nn_indices), L.ptr(g.inter_indptr), L.ptr(g.inter_indices), st)
+           L.ptr(g.nn_indptr), L.ptr(g.nn_indices), L.ptr(g.inter_indptr), L.ptr(g.inter_indices), L.ptr(g.cluster_nl), st)
     return g

@@ -102,6 +102,7 @@ class HGTLayer(nn.Module):
         nn.init.xavier_uniform_(self.relation_msg)
         self._prep = None
         self._prep_key = None
+        self.use_cluster_kernel = True     # False: always go through the generic CSR kernel (tests compare both)
 
     # ------------------------------------------------------------------ weight preparation
     def prepare(self, math_mode: int):
@@ -151,8 +152,11 @@ class HGTLayer(nn.Module):
         d, H = P["d"], self.n_heads
         qkv = _lin(h_n, P["ntgt_qkv"], P["math"], m_dev=n_dev)
         t_agg = torch.empty((h_n.shape[0], d), device=h_n.device, dtype=torch.float32)
-        ops.edge_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.nn_indptr, G.nn_indices, H, t_agg, n_dst_dev=n_dev,
-                      tag="nn_full")
+        if self.use_cluster_kernel and ops.cluster_attn_supported(d, H, qkv.dtype, G.w):
+            ops.cluster_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G, H, t_agg, tag="nn_full")
+        else:
+            ops.edge_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.nn_indptr, G.nn_indices, H, t_agg,
+                          n_dst_dev=n_dev, tag="nn_full")
         return self._out(P, P["n"], t_agg, h_n, n_dev)
 
     def ntgt_centre(self, P, G: TokenGraph, h_n, n_dev, hc, c_dev):
@@ -161,8 +165,11 @@ class HGTLayer(nn.Module):
         kv = _lin(h_n, P["ntgt_qkv"].rows(d, 3 * d), P["math"], m_dev=n_dev)
         qc = _lin(hc, P["ntgt_qkv"].rows(0, d), P["math"], m_dev=c_dev)
         t_agg = torch.empty((hc.shape[0], d), device=h_n.device, dtype=torch.float32)
-        ops.edge_attn(qc, kv[:, :d], kv[:, d:], G.nn_indptr, G.nn_indices, H, t_agg, dst_ids=G.inter_indices,
-                      n_dst_dev=c_dev, tag="nn_centre")
+        if self.use_cluster_kernel and ops.cluster_attn_supported(d, H, qc.dtype, G.w):
+            ops.cluster_attn(qc, kv[:, :d], kv[:, d:], G, H, t_agg, centre_only=True, tag="nn_centre")
+        else:
+            ops.edge_attn(qc, kv[:, :d], kv[:, d:], G.nn_indptr, G.nn_indices, H, t_agg, dst_ids=G.inter_indices,
+                          n_dst_dev=c_dev, tag="nn_centre")
         return self._out(P, P["n"], t_agg, hc, c_dev)
 
     def tgt(self, P, G: TokenGraph, h_t, hc, c_dev):

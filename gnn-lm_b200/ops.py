@@ -100,6 +100,23 @@ def edge_attn(q, k, v, indptr, indices, H, out, *, dst_ids=None, n_dst=None, n_d
     return out
 
 
+def cluster_attn_supported(d: int, H: int, dtype, w: int) -> bool:
+    """Shape envelope of gnnlm_hgt_cluster_attn (else use edge_attn over the CSR)."""
+    cs = 4 if dtype == torch.float32 else 8
+    dk = d // H
+    return (w <= 7 and H & (H - 1) == 0 and H <= 32 and d % (32 * cs) == 0 and dk % cs == 0 and dk // cs <= 32
+            and 32 % (dk // cs) == 0)
+
+
+def cluster_attn(q, k, v, G, H, out, *, centre_only=False, tag=None):
+    """ntgt-intra-ntgt chain attention per (token, neighbour) cluster; G is a TokenGraph."""
+    d = k.shape[1]
+    L.call("gnnlm_hgt_cluster_attn", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0),
+           L.dtype_code(q.dtype), L.ptr(G.node_base), L.ptr(G.valid_base), L.ptr(G.cluster_nl), G.T * G.k, G.w,
+           int(centre_only), H, d // H, L.ptr(out), out.stride(0), L.stream_ptr(), tag=tag)
+    return out
+
+
 def causal_attn(q, k, v, B, Lb, intra_ctx, H, out, *, out_scale=1.0, accumulate=False):
     d = q.shape[1]
     L.call("gnnlm_hgt_causal_attn", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0),

@@ -81,12 +81,14 @@ int32_t gnnlm_graph_count(const int64_t* nbr, const int64_t* tgt_pos, int64_t T,
  *  ntgt_dist    [node_cap]   int32  |sorted position - centre position| in cluster  (nullable)
  *  nn_indptr    [node_cap+1] int32, nn_indices [3*node_cap] int32   ('ntgt','intra','ntgt')
  *  inter_indptr [T+1] int32,        inter_indices [T*k] int32       ('ntgt','inter','tgt'); the
- *               indices are exactly the centre-node ids in creation order. */
+ *               indices are exactly the centre-node ids in creation order.
+ *  cluster_nl   [T*k] int32  number of left-context nodes of each (token, neighbour) cluster, -1 when
+ *               the neighbour is invalid (nullable; consumed by gnnlm_hgt_cluster_attn). */
 int32_t gnnlm_graph_fill(const int64_t* nbr, const int64_t* tgt_pos, int64_t T, int64_t k,
                          int64_t n_datastore, int32_t left_ctx, int32_t right_ctx, int64_t invalid_ctx,
                          const int32_t* node_base, const int32_t* valid_base, int64_t* ntgt_row,
                          int32_t* ntgt_owner, int32_t* ntgt_dist, int32_t* nn_indptr, int32_t* nn_indices,
-                         int32_t* inter_indptr, int32_t* inter_indices, gnnlm_stream_t stream);
+                         int32_t* inter_indptr, int32_t* inter_indices, int32_t* cluster_nl, gnnlm_stream_t stream);
 
 /* ('tgt','intra','tgt') CSR, materialised only for parity checks (the attention kernel treats it as
  * implicit causal).  n_edges = B * sum_v min(v+1, intra_ctx or inf).  indptr [B*L+1], indices [E]. */
@@ -172,6 +174,23 @@ int32_t gnnlm_hgt_edge_attn(const void* q, int64_t ldq, const void* k, int64_t l
                             const int32_t* dst_ids, int64_t n_dst_cap, const int32_t* n_dst_dev, int32_t H,
                             int32_t d_k, float* out, int64_t ldo, float out_scale, int32_t accumulate,
                             gnnlm_stream_t stream);
+
+/* ('ntgt','intra','ntgt') without the CSR indirection: every valid (token, neighbour) pair owns a cluster
+ * of w contiguous node ids (creation order: centre, left ascending, right ascending) whose intra edges
+ * are a chain with self loops (build_ntgt_edges(context=1, bidirect=True), token_block_dataset.py:395-400),
+ * so the node at sorted position p attends to positions p-1, p, p+1.  One warp owns one
+ * (cluster, 128 B feature slice): Q / K' / V' rows of the cluster are read exactly once, all of them in
+ * flight together, and the w outputs are produced from registers -- the same arithmetic as
+ * gnnlm_hgt_edge_attn over nn_indptr / nn_indices (tests compare the two).
+ *  k, v [n_ntgt, H*d_k] indexed by node id.  centre_only == 0: q and out are indexed by node id too and
+ *  every node of every cluster is produced.  centre_only == 1: only the centre node of each cluster is
+ *  produced; q and out rows are compact, indexed by valid_base[cluster] (layer n_layers-1 of the
+ *  decoder's tgt-only mode).  node_base / valid_base / cluster_nl come from gnnlm_graph_count / _fill.
+ *  Supports cluster sizes up to 7 (neighbour context <= 3 per side). */
+int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                               int32_t dtype, const int32_t* node_base, const int32_t* valid_base,
+                               const int32_t* cluster_nl, int64_t n_clusters, int32_t max_cluster, int32_t centre_only,
+                               int32_t H, int32_t d_k, float* out, int64_t ldo, gnnlm_stream_t stream);
 
 /* ('tgt','intra','tgt') as implicit causal attention inside each of B blocks of L tokens
  * (edges u -> v for u <= v, v - u < intra_ctx when intra_ctx > 0; token_block_dataset.py:586-594). */

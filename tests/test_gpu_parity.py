@@ -189,7 +189,8 @@ def test_hgt_golden(case, dev):
     np.testing.assert_allclose(fast.cpu().numpy(), z["out_tgt"], rtol=1e-4, atol=1e-4)
 
 
-@pytest.mark.parametrize("d,H,L,k,c,NL", [(512, 8, 64, 8, 1, 1), (512, 8, 96, 4, 1, 3), (1024, 8, 48, 4, 2, 2), (128, 4, 40, 3, 0, 2)])
+@pytest.mark.parametrize("d,H,L,k,c,NL", [(512, 8, 64, 8, 1, 1), (512, 8, 96, 4, 1, 3), (1024, 8, 48, 4, 2, 2), (128, 4, 40, 3, 0, 2),
+                                          (1024, 8, 40, 4, 3, 3), (256, 4, 70, 5, 1, 2)])
 def test_hgt_vs_oracle(d, H, L, k, c, NL, dev):
     from gnnlm_b200.graph import build_token_graph
     from gnnlm_b200.hgt import HGT
@@ -219,6 +220,13 @@ def test_hgt_vs_oracle(d, H, L, k, c, NL, dev):
     full = m(g, features={"tgt": h_t.to(dev), "ntgt": h_n.to(dev)})
     np.testing.assert_allclose(full["ntgt"].cpu().double().numpy(), ref["ntgt"].numpy(), rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(full["tgt"].cpu().double().numpy(), ref["tgt"].numpy(), rtol=1e-4, atol=1e-4)
+    # generic CSR kernel instead of the cluster kernel for the ntgt-intra-ntgt edges: same results
+    for layer in m.gcs:
+        layer.use_cluster_kernel = False
+    fast2 = m.forward_tgt(g, h_t.to(dev), h_cap)
+    full2 = m(g, features={"tgt": h_t.to(dev), "ntgt": h_n.to(dev)})
+    np.testing.assert_allclose(fast2.cpu().numpy(), fast.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(full2["ntgt"].cpu().numpy(), full["ntgt"].cpu().numpy(), rtol=1e-5, atol=1e-5)
 
 
 @pytest.mark.parametrize("B,L,H,d,ctx", [(2, 37, 4, 128, 5), (2, 200, 8, 1024, 0), (1, 333, 8, 512, 70), (1, 64, 2, 256, 0),
