@@ -37,6 +37,9 @@ def parse():
     p.add_argument("--n-datastore", type=int, default=0, help="override datastore rows (default: the config's)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-tokens", type=int, default=384, help="tokens in the CPU-baseline sample block")
+    p.add_argument("--ncu-range", action="store_true",
+                   help="after warm-up run ONE resident step inside cudaProfilerStart/Stop and exit "
+                        "(use with `ncu --profile-from-start off`); prints no bench line")
     return p.parse_args()
 
 
@@ -196,6 +199,13 @@ def main():
 
     for i in range(max(3, args.warmup)):
         resident(i)
+    if args.ncu_range:
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        resident(0)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        return
     clocks = ClockSampler(local)
     clocks.start()
     l0 = L.launches

@@ -112,7 +112,9 @@ __global__ void __launch_bounds__(256) knn_mix_nll_kernel(const float* __restric
                                                           const void* __restrict__ vals, int val_bytes, int64_t n_datastore,
                                                           const int64_t* __restrict__ target, float sim_sign, float inv_temp,
                                                           float log_lambda, float log_1mlambda, int use_knn,
-                                                          const float* __restrict__ weight, float* __restrict__ out_lp,
+                                                          const float* __restrict__ weight, int64_t pad_id,
+                                                          const int32_t* __restrict__ loss_start, int64_t L,
+                                                          float* __restrict__ out_lp,
                                                           float* __restrict__ out_knn_prob, int32_t* __restrict__ out_recall,
                                                           double* __restrict__ nll_acc, int64_t T) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -159,7 +161,9 @@ __global__ void __launch_bounds__(256) knn_mix_nll_kernel(const float* __restric
     }
     if (lane == 0) {
       if (out_lp) out_lp[t] = lp;
-      const float w = weight ? __ldg(weight + t) : 1.f;
+      float w = weight ? __ldg(weight + t) : 1.f;
+      if (pad_id >= 0 && target && __ldg(target + t) == pad_id) w = 0.f;               // strip_pad (sequence_scorer.py:159,180)
+      if (loss_start && L > 0 && (t % L) < (int64_t)__ldg(loss_start + t / L)) w = 0.f;   // start_indices (:156-162)
       my_sum += (double)lp * (double)w;
       my_cnt += (double)w;
     }
@@ -252,8 +256,9 @@ extern "C" int32_t gnnlm_lse_finish(const float* part_max, const float* part_sum
 extern "C" int32_t gnnlm_knn_mix_nll(const float* lm_lp, const float* orig_lp, float orig_ratio, const float* dists,
                                      const int64_t* ids, int64_t k_nn, const void* vals, int32_t val_bytes,
                                      int64_t n_datastore, const int64_t* target, float sim_sign, float temperature,
-                                     float lambda, const float* weight, float* out_lp, float* out_knn_prob,
-                                     int32_t* out_recall, double* nll_acc, int64_t T, gnnlm_stream_t stream) {
+                                     float lambda, const float* weight, int64_t pad_id, const int32_t* loss_start,
+                                     int64_t L, float* out_lp, float* out_knn_prob, int32_t* out_recall,
+                                     double* nll_acc, int64_t T, gnnlm_stream_t stream) {
   GNNLM_CHECK_ARG(lm_lp, GNNLM_E_ARG, "gnnlm_knn_mix_nll: lm_lp null");
   const int use_knn = (dists != nullptr) && lambda > 0.f;
   if (use_knn) {
@@ -262,6 +267,8 @@ extern "C" int32_t gnnlm_knn_mix_nll(const float* lm_lp, const float* orig_lp, f
     GNNLM_CHECK_ARG(lambda < 1.f && temperature > 0.f, GNNLM_E_ARG, "gnnlm_knn_mix_nll: need 0 < lambda < 1, T > 0");
   }
   GNNLM_CHECK_ARG(!orig_lp || (orig_ratio > 0.f && orig_ratio < 1.f), GNNLM_E_ARG, "gnnlm_knn_mix_nll: orig_ratio in (0,1)");
+  GNNLM_CHECK_ARG((pad_id < 0 && !loss_start) || target, GNNLM_E_ARG, "gnnlm_knn_mix_nll: pad_id / loss_start need target");
+  GNNLM_CHECK_ARG(!loss_start || L > 0, GNNLM_E_ARG, "gnnlm_knn_mix_nll: loss_start needs L");
   if (T == 0) return 0;
   int64_t blocks = ceil_div(T, 8);
   if (blocks > 148 * 8) blocks = 148 * 8;
@@ -270,7 +277,8 @@ extern "C" int32_t gnnlm_knn_mix_nll(const float* lm_lp, const float* orig_lp, f
   const float log_l = use_knn ? (float)log((double)lambda) : 0.f, log_1ml = use_knn ? (float)log(1.0 - (double)lambda) : 0.f;
   knn_mix_nll_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       lm_lp, orig_lp, log_a, log_1ma, dists, ids, k_nn, vals, val_bytes, n_datastore, target, sim_sign,
-      use_knn ? 1.f / temperature : 1.f, log_l, log_1ml, use_knn, weight, out_lp, out_knn_prob, out_recall, nll_acc, T);
+      use_knn ? 1.f / temperature : 1.f, log_l, log_1ml, use_knn, weight, pad_id, loss_start, L, out_lp, out_knn_prob,
+      out_recall, nll_acc, T);
   GNNLM_LAUNCH_CHECK("gnnlm_knn_mix_nll");
   return 0;
 }

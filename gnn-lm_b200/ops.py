@@ -161,7 +161,8 @@ def adapt_target(target, cutoff):
 
 
 def knn_mix_nll(lm_lp, *, target=None, dists=None, ids=None, vals=None, n_datastore=0, sim_sign=1.0, temperature=1.0,
-                lmbda=0.0, orig_lp=None, orig_ratio=0.0, weight=None, nll_acc=None, want_knn=False):
+                lmbda=0.0, orig_lp=None, orig_ratio=0.0, weight=None, nll_acc=None, want_knn=False, pad_id=-1,
+                loss_start=None, block_len=0):
     T = lm_lp.numel()
     dev = lm_lp.device
     out_lp = torch.empty((T,), device=dev, dtype=torch.float32)
@@ -175,7 +176,7 @@ def knn_mix_nll(lm_lp, *, target=None, dists=None, ids=None, vals=None, n_datast
     L.call("gnnlm_knn_mix_nll", L.ptr(lm_lp), L.ptr(orig_lp), float(orig_ratio), L.ptr(dists) if use_knn else None,
            L.ptr(ids) if use_knn else None, dists.shape[1] if use_knn else 0, L.ptr(vals) if use_knn else None, vb,
            n_datastore, L.ptr(target), float(sim_sign), float(temperature), float(lmbda), L.ptr(weight),
-           L.ptr(out_lp), L.ptr(knn_p), L.ptr(recall), L.ptr(nll_acc), T, L.stream_ptr())
+           int(pad_id), L.ptr(loss_start), int(block_len), L.ptr(out_lp), L.ptr(knn_p), L.ptr(recall), L.ptr(nll_acc), T, L.stream_ptr())
     return out_lp, knn_p, recall
 
 

@@ -38,21 +38,22 @@ class SequenceScorer(object):
         dec = model.decoder
         lm_lp = dec.target_log_probs(decoder_out, target).reshape(-1)
         bsz, L = target.shape
-        weight = None
-        if nll_acc is not None:
-            pos = torch.arange(L, device=target.device)[None, :]
-            start = sample["start_indices"].to(target.device).view(bsz, 1) if "start_indices" in sample else 0
-            weight = ((pos >= start) & target.ne(self.pad)).float().reshape(-1).contiguous()
+        mask_kw = {}
+        if nll_acc is not None:     # pad / start_indices masking happens inside the kernel
+            mask_kw = dict(pad_id=self.pad, block_len=L, target=target.reshape(-1))
+            if "start_indices" in sample:
+                mask_kw["loss_start"] = sample["start_indices"].to(target.device, torch.int32).reshape(-1).contiguous()
         lmbda = getattr(self.args, "lmbda", 0.0) if self.args is not None else 0.0
         use_knn = knn_dstore is not None and lmbda > 0.0
         kw = {}
         if use_knn:
             dists, knns = knn_dstore.get_knns(None, positions=sample.get("positions"))
-            kw = dict(target=target.reshape(-1).contiguous(), dists=dists, ids=knns, vals=knn_dstore.vals,
+            kw = dict(target=target.reshape(-1), dists=dists, ids=knns, vals=knn_dstore.vals,
                       n_datastore=knn_dstore.dstore_size, sim_sign=knn_dstore.sim_sign, temperature=temperature,
                       lmbda=lmbda, want_knn=want_knn)
         if use_knn or nll_acc is not None:
-            lp, p, rec = ops.knn_mix_nll(lm_lp, weight=weight, nll_acc=nll_acc, **kw)
+            kw.update(mask_kw)
+            lp, p, rec = ops.knn_mix_nll(lm_lp, nll_acc=nll_acc, **kw)
         else:
             lp, p, rec = lm_lp, None, None
         return lp.view(bsz, L), p, rec, decoder_out

@@ -220,14 +220,17 @@ int32_t gnnlm_adapt_target(const int64_t* target, int64_t T, const int64_t* cuto
  * (sims = dists * sim_sign: +1 do_not_recomp_ip, -1 do_not_recomp_l2); recall = #matches;
  * lp = logsumexp(lm_lp + ln(1-lambda), ln(p_knn + 1e-10) + ln(lambda)).  lambda == 0 or dists == NULL
  * => lp = lm_lp.  Optional orig-LM mixing first: lm_lp = logsumexp(orig_lp + ln(a), lm_lp + ln(1-a)).
- * Accumulates sum(lp * weight) and sum(weight) into nll_acc[0..1] (fp64, device) when non-NULL;
- * weight [T] fp32 nullable (1 everywhere; 0 masks pad / context-window tokens).
+ * Accumulates sum(lp * w) and sum(w) into nll_acc[0..1] (fp64, device) when non-NULL, where
+ * w = weight[t] (fp32, nullable => 1) and w = 0 for pad targets (pad_id >= 0; strip_pad,
+ * sequence_scorer.py:159) and for positions t % L < loss_start[t / L] (loss_start int32 [T/L] nullable;
+ * start_indices of --gcn-context-window, sequence_scorer.py:156-162).
  *  vals: int16/int32 table (val_bytes = 2|4). */
 int32_t gnnlm_knn_mix_nll(const float* lm_lp, const float* orig_lp, float orig_ratio, const float* dists,
                           const int64_t* ids, int64_t k_nn, const void* vals, int32_t val_bytes,
                           int64_t n_datastore, const int64_t* target, float sim_sign, float temperature,
-                          float lambda, const float* weight, float* out_lp, float* out_knn_prob,
-                          int32_t* out_recall, double* nll_acc, int64_t T, gnnlm_stream_t stream);
+                          float lambda, const float* weight, int64_t pad_id, const int32_t* loss_start, int64_t L,
+                          float* out_lp, float* out_knn_prob, int32_t* out_recall, double* nll_acc, int64_t T,
+                          gnnlm_stream_t stream);
 
 /* Full-vocabulary kNN distribution (knn_model.py:202-208): probs [T, V] fp32, zero-filled by the
  * callee, += softmax weights at vals[ids]; kept for API parity with get_knn_prob(targets=None). */

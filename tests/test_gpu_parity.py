@@ -407,3 +407,53 @@ def test_whole_path_fp32_c3mini(dev):
     out = run_gpu(prob, dev, math="fp32")
     np.testing.assert_allclose(out["logprob"], ref["logprob"].numpy(), rtol=1e-4, atol=1e-4)
     assert abs(out["nll"] - ref["nll"]) < 0.01 / 16.8
+
+
+# ------------------------------------------------------------------------------------------ dataset + eval loop
+def test_eval_lm_dataset_vs_oracle(dev):
+    """GraphTokenBlockDataset -> collater -> move_to_cuda (on-device graph assembly) -> evaluate(), over a token
+    stream with a ragged last block and a gcn-context-window, against the CPU oracle run block by block."""
+    from types import SimpleNamespace
+    import copy
+    from gnnlm_b200 import synth
+    from gnnlm_b200.dataset import DeviceDatastore, GraphTokenBlockDataset
+    from gnnlm_b200.eval_lm import evaluate
+    from gnnlm_b200.knn_model import KNNModel
+    from gnnlm_b200.sequence_scorer import SequenceScorer
+    from oracle import model_oracle as mo
+    from tests.synth import oracle_model
+    cfg = dict(synth.CONFIGS["c1"], NL=2, k=4, n_d=1 << 16, k_nn=16)
+    model = synth.make_model(cfg)
+    rng = np.random.RandomState(5)
+    n_tok, blk, cw = 600, 128, 8
+    tables = synth.make_tables(cfg, device="cpu")
+    tokens = rng.randint(4, cfg["V"], size=n_tok).astype(np.int64)
+    nbr = rng.randint(1, cfg["n_d"] - 1, size=(n_tok, cfg["k"])).astype(np.int64)
+    nbr[rng.rand(n_tok, cfg["k"]) < 0.05] = -1
+    feats = rng.randn(n_tok, cfg["d"]).astype(np.float16)
+    kd = rng.randn(n_tok, cfg["k_nn"]).astype(np.float32)
+    ki = rng.randint(0, cfg["n_d"], size=(n_tok, cfg["k_nn"])).astype(np.int64)
+    ds = GraphTokenBlockDataset(tokens, blk, pad=1, eos=2, neighbor_offsets=nbr, n_datastore=cfg["n_d"], neighbor_context=1,
+                                precompute_feats=feats, context_window=cw, knn_dists=kd, knn_ids=ki)
+    dstore = DeviceDatastore(tables["codes"].to(dev), tables["vals"].to(dev))
+    scorer = SequenceScorer(synth.Dictionary(cfg["V"]), args=SimpleNamespace(lmbda=cfg["lmbda"], knn_keytype=None))
+    knn = KNNModel(dstore.vals, vocab_size=cfg["V"])
+    res = evaluate(copy.deepcopy(model).to(dev).set_math("fp32"), ds, dstore, scorer, knn_dstore=knn, temperature=1.0,
+                   max_sentences=2, device=dev)
+    # oracle, block by block (context tokens are scored by the model but excluded from the loss)
+    om = oracle_model(cfg, model)
+    tot, cnt = 0.0, 0
+    for i in range(len(ds)):
+        it = ds[i]
+        cs, e = it["offsets"]
+        batch = {"nbr": nbr[cs:e][None], "offsets": np.arange(cs, e)[None], "tgt_feats": torch.from_numpy(feats[cs:e]).float(),
+                 "target": it["target"], "codes": tables["codes"].numpy(), "cl": 1, "cr": 1, "n_d": cfg["n_d"]}
+        k_ = {"dists": torch.from_numpy(kd[cs:e]), "ids": torch.from_numpy(ki[cs:e]), "vals": tables["vals"].long(),
+              "lmbda": cfg["lmbda"], "temperature": 1.0}
+        out = mo.eval_batch(om, batch, k_)
+        lp = out["logprob"][it["start_idx"]:]
+        tot += float(lp.double().sum())
+        cnt += lp.numel()
+    assert res["count"] == cnt == n_tok
+    assert abs(res["score_sum"] - tot) / abs(tot) < 1e-5
+    assert abs(res["ppl"] - mo.perplexity(tot, cnt)[1]) / res["ppl"] < 1e-4

@@ -1,0 +1,107 @@
+"""N>1 host logic on CPU with world_size-2 gloo: contiguous block sharding and the path's only
+collective -- one all-reduce of {sum log p, n_tokens}.  Per-block scores come from the CPU oracle (test
+infrastructure); the sharded + reduced perplexity must equal the single-process one."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _block_scores(n_blocks, seed=0):
+    """Deterministic stand-in for per-block (score_sum, count): what evaluate() accumulates per batch."""
+    rng = np.random.RandomState(seed)
+    counts = rng.randint(50, 100, size=n_blocks)
+    sums = -rng.rand(n_blocks) * counts * 5.0
+    return sums, counts
+
+
+def _worker(rank, world, port, n_blocks, out):
+    import importlib
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ev = importlib.import_module("gnnlm_b200.eval_lm")
+    lo, hi = ev.shard_range(n_blocks, rank, world)
+    sums, counts = _block_scores(n_blocks)
+    acc = torch.tensor([sums[lo:hi].sum(), counts[lo:hi].sum()], dtype=torch.float64)
+    dist.all_reduce(acc)
+    out[rank] = (lo, hi, acc.tolist())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_blocks", [1, 7, 16])
+def test_sharded_nll_allreduce_gloo(n_blocks):
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n_blocks, out), nprocs=world, join=True)
+    sums, counts = _block_scores(n_blocks)
+    ranges = sorted((out[r][0], out[r][1]) for r in range(world))
+    assert ranges[0][0] == 0 and ranges[-1][1] == n_blocks
+    assert all(ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))        # contiguous, disjoint, complete
+    for r in range(world):
+        s, c = out[r][2]
+        assert c == counts.sum() and abs(s - sums.sum()) < 1e-9
+
+
+def test_shard_range_properties():
+    from gnnlm_b200.eval_lm import shard_range
+    for nb in (0, 1, 5, 8, 33, 1000):
+        for R in (1, 2, 3, 4, 8):
+            rs = [shard_range(nb, r, R) for r in range(R)]
+            assert rs[0][0] == 0 and rs[-1][1] == nb
+            assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+            sizes = [b - a for a, b in rs]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_batches_group_equal_lengths():
+    from gnnlm_b200.dataset import GraphTokenBlockDataset
+    from gnnlm_b200.eval_lm import batches
+    n = 1000
+    ds = GraphTokenBlockDataset(np.arange(n) % 50 + 4, 128, pad=1, eos=2, neighbor_offsets=np.zeros((n, 2), np.int64),
+                                n_datastore=10)
+    got = list(batches(ds, 0, len(ds), 3))
+    assert got == [[0, 1, 2], [3, 4, 5], [6], [7]]        # 7 full blocks (3+3+1) + the ragged last block alone
+    it = ds[0]
+    assert it["source"][0] == 2 and (it["source"][1:] == it["target"][:-1]).all()     # eos-shifted source (:310-311)
+    it3 = ds[3]
+    assert (it3["source"] == torch.from_numpy(ds.tokens[3 * 128 - 1:4 * 128 - 1])).all()   # buffer[s-1:e-1] (:319)
+    dsw = GraphTokenBlockDataset(np.arange(n) % 50 + 4, 128, pad=1, eos=2, neighbor_offsets=np.zeros((n, 2), np.int64),
+                                 n_datastore=10, context_window=16)
+    assert dsw[2]["start_idx"] == 16 and len(dsw[2]["target"]) == 144 and dsw[0]["start_idx"] == 0
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """include/gnnlm_sm100.h <-> libgnnlm_sm100.so <-> ctypes table (no compute calls without a GPU)."""
+    import re
+    from gnnlm_b200 import _lib
+    hdr = open(os.path.join(os.path.dirname(__file__), "..", "include", "gnnlm_sm100.h")).read()
+    declared = set(re.findall(r"\b(gnnlm_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.gnnlm_version() >= 100
+    assert lib.gnnlm_graph_tt_num_edges(2, 6, 0) == 2 * 21 and lib.gnnlm_graph_tt_num_edges(1, 6, 3) == 15
+    assert lib.gnnlm_graph_workspace_bytes(5000) > 0
+    assert lib.gnnlm_lse_num_tiles(20002, 0) == 157
+
+
+def test_product_never_imports_oracle():
+    root = os.path.join(os.path.dirname(__file__), "..", "gnn-lm_b200")
+    for fn in os.listdir(root):
+        if fn.endswith(".py"):
+            src = open(os.path.join(root, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src, fn
