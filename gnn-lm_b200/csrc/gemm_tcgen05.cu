@@ -5,7 +5,8 @@
 // (fairseq/models/hgt.py:320-322,347-348,401; knn/pq_wrapper.py:202;
 // fairseq/modules/adaptive_softmax.py:184,197,202).
 //
-// Structure (persistent, warp-specialised, one CTA per SM, static round-robin tile schedule):
+// Structure (persistent, warp-specialised, one CTA per SM, clusters of 2 CTAs that share the W tile through
+// TMA multicast, static round-robin schedule over tile pairs):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D loads of a 128 x 128B A tile and a 256 x 128B W
 //               tile (SWIZZLE_128B) per k-block into a multi-stage smem ring, mbarrier expect_tx.
 //   warp 1      MMA issuer: one thread issues tcgen05.mma.cta_group::1 (M=128, N=256, K=8 tf32 / 16 bf16)
@@ -21,6 +22,7 @@
 //               the host side once per checkpoint.  D += A_hi*W_lo + A_lo*W_hi + A_hi*W_hi recovers
 //               ~2^-21 relative accuracy from three tf32 passes ("fp32 mode" of the north star).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -73,10 +75,35 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast variant: the box lands at the same smem offset of every CTA in `mask`, each CTA's mbarrier (same
+// offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// commit that arrives on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
 }
 
 // K-major, SWIZZLE_128B smem operand descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
@@ -132,8 +159,97 @@ struct EpiLse {
   int64_t n_tiles;
 };
 
+// One output row per thread: drain 32-column chunks of this warp's TMEM lane quarter and either store them
+// (bias / residual fused) or fold them into the running (max, sum-exp, picked logit) of the row.
+template <bool LSE>
+__device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t M, int64_t n_base, int64_t n_blk, int64_t N,
+                                              const EpiStore& es, const EpiLse& el) {
+        float run_max = -INFINITY, run_sum = 0.f;
+        const int32_t want = (LSE && m < M && el.pick) ? __ldg(el.pick + m) : -1;
+  #pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          if (n_base + c >= N) break;                  // warp-uniform
+          float v[32];
+          tmem_ld32(taddr + (uint32_t)c, v);
+          const int64_t n0 = n_base + c;
+          if constexpr (!LSE) {
+            if (m < M) {
+              if (es.bias) {
+  #pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n0 + j < N) v[j] += __ldg(es.bias + n0 + j);
+              }
+              const bool full = n0 + 32 <= N;
+              if (es.residual) {
+                const float* r = es.residual + m * es.ldr + n0;
+                if (full && (es.ldr & 3) == 0) {
+  #pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(r) + j);
+                    v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                  }
+                } else {
+  #pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (n0 + j < N) v[j] += __ldg(r + j);
+                }
+              }
+              if (!es.c_bf16) {
+                float* o = reinterpret_cast<float*>(es.C) + m * es.ldc + n0;
+                if (full && (es.ldc & 3) == 0) {
+  #pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+  #pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (n0 + j < N) o[j] = v[j];
+                }
+              } else {
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(es.C) + m * es.ldc + n0;
+                if (full && (es.ldc & 7) == 0) {
+  #pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    uint4 u;
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
+                    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
+                    u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
+                    u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
+                    reinterpret_cast<uint4*>(o)[j] = u;
+                  }
+                } else {
+  #pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (n0 + j < N) o[j] = __float2bfloat16(v[j]);
+                }
+              }
+            }
+          } else {
+            float mx = run_max;
+  #pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < N) {
+                mx = fmaxf(mx, v[j]);
+                if (n0 + j == want) el.picked[m] = v[j];
+              }
+            float s = run_sum * __expf(run_max - mx);
+  #pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < N) s += __expf(v[j] - mx);
+            run_max = mx;
+            run_sum = s;
+          }
+        }
+        if constexpr (LSE) {
+          if (m < M) {
+            el.part_max[m * el.n_tiles + n_blk] = run_max;
+            el.part_sum[m * el.n_tiles + n_blk] = run_sum;
+          }
+        }
+}
+
 template <int MODE, bool LSE>
-__global__ void __launch_bounds__(MODE == X3 ? 384 : 256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == X3 ? 384 : 256, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ CUtensorMap map_blo, int64_t M_cap, const int32_t* __restrict__ m_dev, int64_t N,
                    int64_t K, EpiStore es, EpiLse el) {
@@ -155,8 +271,12 @@ __global__ void __launch_bounds__(MODE == X3 ? 384 : 256, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t M = live_rows(M_cap, m_dev);
+  // A CTA pair (cluster of 2 along M) works on two vertically adjacent output tiles that share the W tile:
+  // each CTA fetches half of it and multicasts to both, halving the L2 -> smem traffic of W.
+  const uint32_t crank = cluster_ctarank();
   const int64_t n_m = (M + BLOCK_M - 1) / BLOCK_M, n_n = (N + BLOCK_N - 1) / BLOCK_N;
-  const int64_t total = n_m * n_n;
+  const int64_t total = ((n_m + 1) / 2) * n_n;               // pair tiles; identical in both CTAs
+  const int64_t pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
   const int n_kb = (int)((K + BLOCK_K - 1) / BLOCK_K);
 
   auto sA = [&](int s) { return smem + (size_t)s * STAGE_BYTES; };
@@ -172,7 +292,7 @@ __global__ void __launch_bounds__(MODE == X3 ? 384 : 256, 1)
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], 2);                         // released by the MMA warps of both CTAs
       mbar_init(&conv_bar[s], 4);
     }
     for (int a = 0; a < 2; ++a) {
@@ -189,6 +309,7 @@ __global__ void __launch_bounds__(MODE == X3 ? 384 : 256, 1)
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                                        // peer barriers initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
 
@@ -197,14 +318,16 @@ __global__ void __launch_bounds__(MODE == X3 ? 384 : 256, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int m0 = (int)((tile / n_n) * BLOCK_M), n0 = (int)((tile % n_n) * BLOCK_N);
+      const int half = (int)crank * (BLOCK_N / 2);             // my half of the shared W tile (rows)
+      for (int64_t tile = pair0; tile < total; tile += pair_stride) {
+        const int m0 = (int)(((tile / n_n) * 2 + crank) * BLOCK_M), n0 = (int)((tile % n_n) * BLOCK_N);
         for (int kb = 0; kb < n_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1);           // both CTAs have drained this stage
           mbar_expect_tx(&full_bar[stage], TX_BYTES);
           tma_load_2d(sA(stage), &map_a, kb * BLOCK_K, m0, &full_bar[stage]);
-          tma_load_2d(sB(stage), &map_b, kb * BLOCK_K, n0, &full_bar[stage]);
-          if (MODE == X3) tma_load_2d(sBlo(stage), &map_blo, kb * BLOCK_K, n0, &full_bar[stage]);
+          tma_load_2d_mc(sB(stage) + half * ROW_BYTES, &map_b, kb * BLOCK_K, n0 + half, &full_bar[stage], 3);
+          if (MODE == X3)
+            tma_load_2d_mc(sBlo(stage) + half * ROW_BYTES, &map_blo, kb * BLOCK_K, n0 + half, &full_bar[stage], 3);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -215,7 +338,7 @@ __global__ void __launch_bounds__(MODE == X3 ? 384 : 256, 1)
       int stage = 0;
       uint32_t phase = 0;
       int64_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      for (int64_t tile = pair0; tile < total; tile += pair_stride, ++it) {
         const int acc = (int)(it & 1);
         const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -237,7 +360,7 @@ __global__ void __launch_bounds__(MODE == X3 ? 384 : 256, 1)
               umma<MODE != BF16>(d_tmem, da + koff, db + koff, IDESC, (kb | k) > 0 ? 1u : 0u);
             }
           }
-          tc_commit(&empty_bar[stage]);              // smem stage reusable once these MMAs retire
+          tc_commit_mc(&empty_bar[stage], 3);        // stage reusable (in BOTH CTAs) once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(&tmem_full[acc]);                  // accumulator complete
@@ -247,97 +370,16 @@ __global__ void __launch_bounds__(MODE == X3 ? 384 : 256, 1)
     // ===================== epilogue =====================
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
     int64_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    for (int64_t tile = pair0; tile < total; tile += pair_stride, ++it) {
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      const int64_t m_blk = tile / n_n, n_blk = tile % n_n;
+      const int64_t m_blk = (tile / n_n) * 2 + crank, n_blk = tile % n_n;
       const int64_t m = m_blk * BLOCK_M + q * 32 + lane;
       const int64_t n_base = n_blk * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
-      float run_max = -INFINITY, run_sum = 0.f;
-      const int32_t want = (LSE && m < M && el.pick) ? __ldg(el.pick + m) : -1;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        if (n_base + c >= N) break;                  // warp-uniform
-        float v[32];
-        tmem_ld32(taddr + (uint32_t)c, v);
-        const int64_t n0 = n_base + c;
-        if constexpr (!LSE) {
-          if (m < M) {
-            if (es.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < N) v[j] += __ldg(es.bias + n0 + j);
-            }
-            const bool full = n0 + 32 <= N;
-            if (es.residual) {
-              const float* r = es.residual + m * es.ldr + n0;
-              if (full && (es.ldr & 3) == 0) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 t = __ldg(reinterpret_cast<const float4*>(r) + j);
-                  v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (n0 + j < N) v[j] += __ldg(r + j);
-              }
-            }
-            if (!es.c_bf16) {
-              float* o = reinterpret_cast<float*>(es.C) + m * es.ldc + n0;
-              if (full && (es.ldc & 3) == 0) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (n0 + j < N) o[j] = v[j];
-              }
-            } else {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(es.C) + m * es.ldc + n0;
-              if (full && (es.ldc & 7) == 0) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  uint4 u;
-                  __nv_bfloat162 p0 = __floats2bfloat162_rn(v[8 * j], v[8 * j + 1]), p1 = __floats2bfloat162_rn(v[8 * j + 2], v[8 * j + 3]);
-                  __nv_bfloat162 p2 = __floats2bfloat162_rn(v[8 * j + 4], v[8 * j + 5]), p3 = __floats2bfloat162_rn(v[8 * j + 6], v[8 * j + 7]);
-                  u.x = *reinterpret_cast<uint32_t*>(&p0); u.y = *reinterpret_cast<uint32_t*>(&p1);
-                  u.z = *reinterpret_cast<uint32_t*>(&p2); u.w = *reinterpret_cast<uint32_t*>(&p3);
-                  reinterpret_cast<uint4*>(o)[j] = u;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (n0 + j < N) o[j] = __float2bfloat16(v[j]);
-              }
-            }
-          }
-        } else {
-          float mx = run_max;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < N) {
-              mx = fmaxf(mx, v[j]);
-              if (n0 + j == want) el.picked[m] = v[j];
-            }
-          float s = run_sum * __expf(run_max - mx);
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < N) s += __expf(v[j] - mx);
-          run_max = mx;
-          run_sum = s;
-        }
-      }
-      if constexpr (LSE) {
-        if (m < M) {
-          el.part_max[m * el.n_tiles + n_blk] = run_max;
-          el.part_sum[m * el.n_tiles + n_blk] = run_sum;
-        }
-      }
+      epilogue_tile<LSE>(taddr, m, M, n_base, n_blk, N, es, el);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -347,7 +389,7 @@ __global__ void __launch_bounds__(MODE == X3 ? 384 : 256, 1)
     const int ct = threadIdx.x - CONV_WARP0 * 32;     // 0..127
     int stage = 0;
     uint32_t phase = 0;
-    for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    for (int64_t tile = pair0; tile < total; tile += pair_stride) {
       for (int kb = 0; kb < n_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         float4* a = reinterpret_cast<float4*>(sA(stage));
@@ -373,9 +415,235 @@ __global__ void __launch_bounds__(MODE == X3 ? 384 : 256, 1)
 
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                                        // the peer may still multicast into / arrive on this CTA
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- 2-SM variant
+// cta_group::2: the CTA pair of a cluster issues ONE tcgen05.mma of M = 256 (128 rows per SM), N = 256.  Each
+// CTA stages its own 128-row A tile and HALF of the W tile (128 of the 256 W rows); the tensor cores read the
+// peer's half over the SM-pair link.  Per CTA and k-block that is 16 KB (A) + 16 KB (W) instead of 16 + 32 KB:
+// half the shared-memory operand bandwidth per MMA, half the L2 -> smem traffic for W, and 64 KB instead of
+// 96 KB per 3xTF32 stage (3 stages instead of 2).  Only the even CTA (leader) issues MMAs; the peer's TMA
+// loads, operand splitter and epilogue signal the leader's mbarriers through shared::cluster addresses.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;            // clears the CTA-rank bit of a shared::cluster address
+
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
+// TMA load whose complete_tx goes to the LEADER CTA's mbarrier (executed by both CTAs of the pair)
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {     // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+template <int KIND_TF32>
+__device__ __forceinline__ void umma_2sm(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (KIND_TF32) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+template <int MODE, bool LSE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == X3 ? 384 : 256, 1)
+    gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_blo, int64_t M_cap, const int32_t* __restrict__ m_dev, int64_t N,
+                    int64_t K, EpiStore es, EpiLse el) {
+  constexpr int ELEM = MODE == BF16 ? 2 : 4;
+  constexpr int BLOCK_K = ROW_BYTES / ELEM;
+  constexpr int UMMA_K = 32 / ELEM;
+  constexpr int HALF_B = B_TILE / 2;                                   // this CTA's 128 W rows: 16 KB
+  constexpr int STAGE_BYTES = MODE == X3 ? 2 * (A_TILE + HALF_B) : (A_TILE + HALF_B);
+  constexpr int STAGES = MODE == X3 ? 3 : 6;
+  // bytes that land on the LEADER's w_full barrier per stage (both CTAs): W halves, plus A tiles when nobody
+  // has to post-process A locally
+  constexpr uint32_t W_TX = MODE == X3 ? 2u * 2u * HALF_B : 2u * (A_TILE + HALF_B);
+  constexpr uint32_t FMT = MODE == BF16 ? 1u : 2u;
+  constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(BLOCK_N >> 3) << 17) |
+                             ((uint32_t)((2 * BLOCK_M) >> 4) << 24);     // M = 256 across the pair
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t a_full[STAGES], w_full[STAGES], empty_bar[STAGES], conv_bar[STAGES], tmem_full[2],
+      tmem_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int64_t M = live_rows(M_cap, m_dev);
+  const int64_t n_m = (M + BLOCK_M - 1) / BLOCK_M, n_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int64_t total = ((n_m + 1) / 2) * n_n;
+  const int64_t pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+  const int n_kb = (int)((K + BLOCK_K - 1) / BLOCK_K);
+
+  auto sA = [&](int s) { return smem + (size_t)s * STAGE_BYTES; };
+  auto sB = [&](int s) { return smem + (size_t)s * STAGE_BYTES + A_TILE; };
+  auto sAlo = [&](int s) { return smem + (size_t)s * STAGE_BYTES + A_TILE + HALF_B; };
+  auto sBlo = [&](int s) { return smem + (size_t)s * STAGE_BYTES + 2 * A_TILE + HALF_B; };
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    if (MODE == X3) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&a_full[s], 1);          // own A tile landed (3xTF32: the local splitter waits on it)
+      mbar_init(&w_full[s], 1);          // leader: operands of BOTH CTAs landed
+      mbar_init(&empty_bar[s], 1);       // one multicast commit per CTA
+      mbar_init(&conv_bar[s], 8);        // leader: 4 splitter warps x 2 CTAs
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 8);      // leader: 4 epilogue warps x 2 CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int half = (int)crank * (BLOCK_N / 2);
+      for (int64_t tile = pair0; tile < total; tile += pair_stride) {
+        const int m0 = (int)(((tile / n_n) * 2 + crank) * BLOCK_M), n0 = (int)((tile % n_n) * BLOCK_N) + half;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&w_full[stage], W_TX);
+          if (MODE == X3) {
+            mbar_expect_tx(&a_full[stage], A_TILE);
+            tma_load_2d(sA(stage), &map_a, kb * BLOCK_K, m0, &a_full[stage]);
+            tma_load_2d_2sm(sBlo(stage), &map_blo, kb * BLOCK_K, n0, &w_full[stage]);
+          } else {
+            tma_load_2d_2sm(sA(stage), &map_a, kb * BLOCK_K, m0, &w_full[stage]);
+          }
+          tma_load_2d_2sm(sB(stage), &map_b, kb * BLOCK_K, n0, &w_full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int64_t it = 0;
+      for (int64_t tile = pair0; tile < total; tile += pair_stride, ++it) {
+        const int acc = (int)(it & 1);
+        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BLOCK_N;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&w_full[stage], phase);
+          if (MODE == X3) mbar_wait(&conv_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t da = make_desc(smem_u32(sA(stage))), db = make_desc(smem_u32(sB(stage)));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * ELEM) >> 4);
+            if (MODE == X3) {
+              const uint64_t dal = make_desc(smem_u32(sAlo(stage))), dbl = make_desc(smem_u32(sBlo(stage)));
+              umma_2sm<1>(d_tmem, da + koff, dbl + koff, IDESC, (kb | k) > 0 ? 1u : 0u);
+              umma_2sm<1>(d_tmem, dal + koff, db + koff, IDESC, 1u);
+              umma_2sm<1>(d_tmem, da + koff, db + koff, IDESC, 1u);
+            } else {
+              umma_2sm<MODE != BF16>(d_tmem, da + koff, db + koff, IDESC, (kb | k) > 0 ? 1u : 0u);
+            }
+          }
+          tc_commit_2sm(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&tmem_full[acc]);
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int q = warp & 3;
+    int64_t it = 0;
+    for (int64_t tile = pair0; tile < total; tile += pair_stride, ++it) {
+      const int acc = (int)(it & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      const int64_t m_blk = (tile / n_n) * 2 + crank, n_blk = tile % n_n;
+      const int64_t m = m_blk * BLOCK_M + q * 32 + lane;
+      const int64_t n_base = n_blk * BLOCK_N;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      epilogue_tile<LSE>(taddr, m, M, n_base, n_blk, N, es, el);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+    }
+  } else if (MODE == X3 && warp >= CONV_WARP0) {
+    // ===================== operand splitter (both CTAs, own A tile) =====================
+    const int ct = threadIdx.x - CONV_WARP0 * 32;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t tile = pair0; tile < total; tile += pair_stride) {
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(&a_full[stage], phase);
+        float4* a = reinterpret_cast<float4*>(sA(stage));
+        float4* lo = reinterpret_cast<float4*>(sAlo(stage));
+#pragma unroll
+        for (int i = 0; i < A_TILE / 16 / 128; ++i) {
+          const int idx = ct + i * 128;
+          float4 x = a[idx], h;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+          a[idx] = h;
+          lo[idx] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&conv_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -425,16 +693,28 @@ static int make_map(CUtensorMap* map, const void* base, int bf16, int64_t rows, 
   return (int)r;
 }
 
+static int use_2sm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GNNLM_GEMM_2SM");
+    v = e ? atoi(e) : 1;                    // default: cta_group::2 kernel; GNNLM_GEMM_2SM=0 -> 1-SM + W multicast
+  }
+  return v;
+}
+
 template <int MODE, bool LSE>
 static int32_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mblo, int64_t M, const int32_t* m_dev,
                       int64_t N, int64_t K, const EpiStore& es, const EpiLse& el, cudaStream_t st) {
-  constexpr int STAGE_BYTES = MODE == X3 ? 2 * (A_TILE + B_TILE) : (A_TILE + B_TILE);
-  constexpr int STAGES = MODE == X3 ? 2 : 4;
-  const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GNNLM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+  const bool two = use_2sm() != 0;
+  const int stage_bytes = two ? (MODE == X3 ? 2 * (A_TILE + B_TILE / 2) : (A_TILE + B_TILE / 2))
+                              : (MODE == X3 ? 2 * (A_TILE + B_TILE) : (A_TILE + B_TILE));
+  const int stages = two ? (MODE == X3 ? 3 : 6) : (MODE == X3 ? 2 : 4);
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[two]) {
+    if (two) GNNLM_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<MODE, LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else GNNLM_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<MODE, LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set[two] = true;
   }
   static int n_sm = 0;
   if (!n_sm) {
@@ -442,9 +722,11 @@ static int32_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
     GNNLM_CUDA(cudaGetDevice(&dev));
     GNNLM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int64_t tiles = ceil_div(M, BLOCK_M) * ceil_div(N, BLOCK_N);
-  const unsigned grid = (unsigned)(tiles < n_sm ? tiles : n_sm);
-  gemm_tc_kernel<MODE, LSE><<<grid, MODE == X3 ? 384 : 256, smem, st>>>(ma, mb, mblo, M, m_dev, N, K, es, el);
+  const int64_t pairs = ceil_div(ceil_div(M, BLOCK_M), 2) * ceil_div(N, BLOCK_N);
+  const int64_t max_pairs = n_sm / 2;
+  const unsigned grid = 2u * (unsigned)(pairs < max_pairs ? pairs : max_pairs);     // clusters of 2 CTAs
+  if (two) gemm_tc2_kernel<MODE, LSE><<<grid, MODE == X3 ? 384 : 256, smem, st>>>(ma, mb, mblo, M, m_dev, N, K, es, el);
+  else gemm_tc_kernel<MODE, LSE><<<grid, MODE == X3 ? 384 : 256, smem, st>>>(ma, mb, mblo, M, m_dev, N, K, es, el);
   GNNLM_LAUNCH_CHECK("gemm_tcgen05");
   return 0;
 }
@@ -466,8 +748,8 @@ static int32_t tc_prepare(const char* who, const void* A, int32_t a_dtype, int64
   GNNLM_CHECK_ARG(math != GNNLM_MATH_TF32X3 || (W_lo && (uintptr_t)W_lo % 16 == 0), GNNLM_E_ARG,
                   "%s: MATH_TF32X3 needs W_lo (gnnlm_split_tf32)", who);
   int r = tc::make_map(ma, A, bf16, M, K, lda, tc::BLOCK_M);
-  if (!r) r = tc::make_map(mb, W, bf16, N, K, ldw, tc::BLOCK_N);
-  if (!r) r = tc::make_map(mblo, math == GNNLM_MATH_TF32X3 ? W_lo : W, bf16, N, K, ldw, tc::BLOCK_N);
+  if (!r) r = tc::make_map(mb, W, bf16, N, K, ldw, tc::BLOCK_N / 2);       // each CTA of a pair loads half the W tile
+  if (!r) r = tc::make_map(mblo, math == GNNLM_MATH_TF32X3 ? W_lo : W, bf16, N, K, ldw, tc::BLOCK_N / 2);
   GNNLM_CHECK_ARG(r == 0, GNNLM_E_ARG, "%s: cuTensorMapEncodeTiled failed (%d)", who, r);
   return 0;
 }
