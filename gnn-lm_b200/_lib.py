@@ -26,7 +26,7 @@ SIGNATURES = {
     "gnnlm_graph_tt_csr": (_i32, [_i64, _i64, _i64, _p, _p, _p]),
     "gnnlm_pq_gather_decode": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _i32, _p, _p, _p]),
     "gnnlm_split_tf32": (_i32, [_p, _p, _p, _i64, _p]),
-    "gnnlm_linear": (_i32, [_p, _i32, _i64, _p, _p, _i64, _p, _p, _i64, _p, _i32, _i64, _i64, _p, _i64, _i64, _i32, _p]),
+    "gnnlm_linear": (_i32, [_p, _i32, _i64, _p, _p, _i64, _p, _p, _i32, _i64, _p, _i32, _i64, _i64, _p, _i64, _i64, _i32, _p]),
     "gnnlm_lse_num_tiles": (_i64, [_i64, _i32]),
     "gnnlm_linear_lse": (_i32, [_p, _i32, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _p]),
     "gnnlm_lse_finish": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _p]),
@@ -34,7 +34,7 @@ SIGNATURES = {
     "gnnlm_layernorm": (_i32, [_p, _i64, _p, _p, _f32, _p, _i32, _i64, _i64, _p, _i64, _p]),
     "gnnlm_convert": (_i32, [_p, _i32, _p, _i32, _i64, _p]),
     "gnnlm_hgt_edge_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _i64, _p, _i32, _i32, _p, _i64, _f32, _i32, _p]),
-    "gnnlm_hgt_cluster_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i64, _p]),
+    "gnnlm_hgt_cluster_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p]),
     "gnnlm_hgt_causal_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _i64, _i64, _i64, _i32, _i32, _p, _i64, _f32, _i32, _p]),
     "gnnlm_adapt_target": (_i32, [_p, _i64, _p, _i32, _p, _p, _p, _p, _p]),
     "gnnlm_knn_mix_nll": (_i32, [_p, _p, _f32, _p, _p, _i64, _p, _i32, _i64, _p, _f32, _f32, _f32, _p, _i64, _p, _i64, _p, _p, _p,

@@ -25,8 +25,8 @@ int32_t gemm_simt_lse(const float* A, int64_t lda, const float* W, int64_t ldw, 
 int32_t gemm_tc_supported();
 int64_t gemm_tc_lse_tile_n();
 int32_t gemm_tc_store(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, int64_t ldw,
-                      const float* bias, const float* residual, int64_t ldr, void* C, int32_t c_dtype, int64_t ldc,
-                      int64_t M, const int32_t* m_dev, int64_t N, int64_t K, int32_t math, cudaStream_t st);
+                      const float* bias, const void* residual, int32_t r_dtype, int64_t ldr, void* C, int32_t c_dtype,
+                      int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, int64_t K, int32_t math, cudaStream_t st);
 int32_t gemm_tc_lse(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, int64_t ldw,
                     const int32_t* pick, float* part_max, float* part_sum, float* picked, int64_t M,
                     const int32_t* m_dev, int64_t N, int64_t K, int32_t math, cudaStream_t st);
@@ -58,18 +58,20 @@ static int32_t check_linear(const char* who, const void* A, int32_t a_dtype, con
 }
 
 extern "C" int32_t gnnlm_linear(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, int64_t ldw,
-                                const float* bias, const float* residual, int64_t ldr, void* C, int32_t c_dtype,
-                                int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, int64_t K, int32_t math,
-                                gnnlm_stream_t stream) {
+                                const float* bias, const void* residual, int32_t r_dtype, int64_t ldr, void* C,
+                                int32_t c_dtype, int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, int64_t K,
+                                int32_t math, gnnlm_stream_t stream) {
   int32_t rc = check_linear("gnnlm_linear", A, a_dtype, W, lda, ldw, M, N, K, math);
   if (rc) return rc;
   GNNLM_CHECK_ARG(C && ldc >= N, GNNLM_E_ARG, "gnnlm_linear: bad C/ldc");
   GNNLM_CHECK_ARG(c_dtype == GNNLM_F32 || c_dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED, "gnnlm_linear: C dtype");
   GNNLM_CHECK_ARG(!residual || ldr >= N, GNNLM_E_SHAPE, "gnnlm_linear: ldr < N");
+  GNNLM_CHECK_ARG(!residual || r_dtype == GNNLM_F32 || (r_dtype == GNNLM_BF16 && math != GNNLM_MATH_FP32_SIMT),
+                  GNNLM_E_UNSUPPORTED, "gnnlm_linear: residual must be F32 (or BF16 on the tensor-core path)");
   if (math == GNNLM_MATH_FP32_SIMT)
-    return gemm_simt_store((const float*)A, lda, (const float*)W, ldw, bias, residual, ldr, C, c_dtype, ldc, M, m_dev, N, K,
-                           (cudaStream_t)stream);
-  return gemm_tc_store(A, a_dtype, lda, W, W_lo, ldw, bias, residual, ldr, C, c_dtype, ldc, M, m_dev, N, K, math,
+    return gemm_simt_store((const float*)A, lda, (const float*)W, ldw, bias, (const float*)residual, ldr, C, c_dtype, ldc, M,
+                           m_dev, N, K, (cudaStream_t)stream);
+  return gemm_tc_store(A, a_dtype, lda, W, W_lo, ldw, bias, residual, r_dtype, ldr, C, c_dtype, ldc, M, m_dev, N, K, math,
                        (cudaStream_t)stream);
 }
 

@@ -28,14 +28,38 @@ __device__ __forceinline__ float group_dot(const float (&a)[C], const float (&b)
   return p;
 }
 
-template <typename T, int C, int WMAX>
+template <typename OutT, int C>
+__device__ __forceinline__ void store_out(OutT* __restrict__ p, const float (&r)[C]) {
+  if constexpr (sizeof(OutT) == 4) {
+    store_f32<C>(reinterpret_cast<float*>(p), r);
+  } else {
+    static_assert(C % 8 == 0 || C == 4, "bf16 output needs 8 B / 16 B chunks");
+    if constexpr (C == 4) {
+      __nv_bfloat162 a = __floats2bfloat162_rn(r[0], r[1]), b = __floats2bfloat162_rn(r[2], r[3]);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&a);
+      u.y = *reinterpret_cast<uint32_t*>(&b);
+      *reinterpret_cast<uint2*>(p) = u;
+    } else {
+#pragma unroll
+      for (int i = 0; i < C / 8; ++i) {
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(r[8 * i + 2 * j], r[8 * i + 2 * j + 1]);
+        reinterpret_cast<uint4*>(p)[i] = *reinterpret_cast<uint4*>(h);
+      }
+    }
+  }
+}
+
+template <typename T, typename OutT, int C, int WMAX>
 __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k,
                                                                   int64_t ldk, const T* __restrict__ v, int64_t ldv,
                                                                   const int32_t* __restrict__ node_base,
                                                                   const int32_t* __restrict__ valid_base,
                                                                   const int32_t* __restrict__ cluster_nl, int64_t n_clusters,
                                                                   int centre_only, int group, int n_slices,
-                                                                  float* __restrict__ out, int64_t ldo) {
+                                                                  OutT* __restrict__ out, int64_t ldo) {
   const int lane = threadIdx.x & 31;
   const int64_t n_items = n_clusters * n_slices;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -75,7 +99,7 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
             if (p + 1 < WMAX && p + 1 < w) a = fmaf(e2, vv[p + 1 < WMAX ? p + 1 : p][cc], a);
             r[cc] = a * inv;
           }
-          store_f32<C>(out + (int64_t)(base + ca_pos_to_id(p, nl)) * ldo + col, r);
+          store_out<OutT, C>(out + (int64_t)(base + ca_pos_to_id(p, nl)) * ldo + col, r);
         }
       }
     } else {
@@ -104,34 +128,38 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
         if (has_r) a = fmaf(e2, vv[2][cc], a);
         r[cc] = a * inv;
       }
-      store_f32<C>(out + ci * ldo + col, r);
+      store_out<OutT, C>(out + ci * ldo + col, r);
     }
   }
 }
 
-template <typename T, int C, int WMAX>
+template <typename T, typename OutT, int C, int WMAX>
 static int32_t launch_cluster(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                               const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl,
-                              int64_t n_clusters, int centre_only, int group, int n_slices, float* out, int64_t ldo,
+                              int64_t n_clusters, int centre_only, int group, int n_slices, void* out, int64_t ldo,
                               cudaStream_t st) {
   int64_t blocks = ceil_div(n_clusters * n_slices, CA_THREADS / 32);
   const int64_t max_blocks = 148 * 8 * 8;
   if (blocks > max_blocks) blocks = max_blocks;
-  cluster_attn_kernel<T, C, WMAX><<<(unsigned)blocks, CA_THREADS, 0, st>>>(
+  cluster_attn_kernel<T, OutT, C, WMAX><<<(unsigned)blocks, CA_THREADS, 0, st>>>(
       (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, group,
-      n_slices, out, ldo);
+      n_slices, (OutT*)out, ldo);
   GNNLM_LAUNCH_CHECK("gnnlm_hgt_cluster_attn");
   return 0;
 }
 
-template <typename T, int C>
+template <typename T, typename OutT, int C>
 static int32_t dispatch_w(int wmax, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                           const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl, int64_t n_clusters,
-                          int centre_only, int group, int n_slices, float* out, int64_t ldo, cudaStream_t st) {
-  if (wmax <= 1) return launch_cluster<T, C, 1>(q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, group, n_slices, out, ldo, st);
-  if (wmax <= 3) return launch_cluster<T, C, 3>(q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, group, n_slices, out, ldo, st);
-  if (wmax <= 5) return launch_cluster<T, C, 5>(q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, group, n_slices, out, ldo, st);
-  return launch_cluster<T, C, 7>(q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, group, n_slices, out, ldo, st);
+                          int centre_only, int group, int n_slices, void* out, int64_t ldo, cudaStream_t st) {
+#define GNNLM_CL(W)                                                                                                       \
+  return launch_cluster<T, OutT, C, W>(q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, \
+                                       group, n_slices, out, ldo, st)
+  if (wmax <= 1) GNNLM_CL(1);
+  if (wmax <= 3) GNNLM_CL(3);
+  if (wmax <= 5) GNNLM_CL(5);
+  GNNLM_CL(7);
+#undef GNNLM_CL
 }
 
 }  // namespace gnnlm
@@ -141,11 +169,12 @@ using namespace gnnlm;
 extern "C" int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                           int32_t dtype, const int32_t* node_base, const int32_t* valid_base,
                                           const int32_t* cluster_nl, int64_t n_clusters, int32_t max_cluster,
-                                          int32_t centre_only, int32_t H, int32_t d_k, float* out, int64_t ldo,
-                                          gnnlm_stream_t stream) {
+                                          int32_t centre_only, int32_t H, int32_t d_k, void* out, int32_t out_dtype,
+                                          int64_t ldo, gnnlm_stream_t stream) {
   GNNLM_CHECK_ARG(q && k && v && node_base && cluster_nl && out, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn: null pointer");
   GNNLM_CHECK_ARG(!centre_only || valid_base, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn: centre_only needs valid_base");
   GNNLM_CHECK_ARG(dtype == GNNLM_F32 || dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED, "gnnlm_hgt_cluster_attn: dtype");
+  GNNLM_CHECK_ARG(out_dtype == GNNLM_F32 || out_dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED, "gnnlm_hgt_cluster_attn: out dtype");
   GNNLM_CHECK_ARG(max_cluster >= 1 && max_cluster <= 7, GNNLM_E_UNSUPPORTED,
                   "gnnlm_hgt_cluster_attn: cluster size %d > 7 (use gnnlm_hgt_edge_attn)", max_cluster);
   GNNLM_CHECK_ARG(H > 0 && H <= 32 && (H & (H - 1)) == 0, GNNLM_E_UNSUPPORTED, "gnnlm_hgt_cluster_attn: H must be a power of two <= 32");
@@ -154,14 +183,17 @@ extern "C" int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void
   // a warp covers 32*Cs features; a head (d_k features) must live inside one warp and heads may not straddle warps
   GNNLM_CHECK_ARG(d % (32 * Cs) == 0 && d_k % Cs == 0 && d_k / Cs <= 32 && 32 % (d_k / Cs) == 0, GNNLM_E_UNSUPPORTED,
                   "gnnlm_hgt_cluster_attn: unsupported (H=%d, d_k=%d) -- use gnnlm_hgt_edge_attn", H, d_k);
-  GNNLM_CHECK_ARG(ldq % Cs == 0 && ldk % Cs == 0 && ldv % Cs == 0 && ldo % 4 == 0, GNNLM_E_SHAPE,
+  GNNLM_CHECK_ARG(ldq % Cs == 0 && ldk % Cs == 0 && ldv % Cs == 0 && ldo % 8 == 0, GNNLM_E_SHAPE,
                   "gnnlm_hgt_cluster_attn: leading dimensions must keep 16 B alignment");
   if (n_clusters == 0) return 0;
   const int group = d_k / Cs, n_slices = (int)(d / (32 * Cs));
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == GNNLM_F32)
-    return dispatch_w<float, 4>(max_cluster, q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only,
-                                group, n_slices, out, ldo, st);
-  return dispatch_w<__nv_bfloat16, 8>(max_cluster, q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters,
-                                      centre_only, group, n_slices, out, ldo, st);
+#define GNNLM_DW(T, OT, C)                                                                                                    \
+  return dispatch_w<T, OT, C>(max_cluster, q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, \
+                              group, n_slices, out, ldo, st)
+  if (dtype == GNNLM_F32 && out_dtype == GNNLM_F32) GNNLM_DW(float, float, 4);
+  if (dtype == GNNLM_F32) GNNLM_DW(float, __nv_bfloat16, 4);
+  if (out_dtype == GNNLM_F32) GNNLM_DW(__nv_bfloat16, float, 8);
+  GNNLM_DW(__nv_bfloat16, __nv_bfloat16, 8);
+#undef GNNLM_DW
 }

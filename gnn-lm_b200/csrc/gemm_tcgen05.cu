@@ -145,11 +145,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 
 struct EpiStore {
   const float* bias;
-  const float* residual;
+  const void* residual;
   int64_t ldr;
   void* C;
   int64_t ldc;
   int c_bf16;
+  int r_bf16;
 };
 struct EpiLse {
   const int32_t* pick;
@@ -180,18 +181,36 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t
                   if (n0 + j < N) v[j] += __ldg(es.bias + n0 + j);
               }
               const bool full = n0 + 32 <= N;
-              if (es.residual) {
-                const float* r = es.residual + m * es.ldr + n0;
+              if (es.residual && !es.r_bf16) {
+                const float* r = reinterpret_cast<const float*>(es.residual) + m * es.ldr + n0;
                 if (full && (es.ldr & 3) == 0) {
-  #pragma unroll
+#pragma unroll
                   for (int j = 0; j < 8; ++j) {
                     const float4 t = __ldg(reinterpret_cast<const float4*>(r) + j);
                     v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
                   }
                 } else {
-  #pragma unroll
+#pragma unroll
                   for (int j = 0; j < 32; ++j)
                     if (n0 + j < N) v[j] += __ldg(r + j);
+                }
+              } else if (es.residual) {
+                const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(es.residual) + m * es.ldr + n0;
+                if (full && (es.ldr & 7) == 0) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint4 t = __ldg(reinterpret_cast<const uint4*>(r) + j);
+                    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 f = __bfloat1622float2(hh[e]);
+                      v[8 * j + 2 * e] += f.x; v[8 * j + 2 * e + 1] += f.y;
+                    }
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (n0 + j < N) v[j] += __bfloat162float(r[j]);
                 }
               }
               if (!es.c_bf16) {
@@ -755,13 +774,13 @@ static int32_t tc_prepare(const char* who, const void* A, int32_t a_dtype, int64
 }
 
 int32_t gemm_tc_store(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, int64_t ldw,
-                      const float* bias, const float* residual, int64_t ldr, void* C, int32_t c_dtype, int64_t ldc,
-                      int64_t M, const int32_t* m_dev, int64_t N, int64_t K, int32_t math, cudaStream_t st) {
+                      const float* bias, const void* residual, int32_t r_dtype, int64_t ldr, void* C, int32_t c_dtype,
+                      int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, int64_t K, int32_t math, cudaStream_t st) {
   if (M == 0) return 0;
   CUtensorMap ma, mb, mblo;
   int32_t rc = tc_prepare("gnnlm_linear", A, a_dtype, lda, W, W_lo, ldw, M, N, K, math, &ma, &mb, &mblo);
   if (rc) return rc;
-  tc::EpiStore es{bias, residual, ldr, C, ldc, c_dtype == GNNLM_BF16};
+  tc::EpiStore es{bias, residual, ldr, C, ldc, c_dtype == GNNLM_BF16, r_dtype == GNNLM_BF16};
   tc::EpiLse el{};
   if (math == GNNLM_MATH_TF32X3) return tc::launch<tc::X3, false>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
   if (math == GNNLM_MATH_TF32) return tc::launch<tc::TF32, false>(ma, mb, mblo, M, m_dev, N, K, es, el, st);

@@ -65,6 +65,18 @@ def _lin(x, w: _Weight, math_mode, **kw):
     return ops.linear(x, w.W, w.b, W_lo=w.lo, math=math_mode, **kw)
 
 
+def act_dtype(math_mode: int):
+    """Activation storage type of a math mode: bf16 end to end in MATH_BF16, fp32 otherwise."""
+    return torch.bfloat16 if math_mode == L.MATH_BF16 else torch.float32
+
+
+def as_act(x: torch.Tensor, math_mode: int) -> torch.Tensor:
+    dt = act_dtype(math_mode)
+    if x.dtype == dt:
+        return x if x.is_contiguous() else x.contiguous()
+    return ops.convert(x, dt)
+
+
 class HGTLayer(nn.Module):
     """Same parameters as the reference layer (hgt.py:27-79)."""
 
@@ -143,37 +155,50 @@ class HGTLayer(nn.Module):
 
     # ------------------------------------------------------------------ building blocks
     def _out(self, P, tau, t_agg, h_in, n_dev):
-        o = _lin(t_agg, P["a"][tau], P["math"], residual=h_in, m_dev=n_dev)              # hgt.py:401-403
+        """LayerNorm(A-linear(t) + h) (hgt.py:401-405); the pre-norm sum is fp32 in every mode."""
+        o = _lin(t_agg, P["a"][tau], P["math"], residual=h_in, m_dev=n_dev)
         g, b, eps = P["ln"][tau]
-        return ops.layernorm(o, g, b, eps, out=o, n_dev=n_dev)                            # :405
+        act = act_dtype(P["math"])
+        if act == torch.float32:
+            return ops.layernorm(o, g, b, eps, out=o, n_dev=n_dev)
+        return ops.layernorm(o, g, b, eps, out_dtype=act, n_dev=n_dev)
+
+    def _nn_attn(self, P, G, q, k, v, rows, *, centre: bool, n_dev, c_dev):
+        """ntgt-intra-ntgt attention -> [rows, d] in the activation dtype."""
+        d, H = P["d"], self.n_heads
+        act = act_dtype(P["math"])
+        tag = "nn_centre" if centre else "nn_full"
+        if self.use_cluster_kernel and ops.cluster_attn_supported(d, H, q.dtype, G.w):
+            t_agg = torch.empty((rows, d), device=q.device, dtype=act)
+            ops.cluster_attn(q, k, v, G, H, t_agg, centre_only=centre, tag=tag)
+            return t_agg
+        t_agg = torch.empty((rows, d), device=q.device, dtype=torch.float32)
+        if centre:
+            ops.edge_attn(q, k, v, G.nn_indptr, G.nn_indices, H, t_agg, dst_ids=G.inter_indices, n_dst_dev=c_dev, tag=tag)
+        else:
+            ops.edge_attn(q, k, v, G.nn_indptr, G.nn_indices, H, t_agg, n_dst_dev=n_dev, tag=tag)
+        return as_act(t_agg, P["math"])
 
     def ntgt_full(self, P, G: TokenGraph, h_n, n_dev):
         """All ntgt nodes: Q|K'|V' -> chain attention -> A-linear + residual + LN."""
-        d, H = P["d"], self.n_heads
-        qkv = _lin(h_n, P["ntgt_qkv"], P["math"], m_dev=n_dev)
-        t_agg = torch.empty((h_n.shape[0], d), device=h_n.device, dtype=torch.float32)
-        if self.use_cluster_kernel and ops.cluster_attn_supported(d, H, qkv.dtype, G.w):
-            ops.cluster_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G, H, t_agg, tag="nn_full")
-        else:
-            ops.edge_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.nn_indptr, G.nn_indices, H, t_agg,
-                          n_dst_dev=n_dev, tag="nn_full")
+        d = P["d"]
+        qkv = _lin(h_n, P["ntgt_qkv"], P["math"], m_dev=n_dev, out_dtype=act_dtype(P["math"]))
+        t_agg = self._nn_attn(P, G, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h_n.shape[0], centre=False, n_dev=n_dev,
+                              c_dev=None)
         return self._out(P, P["n"], t_agg, h_n, n_dev)
 
     def ntgt_centre(self, P, G: TokenGraph, h_n, n_dev, hc, c_dev):
         """Centre nodes only (compact rows): K'|V' for every node, Q / A-linear / LN for centres."""
-        d, H = P["d"], self.n_heads
-        kv = _lin(h_n, P["ntgt_qkv"].rows(d, 3 * d), P["math"], m_dev=n_dev)
-        qc = _lin(hc, P["ntgt_qkv"].rows(0, d), P["math"], m_dev=c_dev)
-        t_agg = torch.empty((hc.shape[0], d), device=h_n.device, dtype=torch.float32)
-        if self.use_cluster_kernel and ops.cluster_attn_supported(d, H, qc.dtype, G.w):
-            ops.cluster_attn(qc, kv[:, :d], kv[:, d:], G, H, t_agg, centre_only=True, tag="nn_centre")
-        else:
-            ops.edge_attn(qc, kv[:, :d], kv[:, d:], G.nn_indptr, G.nn_indices, H, t_agg, dst_ids=G.inter_indices,
-                          n_dst_dev=c_dev, tag="nn_centre")
+        d = P["d"]
+        act = act_dtype(P["math"])
+        kv = _lin(h_n, P["ntgt_qkv"].rows(d, 3 * d), P["math"], m_dev=n_dev, out_dtype=act)
+        qc = _lin(hc, P["ntgt_qkv"].rows(0, d), P["math"], m_dev=c_dev, out_dtype=act)
+        t_agg = self._nn_attn(P, G, qc, kv[:, :d], kv[:, d:], hc.shape[0], centre=True, n_dev=n_dev, c_dev=c_dev)
         return self._out(P, P["n"], t_agg, hc, c_dev)
 
     def tgt(self, P, G: TokenGraph, h_t, hc, c_dev):
-        """tgt nodes: mean of (centre ntgt -> tgt) attention and causal tgt -> tgt attention."""
+        """tgt nodes: mean of (centre ntgt -> tgt) attention and causal tgt -> tgt attention.  Q/K'/V' of this
+        (small) side are kept in fp32 in every mode."""
         d, H = P["d"], self.n_heads
         qkv = _lin(h_t, P["tgt_qkv"], P["math"])
         kvi = _lin(hc, P["ntgt_kv_inter"], P["math"], m_dev=c_dev)
@@ -182,7 +207,7 @@ class HGTLayer(nn.Module):
         ops.edge_attn(qkv[:, :d], kvi[:, :d], kvi[:, d:], G.inter_indptr, None, H, t_agg, out_scale=0.5, tag="inter")
         ops.causal_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5,
                         accumulate=True)
-        return self._out(P, P["t"], t_agg, h_t, None)
+        return self._out(P, P["t"], as_act(t_agg, P["math"]), h_t, None)
 
     def forward(self, G: TokenGraph, h: Dict[str, torch.Tensor], etypes=None, incremental_state=None,
                 math_mode: int = L.MATH_FP32_SIMT) -> Dict[str, torch.Tensor]:
@@ -190,9 +215,10 @@ class HGTLayer(nn.Module):
         assert incremental_state is None, "only support lm (transformer.py:1028)"
         P = self.prepare(math_mode)
         n_valid = G.counts()[1]
-        hc = ops.gather_rows(h["ntgt"], G.inter_indices, n_cap=n_valid)
-        new_t = self.tgt(P, G, h["tgt"], hc, None)
-        new_n = self.ntgt_full(P, G, h["ntgt"], None)
+        h_t, h_n = as_act(h["tgt"], math_mode), as_act(h["ntgt"], math_mode)
+        hc = ops.gather_rows(h_n, G.inter_indices, n_cap=n_valid)
+        new_t = self.tgt(P, G, h_t, hc, None)
+        new_n = self.ntgt_full(P, G, h_n, None)
         return {"tgt": new_t, "ntgt": new_n}
 
 
@@ -224,7 +250,7 @@ class HGT(nn.Module):
             x = None if not features else features.get(ntype)
             if x is None:
                 x = G.nodes[ntype].data["h"]
-            h[ntype] = x.float().contiguous()
+            h[ntype] = x if x.dtype == torch.bfloat16 else x.float().contiguous()
         for layer in self.gcs:
             h = layer(G, h, etypes=etypes, incremental_state=incremental_state, math_mode=self.math_mode)
         return h
@@ -243,6 +269,8 @@ class HGT(nn.Module):
         prep = [layer.prepare(mode) for layer in self.gcs]
         # ---- ntgt side: compact centre features entering each layer
         hc: List[torch.Tensor] = []
+        if h_ntgt is not None:
+            h_ntgt = as_act(h_ntgt, mode)
         if hc0 is None:
             hc0 = ops.gather_rows(h_ntgt, G.inter_indices, n_dev=c_dev)
         hc.append(hc0)
@@ -254,7 +282,7 @@ class HGT(nn.Module):
             else:
                 hc.append(self.gcs[l].ntgt_centre(prep[l], G, h_n, n_dev, hc[l], c_dev))
         # ---- tgt side
-        h_t = h_tgt.float().contiguous()
+        h_t = as_act(h_tgt, mode)
         for l in range(NL):
             h_t = self.gcs[l].tgt(prep[l], G, h_t, hc[l], c_dev)
         return h_t

@@ -22,7 +22,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import ops
 from .graph import ETYPES, TokenGraph
-from .hgt import HGT, _Weight
+from .hgt import HGT, _Weight, act_dtype, as_act
 from .pq_codec import TorchPQCodec
 
 
@@ -93,7 +93,7 @@ class AdaptiveSoftmax(nn.Module):
     def target_log_prob(self, x: torch.Tensor, target: torch.Tensor, math_mode: int = L.MATH_FP32_SIMT) -> torch.Tensor:
         """log p(target) per row: the only entries of get_log_prob's [T, V] tensor that the scorer reads
         (adaptive_softmax.py:170-206 + sequence_scorer.py:48-53), computed without materialising it."""
-        x = x.reshape(-1, x.shape[-1])
+        x = as_act(x.reshape(-1, x.shape[-1]), math_mode)
         target = target.reshape(-1).contiguous()
         P = self.prepare(math_mode)
         head_pick, tail_rows, tail_pick, tail_count = ops.adapt_target(target, self.cutoff)
@@ -103,7 +103,8 @@ class AdaptiveSoftmax(nn.Module):
         for i in range(len(self.tail)):
             cnt = tail_count[i:i + 1]
             xi = ops.gather_rows(x, tail_rows[i], n_dev=cnt)
-            hi = ops.linear(xi, P["proj"][i].W, None, W_lo=P["proj"][i].lo, m_dev=cnt, math=math_mode)
+            hi = ops.linear(xi, P["proj"][i].W, None, W_lo=P["proj"][i].lo, m_dev=cnt, math=math_mode,
+                            out_dtype=act_dtype(math_mode))
             pm, ps, pk, nt = ops.linear_lse(hi, P["out"][i].W, tail_pick[i], W_lo=P["out"][i].lo, m_dev=cnt, math=math_mode)
             ops.lse_finish(pm, ps, pk, nt, lp, row_map=tail_rows[i], accumulate=True, m_dev=cnt)
         return lp
@@ -184,9 +185,7 @@ class TokenGraphTransformerDecoder(nn.Module):
         if "h" not in graph.nodes["tgt"].data:
             raise NotImplementedError("the base transformer is out of scope: evaluate with --use-precompute-feat "
                                       "(transformer.py:974-976)")
-        x = graph.nodes["tgt"].data["h"]
-        if x.dtype != torch.float32:
-            x = ops.convert(x, torch.float32)                         # token_block_dataset.py:328
+        x = as_act(graph.nodes["tgt"].data["h"], self.math_mode)     # fp16 -> fp32 (token_block_dataset.py:328) / bf16
         x = x.view(bsz, tgt_len, -1)
         extra = {"inner_states": [x.transpose(0, 1)]}
         orig_x = x if self.orig_prob_ratio > 0 else None
@@ -209,8 +208,7 @@ class TokenGraphTransformerDecoder(nn.Module):
         mode = self.math_mode
         NL = self.hgt_decoder.n_layers
         if "h" in nd and nd["h"].dtype != torch.uint8:               # caller supplied decoded features
-            h_n = nd["h"].float()
-            out = self.hgt_decoder.forward_tgt(graph, h_tgt, h_n)
+            out = self.hgt_decoder.forward_tgt(graph, h_tgt, nd["h"])
         elif "h" in nd:                                               # explicit uint8 code rows (reference layout)
             h_n = self.tgt_quantizer.decode(nd["h"], math_mode=mode)
             out = self.hgt_decoder.forward_tgt(graph, h_tgt, h_n)
@@ -246,7 +244,7 @@ class TokenGraphTransformerDecoder(nn.Module):
                 lp, _, _ = ops.knn_mix_nll(lp, orig_lp=lo, orig_ratio=self.orig_prob_ratio)
         else:
             w = self._plain_out()
-            pm, ps, pk, nt = ops.linear_lse(x.reshape(-1, x.shape[-1]), w.W, target.reshape(-1).to(torch.int32),
+            pm, ps, pk, nt = ops.linear_lse(as_act(x.reshape(-1, x.shape[-1]), mode), w.W, target.reshape(-1).to(torch.int32),
                                             W_lo=w.lo, math=mode)
             lp = torch.empty(pk.shape[0], device=pk.device, dtype=torch.float32)
             ops.lse_finish(pm, ps, pk, nt, lp)

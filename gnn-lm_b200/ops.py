@@ -28,9 +28,10 @@ def linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None
         out = torch.empty((M, N), device=A.device, dtype=out_dtype or torch.float32)
     assert out.stride(1) == 1 and out.shape == (M, N)
     if residual is not None:
-        assert residual.dtype == torch.float32 and residual.stride(1) == 1
+        assert residual.dtype in (torch.float32, torch.bfloat16) and residual.stride(1) == 1
     L.call("gnnlm_linear", L.ptr(A), L.dtype_code(A.dtype), A.stride(0), L.ptr(W), L.ptr(W_lo), W.stride(0),
-           L.ptr(bias), L.ptr(residual), residual.stride(0) if residual is not None else 0, L.ptr(out),
+           L.ptr(bias), L.ptr(residual), L.dtype_code(residual.dtype) if residual is not None else 0,
+           residual.stride(0) if residual is not None else 0, L.ptr(out),
            L.dtype_code(out.dtype), out.stride(0), M, _dev_count(m_dev), N, K, math, L.stream_ptr(),
            tag=tag or f"linear[{N}x{K}]")
     return out
@@ -113,7 +114,7 @@ def cluster_attn(q, k, v, G, H, out, *, centre_only=False, tag=None):
     d = k.shape[1]
     L.call("gnnlm_hgt_cluster_attn", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0),
            L.dtype_code(q.dtype), L.ptr(G.node_base), L.ptr(G.valid_base), L.ptr(G.cluster_nl), G.T * G.k, G.w,
-           int(centre_only), H, d // H, L.ptr(out), out.stride(0), L.stream_ptr(), tag=tag)
+           int(centre_only), H, d // H, L.ptr(out), L.dtype_code(out.dtype), out.stride(0), L.stream_ptr(), tag=tag)
     return out
 
 

@@ -61,12 +61,14 @@ class TorchPQCodec(nn.Module):
                       n_cap: Optional[int] = None, n_dev: Optional[torch.Tensor] = None,
                       math_mode: int = L.MATH_FP32_SIMT) -> torch.Tensor:
         """Fused `quant_neighbor_feats[rows]` + decode: codes_table [N_d, M] uint8 in HBM."""
+        from .hgt import act_dtype
         b = self.b if self.pre_torch and self.b.numel() > 0 else None
+        act = act_dtype(math_mode)
         x, _, _ = ops.pq_gather_decode(codes_table, self.centroids_torch, rows, bias=b, row_ids=row_ids, n_cap=n_cap,
-                                       n_dev=n_dev)
+                                       n_dev=n_dev, out_dtype=act)
         if self.pre_torch:
             w = self._rotation(math_mode)
-            x = ops.linear(x, w.W, None, W_lo=w.lo, m_dev=n_dev, math=math_mode)
+            x = ops.linear(x, w.W, None, W_lo=w.lo, m_dev=n_dev, math=math_mode, out_dtype=act)
         return x
 
     @torch.no_grad()

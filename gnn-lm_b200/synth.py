@@ -157,4 +157,4 @@ def run_gpu(cfg, model, data, device, math="fp32") -> dict:
     nll2 = -s / n / np.log(2)
     return {"logprob": lp.reshape(-1).cpu().numpy(), "knn_prob": p.cpu().numpy(), "recall": rec.cpu().numpy(),
             "score_sum": s, "count": int(n), "ppl": float(2 ** nll2), "nll": -s / n,
-            "gcn_feat": dec_out[0].reshape(-1, dec_out[0].shape[-1]).cpu().numpy()}
+            "gcn_feat": dec_out[0].reshape(-1, dec_out[0].shape[-1]).float().cpu().numpy()}

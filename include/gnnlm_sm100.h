@@ -121,14 +121,14 @@ int32_t gnnlm_pq_gather_decode(const uint8_t* codes, int64_t n_datastore, int32_
  *     adaptive-softmax projections (fairseq/modules/adaptive_softmax.py:184,197,202).
  *
  *  C[m, n] = sum_k A[m, k] * W[n, k] + bias[n] (+ residual[m, n])          (nn.Linear layout)
- *  A [M, K] a_dtype lda; W [N, K] (same dtype as A) ldw; bias fp32 [N] nullable; residual fp32
- *  [M, N] ldr nullable; C c_dtype ldc.  For GNNLM_MATH_TF32X3, W_lo is the low half of the split
+ *  A [M, K] a_dtype lda; W [N, K] (same dtype as A) ldw; bias fp32 [N] nullable; residual [M, N] of
+ *  r_dtype (F32, or BF16 on the tensor-core path) ldr nullable; C c_dtype ldc.  For GNNLM_MATH_TF32X3, W_lo is the low half of the split
  *  (W - tf32(W)), prepared once by gnnlm_split_tf32; NULL otherwise. */
 int32_t gnnlm_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, gnnlm_stream_t stream);
 int32_t gnnlm_linear(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, int64_t ldw,
-                     const float* bias, const float* residual, int64_t ldr, void* C, int32_t c_dtype,
-                     int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, int64_t K, int32_t math,
-                     gnnlm_stream_t stream);
+                     const float* bias, const void* residual, int32_t r_dtype, int64_t ldr, void* C,
+                     int32_t c_dtype, int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, int64_t K,
+                     int32_t math, gnnlm_stream_t stream);
 
 /* Same contraction, but instead of storing C the epilogue keeps, per row and per column tile,
  * (max, sum exp(x - max)) and the single column `pick[m]` -- the [rows, vocab] tensor of
@@ -186,11 +186,12 @@ int32_t gnnlm_hgt_edge_attn(const void* q, int64_t ldq, const void* k, int64_t l
  *  every node of every cluster is produced.  centre_only == 1: only the centre node of each cluster is
  *  produced; q and out rows are compact, indexed by valid_base[cluster] (layer n_layers-1 of the
  *  decoder's tgt-only mode).  node_base / valid_base / cluster_nl come from gnnlm_graph_count / _fill.
- *  Supports cluster sizes up to 7 (neighbour context <= 3 per side). */
+ *  out is F32 or BF16 (out_dtype).  Supports cluster sizes up to 7 (neighbour context <= 3 per side). */
 int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                int32_t dtype, const int32_t* node_base, const int32_t* valid_base,
                                const int32_t* cluster_nl, int64_t n_clusters, int32_t max_cluster, int32_t centre_only,
-                               int32_t H, int32_t d_k, float* out, int64_t ldo, gnnlm_stream_t stream);
+                               int32_t H, int32_t d_k, void* out, int32_t out_dtype, int64_t ldo,
+                               gnnlm_stream_t stream);
 
 /* ('tgt','intra','tgt') as implicit causal attention inside each of B blocks of L tokens
  * (edges u -> v for u <= v, v - u < intra_ctx when intra_ctx > 0; token_block_dataset.py:586-594). */

@@ -457,3 +457,17 @@ def test_eval_lm_dataset_vs_oracle(dev):
     assert res["count"] == cnt == n_tok
     assert abs(res["score_sum"] - tot) / abs(tot) < 1e-5
     assert abs(res["ppl"] - mo.perplexity(tot, cnt)[1]) / res["ppl"] < 1e-4
+
+
+@pytest.mark.parametrize("name", ["c1", "c3mini"])
+def test_whole_path_bf16(name, dev):
+    """bf16 mode (bf16 activations / operands on the ntgt side, fp32 accumulation, fp32 tgt-side attention,
+    fp32 pre-norm sums): per-token log-probs within 1e-2 relative of the fp32 oracle (north_star)."""
+    _need_tc()
+    from tests.synth import make_problem, run_gpu, run_oracle
+    prob = make_problem(name)
+    ref = run_oracle(prob)
+    out = run_gpu(prob, dev, math="bf16")
+    np.testing.assert_allclose(out["logprob"], ref["logprob"].numpy(), rtol=1e-2, atol=1e-2)
+    assert abs(out["nll"] - ref["nll"]) < 1e-2
+    assert (out["recall"] == ref["knn_recall"].numpy()).all()
