@@ -9,8 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgnnlm_sm100.so")
 
 F32, BF16, F16 = 0, 1, 2
-MATH_FP32_SIMT, MATH_TF32X3, MATH_TF32, MATH_BF16 = 0, 1, 2, 3
-MATH_NAMES = {"fp32": MATH_FP32_SIMT, "tf32x3": MATH_TF32X3, "tf32": MATH_TF32, "bf16": MATH_BF16}
+MATH_FP32_SIMT, MATH_TF32X3, MATH_TF32, MATH_BF16, MATH_F16X3 = 0, 1, 2, 3, 4
+MATH_NAMES = {"fp32": MATH_FP32_SIMT, "tf32x3": MATH_TF32X3, "tf32": MATH_TF32, "bf16": MATH_BF16, "f16x3": MATH_F16X3}
 
 _p, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 
@@ -26,9 +26,10 @@ SIGNATURES = {
     "gnnlm_graph_tt_csr": (_i32, [_i64, _i64, _i64, _p, _p, _p]),
     "gnnlm_pq_gather_decode": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _i32, _p, _p, _p]),
     "gnnlm_split_tf32": (_i32, [_p, _p, _p, _i64, _p]),
-    "gnnlm_linear": (_i32, [_p, _i32, _i64, _p, _p, _i64, _p, _p, _i32, _i64, _p, _i32, _i64, _i64, _p, _i64, _i64, _i32, _p]),
+    "gnnlm_split_f16": (_i32, [_p, _f32, _p, _p, _i64, _p]),
+    "gnnlm_linear": (_i32, [_p, _i32, _i64, _p, _p, _f32, _i64, _p, _p, _i32, _i64, _p, _i32, _i64, _i64, _p, _i64, _i64, _i32, _p]),
     "gnnlm_lse_num_tiles": (_i64, [_i64, _i32]),
-    "gnnlm_linear_lse": (_i32, [_p, _i32, _i64, _p, _p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _p]),
+    "gnnlm_linear_lse": (_i32, [_p, _i32, _i64, _p, _p, _f32, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _p]),
     "gnnlm_lse_finish": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _p]),
     "gnnlm_gather_rows": (_i32, [_p, _i64, _p, _p, _i64, _i64, _p, _i64, _i32, _p]),
     "gnnlm_layernorm": (_i32, [_p, _i64, _p, _p, _f32, _p, _i32, _i64, _i64, _p, _i64, _p]),

@@ -24,10 +24,10 @@ int32_t gemm_simt_lse(const float* A, int64_t lda, const float* W, int64_t ldw, 
 // gemm_tcgen05.cu
 int32_t gemm_tc_supported();
 int64_t gemm_tc_lse_tile_n();
-int32_t gemm_tc_store(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, int64_t ldw,
+int32_t gemm_tc_store(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, float w_scale, int64_t ldw,
                       const float* bias, const void* residual, int32_t r_dtype, int64_t ldr, void* C, int32_t c_dtype,
                       int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, int64_t K, int32_t math, cudaStream_t st);
-int32_t gemm_tc_lse(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, int64_t ldw,
+int32_t gemm_tc_lse(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, float w_scale, int64_t ldw,
                     const int32_t* pick, float* part_max, float* part_sum, float* picked, int64_t M,
                     const int32_t* m_dev, int64_t N, int64_t K, int32_t math, cudaStream_t st);
 
@@ -49,7 +49,7 @@ static int32_t check_linear(const char* who, const void* A, int32_t a_dtype, con
   GNNLM_CHECK_ARG(A && W, GNNLM_E_ARG, "%s: null operand", who);
   GNNLM_CHECK_ARG(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K, GNNLM_E_SHAPE, "%s: bad shape M=%lld N=%lld K=%lld lda=%lld ldw=%lld",
                   who, (long long)M, (long long)N, (long long)K, (long long)lda, (long long)ldw);
-  GNNLM_CHECK_ARG(math >= GNNLM_MATH_FP32_SIMT && math <= GNNLM_MATH_BF16, GNNLM_E_ARG, "%s: unknown math mode %d", who, math);
+  GNNLM_CHECK_ARG(math >= GNNLM_MATH_FP32_SIMT && math <= GNNLM_MATH_F16X3, GNNLM_E_ARG, "%s: unknown math mode %d", who, math);
   if (math == GNNLM_MATH_BF16)
     GNNLM_CHECK_ARG(a_dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED, "%s: MATH_BF16 needs bf16 operands", who);
   else
@@ -57,7 +57,8 @@ static int32_t check_linear(const char* who, const void* A, int32_t a_dtype, con
   return 0;
 }
 
-extern "C" int32_t gnnlm_linear(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, int64_t ldw,
+extern "C" int32_t gnnlm_linear(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, float w_scale,
+                                int64_t ldw,
                                 const float* bias, const void* residual, int32_t r_dtype, int64_t ldr, void* C,
                                 int32_t c_dtype, int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, int64_t K,
                                 int32_t math, gnnlm_stream_t stream) {
@@ -71,12 +72,12 @@ extern "C" int32_t gnnlm_linear(const void* A, int32_t a_dtype, int64_t lda, con
   if (math == GNNLM_MATH_FP32_SIMT)
     return gemm_simt_store((const float*)A, lda, (const float*)W, ldw, bias, (const float*)residual, ldr, C, c_dtype, ldc, M,
                            m_dev, N, K, (cudaStream_t)stream);
-  return gemm_tc_store(A, a_dtype, lda, W, W_lo, ldw, bias, residual, r_dtype, ldr, C, c_dtype, ldc, M, m_dev, N, K, math,
-                       (cudaStream_t)stream);
+  return gemm_tc_store(A, a_dtype, lda, W, W_lo, w_scale, ldw, bias, residual, r_dtype, ldr, C, c_dtype, ldc, M, m_dev, N, K,
+                       math, (cudaStream_t)stream);
 }
 
 extern "C" int32_t gnnlm_linear_lse(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo,
-                                    int64_t ldw, const int32_t* pick, float* part_max, float* part_sum, float* picked,
+                                    float w_scale, int64_t ldw, const int32_t* pick, float* part_max, float* part_sum, float* picked,
                                     int64_t M, const int32_t* m_dev, int64_t N, int64_t K, int32_t math,
                                     gnnlm_stream_t stream) {
   int32_t rc = check_linear("gnnlm_linear_lse", A, a_dtype, W, lda, ldw, M, N, K, math);
@@ -85,6 +86,6 @@ extern "C" int32_t gnnlm_linear_lse(const void* A, int32_t a_dtype, int64_t lda,
   if (math == GNNLM_MATH_FP32_SIMT)
     return gemm_simt_lse((const float*)A, lda, (const float*)W, ldw, pick, part_max, part_sum, picked, M, m_dev, N, K,
                          (cudaStream_t)stream);
-  return gemm_tc_lse(A, a_dtype, lda, W, W_lo, ldw, pick, part_max, part_sum, picked, M, m_dev, N, K, math,
+  return gemm_tc_lse(A, a_dtype, lda, W, W_lo, w_scale, ldw, pick, part_max, part_sum, picked, M, m_dev, N, K, math,
                      (cudaStream_t)stream);
 }

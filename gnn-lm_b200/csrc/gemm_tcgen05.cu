@@ -24,6 +24,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace gnnlm {
@@ -164,7 +166,7 @@ struct EpiLse {
 // (bias / residual fused) or fold them into the running (max, sum-exp, picked logit) of the row.
 template <bool LSE>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t M, int64_t n_base, int64_t n_blk, int64_t N,
-                                              const EpiStore& es, const EpiLse& el) {
+                                              const EpiStore& es, const EpiLse& el, float acc_scale = 1.f) {
         float run_max = -INFINITY, run_sum = 0.f;
         const int32_t want = (LSE && m < M && el.pick) ? __ldg(el.pick + m) : -1;
   #pragma unroll 1
@@ -172,6 +174,10 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t
           if (n_base + c >= N) break;                  // warp-uniform
           float v[32];
           tmem_ld32(taddr + (uint32_t)c, v);
+          if (acc_scale != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= acc_scale;
+          }
           const int64_t n0 = n_base + c;
           if constexpr (!LSE) {
             if (m < M) {
@@ -666,6 +672,206 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == X3 ? 384 : 2
   }
 }
 
+// ---------------------------------------------------------------------------------------------- 3xFP16 variant
+// fp32-parity arithmetic at twice the tensor rate of 3xTF32: every fp32 operand is split into two fp16 numbers,
+//   a = a_h + a_l,  a_h = fp16(a), a_l = fp16(a - a_h)            (22 significant bits, as hi/lo tf32)
+//   w*S = w_h + w_l (S a power of two chosen per weight matrix so that max|w*S| = 2^13: keeps w_l normal)
+// and D = a_h*w_h + a_h*w_l + a_l*w_h is accumulated in fp32 in TMEM by kind::f16 MMAs (K = 16 per
+// instruction instead of 8, operand tiles half the bytes); the epilogue multiplies by 1/S (exact).
+// Same cta_group::2 structure as gemm_tc2_kernel.  A arrives as fp32 (TMA, SWIZZLE_128B); the splitter warps
+// rewrite it as two fp16 tiles in the SWIZZLE_64B K-major layout the MMA descriptors expect; W_h / W_l are
+// pre-split fp16 matrices loaded by TMA with SWIZZLE_64B.  Operands beyond +-65504 are clamped (fp16 range).
+constexpr int F16_BLOCK_K = 32;                           // k elements per stage
+constexpr int F16_RAW_A = BLOCK_M * 128;                  // 16 KB fp32 tile (128 B rows)
+constexpr int F16_OP_A = BLOCK_M * 64;                    // 8 KB fp16 tile (64 B rows)
+constexpr int F16_OP_B = (BLOCK_N / 2) * 64;              // 8 KB: this CTA's 128 W rows
+constexpr int F16_STAGE = F16_RAW_A + 2 * F16_OP_A + 2 * F16_OP_B;   // 48 KB
+constexpr int F16_STAGES = 4;
+
+// K-major SWIZZLE_64B descriptor: 8-row groups are 512 B apart (SBO = 32), layout type 4
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (32ull << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <bool LSE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+    gemm_f16x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      const __grid_constant__ CUtensorMap map_blo, int64_t M_cap, const int32_t* __restrict__ m_dev, int64_t N,
+                      int64_t K, EpiStore es, EpiLse el, float acc_scale) {
+  constexpr int STAGES = F16_STAGES;
+  constexpr uint32_t W_TX = 2u * 2u * F16_OP_B;                         // both CTAs' W_h + W_l halves -> leader
+  // c = F32 | a,b = F16 (0) | N >> 3 | M >> 4 with M = 256 across the pair
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ __align__(8) uint64_t a_full[STAGES], w_full[STAGES], empty_bar[STAGES], conv_bar[STAGES], tmem_full[2],
+      tmem_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int64_t M = live_rows(M_cap, m_dev);
+  const int64_t n_m = (M + BLOCK_M - 1) / BLOCK_M, n_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int64_t total = ((n_m + 1) / 2) * n_n;
+  const int64_t pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+  const int n_kb = (int)((K + F16_BLOCK_K - 1) / F16_BLOCK_K);
+
+  auto sRaw = [&](int s) { return smem + (size_t)s * F16_STAGE; };
+  auto sAh = [&](int s) { return smem + (size_t)s * F16_STAGE + F16_RAW_A; };
+  auto sAl = [&](int s) { return smem + (size_t)s * F16_STAGE + F16_RAW_A + F16_OP_A; };
+  auto sBh = [&](int s) { return smem + (size_t)s * F16_STAGE + F16_RAW_A + 2 * F16_OP_A; };
+  auto sBl = [&](int s) { return smem + (size_t)s * F16_STAGE + F16_RAW_A + 2 * F16_OP_A + F16_OP_B; };
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&w_full[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&conv_bar[s], 8);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {                                   // ---- TMA producer (both CTAs)
+      int stage = 0;
+      uint32_t phase = 0;
+      const int half = (int)crank * (BLOCK_N / 2);
+      for (int64_t tile = pair0; tile < total; tile += pair_stride) {
+        const int m0 = (int)(((tile / n_n) * 2 + crank) * BLOCK_M), n0 = (int)((tile % n_n) * BLOCK_N) + half;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&w_full[stage], W_TX);
+          mbar_expect_tx(&a_full[stage], F16_RAW_A);
+          tma_load_2d(sRaw(stage), &map_a, kb * F16_BLOCK_K, m0, &a_full[stage]);
+          tma_load_2d_2sm(sBh(stage), &map_b, kb * F16_BLOCK_K, n0, &w_full[stage]);
+          tma_load_2d_2sm(sBl(stage), &map_blo, kb * F16_BLOCK_K, n0, &w_full[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {                         // ---- MMA issuer (leader only)
+      int stage = 0;
+      uint32_t phase = 0;
+      int64_t it = 0;
+      for (int64_t tile = pair0; tile < total; tile += pair_stride, ++it) {
+        const int acc = (int)(it & 1);
+        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BLOCK_N;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&w_full[stage], phase);
+          mbar_wait(&conv_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t dah = make_desc_sw64(smem_u32(sAh(stage))), dal = make_desc_sw64(smem_u32(sAl(stage)));
+          const uint64_t dbh = make_desc_sw64(smem_u32(sBh(stage))), dbl = make_desc_sw64(smem_u32(sBl(stage)));
+#pragma unroll
+          for (int k = 0; k < F16_BLOCK_K / 16; ++k) {
+            const uint64_t koff = (uint64_t)(k * 2);                     // 16 fp16 = 32 B inside the 64 B row
+            umma_2sm<0>(d_tmem, dah + koff, dbl + koff, IDESC, (kb | k) > 0 ? 1u : 0u);
+            umma_2sm<0>(d_tmem, dal + koff, dbh + koff, IDESC, 1u);
+            umma_2sm<0>(d_tmem, dah + koff, dbh + koff, IDESC, 1u);
+          }
+          tc_commit_2sm(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&tmem_full[acc]);
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
+    const int q = warp & 3;                            // ---- epilogue (both CTAs)
+    int64_t it = 0;
+    for (int64_t tile = pair0; tile < total; tile += pair_stride, ++it) {
+      const int acc = (int)(it & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      const int64_t m_blk = (tile / n_n) * 2 + crank, n_blk = tile % n_n;
+      const int64_t m = m_blk * BLOCK_M + q * 32 + lane;
+      const int64_t n_base = n_blk * BLOCK_N;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      epilogue_tile<LSE>(taddr, m, M, n_base, n_blk, N, es, el, acc_scale);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+    }
+  } else if (warp >= CONV_WARP0) {
+    // ---- operand splitter: fp32 [128 x 32] (SWIZZLE_128B) -> fp16 hi / lo [128 x 32] (SWIZZLE_64B)
+    const int ct = threadIdx.x - CONV_WARP0 * 32;      // 0..127
+    const int qd = ct & 3;                             // which 8 k-elements of the row
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t tile = pair0; tile < total; tile += pair_stride) {
+      for (int kb = 0; kb < n_kb; ++kb) {
+        mbar_wait(&a_full[stage], phase);
+        const uint8_t* raw = sRaw(stage);
+        uint8_t* oh = sAh(stage);
+        uint8_t* ol = sAl(stage);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = (ct >> 2) + 32 * i;
+          const float4 x0 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * qd) ^ (r & 7)) << 4));
+          const float4 x1 = *reinterpret_cast<const float4*>(raw + r * 128 + (((2 * qd + 1) ^ (r & 7)) << 4));
+          float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          float hs[8], ls[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float c = fminf(fmaxf(xs[e], -65504.f), 65504.f);
+            hs[e] = __half2float(__float2half_rn(c));
+            ls[e] = c - hs[e];
+          }
+          uint4 ph, pl;
+          ph.x = pack_h2(hs[0], hs[1]); ph.y = pack_h2(hs[2], hs[3]); ph.z = pack_h2(hs[4], hs[5]); ph.w = pack_h2(hs[6], hs[7]);
+          pl.x = pack_h2(ls[0], ls[1]); pl.y = pack_h2(ls[2], ls[3]); pl.z = pack_h2(ls[4], ls[5]); pl.w = pack_h2(ls[6], ls[7]);
+          const int off = r * 64 + ((qd ^ ((r >> 1) & 3)) << 4);
+          *reinterpret_cast<uint4*>(oh + off) = ph;
+          *reinterpret_cast<uint4*>(ol + off) = pl;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&conv_bar[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -698,6 +904,22 @@ static int device_is_sm100() {
   }
   return cached;
 }
+
+// fp16 [rows, K] K-major matrix, SWIZZLE_64B boxes of 32 elements x box_rows
+static int make_map_f16(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)F16_BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return (int)encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+template <bool LSE>
+static int32_t launch_f16x3(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mblo, int64_t M,
+                            const int32_t* m_dev, int64_t N, int64_t K, const EpiStore& es, const EpiLse& el, float acc_scale,
+                            cudaStream_t st);
 
 static int make_map(CUtensorMap* map, const void* base, int bf16, int64_t rows, int64_t K, int64_t ld, int box_rows) {
   const int elem = bf16 ? 2 : 4;
@@ -750,6 +972,30 @@ static int32_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
   return 0;
 }
 
+template <bool LSE>
+static int32_t launch_f16x3(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mblo, int64_t M,
+                            const int32_t* m_dev, int64_t N, int64_t K, const EpiStore& es, const EpiLse& el, float acc_scale,
+                            cudaStream_t st) {
+  const size_t smem = (size_t)F16_STAGES * F16_STAGE + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GNNLM_CUDA(cudaFuncSetAttribute(gemm_f16x3_kernel<LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    GNNLM_CUDA(cudaGetDevice(&dev));
+    GNNLM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int64_t pairs = ceil_div(ceil_div(M, BLOCK_M), 2) * ceil_div(N, BLOCK_N);
+  const int64_t max_pairs = n_sm / 2;
+  const unsigned grid = 2u * (unsigned)(pairs < max_pairs ? pairs : max_pairs);
+  gemm_f16x3_kernel<LSE><<<grid, 384, smem, st>>>(ma, mb, mblo, M, m_dev, N, K, es, el, acc_scale);
+  GNNLM_LAUNCH_CHECK("gemm_f16x3");
+  return 0;
+}
+
 }  // namespace tc
 
 int32_t gemm_tc_supported() { return tc::encode_fn() != nullptr && tc::device_is_sm100(); }
@@ -759,6 +1005,18 @@ static int32_t tc_prepare(const char* who, const void* A, int32_t a_dtype, int64
                           int64_t ldw, int64_t M, int64_t N, int64_t K, int32_t math, CUtensorMap* ma, CUtensorMap* mb,
                           CUtensorMap* mblo) {
   GNNLM_CHECK_ARG(gemm_tc_supported(), GNNLM_E_UNSUPPORTED, "%s: tcgen05 path needs an sm_100 device and driver TMA support", who);
+  if (math == GNNLM_MATH_F16X3) {
+    GNNLM_CHECK_ARG(W_lo, GNNLM_E_ARG, "%s: MATH_F16X3 needs W_lo (gnnlm_split_f16)", who);
+    GNNLM_CHECK_ARG((lda * 4) % 16 == 0 && (ldw * 2) % 16 == 0 && (uintptr_t)A % 16 == 0 && (uintptr_t)W % 16 == 0 &&
+                        (uintptr_t)W_lo % 16 == 0,
+                    GNNLM_E_SHAPE, "%s: TMA needs 16 B aligned bases and row strides (lda=%lld ldw=%lld)", who, (long long)lda,
+                    (long long)ldw);
+    int r = tc::make_map(ma, A, 0, M, K, lda, tc::BLOCK_M);                // fp32 A, SWIZZLE_128B, 32-element rows
+    if (!r) r = tc::make_map_f16(mb, W, N, K, ldw, tc::BLOCK_N / 2);
+    if (!r) r = tc::make_map_f16(mblo, W_lo, N, K, ldw, tc::BLOCK_N / 2);
+    GNNLM_CHECK_ARG(r == 0, GNNLM_E_ARG, "%s: cuTensorMapEncodeTiled failed (%d)", who, r);
+    return 0;
+  }
   const int bf16 = math == GNNLM_MATH_BF16;
   const int elem = bf16 ? 2 : 4;
   GNNLM_CHECK_ARG((lda * elem) % 16 == 0 && (ldw * elem) % 16 == 0 && (uintptr_t)A % 16 == 0 && (uintptr_t)W % 16 == 0,
@@ -773,7 +1031,7 @@ static int32_t tc_prepare(const char* who, const void* A, int32_t a_dtype, int64
   return 0;
 }
 
-int32_t gemm_tc_store(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, int64_t ldw,
+int32_t gemm_tc_store(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, float w_scale, int64_t ldw,
                       const float* bias, const void* residual, int32_t r_dtype, int64_t ldr, void* C, int32_t c_dtype,
                       int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, int64_t K, int32_t math, cudaStream_t st) {
   if (M == 0) return 0;
@@ -782,12 +1040,13 @@ int32_t gemm_tc_store(const void* A, int32_t a_dtype, int64_t lda, const void* W
   if (rc) return rc;
   tc::EpiStore es{bias, residual, ldr, C, ldc, c_dtype == GNNLM_BF16, r_dtype == GNNLM_BF16};
   tc::EpiLse el{};
+  if (math == GNNLM_MATH_F16X3) return tc::launch_f16x3<false>(ma, mb, mblo, M, m_dev, N, K, es, el, 1.f / w_scale, st);
   if (math == GNNLM_MATH_TF32X3) return tc::launch<tc::X3, false>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
   if (math == GNNLM_MATH_TF32) return tc::launch<tc::TF32, false>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
   return tc::launch<tc::BF16, false>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
 }
 
-int32_t gemm_tc_lse(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, int64_t ldw,
+int32_t gemm_tc_lse(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, float w_scale, int64_t ldw,
                     const int32_t* pick, float* part_max, float* part_sum, float* picked, int64_t M,
                     const int32_t* m_dev, int64_t N, int64_t K, int32_t math, cudaStream_t st) {
   if (M == 0) return 0;
@@ -796,6 +1055,7 @@ int32_t gemm_tc_lse(const void* A, int32_t a_dtype, int64_t lda, const void* W, 
   if (rc) return rc;
   tc::EpiStore es{};
   tc::EpiLse el{pick, part_max, part_sum, picked, ceil_div(N, tc::BLOCK_N)};
+  if (math == GNNLM_MATH_F16X3) return tc::launch_f16x3<true>(ma, mb, mblo, M, m_dev, N, K, es, el, 1.f / w_scale, st);
   if (math == GNNLM_MATH_TF32X3) return tc::launch<tc::X3, true>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
   if (math == GNNLM_MATH_TF32) return tc::launch<tc::TF32, true>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
   return tc::launch<tc::BF16, true>(ma, mb, mblo, M, m_dev, N, K, es, el, st);

@@ -118,6 +118,16 @@ __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict
   }
 }
 
+__global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ w, float scale, __half* __restrict__ hi,
+                                                        __half* __restrict__ lo, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = fminf(fmaxf(w[i] * scale, -65504.f), 65504.f);
+    const __half h = __float2half_rn(x);
+    hi[i] = h;
+    lo[i] = __float2half_rn(x - __half2float(h));
+  }
+}
+
 static inline unsigned grid_for(int64_t n, int per_block) {
   int64_t b = ceil_div(n, per_block);
   const int64_t cap = 148 * 32;
@@ -204,5 +214,14 @@ extern "C" int32_t gnnlm_split_tf32(const float* w, float* w_hi, float* w_lo, in
   if (n == 0) return 0;
   split_tf32_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(w, w_hi, w_lo, n);
   GNNLM_LAUNCH_CHECK("gnnlm_split_tf32");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_split_f16(const float* w, float scale, void* w_hi, void* w_lo, int64_t n, gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(w && w_hi && w_lo, GNNLM_E_ARG, "gnnlm_split_f16: null pointer");
+  GNNLM_CHECK_ARG(scale > 0.f, GNNLM_E_ARG, "gnnlm_split_f16: scale must be positive");
+  if (n == 0) return 0;
+  split_f16_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(w, scale, (__half*)w_hi, (__half*)w_lo, n);
+  GNNLM_LAUNCH_CHECK("gnnlm_split_f16");
   return 0;
 }

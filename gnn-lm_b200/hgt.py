@@ -46,8 +46,11 @@ class _Weight:
         W = W.contiguous().float()
         self.b = None if b is None else b.contiguous().float()
         self.lo = None
+        self.scale = 1.0
         if math_mode == L.MATH_TF32X3:
             self.W, self.lo = ops.split_tf32(W)
+        elif math_mode == L.MATH_F16X3:
+            self.W, self.lo, self.scale = ops.split_f16(W)
         elif math_mode == L.MATH_BF16:
             self.W = ops.convert(W, torch.bfloat16)
         else:
@@ -58,11 +61,12 @@ class _Weight:
         v.W = self.W[a:b_]
         v.lo = None if self.lo is None else self.lo[a:b_]
         v.b = None if self.b is None else self.b[a:b_]
+        v.scale = self.scale
         return v
 
 
 def _lin(x, w: _Weight, math_mode, **kw):
-    return ops.linear(x, w.W, w.b, W_lo=w.lo, math=math_mode, **kw)
+    return ops.linear(x, w.W, w.b, W_lo=w.lo, w_scale=w.scale, math=math_mode, **kw)
 
 
 def act_dtype(math_mode: int):

@@ -98,14 +98,15 @@ class AdaptiveSoftmax(nn.Module):
         P = self.prepare(math_mode)
         head_pick, tail_rows, tail_pick, tail_count = ops.adapt_target(target, self.cutoff)
         lp = torch.empty(x.shape[0], device=x.device, dtype=torch.float32)
-        pm, ps, pk, nt = ops.linear_lse(x, P["head"].W, head_pick, W_lo=P["head"].lo, math=math_mode)
+        pm, ps, pk, nt = ops.linear_lse(x, P["head"].W, head_pick, W_lo=P["head"].lo, w_scale=P["head"].scale, math=math_mode)
         ops.lse_finish(pm, ps, pk, nt, lp)
         for i in range(len(self.tail)):
             cnt = tail_count[i:i + 1]
             xi = ops.gather_rows(x, tail_rows[i], n_dev=cnt)
-            hi = ops.linear(xi, P["proj"][i].W, None, W_lo=P["proj"][i].lo, m_dev=cnt, math=math_mode,
-                            out_dtype=act_dtype(math_mode))
-            pm, ps, pk, nt = ops.linear_lse(hi, P["out"][i].W, tail_pick[i], W_lo=P["out"][i].lo, m_dev=cnt, math=math_mode)
+            hi = ops.linear(xi, P["proj"][i].W, None, W_lo=P["proj"][i].lo, w_scale=P["proj"][i].scale, m_dev=cnt,
+                            math=math_mode, out_dtype=act_dtype(math_mode))
+            pm, ps, pk, nt = ops.linear_lse(hi, P["out"][i].W, tail_pick[i], W_lo=P["out"][i].lo, w_scale=P["out"][i].scale,
+                                            m_dev=cnt, math=math_mode)
             ops.lse_finish(pm, ps, pk, nt, lp, row_map=tail_rows[i], accumulate=True, m_dev=cnt)
         return lp
 
@@ -120,11 +121,12 @@ class AdaptiveSoftmax(nn.Module):
         x = input.reshape(-1, dim).contiguous()
         P = self.prepare(math_mode)
         c0 = self.cutoff[0]
-        head = torch.log_softmax(ops.linear(x, P["head"].W, None, W_lo=P["head"].lo, math=math_mode), dim=1)
+        lin = lambda a, w: ops.linear(a, w.W, None, W_lo=w.lo, w_scale=w.scale, math=math_mode)
+        head = torch.log_softmax(lin(x, P["head"]), dim=1)
         cols = [head[:, :c0]]
         for i in range(len(self.tail)):
-            hi = ops.linear(x, P["proj"][i].W, None, W_lo=P["proj"][i].lo, math=math_mode)
-            ti = ops.linear(hi, P["out"][i].W, None, W_lo=P["out"][i].lo, math=math_mode)
+            hi = lin(x, P["proj"][i])
+            ti = lin(hi, P["out"][i])
             cols.append(torch.log_softmax(ti, dim=1) + head[:, c0 + i, None])
         return torch.cat(cols, 1).view(bsz, length, -1)
 
@@ -245,7 +247,7 @@ class TokenGraphTransformerDecoder(nn.Module):
         else:
             w = self._plain_out()
             pm, ps, pk, nt = ops.linear_lse(as_act(x.reshape(-1, x.shape[-1]), mode), w.W, target.reshape(-1).to(torch.int32),
-                                            W_lo=w.lo, math=mode)
+                                            W_lo=w.lo, w_scale=w.scale, math=mode)
             lp = torch.empty(pk.shape[0], device=pk.device, dtype=torch.float32)
             ops.lse_finish(pm, ps, pk, nt, lp)
         return lp.view(target.shape)
@@ -263,7 +265,8 @@ class TokenGraphTransformerDecoder(nn.Module):
                 out = torch.logsumexp(torch.stack([o + math.log(a), out + math.log(1 - a)]), 0)
         else:
             w = self._plain_out()
-            logits = ops.linear(x.reshape(-1, x.shape[-1]).contiguous(), w.W, None, W_lo=w.lo, math=self.math_mode)
+            logits = ops.linear(x.reshape(-1, x.shape[-1]).contiguous(), w.W, None, W_lo=w.lo, w_scale=w.scale,
+                                math=self.math_mode)
             out = torch.log_softmax(logits, dim=-1).view(x.shape[0], x.shape[1], -1)
         return out if log_probs else out.exp_()
 

@@ -18,7 +18,7 @@ def _dev_count(t: Optional[torch.Tensor]):
 
 def linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, *, W_lo: Optional[torch.Tensor] = None,
            residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_dtype=None,
-           m_dev: Optional[torch.Tensor] = None, math: int = L.MATH_FP32_SIMT, tag=None) -> torch.Tensor:
+           m_dev: Optional[torch.Tensor] = None, math: int = L.MATH_FP32_SIMT, tag=None, w_scale: float = 1.0) -> torch.Tensor:
     """C = A @ W^T + bias (+ residual).  A [M,K] (row stride arbitrary), W [N,K]."""
     assert A.dim() == 2 and W.dim() == 2 and A.stride(1) == 1 and W.stride(1) == 1
     M, K = A.shape
@@ -29,7 +29,7 @@ def linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None
     assert out.stride(1) == 1 and out.shape == (M, N)
     if residual is not None:
         assert residual.dtype in (torch.float32, torch.bfloat16) and residual.stride(1) == 1
-    L.call("gnnlm_linear", L.ptr(A), L.dtype_code(A.dtype), A.stride(0), L.ptr(W), L.ptr(W_lo), W.stride(0),
+    L.call("gnnlm_linear", L.ptr(A), L.dtype_code(A.dtype), A.stride(0), L.ptr(W), L.ptr(W_lo), float(w_scale), W.stride(0),
            L.ptr(bias), L.ptr(residual), L.dtype_code(residual.dtype) if residual is not None else 0,
            residual.stride(0) if residual is not None else 0, L.ptr(out),
            L.dtype_code(out.dtype), out.stride(0), M, _dev_count(m_dev), N, K, math, L.stream_ptr(),
@@ -37,7 +37,7 @@ def linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out
 
 
-def linear_lse(A, W, pick, *, W_lo=None, m_dev=None, math=L.MATH_FP32_SIMT):
+def linear_lse(A, W, pick, *, W_lo=None, m_dev=None, math=L.MATH_FP32_SIMT, w_scale=1.0):
     """Row log-sum-exp partials + picked column of A @ W^T without materialising it."""
     M, K = A.shape
     N = W.shape[0]
@@ -45,7 +45,7 @@ def linear_lse(A, W, pick, *, W_lo=None, m_dev=None, math=L.MATH_FP32_SIMT):
     pmax = torch.empty((M, nt), device=A.device, dtype=torch.float32)
     psum = torch.empty((M, nt), device=A.device, dtype=torch.float32)
     picked = torch.zeros((M,), device=A.device, dtype=torch.float32)
-    L.call("gnnlm_linear_lse", L.ptr(A), L.dtype_code(A.dtype), A.stride(0), L.ptr(W), L.ptr(W_lo), W.stride(0),
+    L.call("gnnlm_linear_lse", L.ptr(A), L.dtype_code(A.dtype), A.stride(0), L.ptr(W), L.ptr(W_lo), float(w_scale), W.stride(0),
            L.ptr(pick), L.ptr(pmax), L.ptr(psum), L.ptr(picked), M, _dev_count(m_dev), N, K, math, L.stream_ptr())
     return pmax, psum, picked, nt
 
@@ -88,6 +88,18 @@ def split_tf32(w):
     hi, lo = torch.empty_like(w), torch.empty_like(w)
     L.call("gnnlm_split_tf32", L.ptr(w), L.ptr(hi), L.ptr(lo), w.numel(), L.stream_ptr())
     return hi, lo
+
+
+def split_f16(w):
+    """fp32 [N, K] -> (fp16 hi, fp16 lo, power-of-two scale) for MATH_F16X3."""
+    import math
+    w = w.contiguous()
+    amax = float(w.abs().max().item()) if w.numel() else 1.0
+    scale = 2.0 ** math.floor(math.log2(8192.0 / amax)) if amax > 0 else 1.0
+    hi = torch.empty(w.shape, device=w.device, dtype=torch.float16)
+    lo = torch.empty(w.shape, device=w.device, dtype=torch.float16)
+    L.call("gnnlm_split_f16", L.ptr(w), float(scale), L.ptr(hi), L.ptr(lo), w.numel(), L.stream_ptr())
+    return hi, lo, scale
 
 
 def edge_attn(q, k, v, indptr, indices, H, out, *, dst_ids=None, n_dst=None, n_dst_dev=None, out_scale=1.0,

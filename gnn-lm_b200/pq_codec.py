@@ -68,7 +68,7 @@ class TorchPQCodec(nn.Module):
                                        n_dev=n_dev, out_dtype=act)
         if self.pre_torch:
             w = self._rotation(math_mode)
-            x = ops.linear(x, w.W, None, W_lo=w.lo, m_dev=n_dev, math=math_mode, out_dtype=act)
+            x = ops.linear(x, w.W, None, W_lo=w.lo, w_scale=w.scale, m_dev=n_dev, math=math_mode, out_dtype=act)
         return x
 
     @torch.no_grad()

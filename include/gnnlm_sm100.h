@@ -45,6 +45,7 @@ typedef struct CUstream_st* gnnlm_stream_t; /* == cudaStream_t */
 #define GNNLM_MATH_TF32X3 1     /* tcgen05 kind::tf32, 3-pass split (hi*hi + hi*lo + lo*hi)      */
 #define GNNLM_MATH_TF32 2       /* tcgen05 kind::tf32, single pass                              */
 #define GNNLM_MATH_BF16 3       /* tcgen05 kind::f16 with bf16 operands, fp32 accumulate        */
+#define GNNLM_MATH_F16X3 4      /* tcgen05 kind::f16, fp32 operands split into 2 x fp16, 3 passes   */
 
 int32_t gnnlm_version(void);
 const char* gnnlm_last_error(void);
@@ -121,11 +122,15 @@ int32_t gnnlm_pq_gather_decode(const uint8_t* codes, int64_t n_datastore, int32_
  *     adaptive-softmax projections (fairseq/modules/adaptive_softmax.py:184,197,202).
  *
  *  C[m, n] = sum_k A[m, k] * W[n, k] + bias[n] (+ residual[m, n])          (nn.Linear layout)
- *  A [M, K] a_dtype lda; W [N, K] (same dtype as A) ldw; bias fp32 [N] nullable; residual [M, N] of
+ *  A [M, K] a_dtype lda; W [N, K] (same dtype as A; fp16 hi/lo pair for MATH_F16X3, whose A is fp32) ldw; bias fp32 [N] nullable; residual [M, N] of
  *  r_dtype (F32, or BF16 on the tensor-core path) ldr nullable; C c_dtype ldc.  For GNNLM_MATH_TF32X3, W_lo is the low half of the split
  *  (W - tf32(W)), prepared once by gnnlm_split_tf32; NULL otherwise. */
 int32_t gnnlm_split_tf32(const float* w, float* w_hi, float* w_lo, int64_t n, gnnlm_stream_t stream);
-int32_t gnnlm_linear(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, int64_t ldw,
+/* MATH_F16X3 weight preparation: w_hi = fp16(w * scale), w_lo = fp16(w * scale - w_hi) (both fp16 arrays of n
+ * elements); `scale` must be a power of two with max|w * scale| <= 2^15; pass it as w_scale to gnnlm_linear*
+ * (the epilogue multiplies by 1 / w_scale).  w_scale is ignored by every other math mode. */
+int32_t gnnlm_split_f16(const float* w, float scale, void* w_hi, void* w_lo, int64_t n, gnnlm_stream_t stream);
+int32_t gnnlm_linear(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, float w_scale, int64_t ldw,
                      const float* bias, const void* residual, int32_t r_dtype, int64_t ldr, void* C,
                      int32_t c_dtype, int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, int64_t K,
                      int32_t math, gnnlm_stream_t stream);
@@ -137,7 +142,7 @@ int32_t gnnlm_linear(const void* A, int32_t a_dtype, int64_t lda, const void* W,
  *  n_tiles = gnnlm_lse_num_tiles(N, math); picked [M] fp32. */
 int64_t gnnlm_lse_num_tiles(int64_t N, int32_t math);
 int32_t gnnlm_linear_lse(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo,
-                         int64_t ldw, const int32_t* pick, float* part_max, float* part_sum, float* picked,
+                         float w_scale, int64_t ldw, const int32_t* pick, float* part_max, float* part_sum, float* picked,
                          int64_t M, const int32_t* m_dev, int64_t N, int64_t K, int32_t math,
                          gnnlm_stream_t stream);
 /* out[row_map ? row_map[m] : m] (+)= picked[m] - logsumexp_m   (log-softmax at the picked column). */

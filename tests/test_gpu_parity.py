@@ -349,13 +349,15 @@ def _need_tc():
 # tf32x3: the split recovers the operands to ~2^-21, what remains is the tensor core's fp32 accumulation
 # rounding over 3*K/8 partial products (measured max |err| 4e-5 on O(3) outputs at K=1024) -> held to the
 # north star's 1e-4; tf32: 10-bit mantissas; bf16: exact products of the bf16-rounded operands, fp32 accumulate.
-@pytest.mark.parametrize("math,rtol,atol", [("tf32x3", 1e-4, 1e-4), ("tf32", 5e-3, 5e-3), ("bf16", 1e-4, 1e-4)])
+# f16x3: operands split into two fp16 halves (22 significant bits), kind::f16 MMAs, same accumulation floor.
+@pytest.mark.parametrize("math,rtol,atol", [("tf32x3", 1e-4, 1e-4), ("f16x3", 1e-4, 1e-4), ("tf32", 5e-3, 5e-3), ("bf16", 1e-4, 1e-4)])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 32), (300, 200, 64), (1000, 20002, 128), (4096, 3072, 1024), (5000, 1024, 1024), (129, 72, 256)])
 def test_linear_tcgen05(math, rtol, atol, M, N, K, dev):
     _need_tc()
     from gnnlm_b200 import _lib as L, ops
     torch.manual_seed(M + N + K)
     mode = L.MATH_NAMES[math]
+    ws = 1.0
     A, W, b = torch.randn(M, K), torch.randn(N, K) / K ** 0.5, torch.randn(N)
     R = torch.randn(M, N)
     if math == "bf16":
@@ -368,33 +370,36 @@ def test_linear_tcgen05(math, rtol, atol, M, N, K, dev):
         lo = None
         if math == "tf32x3":
             Wd, lo = ops.split_tf32(Wd)
+        elif math == "f16x3":
+            Wd, lo, ws = ops.split_f16(Wd)
     ref = A64 @ W64.t() + b.double() + R.double()
-    out = ops.linear(Ad, Wd, b.to(dev), W_lo=lo, residual=R.to(dev), math=mode)
+    out = ops.linear(Ad, Wd, b.to(dev), W_lo=lo, w_scale=ws, residual=R.to(dev), math=mode)
     np.testing.assert_allclose(out.cpu().double().numpy(), ref.numpy(), rtol=rtol, atol=atol)
     # device-side row count: rows >= m_dev must stay untouched
     cnt = torch.tensor([M // 2 + 1], dtype=torch.int32, device=dev)
     out2 = torch.full((M, N), 7.0, device=dev)
-    ops.linear(Ad, Wd, b.to(dev), W_lo=lo, out=out2, m_dev=cnt, math=mode)
+    ops.linear(Ad, Wd, b.to(dev), W_lo=lo, w_scale=ws, out=out2, m_dev=cnt, math=mode)
     live = M // 2 + 1
     np.testing.assert_allclose(out2[:live].cpu().double().numpy(), (ref - R.double())[:live].numpy(), rtol=rtol, atol=atol)
     assert (out2[live:] == 7.0).all()
     # fused log-sum-exp epilogue
     pick = torch.randint(0, N, (M,), dtype=torch.int32)
-    pm, ps, pk, nt = ops.linear_lse(Ad, Wd, pick.to(dev), W_lo=lo, math=mode)
+    pm, ps, pk, nt = ops.linear_lse(Ad, Wd, pick.to(dev), W_lo=lo, w_scale=ws, math=mode)
     lp = torch.empty(M, device=dev)
     ops.lse_finish(pm, ps, pk, nt, lp)
     ref_lp = torch.log_softmax(A64 @ W64.t(), 1).gather(1, pick.long()[:, None]).squeeze(1)
     np.testing.assert_allclose(lp.cpu().double().numpy(), ref_lp.numpy(), rtol=rtol, atol=max(atol, 2e-5))
 
 
+@pytest.mark.parametrize("math", ["tf32x3", "f16x3"])
 @pytest.mark.parametrize("name", ["c1", "c3mini"])
-def test_whole_path_tf32x3(name, dev):
-    """fp32-parity mode on tensor cores (3xTF32 split): same 1e-4 bar as the CUDA-core fp32 mode."""
+def test_whole_path_tf32x3(name, math, dev):
+    """fp32-parity modes on tensor cores (3xTF32 / 3xFP16 splits): same 1e-4 bar as the CUDA-core fp32 mode."""
     _need_tc()
     from tests.synth import make_problem, run_gpu, run_oracle
     prob = make_problem(name)
     ref = run_oracle(prob)
-    out = run_gpu(prob, dev, math="tf32x3")
+    out = run_gpu(prob, dev, math=math)
     np.testing.assert_allclose(out["logprob"], ref["logprob"].numpy(), rtol=1e-4, atol=1e-4)
     assert abs(out["nll"] - ref["nll"]) < 0.01 / 16.8
     assert (out["recall"] == ref["knn_recall"].numpy()).all()
