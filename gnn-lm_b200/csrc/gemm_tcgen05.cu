@@ -145,6 +145,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct EpiStore {
   const float* bias;
   const void* residual;
@@ -181,12 +187,20 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t
           const int64_t n0 = n_base + c;
           if constexpr (!LSE) {
             if (m < M) {
-              if (es.bias) {
-  #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (n0 + j < N) v[j] += __ldg(es.bias + n0 + j);
-              }
               const bool full = n0 + 32 <= N;
+              if (es.bias) {
+                if (full) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(es.bias + n0) + j);
+                    v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (n0 + j < N) v[j] += __ldg(es.bias + n0 + j);
+                }
+              }
               if (es.residual && !es.r_bf16) {
                 const float* r = reinterpret_cast<const float*>(es.residual) + m * es.ldr + n0;
                 if (full && (es.ldr & 3) == 0) {
@@ -250,17 +264,40 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t
               }
             }
           } else {
-            float mx = run_max;
-  #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < N) {
-                mx = fmaxf(mx, v[j]);
+            // online log-sum-exp in the base-2 domain: one FFMA + one MUFU.EX2 per logit
+            constexpr float L2E = 1.4426950408889634f;
+            const int nv = (int)((N - n0) < 32 ? (N - n0) : 32);          // valid columns of this chunk (warp-uniform)
+            if (want >= n0 && want < n0 + nv) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
                 if (n0 + j == want) el.picked[m] = v[j];
+            }
+            float m0 = run_max, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+            if (nv == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                m0 = fmaxf(m0, v[j]); m1 = fmaxf(m1, v[j + 1]); m2 = fmaxf(m2, v[j + 2]); m3 = fmaxf(m3, v[j + 3]);
               }
-            float s = run_sum * __expf(run_max - mx);
-  #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < N) s += __expf(v[j] - mx);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) m0 = fmaxf(m0, v[j]);
+            }
+            const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+            const float mxl = mx * L2E;
+            float s0 = run_sum * fast_exp2(run_max * L2E - mxl), s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            if (nv == 32) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                s0 += fast_exp2(fmaf(v[j], L2E, -mxl)); s1 += fast_exp2(fmaf(v[j + 1], L2E, -mxl));
+                s2 += fast_exp2(fmaf(v[j + 2], L2E, -mxl)); s3 += fast_exp2(fmaf(v[j + 3], L2E, -mxl));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < nv) s0 += fast_exp2(fmaf(v[j], L2E, -mxl));
+            }
+            const float s = (s0 + s1) + (s2 + s3);
             run_max = mx;
             run_sum = s;
           }
