@@ -8,7 +8,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgnnlm_sm100.so")
 
-F32, BF16, F16 = 0, 1, 2
+F32, BF16, F16, F16X2 = 0, 1, 2, 3
 MATH_FP32_SIMT, MATH_TF32X3, MATH_TF32, MATH_BF16, MATH_F16X3 = 0, 1, 2, 3, 4
 MATH_NAMES = {"fp32": MATH_FP32_SIMT, "tf32x3": MATH_TF32X3, "tf32": MATH_TF32, "bf16": MATH_BF16, "f16x3": MATH_F16X3}
 
@@ -32,8 +32,9 @@ SIGNATURES = {
     "gnnlm_linear_lse": (_i32, [_p, _i32, _i64, _p, _p, _f32, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _p]),
     "gnnlm_lse_finish": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _p]),
     "gnnlm_gather_rows": (_i32, [_p, _i64, _p, _p, _i64, _i64, _p, _i64, _i32, _p]),
-    "gnnlm_layernorm": (_i32, [_p, _i64, _p, _p, _f32, _p, _i32, _i64, _i64, _p, _i64, _p]),
+    "gnnlm_layernorm": (_i32, [_p, _i64, _p, _i32, _i64, _p, _p, _f32, _p, _i32, _i64, _i64, _p, _i64, _p]),
     "gnnlm_convert": (_i32, [_p, _i32, _p, _i32, _i64, _p]),
+    "gnnlm_to_split_f16": (_i32, [_p, _i32, _i64, _p, _i64, _i64, _p, _i64, _p]),
     "gnnlm_hgt_edge_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _i64, _p, _i32, _i32, _p, _i64, _f32, _i32, _p]),
     "gnnlm_hgt_cluster_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p]),
     "gnnlm_hgt_causal_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _i64, _i64, _i64, _i32, _i32, _p, _i64, _f32, _i32, _p]),

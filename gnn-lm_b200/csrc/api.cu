@@ -47,11 +47,16 @@ extern "C" int64_t gnnlm_lse_num_tiles(int64_t N, int32_t math) {
 static int32_t check_linear(const char* who, const void* A, int32_t a_dtype, const void* W, int64_t lda, int64_t ldw,
                             int64_t M, int64_t N, int64_t K, int32_t math) {
   GNNLM_CHECK_ARG(A && W, GNNLM_E_ARG, "%s: null operand", who);
+  GNNLM_CHECK_ARG(a_dtype != GNNLM_F16X2 || math == GNNLM_MATH_F16X3, GNNLM_E_UNSUPPORTED,
+                  "%s: split-fp16 operands are the MATH_F16X3 activation format", who);
   GNNLM_CHECK_ARG(M >= 0 && N > 0 && K > 0 && lda >= K && ldw >= K, GNNLM_E_SHAPE, "%s: bad shape M=%lld N=%lld K=%lld lda=%lld ldw=%lld",
                   who, (long long)M, (long long)N, (long long)K, (long long)lda, (long long)ldw);
   GNNLM_CHECK_ARG(math >= GNNLM_MATH_FP32_SIMT && math <= GNNLM_MATH_F16X3, GNNLM_E_ARG, "%s: unknown math mode %d", who, math);
   if (math == GNNLM_MATH_BF16)
     GNNLM_CHECK_ARG(a_dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED, "%s: MATH_BF16 needs bf16 operands", who);
+  else if (math == GNNLM_MATH_F16X3)
+    GNNLM_CHECK_ARG(a_dtype == GNNLM_F32 || a_dtype == GNNLM_F16X2, GNNLM_E_UNSUPPORTED,
+                    "%s: MATH_F16X3 takes fp32 or split-fp16 A", who);
   else
     GNNLM_CHECK_ARG(a_dtype == GNNLM_F32, GNNLM_E_UNSUPPORTED, "%s: fp32/tf32 math needs fp32 operands", who);
   return 0;
@@ -64,11 +69,13 @@ extern "C" int32_t gnnlm_linear(const void* A, int32_t a_dtype, int64_t lda, con
                                 int32_t math, gnnlm_stream_t stream) {
   int32_t rc = check_linear("gnnlm_linear", A, a_dtype, W, lda, ldw, M, N, K, math);
   if (rc) return rc;
-  GNNLM_CHECK_ARG(C && ldc >= N, GNNLM_E_ARG, "gnnlm_linear: bad C/ldc");
-  GNNLM_CHECK_ARG(c_dtype == GNNLM_F32 || c_dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED, "gnnlm_linear: C dtype");
-  GNNLM_CHECK_ARG(!residual || ldr >= N, GNNLM_E_SHAPE, "gnnlm_linear: ldr < N");
-  GNNLM_CHECK_ARG(!residual || r_dtype == GNNLM_F32 || (r_dtype == GNNLM_BF16 && math != GNNLM_MATH_FP32_SIMT),
-                  GNNLM_E_UNSUPPORTED, "gnnlm_linear: residual must be F32 (or BF16 on the tensor-core path)");
+  GNNLM_CHECK_ARG(C && ldc >= N * (c_dtype == GNNLM_F16X2 ? 2 : 1), GNNLM_E_ARG, "gnnlm_linear: bad C/ldc");
+  GNNLM_CHECK_ARG(c_dtype == GNNLM_F32 || c_dtype == GNNLM_BF16 || (c_dtype == GNNLM_F16X2 && math != GNNLM_MATH_FP32_SIMT),
+                  GNNLM_E_UNSUPPORTED, "gnnlm_linear: C dtype");
+  GNNLM_CHECK_ARG(!residual || ldr >= N * (r_dtype == GNNLM_F16X2 ? 2 : 1), GNNLM_E_SHAPE, "gnnlm_linear: ldr too small");
+  GNNLM_CHECK_ARG(!residual || r_dtype == GNNLM_F32 ||
+                      ((r_dtype == GNNLM_BF16 || r_dtype == GNNLM_F16X2) && math != GNNLM_MATH_FP32_SIMT),
+                  GNNLM_E_UNSUPPORTED, "gnnlm_linear: residual must be F32 (or BF16 / F16X2 on the tensor-core path)");
   if (math == GNNLM_MATH_FP32_SIMT)
     return gemm_simt_store((const float*)A, lda, (const float*)W, ldw, bias, (const float*)residual, ldr, C, c_dtype, ldc, M,
                            m_dev, N, K, (cudaStream_t)stream);

@@ -11,6 +11,8 @@
 // one (cluster, feature slice): one round trip for (node_base, cluster_nl), then the 3w row segments of
 // Q / K' / V' are all in flight together and each is read exactly once -- HBM traffic equals the
 // algorithmic bytes of SURVEY.md 8(d): N*(2+1)*d*s read + N*d*4 written.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gnnlm {
@@ -29,9 +31,18 @@ __device__ __forceinline__ float group_dot(const float (&a)[C], const float (&b)
 }
 
 template <typename OutT, int C>
-__device__ __forceinline__ void store_out(OutT* __restrict__ p, const float (&r)[C]) {
+__device__ __forceinline__ void store_out(OutT* __restrict__ p, const float (&r)[C], int lo_off) {
   if constexpr (sizeof(OutT) == 4) {
     store_f32<C>(reinterpret_cast<float*>(p), r);
+  } else if constexpr (std::is_same<OutT, __half>::value) {     // split-fp16: hi at p, lo at p + lo_off
+    static_assert(C % 4 == 0, "split output needs 8 B chunks");
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i) {
+      uint2 hi, lo;
+      split4_f16(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3], hi, lo);
+      reinterpret_cast<uint2*>(p)[i] = hi;
+      reinterpret_cast<uint2*>(p + lo_off)[i] = lo;
+    }
   } else {
     static_assert(C % 8 == 0 || C == 4, "bf16 output needs 8 B / 16 B chunks");
     if constexpr (C == 4) {
@@ -59,7 +70,7 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
                                                                   const int32_t* __restrict__ valid_base,
                                                                   const int32_t* __restrict__ cluster_nl, int64_t n_clusters,
                                                                   int centre_only, int group, int n_slices,
-                                                                  OutT* __restrict__ out, int64_t ldo) {
+                                                                  OutT* __restrict__ out, int64_t ldo, int lo_off) {
   const int lane = threadIdx.x & 31;
   const int64_t n_items = n_clusters * n_slices;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -99,7 +110,7 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
             if (p + 1 < WMAX && p + 1 < w) a = fmaf(e2, vv[p + 1 < WMAX ? p + 1 : p][cc], a);
             r[cc] = a * inv;
           }
-          store_out<OutT, C>(out + (int64_t)(base + ca_pos_to_id(p, nl)) * ldo + col, r);
+          store_out<OutT, C>(out + (int64_t)(base + ca_pos_to_id(p, nl)) * ldo + col, r, lo_off);
         }
       }
     } else {
@@ -128,7 +139,7 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
         if (has_r) a = fmaf(e2, vv[2][cc], a);
         r[cc] = a * inv;
       }
-      store_out<OutT, C>(out + ci * ldo + col, r);
+      store_out<OutT, C>(out + ci * ldo + col, r, lo_off);
     }
   }
 }
@@ -137,13 +148,13 @@ template <typename T, typename OutT, int C, int WMAX>
 static int32_t launch_cluster(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                               const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl,
                               int64_t n_clusters, int centre_only, int group, int n_slices, void* out, int64_t ldo,
-                              cudaStream_t st) {
+                              int lo_off, cudaStream_t st) {
   int64_t blocks = ceil_div(n_clusters * n_slices, CA_THREADS / 32);
   const int64_t max_blocks = 148 * 8 * 8;
   if (blocks > max_blocks) blocks = max_blocks;
   cluster_attn_kernel<T, OutT, C, WMAX><<<(unsigned)blocks, CA_THREADS, 0, st>>>(
       (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, group,
-      n_slices, (OutT*)out, ldo);
+      n_slices, (OutT*)out, ldo, lo_off);
   GNNLM_LAUNCH_CHECK("gnnlm_hgt_cluster_attn");
   return 0;
 }
@@ -151,10 +162,10 @@ static int32_t launch_cluster(const void* q, int64_t ldq, const void* k, int64_t
 template <typename T, typename OutT, int C>
 static int32_t dispatch_w(int wmax, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                           const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl, int64_t n_clusters,
-                          int centre_only, int group, int n_slices, void* out, int64_t ldo, cudaStream_t st) {
+                          int centre_only, int group, int n_slices, void* out, int64_t ldo, int lo_off, cudaStream_t st) {
 #define GNNLM_CL(W)                                                                                                       \
   return launch_cluster<T, OutT, C, W>(q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, \
-                                       group, n_slices, out, ldo, st)
+                                       group, n_slices, out, ldo, lo_off, st)
   if (wmax <= 1) GNNLM_CL(1);
   if (wmax <= 3) GNNLM_CL(3);
   if (wmax <= 5) GNNLM_CL(5);
@@ -174,7 +185,9 @@ extern "C" int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void
   GNNLM_CHECK_ARG(q && k && v && node_base && cluster_nl && out, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn: null pointer");
   GNNLM_CHECK_ARG(!centre_only || valid_base, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn: centre_only needs valid_base");
   GNNLM_CHECK_ARG(dtype == GNNLM_F32 || dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED, "gnnlm_hgt_cluster_attn: dtype");
-  GNNLM_CHECK_ARG(out_dtype == GNNLM_F32 || out_dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED, "gnnlm_hgt_cluster_attn: out dtype");
+  GNNLM_CHECK_ARG(out_dtype == GNNLM_F32 || out_dtype == GNNLM_BF16 || out_dtype == GNNLM_F16X2, GNNLM_E_UNSUPPORTED,
+                  "gnnlm_hgt_cluster_attn: out dtype");
+  GNNLM_CHECK_ARG(out_dtype != GNNLM_F16X2 || ldo >= 2 * (int64_t)H * d_k, GNNLM_E_SHAPE, "gnnlm_hgt_cluster_attn: split output needs ldo >= 2d");
   GNNLM_CHECK_ARG(max_cluster >= 1 && max_cluster <= 7, GNNLM_E_UNSUPPORTED,
                   "gnnlm_hgt_cluster_attn: cluster size %d > 7 (use gnnlm_hgt_edge_attn)", max_cluster);
   GNNLM_CHECK_ARG(H > 0 && H <= 32 && (H & (H - 1)) == 0, GNNLM_E_UNSUPPORTED, "gnnlm_hgt_cluster_attn: H must be a power of two <= 32");
@@ -190,8 +203,10 @@ extern "C" int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void
   cudaStream_t st = (cudaStream_t)stream;
 #define GNNLM_DW(T, OT, C)                                                                                                    \
   return dispatch_w<T, OT, C>(max_cluster, q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, \
-                              group, n_slices, out, ldo, st)
+                              group, n_slices, out, ldo, (int)d, st)
   if (dtype == GNNLM_F32 && out_dtype == GNNLM_F32) GNNLM_DW(float, float, 4);
+  if (dtype == GNNLM_F32 && out_dtype == GNNLM_F16X2) GNNLM_DW(float, __half, 4);
+  if (out_dtype == GNNLM_F16X2) GNNLM_DW(__nv_bfloat16, __half, 8);
   if (dtype == GNNLM_F32) GNNLM_DW(float, __nv_bfloat16, 4);
   if (out_dtype == GNNLM_F32) GNNLM_DW(__nv_bfloat16, float, 8);
   GNNLM_DW(__nv_bfloat16, __nv_bfloat16, 8);

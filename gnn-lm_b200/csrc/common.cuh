@@ -117,4 +117,20 @@ __device__ __forceinline__ void store_f32(float* __restrict__ p, const float (&r
   }
 }
 
+// ---- split-fp16 (GNNLM_F16X2) helpers: 4 floats <-> (hi, lo) packed fp16 quads ----
+__device__ __forceinline__ void split4_f16(float x0, float x1, float x2, float x3, uint2& hi, uint2& lo) {
+  x0 = fminf(fmaxf(x0, -65504.f), 65504.f); x1 = fminf(fmaxf(x1, -65504.f), 65504.f);
+  x2 = fminf(fmaxf(x2, -65504.f), 65504.f); x3 = fminf(fmaxf(x3, -65504.f), 65504.f);
+  const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y), l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+  hi.x = *reinterpret_cast<const uint32_t*>(&h01); hi.y = *reinterpret_cast<const uint32_t*>(&h23);
+  lo.x = *reinterpret_cast<const uint32_t*>(&l01); lo.y = *reinterpret_cast<const uint32_t*>(&l23);
+}
+__device__ __forceinline__ float4 join4_f16(uint2 hi, uint2 lo) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
+  const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&lo.x)), d = __half22float2(*reinterpret_cast<const __half2*>(&lo.y));
+  return make_float4(a.x + c.x, a.y + c.y, b.x + d.x, b.y + d.y);
+}
+
 }  // namespace gnnlm

@@ -157,8 +157,9 @@ struct EpiStore {
   int64_t ldr;
   void* C;
   int64_t ldc;
-  int c_bf16;
-  int r_bf16;
+  int c_bf16;      // C element type: 0 = f32, 1 = bf16, 2 = split-fp16 (hi | lo, lo at column offset c_lo)
+  int r_bf16;      // residual type, same encoding (lo at column offset r_lo)
+  int64_t c_lo, r_lo;
 };
 struct EpiLse {
   const int32_t* pick;
@@ -188,7 +189,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t
             const int lane_ = threadIdx.x & 31;
             const int cq_ = (lane_ & 7) * 4;
             const int64_t n0_ = n_base + c;
-            const bool ok_ = es.residual && (n0_ + cq_ + 3 < N) && ((es.ldc & 3) == 0) && ((es.ldr & (es.r_bf16 ? 7 : 3)) == 0);
+            const bool ok_ = es.residual && (n0_ + cq_ + 3 < N) && ((es.ldc & 3) == 0) && ((es.ldr & 3) == 0) &&
+                             (es.r_bf16 != 2 || (es.r_lo & 3) == 0) && (es.c_bf16 != 2 || (es.c_lo & 3) == 0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int64_t mr = (m - lane_) + j * 4 + (lane_ >> 3);
@@ -196,6 +198,9 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t
               if (ok_ && mr < M) {
                 if (!es.r_bf16) {
                   res[j] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(es.residual) + mr * es.ldr + n0_ + cq_));
+                } else if (es.r_bf16 == 2) {
+                  const __half* rp = reinterpret_cast<const __half*>(es.residual) + mr * es.ldr + n0_ + cq_;
+                  res[j] = join4_f16(__ldg(reinterpret_cast<const uint2*>(rp)), __ldg(reinterpret_cast<const uint2*>(rp + es.r_lo)));
                 } else {
                   const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(es.residual) + mr * es.ldr + n0_ + cq_));
                   const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
@@ -234,7 +239,8 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t
               }
             }
             const int64_t m_warp = m - lane;                             // first row of this warp's 32 rows
-            const bool vec_ok = col_ok && ((es.ldc & 3) == 0) && (!es.residual || (es.ldr & (es.r_bf16 ? 7 : 3)) == 0);
+            const bool vec_ok = col_ok && ((es.ldc & 3) == 0) && (!es.residual || (es.ldr & 3) == 0) &&
+                                (es.r_bf16 != 2 || (es.r_lo & 3) == 0) && (es.c_bf16 != 2 || (es.c_lo & 3) == 0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int r = j * 4 + (lane >> 3);
@@ -247,6 +253,12 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t
                 xs[0] += res[j].x; xs[1] += res[j].y; xs[2] += res[j].z; xs[3] += res[j].w;     // prefetched above
                 if (!es.c_bf16) {
                   *reinterpret_cast<float4*>(reinterpret_cast<float*>(es.C) + mr * es.ldc + n0 + cq) = make_float4(xs[0], xs[1], xs[2], xs[3]);
+                } else if (es.c_bf16 == 2) {
+                  uint2 hi, lo;
+                  split4_f16(xs[0], xs[1], xs[2], xs[3], hi, lo);
+                  __half* cp = reinterpret_cast<__half*>(es.C) + mr * es.ldc + n0 + cq;
+                  *reinterpret_cast<uint2*>(cp) = hi;
+                  *reinterpret_cast<uint2*>(cp + es.c_lo) = lo;
                 } else {
                   __nv_bfloat162 p0 = __floats2bfloat162_rn(xs[0], xs[1]), p1 = __floats2bfloat162_rn(xs[2], xs[3]);
                   uint2 u;
@@ -260,11 +272,23 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t
                   const int64_t n = n0 + cq + e;
                   if (n >= N) continue;
                   float y = xs[e];
-                  if (es.residual)
-                    y += es.r_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(es.residual)[mr * es.ldr + n])
-                                   : __ldg(reinterpret_cast<const float*>(es.residual) + mr * es.ldr + n);
+                  if (es.residual) {
+                    if (es.r_bf16 == 2) {
+                      const __half* rp = reinterpret_cast<const __half*>(es.residual) + mr * es.ldr + n;
+                      y += __half2float(rp[0]) + __half2float(rp[es.r_lo]);
+                    } else {
+                      y += es.r_bf16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(es.residual)[mr * es.ldr + n])
+                                     : __ldg(reinterpret_cast<const float*>(es.residual) + mr * es.ldr + n);
+                    }
+                  }
                   if (!es.c_bf16) reinterpret_cast<float*>(es.C)[mr * es.ldc + n] = y;
-                  else reinterpret_cast<__nv_bfloat16*>(es.C)[mr * es.ldc + n] = __float2bfloat16(y);
+                  else if (es.c_bf16 == 2) {
+                    const float yc = fminf(fmaxf(y, -65504.f), 65504.f);
+                    const __half h = __float2half_rn(yc);
+                    __half* cp = reinterpret_cast<__half*>(es.C) + mr * es.ldc + n;
+                    cp[0] = h;
+                    cp[es.c_lo] = __float2half_rn(yc - __half2float(h));
+                  } else reinterpret_cast<__nv_bfloat16*>(es.C)[mr * es.ldc + n] = __float2bfloat16(y);
                 }
               }
             }
@@ -933,6 +957,147 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F16_THREADS, 1)
   }
 }
 
+// ---------------------------------------------------------------------------------------------- 3xFP16, pre-split A
+// Same arithmetic as gemm_f16x3_kernel, but A arrives already in the split-fp16 activation format (GNNLM_F16X2:
+// hi | lo halves of one fp16 buffer, written by the producing kernel's epilogue), so the four operand tiles
+// A_h, A_l, W_h, W_l come straight from TMA (SWIZZLE_64B) and there are no splitter warps: a stage is 32 KB
+// (6 stages in flight instead of 4) and the TMA -> MMA hand-off has no generic-proxy hop.
+constexpr int F16S_STAGE = 2 * F16_OP_A + 2 * F16_OP_B;   // 32 KB
+constexpr int F16S_STAGES = 6;
+
+template <bool LSE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+    gemm_f16s_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                     const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_blo, int64_t M_cap,
+                     const int32_t* __restrict__ m_dev, int64_t N, int64_t K, EpiStore es, EpiLse el, float acc_scale) {
+  constexpr int STAGES = F16S_STAGES;
+  constexpr uint32_t TX = 2u * F16S_STAGE;                                // both CTAs' four operand tiles -> leader
+  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* epi_smem = reinterpret_cast<float*>(smem + (size_t)STAGES * F16S_STAGE);
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  const int64_t M = live_rows(M_cap, m_dev);
+  const int64_t n_m = (M + BLOCK_M - 1) / BLOCK_M, n_n = (N + BLOCK_N - 1) / BLOCK_N;
+  const int64_t total = ((n_m + 1) / 2) * n_n;
+  const int64_t pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
+  const int n_kb = (int)((K + F16_BLOCK_K - 1) / F16_BLOCK_K);
+
+  auto sAh = [&](int s) { return smem + (size_t)s * F16S_STAGE; };
+  auto sAl = [&](int s) { return smem + (size_t)s * F16S_STAGE + F16_OP_A; };
+  auto sBh = [&](int s) { return smem + (size_t)s * F16S_STAGE + 2 * F16_OP_A; };
+  auto sBl = [&](int s) { return smem + (size_t)s * F16S_STAGE + 2 * F16_OP_A + F16_OP_B; };
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ah) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_al) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 8);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {                                   // ---- TMA producer (both CTAs)
+      int stage = 0;
+      uint32_t phase = 0;
+      const int half = (int)crank * (BLOCK_N / 2);
+      for (int64_t tile = pair0; tile < total; tile += pair_stride) {
+        const int m0 = (int)(((tile / n_n) * 2 + crank) * BLOCK_M), n0 = (int)((tile % n_n) * BLOCK_N) + half;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[stage], TX);
+          tma_load_2d_2sm(sAh(stage), &map_ah, kb * F16_BLOCK_K, m0, &full_bar[stage]);
+          tma_load_2d_2sm(sAl(stage), &map_al, kb * F16_BLOCK_K, m0, &full_bar[stage]);
+          tma_load_2d_2sm(sBh(stage), &map_b, kb * F16_BLOCK_K, n0, &full_bar[stage]);
+          tma_load_2d_2sm(sBl(stage), &map_blo, kb * F16_BLOCK_K, n0, &full_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {                         // ---- MMA issuer (leader only)
+      int stage = 0;
+      uint32_t phase = 0;
+      int64_t it = 0;
+      for (int64_t tile = pair0; tile < total; tile += pair_stride, ++it) {
+        const int acc = (int)(it & 1);
+        const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BLOCK_N;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t dah = make_desc_sw64(smem_u32(sAh(stage))), dal = make_desc_sw64(smem_u32(sAl(stage)));
+          const uint64_t dbh = make_desc_sw64(smem_u32(sBh(stage))), dbl = make_desc_sw64(smem_u32(sBl(stage)));
+#pragma unroll
+          for (int k = 0; k < F16_BLOCK_K / 16; ++k) {
+            const uint64_t koff = (uint64_t)(k * 2);
+            umma_2sm<0>(d_tmem, dah + koff, dbl + koff, IDESC, (kb | k) > 0 ? 1u : 0u);
+            umma_2sm<0>(d_tmem, dal + koff, dbh + koff, IDESC, 1u);
+            umma_2sm<0>(d_tmem, dah + koff, dbh + koff, IDESC, 1u);
+          }
+          tc_commit_2sm(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_2sm(&tmem_full[acc]);
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
+    const int q = warp & 3;                            // ---- epilogue (both CTAs)
+    int64_t it = 0;
+    for (int64_t tile = pair0; tile < total; tile += pair_stride, ++it) {
+      const int acc = (int)(it & 1);
+      const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      const int64_t m_blk = (tile / n_n) * 2 + crank, n_blk = tile % n_n;
+      const int64_t m = m_blk * BLOCK_M + q * 32 + lane;
+      const int64_t n_base = n_blk * BLOCK_N;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      epilogue_tile<LSE>(taddr, m, M, n_base, n_blk, N, es, el, epi_smem + (warp & 3) * 32 * EPI_LD, acc_scale);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1059,6 +1224,30 @@ static int32_t launch_f16x3(const CUtensorMap& ma, const CUtensorMap& mb, const 
   return 0;
 }
 
+template <bool LSE>
+static int32_t launch_f16s(const CUtensorMap& mah, const CUtensorMap& mal, const CUtensorMap& mb, const CUtensorMap& mblo,
+                           int64_t M, const int32_t* m_dev, int64_t N, int64_t K, const EpiStore& es, const EpiLse& el,
+                           float acc_scale, cudaStream_t st) {
+  const size_t smem = (size_t)F16S_STAGES * F16S_STAGE + EPI_SMEM + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GNNLM_CUDA(cudaFuncSetAttribute(gemm_f16s_kernel<LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    GNNLM_CUDA(cudaGetDevice(&dev));
+    GNNLM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int64_t pairs = ceil_div(ceil_div(M, BLOCK_M), 2) * ceil_div(N, BLOCK_N);
+  const int64_t max_pairs = n_sm / 2;
+  const unsigned grid = 2u * (unsigned)(pairs < max_pairs ? pairs : max_pairs);
+  gemm_f16s_kernel<LSE><<<grid, 256, smem, st>>>(mah, mal, mb, mblo, M, m_dev, N, K, es, el, acc_scale);
+  GNNLM_LAUNCH_CHECK("gemm_f16s");
+  return 0;
+}
+
 }  // namespace tc
 
 int32_t gemm_tc_supported() { return tc::encode_fn() != nullptr && tc::device_is_sm100(); }
@@ -1094,15 +1283,42 @@ static int32_t tc_prepare(const char* who, const void* A, int32_t a_dtype, int64
   return 0;
 }
 
+static inline int epi_mode(int32_t dtype) { return dtype == GNNLM_BF16 ? 1 : (dtype == GNNLM_F16X2 ? 2 : 0); }
+
+// split-fp16 A (GNNLM_F16X2): four SWIZZLE_64B maps, no in-kernel operand split
+static int32_t f16s_maps(const char* who, const void* A, int64_t lda, const void* W, const void* W_lo, int64_t ldw, int64_t M,
+                         int64_t N, int64_t K, CUtensorMap* mah, CUtensorMap* mal, CUtensorMap* mb, CUtensorMap* mblo) {
+  GNNLM_CHECK_ARG(gemm_tc_supported(), GNNLM_E_UNSUPPORTED, "%s: tcgen05 path needs an sm_100 device and driver TMA support", who);
+  GNNLM_CHECK_ARG(W_lo, GNNLM_E_ARG, "%s: MATH_F16X3 needs W_lo (gnnlm_split_f16)", who);
+  GNNLM_CHECK_ARG(lda >= 2 * K && (lda * 2) % 16 == 0 && (K * 2) % 16 == 0 && (ldw * 2) % 16 == 0 && (uintptr_t)A % 16 == 0 &&
+                      (uintptr_t)W % 16 == 0 && (uintptr_t)W_lo % 16 == 0,
+                  GNNLM_E_SHAPE, "%s: split-fp16 A needs lda >= 2K and 16 B aligned halves (lda=%lld K=%lld)", who,
+                  (long long)lda, (long long)K);
+  const __half* a = reinterpret_cast<const __half*>(A);
+  int r = tc::make_map_f16(mah, a, M, K, lda, tc::BLOCK_M);
+  if (!r) r = tc::make_map_f16(mal, a + K, M, K, lda, tc::BLOCK_M);
+  if (!r) r = tc::make_map_f16(mb, W, N, K, ldw, tc::BLOCK_N / 2);
+  if (!r) r = tc::make_map_f16(mblo, W_lo, N, K, ldw, tc::BLOCK_N / 2);
+  GNNLM_CHECK_ARG(r == 0, GNNLM_E_ARG, "%s: cuTensorMapEncodeTiled failed (%d)", who, r);
+  return 0;
+}
+
 int32_t gemm_tc_store(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, float w_scale, int64_t ldw,
                       const float* bias, const void* residual, int32_t r_dtype, int64_t ldr, void* C, int32_t c_dtype,
                       int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, int64_t K, int32_t math, cudaStream_t st) {
   if (M == 0) return 0;
+  // split-fp16 buffers keep their lo half N (resp. the residual's logical width = N) columns after the hi half
+  tc::EpiStore es{bias, residual, ldr, C, ldc, epi_mode(c_dtype), epi_mode(r_dtype), N, N};
+  tc::EpiLse el{};
+  if (math == GNNLM_MATH_F16X3 && a_dtype == GNNLM_F16X2) {
+    CUtensorMap mah, mal, mb, mblo;
+    int32_t rc = f16s_maps("gnnlm_linear", A, lda, W, W_lo, ldw, M, N, K, &mah, &mal, &mb, &mblo);
+    if (rc) return rc;
+    return tc::launch_f16s<false>(mah, mal, mb, mblo, M, m_dev, N, K, es, el, 1.f / w_scale, st);
+  }
   CUtensorMap ma, mb, mblo;
   int32_t rc = tc_prepare("gnnlm_linear", A, a_dtype, lda, W, W_lo, ldw, M, N, K, math, &ma, &mb, &mblo);
   if (rc) return rc;
-  tc::EpiStore es{bias, residual, ldr, C, ldc, c_dtype == GNNLM_BF16, r_dtype == GNNLM_BF16};
-  tc::EpiLse el{};
   if (math == GNNLM_MATH_F16X3) return tc::launch_f16x3<false>(ma, mb, mblo, M, m_dev, N, K, es, el, 1.f / w_scale, st);
   if (math == GNNLM_MATH_TF32X3) return tc::launch<tc::X3, false>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
   if (math == GNNLM_MATH_TF32) return tc::launch<tc::TF32, false>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
@@ -1113,11 +1329,17 @@ int32_t gemm_tc_lse(const void* A, int32_t a_dtype, int64_t lda, const void* W, 
                     const int32_t* pick, float* part_max, float* part_sum, float* picked, int64_t M,
                     const int32_t* m_dev, int64_t N, int64_t K, int32_t math, cudaStream_t st) {
   if (M == 0) return 0;
+  tc::EpiStore es{};
+  tc::EpiLse el{pick, part_max, part_sum, picked, ceil_div(N, tc::BLOCK_N)};
+  if (math == GNNLM_MATH_F16X3 && a_dtype == GNNLM_F16X2) {
+    CUtensorMap mah, mal, mb, mblo;
+    int32_t rc = f16s_maps("gnnlm_linear_lse", A, lda, W, W_lo, ldw, M, N, K, &mah, &mal, &mb, &mblo);
+    if (rc) return rc;
+    return tc::launch_f16s<true>(mah, mal, mb, mblo, M, m_dev, N, K, es, el, 1.f / w_scale, st);
+  }
   CUtensorMap ma, mb, mblo;
   int32_t rc = tc_prepare("gnnlm_linear_lse", A, a_dtype, lda, W, W_lo, ldw, M, N, K, math, &ma, &mb, &mblo);
   if (rc) return rc;
-  tc::EpiStore es{};
-  tc::EpiLse el{pick, part_max, part_sum, picked, ceil_div(N, tc::BLOCK_N)};
   if (math == GNNLM_MATH_F16X3) return tc::launch_f16x3<true>(ma, mb, mblo, M, m_dev, N, K, es, el, 1.f / w_scale, st);
   if (math == GNNLM_MATH_TF32X3) return tc::launch<tc::X3, true>(ma, mb, mblo, M, m_dev, N, K, es, el, st);
   if (math == GNNLM_MATH_TF32) return tc::launch<tc::TF32, true>(ma, mb, mblo, M, m_dev, N, K, es, el, st);

@@ -13,6 +13,8 @@
 // nodes: each warp takes one node at a time, each lane owns 4 consecutive output floats
 // (one float4 smem read indexed by the code byte, one coalesced 16 B global store; a warp writes
 // 512 contiguous bytes).  Code bytes are read with one 32-bit load per 4 subspaces.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gnnlm {
@@ -50,13 +52,20 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 }
 
 template <typename OutT>
-__device__ __forceinline__ void store4(OutT* p, float4 v);
+__device__ __forceinline__ void store4(OutT* p, float4 v, int lo_off = 0);
 template <>
-__device__ __forceinline__ void store4<float>(float* p, float4 v) {
+__device__ __forceinline__ void store4<float>(float* p, float4 v, int) {
   *reinterpret_cast<float4*>(p) = v;
 }
 template <>
-__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+__device__ __forceinline__ void store4<__half>(__half* p, float4 v, int lo_off) {       // split-fp16: hi | lo
+  uint2 hi, lo;
+  split4_f16(v.x, v.y, v.z, v.w, hi, lo);
+  *reinterpret_cast<uint2*>(p) = hi;
+  *reinterpret_cast<uint2*>(p + lo_off) = lo;
+}
+template <>
+__device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float4 v, int) {
   __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
   uint2 u;
   u.x = *reinterpret_cast<uint32_t*>(&a);
@@ -128,7 +137,7 @@ __global__ void __launch_bounds__(PQ_THREADS, 1)
       if (r[u] >= 0 && active) {
         float4 v = cb4[((size_t)sub * 256 + c[u]) * f4_per_sub + part];
         v.x -= bsub.x; v.y -= bsub.y; v.z -= bsub.z; v.w -= bsub.w;
-        store4<OutT>(out + (size_t)(i + u) * ld_out + (size_t)(m0 + sub) * dsub + part * 4, v);
+        store4<OutT>(out + (size_t)(i + u) * ld_out + (size_t)(m0 + sub) * dsub + part * 4, v, M * dsub);
       }
     }
   }
@@ -155,7 +164,12 @@ __global__ void __launch_bounds__(256) pq_decode_generic_kernel(const uint8_t* _
   for (int j = 0; j < dsub; ++j) {
     float v = __ldg(src + j) - (bias ? __ldg(bias + m * dsub + j) : 0.f);
     if constexpr (sizeof(OutT) == 4) out[(size_t)node * ld_out + m * dsub + j] = v;
-    else out[(size_t)node * ld_out + m * dsub + j] = __float2bfloat16(v);
+    else if constexpr (std::is_same<OutT, __half>::value) {
+      const float c_ = fminf(fmaxf(v, -65504.f), 65504.f);
+      const __half h = __float2half_rn(c_);
+      out[(size_t)node * ld_out + m * dsub + j] = h;
+      out[(size_t)node * ld_out + (size_t)M * dsub + m * dsub + j] = __float2half_rn(c_ - __half2float(h));
+    } else out[(size_t)node * ld_out + m * dsub + j] = __float2bfloat16(v);
   }
 }
 
@@ -192,15 +206,16 @@ extern "C" int32_t gnnlm_pq_gather_decode(const uint8_t* codes, int64_t n_datast
                                           int64_t* labels_out, uint8_t* codes_out, gnnlm_stream_t stream) {
   GNNLM_CHECK_ARG(codes && rows, GNNLM_E_ARG, "gnnlm_pq_gather_decode: null pointer");
   GNNLM_CHECK_ARG(M > 0 && dsub > 0 && n_cap >= 0 && n_datastore > 0, GNNLM_E_SHAPE, "gnnlm_pq_gather_decode: bad sizes");
-  GNNLM_CHECK_ARG(out_dtype == GNNLM_F32 || out_dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED,
-                  "gnnlm_pq_gather_decode: out dtype must be F32 or BF16");
+  GNNLM_CHECK_ARG(out_dtype == GNNLM_F32 || out_dtype == GNNLM_BF16 || out_dtype == GNNLM_F16X2, GNNLM_E_UNSUPPORTED,
+                  "gnnlm_pq_gather_decode: out dtype must be F32, BF16 or F16X2");
   GNNLM_CHECK_ARG(!labels_out || (labels_table && (label_bytes == 2 || label_bytes == 4)), GNNLM_E_ARG,
                   "gnnlm_pq_gather_decode: labels_table/label_bytes");
   cudaStream_t st = (cudaStream_t)stream;
   if (n_cap == 0) return 0;
   if (out) {
     GNNLM_CHECK_ARG(centroids, GNNLM_E_ARG, "gnnlm_pq_gather_decode: centroids null");
-    GNNLM_CHECK_ARG(ld_out >= (int64_t)M * dsub, GNNLM_E_SHAPE, "gnnlm_pq_gather_decode: ld_out < M*dsub");
+    GNNLM_CHECK_ARG(ld_out >= (int64_t)M * dsub * (out_dtype == GNNLM_F16X2 ? 2 : 1), GNNLM_E_SHAPE,
+                    "gnnlm_pq_gather_decode: ld_out too small");
     const bool vec = (dsub % 4 == 0) && (PQ_CHUNK_FLOATS % dsub == 0) && (ld_out % 4 == 0) &&
                      ((uintptr_t)out % 16 == 0) && ((uintptr_t)centroids % 16 == 0) &&
                      (!bias || (uintptr_t)bias % 16 == 0);
@@ -216,6 +231,10 @@ extern "C" int32_t gnnlm_pq_gather_decode(const uint8_t* codes, int64_t n_datast
         GNNLM_CUDA(cudaFuncSetAttribute(pq_decode_smem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         pq_decode_smem_kernel<float><<<grid, PQ_THREADS, smem, st>>>(codes, M, centroids, dsub, bias, rows, row_ids, n_cap,
                                                                      n_dev, (float*)out, ld_out, mc, nodes_per_cta);
+      } else if (out_dtype == GNNLM_F16X2) {
+        GNNLM_CUDA(cudaFuncSetAttribute(pq_decode_smem_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pq_decode_smem_kernel<__half><<<grid, PQ_THREADS, smem, st>>>(codes, M, centroids, dsub, bias, rows, row_ids, n_cap,
+                                                                      n_dev, (__half*)out, ld_out, mc, nodes_per_cta);
       } else {
         GNNLM_CUDA(cudaFuncSetAttribute(pq_decode_smem_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         pq_decode_smem_kernel<__nv_bfloat16><<<grid, PQ_THREADS, smem, st>>>(
@@ -226,6 +245,9 @@ extern "C" int32_t gnnlm_pq_gather_decode(const uint8_t* codes, int64_t n_datast
       if (out_dtype == GNNLM_F32)
         pq_decode_generic_kernel<float><<<blocks, 256, 0, st>>>(codes, M, centroids, dsub, bias, rows, row_ids, n_cap, n_dev,
                                                                  (float*)out, ld_out);
+      else if (out_dtype == GNNLM_F16X2)
+        pq_decode_generic_kernel<__half><<<blocks, 256, 0, st>>>(codes, M, centroids, dsub, bias, rows, row_ids, n_cap, n_dev,
+                                                                  (__half*)out, ld_out);
       else
         pq_decode_generic_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(codes, M, centroids, dsub, bias, rows, row_ids, n_cap,
                                                                          n_dev, (__nv_bfloat16*)out, ld_out);

@@ -2,6 +2,8 @@
 // Reference call sites: nn.LayerNorm of HGTLayer.forward (fairseq/models/hgt.py:404-405),
 // `precompute_feats[offsets].astype(np.float32)` (fairseq/data/token_block_dataset.py:327-329).
 // All are HBM-bound streaming kernels: vectorised 16 B accesses, one warp per row.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gnnlm {
@@ -22,9 +24,29 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const V* __restrict__ 
   }
 }
 
+// residual operand of the fused add + LayerNorm: mode 0 none, 1 fp32, 2 bf16, 3 split-fp16 (lo half d columns later)
+__device__ __forceinline__ float res_at(const void* res, int mode, int64_t ld, int64_t row, int64_t j, int64_t d) {
+  if (mode == 1) return __ldg(reinterpret_cast<const float*>(res) + row * ld + j);
+  if (mode == 2) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(res)[row * ld + j]);
+  const __half* p = reinterpret_cast<const __half*>(res) + row * ld + j;
+  return __half2float(p[0]) + __half2float(p[d]);
+}
+__device__ __forceinline__ float4 res4_at(const void* res, int mode, int64_t ld, int64_t row, int64_t j, int64_t d) {
+  if (mode == 1) return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(res) + row * ld + j));
+  if (mode == 2) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(res) + row * ld + j));
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  const __half* p = reinterpret_cast<const __half*>(res) + row * ld + j;
+  return join4_f16(__ldg(reinterpret_cast<const uint2*>(p)), __ldg(reinterpret_cast<const uint2*>(p + d)));
+}
+
 // one warp per row, two passes over registers-resident data when d <= 32*MAXV*4, else re-read
 template <typename OutT>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t ldx,
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int64_t ldx, const void* __restrict__ res,
+                                                        int res_mode, int64_t ldres,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         float eps, OutT* __restrict__ y, int64_t ldy, int64_t n_cap,
                                                         const int32_t* __restrict__ n_dev, int64_t d) {
@@ -33,19 +55,25 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
     const float* xr = x + i * ldx;
+    auto at = [&](int64_t j) { return res_mode ? xr[j] + res_at(res, res_mode, ldres, i, j, d) : xr[j]; };
     float s = 0.f;
-    for (int64_t j = lane; j < d; j += 32) s += xr[j];
+    for (int64_t j = lane; j < d; j += 32) s += at(j);
     const float mean = warp_sum(s) / (float)d;
     float vs = 0.f;
     for (int64_t j = lane; j < d; j += 32) {
-      float t = xr[j] - mean;
+      float t = at(j) - mean;
       vs = fmaf(t, t, vs);
     }
     const float rstd = rsqrtf(warp_sum(vs) / (float)d + eps);
     for (int64_t j = lane; j < d; j += 32) {
-      float v = (xr[j] - mean) * rstd * __ldg(gamma + j) + __ldg(beta + j);
+      float v = (at(j) - mean) * rstd * __ldg(gamma + j) + __ldg(beta + j);
       if constexpr (sizeof(OutT) == 4) y[i * ldy + j] = v;
-      else y[i * ldy + j] = __float2bfloat16(v);
+      else if constexpr (std::is_same<OutT, __half>::value) {          // split-fp16: hi | lo
+        v = fminf(fmaxf(v, -65504.f), 65504.f);
+        const __half h = __float2half_rn(v);
+        y[i * ldy + j] = h;
+        y[i * ldy + d + j] = __float2half_rn(v - __half2float(h));
+      } else y[i * ldy + j] = __float2bfloat16(v);
     }
   }
 }
@@ -53,6 +81,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 // vectorised variant: d % 128 == 0, row held in registers (d <= 4096)
 template <typename OutT, int NV>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, int64_t ldx,
+                                                            const void* __restrict__ res, int res_mode, int64_t ldres,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps,
                                                             OutT* __restrict__ y, int64_t ldy, int64_t n_cap,
@@ -66,10 +95,16 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
     float4 r[NV];
     float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < NV; ++j) {
-      r[j] = xr[lane + 32 * j];
-      s += r[j].x + r[j].y + r[j].z + r[j].w;
+    for (int j = 0; j < NV; ++j) r[j] = xr[lane + 32 * j];
+    if (res_mode) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const float4 t = res4_at(res, res_mode, ldres, i, (int64_t)(lane + 32 * j) * 4, d);
+        r[j].x += t.x; r[j].y += t.y; r[j].z += t.z; r[j].w += t.w;
+      }
     }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) s += r[j].x + r[j].y + r[j].z + r[j].w;
     const float mean = warp_sum(s) * (1.f / d);
     float vs = 0.f;
 #pragma unroll
@@ -86,6 +121,11 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restr
                              r[j].w * rstd * g.w + b.w);
       if constexpr (sizeof(OutT) == 4) {
         reinterpret_cast<float4*>(y + i * ldy)[lane + 32 * j] = o;
+      } else if constexpr (std::is_same<OutT, __half>::value) {        // split-fp16: hi | lo
+        uint2 hi, lo;
+        split4_f16(o.x, o.y, o.z, o.w, hi, lo);
+        reinterpret_cast<uint2*>(y + i * ldy)[lane + 32 * j] = hi;
+        reinterpret_cast<uint2*>(y + i * ldy + d)[lane + 32 * j] = lo;
       } else {
         __nv_bfloat162 a = __floats2bfloat162_rn(o.x, o.y), c = __floats2bfloat162_rn(o.z, o.w);
         uint2 u;
@@ -105,6 +145,35 @@ __global__ void __launch_bounds__(256) convert_kernel(const S* __restrict__ src,
     else v = (float)src[i];
     if constexpr (sizeof(D) == 4) dst[i] = v;
     else dst[i] = (D)v;
+  }
+}
+
+// [rows, d] fp16/fp32 -> split-fp16 [rows, 2d]; one warp per row, 4 elements per lane per step
+template <typename S>
+__global__ void __launch_bounds__(256) to_split_kernel(const S* __restrict__ src, int64_t ld_src, __half* __restrict__ dst,
+                                                       int64_t ld_dst, int64_t rows_cap, const int32_t* __restrict__ rows_dev,
+                                                       int64_t d) {
+  const int64_t rows = live_rows(rows_cap, rows_dev);
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const S* s = src + r * ld_src;
+    __half* o = dst + r * ld_dst;
+    for (int64_t c = lane * 4; c < d; c += 128) {
+      float x[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) x[e] = c + e < d ? (float)s[c + e] : 0.f;
+      uint2 hi, lo;
+      split4_f16(x[0], x[1], x[2], x[3], hi, lo);
+      if (c + 3 < d && (d & 3) == 0 && (ld_dst & 3) == 0) {
+        *reinterpret_cast<uint2*>(o + c) = hi;
+        *reinterpret_cast<uint2*>(o + d + c) = lo;
+      } else {
+        const __half* hh = reinterpret_cast<const __half*>(&hi);
+        const __half* ll = reinterpret_cast<const __half*>(&lo);
+        for (int e = 0; e < 4 && c + e < d; ++e) { o[c + e] = hh[e]; o[d + c + e] = ll[e]; }
+      }
+    }
   }
 }
 
@@ -160,30 +229,41 @@ extern "C" int32_t gnnlm_gather_rows(const void* src, int64_t ld_src, const int3
   return 0;
 }
 
-extern "C" int32_t gnnlm_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y,
-                                   int32_t out_dtype, int64_t ldy, int64_t n_cap, const int32_t* n_dev, int64_t d,
-                                   gnnlm_stream_t stream) {
+extern "C" int32_t gnnlm_layernorm(const float* x, int64_t ldx, const void* residual, int32_t r_dtype, int64_t ldr,
+                                   const float* gamma, const float* beta, float eps, void* y, int32_t out_dtype, int64_t ldy,
+                                   int64_t n_cap, const int32_t* n_dev, int64_t d, gnnlm_stream_t stream) {
   GNNLM_CHECK_ARG(x && gamma && beta && y, GNNLM_E_ARG, "gnnlm_layernorm: null pointer");
-  GNNLM_CHECK_ARG(out_dtype == GNNLM_F32 || out_dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED, "gnnlm_layernorm: out dtype");
+  const int res_mode = !residual ? 0 : (r_dtype == GNNLM_F32 ? 1 : (r_dtype == GNNLM_BF16 ? 2 : (r_dtype == GNNLM_F16X2 ? 3 : -1)));
+  GNNLM_CHECK_ARG(res_mode >= 0, GNNLM_E_UNSUPPORTED, "gnnlm_layernorm: residual dtype");
+  GNNLM_CHECK_ARG(!residual || ldr >= d * (res_mode == 3 ? 2 : 1), GNNLM_E_SHAPE, "gnnlm_layernorm: ldr too small");
+  const void* res = residual;
+  const int64_t ldres = ldr;
+  GNNLM_CHECK_ARG(out_dtype == GNNLM_F32 || out_dtype == GNNLM_BF16 || out_dtype == GNNLM_F16X2, GNNLM_E_UNSUPPORTED,
+                  "gnnlm_layernorm: out dtype");
+  GNNLM_CHECK_ARG(out_dtype != GNNLM_F16X2 || ldy >= 2 * d, GNNLM_E_SHAPE, "gnnlm_layernorm: split output needs ldy >= 2d");
   GNNLM_CHECK_ARG(d > 0, GNNLM_E_SHAPE, "gnnlm_layernorm: d");
   if (n_cap == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned g = grid_for(n_cap, 8);
   const bool vec = d % 128 == 0 && d <= 1024 && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)x % 16 == 0 &&
-                   (uintptr_t)y % 16 == 0 && (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0;
+                   (!residual || ((uintptr_t)residual % 16 == 0 && ldr % 8 == 0)) && (uintptr_t)y % 16 == 0 && (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0;
 #define LN_VEC(NV)                                                                                                      \
   if (out_dtype == GNNLM_F32)                                                                                           \
-    layernorm_vec_kernel<float, NV><<<g, 256, 0, st>>>(x, ldx, gamma, beta, eps, (float*)y, ldy, n_cap, n_dev);          \
+    layernorm_vec_kernel<float, NV><<<g, 256, 0, st>>>(x, ldx, res, res_mode, ldres, gamma, beta, eps, (float*)y, ldy, n_cap, n_dev);          \
+  else if (out_dtype == GNNLM_F16X2)                                                                                    \
+    layernorm_vec_kernel<__half, NV><<<g, 256, 0, st>>>(x, ldx, res, res_mode, ldres, gamma, beta, eps, (__half*)y, ldy, n_cap, n_dev);        \
   else                                                                                                                  \
-    layernorm_vec_kernel<__nv_bfloat16, NV><<<g, 256, 0, st>>>(x, ldx, gamma, beta, eps, (__nv_bfloat16*)y, ldy, n_cap, n_dev);
+    layernorm_vec_kernel<__nv_bfloat16, NV><<<g, 256, 0, st>>>(x, ldx, res, res_mode, ldres, gamma, beta, eps, (__nv_bfloat16*)y, ldy, n_cap, n_dev);
   if (vec && d == 1024) { LN_VEC(8) }
   else if (vec && d == 512) { LN_VEC(4) }
   else if (vec && d == 256) { LN_VEC(2) }
   else if (vec && d == 128) { LN_VEC(1) }
   else if (out_dtype == GNNLM_F32)
-    layernorm_kernel<float><<<g, 256, 0, st>>>(x, ldx, gamma, beta, eps, (float*)y, ldy, n_cap, n_dev, d);
+    layernorm_kernel<float><<<g, 256, 0, st>>>(x, ldx, res, res_mode, ldres, gamma, beta, eps, (float*)y, ldy, n_cap, n_dev, d);
+  else if (out_dtype == GNNLM_F16X2)
+    layernorm_kernel<__half><<<g, 256, 0, st>>>(x, ldx, res, res_mode, ldres, gamma, beta, eps, (__half*)y, ldy, n_cap, n_dev, d);
   else
-    layernorm_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(x, ldx, gamma, beta, eps, (__nv_bfloat16*)y, ldy, n_cap, n_dev, d);
+    layernorm_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(x, ldx, res, res_mode, ldres, gamma, beta, eps, (__nv_bfloat16*)y, ldy, n_cap, n_dev, d);
 #undef LN_VEC
   GNNLM_LAUNCH_CHECK("gnnlm_layernorm");
   return 0;
@@ -223,5 +303,19 @@ extern "C" int32_t gnnlm_split_f16(const float* w, float scale, void* w_hi, void
   if (n == 0) return 0;
   split_f16_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(w, scale, (__half*)w_hi, (__half*)w_lo, n);
   GNNLM_LAUNCH_CHECK("gnnlm_split_f16");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_to_split_f16(const void* src, int32_t src_dtype, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows,
+                                      const int32_t* rows_dev, int64_t d, gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(src && dst, GNNLM_E_ARG, "gnnlm_to_split_f16: null pointer");
+  GNNLM_CHECK_ARG(src_dtype == GNNLM_F32 || src_dtype == GNNLM_F16, GNNLM_E_UNSUPPORTED, "gnnlm_to_split_f16: source must be F32 or F16");
+  GNNLM_CHECK_ARG(d > 0 && ld_src >= d && ld_dst >= 2 * d, GNNLM_E_SHAPE, "gnnlm_to_split_f16: bad shape");
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g = grid_for(rows, 8);
+  if (src_dtype == GNNLM_F32) to_split_kernel<float><<<g, 256, 0, st>>>((const float*)src, ld_src, (__half*)dst, ld_dst, rows, rows_dev, d);
+  else to_split_kernel<__half><<<g, 256, 0, st>>>((const __half*)src, ld_src, (__half*)dst, ld_dst, rows, rows_dev, d);
+  GNNLM_LAUNCH_CHECK("gnnlm_to_split_f16");
   return 0;
 }

@@ -70,15 +70,35 @@ def _lin(x, w: _Weight, math_mode, **kw):
 
 
 def act_dtype(math_mode: int):
-    """Activation storage type of a math mode: bf16 end to end in MATH_BF16, fp32 otherwise."""
-    return torch.bfloat16 if math_mode == L.MATH_BF16 else torch.float32
+    """Activation storage type of a math mode: bf16 end to end in MATH_BF16, split fp16 (same bytes as fp32, consumed
+    by the GEMMs without an operand-split pass) in MATH_F16X3, fp32 otherwise."""
+    if math_mode == L.MATH_BF16:
+        return torch.bfloat16
+    return ops.SPLIT if math_mode == L.MATH_F16X3 else torch.float32
 
 
-def as_act(x: torch.Tensor, math_mode: int) -> torch.Tensor:
+def as_act(x, math_mode: int):
     dt = act_dtype(math_mode)
+    if dt == ops.SPLIT:
+        if isinstance(x, ops.Split):
+            return x
+        if x.dtype not in (torch.float16, torch.float32):
+            x = x.float()
+        return ops.to_split(x if x.stride(-1) == 1 else x.contiguous())
+    if isinstance(x, ops.Split):
+        x = x.float()
     if x.dtype == dt:
         return x if x.is_contiguous() else x.contiguous()
     return ops.convert(x, dt)
+
+
+def _attn_in_dtype(math_mode: int):
+    """Q | K' | V' storage: bf16 in MATH_BF16, fp32 otherwise (the attention kernels read fp32 / bf16)."""
+    return torch.bfloat16 if math_mode == L.MATH_BF16 else torch.float32
+
+
+def as_float(x) -> torch.Tensor:
+    return x.float() if isinstance(x, ops.Split) or x.dtype != torch.float32 else x
 
 
 class HGTLayer(nn.Module):
@@ -159,13 +179,14 @@ class HGTLayer(nn.Module):
 
     # ------------------------------------------------------------------ building blocks
     def _out(self, P, tau, t_agg, h_in, n_dev):
-        """LayerNorm(A-linear(t) + h) (hgt.py:401-405); the pre-norm sum is fp32 in every mode."""
-        o = _lin(t_agg, P["a"][tau], P["math"], residual=h_in, m_dev=n_dev)
+        """LayerNorm(A-linear(t) + h) (hgt.py:401-405).  The residual add is fused into the LayerNorm kernel (fp32 sum
+        before the statistics) instead of the GEMM epilogue: same bytes, no load latency inside the GEMM."""
+        o = _lin(t_agg, P["a"][tau], P["math"], m_dev=n_dev)
         g, b, eps = P["ln"][tau]
         act = act_dtype(P["math"])
         if act == torch.float32:
-            return ops.layernorm(o, g, b, eps, out=o, n_dev=n_dev)
-        return ops.layernorm(o, g, b, eps, out_dtype=act, n_dev=n_dev)
+            return ops.layernorm(o, g, b, eps, out=o, n_dev=n_dev, residual=h_in)
+        return ops.layernorm(o, g, b, eps, out_dtype=act, n_dev=n_dev, residual=h_in)       # bf16 or split fp16
 
     def _nn_attn(self, P, G, q, k, v, rows, *, centre: bool, n_dev, c_dev):
         """ntgt-intra-ntgt attention -> [rows, d] in the activation dtype."""
@@ -173,7 +194,7 @@ class HGTLayer(nn.Module):
         act = act_dtype(P["math"])
         tag = "nn_centre" if centre else "nn_full"
         if self.use_cluster_kernel and ops.cluster_attn_supported(d, H, q.dtype, G.w):
-            t_agg = torch.empty((rows, d), device=q.device, dtype=act)
+            t_agg = ops.empty_act(rows, d, act, q.device)
             ops.cluster_attn(q, k, v, G, H, t_agg, centre_only=centre, tag=tag)
             return t_agg
         t_agg = torch.empty((rows, d), device=q.device, dtype=torch.float32)
@@ -186,7 +207,7 @@ class HGTLayer(nn.Module):
     def ntgt_full(self, P, G: TokenGraph, h_n, n_dev):
         """All ntgt nodes: Q|K'|V' -> chain attention -> A-linear + residual + LN."""
         d = P["d"]
-        qkv = _lin(h_n, P["ntgt_qkv"], P["math"], m_dev=n_dev, out_dtype=act_dtype(P["math"]))
+        qkv = _lin(h_n, P["ntgt_qkv"], P["math"], m_dev=n_dev, out_dtype=_attn_in_dtype(P["math"]))
         t_agg = self._nn_attn(P, G, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h_n.shape[0], centre=False, n_dev=n_dev,
                               c_dev=None)
         return self._out(P, P["n"], t_agg, h_n, n_dev)
@@ -194,7 +215,7 @@ class HGTLayer(nn.Module):
     def ntgt_centre(self, P, G: TokenGraph, h_n, n_dev, hc, c_dev):
         """Centre nodes only (compact rows): K'|V' for every node, Q / A-linear / LN for centres."""
         d = P["d"]
-        act = act_dtype(P["math"])
+        act = _attn_in_dtype(P["math"])
         kv = _lin(h_n, P["ntgt_qkv"].rows(d, 3 * d), P["math"], m_dev=n_dev, out_dtype=act)
         qc = _lin(hc, P["ntgt_qkv"].rows(0, d), P["math"], m_dev=c_dev, out_dtype=act)
         t_agg = self._nn_attn(P, G, qc, kv[:, :d], kv[:, d:], hc.shape[0], centre=True, n_dev=n_dev, c_dev=c_dev)
@@ -223,7 +244,7 @@ class HGTLayer(nn.Module):
         hc = ops.gather_rows(h_n, G.inter_indices, n_cap=n_valid)
         new_t = self.tgt(P, G, h_t, hc, None)
         new_n = self.ntgt_full(P, G, h_n, None)
-        return {"tgt": new_t, "ntgt": new_n}
+        return {"tgt": new_t, "ntgt": new_n}       # activation format of the math mode (HGT.forward converts back)
 
 
 class HGT(nn.Module):
@@ -257,7 +278,7 @@ class HGT(nn.Module):
             h[ntype] = x if x.dtype == torch.bfloat16 else x.float().contiguous()
         for layer in self.gcs:
             h = layer(G, h, etypes=etypes, incremental_state=incremental_state, math_mode=self.math_mode)
-        return h
+        return {k_: as_float(v) for k_, v in h.items()}
 
     @torch.no_grad()
     def forward_tgt(self, G: TokenGraph, h_tgt: torch.Tensor, h_ntgt: Optional[torch.Tensor],

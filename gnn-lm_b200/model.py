@@ -22,7 +22,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import ops
 from .graph import ETYPES, TokenGraph
-from .hgt import HGT, _Weight, act_dtype, as_act
+from .hgt import HGT, _Weight, act_dtype, as_act, as_float
 from .pq_codec import TorchPQCodec
 
 
@@ -187,12 +187,14 @@ class TokenGraphTransformerDecoder(nn.Module):
         if "h" not in graph.nodes["tgt"].data:
             raise NotImplementedError("the base transformer is out of scope: evaluate with --use-precompute-feat "
                                       "(transformer.py:974-976)")
-        x = as_act(graph.nodes["tgt"].data["h"], self.math_mode)     # fp16 -> fp32 (token_block_dataset.py:328) / bf16
-        x = x.view(bsz, tgt_len, -1)
+        feats = graph.nodes["tgt"].data["h"]                         # [T, d] fp16 / fp32 rows of keys.npy
+        x = feats.view(bsz, tgt_len, -1)
         extra = {"inner_states": [x.transpose(0, 1)]}
         orig_x = x if self.orig_prob_ratio > 0 else None
         if not self.short_cut:
-            x = self.extract_graph_features(x, prev_output_tokens, graph, encoder_out, incremental_state)
+            # fp16 -> fp32 (token_block_dataset.py:328), or the activation format of the math mode
+            x = self.extract_graph_features(as_act(feats, self.math_mode), prev_output_tokens, graph, encoder_out,
+                                            incremental_state, shape=(bsz, tgt_len))
         extra["gcn_feat"] = x.transpose(0, 1)
         if self.orig_prob_ratio > 0:
             if self.adaptive_softmax is None:
@@ -202,10 +204,16 @@ class TokenGraphTransformerDecoder(nn.Module):
         return x, extra      # adaptive softmax: output_layer is the identity (transformer.py:843-852)
 
     def extract_graph_features(self, tgt_features, prev_output_tokens, graph: TokenGraph, encoder_out=None,
-                               incremental_state=None):
-        bsz, seq_len, h = tgt_features.shape
+                               incremental_state=None, shape=None):
+        """tgt_features: [bsz, len, d] tensor (reference signature) or a flat [T, d] activation (Tensor / Split)
+        together with shape=(bsz, len)."""
         assert encoder_out is None and incremental_state is None, "only support lm"
-        h_tgt = tgt_features.reshape(-1, self.embed_dim)
+        if shape is None:
+            bsz, seq_len, _ = tgt_features.shape
+            h_tgt = tgt_features.reshape(-1, self.embed_dim)
+        else:
+            bsz, seq_len = shape
+            h_tgt = tgt_features
         nd = graph.nodes["ntgt"].data
         mode = self.math_mode
         NL = self.hgt_decoder.n_layers
@@ -224,7 +232,7 @@ class TokenGraphTransformerDecoder(nn.Module):
                 h_n = self.tgt_quantizer.gather_decode(codes, graph.ntgt_row, n_cap=graph.node_cap,
                                                        n_dev=graph.n_ntgt_dev, math_mode=mode)
                 out = self.hgt_decoder.forward_tgt(graph, h_tgt, h_n)
-        return out.view(bsz, seq_len, -1)
+        return as_float(out).view(bsz, seq_len, -1)
 
     # ------------------------------------------------------------------ probabilities
     def _plain_out(self):

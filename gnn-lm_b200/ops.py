@@ -10,43 +10,93 @@ import torch
 from . import _lib as L
 
 _I32 = torch.int32
+SPLIT = "split"          # out_dtype selector for the split-fp16 activation format (GNNLM_F16X2)
+
+
+class Split:
+    """An fp32 matrix [rows, d] stored as split fp16 (GNNLM_F16X2): `.data` is [rows, 2d] float16 with
+    hi = fp16(x) in columns [0, d) and lo = fp16(x - hi) in [d, 2d).  Activation format of MATH_F16X3."""
+
+    def __init__(self, data: torch.Tensor, d: int):
+        assert data.dtype == torch.float16 and data.dim() == 2 and data.shape[1] == 2 * d and data.stride(1) == 1
+        self.data, self.d = data, d
+
+    @staticmethod
+    def empty(rows: int, d: int, device) -> "Split":
+        return Split(torch.empty((rows, 2 * d), device=device, dtype=torch.float16), d)
+
+    @property
+    def shape(self):
+        return (self.data.shape[0], self.d)
+
+    @property
+    def device(self):
+        return self.data.device
+
+    def float(self) -> torch.Tensor:
+        """fp32 reconstruction (API-boundary convenience, torch ops)."""
+        return self.data[:, :self.d].float() + self.data[:, self.d:].float()
+
+
+def empty_act(rows: int, d: int, act, device):
+    return Split.empty(rows, d, device) if act == SPLIT else torch.empty((rows, d), device=device, dtype=act)
+
+
+def _mat(x):
+    """(pointer, dtype code, leading dimension, logical columns) of a Tensor or Split."""
+    if isinstance(x, Split):
+        return L.ptr(x.data), L.F16X2, x.data.stride(0), x.d
+    assert x.dim() == 2 and x.stride(1) == 1
+    return L.ptr(x), L.dtype_code(x.dtype), x.stride(0), x.shape[1]
+
+
+def to_split(x: torch.Tensor, rows_dev=None) -> Split:
+    """fp16 / fp32 [rows, d] -> split fp16."""
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype in (torch.float16, torch.float32)
+    out = Split.empty(x.shape[0], x.shape[1], x.device)
+    L.call("gnnlm_to_split_f16", L.ptr(x), L.dtype_code(x.dtype), x.stride(0), L.ptr(out.data), out.data.stride(0), x.shape[0],
+           L.ptr(rows_dev), x.shape[1], L.stream_ptr())
+    return out
 
 
 def _dev_count(t: Optional[torch.Tensor]):
     return L.ptr(t)
 
 
-def linear(A: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor] = None, *, W_lo: Optional[torch.Tensor] = None,
-           residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out_dtype=None,
-           m_dev: Optional[torch.Tensor] = None, math: int = L.MATH_FP32_SIMT, tag=None, w_scale: float = 1.0) -> torch.Tensor:
-    """C = A @ W^T + bias (+ residual).  A [M,K] (row stride arbitrary), W [N,K]."""
-    assert A.dim() == 2 and W.dim() == 2 and A.stride(1) == 1 and W.stride(1) == 1
-    M, K = A.shape
+def linear(A, W: torch.Tensor, bias: Optional[torch.Tensor] = None, *, W_lo: Optional[torch.Tensor] = None,
+           residual=None, out=None, out_dtype=None, m_dev: Optional[torch.Tensor] = None, math: int = L.MATH_FP32_SIMT,
+           tag=None, w_scale: float = 1.0):
+    """C = A @ W^T + bias (+ residual).  A [M,K] Tensor or Split, W [N,K]; out_dtype a torch dtype or ops.SPLIT."""
+    a_ptr, a_code, lda, K = _mat(A)
+    M = A.shape[0]
     N = W.shape[0]
-    assert W.shape[1] == K, (A.shape, W.shape)
+    assert W.dim() == 2 and W.stride(1) == 1 and W.shape[1] == K, (A.shape, W.shape)
+    dev = W.device
     if out is None:
-        out = torch.empty((M, N), device=A.device, dtype=out_dtype or torch.float32)
-    assert out.stride(1) == 1 and out.shape == (M, N)
+        out = empty_act(M, N, out_dtype or torch.float32, dev)
+    c_ptr, c_code, ldc, n_out = _mat(out)
+    assert n_out == N and out.shape[0] == M
+    r_ptr, r_code, ldr = None, 0, 0
     if residual is not None:
-        assert residual.dtype in (torch.float32, torch.bfloat16) and residual.stride(1) == 1
-    L.call("gnnlm_linear", L.ptr(A), L.dtype_code(A.dtype), A.stride(0), L.ptr(W), L.ptr(W_lo), float(w_scale), W.stride(0),
-           L.ptr(bias), L.ptr(residual), L.dtype_code(residual.dtype) if residual is not None else 0,
-           residual.stride(0) if residual is not None else 0, L.ptr(out),
-           L.dtype_code(out.dtype), out.stride(0), M, _dev_count(m_dev), N, K, math, L.stream_ptr(),
-           tag=tag or f"linear[{N}x{K}]")
+        r_ptr, r_code, ldr, n_r = _mat(residual)
+        assert n_r == N
+    L.call("gnnlm_linear", a_ptr, a_code, lda, L.ptr(W), L.ptr(W_lo), float(w_scale), W.stride(0), L.ptr(bias), r_ptr, r_code,
+           ldr, c_ptr, c_code, ldc, M, _dev_count(m_dev), N, K, math, L.stream_ptr(), tag=tag or f"linear[{N}x{K}]")
     return out
 
 
 def linear_lse(A, W, pick, *, W_lo=None, m_dev=None, math=L.MATH_FP32_SIMT, w_scale=1.0):
     """Row log-sum-exp partials + picked column of A @ W^T without materialising it."""
-    M, K = A.shape
+    a_ptr, a_code, lda, K = _mat(A)
+    M = A.shape[0]
     N = W.shape[0]
+    dev = W.device
     nt = L.load().gnnlm_lse_num_tiles(N, math)
-    pmax = torch.empty((M, nt), device=A.device, dtype=torch.float32)
-    psum = torch.empty((M, nt), device=A.device, dtype=torch.float32)
-    picked = torch.zeros((M,), device=A.device, dtype=torch.float32)
-    L.call("gnnlm_linear_lse", L.ptr(A), L.dtype_code(A.dtype), A.stride(0), L.ptr(W), L.ptr(W_lo), float(w_scale), W.stride(0),
-           L.ptr(pick), L.ptr(pmax), L.ptr(psum), L.ptr(picked), M, _dev_count(m_dev), N, K, math, L.stream_ptr())
+    pmax = torch.empty((M, nt), device=dev, dtype=torch.float32)
+    psum = torch.empty((M, nt), device=dev, dtype=torch.float32)
+    picked = torch.zeros((M,), device=dev, dtype=torch.float32)
+    L.call("gnnlm_linear_lse", a_ptr, a_code, lda, L.ptr(W), L.ptr(W_lo), float(w_scale), W.stride(0), L.ptr(pick), L.ptr(pmax),
+           L.ptr(psum), L.ptr(picked), M, _dev_count(m_dev), N, K, math, L.stream_ptr())
     return pmax, psum, picked, nt
 
 
@@ -57,6 +107,8 @@ def lse_finish(pmax, psum, picked, nt, out, *, row_map=None, accumulate=False, m
 
 
 def gather_rows(src, ids, n_cap=None, n_dev=None, out=None):
+    if isinstance(src, Split):      # a row gather of the [rows, 2d] fp16 buffer
+        return Split(gather_rows(src.data, ids, n_cap, n_dev), src.d)
     n = ids.shape[0] if n_cap is None else n_cap
     d = src.shape[1]
     if out is None:
@@ -66,12 +118,15 @@ def gather_rows(src, ids, n_cap=None, n_dev=None, out=None):
     return out
 
 
-def layernorm(x, gamma, beta, eps=1e-5, out=None, out_dtype=None, n_dev=None):
+def layernorm(x, gamma, beta, eps=1e-5, out=None, out_dtype=None, n_dev=None, residual=None):
+    """LayerNorm(x + residual); residual a Tensor (fp32 / bf16) or Split."""
     n, d = x.shape
     if out is None:
-        out = torch.empty((n, d), device=x.device, dtype=out_dtype or torch.float32)
-    L.call("gnnlm_layernorm", L.ptr(x), x.stride(0), L.ptr(gamma), L.ptr(beta), float(eps), L.ptr(out),
-           L.dtype_code(out.dtype), out.stride(0), n, _dev_count(n_dev), d, L.stream_ptr())
+        out = empty_act(n, d, out_dtype or torch.float32, x.device)
+    o_ptr, o_code, ldy, _ = _mat(out)
+    r_ptr, r_code, ldr = (None, 0, 0) if residual is None else _mat(residual)[:3]
+    L.call("gnnlm_layernorm", L.ptr(x), x.stride(0), r_ptr, r_code, ldr, L.ptr(gamma), L.ptr(beta), float(eps), o_ptr, o_code,
+           ldy, n, _dev_count(n_dev), d, L.stream_ptr())
     return out
 
 
@@ -124,9 +179,10 @@ def cluster_attn_supported(d: int, H: int, dtype, w: int) -> bool:
 def cluster_attn(q, k, v, G, H, out, *, centre_only=False, tag=None):
     """ntgt-intra-ntgt chain attention per (token, neighbour) cluster; G is a TokenGraph."""
     d = k.shape[1]
+    o_ptr, o_code, ldo, _ = _mat(out)
     L.call("gnnlm_hgt_cluster_attn", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0),
            L.dtype_code(q.dtype), L.ptr(G.node_base), L.ptr(G.valid_base), L.ptr(G.cluster_nl), G.T * G.k, G.w,
-           int(centre_only), H, d // H, L.ptr(out), L.dtype_code(out.dtype), out.stride(0), L.stream_ptr(), tag=tag)
+           int(centre_only), H, d // H, o_ptr, o_code, ldo, L.stream_ptr(), tag=tag)
     return out
 
 
@@ -144,7 +200,8 @@ def pq_gather_decode(codes, centroids, rows, *, bias=None, row_ids=None, n_cap=N
     dsub = centroids.shape[2]
     n = (row_ids.shape[0] if row_ids is not None else rows.shape[0]) if n_cap is None else n_cap
     dev = codes.device
-    out = torch.empty((n, M * dsub), device=dev, dtype=out_dtype) if decode else None
+    out = empty_act(n, M * dsub, out_dtype, dev) if decode else None
+    o_ptr, o_code, ld_out = (None, L.F32, M * dsub) if out is None else _mat(out)[:3]
     labels = torch.empty((n,), device=dev, dtype=torch.int64) if labels_table is not None else None
     codes_out = torch.empty((n, M), device=dev, dtype=torch.uint8) if want_codes else None
     lb = 0
@@ -152,7 +209,7 @@ def pq_gather_decode(codes, centroids, rows, *, bias=None, row_ids=None, n_cap=N
         lb = {torch.int16: 2, torch.int32: 4}[labels_table.dtype]
     L.call("gnnlm_pq_gather_decode", L.ptr(codes), n_d, M, L.ptr(centroids), dsub,
            L.ptr(bias) if bias is not None and bias.numel() else None, L.ptr(rows), L.ptr(row_ids), n, _dev_count(n_dev),
-           L.ptr(out), L.dtype_code(out_dtype), M * dsub, L.ptr(labels_table), lb, L.ptr(labels), L.ptr(codes_out),
+           o_ptr, o_code, ld_out, L.ptr(labels_table), lb, L.ptr(labels), L.ptr(codes_out),
            L.stream_ptr())
     return out, labels, codes_out
 

@@ -77,7 +77,8 @@ class TorchPQCodec(nn.Module):
         n, MM = codes.shape
         assert MM == self.M, f"input codes have {MM} subspace, but quantizer have {self.M} subspace"
         rows = torch.arange(n, device=codes.device, dtype=torch.int64)
-        return self.gather_decode(codes.contiguous(), rows, math_mode=math_mode)
+        x = self.gather_decode(codes.contiguous(), rows, math_mode=math_mode)
+        return x.float() if isinstance(x, ops.Split) else x
 
 
 def _arrays_from_faiss(index):

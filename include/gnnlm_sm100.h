@@ -33,6 +33,12 @@ typedef struct CUstream_st* gnnlm_stream_t; /* == cudaStream_t */
 #define GNNLM_F32 0
 #define GNNLM_BF16 1
 #define GNNLM_F16 2
+/* "split fp16": an fp32 matrix [rows, d] stored as two fp16 halves in ONE [rows, 2d] fp16 buffer, hi = fp16(x) in
+ * columns [0, d), lo = fp16(x - hi) in columns [d, 2d) (22 significant bits, |x| clamped to 65504).  Same bytes as
+ * fp32; it is the activation format of GNNLM_MATH_F16X3: GEMMs consume it straight through TMA (no in-kernel
+ * operand split) and the producing kernels (PQ decode, GEMM epilogue, LayerNorm, cluster attention) emit it.
+ * Leading dimensions of F16X2 buffers are in fp16 elements (>= 2d). */
+#define GNNLM_F16X2 3
 
 /* argument errors */
 #define GNNLM_E_ARG (-1)
@@ -154,11 +160,16 @@ int32_t gnnlm_lse_finish(const float* part_max, const float* part_sum, const flo
 /* dst[i, :] = src[ids[i], :]  (n x d elements of `dtype`) */
 int32_t gnnlm_gather_rows(const void* src, int64_t ld_src, const int32_t* ids, void* dst, int64_t ld_dst,
                           int64_t n_cap, const int32_t* n_dev, int64_t d, int32_t dtype, gnnlm_stream_t stream);
-/* y = LayerNorm(x) * gamma + beta over the last dim (hgt.py:404-405; eps as nn.LayerNorm, 1e-5).
- * x fp32 [n, d]; y out_dtype. In-place allowed when out_dtype == F32. */
-int32_t gnnlm_layernorm(const float* x, int64_t ldx, const float* gamma, const float* beta, float eps, void* y,
-                        int32_t out_dtype, int64_t ldy, int64_t n_cap, const int32_t* n_dev, int64_t d,
-                        gnnlm_stream_t stream);
+/* y = LayerNorm(x + residual) * gamma + beta over the last dim (hgt.py:403-405; eps as nn.LayerNorm, 1e-5).
+ * x fp32 [n, d]; residual nullable, [n, d] of r_dtype (F32 / BF16 / F16X2), added in fp32 before the
+ * statistics -- the `trans_out + h[ntype]` of hgt.py:403 fused here rather than in the GEMM epilogue;
+ * y out_dtype (F32 / BF16 / F16X2).  In-place (y == x) allowed when out_dtype == F32. */
+int32_t gnnlm_layernorm(const float* x, int64_t ldx, const void* residual, int32_t r_dtype, int64_t ldr,
+                        const float* gamma, const float* beta, float eps, void* y, int32_t out_dtype, int64_t ldy,
+                        int64_t n_cap, const int32_t* n_dev, int64_t d, gnnlm_stream_t stream);
+/* fp16 / fp32 rows [rows, d] (ld_src elements) -> split-fp16 [rows, 2d] (GNNLM_F16X2, ld_dst >= 2d fp16 elements). */
+int32_t gnnlm_to_split_f16(const void* src, int32_t src_dtype, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows,
+                           const int32_t* rows_dev, int64_t d, gnnlm_stream_t stream);
 /* Convert fp16/fp32 rows (keys.npy slices, token_block_dataset.py:327-329) to fp32/bf16. */
 int32_t gnnlm_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n,
                       gnnlm_stream_t stream);

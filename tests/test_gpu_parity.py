@@ -156,6 +156,12 @@ def test_layernorm_and_gather(dev):
         y = ops.layernorm(x.to(dev), g.to(dev), b.to(dev))
         ref = torch.nn.functional.layer_norm(x, (d,), g, b)
         np.testing.assert_allclose(y.cpu().numpy(), ref.numpy(), rtol=1e-5, atol=1e-5)
+        r = torch.randn(700, d)
+        ref_r = torch.nn.functional.layer_norm(x + r, (d,), g, b)
+        y_r = ops.layernorm(x.to(dev), g.to(dev), b.to(dev), residual=r.to(dev))
+        np.testing.assert_allclose(y_r.cpu().numpy(), ref_r.numpy(), rtol=1e-5, atol=1e-5)
+        y_s = ops.layernorm(x.to(dev), g.to(dev), b.to(dev), residual=ops.to_split(r.to(dev)), out_dtype=ops.SPLIT)
+        np.testing.assert_allclose(y_s.float().cpu().numpy(), ref_r.numpy(), rtol=1e-5, atol=1e-5)
         ids = torch.randint(0, 700, (333,), dtype=torch.int32)
         assert (ops.gather_rows(x.to(dev), ids.to(dev)).cpu() == x[ids.long()]).all()
 
@@ -476,3 +482,35 @@ def test_whole_path_bf16(name, dev):
     np.testing.assert_allclose(out["logprob"], ref["logprob"].numpy(), rtol=1e-2, atol=1e-2)
     assert abs(out["nll"] - ref["nll"]) < 1e-2
     assert (out["recall"] == ref["knn_recall"].numpy()).all()
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 200, 64), (4096, 1024, 1024), (1000, 3072, 256), (129, 72, 32)])
+def test_linear_f16x3_split_format(M, N, K, dev):
+    """MATH_F16X3 with the split-fp16 activation format (GNNLM_F16X2) on A, the residual and C: same 1e-4 bar."""
+    _need_tc()
+    from gnnlm_b200 import _lib as L, ops
+    torch.manual_seed(M + N)
+    A, W, b, R = torch.randn(M, K), torch.randn(N, K) / K ** 0.5, torch.randn(N), torch.randn(M, N)
+    ref = A.double() @ W.double().t() + b.double() + R.double()
+    As, Rs = ops.to_split(A.to(dev)), ops.to_split(R.to(dev))
+    # the format itself: hi + lo reproduces fp32 to ~2^-22
+    np.testing.assert_allclose(As.float().cpu().numpy(), A.numpy(), rtol=1e-6, atol=1e-7)
+    Wh, Wl, ws = ops.split_f16(W.to(dev))
+    out = ops.linear(As, Wh, b.to(dev), W_lo=Wl, w_scale=ws, residual=Rs, out_dtype=ops.SPLIT, math=L.MATH_F16X3)
+    assert isinstance(out, ops.Split)
+    np.testing.assert_allclose(out.float().cpu().double().numpy(), ref.numpy(), rtol=1e-4, atol=1e-4)
+    out32 = ops.linear(As, Wh, b.to(dev), W_lo=Wl, w_scale=ws, residual=R.to(dev), math=L.MATH_F16X3)
+    np.testing.assert_allclose(out32.cpu().double().numpy(), ref.numpy(), rtol=1e-4, atol=1e-4)
+    pick = torch.randint(0, N, (M,), dtype=torch.int32)
+    pm, ps, pk, nt = ops.linear_lse(As, Wh, pick.to(dev), W_lo=Wl, w_scale=ws, math=L.MATH_F16X3)
+    lp = torch.empty(M, device=dev)
+    ops.lse_finish(pm, ps, pk, nt, lp)
+    ref_lp = torch.log_softmax(A.double() @ W.double().t(), 1).gather(1, pick.long()[:, None]).squeeze(1)
+    np.testing.assert_allclose(lp.cpu().double().numpy(), ref_lp.numpy(), rtol=1e-4, atol=1e-4)
+    # LayerNorm -> split, row gather of a split matrix
+    g, be = torch.randn(N), torch.randn(N)
+    y = ops.layernorm(out32, g.to(dev), be.to(dev), out_dtype=ops.SPLIT)
+    np.testing.assert_allclose(y.float().cpu().numpy(), torch.nn.functional.layer_norm(out32.cpu(), (N,), g, be).numpy(),
+                               rtol=1e-5, atol=1e-5)
+    ids = torch.randint(0, M, (77,), dtype=torch.int32)
+    assert (ops.gather_rows(y, ids.to(dev)).data.cpu() == y.data.cpu()[ids.long()]).all()
