@@ -1,0 +1,131 @@
+// Helpers that let the ('tgt','intra','tgt') causal attention of HGTLayer.forward (reference:
+// fairseq/models/hgt.py:354-358 over the edges of token_block_dataset.py:586-594) run on the tensor cores at
+// fp32 parity: per head, S = Q K'^T and O = softmax_causal(S) V' are two 3xFP16 GEMMs (gemm_tcgen05.cu,
+// gemm_f16s_kernel) and everything in between is the three HBM-streaming kernels below.
+//
+//   heads_split      Q / K' [L, H*d_k] fp32 (row stride ld) -> per-head split-fp16 operands:
+//                    A-style [H, L, 2*d_k] (hi | lo in one row) or W-style hi [H, L, d_k], lo [H, L, d_k]
+//   heads_transpose  V' [L, H*d_k] -> W-style transposed operands hi / lo [H, d_k, L]  (P V' = P (V'^T)^T)
+//   causal_softmax   S [H, L, L] fp32 -> P split-fp16 [H, L, 2L]: row i is softmax over j in [max(0, i-ctx+1), i],
+//                    zero elsewhere (the masked products then contribute exact zeros to the GEMM)
+//
+// The full L x L score matrix is materialised per block (H*L*L*4 B = 302 MB at L = 3072, H = 8): 2x the causal
+// FLOPs and ~1.2 GB of HBM traffic per layer, which is still ~3x faster than the fp32 CUDA-core flash kernel.
+#include "common.cuh"
+
+namespace gnnlm {
+
+__global__ void __launch_bounds__(256) heads_split_kernel(const float* __restrict__ src, int64_t ld, int64_t L, int H, int dk,
+                                                          int a_style, __half* __restrict__ hi, __half* __restrict__ lo) {
+  // one thread per 4 consecutive features of one (token, head)
+  const int64_t per_row = (int64_t)H * dk / 4;
+  const int64_t n = L * per_row;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = i / per_row;
+    const int c = (int)(i % per_row) * 4;
+    const int h = c / dk, j = c % dk;
+    const float4 x = __ldg(reinterpret_cast<const float4*>(src + t * ld + c));
+    uint2 ph, pl;
+    split4_f16(x.x, x.y, x.z, x.w, ph, pl);
+    if (a_style) {
+      __half* row = hi + ((int64_t)h * L + t) * 2 * dk;
+      *reinterpret_cast<uint2*>(row + j) = ph;
+      *reinterpret_cast<uint2*>(row + dk + j) = pl;
+    } else {
+      const int64_t o = ((int64_t)h * L + t) * dk + j;
+      *reinterpret_cast<uint2*>(hi + o) = ph;
+      *reinterpret_cast<uint2*>(lo + o) = pl;
+    }
+  }
+}
+
+// 32 x 32 smem tile transpose per (head, token tile, feature tile)
+__global__ void __launch_bounds__(256) heads_transpose_kernel(const float* __restrict__ src, int64_t ld, int64_t L, int H, int dk,
+                                                              __half* __restrict__ hi, __half* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int h = blockIdx.z;
+  const int64_t t0 = (int64_t)blockIdx.x * 32;
+  const int j0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;             // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t t = t0 + r;
+    tile[r][tx] = (t < L && j0 + tx < dk) ? __ldg(src + t * ld + (int64_t)h * dk + j0 + tx) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {                                   // r = feature inside the tile, tx = token
+    const int64_t t = t0 + tx;
+    const int j = j0 + r;
+    if (t < L && j < dk) {
+      const float x = fminf(fmaxf(tile[tx][r], -65504.f), 65504.f);
+      const __half a = __float2half_rn(x);
+      const int64_t o = ((int64_t)h * dk + j) * L + t;
+      hi[o] = a;
+      lo[o] = __float2half_rn(x - __half2float(a));
+    }
+  }
+}
+
+// one warp per (head, query row): two passes over the row (max, then exp + sum), third pass writes hi | lo
+__global__ void __launch_bounds__(256) causal_softmax_kernel(const float* __restrict__ S, int64_t L, int64_t ctx, int H,
+                                                             __half* __restrict__ P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)H * L;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const int64_t i = r % L;
+    const float* s = S + r * L;
+    __half* p = P + r * 2 * L;
+    const int64_t lo_j = (ctx > 0 && i + 1 > ctx) ? i + 1 - ctx : 0;
+    float mx = -INFINITY;
+    for (int64_t j = lo_j + lane; j <= i; j += 32) mx = fmaxf(mx, s[j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int64_t j = lo_j + lane; j <= i; j += 32) sum += __expf(s[j] - mx);
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int64_t j = lane; j < L; j += 32) {
+      const float w = (j >= lo_j && j <= i) ? __expf(s[j] - mx) * inv : 0.f;
+      const __half a = __float2half_rn(w);
+      p[j] = a;
+      p[L + j] = __float2half_rn(w - __half2float(a));
+    }
+  }
+}
+
+}  // namespace gnnlm
+
+using namespace gnnlm;
+
+extern "C" int32_t gnnlm_heads_split_f16(const float* src, int64_t ld, int64_t L, int32_t H, int32_t d_k, int32_t a_style,
+                                         void* hi, void* lo, gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(src && hi && (a_style || lo), GNNLM_E_ARG, "gnnlm_heads_split_f16: null pointer");
+  GNNLM_CHECK_ARG(L > 0 && H > 0 && d_k > 0 && d_k % 4 == 0 && ld % 4 == 0 && (uintptr_t)src % 16 == 0, GNNLM_E_SHAPE,
+                  "gnnlm_heads_split_f16: d_k and ld must be multiples of 4");
+  const int64_t n = L * H * d_k / 4;
+  int64_t blocks = ceil_div(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  heads_split_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, ld, L, H, d_k, a_style, (__half*)hi, (__half*)lo);
+  GNNLM_LAUNCH_CHECK("gnnlm_heads_split_f16");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_heads_transpose_split_f16(const float* src, int64_t ld, int64_t L, int32_t H, int32_t d_k, void* hi,
+                                                   void* lo, gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(src && hi && lo, GNNLM_E_ARG, "gnnlm_heads_transpose_split_f16: null pointer");
+  GNNLM_CHECK_ARG(L > 0 && H > 0 && d_k > 0, GNNLM_E_SHAPE, "gnnlm_heads_transpose_split_f16: bad sizes");
+  dim3 grid((unsigned)ceil_div(L, 32), (unsigned)ceil_div(d_k, 32), (unsigned)H);
+  heads_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, ld, L, H, d_k, (__half*)hi, (__half*)lo);
+  GNNLM_LAUNCH_CHECK("gnnlm_heads_transpose_split_f16");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_causal_softmax_split(const float* S, int64_t L, int64_t intra_ctx, int32_t H, void* P,
+                                              gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(S && P, GNNLM_E_ARG, "gnnlm_causal_softmax_split: null pointer");
+  GNNLM_CHECK_ARG(L > 0 && H > 0, GNNLM_E_SHAPE, "gnnlm_causal_softmax_split: bad sizes");
+  int64_t blocks = ceil_div((int64_t)H * L, 8);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  causal_softmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(S, L, intra_ctx, H, (__half*)P);
+  GNNLM_LAUNCH_CHECK("gnnlm_causal_softmax_split");
+  return 0;
+}

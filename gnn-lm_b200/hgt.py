@@ -139,6 +139,7 @@ class HGTLayer(nn.Module):
         self._prep = None
         self._prep_key = None
         self.use_cluster_kernel = True     # False: always go through the generic CSR kernel (tests compare both)
+        self.use_gemm_attention = True     # MATH_F16X3, long blocks: tgt-intra-tgt attention as tensor-core GEMMs
 
     # ------------------------------------------------------------------ weight preparation
     def prepare(self, math_mode: int):
@@ -230,8 +231,12 @@ class HGTLayer(nn.Module):
         t_agg = torch.empty((h_t.shape[0], d), device=h_t.device, dtype=torch.float32)
         # inter edges in compact centre numbering are the contiguous ranges of inter_indptr
         ops.edge_attn(qkv[:, :d], kvi[:, :d], kvi[:, d:], G.inter_indptr, None, H, t_agg, out_scale=0.5, tag="inter")
-        ops.causal_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5,
-                        accumulate=True)
+        if P["math"] == L.MATH_F16X3 and self.use_gemm_attention and ops.causal_attn_gemm_supported(d, H, G.L) and G.L >= 1024:
+            ops.causal_attn_gemm(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5,
+                                 accumulate=True)
+        else:
+            ops.causal_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5,
+                            accumulate=True)
         return self._out(P, P["t"], as_act(t_agg, P["math"]), h_t, None)
 
     def forward(self, G: TokenGraph, h: Dict[str, torch.Tensor], etypes=None, incremental_state=None,

@@ -194,6 +194,41 @@ def causal_attn(q, k, v, B, Lb, intra_ctx, H, out, *, out_scale=1.0, accumulate=
     return out
 
 
+def causal_attn_gemm_supported(d: int, H: int, Lb: int) -> bool:
+    dk = d // H
+    return Lb % 8 == 0 and dk % 8 == 0 and Lb >= 256
+
+
+def causal_attn_gemm(q, k, v, B, Lb, intra_ctx, H, out, *, out_scale=1.0, accumulate=False):
+    """tgt-intra-tgt attention on the tensor cores at fp32 parity (MATH_F16X3): per block and head two 3xFP16 GEMMs
+    (S = Q K'^T, O = softmax_causal(S) V') with split-fp16 operands; q / k / v fp32 [B*Lb, d] (column slices ok)."""
+    d = q.shape[1]
+    dk = d // H
+    dev = q.device
+    f16 = dict(device=dev, dtype=torch.float16)
+    st = L.stream_ptr
+    for b in range(B):
+        rows = slice(b * Lb, (b + 1) * Lb)
+        qb, kb, vb = q[rows], k[rows], v[rows]
+        qs = torch.empty((H, Lb, 2 * dk), **f16)
+        kh, kl = torch.empty((H, Lb, dk), **f16), torch.empty((H, Lb, dk), **f16)
+        vh, vl = torch.empty((H, dk, Lb), **f16), torch.empty((H, dk, Lb), **f16)
+        L.call("gnnlm_heads_split_f16", L.ptr(qb), qb.stride(0), Lb, H, dk, 1, L.ptr(qs), None, st())
+        L.call("gnnlm_heads_split_f16", L.ptr(kb), kb.stride(0), Lb, H, dk, 0, L.ptr(kh), L.ptr(kl), st())
+        L.call("gnnlm_heads_transpose_split_f16", L.ptr(vb), vb.stride(0), Lb, H, dk, L.ptr(vh), L.ptr(vl), st())
+        S = torch.empty((H, Lb, Lb), device=dev, dtype=torch.float32)
+        for h in range(H):
+            linear(Split(qs[h], dk), kh[h], None, W_lo=kl[h], out=S[h], math=L.MATH_F16X3, tag="attn_qk")
+        P = torch.empty((H, Lb, 2 * Lb), **f16)
+        L.call("gnnlm_causal_softmax_split", L.ptr(S), Lb, intra_ctx, H, L.ptr(P), st())
+        ob = out[rows]
+        for h in range(H):
+            o_h = ob[:, h * dk:(h + 1) * dk]
+            linear(Split(P[h], Lb), vh[h], None, W_lo=vl[h], w_scale=1.0 / out_scale, residual=o_h if accumulate else None,
+                   out=o_h, math=L.MATH_F16X3, tag="attn_pv")
+    return out
+
+
 def pq_gather_decode(codes, centroids, rows, *, bias=None, row_ids=None, n_cap=None, n_dev=None, out_dtype=torch.float32,
                      labels_table=None, want_codes=False, decode=True):
     n_d, M = codes.shape

@@ -216,6 +216,20 @@ int32_t gnnlm_hgt_causal_attn(const void* q, int64_t ldq, const void* k, int64_t
                               int32_t d_k, float* out, int64_t ldo, float out_scale, int32_t accumulate,
                               gnnlm_stream_t stream);
 
+/* Tensor-core form of the same causal attention for MATH_F16X3 (fp32 parity): per block and head,
+ * S = Q K'^T and O = softmax_causal(S) V' are two gnnlm_linear calls on split-fp16 operands; these three
+ * streaming kernels produce the operands.
+ *  gnnlm_heads_split_f16: src fp32 [L, H*d_k] (row stride ld) -> a_style = 1: hi = split-fp16 [H, L, 2*d_k]
+ *    (A operands, lo unused); a_style = 0: hi, lo fp16 [H, L, d_k] each (W operands, scale 1).
+ *  gnnlm_heads_transpose_split_f16: src fp32 [L, H*d_k] -> hi, lo fp16 [H, d_k, L] (W operands of P V').
+ *  gnnlm_causal_softmax_split: S fp32 [H, L, L] -> P split-fp16 [H, L, 2L]; row i = softmax over
+ *    j in [max(0, i - intra_ctx + 1), i] (all j <= i when intra_ctx == 0), zeros elsewhere. */
+int32_t gnnlm_heads_split_f16(const float* src, int64_t ld, int64_t L, int32_t H, int32_t d_k, int32_t a_style, void* hi,
+                              void* lo, gnnlm_stream_t stream);
+int32_t gnnlm_heads_transpose_split_f16(const float* src, int64_t ld, int64_t L, int32_t H, int32_t d_k, void* hi, void* lo,
+                                        gnnlm_stream_t stream);
+int32_t gnnlm_causal_softmax_split(const float* S, int64_t L, int64_t intra_ctx, int32_t H, void* P, gnnlm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (5) Adaptive-softmax bookkeeping + kNN-LM interpolation + NLL -- replaces adapt_target
  *     (adaptive_softmax.py:122-145), KNNModel.get_knn_prob minus the faiss search

@@ -514,3 +514,24 @@ def test_linear_f16x3_split_format(M, N, K, dev):
                                rtol=1e-5, atol=1e-5)
     ids = torch.randint(0, M, (77,), dtype=torch.int32)
     assert (ops.gather_rows(y, ids.to(dev)).data.cpu() == y.data.cpu()[ids.long()]).all()
+
+
+@pytest.mark.parametrize("B,L,H,d,ctx", [(1, 256, 8, 1024, 0), (2, 320, 8, 512, 0), (1, 512, 8, 1024, 100)])
+def test_causal_attn_gemm_form(B, L, H, d, ctx, dev):
+    """Tensor-core (3xFP16 GEMM) form of the tgt-intra-tgt attention vs the fp64 definition and vs the flash kernel."""
+    _need_tc()
+    from gnnlm_b200 import ops
+    torch.manual_seed(7)
+    q, k, v = torch.randn(B * L, d) * 0.3, torch.randn(B * L, d) * 0.3, torch.randn(B * L, d)
+    base = torch.randn(B * L, d)
+    out = base.clone().to(dev)
+    ops.causal_attn_gemm(q.to(dev), k.to(dev), v.to(dev), B, L, ctx, H, out, out_scale=0.5, accumulate=True)
+    out2 = base.clone().to(dev)
+    ops.causal_attn(q.to(dev), k.to(dev), v.to(dev), B, L, ctx, H, out2, out_scale=0.5, accumulate=True)
+    qh, kh, vh = (t.view(B, L, H, d // H).permute(0, 2, 1, 3).double() for t in (q, k, v))
+    s = qh @ kh.transpose(-1, -2)
+    i = torch.arange(L)
+    mask = (i[None, :] <= i[:, None]) & ((i[:, None] - i[None, :] < ctx) if ctx else True)
+    ref = base.double() + 0.5 * (torch.softmax(s.masked_fill(~mask, -float("inf")), -1) @ vh).permute(0, 2, 1, 3).reshape(B * L, d)
+    np.testing.assert_allclose(out.cpu().double().numpy(), ref.numpy(), rtol=1e-4, atol=5e-5)
+    np.testing.assert_allclose(out.cpu().numpy(), out2.cpu().numpy(), rtol=1e-4, atol=5e-5)
