@@ -28,6 +28,8 @@ SIGNATURES = {
     "gnnlm_split_tf32": (_i32, [_p, _p, _p, _i64, _p]),
     "gnnlm_split_f16": (_i32, [_p, _f32, _p, _p, _i64, _p]),
     "gnnlm_linear": (_i32, [_p, _i32, _i64, _p, _p, _f32, _i64, _p, _p, _i32, _i64, _p, _i32, _i64, _i64, _p, _i64, _i64, _i32, _p]),
+    "gnnlm_linear_batched_f16x3": (_i32, [_p, _i64, _i64, _p, _p, _i64, _i64, _f32, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64,
+                                          _i64, _i64, _p]),
     "gnnlm_lse_num_tiles": (_i64, [_i64, _i32]),
     "gnnlm_linear_lse": (_i32, [_p, _i32, _i64, _p, _p, _f32, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _p]),
     "gnnlm_lse_finish": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _p]),

@@ -535,6 +535,13 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* ma
       "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_2sm(uint64_t* bar) {     // arrives on `bar` in both CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
                    smem_u32(bar)),
@@ -969,7 +976,8 @@ template <bool LSE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     gemm_f16s_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                      const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_blo, int64_t M_cap,
-                     const int32_t* __restrict__ m_dev, int64_t N, int64_t K, EpiStore es, EpiLse el, float acc_scale) {
+                     const int32_t* __restrict__ m_dev, int64_t N, int64_t K, EpiStore es, EpiLse el, float acc_scale, int nb,
+                     int64_t c_bs, int64_t r_bs) {
   constexpr int STAGES = F16S_STAGES;
   constexpr uint32_t TX = 2u * F16S_STAGE;                                // both CTAs' four operand tiles -> leader
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
@@ -985,7 +993,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
   const bool leader = crank == 0;
   const int64_t M = live_rows(M_cap, m_dev);
   const int64_t n_m = (M + BLOCK_M - 1) / BLOCK_M, n_n = (N + BLOCK_N - 1) / BLOCK_N;
-  const int64_t total = ((n_m + 1) / 2) * n_n;
+  const int64_t per_batch = ((n_m + 1) / 2) * n_n;               // pair tiles of one batch entry
+  const int64_t total = per_batch * nb;                          // maps are 3-D: (k, row, batch)
   const int64_t pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
   const int n_kb = (int)((K + F16_BLOCK_K - 1) / F16_BLOCK_K);
 
@@ -1029,14 +1038,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
       uint32_t phase = 0;
       const int half = (int)crank * (BLOCK_N / 2);
       for (int64_t tile = pair0; tile < total; tile += pair_stride) {
-        const int m0 = (int)(((tile / n_n) * 2 + crank) * BLOCK_M), n0 = (int)((tile % n_n) * BLOCK_N) + half;
+        const int bi = (int)(tile / per_batch);
+        const int64_t rem = tile % per_batch;
+        const int m0 = (int)(((rem / n_n) * 2 + crank) * BLOCK_M), n0 = (int)((rem % n_n) * BLOCK_N) + half;
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_expect_tx(&full_bar[stage], TX);
-          tma_load_2d_2sm(sAh(stage), &map_ah, kb * F16_BLOCK_K, m0, &full_bar[stage]);
-          tma_load_2d_2sm(sAl(stage), &map_al, kb * F16_BLOCK_K, m0, &full_bar[stage]);
-          tma_load_2d_2sm(sBh(stage), &map_b, kb * F16_BLOCK_K, n0, &full_bar[stage]);
-          tma_load_2d_2sm(sBl(stage), &map_blo, kb * F16_BLOCK_K, n0, &full_bar[stage]);
+          tma_load_3d_2sm(sAh(stage), &map_ah, kb * F16_BLOCK_K, m0, bi, &full_bar[stage]);
+          tma_load_3d_2sm(sAl(stage), &map_al, kb * F16_BLOCK_K, m0, bi, &full_bar[stage]);
+          tma_load_3d_2sm(sBh(stage), &map_b, kb * F16_BLOCK_K, n0, bi, &full_bar[stage]);
+          tma_load_3d_2sm(sBl(stage), &map_blo, kb * F16_BLOCK_K, n0, bi, &full_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -1076,13 +1087,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     for (int64_t tile = pair0; tile < total; tile += pair_stride, ++it) {
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      const int64_t m_blk = (tile / n_n) * 2 + crank, n_blk = tile % n_n;
+      const int64_t bi = tile / per_batch, rem = tile % per_batch;
+      const int64_t m_blk = (rem / n_n) * 2 + crank, n_blk = rem % n_n;
       const int64_t m = m_blk * BLOCK_M + q * 32 + lane;
       const int64_t n_base = n_blk * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<LSE>(taddr, m, M, n_base, n_blk, N, es, el, epi_smem + (warp & 3) * 32 * EPI_LD, acc_scale);
+      EpiStore eb = es;                                  // batch entry bi (fp32 C / residual when nb > 1)
+      if (nb > 1) {
+        eb.C = reinterpret_cast<float*>(es.C) + bi * c_bs;
+        if (es.residual) eb.residual = reinterpret_cast<const float*>(es.residual) + bi * r_bs;
+      }
+      epilogue_tile<LSE>(taddr, m, M, n_base, n_blk, N, eb, el, epi_smem + (warp & 3) * 32 * EPI_LD, acc_scale);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -1138,6 +1155,18 @@ static int make_map_f16(CUtensorMap* map, const void* base, int64_t rows, int64_
   cuuint32_t box[2] = {(cuuint32_t)F16_BLOCK_K, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   return (int)encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+// fp16 [nb, rows, K] K-major, SWIZZLE_64B boxes of 32 elements x box_rows x 1 (batch stride bs elements)
+static int make_map_f16_3d(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int64_t nb, int64_t bs,
+                           int box_rows) {
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)nb};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(nb > 1 ? bs : rows * ld) * 2};
+  cuuint32_t box[3] = {(cuuint32_t)F16_BLOCK_K, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return (int)encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 }
@@ -1227,7 +1256,7 @@ static int32_t launch_f16x3(const CUtensorMap& ma, const CUtensorMap& mb, const 
 template <bool LSE>
 static int32_t launch_f16s(const CUtensorMap& mah, const CUtensorMap& mal, const CUtensorMap& mb, const CUtensorMap& mblo,
                            int64_t M, const int32_t* m_dev, int64_t N, int64_t K, const EpiStore& es, const EpiLse& el,
-                           float acc_scale, cudaStream_t st) {
+                           float acc_scale, cudaStream_t st, int nb = 1, int64_t c_bs = 0, int64_t r_bs = 0) {
   const size_t smem = (size_t)F16S_STAGES * F16S_STAGE + EPI_SMEM + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1240,10 +1269,10 @@ static int32_t launch_f16s(const CUtensorMap& mah, const CUtensorMap& mal, const
     GNNLM_CUDA(cudaGetDevice(&dev));
     GNNLM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int64_t pairs = ceil_div(ceil_div(M, BLOCK_M), 2) * ceil_div(N, BLOCK_N);
+  const int64_t pairs = ceil_div(ceil_div(M, BLOCK_M), 2) * ceil_div(N, BLOCK_N) * nb;
   const int64_t max_pairs = n_sm / 2;
   const unsigned grid = 2u * (unsigned)(pairs < max_pairs ? pairs : max_pairs);
-  gemm_f16s_kernel<LSE><<<grid, 256, smem, st>>>(mah, mal, mb, mblo, M, m_dev, N, K, es, el, acc_scale);
+  gemm_f16s_kernel<LSE><<<grid, 256, smem, st>>>(mah, mal, mb, mblo, M, m_dev, N, K, es, el, acc_scale, nb, c_bs, r_bs);
   GNNLM_LAUNCH_CHECK("gemm_f16s");
   return 0;
 }
@@ -1285,22 +1314,36 @@ static int32_t tc_prepare(const char* who, const void* A, int32_t a_dtype, int64
 
 static inline int epi_mode(int32_t dtype) { return dtype == GNNLM_BF16 ? 1 : (dtype == GNNLM_F16X2 ? 2 : 0); }
 
-// split-fp16 A (GNNLM_F16X2): four SWIZZLE_64B maps, no in-kernel operand split
+// split-fp16 A (GNNLM_F16X2): four SWIZZLE_64B maps (k, row, batch), no in-kernel operand split
 static int32_t f16s_maps(const char* who, const void* A, int64_t lda, const void* W, const void* W_lo, int64_t ldw, int64_t M,
-                         int64_t N, int64_t K, CUtensorMap* mah, CUtensorMap* mal, CUtensorMap* mb, CUtensorMap* mblo) {
+                         int64_t N, int64_t K, CUtensorMap* mah, CUtensorMap* mal, CUtensorMap* mb, CUtensorMap* mblo,
+                         int64_t nb = 1, int64_t a_bs = 0, int64_t w_bs = 0) {
   GNNLM_CHECK_ARG(gemm_tc_supported(), GNNLM_E_UNSUPPORTED, "%s: tcgen05 path needs an sm_100 device and driver TMA support", who);
   GNNLM_CHECK_ARG(W_lo, GNNLM_E_ARG, "%s: MATH_F16X3 needs W_lo (gnnlm_split_f16)", who);
   GNNLM_CHECK_ARG(lda >= 2 * K && (lda * 2) % 16 == 0 && (K * 2) % 16 == 0 && (ldw * 2) % 16 == 0 && (uintptr_t)A % 16 == 0 &&
-                      (uintptr_t)W % 16 == 0 && (uintptr_t)W_lo % 16 == 0,
+                      (uintptr_t)W % 16 == 0 && (uintptr_t)W_lo % 16 == 0 && (a_bs * 2) % 16 == 0 && (w_bs * 2) % 16 == 0,
                   GNNLM_E_SHAPE, "%s: split-fp16 A needs lda >= 2K and 16 B aligned halves (lda=%lld K=%lld)", who,
                   (long long)lda, (long long)K);
   const __half* a = reinterpret_cast<const __half*>(A);
-  int r = tc::make_map_f16(mah, a, M, K, lda, tc::BLOCK_M);
-  if (!r) r = tc::make_map_f16(mal, a + K, M, K, lda, tc::BLOCK_M);
-  if (!r) r = tc::make_map_f16(mb, W, N, K, ldw, tc::BLOCK_N / 2);
-  if (!r) r = tc::make_map_f16(mblo, W_lo, N, K, ldw, tc::BLOCK_N / 2);
+  int r = tc::make_map_f16_3d(mah, a, M, K, lda, nb, a_bs, tc::BLOCK_M);
+  if (!r) r = tc::make_map_f16_3d(mal, a + K, M, K, lda, nb, a_bs, tc::BLOCK_M);
+  if (!r) r = tc::make_map_f16_3d(mb, W, N, K, ldw, nb, w_bs, tc::BLOCK_N / 2);
+  if (!r) r = tc::make_map_f16_3d(mblo, W_lo, N, K, ldw, nb, w_bs, tc::BLOCK_N / 2);
   GNNLM_CHECK_ARG(r == 0, GNNLM_E_ARG, "%s: cuTensorMapEncodeTiled failed (%d)", who, r);
   return 0;
+}
+
+// nb independent products C[b] = acc_scale * A[b] W[b]^T (+ residual[b]) in one launch (per-head attention GEMMs)
+int32_t gemm_tc_batched_f16x3(const void* A, int64_t lda, int64_t a_bs, const void* W_hi, const void* W_lo, int64_t ldw,
+                              int64_t w_bs, float w_scale, const float* residual, int64_t ldr, int64_t r_bs, float* C,
+                              int64_t ldc, int64_t c_bs, int64_t nb, int64_t M, int64_t N, int64_t K, cudaStream_t st) {
+  if (M == 0 || nb == 0) return 0;
+  tc::EpiStore es{nullptr, residual, ldr, C, ldc, 0, 0, N, N};
+  tc::EpiLse el{};
+  CUtensorMap mah, mal, mb, mblo;
+  int32_t rc = f16s_maps("gnnlm_linear_batched_f16x3", A, lda, W_hi, W_lo, ldw, M, N, K, &mah, &mal, &mb, &mblo, nb, a_bs, w_bs);
+  if (rc) return rc;
+  return tc::launch_f16s<false>(mah, mal, mb, mblo, M, nullptr, N, K, es, el, 1.f / w_scale, st, (int)nb, c_bs, r_bs);
 }
 
 int32_t gemm_tc_store(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, float w_scale, int64_t ldw,

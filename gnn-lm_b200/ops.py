@@ -217,15 +217,15 @@ def causal_attn_gemm(q, k, v, B, Lb, intra_ctx, H, out, *, out_scale=1.0, accumu
         L.call("gnnlm_heads_split_f16", L.ptr(kb), kb.stride(0), Lb, H, dk, 0, L.ptr(kh), L.ptr(kl), st())
         L.call("gnnlm_heads_transpose_split_f16", L.ptr(vb), vb.stride(0), Lb, H, dk, L.ptr(vh), L.ptr(vl), st())
         S = torch.empty((H, Lb, Lb), device=dev, dtype=torch.float32)
-        for h in range(H):
-            linear(Split(qs[h], dk), kh[h], None, W_lo=kl[h], out=S[h], math=L.MATH_F16X3, tag="attn_qk")
+        # all heads in one launch each: S[h] = Q_h K'_h^T, then O[:, h] (+)= out_scale * P_h V'_h
+        L.call("gnnlm_linear_batched_f16x3", L.ptr(qs), 2 * dk, Lb * 2 * dk, L.ptr(kh), L.ptr(kl), dk, Lb * dk, 1.0, None, 0, 0,
+               L.ptr(S), Lb, Lb * Lb, H, Lb, Lb, dk, st(), tag="attn_qk")
         P = torch.empty((H, Lb, 2 * Lb), **f16)
         L.call("gnnlm_causal_softmax_split", L.ptr(S), Lb, intra_ctx, H, L.ptr(P), st())
         ob = out[rows]
-        for h in range(H):
-            o_h = ob[:, h * dk:(h + 1) * dk]
-            linear(Split(P[h], Lb), vh[h], None, W_lo=vl[h], w_scale=1.0 / out_scale, residual=o_h if accumulate else None,
-                   out=o_h, math=L.MATH_F16X3, tag="attn_pv")
+        L.call("gnnlm_linear_batched_f16x3", L.ptr(P), 2 * Lb, Lb * 2 * Lb, L.ptr(vh), L.ptr(vl), Lb, dk * Lb, 1.0 / out_scale,
+               L.ptr(ob) if accumulate else None, ob.stride(0), dk, L.ptr(ob), ob.stride(0), dk, H, Lb, dk, Lb, st(),
+               tag="attn_pv")
     return out
 
 

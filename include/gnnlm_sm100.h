@@ -141,6 +141,15 @@ int32_t gnnlm_linear(const void* A, int32_t a_dtype, int64_t lda, const void* W,
                      int32_t c_dtype, int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, int64_t K,
                      int32_t math, gnnlm_stream_t stream);
 
+/* nb independent products in ONE launch (the per-head GEMMs of the tensor-core causal attention):
+ *   C[b] = (1 / w_scale) * A[b] W[b]^T (+ residual[b]),  b = 0..nb-1,   MATH_F16X3 arithmetic.
+ * A[b] split-fp16 [M, 2K] at A + b*a_bs (fp16 elements, lda >= 2K); W_hi[b], W_lo[b] fp16 [N, K] at + b*w_bs;
+ * C[b], residual[b] fp32 at + b*c_bs / b*r_bs (elements; a column offset when the heads share rows). */
+int32_t gnnlm_linear_batched_f16x3(const void* A, int64_t lda, int64_t a_bs, const void* W_hi, const void* W_lo, int64_t ldw,
+                                   int64_t w_bs, float w_scale, const float* residual, int64_t ldr, int64_t r_bs, float* C,
+                                   int64_t ldc, int64_t c_bs, int64_t nb, int64_t M, int64_t N, int64_t K,
+                                   gnnlm_stream_t stream);
+
 /* Same contraction, but instead of storing C the epilogue keeps, per row and per column tile,
  * (max, sum exp(x - max)) and the single column `pick[m]` -- the [rows, vocab] tensor of
  * AdaptiveSoftmax.get_log_prob (adaptive_softmax.py:184-203) is never written.
