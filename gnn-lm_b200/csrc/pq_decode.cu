@@ -19,9 +19,9 @@
 
 namespace gnnlm {
 
-constexpr int PQ_THREADS = 256;
+constexpr int PQ_THREADS = 1024;    // 32 warps x 8 nodes in flight: the kernel is latency-bound, not ALU-bound
 constexpr int PQ_CHUNK_FLOATS = 128;     // output floats per node per chunk == 32 lanes * float4
-constexpr int PQ_NODES_PER_CTA = 2048;
+constexpr int PQ_NODES_PER_CTA = 4096;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
