@@ -41,6 +41,8 @@ class TokenGraph:
         self.nn_indptr = self.nn_indices = self.inter_indptr = self.inter_indices = None
         self.tt_indptr = self.tt_indices = None
         self.cluster_nl = None
+        self.nbr = self.tgt_pos = None        # inputs kept so that token chunks can be re-assembled (chunked ntgt side)
+        self.invalid_ctx = 0
         self._counts_host = None
 
     # ---- device-side counts (no host sync needed by the kernels) ----
@@ -92,6 +94,7 @@ def build_token_graph(nbr: torch.Tensor, n_datastore: int, left_ctx: int, right_
     assert nbr.is_cuda and nbr.dtype == torch.int64 and nbr.dim() == 3 and nbr.is_contiguous()
     B, Lb, k = nbr.shape
     g = TokenGraph(B, Lb, k, left_ctx, right_ctx, intra_ctx, n_datastore)
+    g.nbr, g.tgt_pos, g.invalid_ctx = nbr, tgt_pos, invalid_ctx
     dev = nbr.device
     n = g.T * k
     i32 = dict(dtype=torch.int32, device=dev)
@@ -119,3 +122,12 @@ def build_token_graph(nbr: torch.Tensor, n_datastore: int, left_ctx: int, right_
            L.ptr(g.node_base), L.ptr(g.valid_base), L.ptr(g.ntgt_row), L.ptr(g.ntgt_owner), L.ptr(g.ntgt_dist),
            L.ptr(g.nn_indptr), L.ptr(g.nn_indices), L.ptr(g.inter_indptr), L.ptr(g.inter_indices), L.ptr(g.cluster_nl), st)
     return g
+
+
+def token_chunk_graph(G: TokenGraph, t0: int, t1: int) -> TokenGraph:
+    """The graph of tokens [t0, t1) of the flattened batch on their own (ntgt clusters never cross tokens, so the ntgt
+    side of a chunk is independent of the rest; tgt-intra-tgt is not used on chunk graphs)."""
+    nbr = G.nbr.view(G.T, G.k)[t0:t1].reshape(1, t1 - t0, G.k)
+    pos = None if G.tgt_pos is None else G.tgt_pos.reshape(-1)[t0:t1]
+    return build_token_graph(nbr.contiguous(), G.n_datastore, G.left_ctx, G.right_ctx, tgt_pos=pos,
+                             invalid_ctx=G.invalid_ctx, intra_ctx=G.intra_ctx)

@@ -222,15 +222,22 @@ class HGTLayer(nn.Module):
         t_agg = self._nn_attn(P, G, qc, kv[:, :d], kv[:, d:], hc.shape[0], centre=True, n_dev=n_dev, c_dev=c_dev)
         return self._out(P, P["n"], t_agg, hc, c_dev)
 
-    def tgt(self, P, G: TokenGraph, h_t, hc, c_dev):
+    def tgt(self, P, G: TokenGraph, h_t, hc, c_dev, chunks=None):
         """tgt nodes: mean of (centre ntgt -> tgt) attention and causal tgt -> tgt attention.  Q/K'/V' of this
-        (small) side are kept in fp32 in every mode."""
+        (small) side are kept in fp32 in every mode.  `chunks`: [(t0, t1, chunk_graph, hc_chunk)] when the ntgt side
+        was run in token chunks -- the inter attention is then applied chunk by chunk (hc / c_dev unused)."""
         d, H = P["d"], self.n_heads
         qkv = _lin(h_t, P["tgt_qkv"], P["math"])
-        kvi = _lin(hc, P["ntgt_kv_inter"], P["math"], m_dev=c_dev)
-        t_agg = torch.empty((h_t.shape[0], d), device=h_t.device, dtype=torch.float32)
+        t_agg = torch.empty((h_t.shape[0], d), device=qkv.device, dtype=torch.float32)
         # inter edges in compact centre numbering are the contiguous ranges of inter_indptr
-        ops.edge_attn(qkv[:, :d], kvi[:, :d], kvi[:, d:], G.inter_indptr, None, H, t_agg, out_scale=0.5, tag="inter")
+        if chunks is None:
+            kvi = _lin(hc, P["ntgt_kv_inter"], P["math"], m_dev=c_dev)
+            ops.edge_attn(qkv[:, :d], kvi[:, :d], kvi[:, d:], G.inter_indptr, None, H, t_agg, out_scale=0.5, tag="inter")
+        else:
+            for t0, t1, g_c, hc_c in chunks:
+                kvi = _lin(hc_c, P["ntgt_kv_inter"], P["math"], m_dev=g_c.n_valid_dev)
+                ops.edge_attn(qkv[t0:t1, :d], kvi[:, :d], kvi[:, d:], g_c.inter_indptr, None, H, t_agg[t0:t1], out_scale=0.5,
+                              tag="inter")
         if P["math"] == L.MATH_F16X3 and self.use_gemm_attention and ops.causal_attn_gemm_supported(d, H, G.L) and G.L >= 1024:
             ops.causal_attn_gemm(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5,
                                  accumulate=True)
@@ -293,12 +300,19 @@ class HGT(nn.Module):
 
         h_ntgt [node_cap, d] decoded features of every ntgt node (may be None when n_layers == 1 and
         hc0, the decoded centre rows [T*k, d], is given)."""
-        n_dev, c_dev = G.n_ntgt_dev, G.n_valid_dev
-        NL = self.n_layers
         mode = self.math_mode
         prep = [layer.prepare(mode) for layer in self.gcs]
-        # ---- ntgt side: compact centre features entering each layer
-        hc: List[torch.Tensor] = []
+        hc = self._ntgt_side(prep, G, h_ntgt, hc0)
+        h_t = as_act(h_tgt, mode)
+        for l in range(self.n_layers):
+            h_t = self.gcs[l].tgt(prep[l], G, h_t, hc[l], G.n_valid_dev)
+        return h_t
+
+    def _ntgt_side(self, prep, G: TokenGraph, h_ntgt, hc0=None) -> List:
+        """All layers of the ntgt side of one (chunk) graph -> compact centre features entering each layer."""
+        n_dev, c_dev = G.n_ntgt_dev, G.n_valid_dev
+        NL, mode = self.n_layers, self.math_mode
+        hc: List = []
         if h_ntgt is not None:
             h_ntgt = as_act(h_ntgt, mode)
         if hc0 is None:
@@ -311,8 +325,27 @@ class HGT(nn.Module):
                 hc.append(ops.gather_rows(h_n, G.inter_indices, n_dev=c_dev))
             else:
                 hc.append(self.gcs[l].ntgt_centre(prep[l], G, h_n, n_dev, hc[l], c_dev))
-        # ---- tgt side
+        return hc
+
+    @torch.no_grad()
+    def forward_tgt_chunked(self, G: TokenGraph, h_tgt, decode, chunk_tokens: int):
+        """Same result as forward_tgt with the ntgt side run in chunks of `chunk_tokens` target tokens, so that the
+        ntgt activations (T*k*w rows per buffer) never exceed a memory budget: ntgt clusters belong to exactly one
+        token and only ever exchange messages inside their cluster.  `decode(chunk_graph, centre_only)`
+        returns the decoded ntgt features of a chunk graph (all nodes, or compact centre rows)."""
+        from .graph import token_chunk_graph
+        mode = self.math_mode
+        prep = [layer.prepare(mode) for layer in self.gcs]
+        chunks = []
+        for t0 in range(0, G.T, chunk_tokens):
+            t1 = min(G.T, t0 + chunk_tokens)
+            g_c = token_chunk_graph(G, t0, t1)
+            if self.n_layers == 1:
+                hc_c = self._ntgt_side(prep, g_c, None, hc0=decode(g_c, True))
+            else:
+                hc_c = self._ntgt_side(prep, g_c, decode(g_c, False))
+            chunks.append((t0, t1, g_c, hc_c))
         h_t = as_act(h_tgt, mode)
-        for l in range(NL):
-            h_t = self.gcs[l].tgt(prep[l], G, h_t, hc[l], c_dev)
+        for l in range(self.n_layers):
+            h_t = self.gcs[l].tgt(prep[l], G, h_t, None, None, chunks=[(t0, t1, g_c, hc_c[l]) for t0, t1, g_c, hc_c in chunks])
         return h_t

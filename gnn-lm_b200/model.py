@@ -224,14 +224,23 @@ class TokenGraphTransformerDecoder(nn.Module):
             out = self.hgt_decoder.forward_tgt(graph, h_tgt, h_n)
         else:                                                         # fused gather from the HBM-resident datastore
             codes = graph.codes_table
-            if NL == 1:   # only centre nodes are ever read
-                hc0 = self.tgt_quantizer.gather_decode(codes, graph.ntgt_row, row_ids=graph.inter_indices,
-                                                       n_dev=graph.n_valid_dev, math_mode=mode)
-                out = self.hgt_decoder.forward_tgt(graph, h_tgt, None, hc0=hc0)
+            q = self.tgt_quantizer
+
+            def decode(g, centre_only):
+                if centre_only:   # only centre nodes are ever read (single layer)
+                    return q.gather_decode(codes, g.ntgt_row, row_ids=g.inter_indices, n_dev=g.n_valid_dev, math_mode=mode)
+                return q.gather_decode(codes, g.ntgt_row, n_cap=g.node_cap, n_dev=g.n_ntgt_dev, math_mode=mode)
+
+            # ~11 live [rows, d] fp32-sized buffers on the ntgt side; chunk over target tokens above the budget
+            per_token = graph.k * graph.w * self.embed_dim * 4 * 11
+            budget = float(_get(self.args, "ntgt_memory_budget_gb", 48.0)) * 1e9
+            chunk = max(64, int(budget // per_token) // 64 * 64)
+            if NL > 1 and graph.T > chunk:
+                out = self.hgt_decoder.forward_tgt_chunked(graph, h_tgt, decode, chunk)
+            elif NL == 1:
+                out = self.hgt_decoder.forward_tgt(graph, h_tgt, None, hc0=decode(graph, True))
             else:
-                h_n = self.tgt_quantizer.gather_decode(codes, graph.ntgt_row, n_cap=graph.node_cap,
-                                                       n_dev=graph.n_ntgt_dev, math_mode=mode)
-                out = self.hgt_decoder.forward_tgt(graph, h_tgt, h_n)
+                out = self.hgt_decoder.forward_tgt(graph, h_tgt, decode(graph, False))
         return as_float(out).view(bsz, seq_len, -1)
 
     # ------------------------------------------------------------------ probabilities

@@ -535,3 +535,29 @@ def test_causal_attn_gemm_form(B, L, H, d, ctx, dev):
     ref = base.double() + 0.5 * (torch.softmax(s.masked_fill(~mask, -float("inf")), -1) @ vh).permute(0, 2, 1, 3).reshape(B * L, d)
     np.testing.assert_allclose(out.cpu().double().numpy(), ref.numpy(), rtol=1e-4, atol=5e-5)
     np.testing.assert_allclose(out.cpu().numpy(), out2.cpu().numpy(), rtol=1e-4, atol=5e-5)
+
+
+@pytest.mark.parametrize("math", ["fp32", "f16x3"])
+def test_token_chunked_ntgt_side_matches(math, dev):
+    """forward_tgt_chunked (ntgt side in token chunks, inter attention per chunk) == forward_tgt."""
+    if math != "fp32":
+        _need_tc()
+    import copy
+    from gnnlm_b200 import synth
+    from gnnlm_b200.graph import build_token_graph
+    cfg = dict(synth.CONFIGS["c3mini"], B=2, L=96, NL=3)
+    model = copy.deepcopy(synth.make_model(cfg)).to(dev).set_math(math)
+    tables = synth.make_tables(cfg, device=dev)
+    batch = synth.make_batch(cfg, tables, device=dev)
+    dec, hgt = model.decoder, model.decoder.hgt_decoder
+    g = build_token_graph(batch["nbr"], tables["n_d"], cfg["c"], cfg["c"])
+    h_t = batch["feats"].float()
+    mode = dec.math_mode
+    decode = lambda gg, centre: dec.tgt_quantizer.gather_decode(
+        tables["codes"], gg.ntgt_row, row_ids=gg.inter_indices if centre else None,
+        n_cap=None if centre else gg.node_cap, n_dev=gg.n_valid_dev if centre else gg.n_ntgt_dev, math_mode=mode)
+    from gnnlm_b200.hgt import as_float
+    ref = as_float(hgt.forward_tgt(g, h_t, decode(g, False)))
+    for chunk in (64, 80, 192):
+        out = as_float(hgt.forward_tgt_chunked(g, h_t, decode, chunk))
+        np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-5)
