@@ -5,11 +5,16 @@ Differences that do not change results: the per-hypothesis `score_sum += pos_sco
 the scoring kernel with a single read-back at the end; blocks are sharded over ranks as contiguous
 ranges and the two scalars {sum log p, n_tokens} are all-reduced once (the reference's sharded
 eval never combines its shards)."""
+import json
 import math
+import os
 import time
 from typing import Optional
 
+import numpy as np
 import torch
+
+from . import ops
 
 from .dataset import DeviceDatastore, GraphTokenBlockDataset, move_to_cuda
 from .sequence_scorer import SequenceScorer
@@ -37,10 +42,48 @@ def batches(dataset: GraphTokenBlockDataset, lo: int, hi: int, max_sentences: in
         yield cur
 
 
+class DstoreWriter:
+    """--save-knnlm-dstore (fairseq_cli/eval_lm.py:178-244): keys.npy / vals.npy raw memmaps + info.json, same names,
+    dtypes and shapes; keys are the features selected by --knn-keytype (e.g. `gcn_feat`), written in token order.
+    The fp32 -> fp16 cast runs on the device (gnnlm_convert) before the D2H copy."""
+
+    def __init__(self, dstore_mmap: str, subset: str, dstore_size: int, hidden: int, vocab: int, dstore_fp16: bool,
+                 knn_keytype: Optional[str] = None):
+        suffix = "" if not knn_keytype else f"-{knn_keytype}"
+        self.dir = os.path.join(dstore_mmap, f"{subset}_dstore{suffix}")
+        os.makedirs(self.dir, exist_ok=True)
+        self.fp16, self.size, self.idx = dstore_fp16, int(dstore_size), 0
+        info = {"dstore_size": int(dstore_size), "hidden_size": hidden, "vocab_size": vocab, "dstore_fp16": dstore_fp16,
+                "val_size": 1}
+        json.dump(info, open(os.path.join(self.dir, "info.json"), "w"), indent=4, sort_keys=True)
+        self.keys = np.memmap(os.path.join(self.dir, "keys.npy"), dtype=np.float16 if dstore_fp16 else np.float32, mode="w+",
+                              shape=(self.size, hidden))
+        vdt = np.int16 if dstore_fp16 and vocab < 2 ** 15 else np.int32
+        self.vals = np.memmap(os.path.join(self.dir, "vals.npy"), dtype=vdt, mode="w+", shape=(self.size, 1))
+
+    def add(self, feats: torch.Tensor, tokens: torch.Tensor):
+        """feats [n, d] fp32 on the device, tokens [n]."""
+        n = min(feats.shape[0], self.size - self.idx)            # eval_lm.py:227-230 (clip at dstore_size)
+        if n <= 0:
+            return
+        f = feats[:n].contiguous()
+        if self.fp16:
+            f = ops.convert(f, torch.float16)
+        self.keys[self.idx:self.idx + n] = f.cpu().numpy()
+        self.vals[self.idx:self.idx + n] = tokens[:n].view(-1, 1).cpu().numpy().astype(self.vals.dtype)
+        self.idx += n
+
+    def close(self):
+        self.keys.flush()
+        self.vals.flush()
+        return self.idx
+
+
 @torch.no_grad()
 def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, scorer: SequenceScorer, *,
              knn_dstore=None, temperature: float = 1.0, max_sentences: int = 1, device="cuda", rank: int = 0,
-             world_size: int = 1, process_group=None, log=None) -> dict:
+             world_size: int = 1, process_group=None, log=None, dstore_writer: Optional[DstoreWriter] = None,
+             knn_keytype: Optional[str] = None) -> dict:
     lo, hi = shard_range(len(dataset), rank, world_size)
     acc = torch.zeros(2, dtype=torch.float64, device=device)
     ntok = 0
@@ -51,8 +94,15 @@ def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, sc
         sample = move_to_cuda(batch, dataset, dstore, device)
         if knn_dstore is not None and "knn_ids" in sample:
             knn_dstore.set_search_results(sample["knn_dists"], sample["knn_ids"])
-        scorer.score_tokens(model, sample, knn_dstore, temperature, nll_acc=acc)
+        _, _, _, dec_out = scorer.score_tokens(model, sample, knn_dstore, temperature, nll_acc=acc)
         ntok += sample["ntokens"]
+        if dstore_writer is not None:                           # sequence_scorer.py:180-183 + eval_lm.py:223-244
+            extra = dec_out[1]
+            feat = extra[knn_keytype] if knn_keytype in extra else extra["inner_states"][-1]     # [L, B, d]
+            starts = sample["start_indices"].view(-1).tolist()
+            for i in range(sample["target"].shape[0]):
+                mask = sample["target"][i, starts[i]:].ne(scorer.pad)
+                dstore_writer.add(feat[starts[i]:, i, :][mask].float(), sample["target"][i, starts[i]:][mask])
     if world_size > 1:
         torch.distributed.all_reduce(acc, group=process_group)          # the path's only collective
     torch.cuda.synchronize(device)

@@ -72,6 +72,20 @@ class TorchPQCodec(nn.Module):
         return x
 
     @torch.no_grad()
+    def encode(self, x: torch.Tensor, math_mode: int = L.MATH_FP32_SIMT) -> torch.Tensor:
+        """x [n, D] fp32 -> codes [n, M] uint8 (pq_wrapper.py:131-167): OPQ pre-rotation `x @ A.T + b`, then the
+        per-subspace nearest centroid under ||c||^2 - 2 x.c."""
+        x = x.float().contiguous()
+        if self.pre_torch:
+            b = self.b if self.b.numel() > 0 else None
+            x = ops.linear(x, self.A.contiguous(), b, math=L.MATH_FP32_SIMT)       # F.linear(x, A) == x @ A.T
+        n = x.shape[0]
+        codes = torch.empty((n, self.M), device=x.device, dtype=torch.uint8)
+        L.call("gnnlm_pq_encode", L.ptr(x), x.stride(0), n, self.M, self.dsub, L.ptr(self.centroids_torch),
+               L.ptr(self.norm2_centroids_torch), L.ptr(codes), L.stream_ptr())
+        return codes
+
+    @torch.no_grad()
     def decode(self, codes: torch.Tensor, math_mode: int = L.MATH_FP32_SIMT) -> torch.Tensor:
         """codes [n, M] uint8 -> [n, M*dsub] (pq_wrapper.py:169-203)."""
         n, MM = codes.shape

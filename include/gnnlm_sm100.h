@@ -122,6 +122,13 @@ int32_t gnnlm_pq_gather_decode(const uint8_t* codes, int64_t n_datastore, int32_
                                int64_t ld_out, const void* labels_table, int32_t label_bytes,
                                int64_t* labels_out, uint8_t* codes_out, gnnlm_stream_t stream);
 
+/* PQ encode (the producer of quantized-keys.npy; knn/pq_wrapper.py:51-68,131-167, knn/quantize_features.py:115-152):
+ *  codes[n, m] = argmin_c (norm2[m, c] - 2 <x[n, m*dsub:(m+1)*dsub], centroids[m, c]>), first minimum wins.
+ *  x fp32 [n, M*dsub] (ldx) must already carry the OPQ pre-rotation `x @ A.T (+ b)` (a gnnlm_linear call);
+ *  norm2 [M, 256] = ||centroid||^2 (`norm2_centroids_torch`).  dsub in {1, 2, 4, 8, 16}. */
+int32_t gnnlm_pq_encode(const float* x, int64_t ldx, int64_t n, int32_t M, int32_t dsub, const float* centroids,
+                        const float* norm2, uint8_t* codes, gnnlm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (3) Dense projections -- replace the nn.Linear / einsum calls of HGTLayer.forward
  *     (fairseq/models/hgt.py:320-322,347-348,401), the OPQ rotation (knn/pq_wrapper.py:202) and the

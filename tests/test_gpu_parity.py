@@ -467,6 +467,26 @@ def test_eval_lm_dataset_vs_oracle(dev):
         cnt += lp.numel()
     assert res["count"] == cnt == n_tok
     assert abs(res["score_sum"] - tot) / abs(tot) < 1e-5
+    # --save-knnlm-dstore with gcn_feat keys: same files / dtypes as eval_lm.py:178-244
+    import tempfile, json as _json
+    from gnnlm_b200.eval_lm import DstoreWriter
+    with tempfile.TemporaryDirectory() as tmp:
+        w = DstoreWriter(tmp, "valid", n_tok, cfg["d"], cfg["V"], dstore_fp16=True, knn_keytype="gcn_feat")
+        m2 = copy.deepcopy(model).to(dev).set_math("fp32")
+        evaluate(m2, ds, dstore, scorer, knn_dstore=knn, max_sentences=2, device=dev, dstore_writer=w, knn_keytype="gcn_feat")
+        assert w.close() == n_tok
+        d_ = os.path.join(tmp, "valid_dstore-gcn_feat")
+        info = _json.load(open(os.path.join(d_, "info.json")))
+        assert info == {"dstore_size": n_tok, "hidden_size": cfg["d"], "vocab_size": cfg["V"], "dstore_fp16": True, "val_size": 1}
+        keys = np.memmap(os.path.join(d_, "keys.npy"), dtype=np.float16, mode="r", shape=(n_tok, cfg["d"]))
+        vals = np.memmap(os.path.join(d_, "vals.npy"), dtype=np.int16, mode="r", shape=(n_tok, 1))
+        assert (vals.reshape(-1) == tokens).all()
+        # keys of the first block == oracle gcn features, fp16-rounded
+        it = ds[0]
+        batch0 = {"nbr": nbr[:blk][None], "offsets": np.arange(blk)[None], "tgt_feats": torch.from_numpy(feats[:blk]).float(),
+                  "target": it["target"], "codes": tables["codes"].numpy(), "cl": 1, "cr": 1, "n_d": cfg["n_d"]}
+        o0 = mo.eval_batch(om, batch0, None)
+        np.testing.assert_allclose(np.asarray(keys[:blk], dtype=np.float32), o0["gcn_feat"].numpy(), rtol=2e-3, atol=2e-3)
     assert abs(res["ppl"] - mo.perplexity(tot, cnt)[1]) / res["ppl"] < 1e-4
 
 
@@ -561,3 +581,30 @@ def test_token_chunked_ntgt_side_matches(math, dev):
     for chunk in (64, 80, 192):
         out = as_float(hgt.forward_tgt_chunked(g, h_t, decode, chunk))
         np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("M,dsub,with_pre", [(128, 8, True), (64, 8, False), (32, 4, True), (16, 16, False)])
+def test_pq_encode_vs_oracle(M, dsub, with_pre, dev):
+    """PQ encode (knn/pq_wrapper.py:131-167).  Codes equal the oracle's except where the two best
+    centroids are closer than fp32 summation-order noise (the reference's matmul order is unspecified)."""
+    from gnnlm_b200.pq_codec import TorchPQCodec
+    from oracle import model_oracle as mo
+    rng = np.random.RandomState(M)
+    d, n = M * dsub, 3000
+    cen = rng.randn(M, 256, dsub).astype(np.float32)
+    A = np.linalg.qr(rng.randn(d, d))[0].astype(np.float32) if with_pre else None
+    b = rng.randn(d).astype(np.float32) if with_pre else None
+    x = rng.randn(n, d).astype(np.float32)
+    codec = TorchPQCodec(centroids=cen, A=A, b=b).to(dev)
+    codes = codec.encode(torch.from_numpy(x).to(dev)).cpu().numpy()
+    ref_codes, dist = mo.pq_encode(x, cen, A, b)
+    diff = codes != ref_codes
+    assert diff.mean() < 2e-3
+    if diff.any():      # every disagreement is a numerical tie
+        nn_, mm = np.nonzero(diff)
+        gap = np.abs(dist[nn_, mm, codes[nn_, mm]] - dist[nn_, mm, ref_codes[nn_, mm]])
+        assert (gap <= 1e-4 * np.maximum(1.0, np.abs(dist[nn_, mm, ref_codes[nn_, mm]]))).all()
+    # round trip: decode(encode(x)) is the nearest-centroid reconstruction
+    rec = codec.decode(torch.from_numpy(codes).to(dev)).cpu().numpy()
+    ref_rec = mo.pq_decode(ref_codes, cen, A, b)
+    assert np.abs(rec - ref_rec).mean() < 1e-3
