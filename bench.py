@@ -39,6 +39,8 @@ def parse():
     p.add_argument("--cpu-tokens", type=int, default=384, help="tokens in the CPU-baseline sample block")
     p.add_argument("--also-modes", default="tf32x3,tf32,bf16",
                    help="extra arithmetic modes timed briefly (resident inputs) and reported under `other_modes`")
+    p.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
+                   help="launch the step's kernels one by one instead of replaying the captured whole-step CUDA graph")
     p.add_argument("--ncu-range", action="store_true",
                    help="after warm-up run ONE resident step inside cudaProfilerStart/Stop and exit "
                         "(use with `ncu --profile-from-start off`); prints no bench line")
@@ -196,23 +198,26 @@ def main():
         barrier()
         return float(ms.item())
 
-    resident = lambda i: runner.step_resident(dev_batches[i % NB])
-    host = lambda i: runner.step_host(host_batches[i % NB])
+    eager = lambda i: runner.step_resident(dev_batches[i % NB])
+    resident = lambda i: runner.step_resident(dev_batches[i % NB], cuda_graph=args.cuda_graph)
+    host = lambda i: runner.step_host(host_batches[i % NB], cuda_graph=args.cuda_graph)
 
+    l0 = L.launches
+    eager(0)
+    launches_per_step = L.launches - l0                              # graph replays launch the same kernels
     for i in range(max(3, args.warmup)):
         resident(i)
     if args.ncu_range:
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.start()
-        resident(0)
+        eager(0)
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.stop()
         return
     clocks = ClockSampler(local)
     clocks.start()
-    l0 = L.launches
     ms = timed(resident, args.steps)
-    launches = L.launches - l0
+    launches = launches_per_step * args.steps
     clk = clocks.stop()
     for i in range(2):
         host(i)
@@ -227,7 +232,7 @@ def main():
     # ---- per-kernel pass (CUDA events around every C-ABI launch, same workload, separately timed region)
     L.TIMING = []
     for i in range(args.steps):
-        resident(i)
+        eager(i)
     torch.cuda.synchronize(dev)
     per = {}
     for name, tag, a, b in L.TIMING:
@@ -304,6 +309,7 @@ def main():
                                                            "tf32": "tf32", "bf16": "bf16"}[math],
         "data": "synthetic", "impl": "ours",
         "config": {"workload": workload_name(args.config), "math": math, "n_datastore": tables["n_d"],
+                   "cuda_graph": bool(args.cuda_graph),
                    "parallelism": f"dp{world} (contiguous block shards, replicated datastore, one 16 B all-reduce)",
                    "l2_policy": "inputs larger than L2 (datastore + activations are GBs); 4 distinct batches rotated",
                    "n_ntgt": n_ntgt, "n_valid_neighbours": n_valid},

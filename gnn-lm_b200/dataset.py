@@ -130,25 +130,37 @@ class GraphTokenBlockDataset:
         return np.arange(len(self))                                       # monolingual_dataset.py:264-266
 
 
-def move_to_cuda(batch: dict, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, device="cuda") -> dict:
-    """utils.move_to_cuda (fairseq/utils.py:43-67) + on-device graph assembly.  Returns the fairseq
-    `sample` dict with net_input.graph = TokenGraph."""
-    nb = lambda t: t.to(device, non_blocking=True)
-    nbr = nb(batch["nbr"])
-    pos = nb(batch["positions"])
-    g = build_token_graph(nbr, dstore.size, dataset.left_neighbor_context, dataset.right_neighbor_context,
+def sample_from_inputs(inp: dict, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore) -> dict:
+    """Device tensors of one batch -> the fairseq `sample` dict with net_input.graph = TokenGraph.  Device work only (no
+    host synchronisation), so the whole step can be captured in a CUDA graph (eval_lm.GraphedScorer)."""
+    pos = inp["positions"]
+    g = build_token_graph(inp["nbr"], dstore.size, dataset.left_neighbor_context, dataset.right_neighbor_context,
                           tgt_pos=pos if dataset.invalid_neighbor_context > 0 else None,
                           invalid_ctx=dataset.invalid_neighbor_context, intra_ctx=dataset.max_intra_context)
     g.codes_table = dstore.codes
     g.labels_table = dstore.vals
-    if "feats" in batch:
-        feats = nb(batch["feats"])
-        g.nodes["tgt"].data["h"] = feats.view(-1, feats.shape[-1])
-    sample = {"id": batch["id"], "nsentences": batch["nsentences"], "ntokens": batch["ntokens"],
-              "net_input": {"src_tokens": nb(batch["net_input"]["src_tokens"]), "src_lengths": batch["net_input"]["src_lengths"],
-                            "graph": g},
-              "target": nb(batch["target"]), "start_indices": batch["start_indices"], "positions": pos}
-    if "knn_ids" in batch:
-        sample["knn_dists"] = nb(batch["knn_dists"]).view(-1, batch["knn_dists"].shape[-1])
-        sample["knn_ids"] = nb(batch["knn_ids"]).view(-1, batch["knn_ids"].shape[-1])
+    if "feats" in inp:
+        g.nodes["tgt"].data["h"] = inp["feats"].view(-1, inp["feats"].shape[-1])
+    target = inp["target"]
+    sample = {"ntokens": target.numel(), "nsentences": target.shape[0],
+              "net_input": {"src_tokens": inp["src_tokens"], "graph": g},
+              "target": target, "start_indices": inp["start_indices"], "positions": pos}
+    if "knn_ids" in inp:
+        sample["knn_dists"] = inp["knn_dists"].view(-1, inp["knn_dists"].shape[-1])
+        sample["knn_ids"] = inp["knn_ids"].view(-1, inp["knn_ids"].shape[-1])
+    return sample
+
+
+def move_to_cuda(batch: dict, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, device="cuda") -> dict:
+    """utils.move_to_cuda (fairseq/utils.py:43-67) + on-device graph assembly.  Returns the fairseq
+    `sample` dict with net_input.graph = TokenGraph."""
+    nb = lambda t: t.to(device, non_blocking=True)
+    inp = {"nbr": nb(batch["nbr"]), "positions": nb(batch["positions"]), "src_tokens": nb(batch["net_input"]["src_tokens"]),
+           "target": nb(batch["target"]), "start_indices": batch["start_indices"]}
+    for k in ("feats", "knn_dists", "knn_ids"):
+        if k in batch:
+            inp[k] = nb(batch[k])
+    sample = sample_from_inputs(inp, dataset, dstore)
+    sample.update({"id": batch["id"], "nsentences": batch["nsentences"], "ntokens": batch["ntokens"]})
+    sample["net_input"]["src_lengths"] = batch["net_input"]["src_lengths"]
     return sample

@@ -16,7 +16,7 @@ import torch
 
 from . import ops
 
-from .dataset import DeviceDatastore, GraphTokenBlockDataset, move_to_cuda
+from .dataset import DeviceDatastore, GraphTokenBlockDataset, move_to_cuda, sample_from_inputs
 from .sequence_scorer import SequenceScorer
 
 
@@ -79,30 +79,87 @@ class DstoreWriter:
         return self.idx
 
 
+class GraphedScorer:
+    """One whole scoring step (graph assembly -> PQ decode -> HGT -> log-probs -> kNN mix -> NLL) captured as a CUDA
+    graph per input-shape signature and replayed for every later batch of that shape.  Possible because the path has
+    no host synchronisation: node / edge counts stay on the device and every buffer is sized by its host-known
+    capacity.  Inputs are copied into the graph's static buffers on the current stream before each replay; outputs
+    are the capture's own tensors (valid until the next replay of the same signature)."""
+
+    def __init__(self, fn, warmup: int = 2, device=None):
+        self.fn, self.warmup, self.cache, self.device = fn, warmup, {}, device
+
+    @staticmethod
+    def signature(inputs: dict):
+        return tuple((k, tuple(v.shape), str(v.dtype)) for k, v in sorted(inputs.items()))
+
+    def __call__(self, inputs: dict):
+        key = self.signature(inputs)
+        ent = self.cache.get(key)
+        if ent is None:
+            static = {k: torch.empty_like(v, device=self.device or v.device) for k, v in inputs.items()}   # inputs may be pinned host
+            for k, v in inputs.items():
+                static[k].copy_(v, non_blocking=True)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                       # lazy one-time setup (func attributes, workspaces) outside capture
+                for _ in range(self.warmup):
+                    self.fn(static, dry=True)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.fn(static, dry=False)
+            ent = self.cache[key] = (graph, static, out)
+        graph, static, out = ent
+        for k, v in inputs.items():
+            static[k].copy_(v, non_blocking=True)
+        graph.replay()
+        return out
+
+
+def device_inputs(batch: dict, device) -> dict:
+    """The tensors of a collated batch the device step consumes (utils.move_to_cuda, fairseq/utils.py:43-67)."""
+    nb = lambda t: t.to(device, non_blocking=True)
+    d = {"nbr": nb(batch["nbr"]), "positions": nb(batch["positions"]), "src_tokens": nb(batch["net_input"]["src_tokens"]),
+         "target": nb(batch["target"]), "start_indices": nb(batch["start_indices"].to(torch.int32).reshape(-1))}
+    for k in ("feats", "knn_dists", "knn_ids"):
+        if k in batch:
+            d[k] = nb(batch[k])
+    return d
+
+
 @torch.no_grad()
 def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, scorer: SequenceScorer, *,
              knn_dstore=None, temperature: float = 1.0, max_sentences: int = 1, device="cuda", rank: int = 0,
              world_size: int = 1, process_group=None, log=None, dstore_writer: Optional[DstoreWriter] = None,
-             knn_keytype: Optional[str] = None) -> dict:
+             knn_keytype: Optional[str] = None, cuda_graph: bool = False) -> dict:
+    """`cuda_graph=True` replays one captured CUDA graph per batch shape instead of launching the ~100 kernels of a
+    step one by one (same kernels, same results; pays off when blocks are small enough to be launch-bound)."""
     lo, hi = shard_range(len(dataset), rank, world_size)
     acc = torch.zeros(2, dtype=torch.float64, device=device)
     ntok = 0
+
+    def score(inp: dict, dry: bool = False):
+        sample = sample_from_inputs(inp, dataset, dstore)
+        if knn_dstore is not None and "knn_ids" in sample:
+            knn_dstore.set_search_results(sample["knn_dists"], sample["knn_ids"])
+        return scorer.score_tokens(model, sample, knn_dstore, temperature, nll_acc=None if dry else acc)
+
+    step = GraphedScorer(score) if cuda_graph else score
     torch.cuda.synchronize(device)
     t0 = time.perf_counter()
     for ids in batches(dataset, lo, hi, max_sentences):
         batch = dataset.collater([dataset[i] for i in ids])
-        sample = move_to_cuda(batch, dataset, dstore, device)
-        if knn_dstore is not None and "knn_ids" in sample:
-            knn_dstore.set_search_results(sample["knn_dists"], sample["knn_ids"])
-        _, _, _, dec_out = scorer.score_tokens(model, sample, knn_dstore, temperature, nll_acc=acc)
-        ntok += sample["ntokens"]
+        inp = device_inputs(batch, device)
+        _, _, _, dec_out = step(inp)
+        ntok += batch["ntokens"]
         if dstore_writer is not None:                           # sequence_scorer.py:180-183 + eval_lm.py:223-244
             extra = dec_out[1]
             feat = extra[knn_keytype] if knn_keytype in extra else extra["inner_states"][-1]     # [L, B, d]
-            starts = sample["start_indices"].view(-1).tolist()
-            for i in range(sample["target"].shape[0]):
-                mask = sample["target"][i, starts[i]:].ne(scorer.pad)
-                dstore_writer.add(feat[starts[i]:, i, :][mask].float(), sample["target"][i, starts[i]:][mask])
+            starts = batch["start_indices"].view(-1).tolist()
+            for i in range(inp["target"].shape[0]):
+                mask = inp["target"][i, starts[i]:].ne(scorer.pad)
+                dstore_writer.add(feat[starts[i]:, i, :][mask].float(), inp["target"][i, starts[i]:][mask])
     if world_size > 1:
         torch.distributed.all_reduce(acc, group=process_group)          # the path's only collective
     torch.cuda.synchronize(device)

@@ -127,6 +127,8 @@ class Runner:
         self.args = Namespace(lmbda=self.c.lmbda, knn_keytype=None)
         self.scorer = SequenceScorer(Dictionary(self.c.V), args=self.args)
         self.acc = torch.zeros(2, dtype=torch.float64, device=device)
+        from .eval_lm import GraphedScorer
+        self._graphed = GraphedScorer(self._score, device=device)
 
     def sample_from(self, nbr, feats, target, dists, ids):
         c = self.c
@@ -136,16 +138,26 @@ class Runner:
         self.knn.set_search_results(dists, ids)
         return {"net_input": {"src_tokens": target, "graph": g}, "target": target, "ntokens": target.numel()}
 
-    def step_resident(self, dev_batch: dict, want_knn=False):
-        s = self.sample_from(dev_batch["nbr"], dev_batch["feats"], dev_batch["target"], dev_batch["knn_dists"],
-                             dev_batch["knn_ids"])
-        return self.scorer.score_tokens(self.model, s, self.knn, self.c.temp, nll_acc=self.acc, want_knn=want_knn)
+    KEYS = ("nbr", "feats", "target", "knn_dists", "knn_ids")
 
-    def step_host(self, host_batch: dict):
+    def _score(self, inp: dict, dry: bool = False, want_knn: bool = False):
+        s = self.sample_from(inp["nbr"], inp["feats"], inp["target"], inp["knn_dists"], inp["knn_ids"])
+        return self.scorer.score_tokens(self.model, s, self.knn, self.c.temp, nll_acc=None if dry else self.acc,
+                                        want_knn=want_knn)
+
+    def step_resident(self, dev_batch: dict, want_knn=False, cuda_graph=False):
+        """cuda_graph=True: replay the step as one captured CUDA graph (eval_lm.GraphedScorer)."""
+        inp = {k: dev_batch[k] for k in self.KEYS}
+        if cuda_graph and not want_knn:
+            return self._graphed(inp)
+        return self._score(inp, want_knn=want_knn)
+
+    def step_host(self, host_batch: dict, cuda_graph=False):
         """host_batch: pinned CPU tensors.  Copies in, scores, reads the scalar result back."""
-        nb = lambda k: host_batch[k].to(self.device, non_blocking=True)
-        s = self.sample_from(nb("nbr"), nb("feats"), nb("target"), nb("knn_dists"), nb("knn_ids"))
-        self.scorer.score_tokens(self.model, s, self.knn, self.c.temp, nll_acc=self.acc)
+        if cuda_graph:       # pinned host -> the graph's static device buffers, then one replay
+            self._graphed({k: host_batch[k] for k in self.KEYS})
+        else:
+            self._score({k: host_batch[k].to(self.device, non_blocking=True) for k in self.KEYS})
         return self.acc.cpu()     # D2H read of the step's result (16 B), synchronises
 
 

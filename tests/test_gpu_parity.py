@@ -488,6 +488,15 @@ def test_eval_lm_dataset_vs_oracle(dev):
         o0 = mo.eval_batch(om, batch0, None)
         np.testing.assert_allclose(np.asarray(keys[:blk], dtype=np.float32), o0["gcn_feat"].numpy(), rtol=2e-3, atol=2e-3)
     assert abs(res["ppl"] - mo.perplexity(tot, cnt)[1]) / res["ppl"] < 1e-4
+    # whole-step CUDA-graph replay (one capture per batch shape: 2-block batches, then the ragged tail) == eager
+    for math_ in ("fp32", "f16x3"):
+        if math_ != "fp32":
+            _need_tc()
+        m3 = copy.deepcopy(model).to(dev).set_math(math_)
+        eager = evaluate(m3, ds, dstore, scorer, knn_dstore=knn, max_sentences=2, device=dev)
+        graphed = evaluate(m3, ds, dstore, scorer, knn_dstore=knn, max_sentences=2, device=dev, cuda_graph=True)
+        assert graphed["count"] == eager["count"] == n_tok
+        assert abs(graphed["score_sum"] - eager["score_sum"]) <= 1e-9 * abs(eager["score_sum"])
 
 
 @pytest.mark.parametrize("name", ["c1", "c3mini"])
