@@ -48,6 +48,8 @@ SIGNATURES = {
     "gnnlm_knn_mix_nll": (_i32, [_p, _p, _f32, _p, _p, _i64, _p, _i32, _i64, _p, _f32, _f32, _f32, _p, _i64, _p, _i64, _p, _p, _p,
                                  _p, _i64, _p]),
     "gnnlm_knn_full_prob": (_i32, [_p, _p, _i64, _p, _i32, _i64, _f32, _f32, _p, _i64, _i64, _p]),
+    "gnnlm_knn_sims_keys": (_i32, [_p, _i64, _p, _i32, _i64, _i32, _p, _i64, _i32, _i32, _p, _i64, _p]),
+    "gnnlm_knn_sims_pq": (_i32, [_p, _i64, _i32, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _i64, _i32, _p, _i64, _p]),
 }
 
 _lib = None

@@ -11,6 +11,8 @@
 // one (cluster, feature slice): one round trip for (node_base, cluster_nl), then the 3w row segments of
 // Q / K' / V' are all in flight together and each is read exactly once -- HBM traffic equals the
 // algorithmic bytes of SURVEY.md 8(d): N*(2+1)*d*s read + N*d*4 written.
+#include <stdlib.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -63,14 +65,18 @@ __device__ __forceinline__ void store_out(OutT* __restrict__ p, const float (&r)
   }
 }
 
+// WMAX == 0 selects the centre-only variant (its own instantiation: 3 rows of K'/V' per cluster, a third of the registers of
+// the all-nodes form, so twice the resident warps)
 template <typename T, typename OutT, int C, int WMAX>
 __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k,
                                                                   int64_t ldk, const T* __restrict__ v, int64_t ldv,
                                                                   const int32_t* __restrict__ node_base,
                                                                   const int32_t* __restrict__ valid_base,
                                                                   const int32_t* __restrict__ cluster_nl, int64_t n_clusters,
-                                                                  int centre_only, int group, int n_slices,
+                                                                  int group, int n_slices,
                                                                   OutT* __restrict__ out, int64_t ldo, int lo_off) {
+  constexpr bool centre_only = WMAX == 0;
+  constexpr int WM = WMAX > 0 ? WMAX : 1;
   const int lane = threadIdx.x & 31;
   const int64_t n_items = n_clusters * n_slices;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -81,10 +87,10 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
     const int w = __ldg(node_base + c + 1) - base;
     if (w <= 0) continue;                                    // invalid neighbour: no cluster
     const int nl = __ldg(cluster_nl + c);
-    if (!centre_only) {
-      float qq[WMAX][C], kk[WMAX][C], vv[WMAX][C];
+    if constexpr (!centre_only) {
+      float qq[WM][C], kk[WM][C], vv[WM][C];
 #pragma unroll
-      for (int p = 0; p < WMAX; ++p) {
+      for (int p = 0; p < WM; ++p) {
         if (p < w) {
           const int64_t id = base + ca_pos_to_id(p, nl);
           load_row<T, C>(q + id * ldq + col, qq[p]);
@@ -93,12 +99,12 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
         }
       }
 #pragma unroll
-      for (int p = 0; p < WMAX; ++p) {
+      for (int p = 0; p < WM; ++p) {
         if (p < w) {
           const float s1 = group_dot<C>(qq[p], kk[p], group);
           float s0 = -INFINITY, s2 = -INFINITY;
           if (p > 0) s0 = group_dot<C>(qq[p], kk[p > 0 ? p - 1 : 0], group);
-          if (p + 1 < WMAX && p + 1 < w) s2 = group_dot<C>(qq[p], kk[p + 1 < WMAX ? p + 1 : p], group);
+          if (p + 1 < WM && p + 1 < w) s2 = group_dot<C>(qq[p], kk[p + 1 < WM ? p + 1 : p], group);
           const float mx = fmaxf(s1, fmaxf(s0, s2));
           const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx), e2 = __expf(s2 - mx);
           const float inv = 1.f / (e0 + e1 + e2);
@@ -107,7 +113,7 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
           for (int cc = 0; cc < C; ++cc) {
             float a = e1 * vv[p][cc];
             if (p > 0) a = fmaf(e0, vv[p > 0 ? p - 1 : 0][cc], a);
-            if (p + 1 < WMAX && p + 1 < w) a = fmaf(e2, vv[p + 1 < WMAX ? p + 1 : p][cc], a);
+            if (p + 1 < WM && p + 1 < w) a = fmaf(e2, vv[p + 1 < WM ? p + 1 : p][cc], a);
             r[cc] = a * inv;
           }
           store_out<OutT, C>(out + (int64_t)(base + ca_pos_to_id(p, nl)) * ldo + col, r, lo_off);
@@ -144,17 +150,86 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
   }
 }
 
+// Clusters of any size (used for w > 3): walk the chain in sorted order with a three-row window of K' / V' in registers
+// and the next row's loads already in flight, so the register count (and with it the number of resident warps) does not
+// grow with w the way the fully unrolled form above does.
+template <typename T, typename OutT, int C>
+__global__ void __launch_bounds__(CA_THREADS, C == 4 ? 4 : 2) cluster_attn_window_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k,
+                                                                         int64_t ldk, const T* __restrict__ v, int64_t ldv,
+                                                                         const int32_t* __restrict__ node_base,
+                                                                         const int32_t* __restrict__ cluster_nl, int64_t n_clusters,
+                                                                         int group, int n_slices, OutT* __restrict__ out,
+                                                                         int64_t ldo, int lo_off) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_items = n_clusters * n_slices;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n_items; it += warps) {
+    const int64_t c = it / n_slices;
+    const int col = ((int)(it % n_slices) * 32 + lane) * C;
+    const int base = __ldg(node_base + c);
+    const int w = __ldg(node_base + c + 1) - base;
+    if (w <= 0) continue;
+    const int nl = __ldg(cluster_nl + c);
+    float qc[C], qn[C], kp[C], kc[C], kn[C], vp[C], vc[C], vn[C];
+    {
+      const int64_t id = base + ca_pos_to_id(0, nl);
+      load_row<T, C>(q + id * ldq + col, qc);
+      load_row<T, C>(k + id * ldk + col, kc);
+      load_row<T, C>(v + id * ldv + col, vc);
+    }
+    if (w > 1) {
+      const int64_t id = base + ca_pos_to_id(1, nl);
+      load_row<T, C>(q + id * ldq + col, qn);
+      load_row<T, C>(k + id * ldk + col, kn);
+      load_row<T, C>(v + id * ldv + col, vn);
+    }
+#pragma unroll 1
+    for (int p = 0; p < w; ++p) {
+      float q2[C], k2[C], v2[C];
+      if (p + 2 < w) {                                        // in flight while position p is being computed
+        const int64_t id = base + ca_pos_to_id(p + 2, nl);
+        load_row<T, C>(q + id * ldq + col, q2);
+        load_row<T, C>(k + id * ldk + col, k2);
+        load_row<T, C>(v + id * ldv + col, v2);
+      }
+      const bool has_l = p > 0, has_r = p + 1 < w;
+      const float s1 = group_dot<C>(qc, kc, group);
+      float s0 = -INFINITY, s2 = -INFINITY;
+      if (has_l) s0 = group_dot<C>(qc, kp, group);
+      if (has_r) s2 = group_dot<C>(qc, kn, group);
+      const float mx = fmaxf(s1, fmaxf(s0, s2));
+      const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx), e2 = __expf(s2 - mx);
+      const float inv = 1.f / (e0 + e1 + e2);
+      float r[C];
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) {
+        float a = e1 * vc[cc];
+        if (has_l) a = fmaf(e0, vp[cc], a);
+        if (has_r) a = fmaf(e2, vn[cc], a);
+        r[cc] = a * inv;
+      }
+      store_out<OutT, C>(out + (int64_t)(base + ca_pos_to_id(p, nl)) * ldo + col, r, lo_off);
+#pragma unroll
+      for (int cc = 0; cc < C; ++cc) {
+        kp[cc] = kc[cc]; vp[cc] = vc[cc];
+        kc[cc] = kn[cc]; vc[cc] = vn[cc]; qc[cc] = qn[cc];
+        kn[cc] = k2[cc]; vn[cc] = v2[cc]; qn[cc] = q2[cc];
+      }
+    }
+  }
+}
+
 template <typename T, typename OutT, int C, int WMAX>
 static int32_t launch_cluster(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                               const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl,
-                              int64_t n_clusters, int centre_only, int group, int n_slices, void* out, int64_t ldo,
-                              int lo_off, cudaStream_t st) {
+                              int64_t n_clusters, int group, int n_slices, void* out, int64_t ldo, int lo_off,
+                              cudaStream_t st) {
   int64_t blocks = ceil_div(n_clusters * n_slices, CA_THREADS / 32);
   const int64_t max_blocks = 148 * 8 * 8;
   if (blocks > max_blocks) blocks = max_blocks;
   cluster_attn_kernel<T, OutT, C, WMAX><<<(unsigned)blocks, CA_THREADS, 0, st>>>(
-      (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, group,
-      n_slices, (OutT*)out, ldo, lo_off);
+      (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, node_base, valid_base, cluster_nl, n_clusters, group, n_slices,
+      (OutT*)out, ldo, lo_off);
   GNNLM_LAUNCH_CHECK("gnnlm_hgt_cluster_attn");
   return 0;
 }
@@ -164,13 +239,19 @@ static int32_t dispatch_w(int wmax, const void* q, int64_t ldq, const void* k, i
                           const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl, int64_t n_clusters,
                           int centre_only, int group, int n_slices, void* out, int64_t ldo, int lo_off, cudaStream_t st) {
 #define GNNLM_CL(W)                                                                                                       \
-  return launch_cluster<T, OutT, C, W>(q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, \
-                                       group, n_slices, out, ldo, lo_off, st)
+  return launch_cluster<T, OutT, C, W>(q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, group, n_slices, \
+                                       out, ldo, lo_off, st)
+  if (centre_only) GNNLM_CL(0);
   if (wmax <= 1) GNNLM_CL(1);
   if (wmax <= 3) GNNLM_CL(3);
-  if (wmax <= 5) GNNLM_CL(5);
-  GNNLM_CL(7);
 #undef GNNLM_CL
+  int64_t blocks = ceil_div(n_clusters * n_slices, CA_THREADS / 32);
+  if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
+  cluster_attn_window_kernel<T, OutT, C><<<(unsigned)blocks, CA_THREADS, 0, st>>>(
+      (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, node_base, cluster_nl, n_clusters, group, n_slices, (OutT*)out, ldo,
+      lo_off);
+  GNNLM_LAUNCH_CHECK("gnnlm_hgt_cluster_attn");
+  return 0;
 }
 
 }  // namespace gnnlm
@@ -188,11 +269,15 @@ extern "C" int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void
   GNNLM_CHECK_ARG(out_dtype == GNNLM_F32 || out_dtype == GNNLM_BF16 || out_dtype == GNNLM_F16X2, GNNLM_E_UNSUPPORTED,
                   "gnnlm_hgt_cluster_attn: out dtype");
   GNNLM_CHECK_ARG(out_dtype != GNNLM_F16X2 || ldo >= 2 * (int64_t)H * d_k, GNNLM_E_SHAPE, "gnnlm_hgt_cluster_attn: split output needs ldo >= 2d");
-  GNNLM_CHECK_ARG(max_cluster >= 1 && max_cluster <= 7, GNNLM_E_UNSUPPORTED,
-                  "gnnlm_hgt_cluster_attn: cluster size %d > 7 (use gnnlm_hgt_edge_attn)", max_cluster);
+  GNNLM_CHECK_ARG(max_cluster >= 1, GNNLM_E_SHAPE, "gnnlm_hgt_cluster_attn: max_cluster must be >= 1");
   GNNLM_CHECK_ARG(H > 0 && H <= 32 && (H & (H - 1)) == 0, GNNLM_E_UNSUPPORTED, "gnnlm_hgt_cluster_attn: H must be a power of two <= 32");
   const int64_t d = (int64_t)H * d_k;
-  const int Cs = dtype == GNNLM_F32 ? 4 : 8;                 // 16 B per lane per row
+  // 16 B per lane per row; fp32 chains longer than 3 take 32 B per lane: half the shuffle / exp / address
+  // instructions per byte, which is what bounds the windowed kernel (issue-bound at ~55 % of HBM peak with 16 B)
+  static const bool wide_ok = [] { const char* e = getenv("GNNLM_CLUSTER_WIDE"); return !(e && e[0] == '0'); }();
+  const bool wide = dtype == GNNLM_F32 && !centre_only && max_cluster > 3 && wide_ok && d % 256 == 0 && d_k % 8 == 0 &&
+                    d_k / 8 <= 32 && 32 % (d_k / 8) == 0;
+  const int Cs = (dtype == GNNLM_F32 && !wide) ? 4 : 8;
   // a warp covers 32*Cs features; a head (d_k features) must live inside one warp and heads may not straddle warps
   GNNLM_CHECK_ARG(d % (32 * Cs) == 0 && d_k % Cs == 0 && d_k / Cs <= 32 && 32 % (d_k / Cs) == 0, GNNLM_E_UNSUPPORTED,
                   "gnnlm_hgt_cluster_attn: unsupported (H=%d, d_k=%d) -- use gnnlm_hgt_edge_attn", H, d_k);
@@ -204,6 +289,9 @@ extern "C" int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void
 #define GNNLM_DW(T, OT, C)                                                                                                    \
   return dispatch_w<T, OT, C>(max_cluster, q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, \
                               group, n_slices, out, ldo, (int)d, st)
+  if (wide && out_dtype == GNNLM_F32) GNNLM_DW(float, float, 8);
+  if (wide && out_dtype == GNNLM_F16X2) GNNLM_DW(float, __half, 8);
+  if (wide) GNNLM_DW(float, __nv_bfloat16, 8);
   if (dtype == GNNLM_F32 && out_dtype == GNNLM_F32) GNNLM_DW(float, float, 4);
   if (dtype == GNNLM_F32 && out_dtype == GNNLM_F16X2) GNNLM_DW(float, __half, 4);
   if (out_dtype == GNNLM_F16X2) GNNLM_DW(__nv_bfloat16, __half, 8);

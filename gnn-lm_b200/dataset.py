@@ -130,13 +130,13 @@ class GraphTokenBlockDataset:
         return np.arange(len(self))                                       # monolingual_dataset.py:264-266
 
 
-def sample_from_inputs(inp: dict, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore) -> dict:
+def sample_from_inputs(inp: dict, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, reach=None) -> dict:
     """Device tensors of one batch -> the fairseq `sample` dict with net_input.graph = TokenGraph.  Device work only (no
     host synchronisation), so the whole step can be captured in a CUDA graph (eval_lm.GraphedScorer)."""
     pos = inp["positions"]
     g = build_token_graph(inp["nbr"], dstore.size, dataset.left_neighbor_context, dataset.right_neighbor_context,
                           tgt_pos=pos if dataset.invalid_neighbor_context > 0 else None,
-                          invalid_ctx=dataset.invalid_neighbor_context, intra_ctx=dataset.max_intra_context)
+                          invalid_ctx=dataset.invalid_neighbor_context, intra_ctx=dataset.max_intra_context, reach=reach)
     g.codes_table = dstore.codes
     g.labels_table = dstore.vals
     if "feats" in inp:

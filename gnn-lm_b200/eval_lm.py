@@ -132,15 +132,18 @@ def device_inputs(batch: dict, device) -> dict:
 def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, scorer: SequenceScorer, *,
              knn_dstore=None, temperature: float = 1.0, max_sentences: int = 1, device="cuda", rank: int = 0,
              world_size: int = 1, process_group=None, log=None, dstore_writer: Optional[DstoreWriter] = None,
-             knn_keytype: Optional[str] = None, cuda_graph: bool = False) -> dict:
+             knn_keytype: Optional[str] = None, cuda_graph: bool = False, prune_unreachable: bool = True) -> dict:
     """`cuda_graph=True` replays one captured CUDA graph per batch shape instead of launching the ~100 kernels of a
-    step one by one (same kernels, same results; pays off when blocks are small enough to be launch-bound)."""
+    step one by one (same kernels, same results; pays off when blocks are small enough to be launch-bound).
+    `prune_unreachable` drops context nodes further than graph_layer-1 hops from their centre (graph.build_token_graph
+    `reach`): they cannot reach a tgt node, so scores are unchanged."""
+    reach = model.decoder.hgt_decoder.n_layers - 1 if prune_unreachable else None
     lo, hi = shard_range(len(dataset), rank, world_size)
     acc = torch.zeros(2, dtype=torch.float64, device=device)
     ntok = 0
 
     def score(inp: dict, dry: bool = False):
-        sample = sample_from_inputs(inp, dataset, dstore)
+        sample = sample_from_inputs(inp, dataset, dstore, reach=reach)
         if knn_dstore is not None and "knn_ids" in sample:
             knn_dstore.set_search_results(sample["knn_dists"], sample["knn_ids"])
         return scorer.score_tokens(model, sample, knn_dstore, temperature, nll_acc=None if dry else acc)

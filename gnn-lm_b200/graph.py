@@ -89,8 +89,16 @@ class TokenGraph:
 
 def build_token_graph(nbr: torch.Tensor, n_datastore: int, left_ctx: int, right_ctx: int, *,
                       tgt_pos: Optional[torch.Tensor] = None, invalid_ctx: int = 0, intra_ctx: int = 0,
-                      with_owner: bool = False) -> TokenGraph:
-    """nbr [B, L, k] int64 on the device (= neighbor_offsets[offsets], token_block_dataset.py:309)."""
+                      with_owner: bool = False, reach: Optional[int] = None) -> TokenGraph:
+    """nbr [B, L, k] int64 on the device (= neighbor_offsets[offsets], token_block_dataset.py:309).
+
+    `reach`: keep only context nodes within `reach` chain hops of their centre.  With NL graph layers a tgt node sees its
+    neighbour clusters through the centre after NL-1 ntgt-intra-ntgt hops, so nodes further than NL-1 from the centre
+    cannot influence any tgt output (the decoder reads tgt rows only, transformer.py:1053): reach = NL-1 gives the same
+    tgt features as the reference's full clusters with fewer rows to decode and project (e.g. w = 7 -> 5 at c = 3, NL = 3).
+    The ntgt numbering then differs from the reference's, so leave it None when ntgt outputs are wanted."""
+    if reach is not None:
+        left_ctx, right_ctx = min(left_ctx, reach), min(right_ctx, reach)
     assert nbr.is_cuda and nbr.dtype == torch.int64 and nbr.dim() == 3 and nbr.is_contiguous()
     B, Lb, k = nbr.shape
     g = TokenGraph(B, Lb, k, left_ctx, right_ctx, intra_ctx, n_datastore)

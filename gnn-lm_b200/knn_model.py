@@ -14,13 +14,29 @@ from . import ops
 
 class KNNModel(object):
     def __init__(self, vals: torch.Tensor, vocab_size: Optional[int] = None, metric_type: str = "do_not_recomp_ip",
-                 k: int = 1024, dists: Optional[torch.Tensor] = None, knns: Optional[torch.Tensor] = None):
+                 k: int = 1024, dists: Optional[torch.Tensor] = None, knns: Optional[torch.Tensor] = None,
+                 keys: Optional[torch.Tensor] = None, pq_codes: Optional[torch.Tensor] = None, quantizer=None,
+                 index_file: str = ""):
         """vals: [N_d] (or [N_d,1]) int16/int32 datastore values resident in HBM (vals.npy);
-        dists/knns: optional whole-split precomputed search results [N_split, k] indexed by stream position."""
+        dists/knns: optional whole-split precomputed search results [N_split, k] indexed by stream position.
+        metric_type `l2` / `ip` recompute the similarities (knn_model.py:159-177) from `keys` ([N_d, d] fp16/fp32 in
+        HBM, the reference's keys.npy) or, when the keys only exist PQ-compressed, from `pq_codes` [N_d, M] uint8 +
+        `quantizer` (TorchPQCodec) -- then against the decoded keys.  `index_file`: as in the reference, a name
+        containing "cosine" switches on the query / key normalisation (:171-172,181-184)."""
         assert metric_type in ["do_not_recomp_l2", "do_not_recomp_ip", "l2", "ip"]
-        if metric_type in ("l2", "ip"):
-            raise NotImplementedError("similarity recompute from keys (knn_model.py:159-177) is a 'next' row "
-                                      "(SURVEY.md 8f-3); use do_not_recomp_*")
+        self.recompute = metric_type in ("l2", "ip")
+        if self.recompute and keys is None and pq_codes is None:
+            raise ValueError(f"metric_type={metric_type} needs the datastore keys (keys=...) or their PQ codes "
+                             "(pq_codes=..., quantizer=...)")
+        self.keys, self.pq_codes, self.quantizer, self.index_file = keys, pq_codes, quantizer, index_file
+        self.cosine = "cosine" in index_file
+        if self.recompute and keys is None:
+            if self.cosine:
+                raise NotImplementedError("cosine similarity against PQ-decoded keys")
+            if metric_type == "l2" and quantizer.pre_torch:
+                A = quantizer.A.double()
+                if not torch.allclose(A @ A.T, torch.eye(A.shape[0], dtype=A.dtype, device=A.device), atol=1e-4):
+                    raise NotImplementedError("l2 against PQ-decoded keys needs an orthonormal OPQ transform")
         self.vals = vals.reshape(-1)
         assert self.vals.dtype in (torch.int16, torch.int32)
         self.dstore_size = self.vals.numel()
@@ -32,25 +48,42 @@ class KNNModel(object):
 
     @property
     def sim_sign(self):
-        return -1.0 if self.metric_type == "do_not_recomp_l2" else 1.0      # knn_model.py:153-157
+        return -1.0 if self.metric_type == "do_not_recomp_l2" else 1.0      # knn_model.py:153-157 (recomputed sims carry their sign)
 
-    def set_search_results(self, dists: torch.Tensor, knns: torch.Tensor):
-        """Provide the (out-of-scope) search output for the next get_knn_prob call: [num, k] each."""
-        self._pending = (dists.contiguous().float(), knns.contiguous().long())
+    def similarities(self, queries: torch.Tensor, dists: Optional[torch.Tensor], knns: torch.Tensor) -> torch.Tensor:
+        """sim_func of knn_model.py:137-177 up to the sign handled by `sim_sign`: the search distances for
+        do_not_recomp_*, else recomputed from the keys.  queries [num, d] fp32 on the device."""
+        if not self.recompute:
+            return dists
+        q = queries.float()
+        if q.stride(-1) != 1:
+            q = q.contiguous()
+        if self.keys is not None:
+            return ops.knn_sims_keys(q, self.keys, knns, self.metric_type, cosine=self.cosine)
+        qz = self.quantizer
+        rot = ops.linear(q, qz.A.contiguous(), None, math=0) if qz.pre_torch else q        # q @ A.T, fp32
+        b = qz.b if qz.pre_torch and qz.b.numel() > 0 else None
+        return ops.knn_sims_pq(q, rot, self.pq_codes, qz.centroids_torch, b, knns, self.metric_type)
+
+    def set_search_results(self, dists: Optional[torch.Tensor], knns: torch.Tensor):
+        """Provide the (out-of-scope) search output for the next get_knn_prob call: [num, k] each; dists may be None
+        when the metric recomputes them."""
+        self._pending = (None if dists is None else dists.contiguous().float(), knns.contiguous().long())
 
     def get_knns(self, queries, k: int = 0, positions: Optional[torch.Tensor] = None):
         if self._pending is not None:
             out, self._pending = self._pending, None
             return out
-        if positions is not None and self.dists is not None:
-            return self.dists[positions].contiguous(), self.knns[positions].contiguous()
+        if positions is not None and self.knns is not None and (self.dists is not None or self.recompute):
+            return (None if self.dists is None else self.dists[positions].contiguous()), self.knns[positions].contiguous()
         raise RuntimeError("faiss search is out of scope: call set_search_results() or pass precomputed arrays")
 
     @torch.no_grad()
     def get_knn_prob(self, queries, k: int = 0, output_size: int = None, return_knn: bool = False, t: float = 1.0,
                      targets: torch.Tensor = None, return_recall: bool = False, positions=None):
-        """knn_model.py:103-217.  `queries` is only used for its leading dimension."""
+        """knn_model.py:103-217.  `queries` [num, d] is read only by the recomputing metrics (l2 / ip)."""
         dists, knns = self.get_knns(queries, k=k, positions=positions)
+        dists = self.similarities(queries, dists, knns)
         if targets is None:
             output_size = output_size or self.vocab_size
             if not output_size:

@@ -172,7 +172,7 @@ def cluster_attn_supported(d: int, H: int, dtype, w: int) -> bool:
     """Shape envelope of gnnlm_hgt_cluster_attn (else use edge_attn over the CSR)."""
     cs = 4 if dtype == torch.float32 else 8
     dk = d // H
-    return (w <= 7 and H & (H - 1) == 0 and H <= 32 and d % (32 * cs) == 0 and dk % cs == 0 and dk // cs <= 32
+    return (H & (H - 1) == 0 and H <= 32 and d % (32 * cs) == 0 and dk % cs == 0 and dk // cs <= 32
             and 32 % (dk // cs) == 0)
 
 
@@ -292,3 +292,31 @@ def knn_full_prob(dists, ids, vals, vocab, n_datastore, sim_sign=1.0, temperatur
     L.call("gnnlm_knn_full_prob", L.ptr(dists), L.ptr(ids), k, L.ptr(vals), vb, n_datastore, float(sim_sign),
            float(temperature), L.ptr(probs), vocab, T, L.stream_ptr())
     return probs
+
+
+METRICS = {"l2": 0, "ip": 1}
+
+
+def knn_sims_keys(queries, keys, ids, metric: str, cosine: bool = False):
+    """sims [T, k] from the datastore's own key rows (knn_model.py:159-177); keys [N_d, d] fp16 / fp32 on the device."""
+    T, d = queries.shape
+    assert queries.dtype == torch.float32 and queries.stride(1) == 1 and ids.dtype == torch.int64 and ids.is_contiguous()
+    assert keys.is_contiguous() and keys.shape[1] == d and keys.dtype in (torch.float16, torch.float32)
+    sims = torch.empty(ids.shape, device=queries.device, dtype=torch.float32)
+    norm = (3 if metric == "ip" else 2) if cosine else 0
+    L.call("gnnlm_knn_sims_keys", L.ptr(queries), queries.stride(0), L.ptr(keys), L.F16 if keys.dtype == torch.float16 else L.F32,
+           keys.shape[0], d, L.ptr(ids), ids.shape[1], METRICS[metric], norm, L.ptr(sims), T, L.stream_ptr())
+    return sims
+
+
+def knn_sims_pq(queries, rotated, codes, centroids, bias, ids, metric: str):
+    """sims [T, k] against the PQ-decoded keys by asymmetric distance computation; rotated = queries @ A.T."""
+    T = queries.shape[0]
+    M, ksub, dsub = centroids.shape
+    assert ksub == 256 and codes.dtype == torch.uint8 and codes.is_contiguous() and codes.shape[1] == M
+    assert rotated.shape == (T, M * dsub) and rotated.stride(1) == 1 and queries.stride(1) == 1
+    sims = torch.empty(ids.shape, device=queries.device, dtype=torch.float32)
+    L.call("gnnlm_knn_sims_pq", L.ptr(queries), queries.stride(0), queries.shape[1], L.ptr(rotated), rotated.stride(0),
+           L.ptr(codes), codes.shape[0], M, dsub, L.ptr(centroids), L.ptr(bias), L.ptr(ids), ids.shape[1], METRICS[metric],
+           L.ptr(sims), T, L.stream_ptr())
+    return sims

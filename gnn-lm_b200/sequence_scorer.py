@@ -48,6 +48,12 @@ class SequenceScorer(object):
         kw = {}
         if use_knn:
             dists, knns = knn_dstore.get_knns(None, positions=sample.get("positions"))
+            if getattr(knn_dstore, "recompute", False):       # metric l2 / ip: queries = the --knn-keytype features (:105)
+                keytype = getattr(self.args, "knn_keytype", None)
+                extra = decoder_out[1]
+                feat = extra[keytype] if keytype in extra else extra["inner_states"][-1]          # [L, B, d]
+                queries = feat.float().permute(1, 0, 2).reshape(bsz * L, -1)                     # B-major, like the targets
+                dists = knn_dstore.similarities(queries, dists, knns)
             kw = dict(target=target.reshape(-1), dists=dists, ids=knns, vals=knn_dstore.vals,
                       n_datastore=knn_dstore.dstore_size, sim_sign=knn_dstore.sim_sign, temperature=temperature,
                       lmbda=lmbda, want_knn=want_knn)

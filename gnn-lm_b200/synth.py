@@ -119,8 +119,9 @@ class Runner:
     log-probs -> kNN mix -> NLL accumulation.  `step(host_batch)` is the e2e variant (pinned host
     inputs, H2D inside)."""
 
-    def __init__(self, cfg: dict, model: TransformerLanguageModel, data: dict, device, math: str = "fp32"):
-        self.cfg, self.c, self.device = cfg, SimpleNamespace(**cfg), device
+    def __init__(self, cfg: dict, model: TransformerLanguageModel, data: dict, device, math: str = "fp32",
+                 prune_unreachable: bool = True):
+        self.cfg, self.c, self.device, self.prune_unreachable = cfg, SimpleNamespace(**cfg), device, prune_unreachable
         self.model = model.to(device).set_math(math)
         self.dstore = DeviceDatastore(data["codes"].to(device), data["vals"].to(device))
         self.knn = KNNModel(self.dstore.vals, vocab_size=self.c.V, metric_type="do_not_recomp_ip", k=self.c.k_nn)
@@ -132,7 +133,7 @@ class Runner:
 
     def sample_from(self, nbr, feats, target, dists, ids):
         c = self.c
-        g = build_token_graph(nbr, self.dstore.size, c.c, c.c)
+        g = build_token_graph(nbr, self.dstore.size, c.c, c.c, reach=c.NL - 1 if self.prune_unreachable else None)
         g.codes_table = self.dstore.codes
         g.nodes["tgt"].data["h"] = feats.view(-1, feats.shape[-1])
         self.knn.set_search_results(dists, ids)

@@ -285,6 +285,26 @@ int32_t gnnlm_knn_full_prob(const float* dists, const int64_t* ids, int64_t k_nn
                             int32_t val_bytes, int64_t n_datastore, float sim_sign, float temperature,
                             float* probs, int64_t V, int64_t T, gnnlm_stream_t stream);
 
+/* Similarity recompute -- metric_type `l2` / `ip` of KNNModel.get_knn_prob (knn/knn_model.py:159-177), for pipelines
+ * that keep only the neighbour ids (knn/find_knn.py:65-66).  metric: 0 = l2 (sims = -||q - key||^2), 1 = ip.
+ * sims [T, k_nn] fp32 feed gnnlm_knn_mix_nll / gnnlm_knn_full_prob as `dists` with sim_sign = +1.  ids == -1 wrap to
+ * the last datastore row like numpy indexing (:163,:169); the consumer masks them (:193).
+ *
+ *  _keys: keys [n_datastore, d] fp32 / fp16 (GNNLM_F32 / GNNLM_F16; the datastore's keys.npy), d % 8 == 0.
+ *         normalise bit 0: L2-normalise the gathered keys (cosine index, `ip`, :171-172);
+ *         bit 1: L2-normalise the queries first (cosine index, :181-184).
+ *  _pq:   keys only as PQ codes [n_datastore, M] uint8 + centroids [M, 256, dsub] (+ OPQ bias [M*dsub], nullable):
+ *         similarity to the DECODED key x^ = (y - b) A (knn/pq_wrapper.py:169-203) by asymmetric distance computation.
+ *         rotated [T, M*dsub] = queries A^T (a gnnlm_linear call; pass the queries themselves when there is no OPQ
+ *         transform).  l2 assumes A A^T = I (OPQ rotations are orthonormal).  M % 4 == 0, M*(256+dsub)*4 B <= 220 KB. */
+int32_t gnnlm_knn_sims_keys(const float* queries, int64_t ldq, const void* keys, int32_t key_dtype, int64_t n_datastore,
+                            int32_t d, const int64_t* ids, int64_t k_nn, int32_t metric, int32_t normalise, float* sims,
+                            int64_t T, gnnlm_stream_t stream);
+int32_t gnnlm_knn_sims_pq(const float* queries, int64_t ldq, int32_t d_q, const float* rotated, int64_t ldr,
+                          const uint8_t* codes, int64_t n_datastore, int32_t M, int32_t dsub, const float* centroids,
+                          const float* bias, const int64_t* ids, int64_t k_nn, int32_t metric, float* sims, int64_t T,
+                          gnnlm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,17 +11,21 @@ base = dict(synth.CONFIGS['c3'], n_d=1 << 24)
 model = synth.make_model(base)
 tables = synth.make_tables(base, device=dev)
 rows = []
-for k in (8, 32, 128, 512):
-    for c in (0, 1, 3):
+KS = [int(x) for x in os.environ.get('SWEEP_K', '8,32,128,512').split(',')]
+CS = [int(x) for x in os.environ.get('SWEEP_C', '0,1,3').split(',')]
+PRUNE = os.environ.get('SWEEP_PRUNE', '1') == '1'      # drop context nodes that cannot reach a tgt node (reach = NL-1)
+for k in KS:
+    for c in CS:
         cfg = dict(base, k=k, c=c)
         T, d = cfg['L'], cfg['d']
-        n_cap = T * k * (2 * c + 1)
+        c_eff = min(c, cfg['NL'] - 1) if PRUNE else c
+        n_cap = T * k * (2 * c_eff + 1)
         est_gb = n_cap * d * 4 * 11 / 1e9          # live activation buffers of the ntgt side (x, h0, qkv(3), t, o, h1, kv(2))
-        rec = dict(k=k, c=c, n_ntgt_cap=n_cap, est_activation_gb=round(est_gb, 1))
+        rec = dict(k=k, c=c, w_built=2 * c_eff + 1, n_ntgt_cap=n_cap, est_activation_gb=round(est_gb, 1))
         rec['token_chunked'] = est_gb > 48      # decoder budget: ntgt side runs in token chunks above 48 GB
         try:
             batch = synth.make_batch(cfg, tables, seed=k * 10 + c, device=dev)
-            r = synth.Runner(cfg, model, tables, dev, 'f16x3')
+            r = synth.Runner(cfg, model, tables, dev, 'f16x3', prune_unreachable=PRUNE)
             for _ in range(2 if est_gb < 100 else 1): r.step_resident(batch)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -35,7 +39,7 @@ for k in (8, 32, 128, 512):
             t_nn = sum(a.elapsed_time(b) for n, tag, a, b in L.TIMING if tag == 'nn_full')
             t_nc = sum(a.elapsed_time(b) for n, tag, a, b in L.TIMING if tag == 'nn_centre')
             L.TIMING = None
-            g = synth.build_token_graph(batch['nbr'], tables['n_d'], c, c)
+            g = synth.build_token_graph(batch['nbr'], tables['n_d'], c_eff, c_eff)
             n_ntgt, n_valid = g.counts()
             del g
             rec.update(status='ok', ms_per_step=ms, tokens_per_s=T / ms * 1e3, n_ntgt=n_ntgt, n_valid=n_valid)
@@ -50,4 +54,4 @@ for k in (8, 32, 128, 512):
             rec['status'] = 'OOM'
         torch.cuda.empty_cache()
         rows.append(rec); print(rec, flush=True)
-json.dump(rows, open('gpurun_out/r1_sweep_c5.json', 'w'), indent=1)
+json.dump(rows, open(os.environ.get('SWEEP_OUT', 'gpurun_out/r1_sweep_c5.json'), 'w'), indent=1)

@@ -267,6 +267,31 @@ def make_knn_case(name, T, knn, n_d, V, temp, metric, seed, with_missing):
     print(f"knn_{name}: mean p={float(p_t.mean()):.4f}")
 
 
+def make_knn_recompute_case(name, T, knn, n_d, d, V, temp, metric, index_file, seed, fp16_keys):
+    """metric_type l2 / ip: similarities recomputed from keys[knns] (knn_model.py:159-177), cosine index included."""
+    rng = np.random.RandomState(seed)
+    keys = rng.randn(n_d, d).astype(np.float16 if fp16_keys else np.float32)
+    queries = rng.randn(T, d).astype(np.float32)
+    ids = rng.randint(0, n_d, size=(T, knn)).astype(np.int64)
+    ids[rng.rand(T, knn) < 0.05] = -1
+    vals = rng.randint(4, V, size=(n_d,)).astype(np.int32)
+    targets = torch.from_numpy(rng.randint(4, V, size=(T,)).astype(np.int64))
+    for t in range(0, T, 2):
+        j = rng.randint(0, knn)
+        if ids[t, j] >= 0:
+            targets[t] = int(vals[ids[t, j]])
+    m = _FakeKNN(np.zeros((T, knn), np.float32), ids, vals, V, metric)
+    m.index_file, m.keys = index_file, keys
+    q = torch.from_numpy(queries)
+    p_t, recall = m.get_knn_prob(q, t=temp, targets=targets, return_recall=True)
+    _, sims, _ = m.get_knn_prob(q, t=temp, return_knn=True)
+    np.savez_compressed(os.path.join(OUT, f"knn_{name}.npz"), keys=keys, queries=queries, ids=ids, vals=vals,
+                        targets=targets.numpy(), temp=np.float64(temp), metric=np.array(metric),
+                        cosine=np.bool_("cosine" in index_file), V=V, p_target=p_t.numpy(), recall=recall.numpy(),
+                        sims=sims.numpy())
+    print(f"knn_{name}: mean p={float(p_t.mean()):.4f}")
+
+
 def make_scorer_case(name, B, L, d, V, cutoff, knn, lmbda, temp, seed):
     asm, _ = _ref_adaptive()
     torch.manual_seed(seed)
@@ -497,6 +522,12 @@ if __name__ == "__main__":
     make_pq_case("m16b", n=30, M=16, dsub=8, with_b=True, seed=1)
     make_knn_case("ip_t1", T=24, knn=16, n_d=2000, V=300, temp=1.0, metric="do_not_recomp_ip", seed=0, with_missing=True)
     make_knn_case("l2_t001", T=24, knn=32, n_d=2000, V=300, temp=0.01, metric="do_not_recomp_l2", seed=1, with_missing=False)
+    make_knn_recompute_case("recomp_l2", T=12, knn=16, n_d=500, d=64, V=300, temp=10.0, metric="l2",
+                            index_file="faiss_store.l2", seed=2, fp16_keys=True)
+    make_knn_recompute_case("recomp_ip", T=12, knn=16, n_d=500, d=64, V=300, temp=10.0, metric="ip",
+                            index_file="faiss_store.ip", seed=3, fp16_keys=False)
+    make_knn_recompute_case("recomp_cos", T=12, knn=16, n_d=500, d=96, V=300, temp=0.1, metric="ip",
+                            index_file="faiss_store.cosine", seed=4, fp16_keys=True)
     make_scorer_case("b1_knn", B=1, L=20, d=64, V=300, cutoff=[40, 120], knn=16, lmbda=0.25, temp=1.0, seed=0)
     make_scorer_case("b2_lm", B=2, L=12, d=64, V=300, cutoff=[40, 120], knn=8, lmbda=0.25, temp=1.0, seed=1)
     make_hgt_case("l2_c1", B=2, L=6, k=3, cl=1, cr=1, d=32, H=4, n_layers=2, seed=0)

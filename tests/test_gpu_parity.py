@@ -592,6 +592,31 @@ def test_token_chunked_ntgt_side_matches(math, dev):
         np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-5)
 
 
+@pytest.mark.parametrize("c,NL", [(3, 2), (3, 3), (2, 1), (2, 4)])
+def test_unreachable_context_pruning(c, NL, dev):
+    """Context nodes further than NL-1 chain hops from their centre cannot reach a tgt node: the pruned graph
+    (build_token_graph reach=NL-1, the default of Runner / evaluate) scores exactly like the reference's full
+    clusters -- checked against the oracle on the FULL graph and against the unpruned CUDA path."""
+    import copy
+    from gnnlm_b200 import synth
+    from tests.synth import run_oracle
+    cfg = dict(synth.CONFIGS["c3mini"], c=c, NL=NL, L=64, k=6, n_d=1 << 14)
+    model = synth.make_model(cfg)
+    data = synth.make_data(cfg, seed=3, device="cpu")
+    data["nbr"][0, :4, 0] = torch.tensor([0, 1, cfg["n_d"] - 1, cfg["n_d"] - 2])       # clusters clipped at both ends
+    ref = run_oracle((cfg, model, data))
+    d = synth.to_device({k: data[k] for k in ("nbr", "feats", "target", "knn_dists", "knn_ids")}, dev)
+    outs = []
+    for prune in (True, False):
+        r = synth.Runner(cfg, copy.deepcopy(model), data, dev, "fp32", prune_unreachable=prune)
+        lp = r.step_resident(d)[0].reshape(-1).cpu().numpy()
+        np.testing.assert_allclose(lp, ref["logprob"].numpy(), rtol=1e-4, atol=1e-4)
+        outs.append(lp)
+        g = r.sample_from(d["nbr"], d["feats"], d["target"], d["knn_dists"], d["knn_ids"])["net_input"]["graph"]
+        assert g.left_ctx == (min(c, NL - 1) if prune else c)
+    np.testing.assert_allclose(outs[0], outs[1], rtol=1e-6, atol=1e-6)
+
+
 @pytest.mark.parametrize("M,dsub,with_pre", [(128, 8, True), (64, 8, False), (32, 4, True), (16, 16, False)])
 def test_pq_encode_vs_oracle(M, dsub, with_pre, dev):
     """PQ encode (knn/pq_wrapper.py:131-167).  Codes equal the oracle's except where the two best
@@ -617,3 +642,86 @@ def test_pq_encode_vs_oracle(M, dsub, with_pre, dev):
     rec = codec.decode(torch.from_numpy(codes).to(dev)).cpu().numpy()
     ref_rec = mo.pq_decode(ref_codes, cen, A, b)
     assert np.abs(rec - ref_rec).mean() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------ kNN similarity recompute (8f-3)
+@pytest.mark.parametrize("case", ["recomp_l2", "recomp_ip", "recomp_cos"])
+def test_knn_sims_keys_golden(case, dev, golden_dir):
+    """metric_type l2 / ip (knn/knn_model.py:159-177) against vectors produced by the reference's get_knn_prob."""
+    from gnnlm_b200.knn_model import KNNModel
+    z = np.load(os.path.join(golden_dir, f"knn_{case}.npz"))
+    t = lambda a: torch.from_numpy(np.asarray(a)).to(dev)
+    metric, cosine = str(z["metric"]), bool(z["cosine"])
+    m = KNNModel(t(z["vals"]), vocab_size=int(z["V"]), metric_type=metric, keys=t(z["keys"]),
+                 index_file="faiss_store.cosine" if cosine else "faiss_store." + metric)
+    sims = m.similarities(t(z["queries"]), None, t(z["ids"])).cpu().numpy()
+    live = z["ids"] != -1
+    np.testing.assert_allclose(sims[live], z["sims"][live], rtol=1e-5, atol=1e-4)
+    m.set_search_results(None, t(z["ids"]))
+    p, rec = m.get_knn_prob(t(z["queries"]), t=float(z["temp"]), targets=t(z["targets"]), return_recall=True)
+    np.testing.assert_allclose(p.cpu().numpy(), z["p_target"], rtol=2e-4, atol=1e-7)
+    assert (rec.cpu().numpy() == z["recall"]).all()
+
+
+@pytest.mark.parametrize("M,dsub,opq,with_b", [(128, 8, True, True), (64, 8, True, False), (16, 4, False, False), (32, 16, True, True)])
+@pytest.mark.parametrize("metric", ["l2", "ip"])
+def test_knn_sims_pq_vs_oracle(M, dsub, opq, with_b, metric, dev):
+    """Similarities against the PQ-decoded keys (asymmetric distance computation on the codes) == the oracle's
+    recompute on pq_decode(codes)."""
+    from gnnlm_b200.knn_model import KNNModel
+    from gnnlm_b200.pq_codec import TorchPQCodec
+    from oracle import model_oracle as mo
+    rng = np.random.RandomState(M + dsub)
+    d, n_d, T, k = M * dsub, 4000, 37, 50
+    cen = rng.randn(M, 256, dsub).astype(np.float32)
+    A = np.linalg.qr(rng.randn(d, d))[0].astype(np.float32) if opq else None
+    b = (rng.randn(d).astype(np.float32) if with_b else np.zeros(0, np.float32)) if opq else None
+    codes = rng.randint(0, 256, size=(n_d, M)).astype(np.uint8)
+    q = rng.randn(T, d).astype(np.float32)
+    ids = rng.randint(0, n_d, size=(T, k)).astype(np.int64)
+    ids[rng.rand(T, k) < 0.05] = -1
+    keys_hat = mo.pq_decode(codes, cen, A, b if (b is not None and b.size) else None)
+    ref = mo.knn_sims(None, metric, torch.from_numpy(q), keys_hat, torch.from_numpy(ids)).numpy()
+    codec = TorchPQCodec(centroids=cen, A=A, b=b).to(dev)
+    vals = torch.zeros(n_d, dtype=torch.int32, device=dev)
+    m = KNNModel(vals, vocab_size=10, metric_type=metric, pq_codes=torch.from_numpy(codes).to(dev), quantizer=codec)
+    sims = m.similarities(torch.from_numpy(q).to(dev), None, torch.from_numpy(ids).to(dev)).cpu().numpy()
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(sims, ref, rtol=1e-4, atol=1e-5 * scale)
+
+
+@pytest.mark.parametrize("source", ["keys", "pq"])
+def test_whole_path_recomputed_similarities(source, dev):
+    """The path with --knn-sim-func style recompute: no dists input at all; kNN queries are the block's precomputed
+    features.  Per-token log-probs vs the oracle (which recomputes from the same keys)."""
+    import copy
+    from types import SimpleNamespace
+    from gnnlm_b200 import synth
+    from gnnlm_b200.knn_model import KNNModel
+    from gnnlm_b200.sequence_scorer import SequenceScorer
+    from oracle import model_oracle as mo
+    from tests.synth import oracle_model
+    cfg = dict(synth.CONFIGS["c1"], n_d=1 << 14, k_nn=32, L=96)
+    model = synth.make_model(cfg)
+    data = synth.make_data(cfg, seed=11, device="cpu")
+    q_ = model.decoder.tgt_quantizer
+    if source == "keys":
+        keys = (0.05 * torch.randn(cfg["n_d"], cfg["d"])).half()
+    else:       # the datastore keys as the PQ codes decode them
+        keys = torch.from_numpy(mo.pq_decode(data["codes"].numpy(), q_.centroids_torch.numpy(), q_.A.numpy(), None)).float() * 1.0
+    om = oracle_model(cfg, model)
+    batch = {"nbr": data["nbr"].numpy(), "offsets": data["positions"].numpy(), "tgt_feats": data["feats"].float(),
+             "target": data["target"], "codes": data["codes"].numpy(), "cl": cfg["c"], "cr": cfg["c"], "n_d": data["n_d"]}
+    temp = 20.0
+    knn = {"dists": torch.zeros(data["knn_ids"].shape), "ids": data["knn_ids"], "vals": data["vals"].long(), "lmbda": cfg["lmbda"],
+           "temperature": temp, "metric": "ip", "keys": keys.numpy(), "queries": "inner"}
+    ref = mo.eval_batch(om, batch, knn)
+    r = synth.Runner(cfg, copy.deepcopy(model), data, dev, "fp32")
+    kw = dict(keys=keys.to(dev)) if source == "keys" else dict(pq_codes=r.dstore.codes, quantizer=r.model.decoder.tgt_quantizer)
+    r.knn = KNNModel(r.dstore.vals, vocab_size=cfg["V"], metric_type="ip", k=cfg["k_nn"], **kw)
+    d = synth.to_device({k: data[k] for k in ("nbr", "feats", "target", "knn_ids")}, dev)
+    s = r.sample_from(d["nbr"], d["feats"], d["target"], None, d["knn_ids"])
+    lp, p, rec, _ = r.scorer.score_tokens(r.model, s, r.knn, temp, want_knn=True)
+    np.testing.assert_allclose(p.cpu().numpy(), ref["knn_prob"].numpy(), rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(lp.reshape(-1).cpu().numpy(), ref["logprob"].numpy(), rtol=1e-4, atol=1e-4)
+    assert (rec.cpu().numpy() == ref["knn_recall"].numpy()).all()

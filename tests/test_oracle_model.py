@@ -52,6 +52,21 @@ def test_knn_prob(case, golden_dir):
     np.testing.assert_allclose(full.numpy(), z["p_full"], rtol=1e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("case", ["recomp_l2", "recomp_ip", "recomp_cos"])
+def test_knn_sims_recompute(case, golden_dir):
+    """metric_type l2 / ip (knn_model.py:159-177): similarities from keys[knns], fp16 and fp32 keys, cosine index."""
+    z = np.load(os.path.join(golden_dir, f"knn_{case}.npz"))
+    q, ids, cosine = torch.from_numpy(z["queries"]), torch.from_numpy(z["ids"]), bool(z["cosine"])
+    sims = mo.knn_sims(None, str(z["metric"]), mo.knn_queries(q, cosine), z["keys"], ids, cosine)
+    live = z["ids"] != -1
+    np.testing.assert_allclose(sims.numpy()[live], z["sims"][live], rtol=1e-5, atol=1e-5)
+    assert (z["sims"][~live] == np.float32(-1e10)).all()
+    p, rec = mo.knn_target_prob(torch.zeros_like(sims), ids, torch.from_numpy(z["vals"]), torch.from_numpy(z["targets"]),
+                                float(z["temp"]), str(z["metric"]), queries=q, keys=z["keys"], cosine=cosine)
+    np.testing.assert_allclose(p.numpy(), z["p_target"], rtol=1e-4, atol=1e-7)
+    assert (rec.numpy() == z["recall"]).all()
+
+
 def test_scorer_knn_mix(golden_dir):
     z = np.load(os.path.join(golden_dir, "scorer_b1_knn.npz"))
     w = mo.adaptive_weights(_sd(z, "sd."))
