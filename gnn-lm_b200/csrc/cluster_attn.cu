@@ -23,13 +23,38 @@ constexpr int CA_THREADS = 256;
 
 __device__ __forceinline__ int ca_pos_to_id(int q, int nl) { return q == nl ? 0 : (q < nl ? q + 1 : q); }
 
-template <int C>
+// dot product of the lane's C features, reduced over the GROUP lanes that share a head (GROUP == 0: run-time `group`)
+template <int C, int GROUP>
 __device__ __forceinline__ float group_dot(const float (&a)[C], const float (&b)[C], int group) {
   float p = 0.f;
 #pragma unroll
   for (int c = 0; c < C; ++c) p = fmaf(a[c], b[c], p);
-  for (int o = group >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+  if constexpr (GROUP > 0) {
+#pragma unroll
+    for (int o = GROUP >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+  } else {
+    for (int o = group >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+  }
   return p;
+}
+
+// softmax over the (up to) three chain scores and the weighted sum of the matching V' rows
+template <int C>
+__device__ __forceinline__ void chain_mix(float s0, float s1, float s2, bool has_l, bool has_r, const float (&vp)[C],
+                                          const float (&vc)[C], const float (&vn)[C], float (&r)[C]) {
+  if (!has_l) s0 = -INFINITY;
+  if (!has_r) s2 = -INFINITY;
+  const float mx = fmaxf(s1, fmaxf(s0, s2));
+  const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx), e2 = __expf(s2 - mx);      // exp(-inf) = 0 for a missing side
+  const float inv = __fdividef(1.f, e0 + e1 + e2);
+  const float w0 = e0 * inv, w1 = e1 * inv, w2 = e2 * inv;
+#pragma unroll
+  for (int cc = 0; cc < C; ++cc) {
+    float a = w1 * vc[cc];
+    if (has_l) a = fmaf(w0, vp[cc], a);
+    if (has_r) a = fmaf(w2, vn[cc], a);
+    r[cc] = a;
+  }
 }
 
 template <typename OutT, int C>
@@ -65,9 +90,10 @@ __device__ __forceinline__ void store_out(OutT* __restrict__ p, const float (&r)
   }
 }
 
-// WMAX == 0 selects the centre-only variant (its own instantiation: 3 rows of K'/V' per cluster, a third of the registers of
-// the all-nodes form, so twice the resident warps)
-template <typename T, typename OutT, int C, int WMAX>
+// One warp per (cluster, 32*C-feature slice).  WMAX > 0: all nodes of clusters of at most WMAX (<= 3) nodes, every row
+// loaded up front.  WMAX == 0: centre-only variant (its own instantiation: 3 rows of K'/V' per cluster and a third of the
+// registers of the all-nodes form).  GROUP: lanes per head (0 = run time).
+template <typename T, typename OutT, int C, int WMAX, int GROUP>
 __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k,
                                                                   int64_t ldk, const T* __restrict__ v, int64_t ldv,
                                                                   const int32_t* __restrict__ node_base,
@@ -82,40 +108,37 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n_items; it += warps) {
     const int64_t c = it / n_slices;
-    const int col = ((int)(it % n_slices) * 32 + lane) * C;
+    const int col = ((int)(it - c * n_slices) * 32 + lane) * C;
     const int base = __ldg(node_base + c);
     const int w = __ldg(node_base + c + 1) - base;
     if (w <= 0) continue;                                    // invalid neighbour: no cluster
     const int nl = __ldg(cluster_nl + c);
     if constexpr (!centre_only) {
+      // rows in sorted (chain) order: position p holds node id base + ca_pos_to_id(p, nl)
+      const T* qb = q + (int64_t)base * ldq + col;
+      const T* kb = k + (int64_t)base * ldk + col;
+      const T* vb = v + (int64_t)base * ldv + col;
       float qq[WM][C], kk[WM][C], vv[WM][C];
 #pragma unroll
       for (int p = 0; p < WM; ++p) {
         if (p < w) {
-          const int64_t id = base + ca_pos_to_id(p, nl);
-          load_row<T, C>(q + id * ldq + col, qq[p]);
-          load_row<T, C>(k + id * ldk + col, kk[p]);
-          load_row<T, C>(v + id * ldv + col, vv[p]);
+          const int64_t id = ca_pos_to_id(p, nl);
+          load_row<T, C>(qb + id * ldq, qq[p]);
+          load_row<T, C>(kb + id * ldk, kk[p]);
+          load_row<T, C>(vb + id * ldv, vv[p]);
         }
       }
 #pragma unroll
       for (int p = 0; p < WM; ++p) {
         if (p < w) {
-          const float s1 = group_dot<C>(qq[p], kk[p], group);
-          float s0 = -INFINITY, s2 = -INFINITY;
-          if (p > 0) s0 = group_dot<C>(qq[p], kk[p > 0 ? p - 1 : 0], group);
-          if (p + 1 < WM && p + 1 < w) s2 = group_dot<C>(qq[p], kk[p + 1 < WM ? p + 1 : p], group);
-          const float mx = fmaxf(s1, fmaxf(s0, s2));
-          const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx), e2 = __expf(s2 - mx);
-          const float inv = 1.f / (e0 + e1 + e2);
+          constexpr int pl = 0;
+          const int pp = p > 0 ? p - 1 : pl, pn = p + 1 < WM ? p + 1 : p;
+          const bool has_l = p > 0, has_r = p + 1 < WM && p + 1 < w;
+          const float s1 = group_dot<C, GROUP>(qq[p], kk[p], group);
+          const float s0 = has_l ? group_dot<C, GROUP>(qq[p], kk[pp], group) : 0.f;
+          const float s2 = p + 1 < WM ? group_dot<C, GROUP>(qq[p], kk[pn], group) : 0.f;
           float r[C];
-#pragma unroll
-          for (int cc = 0; cc < C; ++cc) {
-            float a = e1 * vv[p][cc];
-            if (p > 0) a = fmaf(e0, vv[p > 0 ? p - 1 : 0][cc], a);
-            if (p + 1 < WM && p + 1 < w) a = fmaf(e2, vv[p + 1 < WM ? p + 1 : p][cc], a);
-            r[cc] = a * inv;
-          }
+          chain_mix<C>(s0, s1, s2, has_l, has_r, vv[pp], vv[p], vv[pn], r);
           store_out<OutT, C>(out + (int64_t)(base + ca_pos_to_id(p, nl)) * ldo + col, r, lo_off);
         }
       }
@@ -128,33 +151,26 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
       const int64_t idl = base + (has_l ? ca_pos_to_id(nl - 1, nl) : 0), idr = base + (has_r ? ca_pos_to_id(nl + 1, nl) : 0);
       load_row<T, C>(k + (int64_t)base * ldk + col, kk[1]);
       load_row<T, C>(v + (int64_t)base * ldv + col, vv[1]);
-      if (has_l) { load_row<T, C>(k + idl * ldk + col, kk[0]); load_row<T, C>(v + idl * ldv + col, vv[0]); }
-      if (has_r) { load_row<T, C>(k + idr * ldk + col, kk[2]); load_row<T, C>(v + idr * ldv + col, vv[2]); }
-      const float s1 = group_dot<C>(qq, kk[1], group);
-      float s0 = -INFINITY, s2 = -INFINITY;
-      if (has_l) s0 = group_dot<C>(qq, kk[0], group);
-      if (has_r) s2 = group_dot<C>(qq, kk[2], group);
-      const float mx = fmaxf(s1, fmaxf(s0, s2));
-      const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx), e2 = __expf(s2 - mx);
-      const float inv = 1.f / (e0 + e1 + e2);
+      load_row<T, C>(k + idl * ldk + col, kk[0]);            // an absent side re-reads the centre row (L1 hit), masked below
+      load_row<T, C>(v + idl * ldv + col, vv[0]);
+      load_row<T, C>(k + idr * ldk + col, kk[2]);
+      load_row<T, C>(v + idr * ldv + col, vv[2]);
+      const float s1 = group_dot<C, GROUP>(qq, kk[1], group);
+      const float s0 = group_dot<C, GROUP>(qq, kk[0], group);
+      const float s2 = group_dot<C, GROUP>(qq, kk[2], group);
       float r[C];
-#pragma unroll
-      for (int cc = 0; cc < C; ++cc) {
-        float a = e1 * vv[1][cc];
-        if (has_l) a = fmaf(e0, vv[0][cc], a);
-        if (has_r) a = fmaf(e2, vv[2][cc], a);
-        r[cc] = a * inv;
-      }
+      chain_mix<C>(s0, s1, s2, has_l, has_r, vv[0], vv[1], vv[2], r);
       store_out<OutT, C>(out + ci * ldo + col, r, lo_off);
     }
   }
 }
 
-// Clusters of any size (used for w > 3): walk the chain in sorted order with a three-row window of K' / V' in registers
-// and the next row's loads already in flight, so the register count (and with it the number of resident warps) does not
-// grow with w the way the fully unrolled form above does.
-template <typename T, typename OutT, int C>
-__global__ void __launch_bounds__(CA_THREADS, C == 4 ? 4 : 2) cluster_attn_window_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k,
+// Clusters of any size (used for w > 3): walk the chain in sorted order with a ring of four (Q, K', V') row slots --
+// position p reads slots p-1, p, p+1 while the loads of position p+2 are in flight -- so the register count (and the
+// number of resident warps) does not grow with w the way the fully unrolled form above does.  The ring is unrolled by
+// four so that every slot index is a compile-time constant (no register moves).
+template <typename T, typename OutT, int C, int GROUP>
+__global__ void __launch_bounds__(CA_THREADS) cluster_attn_window_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k,
                                                                          int64_t ldk, const T* __restrict__ v, int64_t ldv,
                                                                          const int32_t* __restrict__ node_base,
                                                                          const int32_t* __restrict__ cluster_nl, int64_t n_clusters,
@@ -165,93 +181,84 @@ __global__ void __launch_bounds__(CA_THREADS, C == 4 ? 4 : 2) cluster_attn_windo
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n_items; it += warps) {
     const int64_t c = it / n_slices;
-    const int col = ((int)(it % n_slices) * 32 + lane) * C;
+    const int col = ((int)(it - c * n_slices) * 32 + lane) * C;
     const int base = __ldg(node_base + c);
     const int w = __ldg(node_base + c + 1) - base;
     if (w <= 0) continue;
     const int nl = __ldg(cluster_nl + c);
-    float qc[C], qn[C], kp[C], kc[C], kn[C], vp[C], vc[C], vn[C];
-    {
-      const int64_t id = base + ca_pos_to_id(0, nl);
-      load_row<T, C>(q + id * ldq + col, qc);
-      load_row<T, C>(k + id * ldk + col, kc);
-      load_row<T, C>(v + id * ldv + col, vc);
-    }
-    if (w > 1) {
-      const int64_t id = base + ca_pos_to_id(1, nl);
-      load_row<T, C>(q + id * ldq + col, qn);
-      load_row<T, C>(k + id * ldk + col, kn);
-      load_row<T, C>(v + id * ldv + col, vn);
-    }
-#pragma unroll 1
-    for (int p = 0; p < w; ++p) {
-      float q2[C], k2[C], v2[C];
-      if (p + 2 < w) {                                        // in flight while position p is being computed
-        const int64_t id = base + ca_pos_to_id(p + 2, nl);
-        load_row<T, C>(q + id * ldq + col, q2);
-        load_row<T, C>(k + id * ldk + col, k2);
-        load_row<T, C>(v + id * ldv + col, v2);
-      }
-      const bool has_l = p > 0, has_r = p + 1 < w;
-      const float s1 = group_dot<C>(qc, kc, group);
-      float s0 = -INFINITY, s2 = -INFINITY;
-      if (has_l) s0 = group_dot<C>(qc, kp, group);
-      if (has_r) s2 = group_dot<C>(qc, kn, group);
-      const float mx = fmaxf(s1, fmaxf(s0, s2));
-      const float e0 = __expf(s0 - mx), e1 = __expf(s1 - mx), e2 = __expf(s2 - mx);
-      const float inv = 1.f / (e0 + e1 + e2);
-      float r[C];
+    const T* qb = q + (int64_t)base * ldq + col;
+    const T* kb = k + (int64_t)base * ldk + col;
+    const T* vb = v + (int64_t)base * ldv + col;
+    OutT* ob = out + (int64_t)base * ldo + col;
+    float Q[4][C], K[4][C], V[4][C];
 #pragma unroll
-      for (int cc = 0; cc < C; ++cc) {
-        float a = e1 * vc[cc];
-        if (has_l) a = fmaf(e0, vp[cc], a);
-        if (has_r) a = fmaf(e2, vn[cc], a);
-        r[cc] = a * inv;
+    for (int p = 0; p < 2; ++p) {
+      if (p < w) {
+        const int64_t id = ca_pos_to_id(p, nl);
+        load_row<T, C>(qb + id * ldq, Q[p]);
+        load_row<T, C>(kb + id * ldk, K[p]);
+        load_row<T, C>(vb + id * ldv, V[p]);
       }
-      store_out<OutT, C>(out + (int64_t)(base + ca_pos_to_id(p, nl)) * ldo + col, r, lo_off);
+    }
+    for (int p0 = 0; p0 < w; p0 += 4) {
 #pragma unroll
-      for (int cc = 0; cc < C; ++cc) {
-        kp[cc] = kc[cc]; vp[cc] = vc[cc];
-        kc[cc] = kn[cc]; vc[cc] = vn[cc]; qc[cc] = qn[cc];
-        kn[cc] = k2[cc]; vn[cc] = v2[cc]; qn[cc] = q2[cc];
+      for (int u = 0; u < 4; ++u) {
+        const int p = p0 + u;
+        if (p < w) {
+          const int sp = (u + 3) & 3, sn = (u + 1) & 3, s2_ = (u + 2) & 3;       // constants once unrolled
+          if (p + 2 < w) {                                      // in flight while position p is being computed
+            const int64_t id = ca_pos_to_id(p + 2, nl);
+            load_row<T, C>(qb + id * ldq, Q[s2_]);
+            load_row<T, C>(kb + id * ldk, K[s2_]);
+            load_row<T, C>(vb + id * ldv, V[s2_]);
+          }
+          const bool has_l = p > 0, has_r = p + 1 < w;
+          const float s1 = group_dot<C, GROUP>(Q[u], K[u], group);
+          const float s0 = group_dot<C, GROUP>(Q[u], K[sp], group);
+          const float s2 = group_dot<C, GROUP>(Q[u], K[sn], group);
+          float r[C];
+          chain_mix<C>(s0, s1, s2, has_l, has_r, V[sp], V[u], V[sn], r);
+          store_out<OutT, C>(ob + (int64_t)ca_pos_to_id(p, nl) * ldo, r, lo_off);
+        }
       }
     }
   }
 }
 
-template <typename T, typename OutT, int C, int WMAX>
-static int32_t launch_cluster(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                              const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl,
-                              int64_t n_clusters, int group, int n_slices, void* out, int64_t ldo, int lo_off,
-                              cudaStream_t st) {
+template <typename T, typename OutT, int C, int GROUP>
+static int32_t dispatch_w(int wmax, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                          const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl, int64_t n_clusters,
+                          int centre_only, int group, int n_slices, void* out, int64_t ldo, int lo_off, cudaStream_t st) {
   int64_t blocks = ceil_div(n_clusters * n_slices, CA_THREADS / 32);
-  const int64_t max_blocks = 148 * 8 * 8;
-  if (blocks > max_blocks) blocks = max_blocks;
-  cluster_attn_kernel<T, OutT, C, WMAX><<<(unsigned)blocks, CA_THREADS, 0, st>>>(
-      (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, node_base, valid_base, cluster_nl, n_clusters, group, n_slices,
-      (OutT*)out, ldo, lo_off);
+  if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
+#define GNNLM_CL(W)                                                                                                       \
+  cluster_attn_kernel<T, OutT, C, W, GROUP><<<(unsigned)blocks, CA_THREADS, 0, st>>>(                                     \
+      (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, node_base, valid_base, cluster_nl, n_clusters, group, n_slices, \
+      (OutT*)out, ldo, lo_off)
+  if (centre_only) GNNLM_CL(0);
+  else if (wmax <= 1) GNNLM_CL(1);
+  else if (wmax <= 3) GNNLM_CL(3);
+  else
+    cluster_attn_window_kernel<T, OutT, C, GROUP><<<(unsigned)blocks, CA_THREADS, 0, st>>>(
+        (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, node_base, cluster_nl, n_clusters, group, n_slices, (OutT*)out,
+        ldo, lo_off);
+#undef GNNLM_CL
   GNNLM_LAUNCH_CHECK("gnnlm_hgt_cluster_attn");
   return 0;
 }
 
 template <typename T, typename OutT, int C>
-static int32_t dispatch_w(int wmax, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
-                          const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl, int64_t n_clusters,
-                          int centre_only, int group, int n_slices, void* out, int64_t ldo, int lo_off, cudaStream_t st) {
-#define GNNLM_CL(W)                                                                                                       \
-  return launch_cluster<T, OutT, C, W>(q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, group, n_slices, \
-                                       out, ldo, lo_off, st)
-  if (centre_only) GNNLM_CL(0);
-  if (wmax <= 1) GNNLM_CL(1);
-  if (wmax <= 3) GNNLM_CL(3);
-#undef GNNLM_CL
-  int64_t blocks = ceil_div(n_clusters * n_slices, CA_THREADS / 32);
-  if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
-  cluster_attn_window_kernel<T, OutT, C><<<(unsigned)blocks, CA_THREADS, 0, st>>>(
-      (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, node_base, cluster_nl, n_clusters, group, n_slices, (OutT*)out, ldo,
-      lo_off);
-  GNNLM_LAUNCH_CHECK("gnnlm_hgt_cluster_attn");
-  return 0;
+static int32_t dispatch_group(int wmax, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                              const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl,
+                              int64_t n_clusters, int centre_only, int group, int n_slices, void* out, int64_t ldo, int lo_off,
+                              cudaStream_t st) {
+#define GNNLM_DG(G)                                                                                                          \
+  return dispatch_w<T, OutT, C, G>(wmax, q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, \
+                                   group, n_slices, out, ldo, lo_off, st)
+  if (group == 32) GNNLM_DG(32);
+  if (group == 16) GNNLM_DG(16);
+  GNNLM_DG(0);
+#undef GNNLM_DG
 }
 
 }  // namespace gnnlm
@@ -272,12 +279,7 @@ extern "C" int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void
   GNNLM_CHECK_ARG(max_cluster >= 1, GNNLM_E_SHAPE, "gnnlm_hgt_cluster_attn: max_cluster must be >= 1");
   GNNLM_CHECK_ARG(H > 0 && H <= 32 && (H & (H - 1)) == 0, GNNLM_E_UNSUPPORTED, "gnnlm_hgt_cluster_attn: H must be a power of two <= 32");
   const int64_t d = (int64_t)H * d_k;
-  // 16 B per lane per row; fp32 chains longer than 3 take 32 B per lane: half the shuffle / exp / address
-  // instructions per byte, which is what bounds the windowed kernel (issue-bound at ~55 % of HBM peak with 16 B)
-  static const bool wide_ok = [] { const char* e = getenv("GNNLM_CLUSTER_WIDE"); return !(e && e[0] == '0'); }();
-  const bool wide = dtype == GNNLM_F32 && !centre_only && max_cluster > 3 && wide_ok && d % 256 == 0 && d_k % 8 == 0 &&
-                    d_k / 8 <= 32 && 32 % (d_k / 8) == 0;
-  const int Cs = (dtype == GNNLM_F32 && !wide) ? 4 : 8;
+  const int Cs = dtype == GNNLM_F32 ? 4 : 8;                 // 16 B per lane per row
   // a warp covers 32*Cs features; a head (d_k features) must live inside one warp and heads may not straddle warps
   GNNLM_CHECK_ARG(d % (32 * Cs) == 0 && d_k % Cs == 0 && d_k / Cs <= 32 && 32 % (d_k / Cs) == 0, GNNLM_E_UNSUPPORTED,
                   "gnnlm_hgt_cluster_attn: unsupported (H=%d, d_k=%d) -- use gnnlm_hgt_edge_attn", H, d_k);
@@ -287,11 +289,8 @@ extern "C" int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void
   const int group = d_k / Cs, n_slices = (int)(d / (32 * Cs));
   cudaStream_t st = (cudaStream_t)stream;
 #define GNNLM_DW(T, OT, C)                                                                                                    \
-  return dispatch_w<T, OT, C>(max_cluster, q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, \
+  return dispatch_group<T, OT, C>(max_cluster, q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, \
                               group, n_slices, out, ldo, (int)d, st)
-  if (wide && out_dtype == GNNLM_F32) GNNLM_DW(float, float, 8);
-  if (wide && out_dtype == GNNLM_F16X2) GNNLM_DW(float, __half, 8);
-  if (wide) GNNLM_DW(float, __nv_bfloat16, 8);
   if (dtype == GNNLM_F32 && out_dtype == GNNLM_F32) GNNLM_DW(float, float, 4);
   if (dtype == GNNLM_F32 && out_dtype == GNNLM_F16X2) GNNLM_DW(float, __half, 4);
   if (out_dtype == GNNLM_F16X2) GNNLM_DW(__nv_bfloat16, __half, 8);
