@@ -30,7 +30,7 @@ SIGNATURES = {
     "gnnlm_split_f16": (_i32, [_p, _f32, _p, _p, _i64, _p]),
     "gnnlm_linear": (_i32, [_p, _i32, _i64, _p, _p, _f32, _i64, _p, _p, _i32, _i64, _p, _i32, _i64, _i64, _p, _i64, _i64, _i32, _p]),
     "gnnlm_linear_batched_f16x3": (_i32, [_p, _i64, _i64, _p, _p, _i64, _i64, _f32, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64,
-                                          _i64, _i64, _p]),
+                                          _i64, _i64, _i32, _p]),
     "gnnlm_lse_num_tiles": (_i64, [_i64, _i32]),
     "gnnlm_linear_lse": (_i32, [_p, _i32, _i64, _p, _p, _f32, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _p]),
     "gnnlm_lse_finish": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _p]),
@@ -43,7 +43,7 @@ SIGNATURES = {
     "gnnlm_hgt_causal_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _i64, _i64, _i64, _i32, _i32, _p, _i64, _f32, _i32, _p]),
     "gnnlm_heads_split_f16": (_i32, [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p]),
     "gnnlm_heads_transpose_split_f16": (_i32, [_p, _i64, _i64, _i32, _i32, _p, _p, _p]),
-    "gnnlm_causal_softmax_split": (_i32, [_p, _i64, _i64, _i32, _p, _p]),
+    "gnnlm_causal_softmax_split": (_i32, [_p, _i64, _i64, _i32, _i64, _p, _p]),
     "gnnlm_adapt_target": (_i32, [_p, _i64, _p, _i32, _p, _p, _p, _p, _p]),
     "gnnlm_knn_mix_nll": (_i32, [_p, _p, _f32, _p, _p, _i64, _p, _i32, _i64, _p, _f32, _f32, _f32, _p, _i64, _p, _i64, _p, _p, _p,
                                  _p, _i64, _p]),

@@ -33,7 +33,8 @@ int32_t gemm_tc_lse(const void* A, int32_t a_dtype, int64_t lda, const void* W, 
 
 int32_t gemm_tc_batched_f16x3(const void* A, int64_t lda, int64_t a_bs, const void* W_hi, const void* W_lo, int64_t ldw,
                               int64_t w_bs, float w_scale, const float* residual, int64_t ldr, int64_t r_bs, float* C,
-                              int64_t ldc, int64_t c_bs, int64_t nb, int64_t M, int64_t N, int64_t K, cudaStream_t st);
+                              int64_t ldc, int64_t c_bs, int64_t nb, int64_t M, int64_t N, int64_t K, int32_t causal,
+                              cudaStream_t st);
 
 }  // namespace gnnlm
 
@@ -104,10 +105,11 @@ extern "C" int32_t gnnlm_linear_lse(const void* A, int32_t a_dtype, int64_t lda,
 extern "C" int32_t gnnlm_linear_batched_f16x3(const void* A, int64_t lda, int64_t a_bs, const void* W_hi, const void* W_lo,
                                               int64_t ldw, int64_t w_bs, float w_scale, const float* residual, int64_t ldr,
                                               int64_t r_bs, float* C, int64_t ldc, int64_t c_bs, int64_t nb, int64_t M,
-                                              int64_t N, int64_t K, gnnlm_stream_t stream) {
+                                              int64_t N, int64_t K, int32_t causal, gnnlm_stream_t stream) {
   GNNLM_CHECK_ARG(A && W_hi && W_lo && C, GNNLM_E_ARG, "gnnlm_linear_batched_f16x3: null pointer");
+  GNNLM_CHECK_ARG(causal >= 0 && causal <= 2, GNNLM_E_ARG, "gnnlm_linear_batched_f16x3: causal must be 0, 1 or 2");
   GNNLM_CHECK_ARG(nb >= 1 && M >= 0 && N > 0 && K > 0 && ldc >= N && (!residual || ldr >= N) && w_scale > 0.f, GNNLM_E_SHAPE,
                   "gnnlm_linear_batched_f16x3: bad shape");
   return gemm_tc_batched_f16x3(A, lda, a_bs, W_hi, W_lo, ldw, w_bs, w_scale, residual, ldr, r_bs, C, ldc, c_bs, nb, M, N, K,
-                               (cudaStream_t)stream);
+                               causal, (cudaStream_t)stream);
 }

@@ -9,8 +9,11 @@
 //   causal_softmax   S [H, L, L] fp32 -> P split-fp16 [H, L, 2L]: row i is softmax over j in [max(0, i-ctx+1), i],
 //                    zero elsewhere (the masked products then contribute exact zeros to the GEMM)
 //
-// The full L x L score matrix is materialised per block (H*L*L*4 B = 302 MB at L = 3072, H = 8): 2x the causal
-// FLOPs and ~1.2 GB of HBM traffic per layer, which is still ~3x faster than the fp32 CUDA-core flash kernel.
+// Both GEMMs run with causal tile scheduling (gnnlm_linear_batched_f16x3 `causal`): S tiles entirely above the diagonal are
+// never computed (nor read here), and P V' contracts row pair r only over k < (r+1)*256, so P is written up to there only.
+//
+// The lower-triangular tiles of the L x L score matrix are materialised per block (H*L*L*4 B = 302 MB allocated at
+// L = 3072, H = 8, ~54 % of it touched), still ~3x faster than the fp32 CUDA-core flash kernel.
 #include "common.cuh"
 
 namespace gnnlm {
@@ -65,9 +68,10 @@ __global__ void __launch_bounds__(256) heads_transpose_kernel(const float* __res
   }
 }
 
-// one warp per (head, query row): two passes over the row (max, then exp + sum), third pass writes hi | lo
+// one warp per (head, query row), four columns per lane per step (L % 4 == 0): pass 1 keeps an online (max, sum) per lane,
+// pass 2 writes hi | lo quads.  Columns j > i are never read (their tiles may be unwritten).
 __global__ void __launch_bounds__(256) causal_softmax_kernel(const float* __restrict__ S, int64_t L, int64_t ctx, int H,
-                                                             __half* __restrict__ P) {
+                                                             int64_t k_tile, __half* __restrict__ P) {
   const int lane = threadIdx.x & 31;
   const int64_t rows = (int64_t)H * L;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -76,18 +80,43 @@ __global__ void __launch_bounds__(256) causal_softmax_kernel(const float* __rest
     const float* s = S + r * L;
     __half* p = P + r * 2 * L;
     const int64_t lo_j = (ctx > 0 && i + 1 > ctx) ? i + 1 - ctx : 0;
-    float mx = -INFINITY;
-    for (int64_t j = lo_j + lane; j <= i; j += 32) mx = fmaxf(mx, s[j]);
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int64_t j = lo_j + lane; j <= i; j += 32) sum += __expf(s[j] - mx);
-    sum = warp_sum(sum);
-    const float inv = 1.f / sum;
-    for (int64_t j = lane; j < L; j += 32) {
-      const float w = (j >= lo_j && j <= i) ? __expf(s[j] - mx) * inv : 0.f;
-      const __half a = __float2half_rn(w);
-      p[j] = a;
-      p[L + j] = __float2half_rn(w - __half2float(a));
+    float m = -INFINITY, l = 0.f;
+    for (int64_t j = (lo_j & ~(int64_t)3) + lane * 4; j <= i; j += 128) {
+      const float4 x4 = *reinterpret_cast<const float4*>(s + j);
+      float x[4] = {x4.x, x4.y, x4.z, x4.w};
+      float mx = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (j + e < lo_j || j + e > i) x[e] = -INFINITY;
+        mx = fmaxf(mx, x[e]);
+      }
+      if (mx > m) {                       // rescale the running sum (m == -inf: l is still 0)
+        l *= __expf(m - mx);
+        m = mx;
+      }
+      if (m > -INFINITY) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) l += __expf(x[e] - m);
+      }
+    }
+    const float M = warp_max(m);          // the diagonal is always valid, so M is finite
+    l = warp_sum(m > -INFINITY ? l * __expf(m - M) : 0.f);
+    const float inv = 1.f / l;
+    // the consumer (P V' with causal == 2) contracts row i over k < (i / k_tile + 1) * k_tile only
+    const int64_t j_end = k_tile > 0 ? min(L, (i / k_tile + 1) * k_tile) : L;
+    for (int64_t j = lane * 4; j < j_end; j += 128) {
+      float w[4] = {0.f, 0.f, 0.f, 0.f};
+      if (j <= i && j + 3 >= lo_j) {
+        const float4 x4 = *reinterpret_cast<const float4*>(s + j);
+        const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (j + e >= lo_j && j + e <= i) w[e] = __expf(x[e] - M) * inv;
+      }
+      uint2 hi, lo;
+      split4_f16(w[0], w[1], w[2], w[3], hi, lo);
+      *reinterpret_cast<uint2*>(p + j) = hi;
+      *reinterpret_cast<uint2*>(p + L + j) = lo;
     }
   }
 }
@@ -119,13 +148,14 @@ extern "C" int32_t gnnlm_heads_transpose_split_f16(const float* src, int64_t ld,
   return 0;
 }
 
-extern "C" int32_t gnnlm_causal_softmax_split(const float* S, int64_t L, int64_t intra_ctx, int32_t H, void* P,
+extern "C" int32_t gnnlm_causal_softmax_split(const float* S, int64_t L, int64_t intra_ctx, int32_t H, int64_t k_tile, void* P,
                                               gnnlm_stream_t stream) {
   GNNLM_CHECK_ARG(S && P, GNNLM_E_ARG, "gnnlm_causal_softmax_split: null pointer");
-  GNNLM_CHECK_ARG(L > 0 && H > 0, GNNLM_E_SHAPE, "gnnlm_causal_softmax_split: bad sizes");
+  GNNLM_CHECK_ARG(L > 0 && L % 4 == 0 && H > 0 && k_tile >= 0 && (uintptr_t)S % 16 == 0 && (uintptr_t)P % 8 == 0, GNNLM_E_SHAPE,
+                  "gnnlm_causal_softmax_split: L must be a multiple of 4 and S / P 16 B / 8 B aligned");
   int64_t blocks = ceil_div((int64_t)H * L, 8);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  causal_softmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(S, L, intra_ctx, H, (__half*)P);
+  causal_softmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(S, L, intra_ctx, H, k_tile, (__half*)P);
   GNNLM_LAUNCH_CHECK("gnnlm_causal_softmax_split");
   return 0;
 }

@@ -972,12 +972,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(F16_THREADS, 1)
 constexpr int F16S_STAGE = 2 * F16_OP_A + 2 * F16_OP_B;   // 32 KB
 constexpr int F16S_STAGES = 6;
 
+__host__ __device__ inline int64_t f16s_causal_tiles(int64_t n_p, int64_t n_n) {     // sum_{r < n_p} min(r + 1, n_n)
+  const int64_t full = n_p < n_n ? n_p : n_n;
+  return full * (full + 1) / 2 + (n_p - full) * n_n;
+}
+
 template <bool LSE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     gemm_f16s_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                      const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_blo, int64_t M_cap,
                      const int32_t* __restrict__ m_dev, int64_t N, int64_t K, EpiStore es, EpiLse el, float acc_scale, int nb,
-                     int64_t c_bs, int64_t r_bs) {
+                     int64_t c_bs, int64_t r_bs, int causal) {
   constexpr int STAGES = F16S_STAGES;
   constexpr uint32_t TX = 2u * F16S_STAGE;                                // both CTAs' four operand tiles -> leader
   constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
@@ -993,10 +998,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
   const bool leader = crank == 0;
   const int64_t M = live_rows(M_cap, m_dev);
   const int64_t n_m = (M + BLOCK_M - 1) / BLOCK_M, n_n = (N + BLOCK_N - 1) / BLOCK_N;
-  const int64_t per_batch = ((n_m + 1) / 2) * n_n;               // pair tiles of one batch entry
+  const int64_t n_p = (n_m + 1) / 2;                             // row pairs (2 * BLOCK_M = BLOCK_N rows each)
+  // causal == 1 (S = Q K'^T of causal attention): only column tiles c <= row pair r are ever read (column j <= row i),
+  //   so a batch entry has sum_r min(r + 1, n_n) tiles instead of n_p * n_n;
+  // causal == 2 (O = P V'): row pair r only contracts over k < (r + 1) * 2 * BLOCK_M (P is zero / unread beyond),
+  //   heaviest row pairs first.
+  const int64_t per_batch = causal == 1 ? f16s_causal_tiles(n_p, n_n) : n_p * n_n;   // pair tiles of one batch entry
   const int64_t total = per_batch * nb;                          // maps are 3-D: (k, row, batch)
   const int64_t pair0 = blockIdx.x >> 1, pair_stride = gridDim.x >> 1;
   const int n_kb = (int)((K + F16_BLOCK_K - 1) / F16_BLOCK_K);
+  // tile index -> (batch entry, row pair, column tile, k blocks); identical in every warp role
+  auto decode = [&](int64_t tile, int& bi, int64_t& r, int64_t& c, int& kbs) {
+    bi = (int)(tile / per_batch);
+    int64_t rem = tile % per_batch;
+    kbs = n_kb;
+    if (causal == 1) {
+      r = 0;
+      for (int64_t cnt = 1 < n_n ? 1 : n_n; rem >= cnt; cnt = (r + 1 < n_n ? r + 1 : n_n)) { rem -= cnt; ++r; }
+      c = rem;
+    } else if (causal == 2) {
+      r = n_p - 1 - rem / n_n;
+      c = rem % n_n;
+      const int64_t lim = ((r + 1) * 2 * BLOCK_M + F16_BLOCK_K - 1) / F16_BLOCK_K;
+      if (lim < kbs) kbs = (int)lim;
+    } else {
+      r = rem / n_n;
+      c = rem % n_n;
+    }
+  };
 
   auto sAh = [&](int s) { return smem + (size_t)s * F16S_STAGE; };
   auto sAl = [&](int s) { return smem + (size_t)s * F16S_STAGE + F16_OP_A; };
@@ -1038,10 +1067,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
       uint32_t phase = 0;
       const int half = (int)crank * (BLOCK_N / 2);
       for (int64_t tile = pair0; tile < total; tile += pair_stride) {
-        const int bi = (int)(tile / per_batch);
-        const int64_t rem = tile % per_batch;
-        const int m0 = (int)(((rem / n_n) * 2 + crank) * BLOCK_M), n0 = (int)((rem % n_n) * BLOCK_N) + half;
-        for (int kb = 0; kb < n_kb; ++kb) {
+        int bi, kbs;
+        int64_t r, c;
+        decode(tile, bi, r, c, kbs);
+        const int m0 = (int)((r * 2 + crank) * BLOCK_M), n0 = (int)(c * BLOCK_N) + half;
+        for (int kb = 0; kb < kbs; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_expect_tx(&full_bar[stage], TX);
           tma_load_3d_2sm(sAh(stage), &map_ah, kb * F16_BLOCK_K, m0, bi, &full_bar[stage]);
@@ -1063,7 +1093,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * BLOCK_N;
-        for (int kb = 0; kb < n_kb; ++kb) {
+        int bi, kbs;
+        int64_t r, c;
+        decode(tile, bi, r, c, kbs);
+        for (int kb = 0; kb < kbs; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint64_t dah = make_desc_sw64(smem_u32(sAh(stage))), dal = make_desc_sw64(smem_u32(sAl(stage)));
@@ -1087,8 +1120,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     for (int64_t tile = pair0; tile < total; tile += pair_stride, ++it) {
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      const int64_t bi = tile / per_batch, rem = tile % per_batch;
-      const int64_t m_blk = (rem / n_n) * 2 + crank, n_blk = rem % n_n;
+      int bi, kbs;
+      int64_t r, n_blk;
+      decode(tile, bi, r, n_blk, kbs);
+      const int64_t m_blk = r * 2 + crank;
       const int64_t m = m_blk * BLOCK_M + q * 32 + lane;
       const int64_t n_base = n_blk * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -1256,7 +1291,7 @@ static int32_t launch_f16x3(const CUtensorMap& ma, const CUtensorMap& mb, const 
 template <bool LSE>
 static int32_t launch_f16s(const CUtensorMap& mah, const CUtensorMap& mal, const CUtensorMap& mb, const CUtensorMap& mblo,
                            int64_t M, const int32_t* m_dev, int64_t N, int64_t K, const EpiStore& es, const EpiLse& el,
-                           float acc_scale, cudaStream_t st, int nb = 1, int64_t c_bs = 0, int64_t r_bs = 0) {
+                           float acc_scale, cudaStream_t st, int nb = 1, int64_t c_bs = 0, int64_t r_bs = 0, int causal = 0) {
   const size_t smem = (size_t)F16S_STAGES * F16S_STAGE + EPI_SMEM + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -1269,10 +1304,11 @@ static int32_t launch_f16s(const CUtensorMap& mah, const CUtensorMap& mal, const
     GNNLM_CUDA(cudaGetDevice(&dev));
     GNNLM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int64_t pairs = ceil_div(ceil_div(M, BLOCK_M), 2) * ceil_div(N, BLOCK_N) * nb;
+  const int64_t n_p = ceil_div(ceil_div(M, BLOCK_M), 2), n_n = ceil_div(N, BLOCK_N);
+  const int64_t pairs = (causal == 1 ? f16s_causal_tiles(n_p, n_n) : n_p * n_n) * nb;
   const int64_t max_pairs = n_sm / 2;
   const unsigned grid = 2u * (unsigned)(pairs < max_pairs ? pairs : max_pairs);
-  gemm_f16s_kernel<LSE><<<grid, 256, smem, st>>>(mah, mal, mb, mblo, M, m_dev, N, K, es, el, acc_scale, nb, c_bs, r_bs);
+  gemm_f16s_kernel<LSE><<<grid, 256, smem, st>>>(mah, mal, mb, mblo, M, m_dev, N, K, es, el, acc_scale, nb, c_bs, r_bs, causal);
   GNNLM_LAUNCH_CHECK("gemm_f16s");
   return 0;
 }
@@ -1336,14 +1372,15 @@ static int32_t f16s_maps(const char* who, const void* A, int64_t lda, const void
 // nb independent products C[b] = acc_scale * A[b] W[b]^T (+ residual[b]) in one launch (per-head attention GEMMs)
 int32_t gemm_tc_batched_f16x3(const void* A, int64_t lda, int64_t a_bs, const void* W_hi, const void* W_lo, int64_t ldw,
                               int64_t w_bs, float w_scale, const float* residual, int64_t ldr, int64_t r_bs, float* C,
-                              int64_t ldc, int64_t c_bs, int64_t nb, int64_t M, int64_t N, int64_t K, cudaStream_t st) {
+                              int64_t ldc, int64_t c_bs, int64_t nb, int64_t M, int64_t N, int64_t K, int32_t causal,
+                              cudaStream_t st) {
   if (M == 0 || nb == 0) return 0;
   tc::EpiStore es{nullptr, residual, ldr, C, ldc, 0, 0, N, N};
   tc::EpiLse el{};
   CUtensorMap mah, mal, mb, mblo;
   int32_t rc = f16s_maps("gnnlm_linear_batched_f16x3", A, lda, W_hi, W_lo, ldw, M, N, K, &mah, &mal, &mb, &mblo, nb, a_bs, w_bs);
   if (rc) return rc;
-  return tc::launch_f16s<false>(mah, mal, mb, mblo, M, nullptr, N, K, es, el, 1.f / w_scale, st, (int)nb, c_bs, r_bs);
+  return tc::launch_f16s<false>(mah, mal, mb, mblo, M, nullptr, N, K, es, el, 1.f / w_scale, st, (int)nb, c_bs, r_bs, causal);
 }
 
 int32_t gemm_tc_store(const void* A, int32_t a_dtype, int64_t lda, const void* W, const void* W_lo, float w_scale, int64_t ldw,

@@ -194,6 +194,9 @@ def causal_attn(q, k, v, B, Lb, intra_ctx, H, out, *, out_scale=1.0, accumulate=
     return out
 
 
+CAUSAL_K_TILE = 256      # rows per tile pair of the batched GEMM (2 * BLOCK_M): the contraction limit of `causal = 2`
+
+
 def causal_attn_gemm_supported(d: int, H: int, Lb: int) -> bool:
     dk = d // H
     return Lb % 8 == 0 and dk % 8 == 0 and Lb >= 256
@@ -219,13 +222,13 @@ def causal_attn_gemm(q, k, v, B, Lb, intra_ctx, H, out, *, out_scale=1.0, accumu
         S = torch.empty((H, Lb, Lb), device=dev, dtype=torch.float32)
         # all heads in one launch each: S[h] = Q_h K'_h^T, then O[:, h] (+)= out_scale * P_h V'_h
         L.call("gnnlm_linear_batched_f16x3", L.ptr(qs), 2 * dk, Lb * 2 * dk, L.ptr(kh), L.ptr(kl), dk, Lb * dk, 1.0, None, 0, 0,
-               L.ptr(S), Lb, Lb * Lb, H, Lb, Lb, dk, st(), tag="attn_qk")
+               L.ptr(S), Lb, Lb * Lb, H, Lb, Lb, dk, 1, st(), tag="attn_qk")      # causal = 1: tiles above the diagonal skipped
         P = torch.empty((H, Lb, 2 * Lb), **f16)
-        L.call("gnnlm_causal_softmax_split", L.ptr(S), Lb, intra_ctx, H, L.ptr(P), st())
+        L.call("gnnlm_causal_softmax_split", L.ptr(S), Lb, intra_ctx, H, CAUSAL_K_TILE, L.ptr(P), st())
         ob = out[rows]
         L.call("gnnlm_linear_batched_f16x3", L.ptr(P), 2 * Lb, Lb * 2 * Lb, L.ptr(vh), L.ptr(vl), Lb, dk * Lb, 1.0 / out_scale,
-               L.ptr(ob) if accumulate else None, ob.stride(0), dk, L.ptr(ob), ob.stride(0), dk, H, Lb, dk, Lb, st(),
-               tag="attn_pv")
+               L.ptr(ob) if accumulate else None, ob.stride(0), dk, L.ptr(ob), ob.stride(0), dk, H, Lb, dk, Lb, 2, st(),
+               tag="attn_pv")                                                     # causal = 2: k < 256 (r + 1) per row pair
     return out
 
 

@@ -151,10 +151,13 @@ int32_t gnnlm_linear(const void* A, int32_t a_dtype, int64_t lda, const void* W,
 /* nb independent products in ONE launch (the per-head GEMMs of the tensor-core causal attention):
  *   C[b] = (1 / w_scale) * A[b] W[b]^T (+ residual[b]),  b = 0..nb-1,   MATH_F16X3 arithmetic.
  * A[b] split-fp16 [M, 2K] at A + b*a_bs (fp16 elements, lda >= 2K); W_hi[b], W_lo[b] fp16 [N, K] at + b*w_bs;
- * C[b], residual[b] fp32 at + b*c_bs / b*r_bs (elements; a column offset when the heads share rows). */
+ * C[b], residual[b] fp32 at + b*c_bs / b*r_bs (elements; a column offset when the heads share rows).
+ * causal: 0 = plain; 1 = scores of causal attention: 256 x 256 output tiles entirely above the diagonal (first column >
+ *   last row) are skipped and left unwritten; 2 = probabilities x values: rows [256 r, 256 (r+1)) contract over
+ *   k < 256 (r+1) only (the caller guarantees A is zero -- or never meant to be read -- beyond that). */
 int32_t gnnlm_linear_batched_f16x3(const void* A, int64_t lda, int64_t a_bs, const void* W_hi, const void* W_lo, int64_t ldw,
                                    int64_t w_bs, float w_scale, const float* residual, int64_t ldr, int64_t r_bs, float* C,
-                                   int64_t ldc, int64_t c_bs, int64_t nb, int64_t M, int64_t N, int64_t K,
+                                   int64_t ldc, int64_t c_bs, int64_t nb, int64_t M, int64_t N, int64_t K, int32_t causal,
                                    gnnlm_stream_t stream);
 
 /* Same contraction, but instead of storing C the epilogue keeps, per row and per column tile,
@@ -239,12 +242,15 @@ int32_t gnnlm_hgt_causal_attn(const void* q, int64_t ldq, const void* k, int64_t
  *    (A operands, lo unused); a_style = 0: hi, lo fp16 [H, L, d_k] each (W operands, scale 1).
  *  gnnlm_heads_transpose_split_f16: src fp32 [L, H*d_k] -> hi, lo fp16 [H, d_k, L] (W operands of P V').
  *  gnnlm_causal_softmax_split: S fp32 [H, L, L] -> P split-fp16 [H, L, 2L]; row i = softmax over
- *    j in [max(0, i - intra_ctx + 1), i] (all j <= i when intra_ctx == 0), zeros elsewhere. */
+ *    j in [max(0, i - intra_ctx + 1), i] (all j <= i when intra_ctx == 0), zeros elsewhere -- written for
+ *    j < (i / k_tile + 1) * k_tile only when k_tile > 0 (256 for a `causal = 2` consumer), the whole row when 0;
+ *    S entries with j > i are never read (a `causal = 1` producer leaves tiles above the diagonal unwritten). */
 int32_t gnnlm_heads_split_f16(const float* src, int64_t ld, int64_t L, int32_t H, int32_t d_k, int32_t a_style, void* hi,
                               void* lo, gnnlm_stream_t stream);
 int32_t gnnlm_heads_transpose_split_f16(const float* src, int64_t ld, int64_t L, int32_t H, int32_t d_k, void* hi, void* lo,
                                         gnnlm_stream_t stream);
-int32_t gnnlm_causal_softmax_split(const float* S, int64_t L, int64_t intra_ctx, int32_t H, void* P, gnnlm_stream_t stream);
+int32_t gnnlm_causal_softmax_split(const float* S, int64_t L, int64_t intra_ctx, int32_t H, int64_t k_tile, void* P,
+                                   gnnlm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (5) Adaptive-softmax bookkeeping + kNN-LM interpolation + NLL -- replaces adapt_target

@@ -545,7 +545,8 @@ def test_linear_f16x3_split_format(M, N, K, dev):
     assert (ops.gather_rows(y, ids.to(dev)).data.cpu() == y.data.cpu()[ids.long()]).all()
 
 
-@pytest.mark.parametrize("B,L,H,d,ctx", [(1, 256, 8, 1024, 0), (2, 320, 8, 512, 0), (1, 512, 8, 1024, 100)])
+@pytest.mark.parametrize("B,L,H,d,ctx", [(1, 256, 8, 1024, 0), (2, 320, 8, 512, 0), (1, 512, 8, 1024, 100), (1, 1288, 8, 1024, 0),
+                                          (1, 3072, 8, 1024, 0), (1, 1024, 4, 512, 300)])
 def test_causal_attn_gemm_form(B, L, H, d, ctx, dev):
     """Tensor-core (3xFP16 GEMM) form of the tgt-intra-tgt attention vs the fp64 definition and vs the flash kernel."""
     _need_tc()
