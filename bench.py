@@ -137,6 +137,19 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def ncu_traffic(key, cfg):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind `key`, from the committed
+    `ncu --set full` capture of this workload (profiles/r1_ncu_traffic.json, written by profiles/ncu_metrics.py);
+    None when the capture does not cover this kernel / config."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if not os.path.exists(path) or cfg.get("L") != 3072 or cfg.get("k") != 32 or cfg.get("c") != 1:
+        return None
+    want = {"hgt_cluster_attn:nn_full": "cluster_attn_kernel<float, __half, 4, 3, 32>",
+            "hgt_cluster_attn:nn_centre": "cluster_attn_kernel<float, __half, 4, 0, 32>"}.get(key)
+    db = json.load(open(path))
+    return db[want]["dram_bytes"] if want in db else None
+
+
 def workload_name(cfg_name):
     from gnnlm_b200 import synth
     c = synth.CONFIGS[cfg_name]
@@ -271,7 +284,7 @@ def main():
                 alg = n_valid * 2 * d * s + T * d * s + T * d * 4 + (T + 1) * 4
             ach = alg / (kernels[key]["ms_per_launch"] * 1e-3) / 1e9
             roof = {"kernel": key, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": hbm_src,
-                    "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "algorithmic_bytes": alg,
+                    "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic(key, cfg), "algorithmic_bytes": alg,
                     "nominal_peak": 7700.0, "frac_of_nominal": ach / 7700.0,
                     "peak_note": "peak = driver-measured copy bandwidth (1:1 read:write); this kernel reads 3 bytes per "
                                  "byte written and can exceed it -- nominal HBM3e is 7.7 TB/s",

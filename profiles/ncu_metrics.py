@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""Print the roofline-relevant counters of every launch in an .ncu-rep (needs `ncu` on PATH)."""
+"""Print the roofline-relevant counters of every launch in an .ncu-rep (needs `ncu` on PATH).
+  ncu_metrics.py report.ncu-rep [--traffic-json out.json]
+--traffic-json merges {kernel name (template arguments kept, parameters dropped): dram bytes read + written per launch,
+duration} into out.json -- the file bench.py reads for `roofline.traffic`."""
 import csv
 import io
 import subprocess
@@ -19,3 +22,19 @@ for r in rows[2:]:
         if w in hdr:
             i = hdr.index(w)
             print(f"{w:70s} {r[i][:70]} {units[i]}")
+
+if "--traffic-json" in sys.argv:
+    import json, os
+    path = sys.argv[sys.argv.index("--traffic-json") + 1]
+    db = json.load(open(path)) if os.path.exists(path) else {}
+    to_bytes = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").strip()
+        tot = 0.0
+        for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(m)
+            tot += float(r[i]) * to_bytes[units[i]]
+        i = hdr.index("gpu__time_duration.sum")
+        us = float(r[i]) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[i], 1.0)
+        db[name] = {"dram_bytes": tot, "duration_us": us, "report": os.path.basename(sys.argv[1])}
+    json.dump(db, open(path, "w"), indent=1, sort_keys=True)
