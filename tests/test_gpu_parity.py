@@ -726,3 +726,85 @@ def test_whole_path_recomputed_similarities(source, dev):
     np.testing.assert_allclose(p.cpu().numpy(), ref["knn_prob"].numpy(), rtol=2e-3, atol=1e-6)
     np.testing.assert_allclose(lp.reshape(-1).cpu().numpy(), ref["logprob"].numpy(), rtol=1e-4, atol=1e-4)
     assert (rec.cpu().numpy() == ref["knn_recall"].numpy()).all()
+
+
+# ------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties_wiki103_shape(dev):
+    """BASELINE.json's headline shape (d=1024, H=8, V=267744, L=3072, k=32, c=1, M=128, 3 layers; datastore cut to 2^22
+    rows so that the test fits next to others) is too large for the CPU oracle, so parity is checked through
+    size-independent properties: CSR structure, PQ decode -> encode round trip, log-prob normalisation, the kNN
+    distribution summing to one, agreement of the CUDA-core fp32 path with the tensor-core parity mode, and invariance
+    to the order of a token's neighbours."""
+    _need_tc()
+    import copy
+    from gnnlm_b200 import synth
+    cfg = dict(synth.CONFIGS["c3"], n_d=1 << 22)
+    model = synth.make_model(cfg)
+    tables = synth.make_tables(cfg, device=dev)
+    batch = synth.make_batch(cfg, tables, device=dev)
+    T, k, w, d, V = cfg["L"], cfg["k"], 3, cfg["d"], cfg["V"]
+
+    # (1) graph structure in closed form (token_block_dataset.py:338-412,545-584)
+    g = synth.build_token_graph(batch["nbr"], tables["n_d"], cfg["c"], cfg["c"])
+    n_ntgt, n_valid = g.counts()
+    nbr = batch["nbr"].view(-1)
+    assert n_valid == int((nbr >= 0).sum())
+    size = (g.node_base[1:] - g.node_base[:-1]).long()
+    exp_size = torch.where(nbr >= 0, 1 + torch.minimum(nbr, torch.tensor(cfg["c"], device=dev)).clamp(min=0)
+                           + torch.minimum(tables["n_d"] - 1 - nbr, torch.tensor(cfg["c"], device=dev)).clamp(min=0), 0)
+    assert torch.equal(size, exp_size)
+    assert n_ntgt == int(exp_size.sum())
+    indptr = g.nn_indptr[:n_ntgt + 1].long()
+    assert int(indptr[-1]) == 3 * n_ntgt - 2 * n_valid                     # chain with self loops: 3w - 2 edges per cluster
+    deg = indptr[1:] - indptr[:-1]
+    assert int(deg.min()) >= 1 and int(deg.max()) <= 3
+    src = g.nn_indices[:int(indptr[-1])].long()
+    dst = torch.repeat_interleave(torch.arange(n_ntgt, device=dev), deg)
+    off = g.ntgt_row[:n_ntgt]
+    assert int((off[src] - off[dst]).abs().max()) <= 1                     # context = 1: datastore rows at distance <= 1
+    inter = g.inter_indptr.long()
+    assert torch.equal(inter[1:] - inter[:-1], (batch["nbr"].view(T, k) >= 0).sum(1))
+    centre = g.inter_indices[:n_valid].long()
+    assert torch.equal(off[centre], nbr[nbr >= 0])                         # tgt2ntgt edges start at the centre node
+
+    # (2) PQ decode -> encode round trip on every ntgt node (pq_wrapper.py:131-203): bit-exact codes
+    q = copy.deepcopy(model.decoder.tgt_quantizer).to(dev)
+    rows = g.ntgt_row[:n_ntgt]
+    x = q.gather_decode(tables["codes"], rows)
+    assert torch.equal(q.encode(x if torch.is_tensor(x) else x.float()), tables["codes"][rows])
+
+    # (3) whole path: CUDA-core fp32 vs 3xFP16 tensor-core mode
+    d_in = {k_: batch[k_] for k_ in ("nbr", "feats", "target", "knn_dists", "knn_ids")}
+    outs = {}
+    for math_ in ("fp32", "f16x3"):
+        r = synth.Runner(cfg, copy.deepcopy(model), tables, dev, math_)
+        lp, p, rec, dec_out = r.step_resident(d_in, want_knn=True)
+        outs[math_] = (lp.reshape(-1).float().cpu().numpy(), p.cpu().numpy(), rec.cpu().numpy(), r)
+        feat = dec_out[0]
+    np.testing.assert_allclose(outs["f16x3"][0], outs["fp32"][0], rtol=1e-4, atol=1e-4)
+    assert (outs["f16x3"][2] == outs["fp32"][2]).all()
+    nll = {m: -o[0].astype(np.float64).mean() for m, o in outs.items()}
+    assert abs(nll["f16x3"] - nll["fp32"]) < 0.01 / 16.8
+
+    # (4) normalisation: the full adaptive-softmax rows exponentiate to one and contain the fused target log-prob
+    r = outs["f16x3"][3]
+    dec = r.model.decoder
+    xs = feat.reshape(-1, d)[:16].float().contiguous()
+    tg = batch["target"].reshape(-1)[:16]
+    full = dec.adaptive_softmax.get_log_prob(xs.view(1, 16, d), None, dec.math_mode).view(16, V)
+    np.testing.assert_allclose(torch.logsumexp(full.double(), 1).cpu().numpy(), 0.0, atol=1e-4)
+    fused = dec.adaptive_softmax.target_log_prob(xs.view(1, 16, d), tg.view(1, 16), dec.math_mode).reshape(-1)
+    np.testing.assert_allclose(fused.cpu().numpy(), full[torch.arange(16), tg].cpu().numpy(), rtol=1e-4, atol=1e-4)
+
+    # (5) the kNN distribution over the vocabulary sums to one and its target column is p_knn
+    r.knn.set_search_results(batch["knn_dists"][:64], batch["knn_ids"][:64])
+    pf = r.knn.get_knn_prob(None, t=cfg["temp"], output_size=V)
+    np.testing.assert_allclose(pf.sum(1).cpu().numpy(), 1.0, atol=1e-5)
+    np.testing.assert_allclose(pf[torch.arange(64), batch["target"].reshape(-1)[:64]].cpu().numpy(), outs["f16x3"][1][:64],
+                               rtol=1e-4, atol=1e-7)
+
+    # (6) a token's neighbours are a set: permuting them changes nothing but summation order
+    perm = torch.randperm(k, device=dev)
+    d_perm = dict(d_in, nbr=batch["nbr"][:, :, perm].contiguous())
+    lp2 = r.step_resident(d_perm)[0].reshape(-1).float().cpu().numpy()
+    np.testing.assert_allclose(lp2, outs["f16x3"][0], rtol=1e-4, atol=1e-4)
