@@ -117,15 +117,80 @@ class GraphedScorer:
         return out
 
 
-def device_inputs(batch: dict, device) -> dict:
-    """The tensors of a collated batch the device step consumes (utils.move_to_cuda, fairseq/utils.py:43-67)."""
-    nb = lambda t: t.to(device, non_blocking=True)
-    d = {"nbr": nb(batch["nbr"]), "positions": nb(batch["positions"]), "src_tokens": nb(batch["net_input"]["src_tokens"]),
-         "target": nb(batch["target"]), "start_indices": nb(batch["start_indices"].to(torch.int32).reshape(-1))}
+def host_inputs(batch: dict) -> dict:
+    """The tensors of a collated batch the device step consumes (what utils.move_to_cuda moves, fairseq/utils.py:43-67)."""
+    d = {"nbr": batch["nbr"], "positions": batch["positions"], "src_tokens": batch["net_input"]["src_tokens"],
+         "target": batch["target"], "start_indices": batch["start_indices"].to(torch.int32).reshape(-1)}
     for k in ("feats", "knn_dists", "knn_ids"):
         if k in batch:
-            d[k] = nb(batch[k])
+            d[k] = batch[k]
     return d
+
+
+def device_inputs(batch: dict, device) -> dict:
+    return {k: v.to(device, non_blocking=True) for k, v in host_inputs(batch).items()}
+
+
+class Stager:
+    """Host -> device staging on a copy stream (pageable -> pinned -> device) into two reusable sets of device buffers, so
+    the H2D copy of step i+1 runs under the kernels of step i without touching the allocator (a fresh cross-stream
+    allocation per step ends in cudaMalloc, which synchronises the device).  Protocol per batch:
+    `s = stage(host)` (copy stream) ... `dev = wait(s)` (compute stream waits for the copy) ... launch ... `done(s)`."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.copy = torch.cuda.Stream(self.device)
+        self.slots = [None, None]            # (signature, {name: device tensor}, consumed event)
+        self.n = 0
+
+    def stage(self, host: dict):
+        i = self.n & 1
+        self.n += 1
+        sig = tuple((k, tuple(v.shape), v.dtype) for k, v in host.items())
+        if self.slots[i] is None or self.slots[i][0] != sig:
+            if self.slots[i] is not None:
+                self.slots[i][2].synchronize()
+            self.slots[i] = (sig, {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host.items()},
+                             torch.cuda.Event())
+            self.slots[i][2].record(torch.cuda.current_stream(self.device))
+        _, dev, consumed = self.slots[i]
+        ev = torch.cuda.Event()
+        with torch.cuda.stream(self.copy):
+            self.copy.wait_event(consumed)                   # the previous user of this slot has been launched and finished
+            for k, v in host.items():
+                dev[k].copy_(v if v.is_pinned() else v.pin_memory(), non_blocking=True)
+            ev.record(self.copy)
+        return i, dev, ev
+
+    def wait(self, staged):
+        _, dev, ev = staged
+        torch.cuda.current_stream(self.device).wait_event(ev)
+        return dev
+
+    def done(self, staged):
+        self.slots[staged[0]][2].record(torch.cuda.current_stream(self.device))
+
+
+def prefetch(items, to_host_inputs, device):
+    """Double-buffered input pipeline: yields (item, device tensors) while the NEXT item's tensors are already being staged,
+    so the H2D copy of step i+1 overlaps the kernels of step i.  The reference stages every batch synchronously inside the
+    loop (utils.move_to_cuda, fairseq_cli/eval_lm.py:217).  The yielded tensors are only valid until the next iteration."""
+    st = Stager(device)
+    it = iter(items)
+    try:
+        item = next(it)
+    except StopIteration:
+        return
+    nxt = (item, st.stage(to_host_inputs(item)))
+    while nxt is not None:
+        item, staged = nxt
+        try:
+            n_item = next(it)
+            nxt = (n_item, st.stage(to_host_inputs(n_item)))
+        except StopIteration:
+            nxt = None
+        yield item, st.wait(staged)
+        st.done(staged)
 
 
 @torch.no_grad()
@@ -151,9 +216,8 @@ def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, sc
     step = GraphedScorer(score) if cuda_graph else score
     torch.cuda.synchronize(device)
     t0 = time.perf_counter()
-    for ids in batches(dataset, lo, hi, max_sentences):
-        batch = dataset.collater([dataset[i] for i in ids])
-        inp = device_inputs(batch, device)
+    collated = (dataset.collater([dataset[i] for i in ids]) for ids in batches(dataset, lo, hi, max_sentences))
+    for batch, inp in prefetch(collated, host_inputs, device):
         _, _, _, dec_out = step(inp)
         ntok += batch["ntokens"]
         if dstore_writer is not None:                           # sequence_scorer.py:180-183 + eval_lm.py:223-244

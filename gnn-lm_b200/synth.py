@@ -130,6 +130,7 @@ class Runner:
         self.acc = torch.zeros(2, dtype=torch.float64, device=device)
         from .eval_lm import GraphedScorer
         self._graphed = GraphedScorer(self._score, device=device)
+        self._stager = None
 
     def sample_from(self, nbr, feats, target, dists, ids):
         c = self.c
@@ -152,6 +153,28 @@ class Runner:
         if cuda_graph and not want_knn:
             return self._graphed(inp)
         return self._score(inp, want_knn=want_knn)
+
+    def run_host(self, host_batches, steps: int, cuda_graph=False):
+        """`steps` e2e steps over pinned host batches (rotated), inputs double-buffered: step i is launched, then the H2D
+        copy of step i+1 is issued on a copy stream (it runs under the kernels of step i), then the step's result (the
+        16 B accumulator) is read back.  Returns the last read-back."""
+        from .eval_lm import Stager
+        if self._stager is None:
+            self._stager = Stager(self.device)
+        st, n, out = self._stager, len(host_batches), None
+        pick = lambda i: {k: host_batches[i % n][k] for k in self.KEYS}
+        staged = st.stage(pick(0))
+        for i in range(steps):
+            inp = st.wait(staged)
+            if cuda_graph:
+                self._graphed(inp)
+            else:
+                self._score(inp)
+            st.done(staged)
+            if i + 1 < steps:
+                staged = st.stage(pick(i + 1))
+            out = self.acc.cpu()      # D2H read of the step's result, synchronises
+        return out
 
     def step_host(self, host_batch: dict, cuda_graph=False):
         """host_batch: pinned CPU tensors.  Copies in, scores, reads the scalar result back."""
