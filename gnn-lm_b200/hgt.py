@@ -181,7 +181,9 @@ class HGTLayer(nn.Module):
     # ------------------------------------------------------------------ building blocks
     def _out(self, P, tau, t_agg, h_in, n_dev):
         """LayerNorm(A-linear(t) + h) (hgt.py:401-405).  The residual add is fused into the LayerNorm kernel (fp32 sum
-        before the statistics) instead of the GEMM epilogue: same bytes, no load latency inside the GEMM."""
+        before the statistics) instead of the GEMM epilogue.  Measured on the wiki103 shape: moving it into the epilogue
+        halves LayerNorm (1.0 -> 0.5 ms per step) but makes the epilogue the GEMM's bottleneck (a split-fp16 residual
+        turns the 1.3 ms A-linear into 3.4 ms, an fp32 one into 1.7 ms; profiles/gemm_probe_split.py)."""
         o = _lin(t_agg, P["a"][tau], P["math"], m_dev=n_dev)
         g, b, eps = P["ln"][tau]
         act = act_dtype(P["math"])
