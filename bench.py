@@ -153,7 +153,8 @@ def ncu_traffic(key, cfg):
 def workload_name(cfg_name):
     from gnnlm_b200 import synth
     c = synth.CONFIGS[cfg_name]
-    return (f"{cfg_name}: wiki103-shape GNN+kNN eval" if cfg_name == "c3" else f"{cfg_name}") + \
+    names = {"c1": "tiny", "c2": "enwik8-shape", "c3": "wiki103-shape", "c4": "one-billion-word-shape"}
+    return f"{cfg_name}: {names.get(cfg_name, cfg_name)} GNN+kNN eval" + \
         f" d={c['d']} H={c['H']} V={c['V']} B={c['B']}xL={c['L']} k={c['k']} c={c['c']} M={c['M']} layers={c['NL']} k_nn={c['k_nn']}"
 
 

@@ -25,6 +25,11 @@ CONFIGS = {
     # configs[2]: wiki103 shape (the headline metric's config)
     "c3": dict(d=1024, H=8, V=267744, cutoff=[20000, 60000], tied=True, B=1, L=3072, k=32, c=1, M=128, NL=3,
                n_d=103227021, k_nn=1024, lmbda=0.25, temp=1.0),
+    # configs[3]: One-Billion-Word shape (vocab 793,471, SURVEY.md 8 C4: d=1024 inferred from the +0.02B parameters; adaptive
+    # cutoffs are the checkpoint's -- 60000/160000 assumed; ~0.8 G datastore tokens x 128 B = 98 GB of codes in HBM).  The
+    # reference batches this corpus by sentence (--sample-break-mode eos); blocks here are packed to 3072 tokens.
+    "c4": dict(d=1024, H=8, V=793471, cutoff=[60000, 160000], tied=True, B=1, L=3072, k=32, c=1, M=128, NL=3,
+               n_d=768 * 1000 * 1000, k_nn=1024, lmbda=0.25, temp=1.0),
     # a small wiki103-like problem for tests (adaptive, tied, 3 layers)
     "c3mini": dict(d=1024, H=8, V=30000, cutoff=[4000, 12000], tied=True, B=1, L=192, k=8, c=1, M=128, NL=3,
                    n_d=1 << 18, k_nn=128, lmbda=0.25, temp=1.0),
