@@ -9,8 +9,9 @@ What changes: the reference builds a DGL graph per block in Python inside DataLo
 ships codes/edges over PCIe; here __getitem__ only slices the *inputs* of graph assembly (neighbour
 ids, fp16 features, tokens -- contiguous slices in `none` break mode) and the graph is assembled on
 the device from the HBM-resident datastore (`DeviceDatastore`) by graph_build.cu / pq_decode.cu.
-Only `--sample-break-mode none` (the wiki103 / enwik8 scripts) is implemented; `eos` mode
-(one_billion scripts) is a ragged variant left for a later round."""
+Every `--sample-break-mode` is sliced (`none` for the wiki103 / enwik8 scripts, `eos` for one_billion); blocks of
+different lengths are never padded into one batch (the reference's graph decoder cannot take padded batches either,
+transformer.py:975) -- eval_lm.batches groups equal lengths, across the whole shard when asked to."""
 import json
 import os
 from typing import List, Optional, Tuple, Union
@@ -51,16 +52,52 @@ class DeviceDatastore:
                    torch.from_numpy(np.ascontiguousarray(vals)).to(device))
 
 
+def get_slice_indices(sizes, break_mode: Optional[str], block_size: int, document_sep_len: int = 1) -> np.ndarray:
+    """Block boundaries [n_blocks, 2] over the flat token stream (token_block_utils_fast.pyx:22-105):
+    none = fixed block_size windows; eos = one sentence per block; complete = whole sentences packed greedily up to
+    block_size (an oversize sentence is its own block); complete_doc = the same inside documents, where a sentence of
+    document_sep_len tokens separates documents and blocks of <= 1 token are dropped."""
+    sizes = np.asarray(sizes, dtype=np.int64).reshape(-1)
+    cum = np.concatenate([np.zeros(1, np.int64), np.cumsum(sizes)])
+    total = int(cum[-1])
+    if break_mode is None or break_mode == "none":
+        starts = np.arange(0, total, block_size, dtype=np.int64)
+        return np.stack([starts, np.minimum(starts + block_size, total)], 1)
+    if break_mode == "eos":
+        return np.stack([cum[:-1], cum[1:]], 1)
+    if break_mode not in ("complete", "complete_doc"):
+        raise ValueError("Invalid break_mode: " + str(break_mode))
+    n = len(sizes)
+    if break_mode == "complete":
+        docs, keep = [(0, n)], 0
+    else:
+        seps = np.flatnonzero(sizes == document_sep_len)
+        edges = np.concatenate([[-1], seps, [n]])
+        docs, keep = [(int(a) + 1, int(b)) for a, b in zip(edges[:-1], edges[1:]) if b > a + 1], 1
+    out = []
+    for a, b in docs:
+        i = a
+        while i < b:
+            j = int(np.searchsorted(cum, cum[i] + block_size, side="right")) - 1      # last boundary within block_size
+            j = min(max(j, i + 1), b)
+            if cum[j] - cum[i] > keep:
+                out.append((int(cum[i]), int(cum[j])))
+            i = j
+    return np.asarray(out, dtype=np.int64).reshape(-1, 2)
+
+
 class GraphTokenBlockDataset:
-    """token_block_dataset.py:172-333 for break_mode='none' over a flat token stream."""
+    """token_block_dataset.py:172-333 over a flat token stream.  `sizes` (sentence lengths, summing to len(tokens)) is
+    needed by every break mode except `none`."""
 
     def __init__(self, tokens: np.ndarray, block_size: int, pad: int, eos: int, neighbor_offsets: np.ndarray,
                  n_datastore: int, neighbor_context: Union[int, Tuple[int, int]] = 1,
                  precompute_feats: Optional[np.ndarray] = None, invalid_neighbor_context: int = 0,
                  context_window: int = 0, intra_context: int = 0, knn_dists: Optional[np.ndarray] = None,
-                 knn_ids: Optional[np.ndarray] = None, break_mode: str = "none", deprecated: bool = False):
-        if break_mode not in (None, "none"):
-            raise NotImplementedError("only --sample-break-mode none")
+                 knn_ids: Optional[np.ndarray] = None, break_mode: str = "none", deprecated: bool = False,
+                 sizes: Optional[np.ndarray] = None, document_sep_len: int = 1):
+        if break_mode not in (None, "none") and sizes is None:
+            raise ValueError(f"--sample-break-mode {break_mode} needs the sentence lengths (sizes=...)")
         if deprecated:
             raise NotImplementedError("--deprecated (dedup) graph build is a 'next' row (SURVEY.md 8f-4)")
         self.tokens = tokens
@@ -77,7 +114,11 @@ class GraphTokenBlockDataset:
         self.max_intra_context = intra_context
         self.knn_dists, self.knn_ids = knn_dists, knn_ids
         n = len(tokens)
-        self.slice_indices = [(s, min(s + block_size, n)) for s in range(0, n, block_size)]   # token_block_utils_fast.pyx:22-35
+        if sizes is not None and int(np.sum(sizes)) != n:
+            raise ValueError("sizes must sum to the number of tokens")
+        sl = get_slice_indices(np.array([n]) if sizes is None else sizes, break_mode, block_size, document_sep_len)
+        self.break_mode = break_mode or "none"
+        self.slice_indices = [(int(s), int(e)) for s, e in sl]
         self.sizes = np.array([e - s for s, e in self.slice_indices])
 
     def __len__(self):

@@ -27,13 +27,26 @@ def shard_range(n_blocks: int, rank: int, world: int):
     return lo, hi
 
 
-def batches(dataset: GraphTokenBlockDataset, lo: int, hi: int, max_sentences: int):
-    """Equal-length blocks batched together in order; a ragged last block is its own batch."""
+def batches(dataset: GraphTokenBlockDataset, lo: int, hi: int, max_sentences: int, max_tokens: Optional[int] = None,
+            bucket_by_length: bool = False):
+    """Batches of equal-length blocks (never padded), at most max_sentences blocks / max_tokens tokens each.
+    In order (consecutive blocks; a ragged last block is its own batch), or -- bucket_by_length, for sentence-per-block
+    corpora (--sample-break-mode eos) where consecutive lengths rarely match -- grouped by length over the whole shard,
+    shortest first (the total score does not depend on the order)."""
+    def length(i):
+        return int(dataset.sizes[i]) + (0 if (dataset.context_window == 0 or i == 0) else
+                                         min(dataset.context_window, dataset.slice_indices[i][0]))
+
+    def full(cur, n):
+        return len(cur) >= max_sentences or (max_tokens is not None and (len(cur) + 1) * n > max_tokens)
+
+    order = range(lo, hi)
+    if bucket_by_length:
+        order = sorted(order, key=lambda i: (length(i), i))
     cur, cur_len = [], None
-    for i in range(lo, hi):
-        n = int(dataset.sizes[i]) + (0 if (dataset.context_window == 0 or i == 0) else
-                                     min(dataset.context_window, dataset.slice_indices[i][0]))
-        if cur and (n != cur_len or len(cur) >= max_sentences):
+    for i in order:
+        n = length(i)
+        if cur and (n != cur_len or full(cur, n)):
             yield cur
             cur = []
         cur.append(i)
@@ -197,7 +210,8 @@ def prefetch(items, to_host_inputs, device):
 def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, scorer: SequenceScorer, *,
              knn_dstore=None, temperature: float = 1.0, max_sentences: int = 1, device="cuda", rank: int = 0,
              world_size: int = 1, process_group=None, log=None, dstore_writer: Optional[DstoreWriter] = None,
-             knn_keytype: Optional[str] = None, cuda_graph: bool = False, prune_unreachable: bool = True) -> dict:
+             knn_keytype: Optional[str] = None, cuda_graph: bool = False, prune_unreachable: bool = True,
+             max_tokens: Optional[int] = None, bucket_by_length: bool = False) -> dict:
     """`cuda_graph=True` replays one captured CUDA graph per batch shape instead of launching the ~100 kernels of a
     step one by one (same kernels, same results; pays off when blocks are small enough to be launch-bound).
     `prune_unreachable` drops context nodes further than graph_layer-1 hops from their centre (graph.build_token_graph
@@ -216,7 +230,10 @@ def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, sc
     step = GraphedScorer(score) if cuda_graph else score
     torch.cuda.synchronize(device)
     t0 = time.perf_counter()
-    collated = (dataset.collater([dataset[i] for i in ids]) for ids in batches(dataset, lo, hi, max_sentences))
+    if bucket_by_length and dstore_writer is not None:
+        raise ValueError("--save-knnlm-dstore writes keys in corpus order: do not bucket by length")
+    collated = (dataset.collater([dataset[i] for i in ids])
+                for ids in batches(dataset, lo, hi, max_sentences, max_tokens, bucket_by_length))
     for batch, inp in prefetch(collated, host_inputs, device):
         _, _, _, dec_out = step(inp)
         ntok += batch["ntokens"]

@@ -203,3 +203,42 @@ def build_batch_vectorised(neighbor_idxs: np.ndarray, offsets: np.ndarray, n_dat
     inter_indices = base[:-1][valid].astype(np.int32)
     return {"n_tgt": B * L, "n_ntgt": n_ntgt, "ntgt_offsets": node_off,
             "nn_csr": (indptr, indices), "inter_csr": (inter_indptr, inter_indices)}
+
+
+# --------------------------------------------------------------------------- block boundaries
+def slice_indices(sizes, break_mode, block_size: int, document_sep_len: int = 1) -> np.ndarray:
+    """Block boundaries [n_blocks, 2] over the flat token stream for --sample-break-mode none / complete /
+    complete_doc / eos (fairseq/data/token_block_utils_fast.pyx:22-105).  Plain loops on purpose."""
+    sizes = [int(x) for x in sizes]
+    total = sum(sizes)
+    out = []
+    if break_mode is None or break_mode == "none":                      # :22-35
+        n = -(-total // block_size)
+        out = [(i * block_size, min(i * block_size + block_size, total)) for i in range(n)]
+    elif break_mode == "eos":                                           # :96-100: one sentence per block
+        pos = 0
+        for sz in sizes:
+            out.append((pos, pos + sz))
+            pos += sz
+    elif break_mode in ("complete", "complete_doc"):                    # :63-95: whole sentences up to block_size
+        doc = break_mode == "complete_doc"
+        keep = 1 if doc else 0                                          # complete_doc drops blocks of <= 1 token
+        tok, cur, i = 0, 0, 0
+        while i < len(sizes):
+            fits = cur + sizes[i] <= block_size or cur == 0
+            if fits and not (doc and sizes[i] == document_sep_len):
+                cur += sizes[i]
+                i += 1
+            else:
+                if cur > keep:
+                    out.append((tok, tok + cur))
+                tok += cur
+                cur = 0
+                if doc and sizes[i] == document_sep_len:               # an empty sentence ends the document
+                    tok += sizes[i]
+                    i += 1
+        if cur > keep:
+            out.append((tok, tok + cur))
+    else:
+        raise ValueError("Invalid break_mode: " + str(break_mode))
+    return np.asarray(out, dtype=np.int64).reshape(-1, 2)

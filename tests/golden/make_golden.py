@@ -292,6 +292,54 @@ def make_knn_recompute_case(name, T, knn, n_d, d, V, temp, metric, index_file, s
     print(f"knn_{name}: mean p={float(p_t.mean()):.4f}")
 
 
+def _ref_slice_indices():
+    """fairseq/data/token_block_utils_fast.pyx:22-105 is Cython whose body is plain Python once the C declarations are
+    stripped: drop `cdef` lines / decorators / casts, turn the two `cdef`/`cpdef` signatures into `def`s, and exec it."""
+    import re
+    from itertools import chain
+    from math import ceil
+    src = open(os.path.join(REF, "fairseq/data/token_block_utils_fast.pyx")).read()
+    start = src.index("cdef np.ndarray[DTYPE_t, ndim=2] _get_slice_indices_none_mode")
+    end = src.index("cpdef np.ndarray[DTYPE_t, ndim=2] _get_block_to_dataset_index_fast")
+    out = []
+    for line in src[start:end].splitlines():
+        st = line.strip()
+        if st.startswith("@cython"):
+            continue
+        m = re.match(r"^c?p?def np\.ndarray\[DTYPE_t, ndim=\d\] (\w+)\((.*)\):$", line)
+        if m:
+            args = ", ".join(a.strip().split(" ")[-1] for a in re.sub(r"\[[^\]]*\]", "", m.group(2)).split(","))
+            out.append(f"def {m.group(1)}({args}):")
+            continue
+        if st.startswith("cdef "):
+            d = re.match(r"^cdef\s+[\w\.]+(?:\[[^\]]*\])?\s+(\w+)\s*=\s*(.*)$", st)
+            if d:              # typed declaration with an initialiser -> plain assignment
+                out.append(line[:len(line) - len(line.lstrip())] + d.group(1) + " = " + d.group(2))
+            continue
+        out.append(line)
+    code = "\n".join(out).replace("<DTYPE_t> ", "").replace("<double> ", "")
+    ns = {"np": np, "DTYPE": np.int64, "chain": chain, "ceil": ceil}
+    exec(code, ns)
+    return ns["_get_slice_indices_fast"]
+
+
+def make_slice_cases():
+    """--sample-break-mode none / complete / complete_doc / eos block boundaries for a few sentence-length vectors."""
+    f = _ref_slice_indices()
+    rng = np.random.RandomState(0)
+    out = {}
+    cases = {"short": rng.randint(1, 12, size=40), "long": rng.randint(1, 60, size=25), "one": np.array([7]),
+             "docs": np.array([5, 9, 1, 4, 4, 1, 1, 30, 2, 1, 8])}
+    for name, sizes in cases.items():
+        sizes = sizes.astype(np.int64)
+        out[f"{name}.sizes"] = sizes
+        for mode in ("none", "complete", "complete_doc", "eos"):
+            for bs in (16, 50):
+                out[f"{name}.{mode}.{bs}"] = np.asarray(f(sizes, mode, bs, 1), dtype=np.int64).reshape(-1, 2)
+    np.savez_compressed(os.path.join(OUT, "slices.npz"), **out)
+    print("slices:", len(out), "arrays")
+
+
 def make_scorer_case(name, B, L, d, V, cutoff, knn, lmbda, temp, seed):
     asm, _ = _ref_adaptive()
     torch.manual_seed(seed)
@@ -510,6 +558,7 @@ def make_hgt_case(name, B, L, k, cl, cr, d, H, n_layers, seed, stress=True):
 
 
 if __name__ == "__main__":
+    make_slice_cases()
     make_edges_doctest()
     make_graph_case("c1_c1", L=24, k=4, n_d=400, cl=1, cr=1, invalid_ctx=0, intra_ctx=0, M=8, seed=0, stress=True)
     make_graph_case("c2_c0", L=16, k=3, n_d=300, cl=2, cr=0, invalid_ctx=0, intra_ctx=0, M=8, seed=1, stress=True)

@@ -808,3 +808,50 @@ def test_full_size_properties_wiki103_shape(dev):
     d_perm = dict(d_in, nbr=batch["nbr"][:, :, perm].contiguous())
     lp2 = r.step_resident(d_perm)[0].reshape(-1).float().cpu().numpy()
     np.testing.assert_allclose(lp2, outs["f16x3"][0], rtol=1e-4, atol=1e-4)
+
+
+def test_eval_lm_sentence_blocks_eos_mode(dev):
+    """--sample-break-mode eos (the one_billion scripts): one sentence per block, lengths 1..24.  Blocks are batched by
+    equal length over the whole shard (never padded) and replayed through per-shape CUDA graphs; the summed score equals
+    the CPU oracle run sentence by sentence."""
+    from types import SimpleNamespace
+    import copy
+    from gnnlm_b200 import synth
+    from gnnlm_b200.dataset import DeviceDatastore, GraphTokenBlockDataset
+    from gnnlm_b200.eval_lm import evaluate
+    from gnnlm_b200.knn_model import KNNModel
+    from gnnlm_b200.sequence_scorer import SequenceScorer
+    from oracle import model_oracle as mo
+    from tests.synth import oracle_model
+    cfg = dict(synth.CONFIGS["c1"], NL=2, k=4, n_d=1 << 16, k_nn=16)
+    model = synth.make_model(cfg)
+    rng = np.random.RandomState(9)
+    sizes = np.concatenate([[1, 2], rng.randint(3, 25, size=38)])
+    n_tok = int(sizes.sum())
+    tables = synth.make_tables(cfg, device="cpu")
+    tokens = rng.randint(4, cfg["V"], size=n_tok).astype(np.int64)
+    nbr = rng.randint(1, cfg["n_d"] - 1, size=(n_tok, cfg["k"])).astype(np.int64)
+    nbr[rng.rand(n_tok, cfg["k"]) < 0.05] = -1
+    feats = rng.randn(n_tok, cfg["d"]).astype(np.float16)
+    kd = rng.randn(n_tok, cfg["k_nn"]).astype(np.float32)
+    ki = rng.randint(0, cfg["n_d"], size=(n_tok, cfg["k_nn"])).astype(np.int64)
+    ds = GraphTokenBlockDataset(tokens, 3072, pad=1, eos=2, neighbor_offsets=nbr, n_datastore=cfg["n_d"], neighbor_context=1,
+                                precompute_feats=feats, knn_dists=kd, knn_ids=ki, break_mode="eos", sizes=sizes)
+    assert len(ds) == len(sizes)
+    dstore = DeviceDatastore(tables["codes"].to(dev), tables["vals"].to(dev))
+    scorer = SequenceScorer(synth.Dictionary(cfg["V"]), args=SimpleNamespace(lmbda=cfg["lmbda"], knn_keytype=None))
+    knn = KNNModel(dstore.vals, vocab_size=cfg["V"])
+    om = oracle_model(cfg, model)
+    tot = 0.0
+    for i in range(len(ds)):
+        cs, e = ds[i]["offsets"]
+        batch = {"nbr": nbr[cs:e][None], "offsets": np.arange(cs, e)[None], "tgt_feats": torch.from_numpy(feats[cs:e]).float(),
+                 "target": ds[i]["target"], "codes": tables["codes"].numpy(), "cl": 1, "cr": 1, "n_d": cfg["n_d"]}
+        k_ = {"dists": torch.from_numpy(kd[cs:e]), "ids": torch.from_numpy(ki[cs:e]), "vals": tables["vals"].long(),
+              "lmbda": cfg["lmbda"], "temperature": 1.0}
+        tot += float(mo.eval_batch(om, batch, k_)["logprob"].double().sum())
+    m = copy.deepcopy(model).to(dev).set_math("fp32")
+    for kw in (dict(), dict(bucket_by_length=True, max_tokens=96), dict(bucket_by_length=True, cuda_graph=True)):
+        res = evaluate(m, ds, dstore, scorer, knn_dstore=knn, temperature=1.0, max_sentences=8, device=dev, **kw)
+        assert res["count"] == n_tok
+        assert abs(res["score_sum"] - tot) / abs(tot) < 1e-5, kw

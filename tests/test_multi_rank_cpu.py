@@ -105,3 +105,36 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(root, fn)).read()
             assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_break_mode_slicing_matches_reference():
+    """dataset.get_slice_indices (host logic) against the reference's slicing function for every --sample-break-mode."""
+    import os
+    import numpy as np
+    from gnnlm_b200.dataset import get_slice_indices
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "slices.npz"))
+    for key in z.files:
+        if key.endswith(".sizes"):
+            continue
+        name, mode, bs = key.split(".")
+        assert np.array_equal(get_slice_indices(z[f"{name}.sizes"], mode, int(bs)), z[key]), key
+
+
+def test_batches_bucket_by_length():
+    import numpy as np
+    from gnnlm_b200.dataset import GraphTokenBlockDataset
+    from gnnlm_b200.eval_lm import batches
+    rng = np.random.RandomState(0)
+    sizes = rng.randint(1, 9, size=200)
+    n = int(sizes.sum())
+    ds = GraphTokenBlockDataset(np.arange(n), 3072, pad=1, eos=2, neighbor_offsets=np.zeros((n, 2), np.int64), n_datastore=10,
+                                break_mode="eos", sizes=sizes)
+    assert len(ds) == 200 and [e - s for s, e in ds.slice_indices] == sizes.tolist()
+    seen = []
+    for b in batches(ds, 10, 190, max_sentences=16, max_tokens=64, bucket_by_length=True):
+        lens = {int(ds.sizes[i]) for i in b}
+        assert len(lens) == 1 and len(b) <= 16 and len(b) * lens.pop() <= 64
+        seen += b
+    assert sorted(seen) == list(range(10, 190))
+    in_order = [i for b in batches(ds, 10, 190, max_sentences=16) for i in b]
+    assert in_order == list(range(10, 190))

@@ -66,3 +66,17 @@ def test_batching_offsets():
     # tgt-intra-tgt never crosses a block
     assert ((g["tt"][0] // 5) == (g["tt"][1] // 5)).all()
     assert g["inter_csr"][0][-1] == len(g["inter"][0])
+
+
+def test_slice_indices_all_break_modes(golden_dir):
+    """Block boundaries of every --sample-break-mode against the reference's (de-cythonised) slicing function."""
+    z = np.load(os.path.join(golden_dir, "slices.npz"))
+    n = 0
+    for key in z.files:
+        if key.endswith(".sizes"):
+            continue
+        name, mode, bs = key.split(".")
+        got = go.slice_indices(z[f"{name}.sizes"], mode, int(bs))
+        assert np.array_equal(got, z[key]), key
+        n += 1
+    assert n == 32
