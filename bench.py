@@ -303,10 +303,10 @@ def main():
     edge_all = {key: {"GB/s": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9,
                       "frac": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
                 for key, kv in kernels.items() if key.startswith(("hgt_cluster_attn", "hgt_edge_attn"))}
-    pq_key = "pq_gather_decode"
+    pq_key = next((k_ for k_ in kernels if k_.startswith("pq_gather_decode")), "pq_gather_decode")
     if pq_key in kernels:
         pq_bytes = n_ntgt * (cfg["M"] + 8 + d * 4)
-        edge_all[pq_key] = {"GB/s": pq_bytes / (kernels[pq_key]["ms_per_launch"] * 1e-3) / 1e9,
+        edge_all["pq_gather_decode"] = {"GB/s": pq_bytes / (kernels[pq_key]["ms_per_launch"] * 1e-3) / 1e9,
                             "frac": pq_bytes / (kernels[pq_key]["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
     # dominant dense kernel: the Q|K'|V' projection of all ntgt nodes
     gemm_roof = None

@@ -25,6 +25,7 @@ SIGNATURES = {
     "gnnlm_graph_tt_num_edges": (_i64, [_i64, _i64, _i64]),
     "gnnlm_graph_tt_csr": (_i32, [_i64, _i64, _i64, _p, _p, _p]),
     "gnnlm_pq_gather_decode": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _i32, _p, _p, _p]),
+    "gnnlm_pq_gather_decode_presplit": (_i32, [_p, _i64, _i32, _p, _p, _i32, _p, _p, _i64, _p, _p, _i64, _p]),
     "gnnlm_pq_encode": (_i32, [_p, _i64, _i64, _i32, _i32, _p, _p, _p, _p]),
     "gnnlm_split_tf32": (_i32, [_p, _p, _p, _i64, _p]),
     "gnnlm_split_f16": (_i32, [_p, _f32, _p, _p, _i64, _p]),

@@ -7,8 +7,9 @@
 //
 // Layout / roofline.  HBM-bound byte work: per node M code bytes are read (one 128 B line at
 // M=128) and M*dsub*4 B (4 KB at d=1024) are written.  The codebook [M,256,dsub] fp32 (1 MB at
-// d=1024) does not fit in shared memory, so the grid is 2-D: blockIdx.y picks a chunk of MC
-// subspaces whose centroids (MC*256*dsub*4 B = 128 KB) are staged ONCE per CTA into shared memory
+// d=1024) does not fit in shared memory, so the grid is 2-D: blockIdx.x (fastest, so that the CTAs
+// writing the pieces of one output row are resident together and the row's lines fill up in L2 within a short
+// window) picks a chunk of MC subspaces whose centroids (MC*256*dsub*4 B = 128 KB) are staged ONCE per CTA into shared memory
 // with TMA bulk copies (cp.async.bulk + mbarrier expect_tx), and the CTA then streams over many
 // nodes: each warp takes one node at a time, each lane owns 4 consecutive output floats
 // (one float4 smem read indexed by the code byte, one coalesced 16 B global store; a warp writes
@@ -85,9 +86,9 @@ __global__ void __launch_bounds__(PQ_THREADS, 1)
   __shared__ __align__(8) uint64_t bar;
 
   const int64_t n = live_rows(n_cap, n_dev);
-  const int64_t node0 = (int64_t)blockIdx.x * nodes_per_cta;
+  const int64_t node0 = (int64_t)blockIdx.y * nodes_per_cta;
   if (node0 >= n) return;
-  const int m0 = blockIdx.y * mc;
+  const int m0 = blockIdx.x * mc;
   const int mc_here = min(mc, M - m0);
   const uint32_t chunk_bytes = (uint32_t)mc_here * 256u * (uint32_t)dsub * 4u;
 
@@ -138,6 +139,75 @@ __global__ void __launch_bounds__(PQ_THREADS, 1)
         float4 v = cb4[((size_t)sub * 256 + c[u]) * f4_per_sub + part];
         v.x -= bsub.x; v.y -= bsub.y; v.z -= bsub.z; v.w -= bsub.w;
         store4<OutT>(out + (size_t)(i + u) * ld_out + (size_t)(m0 + sub) * dsub + part * 4, v, M * dsub);
+      }
+    }
+  }
+}
+
+// Split-fp16 output from a codebook that is ALREADY split (hi / lo fp16 halves of `centroid - bias`, prepared once per
+// quantizer): with dsub == 8 a centroid is one 16 B quad per half, so a lane moves one (node, subspace) pair with two 16 B
+// shared-memory reads and two 16 B global stores and no arithmetic at all -- the fp32 form above spends ~25 instructions
+// per 16 B on the split and was issue-bound at 60 % of the HBM roofline.  16 subspaces per chunk (64 KB hi + 64 KB lo in
+// shared memory): a half-warp owns a node, a warp two.
+constexpr int PQS_MC = 16;
+constexpr int PQS_INFLIGHT = 8;     // x 2 nodes per warp in flight
+
+__global__ void __launch_bounds__(PQ_THREADS, 1)
+    pq_decode_presplit_kernel(const uint8_t* __restrict__ codes, int M, const uint4* __restrict__ cb_hi,
+                              const uint4* __restrict__ cb_lo, const int64_t* __restrict__ rows,
+                              const int32_t* __restrict__ row_ids, int64_t n_cap, const int32_t* __restrict__ n_dev,
+                              __half* __restrict__ out, int64_t ld_out, int nodes_per_cta) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint4* s_hi = reinterpret_cast<uint4*>(smem_raw);                  // [PQS_MC][256] quads
+  uint4* s_lo = s_hi + PQS_MC * 256;
+  __shared__ __align__(8) uint64_t bar;
+
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int64_t node0 = (int64_t)blockIdx.y * nodes_per_cta;
+  if (node0 >= n) return;
+  const int m0 = blockIdx.x * PQS_MC;
+  const int mc_here = min(PQS_MC, M - m0);
+  const uint32_t half_bytes = (uint32_t)mc_here * 256u * 16u;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, 2 * half_bytes);
+    for (uint32_t off = 0; off < half_bytes; off += 32768u) {
+      const uint32_t sz = min(32768u, half_bytes - off);
+      bulk_g2s(reinterpret_cast<uint8_t*>(s_hi) + off, reinterpret_cast<const uint8_t*>(cb_hi + (size_t)m0 * 256) + off, sz, &bar);
+      bulk_g2s(reinterpret_cast<uint8_t*>(s_lo) + off, reinterpret_cast<const uint8_t*>(cb_lo + (size_t)m0 * 256) + off, sz, &bar);
+    }
+  }
+  mbar_wait(&bar, 0);
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane & (PQS_MC - 1), half = lane >> 4;             // lane -> (subspace, which of the warp's two nodes)
+  const bool active = sub < mc_here;
+  const int64_t node_end = min(n, node0 + nodes_per_cta);
+  const int64_t lo_off = (int64_t)M * 8;                              // lo half of the row, in fp16 elements
+  for (int64_t i = node0 + warp * (2 * PQS_INFLIGHT); i < node_end; i += (PQ_THREADS / 32) * (2 * PQS_INFLIGHT)) {
+    int64_t r[PQS_INFLIGHT];
+    uint32_t c[PQS_INFLIGHT];
+#pragma unroll
+    for (int u = 0; u < PQS_INFLIGHT; ++u) {
+      const int64_t node = i + 2 * u + half;
+      const bool ok = node < node_end;
+      const int64_t nid = ok ? (row_ids ? (int64_t)__ldg(row_ids + node) : node) : 0;
+      r[u] = ok ? __ldg(rows + nid) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < PQS_INFLIGHT; ++u)
+      c[u] = (r[u] >= 0 && active) ? (uint32_t)__ldg(codes + (size_t)r[u] * M + m0 + sub) : 0u;
+#pragma unroll
+    for (int u = 0; u < PQS_INFLIGHT; ++u) {
+      if (r[u] >= 0 && active) {
+        __half* dst = out + (size_t)(i + 2 * u + half) * ld_out + (size_t)(m0 + sub) * 8;
+        *reinterpret_cast<uint4*>(dst) = s_hi[sub * 256 + c[u]];
+        *reinterpret_cast<uint4*>(dst + lo_off) = s_lo[sub * 256 + c[u]];
       }
     }
   }
@@ -226,7 +296,7 @@ extern "C" int32_t gnnlm_pq_gather_decode(const uint8_t* codes, int64_t n_datast
       int nodes_per_cta = PQ_NODES_PER_CTA;
       // keep at least ~2 waves of CTAs on small inputs
       while (nodes_per_cta > 64 && ceil_div(n_cap, nodes_per_cta) * ceil_div(M, mc) < 296) nodes_per_cta >>= 1;
-      dim3 grid((unsigned)ceil_div(n_cap, nodes_per_cta), (unsigned)ceil_div(M, mc));
+      dim3 grid((unsigned)ceil_div(M, mc), (unsigned)ceil_div(n_cap, nodes_per_cta));
       if (out_dtype == GNNLM_F32) {
         GNNLM_CUDA(cudaFuncSetAttribute(pq_decode_smem_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         pq_decode_smem_kernel<float><<<grid, PQ_THREADS, smem, st>>>(codes, M, centroids, dsub, bias, rows, row_ids, n_cap,
@@ -260,5 +330,31 @@ extern "C" int32_t gnnlm_pq_gather_decode(const uint8_t* codes, int64_t n_datast
                                                                                 codes_out);
     GNNLM_LAUNCH_CHECK("gnnlm_pq_gather_side");
   }
+  return 0;
+}
+
+extern "C" int32_t gnnlm_pq_gather_decode_presplit(const uint8_t* codes, int64_t n_datastore, int32_t M, const void* cb_hi,
+                                                   const void* cb_lo, int32_t dsub, const int64_t* rows,
+                                                   const int32_t* row_ids, int64_t n_cap, const int32_t* n_dev, void* out,
+                                                   int64_t ld_out, gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(codes && rows && cb_hi && cb_lo && out, GNNLM_E_ARG, "gnnlm_pq_gather_decode_presplit: null pointer");
+  GNNLM_CHECK_ARG(M > 0 && n_cap >= 0 && n_datastore > 0, GNNLM_E_SHAPE, "gnnlm_pq_gather_decode_presplit: bad sizes");
+  GNNLM_CHECK_ARG(dsub == 8, GNNLM_E_UNSUPPORTED, "gnnlm_pq_gather_decode_presplit: dsub must be 8 (use gnnlm_pq_gather_decode)");
+  GNNLM_CHECK_ARG(ld_out >= 2 * (int64_t)M * 8 && ld_out % 8 == 0 && (uintptr_t)out % 16 == 0 && (uintptr_t)cb_hi % 16 == 0 &&
+                      (uintptr_t)cb_lo % 16 == 0,
+                  GNNLM_E_SHAPE, "gnnlm_pq_gather_decode_presplit: out / codebooks must be 16 B aligned, ld_out >= 2*M*8");
+  if (n_cap == 0) return 0;
+  const size_t smem = (size_t)2 * PQS_MC * 256 * 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GNNLM_CUDA(cudaFuncSetAttribute(pq_decode_presplit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int nodes_per_cta = PQ_NODES_PER_CTA;
+  while (nodes_per_cta > 64 && ceil_div(n_cap, nodes_per_cta) * ceil_div(M, PQS_MC) < 296) nodes_per_cta >>= 1;
+  dim3 grid((unsigned)ceil_div(M, PQS_MC), (unsigned)ceil_div(n_cap, nodes_per_cta));
+  pq_decode_presplit_kernel<<<grid, PQ_THREADS, smem, (cudaStream_t)stream>>>(
+      codes, M, (const uint4*)cb_hi, (const uint4*)cb_lo, rows, row_ids, n_cap, n_dev, (__half*)out, ld_out, nodes_per_cta);
+  GNNLM_LAUNCH_CHECK("gnnlm_pq_gather_decode_presplit");
   return 0;
 }

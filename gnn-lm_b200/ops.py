@@ -252,6 +252,18 @@ def pq_gather_decode(codes, centroids, rows, *, bias=None, row_ids=None, n_cap=N
     return out, labels, codes_out
 
 
+def pq_gather_decode_presplit(codes, cb_hi, cb_lo, rows, *, row_ids=None, n_cap=None, n_dev=None):
+    """Gather + decode straight into the split-fp16 format from a pre-split codebook (dsub == 8)."""
+    n_d, M = codes.shape
+    assert cb_hi.dtype == torch.float16 and cb_hi.shape == cb_lo.shape == (M, 256, 8) and cb_hi.is_contiguous()
+    n = (row_ids.shape[0] if row_ids is not None else rows.shape[0]) if n_cap is None else n_cap
+    out = empty_act(n, M * 8, SPLIT, codes.device)
+    o_ptr, _, ld_out, _ = _mat(out)
+    L.call("gnnlm_pq_gather_decode_presplit", L.ptr(codes), n_d, M, L.ptr(cb_hi), L.ptr(cb_lo), 8, L.ptr(rows), L.ptr(row_ids),
+           n, _dev_count(n_dev), o_ptr, ld_out, L.stream_ptr(), tag="pq_gather_decode")
+    return out
+
+
 def adapt_target(target, cutoff):
     """target [T] int64 (device), cutoff: python list ending with vocab size."""
     T = target.numel()

@@ -39,6 +39,8 @@ class TorchPQCodec(nn.Module):
         self.register_buffer("sdc_table_torch", sdc)
         self._rot = None
         self._rot_key = None
+        self._split = None
+        self._split_key = None
 
     @property
     def M(self):
@@ -56,6 +58,21 @@ class TorchPQCodec(nn.Module):
             self._rot, self._rot_key = _Weight(self.A.t().contiguous(), None, math_mode), key
         return self._rot
 
+    def _split_codebook(self):
+        """(hi, lo) fp16 halves of `centroid - b` [M, 256, dsub]: the split-fp16 activation format applied to the
+        codebook once, so that decoding into that format needs no arithmetic (same values as splitting after the lookup)."""
+        cen = self.centroids_torch
+        key = (cen.device, int(cen._version), int(self.b._version) if self.pre_torch else -1)
+        if self._split is None or self._split_key != key:
+            v = cen
+            if self.pre_torch and self.b.numel() > 0:
+                v = cen - self.b.view(self.M, 1, self.dsub)
+            v = v.clamp(-65504.0, 65504.0)
+            hi = v.half()
+            lo = (v - hi.float()).half()
+            self._split, self._split_key = (hi.contiguous(), lo.contiguous()), key
+        return self._split
+
     @torch.no_grad()
     def gather_decode(self, codes_table: torch.Tensor, rows: torch.Tensor, *, row_ids: Optional[torch.Tensor] = None,
                       n_cap: Optional[int] = None, n_dev: Optional[torch.Tensor] = None,
@@ -64,8 +81,12 @@ class TorchPQCodec(nn.Module):
         from .hgt import act_dtype
         b = self.b if self.pre_torch and self.b.numel() > 0 else None
         act = act_dtype(math_mode)
-        x, _, _ = ops.pq_gather_decode(codes_table, self.centroids_torch, rows, bias=b, row_ids=row_ids, n_cap=n_cap,
-                                       n_dev=n_dev, out_dtype=act)
+        if act == ops.SPLIT and self.dsub == 8:        # pre-split codebook: pure byte movement (pq_decode_presplit_kernel)
+            hi, lo = self._split_codebook()
+            x = ops.pq_gather_decode_presplit(codes_table, hi, lo, rows, row_ids=row_ids, n_cap=n_cap, n_dev=n_dev)
+        else:
+            x, _, _ = ops.pq_gather_decode(codes_table, self.centroids_torch, rows, bias=b, row_ids=row_ids, n_cap=n_cap,
+                                           n_dev=n_dev, out_dtype=act)
         if self.pre_torch:
             w = self._rotation(math_mode)
             x = ops.linear(x, w.W, None, W_lo=w.lo, w_scale=w.scale, m_dev=n_dev, math=math_mode, out_dtype=act)

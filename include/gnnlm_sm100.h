@@ -122,6 +122,14 @@ int32_t gnnlm_pq_gather_decode(const uint8_t* codes, int64_t n_datastore, int32_
                                int64_t ld_out, const void* labels_table, int32_t label_bytes,
                                int64_t* labels_out, uint8_t* codes_out, gnnlm_stream_t stream);
 
+/* Same gather + decode for the split-fp16 activation format from a codebook that is already split: cb_hi / cb_lo
+ * [M, 256, 8] fp16 = hi / lo halves of (centroid - bias) (prepared once per quantizer; dsub == 8 only, i.e. one 16 B quad per
+ * centroid half).  out [n_cap, 2*M*8] split fp16 (leading dimension ld_out, in fp16 elements).  Pure byte movement. */
+int32_t gnnlm_pq_gather_decode_presplit(const uint8_t* codes, int64_t n_datastore, int32_t M, const void* cb_hi,
+                                        const void* cb_lo, int32_t dsub, const int64_t* rows, const int32_t* row_ids,
+                                        int64_t n_cap, const int32_t* n_dev, void* out, int64_t ld_out,
+                                        gnnlm_stream_t stream);
+
 /* PQ encode (the producer of quantized-keys.npy; knn/pq_wrapper.py:51-68,131-167, knn/quantize_features.py:115-152):
  *  codes[n, m] = argmin_c (norm2[m, c] - 2 <x[n, m*dsub:(m+1)*dsub], centroids[m, c]>), first minimum wins.
  *  x fp32 [n, M*dsub] (ldx) must already carry the OPQ pre-rotation `x @ A.T (+ b)` (a gnnlm_linear call);

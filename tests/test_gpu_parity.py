@@ -855,3 +855,29 @@ def test_eval_lm_sentence_blocks_eos_mode(dev):
         res = evaluate(m, ds, dstore, scorer, knn_dstore=knn, temperature=1.0, max_sentences=8, device=dev, **kw)
         assert res["count"] == n_tok
         assert abs(res["score_sum"] - tot) / abs(tot) < 1e-5, kw
+
+
+@pytest.mark.parametrize("M,with_b", [(128, True), (64, False), (24, True)])
+def test_pq_decode_presplit_codebook(M, with_b, dev):
+    """Decoding into the split-fp16 format from the pre-split codebook is bit-identical to splitting after the fp32
+    lookup (and so inherits its parity with pq_wrapper.py:169-201), incl. row indirection, a device-side count and M not
+    a multiple of the 16-subspace chunk."""
+    from gnnlm_b200 import ops
+    from gnnlm_b200.pq_codec import TorchPQCodec
+    rng = np.random.RandomState(M)
+    d, n_d, n = M * 8, 5000, 3001
+    cen = (rng.randn(M, 256, 8) * 3).astype(np.float32)
+    A = np.linalg.qr(rng.randn(d, d))[0].astype(np.float32)
+    b = rng.randn(d).astype(np.float32) if with_b else np.zeros(0, np.float32)
+    codec = TorchPQCodec(centroids=cen, A=A, b=b).to(dev)
+    codes = torch.from_numpy(rng.randint(0, 256, size=(n_d, M)).astype(np.uint8)).to(dev)
+    rows = torch.from_numpy(rng.randint(0, n_d, size=n).astype(np.int64)).to(dev)
+    ids = torch.from_numpy(rng.permutation(n)[:1777].astype(np.int32)).to(dev)
+    n_dev = torch.tensor([1500], dtype=torch.int32, device=dev)
+    hi, lo = codec._split_codebook()
+    bias = codec.b if with_b else None
+    for kw in (dict(), dict(row_ids=ids), dict(row_ids=ids, n_cap=1777, n_dev=n_dev)):
+        ref, _, _ = ops.pq_gather_decode(codes, codec.centroids_torch, rows, bias=bias, out_dtype=ops.SPLIT, **kw)
+        out = ops.pq_gather_decode_presplit(codes, hi, lo, rows, **kw)
+        live = 1500 if "n_dev" in kw else ref.data.shape[0]
+        assert torch.equal(out.data[:live], ref.data[:live])
