@@ -138,3 +138,73 @@ def test_batches_bucket_by_length():
     assert sorted(seen) == list(range(10, 190))
     in_order = [i for b in batches(ds, 10, 190, max_sentences=16) for i in b]
     assert in_order == list(range(10, 190))
+
+
+# ---- the reference's own known-answer tests for the host logic of the path
+def _blocks(data, block_size, mode):
+    import numpy as np
+    from gnnlm_b200.dataset import GraphTokenBlockDataset
+    from oracle import graph_oracle as go
+    tokens = np.concatenate([np.asarray(x) for x in data])
+    sizes = np.array([len(x) for x in data])
+    ds = GraphTokenBlockDataset(tokens, block_size, pad=0, eos=1, neighbor_offsets=np.zeros((len(tokens), 1), np.int64),
+                                n_datastore=4, break_mode=mode, sizes=sizes)
+    got = [ds[i]["target"].tolist() for i in range(len(ds))]
+    assert got == [tokens[s:e].tolist() for s, e in go.slice_indices(sizes, mode, block_size)]       # oracle agrees
+    return got
+
+
+def test_token_block_known_answers():
+    """The vectors of the reference's tests/test_token_block_dataset.py:22-78 (eos / none / complete break modes)."""
+    assert _blocks([[5, 4, 3, 2, 1], [1], [8, 7, 6, 1]], 10 ** 9, "eos") == [[5, 4, 3, 2, 1], [1], [8, 7, 6, 1]]
+    assert _blocks([[5, 4, 3, 2, 1], [8, 7, 6, 1], [1]], 10 ** 9, "eos") == [[5, 4, 3, 2, 1], [8, 7, 6, 1], [1]]
+    assert _blocks([[5, 4, 3, 2, 1], [8, 7, 6, 1], [9, 1]], 3, "none") == [[5, 4, 3], [2, 1, 8], [7, 6, 1], [9, 1]]
+    assert _blocks([[5, 4, 3, 2, 1], [8, 7, 6, 1], [9, 1]], 6, "complete") == [[5, 4, 3, 2, 1], [8, 7, 6, 1, 9, 1]]
+    assert _blocks([[4, 3, 2, 1], [5, 1], [1], [6, 1]], 3, "complete") == [[4, 3, 2, 1], [5, 1, 1], [6, 1]]
+
+
+def test_sequence_scorer_known_answers():
+    """The vectors of the reference's tests/test_sequence_scorer.py:17-91: a scripted model emits the per-step
+    distributions, the scorer must return the target tokens (pad stripped), their positional log-probs and the mean
+    score.  Runs without the kNN stage, so no kernel is involved: this is SequenceScorer.generate's host logic."""
+    import math
+    from types import SimpleNamespace
+    import torch
+    from gnnlm_b200.sequence_scorer import SequenceScorer
+    pad, eos, w1, w2 = 1, 2, 4, 5
+    targets = [[w1, w2, w1, eos], [w2, w1, eos], [w2, eos]]
+    beam_probs = [torch.tensor([[0.0, 0.0, 0.6, 0.4], [0.0, 0.0, 0.4, 0.6], [0.0, 0.0, 0.7, 0.3]]),
+                  torch.tensor([[0.0, 0.0, 0.2, 0.7], [0.0, 0.0, 0.8, 0.2], [0.7, 0.0, 0.1, 0.2]]),
+                  torch.tensor([[0.10, 0.0, 0.50, 0.4], [0.15, 0.0, 0.15, 0.7], [0.0, 0.0, 0.0, 0.0]]),
+                  torch.tensor([[0.9, 0.0, 0.05, 0.05], [0.0, 0.0, 0.0, 0.0], [0.0, 0.0, 0.0, 0.0]])]
+    expected = [[0.6, 0.7, 0.5, 0.9], [0.6, 0.8, 0.15], [0.3, 0.7]]
+    col = {eos: 0, 3: 1, w1: 2, w2: 3}                                   # columns of beam_probs: eos, unk, w1, w2
+    L = 4
+    tgt = torch.full((3, L), pad, dtype=torch.long)
+    for i, t in enumerate(targets):
+        tgt[i, :len(t)] = torch.tensor(t)
+
+    class Decoder:
+        def target_log_probs(self, net_output, target):
+            probs = torch.stack(beam_probs, 1)                            # [bsz, step, 4]
+            idx = torch.tensor([[col.get(int(v), 1) for v in row] for row in target])
+            return torch.log(probs.gather(2, idx.unsqueeze(-1)).squeeze(-1))
+
+    class Model:
+        decoder = Decoder()
+
+        def eval(self):
+            return self
+
+        def __call__(self, **net_input):
+            feat = torch.zeros(L, 3, 2)
+            return feat.transpose(0, 1), {"inner_states": [feat]}
+
+    d = SimpleNamespace(pad=lambda: pad, eos=lambda: eos)
+    scorer = SequenceScorer(d)
+    hypos = scorer.generate([Model()], {"net_input": {"src_tokens": tgt}, "target": tgt})
+    for i, h in enumerate(hypos):
+        assert h[0]["tokens"].tolist() == targets[i]
+        want = torch.log(torch.tensor(expected[i]))
+        assert (h[0]["positional_scores"] - want).abs().max() < 1e-4
+        assert abs(float(h[0]["score"]) - float(want.sum()) / len(expected[i])) < 1e-6
