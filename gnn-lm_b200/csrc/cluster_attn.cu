@@ -277,7 +277,7 @@ extern "C" int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void
                   "gnnlm_hgt_cluster_attn: out dtype");
   GNNLM_CHECK_ARG(out_dtype != GNNLM_F16X2 || ldo >= 2 * (int64_t)H * d_k, GNNLM_E_SHAPE, "gnnlm_hgt_cluster_attn: split output needs ldo >= 2d");
   GNNLM_CHECK_ARG(max_cluster >= 1, GNNLM_E_SHAPE, "gnnlm_hgt_cluster_attn: max_cluster must be >= 1");
-  GNNLM_CHECK_ARG(H > 0 && H <= 32 && (H & (H - 1)) == 0, GNNLM_E_UNSUPPORTED, "gnnlm_hgt_cluster_attn: H must be a power of two <= 32");
+  GNNLM_CHECK_ARG(H > 0 && d_k > 0, GNNLM_E_SHAPE, "gnnlm_hgt_cluster_attn: H and d_k must be positive");
   const int64_t d = (int64_t)H * d_k;
   const int Cs = dtype == GNNLM_F32 ? 4 : 8;                 // 16 B per lane per row
   // a warp covers 32*Cs features; a head (d_k features) must live inside one warp and heads may not straddle warps

@@ -370,19 +370,33 @@ static int32_t launch_causal(const void* q, int64_t ldq, const void* k, int64_t 
   return 0;
 }
 
+// Two lane mappings: "whole" -- a warp spans the whole row, d/32 features per lane, 32/H lanes per head (H a power of
+// two); "sliced" -- a lane owns 16 B, a warp spans 32 lanes * 16 B of the row and the row takes d / that many slices
+// (any H as long as a head's lanes divide the warp: d_k = 64, 128, ... in fp32).
 static int32_t check_shape(const char* who, int32_t H, int32_t d_k, int32_t dtype, int64_t ldq, int64_t ldk, int64_t ldv,
-                           int64_t ldo, int* C_out, int* group_out) {
+                           int64_t ldo, int* C_out, int* group_out, int* slices_out, bool need_whole) {
   GNNLM_CHECK_ARG(dtype == GNNLM_F32 || dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED, "%s: dtype must be F32 or BF16", who);
-  GNNLM_CHECK_ARG(H > 0 && H <= 32 && (H & (H - 1)) == 0, GNNLM_E_UNSUPPORTED, "%s: H must be a power of two <= 32 (H=%d)", who, H);
+  GNNLM_CHECK_ARG(H > 0 && d_k > 0, GNNLM_E_SHAPE, "%s: H and d_k must be positive", who);
   const int64_t d = (int64_t)H * d_k;
-  GNNLM_CHECK_ARG(d % 32 == 0, GNNLM_E_UNSUPPORTED, "%s: H*d_k must be a multiple of 32 (d=%lld)", who, (long long)d);
-  const int C = (int)(d / 32);
-  GNNLM_CHECK_ARG(C == 1 || C == 2 || C == 4 || C == 8 || C == 16 || C == 32, GNNLM_E_UNSUPPORTED,
-                  "%s: d/32 must be in {1,2,4,8,16,32} (d=%lld)", who, (long long)d);
-  GNNLM_CHECK_ARG(ldq % C == 0 && ldk % C == 0 && ldv % C == 0 && ldo % C == 0, GNNLM_E_SHAPE,
-                  "%s: leading dimensions must be multiples of d/32", who);
-  *C_out = C;
-  *group_out = 32 / H;
+  const int Cs = dtype == GNNLM_F32 ? 4 : 8;                   // 16 B per lane per row
+  const bool sliced_ok = d % (32 * Cs) == 0 && d_k % Cs == 0 && d_k / Cs <= 32 && 32 % (d_k / Cs) == 0;
+  const int64_t Cw = d / 32;
+  const bool whole_ok = H <= 32 && (H & (H - 1)) == 0 && d % 32 == 0 &&
+                        (Cw == 1 || Cw == 2 || Cw == 4 || Cw == 8 || Cw == 16 || Cw == 32);
+  GNNLM_CHECK_ARG(whole_ok || (sliced_ok && !need_whole), GNNLM_E_UNSUPPORTED,
+                  "%s: unsupported head layout (H=%d, d_k=%d): need H a power of two <= 32 with H*d_k/32 in {1..32}%s", who, H,
+                  d_k, need_whole ? "" : ", or d_k a multiple of 4 (fp32) / 8 (bf16) whose lanes divide a warp");
+  if (!need_whole && sliced_ok && (Cw > Cs || !whole_ok)) {
+    *C_out = Cs;
+    *group_out = d_k / Cs;                                     // lanes per head inside a slice
+    *slices_out = (int)(d / (32 * Cs));
+  } else {
+    *C_out = (int)Cw;
+    *group_out = 32 / H;
+    *slices_out = 1;
+  }
+  GNNLM_CHECK_ARG(ldq % *C_out == 0 && ldk % *C_out == 0 && ldv % *C_out == 0 && ldo % *C_out == 0, GNNLM_E_SHAPE,
+                  "%s: leading dimensions must be multiples of the per-lane width (%d)", who, *C_out);
   return 0;
 }
 
@@ -406,19 +420,11 @@ extern "C" int32_t gnnlm_hgt_edge_attn(const void* q, int64_t ldq, const void* k
                                        int32_t d_k, float* out, int64_t ldo, float out_scale, int32_t accumulate,
                                        gnnlm_stream_t stream) {
   GNNLM_CHECK_ARG(q && k && v && indptr && out, GNNLM_E_ARG, "gnnlm_hgt_edge_attn: null pointer");
-  int C, group;
-  int32_t rc = check_shape("gnnlm_hgt_edge_attn", H, d_k, dtype, ldq, ldk, ldv, ldo, &C, &group);
+  int C, group, n_slices;
+  int32_t rc = check_shape("gnnlm_hgt_edge_attn", H, d_k, dtype, ldq, ldk, ldv, ldo, &C, &group, &n_slices, false);
   if (rc) return rc;
   if (n_dst_cap == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  // feature slicing: lanes own Cs floats; a warp covers 32*Cs features; heads must not straddle lanes
-  int n_slices = 1;
-  const int Cs = dtype == GNNLM_F32 ? 4 : 8;                   // 16 B per lane per row
-  if (C > Cs && d_k % Cs == 0 && d_k / Cs <= 32 && 32 % (d_k / Cs) == 0) {   // a head must live inside one warp
-    n_slices = C / Cs;
-    group = d_k / Cs;                                          // lanes per head inside a slice
-    C = Cs;
-  }
   if (dtype == GNNLM_F32) {
     DISPATCH_C(launch_edge, float, q, ldq, k, ldk, v, ldv, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, group, n_slices,
                out, ldo, out_scale, accumulate, st)
@@ -434,20 +440,20 @@ extern "C" int32_t gnnlm_hgt_causal_attn(const void* q, int64_t ldq, const void*
                                          gnnlm_stream_t stream) {
   GNNLM_CHECK_ARG(q && k && v && out, GNNLM_E_ARG, "gnnlm_hgt_causal_attn: null pointer");
   GNNLM_CHECK_ARG(B >= 0 && L > 0, GNNLM_E_SHAPE, "gnnlm_hgt_causal_attn: bad sizes");
-  int C, group;
-  int32_t rc = check_shape("gnnlm_hgt_causal_attn", H, d_k, dtype, ldq, ldk, ldv, ldo, &C, &group);
-  if (rc) return rc;
-  if (B == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const bool al16 = ((uintptr_t)q % 16 == 0) && ((uintptr_t)k % 16 == 0) && ((uintptr_t)v % 16 == 0) &&
                     ((uintptr_t)out % 16 == 0) && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0;
-  if (dtype == GNNLM_F32 && al16 && L >= 64 && B <= 65535 && (d_k == 128 || d_k == 64)) {
+  if (dtype == GNNLM_F32 && al16 && L >= 64 && B <= 65535 && B > 0 && H > 0 && (d_k == 128 || d_k == 64)) {   // any H
     if (d_k == 128)
       return launch_flash<128>((const float*)q, ldq, (const float*)k, ldk, (const float*)v, ldv, B, L, intra_ctx, H, out,
                                ldo, out_scale, accumulate, st);
     return launch_flash<64>((const float*)q, ldq, (const float*)k, ldk, (const float*)v, ldv, B, L, intra_ctx, H, out, ldo,
                             out_scale, accumulate, st);
   }
+  int C, group, n_slices;
+  int32_t rc = check_shape("gnnlm_hgt_causal_attn", H, d_k, dtype, ldq, ldk, ldv, ldo, &C, &group, &n_slices, true);
+  if (rc) return rc;
+  if (B == 0) return 0;
   if (dtype == GNNLM_F32) {
     DISPATCH_C(launch_causal, float, q, ldq, k, ldk, v, ldv, B, L, intra_ctx, group, out, ldo, out_scale, accumulate, st)
   } else {

@@ -881,3 +881,21 @@ def test_pq_decode_presplit_codebook(M, with_b, dev):
         out = ops.pq_gather_decode_presplit(codes, hi, lo, rows, **kw)
         live = 1500 if "n_dev" in kw else ref.data.shape[0]
         assert torch.equal(out.data[:live], ref.data[:live])
+
+
+@pytest.mark.parametrize("math", ["fp32", "f16x3"])
+def test_whole_path_heads_not_power_of_two(math, dev):
+    """d=768, H=12 (d_k=64), M=96: shapes outside the cluster-attention envelope fall back to the CSR edge kernel;
+    everything else (GEMM tiles with ragged N / K, PQ chunks, causal attention) must cope too."""
+    if math != "fp32":
+        _need_tc()
+    import copy
+    from gnnlm_b200 import synth
+    from tests.synth import run_oracle
+    cfg = dict(synth.CONFIGS["c3mini"], d=768, H=12, M=96, L=80, k=6, c=2, NL=3, n_d=1 << 14, V=5000, cutoff=[1000, 3000])
+    model = synth.make_model(cfg)
+    data = synth.make_data(cfg, seed=21, device="cpu")
+    ref = run_oracle((cfg, model, data))
+    out = synth.run_gpu(cfg, copy.deepcopy(model), data, dev, math)
+    np.testing.assert_allclose(out["logprob"], ref["logprob"].numpy(), rtol=1e-4, atol=1e-4)
+    assert abs(out["nll"] - ref["nll"]) < 0.01 / 16.8
