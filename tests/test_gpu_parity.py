@@ -899,3 +899,57 @@ def test_whole_path_heads_not_power_of_two(math, dev):
     out = synth.run_gpu(cfg, copy.deepcopy(model), data, dev, math)
     np.testing.assert_allclose(out["logprob"], ref["logprob"].numpy(), rtol=1e-4, atol=1e-4)
     assert abs(out["nll"] - ref["nll"]) < 0.01 / 16.8
+
+
+@pytest.mark.parametrize("cl,cr,NL,intra,cw,math", [(2, 0, 2, 0, 0, "fp32"), (0, 2, 3, 5, 4, "fp32"), (1, 2, 3, 0, 0, "f16x3"),
+                                                    (3, 1, 1, 7, 0, "fp32"), (0, 0, 2, 0, 3, "f16x3"), (2, 2, 4, 9, 0, "f16x3")])
+def test_eval_lm_option_matrix(cl, cr, NL, intra, cw, math, dev):
+    """Asymmetric neighbour context (--neighbor-context "(l, r)"), --intra-context, --gcn-context-window and 1..4 graph
+    layers through dataset -> evaluate(), against the CPU oracle block by block (unpruned reference graph)."""
+    if math != "fp32":
+        _need_tc()
+    from types import SimpleNamespace
+    import copy
+    from gnnlm_b200 import synth
+    from gnnlm_b200.dataset import DeviceDatastore, GraphTokenBlockDataset
+    from gnnlm_b200.eval_lm import evaluate
+    from gnnlm_b200.knn_model import KNNModel
+    from gnnlm_b200.sequence_scorer import SequenceScorer
+    from oracle import model_oracle as mo
+    from tests.synth import oracle_model
+    cfg = dict(synth.CONFIGS["c1"], NL=NL, k=5, n_d=1 << 12, k_nn=8)
+    model = synth.make_model(cfg)
+    rng = np.random.RandomState(cl * 7 + cr * 3 + NL)
+    n_tok, blk = 230, 64
+    tables = synth.make_tables(cfg, device="cpu")
+    tokens = rng.randint(4, cfg["V"], size=n_tok).astype(np.int64)
+    nbr = rng.randint(0, cfg["n_d"], size=(n_tok, cfg["k"])).astype(np.int64)
+    nbr[rng.rand(n_tok, cfg["k"]) < 0.1] = -1
+    nbr[:3, 0] = [0, 1, cfg["n_d"] - 1]
+    feats = rng.randn(n_tok, cfg["d"]).astype(np.float16)
+    kd = rng.randn(n_tok, cfg["k_nn"]).astype(np.float32)
+    ki = rng.randint(0, cfg["n_d"], size=(n_tok, cfg["k_nn"])).astype(np.int64)
+    ds = GraphTokenBlockDataset(tokens, blk, pad=1, eos=2, neighbor_offsets=nbr, n_datastore=cfg["n_d"],
+                                neighbor_context=(cl, cr), precompute_feats=feats, context_window=cw, intra_context=intra,
+                                knn_dists=kd, knn_ids=ki)
+    dstore = DeviceDatastore(tables["codes"].to(dev), tables["vals"].to(dev))
+    scorer = SequenceScorer(synth.Dictionary(cfg["V"]), args=SimpleNamespace(lmbda=cfg["lmbda"], knn_keytype=None))
+    knn = KNNModel(dstore.vals, vocab_size=cfg["V"])
+    om = oracle_model(cfg, model)
+    tot, cnt = 0.0, 0
+    for i in range(len(ds)):
+        it = ds[i]
+        cs, e = it["offsets"]
+        batch = {"nbr": nbr[cs:e][None], "offsets": np.arange(cs, e)[None], "tgt_feats": torch.from_numpy(feats[cs:e]).float(),
+                 "target": it["target"], "codes": tables["codes"].numpy(), "cl": cl, "cr": cr, "n_d": cfg["n_d"],
+                 "intra_ctx": intra}
+        k_ = {"dists": torch.from_numpy(kd[cs:e]), "ids": torch.from_numpy(ki[cs:e]), "vals": tables["vals"].long(),
+              "lmbda": cfg["lmbda"], "temperature": 1.0}
+        lp = mo.eval_batch(om, batch, k_)["logprob"][it["start_idx"]:]
+        tot += float(lp.double().sum())
+        cnt += lp.numel()
+    m = copy.deepcopy(model).to(dev).set_math(math)
+    for kw in (dict(), dict(cuda_graph=True, prune_unreachable=False)):
+        res = evaluate(m, ds, dstore, scorer, knn_dstore=knn, temperature=1.0, max_sentences=2, device=dev, **kw)
+        assert res["count"] == cnt == n_tok
+        assert abs(res["score_sum"] - tot) / abs(tot) < 2e-5, (kw, res["score_sum"], tot)
