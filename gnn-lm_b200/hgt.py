@@ -240,7 +240,10 @@ class HGTLayer(nn.Module):
                 kvi = _lin(hc_c, P["ntgt_kv_inter"], P["math"], m_dev=g_c.n_valid_dev)
                 ops.edge_attn(qkv[t0:t1, :d], kvi[:, :d], kvi[:, d:], g_c.inter_indptr, None, H, t_agg[t0:t1], out_scale=0.5,
                               tag="inter")
-        if P["math"] == L.MATH_F16X3 and self.use_gemm_attention and ops.causal_attn_gemm_supported(d, H, G.L) and G.L >= 1024:
+        # tensor-core form (3xFP16 GEMMs on the fp32 Q / K' / V', fp32-level accuracy) in every mode that already puts fp16-range
+        # operands on the tensor cores; tf32x3 / fp32 keep the CUDA-core kernel (no fp16 range limit on Q / K' / V')
+        gemm_modes = (L.MATH_F16X3, L.MATH_BF16, L.MATH_TF32)
+        if P["math"] in gemm_modes and self.use_gemm_attention and ops.causal_attn_gemm_supported(d, H, G.L) and G.L >= 1024:
             ops.causal_attn_gemm(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5,
                                  accumulate=True)
         else:
