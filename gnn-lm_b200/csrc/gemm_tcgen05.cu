@@ -213,7 +213,7 @@ constexpr int EPI_SMEM = 4 * 32 * EPI_LD * 4;               // 4 epilogue warps
 // three times the single-pass (bf16) main loop.
 template <int CMODE>      // 0 = f32, 1 = bf16, 2 = split fp16
 __device__ __forceinline__ void epilogue_store_fast(uint32_t taddr, int64_t m, int64_t M, int64_t n_base, int64_t N,
-                                                    const EpiStore& es, float* stage_smem, float acc_scale) {
+                                                    const EpiStore& es, float* stage_smem, float acc_scale, int tile_cols) {
   constexpr int ES = CMODE == 0 ? 4 : 2;
   const int lane = threadIdx.x & 31;
   const int cq = (lane & 7) * 4, rsub = lane >> 3;
@@ -229,7 +229,7 @@ __device__ __forceinline__ void epilogue_store_fast(uint32_t taddr, int64_t m, i
   const uint32_t st_w = st_base + (uint32_t)lane * (EPI_LD * 4);                     // my TMEM row
   const uint32_t st_r = st_base + (uint32_t)(rsub * EPI_LD + cq) * 4;                // row rsub, my 4 columns
   const int64_t cols = N - n_base;                            // valid columns of this tile (multiple of 4)
-  const int n_chunks = (int)((cols < BLOCK_N ? cols : BLOCK_N) + 31) >> 5;
+  const int n_chunks = cols <= 0 ? 0 : (int)((cols < tile_cols ? cols : tile_cols) + 31) >> 5;
   float v[32];
   if (n_chunks > 0) tmem_ld32_issue(taddr, v);
 #pragma unroll 1
@@ -273,21 +273,22 @@ __device__ __forceinline__ void epilogue_store_fast(uint32_t taddr, int64_t m, i
 
 template <bool LSE>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t M, int64_t n_base, int64_t n_blk, int64_t N,
-                                              const EpiStore& es, const EpiLse& el, float* stage_smem, float acc_scale = 1.f) {
+                                              const EpiStore& es, const EpiLse& el, float* stage_smem, float acc_scale = 1.f,
+                                              int tile_cols = BLOCK_N) {
         if constexpr (!LSE) {
           // warp-uniform launch properties
           if (!es.residual && (N & 3) == 0 && (es.ldc & 3) == 0 && (es.c_bf16 != 2 || (es.c_lo & 3) == 0) &&
               (reinterpret_cast<uintptr_t>(es.C) & 15) == 0 && (!es.bias || (reinterpret_cast<uintptr_t>(es.bias) & 15) == 0)) {
-            if (es.c_bf16 == 0) epilogue_store_fast<0>(taddr, m, M, n_base, N, es, stage_smem, acc_scale);
-            else if (es.c_bf16 == 2) epilogue_store_fast<2>(taddr, m, M, n_base, N, es, stage_smem, acc_scale);
-            else epilogue_store_fast<1>(taddr, m, M, n_base, N, es, stage_smem, acc_scale);
+            if (es.c_bf16 == 0) epilogue_store_fast<0>(taddr, m, M, n_base, N, es, stage_smem, acc_scale, tile_cols);
+            else if (es.c_bf16 == 2) epilogue_store_fast<2>(taddr, m, M, n_base, N, es, stage_smem, acc_scale, tile_cols);
+            else epilogue_store_fast<1>(taddr, m, M, n_base, N, es, stage_smem, acc_scale, tile_cols);
             return;
           }
         }
         float run_max = -INFINITY, run_sum = 0.f;
         const int32_t want = (LSE && m < M && el.pick) ? __ldg(el.pick + m) : -1;
   #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
+        for (int c = 0; c < tile_cols; c += 32) {
           if (n_base + c >= N) break;                  // warp-uniform
           // residual rows of this chunk in the *transposed* (coalesced) mapping, issued as one batch before the
           // TMEM load so that their DRAM latency overlaps it
@@ -672,8 +673,14 @@ __device__ __forceinline__ void umma_2sm(uint32_t d_tmem, uint64_t da, uint64_t 
   }
 }
 
+// Single-pass (bf16 / tf32) store GEMMs are paced by the epilogue, not by the MMAs (5 us of main loop per tile against
+// ~8 us of TMEM drain + stores with one warp per TMEM lane quarter): they run EIGHT epilogue warps, two per lane quarter,
+// each draining half of the tile's columns, and give up one pipeline stage for the extra staging tiles.
 template <int MODE, bool LSE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == X3 ? 384 : 256, 1)
+__host__ __device__ constexpr bool tc2_epi8() { return MODE != X3 && !LSE; }
+
+template <int MODE, bool LSE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((MODE == X3 || tc2_epi8<MODE, LSE>()) ? 384 : 256, 1)
     gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_blo, int64_t M_cap, const int32_t* __restrict__ m_dev, int64_t N,
                     int64_t K, EpiStore es, EpiLse el) {
@@ -682,7 +689,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == X3 ? 384 : 2
   constexpr int UMMA_K = 32 / ELEM;
   constexpr int HALF_B = B_TILE / 2;                                   // this CTA's 128 W rows: 16 KB
   constexpr int STAGE_BYTES = MODE == X3 ? 2 * (A_TILE + HALF_B) : (A_TILE + HALF_B);
-  constexpr int STAGES = MODE == X3 ? 3 : 6;
+  constexpr bool EPI8 = tc2_epi8<MODE, LSE>();
+  constexpr int EPI_WARPS = EPI8 ? 8 : 4;
+  constexpr int STAGES = MODE == X3 ? 3 : (EPI8 ? 5 : 6);
   // bytes that land on the LEADER's w_full barrier per stage (both CTAs): W halves, plus A tiles when nobody
   // has to post-process A locally
   constexpr uint32_t W_TX = MODE == X3 ? 2u * 2u * HALF_B : 2u * (A_TILE + HALF_B);
@@ -725,7 +734,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == X3 ? 384 : 2
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 8);      // leader: 4 epilogue warps x 2 CTAs
+      mbar_init(&tmem_empty[a], 2 * EPI_WARPS);      // leader: every epilogue warp of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -799,9 +808,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == X3 ? 384 : 2
         tc_commit_2sm(&tmem_full[acc]);
       }
     }
-  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
     // ===================== epilogue (both CTAs, own 128 rows) =====================
-    const int q = warp & 3;
+    const int q = warp & 3;                                   // TMEM lane quarter
+    const int ew = warp - EPI_WARP0;
+    constexpr int COLS = EPI8 ? BLOCK_N / 2 : BLOCK_N;        // columns per epilogue warp
+    const int c0 = (ew >> 2) * COLS;
     int64_t it = 0;
     for (int64_t tile = pair0; tile < total; tile += pair_stride, ++it) {
       const int acc = (int)(it & 1);
@@ -811,8 +823,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == X3 ? 384 : 2
       const int64_t n_base = n_blk * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<LSE>(taddr, m, M, n_base, n_blk, N, es, el, epi_smem + (warp & 3) * 32 * EPI_LD);
+      const uint32_t taddr = tmem_base + (uint32_t)acc * BLOCK_N + (uint32_t)c0 + ((uint32_t)(q * 32) << 16);
+      epilogue_tile<LSE>(taddr, m, M, n_base + c0, n_blk, N, es, el, epi_smem + ew * 32 * EPI_LD, 1.f, COLS);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -1346,8 +1358,9 @@ static int32_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
   const bool two = use_2sm() != 0;
   const int stage_bytes = two ? (MODE == X3 ? 2 * (A_TILE + B_TILE / 2) : (A_TILE + B_TILE / 2))
                               : (MODE == X3 ? 2 * (A_TILE + B_TILE) : (A_TILE + B_TILE));
-  const int stages = two ? (MODE == X3 ? 3 : 6) : (MODE == X3 ? 2 : 4);
-  const size_t smem = (size_t)stages * stage_bytes + EPI_SMEM + 1024;
+  const bool epi8 = two && tc2_epi8<MODE, LSE>();
+  const int stages = two ? (MODE == X3 ? 3 : (epi8 ? 5 : 6)) : (MODE == X3 ? 2 : 4);
+  const size_t smem = (size_t)stages * stage_bytes + (epi8 ? 2 : 1) * EPI_SMEM + 1024;
   static bool attr_set[2] = {false, false};
   if (!attr_set[two]) {
     if (two) GNNLM_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<MODE, LSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1363,7 +1376,7 @@ static int32_t launch(const CUtensorMap& ma, const CUtensorMap& mb, const CUtens
   const int64_t pairs = ceil_div(ceil_div(M, BLOCK_M), 2) * ceil_div(N, BLOCK_N);
   const int64_t max_pairs = n_sm / 2;
   const unsigned grid = 2u * (unsigned)(pairs < max_pairs ? pairs : max_pairs);     // clusters of 2 CTAs
-  if (two) gemm_tc2_kernel<MODE, LSE><<<grid, MODE == X3 ? 384 : 256, smem, st>>>(ma, mb, mblo, M, m_dev, N, K, es, el);
+  if (two) gemm_tc2_kernel<MODE, LSE><<<grid, (MODE == X3 || epi8) ? 384 : 256, smem, st>>>(ma, mb, mblo, M, m_dev, N, K, es, el);
   else gemm_tc_kernel<MODE, LSE><<<grid, MODE == X3 ? 384 : 256, smem, st>>>(ma, mb, mblo, M, m_dev, N, K, es, el);
   GNNLM_LAUNCH_CHECK("gemm_tcgen05");
   return 0;
