@@ -38,6 +38,7 @@ SIGNATURES = {
     "gnnlm_gather_rows": (_i32, [_p, _i64, _p, _p, _i64, _i64, _p, _i64, _i32, _p]),
     "gnnlm_layernorm": (_i32, [_p, _i64, _p, _i32, _i64, _p, _p, _f32, _p, _i32, _i64, _i64, _p, _i64, _p]),
     "gnnlm_convert": (_i32, [_p, _i32, _p, _i32, _i64, _p]),
+    "gnnlm_gelu": (_i32, [_p, _i64, _p, _i32, _i64, _i64, _p, _i64, _p]),
     "gnnlm_to_split_f16": (_i32, [_p, _i32, _i64, _p, _i64, _i64, _p, _i64, _p]),
     "gnnlm_hgt_edge_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _i64, _p, _i32, _i32, _p, _i64, _f32, _i32, _p]),
     "gnnlm_hgt_cluster_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p]),

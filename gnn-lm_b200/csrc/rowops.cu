@@ -177,6 +177,40 @@ __global__ void __launch_bounds__(256) to_split_kernel(const S* __restrict__ src
   }
 }
 
+// y = gelu(x) (exact erf form, torch.nn.functional.gelu's default; hgt.py:506) for fp32 rows, written in an activation format
+template <int OMODE>      // 0 = f32, 1 = bf16, 2 = split fp16
+__global__ void __launch_bounds__(256) gelu_kernel(const float* __restrict__ src, int64_t ld_src, void* __restrict__ dst,
+                                                   int64_t ld_dst, int64_t rows_cap, const int32_t* __restrict__ rows_dev,
+                                                   int64_t d) {
+  const int64_t rows = live_rows(rows_cap, rows_dev);
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const float* s = src + r * ld_src;
+    for (int64_t c = lane * 4; c < d; c += 128) {             // d % 4 == 0
+      const float4 x4 = *reinterpret_cast<const float4*>(s + c);
+      float x[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) x[e] = 0.5f * x[e] * (1.f + erff(x[e] * 0.70710678118654752f));
+      if constexpr (OMODE == 0) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst) + r * ld_dst + c) = make_float4(x[0], x[1], x[2], x[3]);
+      } else if constexpr (OMODE == 2) {
+        uint2 hi, lo;
+        split4_f16(x[0], x[1], x[2], x[3], hi, lo);
+        __half* o = reinterpret_cast<__half*>(dst) + r * ld_dst;
+        *reinterpret_cast<uint2*>(o + c) = hi;
+        *reinterpret_cast<uint2*>(o + d + c) = lo;
+      } else {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(x[0], x[1]), b = __floats2bfloat162_rn(x[2], x[3]);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&a);
+        u.y = *reinterpret_cast<const uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(dst) + r * ld_dst + c) = u;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi,
                                                          float* __restrict__ lo, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -317,5 +351,23 @@ extern "C" int32_t gnnlm_to_split_f16(const void* src, int32_t src_dtype, int64_
   if (src_dtype == GNNLM_F32) to_split_kernel<float><<<g, 256, 0, st>>>((const float*)src, ld_src, (__half*)dst, ld_dst, rows, rows_dev, d);
   else to_split_kernel<__half><<<g, 256, 0, st>>>((const __half*)src, ld_src, (__half*)dst, ld_dst, rows, rows_dev, d);
   GNNLM_LAUNCH_CHECK("gnnlm_to_split_f16");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_gelu(const float* src, int64_t ld_src, void* dst, int32_t dst_dtype, int64_t ld_dst, int64_t rows,
+                              const int32_t* rows_dev, int64_t d, gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(src && dst, GNNLM_E_ARG, "gnnlm_gelu: null pointer");
+  GNNLM_CHECK_ARG(dst_dtype == GNNLM_F32 || dst_dtype == GNNLM_BF16 || dst_dtype == GNNLM_F16X2, GNNLM_E_UNSUPPORTED,
+                  "gnnlm_gelu: output must be F32, BF16 or F16X2");
+  GNNLM_CHECK_ARG(d > 0 && d % 4 == 0 && ld_src % 4 == 0 && ld_dst % 4 == 0 && ld_src >= d &&
+                      ld_dst >= (dst_dtype == GNNLM_F16X2 ? 2 * d : d) && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0,
+                  GNNLM_E_SHAPE, "gnnlm_gelu: d and the leading dimensions must be multiples of 4, pointers 16 B aligned");
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g = grid_for(rows, 8);
+  if (dst_dtype == GNNLM_F32) gelu_kernel<0><<<g, 256, 0, st>>>(src, ld_src, dst, ld_dst, rows, rows_dev, d);
+  else if (dst_dtype == GNNLM_F16X2) gelu_kernel<2><<<g, 256, 0, st>>>(src, ld_src, dst, ld_dst, rows, rows_dev, d);
+  else gelu_kernel<1><<<g, 256, 0, st>>>(src, ld_src, dst, ld_dst, rows, rows_dev, d);
+  GNNLM_LAUNCH_CHECK("gnnlm_gelu");
   return 0;
 }

@@ -270,12 +270,15 @@ class HGT(nn.Module):
     def __init__(self, ntype2idx, etype2idx, in_dim, hidden_dim, out_dim, n_layers, n_heads, use_norm=True,
                  dropout=0.0, two_stream=False, attn_drop=0.0):
         super().__init__()
-        if in_dim != hidden_dim or hidden_dim != out_dim:
-            raise NotImplementedError("adapt_ws / out projections (hgt.py:482-492) are unused by every reference "
-                                      "config (decoder_gcn_dim == decoder_embed_dim)")
         self.ntype2idx, self.etype2idx = ntype2idx, etype2idx
         self.in_dim, self.hidden_dim, self.out_dim, self.n_layers = in_dim, hidden_dim, out_dim, n_layers
-        self.adapt_ws = nn.ModuleList()
+        self.adapt_ws = nn.ModuleList()                       # hgt.py:482-492: only when --decoder_gcn_dim != embedding width
+        if in_dim != hidden_dim:
+            for _ in range(len(ntype2idx)):
+                self.adapt_ws.append(nn.Linear(in_dim, hidden_dim))
+        if hidden_dim != out_dim:
+            self.out = nn.Linear(hidden_dim, out_dim)
+        self._io_prep, self._io_key = None, None
         self.gcs = nn.ModuleList(HGTLayer(hidden_dim, hidden_dim, ntype2idx, etype2idx, n_heads, use_norm=use_norm,
                                           dropout=dropout, two_stream=two_stream, attn_drop=attn_drop)
                                  for _ in range(n_layers))
@@ -285,6 +288,32 @@ class HGT(nn.Module):
         self.math_mode = L.MATH_NAMES[mode] if isinstance(mode, str) else int(mode)
         return self
 
+    def _io(self):
+        """Prepared weights of the input adapters / output projection for the current math mode."""
+        mode = self.math_mode
+        ws = list(self.adapt_ws) + ([self.out] if self.hidden_dim != self.out_dim else [])
+        key = (mode,) + tuple((w.weight.device, int(w.weight._version), int(w.bias._version)) for w in ws)
+        if self._io_prep is None or self._io_key != key:
+            mk = lambda lin: _Weight(lin.weight.detach(), lin.bias.detach(), mode)
+            self._io_prep = {"adapt": [mk(w) for w in self.adapt_ws],
+                             "out": mk(self.out) if self.hidden_dim != self.out_dim else None}
+            self._io_key = key
+        return self._io_prep
+
+    def adapt(self, x, ntype: str, n_dev=None):
+        """h = gelu(adapt_ws[t](x)) when in_dim != hidden_dim (hgt.py:505-507), in the activation format; else x."""
+        if self.in_dim == self.hidden_dim or x is None:
+            return x
+        w = self._io()["adapt"][self.ntype2idx[ntype]]
+        y = _lin(as_act(x, self.math_mode), w, self.math_mode, m_dev=n_dev)                 # fp32 pre-activation
+        return ops.gelu(y, act_dtype(self.math_mode), n_dev=n_dev)
+
+    def project_out(self, h, n_dev=None):
+        """self.out(h) when hidden_dim != out_dim (hgt.py:513)."""
+        if self.hidden_dim == self.out_dim:
+            return h
+        return _lin(as_act(h, self.math_mode), self._io()["out"], self.math_mode, m_dev=n_dev)
+
     def forward(self, G: TokenGraph, features: Dict[str, torch.Tensor] = None, etypes=None, incremental_state=None):
         """Reference-shaped call (hgt.py:494-513): returns features of every node of both types."""
         h = {}
@@ -292,10 +321,11 @@ class HGT(nn.Module):
             x = None if not features else features.get(ntype)
             if x is None:
                 x = G.nodes[ntype].data["h"]
-            h[ntype] = x if x.dtype == torch.bfloat16 else x.float().contiguous()
+            x = x if x.dtype == torch.bfloat16 else x.float().contiguous()
+            h[ntype] = self.adapt(x, ntype)
         for layer in self.gcs:
             h = layer(G, h, etypes=etypes, incremental_state=incremental_state, math_mode=self.math_mode)
-        return {k_: as_float(v) for k_, v in h.items()}
+        return {k_: as_float(self.project_out(v)) for k_, v in h.items()}
 
     @torch.no_grad()
     def forward_tgt(self, G: TokenGraph, h_tgt: torch.Tensor, h_ntgt: Optional[torch.Tensor],
@@ -308,10 +338,10 @@ class HGT(nn.Module):
         mode = self.math_mode
         prep = [layer.prepare(mode) for layer in self.gcs]
         hc = self._ntgt_side(prep, G, h_ntgt, hc0)
-        h_t = as_act(h_tgt, mode)
+        h_t = as_act(self.adapt(h_tgt, "tgt"), mode)
         for l in range(self.n_layers):
             h_t = self.gcs[l].tgt(prep[l], G, h_t, hc[l], G.n_valid_dev)
-        return h_t
+        return self.project_out(h_t)
 
     def _ntgt_side(self, prep, G: TokenGraph, h_ntgt, hc0=None) -> List:
         """All layers of the ntgt side of one (chunk) graph -> compact centre features entering each layer."""
@@ -319,7 +349,9 @@ class HGT(nn.Module):
         NL, mode = self.n_layers, self.math_mode
         hc: List = []
         if h_ntgt is not None:
-            h_ntgt = as_act(h_ntgt, mode)
+            h_ntgt = as_act(self.adapt(h_ntgt, "ntgt", n_dev), mode)
+        elif hc0 is not None:
+            hc0 = self.adapt(hc0, "ntgt", c_dev)
         if hc0 is None:
             hc0 = ops.gather_rows(h_ntgt, G.inter_indices, n_dev=c_dev)
         hc.append(hc0)
@@ -350,7 +382,7 @@ class HGT(nn.Module):
             else:
                 hc_c = self._ntgt_side(prep, g_c, decode(g_c, False))
             chunks.append((t0, t1, g_c, hc_c))
-        h_t = as_act(h_tgt, mode)
+        h_t = as_act(self.adapt(h_tgt, "tgt"), mode)
         for l in range(self.n_layers):
             h_t = self.gcs[l].tgt(prep[l], G, h_t, None, None, chunks=[(t0, t1, g_c, hc_c[l]) for t0, t1, g_c, hc_c in chunks])
-        return h_t
+        return self.project_out(h_t)

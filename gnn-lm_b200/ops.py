@@ -251,6 +251,16 @@ def pq_gather_decode(codes, centroids, rows, *, bias=None, row_ids=None, n_cap=N
     return out, labels, codes_out
 
 
+def gelu(x, out_dtype=torch.float32, n_dev=None):
+    """gelu(x) (erf form) of fp32 rows into an activation format (torch dtype or SPLIT)."""
+    n, d = x.shape
+    assert x.dtype == torch.float32 and x.stride(1) == 1
+    out = empty_act(n, d, out_dtype, x.device)
+    o_ptr, o_code, ldo, _ = _mat(out)
+    L.call("gnnlm_gelu", L.ptr(x), x.stride(0), o_ptr, o_code, ldo, n, _dev_count(n_dev), d, L.stream_ptr())
+    return out
+
+
 def pq_gather_decode_presplit(codes, cb_hi, cb_lo, rows, *, row_ids=None, n_cap=None, n_dev=None):
     """Gather + decode straight into the split-fp16 format from a pre-split codebook (dsub == 8)."""
     n_d, M = codes.shape

@@ -59,7 +59,7 @@ def make_model(cfg: dict, seed: int = 1) -> TransformerLanguageModel:
     cen = rng.randn(c.M, 256, dsub).astype(np.float32)
     A = np.linalg.qr(rng.randn(c.d, c.d))[0].astype(np.float32)
     codec = TorchPQCodec(centroids=cen, A=A, b=np.zeros(0, np.float32))
-    args = default_args(decoder_embed_dim=c.d, decoder_attention_heads=c.H, graph_layer=c.NL,
+    args = default_args(decoder_embed_dim=c.d, decoder_attention_heads=c.H, graph_layer=c.NL, decoder_gcn_dim=cfg.get("gcn_dim"),
                         adaptive_softmax_cutoff=c.cutoff, tie_adaptive_weights=c.tied)
     model = TransformerLanguageModel.build_model(args, dictionary=Dictionary(c.V), quantizer=codec)
     with torch.no_grad():   # make biases / pri / LN affine non-trivial so that parity exercises them

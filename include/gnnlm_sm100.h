@@ -197,6 +197,10 @@ int32_t gnnlm_layernorm(const float* x, int64_t ldx, const void* residual, int32
 /* fp16 / fp32 rows [rows, d] (ld_src elements) -> split-fp16 [rows, 2d] (GNNLM_F16X2, ld_dst >= 2d fp16 elements). */
 int32_t gnnlm_to_split_f16(const void* src, int32_t src_dtype, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows,
                            const int32_t* rows_dev, int64_t d, gnnlm_stream_t stream);
+/* y = gelu(x), exact erf form -- the activation of HGT's input adapters `gelu(adapt_ws[t](h))` (hgt.py:505-507), used when
+ * --decoder_gcn_dim differs from the embedding width.  x fp32 [rows, d]; y F32 / BF16 / F16X2. */
+int32_t gnnlm_gelu(const float* src, int64_t ld_src, void* dst, int32_t dst_dtype, int64_t ld_dst, int64_t rows,
+                   const int32_t* rows_dev, int64_t d, gnnlm_stream_t stream);
 /* Convert fp16/fp32 rows (keys.npy slices, token_block_dataset.py:327-329) to fp32/bf16. */
 int32_t gnnlm_convert(const void* src, int32_t src_dtype, void* dst, int32_t dst_dtype, int64_t n,
                       gnnlm_stream_t stream);

@@ -502,7 +502,7 @@ def _ref_hgt():
     return mod
 
 
-def make_hgt_case(name, B, L, k, cl, cr, d, H, n_layers, seed, stress=True):
+def make_hgt_case(name, B, L, k, cl, cr, d, H, n_layers, seed, stress=True, hidden=None, out_dim=None):
     sys.path.insert(0, os.path.join(OUT, "..", ".."))
     from oracle import graph_oracle as go
     rng = np.random.RandomState(seed)
@@ -535,7 +535,8 @@ def make_hgt_case(name, B, L, k, cl, cr, d, H, n_layers, seed, stress=True):
     hgt = _ref_hgt()
     torch.manual_seed(seed)
     model = hgt.HGT(ntype2idx={"tgt": 0, "ntgt": 1}, etype2idx={"intra": 0, "inter": 1}, in_dim=d,
-                    hidden_dim=d, out_dim=d, n_layers=n_layers, n_heads=H, dropout=0.0, attn_drop=0.0).eval()
+                    hidden_dim=hidden or d, out_dim=out_dim or d, n_layers=n_layers, n_heads=H, dropout=0.0,
+                    attn_drop=0.0).eval()
     with torch.no_grad():
         for p in model.parameters():          # make every parameter non-trivial (biases, pri, LN affine)
             if p.dim() <= 2 and p.shape[-1] != d or p.dim() == 1:
@@ -581,3 +582,4 @@ if __name__ == "__main__":
     make_scorer_case("b2_lm", B=2, L=12, d=64, V=300, cutoff=[40, 120], knn=8, lmbda=0.25, temp=1.0, seed=1)
     make_hgt_case("l2_c1", B=2, L=6, k=3, cl=1, cr=1, d=32, H=4, n_layers=2, seed=0)
     make_hgt_case("l3_c2", B=1, L=8, k=2, cl=2, cr=2, d=32, H=2, n_layers=3, seed=1)
+    make_hgt_case("l2_adapt", B=1, L=7, k=3, cl=1, cr=1, d=24, H=4, n_layers=2, seed=2, hidden=32, out_dim=24)

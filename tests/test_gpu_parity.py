@@ -169,13 +169,13 @@ def test_layernorm_and_gather(dev):
 # ------------------------------------------------------------------------------------------ HGT
 def _hgt_from_golden(z, dev):
     from gnnlm_b200.hgt import HGT
-    d = z["h_tgt"].shape[1]
-    m = HGT({"tgt": 0, "ntgt": 1}, {"intra": 0, "inter": 1}, d, d, d, int(z["n_layers"]), int(z["H"]))
+    d, hidden, d_out = z["h_tgt"].shape[1], z["sd.gcs.0.k_linears.0.weight"].shape[0], z["out_tgt"].shape[1]
+    m = HGT({"tgt": 0, "ntgt": 1}, {"intra": 0, "inter": 1}, d, hidden, d_out, int(z["n_layers"]), int(z["H"]))
     m.load_state_dict(_sd(z, "sd."), strict=True)
     return m.to(dev).eval()
 
 
-@pytest.mark.parametrize("case", ["l2_c1", "l3_c2"])
+@pytest.mark.parametrize("case", ["l2_c1", "l3_c2", "l2_adapt"])      # l2_adapt: in_dim 24 -> hidden 32 -> out 24 (adapt_ws / out)
 def test_hgt_golden(case, dev):
     """Reference hgt.py executed under the DGL stub (tests/golden/make_golden.py) vs the CUDA path."""
     from gnnlm_b200.graph import build_token_graph
@@ -953,3 +953,22 @@ def test_eval_lm_option_matrix(cl, cr, NL, intra, cw, math, dev):
         res = evaluate(m, ds, dstore, scorer, knn_dstore=knn, temperature=1.0, max_sentences=2, device=dev, **kw)
         assert res["count"] == cnt == n_tok
         assert abs(res["score_sum"] - tot) / abs(tot) < 2e-5, (kw, res["score_sum"], tot)
+
+
+@pytest.mark.parametrize("math", ["fp32", "f16x3", "bf16"])
+def test_whole_path_gcn_dim_differs(math, dev):
+    """--decoder_gcn_dim != embedding width: HGT's input adapters gelu(adapt_ws[t](h)) and output projection
+    (hgt.py:482-492,505-513) are live; d = 512 -> hidden 256 -> 512, two layers."""
+    if math != "fp32":
+        _need_tc()
+    import copy
+    from gnnlm_b200 import synth
+    from tests.synth import run_oracle
+    cfg = dict(synth.CONFIGS["c1"], NL=2, L=96, k=6, n_d=1 << 14, gcn_dim=256)
+    model = synth.make_model(cfg)
+    assert len(model.decoder.hgt_decoder.adapt_ws) == 2 and model.decoder.hgt_decoder.out.weight.shape == (512, 256)
+    data = synth.make_data(cfg, seed=5, device="cpu")
+    ref = run_oracle((cfg, model, data))
+    out = synth.run_gpu(cfg, copy.deepcopy(model), data, dev, math)
+    tol = 1e-2 if math == "bf16" else 1e-4
+    np.testing.assert_allclose(out["logprob"], ref["logprob"].numpy(), rtol=tol, atol=tol)

@@ -91,7 +91,7 @@ def test_scorer_lm_b2_start_indices(golden_dir):
         np.testing.assert_allclose(lm[i, s:].numpy(), z[f"lm_pos_{i}"], rtol=1e-5, atol=1e-5)
 
 
-@pytest.mark.parametrize("case", ["l2_c1", "l3_c2"])
+@pytest.mark.parametrize("case", ["l2_c1", "l3_c2", "l2_adapt"])
 def test_hgt_matches_reference_layer_code(case, golden_dir):
     z = np.load(os.path.join(golden_dir, f"hgt_{case}.npz"))
     g = go.build_batch(z["nbr"], z["offsets"], int(z["n_d"]), int(z["cl"]), int(z["cr"]))
