@@ -115,6 +115,46 @@ def new_build_graph(offsets: np.ndarray, neighbor_idxs: np.ndarray, n_datastore:
     return out
 
 
+def deprecated_build_graph(offsets: np.ndarray, neighbor_idxs: np.ndarray, n_datastore: int, left_ctx: int,
+                           right_ctx: int, invalid_ctx: int = 0, max_intra_context: int = 0,
+                           quant_feats: np.ndarray = None) -> dict:
+    """token_block_dataset.py:414-479 (`--deprecated`), one block: datastore rows are DE-DUPLICATED -- one ntgt node per
+    distinct row of the block, numbered by first appearance (centre, then its left context ascending, then its right
+    context ascending, neighbour by neighbour); ntgt-ntgt edges by build_ntgt_edges over ALL nodes of the block
+    (context 1, bidirectional): rows at distance <= 1 are connected wherever they came from."""
+    L = len(offsets)
+    off2id: Dict[int, int] = {}
+    tgt2ntgt = [[], []]
+    for tgt_idx in range(L):
+        for offset in neighbor_idxs[tgt_idx]:
+            offset = int(offset)
+            if offset == -1:                                                  # :432
+                continue
+            if abs(int(offsets[tgt_idx]) - offset) < invalid_ctx:             # :435
+                continue
+            if offset not in off2id:                                          # :440-448
+                off2id[offset] = len(off2id)
+            tgt2ntgt[0].append(tgt_idx)
+            tgt2ntgt[1].append(off2id[offset])
+            ctx = []
+            if left_ctx:                                                      # :452-455
+                ctx.extend(range(max(0, offset - left_ctx), offset))
+            if right_ctx:                                                     # :456-460
+                ctx.extend(range(offset + 1, min(n_datastore, offset + 1 + right_ctx)))
+            for o in ctx:                                                     # :461-466
+                if o not in off2id:
+                    off2id[o] = len(off2id)
+    s, t = build_ntgt_edges(off2id, 1, bidirect=True)                         # :469
+    us, vs = auto_regressive_edges(L, max_intra_context)
+    ntgt_offsets = np.asarray(list(off2id.keys()), dtype=np.int64)            # insertion order == node id order
+    out = {"n_tgt": L, "n_ntgt": len(off2id), "tt": (us, vs),
+           "inter": (np.asarray(tgt2ntgt[1], np.int64), np.asarray(tgt2ntgt[0], np.int64)),
+           "nn": (np.asarray(s, np.int64), np.asarray(t, np.int64)), "ntgt_offsets": ntgt_offsets}
+    if quant_feats is not None:
+        out["ntgt_codes"] = quant_feats[ntgt_offsets] if len(off2id) else np.zeros((0, quant_feats.shape[1]), quant_feats.dtype)
+    return out
+
+
 def batch_graphs(graphs: List[dict]) -> dict:
     """dgl.batch semantics (monolingual_dataset.py:261): per-type node ids are offset by the
     cumulative node counts of the preceding graphs; edge lists are concatenated."""
@@ -152,10 +192,11 @@ def canonical_csr(src: np.ndarray, dst: np.ndarray, n_dst: int) -> Tuple[np.ndar
 
 
 def build_batch(neighbor_idxs: np.ndarray, offsets: np.ndarray, n_datastore: int, left_ctx: int,
-                right_ctx: int, invalid_ctx: int = 0, max_intra_context: int = 0) -> dict:
+                right_ctx: int, invalid_ctx: int = 0, max_intra_context: int = 0, deprecated: bool = False) -> dict:
     """[B, L, k] neighbour ids + [B, L] stream positions -> batched graph + canonical CSRs."""
-    graphs = [new_build_graph(offsets[b], neighbor_idxs[b], n_datastore, left_ctx, right_ctx,
-                              invalid_ctx, max_intra_context) for b in range(neighbor_idxs.shape[0])]
+    one = deprecated_build_graph if deprecated else new_build_graph
+    graphs = [one(offsets[b], neighbor_idxs[b], n_datastore, left_ctx, right_ctx,
+                  invalid_ctx, max_intra_context) for b in range(neighbor_idxs.shape[0])]
     g = batch_graphs(graphs)
     g["tt_csr"] = canonical_csr(*g["tt"], g["n_tgt"])
     g["inter_csr"] = canonical_csr(*g["inter"], g["n_tgt"])

@@ -96,7 +96,7 @@ def _graph_builder(fix_q1):
     ns = {"torch": torch, "np": np, "lru_cache": lru_cache, "Dict": Dict, "Tuple": Tuple, "List": List,
           "dgl": types.SimpleNamespace(heterograph=lambda e: _RecGraph(e))}
     body = []
-    for m in ("new_build_graph", "build_ntgt_edges", "auto_regressive_edges"):
+    for m in ("new_build_graph", "deprecated_build_graph", "build_ntgt_edges", "auto_regressive_edges"):
         s = _method_source("fairseq/data/token_block_dataset.py", "GraphTokenBlockDataset", m)
         if fix_q1 and m == "new_build_graph":
             assert "len(self.neighbor_offsets.shape[0])" in s
@@ -140,6 +140,39 @@ def make_graph_case(name, L, k, n_d, cl, cr, invalid_ctx, intra_ctx, M, seed, st
     )
     np.savez_compressed(os.path.join(OUT, f"graph_{name}.npz"), **out)
     print(f"graph_{name}: ntgt={len(out['ntgt_labels'])} E_nn={len(out['nn_src'])}")
+
+
+def make_dedup_case(name, L, k, n_d, cl, cr, invalid_ctx, intra_ctx, M, seed):
+    """`--deprecated` graph build (token_block_dataset.py:414-479): runs unmodified (it clips the right context with
+    len(self.neighbor_tokens), :458).  Neighbour ids are drawn from a narrow range so that rows repeat and runs of
+    consecutive rows form across neighbours and tokens."""
+    rng = np.random.RandomState(seed)
+    g = _graph_builder(False)()
+    start = int(rng.randint(0, 1000))
+    offsets = np.arange(start, start + L, dtype=np.int64)
+    nbr = rng.randint(0, min(n_d, 6 * L), size=(L, k)).astype(np.int64)
+    nbr[rng.rand(L, k) < 0.1] = -1
+    edge = rng.rand(L, k) < 0.1
+    nbr[edge] = rng.choice([0, 1, n_d - 1, n_d - 2], size=int(edge.sum()))
+    nbr[L // 3] = -1
+    nbr[1, :] = nbr[0, :]                     # a token repeating its predecessor's neighbours
+    if k > 1:
+        nbr[2, 1] = nbr[2, 0]                 # the same row twice for one token
+    codes = rng.randint(0, 256, size=(n_d, M)).astype(np.uint8)
+    vals = rng.randint(4, 1000, size=(n_d, 1)).astype(np.int32)
+    g.neighbor_offsets, g.neighbor_tokens, g.quant_neighbor_feats = nbr, vals, codes
+    g.left_neighbor_context, g.right_neighbor_context = cl, cr
+    g.invalid_neighbor_context, g.max_intra_context = invalid_ctx, intra_ctx
+    z = torch.zeros(L, dtype=torch.long)
+    graph = g.deprecated_build_graph(z, offsets, nbr, z)
+    e = graph.edges
+    out = dict(L=L, k=k, n_d=n_d, cl=cl, cr=cr, invalid_ctx=invalid_ctx, intra_ctx=intra_ctx, offsets=offsets, nbr=nbr, codes=codes,
+               tt_src=e[("tgt", "intra", "tgt")][0].numpy(), tt_dst=e[("tgt", "intra", "tgt")][1].numpy(),
+               inter_src=e[("ntgt", "inter", "tgt")][0].numpy(), inter_dst=e[("ntgt", "inter", "tgt")][1].numpy(),
+               nn_src=e[("ntgt", "intra", "ntgt")][0].numpy(), nn_dst=e[("ntgt", "intra", "ntgt")][1].numpy(),
+               ntgt_codes=graph.nodes["ntgt"].data["h"].numpy())
+    np.savez_compressed(os.path.join(OUT, f"dedup_{name}.npz"), **out)
+    print(f"dedup_{name}: ntgt={len(out['ntgt_codes'])} (of {int((nbr >= 0).sum())} neighbours) E_nn={len(out['nn_src'])}")
 
 
 def make_edges_doctest():
@@ -566,6 +599,10 @@ if __name__ == "__main__":
     make_graph_case("c3_c3_intra5", L=20, k=5, n_d=600, cl=3, cr=3, invalid_ctx=0, intra_ctx=5, M=16, seed=2, stress=True)
     make_graph_case("c0_c0", L=12, k=6, n_d=200, cl=0, cr=0, invalid_ctx=0, intra_ctx=0, M=8, seed=3, stress=False)
     make_graph_case("c1_c2_invalid", L=32, k=4, n_d=1200, cl=1, cr=2, invalid_ctx=300, intra_ctx=0, M=8, seed=4, stress=True)
+    make_dedup_case("c1", L=24, k=4, n_d=400, cl=1, cr=1, invalid_ctx=0, intra_ctx=0, M=8, seed=0)
+    make_dedup_case("c2_c0", L=16, k=3, n_d=300, cl=2, cr=0, invalid_ctx=0, intra_ctx=0, M=8, seed=1)
+    make_dedup_case("c0", L=12, k=5, n_d=60, cl=0, cr=0, invalid_ctx=0, intra_ctx=4, M=8, seed=2)
+    make_dedup_case("c1_c3_invalid", L=32, k=4, n_d=1200, cl=1, cr=3, invalid_ctx=300, intra_ctx=0, M=16, seed=3)
     make_adaptive_case("untied", V=300, d=64, cutoff=[40, 120], tied=False, T=40, seed=0)
     make_adaptive_case("tied", V=300, d=64, cutoff=[40, 120], tied=True, T=40, seed=1)
     make_pq_case("m8", n=50, M=8, dsub=4, with_b=False, seed=0)

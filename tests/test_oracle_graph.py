@@ -80,3 +80,20 @@ def test_slice_indices_all_break_modes(golden_dir):
         assert np.array_equal(got, z[key]), key
         n += 1
     assert n == 32
+
+
+DEDUP = sorted(os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "dedup_*.npz")))
+
+
+@pytest.mark.parametrize("case", DEDUP)
+def test_deprecated_build_graph_matches_reference(case, golden_dir):
+    """`--deprecated` (de-duplicating) builder, token_block_dataset.py:414-479, executed from the reference source."""
+    z = np.load(os.path.join(golden_dir, f"dedup_{case}.npz"))
+    g = go.deprecated_build_graph(z["offsets"], z["nbr"], int(z["n_d"]), int(z["cl"]), int(z["cr"]), int(z["invalid_ctx"]),
+                                  int(z["intra_ctx"]), quant_feats=z["codes"])
+    assert g["n_ntgt"] == z["ntgt_codes"].shape[0]
+    for name in ("tt", "inter", "nn"):
+        assert np.array_equal(g[name][0], z[f"{name}_src"]), name
+        assert np.array_equal(g[name][1], z[f"{name}_dst"]), name
+    assert np.array_equal(g["ntgt_codes"], z["ntgt_codes"])
+    assert len(set(g["ntgt_offsets"].tolist())) == g["n_ntgt"]            # one node per distinct datastore row
