@@ -16,39 +16,13 @@
 // HBM-bound integer work: 8 B read per (token, neighbour), ~(8+4+4) B + 4*(3w-2)/w B written per
 // node.  One thread per cluster; scans are block-local + a single-block pass over block sums.
 #include "common.cuh"
+#include "graph_shape.cuh"
 
 namespace gnnlm {
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 4;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-
-struct ClusterShape {
-  int nl, nr, valid;
-};
-
-__device__ __forceinline__ ClusterShape cluster_shape(int64_t o, int64_t pos, int64_t n_datastore, int left_ctx,
-                                                      int right_ctx, int64_t invalid_ctx) {
-  ClusterShape s{0, 0, 0};
-  if (o == -1) return s;                                       // token_block_dataset.py:358
-  if (invalid_ctx > 0) {
-    int64_t dlt = pos - o;
-    if (dlt < 0) dlt = -dlt;
-    if (dlt < invalid_ctx) return s;                           // :361
-  }
-  s.valid = 1;
-  // left: range(max(0, o - c_l), o)            (:380)
-  int64_t lo = o - left_ctx;
-  if (lo < 0) lo = 0;
-  int64_t nl = o - lo;
-  s.nl = nl > 0 ? (int)nl : 0;
-  // right: range(o + 1, min(N, o + 1 + c_r))   (:384, with the Q1 fix)
-  int64_t hi = o + 1 + right_ctx;
-  if (hi > n_datastore) hi = n_datastore;
-  int64_t nr = hi - (o + 1);
-  s.nr = nr > 0 ? (int)nr : 0;
-  return s;
-}
 
 __device__ __forceinline__ int2 add2(int2 a, int2 b) { return make_int2(a.x + b.x, a.y + b.y); }
 

@@ -98,8 +98,7 @@ class GraphTokenBlockDataset:
                  sizes: Optional[np.ndarray] = None, document_sep_len: int = 1):
         if break_mode not in (None, "none") and sizes is None:
             raise ValueError(f"--sample-break-mode {break_mode} needs the sentence lengths (sizes=...)")
-        if deprecated:
-            raise NotImplementedError("--deprecated (dedup) graph build is a 'next' row (SURVEY.md 8f-4)")
+        self.deprecated = deprecated                # --deprecated: de-duplicating builder (token_block_dataset.py:305,414-479)
         self.tokens = tokens
         self.block_size, self.pad, self.eos = block_size, pad, eos
         self.neighbor_offsets = neighbor_offsets
@@ -177,7 +176,8 @@ def sample_from_inputs(inp: dict, dataset: GraphTokenBlockDataset, dstore: Devic
     pos = inp["positions"]
     g = build_token_graph(inp["nbr"], dstore.size, dataset.left_neighbor_context, dataset.right_neighbor_context,
                           tgt_pos=pos if dataset.invalid_neighbor_context > 0 else None,
-                          invalid_ctx=dataset.invalid_neighbor_context, intra_ctx=dataset.max_intra_context, reach=reach)
+                          invalid_ctx=dataset.invalid_neighbor_context, intra_ctx=dataset.max_intra_context, reach=reach,
+                          dedup=getattr(dataset, "deprecated", False))
     g.codes_table = dstore.codes
     g.labels_table = dstore.vals
     if "feats" in inp:

@@ -44,11 +44,13 @@ class TokenGraph:
         self.nbr = self.tgt_pos = None        # inputs kept so that token chunks can be re-assembled (chunked ntgt side)
         self.invalid_ctx = 0
         self._counts_host = None
+        self.dedup = False                    # --deprecated builder: one node per distinct datastore row, general CSR
+        self._n_ntgt = None
 
     # ---- device-side counts (no host sync needed by the kernels) ----
     @property
     def n_ntgt_dev(self) -> torch.Tensor:
-        return self.node_base[-1:]
+        return self._n_ntgt if self.dedup else self.node_base[-1:]
 
     @property
     def n_valid_dev(self) -> torch.Tensor:
@@ -57,7 +59,7 @@ class TokenGraph:
     def counts(self):
         """(n_ntgt, n_valid) on the host -- synchronises; only tests / full-mode outputs use it."""
         if self._counts_host is None:
-            self._counts_host = (int(self.node_base[-1].item()), int(self.valid_base[-1].item()))
+            self._counts_host = (int(self.n_ntgt_dev.item()), int(self.valid_base[-1].item()))
         return self._counts_host
 
     def num_nodes(self, ntype: str) -> int:
@@ -89,7 +91,7 @@ class TokenGraph:
 
 def build_token_graph(nbr: torch.Tensor, n_datastore: int, left_ctx: int, right_ctx: int, *,
                       tgt_pos: Optional[torch.Tensor] = None, invalid_ctx: int = 0, intra_ctx: int = 0,
-                      with_owner: bool = False, reach: Optional[int] = None) -> TokenGraph:
+                      with_owner: bool = False, reach: Optional[int] = None, dedup: bool = False) -> TokenGraph:
     """nbr [B, L, k] int64 on the device (= neighbor_offsets[offsets], token_block_dataset.py:309).
 
     `reach`: keep only context nodes within `reach` chain hops of their centre.  With NL graph layers a tgt node sees its
@@ -97,7 +99,7 @@ def build_token_graph(nbr: torch.Tensor, n_datastore: int, left_ctx: int, right_
     cannot influence any tgt output (the decoder reads tgt rows only, transformer.py:1053): reach = NL-1 gives the same
     tgt features as the reference's full clusters with fewer rows to decode and project (e.g. w = 7 -> 5 at c = 3, NL = 3).
     The ntgt numbering then differs from the reference's, so leave it None when ntgt outputs are wanted."""
-    if reach is not None:
+    if reach is not None and not dedup:      # de-duplicated context rows can be adjacent to OTHER centres: no pruning there
         left_ctx, right_ctx = min(left_ctx, reach), min(right_ctx, reach)
     assert nbr.is_cuda and nbr.dtype == torch.int64 and nbr.dim() == 3 and nbr.is_contiguous()
     B, Lb, k = nbr.shape
@@ -118,6 +120,8 @@ def build_token_graph(nbr: torch.Tensor, n_datastore: int, left_ctx: int, right_
     L.call("gnnlm_graph_count", L.ptr(nbr), L.ptr(tgt_pos), g.T, k, n_datastore, left_ctx, right_ctx, invalid_ctx,
            L.ptr(g.node_base), L.ptr(g.valid_base), L.ptr(ws), ws.numel(), st)
     cap = g.node_cap
+    if dedup:
+        return _build_dedup(g, nbr, tgt_pos, n, cap, st)
     g.ntgt_row = torch.empty(cap, dtype=torch.int64, device=dev)
     g.ntgt_dist = torch.empty(cap, **i32)
     g.ntgt_owner = torch.empty(cap, **i32) if with_owner else None
@@ -129,6 +133,26 @@ def build_token_graph(nbr: torch.Tensor, n_datastore: int, left_ctx: int, right_
     L.call("gnnlm_graph_fill", L.ptr(nbr), L.ptr(tgt_pos), g.T, k, n_datastore, left_ctx, right_ctx, invalid_ctx,
            L.ptr(g.node_base), L.ptr(g.valid_base), L.ptr(g.ntgt_row), L.ptr(g.ntgt_owner), L.ptr(g.ntgt_dist),
            L.ptr(g.nn_indptr), L.ptr(g.nn_indices), L.ptr(g.inter_indptr), L.ptr(g.inter_indices), L.ptr(g.cluster_nl), st)
+    return g
+
+
+def _build_dedup(g: TokenGraph, nbr, tgt_pos, n: int, cap: int, st) -> TokenGraph:
+    """`--deprecated` builder (token_block_dataset.py:414-479) -> gnnlm_graph_dedup; valid_base is already counted."""
+    dev = nbr.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    g.dedup = True
+    g.ntgt_row = torch.empty(cap, dtype=torch.int64, device=dev)
+    g._n_ntgt = torch.empty(1, **i32)
+    g.nn_indptr = torch.empty(cap + 1, **i32)
+    g.nn_indices = torch.empty(3 * cap, **i32)
+    g.inter_indptr = torch.empty(g.T + 1, **i32)
+    g.inter_indices = torch.empty(n, **i32)
+    ws_bytes = L.load().gnnlm_graph_dedup_workspace_bytes(g.T, g.k, g.w)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    L.call("gnnlm_graph_dedup", L.ptr(nbr), L.ptr(tgt_pos), g.T, g.L, g.k, g.n_datastore, g.left_ctx, g.right_ctx,
+           g.invalid_ctx, L.ptr(g.valid_base), L.ptr(g.ntgt_row), L.ptr(g._n_ntgt), L.ptr(g.nn_indptr), L.ptr(g.nn_indices),
+           L.ptr(g.inter_indptr), L.ptr(g.inter_indices), L.ptr(ws), ws.numel(), st)
+    g.node_base = None                        # no cluster structure in this mode
     return g
 
 

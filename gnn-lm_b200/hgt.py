@@ -196,7 +196,7 @@ class HGTLayer(nn.Module):
         d, H = P["d"], self.n_heads
         act = act_dtype(P["math"])
         tag = "nn_centre" if centre else "nn_full"
-        if self.use_cluster_kernel and ops.cluster_attn_supported(d, H, q.dtype, G.w):
+        if self.use_cluster_kernel and not G.dedup and ops.cluster_attn_supported(d, H, q.dtype, G.w):
             t_agg = ops.empty_act(rows, d, act, q.device)
             ops.cluster_attn(q, k, v, G, H, t_agg, centre_only=centre, tag=tag)
             return t_agg

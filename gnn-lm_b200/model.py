@@ -235,6 +235,9 @@ class TokenGraphTransformerDecoder(nn.Module):
             per_token = graph.k * graph.w * self.embed_dim * 4 * 11
             budget = float(_get(self.args, "ntgt_memory_budget_gb", 48.0)) * 1e9
             chunk = max(64, int(budget // per_token) // 64 * 64)
+            if NL > 1 and graph.T > chunk and graph.dedup:
+                raise NotImplementedError("--deprecated graphs share ntgt nodes between tokens, so the ntgt side cannot run "
+                                          "in token chunks: raise ntgt_memory_budget_gb or evaluate shorter blocks")
             if NL > 1 and graph.T > chunk:
                 out = self.hgt_decoder.forward_tgt_chunked(graph, h_tgt, decode, chunk)
             elif NL == 1:

@@ -103,6 +103,21 @@ int64_t gnnlm_graph_tt_num_edges(int64_t B, int64_t L, int64_t intra_ctx);
 int32_t gnnlm_graph_tt_csr(int64_t B, int64_t L, int64_t intra_ctx, int32_t* indptr, int32_t* indices,
                            gnnlm_stream_t stream);
 
+/* `--deprecated` graph assembly (GraphTokenBlockDataset.deprecated_build_graph, token_block_dataset.py:414-479): ONE ntgt
+ * node per distinct datastore row of a block, numbered by first appearance (centre, left context ascending, right context
+ * ascending, neighbour by neighbour, token by token); ntgt-ntgt edges between rows at distance <= 1 wherever they came
+ * from (+ self loops); blocks of a batch share no nodes.  T = B * L tokens, block length L.
+ *  valid_base   [T*k + 1] from gnnlm_graph_count (same contexts / invalid_ctx)
+ *  ntgt_row     [T*k*w] int64 datastore row per node; n_ntgt [1] live node count (device)
+ *  nn_indptr [T*k*w + 1], nn_indices [3*T*k*w]: canonical CSR by destination, sources in row order (o-1, o, o+1)
+ *  inter_indptr [T + 1], inter_indices [T*k]: the centre node of every valid (token, neighbour), in that order
+ *  workspace: gnnlm_graph_dedup_workspace_bytes(T, k, w) bytes, 256 B aligned. */
+int64_t gnnlm_graph_dedup_workspace_bytes(int64_t T, int64_t k, int32_t w);
+int32_t gnnlm_graph_dedup(const int64_t* nbr, const int64_t* tgt_pos, int64_t T, int64_t L, int64_t k, int64_t n_datastore,
+                          int32_t left_ctx, int32_t right_ctx, int64_t invalid_ctx, const int32_t* valid_base,
+                          int64_t* ntgt_row, int32_t* n_ntgt, int32_t* nn_indptr, int32_t* nn_indices, int32_t* inter_indptr,
+                          int32_t* inter_indices, void* workspace, int64_t workspace_bytes, gnnlm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (2) Datastore gather + PQ decode -- replaces `quant_neighbor_feats[offset]` /
  *     `neighbor_tokens[offset]` (token_block_dataset.py:369-371,392-394) and the centroid gather of

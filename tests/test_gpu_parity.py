@@ -972,3 +972,108 @@ def test_whole_path_gcn_dim_differs(math, dev):
     out = synth.run_gpu(cfg, copy.deepcopy(model), data, dev, math)
     tol = 1e-2 if math == "bf16" else 1e-4
     np.testing.assert_allclose(out["logprob"], ref["logprob"].numpy(), rtol=tol, atol=tol)
+
+
+# ------------------------------------------------------------------------------------------ --deprecated (dedup) graphs
+_DEDUP = sorted(os.path.basename(p)[6:-4] for p in __import__("glob").glob(os.path.join(GOLD, "dedup_*.npz")))
+
+
+def _check_dedup_graph(g, ref, n_tgt, dev):
+    n_ntgt, n_valid = g.counts()
+    assert n_ntgt == ref["n_ntgt"] and n_valid == len(ref["inter"][0])
+    from oracle import graph_oracle as go
+    nn_ip, nn_ix = go.canonical_csr(*ref["nn"], n_ntgt)
+    in_ip, in_ix = go.canonical_csr(*ref["inter"], n_tgt)
+    assert (g.ntgt_row[:n_ntgt].cpu().numpy() == ref["ntgt_offsets"]).all()             # first-appearance numbering
+    assert (g.nn_indptr[:n_ntgt + 1].cpu().numpy() == nn_ip).all()
+    assert (g.nn_indices[:len(nn_ix)].cpu().numpy() == nn_ix).all()
+    assert (g.inter_indptr.cpu().numpy() == in_ip).all()
+    assert (g.inter_indices[:n_valid].cpu().numpy() == in_ix).all()
+
+
+@pytest.mark.parametrize("case", _DEDUP)
+def test_graph_dedup_matches_reference_builder(case, dev):
+    """gnnlm_graph_dedup vs deprecated_build_graph executed from the reference source: node numbering, canonical CSRs and
+    the gathered code rows are bit-exact."""
+    from gnnlm_b200 import ops
+    from gnnlm_b200.graph import build_token_graph
+    z = np.load(os.path.join(GOLD, f"dedup_{case}.npz"))
+    nbr = torch.from_numpy(z["nbr"])[None].contiguous().to(dev)
+    pos = torch.from_numpy(z["offsets"])[None].contiguous().to(dev)
+    g = build_token_graph(nbr, int(z["n_d"]), int(z["cl"]), int(z["cr"]), tgt_pos=pos, invalid_ctx=int(z["invalid_ctx"]),
+                          intra_ctx=int(z["intra_ctx"]), dedup=True)
+    n = z["ntgt_codes"].shape[0]
+    ref = {"n_ntgt": n, "inter": (z["inter_src"], z["inter_dst"]), "nn": (z["nn_src"], z["nn_dst"]),
+           "ntgt_offsets": None}
+    # rows of the reference's nodes: recover from the gathered code rows is ambiguous, so take them from the oracle
+    from oracle import graph_oracle as go
+    o = go.deprecated_build_graph(z["offsets"], z["nbr"], int(z["n_d"]), int(z["cl"]), int(z["cr"]), int(z["invalid_ctx"]))
+    ref["ntgt_offsets"] = o["ntgt_offsets"]
+    _check_dedup_graph(g, ref, int(z["L"]), dev)
+    codes = torch.from_numpy(z["codes"]).to(dev)
+    cen = torch.zeros(codes.shape[1], 256, 4, device=dev)
+    _, _, codes_out = ops.pq_gather_decode(codes, cen, g.ntgt_row, n_cap=n, want_codes=True, decode=False)
+    assert (codes_out.cpu().numpy() == z["ntgt_codes"]).all()
+
+
+@pytest.mark.parametrize("B,L,k,cl,cr,span", [(2, 64, 8, 1, 1, 300), (3, 40, 16, 2, 0, 100), (1, 512, 32, 1, 1, 20000),
+                                              (2, 33, 5, 0, 0, 50), (1, 96, 12, 3, 3, 400)])
+def test_graph_dedup_vs_oracle_random(B, L, k, cl, cr, span, dev):
+    """Heavier collision patterns (neighbours drawn from `span` rows), several blocks per batch, clipping at both ends."""
+    from gnnlm_b200.graph import build_token_graph
+    from oracle import graph_oracle as go
+    rng = np.random.RandomState(B * 100 + L + k)
+    n_d = span + 7
+    nbr = rng.randint(0, n_d, size=(B, L, k)).astype(np.int64)
+    nbr[rng.rand(B, L, k) < 0.05] = -1
+    off = np.arange(B * L, dtype=np.int64).reshape(B, L)
+    ref = go.build_batch(nbr, off, n_d, cl, cr, deprecated=True)
+    g = build_token_graph(torch.from_numpy(nbr).to(dev), n_d, cl, cr, dedup=True)
+    _check_dedup_graph(g, ref, B * L, dev)
+
+
+@pytest.mark.parametrize("math,NL", [("fp32", 1), ("fp32", 3), ("f16x3", 2)])
+def test_eval_lm_deprecated_graph(math, NL, dev):
+    """The whole path over --deprecated graphs (shared ntgt nodes, general CSR attention) vs the CPU oracle."""
+    if math != "fp32":
+        _need_tc()
+    from types import SimpleNamespace
+    import copy
+    from gnnlm_b200 import synth
+    from gnnlm_b200.dataset import DeviceDatastore, GraphTokenBlockDataset
+    from gnnlm_b200.eval_lm import evaluate
+    from gnnlm_b200.knn_model import KNNModel
+    from gnnlm_b200.sequence_scorer import SequenceScorer
+    from oracle import model_oracle as mo
+    from tests.synth import oracle_model
+    cfg = dict(synth.CONFIGS["c1"], NL=NL, k=6, n_d=900, k_nn=8)
+    model = synth.make_model(cfg)
+    rng = np.random.RandomState(NL)
+    n_tok, blk = 150, 48
+    tables = synth.make_tables(cfg, device="cpu")
+    tokens = rng.randint(4, cfg["V"], size=n_tok).astype(np.int64)
+    nbr = rng.randint(0, 300, size=(n_tok, cfg["k"])).astype(np.int64)          # many repeated / adjacent rows
+    nbr[rng.rand(n_tok, cfg["k"]) < 0.1] = -1
+    feats = rng.randn(n_tok, cfg["d"]).astype(np.float16)
+    kd = rng.randn(n_tok, cfg["k_nn"]).astype(np.float32)
+    ki = rng.randint(0, cfg["n_d"], size=(n_tok, cfg["k_nn"])).astype(np.int64)
+    ds = GraphTokenBlockDataset(tokens, blk, pad=1, eos=2, neighbor_offsets=nbr, n_datastore=cfg["n_d"], neighbor_context=1,
+                                precompute_feats=feats, knn_dists=kd, knn_ids=ki, deprecated=True)
+    dstore = DeviceDatastore(tables["codes"].to(dev), tables["vals"].to(dev))
+    scorer = SequenceScorer(synth.Dictionary(cfg["V"]), args=SimpleNamespace(lmbda=cfg["lmbda"], knn_keytype=None))
+    knn = KNNModel(dstore.vals, vocab_size=cfg["V"])
+    om = oracle_model(cfg, model)
+    tot = 0.0
+    for i in range(len(ds)):
+        cs, e = ds[i]["offsets"]
+        batch = {"nbr": nbr[cs:e][None], "offsets": np.arange(cs, e)[None], "tgt_feats": torch.from_numpy(feats[cs:e]).float(),
+                 "target": ds[i]["target"], "codes": tables["codes"].numpy(), "cl": 1, "cr": 1, "n_d": cfg["n_d"],
+                 "deprecated": True}
+        k_ = {"dists": torch.from_numpy(kd[cs:e]), "ids": torch.from_numpy(ki[cs:e]), "vals": tables["vals"].long(),
+              "lmbda": cfg["lmbda"], "temperature": 1.0}
+        tot += float(mo.eval_batch(om, batch, k_)["logprob"].double().sum())
+    m = copy.deepcopy(model).to(dev).set_math(math)
+    for kw in (dict(), dict(cuda_graph=True)):
+        res = evaluate(m, ds, dstore, scorer, knn_dstore=knn, temperature=1.0, max_sentences=2, device=dev, **kw)
+        assert res["count"] == n_tok
+        assert abs(res["score_sum"] - tot) / abs(tot) < 2e-5, (kw, res["score_sum"], tot)
