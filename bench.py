@@ -35,6 +35,7 @@ def parse():
     p.add_argument("--config", default="c3")
     p.add_argument("--math", default="auto")
     p.add_argument("--n-datastore", type=int, default=0, help="override datastore rows (default: the config's)")
+    p.add_argument("--deprecated", action="store_true", help="--deprecated (de-duplicating) graph builder, general CSR attention")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-tokens", type=int, default=384, help="tokens in the CPU-baseline sample block")
     p.add_argument("--also-modes", default="tf32x3,tf32,bf16",
@@ -184,6 +185,8 @@ def main():
     cfg = dict(synth.CONFIGS[args.config])
     if args.n_datastore:
         cfg["n_d"] = args.n_datastore
+    if args.deprecated:
+        cfg["deprecated"] = True
     T = cfg["B"] * cfg["L"]
 
     model = synth.make_model(cfg)
@@ -329,7 +332,7 @@ def main():
                                                            "tf32": "tf32", "bf16": "bf16"}[math],
         "data": "synthetic", "impl": "ours",
         "config": {"workload": workload_name(args.config), "math": math, "n_datastore": tables["n_d"],
-                   "cuda_graph": bool(args.cuda_graph),
+                   "cuda_graph": bool(args.cuda_graph), "graph_builder": "deprecated (dedup)" if args.deprecated else "new",
                    "parallelism": f"dp{world} (contiguous block shards, replicated datastore, one 16 B all-reduce)",
                    "l2_policy": "inputs larger than L2 (datastore + activations are GBs); 4 distinct batches rotated",
                    "n_ntgt": n_ntgt, "n_valid_neighbours": n_valid},

@@ -139,7 +139,8 @@ class Runner:
 
     def sample_from(self, nbr, feats, target, dists, ids):
         c = self.c
-        g = build_token_graph(nbr, self.dstore.size, c.c, c.c, reach=c.NL - 1 if self.prune_unreachable else None)
+        g = build_token_graph(nbr, self.dstore.size, c.c, c.c, reach=c.NL - 1 if self.prune_unreachable else None,
+                              dedup=bool(self.cfg.get("deprecated", False)))
         g.codes_table = self.dstore.codes
         g.nodes["tgt"].data["h"] = feats.view(-1, feats.shape[-1])
         self.knn.set_search_results(dists, ids)
