@@ -1077,3 +1077,35 @@ def test_eval_lm_deprecated_graph(math, NL, dev):
         res = evaluate(m, ds, dstore, scorer, knn_dstore=knn, temperature=1.0, max_sentences=2, device=dev, **kw)
         assert res["count"] == n_tok
         assert abs(res["score_sum"] - tot) / abs(tot) < 2e-5, (kw, res["score_sum"], tot)
+
+
+# ------------------------------------------------------------------------------------------ error behaviour of the C-ABI
+def test_c_abi_rejects_bad_arguments(dev):
+    """Argument / shape problems come back as a status code + message (GnnlmError), never as a crash or a silent
+    fallback -- the places where the reference asserts or raises."""
+    from gnnlm_b200 import _lib as L, ops
+    from gnnlm_b200._lib import GnnlmError
+    from gnnlm_b200.graph import build_token_graph
+    x = torch.randn(64, 96, device=dev)
+    w = torch.randn(32, 96, device=dev)
+    with pytest.raises(GnnlmError, match="gnnlm_linear"):
+        L.call("gnnlm_linear", None, 0, 96, L.ptr(w), None, 1.0, 96, None, None, 0, 0, L.ptr(x), 0, 32, 64, None, 32, 96, 0,
+               L.stream_ptr())                                                         # null A
+    with pytest.raises(GnnlmError, match="W_lo"):
+        ops.linear(x, w, None, math=L.MATH_F16X3)                                      # 3xFP16 without the split weights
+    with pytest.raises(GnnlmError, match="dsub must be 8"):
+        L.call("gnnlm_pq_gather_decode_presplit", L.ptr(x), 10, 8, L.ptr(x), L.ptr(x), 4, L.ptr(x), None, 4, None, L.ptr(x), 128,
+               L.stream_ptr())
+    q = torch.randn(10, 60, device=dev)                                                # d_k = 30: no lane mapping
+    with pytest.raises(GnnlmError, match="head layout"):
+        ops.edge_attn(q, q, q, torch.zeros(11, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int32, device=dev), 2,
+                      torch.empty(10, 60, device=dev))
+    nbr = torch.zeros(1, 7, 2, dtype=torch.int64, device=dev)
+    with pytest.raises(GnnlmError, match="multiple of the block length"):
+        L.call("gnnlm_graph_dedup", L.ptr(nbr), None, 7, 3, 2, 100, 1, 1, 0, L.ptr(nbr), L.ptr(nbr), L.ptr(nbr), L.ptr(nbr),
+               L.ptr(nbr), L.ptr(nbr), L.ptr(nbr), L.ptr(nbr), 1 << 20, L.stream_ptr())
+    with pytest.raises(GnnlmError, match="metric"):
+        L.call("gnnlm_knn_sims_keys", L.ptr(x), 96, L.ptr(x), 0, 64, 96, L.ptr(nbr), 2, 7, 0, L.ptr(x), 1, L.stream_ptr())
+    # the library is still usable afterwards
+    g = build_token_graph(torch.full((1, 4, 2), -1, dtype=torch.int64, device=dev), 100, 1, 1)
+    assert g.counts() == (0, 0)
