@@ -10,7 +10,7 @@ SOURCES = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")))
 HEADERS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + [
     os.path.join(os.path.dirname(HERE), "include", "gnnlm_sm100.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "--threads", "0"]      # one compile per source file in parallel
 
 
 def is_stale() -> bool:

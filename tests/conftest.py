@@ -17,3 +17,11 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
+
+
+@pytest.fixture(scope="session")
+def built_library():
+    """The in-tree C-ABI library, built here when the checkout is fresh (nvcc cross-compiles without a GPU); loading it
+    and listing its symbols is all the CPU suite does with it."""
+    from gnnlm_b200 import build
+    return build.build()

@@ -83,7 +83,7 @@ def test_batches_group_equal_lengths():
     assert dsw[2]["start_idx"] == 16 and len(dsw[2]["target"]) == 144 and dsw[0]["start_idx"] == 0
 
 
-def test_c_abi_exports_every_declared_symbol():
+def test_c_abi_exports_every_declared_symbol(built_library):
     """include/gnnlm_sm100.h <-> libgnnlm_sm100.so <-> ctypes table (no compute calls without a GPU)."""
     import re
     from gnnlm_b200 import _lib
