@@ -25,7 +25,7 @@ namespace gnnlm {
 
 constexpr int EA_THREADS = 256;
 
-template <typename T, int C, int UNROLL>
+template <typename T, int C, int UNROLL, int GROUP = 0>      // GROUP: lanes per head when known at compile time (0 = `group`)
 __device__ __forceinline__ void attend_range(const float (&q)[C], const T* __restrict__ k, int64_t ldk,
                                              const T* __restrict__ v, int64_t ldv, const int32_t* __restrict__ indices,
                                              int64_t e_begin, int64_t e_end, int col, int group, float& m_run,
@@ -57,7 +57,12 @@ __device__ __forceinline__ void attend_range(const float (&q)[C], const T* __res
       float p = 0.f;
 #pragma unroll
       for (int c = 0; c < C; ++c) p = fmaf(q[c], kk[u][c], p);
-      for (int o = group >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      if constexpr (GROUP > 0) {
+#pragma unroll
+        for (int o = GROUP >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      } else {
+        for (int o = group >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      }
       s[u] = src[u] >= 0 ? p : -INFINITY;
       mx = fmaxf(mx, s[u]);
     }
@@ -95,7 +100,7 @@ __device__ __forceinline__ void write_out(float* __restrict__ o, const float (&a
 // CSR edge attention.  Work item = (destination, feature slice of 32*C floats): a warp reads 128*C
 // contiguous bytes of each Q / K' / V' row, so registers stay small (many warps resident, several rows in
 // flight per warp) and every row segment is one coalesced request.  `group` = lanes per head.
-template <typename T, int C, int UNROLL>
+template <typename T, int C, int UNROLL, int GROUP>
 __global__ void __launch_bounds__(EA_THREADS) edge_attn_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k,
                                                                int64_t ldk, const T* __restrict__ v, int64_t ldv,
                                                                const int32_t* __restrict__ indptr,
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(EA_THREADS) edge_attn_kernel(const T* __restri
 #pragma unroll
     for (int c = 0; c < C; ++c) acc[c] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
-    attend_range<T, C, UNROLL>(qr, k, ldk, v, ldv, indices, e0, e1, col, group, m_run, l_run, acc);
+    attend_range<T, C, UNROLL, GROUP>(qr, k, ldk, v, ldv, indices, e0, e1, col, group, m_run, l_run, acc);
     write_out<C>(out + i * ldo + col, acc, l_run, out_scale, accumulate);
   }
 }
@@ -350,9 +355,14 @@ static int32_t launch_edge(const void* q, int64_t ldq, const void* k, int64_t ld
   int64_t blocks = ceil_div(items, EA_THREADS / 32);
   const int64_t max_blocks = 148 * 8 * 8;
   if (blocks > max_blocks) blocks = max_blocks;
-  edge_attn_kernel<T, C, UNROLL><<<(unsigned)blocks, EA_THREADS, 0, st>>>(
-      (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, group, n_slices,
-      out, ldo, out_scale, accumulate);
+#define GNNLM_EA(G)                                                                                                         \
+  edge_attn_kernel<T, C, UNROLL, G><<<(unsigned)blocks, EA_THREADS, 0, st>>>(                                                \
+      (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, group, n_slices, \
+      out, ldo, out_scale, accumulate)
+  if (group == 32) GNNLM_EA(32);           // d_k = 128 fp32 / 256 bf16: fully unrolled reductions, no divergent-collective code
+  else if (group == 16) GNNLM_EA(16);
+  else GNNLM_EA(0);
+#undef GNNLM_EA
   GNNLM_LAUNCH_CHECK("gnnlm_hgt_edge_attn");
   return 0;
 }
