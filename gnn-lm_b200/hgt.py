@@ -65,6 +65,9 @@ class _Weight:
         return v
 
 
+FUSED_INTER_MODES = (L.MATH_F16X3, L.MATH_BF16, L.MATH_TF32)     # modes whose operands are already fp16-range on tensor cores
+
+
 def _lin(x, w: _Weight, math_mode, **kw):
     return ops.linear(x, w.W, w.b, W_lo=w.lo, w_scale=w.scale, math=math_mode, **kw)
 
@@ -139,6 +142,7 @@ class HGTLayer(nn.Module):
         self._prep = None
         self._prep_key = None
         self.use_cluster_kernel = True     # False: always go through the generic CSR kernel (tests compare both)
+        self.use_fused_inter = True        # False: project every centre node to K' / V' and use the CSR kernel
         self.use_gemm_attention = True     # MATH_F16X3, long blocks: tgt-intra-tgt attention as tensor-core GEMMs
 
     # ------------------------------------------------------------------ weight preparation
@@ -166,6 +170,13 @@ class HGTLayer(nn.Module):
             return _Weight(W, b, math_mode)
 
         Wk, bk, Wv, bv = kv(n, inter)
+        fused = None
+        if math_mode in FUSED_INTER_MODES and ops.inter_fused_supported(d, self.n_heads):
+            # token-side form of the inter projections (inter_attn.cu): W_k'[h]^T [H, d, d_k] and W_v'[h] [H, d_k, d] as
+            # fp16 splits; b_k' drops out of the softmax, b_v' is added once per token
+            Hh, dk = self.n_heads, d // self.n_heads
+            fused = {"wk_t": ops.split_f16(Wk.view(Hh, dk, d).transpose(1, 2).contiguous().view(Hh * d, dk)),
+                     "wv": ops.split_f16(Wv.contiguous()), "bv": bv.contiguous().float()}
         P = {
             "tgt_qkv": qkv(t), "ntgt_qkv": qkv(n),
             "ntgt_kv_inter": _Weight(torch.cat([Wk, Wv], 0), torch.cat([bk, bv], 0), math_mode),
@@ -173,7 +184,7 @@ class HGTLayer(nn.Module):
                   for tau in (t, n)},
             "ln": {tau: (self.norms[tau].weight.detach().float().contiguous(),
                          self.norms[tau].bias.detach().float().contiguous(), self.norms[tau].eps) for tau in (t, n)},
-            "math": math_mode, "d": d, "t": t, "n": n,
+            "math": math_mode, "d": d, "t": t, "n": n, "inter_fused": fused,
         }
         self._prep, self._prep_key = P, key
         return P
@@ -232,7 +243,12 @@ class HGTLayer(nn.Module):
         qkv = _lin(h_t, P["tgt_qkv"], P["math"])
         t_agg = torch.empty((h_t.shape[0], d), device=qkv.device, dtype=torch.float32)
         # inter edges in compact centre numbering are the contiguous ranges of inter_indptr
-        if chunks is None:
+        if P["inter_fused"] is not None and self.use_fused_inter:
+            F_ = P["inter_fused"]
+            parts = [(0, G.T, G.inter_indptr, hc)] if chunks is None else [(t0, t1 - t0, g_c.inter_indptr, hc_c)
+                                                                          for t0, t1, g_c, hc_c in chunks]
+            ops.inter_attn_fused(qkv[:, :d], parts, H, t_agg, F_["wk_t"], F_["wv"], F_["bv"], out_scale=0.5)
+        elif chunks is None:
             kvi = _lin(hc, P["ntgt_kv_inter"], P["math"], m_dev=c_dev)
             ops.edge_attn(qkv[:, :d], kvi[:, :d], kvi[:, d:], G.inter_indptr, None, H, t_agg, out_scale=0.5, tag="inter")
         else:

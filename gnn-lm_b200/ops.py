@@ -185,6 +185,34 @@ def cluster_attn(q, k, v, G, H, out, *, centre_only=False, tag=None):
     return out
 
 
+def inter_fused_supported(d: int, H: int) -> bool:
+    dk = d // H
+    return H in (4, 8, 12, 16) and d % 8 == 0 and d <= 1024 and dk % 8 == 0 and (32 * (d + 4) + H * d + 35 * H) * 4 <= 220 * 1024
+
+
+def inter_attn_fused(q, hc_chunks, H, t_agg, wk_t, wv, bias_v, out_scale=0.5):
+    """('ntgt','inter','tgt') attention with the K' / V' projections on the token side (gnnlm_hgt_inter_fused).
+    q fp32 [T, d] (column slice ok); hc_chunks: [(t0, n_tokens, inter_indptr, hc)] covering all T tokens; t_agg fp32 [T, d] is
+    OVERWRITTEN with out_scale * inter.  wk_t / wv: (hi, lo, scale) fp16 splits of W_k'[h]^T [H, d, d_k] and W_v'[h] [H, d_k, d]."""
+    T, d = q.shape
+    dk = d // H
+    dev = q.device
+    st = L.stream_ptr
+    qs = torch.empty((H, T, 2 * dk), device=dev, dtype=torch.float16)
+    L.call("gnnlm_heads_split_f16", L.ptr(q), q.stride(0), T, H, dk, 1, L.ptr(qs), None, st())
+    qt = torch.empty((H, T, d), device=dev, dtype=torch.float32)
+    L.call("gnnlm_linear_batched_f16x3", L.ptr(qs), 2 * dk, T * 2 * dk, L.ptr(wk_t[0]), L.ptr(wk_t[1]), dk, d * dk, float(wk_t[2]),
+           None, 0, 0, L.ptr(qt), d, T * d, H, T, d, dk, 0, st(), tag="inter_q")
+    a = torch.empty((H, T, 2 * d), device=dev, dtype=torch.float16)
+    for t0, n_tok, indptr, hc in hc_chunks:
+        h_ptr, h_code, ldh, _ = _mat(hc)
+        L.call("gnnlm_hgt_inter_fused", L.ptr(qt), T * d, h_ptr, h_code, ldh, L.ptr(indptr), t0, n_tok, H, d, L.ptr(a), T * 2 * d,
+               2 * d, L.ptr(bias_v), float(out_scale), L.ptr(t_agg), t_agg.stride(0), st(), tag="inter_fused")
+    L.call("gnnlm_linear_batched_f16x3", L.ptr(a), 2 * d, T * 2 * d, L.ptr(wv[0]), L.ptr(wv[1]), d, dk * d, float(wv[2]) / out_scale,
+           L.ptr(t_agg), t_agg.stride(0), dk, L.ptr(t_agg), t_agg.stride(0), dk, H, T, dk, d, 0, st(), tag="inter_v")
+    return t_agg
+
+
 def causal_attn(q, k, v, B, Lb, intra_ctx, H, out, *, out_scale=1.0, accumulate=False):
     d = q.shape[1]
     L.call("gnnlm_hgt_causal_attn", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0),

@@ -262,6 +262,22 @@ int32_t gnnlm_hgt_causal_attn(const void* q, int64_t ldq, const void* k, int64_t
                               int32_t d_k, float* out, int64_t ldo, float out_scale, int32_t accumulate,
                               gnnlm_stream_t stream);
 
+/* ('ntgt','inter','tgt') attention with the K' / V' projections moved from the ~k*T centre nodes to the T target tokens
+ * (every centre row is used by exactly one (token, neighbour) pair): with q~[t,h] = W_k'[h]^T q[t,h] in R^d (a per-head GEMM
+ * of the caller) this kernel computes, per token and head, alpha = softmax_c <h_c, q~[t,h]> over the token's centre rows and
+ * a[t,h] = sum_c alpha_c h_c; the caller finishes with out[t,h] = W_v'[h] a[t,h] (+ b_v' when the token has a neighbour).
+ * Same value as hgt.py:339-358 for this edge type up to fp32 re-association (b_k' cancels inside the softmax).
+ *  q_tilde [H, n_all, d] fp32 (head stride q_head_stride, row stride d), rows t0 .. t0 + n_tokens are processed
+ *  hc      compact centre features, row i = i-th inter edge (F32 [*, d] / BF16 [*, d] / F16X2 [*, 2d]; ldh elements)
+ *  inter_indptr [n_tokens + 1]: token t0 + i owns rows [indptr[i], indptr[i+1]) of hc
+ *  a_out   [H, n_all, 2d] split fp16 (head stride a_head_stride, row stride lda): zero rows for tokens without neighbours
+ *  t_agg   [n_all, d] fp32 (ldt): row t := out_scale * b_v' if the token has a neighbour else 0 (the caller's final
+ *          per-head GEMM accumulates out_scale * W_v' a on top).  H in {4, 8, 12, 16}, d % 4 == 0, d <= 1024. */
+int32_t gnnlm_hgt_inter_fused(const float* q_tilde, int64_t q_head_stride, const void* hc, int32_t hc_dtype, int64_t ldh,
+                              const int32_t* inter_indptr, int64_t t0, int64_t n_tokens, int32_t H, int64_t d, void* a_out,
+                              int64_t a_head_stride, int64_t lda, const float* bias_v, float out_scale, float* t_agg,
+                              int64_t ldt, gnnlm_stream_t stream);
+
 /* Tensor-core form of the same causal attention for MATH_F16X3 (fp32 parity): per block and head,
  * S = Q K'^T and O = softmax_causal(S) V' are two gnnlm_linear calls on split-fp16 operands; these three
  * streaming kernels produce the operands.
