@@ -66,30 +66,44 @@ __global__ void __launch_bounds__(IA_THREADS) inter_fused_kernel(const float* __
   const int64_t e0 = __ldg(indptr + tl), e1 = __ldg(indptr + tl + 1);
   const int64_t deg = e1 - e0;
 
-  for (int64_t i = tid * 4; i < (int64_t)H * d; i += IA_THREADS * 4) {
-    const int64_t h = i / d, c = i - h * d;
-    *reinterpret_cast<float4*>(qs + i) = __ldg(reinterpret_cast<const float4*>(qt + h * q_hs + t * d + c));
+  const int di = (int)d;                                    // 32-bit index arithmetic below (d <= 1024)
+  for (int h = warp; h < H; h += IA_THREADS / 32) {         // warp per head row: no divisions in the copy loops
+    const float* src = qt + h * q_hs + t * d;
+    for (int c = lane * 4; c < di; c += 128)
+      *reinterpret_cast<float4*>(qs + h * di + c) = __ldg(reinterpret_cast<const float4*>(src + c));
   }
   if (tid < H) {
     l_s[tid] = 0.f;
     m_s[tid] = -INFINITY;
   }
   // phase 2 ownership: 4 columns x HH heads per thread
-  const int64_t col = (int64_t)(tid & (IA_THREADS / 2 - 1)) * 4;
+  const int col = (tid & (IA_THREADS / 2 - 1)) * 4;
   const int h0 = (tid >= IA_THREADS / 2) ? HH : 0;
   float acc[HH][4];
 #pragma unroll
   for (int h = 0; h < HH; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
   // phase 1 ownership: warp -> (head mod 8, half of the tile's rows); lane -> (half of the columns, row)
   const int p1_rh = warp >> 3, p1_r = p1_rh * 16 + (lane & 15), p1_ch = lane >> 4;
-  const int64_t half_q = d / 8;                            // float4 per column half
+  const int half_q = (int)(d / 8);                         // float4 per column half
 
   for (int64_t r0 = 0; r0 < deg; r0 += IA_ROWS) {
     const int nr = (int)((deg - r0) < IA_ROWS ? (deg - r0) : IA_ROWS);
     __syncthreads();                                       // previous tile fully consumed (and qs / l_s / m_s visible)
-    for (int64_t i = tid * 4; i < (int64_t)nr * d; i += IA_THREADS * 4) {
-      const int64_t r = i / d, c = i - r * d;
-      *reinterpret_cast<float4*>(rows + r * ldr + c) = ia_load4<InT>(hc + (e0 + r0 + r) * ldh, c, d);
+    // global -> shared, one warp per centre row (two rows per warp per tile), all loads of a row issued before its stores
+    for (int r = warp; r < nr; r += IA_THREADS / 32) {
+      const InT* src = hc + (e0 + r0 + r) * ldh;
+      float* dst = rows + r * (int)ldr;
+      float4 buf[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = lane * 4 + u * 128;
+        if (c < di) buf[u] = ia_load4<InT>(src, c, d);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = lane * 4 + u * 128;
+        if (c < di) *reinterpret_cast<float4*>(dst + c) = buf[u];
+      }
     }
     __syncthreads();
     // ---- phase 1a: scores of the tile
@@ -99,10 +113,11 @@ __global__ void __launch_bounds__(IA_THREADS) inter_fused_kernel(const float* __
       if (h < H) {
         float s = 0.f;
         if (p1_r < nr) {
-          const float4* rp = reinterpret_cast<const float4*>(rows + p1_r * ldr) + p1_ch * half_q;
-          const float4* qp = reinterpret_cast<const float4*>(qs + (int64_t)h * d) + p1_ch * half_q;
+          const float4* rp = reinterpret_cast<const float4*>(rows + p1_r * (int)ldr) + p1_ch * half_q;
+          const float4* qp = reinterpret_cast<const float4*>(qs + h * di) + p1_ch * half_q;
           float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f, s5 = 0.f, s6 = 0.f, s7 = 0.f;
-          int64_t j = 0;
+          int j = 0;
+#pragma unroll 4
           for (; j + 1 < half_q; j += 2) {
             const float4 a = rp[j], b = qp[j], a2 = rp[j + 1], b2 = qp[j + 1];
             s0 = fmaf(a.x, b.x, s0); s1 = fmaf(a.y, b.y, s1); s2 = fmaf(a.z, b.z, s2); s3 = fmaf(a.w, b.w, s3);
@@ -145,7 +160,7 @@ __global__ void __launch_bounds__(IA_THREADS) inter_fused_kernel(const float* __
       }
 #pragma unroll 4
       for (int r = 0; r < nr; ++r) {
-        const float4 x = *reinterpret_cast<const float4*>(rows + r * ldr + col);
+        const float4 x = *reinterpret_cast<const float4*>(rows + r * (int)ldr + col);
 #pragma unroll
         for (int h = 0; h < HH; ++h) {
           const float p = ss[r * H + h0 + h];
