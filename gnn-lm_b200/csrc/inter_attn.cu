@@ -13,17 +13,17 @@
 // its <= k centre rows once, scores them against the H transformed queries, and writes the H alpha-weighted row sums:
 // d reads + H*d writes per token instead of 2 d^2 MACs per centre.  Same result up to fp32 re-association.
 //
-// One CTA (512 threads) per token; centre rows in tiles of 32 through shared memory (fp32, row stride d + 4 floats:
-// conflict-free for both access patterns), online softmax across tiles.  Phase 1: warp -> (head, half of the rows),
-// lane -> (half of the columns, row).  Phase 2: thread -> 4 columns of half of the H sums.
+// One CTA (256 threads) per token, two CTAs per SM; centre rows in tiles of 16 through shared memory (fp32, row stride
+// d + 4 floats: conflict-free for both access patterns), online softmax across tiles.  Phase 1: warp -> head,
+// lane -> (half of the columns, row).  Phase 2: thread -> 4 columns of all H sums.
 #include <type_traits>
 
 #include "common.cuh"
 
 namespace gnnlm {
 
-constexpr int IA_THREADS = 512;
-constexpr int IA_ROWS = 32;
+constexpr int IA_THREADS = 256;
+constexpr int IA_ROWS = 16;          // centre rows per tile: 2 CTAs per SM at d = 1024, H = 8 (copy of one overlaps the math of the other)
 
 template <typename InT>
 __device__ __forceinline__ float4 ia_load4(const InT* row, int64_t c, int64_t d);
@@ -44,13 +44,13 @@ __device__ __forceinline__ float4 ia_load4<__nv_bfloat16>(const __nv_bfloat16* r
 }
 
 template <typename InT, int H>
-__global__ void __launch_bounds__(IA_THREADS) inter_fused_kernel(const float* __restrict__ qt, int64_t q_hs,   // [H, T, d], head stride
+__global__ void __launch_bounds__(IA_THREADS, 2) inter_fused_kernel(const float* __restrict__ qt, int64_t q_hs,   // [H, T, d], head stride
                                                                  const InT* __restrict__ hc, int64_t ldh,
                                                                  const int32_t* __restrict__ indptr, int64_t t0, int64_t d,
                                                                  __half* __restrict__ a_out, int64_t a_hs, int64_t lda,
                                                                  const float* __restrict__ bias_v, float out_scale,
                                                                  float* __restrict__ t_agg, int64_t ldt) {
-  constexpr int HH = H / 2;                                // heads per thread in phase 2
+  constexpr int HH = H;                                    // heads per thread in phase 2
   extern __shared__ __align__(16) float ia_smem[];
   const int64_t ldr = d + 4;
   float* rows = ia_smem;                                   // [IA_ROWS][d + 4]
@@ -77,13 +77,13 @@ __global__ void __launch_bounds__(IA_THREADS) inter_fused_kernel(const float* __
     m_s[tid] = -INFINITY;
   }
   // phase 2 ownership: 4 columns x HH heads per thread
-  const int col = (tid & (IA_THREADS / 2 - 1)) * 4;
-  const int h0 = (tid >= IA_THREADS / 2) ? HH : 0;
+  const int col = tid * 4;
+  constexpr int h0 = 0;
   float acc[HH][4];
 #pragma unroll
   for (int h = 0; h < HH; ++h) acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
-  // phase 1 ownership: warp -> (head mod 8, half of the tile's rows); lane -> (half of the columns, row)
-  const int p1_rh = warp >> 3, p1_r = p1_rh * 16 + (lane & 15), p1_ch = lane >> 4;
+  // phase 1 ownership: warp -> head (mod 8); lane -> (half of the columns, row)
+  const int p1_r = lane & 15, p1_ch = lane >> 4;
   const int half_q = (int)(d / 8);                         // float4 per column half
 
   for (int64_t r0 = 0; r0 < deg; r0 += IA_ROWS) {
@@ -136,13 +136,13 @@ __global__ void __launch_bounds__(IA_THREADS) inter_fused_kernel(const float* __
     __syncthreads();
     // ---- phase 1b: online softmax bookkeeping (warp h, lane -> row)
     for (int h = warp; h < H; h += IA_THREADS / 32) {
-      const float s = ss[lane * H + h];
+      const float s = lane < IA_ROWS ? ss[lane * H + h] : -INFINITY;
       const float m_old = m_s[h];
       const float mx = fmaxf(m_old, warp_max(s));
       const float p = lane < nr ? __expf(s - mx) : 0.f;
       const float tile_sum = warp_sum(p);
       __syncwarp();
-      ss[lane * H + h] = p;
+      if (lane < IA_ROWS) ss[lane * H + h] = p;
       if (lane == 0) {
         const float c = __expf(m_old - mx);                  // first tile: exp(-inf) = 0
         corr_s[h] = c;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(IA_THREADS) inter_fused_kernel(const float* __
       *reinterpret_cast<uint2*>(o) = hi;
       *reinterpret_cast<uint2*>(o + d) = lo;
     }
-    if (h0 == 0) {
+    {
       float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
       if (deg > 0 && bias_v) b = __ldg(reinterpret_cast<const float4*>(bias_v + col));
       *reinterpret_cast<float4*>(t_agg + t * ldt + col) =
@@ -219,11 +219,11 @@ extern "C" int32_t gnnlm_hgt_inter_fused(const float* q_tilde, int64_t q_head_st
   GNNLM_CHECK_ARG(q_tilde && hc && inter_indptr && a_out && t_agg, GNNLM_E_ARG, "gnnlm_hgt_inter_fused: null pointer");
   GNNLM_CHECK_ARG(hc_dtype == GNNLM_F32 || hc_dtype == GNNLM_BF16 || hc_dtype == GNNLM_F16X2, GNNLM_E_UNSUPPORTED,
                   "gnnlm_hgt_inter_fused: centre features must be F32, BF16 or F16X2");
-  GNNLM_CHECK_ARG(d > 0 && d % 8 == 0 && d <= IA_THREADS * 2 && ldh % 4 == 0 && lda % 4 == 0 && lda >= 2 * d && ldt % 4 == 0 &&
+  GNNLM_CHECK_ARG(d > 0 && d % 8 == 0 && d <= IA_THREADS * 4 && ldh % 4 == 0 && lda % 4 == 0 && lda >= 2 * d && ldt % 4 == 0 &&
                       ldt >= d && (uintptr_t)q_tilde % 16 == 0 && (uintptr_t)hc % 16 == 0 && (uintptr_t)a_out % 16 == 0 &&
                       (uintptr_t)t_agg % 16 == 0 && q_head_stride % 4 == 0 && a_head_stride % 4 == 0,
                   GNNLM_E_SHAPE, "gnnlm_hgt_inter_fused: d must be a multiple of 8 and <= %d, strides multiples of 4, pointers 16 B aligned",
-                  IA_THREADS * 2);
+                  IA_THREADS * 4);
   GNNLM_CHECK_ARG(n_tokens >= 0 && t0 >= 0, GNNLM_E_SHAPE, "gnnlm_hgt_inter_fused: bad token range");
   if (n_tokens == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;

@@ -187,7 +187,7 @@ def cluster_attn(q, k, v, G, H, out, *, centre_only=False, tag=None):
 
 def inter_fused_supported(d: int, H: int) -> bool:
     dk = d // H
-    return H in (4, 8, 12, 16) and d % 8 == 0 and d <= 1024 and dk % 8 == 0 and (32 * (d + 4) + H * d + 35 * H) * 4 <= 220 * 1024
+    return H in (4, 8, 12, 16) and d % 8 == 0 and d <= 1024 and dk % 8 == 0 and (16 * (d + 4) + H * d + 19 * H) * 4 <= 220 * 1024
 
 
 def inter_attn_fused(q, hc_chunks, H, t_agg, wk_t, wv, bias_v, out_scale=0.5):
