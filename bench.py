@@ -306,6 +306,14 @@ def main():
     edge_all = {key: {"GB/s": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9,
                       "frac": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
                 for key, kv in kernels.items() if key.startswith(("hgt_cluster_attn", "hgt_edge_attn"))}
+    if "hgt_inter_fused:inter_fused" in kernels:
+        # token-side form of the inter edges (inter_attn.cu): centre rows once + H transformed queries in + H weighted row sums out
+        Hh = cfg["H"]
+        ib = n_valid * d * s + T * Hh * d * 4 + T * Hh * d * 4 + T * d * 4 + (T + 1) * 4
+        kv = kernels["hgt_inter_fused:inter_fused"]
+        edge_all["hgt_inter_fused:inter"] = {"GB/s": ib / (kv["ms_per_launch"] * 1e-3) / 1e9,
+                                             "frac": ib / (kv["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak,
+                                             "note": "CUDA-core FMA bound (2 H d FMAs per centre row), not HBM bound"}
     pq_key = next((k_ for k_ in kernels if k_.startswith("pq_gather_decode")), "pq_gather_decode")
     if pq_key in kernels:
         pq_bytes = n_ntgt * (cfg["M"] + 8 + d * 4)

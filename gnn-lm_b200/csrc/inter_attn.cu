@@ -16,6 +16,9 @@
 // One CTA (256 threads) per token, two CTAs per SM; centre rows in tiles of 16 through shared memory (fp32, row stride
 // d + 4 floats: conflict-free for both access patterns), online softmax across tiles.  Phase 1: warp -> head,
 // lane -> (half of the columns, row).  Phase 2: thread -> 4 columns of all H sums.
+#include <stdlib.h>
+#include <string.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -161,9 +164,15 @@ __global__ void __launch_bounds__(IA_THREADS, 2) inter_fused_kernel(const float*
 #pragma unroll 4
       for (int r = 0; r < nr; ++r) {
         const float4 x = *reinterpret_cast<const float4*>(rows + r * (int)ldr + col);
+        float pr[HH];                                        // the row's H softmax numerators: H / 4 broadcast 16 B reads
+#pragma unroll
+        for (int h4 = 0; h4 < HH / 4; ++h4) {
+          const float4 p4 = *reinterpret_cast<const float4*>(ss + r * H + h0 + 4 * h4);
+          pr[4 * h4] = p4.x; pr[4 * h4 + 1] = p4.y; pr[4 * h4 + 2] = p4.z; pr[4 * h4 + 3] = p4.w;
+        }
 #pragma unroll
         for (int h = 0; h < HH; ++h) {
-          const float p = ss[r * H + h0 + h];
+          const float p = pr[h];
           acc[h][0] = fmaf(p, x.x, acc[h][0]); acc[h][1] = fmaf(p, x.y, acc[h][1]);
           acc[h][2] = fmaf(p, x.z, acc[h][2]); acc[h][3] = fmaf(p, x.w, acc[h][3]);
         }
@@ -190,10 +199,555 @@ __global__ void __launch_bounds__(IA_THREADS, 2) inter_fused_kernel(const float*
   }
 }
 
+// ---- register-resident q~ form (H <= 8): persistent, cp.async-pipelined, thread -> 4 columns of every head in BOTH phases ------
+// ncu on the shared-memory form above (one token per CTA, synchronous copies): 27 % of the issue slots busy, warps stalled on
+// the global loads of the next tile (long scoreboard 4.7 cycles per issue), on shared-memory operands (short scoreboard 5.5)
+// and on the barriers around the copy -- a latency-bound kernel at 25 % of the HBM time it needs.  This form removes the exposed
+// latencies instead of adding bandwidth:
+//   * every thread keeps its 4 columns of all H transformed queries in registers and only ever touches ITS OWN 4 columns of a
+//     centre row, in the score phase and in the weighted-sum phase alike, so rows are copied global -> shared with per-thread
+//     cp.async (raw bytes; split-fp16 halves are joined when read) and need NO barrier: cp.async.wait_group is enough;
+//   * CTAs are persistent (two per SM) and walk a stream of 8-row tiles that crosses token boundaries: while tile i is being
+//     computed, tile i + 1 -- possibly the first tile of the NEXT token, together with that token's q~ -- is in flight;
+//   * the 256-thread sum of the per-thread partial dot products is taken with a transposing butterfly: NV partial sums
+//     (NV / H rows x H heads) are reduced over a warp with NV - 1 + log2(32 / NV) shuffles, after which lane l holds the warp
+//     total of partial l % NV; the 8 warp totals meet in shared memory (one 16 B read per 4 H FMAs instead of two per 4).
+constexpr int IB_ROWS = 8;           // rows per tile
+constexpr int IB_STAGES = 2;
+
+template <int N>
+__device__ __forceinline__ void bfly_reduce(float* v, int lane) {     // N live values -> N / 2 ... -> 1: lane l then holds sum (l % N0)
+  if constexpr (N >= 2) {
+    constexpr int n = N / 2;
+    const bool up = (lane & n) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = up ? v[i] : v[i + n];
+      const float keep = up ? v[i + n] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+    }
+    bfly_reduce<n>(v, lane);
+  }
+}
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// raw row bytes in shared memory: fp32 4 d, split fp16 4 d (hi | lo), bf16 2 d; `col` = first of the thread's 4 columns
+template <typename InT>
+__device__ __forceinline__ void ib_copy_row(char* dst_row, const InT* src_row, int col, int d) {
+  if constexpr (std::is_same<InT, float>::value) {
+    cp_async16(dst_row + col * 4, src_row + col);
+  } else if constexpr (std::is_same<InT, __half>::value) {
+    cp_async8(dst_row + col * 2, src_row + col);
+    cp_async8(dst_row + (d + col) * 2, src_row + d + col);
+  } else {
+    cp_async8(dst_row + col * 2, src_row + col);
+  }
+}
+template <typename InT>
+__device__ __forceinline__ float4 ib_read_row(const char* row, int col, int d) {
+  if constexpr (std::is_same<InT, float>::value) {
+    return *reinterpret_cast<const float4*>(row + col * 4);
+  } else if constexpr (std::is_same<InT, __half>::value) {
+    return join4_f16(*reinterpret_cast<const uint2*>(row + col * 2), *reinterpret_cast<const uint2*>(row + (d + col) * 2));
+  } else {
+    const uint2 t = *reinterpret_cast<const uint2*>(row + col * 2);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&t.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+}
+
+struct IbTile {            // one step of the tile stream: token, its edge range, first row of the tile
+  int64_t tok;
+  int64_t e0;
+  int deg, r0;
+};
+
+template <typename InT, int H, int NV>
+__global__ void __launch_bounds__(IA_THREADS, 2) inter_regq_kernel(const float* __restrict__ qt, int64_t q_hs,   // [H, T, d], head stride
+                                                                const InT* __restrict__ hc, int64_t ldh,
+                                                                const int32_t* __restrict__ indptr, int64_t t0, int64_t n_tokens,
+                                                                int64_t d, __half* __restrict__ a_out, int64_t a_hs, int64_t lda,
+                                                                const float* __restrict__ bias_v, float out_scale,
+                                                                float* __restrict__ t_agg, int64_t ldt) {
+  static_assert(NV % H == 0 && NV <= 32 && IB_ROWS % (NV / H) == 0, "NV / H rows per reduction group");
+  constexpr int RG = NV / H;                               // rows per reduction group
+  constexpr int NW = IA_THREADS / 32;
+  constexpr int ROW_B = std::is_same<InT, __nv_bfloat16>::value ? 2 : 4;   // raw bytes per column
+  extern __shared__ __align__(16) char ib_smem[];
+  const int di = (int)d;
+  const int row_bytes = di * ROW_B;
+  char* rows = ib_smem;                                                    // [IB_STAGES][IB_ROWS][row_bytes], thread-private columns
+  float* qbuf = reinterpret_cast<float*>(rows + IB_STAGES * IB_ROWS * row_bytes);   // [H][d] q~ of the token whose first tile is in flight
+  float* wsum = qbuf + H * di;                             // [NW][H][IB_ROWS] warp totals of the tile's scores
+  float* ss = wsum + NW * H * IB_ROWS;                     // [IB_ROWS][H] softmax numerators of the tile
+  float* corr_s = ss + IB_ROWS * H;                        // [H] rescale of the running sums
+  float* l_s = corr_s + H;                                 // [H] running denominators
+  float* m_s = l_s + H;                                    // [H] running maxima
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int col = tid * 4;
+  const bool active = col < di;
+
+  // producer side of the tile stream (one tile ahead of the consumer); a token without centres is one empty tile
+  auto token_tile = [&](int64_t tok) {
+    IbTile it;
+    it.tok = tok; it.r0 = 0; it.e0 = 0; it.deg = 0;
+    if (tok < n_tokens) {
+      it.e0 = __ldg(indptr + tok);
+      it.deg = (int)(__ldg(indptr + tok + 1) - it.e0);
+    }
+    return it;
+  };
+  auto advance = [&](IbTile it) {
+    it.r0 += IB_ROWS;
+    if (it.r0 >= it.deg) it = token_tile(it.tok + gridDim.x);
+    return it;
+  };
+  auto issue = [&](const IbTile& it, int stage) {           // cp.async of the tile (+ q~ when it opens a token); always one commit
+    if (it.tok < n_tokens && active) {
+      if (it.r0 == 0) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) cp_async16(qbuf + h * di + col, qt + h * q_hs + (t0 + it.tok) * d + col);
+      }
+      const int nr = (it.deg - it.r0) < IB_ROWS ? (it.deg - it.r0) : IB_ROWS;
+      char* dst = rows + stage * IB_ROWS * row_bytes;
+      const InT* src = hc + (it.e0 + it.r0) * ldh;
+#pragma unroll
+      for (int r = 0; r < IB_ROWS; ++r)
+        if (r < nr) ib_copy_row<InT>(dst + r * row_bytes, src + r * ldh, col, di);
+    }
+    cp_async_commit();
+  };
+
+  IbTile cur = token_tile(blockIdx.x);
+  issue(cur, 0);
+  float q[H][4], acc[H][4];
+  int stage = 0;
+  while (cur.tok < n_tokens) {
+    const bool first = cur.r0 == 0;
+    const int nr = (cur.deg - cur.r0) < IB_ROWS ? (cur.deg - cur.r0) : IB_ROWS;       // <= 0 for a token without centres
+    const bool last = cur.r0 + IB_ROWS >= cur.deg;
+    cp_async_wait_all();
+    if (first) {
+#pragma unroll
+      for (int h = 0; h < H; ++h) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) v = *reinterpret_cast<const float4*>(qbuf + h * di + col);
+        q[h][0] = v.x; q[h][1] = v.y; q[h][2] = v.z; q[h][3] = v.w;
+        acc[h][0] = acc[h][1] = acc[h][2] = acc[h][3] = 0.f;
+      }
+    }
+    const IbTile nxt = advance(cur);
+    issue(nxt, stage ^ 1);                                  // its buffer (and qbuf) were last read by this thread, before this point
+    const char* my_rows = rows + stage * IB_ROWS * row_bytes;
+    // ---- phase 1a: per-thread partial scores, reduced over the warp NV at a time
+    for (int g0 = 0; g0 < nr; g0 += RG) {
+      float v[NV];
+#pragma unroll
+      for (int rr = 0; rr < RG; ++rr) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active && g0 + rr < nr) x = ib_read_row<InT>(my_rows + (g0 + rr) * row_bytes, col, di);
+#pragma unroll
+        for (int h = 0; h < H; ++h)
+          v[rr * H + h] = fmaf(x.x, q[h][0], fmaf(x.y, q[h][1], fmaf(x.z, q[h][2], x.w * q[h][3])));
+      }
+      bfly_reduce<NV>(v, lane);
+      float tot = v[0];
+#pragma unroll
+      for (int o = NV; o < 32; o <<= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+      if (lane < NV) wsum[(warp * H + (lane % H)) * IB_ROWS + g0 + lane / H] = tot;
+    }
+    __syncthreads();
+    // ---- phase 1b: block totals + online softmax bookkeeping (warp h, lane -> row)
+    if (warp < H) {
+      const int h = warp;
+      float s = -INFINITY;
+      if (lane < nr) {
+        s = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += wsum[(w * H + h) * IB_ROWS + lane];
+      }
+      const float m_old = first ? -INFINITY : m_s[h];
+      const float l_old = first ? 0.f : l_s[h];
+      const float mx = fmaxf(m_old, warp_max(s));
+      const float p = lane < nr ? __expf(s - mx) : 0.f;
+      const float tile_sum = warp_sum(p);
+      if (lane < IB_ROWS) ss[lane * H + h] = p;
+      if (lane == 0) {
+        const float c = nr > 0 ? __expf(m_old - mx) : 0.f;   // first tile: exp(-inf) = 0
+        corr_s[h] = c;
+        l_s[h] = l_old * c + tile_sum;
+        m_s[h] = mx;
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: rescale and add the tile's weighted rows
+    if (active) {
+      if (!first) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float cr = corr_s[h];
+          acc[h][0] *= cr; acc[h][1] *= cr; acc[h][2] *= cr; acc[h][3] *= cr;
+        }
+      }
+#pragma unroll 2
+      for (int r = 0; r < nr; ++r) {
+        const float4 x = ib_read_row<InT>(my_rows + r * row_bytes, col, di);
+        float pr[H];
+#pragma unroll
+        for (int h4 = 0; h4 < H / 4; ++h4) {
+          const float4 p4 = *reinterpret_cast<const float4*>(ss + r * H + 4 * h4);
+          pr[4 * h4] = p4.x; pr[4 * h4 + 1] = p4.y; pr[4 * h4 + 2] = p4.z; pr[4 * h4 + 3] = p4.w;
+        }
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          acc[h][0] = fmaf(pr[h], x.x, acc[h][0]); acc[h][1] = fmaf(pr[h], x.y, acc[h][1]);
+          acc[h][2] = fmaf(pr[h], x.z, acc[h][2]); acc[h][3] = fmaf(pr[h], x.w, acc[h][3]);
+        }
+      }
+      if (last) {
+        const int64_t t = t0 + cur.tok;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float inv = cur.deg > 0 ? 1.f / l_s[h] : 0.f;
+          uint2 hi, lo;
+          split4_f16(acc[h][0] * inv, acc[h][1] * inv, acc[h][2] * inv, acc[h][3] * inv, hi, lo);
+          __half* o = a_out + h * a_hs + t * lda + col;
+          *reinterpret_cast<uint2*>(o) = hi;
+          *reinterpret_cast<uint2*>(o + d) = lo;
+        }
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cur.deg > 0 && bias_v) b = __ldg(reinterpret_cast<const float4*>(bias_v + col));
+        *reinterpret_cast<float4*>(t_agg + t * ldt + col) =
+            make_float4(b.x * out_scale, b.y * out_scale, b.z * out_scale, b.w * out_scale);
+      }
+    }
+    cur = nxt;
+    stage ^= 1;
+  }
+  cp_async_wait_all();
+}
+
+// ---- tensor-core form (split-fp16 centre rows, H = 8, d = 128 KS): mma.sync m16n8k16, three fp16 passes --------------------------
+// ncu on the register-q~ form: 170 M warp instructions per launch, 68 % of the issue slots busy -- the CUDA-core form is bound by
+// instruction issue (64 FMAs per row per thread plus the butterfly and the hi + lo joins), 3x above the HBM time.  The centre rows
+// already ARE fp16 pairs (hi | lo, the activation format of MATH_F16X3), and H = 8 is exactly the N of mma.m16n8k16, so both
+// contractions go to the tensor cores with the same three-pass split the projections use (x_hi q_hi + x_hi q_lo + x_lo q_hi, fp32
+// accumulation; the dropped x_lo q_lo term is 2^-22 relative):
+//   scores   S[16 rows, 8 heads] = X[16, d] Q~^T      warp w contracts its d / 8 columns (A: ldmatrix of the row tile, B: the
+//                                                     warp's slice of q~ as fp16 hi / lo fragments held in registers for the
+//                                                     whole token, scaled by a power of two per (token, head) so that the lo
+//                                                     halves stay normal); the 8 warp partials meet in shared memory
+//   sums     A^T[d, 8 heads] += X^T[d, 16] P[16, 8]   warp w owns its d / 8 columns of all heads (A: ldmatrix.trans of the same
+//                                                     tile, B: the tile's softmax numerators x 1024 as fp16 hi / lo)
+// Same persistent tile stream as above (cp.async, one 16-row tile in flight under the math of the previous one, crossing
+// token boundaries), one CTA per SM.  ~100 warp instructions per tile and warp instead of ~2000.
+constexpr int IM_ROWS = 16;
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split2_f16(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x, y);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x - f.x, y - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+template <int KS>
+__global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* __restrict__ qt, int64_t q_hs,   // [8, T, d], head stride
+                                                               const __half* __restrict__ hc, int64_t ldh,
+                                                               const int32_t* __restrict__ indptr, int64_t t0, int64_t n_tokens,
+                                                               __half* __restrict__ a_out, int64_t a_hs, int64_t lda,
+                                                               const float* __restrict__ bias_v, float out_scale,
+                                                               float* __restrict__ t_agg, int64_t ldt) {
+  constexpr int H = 8, NW = IA_THREADS / 32, D = 128 * KS;
+  constexpr int RS = 4 * D + 16;                           // row stride in bytes (hi | lo + 16: conflict-free ldmatrix)
+  constexpr int QS = D + 8;                                // q~ head stride in floats
+  constexpr int OS = D + 4;                                // output staging head stride in floats
+  extern __shared__ __align__(128) char im_smem[];
+  char* rows = im_smem;                                                  // [2][16][RS]
+  float* qbuf = reinterpret_cast<float*>(rows + 2 * IM_ROWS * RS);       // [8][QS] q~ of the token whose first tile is in flight
+  float* obuf = qbuf + H * QS;                                           // [8][OS] normalised sums before the coalesced store
+  float* wsum = obuf + H * OS;                                           // [NW][16][8] per-warp partial scores
+  float* amax_s = wsum + NW * IM_ROWS * H;                               // [NW][8]
+  float* corr_s = amax_s + NW * H;                                       // [8] each:
+  float* l_s = corr_s + H;
+  float* m_s = l_s + H;
+  float* isc_s = m_s + H;                                                // 1 / (power-of-two scale of q~[head])
+  __half* p_hi = reinterpret_cast<__half*>(isc_s + H);                   // [8][16] softmax numerators x 1024, hi / lo
+  __half* p_lo = p_hi + H * IM_ROWS;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  const bool active = tid * 4 < D;                         // owner of 16 B chunk `tid` of every row (copies, final store)
+  const int wcol0 = warp * KS * 16;                        // first of the warp's columns
+  const int mi = lane >> 3, r8 = lane & 7;
+  const int p1_off = (r8 + (mi & 1) * 8) * RS + (mi >> 1) * 16 + wcol0 * 2;     // A = X      (rows x columns)
+  const int p2_off = (r8 + (mi >> 1) * 8) * RS + (mi & 1) * 16 + wcol0 * 2;     // A = X^T    (columns x rows), ldmatrix.trans
+
+  auto token_tile = [&](int64_t tok) {
+    IbTile it;
+    it.tok = tok; it.r0 = 0; it.e0 = 0; it.deg = 0;
+    if (tok < n_tokens) {
+      it.e0 = __ldg(indptr + tok);
+      it.deg = (int)(__ldg(indptr + tok + 1) - it.e0);
+    }
+    return it;
+  };
+  auto advance = [&](IbTile it) {
+    it.r0 += IM_ROWS;
+    if (it.r0 >= it.deg) it = token_tile(it.tok + gridDim.x);
+    return it;
+  };
+  auto issue = [&](const IbTile& it, int st) {             // cp.async of one tile (+ q~ when it opens a token); always one commit
+    if (it.tok < n_tokens && active) {
+      if (it.r0 == 0) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) cp_async16(qbuf + h * QS + tid * 4, qt + h * q_hs + (t0 + it.tok) * D + tid * 4);
+      }
+      const int nr = (it.deg - it.r0) < IM_ROWS ? (it.deg - it.r0) : IM_ROWS;
+      char* dst = rows + st * IM_ROWS * RS + tid * 16;
+      const char* src = reinterpret_cast<const char*>(hc + (it.e0 + it.r0) * ldh) + tid * 16;
+#pragma unroll
+      for (int r = 0; r < IM_ROWS; ++r) {
+        if (r < nr) cp_async16(dst + r * RS, src + (int64_t)r * ldh * 2);
+        else *reinterpret_cast<uint4*>(dst + r * RS) = make_uint4(0u, 0u, 0u, 0u);       // rows past the token's last centre: finite
+      }
+    }
+    cp_async_commit();
+  };
+
+  IbTile cur = token_tile(blockIdx.x);
+  issue(cur, 0);
+  uint32_t qh[KS][2], ql[KS][2];
+  float acc[KS][4];
+  int stage = 0;
+  while (cur.tok < n_tokens) {
+    const bool first = cur.r0 == 0;
+    const int nr = (cur.deg - cur.r0) < IM_ROWS ? (cur.deg - cur.r0) : IM_ROWS;        // 0 for a token without centres
+    const bool last = cur.r0 + IM_ROWS >= cur.deg;
+    cp_async_wait_all();
+    __syncthreads();                                       // tile (and q~) visible; everyone is past the previous tile
+    if (first) {
+      // q~ slice of this warp -> fp16 hi / lo B fragments, scaled per head by a power of two (amax -> [4096, 8192])
+      const float* qrow = qbuf + g * QS + wcol0 + 2 * tq;
+      float am = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const float2 v0 = *reinterpret_cast<const float2*>(qrow + ks * 16), v1 = *reinterpret_cast<const float2*>(qrow + ks * 16 + 8);
+        am = fmaxf(fmaxf(am, fmaxf(fabsf(v0.x), fabsf(v0.y))), fmaxf(fabsf(v1.x), fabsf(v1.y)));
+      }
+      am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
+      am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
+      if (tq == 0) amax_s[warp * H + g] = am;
+      __syncthreads();
+      float amx = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) amx = fmaxf(amx, amax_s[w * H + g]);
+      float scale = 1.f;
+      if (amx > 0.f && amx < INFINITY) scale = exp2f(fminf(fmaxf(floorf(log2f(8192.f / amx)), -100.f), 100.f));
+      if (warp == 0 && tq == 0) isc_s[g] = 1.f / scale;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        const float2 v0 = *reinterpret_cast<const float2*>(qrow + ks * 16), v1 = *reinterpret_cast<const float2*>(qrow + ks * 16 + 8);
+        split2_f16(v0.x * scale, v0.y * scale, qh[ks][0], ql[ks][0]);
+        split2_f16(v1.x * scale, v1.y * scale, qh[ks][1], ql[ks][1]);
+        acc[ks][0] = acc[ks][1] = acc[ks][2] = acc[ks][3] = 0.f;
+      }
+    }
+    const char* tile = rows + stage * IM_ROWS * RS;
+    // ---- phase 1a: this warp's partial scores of the tile (tensor cores)
+    {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t ah[4], al[4];
+        ldsm_x4(ah, tile + p1_off + ks * 32);
+        ldsm_x4(al, tile + p1_off + ks * 32 + D * 2);
+        mma16816(c, al, qh[ks][0], qh[ks][1]);
+        mma16816(c, ah, ql[ks][0], ql[ks][1]);
+        mma16816(c, ah, qh[ks][0], qh[ks][1]);
+      }
+      *reinterpret_cast<float2*>(wsum + (warp * IM_ROWS + g) * H + 2 * tq) = make_float2(c[0], c[1]);
+      *reinterpret_cast<float2*>(wsum + (warp * IM_ROWS + g + 8) * H + 2 * tq) = make_float2(c[2], c[3]);
+    }
+    __syncthreads();
+    const IbTile nxt = advance(cur);
+    issue(nxt, stage ^ 1);                                  // that buffer and qbuf were last read before the barrier above
+    // ---- phase 1b: block totals + online softmax bookkeeping (warp -> head, lane -> row)
+    {
+      const int h = warp;
+      float s = -INFINITY;
+      if (lane < nr) {
+        s = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += wsum[(w * IM_ROWS + lane) * H + h];
+        s *= isc_s[h];
+      }
+      const float m_old = first ? -INFINITY : m_s[h];
+      const float l_old = first ? 0.f : l_s[h];
+      const float mx = fmaxf(m_old, warp_max(s));
+      const float p = lane < nr ? __expf(s - mx) : 0.f;
+      const float tile_sum = warp_sum(p);
+      if (lane < IM_ROWS) {
+        const float ps = p * 1024.f;
+        const __half hi = __float2half_rn(ps);
+        p_hi[h * IM_ROWS + lane] = hi;
+        p_lo[h * IM_ROWS + lane] = __float2half_rn(ps - __half2float(hi));
+      }
+      if (lane == 0) {
+        const float cr = nr > 0 ? __expf(m_old - mx) : 0.f;  // first tile: exp(-inf) = 0
+        corr_s[h] = cr;
+        l_s[h] = l_old * cr + tile_sum;
+        m_s[h] = mx;
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: rescale, add the tile's weighted rows (tensor cores); accumulator (column g / g + 8 of tile mt, heads 2 tq, 2 tq + 1)
+    if (!first) {
+      const float c0 = corr_s[2 * tq], c1 = corr_s[2 * tq + 1];
+#pragma unroll
+      for (int mt = 0; mt < KS; ++mt) {
+        acc[mt][0] *= c0; acc[mt][1] *= c1; acc[mt][2] *= c0; acc[mt][3] *= c1;
+      }
+    }
+    if (nr > 0) {
+      const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(p_hi + g * IM_ROWS + 2 * tq);
+      const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(p_hi + g * IM_ROWS + 2 * tq + 8);
+      const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(p_lo + g * IM_ROWS + 2 * tq);
+      const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(p_lo + g * IM_ROWS + 2 * tq + 8);
+#pragma unroll
+      for (int mt = 0; mt < KS; ++mt) {
+        uint32_t ah[4], al[4];
+        ldsm_x4_t(ah, tile + p2_off + mt * 32);
+        ldsm_x4_t(al, tile + p2_off + mt * 32 + D * 2);
+        mma16816(acc[mt], al, bh0, bh1);
+        mma16816(acc[mt], ah, bl0, bl1);
+        mma16816(acc[mt], ah, bh0, bh1);
+      }
+    }
+    if (last) {
+      const float i0 = cur.deg > 0 ? 1.f / (1024.f * l_s[2 * tq]) : 0.f;
+      const float i1 = cur.deg > 0 ? 1.f / (1024.f * l_s[2 * tq + 1]) : 0.f;
+#pragma unroll
+      for (int mt = 0; mt < KS; ++mt) {
+        float* o0 = obuf + (2 * tq) * OS + wcol0 + mt * 16 + g;
+        float* o1 = o0 + OS;
+        o0[0] = acc[mt][0] * i0; o1[0] = acc[mt][1] * i1; o0[8] = acc[mt][2] * i0; o1[8] = acc[mt][3] * i1;
+      }
+      __syncthreads();
+      if (active) {
+        const int64_t t = t0 + cur.tok;
+        const int col = tid * 4;
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          const float4 v = *reinterpret_cast<const float4*>(obuf + h * OS + col);
+          uint2 hi, lo;
+          split4_f16(v.x, v.y, v.z, v.w, hi, lo);
+          __half* o = a_out + h * a_hs + t * lda + col;
+          *reinterpret_cast<uint2*>(o) = hi;
+          *reinterpret_cast<uint2*>(o + D) = lo;
+        }
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (cur.deg > 0 && bias_v) b = __ldg(reinterpret_cast<const float4*>(bias_v + col));
+        *reinterpret_cast<float4*>(t_agg + t * ldt + col) =
+            make_float4(b.x * out_scale, b.y * out_scale, b.z * out_scale, b.w * out_scale);
+      }
+    }
+    cur = nxt;
+    stage ^= 1;
+  }
+  cp_async_wait_all();
+}
+
+template <int KS>
+static int32_t launch_inter_mma(const float* qt, int64_t q_hs, const __half* hc, int64_t ldh, const int32_t* indptr, int64_t t0,
+                                int64_t n_tokens, void* a_out, int64_t a_hs, int64_t lda, const float* bias_v, float out_scale,
+                                float* t_agg, int64_t ldt, int n_sm, cudaStream_t st) {
+  constexpr int D = 128 * KS;
+  const size_t smem = (size_t)2 * IM_ROWS * (4 * D + 16) +
+                      ((size_t)8 * (D + 8) + 8 * (D + 4) + 8 * IM_ROWS * 8 + 8 * 8 + 4 * 8) * sizeof(float) + 2 * 8 * IM_ROWS * sizeof(__half);
+  static bool configured = false;
+  if (!configured) {
+    GNNLM_CUDA(cudaFuncSetAttribute(inter_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int64_t grid = n_tokens < n_sm ? n_tokens : n_sm;   // persistent: one CTA per SM
+  inter_mma_kernel<KS><<<(unsigned)grid, IA_THREADS, smem, st>>>(qt, q_hs, hc, ldh, indptr, t0, n_tokens, (__half*)a_out, a_hs, lda,
+                                                                bias_v, out_scale, t_agg, ldt);
+  GNNLM_LAUNCH_CHECK("gnnlm_hgt_inter_fused");
+  return 0;
+}
+
 template <typename InT, int H>
 static int32_t launch_inter(const float* qt, int64_t q_hs, const void* hc, int64_t ldh, const int32_t* indptr, int64_t t0,
                             int64_t n_tokens, int64_t d, void* a_out, int64_t a_hs, int64_t lda, const float* bias_v,
                             float out_scale, float* t_agg, int64_t ldt, cudaStream_t st) {
+  // GNNLM_INTER_KERNEL=smemq | regq selects the shared-memory q~ / register q~ CUDA-core forms where the tensor-core form
+  // would run (A/B timing switch)
+  static const int force = [] {
+    const char* e = getenv("GNNLM_INTER_KERNEL");
+    return !e ? 0 : strcmp(e, "smemq") == 0 ? 1 : strcmp(e, "regq") == 0 ? 2 : 0;
+  }();
+  const bool force_smemq = force == 1;
+  static int n_sm = 0;
+  if (n_sm == 0) {
+    int dev = 0;
+    GNNLM_CUDA(cudaGetDevice(&dev));
+    GNNLM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  if constexpr (std::is_same<InT, __half>::value && H == 8) {
+    if (force == 0 && ldh % 8 == 0 && d % 128 == 0) {
+#define GNNLM_IM(KS) \
+  return launch_inter_mma<KS>(qt, q_hs, (const __half*)hc, ldh, indptr, t0, n_tokens, a_out, a_hs, lda, bias_v, out_scale, t_agg, ldt, n_sm, st)
+      switch (d / 128) {
+        case 4: GNNLM_IM(4);
+        case 6: GNNLM_IM(6);
+        case 8: GNNLM_IM(8);
+        default: break;
+      }
+#undef GNNLM_IM
+    }
+  }
+  if constexpr (H <= 8) {
+    if (!force_smemq) {
+      constexpr int NV = 16;                                 // partial sums per butterfly (16: 2 rows x 8 heads / 4 rows x 4 heads)
+      const size_t row_b = (size_t)d * (std::is_same<InT, __nv_bfloat16>::value ? 2 : 4);
+      const size_t smem = (size_t)IB_STAGES * IB_ROWS * row_b +
+                          ((size_t)H * d + (size_t)(IA_THREADS / 32) * H * IB_ROWS + IB_ROWS * H + 3 * H) * sizeof(float);
+      static size_t configured = 0;
+      if (smem > configured) {
+        GNNLM_CUDA(cudaFuncSetAttribute(inter_regq_kernel<InT, H, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+      }
+      const int64_t grid = n_tokens < 2 * (int64_t)n_sm ? n_tokens : 2 * (int64_t)n_sm;      // persistent: two CTAs per SM
+      inter_regq_kernel<InT, H, NV><<<(unsigned)grid, IA_THREADS, smem, st>>>(qt, q_hs, (const InT*)hc, ldh, indptr, t0, n_tokens, d,
+                                                                             (__half*)a_out, a_hs, lda, bias_v, out_scale, t_agg,
+                                                                             ldt);
+      GNNLM_LAUNCH_CHECK("gnnlm_hgt_inter_fused");
+      return 0;
+    }
+  }
   const size_t smem = ((size_t)IA_ROWS * (d + 4) + (size_t)H * d + IA_ROWS * H + 3 * H) * sizeof(float);
   GNNLM_CHECK_ARG(smem <= 220 * 1024, GNNLM_E_UNSUPPORTED, "gnnlm_hgt_inter_fused: H * d too large for shared memory (%zu B)", smem);
   static size_t configured = 0;

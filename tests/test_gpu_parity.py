@@ -1080,6 +1080,52 @@ def test_eval_lm_deprecated_graph(math, NL, dev):
 
 
 # ------------------------------------------------------------------------------------------ error behaviour of the C-ABI
+@pytest.mark.parametrize("d,H,fmt", [(1024, 8, "split"), (1024, 8, "f32"), (1024, 8, "bf16"), (512, 8, "split"), (768, 8, "split"), (256, 4, "split"), (512, 8, "f32"),
+                                     (768, 12, "split"), (1024, 16, "f32")])
+def test_inter_attn_token_side_form(d, H, fmt, dev):
+    """('ntgt','inter','tgt') attention with the K' / V' projections moved to the token side (inter_attn.cu: register-q~ kernel
+    for H <= 8, shared-memory q~ kernel above) against hgt.py:339-358 evaluated in fp64: ragged degrees around the 16-row tile
+    (0, 1, 15, 16, 17, 32, 33, 40), bias b_v' only for tokens with at least one centre."""
+    from gnnlm_b200 import ops
+    dk = d // H
+    g = torch.Generator().manual_seed(d + H)
+    degs = torch.tensor([0, 1, 15, 16, 17, 32, 33, 40, 0, 3, 32, 32], dtype=torch.int64)
+    T, n_c = len(degs), int(degs.sum())
+    indptr = torch.zeros(T + 1, dtype=torch.int32)
+    indptr[1:] = torch.cumsum(degs, 0)
+    q = torch.randn(T, d, generator=g)
+    hc = torch.randn(n_c, d, generator=g)
+    if fmt == "bf16":
+        hc = hc.bfloat16().float()
+    Wk = torch.randn(d, d, generator=g) / d ** 0.5 * 0.3
+    Wv = torch.randn(d, d, generator=g) / d ** 0.5
+    bk, bv = torch.randn(d, generator=g), torch.randn(d, generator=g)
+    # fp64 statement of the reference: project every centre, score against q, softmax per (token, head), weighted V' sum
+    K = (hc.double() @ Wk.double().T + bk.double()).view(n_c, H, dk)
+    V = (hc.double() @ Wv.double().T + bv.double()).view(n_c, H, dk)
+    ref = torch.zeros(T, H, dk, dtype=torch.float64)
+    for t in range(T):
+        e0, e1 = int(indptr[t]), int(indptr[t + 1])
+        if e1 > e0:
+            s = torch.einsum("hj,chj->ch", q[t].double().view(H, dk), K[e0:e1])
+            ref[t] = torch.einsum("ch,chj->hj", torch.softmax(s, 0), V[e0:e1])
+    ref = 0.5 * ref.view(T, d)
+    assert ops.inter_fused_supported(d, H)
+    Wk_d, Wv_d = Wk.to(dev), Wv.to(dev)
+    wk_t = ops.split_f16(Wk_d.view(H, dk, d).transpose(1, 2).contiguous().view(H * d, dk))
+    wv = ops.split_f16(Wv_d.contiguous())
+    hc_d = hc.to(dev)
+    hc_in = ops.to_split(hc_d) if fmt == "split" else (hc_d.bfloat16() if fmt == "bf16" else hc_d)
+    t_agg = torch.full((T, d), float("nan"), device=dev)
+    ops.inter_attn_fused(q.to(dev), [(0, T, indptr.to(dev), hc_in)], H, t_agg, wk_t, wv, bv.to(dev), out_scale=0.5)
+    got = t_agg.cpu().double()
+    assert torch.isfinite(got).all()
+    # fp32 re-association + 3xFP16 GEMMs (22 significant bits): 1e-4 relative to the row scale, the path's fp32 bar
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 1e-4, err
+    assert (got[degs == 0] == 0).all()            # no centre: no message and no bias
+
+
 def test_c_abi_rejects_bad_arguments(dev):
     """Argument / shape problems come back as a status code + message (GnnlmError), never as a crash or a silent
     fallback -- the places where the reference asserts or raises."""
