@@ -313,7 +313,8 @@ def main():
         kv = kernels["hgt_inter_fused:inter_fused"]
         edge_all["hgt_inter_fused:inter"] = {"GB/s": ib / (kv["ms_per_launch"] * 1e-3) / 1e9,
                                              "frac": ib / (kv["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak,
-                                             "note": "CUDA-core FMA bound (2 H d FMAs per centre row), not HBM bound"}
+                                             "note": "token-side form: replaces the K'|V' projection of every centre (2 d^2 MACs each); latency-bound "
+                                                     "per 16-row tile (two block barriers), one persistent CTA per SM"}
     pq_key = next((k_ for k_ in kernels if k_.startswith("pq_gather_decode")), "pq_gather_decode")
     if pq_key in kernels:
         pq_bytes = n_ntgt * (cfg["M"] + 8 + d * 4)

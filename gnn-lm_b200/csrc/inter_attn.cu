@@ -473,6 +473,14 @@ __device__ __forceinline__ void split2_f16(float x, float y, uint32_t& hi, uint3
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+constexpr int IM_STAGES = 3;         // two 16-row tiles (128 KB at d = 1024) in flight per SM under the math of a third
+constexpr int IM_TAB = 512;          // tokens per CTA and launch whose edge ranges are staged in shared memory
+
+// Two block barriers per tile: (1) tile landed / previous tile consumed, (2) the 8 per-warp partial score tiles are in shared
+// memory.  Everything after that is per warp: every warp sums the partials, runs the online softmax of all 8 heads redundantly
+// with lane (g, tq) owning head g and rows {2 tq, 2 tq + 1, 2 tq + 8, 2 tq + 9} -- exactly its B fragment of P -- and keeps the
+// running maxima / denominators in registers; q~ is scaled per (warp, head); the normalised sums leave the accumulator fragments
+// as 2-byte stores (8 consecutive lanes cover 16 contiguous bytes of a hi or lo row).
 template <int KS>
 __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* __restrict__ qt, int64_t q_hs,   // [8, T, d], head stride
                                                                const __half* __restrict__ hc, int64_t ldh,
@@ -482,52 +490,52 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
                                                                float* __restrict__ t_agg, int64_t ldt) {
   constexpr int H = 8, NW = IA_THREADS / 32, D = 128 * KS;
   constexpr int RS = 4 * D + 16;                           // row stride in bytes (hi | lo + 16: conflict-free ldmatrix)
-  constexpr int QS = D + 8;                                // q~ head stride in floats
-  constexpr int OS = D + 4;                                // output staging head stride in floats
   extern __shared__ __align__(128) char im_smem[];
-  char* rows = im_smem;                                                  // [2][16][RS]
-  float* qbuf = reinterpret_cast<float*>(rows + 2 * IM_ROWS * RS);       // [8][QS] q~ of the token whose first tile is in flight
-  float* obuf = qbuf + H * QS;                                           // [8][OS] normalised sums before the coalesced store
-  float* wsum = obuf + H * OS;                                           // [NW][16][8] per-warp partial scores
-  float* amax_s = wsum + NW * IM_ROWS * H;                               // [NW][8]
-  float* corr_s = amax_s + NW * H;                                       // [8] each:
-  float* l_s = corr_s + H;
-  float* m_s = l_s + H;
-  float* isc_s = m_s + H;                                                // 1 / (power-of-two scale of q~[head])
-  __half* p_hi = reinterpret_cast<__half*>(isc_s + H);                   // [8][16] softmax numerators x 1024, hi / lo
-  __half* p_lo = p_hi + H * IM_ROWS;
+  char* rows = im_smem;                                                  // [IM_STAGES][16][RS]
+  float* wsum = reinterpret_cast<float*>(rows + IM_STAGES * IM_ROWS * RS);   // [NW][16][8] per-warp partial scores
+  float* isc_s = wsum + NW * IM_ROWS * H;                                // [NW][8] 1 / (power-of-two scale of the warp's q~ slice)
+  int2* tab = reinterpret_cast<int2*>(isc_s + NW * H);                   // [IM_TAB] (first edge, degree) of this CTA's tokens
+  constexpr int OSW = KS * 16 + 4;                                       // staging row stride in floats
+  float* ostage = reinterpret_cast<float*>(tab + IM_TAB);                // [NW][4][OSW] per-warp output staging
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3;
-  const bool active = tid * 4 < D;                         // owner of 16 B chunk `tid` of every row (copies, final store)
+  const bool active = tid * 4 < D;                         // owner of 16 B chunk `tid` of every row (copies, bias store)
   const int wcol0 = warp * KS * 16;                        // first of the warp's columns
   const int mi = lane >> 3, r8 = lane & 7;
   const int p1_off = (r8 + (mi & 1) * 8) * RS + (mi >> 1) * 16 + wcol0 * 2;     // A = X      (rows x columns)
   const int p2_off = (r8 + (mi >> 1) * 8) * RS + (mi & 1) * 16 + wcol0 * 2;     // A = X^T    (columns x rows), ldmatrix.trans
 
-  auto token_tile = [&](int64_t tok) {
-    IbTile it;
-    it.tok = tok; it.r0 = 0; it.e0 = 0; it.deg = 0;
-    if (tok < n_tokens) {
-      it.e0 = __ldg(indptr + tok);
-      it.deg = (int)(__ldg(indptr + tok + 1) - it.e0);
+  // edge ranges of this CTA's tokens (token j of the CTA = blockIdx.x + j gridDim.x): one strided read up front instead of a
+  // dependent global load at every token switch (ncu: 12 % of the stall samples)
+  const int n_mine = n_tokens > blockIdx.x ? (int)((n_tokens - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+  for (int j = tid; j < n_mine; j += IA_THREADS) {
+    const int64_t tok = blockIdx.x + (int64_t)j * gridDim.x;
+    const int e0 = __ldg(indptr + tok);
+    tab[j] = make_int2(e0, __ldg(indptr + tok + 1) - e0);
+  }
+  __syncthreads();
+
+  struct Tile { int j, e0, deg, r0; };                     // token j of this CTA, first row of the tile
+  auto token_tile = [&](int j) {
+    Tile it;
+    it.j = j; it.r0 = 0; it.e0 = 0; it.deg = 0;
+    if (j < n_mine) {
+      const int2 e = tab[j];
+      it.e0 = e.x; it.deg = e.y;
     }
     return it;
   };
-  auto advance = [&](IbTile it) {
+  auto advance = [&](Tile it) {
     it.r0 += IM_ROWS;
-    if (it.r0 >= it.deg) it = token_tile(it.tok + gridDim.x);
+    if (it.r0 >= it.deg) it = token_tile(it.j + 1);
     return it;
   };
-  auto issue = [&](const IbTile& it, int st) {             // cp.async of one tile (+ q~ when it opens a token); always one commit
-    if (it.tok < n_tokens && active) {
-      if (it.r0 == 0) {
-#pragma unroll
-        for (int h = 0; h < H; ++h) cp_async16(qbuf + h * QS + tid * 4, qt + h * q_hs + (t0 + it.tok) * D + tid * 4);
-      }
+  auto issue = [&](const Tile& it, int st) {               // cp.async of one tile; always exactly one commit
+    if (it.j < n_mine && active) {
       const int nr = (it.deg - it.r0) < IM_ROWS ? (it.deg - it.r0) : IM_ROWS;
       char* dst = rows + st * IM_ROWS * RS + tid * 16;
-      const char* src = reinterpret_cast<const char*>(hc + (it.e0 + it.r0) * ldh) + tid * 16;
+      const char* src = reinterpret_cast<const char*>(hc + (int64_t)(it.e0 + it.r0) * ldh) + tid * 16;
 #pragma unroll
       for (int r = 0; r < IM_ROWS; ++r) {
         if (r < nr) cp_async16(dst + r * RS, src + (int64_t)r * ldh * 2);
@@ -536,106 +544,121 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
     }
     cp_async_commit();
   };
+  // this thread's B-fragment elements of q~ (head g, columns wcol0 + 16 ks + 2 tq + {0, 1, 8, 9}), raw fp32, loaded one token ahead
+  float2 qraw[KS][2];
+  auto load_q = [&](int j) {
+    if (j < n_mine) {
+      const float* qrow = qt + g * q_hs + (t0 + blockIdx.x + (int64_t)j * gridDim.x) * D + wcol0 + 2 * tq;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        qraw[ks][0] = __ldg(reinterpret_cast<const float2*>(qrow + ks * 16));
+        qraw[ks][1] = __ldg(reinterpret_cast<const float2*>(qrow + ks * 16 + 8));
+      }
+    }
+  };
 
-  IbTile cur = token_tile(blockIdx.x);
+  static_assert(IM_STAGES == 3, "cur, n1, n2: the tile being computed and the two in flight");
+  Tile cur = token_tile(0);
+  load_q(0);
+  Tile n1 = advance(cur);
   issue(cur, 0);
+  issue(n1, 1);
+  Tile n2 = advance(n1);                                   // next tile to issue
   uint32_t qh[KS][2], ql[KS][2];
   float acc[KS][4];
+  float m_run = -INFINITY, l_run = 0.f;                    // head g (replicated over tq and over the warps)
+  float isc[NW];                                           // 1 / scale of head g's q~ slice in every warp
   int stage = 0;
-  while (cur.tok < n_tokens) {
+  while (cur.j < n_mine) {
     const bool first = cur.r0 == 0;
     const int nr = (cur.deg - cur.r0) < IM_ROWS ? (cur.deg - cur.r0) : IM_ROWS;        // 0 for a token without centres
     const bool last = cur.r0 + IM_ROWS >= cur.deg;
-    cp_async_wait_all();
-    __syncthreads();                                       // tile (and q~) visible; everyone is past the previous tile
+    asm volatile("cp.async.wait_group %0;" ::"n"(IM_STAGES - 2) : "memory");
+    __syncthreads();                                       // tile visible; everyone is past the previous tile
+    issue(n2, stage == 0 ? IM_STAGES - 1 : stage - 1);     // into the buffer of the previous tile
+    const Tile n3 = advance(n2);
     if (first) {
-      // q~ slice of this warp -> fp16 hi / lo B fragments, scaled per head by a power of two (amax -> [4096, 8192])
-      const float* qrow = qbuf + g * QS + wcol0 + 2 * tq;
+      // q~ slice of this warp -> fp16 hi / lo B fragments, scaled per (warp, head) by a power of two (amax -> [4096, 8192])
       float am = 0.f;
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
-        const float2 v0 = *reinterpret_cast<const float2*>(qrow + ks * 16), v1 = *reinterpret_cast<const float2*>(qrow + ks * 16 + 8);
-        am = fmaxf(fmaxf(am, fmaxf(fabsf(v0.x), fabsf(v0.y))), fmaxf(fabsf(v1.x), fabsf(v1.y)));
-      }
+      for (int ks = 0; ks < KS; ++ks)
+        am = fmaxf(fmaxf(am, fmaxf(fabsf(qraw[ks][0].x), fabsf(qraw[ks][0].y))), fmaxf(fabsf(qraw[ks][1].x), fabsf(qraw[ks][1].y)));
       am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
       am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
-      if (tq == 0) amax_s[warp * H + g] = am;
-      __syncthreads();
-      float amx = 0.f;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) amx = fmaxf(amx, amax_s[w * H + g]);
       float scale = 1.f;
-      if (amx > 0.f && amx < INFINITY) scale = exp2f(fminf(fmaxf(floorf(log2f(8192.f / amx)), -100.f), 100.f));
-      if (warp == 0 && tq == 0) isc_s[g] = 1.f / scale;
+      if (am > 0.f && am < INFINITY) scale = exp2f(fminf(fmaxf(floorf(log2f(8192.f / am)), -100.f), 100.f));
+      if (tq == 0) isc_s[warp * H + g] = 1.f / scale;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        const float2 v0 = *reinterpret_cast<const float2*>(qrow + ks * 16), v1 = *reinterpret_cast<const float2*>(qrow + ks * 16 + 8);
-        split2_f16(v0.x * scale, v0.y * scale, qh[ks][0], ql[ks][0]);
-        split2_f16(v1.x * scale, v1.y * scale, qh[ks][1], ql[ks][1]);
+        split2_f16(qraw[ks][0].x * scale, qraw[ks][0].y * scale, qh[ks][0], ql[ks][0]);
+        split2_f16(qraw[ks][1].x * scale, qraw[ks][1].y * scale, qh[ks][1], ql[ks][1]);
         acc[ks][0] = acc[ks][1] = acc[ks][2] = acc[ks][3] = 0.f;
       }
+      m_run = -INFINITY;
+      l_run = 0.f;
+      load_q(cur.j + 1);                                   // in flight for the whole token
     }
     const char* tile = rows + stage * IM_ROWS * RS;
-    // ---- phase 1a: this warp's partial scores of the tile (tensor cores)
+    // ---- phase 1a: this warp's partial scores of the tile (tensor cores; one accumulator per pass: three independent chains)
     {
-      float c[4] = {0.f, 0.f, 0.f, 0.f};
+      float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         uint32_t ah[4], al[4];
         ldsm_x4(ah, tile + p1_off + ks * 32);
         ldsm_x4(al, tile + p1_off + ks * 32 + D * 2);
-        mma16816(c, al, qh[ks][0], qh[ks][1]);
-        mma16816(c, ah, ql[ks][0], ql[ks][1]);
-        mma16816(c, ah, qh[ks][0], qh[ks][1]);
+        mma16816(c0, ah, qh[ks][0], qh[ks][1]);
+        mma16816(c1, ah, ql[ks][0], ql[ks][1]);
+        mma16816(c2, al, qh[ks][0], qh[ks][1]);
       }
-      *reinterpret_cast<float2*>(wsum + (warp * IM_ROWS + g) * H + 2 * tq) = make_float2(c[0], c[1]);
-      *reinterpret_cast<float2*>(wsum + (warp * IM_ROWS + g + 8) * H + 2 * tq) = make_float2(c[2], c[3]);
+      *reinterpret_cast<float2*>(wsum + (warp * IM_ROWS + g) * H + 2 * tq) = make_float2(c0[0] + (c1[0] + c2[0]), c0[1] + (c1[1] + c2[1]));
+      *reinterpret_cast<float2*>(wsum + (warp * IM_ROWS + g + 8) * H + 2 * tq) =
+          make_float2(c0[2] + (c1[2] + c2[2]), c0[3] + (c1[3] + c2[3]));
     }
     __syncthreads();
-    const IbTile nxt = advance(cur);
-    issue(nxt, stage ^ 1);                                  // that buffer and qbuf were last read before the barrier above
-    // ---- phase 1b: block totals + online softmax bookkeeping (warp -> head, lane -> row)
-    {
-      const int h = warp;
-      float s = -INFINITY;
-      if (lane < nr) {
-        s = 0.f;
+    // ---- phase 1b (every warp): scores of head g at rows 2 tq + {0, 1, 8, 9}, online softmax, P fragments
+    if (first) {
 #pragma unroll
-        for (int w = 0; w < NW; ++w) s += wsum[(w * IM_ROWS + lane) * H + h];
-        s *= isc_s[h];
-      }
-      const float m_old = first ? -INFINITY : m_s[h];
-      const float l_old = first ? 0.f : l_s[h];
-      const float mx = fmaxf(m_old, warp_max(s));
-      const float p = lane < nr ? __expf(s - mx) : 0.f;
-      const float tile_sum = warp_sum(p);
-      if (lane < IM_ROWS) {
-        const float ps = p * 1024.f;
-        const __half hi = __float2half_rn(ps);
-        p_hi[h * IM_ROWS + lane] = hi;
-        p_lo[h * IM_ROWS + lane] = __float2half_rn(ps - __half2float(hi));
-      }
-      if (lane == 0) {
-        const float cr = nr > 0 ? __expf(m_old - mx) : 0.f;  // first tile: exp(-inf) = 0
-        corr_s[h] = cr;
-        l_s[h] = l_old * cr + tile_sum;
-        m_s[h] = mx;
-      }
+      for (int w = 0; w < NW; ++w) isc[w] = isc_s[w * H + g];
     }
-    __syncthreads();
+    float sc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int row = 2 * tq + (j & 1) + (j >> 1) * 8;
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) s = fmaf(wsum[(w * IM_ROWS + row) * H + g], isc[w], s);
+      sc[j] = row < nr ? s : -INFINITY;
+    }
+    float mx = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = fmaxf(mx, m_run);
+    float pj[4], tile_sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      pj[j] = sc[j] > -INFINITY ? __expf(sc[j] - mx) : 0.f;
+      tile_sum += pj[j];
+    }
+    tile_sum += __shfl_xor_sync(0xffffffffu, tile_sum, 1);
+    tile_sum += __shfl_xor_sync(0xffffffffu, tile_sum, 2);
+    const float corr = nr > 0 && m_run > -INFINITY ? __expf(m_run - mx) : 0.f;
+    l_run = l_run * corr + tile_sum;
+    m_run = mx;
     // ---- phase 2: rescale, add the tile's weighted rows (tensor cores); accumulator (column g / g + 8 of tile mt, heads 2 tq, 2 tq + 1)
-    if (!first) {
-      const float c0 = corr_s[2 * tq], c1 = corr_s[2 * tq + 1];
+    {
+      const float cr0 = __shfl_sync(0xffffffffu, corr, 8 * tq), cr1 = __shfl_sync(0xffffffffu, corr, 8 * tq + 4);
+      if (!first) {
 #pragma unroll
-      for (int mt = 0; mt < KS; ++mt) {
-        acc[mt][0] *= c0; acc[mt][1] *= c1; acc[mt][2] *= c0; acc[mt][3] *= c1;
+        for (int mt = 0; mt < KS; ++mt) {
+          acc[mt][0] *= cr0; acc[mt][1] *= cr1; acc[mt][2] *= cr0; acc[mt][3] *= cr1;
+        }
       }
     }
     if (nr > 0) {
-      const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(p_hi + g * IM_ROWS + 2 * tq);
-      const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(p_hi + g * IM_ROWS + 2 * tq + 8);
-      const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(p_lo + g * IM_ROWS + 2 * tq);
-      const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(p_lo + g * IM_ROWS + 2 * tq + 8);
+      uint32_t bh0, bl0, bh1, bl1;
+      split2_f16(pj[0] * 1024.f, pj[1] * 1024.f, bh0, bl0);
+      split2_f16(pj[2] * 1024.f, pj[3] * 1024.f, bh1, bl1);
 #pragma unroll
       for (int mt = 0; mt < KS; ++mt) {
         uint32_t ah[4], al[4];
@@ -647,35 +670,46 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
       }
     }
     if (last) {
-      const float i0 = cur.deg > 0 ? 1.f / (1024.f * l_s[2 * tq]) : 0.f;
-      const float i1 = cur.deg > 0 ? 1.f / (1024.f * l_s[2 * tq + 1]) : 0.f;
+      const float l0 = __shfl_sync(0xffffffffu, l_run, 8 * tq), l1 = __shfl_sync(0xffffffffu, l_run, 8 * tq + 4);
+      const float i0 = cur.deg > 0 ? 1.f / (1024.f * l0) : 0.f;
+      const float i1 = cur.deg > 0 ? 1.f / (1024.f * l1) : 0.f;
+      const int64_t t = t0 + blockIdx.x + (int64_t)cur.j * gridDim.x;
+      // the warp's [8 heads x 16 KS columns] block leaves through a private staging area, four heads at a time (lanes with
+      // tq < 2 hold heads 0-3), as coalesced split-fp16 row segments: no block barrier
+      float* stg = ostage + warp * (4 * OSW);
 #pragma unroll
-      for (int mt = 0; mt < KS; ++mt) {
-        float* o0 = obuf + (2 * tq) * OS + wcol0 + mt * 16 + g;
-        float* o1 = o0 + OS;
-        o0[0] = acc[mt][0] * i0; o1[0] = acc[mt][1] * i1; o0[8] = acc[mt][2] * i0; o1[8] = acc[mt][3] * i1;
-      }
-      __syncthreads();
-      if (active) {
-        const int64_t t = t0 + cur.tok;
-        const int col = tid * 4;
+      for (int half = 0; half < 2; ++half) {
+        __syncwarp();
+        if ((tq >> 1) == half) {
 #pragma unroll
-        for (int h = 0; h < H; ++h) {
-          const float4 v = *reinterpret_cast<const float4*>(obuf + h * OS + col);
+          for (int mt = 0; mt < KS; ++mt) {
+            float* o = stg + (2 * (tq & 1)) * OSW + mt * 16 + g;
+            o[0] = acc[mt][0] * i0; o[OSW] = acc[mt][1] * i1; o[8] = acc[mt][2] * i0; o[OSW + 8] = acc[mt][3] * i1;
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < (4 * KS * 16) / 128; ++i) {                  // 4 heads x 16 KS columns, 4 per lane and step
+          const int idx = i * 128 + lane * 4;
+          const int hh = idx / (KS * 16), cc = idx % (KS * 16);
+          const float4 v = *reinterpret_cast<const float4*>(stg + hh * OSW + cc);
           uint2 hi, lo;
           split4_f16(v.x, v.y, v.z, v.w, hi, lo);
-          __half* o = a_out + h * a_hs + t * lda + col;
+          __half* o = a_out + (4 * half + hh) * a_hs + t * lda + wcol0 + cc;
           *reinterpret_cast<uint2*>(o) = hi;
           *reinterpret_cast<uint2*>(o + D) = lo;
         }
+      }
+      if (active) {
+        const int col = tid * 4;
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         if (cur.deg > 0 && bias_v) b = __ldg(reinterpret_cast<const float4*>(bias_v + col));
         *reinterpret_cast<float4*>(t_agg + t * ldt + col) =
             make_float4(b.x * out_scale, b.y * out_scale, b.z * out_scale, b.w * out_scale);
       }
     }
-    cur = nxt;
-    stage ^= 1;
+    cur = n1; n1 = n2; n2 = n3;
+    stage = stage + 1 == IM_STAGES ? 0 : stage + 1;
   }
   cp_async_wait_all();
 }
@@ -685,17 +719,22 @@ static int32_t launch_inter_mma(const float* qt, int64_t q_hs, const __half* hc,
                                 int64_t n_tokens, void* a_out, int64_t a_hs, int64_t lda, const float* bias_v, float out_scale,
                                 float* t_agg, int64_t ldt, int n_sm, cudaStream_t st) {
   constexpr int D = 128 * KS;
-  const size_t smem = (size_t)2 * IM_ROWS * (4 * D + 16) +
-                      ((size_t)8 * (D + 8) + 8 * (D + 4) + 8 * IM_ROWS * 8 + 8 * 8 + 4 * 8) * sizeof(float) + 2 * 8 * IM_ROWS * sizeof(__half);
+  const size_t smem = (size_t)IM_STAGES * IM_ROWS * (4 * D + 16) + ((size_t)8 * IM_ROWS * 8 + 8 * 8) * sizeof(float) +
+                      (size_t)IM_TAB * sizeof(int2) + (size_t)8 * 4 * (KS * 16 + 4) * sizeof(float);
   static bool configured = false;
   if (!configured) {
     GNNLM_CUDA(cudaFuncSetAttribute(inter_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  const int64_t grid = n_tokens < n_sm ? n_tokens : n_sm;   // persistent: one CTA per SM
-  inter_mma_kernel<KS><<<(unsigned)grid, IA_THREADS, smem, st>>>(qt, q_hs, hc, ldh, indptr, t0, n_tokens, (__half*)a_out, a_hs, lda,
-                                                                bias_v, out_scale, t_agg, ldt);
-  GNNLM_LAUNCH_CHECK("gnnlm_hgt_inter_fused");
+  // persistent: one CTA per SM; a launch covers at most IM_TAB tokens per CTA (their edge ranges are staged in shared memory)
+  const int64_t per_launch = (int64_t)n_sm * IM_TAB;
+  for (int64_t b0 = 0; b0 < n_tokens; b0 += per_launch) {
+    const int64_t n = n_tokens - b0 < per_launch ? n_tokens - b0 : per_launch;
+    const int64_t grid = n < n_sm ? n : n_sm;
+    inter_mma_kernel<KS><<<(unsigned)grid, IA_THREADS, smem, st>>>(qt, q_hs, hc, ldh, indptr + b0, t0 + b0, n, (__half*)a_out, a_hs, lda,
+                                                                  bias_v, out_scale, t_agg, ldt);
+    GNNLM_LAUNCH_CHECK("gnnlm_hgt_inter_fused");
+  }
   return 0;
 }
 
