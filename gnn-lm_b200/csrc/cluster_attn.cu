@@ -90,7 +90,7 @@ __device__ __forceinline__ void store_out(OutT* __restrict__ p, const float (&r)
   }
 }
 
-// One warp per (cluster, 32*C-feature slice).  WMAX > 0: all nodes of clusters of at most WMAX (<= 3) nodes, every row
+// One warp per (cluster, 32*C-feature slice).  WMAX > 0: all nodes of clusters of at most WMAX (1, 3, 5, 7) nodes, every row
 // loaded up front.  WMAX == 0: centre-only variant (its own instantiation: 3 rows of K'/V' per cluster and a third of the
 // registers of the all-nodes form).  GROUP: lanes per head (0 = run time).
 template <typename T, typename OutT, int C, int WMAX, int GROUP>
@@ -225,6 +225,12 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_window_kernel(const T
   }
 }
 
+// GNNLM_CLUSTER_WINDOW=1: use the ring-of-four window kernel for every chain longer than 3 (A/B timing switch)
+static bool window_forced() {
+  static const bool f = [] { const char* e = getenv("GNNLM_CLUSTER_WINDOW"); return e && e[0] == '1'; }();
+  return f;
+}
+
 template <typename T, typename OutT, int C, int GROUP>
 static int32_t dispatch_w(int wmax, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                           const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl, int64_t n_clusters,
@@ -238,6 +244,8 @@ static int32_t dispatch_w(int wmax, const void* q, int64_t ldq, const void* k, i
   if (centre_only) GNNLM_CL(0);
   else if (wmax <= 1) GNNLM_CL(1);
   else if (wmax <= 3) GNNLM_CL(3);
+  else if (wmax <= 5 && !window_forced()) GNNLM_CL(5);      // c = 2 (or c = 3 pruned to reach 2): 15 rows in flight per warp
+  else if (wmax <= 7 && !window_forced()) GNNLM_CL(7);
   else
     cluster_attn_window_kernel<T, OutT, C, GROUP><<<(unsigned)blocks, CA_THREADS, 0, st>>>(
         (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, node_base, cluster_nl, n_clusters, group, n_slices, (OutT*)out,
