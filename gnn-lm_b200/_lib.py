@@ -38,6 +38,7 @@ SIGNATURES = {
     "gnnlm_linear_lse": (_i32, [_p, _i32, _i64, _p, _p, _f32, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _p]),
     "gnnlm_lse_finish": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _p]),
     "gnnlm_gather_rows": (_i32, [_p, _i64, _p, _p, _i64, _i64, _p, _i64, _i32, _p]),
+    "gnnlm_embed_gather": (_i32, [_p, _i64, _i64, _p, _i32, _i64, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p, _p]),
     "gnnlm_layernorm": (_i32, [_p, _i64, _p, _i32, _i64, _p, _p, _f32, _p, _i32, _i64, _i64, _p, _i64, _p]),
     "gnnlm_convert": (_i32, [_p, _i32, _p, _i32, _i64, _p]),
     "gnnlm_gelu": (_i32, [_p, _i64, _p, _i32, _i64, _i64, _p, _i64, _p]),

@@ -24,6 +24,33 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const V* __restrict__ 
   }
 }
 
+// --reinit-nfeat (transformer.py:1046-1048): ntgt features are embeddings of the neighbour TOKENS instead of decoded keys.
+// out[i, :] = table[labels[rows[i]], :] -- datastore row -> value (the `neighbor_tokens[offset]` of token_block_dataset.py:371,394)
+// -> row of the projected embedding table, one warp per node; an out-of-vocabulary value sets *err and yields zeros.
+template <typename LT>
+__global__ void __launch_bounds__(256) embed_gather_kernel(const uint4* __restrict__ table, int64_t ld_vec, int64_t vocab,
+                                                           const LT* __restrict__ labels, int64_t n_datastore,
+                                                           const int64_t* __restrict__ rows, const int32_t* __restrict__ row_ids,
+                                                           uint4* __restrict__ dst, int64_t ld_dst_vec, int64_t n_cap,
+                                                           const int32_t* __restrict__ n_dev, int64_t d_vec,
+                                                           int64_t* __restrict__ labels_out, int32_t* __restrict__ err) {
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    const int64_t node = row_ids ? (int64_t)__ldg(row_ids + i) : i;
+    const int64_t r = __ldg(rows + node);
+    int64_t tok = -1;
+    if (r >= 0 && r < n_datastore) tok = (int64_t)__ldg(labels + r);
+    if (lane == 0 && labels_out) labels_out[i] = tok;
+    const bool ok = tok >= 0 && tok < vocab;
+    if (!ok && lane == 0 && err) atomicExch(err, 1);
+    const uint4* s = table + (ok ? tok : 0) * ld_vec;
+    uint4* o = dst + i * ld_dst_vec;
+    for (int64_t j = lane; j < d_vec; j += 32) o[j] = ok ? __ldg(s + j) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // residual operand of the fused add + LayerNorm: mode 0 none, 1 fp32, 2 bf16, 3 split-fp16 (lo half d columns later)
 __device__ __forceinline__ float res_at(const void* res, int mode, int64_t ld, int64_t row, int64_t j, int64_t d) {
   if (mode == 1) return __ldg(reinterpret_cast<const float*>(res) + row * ld + j);
@@ -260,6 +287,28 @@ extern "C" int32_t gnnlm_gather_rows(const void* src, int64_t ld_src, const int3
     gather_rows_kernel<uint16_t><<<g, 256, 0, st>>>((const uint16_t*)src, ld_src, ids, (uint16_t*)dst, ld_dst, n_cap, n_dev, d);
   }
   GNNLM_LAUNCH_CHECK("gnnlm_gather_rows");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_embed_gather(const float* table, int64_t ld_table, int64_t vocab, const void* labels, int32_t label_bytes,
+                                      int64_t n_datastore, const int64_t* rows, const int32_t* row_ids, float* dst, int64_t ld_dst,
+                                      int64_t n_cap, const int32_t* n_dev, int64_t d, int64_t* labels_out, int32_t* err,
+                                      gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(table && labels && rows && dst, GNNLM_E_ARG, "gnnlm_embed_gather: null pointer");
+  GNNLM_CHECK_ARG(label_bytes == 2 || label_bytes == 4, GNNLM_E_UNSUPPORTED, "gnnlm_embed_gather: labels must be int16 or int32");
+  GNNLM_CHECK_ARG(d > 0 && d % 4 == 0 && ld_table % 4 == 0 && ld_dst % 4 == 0 && (uintptr_t)table % 16 == 0 && (uintptr_t)dst % 16 == 0,
+                  GNNLM_E_SHAPE, "gnnlm_embed_gather: d and leading dimensions must be multiples of 4 floats, pointers 16 B aligned");
+  GNNLM_CHECK_ARG(vocab > 0 && n_datastore > 0 && n_cap >= 0, GNNLM_E_SHAPE, "gnnlm_embed_gather: sizes");
+  if (n_cap == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g = grid_for(n_cap, 8);
+  if (label_bytes == 2)
+    embed_gather_kernel<int16_t><<<g, 256, 0, st>>>((const uint4*)table, ld_table / 4, vocab, (const int16_t*)labels, n_datastore, rows,
+                                                   row_ids, (uint4*)dst, ld_dst / 4, n_cap, n_dev, d / 4, labels_out, err);
+  else
+    embed_gather_kernel<int32_t><<<g, 256, 0, st>>>((const uint4*)table, ld_table / 4, vocab, (const int32_t*)labels, n_datastore, rows,
+                                                   row_ids, (uint4*)dst, ld_dst / 4, n_cap, n_dev, d / 4, labels_out, err);
+  GNNLM_LAUNCH_CHECK("gnnlm_embed_gather");
   return 0;
 }
 

@@ -34,22 +34,27 @@ class DeviceDatastore:
     """The quantised datastore replicated in one GPU's HBM: codes [N_d, M] uint8
     (train_dstore/quantized-keys.npy) and values [N_d] int16/int32 (train_dstore/vals.npy)."""
 
-    def __init__(self, codes: torch.Tensor, vals: torch.Tensor):
-        assert codes.dtype == torch.uint8 and codes.dim() == 2
-        self.codes = codes.contiguous()
+    def __init__(self, codes: Optional[torch.Tensor], vals: torch.Tensor):
+        """codes=None is `--reinit-nfeat` (language_modeling.py:273-278: no quantized features are loaded; the ntgt features are
+        embeddings of the datastore VALUES)."""
         self.vals = vals.reshape(-1).contiguous()
-        assert self.vals.dtype in (torch.int16, torch.int32) and self.vals.numel() == codes.shape[0]
-        self.size = codes.shape[0]
+        assert self.vals.dtype in (torch.int16, torch.int32)
+        if codes is not None:
+            assert codes.dtype == torch.uint8 and codes.dim() == 2 and self.vals.numel() == codes.shape[0]
+            codes = codes.contiguous()
+        self.codes = codes
+        self.size = self.vals.numel()
 
     @classmethod
-    def from_dir(cls, data_dir: str, vocab_size: int, device) -> "DeviceDatastore":
+    def from_dir(cls, data_dir: str, vocab_size: int, device, reinit_nfeat: bool = False) -> "DeviceDatastore":
         info = json.load(open(os.path.join(dstore_path(data_dir, "train"), "info.json")))
         n = info["dstore_size"]
         vdt = np.int16 if info.get("dstore_fp16") and vocab_size < 2 ** 15 else np.int32   # language_modeling.py:272
         vals = np.memmap(value_path(data_dir, "train"), dtype=vdt, mode="r", shape=(n, 1))
-        codes = np.load(quantized_feature_path(data_dir, "train"), mmap_mode="r")
-        return cls(torch.from_numpy(np.ascontiguousarray(codes)).to(device),
-                   torch.from_numpy(np.ascontiguousarray(vals)).to(device))
+        codes = None
+        if not reinit_nfeat:
+            codes = torch.from_numpy(np.array(np.load(quantized_feature_path(data_dir, "train"), mmap_mode="r"))).to(device)
+        return cls(codes, torch.from_numpy(np.array(vals)).to(device))
 
 
 def get_slice_indices(sizes, break_mode: Optional[str], block_size: int, document_sep_len: int = 1) -> np.ndarray:
@@ -132,12 +137,12 @@ class GraphTokenBlockDataset:
         else:
             source = torch.from_numpy(np.asarray(self.tokens[cs - 1:e - 1]).astype(np.int64))
         out = {"id": index, "source": source, "target": item, "offsets": (cs, e), "start_idx": s - cs,
-               "nbr": torch.from_numpy(np.ascontiguousarray(self.neighbor_offsets[cs:e]))}
+               "nbr": torch.from_numpy(np.array(self.neighbor_offsets[cs:e]))}
         if self.precompute_feats is not None:
-            out["feats"] = torch.from_numpy(np.ascontiguousarray(self.precompute_feats[cs:e]))
+            out["feats"] = torch.from_numpy(np.array(self.precompute_feats[cs:e]))
         if self.knn_ids is not None:
-            out["knn_dists"] = torch.from_numpy(np.ascontiguousarray(self.knn_dists[cs:e]))
-            out["knn_ids"] = torch.from_numpy(np.ascontiguousarray(self.knn_ids[cs:e]))
+            out["knn_dists"] = torch.from_numpy(np.array(self.knn_dists[cs:e]))
+            out["knn_ids"] = torch.from_numpy(np.array(self.knn_ids[cs:e]))
         return out
 
     def collater(self, samples: List[dict]) -> dict:

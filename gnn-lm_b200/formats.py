@@ -1,0 +1,172 @@
+"""On-disk formats either side of the hot path -- host-side readers for the files the reference's task opens
+(fairseq/tasks/language_modeling.py:216-319), so that `evaluate()` runs on a reference data directory as it is:
+
+  {split}.bin / {split}.idx      fairseq MMapIndexedDataset (fairseq/data/indexed_dataset.py:351-494)
+  dict.txt                       fairseq Dictionary (fairseq/data/dictionary.py:18-60,183-228)
+  {split}_dstore/info.json       {dstore_size, hidden_size, vocab_size, dstore_fp16, val_size} (knn/data_store.py:78-88)
+  {split}_dstore/keys.npy        RAW memmap fp16/fp32 [N, hidden]   (not NPY despite the name; knn/data_store.py)
+  {split}_dstore/vals.npy        RAW memmap int16/int32 [N, 1]
+  {split}_dstore/neighbors.mmap.{k}   RAW memmap int64 [N_split, k], -1 = missing (knn/find_knn.py:45-66)
+  train_dstore/quantized-keys.npy     real NPY uint8 [N_d, M] (knn/quantize_features.py:151-152; read by DeviceDatastore)
+
+Nothing here touches the GPU; arrays stay memory-mapped and `GraphTokenBlockDataset` slices them per block."""
+import json
+import os
+import struct
+from typing import Optional, Tuple, Union
+
+import numpy as np
+
+from .dataset import GraphTokenBlockDataset, dstore_path, feature_path, neighbor_path
+
+_HDR_MAGIC = b"MMIDIDX\x00\x00"
+# element type codes of the index header (indexed_dataset.py:83-92; code 6 is the reference's `np.float` = float64)
+_DTYPES = {1: np.uint8, 2: np.int8, 3: np.int16, 4: np.int32, 5: np.int64, 6: np.float64, 7: np.float64, 8: np.uint16}
+
+
+class MMapIndexedDataset:
+    """Reader of fairseq's mmap token storage: `prefix.idx` = magic, version (u64 = 1), dtype code (u8), sentence count
+    (u64), sizes int32[n], byte pointers int64[n]; `prefix.bin` = the sentences back to back (indexed_dataset.py:395-417)."""
+
+    def __init__(self, path_prefix: str):
+        idx, data = path_prefix + ".idx", path_prefix + ".bin"
+        if not (os.path.exists(idx) and os.path.exists(data)):
+            raise FileNotFoundError("Dataset not found: {}".format(path_prefix))      # language_modeling.py:232-235
+        with open(idx, "rb") as f:
+            if f.read(9) != _HDR_MAGIC:
+                raise ValueError("Index file doesn't match expected format. Make sure that --dataset-impl is configured properly.")
+            (version,) = struct.unpack("<Q", f.read(8))
+            if version != 1:
+                raise ValueError(f"unsupported MMapIndexedDataset index version {version}")
+            (code,) = struct.unpack("<B", f.read(1))
+            if code not in _DTYPES:
+                raise ValueError(f"unknown element type code {code} in {idx}")
+            self.dtype = np.dtype(_DTYPES[code])
+            (self._len,) = struct.unpack("<Q", f.read(8))
+            offset = f.tell()
+        index = np.memmap(idx, mode="r", order="C")
+        self.sizes = np.frombuffer(index, dtype=np.int32, count=self._len, offset=offset)
+        self._pointers = np.frombuffer(index, dtype=np.int64, count=self._len, offset=offset + self.sizes.nbytes)
+        self._bin = np.memmap(data, mode="r", order="C")
+
+    def __len__(self):
+        return self._len
+
+    def __getitem__(self, i) -> np.ndarray:                     # :469-476 (always int64 to the caller)
+        a = np.frombuffer(self._bin, dtype=self.dtype, count=int(self.sizes[i]), offset=int(self._pointers[i]))
+        return a.astype(np.int64) if self.dtype != np.int64 else a
+
+    def tokens(self) -> np.ndarray:
+        """The flat token stream (all sentences back to back) as a zero-copy view of the .bin file.  The builder writes
+        sentences contiguously (pointers are the running byte sum of the sizes, :371-380), which is checked."""
+        total = int(self.sizes.astype(np.int64).sum())
+        if self._len:
+            expect = np.concatenate([[0], np.cumsum(self.sizes[:-1].astype(np.int64) * self.dtype.itemsize)])
+            if not np.array_equal(expect, self._pointers):
+                raise ValueError("non-contiguous MMapIndexedDataset: sentence pointers are not the running sum of the sizes")
+        return np.frombuffer(self._bin, dtype=self.dtype, count=total, offset=0)
+
+
+class Dictionary:
+    """dict.txt reader with the reference's numbering: <s>=0, <pad>=1, </s>=2, <unk>=3, then the file's symbols in
+    order (dictionary.py:18-39,183-228).  A line is '<symbol> <count>', split at the LAST space."""
+
+    def __init__(self, pad="<pad>", eos="</s>", unk="<unk>", bos="<s>"):
+        self.symbols, self.count, self.indices = [], [], {}
+        self.unk_word, self.pad_word, self.eos_word = unk, pad, eos
+        self.bos_index = self.add_symbol(bos)
+        self.pad_index = self.add_symbol(pad)
+        self.eos_index = self.add_symbol(eos)
+        self.unk_index = self.add_symbol(unk)
+        self.nspecial = len(self.symbols)
+
+    def add_symbol(self, word, n=1):                            # dictionary.py:108-120
+        if word in self.indices:
+            idx = self.indices[word]
+            self.count[idx] += n
+            return idx
+        idx = len(self.symbols)
+        self.indices[word] = idx
+        self.symbols.append(word)
+        self.count.append(n)
+        return idx
+
+    @classmethod
+    def load(cls, path: str) -> "Dictionary":
+        d = cls()
+        with open(path, "r", encoding="utf-8") as f:
+            for line in f.readlines():
+                i = line.rfind(" ")
+                if i == -1:
+                    raise ValueError("Incorrect dictionary format, expected '<token> <cnt>'")
+                # the reference appends unconditionally (a duplicate symbol keeps both slots; `indices` points at the last)
+                d.indices[line[:i]] = len(d.symbols)
+                d.symbols.append(line[:i])
+                d.count.append(int(line[i + 1:]))
+        return d
+
+    def __len__(self):
+        return len(self.symbols)
+
+    def __getitem__(self, idx):
+        return self.symbols[idx] if idx < len(self.symbols) else self.unk_word
+
+    def index(self, sym):
+        return self.indices.get(sym, self.unk_index)
+
+    def bos(self): return self.bos_index
+    def pad(self): return self.pad_index
+    def eos(self): return self.eos_index
+    def unk(self): return self.unk_index
+
+
+class MmapDataset:
+    """Raw memmap with a shape and dtype (fairseq/data/mmap_dataset.py:28-58)."""
+
+    def __init__(self, path, shape, dtype, warmup=False, verbose=False):
+        need = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        have = os.path.getsize(path)                             # FileNotFoundError if absent, like np.memmap
+        if have < need:
+            raise ValueError(f"{path}: {have} bytes on disk, {need} needed for shape {tuple(shape)} of {np.dtype(dtype)}")
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        self._mmap = np.memmap(path, mode="r", shape=self.shape, dtype=self.dtype)
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, item):
+        return self._mmap[item]
+
+    def array(self) -> np.ndarray:
+        return self._mmap
+
+
+def load_graph_lm_dataset(data_path: str, split: str, *, tokens_per_sample: int, gcn_k: int = 32,
+                          neighbor_context: Union[int, Tuple[int, int], str] = 1, use_precompute_feat: bool = True,
+                          invalid_neighbor_context: int = 0, gcn_context_window: int = 0, intra_context: int = 0,
+                          sample_break_mode: Optional[str] = "none", deprecated: bool = False,
+                          knn_dists: Optional[np.ndarray] = None, knn_ids: Optional[np.ndarray] = None):
+    """The `--graph` branch of LanguageModelingTask.load_dataset (language_modeling.py:216-232,265-303) over a reference
+    data directory; keyword names are the task's flags.  Returns (GraphTokenBlockDataset, Dictionary).
+    `neighbor_context` may be the flag's string form ("1" or "(2,0)"; the task evals it, :289)."""
+    dictionary = Dictionary.load(os.path.join(data_path, "dict.txt"))
+    sentences = MMapIndexedDataset(os.path.join(data_path, split))
+    tokens = sentences.tokens()
+    num_tokens = int(tokens.shape[0])
+    neighbor_info = json.load(open(os.path.join(dstore_path(data_path, "train"), "info.json")))
+    info = json.load(open(os.path.join(dstore_path(data_path, split), "info.json")))
+    if isinstance(neighbor_context, str):
+        import ast
+        neighbor_context = ast.literal_eval(neighbor_context)
+    neighbors = MmapDataset(neighbor_path(data_path, split, gcn_k), shape=(num_tokens, gcn_k), dtype=np.int64)
+    feats = None
+    if use_precompute_feat:                                       # :291-294
+        feats = MmapDataset(feature_path(data_path, split), shape=(num_tokens, info["hidden_size"]),
+                            dtype=np.float16 if info["dstore_fp16"] else np.float32).array()
+    ds = GraphTokenBlockDataset(
+        tokens, tokens_per_sample, pad=dictionary.pad(), eos=dictionary.eos(), neighbor_offsets=neighbors.array(),
+        n_datastore=int(neighbor_info["dstore_size"]), neighbor_context=neighbor_context, precompute_feats=feats,
+        invalid_neighbor_context=invalid_neighbor_context if split == "train" else 0,      # :295
+        context_window=gcn_context_window, intra_context=intra_context, knn_dists=knn_dists, knn_ids=knn_ids,
+        break_mode=sample_break_mode, deprecated=deprecated, sizes=np.asarray(sentences.sizes))
+    return ds, dictionary

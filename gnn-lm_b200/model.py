@@ -135,6 +135,66 @@ def _get(args, name, default=None):
     return getattr(args, name, default)
 
 
+class AdaptiveInput(nn.Module):
+    """fairseq/modules/adaptive_input.py:13-74 -- same constructor, same state_dict keys (`embeddings.{i}.0.weight` [size_i, dim_i],
+    `embeddings.{i}.1.weight` [d, dim_i], `_float_tensor`).  Only used for `--reinit-nfeat` (ntgt features = embeddings of the
+    neighbour tokens, transformer.py:1046-1048).  On the device the band-wise Embedding -> Linear is evaluated ONCE per
+    checkpoint into a projected table [V, d] fp32 (1.1 GB at the wiki103 shape; HBM is sized for it), so a lookup is one row
+    gather (gnnlm_embed_gather) instead of a mask / index / GEMM / scatter per band and batch."""
+
+    def __init__(self, vocab_size: int, padding_idx: int, initial_dim: int, factor: float, output_dim: int, cutoff: List[int]):
+        super().__init__()
+        cutoff = list(cutoff)
+        if vocab_size > cutoff[-1]:
+            cutoff = cutoff + [vocab_size]
+        else:
+            assert vocab_size == cutoff[-1], "cannot specify cutoff larger than vocab size"
+        self.cutoff, self.embedding_dim, self.padding_idx = cutoff, output_dim, padding_idx
+        self.embeddings = nn.ModuleList()
+        for i in range(len(cutoff)):
+            size = cutoff[i] - (cutoff[i - 1] if i > 0 else 0)
+            dim = int(initial_dim // (factor ** i))
+            self.embeddings.append(nn.Sequential(nn.Embedding(size, dim, padding_idx if i == 0 else None),
+                                                 nn.Linear(dim, output_dim, bias=False)))
+        for m in self.modules():                                  # adaptive_input.py:48-55
+            if isinstance(m, nn.Embedding):
+                nn.init.normal_(m.weight, mean=0, std=m.weight.shape[1] ** -0.5)
+                nn.init.constant_(m.weight[padding_idx], 0)
+            elif isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+        self.register_buffer("_float_tensor", torch.FloatTensor(1))
+        self._table, self._table_key = None, None
+
+    def weights_for_band(self, band: int):
+        return self.embeddings[band][0].weight, self.embeddings[band][1].weight
+
+    @torch.no_grad()
+    def table(self) -> torch.Tensor:
+        """[V, d] fp32: row v = Linear_i(Embedding_i[v - cutoff[i-1]]) for the band i of v (fp32 CUDA-core GEMM)."""
+        key = (self.embeddings[0][0].weight.device, tuple(int(p._version) for p in self.parameters()))
+        if self._table is None or self._table_key != key:
+            dev = key[0]
+            t = torch.empty((self.cutoff[-1], self.embedding_dim), device=dev, dtype=torch.float32)
+            for i, seq in enumerate(self.embeddings):
+                lo = self.cutoff[i - 1] if i > 0 else 0
+                ops.linear(seq[0].weight.detach().float().contiguous(), seq[1].weight.detach().float().contiguous(),
+                           out=t[lo:self.cutoff[i]], math=L.MATH_FP32_SIMT, tag="embed_table")
+            self._table, self._table_key = t, key
+        return self._table
+
+    @torch.no_grad()
+    def forward(self, input: torch.Tensor) -> torch.Tensor:
+        flat = input.reshape(-1).to(torch.int32)
+        return ops.gather_rows(self.table(), flat).view(*input.shape, self.embedding_dim)
+
+
+class Embedding(nn.Embedding):
+    """Plain input embedding (transformer_lm.py:173-175) with the `table()` face of AdaptiveInput."""
+
+    def table(self) -> torch.Tensor:
+        return self.weight.detach().float().contiguous()
+
+
 class TokenGraphTransformerDecoder(nn.Module):
     """transformer.py:910-1085.  `dictionary` only needs __len__ and eos()."""
 
@@ -150,6 +210,10 @@ class TokenGraphTransformerDecoder(nn.Module):
                                attn_drop=_get(args, "attention_dropout", 0.0))
         self.num_classes = len(dictionary)
         self.eos_idx = dictionary.eos() if hasattr(dictionary, "eos") else 2
+        if embed_tokens is not None:              # only read by --reinit-nfeat (the base transformer is bypassed)
+            self.embed_tokens = embed_tokens
+        else:
+            self.embed_tokens = None
         if quantizer is not None:
             self.tgt_quantizer = quantizer
         elif _get(args, "quantizer_path"):
@@ -225,11 +289,26 @@ class TokenGraphTransformerDecoder(nn.Module):
         else:                                                         # fused gather from the HBM-resident datastore
             codes = graph.codes_table
             q = self.tgt_quantizer
+            if codes is None:
+                # --reinit-nfeat: the dataset carries no code rows, ntgt.h = embed_tokens(ntgt.labels) (transformer.py:1046-1048)
+                if self.embed_tokens is None:
+                    raise ValueError("the graph has no ntgt features (--reinit-nfeat) and the model was built without embed_tokens")
+                table, labels = self.embed_tokens.table(), graph.labels_table
+                if table.shape[1] != self.embed_dim:
+                    raise ValueError("--reinit-nfeat needs decoder_input_dim == decoder_embed_dim")
 
-            def decode(g, centre_only):
-                if centre_only:   # only centre nodes are ever read (single layer)
-                    return q.gather_decode(codes, g.ntgt_row, row_ids=g.inter_indices, n_dev=g.n_valid_dev, math_mode=mode)
-                return q.gather_decode(codes, g.ntgt_row, n_cap=g.node_cap, n_dev=g.n_ntgt_dev, math_mode=mode)
+                def decode(g, centre_only):
+                    ids, cap, n_dev = (g.inter_indices, None, g.n_valid_dev) if centre_only else (None, g.node_cap, g.n_ntgt_dev)
+                    x, _ = ops.embed_gather(table, labels, g.ntgt_row, row_ids=ids, n_cap=cap, n_dev=n_dev)
+                    act = act_dtype(mode)
+                    if act == ops.SPLIT:
+                        return ops.to_split(x, n_dev)
+                    return x if act == torch.float32 else ops.convert(x, act)
+            else:
+                def decode(g, centre_only):
+                    if centre_only:   # only centre nodes are ever read (single layer)
+                        return q.gather_decode(codes, g.ntgt_row, row_ids=g.inter_indices, n_dev=g.n_valid_dev, math_mode=mode)
+                    return q.gather_decode(codes, g.ntgt_row, n_cap=g.node_cap, n_dev=g.n_ntgt_dev, math_mode=mode)
 
             # ~11 live [rows, d] fp32-sized buffers on the ntgt side; chunk over target tokens above the budget
             per_token = graph.k * graph.w * self.embed_dim * 4 * 11
@@ -307,7 +386,19 @@ class TransformerLanguageModel(nn.Module):
         dictionary = dictionary if dictionary is not None else task.source_dictionary
         if _get(args, "graph_layer", 0) <= 0:
             raise NotImplementedError("only the --graph_layer > 0 decoder is on the hot path")
-        dec = TokenGraphTransformerDecoder(args, dictionary, None, no_encoder_attn=True, quantizer=quantizer)
+        embed_tokens = None
+        if _get(args, "reinit_nfeat", False):                    # transformer_lm.py:160-175 (only --reinit-nfeat reads it here)
+            d_in = _get(args, "decoder_input_dim", args.decoder_embed_dim)
+            if _get(args, "adaptive_input", False):
+                cut = _get(args, "adaptive_input_cutoff")
+                cut = [int(c) for c in cut.split(",")] if isinstance(cut, str) else list(cut)
+                embed_tokens = AdaptiveInput(len(dictionary), dictionary.pad(), d_in, _get(args, "adaptive_input_factor", 4),
+                                             args.decoder_embed_dim, cut)
+            else:
+                embed_tokens = Embedding(len(dictionary), d_in, dictionary.pad())
+                nn.init.normal_(embed_tokens.weight, mean=0, std=d_in ** -0.5)
+                nn.init.constant_(embed_tokens.weight[dictionary.pad()], 0)
+        dec = TokenGraphTransformerDecoder(args, dictionary, embed_tokens, no_encoder_attn=True, quantizer=quantizer)
         return cls(dec)
 
     def forward(self, src_tokens, **kwargs):

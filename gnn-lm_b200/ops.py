@@ -118,6 +118,18 @@ def gather_rows(src, ids, n_cap=None, n_dev=None, out=None):
     return out
 
 
+def embed_gather(table, labels_table, rows, *, row_ids=None, n_cap=None, n_dev=None, want_labels=False, err=None):
+    """`embed_tokens(neighbor_tokens[rows])` (--reinit-nfeat): table fp32 [V, d], labels_table int16/int32 [N_d], rows int64."""
+    n = (row_ids.shape[0] if row_ids is not None else rows.shape[0]) if n_cap is None else n_cap
+    V, d = table.shape
+    out = torch.empty((n, d), device=table.device, dtype=torch.float32)
+    labels = torch.empty((n,), device=table.device, dtype=torch.int64) if want_labels else None
+    lb = {torch.int16: 2, torch.int32: 4}[labels_table.dtype]
+    L.call("gnnlm_embed_gather", L.ptr(table), table.stride(0), V, L.ptr(labels_table), lb, labels_table.numel(), L.ptr(rows),
+           L.ptr(row_ids), L.ptr(out), out.stride(0), n, _dev_count(n_dev), d, L.ptr(labels), L.ptr(err), L.stream_ptr())
+    return out, labels
+
+
 def layernorm(x, gamma, beta, eps=1e-5, out=None, out_dtype=None, n_dev=None, residual=None):
     """LayerNorm(x + residual); residual a Tensor (fp32 / bf16) or Split."""
     n, d = x.shape

@@ -202,6 +202,15 @@ int32_t gnnlm_lse_finish(const float* part_max, const float* part_sum, const flo
 /* dst[i, :] = src[ids[i], :]  (n x d elements of `dtype`) */
 int32_t gnnlm_gather_rows(const void* src, int64_t ld_src, const int32_t* ids, void* dst, int64_t ld_dst,
                           int64_t n_cap, const int32_t* n_dev, int64_t d, int32_t dtype, gnnlm_stream_t stream);
+/* --reinit-nfeat (fairseq/models/transformer.py:1046-1048; fairseq/data/token_block_dataset.py:371,394): ntgt features are
+ * `embed_tokens(labels)` instead of decoded keys.  dst[i, :] = table[labels[rows[node(i)]], :], node(i) = row_ids ? row_ids[i] : i;
+ * table fp32 [vocab, d] = the (projected) input-embedding table, labels = the datastore values (int16 / int32, vals.npy),
+ * rows = datastore row of every ntgt node (int64).  labels_out (nullable) receives the int64 token of every node (`ntgt.labels`);
+ * *err (nullable) is set to 1 if a value falls outside [0, vocab) (that row is zero-filled). */
+int32_t gnnlm_embed_gather(const float* table, int64_t ld_table, int64_t vocab, const void* labels, int32_t label_bytes,
+                           int64_t n_datastore, const int64_t* rows, const int32_t* row_ids, float* dst, int64_t ld_dst,
+                           int64_t n_cap, const int32_t* n_dev, int64_t d, int64_t* labels_out, int32_t* err,
+                           gnnlm_stream_t stream);
 /* y = LayerNorm(x + residual) * gamma + beta over the last dim (hgt.py:403-405; eps as nn.LayerNorm, 1e-5).
  * x fp32 [n, d]; residual nullable, [n, d] of r_dtype (F32 / BF16 / F16X2), added in fp32 before the
  * statistics -- the `trans_out + h[ntype]` of hgt.py:403 fused here rather than in the GEMM epilogue;

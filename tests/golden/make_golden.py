@@ -28,6 +28,9 @@ faiss and pyarrow.plasma are not installed), so each function is lifted out of i
                    five calls the layer makes.  This pins the layer code (projection order,
                    einsum, scaling, residual, LayerNorm); the DGL semantics themselves are
                    restated, not executed (DGL is absent) -> "parity unpinned" at that boundary.
+  adaptive_input_* fairseq/modules/adaptive_input.py AdaptiveInput.forward (the `--reinit-nfeat` ntgt features).
+  fmt_*            {split}.bin/.idx + dict.txt written AND read back by the reference's own
+                   MMapIndexedDatasetBuilder / MMapIndexedDataset / Dictionary (fmt.npz = what its readers return).
 """
 import ast
 import importlib.util
@@ -591,7 +594,85 @@ def make_hgt_case(name, B, L, k, cl, cr, d, H, n_layers, seed, stress=True, hidd
     print(f"hgt_{name}: n_tgt={bg['n_tgt']} n_ntgt={bg['n_ntgt']} |out|={float(out['tgt'].abs().mean()):.3f}")
 
 
+def make_adaptive_input_case(name, V, d, cutoff, T, seed):
+    """adaptive_input_*.npz: the reference's AdaptiveInput (fairseq/modules/adaptive_input.py, loaded by file path) on random
+    tokens that hit every band and both edges of every cutoff -- what `--reinit-nfeat` feeds the ntgt nodes."""
+    _, ain = _ref_adaptive()
+    torch.manual_seed(seed)
+    m = ain.AdaptiveInput(V, 1, d, 4, d, list(cutoff))
+    m.eval()
+    g = torch.Generator().manual_seed(seed)
+    tok = torch.randint(0, V, (T,), generator=g)
+    edge = [0, 1, cutoff[0] - 1, cutoff[0], cutoff[1] - 1, cutoff[1], V - 1]
+    tok[:len(edge)] = torch.tensor(edge)
+    with torch.no_grad():
+        out = m(tok)
+    rec = {"tokens": tok.numpy(), "out": out.numpy(), "cutoff": np.array(m.cutoff), "V": np.array(V), "d": np.array(d)}
+    for k_, v_ in m.state_dict().items():
+        rec["sd." + k_] = v_.numpy()
+    np.savez_compressed(os.path.join(OUT, f"adaptive_input_{name}.npz"), **rec)
+    print(f"adaptive_input_{name}: keys={[k for k in rec if k.startswith('sd.')]}")
+
+
+# ---------------------------------------------------------------------------------------- on-disk formats
+def make_format_fixtures():
+    """fmt_uint16.{bin,idx}, fmt_int32.{bin,idx}, fmt_dict.txt written by the reference's OWN writers
+    (MMapIndexedDatasetBuilder, fairseq/data/indexed_dataset.py:496-523; Dictionary.save, fairseq/data/dictionary.py:230-252)
+    and fmt.npz = what the reference's own readers return for them (MMapIndexedDataset.__getitem__ / .sizes,
+    Dictionary.load numbering).  indexed_dataset.py is executed whole with only its package-relative import stubbed and
+    `np.float` (removed in numpy 2) aliased to float; Dictionary is lifted by ast with its fairseq imports stubbed."""
+    src = _src("fairseq/data/indexed_dataset.py").replace("from . import FairseqDataset", "FairseqDataset = object")
+    had = hasattr(np, "float")
+    if not had:
+        np.float = float
+    ns = {"__name__": "ref_indexed_dataset"}
+    exec(compile(src, "indexed_dataset.py", "exec"), ns)
+    dsrc = _class_source("fairseq/data/dictionary.py", "Dictionary")
+    dns = {"torch": torch, "os": os, "Counter": __import__("collections").Counter,
+           "PathManager": types.SimpleNamespace(open=open, mkdirs=lambda p: os.makedirs(p, exist_ok=True)),
+           "data_utils": None, "safe_readline": None, "tokenize_line": lambda l: l.split(), "Pool": None}
+    exec(compile(dsrc, "dictionary.py", "exec"), dns)
+    RefDict = dns["Dictionary"]
+
+    rng = np.random.RandomState(7)
+    d = RefDict()
+    words = [f"w{i}" for i in range(40)] + ["with space", "ünï", "madeupword0000", "madeupword0001"]
+    for i, w in enumerate(words):
+        d.add_symbol(w, n=1000 - i)
+    dict_path = os.path.join(OUT, "fmt_dict.txt")
+    d.save(dict_path)
+    d2 = RefDict.load(dict_path)
+    out = {"dict_len": len(d2), "dict_pad": d2.pad(), "dict_eos": d2.eos(), "dict_unk": d2.unk(), "dict_bos": d2.bos(),
+           "dict_symbols": np.array(d2.symbols), "dict_index_w7": d2.index("w7"), "dict_index_missing": d2.index("nope")}
+    for tag, dt in (("uint16", np.uint16), ("int32", np.int32)):
+        prefix = os.path.join(OUT, f"fmt_{tag}")
+        b = ns["MMapIndexedDatasetBuilder"](prefix + ".bin", dtype=dt)
+        sents = []
+        for n in (5, 1, 9, 3, 17, 2):
+            sent = np.concatenate([rng.randint(4, len(d2), size=n - 1), [d2.eos()]]).astype(np.int64)
+            sents.append(sent)
+            b.add_item(torch.from_numpy(sent))
+        b.finalize(prefix + ".idx")
+        ref = ns["MMapIndexedDataset"](prefix)
+        assert len(ref) == len(sents)
+        out[f"{tag}_sizes"] = np.array(ref.sizes)
+        out[f"{tag}_flat"] = np.concatenate([ref[i].numpy() for i in range(len(ref))])
+        for i in range(len(ref)):
+            out[f"{tag}_sent{i}"] = ref[i].numpy()
+        del ref
+    np.savez(os.path.join(OUT, "fmt.npz"), **out)
+    if not had:
+        del np.float
+    print("fmt fixtures written")
+
+
 if __name__ == "__main__":
+    if "--formats-only" in sys.argv:
+        make_format_fixtures()
+        sys.exit(0)
+    if "--adaptive-input-only" in sys.argv:
+        make_adaptive_input_case("v300", V=300, d=64, cutoff=[40, 120], T=64, seed=0)
+        sys.exit(0)
     make_slice_cases()
     make_edges_doctest()
     make_graph_case("c1_c1", L=24, k=4, n_d=400, cl=1, cr=1, invalid_ctx=0, intra_ctx=0, M=8, seed=0, stress=True)
@@ -620,3 +701,5 @@ if __name__ == "__main__":
     make_hgt_case("l2_c1", B=2, L=6, k=3, cl=1, cr=1, d=32, H=4, n_layers=2, seed=0)
     make_hgt_case("l3_c2", B=1, L=8, k=2, cl=2, cr=2, d=32, H=2, n_layers=3, seed=1)
     make_hgt_case("l2_adapt", B=1, L=7, k=3, cl=1, cr=1, d=24, H=4, n_layers=2, seed=2, hidden=32, out_dim=24)
+    make_format_fixtures()
+    make_adaptive_input_case("v300", V=300, d=64, cutoff=[40, 120], T=64, seed=0)

@@ -499,6 +499,134 @@ def test_eval_lm_dataset_vs_oracle(dev):
         assert abs(graphed["score_sum"] - eager["score_sum"]) <= 1e-9 * abs(eager["score_sum"])
 
 
+def test_adaptive_input_mirror_golden(dev):
+    """model.AdaptiveInput (projected-table form) against the reference's AdaptiveInput.forward: strict state_dict load with the
+    reference's keys, every band and cutoff edge."""
+    from gnnlm_b200.model import AdaptiveInput
+    z = np.load(os.path.join(GOLD, "adaptive_input_v300.npz"))
+    cutoff = [int(c) for c in z["cutoff"]]
+    m = AdaptiveInput(int(z["V"]), 1, int(z["d"]), 4, int(z["d"]), cutoff[:-1])
+    m.load_state_dict(_sd(z, "sd."), strict=True)
+    m = m.to(dev)
+    out = m(torch.from_numpy(z["tokens"]).to(dev))
+    np.testing.assert_allclose(out.cpu().numpy(), z["out"], rtol=1e-5, atol=1e-6)     # fp32 GEMM re-association only
+    assert m.table().shape == (int(z["V"]), int(z["d"]))
+
+
+@pytest.mark.parametrize("math,adaptive,NL", [("fp32", True, 2), ("f16x3", True, 3), ("fp32", False, 1)])
+def test_eval_lm_reinit_nfeat(math, adaptive, NL, dev):
+    """--reinit-nfeat (language_modeling.py:273-278, transformer.py:1046-1048): no code rows, ntgt features =
+    embed_tokens(neighbour tokens) -- adaptive input and plain embedding -- through evaluate() against the oracle."""
+    from types import SimpleNamespace
+    import copy
+    from gnnlm_b200 import synth
+    from gnnlm_b200.dataset import DeviceDatastore, GraphTokenBlockDataset
+    from gnnlm_b200.eval_lm import evaluate
+    from gnnlm_b200.model import TransformerLanguageModel, default_args
+    from gnnlm_b200.sequence_scorer import SequenceScorer
+    from oracle import model_oracle as mo
+    from tests.synth import oracle_model
+    if math != "fp32":
+        _need_tc()
+    cfg = dict(synth.CONFIGS["c1"], NL=NL, k=4, n_d=1 << 14, V=1000, cutoff=[200, 600])
+    torch.manual_seed(3)
+    args = default_args(decoder_embed_dim=cfg["d"], decoder_attention_heads=cfg["H"], graph_layer=NL,
+                        adaptive_softmax_cutoff=cfg["cutoff"], reinit_nfeat=True, adaptive_input=adaptive,
+                        adaptive_input_cutoff="200,600", adaptive_input_factor=4)
+    model = TransformerLanguageModel.build_model(args, dictionary=synth.Dictionary(cfg["V"])).eval()
+    assert model.decoder.tgt_quantizer is None
+    sd_keys = set(model.state_dict())
+    want_key = "decoder.embed_tokens.embeddings.1.1.weight" if adaptive else "decoder.embed_tokens.weight"
+    assert want_key in sd_keys
+    tables = synth.make_tables(cfg, device="cpu")
+    rng = np.random.RandomState(5)
+    n_tok, blk = 200, 64
+    tokens = rng.randint(4, cfg["V"], size=n_tok).astype(np.int64)
+    nbr = rng.randint(1, cfg["n_d"] - 1, size=(n_tok, cfg["k"])).astype(np.int64)
+    nbr[rng.rand(n_tok, cfg["k"]) < 0.05] = -1
+    feats = rng.randn(n_tok, cfg["d"]).astype(np.float16)
+    ds = GraphTokenBlockDataset(tokens, blk, pad=1, eos=2, neighbor_offsets=nbr, n_datastore=cfg["n_d"], neighbor_context=1,
+                                precompute_feats=feats)
+    dstore = DeviceDatastore(None, tables["vals"].to(dev))
+    scorer = SequenceScorer(synth.Dictionary(cfg["V"]), args=SimpleNamespace(lmbda=0.0, knn_keytype=None))
+    res = evaluate(copy.deepcopy(model).to(dev).set_math(math), ds, dstore, scorer, max_sentences=1, device=dev)
+    # oracle
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    om = {"sd": {k[len("decoder.hgt_decoder."):]: v for k, v in sd.items() if k.startswith("decoder.hgt_decoder.")},
+          "n_heads": cfg["H"], "n_layers": NL, "cutoff": list(cfg["cutoff"]) + [cfg["V"]],
+          "softmax": mo.adaptive_weights({k[len("decoder.adaptive_softmax."):]: v for k, v in sd.items()
+                                          if k.startswith("decoder.adaptive_softmax.")})}
+    if adaptive:
+        om["embed_cutoff"] = [200, 600, cfg["V"]]
+        om["embed_bands"] = [(sd[f"decoder.embed_tokens.embeddings.{i}.0.weight"], sd[f"decoder.embed_tokens.embeddings.{i}.1.weight"])
+                             for i in range(3)]
+    else:
+        om["embed_cutoff"], om["embed_bands"] = [cfg["V"]], [(sd["decoder.embed_tokens.weight"], None)]
+    tot, cnt = 0.0, 0
+    for i in range(len(ds)):
+        it = ds[i]
+        cs, e = it["offsets"]
+        batch = {"nbr": nbr[cs:e][None], "offsets": np.arange(cs, e)[None], "tgt_feats": torch.from_numpy(feats[cs:e]).float(),
+                 "target": it["target"], "vals": tables["vals"].numpy(), "reinit_nfeat": True, "cl": 1, "cr": 1, "n_d": cfg["n_d"]}
+        out = mo.eval_batch(om, batch, None)
+        tot += float(out["logprob"].double().sum())
+        cnt += out["logprob"].numel()
+    assert res["count"] == cnt == n_tok
+    assert abs(res["score_sum"] - tot) / abs(tot) < 1e-5        # summed log-probs; per-token parity is covered by the kernels' own tests
+
+
+def test_eval_lm_from_reference_data_dir(dev, tmp_path):
+    """A data directory laid out as the reference's task expects it (dict.txt, valid.bin/.idx, {valid,train}_dstore/ with
+    info.json, raw keys / vals / neighbour memmaps, quantized-keys.npy; knn/path_utils.py:13-41) -> formats.load_graph_lm_dataset
+    + DeviceDatastore.from_dir -> evaluate(): identical to evaluating the same arrays handed over in memory."""
+    from types import SimpleNamespace
+    import copy, json as _json
+    from gnnlm_b200 import synth
+    from gnnlm_b200.dataset import DeviceDatastore, GraphTokenBlockDataset
+    from gnnlm_b200.eval_lm import evaluate
+    from gnnlm_b200.formats import load_graph_lm_dataset
+    from gnnlm_b200.sequence_scorer import SequenceScorer
+    from tests.test_formats import write_mmap_indexed
+    cfg = dict(synth.CONFIGS["c1"], NL=2, k=4, n_d=1 << 14, V=1000, cutoff=[200, 600])
+    model = synth.make_model(cfg)
+    tables = synth.make_tables(cfg, device="cpu")
+    rng = np.random.RandomState(11)
+    lens = [40, 7, 64, 1, 90, 33, 65]
+    sents = [np.concatenate([rng.randint(4, cfg["V"], size=n - 1), [2]]).astype(np.int64) for n in lens]
+    n_tok = sum(lens)
+    root = str(tmp_path / "data-bin")
+    os.makedirs(os.path.join(root, "valid_dstore"))
+    os.makedirs(os.path.join(root, "train_dstore"))
+    with open(os.path.join(root, "dict.txt"), "w") as f:
+        for i in range(4, cfg["V"]):
+            f.write(f"w{i} {cfg['V'] - i}\n")
+    write_mmap_indexed(os.path.join(root, "valid"), sents, np.uint16)
+    nbr = rng.randint(1, cfg["n_d"] - 1, size=(n_tok, cfg["k"])).astype(np.int64)
+    nbr[rng.rand(n_tok, cfg["k"]) < 0.05] = -1
+    feats = rng.randn(n_tok, cfg["d"]).astype(np.float16)
+    nbr.tofile(os.path.join(root, "valid_dstore", f"neighbors.mmap.{cfg['k']}"))
+    feats.tofile(os.path.join(root, "valid_dstore", "keys.npy"))
+    info = {"hidden_size": cfg["d"], "vocab_size": cfg["V"], "dstore_fp16": True, "val_size": 1}
+    _json.dump(dict(info, dstore_size=n_tok), open(os.path.join(root, "valid_dstore", "info.json"), "w"))
+    _json.dump(dict(info, dstore_size=cfg["n_d"]), open(os.path.join(root, "train_dstore", "info.json"), "w"))
+    tables["vals"].numpy().astype(np.int16).reshape(-1, 1).tofile(os.path.join(root, "train_dstore", "vals.npy"))   # fp16 & V < 2^15
+    np.save(os.path.join(root, "train_dstore", "quantized-keys.npy"), tables["codes"].numpy())
+    ds, dictionary = load_graph_lm_dataset(root, "valid", tokens_per_sample=64, gcn_k=cfg["k"], neighbor_context="1")
+    assert len(dictionary) == cfg["V"]
+    dstore = DeviceDatastore.from_dir(root, len(dictionary), dev)
+    assert dstore.vals.dtype == torch.int16 and (dstore.codes.cpu() == tables["codes"]).all()
+    scorer = SequenceScorer(dictionary, args=SimpleNamespace(lmbda=0.0, knn_keytype=None))
+    m = copy.deepcopy(model).to(dev).set_math("fp32")
+    got = evaluate(m, ds, dstore, scorer, max_sentences=2, device=dev)
+    flat = np.concatenate(sents)
+    ds_mem = GraphTokenBlockDataset(flat, 64, pad=1, eos=2, neighbor_offsets=nbr, n_datastore=cfg["n_d"], neighbor_context=1,
+                                    precompute_feats=feats)
+    dstore_mem = DeviceDatastore(tables["codes"].to(dev), tables["vals"].to(dev))
+    want = evaluate(m, ds_mem, dstore_mem, scorer, max_sentences=2, device=dev)
+    assert got["count"] == want["count"] == n_tok
+    assert got["score_sum"] == want["score_sum"]              # same kernels, same inputs: bit-identical
+
+
 @pytest.mark.parametrize("name", ["c1", "c3mini"])
 def test_whole_path_bf16(name, dev):
     """bf16 mode (bf16 activations / operands on the ntgt side, fp32 accumulation, fp32 tgt-side attention,

@@ -116,3 +116,15 @@ def test_zero_in_degree_tgt_gets_half_intra(golden_dir):
 def test_perplexity():
     nll2, ppl = mo.perplexity(-10.0 * np.log(2), 10)
     assert abs(nll2 - 1.0) < 1e-12 and abs(ppl - 2.0) < 1e-12
+
+
+def test_adaptive_input_oracle_matches_reference(golden_dir):
+    """oracle adaptive_input_forward == the reference's AdaptiveInput.forward (fixture generated by executing
+    fairseq/modules/adaptive_input.py): every band, both edges of every cutoff."""
+    from oracle import model_oracle as mo
+    z = np.load(os.path.join(golden_dir, "adaptive_input_v300.npz"))
+    cutoff = [int(c) for c in z["cutoff"]]
+    bands = [(torch.from_numpy(z[f"sd.embeddings.{i}.0.weight"]), torch.from_numpy(z[f"sd.embeddings.{i}.1.weight"]))
+             for i in range(len(cutoff))]
+    out = mo.adaptive_input_forward(bands, cutoff, torch.from_numpy(z["tokens"]))
+    np.testing.assert_allclose(out.numpy(), z["out"], rtol=1e-6, atol=1e-7)
