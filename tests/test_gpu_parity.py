@@ -499,6 +499,42 @@ def test_eval_lm_dataset_vs_oracle(dev):
         assert abs(graphed["score_sum"] - eager["score_sum"]) <= 1e-9 * abs(eager["score_sum"])
 
 
+def test_inter_attn_many_tokens_split_launches(dev):
+    """More tokens than one launch of the tensor-core inter kernel stages edge ranges for (148 SMs x 512): the library splits the
+    token range over several launches.  Scoring the range in one call == scoring it in slices of 9,000 tokens (bit-identical), and
+    sampled tokens match the fp64 statement of hgt.py:339-358."""
+    from gnnlm_b200 import ops
+    _need_tc()
+    d, H, T = 512, 8, 80000
+    dk = d // H
+    g = torch.Generator().manual_seed(1)
+    degs = (torch.arange(T) % 4 == 0).long() * 0 + (torch.arange(T) % 4).clamp(max=2)          # 0, 1, 2, 2, 0, 1, ...
+    degs[-1] = 19                                                                             # a two-tile token at the very end
+    indptr = torch.zeros(T + 1, dtype=torch.int32)
+    indptr[1:] = torch.cumsum(degs, 0)
+    n_c = int(indptr[-1])
+    q = torch.randn(T, d, generator=g).to(dev)
+    hc = torch.randn(n_c, d, generator=g).to(dev)
+    Wk = (torch.randn(d, d, generator=g) / d ** 0.5 * 0.3).to(dev)
+    Wv = (torch.randn(d, d, generator=g) / d ** 0.5).to(dev)
+    bv = torch.randn(d, generator=g).to(dev)
+    wk_t = ops.split_f16(Wk.view(H, dk, d).transpose(1, 2).contiguous().view(H * d, dk))
+    wv = ops.split_f16(Wv.contiguous())
+    hs, ip = ops.to_split(hc), indptr.to(dev)
+    whole = torch.full((T, d), float("nan"), device=dev)
+    ops.inter_attn_fused(q, [(0, T, ip, hs)], H, whole, wk_t, wv, bv, out_scale=0.5)
+    sliced = torch.full((T, d), float("nan"), device=dev)
+    ops.inter_attn_fused(q, [(t0, min(9000, T - t0), ip[t0:], hs) for t0 in range(0, T, 9000)], H, sliced, wk_t, wv, bv, out_scale=0.5)
+    assert torch.isfinite(whole).all() and torch.equal(whole, sliced)
+    for t in (1, 2, 3, 75775, 75776, 75777, 79998, T - 1):
+        e0, e1 = int(indptr[t]), int(indptr[t + 1])
+        K = (hc[e0:e1].double() @ Wk.double().T).view(-1, H, dk)
+        V = (hc[e0:e1].double() @ Wv.double().T + bv.double()).view(-1, H, dk)
+        s_ = torch.einsum("hj,chj->ch", q[t].double().view(H, dk), K)
+        ref = 0.5 * torch.einsum("ch,chj->hj", torch.softmax(s_, 0), V).reshape(d)
+        assert (whole[t].double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()      # a token without centres: 0 == 0
+
+
 def test_adaptive_input_mirror_golden(dev):
     """model.AdaptiveInput (projected-table form) against the reference's AdaptiveInput.forward: strict state_dict load with the
     reference's keys, every band and cutoff edge."""
