@@ -276,17 +276,17 @@ def main():
     # algorithmic bytes: K',V' rows once + Q + out + CSR
     g = synth.build_token_graph(dev_batches[0]["nbr"], tables["n_d"], cfg["c"], cfg["c"], reach=cfg["NL"] - 1)
     n_ntgt, n_valid = g.counts()
-    d, s = cfg["d"], 4
+    d, s = cfg["d"], (2 if math == "bf16" else 4)          # bytes per activation element (bf16 mode: Q | K' | V' and outputs in bf16)
     roof = None
     for key in ("hgt_cluster_attn:nn_full", "hgt_edge_attn:nn_full", "hgt_cluster_attn:nn_centre", "hgt_edge_attn:nn_centre",
                 "hgt_edge_attn:inter"):
         if key in kernels:
             if key.endswith("nn_full"):
                 E = 3 * n_ntgt - 2 * n_valid
-                alg = n_ntgt * 2 * d * s + n_ntgt * d * s + n_ntgt * d * 4 + E * 4 + (n_ntgt + 1) * 4
+                alg = n_ntgt * 2 * d * s + n_ntgt * d * s + n_ntgt * d * s + E * 4 + (n_ntgt + 1) * 4
             elif key.endswith("nn_centre"):
                 E = 3 * n_valid
-                alg = n_ntgt * 2 * d * s + n_valid * d * s + n_valid * d * 4 + E * 4 + 2 * n_valid * 4
+                alg = n_ntgt * 2 * d * s + n_valid * d * s + n_valid * d * s + E * 4 + 2 * n_valid * 4
             else:
                 alg = n_valid * 2 * d * s + T * d * s + T * d * 4 + (T + 1) * 4
             ach = alg / (kernels[key]["ms_per_launch"] * 1e-3) / 1e9
@@ -299,9 +299,9 @@ def main():
             break
     def _edge_bytes(key):
         if key.endswith("nn_full"):
-            return n_ntgt * 2 * d * s + n_ntgt * d * s + n_ntgt * d * 4 + (3 * n_ntgt - 2 * n_valid) * 4 + (n_ntgt + 1) * 4
+            return n_ntgt * 2 * d * s + n_ntgt * d * s + n_ntgt * d * s + (3 * n_ntgt - 2 * n_valid) * 4 + (n_ntgt + 1) * 4
         if key.endswith("nn_centre"):
-            return n_ntgt * 2 * d * s + n_valid * d * s + n_valid * d * 4 + 3 * n_valid * 4 + 2 * n_valid * 4
+            return n_ntgt * 2 * d * s + n_valid * d * s + n_valid * d * s + 3 * n_valid * 4 + 2 * n_valid * 4
         return n_valid * 2 * d * s + T * d * s + T * d * 4 + (T + 1) * 4
     edge_all = {key: {"GB/s": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9,
                       "frac": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
@@ -317,7 +317,7 @@ def main():
                                                      "per 16-row tile (two block barriers), one persistent CTA per SM"}
     pq_key = next((k_ for k_ in kernels if k_.startswith("pq_gather_decode")), "pq_gather_decode")
     if pq_key in kernels:
-        pq_bytes = n_ntgt * (cfg["M"] + 8 + d * 4)
+        pq_bytes = n_ntgt * (cfg["M"] + 8 + d * s)
         edge_all["pq_gather_decode"] = {"GB/s": pq_bytes / (kernels[pq_key]["ms_per_launch"] * 1e-3) / 1e9,
                             "frac": pq_bytes / (kernels[pq_key]["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
     # dominant dense kernel: the Q|K'|V' projection of all ntgt nodes

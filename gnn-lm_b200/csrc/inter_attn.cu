@@ -465,6 +465,17 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void mma16816_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split2_bf16(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  const float2 f = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x - f.x, y - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void split2_f16(float x, float y, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(x, y);
   const float2 f = __half22float2(h);
@@ -481,15 +492,19 @@ constexpr int IM_TAB = 512;          // tokens per CTA and launch whose edge ran
 // with lane (g, tq) owning head g and rows {2 tq, 2 tq + 1, 2 tq + 8, 2 tq + 9} -- exactly its B fragment of P -- and keeps the
 // running maxima / denominators in registers; q~ is scaled per (warp, head); the normalised sums leave the accumulator fragments
 // as 2-byte stores (8 consecutive lanes cover 16 contiguous bytes of a hi or lo row).
-template <int KS>
+// BF16: centre rows are bf16 (MATH_BF16 activations) -- one A operand, q~ and P split into bf16 hi / lo (two passes, no scaling:
+// bf16 has the fp32 exponent range); otherwise split fp16 rows, three passes.
+template <int KS, bool BF16>
 __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* __restrict__ qt, int64_t q_hs,   // [8, T, d], head stride
-                                                               const __half* __restrict__ hc, int64_t ldh,
+                                                               const void* __restrict__ hc_, int64_t ldh,
                                                                const int32_t* __restrict__ indptr, int64_t t0, int64_t n_tokens,
                                                                __half* __restrict__ a_out, int64_t a_hs, int64_t lda,
                                                                const float* __restrict__ bias_v, float out_scale,
                                                                float* __restrict__ t_agg, int64_t ldt) {
   constexpr int H = 8, NW = IA_THREADS / 32, D = 128 * KS;
-  constexpr int RS = 4 * D + 16;                           // row stride in bytes (hi | lo + 16: conflict-free ldmatrix)
+  constexpr int ROWB = BF16 ? 2 * D : 4 * D;               // bytes of one centre row (bf16, or fp16 hi | lo)
+  constexpr int RS = ROWB + 16;                            // row stride in shared memory (+ 16: conflict-free ldmatrix)
+  const char* hc = reinterpret_cast<const char*>(hc_);
   extern __shared__ __align__(128) char im_smem[];
   char* rows = im_smem;                                                  // [IM_STAGES][16][RS]
   float* wsum = reinterpret_cast<float*>(rows + IM_STAGES * IM_ROWS * RS);   // [NW][16][8] per-warp partial scores
@@ -500,7 +515,8 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3;
-  const bool active = tid * 4 < D;                         // owner of 16 B chunk `tid` of every row (copies, bias store)
+  const bool active = tid * 4 < D;                         // owner of 4 output columns (bias store)
+  const bool copier = tid * 16 < ROWB;                     // owner of 16 B chunk `tid` of every row
   const int wcol0 = warp * KS * 16;                        // first of the warp's columns
   const int mi = lane >> 3, r8 = lane & 7;
   const int p1_off = (r8 + (mi & 1) * 8) * RS + (mi >> 1) * 16 + wcol0 * 2;     // A = X      (rows x columns)
@@ -532,10 +548,10 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
     return it;
   };
   auto issue = [&](const Tile& it, int st) {               // cp.async of one tile; always exactly one commit
-    if (it.j < n_mine && active) {
+    if (it.j < n_mine && copier) {
       const int nr = (it.deg - it.r0) < IM_ROWS ? (it.deg - it.r0) : IM_ROWS;
       char* dst = rows + st * IM_ROWS * RS + tid * 16;
-      const char* src = reinterpret_cast<const char*>(hc + (int64_t)(it.e0 + it.r0) * ldh) + tid * 16;
+      const char* src = hc + (int64_t)(it.e0 + it.r0) * ldh * 2 + tid * 16;
 #pragma unroll
       for (int r = 0; r < IM_ROWS; ++r) {
         if (r < nr) cp_async16(dst + r * RS, src + (int64_t)r * ldh * 2);
@@ -586,12 +602,17 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
       am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
       am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
       float scale = 1.f;
-      if (am > 0.f && am < INFINITY) scale = exp2f(fminf(fmaxf(floorf(log2f(8192.f / am)), -100.f), 100.f));
+      if (!BF16 && am > 0.f && am < INFINITY) scale = exp2f(fminf(fmaxf(floorf(log2f(8192.f / am)), -100.f), 100.f));
       if (tq == 0) isc_s[warp * H + g] = 1.f / scale;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        split2_f16(qraw[ks][0].x * scale, qraw[ks][0].y * scale, qh[ks][0], ql[ks][0]);
-        split2_f16(qraw[ks][1].x * scale, qraw[ks][1].y * scale, qh[ks][1], ql[ks][1]);
+        if constexpr (BF16) {
+          split2_bf16(qraw[ks][0].x, qraw[ks][0].y, qh[ks][0], ql[ks][0]);
+          split2_bf16(qraw[ks][1].x, qraw[ks][1].y, qh[ks][1], ql[ks][1]);
+        } else {
+          split2_f16(qraw[ks][0].x * scale, qraw[ks][0].y * scale, qh[ks][0], ql[ks][0]);
+          split2_f16(qraw[ks][1].x * scale, qraw[ks][1].y * scale, qh[ks][1], ql[ks][1]);
+        }
         acc[ks][0] = acc[ks][1] = acc[ks][2] = acc[ks][3] = 0.f;
       }
       m_run = -INFINITY;
@@ -604,12 +625,18 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
       float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
-        uint32_t ah[4], al[4];
+        uint32_t ah[4];
         ldsm_x4(ah, tile + p1_off + ks * 32);
-        ldsm_x4(al, tile + p1_off + ks * 32 + D * 2);
-        mma16816(c0, ah, qh[ks][0], qh[ks][1]);
-        mma16816(c1, ah, ql[ks][0], ql[ks][1]);
-        mma16816(c2, al, qh[ks][0], qh[ks][1]);
+        if constexpr (BF16) {
+          mma16816_bf16(c0, ah, qh[ks][0], qh[ks][1]);
+          mma16816_bf16(c1, ah, ql[ks][0], ql[ks][1]);
+        } else {
+          uint32_t al[4];
+          ldsm_x4(al, tile + p1_off + ks * 32 + D * 2);
+          mma16816(c0, ah, qh[ks][0], qh[ks][1]);
+          mma16816(c1, ah, ql[ks][0], ql[ks][1]);
+          mma16816(c2, al, qh[ks][0], qh[ks][1]);
+        }
       }
       *reinterpret_cast<float2*>(wsum + (warp * IM_ROWS + g) * H + 2 * tq) = make_float2(c0[0] + (c1[0] + c2[0]), c0[1] + (c1[1] + c2[1]));
       *reinterpret_cast<float2*>(wsum + (warp * IM_ROWS + g + 8) * H + 2 * tq) =
@@ -657,16 +684,27 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
     }
     if (nr > 0) {
       uint32_t bh0, bl0, bh1, bl1;
-      split2_f16(pj[0] * 1024.f, pj[1] * 1024.f, bh0, bl0);
-      split2_f16(pj[2] * 1024.f, pj[3] * 1024.f, bh1, bl1);
+      if constexpr (BF16) {
+        split2_bf16(pj[0] * 1024.f, pj[1] * 1024.f, bh0, bl0);
+        split2_bf16(pj[2] * 1024.f, pj[3] * 1024.f, bh1, bl1);
+      } else {
+        split2_f16(pj[0] * 1024.f, pj[1] * 1024.f, bh0, bl0);
+        split2_f16(pj[2] * 1024.f, pj[3] * 1024.f, bh1, bl1);
+      }
 #pragma unroll
       for (int mt = 0; mt < KS; ++mt) {
-        uint32_t ah[4], al[4];
+        uint32_t ah[4];
         ldsm_x4_t(ah, tile + p2_off + mt * 32);
-        ldsm_x4_t(al, tile + p2_off + mt * 32 + D * 2);
-        mma16816(acc[mt], al, bh0, bh1);
-        mma16816(acc[mt], ah, bl0, bl1);
-        mma16816(acc[mt], ah, bh0, bh1);
+        if constexpr (BF16) {
+          mma16816_bf16(acc[mt], ah, bl0, bl1);
+          mma16816_bf16(acc[mt], ah, bh0, bh1);
+        } else {
+          uint32_t al[4];
+          ldsm_x4_t(al, tile + p2_off + mt * 32 + D * 2);
+          mma16816(acc[mt], al, bh0, bh1);
+          mma16816(acc[mt], ah, bl0, bl1);
+          mma16816(acc[mt], ah, bh0, bh1);
+        }
       }
     }
     if (last) {
@@ -714,16 +752,16 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
   cp_async_wait_all();
 }
 
-template <int KS>
-static int32_t launch_inter_mma(const float* qt, int64_t q_hs, const __half* hc, int64_t ldh, const int32_t* indptr, int64_t t0,
+template <int KS, bool BF16>
+static int32_t launch_inter_mma(const float* qt, int64_t q_hs, const void* hc, int64_t ldh, const int32_t* indptr, int64_t t0,
                                 int64_t n_tokens, void* a_out, int64_t a_hs, int64_t lda, const float* bias_v, float out_scale,
                                 float* t_agg, int64_t ldt, int n_sm, cudaStream_t st) {
   constexpr int D = 128 * KS;
-  const size_t smem = (size_t)IM_STAGES * IM_ROWS * (4 * D + 16) + ((size_t)8 * IM_ROWS * 8 + 8 * 8) * sizeof(float) +
+  const size_t smem = (size_t)IM_STAGES * IM_ROWS * ((BF16 ? 2 : 4) * D + 16) + ((size_t)8 * IM_ROWS * 8 + 8 * 8) * sizeof(float) +
                       (size_t)IM_TAB * sizeof(int2) + (size_t)8 * 4 * (KS * 16 + 4) * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    GNNLM_CUDA(cudaFuncSetAttribute(inter_mma_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GNNLM_CUDA(cudaFuncSetAttribute(inter_mma_kernel<KS, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   // persistent: one CTA per SM; a launch covers at most IM_TAB tokens per CTA (their edge ranges are staged in shared memory)
@@ -731,8 +769,8 @@ static int32_t launch_inter_mma(const float* qt, int64_t q_hs, const __half* hc,
   for (int64_t b0 = 0; b0 < n_tokens; b0 += per_launch) {
     const int64_t n = n_tokens - b0 < per_launch ? n_tokens - b0 : per_launch;
     const int64_t grid = n < n_sm ? n : n_sm;
-    inter_mma_kernel<KS><<<(unsigned)grid, IA_THREADS, smem, st>>>(qt, q_hs, hc, ldh, indptr + b0, t0 + b0, n, (__half*)a_out, a_hs, lda,
-                                                                  bias_v, out_scale, t_agg, ldt);
+    inter_mma_kernel<KS, BF16><<<(unsigned)grid, IA_THREADS, smem, st>>>(qt, q_hs, hc, ldh, indptr + b0, t0 + b0, n, (__half*)a_out, a_hs,
+                                                                        lda, bias_v, out_scale, t_agg, ldt);
     GNNLM_LAUNCH_CHECK("gnnlm_hgt_inter_fused");
   }
   return 0;
@@ -755,10 +793,11 @@ static int32_t launch_inter(const float* qt, int64_t q_hs, const void* hc, int64
     GNNLM_CUDA(cudaGetDevice(&dev));
     GNNLM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-  if constexpr (std::is_same<InT, __half>::value && H == 8) {
+  if constexpr (!std::is_same<InT, float>::value && H == 8) {
     if (force == 0 && ldh % 8 == 0 && d % 128 == 0) {
-#define GNNLM_IM(KS) \
-  return launch_inter_mma<KS>(qt, q_hs, (const __half*)hc, ldh, indptr, t0, n_tokens, a_out, a_hs, lda, bias_v, out_scale, t_agg, ldt, n_sm, st)
+#define GNNLM_IM(KS)                                                                                                          \
+  return launch_inter_mma<KS, std::is_same<InT, __nv_bfloat16>::value>(qt, q_hs, hc, ldh, indptr, t0, n_tokens, a_out, a_hs, lda, \
+                                                                       bias_v, out_scale, t_agg, ldt, n_sm, st)
       switch (d / 128) {
         case 4: GNNLM_IM(4);
         case 6: GNNLM_IM(6);
