@@ -37,7 +37,7 @@ def parse():
     p.add_argument("--n-datastore", type=int, default=0, help="override datastore rows (default: the config's)")
     p.add_argument("--deprecated", action="store_true", help="--deprecated (de-duplicating) graph builder, general CSR attention")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--cpu-tokens", type=int, default=384, help="tokens in the CPU-baseline sample block")
+    p.add_argument("--cpu-tokens", type=int, default=768, help="tokens in the CPU-baseline sample block")
     p.add_argument("--also-modes", default="tf32x3,tf32,bf16",
                    help="extra arithmetic modes timed briefly (resident inputs) and reported under `other_modes`")
     p.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
@@ -106,6 +106,11 @@ def cpu_sample(cfg_name, n_tokens, n_d=1 << 22):
 def time_oracle(prob, steps, warmup):
     from tests.synth import run_oracle
     torch.set_num_threads(os.cpu_count())
+    try:        # torchrun exports OMP_NUM_THREADS=1: give numpy's BLAS (the oracle's PQ rotation) every host core back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     for _ in range(warmup):
         run_oracle(prob)
     ts = []
@@ -371,11 +376,11 @@ def main():
     line["other_modes"] = other
     if world == 1 and not args.no_cpu_baseline:
         ccfg, cmodel, cdata = cpu_sample(args.config, args.cpu_tokens)
-        sec, _ = time_oracle((ccfg, cmodel, cdata), 1, 0)
+        sec, _ = time_oracle((ccfg, cmodel, cdata), 2, 1)       # ~10 s of CPU work: one warm-up + two timed passes
         line["cpu_baseline"] = {
             "value": ccfg["L"] / sec, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
             "sample": f"CPU oracle (torch fp32, {torch.get_num_threads()} threads), 1 block of {ccfg['L']} tokens at the "
-                      f"{args.config} shape, datastore 2^22 rows, {sec:.1f} s"}
+                      f"{args.config} shape, datastore 2^22 rows, mean of 2 timed passes after 1 warm-up, {sec:.1f} s per pass"}
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:
