@@ -1249,11 +1249,11 @@ def test_eval_lm_deprecated_graph(math, NL, dev):
 def test_inter_attn_token_side_form(d, H, fmt, dev):
     """('ntgt','inter','tgt') attention with the K' / V' projections moved to the token side (inter_attn.cu: register-q~ kernel
     for H <= 8, shared-memory q~ kernel above) against hgt.py:339-358 evaluated in fp64: ragged degrees around the 16-row tile
-    (0, 1, 15, 16, 17, 32, 33, 40), bias b_v' only for tokens with at least one centre."""
+    (0, 1, 15, 16, 17, 32, 33, 40, 48, 100, 512), bias b_v' only for tokens with at least one centre."""
     from gnnlm_b200 import ops
     dk = d // H
     g = torch.Generator().manual_seed(d + H)
-    degs = torch.tensor([0, 1, 15, 16, 17, 32, 33, 40, 0, 3, 32, 32], dtype=torch.int64)
+    degs = torch.tensor([0, 1, 15, 16, 17, 32, 33, 40, 0, 3, 32, 32, 512, 0, 0, 100, 48], dtype=torch.int64)     # k up to 512 (configs[4])
     T, n_c = len(degs), int(degs.sum())
     indptr = torch.zeros(T + 1, dtype=torch.int32)
     indptr[1:] = torch.cumsum(degs, 0)
