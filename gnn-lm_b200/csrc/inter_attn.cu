@@ -9,13 +9,18 @@
 //   s[t,c,h]  = <h_c, q~[t,h]> + <q[t,h], b_k'[h]>,   q~[t,h] = W_k'[h]^T q[t,h]  in R^d      (the bias term is the same for every
 //                                                                                              c of a token: softmax drops it)
 //   out[t,h]  = W_v'[h] a[t,h] + b_v'[h] * [deg(t) > 0],   a[t,h] = sum_c alpha[t,c,h] h_c  in R^d
-// i.e. two per-head GEMMs over the T target rows (gemm_tcgen05.cu, batched) around THIS kernel, which per token streams
+// i.e. two per-head GEMMs over the T target rows (gemm_tcgen05.cu, batched) around the kernel of this file, which per token streams
 // its <= k centre rows once, scores them against the H transformed queries, and writes the H alpha-weighted row sums:
 // d reads + H*d writes per token instead of 2 d^2 MACs per centre.  Same result up to fp32 re-association.
 //
-// One CTA (256 threads) per token, two CTAs per SM; centre rows in tiles of 16 through shared memory (fp32, row stride
-// d + 4 floats: conflict-free for both access patterns), online softmax across tiles.  Phase 1: warp -> head,
-// lane -> (half of the columns, row).  Phase 2: thread -> 4 columns of all H sums.
+// Three forms, chosen by the launcher:
+//   inter_mma_kernel    split-fp16 or bf16 centre rows, H = 8, d in {512, 768, 1024}: both contractions on mma.sync tensor cores,
+//                       persistent CTA per SM, cp.async tile ring (the default path of MATH_F16X3 / MATH_BF16)
+//   inter_regq_kernel   fp32 rows, or H = 4: CUDA cores, q~ in registers, persistent, cp.async tile ring
+//   inter_fused_kernel  H = 12 / 16 (or GNNLM_INTER_KERNEL=smemq): CUDA cores, q~ in shared memory, one CTA (256 threads) per token,
+//                       two CTAs per SM; centre rows in tiles of 16 through shared memory (fp32, row stride d + 4 floats: conflict-free
+//                       for both access patterns), online softmax across tiles.  Phase 1: warp -> head, lane -> (half of the
+//                       columns, row).  Phase 2: thread -> 4 columns of all H sums.
 #include <stdlib.h>
 #include <string.h>
 
