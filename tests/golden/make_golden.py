@@ -29,6 +29,8 @@ faiss and pyarrow.plasma are not installed), so each function is lifted out of i
                    einsum, scaling, residual, LayerNorm); the DGL semantics themselves are
                    restated, not executed (DGL is absent) -> "parity unpinned" at that boundary.
   adaptive_input_* fairseq/modules/adaptive_input.py AdaptiveInput.forward (the `--reinit-nfeat` ntgt features).
+  registry.json    flag defaults of the model / task / eval-lm parsers and the `transformer_lm*` architecture presets, from the
+                   reference's own add_args and architecture functions.
   fmt_*            {split}.bin/.idx + dict.txt written AND read back by the reference's own
                    MMapIndexedDatasetBuilder / MMapIndexedDataset / Dictionary (fmt.npz = what its readers return).
 """
@@ -614,6 +616,73 @@ def make_adaptive_input_case(name, V, d, cutoff, T, seed):
     print(f"adaptive_input_{name}: keys={[k for k in rec if k.startswith('sd.')]}")
 
 
+# ---------------------------------------------------------------------------------------- flags and architecture presets
+def make_registry_fixture():
+    """registry.json: (1) the defaults argparse produces for the reference's own add_args of the transformer_lm model
+    (fairseq/models/transformer_lm.py:52-139), the language_modeling task (fairseq/tasks/language_modeling.py:68-153) and the
+    eval-lm option group (fairseq/options.py:456-501); (2) what each `transformer_lm*` architecture function
+    (transformer_lm.py:190-333) makes of an empty Namespace.  The functions are lifted by ast and executed unmodified; only
+    `utils.get_available_activation_fns` and the registry decorators are stubbed."""
+    import argparse
+    import json as _json
+    out = {}
+    # --- model / task / eval flags
+    src = _method_source("fairseq/models/transformer_lm.py", "TransformerLanguageModel", "add_args")
+    ns = {"utils": types.SimpleNamespace(get_available_activation_fns=lambda: ["relu", "gelu", "gelu_fast", "gelu_accurate", "tanh", "linear"])}
+    exec(textwrap.dedent(src).replace("@staticmethod\n", ""), ns)
+    def options(parser):      # dest -> spelling, kind and type of every option, so that the mirror keeps the command line
+        return {a.dest: {"flags": list(a.option_strings), "action": type(a).__name__,
+                         "type": getattr(a.type, "__name__", None), "choices": list(a.choices) if a.choices else None,
+                         "nargs": a.nargs, "const": a.const}
+                for a in parser._actions if a.dest != "help"}
+    pm = argparse.ArgumentParser()
+    ns["add_args"](pm)
+    out["model_flags"] = vars(pm.parse_args([]))
+    out["model_options"] = options(pm)
+    src = _method_source("fairseq/tasks/language_modeling.py", "LanguageModelingTask", "add_args")
+    ns = {}
+    exec(textwrap.dedent(src).replace("@staticmethod\n", ""), ns)
+    pt = argparse.ArgumentParser()
+    ns["add_args"](pt)
+    out["task_flags"] = vars(pt.parse_args(["DATA"]))
+    out["task_options"] = options(pt)
+    osrc = _src("fairseq/options.py")
+    tree = ast.parse(osrc)
+    ns = {"sys": sys}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in ("add_common_eval_args", "add_eval_lm_args"):
+            exec(ast.get_source_segment(osrc, node), ns)
+    pe = argparse.ArgumentParser()
+    ns["add_eval_lm_args"](pe)
+    out["eval_flags"] = vars(pe.parse_args([]))
+    out["eval_options"] = options(pe)
+    # --- architecture presets
+    msrc = _src("fairseq/models/transformer_lm.py")
+    tree = ast.parse(msrc)
+    ns, archs = {}, {}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef):
+            exec(ast.get_source_segment(msrc, node), ns)      # the function body, unmodified
+            for dec in node.decorator_list:                   # @register_model_architecture('transformer_lm', '<arch>')
+                if isinstance(dec, ast.Call) and getattr(dec.func, "id", "") == "register_model_architecture":
+                    assert dec.args[0].value == "transformer_lm"
+                    archs[dec.args[1].value] = ns[node.name]
+    ns["_archs"] = archs
+    out["archs"] = {}
+    for arch, fn in ns["_archs"].items():
+        a = argparse.Namespace()
+        fn(a)
+        out["archs"][arch] = vars(a)
+    # an "old checkpoint" namespace exercises the backward-compatibility branch of base_lm_architecture (:193-200)
+    a = argparse.Namespace(no_tie_adaptive_proj=False, decoder_final_norm=False)
+    ns["_archs"]["transformer_lm"](a)
+    out["archs_old_checkpoint"] = vars(a)
+    with open(os.path.join(OUT, "registry.json"), "w") as f:
+        _json.dump(out, f, indent=1, sort_keys=True)
+    print("registry.json:", len(out["model_flags"]), "model flags,", len(out["task_flags"]), "task flags,", len(out["eval_flags"]),
+          "eval flags,", len(out["archs"]), "architectures")
+
+
 # ---------------------------------------------------------------------------------------- on-disk formats
 def make_format_fixtures():
     """fmt_uint16.{bin,idx}, fmt_int32.{bin,idx}, fmt_dict.txt written by the reference's OWN writers
@@ -670,6 +739,9 @@ if __name__ == "__main__":
     if "--formats-only" in sys.argv:
         make_format_fixtures()
         sys.exit(0)
+    if "--registry-only" in sys.argv:
+        make_registry_fixture()
+        sys.exit(0)
     if "--adaptive-input-only" in sys.argv:
         make_adaptive_input_case("v300", V=300, d=64, cutoff=[40, 120], T=64, seed=0)
         sys.exit(0)
@@ -703,3 +775,4 @@ if __name__ == "__main__":
     make_hgt_case("l2_adapt", B=1, L=7, k=3, cl=1, cr=1, d=24, H=4, n_layers=2, seed=2, hidden=32, out_dim=24)
     make_format_fixtures()
     make_adaptive_input_case("v300", V=300, d=64, cutoff=[40, 120], T=64, seed=0)
+    make_registry_fixture()

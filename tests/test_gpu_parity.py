@@ -535,6 +535,46 @@ def test_inter_attn_many_tokens_split_launches(dev):
         assert (whole[t].double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()      # a token without centres: 0 == 0
 
 
+def test_eval_lm_through_the_registration_face(dev, tmp_path):
+    """Reference-style command line -> registry.eval_lm_parser -> (stand-in) fairseq registries -> task.setup_task /
+    load_dataset / load_datastore -> ARCH_MODEL_REGISTRY[arch].build_model -> evaluate(): the same score as the same model
+    evaluated over the arrays in memory (`--reinit-nfeat` run: no quantizer file needed)."""
+    from types import SimpleNamespace
+    from gnnlm_b200 import registry
+    from gnnlm_b200.dataset import DeviceDatastore, GraphTokenBlockDataset
+    from gnnlm_b200.eval_lm import evaluate
+    from gnnlm_b200.sequence_scorer import SequenceScorer
+    from tests.test_formats import _write_data_dir
+    from tests.test_multi_rank_cpu import _fake_fairseq
+    fm, ft = _fake_fairseq()
+    registry.register_with_fairseq(fm, ft, override=True)
+    root = str(tmp_path / "data-bin")
+    n_tok, feats, nbr = _write_data_dir(root, k=4, hidden=64, n_d=500)
+    vals = np.random.RandomState(3).randint(4, 48, size=(500, 1)).astype(np.int16)
+    vals.tofile(os.path.join(root, "train_dstore", "vals.npy"))
+    argv = [root, "--graph", "--use-precompute-feat", "--reinit-nfeat", "--graph_layer", "2", "--decoder_gcn_dim", "64",
+            "--decoder-embed-dim", "64", "--decoder-attention-heads", "4", "--adaptive-softmax-cutoff", "10,20", "--adaptive-input",
+            "--adaptive-input-cutoff", "10,20", "--tokens-per-sample", "8", "--gcn-k", "4", "--neighbor-context", "1",
+            "--gen-subset", "valid"]
+    args = registry.eval_lm_parser().parse_args(argv)
+    task = ft.TASK_REGISTRY["language_modeling"].setup_task(args)
+    ds = task.load_dataset(args.gen_subset)
+    dstore = task.load_datastore(dev)
+    assert dstore.codes is None and dstore.vals.dtype == torch.int16
+    torch.manual_seed(0)
+    model = fm.ARCH_MODEL_REGISTRY[args.arch].build_model(args, task).eval().to(dev).set_math("fp32")
+    assert "decoder.embed_tokens.embeddings.2.1.weight" in model.state_dict()
+    assert model.load_reference_state_dict({k: v.clone() for k, v in model.state_dict().items()}) == []     # strict round trip
+    scorer = SequenceScorer(task.target_dictionary, args.softmax_batch, args=args)
+    got = evaluate(model, ds, dstore, scorer, max_sentences=2, device=dev)
+    z = np.load(os.path.join(GOLD, "fmt.npz"))
+    ds_mem = GraphTokenBlockDataset(z["uint16_flat"], 8, pad=1, eos=2, neighbor_offsets=nbr, n_datastore=500, neighbor_context=1,
+                                    precompute_feats=feats)
+    want = evaluate(model, ds_mem, DeviceDatastore(None, torch.from_numpy(vals.reshape(-1)).to(dev)), scorer, max_sentences=2, device=dev)
+    assert got["count"] == want["count"] == n_tok and np.isfinite(got["ppl"])
+    assert got["score_sum"] == want["score_sum"]
+
+
 def test_adaptive_input_mirror_golden(dev):
     """model.AdaptiveInput (projected-table form) against the reference's AdaptiveInput.forward: strict state_dict load with the
     reference's keys, every band and cutoff edge."""

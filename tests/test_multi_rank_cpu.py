@@ -208,3 +208,174 @@ def test_sequence_scorer_known_answers():
         want = torch.log(torch.tensor(expected[i]))
         assert (h[0]["positional_scores"] - want).abs().max() < 1e-4
         assert abs(float(h[0]["score"]) - float(want.sum()) / len(expected[i])) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ registration face
+def _registry_golden():
+    import json
+    return json.load(open(os.path.join(os.path.dirname(__file__), "golden", "registry.json")))
+
+
+@pytest.mark.parametrize("group", ["model", "task", "eval"])
+def test_flags_match_reference_parsers(group):
+    """Every flag of the reference's transformer_lm.add_args / LanguageModelingTask.add_args / add_eval_lm_args exists here with
+    the same spellings, kind, type and default (golden produced by executing the reference's own add_args)."""
+    import argparse
+    from gnnlm_b200 import registry
+    g = _registry_golden()
+    p = argparse.ArgumentParser()
+    {"model": registry.add_model_args, "task": registry.add_task_args, "eval": registry.add_eval_lm_args}[group](p)
+    got = vars(p.parse_args(["DATA"] if group == "task" else []))
+    want = g[group + "_flags"]
+    assert got == want
+    acts = {a.dest: a for a in p._actions if a.dest != "help"}
+    for dest, o in g[group + "_options"].items():
+        a = acts[dest]
+        assert list(a.option_strings) == o["flags"], dest
+        assert type(a).__name__ == o["action"] and getattr(a.type, "__name__", None) == o["type"], dest
+        assert (list(a.choices) if a.choices else None) == o["choices"] and a.nargs == o["nargs"] and a.const == o["const"], dest
+
+
+def test_architecture_presets_match_reference():
+    """apply_architecture == the reference's `transformer_lm*` architecture functions on an empty Namespace, on an old-checkpoint
+    Namespace, and with a pre-set attribute winning over the preset."""
+    import argparse
+    from gnnlm_b200 import registry
+    g = _registry_golden()
+    assert set(registry.ARCHITECTURES) == set(g["archs"])
+    for arch, want in g["archs"].items():
+        assert vars(registry.apply_architecture(argparse.Namespace(), arch)) == want, arch
+    old = registry.apply_architecture(argparse.Namespace(no_tie_adaptive_proj=False, decoder_final_norm=False), "transformer_lm")
+    assert vars(old) == g["archs_old_checkpoint"]
+    a = registry.apply_architecture(argparse.Namespace(decoder_embed_dim=768, dropout=0.0), "transformer_lm_wiki103")
+    assert a.decoder_embed_dim == 768 and a.decoder_input_dim == 768 and a.dropout == 0.0 and a.decoder_layers == 16
+    with pytest.raises(ValueError):
+        registry.apply_architecture(argparse.Namespace(), "transformer_lm_nope")
+
+
+def _fake_fairseq():
+    """Stand-in for fairseq.models / fairseq.tasks with the decorator semantics of fairseq/models/__init__.py:51-119 and
+    fairseq/tasks/__init__.py (duplicate names and wrong base classes raise ValueError)."""
+    import types
+    import torch.nn as nn
+    fm, ft = types.SimpleNamespace(), types.SimpleNamespace()
+    fm.MODEL_REGISTRY, fm.ARCH_MODEL_REGISTRY, fm.ARCH_MODEL_INV_REGISTRY, fm.ARCH_CONFIG_REGISTRY = {}, {}, {}, {}
+
+    class BaseFairseqModel(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self._is_generation_fast = False
+
+    fm.BaseFairseqModel = BaseFairseqModel
+
+    def register_model(name):
+        def deco(cls):
+            if name in fm.MODEL_REGISTRY:
+                raise ValueError("Cannot register duplicate model ({})".format(name))
+            if not issubclass(cls, BaseFairseqModel):
+                raise ValueError("Model ({}: {}) must extend BaseFairseqModel".format(name, cls.__name__))
+            fm.MODEL_REGISTRY[name] = cls
+            return cls
+        return deco
+
+    def register_model_architecture(model_name, arch_name):
+        def deco(fn):
+            if model_name not in fm.MODEL_REGISTRY:
+                raise ValueError("Cannot register model architecture for unknown model type ({})".format(model_name))
+            if arch_name in fm.ARCH_MODEL_REGISTRY:
+                raise ValueError("Cannot register duplicate model architecture ({})".format(arch_name))
+            fm.ARCH_MODEL_REGISTRY[arch_name] = fm.MODEL_REGISTRY[model_name]
+            fm.ARCH_MODEL_INV_REGISTRY.setdefault(model_name, []).append(arch_name)
+            fm.ARCH_CONFIG_REGISTRY[arch_name] = fn
+            return fn
+        return deco
+
+    fm.register_model, fm.register_model_architecture = register_model, register_model_architecture
+
+    class FairseqTask:
+        def __init__(self, args):
+            self.args, self.datasets = args, {}
+
+    ft.FairseqTask, ft.TASK_REGISTRY = FairseqTask, {}
+
+    def register_task(name):
+        def deco(cls):
+            if name in ft.TASK_REGISTRY:
+                raise ValueError("Cannot register duplicate task ({})".format(name))
+            if not issubclass(cls, FairseqTask):
+                raise ValueError("Task ({}: {}) must extend FairseqTask".format(name, cls.__name__))
+            ft.TASK_REGISTRY[name] = cls
+            return cls
+        return deco
+
+    ft.register_task = register_task
+
+    # the stock entries a real fairseq already holds
+    class StockLM(BaseFairseqModel):
+        @classmethod
+        def build_model(cls, args, task):
+            return "stock model"
+
+    class StockTask(FairseqTask):
+        @classmethod
+        def setup_task(cls, args, **kw):
+            return "stock task"
+
+    register_model("transformer_lm")(StockLM)
+    register_model_architecture("transformer_lm", "transformer_lm")(lambda a: None)
+    register_model_architecture("transformer_lm", "transformer_lm_wiki103")(lambda a: None)
+    register_task("language_modeling")(StockTask)
+    return fm, ft
+
+
+def test_fairseq_registration_adds_hgt_lm_and_overrides_on_request():
+    import argparse
+    from gnnlm_b200 import registry
+    from gnnlm_b200.model import TransformerLanguageModel
+    fm, ft = _fake_fairseq()
+    stock = fm.MODEL_REGISTRY["transformer_lm"]
+    names = registry.register_with_fairseq(fm, ft, override=False)
+    assert "hgt_lm" in fm.MODEL_REGISTRY and "hgt_lm_wiki103" in names and "hgt_lm_baevski_gbw" in names
+    assert fm.MODEL_REGISTRY["transformer_lm"] is stock and ft.TASK_REGISTRY["language_modeling"].__name__ == "StockTask"
+    assert issubclass(fm.MODEL_REGISTRY["hgt_lm"], fm.BaseFairseqModel) and issubclass(fm.MODEL_REGISTRY["hgt_lm"], TransformerLanguageModel)
+    a = argparse.Namespace()
+    fm.ARCH_CONFIG_REGISTRY["hgt_lm_wiki103"](a)
+    assert a.decoder_embed_dim == 1024 and a.adaptive_softmax_cutoff == "20000,60000" and a.decoder_attention_heads == 8
+    with pytest.raises(ValueError):                               # fairseq's own duplicate check fires on a second import
+        registry.register_with_fairseq(fm, ft, override=False)
+    # override: existing checkpoints (arch = transformer_lm_wiki103) and scripts (--task language_modeling) resolve here ...
+    fm2, ft2 = _fake_fairseq()
+    registry.register_with_fairseq(fm2, ft2, override=True)
+    cls = fm2.ARCH_MODEL_REGISTRY["transformer_lm_wiki103"]
+    assert cls is fm2.MODEL_REGISTRY["hgt_lm"] is fm2.MODEL_REGISTRY["transformer_lm"]
+    # ... only when they are graph runs: everything else goes back to the stock classes
+    assert cls.build_model(argparse.Namespace(graph_layer=0), None) == "stock model"
+    assert ft2.TASK_REGISTRY["language_modeling"].setup_task(argparse.Namespace(graph=False)) == "stock task"
+
+
+def test_registered_model_and_task_build_from_a_command_line(tmp_path):
+    """The reference's eval command line -> parser -> task.setup_task / load_dataset -> ARCH_MODEL_REGISTRY[arch].build_model:
+    the model carries the reference's state_dict keys and the dataset reads the reference's on-disk layout."""
+    from gnnlm_b200 import registry
+    from tests.test_formats import _write_data_dir
+    fm, ft = _fake_fairseq()
+    registry.register_with_fairseq(fm, ft, override=True)
+    root = str(tmp_path / "data-bin")
+    _write_data_dir(root, k=4, hidden=64)
+    argv = [root, "--graph", "--use-precompute-feat", "--graph_layer", "2", "--decoder_gcn_dim", "64", "--decoder-embed-dim", "64",
+            "--decoder-attention-heads", "4", "--adaptive-softmax-cutoff", "10,20", "--tokens-per-sample", "8", "--gcn-k", "4",
+            "--neighbor-context", "1", "--gen-subset", "valid", "--lmbda", "0.25", "--knn-keytype", "gcn_feat", "--softmax-batch", "1024"]
+    args = registry.eval_lm_parser().parse_args(argv)
+    assert args.graph and args.neighbor_context == "1" and args.k == 1024 and args.softmax_batch == 1024
+    fm.ARCH_CONFIG_REGISTRY[args.arch](args) if args.arch in fm.ARCH_CONFIG_REGISTRY else None
+    task = ft.TASK_REGISTRY["language_modeling"].setup_task(args)
+    assert isinstance(task, ft.FairseqTask) and len(task.source_dictionary) == 48
+    ds = task.load_dataset(args.gen_subset)
+    assert task.dataset("valid") is ds and ds.block_size == 8 and (ds.left_neighbor_context, ds.right_neighbor_context) == (1, 1)
+    model = fm.ARCH_MODEL_REGISTRY[args.arch].build_model(args, task)
+    assert isinstance(model, fm.BaseFairseqModel) and model._is_generation_fast is False
+    keys = set(model.state_dict())
+    for k in ("decoder.hgt_decoder.gcs.1.k_linears.0.weight", "decoder.hgt_decoder.gcs.0.relation_att", "decoder.hgt_decoder.gcs.0.skip",
+              "decoder.adaptive_softmax.head.weight", "decoder.adaptive_softmax.tail.1.2.weight"):
+        assert k in keys, k
+    assert args.decoder_input_dim == 64 and args.decoder_normalize_before is True and args.max_target_positions == 8
