@@ -244,8 +244,9 @@ def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, sc
             for i in range(inp["target"].shape[0]):
                 mask = inp["target"][i, starts[i]:].ne(scorer.pad)
                 dstore_writer.add(feat[starts[i]:, i, :][mask].float(), inp["target"][i, starts[i]:][mask])
-    if world_size > 1:
+    if world_size > 1 and torch.distributed.is_initialized():
         torch.distributed.all_reduce(acc, group=process_group)          # the path's only collective
+    # (--num-shards / --shard-id without a process group: the reference's shards are never combined either)
     torch.cuda.synchronize(device)
     dt = time.perf_counter() - t0
     score_sum, count = acc.tolist()
@@ -256,3 +257,110 @@ def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, sc
         log("Evaluated {} tokens in {:.1f}s ({:.2f} tokens/s)".format(ntok, dt, res["tokens_per_s"]))
         log("Loss (base 2): {:.4f}, Perplexity: {:.2f}".format(avg_nll2, res["ppl"]))
     return res
+
+
+# ---------------------------------------------------------------------------------------------- command line
+def load_model_ensemble(filenames, arg_overrides=None, task=None):
+    """checkpoint_utils.load_model_ensemble (fairseq/checkpoint_utils.py:176-206): every checkpoint is {'args': Namespace,
+    'model': state_dict}; the model is built from the CHECKPOINT's args (+ overrides) and loaded strictly on the hot path
+    (the bypassed base-transformer keys are ignored, model.load_reference_state_dict)."""
+    from .registry import build_model
+    ensemble, args = [], None
+    for filename in filenames:
+        if not os.path.exists(filename):
+            raise IOError("Model file not found: {}".format(filename))
+        state = torch.load(filename, map_location="cpu", weights_only=False)
+        args = state["args"]
+        for k, v in (arg_overrides or {}).items():
+            setattr(args, k, v)
+        if getattr(args, "reinit_nfeat", None) is None and getattr(getattr(task, "args", None), "reinit_nfeat", False):
+            args.reinit_nfeat = True
+        if getattr(args, "quantizer_path", ""):
+            args.quantizer_path = ""        # the codec is in the checkpoint (decoder.tgt_quantizer.*, convert_ckpt.py:40-45)
+        quantizer = None
+        if any(k.startswith("decoder.tgt_quantizer.") for k in state["model"]):
+            from .pq_codec import TorchPQCodec
+            sd = state["model"]
+            quantizer = TorchPQCodec(centroids=sd["decoder.tgt_quantizer.centroids_torch"].numpy(),
+                                     A=sd["decoder.tgt_quantizer.A"].numpy(), b=sd["decoder.tgt_quantizer.b"].numpy())
+        from .registry import apply_architecture
+        apply_architecture(args, getattr(args, "arch", "transformer_lm"))
+        if getattr(args, "max_target_positions", None) is None:
+            args.max_target_positions = getattr(args, "tokens_per_sample", 1024)
+        from .model import TransformerLanguageModel
+        model = TransformerLanguageModel.build_model(args, task, quantizer=quantizer)
+        model.load_reference_state_dict(state["model"])
+        ensemble.append(model)
+    return ensemble, args
+
+
+def main(argv=None, device="cuda", log=print) -> dict:
+    """`fairseq-eval-lm DATA --path ckpt.pt --graph --use-precompute-feat ...` (fairseq_cli/eval_lm.py:61-331) for the graph LM:
+    same flags, same files, same two log lines.  kNN-LM neighbours are read from `{split}_dstore/neighbors.mmap.{--k}` (the
+    precomputed-neighbour pipeline); their distances, which knn/find_knn.py:65-66 does not keep, are either
+    recomputed on the device (`--knn-sim-func l2|ip`, against the PQ-decoded keys) or read from `--knn-dists-file` (raw fp32
+    [N_split, k])."""
+    from . import registry
+    from .formats import MmapDataset
+    from .dataset import neighbor_path
+    from .knn_model import KNNModel
+    parser = registry.eval_lm_parser()
+    parser.add_argument("--knn-dists-file", default=None, help="raw fp32 [N_split, k] distances of neighbors.mmap.{k}")
+    parser.add_argument("--math", default="f16x3", choices=["f16x3", "tf32x3", "fp32", "tf32", "bf16"])
+    parser.add_argument("--cuda-graph", action="store_true")
+    parsed = parser.parse_args(argv)
+    if parsed.path is None:
+        raise ValueError("--path required for evaluation!")
+    if parsed.context_window > 0:
+        raise NotImplementedError("--context-window (LMContextWindowDataset) is not used by the graph LM scripts; "
+                                  "use --gcn-context-window")
+    task = registry.LanguageModelingTask.setup_task(parsed)
+    models, args = load_model_ensemble(parsed.path.split(os.pathsep), arg_overrides=eval(parsed.model_overrides), task=task)
+    if len(models) != 1:
+        raise NotImplementedError("ensembles are not on the graph LM path (sequence_scorer.py:138-152)")
+    for k, v in vars(parsed).items():                             # eval_lm.py:80-86
+        if k not in {"self_target", "future_target", "past_target", "output_size_dictionary", "add_bos_token"}:
+            setattr(args, k, v)
+    task = registry.LanguageModelingTask.setup_task(args)
+    dataset = task.load_dataset(args.gen_subset)
+    if args.knnlm and args.save_knnlm_dstore:
+        raise ValueError("Cannot use knnlm while trying to build the datastore!")
+    model = models[0].eval().to(device).set_math(args.math)
+    dstore = task.load_datastore(device)
+    knn = None
+    if args.knnlm:
+        n = len(dataset.tokens)
+        dataset.knn_ids = MmapDataset(neighbor_path(args.data.split(os.pathsep)[0], args.gen_subset, args.k), (n, args.k),
+                                      np.int64).array()
+        if args.knn_dists_file:
+            dataset.knn_dists = MmapDataset(args.knn_dists_file, (n, args.k), np.float32).array()
+        elif args.knn_sim_func in ("l2", "ip"):
+            dataset.knn_dists = np.broadcast_to(np.zeros((1, 1), np.float32), (n, args.k))       # ignored: recomputed
+        else:
+            raise ValueError("--knn-sim-func {} needs the neighbours' distances: pass --knn-dists-file, or recompute them with "
+                             "--knn-sim-func l2|ip".format(args.knn_sim_func))
+        knn = KNNModel(dstore.vals, vocab_size=len(task.target_dictionary), metric_type=args.knn_sim_func, k=args.k,
+                       pq_codes=dstore.codes, quantizer=model.decoder.tgt_quantizer, index_file=args.index_file or "")
+    writer = None
+    if args.save_knnlm_dstore:
+        writer = DstoreWriter(args.dstore_mmap, args.gen_subset, int(dataset.sizes.sum()), args.decoder_embed_dim,
+                              len(task.target_dictionary), args.dstore_fp16, args.knn_keytype)
+    scorer = SequenceScorer(task.target_dictionary, args.softmax_batch, args=args)
+    rank, world = int(os.environ.get("RANK", args.shard_id)), int(os.environ.get("WORLD_SIZE", args.num_shards))
+    use_dist = "RANK" in os.environ and world > 1
+    if use_dist and not torch.distributed.is_initialized():
+        torch.distributed.init_process_group("nccl" if str(device).startswith("cuda") else "gloo")
+    log("{} {} {} examples".format(args.data, args.gen_subset, len(dataset)))
+    log("num. model params: {}".format(sum(p.numel() for p in model.parameters())))
+    res = evaluate(model, dataset, dstore, scorer, knn_dstore=knn, temperature=args.temperature,
+                   max_sentences=args.max_sentences or 1, max_tokens=args.max_tokens, device=device, rank=rank,
+                   world_size=world, log=log if (rank == 0 or not use_dist) else None, dstore_writer=writer,
+                   knn_keytype=args.knn_keytype, cuda_graph=args.cuda_graph,
+                   bucket_by_length=args.sample_break_mode not in (None, "none") and writer is None)
+    if writer is not None:
+        res["dstore_items"] = writer.close()
+    return res
+
+
+if __name__ == "__main__":
+    main()

@@ -535,6 +535,83 @@ def test_inter_attn_many_tokens_split_launches(dev):
         assert (whole[t].double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()      # a token without centres: 0 == 0
 
 
+def test_eval_lm_main_from_checkpoint_and_data_dir(dev, tmp_path):
+    """eval_lm.main: reference command line + a fairseq-format checkpoint ({'args', 'model'} with the bypassed base-transformer
+    keys still in it) + a reference data directory -> the same scores as evaluate() on the in-memory model and arrays; with
+    --knnlm the neighbours come from neighbors.mmap.{k} and the similarities are recomputed from the PQ codes; two shards
+    (--num-shards 2) partition the blocks."""
+    from argparse import Namespace
+    from types import SimpleNamespace
+    import copy, json as _json
+    from gnnlm_b200 import synth
+    from gnnlm_b200.dataset import DeviceDatastore, GraphTokenBlockDataset
+    from gnnlm_b200.eval_lm import evaluate, main
+    from gnnlm_b200.knn_model import KNNModel
+    from gnnlm_b200.sequence_scorer import SequenceScorer
+    from tests.test_formats import write_mmap_indexed
+    cfg = dict(synth.CONFIGS["c1"], NL=2, k=4, n_d=1 << 14, V=1000, cutoff=[200, 600], k_nn=8)
+    model = synth.make_model(cfg)
+    tables = synth.make_tables(cfg, device="cpu")
+    rng = np.random.RandomState(11)
+    lens = [64, 64, 64, 40]
+    sents = [np.concatenate([rng.randint(4, cfg["V"], size=n - 1), [2]]).astype(np.int64) for n in lens]
+    n_tok = sum(lens)
+    root = str(tmp_path / "data-bin")
+    os.makedirs(os.path.join(root, "valid_dstore"))
+    os.makedirs(os.path.join(root, "train_dstore"))
+    with open(os.path.join(root, "dict.txt"), "w") as f:
+        for i in range(4, cfg["V"]):
+            f.write(f"w{i} {cfg['V'] - i}\n")
+    write_mmap_indexed(os.path.join(root, "valid"), sents, np.uint16)
+    nbr = rng.randint(1, cfg["n_d"] - 1, size=(n_tok, cfg["k"])).astype(np.int64)
+    knn_ids = rng.randint(0, cfg["n_d"], size=(n_tok, cfg["k_nn"])).astype(np.int64)
+    feats = rng.randn(n_tok, cfg["d"]).astype(np.float16)
+    nbr.tofile(os.path.join(root, "valid_dstore", f"neighbors.mmap.{cfg['k']}"))
+    knn_ids.tofile(os.path.join(root, "valid_dstore", f"neighbors.mmap.{cfg['k_nn']}"))
+    feats.tofile(os.path.join(root, "valid_dstore", "keys.npy"))
+    info = {"hidden_size": cfg["d"], "vocab_size": cfg["V"], "dstore_fp16": True, "val_size": 1}
+    _json.dump(dict(info, dstore_size=n_tok), open(os.path.join(root, "valid_dstore", "info.json"), "w"))
+    _json.dump(dict(info, dstore_size=cfg["n_d"]), open(os.path.join(root, "train_dstore", "info.json"), "w"))
+    tables["vals"].numpy().astype(np.int16).reshape(-1, 1).tofile(os.path.join(root, "train_dstore", "vals.npy"))
+    np.save(os.path.join(root, "train_dstore", "quantized-keys.npy"), tables["codes"].numpy())
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["decoder.layers.0.self_attn.k_proj.weight"] = torch.zeros(4, 4)          # the bypassed 16-layer transformer: ignored
+    sd["decoder.embed_tokens.embeddings.0.0.weight"] = torch.zeros(4, 4)
+    sd["decoder.version"] = torch.tensor([3.0])
+    ckpt_args = Namespace(arch="transformer_lm", decoder_embed_dim=cfg["d"], decoder_attention_heads=cfg["H"], graph_layer=2,
+                          decoder_gcn_dim=cfg["d"], adaptive_softmax_cutoff="200,600", tie_adaptive_weights=False,
+                          quantizer_path="/somewhere/else/quantizer", task="language_modeling", tokens_per_sample=3072)
+    ckpt = str(tmp_path / "checkpoint_best.pt")
+    torch.save({"args": ckpt_args, "model": sd}, ckpt)
+    argv = [root, "--path", ckpt, "--graph", "--use-precompute-feat", "--gen-subset", "valid", "--tokens-per-sample", "64",
+            "--gcn-k", str(cfg["k"]), "--neighbor-context", "1", "--math", "fp32", "--max-sentences", "2"]
+    lines = []
+    got = main(argv, device=dev, log=lines.append)
+    assert any(l.startswith("Loss (base 2):") for l in lines) and any("examples" in l for l in lines)
+    flat = np.concatenate(sents)
+    ds_mem = GraphTokenBlockDataset(flat, 64, pad=1, eos=2, neighbor_offsets=nbr, n_datastore=cfg["n_d"], neighbor_context=1,
+                                    precompute_feats=feats, knn_dists=np.zeros((n_tok, cfg["k_nn"]), np.float32), knn_ids=knn_ids)
+    dstore = DeviceDatastore(tables["codes"].to(dev), tables["vals"].to(torch.int16).to(dev))
+    m = copy.deepcopy(model).to(dev).set_math("fp32")
+    plain = SequenceScorer(synth.Dictionary(cfg["V"]), args=SimpleNamespace(lmbda=0.0, knn_keytype=None))
+    want = evaluate(m, ds_mem, dstore, plain, max_sentences=2, device=dev)
+    assert got["count"] == want["count"] == n_tok and got["score_sum"] == want["score_sum"]
+    # kNN-LM from the precomputed neighbour file, similarities recomputed against the PQ-decoded keys
+    got_knn = main(argv + ["--knnlm", "--k", str(cfg["k_nn"]), "--lmbda", "0.25", "--knn-sim-func", "ip", "--temperature", "10"],
+                   device=dev, log=lines.append)
+    knn = KNNModel(dstore.vals, vocab_size=cfg["V"], metric_type="ip", k=cfg["k_nn"], pq_codes=dstore.codes,
+                   quantizer=m.decoder.tgt_quantizer)
+    mixed = SequenceScorer(synth.Dictionary(cfg["V"]), args=SimpleNamespace(lmbda=0.25, knn_keytype=None))
+    want_knn = evaluate(m, ds_mem, dstore, mixed, knn_dstore=knn, temperature=10.0, max_sentences=2, device=dev)
+    assert got_knn["score_sum"] == want_knn["score_sum"] != want["score_sum"]
+    with pytest.raises(ValueError):               # distances are not on disk and the metric does not recompute them
+        main(argv + ["--knnlm", "--k", str(cfg["k_nn"]), "--lmbda", "0.25"], device=dev, log=lines.append)
+    # --num-shards / --shard-id: contiguous block ranges, scores add up
+    parts = [main(argv + ["--num-shards", "2", "--shard-id", str(i)], device=dev, log=lines.append) for i in range(2)]
+    assert parts[0]["count"] + parts[1]["count"] == n_tok
+    assert abs(parts[0]["score_sum"] + parts[1]["score_sum"] - want["score_sum"]) < 1e-9 * abs(want["score_sum"])
+
+
 def test_eval_lm_through_the_registration_face(dev, tmp_path):
     """Reference-style command line -> registry.eval_lm_parser -> (stand-in) fairseq registries -> task.setup_task /
     load_dataset / load_datastore -> ARCH_MODEL_REGISTRY[arch].build_model -> evaluate(): the same score as the same model
