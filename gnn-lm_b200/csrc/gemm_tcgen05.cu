@@ -274,7 +274,8 @@ __device__ __forceinline__ void epilogue_store_fast(uint32_t taddr, int64_t m, i
 template <bool LSE>
 __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t M, int64_t n_base, int64_t n_blk, int64_t N,
                                               const EpiStore& es, const EpiLse& el, float* stage_smem, float acc_scale = 1.f,
-                                              int tile_cols = BLOCK_N) {
+                                              int tile_cols = BLOCK_N, float2* lse_slot = nullptr, int lse_role = 0,
+                                              int lse_bar = 0) {
         if constexpr (!LSE) {
           // warp-uniform launch properties
           if (!es.residual && (N & 3) == 0 && (es.ldc & 3) == 0 && (es.c_bf16 != 2 || (es.c_lo & 3) == 0) &&
@@ -441,6 +442,20 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t
           }
         }
         if constexpr (LSE) {
+          // two epilogue warps per TMEM lane quarter (lse_role 1 / 2: upper / lower half of the tile's columns) meet through
+          // shared memory and a 64-thread named barrier; the lower-half warp merges and writes the tile's partial
+          if (lse_role == 1) {
+            *lse_slot = make_float2(run_max, run_sum);
+            asm volatile("bar.sync %0, 64;" ::"r"(lse_bar) : "memory");
+            return;
+          }
+          if (lse_role == 2) {
+            asm volatile("bar.sync %0, 64;" ::"r"(lse_bar) : "memory");
+            const float2 o = *lse_slot;
+            const float mx = fmaxf(run_max, o.x);
+            run_sum = mx > -INFINITY ? run_sum * __expf(run_max - mx) + o.y * __expf(o.x - mx) : 0.f;
+            run_max = mx;
+          }
           if (m < M) {
             el.part_max[m * el.n_tiles + n_blk] = run_max;
             el.part_sum[m * el.n_tiles + n_blk] = run_sum;
@@ -1096,8 +1111,11 @@ __host__ __device__ inline int64_t f16s_causal_tiles(int64_t n_p, int64_t n_n) {
   return full * (full + 1) / 2 + (n_p - full) * n_n;
 }
 
+// The log-sum-exp epilogue (one FFMA + one MUFU.EX2 per logit, online max) paces the K = 64 tail-cluster GEMMs (ncu: a single
+// epilogue warp per scheduler, 31 % issue-slot use, every other warp parked at the final barrier), so the LSE instantiation runs
+// EIGHT epilogue warps -- two per TMEM lane quarter, each reducing half of the tile's columns -- and 384 threads.
 template <bool LSE>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSE ? 384 : 256, 1)
     gemm_f16s_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                      const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_blo, int64_t M_cap,
                      const int32_t* __restrict__ m_dev, int64_t N, int64_t K, EpiStore es, EpiLse el, float acc_scale, int nb,
@@ -1111,6 +1129,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
   float* epi_smem = reinterpret_cast<float*>(smem + (size_t)STAGES * F16S_STAGE);
   __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_s;
+  constexpr int EPI_WARPS = LSE ? 8 : 4;
+  __shared__ float2 lse_pair[2][4][32];                   // [tile parity][lane quarter][row]: upper-half (max, sum)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = cluster_ctarank();
@@ -1164,7 +1184,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 8);
+      mbar_init(&tmem_empty[a], 2 * EPI_WARPS);        // every epilogue warp of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1233,8 +1253,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         tc_commit_2sm(&tmem_full[acc]);
       }
     }
-  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
     const int q = warp & 3;                            // ---- epilogue (both CTAs)
+    const int half = (warp - EPI_WARP0) >> 2;          // LSE: 0 = lower, 1 = upper half of the tile's columns
+    constexpr int COLS = LSE ? BLOCK_N / 2 : BLOCK_N;
     int64_t it = 0;
     for (int64_t tile = pair0; tile < total; tile += pair_stride, ++it) {
       const int acc = (int)(it & 1);
@@ -1247,13 +1269,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
       const int64_t n_base = n_blk * BLOCK_N;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)acc * BLOCK_N + (uint32_t)(half * COLS) + ((uint32_t)(q * 32) << 16);
       EpiStore eb = es;                                  // batch entry bi (fp32 C / residual when nb > 1)
       if (nb > 1) {
         eb.C = reinterpret_cast<float*>(es.C) + bi * c_bs;
         if (es.residual) eb.residual = reinterpret_cast<const float*>(es.residual) + bi * r_bs;
       }
-      epilogue_tile<LSE>(taddr, m, M, n_base, n_blk, N, eb, el, epi_smem + (warp & 3) * 32 * EPI_LD, acc_scale);
+      if constexpr (LSE)
+        epilogue_tile<LSE>(taddr, m, M, n_base + half * COLS, n_blk, N, eb, el, epi_smem, acc_scale, COLS,
+                           &lse_pair[it & 1][q][lane], half ? 1 : 2, 1 + q);
+      else
+        epilogue_tile<LSE>(taddr, m, M, n_base, n_blk, N, eb, el, epi_smem + (warp & 3) * 32 * EPI_LD, acc_scale);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
@@ -1428,7 +1454,8 @@ static int32_t launch_f16s(const CUtensorMap& mah, const CUtensorMap& mal, const
   const int64_t pairs = (causal == 1 ? f16s_causal_tiles(n_p, n_n) : n_p * n_n) * nb;
   const int64_t max_pairs = n_sm / 2;
   const unsigned grid = 2u * (unsigned)(pairs < max_pairs ? pairs : max_pairs);
-  gemm_f16s_kernel<LSE><<<grid, 256, smem, st>>>(mah, mal, mb, mblo, M, m_dev, N, K, es, el, acc_scale, nb, c_bs, r_bs, causal);
+  gemm_f16s_kernel<LSE><<<grid, LSE ? 384 : 256, smem, st>>>(mah, mal, mb, mblo, M, m_dev, N, K, es, el, acc_scale, nb, c_bs, r_bs,
+                                                             causal);
   GNNLM_LAUNCH_CHECK("gemm_f16s");
   return 0;
 }
