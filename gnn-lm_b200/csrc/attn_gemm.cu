@@ -14,6 +14,8 @@
 //
 // The lower-triangular tiles of the L x L score matrix are materialised per block (H*L*L*4 B = 302 MB allocated at
 // L = 3072, H = 8, ~54 % of it touched), still ~3x faster than the fp32 CUDA-core flash kernel.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gnnlm {
@@ -121,6 +123,59 @@ __global__ void __launch_bounds__(256) causal_softmax_kernel(const float* __rest
   }
 }
 
+// Register-resident form for L <= 128 * NT: the row is read ONCE (NT float4 per lane, all loads in flight together), max / sum / the
+// normalised numerators come from registers -- one exponential per logit instead of two plus the online rescales, and no second
+// pass over S.  Same arithmetic as above up to the order of the (max, sum) reduction.
+template <int NT>
+__global__ void __launch_bounds__(256) causal_softmax_reg_kernel(const float* __restrict__ S, int64_t L, int64_t ctx, int H,
+                                                                 int64_t k_tile, __half* __restrict__ P) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)H * L;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const int i = (int)(r % L);
+    const float* s = S + r * L;
+    __half* p = P + r * 2 * L;
+    const int lo_j = (ctx > 0 && i + 1 > ctx) ? (int)(i + 1 - ctx) : 0;
+    float4 x[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int j = t * 128 + lane * 4;
+      x[t] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (j <= i && j + 3 >= lo_j) {                      // columns j > i are never read (their tiles may be unwritten)
+        x[t] = __ldg(reinterpret_cast<const float4*>(s + j));
+        if (j < lo_j) x[t].x = -INFINITY;
+        if (j + 1 < lo_j || j + 1 > i) x[t].y = -INFINITY;
+        if (j + 2 < lo_j || j + 2 > i) x[t].z = -INFINITY;
+        if (j + 3 < lo_j || j + 3 > i) x[t].w = -INFINITY;
+      }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) m = fmaxf(m, fmaxf(fmaxf(x[t].x, x[t].y), fmaxf(x[t].z, x[t].w)));
+    const float M = warp_max(m);                          // the diagonal is always valid, so M is finite
+    float l = 0.f;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      x[t].x = __expf(x[t].x - M); x[t].y = __expf(x[t].y - M); x[t].z = __expf(x[t].z - M); x[t].w = __expf(x[t].w - M);
+      l += (x[t].x + x[t].y) + (x[t].z + x[t].w);         // exp(-inf) = 0 for masked columns
+    }
+    const float inv = 1.f / warp_sum(l);
+    // the consumer (P V' with causal == 2) contracts row i over k < (i / k_tile + 1) * k_tile only
+    const int j_end = (int)(k_tile > 0 ? min(L, (i / k_tile + 1) * k_tile) : L);
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const int j = t * 128 + lane * 4;
+      if (j < j_end) {
+        uint2 hi, lo;
+        split4_f16(x[t].x * inv, x[t].y * inv, x[t].z * inv, x[t].w * inv, hi, lo);
+        *reinterpret_cast<uint2*>(p + j) = hi;
+        *reinterpret_cast<uint2*>(p + L + j) = lo;
+      }
+    }
+  }
+}
+
 }  // namespace gnnlm
 
 using namespace gnnlm;
@@ -155,7 +210,15 @@ extern "C" int32_t gnnlm_causal_softmax_split(const float* S, int64_t L, int64_t
                   "gnnlm_causal_softmax_split: L must be a multiple of 4 and S / P 16 B / 8 B aligned");
   int64_t blocks = ceil_div((int64_t)H * L, 8);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  causal_softmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(S, L, intra_ctx, H, k_tile, (__half*)P);
+  static const bool two_pass = [] { const char* e = getenv("GNNLM_SOFTMAX_TWO_PASS"); return e && e[0] == '1'; }();   // A/B switch
+  if (!two_pass && L <= 1024)
+    causal_softmax_reg_kernel<8><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(S, L, intra_ctx, H, k_tile, (__half*)P);
+  else if (!two_pass && L <= 2048)
+    causal_softmax_reg_kernel<16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(S, L, intra_ctx, H, k_tile, (__half*)P);
+  else if (!two_pass && L <= 3072)
+    causal_softmax_reg_kernel<24><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(S, L, intra_ctx, H, k_tile, (__half*)P);
+  else
+    causal_softmax_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(S, L, intra_ctx, H, k_tile, (__half*)P);
   GNNLM_LAUNCH_CHECK("gnnlm_causal_softmax_split");
   return 0;
 }
