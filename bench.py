@@ -94,7 +94,6 @@ def cpu_sample(cfg_name, n_tokens, n_d=1 << 22):
     """Bounded sample of the same workload for the CPU oracle: one block of n_tokens tokens with the
     config's d / V / k / c / M / layers / k_nn and a 2^22-row datastore (the CPU cost per token does not
     depend on the datastore size)."""
-    from tests.synth import make_problem
     from gnnlm_b200 import synth
     cfg = dict(synth.CONFIGS[cfg_name])
     cfg.update(B=1, L=n_tokens, n_d=min(cfg["n_d"], n_d))

@@ -264,7 +264,6 @@ def load_model_ensemble(filenames, arg_overrides=None, task=None):
     """checkpoint_utils.load_model_ensemble (fairseq/checkpoint_utils.py:176-206): every checkpoint is {'args': Namespace,
     'model': state_dict}; the model is built from the CHECKPOINT's args (+ overrides) and loaded strictly on the hot path
     (the bypassed base-transformer keys are ignored, model.load_reference_state_dict)."""
-    from .registry import build_model
     ensemble, args = [], None
     for filename in filenames:
         if not os.path.exists(filename):

@@ -15,7 +15,7 @@ B200-first restructuring (results identical up to fp rounding, see tests/test_gp
     rows only (dead-work elimination).
 """
 import math
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Optional
 
 import torch
 import torch.nn as nn

@@ -6,7 +6,6 @@ with, hence precomputable).  Everything after the search -- similarity sign, -1 
 over sims/T, the vote on the target or the full-vocabulary scatter -- runs in logprob_knn.cu."""
 from typing import Optional
 
-import numpy as np
 import torch
 
 from . import ops
