@@ -158,7 +158,8 @@ def ncu_traffic(key, cfg):
 def workload_name(cfg_name):
     from gnnlm_b200 import synth
     c = synth.CONFIGS[cfg_name]
-    names = {"c1": "tiny", "c2": "enwik8-shape", "c3": "wiki103-shape", "c4": "one-billion-word-shape"}
+    names = {"c1": "tiny", "c2": "enwik8-shape", "c3": "wiki103-shape", "c4": "one-billion-word-shape",
+             "c3e": "wiki103-shape at the reference eval script's setting"}
     return f"{cfg_name}: {names.get(cfg_name, cfg_name)} GNN+kNN eval" + \
         f" d={c['d']} H={c['H']} V={c['V']} B={c['B']}xL={c['L']} k={c['k']} c={c['c']} M={c['M']} layers={c['NL']} k_nn={c['k_nn']}"
 
@@ -290,7 +291,7 @@ def main():
                 alg = n_ntgt * 2 * d * s + n_ntgt * d * s + n_ntgt * d * s + E * 4 + (n_ntgt + 1) * 4
             elif key.endswith("nn_centre"):
                 E = 3 * n_valid
-                alg = n_ntgt * 2 * d * s + n_valid * d * s + n_valid * d * s + E * 4 + 2 * n_valid * 4
+                alg = min(n_ntgt, 3 * n_valid) * 2 * d * s + n_valid * d * s + n_valid * d * s + E * 4 + 2 * n_valid * 4
             else:
                 alg = n_valid * 2 * d * s + T * d * s + T * d * 4 + (T + 1) * 4
             ach = alg / (kernels[key]["ms_per_launch"] * 1e-3) / 1e9
@@ -305,7 +306,7 @@ def main():
         if key.endswith("nn_full"):
             return n_ntgt * 2 * d * s + n_ntgt * d * s + n_ntgt * d * s + (3 * n_ntgt - 2 * n_valid) * 4 + (n_ntgt + 1) * 4
         if key.endswith("nn_centre"):
-            return n_ntgt * 2 * d * s + n_valid * d * s + n_valid * d * s + 3 * n_valid * 4 + 2 * n_valid * 4
+            return min(n_ntgt, 3 * n_valid) * 2 * d * s + n_valid * d * s + n_valid * d * s + 3 * n_valid * 4 + 2 * n_valid * 4
         return n_valid * 2 * d * s + T * d * s + T * d * 4 + (T + 1) * 4
     edge_all = {key: {"GB/s": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9,
                       "frac": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}

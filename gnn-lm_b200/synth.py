@@ -25,6 +25,10 @@ CONFIGS = {
     # configs[2]: wiki103 shape (the headline metric's config)
     "c3": dict(d=1024, H=8, V=267744, cutoff=[20000, 60000], tied=True, B=1, L=3072, k=32, c=1, M=128, NL=3,
                n_d=103227021, k_nn=1024, lmbda=0.25, temp=1.0),
+    # the Wiki103 shape at the setting of the reference's own evaluation script (gnnlm_scripts/wiki103/hgt_lm_wiki103_reproduce.sh:
+    # 127-147: one 256-token sample per batch, --gcn-k 128, --neighbor-context 2, --k 1024, --lmbda 0.1, --temperature 0.01)
+    "c3e": dict(d=1024, H=8, V=267744, cutoff=[20000, 60000], tied=True, B=1, L=256, k=128, c=2, M=128, NL=3,
+                n_d=103227021, k_nn=1024, lmbda=0.1, temp=0.01),
     # configs[3]: One-Billion-Word shape (vocab 793,471, SURVEY.md 8 C4: d=1024 inferred from the +0.02B parameters; adaptive
     # cutoffs are the checkpoint's -- 60000/160000 assumed; ~0.8 G datastore tokens x 128 B = 98 GB of codes in HBM).  The
     # reference batches this corpus by sentence (--sample-break-mode eos); blocks here are packed to 3072 tokens.
