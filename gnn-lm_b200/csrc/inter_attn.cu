@@ -386,6 +386,7 @@ __global__ void __launch_bounds__(IA_THREADS, 2) inter_regq_kernel(const float* 
       const float mx = fmaxf(m_old, warp_max(s));
       const float p = lane < nr ? __expf(s - mx) : 0.f;
       const float tile_sum = warp_sum(p);
+      __syncwarp();                                          // every lane has read m_s / l_s before lane 0 rewrites them
       if (lane < IB_ROWS) ss[lane * H + h] = p;
       if (lane == 0) {
         const float c = nr > 0 ? __expf(m_old - mx) : 0.f;   // first tile: exp(-inf) = 0
