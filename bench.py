@@ -368,6 +368,7 @@ def main():
             f2(i)
         ms2 = timed(f2, args.steps)
         other[m] = {"value": world * args.steps * T / (ms2 * 1e-3), "unit": "tokens/s", "ms_per_step": ms2 / args.steps,
+                    "cuda_graph": False,        # launched kernel by kernel; `--math <mode>` times it like the headline
                     "parity": {"tf32": "single-pass tf32: log-probs ~1e-3 of fp32 (not a parity mode)",
                                "bf16": "log-probs within 1e-2 of fp32 (tested)",
                                "tf32x3": "log-probs within 1e-4 of fp32 (tested); no fp16 range limit on operands",
