@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 // vectorised variant: d % 128 == 0, row held in registers (d <= 4096)
 template <typename OutT, int NV>
-__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float* __restrict__ x, int64_t ldx,
+__global__ void __launch_bounds__(256, 4) layernorm_vec_kernel(const float* __restrict__ x, int64_t ldx,
                                                             const void* __restrict__ res, int res_mode, int64_t ldres,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps,
