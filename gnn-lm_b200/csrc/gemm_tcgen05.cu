@@ -1122,7 +1122,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSE ? 384 : 256, 1)
                      int64_t c_bs, int64_t r_bs, int causal) {
   constexpr int STAGES = F16S_STAGES;
   constexpr uint32_t TX = 2u * F16S_STAGE;                                // both CTAs' four operand tiles -> leader
-  constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
+  // N of the instruction: outputs of at most 128 columns (the P V' GEMM of the causal attention, N = d_k = 128; the narrow tail
+  // projections) run N = 128 MMAs -- half the tensor work of a padded 256-column tile.  Each CTA of the pair then supplies
+  // N / 2 = 64 rows of W: its TMA box starts at row crank * 64 and only the first 64 rows of its tile are read.
+  const int n_mma = N <= BLOCK_N / 2 ? BLOCK_N / 2 : BLOCK_N;
+  const uint32_t IDESC = (1u << 4) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)((2 * BLOCK_M) >> 4) << 24);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1204,7 +1208,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(LSE ? 384 : 256, 1)
     if (lane == 0) {                                   // ---- TMA producer (both CTAs)
       int stage = 0;
       uint32_t phase = 0;
-      const int half = (int)crank * (BLOCK_N / 2);
+      const int half = (int)crank * (n_mma / 2);
       for (int64_t tile = pair0; tile < total; tile += pair_stride) {
         int bi, kbs;
         int64_t r, c;
