@@ -12,6 +12,9 @@ __device__ __forceinline__ ClusterShape cluster_shape(int64_t o, int64_t pos, in
                                                       int right_ctx, int64_t invalid_ctx) {
   ClusterShape s{0, 0, 0};
   if (o == -1) return s;                                       // token_block_dataset.py:358
+  // ids outside the datastore never reach the code / label gathers (the host side raises IndexError before a block with
+  // such ids is staged, dataset.GraphTokenBlockDataset.__getitem__; callers that bypass it get an absent neighbour)
+  if (o < 0 || o >= n_datastore) return s;
   if (invalid_ctx > 0) {
     int64_t dlt = pos - o;
     if (dlt < 0) dlt = -dlt;

@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(256) knn_mix_nll_kernel(const float* __restric
         int64_t id = __ldg(ids + t * k_nn + j);
         float s = __ldg(dists + t * k_nn + j) * sim_sign;                              // knn_model.py:153-157
         if (id == -1) { s = -1e10f; id += n_datastore; }                               // :193 mask; :198 numpy wrap
+        if (id < 0 || id >= n_datastore) { s = -1e10f; id = n_datastore - 1; }         // foreign ids: masked, never dereferenced
         s *= inv_temp;                                                                 // :196
         const bool hit = load_val(vals, val_bytes, id) == y;                           // :212
         rec += hit;
@@ -193,14 +194,14 @@ __global__ void __launch_bounds__(256) knn_full_kernel(const float* __restrict__
     float m = -INFINITY;
     for (int64_t j = lane; j < k_nn; j += 32) {
       float s = __ldg(dists + t * k_nn + j) * sim_sign;
-      if (__ldg(ids + t * k_nn + j) == -1) s = -1e10f;
+      { const int64_t id = __ldg(ids + t * k_nn + j); if (id < 0 || id >= n_datastore) s = -1e10f; }
       m = fmaxf(m, s * inv_temp);
     }
     m = warp_max(m);
     float l = 0.f;
     for (int64_t j = lane; j < k_nn; j += 32) {
       float s = __ldg(dists + t * k_nn + j) * sim_sign;
-      if (__ldg(ids + t * k_nn + j) == -1) s = -1e10f;
+      { const int64_t id = __ldg(ids + t * k_nn + j); if (id < 0 || id >= n_datastore) s = -1e10f; }
       l += expf(s * inv_temp - m);
     }
     l = warp_sum(l);
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(256) knn_full_kernel(const float* __restrict__
       int64_t id = __ldg(ids + t * k_nn + j);
       float s = __ldg(dists + t * k_nn + j) * sim_sign;
       if (id == -1) { s = -1e10f; id += n_datastore; }
+      if (id < 0 || id >= n_datastore) continue;                                      // foreign ids are never dereferenced
       const int64_t val = load_val(vals, val_bytes, id);
       if (val >= 0 && val < V) atomicAdd(probs + t * V + val, expf(s * inv_temp - m) / l);   // knn_model.py:205
     }

@@ -136,13 +136,22 @@ class GraphTokenBlockDataset:
             source = torch.cat([item.new_tensor([self.eos]), item[:-1]])
         else:
             source = torch.from_numpy(np.asarray(self.tokens[cs - 1:e - 1]).astype(np.int64))
+        nbr = np.array(self.neighbor_offsets[cs:e])
+        # the files are raw memmaps without a header: a neighbors.mmap built against another datastore would index past
+        # the code table.  The reference raises IndexError at `quant_neighbor_feats[o]` (token_block_dataset.py:369-370)
+        if nbr.size and (int(nbr.min()) < -1 or int(nbr.max()) >= self.n_datastore):
+            raise IndexError(f"block {index}: neighbour id outside [-1, {self.n_datastore}) -- neighbors.mmap does not "
+                             "belong to this train_dstore")
         out = {"id": index, "source": source, "target": item, "offsets": (cs, e), "start_idx": s - cs,
-               "nbr": torch.from_numpy(np.array(self.neighbor_offsets[cs:e]))}
+               "nbr": torch.from_numpy(nbr)}
         if self.precompute_feats is not None:
             out["feats"] = torch.from_numpy(np.array(self.precompute_feats[cs:e]))
         if self.knn_ids is not None:
             out["knn_dists"] = torch.from_numpy(np.array(self.knn_dists[cs:e]))
-            out["knn_ids"] = torch.from_numpy(np.array(self.knn_ids[cs:e]))
+            ids = np.array(self.knn_ids[cs:e])
+            if ids.size and (int(ids.min()) < -1 or int(ids.max()) >= self.n_datastore):
+                raise IndexError(f"block {index}: kNN-LM neighbour id outside [-1, {self.n_datastore})")
+            out["knn_ids"] = torch.from_numpy(ids)
         return out
 
     def collater(self, samples: List[dict]) -> dict:

@@ -58,25 +58,42 @@ def batches(dataset: GraphTokenBlockDataset, lo: int, hi: int, max_sentences: in
 class DstoreWriter:
     """--save-knnlm-dstore (fairseq_cli/eval_lm.py:178-244): keys.npy / vals.npy raw memmaps + info.json, same names,
     dtypes and shapes; keys are the features selected by --knn-keytype (e.g. `gcn_feat`), written in token order.
-    The fp32 -> fp16 cast runs on the device (gnnlm_convert) before the D2H copy."""
+    The fp32 -> fp16 cast runs on the device (gnnlm_convert) before the D2H copy.
+
+    Shard-aware: `offset` is the global token offset of this rank's first block (sum of the sizes of the blocks before its
+    contiguous range), so every rank / shard writes its own row range [offset, offset + its tokens) of the SAME files.  The
+    files are sized with ftruncate (extends with zeros, never clears rows another shard already wrote) and mapped `r+`, so
+    concurrent ranks and separately launched `--shard-id` runs compose into one datastore."""
 
     def __init__(self, dstore_mmap: str, subset: str, dstore_size: int, hidden: int, vocab: int, dstore_fp16: bool,
-                 knn_keytype: Optional[str] = None):
+                 knn_keytype: Optional[str] = None, offset: int = 0, limit: Optional[int] = None, write_info: bool = True):
         suffix = "" if not knn_keytype else f"-{knn_keytype}"
         self.dir = os.path.join(dstore_mmap, f"{subset}_dstore{suffix}")
         os.makedirs(self.dir, exist_ok=True)
-        self.fp16, self.size, self.idx = dstore_fp16, int(dstore_size), 0
+        self.fp16, self.size = dstore_fp16, int(dstore_size)
+        self.start = self.idx = min(int(offset), self.size)
+        self.end = self.size if limit is None else min(self.size, self.start + int(limit))
         info = {"dstore_size": int(dstore_size), "hidden_size": hidden, "vocab_size": vocab, "dstore_fp16": dstore_fp16,
                 "val_size": 1}
-        json.dump(info, open(os.path.join(self.dir, "info.json"), "w"), indent=4, sort_keys=True)
-        self.keys = np.memmap(os.path.join(self.dir, "keys.npy"), dtype=np.float16 if dstore_fp16 else np.float32, mode="w+",
-                              shape=(self.size, hidden))
+        if write_info:
+            json.dump(info, open(os.path.join(self.dir, "info.json"), "w"), indent=4, sort_keys=True)
+        kdt = np.float16 if dstore_fp16 else np.float32
         vdt = np.int16 if dstore_fp16 and vocab < 2 ** 15 else np.int32
-        self.vals = np.memmap(os.path.join(self.dir, "vals.npy"), dtype=vdt, mode="w+", shape=(self.size, 1))
+        self.keys = self._map(os.path.join(self.dir, "keys.npy"), kdt, (self.size, hidden))
+        self.vals = self._map(os.path.join(self.dir, "vals.npy"), vdt, (self.size, 1))
+
+    @staticmethod
+    def _map(path, dtype, shape):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        with open(path, "ab") as f:
+            f.truncate(nbytes)
+        if nbytes == 0:
+            return np.zeros(shape, dtype)
+        return np.memmap(path, dtype=dtype, mode="r+", shape=shape)
 
     def add(self, feats: torch.Tensor, tokens: torch.Tensor):
         """feats [n, d] fp32 on the device, tokens [n]."""
-        n = min(feats.shape[0], self.size - self.idx)            # eval_lm.py:227-230 (clip at dstore_size)
+        n = min(feats.shape[0], self.end - self.idx)             # eval_lm.py:227-230 (clip at dstore_size)
         if n <= 0:
             return
         f = feats[:n].contiguous()
@@ -87,9 +104,11 @@ class DstoreWriter:
         self.idx += n
 
     def close(self):
-        self.keys.flush()
-        self.vals.flush()
-        return self.idx
+        """Rows written by THIS rank / shard."""
+        if hasattr(self.keys, "flush"):
+            self.keys.flush()
+            self.vals.flush()
+        return self.idx - self.start
 
 
 class GraphedScorer:
@@ -280,8 +299,11 @@ def load_model_ensemble(filenames, arg_overrides=None, task=None):
         if any(k.startswith("decoder.tgt_quantizer.") for k in state["model"]):
             from .pq_codec import TorchPQCodec
             sd = state["model"]
+            # A / b exist only for an OPQ index (convert_ckpt.py:40-45 writes them `if QUANTIZER.pre_torch`): a plain
+            # `--index PQ64` checkpoint has the codebook alone
+            A, b = sd.get("decoder.tgt_quantizer.A"), sd.get("decoder.tgt_quantizer.b")
             quantizer = TorchPQCodec(centroids=sd["decoder.tgt_quantizer.centroids_torch"].numpy(),
-                                     A=sd["decoder.tgt_quantizer.A"].numpy(), b=sd["decoder.tgt_quantizer.b"].numpy())
+                                     A=None if A is None else A.numpy(), b=None if b is None else b.numpy())
         from .registry import apply_architecture
         apply_architecture(args, getattr(args, "arch", "transformer_lm"))
         if getattr(args, "max_target_positions", None) is None:
@@ -340,15 +362,19 @@ def main(argv=None, device="cuda", log=print) -> dict:
                              "--knn-sim-func l2|ip".format(args.knn_sim_func))
         knn = KNNModel(dstore.vals, vocab_size=len(task.target_dictionary), metric_type=args.knn_sim_func, k=args.k,
                        pq_codes=dstore.codes, quantizer=model.decoder.tgt_quantizer, index_file=args.index_file or "")
-    writer = None
-    if args.save_knnlm_dstore:
-        writer = DstoreWriter(args.dstore_mmap, args.gen_subset, int(dataset.sizes.sum()), args.decoder_embed_dim,
-                              len(task.target_dictionary), args.dstore_fp16, args.knn_keytype)
     scorer = SequenceScorer(task.target_dictionary, args.softmax_batch, args=args)
     rank, world = int(os.environ.get("RANK", args.shard_id)), int(os.environ.get("WORLD_SIZE", args.num_shards))
     use_dist = "RANK" in os.environ and world > 1
     if use_dist and not torch.distributed.is_initialized():
         torch.distributed.init_process_group("nccl" if str(device).startswith("cuda") else "gloo")
+    writer = None
+    if args.save_knnlm_dstore:
+        # every rank / shard writes the rows of its own contiguous block range into the same files
+        lo, hi = shard_range(len(dataset), rank, world)
+        writer = DstoreWriter(args.dstore_mmap, args.gen_subset, int(dataset.sizes.sum()), args.decoder_embed_dim,
+                              len(task.target_dictionary), args.dstore_fp16, args.knn_keytype,
+                              offset=int(dataset.sizes[:lo].sum()), limit=int(dataset.sizes[lo:hi].sum()),
+                              write_info=rank == 0 or not use_dist)
     log("{} {} {} examples".format(args.data, args.gen_subset, len(dataset)))
     log("num. model params: {}".format(sum(p.numel() for p in model.parameters())))
     res = evaluate(model, dataset, dstore, scorer, knn_dstore=knn, temperature=args.temperature,
@@ -357,7 +383,13 @@ def main(argv=None, device="cuda", log=print) -> dict:
                    knn_keytype=args.knn_keytype, cuda_graph=args.cuda_graph,
                    bucket_by_length=args.sample_break_mode not in (None, "none") and writer is None)
     if writer is not None:
-        res["dstore_items"] = writer.close()
+        n_rows = writer.close()
+        res["dstore_items_this_rank"] = n_rows
+        if use_dist:
+            t = torch.tensor([n_rows], dtype=torch.int64, device=device)
+            torch.distributed.all_reduce(t)
+            n_rows = int(t.item())
+        res["dstore_items"] = n_rows
     return res
 
 

@@ -74,7 +74,9 @@ class KNNModel(object):
             out, self._pending = self._pending, None
             return out
         if positions is not None and self.knns is not None and (self.dists is not None or self.recompute):
-            return (None if self.dists is None else self.dists[positions].contiguous()), self.knns[positions].contiguous()
+            positions = positions.reshape(-1)          # sample['positions'] is [B, L]: one row of search results per token
+            return (None if self.dists is None else self.dists[positions].float().contiguous()), \
+                self.knns[positions].long().contiguous()
         raise RuntimeError("faiss search is out of scope: call set_search_results() or pass precomputed arrays")
 
     @torch.no_grad()

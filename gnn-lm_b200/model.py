@@ -48,12 +48,15 @@ class _TiedHead(nn.Module):
 class AdaptiveSoftmax(nn.Module):
     """Efficient softmax approximation (adaptive_softmax.py:50-115), evaluated at the target only.
 
-    `tied=True` reproduces the key layout of --tie-adaptive-weights/--tie-adaptive-proj checkpoints
-    (wiki103): head.word_proj / head.class_proj, tail.i.0.weight stored [d, dim_i]."""
+    `tied=True` reproduces the key layout of --tie-adaptive-weights checkpoints (wiki103): head.word_proj / head.class_proj;
+    with `tie_proj` (--tie-adaptive-proj, default = `tied`) the tail projection is the adaptive input's TiedLinear, stored
+    [d, dim_i] and applied transposed; without it the reference builds nn.Linear(d, dim_i), stored [dim_i, d]
+    (adaptive_softmax.py:96-101)."""
 
     def __init__(self, vocab_size: int, input_dim: int, cutoff: List[int], dropout: float = 0.0, factor: float = 4.0,
-                 tied: bool = False):
+                 tied: bool = False, tie_proj: Optional[bool] = None):
         super().__init__()
+        self.tie_proj = bool(tied) if tie_proj is None else bool(tie_proj) and bool(tied)
         cutoff = list(cutoff)
         if vocab_size > cutoff[-1]:
             cutoff = cutoff + [vocab_size]
@@ -68,7 +71,7 @@ class AdaptiveSoftmax(nn.Module):
         self.tail = nn.ModuleList()
         for i in range(n_tail):
             dim = int(input_dim // factor ** (i + 1))
-            proj = _W(input_dim, dim) if tied else _W(dim, input_dim)
+            proj = _W(input_dim, dim) if self.tie_proj else _W(dim, input_dim)
             self.tail.append(nn.Sequential(proj, nn.Dropout(dropout), _W(cutoff[i + 1] - cutoff[i], dim)))
         self.register_buffer("version", torch.LongTensor([1]))
         self._prep, self._prep_key = None, None
@@ -84,7 +87,7 @@ class AdaptiveSoftmax(nn.Module):
         P = {"head": _Weight(head, None, math_mode), "proj": [], "out": []}
         for seq in self.tail:
             p = seq[0].weight.detach()
-            P["proj"].append(_Weight(p.t() if self.tied else p, None, math_mode))
+            P["proj"].append(_Weight(p.t() if self.tie_proj else p, None, math_mode))
             P["out"].append(_Weight(seq[2].weight.detach(), None, math_mode))
         self._prep, self._prep_key = P, key
         return P
@@ -227,9 +230,14 @@ class TokenGraphTransformerDecoder(nn.Module):
         if cut is not None:
             if isinstance(cut, str):
                 cut = [int(c) for c in cut.split(",")]
+            tied = bool(_get(args, "tie_adaptive_weights", False))
+            if tied and _get(args, "decoder_input_dim", d) != _get(args, "decoder_output_dim", d):
+                # TiedHeadModule then wraps word_proj in nn.Sequential(Linear, TiedLinear) (adaptive_softmax.py:32-36)
+                raise NotImplementedError("--tie-adaptive-weights with decoder_input_dim != decoder_output_dim "
+                                          "(Sequential head word_proj) is not used by any graph LM config")
             self.adaptive_softmax = AdaptiveSoftmax(self.num_classes, d, cut, dropout=0.0,
-                                                    factor=_get(args, "adaptive_softmax_factor", 4),
-                                                    tied=bool(_get(args, "tie_adaptive_weights", False)))
+                                                    factor=_get(args, "adaptive_softmax_factor", 4), tied=tied,
+                                                    tie_proj=_get(args, "tie_adaptive_proj", None))
             self.embed_out = None
         else:
             self.adaptive_softmax = None

@@ -203,13 +203,14 @@ def _ref_adaptive():
     return asm, ain
 
 
-def make_adaptive_case(name, V, d, cutoff, tied, T, seed):
+def make_adaptive_case(name, V, d, cutoff, tied, T, seed, tie_proj=None):
     asm, ain = _ref_adaptive()
     torch.manual_seed(seed)
     emb = None
     if tied:
         emb = ain.AdaptiveInput(V, 1, d, 4, d, list(cutoff))
-    m = asm.AdaptiveSoftmax(V, d, list(cutoff), dropout=0.0, factor=4.0, adaptive_inputs=emb, tie_proj=tied)
+    tie_proj = tied if tie_proj is None else tie_proj
+    m = asm.AdaptiveSoftmax(V, d, list(cutoff), dropout=0.0, factor=4.0, adaptive_inputs=emb, tie_proj=tie_proj)
     m.eval()
     x = torch.randn(1, T, d)
     g = torch.Generator().manual_seed(seed)
@@ -220,7 +221,7 @@ def make_adaptive_case(name, V, d, cutoff, tied, T, seed):
         lp_f = m.get_log_prob(x, None)
     out = {"x": x.numpy(), "target": target.numpy(), "cutoff": np.array(m.cutoff),
            "lp_target_mode_at_target": lp_t.gather(2, target.unsqueeze(-1)).squeeze(-1).numpy(),
-           "lp_full": lp_f.numpy(), "tied": np.array(int(tied))}
+           "lp_full": lp_f.numpy(), "tied": np.array(int(tied)), "tie_proj": np.array(int(tie_proj))}
     for k_, v_ in m.state_dict().items():
         out["sd." + k_] = v_.numpy()
     if tied:
@@ -742,6 +743,10 @@ if __name__ == "__main__":
     if "--registry-only" in sys.argv:
         make_registry_fixture()
         sys.exit(0)
+    if "--adaptive-noproj-only" in sys.argv:
+        # --tie-adaptive-weights WITHOUT --tie-adaptive-proj: tail projections are nn.Linear(d, dim_i) (adaptive_softmax.py:96-101)
+        make_adaptive_case("tied_noproj", V=300, d=64, cutoff=[40, 120], tied=True, T=40, seed=2, tie_proj=False)
+        sys.exit(0)
     if "--adaptive-input-only" in sys.argv:
         make_adaptive_input_case("v300", V=300, d=64, cutoff=[40, 120], T=64, seed=0)
         sys.exit(0)
@@ -758,6 +763,7 @@ if __name__ == "__main__":
     make_dedup_case("c1_c3_invalid", L=32, k=4, n_d=1200, cl=1, cr=3, invalid_ctx=300, intra_ctx=0, M=16, seed=3)
     make_adaptive_case("untied", V=300, d=64, cutoff=[40, 120], tied=False, T=40, seed=0)
     make_adaptive_case("tied", V=300, d=64, cutoff=[40, 120], tied=True, T=40, seed=1)
+    make_adaptive_case("tied_noproj", V=300, d=64, cutoff=[40, 120], tied=True, T=40, seed=2, tie_proj=False)
     make_pq_case("m8", n=50, M=8, dsub=4, with_b=False, seed=0)
     make_pq_case("m16b", n=30, M=16, dsub=8, with_b=True, seed=1)
     make_knn_case("ip_t1", T=24, knn=16, n_d=2000, V=300, temp=1.0, metric="do_not_recomp_ip", seed=0, with_missing=True)

@@ -257,12 +257,14 @@ def test_causal_attn_with_intra_context(B, L, H, d, ctx, dev):
 
 
 # ------------------------------------------------------------------------------------------ log-probs / kNN
-@pytest.mark.parametrize("case", ["untied", "tied"])
+@pytest.mark.parametrize("case", ["untied", "tied", "tied_noproj"])
 def test_adaptive_softmax_golden(case, dev):
+    """tied_noproj: --tie-adaptive-weights without --tie-adaptive-proj (tail projections stored [dim_i, d])."""
     from gnnlm_b200.model import AdaptiveSoftmax
     z = np.load(os.path.join(GOLD, f"adaptive_{case}.npz"))
     cutoff = z["cutoff"].tolist()
-    m = AdaptiveSoftmax(cutoff[-1], z["x"].shape[-1], cutoff[:-1], tied=bool(z["tied"]))
+    m = AdaptiveSoftmax(cutoff[-1], z["x"].shape[-1], cutoff[:-1], tied=bool(z["tied"]),
+                        tie_proj=bool(z["tie_proj"]) if "tie_proj" in z.files else None)
     sd = _sd(z, "sd.")
     m.load_state_dict(sd, strict=True)
     m = m.to(dev)
@@ -610,6 +612,51 @@ def test_eval_lm_main_from_checkpoint_and_data_dir(dev, tmp_path):
     parts = [main(argv + ["--num-shards", "2", "--shard-id", str(i)], device=dev, log=lines.append) for i in range(2)]
     assert parts[0]["count"] + parts[1]["count"] == n_tok
     assert abs(parts[0]["score_sum"] + parts[1]["score_sum"] - want["score_sum"]) < 1e-9 * abs(want["score_sum"])
+    # --save-knnlm-dstore is shard-aware: two separately launched shards fill the row ranges of ONE keys.npy / vals.npy
+    # (fairseq_cli/eval_lm.py:178-244), identical to the single-process datastore
+    one, two = str(tmp_path / "ds1"), str(tmp_path / "ds2")
+    r1 = main(argv + ["--save-knnlm-dstore", "--dstore-mmap", one, "--knn-keytype", "gcn_feat", "--dstore-fp16"], device=dev,
+              log=lines.append)
+    rs = [main(argv + ["--save-knnlm-dstore", "--dstore-mmap", two, "--knn-keytype", "gcn_feat", "--dstore-fp16", "--num-shards", "2",
+                       "--shard-id", str(i)], device=dev, log=lines.append) for i in (1, 0)]
+    assert r1["dstore_items"] == n_tok and rs[0]["dstore_items"] + rs[1]["dstore_items"] == n_tok
+    for name, dt in (("keys.npy", np.float16), ("vals.npy", np.int16)):
+        a = np.fromfile(os.path.join(one, "valid_dstore-gcn_feat", name), dtype=dt)
+        b = np.fromfile(os.path.join(two, "valid_dstore-gcn_feat", name), dtype=dt)
+        assert a.shape == b.shape and (a == b).all() and np.abs(a.astype(np.float64)).sum() > 0
+    assert (np.fromfile(os.path.join(one, "valid_dstore-gcn_feat", "vals.npy"), dtype=np.int16) == flat).all()
+    # a plain-PQ checkpoint (--index PQ64: no OPQ transform, convert_ckpt.py:40-45 writes neither A nor b) loads and runs
+    sd_pq = {k: v for k, v in sd.items() if k not in ("decoder.tgt_quantizer.A", "decoder.tgt_quantizer.b")}
+    ckpt_pq = str(tmp_path / "checkpoint_pq.pt")
+    torch.save({"args": ckpt_args, "model": sd_pq}, ckpt_pq)
+    got_pq = main([root, "--path", ckpt_pq] + argv[3:], device=dev, log=lines.append)
+    from gnnlm_b200.pq_codec import TorchPQCodec
+    m_pq = copy.deepcopy(model)
+    m_pq.decoder.tgt_quantizer = TorchPQCodec(centroids=model.decoder.tgt_quantizer.centroids_torch.numpy())
+    want_pq = evaluate(m_pq.to(dev).set_math("fp32"), ds_mem, dstore, plain, max_sentences=2, device=dev)
+    assert got_pq["count"] == n_tok and got_pq["score_sum"] == want_pq["score_sum"] != want["score_sum"]
+
+
+def test_knn_model_precomputed_arrays(dev):
+    """KNNModel(knns=..., dists=...) -- the whole-split constructor: get_knns(positions=[B, L]) returns one row of search results
+    per token ([B*L, k], fp32 / int64), and get_knn_prob equals the set_search_results route."""
+    from gnnlm_b200.knn_model import KNNModel
+    g = torch.Generator().manual_seed(4)
+    n_d, V, n_split, k, B, Lb = 5000, 300, 64, 16, 2, 8
+    vals = torch.randint(4, V, (n_d,), generator=g, dtype=torch.int32).to(dev)
+    dists = torch.randn((n_split, k), generator=g).half().to(dev)            # stored fp16: must come back fp32
+    knns = torch.randint(0, n_d, (n_split, k), generator=g, dtype=torch.int32).to(dev)
+    knns[3, 5] = -1
+    pos = torch.randperm(n_split, generator=g)[:B * Lb].view(B, Lb).to(dev)
+    tgt = torch.randint(4, V, (B, Lb), generator=g).to(dev)
+    whole = KNNModel(vals, vocab_size=V, dists=dists, knns=knns, k=k)
+    d_, i_ = whole.get_knns(None, positions=pos)
+    assert d_.shape == i_.shape == (B * Lb, k) and d_.dtype == torch.float32 and i_.dtype == torch.int64
+    p1, r1 = whole.get_knn_prob(None, targets=tgt, return_recall=True, positions=pos)
+    step = KNNModel(vals, vocab_size=V, k=k)
+    step.set_search_results(dists[pos.reshape(-1)].float(), knns[pos.reshape(-1)].long())
+    p2, r2 = step.get_knn_prob(None, targets=tgt, return_recall=True)
+    assert p1.shape == (B * Lb,) and torch.equal(p1, p2) and torch.equal(r1, r2)
 
 
 def test_eval_lm_through_the_registration_face(dev, tmp_path):

@@ -379,3 +379,67 @@ def test_registered_model_and_task_build_from_a_command_line(tmp_path):
               "decoder.adaptive_softmax.head.weight", "decoder.adaptive_softmax.tail.1.2.weight"):
         assert k in keys, k
     assert args.decoder_input_dim == 64 and args.decoder_normalize_before is True and args.max_target_positions == 8
+
+
+def test_adaptive_softmax_key_layouts_match_reference(golden_dir):
+    """state_dict keys and shapes of model.AdaptiveSoftmax against the reference module's own (fixtures written by
+    tests/golden/make_golden.py from fairseq/modules/adaptive_softmax.py): untied, tied + tied projections, and tied weights
+    with untied projections (nn.Linear(d, dim_i), adaptive_softmax.py:96-101)."""
+    from gnnlm_b200.model import AdaptiveSoftmax
+    for case in ("untied", "tied", "tied_noproj"):
+        z = np.load(os.path.join(golden_dir, f"adaptive_{case}.npz"))
+        cutoff = z["cutoff"].tolist()
+        m = AdaptiveSoftmax(cutoff[-1], z["x"].shape[-1], cutoff[:-1], tied=bool(z["tied"]),
+                            tie_proj=bool(z["tie_proj"]) if "tie_proj" in z.files else None)
+        want = {k[3:]: z[k].shape for k in z.files if k.startswith("sd.")}
+        got = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        assert got == want, case
+
+
+def test_dataset_rejects_neighbour_ids_of_another_datastore():
+    """neighbors.mmap is a raw memmap without a header: ids outside [-1, N_d) raise IndexError when the block is sliced, as the
+    reference does at `quant_neighbor_feats[o]` (token_block_dataset.py:369-370), instead of reaching the device gathers."""
+    from gnnlm_b200.dataset import GraphTokenBlockDataset
+    tokens = np.arange(4, 36).astype(np.int64)
+    nbr = np.random.RandomState(0).randint(-1, 100, size=(32, 4)).astype(np.int64)
+    ok = GraphTokenBlockDataset(tokens, 8, pad=1, eos=2, neighbor_offsets=nbr, n_datastore=100)
+    assert ok[3]["nbr"].shape == (8, 4)
+    for bad in (100, -2):
+        nb2 = nbr.copy()
+        nb2[17, 2] = bad
+        ds = GraphTokenBlockDataset(tokens, 8, pad=1, eos=2, neighbor_offsets=nb2, n_datastore=100)
+        assert ds[1]["nbr"].shape == (8, 4)          # other blocks are unaffected
+        with pytest.raises(IndexError):
+            ds[2]
+    ids = np.zeros((32, 3), np.int64)
+    ids[5, 1] = 100
+    ds = GraphTokenBlockDataset(tokens, 8, pad=1, eos=2, neighbor_offsets=nbr, n_datastore=100, knn_ids=ids,
+                                knn_dists=np.zeros((32, 3), np.float32))
+    with pytest.raises(IndexError):
+        ds[0]
+
+
+def test_dstore_writer_shards_compose(tmp_path):
+    """--save-knnlm-dstore under sharding: every shard writes its own row range of the same keys.npy / vals.npy, in any
+    launch order, without clearing rows another shard wrote; the clip at dstore_size (eval_lm.py:227-230) applies per shard."""
+    from gnnlm_b200.eval_lm import DstoreWriter, shard_range
+    rng = np.random.RandomState(0)
+    sizes = np.array([5, 7, 3, 9, 4])
+    n, d = int(sizes.sum()), 6
+    feats, toks = rng.randn(n, d).astype(np.float32), rng.randint(4, 50, size=n)
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    written = 0
+    for rank in (2, 0, 1):                        # any order
+        lo, hi = shard_range(len(sizes), rank, 3)
+        w = DstoreWriter(str(tmp_path), "valid", n, d, 50, dstore_fp16=False, knn_keytype="gcn_feat", offset=int(starts[lo]),
+                         limit=int(starts[hi] - starts[lo]), write_info=rank == 0)
+        for b in range(lo, hi):
+            w.add(torch.from_numpy(feats[starts[b]:starts[b + 1]]), torch.from_numpy(toks[starts[b]:starts[b + 1]]))
+        w.add(torch.zeros(2, d), torch.zeros(2, dtype=torch.int64))          # past the shard's range: dropped
+        written += w.close()
+    assert written == n
+    out = os.path.join(str(tmp_path), "valid_dstore-gcn_feat")
+    assert (np.fromfile(os.path.join(out, "keys.npy"), np.float32).reshape(n, d) == feats).all()
+    assert (np.fromfile(os.path.join(out, "vals.npy"), np.int32) == toks).all()
+    import json
+    assert json.load(open(os.path.join(out, "info.json")))["dstore_size"] == n

@@ -26,7 +26,7 @@ def test_pq_decode(case, golden_dir):
     assert (z["cen"].reshape(-1, z["cen"].shape[2])[idx].reshape(raw.shape) == raw).all()
 
 
-@pytest.mark.parametrize("case", ["untied", "tied"])
+@pytest.mark.parametrize("case", ["untied", "tied", "tied_noproj"])
 def test_adaptive_softmax(case, golden_dir):
     z = np.load(os.path.join(golden_dir, f"adaptive_{case}.npz"))
     w = mo.adaptive_weights(_sd(z, "sd."))
