@@ -25,3 +25,13 @@ def built_library():
     and listing its symbols is all the CPU suite does with it."""
     from gnnlm_b200 import build
     return build.build()
+
+
+@pytest.fixture(scope="session")
+def dev():
+    """cuda:0 for the `-m gpu` tests; fails loudly when the device or the in-tree extension is missing (no fallback)."""
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from gnnlm_b200 import _lib
+    _lib.load()
+    return torch.device("cuda:0")

@@ -34,14 +34,24 @@ def oracle_model(cfg, model) -> dict:
             "A": q.A.numpy(), "b": q.b.numpy(), "softmax": soft, "cutoff": cutoff}
 
 
-def run_oracle(prob, dtype=torch.float32) -> dict:
+def run_oracle(prob, dtype=torch.float32, device="cpu", dense_tt=None) -> dict:
+    """The oracle over one synthetic problem.  device="cpu": everything on the host (data may live anywhere).  A CUDA device:
+    the oracle's torch statements run there (fp64 checker for the full-size configurations); the datastore tables stay where
+    they are (the code rows of the graph's nodes are gathered by torch indexing)."""
     cfg, model, data = prob
     B, L = cfg["B"], cfg["L"]
-    batch = {"nbr": data["nbr"].numpy(), "offsets": data["positions"].numpy(), "tgt_feats": data["feats"].float(),
-             "target": data["target"], "codes": data["codes"].numpy(), "cl": cfg["c"], "cr": cfg["c"], "n_d": data["n_d"]}
+    cpu = lambda t: t.cpu()
+    codes = data["codes"].numpy() if str(device) == "cpu" and data["codes"].device.type == "cpu" else data["codes"]
+    if str(device) == "cpu" and torch.is_tensor(codes):
+        codes = codes.cpu()
+    batch = {"nbr": cpu(data["nbr"]).numpy(), "offsets": cpu(data["positions"]).numpy(), "tgt_feats": data["feats"].float(),
+             "target": data["target"], "codes": codes, "cl": cfg["c"], "cr": cfg["c"], "n_d": data["n_d"]}
     knn = {"dists": data["knn_dists"], "ids": data["knn_ids"], "vals": data["vals"].long(), "lmbda": cfg["lmbda"],
            "temperature": cfg["temp"]}
-    out = mo.eval_batch(oracle_model(cfg, model), batch, knn, dtype=dtype)
+    if str(device) == "cpu":
+        batch = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in batch.items()}
+        knn = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in knn.items()}
+    out = mo.eval_batch(oracle_model(cfg, model), batch, knn, dtype=dtype, device=device, dense_tt=dense_tt)
     nll2, ppl = mo.perplexity(out["score_sum"], out["count"])
     out["ppl"], out["nll"] = ppl, -out["score_sum"] / out["count"]
     return out

@@ -15,14 +15,6 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 GRAPH_CASES = sorted(os.path.basename(p)[6:-4] for p in glob.glob(os.path.join(GOLD, "graph_*.npz")))
 
 
-@pytest.fixture(scope="module")
-def dev():
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
-    from gnnlm_b200 import _lib
-    _lib.load()          # fail loudly if the extension is missing
-    return torch.device("cuda:0")
-
-
 def _sd(z, prefix):
     return {k[len(prefix):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(prefix)}
 
@@ -1059,10 +1051,10 @@ def test_whole_path_recomputed_similarities(source, dev):
 # ------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_properties_wiki103_shape(dev):
     """BASELINE.json's headline shape (d=1024, H=8, V=267744, L=3072, k=32, c=1, M=128, 3 layers; datastore cut to 2^22
-    rows so that the test fits next to others) is too large for the CPU oracle, so parity is checked through
-    size-independent properties: CSR structure, PQ decode -> encode round trip, log-prob normalisation, the kNN
-    distribution summing to one, agreement of the CUDA-core fp32 path with the tensor-core parity mode, and invariance
-    to the order of a token's neighbours."""
+    rows so that the test fits next to others) through size-independent properties, in addition to the direct comparison
+    with the fp64 oracle at this size (tests/test_full_size_parity.py): CSR structure, PQ decode -> encode round trip,
+    log-prob normalisation, the kNN distribution summing to one, agreement of the CUDA-core fp32 path with the
+    tensor-core parity mode, and invariance to the order of a token's neighbours."""
     _need_tc()
     import copy
     from gnnlm_b200 import synth

@@ -128,3 +128,26 @@ def test_adaptive_input_oracle_matches_reference(golden_dir):
              for i in range(len(cutoff))]
     out = mo.adaptive_input_forward(bands, cutoff, torch.from_numpy(z["tokens"]))
     np.testing.assert_allclose(out.numpy(), z["out"], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("name,intra_ctx", [("c1", 0), ("c3mini", 0), ("c3mini", 37)])
+def test_dense_causal_form_equals_coo_form(name, intra_ctx):
+    """The tgt-intra-tgt attention as a masked [L, L] softmax per block and head (DenseCausal -- what makes the oracle
+    runnable on 3072-token blocks) against the COO edge list of auto_regressive_edges (token_block_dataset.py:586-594) it
+    restates: same per-token log-probs to fp64 rounding, whole path, B = 2 included, with and without --intra-context."""
+    from tests.synth import make_problem, oracle_model
+    cfg, model, data = make_problem(name)
+    batch = {"nbr": data["nbr"].numpy(), "offsets": data["positions"].numpy(), "tgt_feats": data["feats"].float(),
+             "target": data["target"], "codes": data["codes"].numpy(), "cl": cfg["c"], "cr": cfg["c"], "n_d": data["n_d"],
+             "intra_ctx": intra_ctx}
+    om = oracle_model(cfg, model)
+    coo = mo.eval_batch(om, batch, None, dtype=torch.float64, dense_tt=False)
+    dense = mo.eval_batch(om, batch, None, dtype=torch.float64, dense_tt=True)
+    assert (coo["logprob"] - dense["logprob"]).abs().max().item() < 1e-11
+    assert (coo["gcn_feat"] - dense["gcn_feat"]).abs().max().item() < 1e-11
+    # the tensor form of the code gather + decode used when the table lives on a device
+    batch_t = dict(batch, codes=data["codes"])
+    via_torch = mo.eval_batch(om, batch_t, None, dtype=torch.float64, dense_tt=True)
+    assert (via_torch["logprob"] - dense["logprob"]).abs().max().item() < 1e-11
+    if intra_ctx:
+        assert (coo["logprob"] - mo.eval_batch(om, dict(batch, intra_ctx=0), None, dtype=torch.float64)["logprob"]).abs().max() > 1e-6
