@@ -4,7 +4,7 @@ adaptive-softmax log-probs -> kNN-LM mix -> NLL) on synthetic data of the Wiki10
 (BASELINE.json configs[2]: d=1024, H=8, V=267,744, cutoffs 20000/60000, L=3072, k=32, c=1, M=128, 3 HGT
 layers, k_nn=1024), one process per GPU.
 
-  python bench.py [--gpus N --steps K --warmup W] [--config c3] [--math f16x3|tf32x3|fp32|tf32|bf16]
+  python bench.py [--gpus N --steps K --warmup W] [--config c3] [--math f16f8|f16x3|tf32x3|fp32|tf32|bf16]
   python bench.py --impl reference ...      # the CPU restatement of the reference path (oracle/) on host cores
 
 A "step" is one pass of the hot path over one batch (B blocks x L tokens).  `value` is measured with all
@@ -38,7 +38,7 @@ def parse():
     p.add_argument("--deprecated", action="store_true", help="--deprecated (de-duplicating) graph builder, general CSR attention")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-tokens", type=int, default=768, help="tokens in the CPU-baseline sample block")
-    p.add_argument("--also-modes", default="tf32x3,tf32,bf16",
+    p.add_argument("--also-modes", default="f16x3,tf32x3,tf32,bf16",
                    help="extra arithmetic modes timed briefly (resident inputs) and reported under `other_modes`")
     p.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
                    help="launch the step's kernels one by one instead of replaying the captured whole-step CUDA graph")
@@ -186,7 +186,7 @@ def main():
     lib = L.load()
     math = args.math
     if math == "auto":
-        math = "f16x3" if lib.gnnlm_has_tcgen05() else "fp32"      # fp32-parity mode with the fewest tensor cycles
+        math = "f16f8" if lib.gnnlm_has_tcgen05() else "fp32"      # fp32-parity mode with the fewest tensor cycles
     cfg = dict(synth.CONFIGS[args.config])
     if args.n_datastore:
         cfg["n_d"] = args.n_datastore
@@ -333,7 +333,7 @@ def main():
         # launched for ntgt (n_ntgt rows) and tgt (T rows) -- take the per-step totals
         flops = 2.0 * (n_ntgt * (cfg["NL"] > 2) + cfg["NL"] * T) * 3 * d * d
         tot_ms = kernels[gk]["ms_per_launch"] * kernels[gk]["launches_per_step"]
-        passes = {"tf32x3": 3, "f16x3": 3, "fp32": 1, "tf32": 1, "bf16": 1}[math]
+        passes = {"tf32x3": 3, "f16x3": 3, "f16f8": 2, "fp32": 1, "tf32": 1, "bf16": 1}[math]
         gemm_roof = {"kernel": gk, "bound": "tensor", "achieved": flops / (tot_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
                      "peak": tf_peak, "peak_note": "measured cuBLAS bf16 sustained; tf32 dense is half of it, "
                                                    "3-pass split another third", "passes": passes}
@@ -344,6 +344,7 @@ def main():
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "f32 (3xTF32 tensor-core split)",
                                                            "f16x3": "f32 (3xFP16 tensor-core split, fp32 accumulate)",
+                                                           "f16f8": "f32 (fp16 main product + FP8 e4m3 correction products, fp32 accumulate)",
                                                            "tf32": "tf32", "bf16": "bf16"}[math],
         "data": "synthetic", "impl": "ours",
         "config": {"workload": workload_name(args.config), "math": math, "n_datastore": tables["n_d"],
@@ -373,7 +374,8 @@ def main():
                     "parity": {"tf32": "single-pass tf32: log-probs ~1e-3 of fp32 (not a parity mode)",
                                "bf16": "log-probs within 1e-2 of fp32 (tested)",
                                "tf32x3": "log-probs within 1e-4 of fp32 (tested); no fp16 range limit on operands",
-                               "f16x3": "log-probs within 1e-4 of fp32 (tested)", "fp32": "fp32 FMA"}.get(m, "")}
+                               "f16x3": "log-probs within 1e-4 of fp32 (tested)", "fp32": "fp32 FMA",
+                               "f16f8": "log-probs within 1e-4 of fp32 (tested)"}.get(m, "")}
         del r2
     line["other_modes"] = other
     if world == 1 and not args.no_cpu_baseline:

@@ -10,7 +10,16 @@ LIB_PATH = os.path.join(HERE, "libgnnlm_sm100.so")
 
 F32, BF16, F16, F16X2 = 0, 1, 2, 3
 MATH_FP32_SIMT, MATH_TF32X3, MATH_TF32, MATH_BF16, MATH_F16X3 = 0, 1, 2, 3, 4
-MATH_NAMES = {"fp32": MATH_FP32_SIMT, "tf32x3": MATH_TF32X3, "tf32": MATH_TF32, "bf16": MATH_BF16, "f16x3": MATH_F16X3}
+# host-level mode: MATH_F16X3 everywhere, except that products whose activation operand carries an e4m3 companion (ops.Split.q8)
+# run gnnlm_linear_f16f8 (fp16 main product + FP8 correction MMAs: two tensor-pass equivalents instead of three)
+MATH_F16F8 = 5
+MATH_NAMES = {"fp32": MATH_FP32_SIMT, "tf32x3": MATH_TF32X3, "tf32": MATH_TF32, "bf16": MATH_BF16, "f16x3": MATH_F16X3,
+              "f16f8": MATH_F16F8}
+
+
+def base_math(mode: int) -> int:
+    """The `math` argument of the C ABI for a host-level mode."""
+    return MATH_F16X3 if mode == MATH_F16F8 else mode
 
 _p, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 
@@ -28,23 +37,32 @@ SIGNATURES = {
     "gnnlm_graph_dedup": (_i32, [_p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
     "gnnlm_pq_gather_decode": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _i32, _p, _p, _p]),
     "gnnlm_pq_gather_decode_presplit": (_i32, [_p, _i64, _i32, _p, _p, _i32, _p, _p, _i64, _p, _p, _i64, _p]),
+    "gnnlm_pq_gather_decode_presplit_q8": (_i32, [_p, _i64, _i32, _p, _p, _i32, _p, _p, _i64, _p, _p, _i64, _p, _i64, _p]),
+    "gnnlm_pq_gather_decode_hiq8": (_i32, [_p, _i64, _i32, _p, _p, _i32, _p, _p, _i64, _p, _p, _i64, _p, _i64, _p]),
     "gnnlm_pq_encode": (_i32, [_p, _i64, _i64, _i32, _i32, _p, _p, _p, _p]),
     "gnnlm_split_tf32": (_i32, [_p, _p, _p, _i64, _p]),
     "gnnlm_split_f16": (_i32, [_p, _f32, _p, _p, _i64, _p]),
     "gnnlm_linear": (_i32, [_p, _i32, _i64, _p, _p, _f32, _i64, _p, _p, _i32, _i64, _p, _i32, _i64, _i64, _p, _i64, _i64, _i32, _p]),
     "gnnlm_linear_batched_f16x3": (_i32, [_p, _i64, _i64, _p, _p, _i64, _i64, _f32, _p, _i64, _i64, _p, _i64, _i64, _i64, _i64,
                                           _i64, _i64, _i32, _p]),
+    "gnnlm_split_to_q8": (_i32, [_p, _i64, _p, _i64, _i64, _p, _i64, _p]),
+    "gnnlm_quant_w8": (_i32, [_p, _p, _i64, _p, _i64, _i64, _i64, _p]),
+    "gnnlm_linear_f16f8": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i64, _i64, _i64, _p, _p, _f32, _i64, _i64, _p, _p, _i32, _i64,
+                                  _i64, _p, _i64, _p]),
     "gnnlm_lse_num_tiles": (_i64, [_i64, _i32]),
     "gnnlm_linear_lse": (_i32, [_p, _i32, _i64, _p, _p, _f32, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _p]),
     "gnnlm_lse_finish": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _p]),
     "gnnlm_gather_rows": (_i32, [_p, _i64, _p, _p, _i64, _i64, _p, _i64, _i32, _p]),
     "gnnlm_embed_gather": (_i32, [_p, _i64, _i64, _p, _i32, _i64, _p, _p, _p, _i64, _i64, _p, _i64, _p, _p, _p]),
     "gnnlm_layernorm": (_i32, [_p, _i64, _p, _i32, _i64, _p, _p, _f32, _p, _i32, _i64, _i64, _p, _i64, _p]),
+    "gnnlm_layernorm_q8": (_i32, [_p, _i64, _p, _i32, _i64, _p, _p, _f32, _p, _i32, _i64, _p, _i64, _i64, _p, _i64, _p]),
     "gnnlm_convert": (_i32, [_p, _i32, _p, _i32, _i64, _p]),
     "gnnlm_gelu": (_i32, [_p, _i64, _p, _i32, _i64, _i64, _p, _i64, _p]),
     "gnnlm_to_split_f16": (_i32, [_p, _i32, _i64, _p, _i64, _i64, _p, _i64, _p]),
     "gnnlm_hgt_edge_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _i64, _p, _i32, _i32, _p, _i64, _f32, _i32, _p]),
     "gnnlm_hgt_cluster_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p]),
+    "gnnlm_hgt_cluster_attn_q8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i64,
+                                         _p, _i64, _i32, _p]),
     "gnnlm_hgt_causal_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _i64, _i64, _i64, _i32, _i32, _p, _i64, _f32, _i32, _p]),
     "gnnlm_hgt_inter_fused": (_i32, [_p, _i64, _p, _i32, _i64, _p, _i64, _i64, _i32, _i64, _p, _i64, _i64, _p, _f32, _p, _i64, _p]),
     "gnnlm_heads_split_f16": (_i32, [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p]),

@@ -57,8 +57,11 @@ __device__ __forceinline__ void chain_mix(float s0, float s1, float s2, bool has
   }
 }
 
+// q8p (nullable): where the e4m3 companion (hi8 at q8p, lo8 at q8p + lo_off) of a split-fp16 output element group goes;
+// write_lo = false: the fp16 lo half is not stored (hi + companion only: the operand set of gnnlm_linear_f16f8)
 template <typename OutT, int C>
-__device__ __forceinline__ void store_out(OutT* __restrict__ p, const float (&r)[C], int lo_off) {
+__device__ __forceinline__ void store_out(OutT* __restrict__ p, const float (&r)[C], int lo_off, uint8_t* q8p = nullptr,
+                                          bool write_lo = true) {
   if constexpr (sizeof(OutT) == 4) {
     store_f32<C>(reinterpret_cast<float*>(p), r);
   } else if constexpr (std::is_same<OutT, __half>::value) {     // split-fp16: hi at p, lo at p + lo_off
@@ -68,7 +71,13 @@ __device__ __forceinline__ void store_out(OutT* __restrict__ p, const float (&r)
       uint2 hi, lo;
       split4_f16(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3], hi, lo);
       reinterpret_cast<uint2*>(p)[i] = hi;
-      reinterpret_cast<uint2*>(p + lo_off)[i] = lo;
+      if (write_lo) reinterpret_cast<uint2*>(p + lo_off)[i] = lo;
+      if (q8p) {
+        uint32_t h8, l8;
+        q8_from_split4(hi, lo, h8, l8);
+        reinterpret_cast<uint32_t*>(q8p)[i] = h8;
+        reinterpret_cast<uint32_t*>(q8p + lo_off)[i] = l8;
+      }
     }
   } else {
     static_assert(C % 8 == 0 || C == 4, "bf16 output needs 8 B / 16 B chunks");
@@ -100,7 +109,8 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
                                                                   const int32_t* __restrict__ valid_base,
                                                                   const int32_t* __restrict__ cluster_nl, int64_t n_clusters,
                                                                   int group, int n_slices,
-                                                                  OutT* __restrict__ out, int64_t ldo, int lo_off) {
+                                                                  OutT* __restrict__ out, int64_t ldo, int lo_off,
+                                                                  uint8_t* __restrict__ q8, int64_t ldq8, bool write_lo) {
   constexpr bool centre_only = WMAX == 0;
   constexpr int WM = WMAX > 0 ? WMAX : 1;
   const int lane = threadIdx.x & 31;
@@ -139,7 +149,8 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
           const float s2 = p + 1 < WM ? group_dot<C, GROUP>(qq[p], kk[pn], group) : 0.f;
           float r[C];
           chain_mix<C>(s0, s1, s2, has_l, has_r, vv[pp], vv[p], vv[pn], r);
-          store_out<OutT, C>(out + (int64_t)(base + ca_pos_to_id(p, nl)) * ldo + col, r, lo_off);
+          const int64_t row = base + ca_pos_to_id(p, nl);
+          store_out<OutT, C>(out + row * ldo + col, r, lo_off, q8 ? q8 + row * ldq8 + col : nullptr, write_lo);
         }
       }
     } else {
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
       const float s2 = group_dot<C, GROUP>(qq, kk[2], group);
       float r[C];
       chain_mix<C>(s0, s1, s2, has_l, has_r, vv[0], vv[1], vv[2], r);
-      store_out<OutT, C>(out + ci * ldo + col, r, lo_off);
+      store_out<OutT, C>(out + ci * ldo + col, r, lo_off, q8 ? q8 + ci * ldq8 + col : nullptr, write_lo);
     }
   }
 }
@@ -175,7 +186,8 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_window_kernel(const T
                                                                          const int32_t* __restrict__ node_base,
                                                                          const int32_t* __restrict__ cluster_nl, int64_t n_clusters,
                                                                          int group, int n_slices, OutT* __restrict__ out,
-                                                                         int64_t ldo, int lo_off) {
+                                                                         int64_t ldo, int lo_off, uint8_t* __restrict__ q8,
+                                                                         int64_t ldq8, bool write_lo) {
   const int lane = threadIdx.x & 31;
   const int64_t n_items = n_clusters * n_slices;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -218,7 +230,8 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_window_kernel(const T
           const float s2 = group_dot<C, GROUP>(Q[u], K[sn], group);
           float r[C];
           chain_mix<C>(s0, s1, s2, has_l, has_r, V[sp], V[u], V[sn], r);
-          store_out<OutT, C>(ob + (int64_t)ca_pos_to_id(p, nl) * ldo, r, lo_off);
+          const int64_t rid = ca_pos_to_id(p, nl);
+          store_out<OutT, C>(ob + rid * ldo, r, lo_off, q8 ? q8 + (base + rid) * ldq8 + col : nullptr, write_lo);
         }
       }
     }
@@ -234,13 +247,14 @@ static bool window_forced() {
 template <typename T, typename OutT, int C, int GROUP>
 static int32_t dispatch_w(int wmax, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                           const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl, int64_t n_clusters,
-                          int centre_only, int group, int n_slices, void* out, int64_t ldo, int lo_off, cudaStream_t st) {
+                          int centre_only, int group, int n_slices, void* out, int64_t ldo, int lo_off, uint8_t* q8,
+                          int64_t ldq8, bool write_lo, cudaStream_t st) {
   int64_t blocks = ceil_div(n_clusters * n_slices, CA_THREADS / 32);
   if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
 #define GNNLM_CL(W)                                                                                                       \
   cluster_attn_kernel<T, OutT, C, W, GROUP><<<(unsigned)blocks, CA_THREADS, 0, st>>>(                                     \
       (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, node_base, valid_base, cluster_nl, n_clusters, group, n_slices, \
-      (OutT*)out, ldo, lo_off)
+      (OutT*)out, ldo, lo_off, q8, ldq8, write_lo)
   if (centre_only) GNNLM_CL(0);
   else if (wmax <= 1) GNNLM_CL(1);
   else if (wmax <= 3) GNNLM_CL(3);
@@ -249,7 +263,7 @@ static int32_t dispatch_w(int wmax, const void* q, int64_t ldq, const void* k, i
   else
     cluster_attn_window_kernel<T, OutT, C, GROUP><<<(unsigned)blocks, CA_THREADS, 0, st>>>(
         (const T*)q, ldq, (const T*)k, ldk, (const T*)v, ldv, node_base, cluster_nl, n_clusters, group, n_slices, (OutT*)out,
-        ldo, lo_off);
+        ldo, lo_off, q8, ldq8, write_lo);
 #undef GNNLM_CL
   GNNLM_LAUNCH_CHECK("gnnlm_hgt_cluster_attn");
   return 0;
@@ -259,10 +273,10 @@ template <typename T, typename OutT, int C>
 static int32_t dispatch_group(int wmax, const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                               const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl,
                               int64_t n_clusters, int centre_only, int group, int n_slices, void* out, int64_t ldo, int lo_off,
-                              cudaStream_t st) {
+                              uint8_t* q8, int64_t ldq8, bool write_lo, cudaStream_t st) {
 #define GNNLM_DG(G)                                                                                                          \
   return dispatch_w<T, OutT, C, G>(wmax, q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, \
-                                   group, n_slices, out, ldo, lo_off, st)
+                                   group, n_slices, out, ldo, lo_off, q8, ldq8, write_lo, st)
   if (group == 32) GNNLM_DG(32);
   if (group == 16) GNNLM_DG(16);
   GNNLM_DG(0);
@@ -278,12 +292,27 @@ extern "C" int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void
                                           const int32_t* cluster_nl, int64_t n_clusters, int32_t max_cluster,
                                           int32_t centre_only, int32_t H, int32_t d_k, void* out, int32_t out_dtype,
                                           int64_t ldo, gnnlm_stream_t stream) {
+  return gnnlm_hgt_cluster_attn_q8(q, ldq, k, ldk, v, ldv, dtype, node_base, valid_base, cluster_nl, n_clusters, max_cluster,
+                                   centre_only, H, d_k, out, out_dtype, ldo, nullptr, 0, 1, stream);
+}
+
+extern "C" int32_t gnnlm_hgt_cluster_attn_q8(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                             int32_t dtype, const int32_t* node_base, const int32_t* valid_base,
+                                             const int32_t* cluster_nl, int64_t n_clusters, int32_t max_cluster,
+                                             int32_t centre_only, int32_t H, int32_t d_k, void* out, int32_t out_dtype,
+                                             int64_t ldo, void* q8v, int64_t ldq8, int32_t write_lo,
+                                             gnnlm_stream_t stream) {
+  uint8_t* q8 = reinterpret_cast<uint8_t*>(q8v);
+  GNNLM_CHECK_ARG(!q8 || (out_dtype == GNNLM_F16X2 && (uintptr_t)q8 % 4 == 0 && ldq8 % 4 == 0 && ldq8 >= 2 * (int64_t)H * d_k),
+                  GNNLM_E_UNSUPPORTED, "gnnlm_hgt_cluster_attn_q8: the e4m3 companion needs a split-fp16 output and ldq8 >= 2d");
+  GNNLM_CHECK_ARG(write_lo || q8, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn_q8: write_lo = 0 (hi + companion only) needs q8");
   GNNLM_CHECK_ARG(q && k && v && node_base && cluster_nl && out, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn: null pointer");
   GNNLM_CHECK_ARG(!centre_only || valid_base, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn: centre_only needs valid_base");
   GNNLM_CHECK_ARG(dtype == GNNLM_F32 || dtype == GNNLM_BF16, GNNLM_E_UNSUPPORTED, "gnnlm_hgt_cluster_attn: dtype");
   GNNLM_CHECK_ARG(out_dtype == GNNLM_F32 || out_dtype == GNNLM_BF16 || out_dtype == GNNLM_F16X2, GNNLM_E_UNSUPPORTED,
                   "gnnlm_hgt_cluster_attn: out dtype");
-  GNNLM_CHECK_ARG(out_dtype != GNNLM_F16X2 || ldo >= 2 * (int64_t)H * d_k, GNNLM_E_SHAPE, "gnnlm_hgt_cluster_attn: split output needs ldo >= 2d");
+  GNNLM_CHECK_ARG(out_dtype != GNNLM_F16X2 || ldo >= (write_lo ? 2 : 1) * (int64_t)H * d_k, GNNLM_E_SHAPE,
+                  "gnnlm_hgt_cluster_attn: split output needs ldo >= 2d (d when only the hi half is written)");
   GNNLM_CHECK_ARG(max_cluster >= 1, GNNLM_E_SHAPE, "gnnlm_hgt_cluster_attn: max_cluster must be >= 1");
   GNNLM_CHECK_ARG(H > 0 && d_k > 0, GNNLM_E_SHAPE, "gnnlm_hgt_cluster_attn: H and d_k must be positive");
   const int64_t d = (int64_t)H * d_k;
@@ -298,7 +327,7 @@ extern "C" int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void
   cudaStream_t st = (cudaStream_t)stream;
 #define GNNLM_DW(T, OT, C)                                                                                                    \
   return dispatch_group<T, OT, C>(max_cluster, q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, centre_only, \
-                              group, n_slices, out, ldo, (int)d, st)
+                              group, n_slices, out, ldo, (int)d, q8, ldq8, write_lo != 0, st)
   if (dtype == GNNLM_F32 && out_dtype == GNNLM_F32) GNNLM_DW(float, float, 4);
   if (dtype == GNNLM_F32 && out_dtype == GNNLM_F16X2) GNNLM_DW(float, __half, 4);
   if (out_dtype == GNNLM_F16X2) GNNLM_DW(__nv_bfloat16, __half, 8);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -131,6 +132,23 @@ __device__ __forceinline__ float4 join4_f16(uint2 hi, uint2 lo) {
   const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hi.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&hi.y));
   const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&lo.x)), d = __half22float2(*reinterpret_cast<const __half2*>(&lo.y));
   return make_float4(a.x + c.x, a.y + c.y, b.x + d.x, b.y + d.y);
+}
+
+// ---- e4m3 companions of a split-fp16 quad (operands of the FP8 correction MMAs of gnnlm_linear_f16f8):
+// hi8 = e4m3(hi), lo8 = e4m3(2^10 * lo), round to nearest even, saturating at +-448
+__device__ __forceinline__ uint32_t e4m3x4(uint2 v) {
+  const __half2_raw a = *reinterpret_cast<const __half2_raw*>(&v.x), b = *reinterpret_cast<const __half2_raw*>(&v.y);
+  return (uint32_t)__nv_cvt_halfraw2_to_fp8x2(a, __NV_SATFINITE, __NV_E4M3) |
+         ((uint32_t)__nv_cvt_halfraw2_to_fp8x2(b, __NV_SATFINITE, __NV_E4M3) << 16);
+}
+__device__ __forceinline__ void q8_from_split4(uint2 hi, uint2 lo, uint32_t& hi8, uint32_t& lo8) {
+  const __half2 s = __floats2half2_rn(1024.f, 1024.f);
+  uint2 ls;
+  const __half2 l0 = __hmul2(*reinterpret_cast<const __half2*>(&lo.x), s), l1 = __hmul2(*reinterpret_cast<const __half2*>(&lo.y), s);
+  ls.x = *reinterpret_cast<const uint32_t*>(&l0);
+  ls.y = *reinterpret_cast<const uint32_t*>(&l1);
+  hi8 = e4m3x4(hi);
+  lo8 = e4m3x4(ls);
 }
 
 }  // namespace gnnlm

@@ -152,11 +152,16 @@ __global__ void __launch_bounds__(PQ_THREADS, 1)
 constexpr int PQS_MC = 16;
 constexpr int PQS_INFLIGHT = 8;     // x 2 nodes per warp in flight
 
+// HIQ8: the second codebook holds the e4m3 companion of every centroid (8 B hi8 | 8 B lo8) instead of its fp16 lo half, and a
+// row is written as fp16 hi [ld_out >= M*8] + companion bytes [ldq >= 2*M*8] only -- the operand set of gnnlm_linear_f16f8,
+// same bytes per node as the plain hi | lo form and no conversion instructions.
+template <bool HIQ8>
 __global__ void __launch_bounds__(PQ_THREADS, 1)
     pq_decode_presplit_kernel(const uint8_t* __restrict__ codes, int M, const uint4* __restrict__ cb_hi,
                               const uint4* __restrict__ cb_lo, const int64_t* __restrict__ rows,
                               const int32_t* __restrict__ row_ids, int64_t n_cap, const int32_t* __restrict__ n_dev,
-                              __half* __restrict__ out, int64_t ld_out, int nodes_per_cta) {
+                              __half* __restrict__ out, int64_t ld_out, int nodes_per_cta, uint8_t* __restrict__ q8,
+                              int64_t ldq) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint4* s_hi = reinterpret_cast<uint4*>(smem_raw);                  // [PQS_MC][256] quads
   uint4* s_lo = s_hi + PQS_MC * 256;
@@ -206,8 +211,23 @@ __global__ void __launch_bounds__(PQ_THREADS, 1)
     for (int u = 0; u < PQS_INFLIGHT; ++u) {
       if (r[u] >= 0 && active) {
         __half* dst = out + (size_t)(i + 2 * u + half) * ld_out + (size_t)(m0 + sub) * 8;
-        *reinterpret_cast<uint4*>(dst) = s_hi[sub * 256 + c[u]];
-        *reinterpret_cast<uint4*>(dst + lo_off) = s_lo[sub * 256 + c[u]];
+        const uint4 vh = s_hi[sub * 256 + c[u]], vl = s_lo[sub * 256 + c[u]];
+        *reinterpret_cast<uint4*>(dst) = vh;
+        if constexpr (HIQ8) {
+          uint8_t* qd = q8 + (size_t)(i + 2 * u + half) * ldq + (size_t)(m0 + sub) * 8;
+          *reinterpret_cast<uint2*>(qd) = make_uint2(vl.x, vl.y);
+          *reinterpret_cast<uint2*>(qd + lo_off) = make_uint2(vl.z, vl.w);
+          continue;
+        }
+        *reinterpret_cast<uint4*>(dst + lo_off) = vl;
+        if (q8) {                                        // e4m3 companion (hi8 | lo8): 8 B per (node, subspace) and half
+          uint2 h8, l8;
+          q8_from_split4(make_uint2(vh.x, vh.y), make_uint2(vl.x, vl.y), h8.x, l8.x);
+          q8_from_split4(make_uint2(vh.z, vh.w), make_uint2(vl.z, vl.w), h8.y, l8.y);
+          uint8_t* qd = q8 + (size_t)(i + 2 * u + half) * ldq + (size_t)(m0 + sub) * 8;
+          *reinterpret_cast<uint2*>(qd) = h8;
+          *reinterpret_cast<uint2*>(qd + lo_off) = l8;
+        }
       }
     }
   }
@@ -337,7 +357,18 @@ extern "C" int32_t gnnlm_pq_gather_decode_presplit(const uint8_t* codes, int64_t
                                                    const void* cb_lo, int32_t dsub, const int64_t* rows,
                                                    const int32_t* row_ids, int64_t n_cap, const int32_t* n_dev, void* out,
                                                    int64_t ld_out, gnnlm_stream_t stream) {
+  return gnnlm_pq_gather_decode_presplit_q8(codes, n_datastore, M, cb_hi, cb_lo, dsub, rows, row_ids, n_cap, n_dev, out, ld_out,
+                                            nullptr, 0, stream);
+}
+
+extern "C" int32_t gnnlm_pq_gather_decode_presplit_q8(const uint8_t* codes, int64_t n_datastore, int32_t M, const void* cb_hi,
+                                                      const void* cb_lo, int32_t dsub, const int64_t* rows,
+                                                      const int32_t* row_ids, int64_t n_cap, const int32_t* n_dev, void* out,
+                                                      int64_t ld_out, void* q8v, int64_t ldq, gnnlm_stream_t stream) {
   GNNLM_CHECK_ARG(codes && rows && cb_hi && cb_lo && out, GNNLM_E_ARG, "gnnlm_pq_gather_decode_presplit: null pointer");
+  uint8_t* q8 = reinterpret_cast<uint8_t*>(q8v);
+  GNNLM_CHECK_ARG(!q8 || (ldq >= 2 * (int64_t)M * 8 && ldq % 8 == 0 && (uintptr_t)q8 % 8 == 0), GNNLM_E_SHAPE,
+                  "gnnlm_pq_gather_decode_presplit_q8: the e4m3 companion needs ldq >= 2*M*8, 8 B aligned rows");
   GNNLM_CHECK_ARG(M > 0 && n_cap >= 0 && n_datastore > 0, GNNLM_E_SHAPE, "gnnlm_pq_gather_decode_presplit: bad sizes");
   GNNLM_CHECK_ARG(dsub == 8, GNNLM_E_UNSUPPORTED, "gnnlm_pq_gather_decode_presplit: dsub must be 8 (use gnnlm_pq_gather_decode)");
   GNNLM_CHECK_ARG(ld_out >= 2 * (int64_t)M * 8 && ld_out % 8 == 0 && (uintptr_t)out % 16 == 0 && (uintptr_t)cb_hi % 16 == 0 &&
@@ -347,14 +378,42 @@ extern "C" int32_t gnnlm_pq_gather_decode_presplit(const uint8_t* codes, int64_t
   const size_t smem = (size_t)2 * PQS_MC * 256 * 16;
   static bool attr_set = false;
   if (!attr_set) {
-    GNNLM_CUDA(cudaFuncSetAttribute(pq_decode_presplit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GNNLM_CUDA(cudaFuncSetAttribute(pq_decode_presplit_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GNNLM_CUDA(cudaFuncSetAttribute(pq_decode_presplit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   int nodes_per_cta = PQ_NODES_PER_CTA;
   while (nodes_per_cta > 64 && ceil_div(n_cap, nodes_per_cta) * ceil_div(M, PQS_MC) < 296) nodes_per_cta >>= 1;
   dim3 grid((unsigned)ceil_div(M, PQS_MC), (unsigned)ceil_div(n_cap, nodes_per_cta));
-  pq_decode_presplit_kernel<<<grid, PQ_THREADS, smem, (cudaStream_t)stream>>>(
-      codes, M, (const uint4*)cb_hi, (const uint4*)cb_lo, rows, row_ids, n_cap, n_dev, (__half*)out, ld_out, nodes_per_cta);
+  pq_decode_presplit_kernel<false><<<grid, PQ_THREADS, smem, (cudaStream_t)stream>>>(
+      codes, M, (const uint4*)cb_hi, (const uint4*)cb_lo, rows, row_ids, n_cap, n_dev, (__half*)out, ld_out, nodes_per_cta, q8, ldq);
   GNNLM_LAUNCH_CHECK("gnnlm_pq_gather_decode_presplit");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_pq_gather_decode_hiq8(const uint8_t* codes, int64_t n_datastore, int32_t M, const void* cb_hi,
+                                               const void* cb_q8, int32_t dsub, const int64_t* rows, const int32_t* row_ids,
+                                               int64_t n_cap, const int32_t* n_dev, void* out_hi, int64_t ld_out, void* q8v,
+                                               int64_t ldq, gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(codes && rows && cb_hi && cb_q8 && out_hi && q8v, GNNLM_E_ARG, "gnnlm_pq_gather_decode_hiq8: null pointer");
+  GNNLM_CHECK_ARG(M > 0 && n_cap >= 0 && n_datastore > 0, GNNLM_E_SHAPE, "gnnlm_pq_gather_decode_hiq8: bad sizes");
+  GNNLM_CHECK_ARG(dsub == 8, GNNLM_E_UNSUPPORTED, "gnnlm_pq_gather_decode_hiq8: dsub must be 8");
+  GNNLM_CHECK_ARG(ld_out >= (int64_t)M * 8 && ld_out % 8 == 0 && ldq >= 2 * (int64_t)M * 8 && ldq % 8 == 0 && (uintptr_t)out_hi % 16 == 0 &&
+                      (uintptr_t)q8v % 8 == 0 && (uintptr_t)cb_hi % 16 == 0 && (uintptr_t)cb_q8 % 16 == 0,
+                  GNNLM_E_SHAPE, "gnnlm_pq_gather_decode_hiq8: 16 B aligned rows, ld_out >= M*8, ldq >= 2*M*8");
+  if (n_cap == 0) return 0;
+  const size_t smem = (size_t)2 * PQS_MC * 256 * 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GNNLM_CUDA(cudaFuncSetAttribute(pq_decode_presplit_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int nodes_per_cta = PQ_NODES_PER_CTA;
+  while (nodes_per_cta > 64 && ceil_div(n_cap, nodes_per_cta) * ceil_div(M, PQS_MC) < 296) nodes_per_cta >>= 1;
+  dim3 grid((unsigned)ceil_div(M, PQS_MC), (unsigned)ceil_div(n_cap, nodes_per_cta));
+  pq_decode_presplit_kernel<true><<<grid, PQ_THREADS, smem, (cudaStream_t)stream>>>(
+      codes, M, (const uint4*)cb_hi, (const uint4*)cb_q8, rows, row_ids, n_cap, n_dev, (__half*)out_hi, ld_out, nodes_per_cta,
+      reinterpret_cast<uint8_t*>(q8v), ldq);
+  GNNLM_LAUNCH_CHECK("gnnlm_pq_gather_decode_hiq8");
   return 0;
 }

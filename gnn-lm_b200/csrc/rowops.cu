@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(256, 4) layernorm_vec_kernel(const float* __re
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps,
                                                             OutT* __restrict__ y, int64_t ldy, int64_t n_cap,
-                                                            const int32_t* __restrict__ n_dev) {
+                                                            const int32_t* __restrict__ n_dev, uint8_t* __restrict__ q8 = nullptr,
+                                                            int64_t ldq = 0) {
   const int64_t n = live_rows(n_cap, n_dev);
   const int lane = threadIdx.x & 31;
   constexpr int d = NV * 128;
@@ -153,6 +154,12 @@ __global__ void __launch_bounds__(256, 4) layernorm_vec_kernel(const float* __re
         split4_f16(o.x, o.y, o.z, o.w, hi, lo);
         reinterpret_cast<uint2*>(y + i * ldy)[lane + 32 * j] = hi;
         reinterpret_cast<uint2*>(y + i * ldy + d)[lane + 32 * j] = lo;
+        if (q8) {                                                     // e4m3 companion (hi8 | lo8) for the FP8 correction MMAs
+          uint32_t h8, l8;
+          q8_from_split4(hi, lo, h8, l8);
+          reinterpret_cast<uint32_t*>(q8 + i * ldq)[lane + 32 * j] = h8;
+          reinterpret_cast<uint32_t*>(q8 + i * ldq + d)[lane + 32 * j] = l8;
+        }
       } else {
         __nv_bfloat162 a = __floats2bfloat162_rn(o.x, o.y), c = __floats2bfloat162_rn(o.z, o.w);
         uint2 u;
@@ -315,7 +322,17 @@ extern "C" int32_t gnnlm_embed_gather(const float* table, int64_t ld_table, int6
 extern "C" int32_t gnnlm_layernorm(const float* x, int64_t ldx, const void* residual, int32_t r_dtype, int64_t ldr,
                                    const float* gamma, const float* beta, float eps, void* y, int32_t out_dtype, int64_t ldy,
                                    int64_t n_cap, const int32_t* n_dev, int64_t d, gnnlm_stream_t stream) {
+  return gnnlm_layernorm_q8(x, ldx, residual, r_dtype, ldr, gamma, beta, eps, y, out_dtype, ldy, nullptr, 0, n_cap, n_dev, d, stream);
+}
+
+extern "C" int32_t gnnlm_layernorm_q8(const float* x, int64_t ldx, const void* residual, int32_t r_dtype, int64_t ldr,
+                                      const float* gamma, const float* beta, float eps, void* y, int32_t out_dtype, int64_t ldy,
+                                      void* q8v, int64_t ldq, int64_t n_cap, const int32_t* n_dev, int64_t d,
+                                      gnnlm_stream_t stream) {
   GNNLM_CHECK_ARG(x && gamma && beta && y, GNNLM_E_ARG, "gnnlm_layernorm: null pointer");
+  uint8_t* q8 = reinterpret_cast<uint8_t*>(q8v);
+  GNNLM_CHECK_ARG(!q8 || (out_dtype == GNNLM_F16X2 && d % 128 == 0 && d <= 1024 && ldq >= 2 * d && ldq % 4 == 0 && (uintptr_t)q8 % 4 == 0),
+                  GNNLM_E_UNSUPPORTED, "gnnlm_layernorm_q8: the e4m3 companion needs a split-fp16 output, d in {128..1024} a multiple of 128, ldq >= 2d");
   const int res_mode = !residual ? 0 : (r_dtype == GNNLM_F32 ? 1 : (r_dtype == GNNLM_BF16 ? 2 : (r_dtype == GNNLM_F16X2 ? 3 : -1)));
   GNNLM_CHECK_ARG(res_mode >= 0, GNNLM_E_UNSUPPORTED, "gnnlm_layernorm: residual dtype");
   GNNLM_CHECK_ARG(!residual || ldr >= d * (res_mode == 3 ? 2 : 1), GNNLM_E_SHAPE, "gnnlm_layernorm: ldr too small");
@@ -330,11 +347,13 @@ extern "C" int32_t gnnlm_layernorm(const float* x, int64_t ldx, const void* resi
   const unsigned g = grid_for(n_cap, 8);
   const bool vec = d % 128 == 0 && d <= 1024 && ldx % 4 == 0 && ldy % 4 == 0 && (uintptr_t)x % 16 == 0 &&
                    (!residual || ((uintptr_t)residual % 16 == 0 && ldr % 8 == 0)) && (uintptr_t)y % 16 == 0 && (uintptr_t)gamma % 16 == 0 && (uintptr_t)beta % 16 == 0;
+  GNNLM_CHECK_ARG(!q8 || (vec && (d == 1024 || d == 512 || d == 256 || d == 128)), GNNLM_E_UNSUPPORTED,
+                  "gnnlm_layernorm_q8: the e4m3 companion is written by the vectorised kernel only (d in {128, 256, 512, 1024}, 16 B aligned rows)");
 #define LN_VEC(NV)                                                                                                      \
   if (out_dtype == GNNLM_F32)                                                                                           \
     layernorm_vec_kernel<float, NV><<<g, 256, 0, st>>>(x, ldx, res, res_mode, ldres, gamma, beta, eps, (float*)y, ldy, n_cap, n_dev);          \
   else if (out_dtype == GNNLM_F16X2)                                                                                    \
-    layernorm_vec_kernel<__half, NV><<<g, 256, 0, st>>>(x, ldx, res, res_mode, ldres, gamma, beta, eps, (__half*)y, ldy, n_cap, n_dev);        \
+    layernorm_vec_kernel<__half, NV><<<g, 256, 0, st>>>(x, ldx, res, res_mode, ldres, gamma, beta, eps, (__half*)y, ldy, n_cap, n_dev, q8, ldq); \
   else                                                                                                                  \
     layernorm_vec_kernel<__nv_bfloat16, NV><<<g, 256, 0, st>>>(x, ldx, res, res_mode, ldres, gamma, beta, eps, (__nv_bfloat16*)y, ldy, n_cap, n_dev);
   if (vec && d == 1024) { LN_VEC(8) }

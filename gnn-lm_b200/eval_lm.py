@@ -327,7 +327,7 @@ def main(argv=None, device="cuda", log=print) -> dict:
     from .knn_model import KNNModel
     parser = registry.eval_lm_parser()
     parser.add_argument("--knn-dists-file", default=None, help="raw fp32 [N_split, k] distances of neighbors.mmap.{k}")
-    parser.add_argument("--math", default="f16x3", choices=["f16x3", "tf32x3", "fp32", "tf32", "bf16"])
+    parser.add_argument("--math", default="f16x3", choices=["f16x3", "f16f8", "tf32x3", "fp32", "tf32", "bf16"])
     parser.add_argument("--cuda-graph", action="store_true")
     parsed = parser.parse_args(argv)
     if parsed.path is None:

@@ -47,17 +47,27 @@ class _Weight:
         self.b = None if b is None else b.contiguous().float()
         self.lo = None
         self.scale = 1.0
+        self._q8 = None
+        self.f8 = math_mode == L.MATH_F16F8
         if math_mode == L.MATH_TF32X3:
             self.W, self.lo = ops.split_tf32(W)
-        elif math_mode == L.MATH_F16X3:
+        elif math_mode in (L.MATH_F16X3, L.MATH_F16F8):
             self.W, self.lo, self.scale = ops.split_f16(W)
         elif math_mode == L.MATH_BF16:
             self.W = ops.convert(W, torch.bfloat16)
         else:
             self.W = W
 
+    def w8(self) -> torch.Tensor:
+        """e4m3 companion [N, 2K] of the fp16 halves (MATH_F16F8), built on first use."""
+        if self._q8 is None:
+            self._q8 = ops.quant_w8(self.W, self.lo)
+        return self._q8
+
     def rows(self, a: int, b_: int) -> "_Weight":
         v = object.__new__(_Weight)
+        v.f8 = self.f8
+        v._q8 = self.w8()[a:b_] if self.f8 else None
         v.W = self.W[a:b_]
         v.lo = None if self.lo is None else self.lo[a:b_]
         v.b = None if self.b is None else self.b[a:b_]
@@ -65,11 +75,37 @@ class _Weight:
         return v
 
 
-FUSED_INTER_MODES = (L.MATH_F16X3, L.MATH_BF16, L.MATH_TF32)     # modes whose operands are already fp16-range on tensor cores
+FUSED_INTER_MODES = (L.MATH_F16X3, L.MATH_F16F8, L.MATH_BF16, L.MATH_TF32)     # modes whose operands are already fp16-range on tensor cores
 
 
-def _lin(x, w: _Weight, math_mode, **kw):
+def _lin(x, w: _Weight, math_mode, x2=None, **kw):
+    """x @ W^T + b; `x2`: second row-aligned source, W = [W1 | W2] along k (MATH_F16F8 only)."""
+    if math_mode == L.MATH_F16F8 and isinstance(x, ops.Split) and x.q8 is not None and "residual" not in kw and \
+            ops.f16f8_supported(x.d, 0 if x2 is None else x2.d):
+        return ops.linear_f16f8(x, w.W, w.w8(), w.b, A2=x2, w_scale=w.scale, **kw)
+    assert x2 is None
     return ops.linear(x, w.W, w.b, W_lo=w.lo, w_scale=w.scale, math=math_mode, **kw)
+
+
+F16F8_MIN_ROWS = 0          # rows below which a split operand is not given an e4m3 companion (0: always in MATH_F16F8)
+
+
+def with_q8(x, math_mode: int, n_dev=None):
+    """MATH_F16F8: make sure a large split-fp16 GEMM operand carries its e4m3 companion (a standalone pass when the
+    producing kernel did not write it)."""
+    if math_mode == L.MATH_F16F8 and isinstance(x, ops.Split) and x.q8 is None and x.shape[0] >= F16F8_MIN_ROWS and \
+            ops.f16f8_supported(x.d):
+        ops.to_q8(x, n_dev)
+    return x
+
+
+def gemm_act(math_mode: int, rows: int, d: int, lo: bool = True):
+    """Output format for an activation that feeds a GEMM: split fp16, with the e4m3 companion in MATH_F16F8 (lo=False: and
+    without the fp16 lo half, for an activation that feeds NOTHING but that product)."""
+    act = act_dtype(math_mode)
+    if math_mode == L.MATH_F16F8 and rows >= F16F8_MIN_ROWS and ops.f16f8_supported(d) and d in (128, 256, 512, 1024):
+        return ops.SPLIT_Q8 if lo else ops.HI_Q8
+    return act
 
 
 def act_dtype(math_mode: int):
@@ -77,7 +113,7 @@ def act_dtype(math_mode: int):
     by the GEMMs without an operand-split pass) in MATH_F16X3, fp32 otherwise."""
     if math_mode == L.MATH_BF16:
         return torch.bfloat16
-    return ops.SPLIT if math_mode == L.MATH_F16X3 else torch.float32
+    return ops.SPLIT if math_mode in (L.MATH_F16X3, L.MATH_F16F8) else torch.float32
 
 
 def as_act(x, math_mode: int):
@@ -146,8 +182,13 @@ class HGTLayer(nn.Module):
         self.use_gemm_attention = True     # MATH_F16X3, long blocks: tgt-intra-tgt attention as tensor-core GEMMs
 
     # ------------------------------------------------------------------ weight preparation
-    def prepare(self, math_mode: int):
-        key = (math_mode, self.relation_pri.device, tuple(int(p._version) for p in self.parameters()))
+    def prepare(self, math_mode: int, rot: Optional[torch.Tensor] = None):
+        """`rot` [d, d_dec] (layer 0, MATH_F16F8): the ntgt input features are given UN-rotated, h = x @ rot^T (the OPQ inverse
+        rotation `x @ A` of pq_wrapper.py:202, rot = A^T), and the rotation is folded into this layer's ntgt-side weights in
+        fp64 -- Q|K'|V' = x (W rot)^T, the inter K' / V' likewise, and the residual of hgt.py:403 inside the output projection:
+        A-linear(t) + h = [t | x] [W_a | rot]^T -- so the rotated features are never materialised."""
+        key = (math_mode, self.relation_pri.device, tuple(int(p._version) for p in self.parameters()),
+               None if rot is None else (rot.data_ptr(), int(rot._version)))
         if self._prep is not None and self._prep_key == key:
             return self._prep
         if not self.use_norm:
@@ -163,13 +204,17 @@ class HGTLayer(nn.Module):
             Wv, bv = _fold(self.v_linears[tau].weight, self.v_linears[tau].bias, self.relation_msg[rel], None)
             return Wk, bk, Wv, bv
 
+        rot64 = None if rot is None else rot.detach().double()
+        through = lambda W: W if rot64 is None else (W.double() @ rot64).float()        # x (W rot)^T == (x rot^T) W^T
+
         def qkv(tau):
             Wk, bk, Wv, bv = kv(tau, intra)
             W = torch.cat([self.q_linears[tau].weight.detach().float(), Wk, Wv], 0)
             b = torch.cat([self.q_linears[tau].bias.detach().float(), bk, bv], 0)
-            return _Weight(W, b, math_mode)
+            return _Weight(through(W) if tau == n else W, b, math_mode)
 
         Wk, bk, Wv, bv = kv(n, inter)
+        Wk, Wv = through(Wk), through(Wv)
         fused = None
         if math_mode in FUSED_INTER_MODES and ops.inter_fused_supported(d, self.n_heads):
             # token-side form of the inter projections (inter_attn.cu): W_k'[h]^T [H, d, d_k] and W_v'[h] [H, d_k, d] as
@@ -185,22 +230,29 @@ class HGTLayer(nn.Module):
             "ln": {tau: (self.norms[tau].weight.detach().float().contiguous(),
                          self.norms[tau].bias.detach().float().contiguous(), self.norms[tau].eps) for tau in (t, n)},
             "math": math_mode, "d": d, "t": t, "n": n, "inter_fused": fused,
+            # [W_a | rot]: output projection and rotation of the residual as one product over [t | x]
+            "a_rot": None if rot is None else _Weight(torch.cat([self.a_linears[n].weight.detach().float(), rot.detach().float()], 1),
+                                                      self.a_linears[n].bias.detach(), math_mode),
         }
         self._prep, self._prep_key = P, key
         return P
 
     # ------------------------------------------------------------------ building blocks
-    def _out(self, P, tau, t_agg, h_in, n_dev):
+    def _out(self, P, tau, t_agg, h_in, n_dev, feeds_gemm: bool = False):
         """LayerNorm(A-linear(t) + h) (hgt.py:401-405).  The residual add is fused into the LayerNorm kernel (fp32 sum
         before the statistics) instead of the GEMM epilogue.  Measured on the wiki103 shape: moving it into the epilogue
         halves LayerNorm (1.0 -> 0.5 ms per step) but makes the epilogue the GEMM's bottleneck (a split-fp16 residual
         turns the 1.3 ms A-linear into 3.4 ms, an fp32 one into 1.7 ms; profiles/gemm_probe_split.py)."""
-        o = _lin(t_agg, P["a"][tau], P["math"], m_dev=n_dev)
+        if tau == P["n"] and P["a_rot"] is not None:      # rotation folded: h_in is un-rotated, the product adds the residual
+            o = _lin(with_q8(t_agg, P["math"], n_dev), P["a_rot"], P["math"], x2=with_q8(h_in, P["math"], n_dev), m_dev=n_dev)
+            h_in = None
+        else:
+            o = _lin(with_q8(t_agg, P["math"], n_dev), P["a"][tau], P["math"], m_dev=n_dev)
         g, b, eps = P["ln"][tau]
-        act = act_dtype(P["math"])
+        act = gemm_act(P["math"], o.shape[0], o.shape[1]) if feeds_gemm else act_dtype(P["math"])
         if act == torch.float32:
             return ops.layernorm(o, g, b, eps, out=o, n_dev=n_dev, residual=h_in)
-        return ops.layernorm(o, g, b, eps, out_dtype=act, n_dev=n_dev, residual=h_in)       # bf16 or split fp16
+        return ops.layernorm(o, g, b, eps, out_dtype=act, n_dev=n_dev, residual=h_in)       # bf16 or split fp16 (+ e4m3 companion)
 
     def _nn_attn(self, P, G, q, k, v, rows, *, centre: bool, n_dev, c_dev):
         """ntgt-intra-ntgt attention -> [rows, d] in the activation dtype."""
@@ -208,7 +260,7 @@ class HGTLayer(nn.Module):
         act = act_dtype(P["math"])
         tag = "nn_centre" if centre else "nn_full"
         if self.use_cluster_kernel and not G.dedup and ops.cluster_attn_supported(d, H, q.dtype, G.w):
-            t_agg = ops.empty_act(rows, d, act, q.device)
+            t_agg = ops.empty_act(rows, d, gemm_act(P["math"], rows, d, lo=False), q.device)   # feeds the A-linear and nothing else
             ops.cluster_attn(q, k, v, G, H, t_agg, centre_only=centre, tag=tag)
             return t_agg
         t_agg = torch.empty((rows, d), device=q.device, dtype=torch.float32)
@@ -221,17 +273,17 @@ class HGTLayer(nn.Module):
     def ntgt_full(self, P, G: TokenGraph, h_n, n_dev):
         """All ntgt nodes: Q|K'|V' -> chain attention -> A-linear + residual + LN."""
         d = P["d"]
-        qkv = _lin(h_n, P["ntgt_qkv"], P["math"], m_dev=n_dev, out_dtype=_attn_in_dtype(P["math"]))
+        qkv = _lin(with_q8(h_n, P["math"], n_dev), P["ntgt_qkv"], P["math"], m_dev=n_dev, out_dtype=_attn_in_dtype(P["math"]))
         t_agg = self._nn_attn(P, G, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h_n.shape[0], centre=False, n_dev=n_dev,
                               c_dev=None)
-        return self._out(P, P["n"], t_agg, h_n, n_dev)
+        return self._out(P, P["n"], t_agg, h_n, n_dev, feeds_gemm=True)        # h of the next layer: a GEMM operand
 
     def ntgt_centre(self, P, G: TokenGraph, h_n, n_dev, hc, c_dev):
         """Centre nodes only (compact rows): K'|V' for every node, Q / A-linear / LN for centres."""
         d = P["d"]
         act = _attn_in_dtype(P["math"])
-        kv = _lin(h_n, P["ntgt_qkv"].rows(d, 3 * d), P["math"], m_dev=n_dev, out_dtype=act)
-        qc = _lin(hc, P["ntgt_qkv"].rows(0, d), P["math"], m_dev=c_dev, out_dtype=act)
+        kv = _lin(with_q8(h_n, P["math"], n_dev), P["ntgt_qkv"].rows(d, 3 * d), P["math"], m_dev=n_dev, out_dtype=act)
+        qc = _lin(with_q8(hc, P["math"], c_dev), P["ntgt_qkv"].rows(0, d), P["math"], m_dev=c_dev, out_dtype=act)
         t_agg = self._nn_attn(P, G, qc, kv[:, :d], kv[:, d:], hc.shape[0], centre=True, n_dev=n_dev, c_dev=c_dev)
         return self._out(P, P["n"], t_agg, hc, c_dev)
 
@@ -258,7 +310,7 @@ class HGTLayer(nn.Module):
                               tag="inter")
         # tensor-core form (3xFP16 GEMMs on the fp32 Q / K' / V', fp32-level accuracy) in every mode that already puts fp16-range
         # operands on the tensor cores; tf32x3 / fp32 keep the CUDA-core kernel (no fp16 range limit on Q / K' / V')
-        gemm_modes = (L.MATH_F16X3, L.MATH_BF16, L.MATH_TF32)
+        gemm_modes = (L.MATH_F16X3, L.MATH_F16F8, L.MATH_BF16, L.MATH_TF32)
         if P["math"] in gemm_modes and self.use_gemm_attention and ops.causal_attn_gemm_supported(d, H, G.L) and G.L >= 1024:
             ops.causal_attn_gemm(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5,
                                  accumulate=True)
@@ -345,19 +397,31 @@ class HGT(nn.Module):
 
     @torch.no_grad()
     def forward_tgt(self, G: TokenGraph, h_tgt: torch.Tensor, h_ntgt: Optional[torch.Tensor],
-                    hc0: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    hc0: Optional[torch.Tensor] = None, rot: Optional[torch.Tensor] = None) -> torch.Tensor:
         """tgt features only (what the decoder consumes, transformer.py:1053), capacity-sized ntgt
         arrays + device-side row counts: no host synchronisation anywhere.
 
         h_ntgt [node_cap, d] decoded features of every ntgt node (may be None when n_layers == 1 and
         hc0, the decoded centre rows [T*k, d], is given)."""
         mode = self.math_mode
-        prep = [layer.prepare(mode) for layer in self.gcs]
+        prep = self._prepare_layers(rot)
         hc = self._ntgt_side(prep, G, h_ntgt, hc0)
         h_t = as_act(self.adapt(h_tgt, "tgt"), mode)
         for l in range(self.n_layers):
             h_t = self.gcs[l].tgt(prep[l], G, h_t, hc[l], G.n_valid_dev)
         return self.project_out(h_t)
+
+    def can_fold_rotation(self, d_dec: int) -> bool:
+        """MATH_F16F8 with no input adapters: the OPQ rotation of the ntgt features can be folded into layer 0
+        (HGTLayer.prepare `rot`); needs the two-source f16f8 product (k-blocks of 64) and the fused inter kernel."""
+        d = self.hidden_dim
+        return (self.math_mode == L.MATH_F16F8 and self.in_dim == self.hidden_dim and d_dec == d and d in (128, 256, 512, 1024)
+                and ops.f16f8_supported(d, d) and ops.inter_fused_supported(d, self.gcs[0].n_heads) and self.gcs[0].use_fused_inter)
+
+    def _prepare_layers(self, rot=None):
+        """`rot`: ntgt input features (h_ntgt / hc0 and whatever `decode` returns) are un-rotated; folded into layer 0."""
+        assert rot is None or self.can_fold_rotation(rot.shape[1])
+        return [layer.prepare(self.math_mode, rot if l == 0 else None) for l, layer in enumerate(self.gcs)]
 
     def _ntgt_side(self, prep, G: TokenGraph, h_ntgt, hc0=None) -> List:
         """All layers of the ntgt side of one (chunk) graph -> compact centre features entering each layer."""
@@ -368,6 +432,8 @@ class HGT(nn.Module):
             h_ntgt = as_act(self.adapt(h_ntgt, "ntgt", n_dev), mode)
         elif hc0 is not None:
             hc0 = self.adapt(hc0, "ntgt", c_dev)
+        # (rotation folded into layer 0: the caller passes both, un-rotated -- h_ntgt as fp16 hi + e4m3 companion only, hc0 as a
+        # full split matrix, because the inter kernel reads both fp16 halves of the centre rows)
         if hc0 is None:
             hc0 = ops.gather_rows(h_ntgt, G.inter_indices, n_dev=c_dev)
         hc.append(hc0)
@@ -381,14 +447,14 @@ class HGT(nn.Module):
         return hc
 
     @torch.no_grad()
-    def forward_tgt_chunked(self, G: TokenGraph, h_tgt, decode, chunk_tokens: int):
+    def forward_tgt_chunked(self, G: TokenGraph, h_tgt, decode, chunk_tokens: int, rot=None):
         """Same result as forward_tgt with the ntgt side run in chunks of `chunk_tokens` target tokens, so that the
         ntgt activations (T*k*w rows per buffer) never exceed a memory budget: ntgt clusters belong to exactly one
         token and only ever exchange messages inside their cluster.  `decode(chunk_graph, centre_only)`
         returns the decoded ntgt features of a chunk graph (all nodes, or compact centre rows)."""
         from .graph import token_chunk_graph
         mode = self.math_mode
-        prep = [layer.prepare(mode) for layer in self.gcs]
+        prep = self._prepare_layers(rot)
         chunks = []
         for t0 in range(0, G.T, chunk_tokens):
             t1 = min(G.T, t0 + chunk_tokens)
@@ -396,7 +462,7 @@ class HGT(nn.Module):
             if self.n_layers == 1:
                 hc_c = self._ntgt_side(prep, g_c, None, hc0=decode(g_c, True))
             else:
-                hc_c = self._ntgt_side(prep, g_c, decode(g_c, False))
+                hc_c = self._ntgt_side(prep, g_c, decode(g_c, False), hc0=decode(g_c, True) if rot is not None else None)
             chunks.append((t0, t1, g_c, hc_c))
         h_t = as_act(self.adapt(h_tgt, "tgt"), mode)
         for l in range(self.n_layers):

@@ -244,6 +244,7 @@ class TokenGraphTransformerDecoder(nn.Module):
             self.embed_out = nn.Parameter(torch.empty(self.num_classes, d))       # transformer.py:650-655
             nn.init.normal_(self.embed_out, mean=0, std=d ** -0.5)
         self.math_mode = L.MATH_FP32_SIMT
+        self.fold_rotation = True          # MATH_F16F8: fold the OPQ rotation into HGT layer 0 (False: explicit rotation GEMM)
         self._out_prep, self._out_key = None, None
 
     def set_math(self, mode):
@@ -297,6 +298,7 @@ class TokenGraphTransformerDecoder(nn.Module):
         else:                                                         # fused gather from the HBM-resident datastore
             codes = graph.codes_table
             q = self.tgt_quantizer
+            fold, rot = False, None
             if codes is None:
                 # --reinit-nfeat: the dataset carries no code rows, ntgt.h = embed_tokens(ntgt.labels) (transformer.py:1046-1048)
                 if self.embed_tokens is None:
@@ -313,10 +315,18 @@ class TokenGraphTransformerDecoder(nn.Module):
                         return ops.to_split(x, n_dev)
                     return x if act == torch.float32 else ops.convert(x, act)
             else:
+                # MATH_F16F8: the OPQ rotation is folded into layer 0's weights (HGTLayer.prepare `rot`): features stay un-rotated
+                fold = (q.pre_torch and q.dsub == 8 and not graph.dedup and self.fold_rotation
+                        and self.hgt_decoder.can_fold_rotation(q.M * q.dsub))
+                rot = q.rotation_weight() if fold else None
+
                 def decode(g, centre_only):
-                    if centre_only:   # only centre nodes are ever read (single layer)
-                        return q.gather_decode(codes, g.ntgt_row, row_ids=g.inter_indices, n_dev=g.n_valid_dev, math_mode=mode)
-                    return q.gather_decode(codes, g.ntgt_row, n_cap=g.node_cap, n_dev=g.n_ntgt_dev, math_mode=mode)
+                    if centre_only:   # only centre nodes are ever read (single layer; every layer's inter edges when folded)
+                        # (folded: their e4m3 companion only when they also feed a projection, i.e. layer 0 is the centre-only layer)
+                        return q.gather_decode(codes, g.ntgt_row, row_ids=g.inter_indices, n_dev=g.n_valid_dev, math_mode=mode,
+                                               rotate=not fold, q8=NL == 2)
+                    return q.gather_decode(codes, g.ntgt_row, n_cap=g.node_cap, n_dev=g.n_ntgt_dev, math_mode=mode,
+                                           rotate=not fold, hi_only=fold)
 
             # ~11 live [rows, d] fp32-sized buffers on the ntgt side; chunk over target tokens above the budget
             per_token = graph.k * graph.w * self.embed_dim * 4 * 11
@@ -326,11 +336,12 @@ class TokenGraphTransformerDecoder(nn.Module):
                 raise NotImplementedError("--deprecated graphs share ntgt nodes between tokens, so the ntgt side cannot run "
                                           "in token chunks: raise ntgt_memory_budget_gb or evaluate shorter blocks")
             if NL > 1 and graph.T > chunk:
-                out = self.hgt_decoder.forward_tgt_chunked(graph, h_tgt, decode, chunk)
+                out = self.hgt_decoder.forward_tgt_chunked(graph, h_tgt, decode, chunk, rot=rot)
             elif NL == 1:
-                out = self.hgt_decoder.forward_tgt(graph, h_tgt, None, hc0=decode(graph, True))
+                out = self.hgt_decoder.forward_tgt(graph, h_tgt, None, hc0=decode(graph, True), rot=rot)
             else:
-                out = self.hgt_decoder.forward_tgt(graph, h_tgt, decode(graph, False))
+                out = self.hgt_decoder.forward_tgt(graph, h_tgt, decode(graph, False), hc0=decode(graph, True) if fold else None,
+                                                   rot=rot)
         return as_float(out).view(bsz, seq_len, -1)
 
     # ------------------------------------------------------------------ probabilities

@@ -11,19 +11,30 @@ from . import _lib as L
 
 _I32 = torch.int32
 SPLIT = "split"          # out_dtype selector for the split-fp16 activation format (GNNLM_F16X2)
+SPLIT_Q8 = "split+q8"    # the same with the e4m3 companion (Split.q8) written by the producing kernel (MATH_F16F8 GEMM operands)
+HI_Q8 = "hi+q8"          # fp16 hi half + companion only (no lo half): for matrices that only feed gnnlm_linear_f16f8
 
 
 class Split:
     """An fp32 matrix [rows, d] stored as split fp16 (GNNLM_F16X2): `.data` is [rows, 2d] float16 with
-    hi = fp16(x) in columns [0, d) and lo = fp16(x - hi) in [d, 2d).  Activation format of MATH_F16X3."""
+    hi = fp16(x) in columns [0, d) and lo = fp16(x - hi) in [d, 2d).  Activation format of MATH_F16X3.
 
-    def __init__(self, data: torch.Tensor, d: int):
-        assert data.dtype == torch.float16 and data.dim() == 2 and data.shape[1] == 2 * d and data.stride(1) == 1
-        self.data, self.d = data, d
+    `.q8` (optional): the e4m3 companion [rows, 2d] bytes (hi8 = e4m3(hi) | lo8 = e4m3(2^10 lo)) -- the operands of the FP8
+    correction MMAs of gnnlm_linear_f16f8 (MATH_F16F8), written by the kernel that produced `data` (or by to_q8).
+    A matrix that only ever feeds that product may drop its lo half: `.data` is then [rows, d] (hi only, `has_lo` False) and
+    nothing but linear_f16f8 accepts it."""
+
+    def __init__(self, data: torch.Tensor, d: int, q8: Optional[torch.Tensor] = None):
+        assert data.dtype == torch.float16 and data.dim() == 2 and data.shape[1] in (d, 2 * d) and data.stride(1) == 1
+        assert q8 is None or (q8.dtype == torch.uint8 and q8.shape == (data.shape[0], 2 * d) and q8.stride(1) == 1)
+        self.data, self.d, self.q8 = data, d, q8
+        self.has_lo = data.shape[1] == 2 * d
+        assert self.has_lo or q8 is not None
 
     @staticmethod
-    def empty(rows: int, d: int, device) -> "Split":
-        return Split(torch.empty((rows, 2 * d), device=device, dtype=torch.float16), d)
+    def empty(rows: int, d: int, device, q8: bool = False, lo: bool = True) -> "Split":
+        return Split(torch.empty((rows, 2 * d if lo else d), device=device, dtype=torch.float16), d,
+                     torch.empty((rows, 2 * d), device=device, dtype=torch.uint8) if q8 else None)
 
     @property
     def shape(self):
@@ -35,16 +46,20 @@ class Split:
 
     def float(self) -> torch.Tensor:
         """fp32 reconstruction (API-boundary convenience, torch ops)."""
+        assert self.has_lo, "hi + e4m3 companion only: not reconstructible to fp32"
         return self.data[:, :self.d].float() + self.data[:, self.d:].float()
 
 
 def empty_act(rows: int, d: int, act, device):
-    return Split.empty(rows, d, device) if act == SPLIT else torch.empty((rows, d), device=device, dtype=act)
+    if act in (SPLIT, SPLIT_Q8, HI_Q8):
+        return Split.empty(rows, d, device, q8=act != SPLIT, lo=act != HI_Q8)
+    return torch.empty((rows, d), device=device, dtype=act)
 
 
 def _mat(x):
     """(pointer, dtype code, leading dimension, logical columns) of a Tensor or Split."""
     if isinstance(x, Split):
+        assert x.has_lo, "this kernel reads / writes both fp16 halves"
         return L.ptr(x.data), L.F16X2, x.data.stride(0), x.d
     assert x.dim() == 2 and x.stride(1) == 1
     return L.ptr(x), L.dtype_code(x.dtype), x.stride(0), x.shape[1]
@@ -70,6 +85,7 @@ def linear(A, W: torch.Tensor, bias: Optional[torch.Tensor] = None, *, W_lo: Opt
     a_ptr, a_code, lda, K = _mat(A)
     M = A.shape[0]
     N = W.shape[0]
+    math = L.base_math(math)
     assert W.dim() == 2 and W.stride(1) == 1 and W.shape[1] == K, (A.shape, W.shape)
     dev = W.device
     if out is None:
@@ -85,12 +101,55 @@ def linear(A, W: torch.Tensor, bias: Optional[torch.Tensor] = None, *, W_lo: Opt
     return out
 
 
+def to_q8(x: Split, rows_dev=None) -> Split:
+    """Attach the e4m3 companion to a split-fp16 matrix (standalone pass; the big producers write it themselves)."""
+    if x.q8 is None:
+        q = torch.empty(x.data.shape, device=x.data.device, dtype=torch.uint8)
+        L.call("gnnlm_split_to_q8", L.ptr(x.data), x.data.stride(0), L.ptr(q), q.stride(0), x.data.shape[0], L.ptr(rows_dev), x.d,
+               L.stream_ptr())
+        x.q8 = q
+    return x
+
+
+def quant_w8(w_hi: torch.Tensor, w_lo: torch.Tensor) -> torch.Tensor:
+    """fp16 (hi, lo) halves of a scaled weight [N, K] -> e4m3 bytes [N, 2K] (lo8 | 2^-10 hi8) for gnnlm_linear_f16f8."""
+    N, K = w_hi.shape
+    q = torch.empty((N, 2 * K), device=w_hi.device, dtype=torch.uint8)
+    L.call("gnnlm_quant_w8", L.ptr(w_hi), L.ptr(w_lo), w_hi.stride(0), L.ptr(q), q.stride(0), N, K, L.stream_ptr())
+    return q
+
+
+def f16f8_supported(K1: int, K2: int = 0) -> bool:
+    return K1 % 64 == 0 and K2 % 16 == 0
+
+
+def linear_f16f8(A1: Split, W_hi, W8, bias=None, *, A2: Optional[Split] = None, w_scale=1.0, out=None, out_dtype=None,
+                 m_dev=None, tag=None):
+    """C = [A1 | A2] @ W^T + bias in two tensor-pass equivalents (fp16 main product + FP8 corrections, MATH_F16F8).
+    A1 / A2 split fp16 with e4m3 companions; W_hi fp16 [N, K1 + K2] (scaled), W8 = quant_w8(W_hi, W_lo)."""
+    M, K1 = A1.shape
+    K2 = 0 if A2 is None else A2.shape[1]
+    N = W_hi.shape[0]
+    assert A1.q8 is not None and (A2 is None or (A2.q8 is not None and A2.shape[0] == M))
+    assert W_hi.shape[1] == K1 + K2 and W8.shape == (N, 2 * (K1 + K2)) and W_hi.dtype == torch.float16
+    if out is None:
+        out = empty_act(M, N, out_dtype or torch.float32, W_hi.device)
+    c_ptr, c_code, ldc, n_out = _mat(out)
+    assert n_out == N and out.shape[0] == M
+    a2 = (None, None, 0, 0) if A2 is None else (L.ptr(A2.data), L.ptr(A2.q8), A2.data.stride(0), A2.q8.stride(0))
+    L.call("gnnlm_linear_f16f8", L.ptr(A1.data), L.ptr(A1.q8), A1.data.stride(0), A1.q8.stride(0), K1, a2[0], a2[1], a2[2], a2[3],
+           K2, L.ptr(W_hi), L.ptr(W8), float(w_scale), W_hi.stride(0), W8.stride(0), L.ptr(bias), c_ptr, c_code, ldc, M,
+           _dev_count(m_dev), N, L.stream_ptr(), tag=tag or f"linear_f16f8[{N}x{K1 + K2}]")
+    return out
+
+
 def linear_lse(A, W, pick, *, W_lo=None, m_dev=None, math=L.MATH_FP32_SIMT, w_scale=1.0):
     """Row log-sum-exp partials + picked column of A @ W^T without materialising it."""
     a_ptr, a_code, lda, K = _mat(A)
     M = A.shape[0]
     N = W.shape[0]
     dev = W.device
+    math = L.base_math(math)
     nt = L.load().gnnlm_lse_num_tiles(N, math)
     pmax = torch.empty((M, nt), device=dev, dtype=torch.float32)
     psum = torch.empty((M, nt), device=dev, dtype=torch.float32)
@@ -107,8 +166,9 @@ def lse_finish(pmax, psum, picked, nt, out, *, row_map=None, accumulate=False, m
 
 
 def gather_rows(src, ids, n_cap=None, n_dev=None, out=None):
-    if isinstance(src, Split):      # a row gather of the [rows, 2d] fp16 buffer
-        return Split(gather_rows(src.data, ids, n_cap, n_dev), src.d)
+    if isinstance(src, Split):      # a row gather of the [rows, 2d] fp16 buffer (and of its e4m3 companion)
+        q8 = None if src.q8 is None else gather_rows(src.q8.view(torch.float16), ids, n_cap, n_dev).view(torch.uint8)   # bytes moved as 2-byte words
+        return Split(gather_rows(src.data, ids, n_cap, n_dev), src.d, q8)
     n = ids.shape[0] if n_cap is None else n_cap
     d = src.shape[1]
     if out is None:
@@ -137,6 +197,10 @@ def layernorm(x, gamma, beta, eps=1e-5, out=None, out_dtype=None, n_dev=None, re
         out = empty_act(n, d, out_dtype or torch.float32, x.device)
     o_ptr, o_code, ldy, _ = _mat(out)
     r_ptr, r_code, ldr = (None, 0, 0) if residual is None else _mat(residual)[:3]
+    if isinstance(out, Split) and out.q8 is not None:
+        L.call("gnnlm_layernorm_q8", L.ptr(x), x.stride(0), r_ptr, r_code, ldr, L.ptr(gamma), L.ptr(beta), float(eps), o_ptr, o_code,
+               ldy, L.ptr(out.q8), out.q8.stride(0), n, _dev_count(n_dev), d, L.stream_ptr(), tag="layernorm")
+        return out
     L.call("gnnlm_layernorm", L.ptr(x), x.stride(0), r_ptr, r_code, ldr, L.ptr(gamma), L.ptr(beta), float(eps), o_ptr, o_code,
            ldy, n, _dev_count(n_dev), d, L.stream_ptr())
     return out
@@ -190,6 +254,12 @@ def cluster_attn_supported(d: int, H: int, dtype, w: int) -> bool:
 def cluster_attn(q, k, v, G, H, out, *, centre_only=False, tag=None):
     """ntgt-intra-ntgt chain attention per (token, neighbour) cluster; G is a TokenGraph."""
     d = k.shape[1]
+    if isinstance(out, Split) and out.q8 is not None:
+        L.call("gnnlm_hgt_cluster_attn_q8", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0),
+               L.dtype_code(q.dtype), L.ptr(G.node_base), L.ptr(G.valid_base), L.ptr(G.cluster_nl), G.T * G.k, G.w,
+               int(centre_only), H, d // H, L.ptr(out.data), L.F16X2, out.data.stride(0), L.ptr(out.q8), out.q8.stride(0),
+               int(out.has_lo), L.stream_ptr(), tag=tag)
+        return out
     o_ptr, o_code, ldo, _ = _mat(out)
     L.call("gnnlm_hgt_cluster_attn", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0),
            L.dtype_code(q.dtype), L.ptr(G.node_base), L.ptr(G.valid_base), L.ptr(G.cluster_nl), G.T * G.k, G.w,
@@ -301,13 +371,29 @@ def gelu(x, out_dtype=torch.float32, n_dev=None):
     return out
 
 
-def pq_gather_decode_presplit(codes, cb_hi, cb_lo, rows, *, row_ids=None, n_cap=None, n_dev=None):
-    """Gather + decode straight into the split-fp16 format from a pre-split codebook (dsub == 8)."""
+def pq_gather_decode_hiq8(codes, cb_hi, cb_q8, rows, *, row_ids=None, n_cap=None, n_dev=None):
+    """Gather + decode into the operand set of linear_f16f8 only (fp16 hi + e4m3 companion) from pre-quantised codebooks."""
+    n_d, M = codes.shape
+    assert cb_hi.dtype == torch.float16 and cb_hi.shape == (M, 256, 8) and cb_q8.dtype == torch.uint8 and cb_q8.shape == (M, 256, 16)
+    n = (row_ids.shape[0] if row_ids is not None else rows.shape[0]) if n_cap is None else n_cap
+    out = empty_act(n, M * 8, HI_Q8, codes.device)
+    L.call("gnnlm_pq_gather_decode_hiq8", L.ptr(codes), n_d, M, L.ptr(cb_hi), L.ptr(cb_q8), 8, L.ptr(rows), L.ptr(row_ids), n,
+           _dev_count(n_dev), L.ptr(out.data), out.data.stride(0), L.ptr(out.q8), out.q8.stride(0), L.stream_ptr(),
+           tag="pq_gather_decode")
+    return out
+
+
+def pq_gather_decode_presplit(codes, cb_hi, cb_lo, rows, *, row_ids=None, n_cap=None, n_dev=None, q8=False):
+    """Gather + decode straight into the split-fp16 format from a pre-split codebook (dsub == 8); q8: also the e4m3 companion."""
     n_d, M = codes.shape
     assert cb_hi.dtype == torch.float16 and cb_hi.shape == cb_lo.shape == (M, 256, 8) and cb_hi.is_contiguous()
     n = (row_ids.shape[0] if row_ids is not None else rows.shape[0]) if n_cap is None else n_cap
-    out = empty_act(n, M * 8, SPLIT, codes.device)
+    out = empty_act(n, M * 8, SPLIT_Q8 if q8 else SPLIT, codes.device)
     o_ptr, _, ld_out, _ = _mat(out)
+    if q8:
+        L.call("gnnlm_pq_gather_decode_presplit_q8", L.ptr(codes), n_d, M, L.ptr(cb_hi), L.ptr(cb_lo), 8, L.ptr(rows), L.ptr(row_ids),
+               n, _dev_count(n_dev), o_ptr, ld_out, L.ptr(out.q8), out.q8.stride(0), L.stream_ptr(), tag="pq_gather_decode")
+        return out
     L.call("gnnlm_pq_gather_decode_presplit", L.ptr(codes), n_d, M, L.ptr(cb_hi), L.ptr(cb_lo), 8, L.ptr(rows), L.ptr(row_ids),
            n, _dev_count(n_dev), o_ptr, ld_out, L.stream_ptr(), tag="pq_gather_decode")
     return out

@@ -41,6 +41,8 @@ class TorchPQCodec(nn.Module):
         self._rot_key = None
         self._split = None
         self._split_key = None
+        self._q8cb, self._q8cb_key = None, None
+        self._rot32, self._rot32_key = None, None
 
     @property
     def M(self):
@@ -73,23 +75,50 @@ class TorchPQCodec(nn.Module):
             self._split, self._split_key = (hi.contiguous(), lo.contiguous()), key
         return self._split
 
+    def rotation_weight(self) -> torch.Tensor:
+        """rot = A^T [d, d_dec] fp32 (x @ A == x @ rot^T), a persistent tensor: HGTLayer.prepare folds it into layer 0 and keys
+        its cache on it."""
+        key = (self.A.device, int(self.A._version))
+        if self._rot32 is None or self._rot32_key != key:
+            self._rot32, self._rot32_key = self.A.detach().t().contiguous().float(), key
+        return self._rot32
+
+    def _q8_codebook(self):
+        """e4m3 companion of the split codebook, [M, 256, 16] bytes (8 B hi8 | 8 B lo8 per centroid)."""
+        hi, lo = self._split_codebook()
+        key = (hi.data_ptr(), lo.data_ptr())
+        if self._q8cb is None or self._q8cb_key != key:
+            both = ops.Split(torch.cat([hi.reshape(-1, 8), lo.reshape(-1, 8)], 1).contiguous(), 8)
+            self._q8cb, self._q8cb_key = ops.to_q8(both).q8.view(self.M, 256, 16), key
+        return self._q8cb
+
     @torch.no_grad()
     def gather_decode(self, codes_table: torch.Tensor, rows: torch.Tensor, *, row_ids: Optional[torch.Tensor] = None,
                       n_cap: Optional[int] = None, n_dev: Optional[torch.Tensor] = None,
-                      math_mode: int = L.MATH_FP32_SIMT) -> torch.Tensor:
-        """Fused `quant_neighbor_feats[rows]` + decode: codes_table [N_d, M] uint8 in HBM."""
-        from .hgt import act_dtype
+                      math_mode: int = L.MATH_FP32_SIMT, rotate: bool = True, hi_only: bool = False, q8: bool = True) -> torch.Tensor:
+        """Fused `quant_neighbor_feats[rows]` + decode: codes_table [N_d, M] uint8 in HBM.
+        rotate=False (MATH_F16F8, dsub == 8): the caller folds `x @ A` into its own weights (rotation_weight()) -- returns the
+        un-rotated features (with their e4m3 companion unless q8=False), as fp16 hi + companion only when hi_only."""
+        from .hgt import act_dtype, gemm_act
         b = self.b if self.pre_torch and self.b.numel() > 0 else None
         act = act_dtype(math_mode)
+        if not rotate:
+            assert math_mode == L.MATH_F16F8 and self.dsub == 8 and self.pre_torch
+            hi, lo = self._split_codebook()
+            if hi_only:
+                return ops.pq_gather_decode_hiq8(codes_table, hi, self._q8_codebook(), rows, row_ids=row_ids, n_cap=n_cap, n_dev=n_dev)
+            return ops.pq_gather_decode_presplit(codes_table, hi, lo, rows, row_ids=row_ids, n_cap=n_cap, n_dev=n_dev, q8=q8)
         if act == ops.SPLIT and self.dsub == 8:        # pre-split codebook: pure byte movement (pq_decode_presplit_kernel)
             hi, lo = self._split_codebook()
-            x = ops.pq_gather_decode_presplit(codes_table, hi, lo, rows, row_ids=row_ids, n_cap=n_cap, n_dev=n_dev)
+            n = (row_ids.shape[0] if row_ids is not None else rows.shape[0]) if n_cap is None else n_cap
+            x = ops.pq_gather_decode_presplit(codes_table, hi, lo, rows, row_ids=row_ids, n_cap=n_cap, n_dev=n_dev,
+                                              q8=self.pre_torch and gemm_act(math_mode, n, self.M * 8) == ops.SPLIT_Q8)
         else:
             x, _, _ = ops.pq_gather_decode(codes_table, self.centroids_torch, rows, bias=b, row_ids=row_ids, n_cap=n_cap,
                                            n_dev=n_dev, out_dtype=act)
         if self.pre_torch:
-            w = self._rotation(math_mode)
-            x = ops.linear(x, w.W, None, W_lo=w.lo, w_scale=w.scale, m_dev=n_dev, math=math_mode, out_dtype=act)
+            from .hgt import _lin, with_q8
+            x = _lin(with_q8(x, math_mode, n_dev), self._rotation(math_mode), math_mode, m_dev=n_dev, out_dtype=act)
         return x
 
     @torch.no_grad()

@@ -145,6 +145,21 @@ int32_t gnnlm_pq_gather_decode_presplit(const uint8_t* codes, int64_t n_datastor
                                         int64_t n_cap, const int32_t* n_dev, void* out, int64_t ld_out,
                                         gnnlm_stream_t stream);
 
+/* ..._q8: additionally writes the e4m3 companion q8 [n_cap, 2*M*8] bytes (ldq; hi8 = e4m3(hi) | lo8 = e4m3(2^10 lo)) that
+ * gnnlm_linear_f16f8 reads; q8 == NULL is the plain call. */
+int32_t gnnlm_pq_gather_decode_presplit_q8(const uint8_t* codes, int64_t n_datastore, int32_t M, const void* cb_hi,
+                                           const void* cb_lo, int32_t dsub, const int64_t* rows, const int32_t* row_ids,
+                                           int64_t n_cap, const int32_t* n_dev, void* out, int64_t ld_out, void* q8,
+                                           int64_t ldq, gnnlm_stream_t stream);
+
+/* The operand set of gnnlm_linear_f16f8 only: out_hi [n_cap, M*8] fp16 (ld_out >= M*8) + q8 [n_cap, 2*M*8] bytes, from cb_hi
+ * [M, 256, 8] fp16 and cb_q8 [M, 256, 16] bytes = the e4m3 companion (8 B hi8 | 8 B lo8) of every centroid, prepared once per
+ * quantizer (gnnlm_split_to_q8 over the split codebook).  Same bytes per node as the plain form, no conversions. */
+int32_t gnnlm_pq_gather_decode_hiq8(const uint8_t* codes, int64_t n_datastore, int32_t M, const void* cb_hi, const void* cb_q8,
+                                    int32_t dsub, const int64_t* rows, const int32_t* row_ids, int64_t n_cap,
+                                    const int32_t* n_dev, void* out_hi, int64_t ld_out, void* q8, int64_t ldq,
+                                    gnnlm_stream_t stream);
+
 /* PQ encode (the producer of quantized-keys.npy; knn/pq_wrapper.py:51-68,131-167, knn/quantize_features.py:115-152):
  *  codes[n, m] = argmin_c (norm2[m, c] - 2 <x[n, m*dsub:(m+1)*dsub], centroids[m, c]>), first minimum wins.
  *  x fp32 [n, M*dsub] (ldx) must already carry the OPQ pre-rotation `x @ A.T (+ b)` (a gnnlm_linear call);
@@ -183,6 +198,25 @@ int32_t gnnlm_linear_batched_f16x3(const void* A, int64_t lda, int64_t a_bs, con
                                    int64_t ldc, int64_t c_bs, int64_t nb, int64_t M, int64_t N, int64_t K, int32_t causal,
                                    gnnlm_stream_t stream);
 
+/* fp32-parity product in TWO tensor-pass equivalents (the large ntgt-side projections of hgt.py:320-322,347-348,401 and the
+ * rotation of pq_wrapper.py:202): the fp16 main product a_hi w_hi (kind::f16) plus the two 2^-11-sized correction products
+ * a_hi w_lo + a_lo w_hi as FP8 MMAs (kind::f8f6f4, e4m3 x e4m3, twice the fp16 rate) into the same fp32 accumulator.
+ *   C[m, n] = (1 / w_scale) * sum_k A[m, k] W[n, k] + bias[n],   A = [A1 | A2] along k (K = K1 + K2; K2 = 0: one source)
+ * A1 / A2: split-fp16 buffers (GNNLM_F16X2; only the hi half [., 0:Ki) is read, so lda >= Ki suffices), lda in fp16 elements;
+ * A1q / A2q: their e4m3 companions [M, 2*Ki] bytes (ldq >= 2*Ki): hi8 = e4m3(hi) in [0, Ki), lo8 = e4m3(2^10 * lo) in [Ki, 2Ki)
+ *   -- written by the producing kernels (gnnlm_layernorm_q8 / gnnlm_hgt_cluster_attn_q8 / gnnlm_pq_gather_decode_presplit_q8)
+ *   or by gnnlm_split_to_q8;
+ * W_hi fp16 [N, K] from gnnlm_split_f16 (scaled by w_scale), W8 [N, 2K] bytes from gnnlm_quant_w8: lo8 = e4m3(w_lo) in [0, K),
+ *   hi8 = e4m3(2^-10 * w_hi) in [K, 2K).  K1 must be a multiple of 64, K2 of 16; C F32 / BF16 / F16X2. */
+int32_t gnnlm_split_to_q8(const void* x, int64_t ldx, void* q, int64_t ldq, int64_t rows, const int32_t* rows_dev, int64_t d,
+                          gnnlm_stream_t stream);
+int32_t gnnlm_quant_w8(const void* w_hi, const void* w_lo, int64_t ldw, void* q, int64_t ldq, int64_t N, int64_t K,
+                       gnnlm_stream_t stream);
+int32_t gnnlm_linear_f16f8(const void* A1, const void* A1q, int64_t lda1, int64_t ldq1, int64_t K1, const void* A2,
+                           const void* A2q, int64_t lda2, int64_t ldq2, int64_t K2, const void* W_hi, const void* W8,
+                           float w_scale, int64_t ldw, int64_t ldw8, const float* bias, void* C, int32_t c_dtype, int64_t ldc,
+                           int64_t M, const int32_t* m_dev, int64_t N, gnnlm_stream_t stream);
+
 /* Same contraction, but instead of storing C the epilogue keeps, per row and per column tile,
  * (max, sum exp(x - max)) and the single column `pick[m]` -- the [rows, vocab] tensor of
  * AdaptiveSoftmax.get_log_prob (adaptive_softmax.py:184-203) is never written.
@@ -218,6 +252,11 @@ int32_t gnnlm_embed_gather(const float* table, int64_t ld_table, int64_t vocab, 
 int32_t gnnlm_layernorm(const float* x, int64_t ldx, const void* residual, int32_t r_dtype, int64_t ldr,
                         const float* gamma, const float* beta, float eps, void* y, int32_t out_dtype, int64_t ldy,
                         int64_t n_cap, const int32_t* n_dev, int64_t d, gnnlm_stream_t stream);
+/* gnnlm_layernorm with a split-fp16 output plus its e4m3 companion q8 [n, 2d] bytes (ldq) for gnnlm_linear_f16f8
+ * (d in {128, 256, 512, 1024}); q8 == NULL is the plain call. */
+int32_t gnnlm_layernorm_q8(const float* x, int64_t ldx, const void* residual, int32_t r_dtype, int64_t ldr, const float* gamma,
+                           const float* beta, float eps, void* y, int32_t out_dtype, int64_t ldy, void* q8, int64_t ldq,
+                           int64_t n_cap, const int32_t* n_dev, int64_t d, gnnlm_stream_t stream);
 /* fp16 / fp32 rows [rows, d] (ld_src elements) -> split-fp16 [rows, 2d] (GNNLM_F16X2, ld_dst >= 2d fp16 elements). */
 int32_t gnnlm_to_split_f16(const void* src, int32_t src_dtype, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows,
                            const int32_t* rows_dev, int64_t d, gnnlm_stream_t stream);
@@ -263,6 +302,14 @@ int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void* k, int64_
                                const int32_t* cluster_nl, int64_t n_clusters, int32_t max_cluster, int32_t centre_only,
                                int32_t H, int32_t d_k, void* out, int32_t out_dtype, int64_t ldo,
                                gnnlm_stream_t stream);
+/* Split-fp16 output plus its e4m3 companion q8 ([rows, hi8 | lo8] bytes, row stride ldq8 >= 2d) for gnnlm_linear_f16f8;
+ * write_lo == 0: only the fp16 hi half is stored (ldo >= d) -- hi + companion is everything that product reads.
+ * q8 == NULL (write_lo = 1) is the plain call. */
+int32_t gnnlm_hgt_cluster_attn_q8(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                  int32_t dtype, const int32_t* node_base, const int32_t* valid_base,
+                                  const int32_t* cluster_nl, int64_t n_clusters, int32_t max_cluster, int32_t centre_only,
+                                  int32_t H, int32_t d_k, void* out, int32_t out_dtype, int64_t ldo, void* q8, int64_t ldq8,
+                                  int32_t write_lo, gnnlm_stream_t stream);
 
 /* ('tgt','intra','tgt') as implicit causal attention inside each of B blocks of L tokens
  * (edges u -> v for u <= v, v - u < intra_ctx when intra_ctx > 0; token_block_dataset.py:586-594). */

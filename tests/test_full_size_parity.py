@@ -17,7 +17,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-REL = {"fp32": 1e-4, "f16x3": 1e-4, "tf32x3": 1e-4, "bf16": 1e-2}
+REL = {"fp32": 1e-4, "f16x3": 1e-4, "f16f8": 1e-4, "tf32x3": 1e-4, "bf16": 1e-2}
 
 
 def _need_tc():
@@ -75,7 +75,7 @@ def test_c2_enwik8_shape_vs_fp64_oracle(dev):
     """BASELINE.json configs[1]: d=512, H=8, char vocab 204 with a plain softmax (transformer.py:1081-1085), 512-token
     blocks, k=32, c=1, M=64, 3 layers, 2^24-row datastore -- every arithmetic mode."""
     _need_tc()
-    _check(_problem("c2", dev), dev, ["fp32", "f16x3", "tf32x3", "bf16"])
+    _check(_problem("c2", dev), dev, ["fp32", "f16x3", "f16f8", "tf32x3", "bf16"])
 
 
 def test_c3_wiki103_shape_full_block_vs_fp64_oracle(dev):
@@ -83,14 +83,14 @@ def test_c3_wiki103_shape_full_block_vs_fp64_oracle(dev):
     the adaptive softmax (cutoffs 20000/60000, tied), k=32, c=1, M=128, 3 layers, k_nn=1024, the 103,227,021-row datastore
     resident in HBM."""
     _need_tc()
-    _check(_problem("c3", dev), dev, ["f16x3", "bf16", "fp32"])
+    _check(_problem("c3", dev), dev, ["f16x3", "f16f8", "bf16", "fp32"])
 
 
 def test_c3e_reference_eval_script_setting_vs_fp64_oracle(dev):
     """The Wiki103 shape at the reference evaluation script's setting (hgt_lm_wiki103_reproduce.sh:127-147): 256-token sample,
     --gcn-k 128, --neighbor-context 2 (clusters of 5), lambda 0.1, temperature 0.01."""
     _need_tc()
-    _check(_problem("c3e", dev), dev, ["f16x3", "bf16"])
+    _check(_problem("c3e", dev), dev, ["f16x3", "f16f8", "bf16"])
 
 
 def test_c5_cell_k128_c3_token_chunked_vs_fp64_oracle(dev, monkeypatch):
@@ -102,14 +102,14 @@ def test_c5_cell_k128_c3_token_chunked_vs_fp64_oracle(dev, monkeypatch):
     from gnnlm_b200.hgt import HGT
     chunks, inner = [], HGT.forward_tgt_chunked
 
-    def spy(self, G, h_tgt, decode, chunk_tokens):
+    def spy(self, G, h_tgt, decode, chunk_tokens, **kw):
         chunks.append(chunk_tokens)
-        return inner(self, G, h_tgt, decode, chunk_tokens)
+        return inner(self, G, h_tgt, decode, chunk_tokens, **kw)
 
     monkeypatch.setattr(HGT, "forward_tgt_chunked", spy)
     prob = _problem("c3", dev, k=128, c=3, L=512, n_d=1 << 24)
-    _check(prob, dev, ["f16x3", "bf16"], budget_gb=4.0)
-    assert chunks == [128, 128]              # both modes ran the ntgt side in four 128-token chunks
+    _check(prob, dev, ["f16x3", "f16f8", "bf16"], budget_gb=4.0)
+    assert chunks == [128, 128, 128]         # every mode ran the ntgt side in four 128-token chunks
 
 
 def test_c4_one_billion_word_vocab_logprob_stage_vs_fp64_oracle(dev):

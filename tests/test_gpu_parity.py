@@ -391,7 +391,125 @@ def test_linear_tcgen05(math, rtol, atol, M, N, K, dev):
     np.testing.assert_allclose(lp.cpu().double().numpy(), ref_lp.numpy(), rtol=rtol, atol=max(atol, 2e-5))
 
 
-@pytest.mark.parametrize("math", ["tf32x3", "f16x3"])
+@pytest.mark.parametrize("M,N,K,K2", [(128, 256, 64, 0), (300, 200, 128, 0), (5000, 1024, 1024, 0), (4097, 3072, 1024, 0), (2500, 1024, 512, 512),
+                                       (129, 72, 256, 48), (70000, 136, 1024, 1024)])
+def test_linear_f16f8(M, N, K, K2, dev):
+    """MATH_F16F8 product (fp16 main product + the two 2^-11-sized correction products as FP8 e4m3 MMAs into the same TMEM
+    accumulator): within 1e-4 of the fp64 product like the other fp32-parity modes (measured ~1e-5 of max|C|), for one and two
+    k-concatenated sources, ragged M / N, device-side row counts; the e4m3 companions against their definition bit for bit."""
+    _need_tc()
+    from gnnlm_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(M + N + K + K2)
+    A = torch.randn((M, K), generator=g, device=dev)
+    A2 = torch.randn((M, K2), generator=g, device=dev) * 3 if K2 else None
+    W = torch.randn((N, K + K2), generator=g, device=dev) / (K + K2) ** 0.5
+    b = torch.randn((N,), generator=g, device=dev)
+    Wh, Wl, sc = ops.split_f16(W)
+    W8 = ops.quant_w8(Wh, Wl)
+    As = ops.to_q8(ops.to_split(A))
+    A2s = ops.to_q8(ops.to_split(A2)) if K2 else None
+    # companions: hi8 = e4m3(hi), lo8 = e4m3(2^10 lo); weights lo8 = e4m3(lo), hi8 = e4m3(2^-10 hi) (round to nearest even, saturating)
+    e4 = lambda t: t.float().clamp(-448, 448).to(torch.float8_e4m3fn).view(torch.uint8)
+    assert torch.equal(As.q8[:, :K], e4(As.data[:, :K])) and torch.equal(As.q8[:, K:], e4(As.data[:, K:].float() * 1024))
+    assert torch.equal(W8[:, :K + K2], e4(Wl)) and torch.equal(W8[:, K + K2:], e4(Wh.float() / 1024))
+    Af = A if not K2 else torch.cat([A, A2], 1)
+    ref = Af.double() @ W.double().T + b.double()
+    out = ops.linear_f16f8(As, Wh, W8, b, A2=A2s, w_scale=sc)
+    # errors are relative to the magnitude of the accumulated terms, not of a (possibly cancelling) result: 3e-5 of max|C|
+    # (measured 8e-6; 3xFP16 3e-6; a single fp16 pass 2e-4)
+    assert (out.double() - ref).abs().max().item() <= 3e-5 * ref.abs().max().item()
+    cnt = torch.tensor([M // 2 + 1], dtype=torch.int32, device=dev)
+    out2 = torch.full((M, N), 7.0, device=dev)
+    ops.linear_f16f8(As, Wh, W8, b, A2=A2s, w_scale=sc, out=out2, m_dev=cnt)
+    live = M // 2 + 1
+    assert torch.equal(out2[:live], out[:live]) and (out2[live:] == 7.0).all()
+    # split-fp16 output epilogue
+    o3 = ops.linear_f16f8(As, Wh, W8, b, A2=A2s, w_scale=sc, out_dtype=ops.SPLIT)
+    assert (o3.float() - out).abs().max().item() <= 2e-7 * out.abs().max().item()
+
+
+def test_e4m3_companions_written_by_the_producers(dev):
+    """LayerNorm, cluster attention (all nodes / centre only) and the pre-split PQ decode write the e4m3 companion of their
+    split-fp16 output themselves in MATH_F16F8: bit-identical to the standalone gnnlm_split_to_q8 pass over the same output,
+    and the split output itself unchanged."""
+    _need_tc()
+    from gnnlm_b200 import ops, synth
+    from gnnlm_b200.graph import build_token_graph
+    g = torch.Generator(device=dev).manual_seed(11)
+    n, d, H = 3000, 1024, 8
+    x = torch.randn((n, d), generator=g, device=dev) * 3
+    res = ops.to_split(torch.randn((n, d), generator=g, device=dev))
+    gam, bet = torch.randn(d, generator=g, device=dev), torch.randn(d, generator=g, device=dev)
+    cnt = torch.tensor([n - 7], dtype=torch.int32, device=dev)
+    plain = ops.layernorm(x, gam, bet, out_dtype=ops.SPLIT, residual=res, n_dev=cnt)
+    both = ops.layernorm(x, gam, bet, out_dtype=ops.SPLIT_Q8, residual=res, n_dev=cnt)
+    live = n - 7
+    assert torch.equal(plain.data[:live], both.data[:live])
+    want = ops.to_q8(ops.Split(both.data.clone(), d), cnt).q8
+    assert torch.equal(both.q8[:live], want[:live])
+    # cluster attention over a small graph (k = 4, c = 1)
+    cfg = dict(synth.CONFIGS["c3mini"], L=96, k=4)
+    tables = synth.make_tables(cfg, device=dev, n_d=1 << 14)
+    batch = synth.make_batch(cfg, tables, device=dev)
+    G = build_token_graph(batch["nbr"], tables["n_d"], 1, 1)
+    n_ntgt, n_valid = G.counts()
+    qkv = torch.randn((G.node_cap, 3 * d), generator=g, device=dev)
+    for centre in (False, True):
+        rows = n_valid if centre else G.node_cap
+        q = qkv[:rows, :d].contiguous() if centre else qkv[:, :d]
+        a = ops.empty_act(rows, d, ops.SPLIT, dev)
+        b = ops.empty_act(rows, d, ops.SPLIT_Q8, dev)
+        b.q8.zero_()
+        ops.cluster_attn(q, qkv[:, d:2 * d], qkv[:, 2 * d:], G, H, a, centre_only=centre)
+        ops.cluster_attn(q, qkv[:, d:2 * d], qkv[:, 2 * d:], G, H, b, centre_only=centre)
+        m = n_valid if centre else n_ntgt
+        assert torch.equal(a.data[:m], b.data[:m])
+        assert torch.equal(b.q8[:m], ops.to_q8(ops.Split(b.data.clone(), d)).q8[:m]) and int(b.q8[:m].max()) > 0
+    # PQ decode from the pre-split codebook
+    model = synth.make_model(cfg)
+    qz = model.decoder.tgt_quantizer.to(dev)
+    hi, lo = qz._split_codebook()
+    rows = G.ntgt_row
+    p0 = ops.pq_gather_decode_presplit(tables["codes"], hi, lo, rows, n_cap=G.node_cap, n_dev=G.n_ntgt_dev)
+    p1 = ops.pq_gather_decode_presplit(tables["codes"], hi, lo, rows, n_cap=G.node_cap, n_dev=G.n_ntgt_dev, q8=True)
+    assert torch.equal(p0.data[:n_ntgt], p1.data[:n_ntgt])
+    assert torch.equal(p1.q8[:n_ntgt], ops.to_q8(ops.Split(p1.data.clone(), d)).q8[:n_ntgt])
+    # ... and the hi + companion only form from the pre-quantised codebook
+    p2 = ops.pq_gather_decode_hiq8(tables["codes"], hi, qz._q8_codebook(), rows, n_cap=G.node_cap, n_dev=G.n_ntgt_dev)
+    assert not p2.has_lo and torch.equal(p2.data[:n_ntgt], p1.data[:n_ntgt, :d]) and torch.equal(p2.q8[:n_ntgt], p1.q8[:n_ntgt])
+    # cluster attention, hi + companion only
+    c = ops.empty_act(G.node_cap, d, ops.HI_Q8, dev)
+    ops.cluster_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G, H, c)
+    full = ops.empty_act(G.node_cap, d, ops.SPLIT_Q8, dev)
+    ops.cluster_attn(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G, H, full)
+    assert torch.equal(c.data[:n_ntgt], full.data[:n_ntgt, :d]) and torch.equal(c.q8[:n_ntgt], full.q8[:n_ntgt])
+
+
+@pytest.mark.parametrize("name,NL", [("c3mini", 3), ("c3mini", 2), ("c1", 1)])
+def test_f16f8_rotation_fold_matches_explicit_rotation(name, NL, dev):
+    """MATH_F16F8 folds the OPQ rotation `x @ A` (pq_wrapper.py:202) into HGT layer 0 (Q|K'|V' = x (W A^T)^T, the residual of
+    hgt.py:403 inside the output projection [t | x] [W_a | A^T]^T, the inter K' / V' on the token side) and decodes straight into
+    fp16 hi + e4m3 companion: same log-probs as the explicit rotation GEMM of the same mode to fp32 re-association, and both
+    within 1e-4 of the oracle; 1, 2 and 3 layers (centre-only decode / centre-only layer 0 / full layer 0)."""
+    _need_tc()
+    import copy
+    from gnnlm_b200 import synth
+    from tests.synth import make_problem, run_oracle
+    cfg, model, data = make_problem(name)
+    cfg = dict(cfg, NL=NL)
+    model = synth.make_model(cfg)
+    ref = run_oracle((cfg, model, data))
+    outs = {}
+    for fold in (True, False):
+        m = copy.deepcopy(model)
+        m.decoder.fold_rotation = fold
+        outs[fold] = synth.run_gpu(cfg, m, data, dev, "f16f8")
+        np.testing.assert_allclose(outs[fold]["logprob"], ref["logprob"].numpy(), rtol=1e-4, atol=1e-4)
+    assert np.abs(outs[True]["logprob"] - outs[False]["logprob"]).max() < 2e-5 * np.abs(outs[False]["logprob"]).max()
+    assert not np.array_equal(outs[True]["gcn_feat"], outs[False]["gcn_feat"])          # two different evaluation orders did run
+
+
+@pytest.mark.parametrize("math", ["tf32x3", "f16x3", "f16f8"])
 @pytest.mark.parametrize("name", ["c1", "c3mini"])
 def test_whole_path_tf32x3(name, math, dev):
     """fp32-parity modes on tensor cores (3xTF32 / 3xFP16 splits): same 1e-4 bar as the CUDA-core fp32 mode."""
