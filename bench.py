@@ -9,7 +9,10 @@ layers, k_nn=1024), one process per GPU.
 
 A "step" is one pass of the hot path over one batch (B blocks x L tokens).  `value` is measured with all
 inputs resident in HBM; `e2e` goes through the same public call with pinned HOST inputs (H2D inside the
-timed region, 16 B result read back per step).  Prints ONE JSON line on rank 0.
+timed region, 16 B result read back per step); `e2e_evaluate` is eval_lm.evaluate() -- the call a user makes -- over a
+reference-layout data directory in tmpfs (mmap slicing, collater, staging, scoring).  Prints ONE JSON line on rank 0.
+
+  python bench.py --gpus N --scaling strong   # a fixed corpus sharded over the ranks through evaluate() (extra evidence)
 """
 import argparse
 import json
@@ -37,11 +40,18 @@ def parse():
     p.add_argument("--n-datastore", type=int, default=0, help="override datastore rows (default: the config's)")
     p.add_argument("--deprecated", action="store_true", help="--deprecated (de-duplicating) graph builder, general CSR attention")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-full-block", action="store_true", help="--impl reference: skip the single pass over a full block")
     p.add_argument("--cpu-tokens", type=int, default=768, help="tokens in the CPU-baseline sample block")
     p.add_argument("--also-modes", default="f16x3,tf32x3,tf32,bf16",
                    help="extra arithmetic modes timed briefly (resident inputs) and reported under `other_modes`")
     p.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
                    help="launch the step's kernels one by one instead of replaying the captured whole-step CUDA graph")
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                   help="weak: one block per step per rank (the headline line).  strong: ONE fixed corpus of --strong-blocks blocks "
+                        "(+ a ragged tail) through eval_lm.evaluate(rank, world_size): contiguous block shards, replicated datastore, "
+                        "one NCCL all-reduce of {sum log p, n_tokens}")
+    p.add_argument("--strong-blocks", type=int, default=64)
+    p.add_argument("--eval-blocks", type=int, default=16, help="blocks of the e2e_evaluate leg (0: skip it)")
     p.add_argument("--ncu-range", action="store_true",
                    help="after warm-up run ONE resident step inside cudaProfilerStart/Stop and exit "
                         "(use with `ncu --profile-from-start off`); prints no bench line")
@@ -96,6 +106,7 @@ def cpu_sample(cfg_name, n_tokens, n_d=1 << 22):
     depend on the datastore size)."""
     from gnnlm_b200 import synth
     cfg = dict(synth.CONFIGS[cfg_name])
+    n_tokens = min(n_tokens, cfg["B"] * cfg["L"])                # never more than the workload's own block
     cfg.update(B=1, L=n_tokens, n_d=min(cfg["n_d"], n_d))
     model = synth.make_model(cfg)
     data = synth.make_data(cfg, seed=0, device="cpu")
@@ -120,39 +131,64 @@ def time_oracle(prob, steps, warmup):
     return float(np.mean(ts)), out
 
 
+def bench_config(cfg_name, world, scaling="weak"):
+    """The `config` object of BOTH arms (the reference arm runs on our arm's config; what it actually times per step is stated
+    in its cpu_baseline.sample)."""
+    return {"workload": workload_name(cfg_name),
+            "parallelism": f"dp{world} (contiguous block shards, replicated datastore, one 16 B all-reduce)",
+            "l2_policy": "inputs larger than L2 (datastore + activations are GBs); 4 distinct batches rotated",
+            "scaling_mode": scaling}
+
+
+def sample_note(cfg, args):
+    full = __import__("gnnlm_b200").synth.CONFIGS[args.config]["L"]
+    return (f"CPU oracle port (torch fp32, {torch.get_num_threads()} threads): each step scores ONE block of {cfg['L']} tokens -- "
+            f"a bounded sample, {cfg['L']}/{full} of the workload's {full}-token block -- at the {args.config} shape (d={cfg['d']}, "
+            f"V={cfg['V']}, k={cfg['k']}, c={cfg['c']}, M={cfg['M']}, {cfg['NL']} HGT layers, k_nn={cfg['k_nn']}), datastore "
+            f"2^22 rows; the CPU cost per token GROWS with the block length (tgt-intra-tgt attention is quadratic), so the "
+            f"sample understates the CPU time of the full block")
+
+
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation cannot run here (needs dgl + faiss;
-    DESIGN.md), so this times the oracle port of it on all host cores."""
+    """--impl reference: the reference's own CPU implementation cannot run here (needs dgl + faiss), so this times
+    the oracle port of it on all host cores.  Same `config` as our arm; each step is a bounded sample of that workload (a
+    768-token block instead of the 3072-token one, stated in cpu_baseline.sample and `sample_tokens`), and one pass over a
+    FULL block is timed once beside it (`full_block`) so that the two can be compared."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from gnnlm_b200 import synth
     cfg, model, data = cpu_sample(args.config, args.cpu_tokens)
     sec, out = time_oracle((cfg, model, data), max(1, args.steps), max(0, min(args.warmup, 1)))
     tps = cfg["L"] / sec
-    sample = (f"1 block of {cfg['L']} tokens per step at the {args.config} shape (d={cfg['d']}, V={cfg['V']}, k={cfg['k']}, "
-              f"c={cfg['c']}, M={cfg['M']}, {cfg['NL']} HGT layers, k_nn={cfg['k_nn']}), datastore 2^22 rows, fp32, "
-              f"torch CPU {torch.get_num_threads()} threads")
+    full = None
+    L_full = synth.CONFIGS[args.config]["L"] * synth.CONFIGS[args.config]["B"]
+    if not args.no_full_block and L_full != cfg["L"]:
+        fcfg, fmodel, fdata = cpu_sample(args.config, L_full)
+        fsec, _ = time_oracle((fcfg, fmodel, fdata), 1, 0)
+        full = {"tokens": L_full, "seconds": fsec, "tokens_per_s": L_full / fsec, "passes": 1,
+                "note": "one un-warmed pass over a full block of the workload (dense-causal oracle form)"}
     line = {"impl": "reference", "metric": "eval tokens/s (HGT+kNN-LM fwd)", "value": tps, "unit": "tokens/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.config)},
-            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+            "config": bench_config(args.config, args.gpus), "sample_tokens": cfg["L"], "full_block": full,
+            "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": sample_note(cfg, args)},
             "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def ncu_traffic(key, cfg):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind `key`, from the committed
-    `ncu --set full` capture of this workload (profiles/r1_ncu_traffic.json, written by profiles/ncu_metrics.py);
-    None when the capture does not cover this kernel / config."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
-    if not os.path.exists(path) or cfg.get("L") != 3072 or cfg.get("k") != 32 or cfg.get("c") != 1:
-        return None
-    want = {"hgt_cluster_attn:nn_full": "cluster_attn_kernel<float, __half, 4, 3, 32>",
-            "hgt_cluster_attn:nn_centre": "cluster_attn_kernel<float, __half, 4, 0, 32>"}.get(key)
-    db = json.load(open(path))
-    return db[want]["dram_bytes"] if want in db else None
+def committed_ncu(kernel_key):
+    """Per-launch counters of a kernel from the committed `ncu --set full` captures of this workload (profiles/*ncu_traffic.json,
+    written by profiles/ncu_metrics.py from captures taken under gpurun -- NOT measured by this run)."""
+    for name in ("r2_ncu_traffic.json", "r1_ncu_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(path):
+            db = json.load(open(path))
+            if kernel_key in db:
+                return dict(db[kernel_key], file=f"profiles/{name}")
+    return None
 
 
 def workload_name(cfg_name):
@@ -162,6 +198,80 @@ def workload_name(cfg_name):
              "c3e": "wiki103-shape at the reference eval script's setting"}
     return f"{cfg_name}: {names.get(cfg_name, cfg_name)} GNN+kNN eval" + \
         f" d={c['d']} H={c['H']} V={c['V']} B={c['B']}xL={c['L']} k={c['k']} c={c['c']} M={c['M']} layers={c['NL']} k_nn={c['k_nn']}"
+
+
+# ----------------------------------------------------------------------------------------------- evaluate() legs
+def build_eval(cfg, model, dev, math, root, n_blocks, tail, seed=0):
+    """A reference-layout data directory under `root` (tmpfs) + everything eval_lm.evaluate() needs, through the same loaders
+    eval_lm.main uses (formats.load_graph_lm_dataset, DeviceDatastore.from_dir, KNNModel over the neighbour memmaps)."""
+    from argparse import Namespace
+    from gnnlm_b200 import synth
+    from gnnlm_b200.dataset import DeviceDatastore, neighbor_path
+    from gnnlm_b200.formats import MmapDataset, load_graph_lm_dataset
+    from gnnlm_b200.knn_model import KNNModel
+    from gnnlm_b200.sequence_scorer import SequenceScorer
+    info = synth.write_data_dir(root, cfg, n_blocks, tail_tokens=tail, seed=seed, device=dev)
+    n = info["n_tokens"]
+    knn_ids = MmapDataset(neighbor_path(root, "valid", cfg["k_nn"]), (n, cfg["k_nn"]), np.int64).array()
+    knn_dists = MmapDataset(info["dists_file"], (n, cfg["k_nn"]), np.float32).array()
+    ds, dictionary = load_graph_lm_dataset(root, "valid", tokens_per_sample=cfg["L"], gcn_k=cfg["k"], neighbor_context=cfg["c"],
+                                           knn_dists=knn_dists, knn_ids=knn_ids)
+    dstore = DeviceDatastore.from_dir(root, len(dictionary), dev)
+    knn = KNNModel(dstore.vals, vocab_size=cfg["V"], metric_type="do_not_recomp_ip", k=cfg["k_nn"])
+    scorer = SequenceScorer(dictionary, args=Namespace(lmbda=cfg["lmbda"], knn_keytype=None))
+    return ds, dstore, knn, scorer, info
+
+
+def run_evaluate(model, ds, dstore, knn, scorer, cfg, dev, rank=0, world=1):
+    from gnnlm_b200.eval_lm import evaluate
+    return evaluate(model, ds, dstore, scorer, knn_dstore=knn, temperature=cfg["temp"], max_sentences=cfg["B"], device=dev,
+                    rank=rank, world_size=world, cuda_graph=True)
+
+
+def tmp_root(tag):
+    import tempfile
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    return tempfile.mkdtemp(prefix=f"gnnlm_bench_{tag}_", dir=base)
+
+
+def run_strong(args, world, rank, dev, dist, math):
+    """Strong scaling through the product API: ONE corpus of --strong-blocks blocks + a ragged tail (not divisible by 2 / 4 / 8),
+    every rank holds the whole data directory and the replicated datastore, evaluates its contiguous block range
+    (eval_lm.shard_range) and joins the single NCCL all-reduce.  Timed: evaluate() on every rank between two barriers, max
+    over ranks.  The combined score_sum must not depend on N."""
+    import shutil
+    from gnnlm_b200 import synth
+    cfg = dict(synth.CONFIGS[args.config])
+    cfg["n_d"] = args.n_datastore or min(cfg["n_d"], 1 << 24)
+    model = synth.make_model(cfg).to(dev).set_math(math)
+    root = tmp_root(f"strong_r{rank}")
+    try:
+        ds, dstore, knn, scorer, info = build_eval(cfg, model, dev, math, root, args.strong_blocks, tail=1000, seed=0)
+        run_evaluate(model, ds, dstore, knn, scorer, cfg, dev, rank, world)            # warm-up pass (graph capture, weight preparation)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        res = run_evaluate(model, ds, dstore, knn, scorer, cfg, dev, rank, world)
+        torch.cuda.synchronize(dev)
+        sec = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        sec = float(sec.item())
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    line = {"metric": "eval tokens/s (HGT+kNN-LM fwd)", "value": res["count"] / sec, "unit": "tokens/s", "n_gpus": world,
+            "steps": 1, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": math, "data": "synthetic", "impl": "ours",
+            "config": dict(bench_config(args.config, world, "strong"), n_datastore=cfg["n_d"], math=math,
+                           corpus=f"{info['n_blocks']} blocks = {info['n_tokens']} tokens ({args.strong_blocks} x {cfg['L']} + a "
+                                  f"1000-token tail), reference-layout data directory in tmpfs, eval_lm.evaluate(cuda_graph=True)"),
+            "score_sum": repr(res["score_sum"]), "count": res["count"], "ppl": res["ppl"],
+            "blocks_this_rank": list(__import__("gnnlm_b200").eval_lm.shard_range(len(ds), rank, world)),
+            "seconds_max_over_ranks": sec}
+    if rank == 0:
+        print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -187,6 +297,11 @@ def main():
     math = args.math
     if math == "auto":
         math = "f16f8" if lib.gnnlm_has_tcgen05() else "fp32"      # fp32-parity mode with the fewest tensor cycles
+    if args.scaling == "strong":
+        run_strong(args, world, rank, dev, dist, math)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     cfg = dict(synth.CONFIGS[args.config])
     if args.n_datastore:
         cfg["n_d"] = args.n_datastore
@@ -260,12 +375,23 @@ def main():
     for i in range(args.steps):
         eager(i)
     torch.cuda.synchronize(dev)
-    per = {}
-    for name, tag, a, b in L.TIMING:
-        key = name.replace("gnnlm_", "") + (f":{tag}" if tag else "")
-        d = per.setdefault(key, [0.0, 0])
-        d[0] += a.elapsed_time(b)
-        d[1] += 1
+    g = synth.build_token_graph(dev_batches[0]["nbr"], tables["n_d"], cfg["c"], cfg["c"], reach=cfg["NL"] - 1)
+    n_ntgt, n_valid = g.counts()
+    live = {g.node_cap: n_ntgt, T * cfg["k"]: n_valid}              # capacity-sized launches -> live rows of batch 0
+    per, gemm = {}, {}
+    for name, tag, a, b, work in L.TIMING:
+        base = name.replace("gnnlm_", "").replace("_q8", "").replace("_hiq8", "").replace("_presplit", "")
+        key = base + (f":{tag}" if tag else "")
+        dt = a.elapsed_time(b)
+        d_ = per.setdefault(key, [0.0, 0])
+        d_[0] += dt
+        d_[1] += 1
+        if work is not None and base in ("linear", "linear_f16f8", "linear_lse"):
+            M_, N_, K_ = work
+            w_ = gemm.setdefault(base, [0.0, 0.0, 0])
+            w_[0] += dt
+            w_[1] += 2.0 * live.get(M_, M_) * N_ * K_
+            w_[2] += 1
     L.TIMING = None
     step_ms_instr = sum(v[0] for v in per.values()) / args.steps
     kernels = {k: {"ms_per_launch": v[0] / v[1], "launches_per_step": v[1] / args.steps,
@@ -276,41 +402,44 @@ def main():
     if os.path.exists(pk):
         peaks = json.load(open(pk))
     hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
-    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    tf_peak, tf_src = (peaks["bf16_tflops_sustained"], "measured (cuBLAS bf16, sustained)") if "bf16_tflops_sustained" in peaks \
+        else (1400.0, "fallback")
 
-    # edge-aggregation roofline (the metric's kernel): ntgt-intra-ntgt attention over all nodes.
-    # algorithmic bytes: K',V' rows once + Q + out + CSR
-    g = synth.build_token_graph(dev_batches[0]["nbr"], tables["n_d"], cfg["c"], cfg["c"], reach=cfg["NL"] - 1)
-    n_ntgt, n_valid = g.counts()
-    d, s = cfg["d"], (2 if math == "bf16" else 4)          # bytes per activation element (bf16 mode: Q | K' | V' and outputs in bf16)
+    # ---- roofline of the DOMINANT kernel: the projection GEMM family of the mode (share of the step in `share_of_step`)
+    passes = {"tf32x3": 3, "f16x3": 3, "f16f8": 2, "fp32": 1, "tf32": 1, "bf16": 1}[math]
+    fam = max(gemm, key=lambda k_: gemm[k_][0]) if gemm else None
     roof = None
-    for key in ("hgt_cluster_attn:nn_full", "hgt_edge_attn:nn_full", "hgt_cluster_attn:nn_centre", "hgt_edge_attn:nn_centre",
-                "hgt_edge_attn:inter"):
-        if key in kernels:
-            if key.endswith("nn_full"):
-                E = 3 * n_ntgt - 2 * n_valid
-                alg = n_ntgt * 2 * d * s + n_ntgt * d * s + n_ntgt * d * s + E * 4 + (n_ntgt + 1) * 4
-            elif key.endswith("nn_centre"):
-                E = 3 * n_valid
-                alg = min(n_ntgt, 3 * n_valid) * 2 * d * s + n_valid * d * s + n_valid * d * s + E * 4 + 2 * n_valid * 4
-            else:
-                alg = n_valid * 2 * d * s + T * d * s + T * d * 4 + (T + 1) * 4
-            ach = alg / (kernels[key]["ms_per_launch"] * 1e-3) / 1e9
-            roof = {"kernel": key, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "peak_source": hbm_src,
-                    "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic(key, cfg), "algorithmic_bytes": alg,
-                    "nominal_peak": 7700.0, "frac_of_nominal": ach / 7700.0,
-                    "peak_note": "peak = driver-measured copy bandwidth (1:1 read:write); this kernel reads 3 bytes per "
-                                 "byte written and can exceed it -- nominal HBM3e is 7.7 TB/s",
-                    "ms_per_launch": kernels[key]["ms_per_launch"], "share_of_step": kernels[key]["share"]}
-            break
+    if fam is not None:
+        ms_f, flops_f, n_f = gemm[fam]
+        useful = flops_f / (ms_f * 1e-3) / 1e12
+        kname = {"linear_f16f8": "gemm_f16f8_kernel", "linear": "gemm_f16s_kernel<0> (3xFP16)" if math in ("f16x3", "f16f8")
+                 else "gnnlm_linear"}.get(fam, fam)
+        ncu = committed_ncu(kname.split(" ")[0])
+        roof = {"kernel": kname, "bound": "tensor", "achieved": useful, "unit": "TFLOP/s", "peak": tf_peak, "peak_source": tf_src,
+                "frac": useful / tf_peak, "achieved_useful": useful, "passes": passes if fam != "linear" or math != "f16f8" else 3,
+                "launches_per_step": n_f / args.steps, "ms_per_step": ms_f / args.steps, "share_of_step": ms_f / args.steps / step_ms_instr,
+                "algorithmic_flops_per_step": flops_f / args.steps,
+                "note": "achieved = useful flops (2 M N K over the live rows) / device time of every launch of the kernel in the "
+                        "step; achieved_executed counts the tensor-pass equivalents the parity arithmetic issues (fp16 main "
+                        "product = 1, the two FP8 correction products = 0.5 each; 3xFP16 = 3)",
+                "traffic": None if ncu is None else ncu.get("dram_bytes"),
+                "traffic_source": None if ncu is None else f"committed ncu capture ({ncu['file']}), largest launch; not measured by this run"}
+        roof["achieved_executed"] = useful * roof["passes"]
+        roof["frac_executed"] = roof["achieved_executed"] / tf_peak
+
+    # ---- edge-aggregation kernels (the metric's second half): algorithmic bytes / device time, vs the HBM peak
+    d, s = cfg["d"], (2 if math == "bf16" else 4)          # bytes per activation element (bf16 mode: Q | K' | V' and outputs in bf16)
+    out_b = {"f16f8": 3}.get(math, s)                       # f16f8: cluster attention writes fp16 hi + 2 companion bytes per element
+
     def _edge_bytes(key):
         if key.endswith("nn_full"):
-            return n_ntgt * 2 * d * s + n_ntgt * d * s + n_ntgt * d * s + (3 * n_ntgt - 2 * n_valid) * 4 + (n_ntgt + 1) * 4
+            return n_ntgt * 2 * d * s + n_ntgt * d * s + n_ntgt * d * out_b + (3 * n_ntgt - 2 * n_valid) * 4 + (n_ntgt + 1) * 4
         if key.endswith("nn_centre"):
-            return min(n_ntgt, 3 * n_valid) * 2 * d * s + n_valid * d * s + n_valid * d * s + 3 * n_valid * 4 + 2 * n_valid * 4
+            return min(n_ntgt, 3 * n_valid) * 2 * d * s + n_valid * d * s + n_valid * d * out_b + 3 * n_valid * 4 + 2 * n_valid * 4
         return n_valid * 2 * d * s + T * d * s + T * d * 4 + (T + 1) * 4
     edge_all = {key: {"GB/s": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9,
-                      "frac": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
+                      "frac": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak,
+                      "algorithmic_bytes": _edge_bytes(key), "ms_per_launch": kv["ms_per_launch"], "share_of_step": kv["share"]}
                 for key, kv in kernels.items() if key.startswith(("hgt_cluster_attn", "hgt_edge_attn"))}
     if "hgt_inter_fused:inter_fused" in kernels:
         # token-side form of the inter edges (inter_attn.cu): centre rows once + H transformed queries in + H weighted row sums out
@@ -318,25 +447,29 @@ def main():
         ib = n_valid * d * s + T * Hh * d * 4 + T * Hh * d * 4 + T * d * 4 + (T + 1) * 4
         kv = kernels["hgt_inter_fused:inter_fused"]
         edge_all["hgt_inter_fused:inter"] = {"GB/s": ib / (kv["ms_per_launch"] * 1e-3) / 1e9,
-                                             "frac": ib / (kv["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak,
-                                             "note": "token-side form: replaces the K'|V' projection of every centre (2 d^2 MACs each); latency-bound "
-                                                     "per 16-row tile (two block barriers), one persistent CTA per SM"}
-    pq_key = next((k_ for k_ in kernels if k_.startswith("pq_gather_decode")), "pq_gather_decode")
-    if pq_key in kernels:
-        pq_bytes = n_ntgt * (cfg["M"] + 8 + d * s)
-        edge_all["pq_gather_decode"] = {"GB/s": pq_bytes / (kernels[pq_key]["ms_per_launch"] * 1e-3) / 1e9,
-                            "frac": pq_bytes / (kernels[pq_key]["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak}
-    # dominant dense kernel: the Q|K'|V' projection of all ntgt nodes
-    gemm_roof = None
-    gk = f"linear:linear[{3 * d}x{d}]"
-    if gk in kernels:
-        # launched for ntgt (n_ntgt rows) and tgt (T rows) -- take the per-step totals
-        flops = 2.0 * (n_ntgt * (cfg["NL"] > 2) + cfg["NL"] * T) * 3 * d * d
-        tot_ms = kernels[gk]["ms_per_launch"] * kernels[gk]["launches_per_step"]
-        passes = {"tf32x3": 3, "f16x3": 3, "f16f8": 2, "fp32": 1, "tf32": 1, "bf16": 1}[math]
-        gemm_roof = {"kernel": gk, "bound": "tensor", "achieved": flops / (tot_ms * 1e-3) / 1e12, "unit": "TFLOP/s",
-                     "peak": tf_peak, "peak_note": "measured cuBLAS bf16 sustained; tf32 dense is half of it, "
-                                                   "3-pass split another third", "passes": passes}
+                                             "frac": ib / (kv["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": ib,
+                                             "ms_per_launch": kv["ms_per_launch"], "share_of_step": kv["share"],
+                                             "note": "token-side form: replaces the K'|V' projection of every centre (2 d^2 MACs each)"}
+    pq_keys = [k_ for k_ in kernels if k_.startswith("pq_gather_decode")]
+    if pq_keys:
+        pq_ms = sum(kernels[k_]["ms_per_launch"] * kernels[k_]["launches_per_step"] for k_ in pq_keys)
+        pq_bytes = n_ntgt * (cfg["M"] + 8 + d * s) + (n_valid * (cfg["M"] + 8 + d * s) if math == "f16f8" else 0)
+        edge_all["pq_gather_decode"] = {"GB/s": pq_bytes / (pq_ms * 1e-3) / 1e9, "frac": pq_bytes / (pq_ms * 1e-3) / 1e9 / hbm_peak,
+                                        "algorithmic_bytes": pq_bytes, "ms_per_step": pq_ms}
+    roof_edge = None
+    for key in ("hgt_cluster_attn:nn_full", "hgt_edge_attn:nn_full", "hgt_cluster_attn:nn_centre", "hgt_edge_attn:nn_centre"):
+        if key in edge_all:
+            e = edge_all[key]
+            kn = "cluster_attn_kernel<float, __half, 4, 3, 32>" if key == "hgt_cluster_attn:nn_full" else key
+            ncu = committed_ncu(kn) if (cfg["L"], cfg["k"], cfg["c"]) == (3072, 32, 1) else None
+            roof_edge = {"kernel": key, "bound": "hbm", "achieved": e["GB/s"], "peak": hbm_peak, "peak_source": hbm_src, "unit": "GB/s",
+                         "frac": e["frac"], "algorithmic_bytes": e["algorithmic_bytes"], "nominal_peak": 7700.0,
+                         "frac_of_nominal": e["GB/s"] / 7700.0, "ms_per_launch": e["ms_per_launch"], "share_of_step": e["share_of_step"],
+                         "peak_note": "peak = driver-measured copy bandwidth (1:1 read:write); this kernel reads 3 bytes per "
+                                      "byte written and can exceed it -- nominal HBM3e is 7.7 TB/s",
+                         "traffic": None if ncu is None else ncu.get("dram_bytes"),
+                         "traffic_source": None if ncu is None else f"committed ncu capture ({ncu['file']}); not measured by this run"}
+            break
 
     tokens_all = world * args.steps * T
     line = {
@@ -347,17 +480,39 @@ def main():
                                                            "f16f8": "f32 (fp16 main product + FP8 e4m3 correction products, fp32 accumulate)",
                                                            "tf32": "tf32", "bf16": "bf16"}[math],
         "data": "synthetic", "impl": "ours",
-        "config": {"workload": workload_name(args.config), "math": math, "n_datastore": tables["n_d"],
-                   "cuda_graph": bool(args.cuda_graph), "graph_builder": "deprecated (dedup)" if args.deprecated else "new",
-                   "parallelism": f"dp{world} (contiguous block shards, replicated datastore, one 16 B all-reduce)",
-                   "l2_policy": "inputs larger than L2 (datastore + activations are GBs); 4 distinct batches rotated",
-                   "n_ntgt": n_ntgt, "n_valid_neighbours": n_valid},
+        "config": bench_config(args.config, world),
+        "run": {"math": math, "n_datastore": tables["n_d"], "cuda_graph": bool(args.cuda_graph),
+                "graph_builder": "deprecated (dedup)" if args.deprecated else "new", "n_ntgt": n_ntgt, "n_valid_neighbours": n_valid},
         "e2e": {"value": tokens_all / (ms_e2e * 1e-3), "unit": "tokens/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for v in host_batches[0].values())),
-                "d2h_bytes_per_step": 16},
-        "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_gemm": gemm_roof, "hbm_kernels": edge_all,
+                "d2h_bytes_per_step": 16,
+                "api": "synth.Runner.run_host: pinned host inputs of one block per step, double-buffered H2D, scoring step, 16 B read-back"},
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_edge": roof_edge, "hbm_kernels": edge_all,
         "kernels": kernels, "score_sum": score_sum, "count": count,
     }
+    # ---- the public call end to end: eval_lm.evaluate() over a reference-layout data directory (rank 0, N = 1 only)
+    if world == 1 and args.eval_blocks > 0:
+        import shutil
+        ecfg = dict(cfg, n_d=min(cfg["n_d"], 1 << 24))
+        root = tmp_root("eval")
+        try:
+            emodel = runner.model                                   # same weights, already prepared
+            ds, dstore_e, knn_e, scorer_e, info = build_eval(ecfg, emodel, dev, math, root, args.eval_blocks, tail=0, seed=3)
+            run_evaluate(emodel, ds, dstore_e, knn_e, scorer_e, ecfg, dev)           # warm-up pass: page cache, graph capture
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            res = run_evaluate(emodel, ds, dstore_e, knn_e, scorer_e, ecfg, dev)
+            torch.cuda.synchronize(dev)
+            sec = time.perf_counter() - t0
+            line["e2e_evaluate"] = {
+                "value": res["count"] / sec, "unit": "tokens/s", "seconds": sec, "blocks": info["n_blocks"], "tokens": int(res["count"]),
+                "ppl": res["ppl"], "loss_base2": res["loss_base2"], "n_datastore": ecfg["n_d"],
+                "api": "eval_lm.evaluate(cuda_graph=True) over formats.load_graph_lm_dataset(<tmpfs data dir>): mmap slicing "
+                       "(dataset.__getitem__), collater, pinned staging + H2D, graph assembly .. NLL, one read-back at the end; "
+                       "wall clock around the call"}
+            del ds, dstore_e, knn_e
+        finally:
+            shutil.rmtree(root, ignore_errors=True)
     # secondary arithmetic modes (same workload, resident inputs, short timed loop) -- information only; the
     # headline stays the fp32-parity mode
     other = {}
@@ -383,8 +538,7 @@ def main():
         sec, _ = time_oracle((ccfg, cmodel, cdata), 2, 1)       # ~10 s of CPU work: one warm-up + two timed passes
         line["cpu_baseline"] = {
             "value": ccfg["L"] / sec, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"CPU oracle (torch fp32, {torch.get_num_threads()} threads), 1 block of {ccfg['L']} tokens at the "
-                      f"{args.config} shape, datastore 2^22 rows, mean of 2 timed passes after 1 warm-up, {sec:.1f} s per pass"}
+            "sample": sample_note(ccfg, args) + f"; mean of 2 timed passes after 1 warm-up, {sec:.1f} s per pass"}
     if rank == 0:
         print(json.dumps(line))
     if dist is not None:

@@ -79,7 +79,7 @@ SIGNATURES = {
 _lib = None
 launches = 0          # number of CUDA kernels launched through the C ABI (bench.py's gpu_launches)
 KERNELS_PER_CALL = {"gnnlm_graph_count": 3, "gnnlm_knn_full_prob": 2, "gnnlm_graph_dedup": 12}   # everything else launches exactly one
-TIMING = None         # when a list: (name, tag, start_event, end_event) per call (bench.py per-kernel pass)
+TIMING = None         # when a list: (name, tag, start_event, end_event, work) per call (bench.py per-kernel pass)
 
 
 class GnnlmError(RuntimeError):
@@ -117,7 +117,8 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name, *args, tag=None):
+def call(name, *args, tag=None, work=None):
+    """`work`: (M_cap, N, K) of a GEMM call, recorded with its timing for the roofline of bench.py."""
     global launches
     lib = load()
     if TIMING is not None:
@@ -128,6 +129,6 @@ def call(name, *args, tag=None):
         raise GnnlmError(f"{name} failed ({rc}): {lib.gnnlm_last_error().decode()}")
     if TIMING is not None:
         e1.record()
-        TIMING.append((name, tag, e0, e1))
+        TIMING.append((name, tag, e0, e1, work))
     launches += KERNELS_PER_CALL.get(name, 1)
     return rc

@@ -67,6 +67,23 @@ class MMapIndexedDataset:
         return np.frombuffer(self._bin, dtype=self.dtype, count=total, offset=0)
 
 
+def write_mmap_indexed(prefix: str, sentences, dtype) -> None:
+    """Writer side of the same storage -- what MMapIndexedDatasetBuilder.add_item / finalize produce
+    (indexed_dataset.py:496-527 with the index layout of :357-393): `prefix.bin` = the sentences back to back in `dtype`,
+    `prefix.idx` = magic, version, dtype code, count, int32 sizes, int64 byte pointers.  Byte-identical to files written by the
+    reference's builder (tests/test_formats.py)."""
+    code = {np.dtype(v): k for k, v in _DTYPES.items() if k != 7}[np.dtype(dtype)]
+    sizes = np.array([len(s_) for s_ in sentences], dtype=np.int32)
+    with open(prefix + ".bin", "wb") as f:
+        for s_ in sentences:
+            f.write(np.asarray(s_, dtype=dtype).tobytes(order="C"))
+    pointers = np.concatenate([[0], np.cumsum(sizes[:-1].astype(np.int64) * np.dtype(dtype).itemsize)]).astype(np.int64)
+    with open(prefix + ".idx", "wb") as f:
+        f.write(_HDR_MAGIC + struct.pack("<Q", 1) + struct.pack("<B", code) + struct.pack("<Q", len(sizes)))
+        f.write(sizes.tobytes(order="C"))
+        f.write(pointers.tobytes(order="C"))
+
+
 class Dictionary:
     """dict.txt reader with the reference's numbering: <s>=0, <pad>=1, </s>=2, <unk>=3, then the file's symbols in
     order (dictionary.py:18-39,183-228).  A line is '<symbol> <count>', split at the LAST space."""

@@ -97,7 +97,7 @@ def linear(A, W: torch.Tensor, bias: Optional[torch.Tensor] = None, *, W_lo: Opt
         r_ptr, r_code, ldr, n_r = _mat(residual)
         assert n_r == N
     L.call("gnnlm_linear", a_ptr, a_code, lda, L.ptr(W), L.ptr(W_lo), float(w_scale), W.stride(0), L.ptr(bias), r_ptr, r_code,
-           ldr, c_ptr, c_code, ldc, M, _dev_count(m_dev), N, K, math, L.stream_ptr(), tag=tag or f"linear[{N}x{K}]")
+           ldr, c_ptr, c_code, ldc, M, _dev_count(m_dev), N, K, math, L.stream_ptr(), tag=tag or f"linear[{N}x{K}]", work=(M, N, K))
     return out
 
 
@@ -139,7 +139,7 @@ def linear_f16f8(A1: Split, W_hi, W8, bias=None, *, A2: Optional[Split] = None, 
     a2 = (None, None, 0, 0) if A2 is None else (L.ptr(A2.data), L.ptr(A2.q8), A2.data.stride(0), A2.q8.stride(0))
     L.call("gnnlm_linear_f16f8", L.ptr(A1.data), L.ptr(A1.q8), A1.data.stride(0), A1.q8.stride(0), K1, a2[0], a2[1], a2[2], a2[3],
            K2, L.ptr(W_hi), L.ptr(W8), float(w_scale), W_hi.stride(0), W8.stride(0), L.ptr(bias), c_ptr, c_code, ldc, M,
-           _dev_count(m_dev), N, L.stream_ptr(), tag=tag or f"linear_f16f8[{N}x{K1 + K2}]")
+           _dev_count(m_dev), N, L.stream_ptr(), tag=tag or f"linear_f16f8[{N}x{K1 + K2}]", work=(M, N, K1 + K2))
     return out
 
 
@@ -155,7 +155,7 @@ def linear_lse(A, W, pick, *, W_lo=None, m_dev=None, math=L.MATH_FP32_SIMT, w_sc
     psum = torch.empty((M, nt), device=dev, dtype=torch.float32)
     picked = torch.zeros((M,), device=dev, dtype=torch.float32)
     L.call("gnnlm_linear_lse", a_ptr, a_code, lda, L.ptr(W), L.ptr(W_lo), float(w_scale), W.stride(0), L.ptr(pick), L.ptr(pmax),
-           L.ptr(psum), L.ptr(picked), M, _dev_count(m_dev), N, K, math, L.stream_ptr())
+           L.ptr(psum), L.ptr(picked), M, _dev_count(m_dev), N, K, math, L.stream_ptr(), work=(M, N, K))
     return pmax, psum, picked, nt
 
 

@@ -123,6 +123,48 @@ def to_device(data: dict, device) -> dict:
     return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in data.items()}
 
 
+def write_data_dir(root: str, cfg: dict, n_blocks: int, tail_tokens: int = 0, seed: int = 0, split: str = "valid",
+                   device="cpu") -> dict:
+    """A synthetic data directory in the reference's layout (knn/path_utils.py:13-41, language_modeling.py:266-298):
+    dict.txt, {split}.bin/.idx, {split}_dstore/{info.json, keys.npy, neighbors.mmap.{k}, neighbors.mmap.{k_nn}, dists.{k_nn}},
+    train_dstore/{info.json, vals.npy, quantized-keys.npy} -- n_blocks blocks of cfg['L'] tokens (+ a ragged tail).  The kNN-LM
+    neighbour distances are not a reference file (find_knn.py:65-66 drops them): they go to `dists.{k_nn}` for
+    eval_lm's --knn-dists-file.  Arrays are generated on `device` and written from the host."""
+    import json
+    import os
+    from .formats import write_mmap_indexed
+    c = SimpleNamespace(**cfg)
+    n_tok = n_blocks * c.L + tail_tokens
+    g = torch.Generator(device=device).manual_seed(seed + 777)
+    os.makedirs(os.path.join(root, f"{split}_dstore"), exist_ok=True)
+    os.makedirs(os.path.join(root, "train_dstore"), exist_ok=True)
+    tables = make_tables(cfg, seed, device=device)
+    host = lambda t: t.cpu().numpy()
+    tokens = host(torch.randint(4, c.V, (n_tok,), generator=g, device=device, dtype=torch.int64))
+    tokens[c.L - 1::c.L] = 2                                             # an eos per block keeps sentences = blocks
+    tokens[-1] = 2
+    bounds = list(range(0, n_tok, c.L)) + [n_tok]
+    tdt = np.uint16 if c.V < 65500 else np.int32                       # indexed_dataset.py:29-33 (__best_fitting_dtype)
+    write_mmap_indexed(os.path.join(root, split), [tokens[a:b] for a, b in zip(bounds[:-1], bounds[1:])], tdt)
+    with open(os.path.join(root, "dict.txt"), "w") as f:
+        f.write("".join(f"w{i} {c.V - i}\n" for i in range(4, c.V)))
+    nbr = torch.randint(c.c, c.n_d - c.c, (n_tok, c.k), generator=g, device=device, dtype=torch.int64)
+    nbr[torch.rand((n_tok, c.k), generator=g, device=device) < 0.01] = -1
+    host(nbr).tofile(os.path.join(root, f"{split}_dstore", f"neighbors.mmap.{c.k}"))
+    host(torch.randn((n_tok, c.d), generator=g, device=device).half()).tofile(os.path.join(root, f"{split}_dstore", "keys.npy"))
+    ids = torch.randint(0, c.n_d, (n_tok, c.k_nn), generator=g, device=device, dtype=torch.int64)
+    host(ids).tofile(os.path.join(root, f"{split}_dstore", f"neighbors.mmap.{c.k_nn}"))
+    host(torch.randn((n_tok, c.k_nn), generator=g, device=device)).tofile(os.path.join(root, f"{split}_dstore", f"dists.{c.k_nn}"))
+    info = {"hidden_size": c.d, "vocab_size": c.V, "dstore_fp16": True, "val_size": 1}
+    json.dump(dict(info, dstore_size=n_tok), open(os.path.join(root, f"{split}_dstore", "info.json"), "w"))
+    json.dump(dict(info, dstore_size=c.n_d), open(os.path.join(root, "train_dstore", "info.json"), "w"))
+    vdt = np.int16 if c.V < 2 ** 15 else np.int32                       # language_modeling.py:272 (dstore_fp16)
+    host(tables["vals"]).astype(vdt).reshape(-1, 1).tofile(os.path.join(root, "train_dstore", "vals.npy"))
+    np.save(os.path.join(root, "train_dstore", "quantized-keys.npy"), host(tables["codes"]))
+    return {"n_tokens": n_tok, "n_blocks": len(bounds) - 1, "tables": tables,
+            "dists_file": os.path.join(root, f"{split}_dstore", f"dists.{c.k_nn}")}
+
+
 class Runner:
     """The call a user makes per batch, on device-resident tables: graph assembly -> PQ decode -> HGT ->
     log-probs -> kNN mix -> NLL accumulation.  `step(host_batch)` is the e2e variant (pinned host

@@ -36,8 +36,8 @@ for k in KS:
             ms = e0.elapsed_time(e1) / n_it
             L.TIMING = []
             r.step_resident(batch); torch.cuda.synchronize()
-            t_nn = sum(a.elapsed_time(b) for n, tag, a, b in L.TIMING if tag == 'nn_full')
-            t_nc = sum(a.elapsed_time(b) for n, tag, a, b in L.TIMING if tag == 'nn_centre')
+            t_nn = sum(a.elapsed_time(b) for n, tag, a, b, _w in L.TIMING if tag == 'nn_full')
+            t_nc = sum(a.elapsed_time(b) for n, tag, a, b, _w in L.TIMING if tag == 'nn_centre')
             L.TIMING = None
             g = synth.build_token_graph(batch['nbr'], tables['n_d'], c_eff, c_eff)
             n_ntgt, n_valid = g.counts()

@@ -12,20 +12,7 @@ import pytest
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def write_mmap_indexed(prefix, sentences, dtype):
-    """Test-side writer of {prefix}.bin/.idx (the layout of indexed_dataset.py:357-393), used to lay out data directories on
-    the GPU box where the reference's builder does not exist; checked byte for byte against the reference-written fixtures."""
-    import struct
-    code = {np.uint8: 1, np.int8: 2, np.int16: 3, np.int32: 4, np.int64: 5, np.uint16: 8}[dtype]
-    sizes = np.array([len(s) for s in sentences], dtype=np.int32)
-    with open(prefix + ".bin", "wb") as f:
-        for s in sentences:
-            f.write(np.asarray(s, dtype=dtype).tobytes(order="C"))
-    pointers = np.concatenate([[0], np.cumsum(sizes[:-1].astype(np.int64) * np.dtype(dtype).itemsize)]).astype(np.int64)
-    with open(prefix + ".idx", "wb") as f:
-        f.write(b"MMIDIDX\x00\x00" + struct.pack("<Q", 1) + struct.pack("<B", code) + struct.pack("<Q", len(sizes)))
-        f.write(sizes.tobytes(order="C"))
-        f.write(pointers.tobytes(order="C"))
+from gnnlm_b200.formats import write_mmap_indexed      # writer of {prefix}.bin/.idx, checked byte for byte below
 
 
 @pytest.mark.parametrize("tag,dtype", [("uint16", np.uint16), ("int32", np.int32)])
