@@ -500,14 +500,18 @@ constexpr int IM_TAB = 512;          // tokens per CTA and launch whose edge ran
 // as 2-byte stores (8 consecutive lanes cover 16 contiguous bytes of a hi or lo row).
 // BF16: centre rows are bf16 (MATH_BF16 activations) -- one A operand, q~ and P split into bf16 hi / lo (two passes, no scaling:
 // bf16 has the fp32 exponent range); otherwise split fp16 rows, three passes.
-template <int KS, bool BF16>
-__global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* __restrict__ qt, int64_t q_hs,   // [8, T, d], head stride
+// NW warps per CTA (8 or 16): with 16, a warp owns d / 16 columns -- half the tensor work and accumulator registers per warp, twice
+// the warps per scheduler to hide the per-tile dependency chain (ldmatrix -> mma -> barrier -> softmax -> mma).
+template <int KS, bool BF16, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) inter_mma_kernel(const float* __restrict__ qt, int64_t q_hs,   // [8, T, d], head stride
                                                                const void* __restrict__ hc_, int64_t ldh,
                                                                const int32_t* __restrict__ indptr, int64_t t0, int64_t n_tokens,
                                                                __half* __restrict__ a_out, int64_t a_hs, int64_t lda,
                                                                const float* __restrict__ bias_v, float out_scale,
                                                                float* __restrict__ t_agg, int64_t ldt) {
-  constexpr int H = 8, NW = IA_THREADS / 32, D = 128 * KS;
+  constexpr int H = 8, D = 128 * KS, NT = NW * 32;
+  constexpr int KW = KS * 8 / NW;                          // 16-column k-steps of a warp
+  static_assert(KW * NW == KS * 8, "d / 16 must divide by the number of warps");
   constexpr int ROWB = BF16 ? 2 * D : 4 * D;               // bytes of one centre row (bf16, or fp16 hi | lo)
   constexpr int RS = ROWB + 16;                            // row stride in shared memory (+ 16: conflict-free ldmatrix)
   const char* hc = reinterpret_cast<const char*>(hc_);
@@ -516,14 +520,15 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
   float* wsum = reinterpret_cast<float*>(rows + IM_STAGES * IM_ROWS * RS);   // [NW][16][8] per-warp partial scores
   float* isc_s = wsum + NW * IM_ROWS * H;                                // [NW][8] 1 / (power-of-two scale of the warp's q~ slice)
   int2* tab = reinterpret_cast<int2*>(isc_s + NW * H);                   // [IM_TAB] (first edge, degree) of this CTA's tokens
-  constexpr int OSW = KS * 16 + 4;                                       // staging row stride in floats
+  constexpr int OSW = KW * 16 + 4;                                       // staging row stride in floats
   float* ostage = reinterpret_cast<float*>(tab + IM_TAB);                // [NW][4][OSW] per-warp output staging
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, tq = lane & 3;
   const bool active = tid * 4 < D;                         // owner of 4 output columns (bias store)
-  const bool copier = tid * 16 < ROWB;                     // owner of 16 B chunk `tid` of every row
-  const int wcol0 = warp * KS * 16;                        // first of the warp's columns
+  const int chunk = tid & 255, rpar = tid >> 8;            // 16 B chunk of a row; rows rpar, rpar + NT / 256, ...
+  const bool copier = chunk * 16 < ROWB;
+  const int wcol0 = warp * KW * 16;                        // first of the warp's columns
   const int mi = lane >> 3, r8 = lane & 7;
   const int p1_off = (r8 + (mi & 1) * 8) * RS + (mi >> 1) * 16 + wcol0 * 2;     // A = X      (rows x columns)
   const int p2_off = (r8 + (mi >> 1) * 8) * RS + (mi & 1) * 16 + wcol0 * 2;     // A = X^T    (columns x rows), ldmatrix.trans
@@ -531,7 +536,7 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
   // edge ranges of this CTA's tokens (token j of the CTA = blockIdx.x + j gridDim.x): one strided read up front instead of a
   // dependent global load at every token switch (ncu: 12 % of the stall samples)
   const int n_mine = n_tokens > blockIdx.x ? (int)((n_tokens - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
-  for (int j = tid; j < n_mine; j += IA_THREADS) {
+  for (int j = tid; j < n_mine; j += NT) {
     const int64_t tok = blockIdx.x + (int64_t)j * gridDim.x;
     const int e0 = __ldg(indptr + tok);
     tab[j] = make_int2(e0, __ldg(indptr + tok + 1) - e0);
@@ -556,10 +561,10 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
   auto issue = [&](const Tile& it, int st) {               // cp.async of one tile; always exactly one commit
     if (it.j < n_mine && copier) {
       const int nr = (it.deg - it.r0) < IM_ROWS ? (it.deg - it.r0) : IM_ROWS;
-      char* dst = rows + st * IM_ROWS * RS + tid * 16;
-      const char* src = hc + (int64_t)(it.e0 + it.r0) * ldh * 2 + tid * 16;
+      char* dst = rows + st * IM_ROWS * RS + chunk * 16;
+      const char* src = hc + (int64_t)(it.e0 + it.r0) * ldh * 2 + chunk * 16;
 #pragma unroll
-      for (int r = 0; r < IM_ROWS; ++r) {
+      for (int r = rpar; r < IM_ROWS; r += NT / 256) {
         if (r < nr) cp_async16(dst + r * RS, src + (int64_t)r * ldh * 2);
         else *reinterpret_cast<uint4*>(dst + r * RS) = make_uint4(0u, 0u, 0u, 0u);       // rows past the token's last centre: finite
       }
@@ -567,12 +572,12 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
     cp_async_commit();
   };
   // this thread's B-fragment elements of q~ (head g, columns wcol0 + 16 ks + 2 tq + {0, 1, 8, 9}), raw fp32, loaded one token ahead
-  float2 qraw[KS][2];
+  float2 qraw[KW][2];
   auto load_q = [&](int j) {
     if (j < n_mine) {
       const float* qrow = qt + g * q_hs + (t0 + blockIdx.x + (int64_t)j * gridDim.x) * D + wcol0 + 2 * tq;
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
+      for (int ks = 0; ks < KW; ++ks) {
         qraw[ks][0] = __ldg(reinterpret_cast<const float2*>(qrow + ks * 16));
         qraw[ks][1] = __ldg(reinterpret_cast<const float2*>(qrow + ks * 16 + 8));
       }
@@ -586,10 +591,10 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
   issue(cur, 0);
   issue(n1, 1);
   Tile n2 = advance(n1);                                   // next tile to issue
-  uint32_t qh[KS][2], ql[KS][2];
-  float acc[KS][4];
+  uint32_t qh[KW][2], ql[KW][2];
+  float acc[KW][4];
   float m_run = -INFINITY, l_run = 0.f;                    // head g (replicated over tq and over the warps)
-  float isc[NW];                                           // 1 / scale of head g's q~ slice in every warp
+  float isc[NW > 8 ? 1 : NW];                              // 1 / scale of head g's q~ slice in every warp (NW > 8: read from shared memory)
   int stage = 0;
   while (cur.j < n_mine) {
     const bool first = cur.r0 == 0;
@@ -603,7 +608,7 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
       // q~ slice of this warp -> fp16 hi / lo B fragments, scaled per (warp, head) by a power of two (amax -> [4096, 8192])
       float am = 0.f;
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks)
+      for (int ks = 0; ks < KW; ++ks)
         am = fmaxf(fmaxf(am, fmaxf(fabsf(qraw[ks][0].x), fabsf(qraw[ks][0].y))), fmaxf(fabsf(qraw[ks][1].x), fabsf(qraw[ks][1].y)));
       am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 1));
       am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, 2));
@@ -611,7 +616,7 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
       if (!BF16 && am > 0.f && am < INFINITY) scale = exp2f(fminf(fmaxf(floorf(log2f(8192.f / am)), -100.f), 100.f));
       if (tq == 0) isc_s[warp * H + g] = 1.f / scale;
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
+      for (int ks = 0; ks < KW; ++ks) {
         if constexpr (BF16) {
           split2_bf16(qraw[ks][0].x, qraw[ks][0].y, qh[ks][0], ql[ks][0]);
           split2_bf16(qraw[ks][1].x, qraw[ks][1].y, qh[ks][1], ql[ks][1]);
@@ -630,7 +635,7 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
     {
       float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int ks = 0; ks < KS; ++ks) {
+      for (int ks = 0; ks < KW; ++ks) {
         uint32_t ah[4];
         ldsm_x4(ah, tile + p1_off + ks * 32);
         if constexpr (BF16) {
@@ -650,9 +655,11 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
     }
     __syncthreads();
     // ---- phase 1b (every warp): scores of head g at rows 2 tq + {0, 1, 8, 9}, online softmax, P fragments
-    if (first) {
+    if constexpr (NW <= 8) {
+      if (first) {
 #pragma unroll
-      for (int w = 0; w < NW; ++w) isc[w] = isc_s[w * H + g];
+        for (int w = 0; w < NW; ++w) isc[w] = isc_s[w * H + g];
+      }
     }
     float sc[4];
 #pragma unroll
@@ -660,7 +667,7 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
       const int row = 2 * tq + (j & 1) + (j >> 1) * 8;
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < NW; ++w) s = fmaf(wsum[(w * IM_ROWS + row) * H + g], isc[w], s);
+      for (int w = 0; w < NW; ++w) s = fmaf(wsum[(w * IM_ROWS + row) * H + g], NW <= 8 ? isc[NW <= 8 ? w : 0] : isc_s[w * H + g], s);
       sc[j] = row < nr ? s : -INFINITY;
     }
     float mx = fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3]));
@@ -683,7 +690,7 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
       const float cr0 = __shfl_sync(0xffffffffu, corr, 8 * tq), cr1 = __shfl_sync(0xffffffffu, corr, 8 * tq + 4);
       if (!first) {
 #pragma unroll
-        for (int mt = 0; mt < KS; ++mt) {
+        for (int mt = 0; mt < KW; ++mt) {
           acc[mt][0] *= cr0; acc[mt][1] *= cr1; acc[mt][2] *= cr0; acc[mt][3] *= cr1;
         }
       }
@@ -698,7 +705,7 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
         split2_f16(pj[2] * 1024.f, pj[3] * 1024.f, bh1, bl1);
       }
 #pragma unroll
-      for (int mt = 0; mt < KS; ++mt) {
+      for (int mt = 0; mt < KW; ++mt) {
         uint32_t ah[4];
         ldsm_x4_t(ah, tile + p2_off + mt * 32);
         if constexpr (BF16) {
@@ -726,16 +733,17 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
         __syncwarp();
         if ((tq >> 1) == half) {
 #pragma unroll
-          for (int mt = 0; mt < KS; ++mt) {
+          for (int mt = 0; mt < KW; ++mt) {
             float* o = stg + (2 * (tq & 1)) * OSW + mt * 16 + g;
             o[0] = acc[mt][0] * i0; o[OSW] = acc[mt][1] * i1; o[8] = acc[mt][2] * i0; o[OSW + 8] = acc[mt][3] * i1;
           }
         }
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < (4 * KS * 16) / 128; ++i) {                  // 4 heads x 16 KS columns, 4 per lane and step
+        for (int i = 0; i < (4 * KW * 16 + 127) / 128; ++i) {            // 4 heads x 16 KW columns, 4 per lane and step
           const int idx = i * 128 + lane * 4;
-          const int hh = idx / (KS * 16), cc = idx % (KS * 16);
+          if (idx >= 4 * KW * 16) break;
+          const int hh = idx / (KW * 16), cc = idx % (KW * 16);
           const float4 v = *reinterpret_cast<const float4*>(stg + hh * OSW + cc);
           uint2 hi, lo;
           split4_f16(v.x, v.y, v.z, v.w, hi, lo);
@@ -758,16 +766,16 @@ __global__ void __launch_bounds__(IA_THREADS, 1) inter_mma_kernel(const float* _
   cp_async_wait_all();
 }
 
-template <int KS, bool BF16>
+template <int KS, bool BF16, int NW>
 static int32_t launch_inter_mma(const float* qt, int64_t q_hs, const void* hc, int64_t ldh, const int32_t* indptr, int64_t t0,
                                 int64_t n_tokens, void* a_out, int64_t a_hs, int64_t lda, const float* bias_v, float out_scale,
                                 float* t_agg, int64_t ldt, int n_sm, cudaStream_t st) {
-  constexpr int D = 128 * KS;
-  const size_t smem = (size_t)IM_STAGES * IM_ROWS * ((BF16 ? 2 : 4) * D + 16) + ((size_t)8 * IM_ROWS * 8 + 8 * 8) * sizeof(float) +
-                      (size_t)IM_TAB * sizeof(int2) + (size_t)8 * 4 * (KS * 16 + 4) * sizeof(float);
+  constexpr int D = 128 * KS, KW = KS * 8 / NW;
+  const size_t smem = (size_t)IM_STAGES * IM_ROWS * ((BF16 ? 2 : 4) * D + 16) + ((size_t)NW * IM_ROWS * 8 + NW * 8) * sizeof(float) +
+                      (size_t)IM_TAB * sizeof(int2) + (size_t)NW * 4 * (KW * 16 + 4) * sizeof(float);
   static bool configured = false;
   if (!configured) {
-    GNNLM_CUDA(cudaFuncSetAttribute(inter_mma_kernel<KS, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GNNLM_CUDA(cudaFuncSetAttribute(inter_mma_kernel<KS, BF16, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
   // persistent: one CTA per SM; a launch covers at most IM_TAB tokens per CTA (their edge ranges are staged in shared memory)
@@ -775,8 +783,8 @@ static int32_t launch_inter_mma(const float* qt, int64_t q_hs, const void* hc, i
   for (int64_t b0 = 0; b0 < n_tokens; b0 += per_launch) {
     const int64_t n = n_tokens - b0 < per_launch ? n_tokens - b0 : per_launch;
     const int64_t grid = n < n_sm ? n : n_sm;
-    inter_mma_kernel<KS, BF16><<<(unsigned)grid, IA_THREADS, smem, st>>>(qt, q_hs, hc, ldh, indptr + b0, t0 + b0, n, (__half*)a_out, a_hs,
-                                                                        lda, bias_v, out_scale, t_agg, ldt);
+    inter_mma_kernel<KS, BF16, NW><<<(unsigned)grid, NW * 32, smem, st>>>(qt, q_hs, hc, ldh, indptr + b0, t0 + b0, n, (__half*)a_out,
+                                                                         a_hs, lda, bias_v, out_scale, t_agg, ldt);
     GNNLM_LAUNCH_CHECK("gnnlm_hgt_inter_fused");
   }
   return 0;
@@ -801,9 +809,15 @@ static int32_t launch_inter(const float* qt, int64_t q_hs, const void* hc, int64
   }
   if constexpr (!std::is_same<InT, float>::value && H == 8) {
     if (force == 0 && ldh % 8 == 0 && d % 128 == 0) {
-#define GNNLM_IM(KS)                                                                                                          \
-  return launch_inter_mma<KS, std::is_same<InT, __nv_bfloat16>::value>(qt, q_hs, hc, ldh, indptr, t0, n_tokens, a_out, a_hs, lda, \
-                                                                       bias_v, out_scale, t_agg, ldt, n_sm, st)
+      // GNNLM_INTER_WARPS=16: the 16-warp form (A/B timing switch).  Measured on the Wiki103 shape (profiles/r2_inter_probe.log):
+      // 8 warps 156 us (3.93 TB/s), 16 warps 197 us -- the softmax every warp repeats and the wider barriers cost more than
+      // the extra warps hide, so 8 stays the default
+      static const int nw = [] { const char* e = getenv("GNNLM_INTER_WARPS"); return e && atoi(e) == 16 ? 16 : 8; }();
+#define GNNLM_IM(KS)                                                                                                              \
+  return nw == 8 ? launch_inter_mma<KS, std::is_same<InT, __nv_bfloat16>::value, 8>(qt, q_hs, hc, ldh, indptr, t0, n_tokens, a_out, a_hs, \
+                                                                                  lda, bias_v, out_scale, t_agg, ldt, n_sm, st)   \
+                 : launch_inter_mma<KS, std::is_same<InT, __nv_bfloat16>::value, 16>(qt, q_hs, hc, ldh, indptr, t0, n_tokens, a_out,      \
+                                                                                   a_hs, lda, bias_v, out_scale, t_agg, ldt, n_sm, st)
       switch (d / 128) {
         case 4: GNNLM_IM(4);
         case 6: GNNLM_IM(6);

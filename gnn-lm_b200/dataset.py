@@ -180,6 +180,55 @@ class GraphTokenBlockDataset:
                 batch[k] = st(k)
         return batch
 
+    # ---- fast host path of evaluate(): block slices copied ONCE, straight from the memmaps into reusable pinned batch buffers
+    def batch_spec(self, ids: List[int]):
+        """(name, shape, dtype) of every tensor the device step consumes for the equal-length blocks `ids` (see collate_into)."""
+        s, e = self.slice_indices[ids[0]]
+        cs = s if (self.context_window == 0 or ids[0] == 0) else max(0, s - self.context_window)
+        B, Lb = len(ids), e - cs
+        spec = [("nbr", (B, Lb, self.neighbor_offsets.shape[1]), torch.int64), ("positions", (B, Lb), torch.int64),
+                ("src_tokens", (B, Lb), torch.int64), ("target", (B, Lb), torch.int64), ("start_indices", (B,), torch.int32)]
+        if self.precompute_feats is not None:
+            spec.append(("feats", (B, Lb, self.precompute_feats.shape[1]), torch.from_numpy(np.zeros(0, self.precompute_feats.dtype)).dtype))
+        if self.knn_ids is not None:
+            spec.append(("knn_dists", (B, Lb, self.knn_dists.shape[1]), torch.float32))
+            spec.append(("knn_ids", (B, Lb, self.knn_ids.shape[1]), torch.int64))
+        return spec
+
+    def collate_into(self, ids: List[int], out: dict) -> dict:
+        """collater([self[i] for i in ids]) without the intermediate copies: the same tensors (eval_lm.host_inputs names),
+        written into the preallocated (pinned) buffers `out` -- one memcpy per array from the page cache.  Same id checks as
+        __getitem__; numpy releases the GIL during the copies, so a producer thread overlaps the device step."""
+        n_tok = 0
+        for b, i in enumerate(ids):
+            s, e = self.slice_indices[i]
+            cs = s if (self.context_window == 0 or i == 0) else max(0, s - self.context_window)
+            nbr = out["nbr"][b].numpy()
+            np.copyto(nbr, self.neighbor_offsets[cs:e])
+            if nbr.size and (int(nbr.min()) < -1 or int(nbr.max()) >= self.n_datastore):
+                raise IndexError(f"block {i}: neighbour id outside [-1, {self.n_datastore}) -- neighbors.mmap does not "
+                                 "belong to this train_dstore")
+            tgt = out["target"][b].numpy()
+            np.copyto(tgt, self.tokens[cs:e], casting="unsafe")
+            src = out["src_tokens"][b].numpy()
+            if cs == 0:
+                src[0] = self.eos
+                src[1:] = tgt[:-1]
+            else:
+                np.copyto(src, self.tokens[cs - 1:e - 1], casting="unsafe")
+            out["positions"][b].copy_(torch.arange(cs, e))
+            out["start_indices"][b] = s - cs
+            if self.precompute_feats is not None:
+                np.copyto(out["feats"][b].numpy(), self.precompute_feats[cs:e])
+            if self.knn_ids is not None:
+                np.copyto(out["knn_dists"][b].numpy(), self.knn_dists[cs:e])
+                kid = out["knn_ids"][b].numpy()
+                np.copyto(kid, self.knn_ids[cs:e])
+                if kid.size and (int(kid.min()) < -1 or int(kid.max()) >= self.n_datastore):
+                    raise IndexError(f"block {i}: kNN-LM neighbour id outside [-1, {self.n_datastore})")
+            n_tok += e - cs
+        return {"ids": list(ids), "nsentences": len(ids), "ntokens": n_tok, "host": out}
+
     def ordered_indices(self):
         return np.arange(len(self))                                       # monolingual_dataset.py:264-266
 

@@ -203,7 +203,62 @@ class Stager:
         self.slots[staged[0]][2].record(torch.cuda.current_stream(self.device))
 
 
-def prefetch(items, to_host_inputs, device):
+class HostBatcher:
+    """Producer thread of evaluate(): walks the batches of a shard, fills reusable PINNED buffer sets straight from the dataset's
+    memmaps (GraphTokenBlockDataset.collate_into: one copy per array) and hands them over through a bounded queue, so that
+    slicing / collation of batch i+1 (+2) runs under the device step of batch i.  The reference does this work in DataLoader
+    worker processes and pickles whole DGL graphs back (fairseq/data/iterators.py:155-167); here only the inputs of graph
+    assembly are sliced and the consumer is the same process.  A buffer set returns to the pool once its H2D copy has completed
+    (`release`)."""
+
+    def __init__(self, dataset, id_lists, depth: int = 3):
+        import queue
+        import threading
+        self.dataset, self.id_lists, self.depth = dataset, list(id_lists), depth
+        self.pools = {}                                  # shape signature -> queue of free buffer sets
+        self.ready = queue.Queue(maxsize=depth)
+        self.error = None
+        self._queue = queue
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _pool(self, spec):
+        key = tuple((n, tuple(sh), str(dt)) for n, sh, dt in spec)
+        if key not in self.pools:
+            pin = torch.cuda.is_available()
+            q = self._queue.Queue()
+            for _ in range(self.depth + 1):
+                q.put({n: torch.empty(sh, dtype=dt, pin_memory=pin) for n, sh, dt in spec})
+            self.pools[key] = q
+        return self.pools[key]
+
+    def _run(self):
+        try:
+            for ids in self.id_lists:
+                pool = self._pool(self.dataset.batch_spec(ids))
+                bufs = pool.get()
+                item = self.dataset.collate_into(ids, bufs)
+                item["pool"] = pool
+                self.ready.put(item)
+        except BaseException as e:          # surfaces in the consumer
+            self.error = e
+        self.ready.put(None)
+
+    def __iter__(self):
+        while True:
+            item = self.ready.get()
+            if item is None:
+                if self.error is not None:
+                    raise self.error
+                return
+            yield item
+
+    @staticmethod
+    def release(item):
+        item["pool"].put(item["host"])
+
+
+def prefetch(items, to_host_inputs, device, release=None):
     """Double-buffered input pipeline: yields (item, device tensors) while the NEXT item's tensors are already being staged,
     so the H2D copy of step i+1 overlaps the kernels of step i.  The reference stages every batch synchronously inside the
     loop (utils.move_to_cuda, fairseq_cli/eval_lm.py:217).  The yielded tensors are only valid until the next iteration."""
@@ -223,6 +278,9 @@ def prefetch(items, to_host_inputs, device):
             nxt = None
         yield item, st.wait(staged)
         st.done(staged)
+        if release is not None:             # the item's H2D copy has completed: its host buffers may be refilled
+            staged[2].synchronize()
+            release(item)
 
 
 @torch.no_grad()
@@ -230,11 +288,13 @@ def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, sc
              knn_dstore=None, temperature: float = 1.0, max_sentences: int = 1, device="cuda", rank: int = 0,
              world_size: int = 1, process_group=None, log=None, dstore_writer: Optional[DstoreWriter] = None,
              knn_keytype: Optional[str] = None, cuda_graph: bool = False, prune_unreachable: bool = True,
-             max_tokens: Optional[int] = None, bucket_by_length: bool = False) -> dict:
+             max_tokens: Optional[int] = None, bucket_by_length: bool = False, host_threads: bool = True) -> dict:
     """`cuda_graph=True` replays one captured CUDA graph per batch shape instead of launching the ~100 kernels of a
     step one by one (same kernels, same results; pays off when blocks are small enough to be launch-bound).
     `prune_unreachable` drops context nodes further than graph_layer-1 hops from their centre (graph.build_token_graph
-    `reach`): they cannot reach a tgt node, so scores are unchanged."""
+    `reach`): they cannot reach a tgt node, so scores are unchanged.
+    `host_threads=False`: slice / collate every batch synchronously on the calling thread through dataset.__getitem__ +
+    collater (the reference-shaped calls) instead of the HostBatcher producer thread -- same tensors, same scores."""
     reach = model.decoder.hgt_decoder.n_layers - 1 if prune_unreachable else None
     lo, hi = shard_range(len(dataset), rank, world_size)
     acc = torch.zeros(2, dtype=torch.float64, device=device)
@@ -251,15 +311,19 @@ def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, sc
     t0 = time.perf_counter()
     if bucket_by_length and dstore_writer is not None:
         raise ValueError("--save-knnlm-dstore writes keys in corpus order: do not bucket by length")
-    collated = (dataset.collater([dataset[i] for i in ids])
-                for ids in batches(dataset, lo, hi, max_sentences, max_tokens, bucket_by_length))
-    for batch, inp in prefetch(collated, host_inputs, device):
+    id_lists = batches(dataset, lo, hi, max_sentences, max_tokens, bucket_by_length)
+    if host_threads:
+        # slicing + collation on a producer thread into reusable pinned buffers (HostBatcher), H2D double-buffered (Stager)
+        stream = prefetch(HostBatcher(dataset, id_lists), lambda item: item["host"], device, release=HostBatcher.release)
+    else:
+        stream = prefetch((dataset.collater([dataset[i] for i in ids]) for ids in id_lists), host_inputs, device)
+    for batch, inp in stream:
         _, _, _, dec_out = step(inp)
         ntok += batch["ntokens"]
         if dstore_writer is not None:                           # sequence_scorer.py:180-183 + eval_lm.py:223-244
             extra = dec_out[1]
             feat = extra[knn_keytype] if knn_keytype in extra else extra["inner_states"][-1]     # [L, B, d]
-            starts = batch["start_indices"].view(-1).tolist()
+            starts = (batch["host"] if "host" in batch else batch)["start_indices"].view(-1).tolist()
             for i in range(inp["target"].shape[0]):
                 mask = inp["target"][i, starts[i]:].ne(scorer.pad)
                 dstore_writer.add(feat[starts[i]:, i, :][mask].float(), inp["target"][i, starts[i]:][mask])

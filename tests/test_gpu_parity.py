@@ -769,6 +769,60 @@ def test_knn_model_precomputed_arrays(dev):
     assert p1.shape == (B * Lb,) and torch.equal(p1, p2) and torch.equal(r1, r2)
 
 
+def test_evaluate_host_pipeline_matches_reference_shaped_calls(dev, tmp_path):
+    """evaluate()'s producer thread (HostBatcher: memmap slices copied once into reusable pinned buffers,
+    GraphTokenBlockDataset.collate_into) against the reference-shaped per-batch calls dataset[i] + collater
+    (token_block_dataset.py:287-333, monolingual_dataset.py:237-262): the same device inputs, hence the same scores -- with a
+    --gcn-context-window, B = 2 batches, a ragged last block and kNN-LM arrays; a foreign neighbour id surfaces as IndexError."""
+    from types import SimpleNamespace
+    import copy
+    from gnnlm_b200 import synth
+    from gnnlm_b200.dataset import DeviceDatastore, GraphTokenBlockDataset
+    from gnnlm_b200.eval_lm import evaluate
+    from gnnlm_b200.knn_model import KNNModel
+    from gnnlm_b200.sequence_scorer import SequenceScorer
+    cfg = dict(synth.CONFIGS["c1"], NL=2, k=4, n_d=1 << 14, V=1000, cutoff=[200, 600], k_nn=8)
+    model = synth.make_model(cfg)
+    tables = synth.make_tables(cfg, device="cpu")
+    rng = np.random.RandomState(7)
+    n_tok = 64 * 7 + 23
+    tokens = rng.randint(4, cfg["V"], size=n_tok).astype(np.uint16)
+    nbr = rng.randint(1, cfg["n_d"] - 1, size=(n_tok, cfg["k"])).astype(np.int64)
+    nbr[rng.rand(n_tok, cfg["k"]) < 0.05] = -1
+    feats = rng.randn(n_tok, cfg["d"]).astype(np.float16)
+    kid = rng.randint(0, cfg["n_d"], size=(n_tok, cfg["k_nn"])).astype(np.int64)
+    kd = rng.randn(n_tok, cfg["k_nn"]).astype(np.float32)
+    dstore = DeviceDatastore(tables["codes"].to(dev), tables["vals"].to(dev))
+    scorer = SequenceScorer(synth.Dictionary(cfg["V"]), args=SimpleNamespace(lmbda=0.25, knn_keytype=None))
+    m = copy.deepcopy(model).to(dev).set_math("fp32")
+    for cw in (0, 16):
+        ds = GraphTokenBlockDataset(tokens, 64, pad=1, eos=2, neighbor_offsets=nbr, n_datastore=cfg["n_d"], neighbor_context=1,
+                                    precompute_feats=feats, context_window=cw, knn_dists=kd, knn_ids=kid)
+        res = {}
+        for threads in (True, False):
+            knn = KNNModel(dstore.vals, vocab_size=cfg["V"], k=cfg["k_nn"])
+            res[threads] = evaluate(m, ds, dstore, scorer, knn_dstore=knn, max_sentences=2, device=dev, host_threads=threads)
+        assert res[True]["count"] == res[False]["count"] == n_tok
+        assert abs(res[True]["score_sum"] - res[False]["score_sum"]) <= 1e-12 * abs(res[False]["score_sum"])
+        # the producer's tensors are the collater's
+        ids = [2, 3]
+        spec = ds.batch_spec(ids)
+        bufs = {n: torch.empty(sh, dtype=dt) for n, sh, dt in spec}
+        fast = ds.collate_into(ids, bufs)["host"]
+        from gnnlm_b200.eval_lm import host_inputs
+        slow = host_inputs(ds.collater([ds[i] for i in ids]))
+        assert set(fast) == set(slow)
+        for k_ in slow:
+            assert torch.equal(fast[k_], slow[k_].reshape(fast[k_].shape)), k_
+    bad = nbr.copy()
+    bad[200, 1] = cfg["n_d"]
+    ds = GraphTokenBlockDataset(tokens, 64, pad=1, eos=2, neighbor_offsets=bad, n_datastore=cfg["n_d"], neighbor_context=1,
+                                precompute_feats=feats)
+    with pytest.raises(IndexError):
+        evaluate(m, ds, dstore, SequenceScorer(synth.Dictionary(cfg["V"]), args=SimpleNamespace(lmbda=0.0, knn_keytype=None)),
+                 max_sentences=2, device=dev)
+
+
 def test_eval_lm_through_the_registration_face(dev, tmp_path):
     """Reference-style command line -> registry.eval_lm_parser -> (stand-in) fairseq registries -> task.setup_task /
     load_dataset / load_datastore -> ARCH_MODEL_REGISTRY[arch].build_model -> evaluate(): the same score as the same model

@@ -443,3 +443,37 @@ def test_dstore_writer_shards_compose(tmp_path):
     assert (np.fromfile(os.path.join(out, "vals.npy"), np.int32) == toks).all()
     import json
     assert json.load(open(os.path.join(out, "info.json")))["dstore_size"] == n
+
+
+def test_host_batcher_fills_the_collaters_tensors():
+    """evaluate()'s fast host path: GraphTokenBlockDataset.collate_into (memmap slices copied once into preallocated batch
+    buffers) produces exactly the tensors of the reference-shaped dataset[i] + collater (token_block_dataset.py:287-333,
+    monolingual_dataset.py:237-262), with and without --gcn-context-window, for full, ragged and single-block batches; the
+    HostBatcher producer thread delivers the batches of eval_lm.batches in order and recycles its buffer sets."""
+    from gnnlm_b200.dataset import GraphTokenBlockDataset
+    from gnnlm_b200.eval_lm import HostBatcher, batches, host_inputs
+    rng = np.random.RandomState(0)
+    n_tok = 64 * 9 + 13
+    tokens = rng.randint(4, 900, size=n_tok).astype(np.uint16)
+    nbr = rng.randint(-1, 5000, size=(n_tok, 4)).astype(np.int64)
+    feats = rng.randn(n_tok, 32).astype(np.float16)
+    kid, kd = rng.randint(0, 5000, size=(n_tok, 8)).astype(np.int64), rng.randn(n_tok, 8).astype(np.float32)
+    for cw in (0, 16):
+        ds = GraphTokenBlockDataset(tokens, 64, pad=1, eos=2, neighbor_offsets=nbr, n_datastore=5000, neighbor_context=1,
+                                    precompute_feats=feats, context_window=cw, knn_dists=kd, knn_ids=kid)
+        want = list(batches(ds, 0, len(ds), 2))
+        got = []
+        for item in HostBatcher(ds, want, depth=2):                  # 3 buffer sets for 5-6 batches: recycling is exercised
+            slow = host_inputs(ds.collater([ds[i] for i in item["ids"]]))
+            assert set(item["host"]) == set(slow)
+            for k_ in slow:
+                assert torch.equal(item["host"][k_], slow[k_].reshape(item["host"][k_].shape)), (cw, item["ids"], k_)
+            assert item["ntokens"] == sum(len(ds[i]["target"]) for i in item["ids"])
+            got.append(item["ids"])
+            HostBatcher.release(item)
+        assert got == want
+    bad = nbr.copy()
+    bad[70, 0] = 5000
+    ds = GraphTokenBlockDataset(tokens, 64, pad=1, eos=2, neighbor_offsets=bad, n_datastore=5000)
+    with pytest.raises(IndexError):
+        list(HostBatcher(ds, [[0], [1]]))
