@@ -50,7 +50,7 @@ def parse():
                    help="weak: one block per step per rank (the headline line).  strong: ONE fixed corpus of --strong-blocks blocks "
                         "(+ a ragged tail) through eval_lm.evaluate(rank, world_size): contiguous block shards, replicated datastore, "
                         "one NCCL all-reduce of {sum log p, n_tokens}")
-    p.add_argument("--strong-blocks", type=int, default=64)
+    p.add_argument("--strong-blocks", type=int, default=128)
     p.add_argument("--eval-blocks", type=int, default=16, help="blocks of the e2e_evaluate leg (0: skip it)")
     p.add_argument("--ncu-range", action="store_true",
                    help="after warm-up run ONE resident step inside cudaProfilerStart/Stop and exit "
@@ -201,7 +201,7 @@ def workload_name(cfg_name):
 
 
 # ----------------------------------------------------------------------------------------------- evaluate() legs
-def build_eval(cfg, model, dev, math, root, n_blocks, tail, seed=0):
+def build_eval(cfg, model, dev, math, root, n_blocks, tail, seed=0, write=True):
     """A reference-layout data directory under `root` (tmpfs) + everything eval_lm.evaluate() needs, through the same loaders
     eval_lm.main uses (formats.load_graph_lm_dataset, DeviceDatastore.from_dir, KNNModel over the neighbour memmaps)."""
     from argparse import Namespace
@@ -210,7 +210,11 @@ def build_eval(cfg, model, dev, math, root, n_blocks, tail, seed=0):
     from gnnlm_b200.formats import MmapDataset, load_graph_lm_dataset
     from gnnlm_b200.knn_model import KNNModel
     from gnnlm_b200.sequence_scorer import SequenceScorer
-    info = synth.write_data_dir(root, cfg, n_blocks, tail_tokens=tail, seed=seed, device=dev)
+    if write:
+        info = synth.write_data_dir(root, cfg, n_blocks, tail_tokens=tail, seed=seed, device=dev)
+    else:
+        info = {"n_tokens": n_blocks * cfg["L"] + tail, "n_blocks": n_blocks + (1 if tail else 0),
+                "dists_file": os.path.join(root, "valid_dstore", f"dists.{cfg['k_nn']}")}
     n = info["n_tokens"]
     knn_ids = MmapDataset(neighbor_path(root, "valid", cfg["k_nn"]), (n, cfg["k_nn"]), np.int64).array()
     knn_dists = MmapDataset(info["dists_file"], (n, cfg["k_nn"]), np.float32).array()
@@ -244,9 +248,17 @@ def run_strong(args, world, rank, dev, dist, math):
     cfg = dict(synth.CONFIGS[args.config])
     cfg["n_d"] = args.n_datastore or min(cfg["n_d"], 1 << 24)
     model = synth.make_model(cfg).to(dev).set_math(math)
-    root = tmp_root(f"strong_r{rank}")
+    # ONE data directory for the node (rank 0 writes it, every rank maps it), as a shared dataset would be
+    name = [tmp_root("strong") if rank == 0 else None]
+    if dist is not None:
+        dist.broadcast_object_list(name, src=0)
+    root = name[0]
     try:
-        ds, dstore, knn, scorer, info = build_eval(cfg, model, dev, math, root, args.strong_blocks, tail=1000, seed=0)
+        if rank == 0:
+            build_eval(cfg, model, dev, math, root, args.strong_blocks, tail=1000, seed=0)
+        if dist is not None:
+            dist.barrier()
+        ds, dstore, knn, scorer, info = build_eval(cfg, model, dev, math, root, args.strong_blocks, tail=1000, seed=0, write=False)
         run_evaluate(model, ds, dstore, knn, scorer, cfg, dev, rank, world)            # warm-up pass (graph capture, weight preparation)
         if dist is not None:
             dist.barrier()
@@ -260,7 +272,10 @@ def run_strong(args, world, rank, dev, dist, math):
             dist.barrier()
         sec = float(sec.item())
     finally:
-        shutil.rmtree(root, ignore_errors=True)
+        if dist is not None:
+            dist.barrier()
+        if rank == 0:
+            shutil.rmtree(root, ignore_errors=True)
     line = {"metric": "eval tokens/s (HGT+kNN-LM fwd)", "value": res["count"] / sec, "unit": "tokens/s", "n_gpus": world,
             "steps": 1, "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": math, "data": "synthetic", "impl": "ours",

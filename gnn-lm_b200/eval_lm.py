@@ -204,53 +204,72 @@ class Stager:
 
 
 class HostBatcher:
-    """Producer thread of evaluate(): walks the batches of a shard, fills reusable PINNED buffer sets straight from the dataset's
-    memmaps (GraphTokenBlockDataset.collate_into: one copy per array) and hands them over through a bounded queue, so that
-    slicing / collation of batch i+1 (+2) runs under the device step of batch i.  The reference does this work in DataLoader
-    worker processes and pickles whole DGL graphs back (fairseq/data/iterators.py:155-167); here only the inputs of graph
-    assembly are sliced and the consumer is the same process.  A buffer set returns to the pool once its H2D copy has completed
-    (`release`)."""
+    """Producer threads of evaluate(): walk the batches of a shard, fill reusable PINNED buffer sets straight from the dataset's
+    memmaps (GraphTokenBlockDataset.collate_into: one copy per array; numpy releases the GIL while copying) and hand them over
+    in order, so that slicing / collation of the next batches runs under the device step of the current one.  A Wiki103-shape
+    block is 45 MB of host copies (~14 ms on one core, as long as its device step): `workers` threads fill different batches
+    concurrently.  The reference does this work in DataLoader worker processes and pickles whole DGL graphs back
+    (fairseq/data/iterators.py:155-167); here only the inputs of graph assembly are sliced and the consumer is the same
+    process.  A buffer set returns to its pool once its H2D copy has completed (`release`); the sets are kept on the dataset, so
+    a second evaluate() over the same shapes allocates nothing (one evaluate() per dataset at a time)."""
 
-    def __init__(self, dataset, id_lists, depth: int = 3):
+    def __init__(self, dataset, id_lists, depth: int = 4, workers: int = 3):
         import queue
         import threading
         self.dataset, self.id_lists, self.depth = dataset, list(id_lists), depth
-        self.pools = {}                                  # shape signature -> queue of free buffer sets
-        self.ready = queue.Queue(maxsize=depth)
-        self.error = None
-        self._queue = queue
-        self.thread = threading.Thread(target=self._run, daemon=True)
-        self.thread.start()
+        if not hasattr(dataset, "_host_bufs"):
+            dataset._host_bufs = {}
+        self.bufs = dataset._host_bufs               # shape signature -> every buffer set ever allocated (kept across calls)
+        self.pools = {}                              # shape signature -> queue of this run's free buffer sets
+        self._queue, self._lock, self._order, self._cv = queue, threading.Lock(), threading.Lock(), threading.Condition()
+        self._next, self._done, self.error = 0, {}, None
+        self.threads = [threading.Thread(target=self._run, daemon=True) for _ in range(max(1, min(workers, len(self.id_lists))))]
+        for t in self.threads:
+            t.start()
 
     def _pool(self, spec):
         key = tuple((n, tuple(sh), str(dt)) for n, sh, dt in spec)
-        if key not in self.pools:
-            pin = torch.cuda.is_available()
-            q = self._queue.Queue()
-            for _ in range(self.depth + 1):
-                q.put({n: torch.empty(sh, dtype=dt, pin_memory=pin) for n, sh, dt in spec})
-            self.pools[key] = q
-        return self.pools[key]
+        with self._lock:
+            if key not in self.pools:                # a new run owns every set of the dataset again (the previous run is over)
+                pin = torch.cuda.is_available()
+                sets = self.bufs.setdefault(key, [])
+                while len(sets) < self.depth + 1:
+                    sets.append({n: torch.empty(sh, dtype=dt, pin_memory=pin) for n, sh, dt in spec})
+                q = self._queue.Queue()
+                for b in sets:
+                    q.put(b)
+                self.pools[key] = q
+            return self.pools[key]
 
     def _run(self):
         try:
-            for ids in self.id_lists:
-                pool = self._pool(self.dataset.batch_spec(ids))
-                bufs = pool.get()
+            while True:
+                with self._order:                    # sequence number AND buffer set are taken in order: the earliest
+                    seq = self._next                 # outstanding batch always owns buffers, so the in-order consumer cannot starve
+                    if seq >= len(self.id_lists) or self.error is not None:
+                        return
+                    self._next += 1
+                    ids = self.id_lists[seq]
+                    pool = self._pool(self.dataset.batch_spec(ids))
+                    bufs = pool.get()                # blocks while every set of this shape is in flight
                 item = self.dataset.collate_into(ids, bufs)
                 item["pool"] = pool
-                self.ready.put(item)
-        except BaseException as e:          # surfaces in the consumer
-            self.error = e
-        self.ready.put(None)
+                with self._cv:
+                    self._done[seq] = item
+                    self._cv.notify_all()
+        except BaseException as e:                   # surfaces in the consumer
+            with self._cv:
+                self.error = e
+                self._cv.notify_all()
 
     def __iter__(self):
-        while True:
-            item = self.ready.get()
-            if item is None:
-                if self.error is not None:
+        for seq in range(len(self.id_lists)):
+            with self._cv:
+                while seq not in self._done and self.error is None:
+                    self._cv.wait()
+                if seq not in self._done:
                     raise self.error
-                return
+                item = self._done.pop(seq)
             yield item
 
     @staticmethod
