@@ -28,6 +28,7 @@ SIGNATURES = {
     "gnnlm_version": (_i32, []),
     "gnnlm_last_error": (C.c_char_p, []),
     "gnnlm_has_tcgen05": (_i32, []),
+    "gnnlm_host_copy": (_i32, [_p, _p, _i64, _i32, _i64, _i64, _i32, _p]),
     "gnnlm_graph_workspace_bytes": (_i64, [_i64]),
     "gnnlm_graph_count": (_i32, [_p, _p, _i64, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _i64, _p]),
     "gnnlm_graph_fill": (_i32, [_p, _p, _i64, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
@@ -78,7 +79,8 @@ SIGNATURES = {
 
 _lib = None
 launches = 0          # number of CUDA kernels launched through the C ABI (bench.py's gpu_launches)
-KERNELS_PER_CALL = {"gnnlm_graph_count": 3, "gnnlm_knn_full_prob": 2, "gnnlm_graph_dedup": 12}   # everything else launches exactly one
+KERNELS_PER_CALL = {"gnnlm_graph_count": 3, "gnnlm_knn_full_prob": 2, "gnnlm_graph_dedup": 12,   # everything else launches exactly one
+                    "gnnlm_host_copy": 0}
 TIMING = None         # when a list: (name, tag, start_event, end_event, work) per call (bench.py per-kernel pass)
 
 

@@ -1,6 +1,11 @@
 // C-ABI glue: version, thread-local error text, GEMM dispatch between the fp32 CUDA-core kernel
 // (gemm_simt.cu) and the tcgen05/TMA kernel (gemm_tcgen05.cu).
 #include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <thread>
+#include <vector>
 
 #include "common.cuh"
 
@@ -112,4 +117,48 @@ extern "C" int32_t gnnlm_linear_batched_f16x3(const void* A, int64_t lda, int64_
                   "gnnlm_linear_batched_f16x3: bad shape");
   return gemm_tc_batched_f16x3(A, lda, a_bs, W_hi, W_lo, ldw, w_bs, w_scale, residual, ldr, r_bs, C, ldc, c_bs, nb, M, N, K,
                                causal, (cudaStream_t)stream);
+}
+
+// ---- host side of a batch (replaces the per-batch numpy copies of GraphTokenBlockDataset.__getitem__ + collater)
+// dst <- src (bytes), split over n_threads host threads; check_i64: the range holds int64 ids, every one of which must lie in
+// [lo, hi) -- *bad is set to 1 otherwise (the copy still completes).  dst == NULL: check only (page-locked sources are not copied).
+// The per-batch host work of GraphTokenBlockDataset.__getitem__ (neighbor_offsets[offsets], precompute_feats[offsets],
+// token_block_dataset.py:309,327-329) as ONE blocking native call without the interpreter lock.
+extern "C" int32_t gnnlm_host_copy(void* dst, const void* src, int64_t bytes, int32_t check_i64, int64_t lo, int64_t hi,
+                                   int32_t n_threads, int32_t* bad) {
+  GNNLM_CHECK_ARG(src && bytes >= 0 && (dst || check_i64), GNNLM_E_ARG, "gnnlm_host_copy: null pointer / bad size");
+  GNNLM_CHECK_ARG(!check_i64 || (bytes % 8 == 0 && (uintptr_t)src % 8 == 0 && bad), GNNLM_E_ARG,
+                  "gnnlm_host_copy: an id check needs 8 B aligned int64 data and a flag");
+  if (bytes == 0) return 0;
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 32) n_threads = 32;
+  const int64_t min_chunk = 1 << 20;                              // below ~1 MB per thread a spawn costs more than it saves
+  int64_t nt = bytes / min_chunk;
+  if (nt < 1) nt = 1;
+  if (nt > n_threads) nt = n_threads;
+  std::atomic<int> any_bad(0);
+  auto work = [&](int64_t b0, int64_t b1) {
+    if (dst) memcpy(reinterpret_cast<char*>(dst) + b0, reinterpret_cast<const char*>(src) + b0, (size_t)(b1 - b0));
+    if (check_i64) {
+      const int64_t* p = reinterpret_cast<const int64_t*>(reinterpret_cast<const char*>(src) + b0);
+      const int64_t n = (b1 - b0) / 8;
+      int64_t mn = lo, mx = lo;
+      for (int64_t i = 0; i < n; ++i) {
+        const int64_t v = p[i];
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+      }
+      if (mn < lo || mx >= hi) any_bad.store(1);
+    }
+  };
+  const int64_t per = ((bytes / nt) + 63) / 64 * 64;              // 64 B aligned pieces (multiples of 8 B)
+  std::vector<std::thread> pool;
+  for (int64_t t = 1; t < nt; ++t) {
+    const int64_t b0 = t * per, b1 = (t + 1 == nt) ? bytes : (t + 1) * per;
+    if (b0 < bytes) pool.emplace_back(work, b0, b1 < bytes ? b1 : bytes);
+  }
+  work(0, per < bytes ? per : bytes);
+  for (auto& th : pool) th.join();
+  if (check_i64 && any_bad.load()) *bad = 1;
+  return 0;
 }

@@ -117,6 +117,7 @@ class GraphTokenBlockDataset:
         self.context_window = context_window
         self.max_intra_context = intra_context
         self.knn_dists, self.knn_ids = knn_dists, knn_ids
+        self.host_copy_threads = 4              # native threads of one batch-slice copy (collate_into)
         n = len(tokens)
         if sizes is not None and int(np.sum(sizes)) != n:
             raise ValueError("sizes must sum to the number of tokens")
@@ -198,16 +199,36 @@ class GraphTokenBlockDataset:
     def collate_into(self, ids: List[int], out: dict) -> dict:
         """collater([self[i] for i in ids]) without the intermediate copies: the same tensors (eval_lm.host_inputs names),
         written into the preallocated (pinned) buffers `out` -- one memcpy per array from the page cache.  Same id checks as
-        __getitem__; numpy releases the GIL during the copies, so a producer thread overlaps the device step."""
+        __getitem__ (range check of the int64 ids fused into the copy)."""
+        import ctypes
+        from . import _lib as L
+        lib = L.load()
         n_tok = 0
+        bad = ctypes.c_int32(0)
+
+        def take(name, b, src, cs, e, ids_check=False):
+            """slice [cs, e) of a per-token array -> the batch buffer: one native multi-threaded copy (gnnlm_host_copy), int64 id
+            arrays range-checked in the same pass"""
+            sl = src[cs:e]
+            dst = out[name][b]
+            if sl.flags["C_CONTIGUOUS"] and dst.is_contiguous() and dst.numel() * dst.element_size() == sl.nbytes:
+                rc = lib.gnnlm_host_copy(dst.data_ptr(), sl.ctypes.data, sl.nbytes, int(ids_check), -1, self.n_datastore,
+                                         self.host_copy_threads, ctypes.byref(bad))
+                if rc != 0:
+                    raise L.GnnlmError(lib.gnnlm_last_error().decode())
+            else:                                                   # broadcast / strided sources
+                np.copyto(dst.numpy(), sl)
+                if ids_check and sl.size and (int(sl.min()) < -1 or int(sl.max()) >= self.n_datastore):
+                    bad.value = 1
+            if bad.value:
+                raise IndexError(f"block {ids[b]}: neighbour id outside [-1, {self.n_datastore}) -- "
+                                 f"{'neighbors.mmap' if name == 'nbr' else 'the kNN-LM neighbour file'} does not belong to this "
+                                 "train_dstore")
+
         for b, i in enumerate(ids):
             s, e = self.slice_indices[i]
             cs = s if (self.context_window == 0 or i == 0) else max(0, s - self.context_window)
-            nbr = out["nbr"][b].numpy()
-            np.copyto(nbr, self.neighbor_offsets[cs:e])
-            if nbr.size and (int(nbr.min()) < -1 or int(nbr.max()) >= self.n_datastore):
-                raise IndexError(f"block {i}: neighbour id outside [-1, {self.n_datastore}) -- neighbors.mmap does not "
-                                 "belong to this train_dstore")
+            take("nbr", b, self.neighbor_offsets, cs, e, ids_check=True)
             tgt = out["target"][b].numpy()
             np.copyto(tgt, self.tokens[cs:e], casting="unsafe")
             src = out["src_tokens"][b].numpy()
@@ -219,13 +240,10 @@ class GraphTokenBlockDataset:
             out["positions"][b].copy_(torch.arange(cs, e))
             out["start_indices"][b] = s - cs
             if self.precompute_feats is not None:
-                np.copyto(out["feats"][b].numpy(), self.precompute_feats[cs:e])
+                take("feats", b, self.precompute_feats, cs, e)
             if self.knn_ids is not None:
-                np.copyto(out["knn_dists"][b].numpy(), self.knn_dists[cs:e])
-                kid = out["knn_ids"][b].numpy()
-                np.copyto(kid, self.knn_ids[cs:e])
-                if kid.size and (int(kid.min()) < -1 or int(kid.max()) >= self.n_datastore):
-                    raise IndexError(f"block {i}: kNN-LM neighbour id outside [-1, {self.n_datastore})")
+                take("knn_dists", b, self.knn_dists, cs, e)
+                take("knn_ids", b, self.knn_ids, cs, e, ids_check=True)
             n_tok += e - cs
         return {"ids": list(ids), "nsentences": len(ids), "ntokens": n_tok, "host": out}
 

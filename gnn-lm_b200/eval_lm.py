@@ -204,16 +204,15 @@ class Stager:
 
 
 class HostBatcher:
-    """Producer threads of evaluate(): walk the batches of a shard, fill reusable PINNED buffer sets straight from the dataset's
-    memmaps (GraphTokenBlockDataset.collate_into: one copy per array; numpy releases the GIL while copying) and hand them over
-    in order, so that slicing / collation of the next batches runs under the device step of the current one.  A Wiki103-shape
-    block is 45 MB of host copies (~14 ms on one core, as long as its device step): `workers` threads fill different batches
-    concurrently.  The reference does this work in DataLoader worker processes and pickles whole DGL graphs back
+    """Host batches of evaluate(): walks the batches of a shard and fills reusable PINNED buffer sets straight from the dataset's
+    memmaps (GraphTokenBlockDataset.collate_into: one native multi-threaded copy per array, 45 MB in ~2 ms for a Wiki103-shape
+    block) -- on the calling thread (workers = 0, the default), or on `workers` producer threads that fill the next batches
+    under the device step of the current one and hand them over in order.  The reference does this work in DataLoader worker processes and pickles whole DGL graphs back
     (fairseq/data/iterators.py:155-167); here only the inputs of graph assembly are sliced and the consumer is the same
     process.  A buffer set returns to its pool once its H2D copy has completed (`release`); the sets are kept on the dataset, so
     a second evaluate() over the same shapes allocates nothing (one evaluate() per dataset at a time)."""
 
-    def __init__(self, dataset, id_lists, depth: int = 4, workers: int = 3):
+    def __init__(self, dataset, id_lists, depth: int = 4, workers: int = 0):
         import queue
         import threading
         self.dataset, self.id_lists, self.depth = dataset, list(id_lists), depth
@@ -223,7 +222,7 @@ class HostBatcher:
         self.pools = {}                              # shape signature -> queue of this run's free buffer sets
         self._queue, self._lock, self._order, self._cv = queue, threading.Lock(), threading.Lock(), threading.Condition()
         self._next, self._done, self.error = 0, {}, None
-        self.threads = [threading.Thread(target=self._run, daemon=True) for _ in range(max(1, min(workers, len(self.id_lists))))]
+        self.threads = [threading.Thread(target=self._run, daemon=True) for _ in range(max(0, min(workers, len(self.id_lists))))]
         for t in self.threads:
             t.start()
 
@@ -263,6 +262,13 @@ class HostBatcher:
                 self._cv.notify_all()
 
     def __iter__(self):
+        if not self.threads:                         # workers = 0: fill on the calling thread (the copies are native and threaded)
+            for ids in self.id_lists:
+                pool = self._pool(self.dataset.batch_spec(ids))
+                item = self.dataset.collate_into(ids, pool.get())
+                item["pool"] = pool
+                yield item
+            return
         for seq in range(len(self.id_lists)):
             with self._cv:
                 while seq not in self._done and self.error is None:
@@ -277,12 +283,16 @@ class HostBatcher:
         item["pool"].put(item["host"])
 
 
-def prefetch(items, to_host_inputs, device, release=None):
+def prefetch(items, to_host_inputs, device, release=None, profile: Optional[dict] = None):
     """Double-buffered input pipeline: yields (item, device tensors) while the NEXT item's tensors are already being staged,
     so the H2D copy of step i+1 overlaps the kernels of step i.  The reference stages every batch synchronously inside the
     loop (utils.move_to_cuda, fairseq_cli/eval_lm.py:217).  The yielded tensors are only valid until the next iteration."""
     st = Stager(device)
     it = iter(items)
+    clock = time.perf_counter
+    prof = profile if profile is not None else {}
+    for k in ("wait_producer_s", "stage_s", "consumer_s", "wait_copy_s"):
+        prof.setdefault(k, 0.0)
     try:
         item = next(it)
     except StopIteration:
@@ -290,16 +300,26 @@ def prefetch(items, to_host_inputs, device, release=None):
     nxt = (item, st.stage(to_host_inputs(item)))
     while nxt is not None:
         item, staged = nxt
+        t0 = clock()
         try:
             n_item = next(it)
+            t1 = clock()
             nxt = (n_item, st.stage(to_host_inputs(n_item)))
         except StopIteration:
+            t1 = clock()
             nxt = None
+        t2 = clock()
         yield item, st.wait(staged)
+        t3 = clock()
         st.done(staged)
         if release is not None:             # the item's H2D copy has completed: its host buffers may be refilled
             staged[2].synchronize()
             release(item)
+        t4 = clock()
+        prof["wait_producer_s"] += t1 - t0
+        prof["stage_s"] += t2 - t1
+        prof["consumer_s"] += t3 - t2
+        prof["wait_copy_s"] += t4 - t3
 
 
 @torch.no_grad()
@@ -307,17 +327,30 @@ def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, sc
              knn_dstore=None, temperature: float = 1.0, max_sentences: int = 1, device="cuda", rank: int = 0,
              world_size: int = 1, process_group=None, log=None, dstore_writer: Optional[DstoreWriter] = None,
              knn_keytype: Optional[str] = None, cuda_graph: bool = False, prune_unreachable: bool = True,
-             max_tokens: Optional[int] = None, bucket_by_length: bool = False, host_threads: bool = True) -> dict:
+             max_tokens: Optional[int] = None, bucket_by_length: bool = False, host_threads: bool = True,
+             host_workers: int = 0, graph_cache: Optional[dict] = None) -> dict:
     """`cuda_graph=True` replays one captured CUDA graph per batch shape instead of launching the ~100 kernels of a
     step one by one (same kernels, same results; pays off when blocks are small enough to be launch-bound).
     `prune_unreachable` drops context nodes further than graph_layer-1 hops from their centre (graph.build_token_graph
     `reach`): they cannot reach a tgt node, so scores are unchanged.
+    Host side: a batch's slices go from the dataset's memmaps into reusable pinned buffers with one native multi-threaded
+    copy per array (gnnlm_host_copy; ~2 ms per Wiki103 block), issued by the calling thread (`host_workers` = 0) or by that many
+    producer threads (HostBatcher), then H2D on a copy stream under the previous step (Stager).
+    `graph_cache`: a dict the caller keeps between calls over the SAME model / dataset settings / datastore / kNN store: the
+    captured CUDA graphs (and their activation pool, ~15 GB at the Wiki103 shape) are reused instead of being re-captured.
     `host_threads=False`: slice / collate every batch synchronously on the calling thread through dataset.__getitem__ +
     collater (the reference-shaped calls) instead of the HostBatcher producer thread -- same tensors, same scores."""
     reach = model.decoder.hgt_decoder.n_layers - 1 if prune_unreachable else None
     lo, hi = shard_range(len(dataset), rank, world_size)
-    acc = torch.zeros(2, dtype=torch.float64, device=device)
+    cached = graph_cache.get("evaluate") if (graph_cache is not None and cuda_graph) else None
+    if cached is not None:
+        assert cached["key"] == (id(model), id(dataset), id(dstore), id(knn_dstore), id(scorer), temperature, reach), \
+            "graph_cache belongs to another evaluate() configuration"
+        acc = cached["acc"].zero_()
+    else:
+        acc = torch.zeros(2, dtype=torch.float64, device=device)
     ntok = 0
+    host_profile = {}                   # seconds the calling thread spent waiting for the producer / staging / in the step / on H2D
 
     def score(inp: dict, dry: bool = False):
         sample = sample_from_inputs(inp, dataset, dstore, reach=reach)
@@ -325,7 +358,13 @@ def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, sc
             knn_dstore.set_search_results(sample["knn_dists"], sample["knn_ids"])
         return scorer.score_tokens(model, sample, knn_dstore, temperature, nll_acc=None if dry else acc)
 
-    step = GraphedScorer(score) if cuda_graph else score
+    if cached is not None:
+        step = cached["step"]
+    else:
+        step = GraphedScorer(score) if cuda_graph else score
+        if graph_cache is not None and cuda_graph:
+            graph_cache["evaluate"] = {"key": (id(model), id(dataset), id(dstore), id(knn_dstore), id(scorer), temperature, reach),
+                                       "acc": acc, "step": step}
     torch.cuda.synchronize(device)
     t0 = time.perf_counter()
     if bucket_by_length and dstore_writer is not None:
@@ -333,9 +372,11 @@ def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, sc
     id_lists = batches(dataset, lo, hi, max_sentences, max_tokens, bucket_by_length)
     if host_threads:
         # slicing + collation on a producer thread into reusable pinned buffers (HostBatcher), H2D double-buffered (Stager)
-        stream = prefetch(HostBatcher(dataset, id_lists), lambda item: item["host"], device, release=HostBatcher.release)
+        stream = prefetch(HostBatcher(dataset, id_lists, workers=host_workers), lambda item: item["host"], device,
+                          release=HostBatcher.release, profile=host_profile)
     else:
-        stream = prefetch((dataset.collater([dataset[i] for i in ids]) for ids in id_lists), host_inputs, device)
+        stream = prefetch((dataset.collater([dataset[i] for i in ids]) for ids in id_lists), host_inputs, device,
+                          profile=host_profile)
     for batch, inp in stream:
         _, _, _, dec_out = step(inp)
         ntok += batch["ntokens"]
@@ -354,7 +395,8 @@ def evaluate(model, dataset: GraphTokenBlockDataset, dstore: DeviceDatastore, sc
     score_sum, count = acc.tolist()
     avg_nll2 = -score_sum / count / math.log(2) if count else float("nan")     # eval_lm.py:325
     res = {"score_sum": score_sum, "count": count, "loss_base2": avg_nll2, "ppl": 2 ** avg_nll2,
-           "tokens_this_rank": ntok, "seconds": dt, "tokens_per_s": ntok / dt if dt > 0 else float("nan")}
+           "tokens_this_rank": ntok, "seconds": dt, "tokens_per_s": ntok / dt if dt > 0 else float("nan"),
+           "host_profile": host_profile}
     if log:
         log("Evaluated {} tokens in {:.1f}s ({:.2f} tokens/s)".format(ntok, dt, res["tokens_per_s"]))
         log("Loss (base 2): {:.4f}, Perplexity: {:.2f}".format(avg_nll2, res["ppl"]))

@@ -118,6 +118,12 @@ int32_t gnnlm_graph_dedup(const int64_t* nbr, const int64_t* tgt_pos, int64_t T,
                           int64_t* ntgt_row, int32_t* n_ntgt, int32_t* nn_indptr, int32_t* nn_indices, int32_t* inter_indptr,
                           int32_t* inter_indices, void* workspace, int64_t workspace_bytes, gnnlm_stream_t stream);
 
+/* Host-side slice copy of a batch's inputs: dst <- src (bytes) over n_threads native threads (one blocking call, no interpreter
+ * lock), optionally checking that the range -- int64 neighbour ids, token_block_dataset.py:309 -- lies in [lo, hi): *bad = 1
+ * otherwise (the reference raises IndexError at quant_neighbor_feats[o], :369-370).  dst == NULL: check only. */
+int32_t gnnlm_host_copy(void* dst, const void* src, int64_t bytes, int32_t check_i64, int64_t lo, int64_t hi, int32_t n_threads,
+                        int32_t* bad);
+
 /* ------------------------------------------------------------------------------------------------
  * (2) Datastore gather + PQ decode -- replaces `quant_neighbor_feats[offset]` /
  *     `neighbor_tokens[offset]` (token_block_dataset.py:369-371,392-394) and the centroid gather of

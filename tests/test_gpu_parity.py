@@ -799,11 +799,21 @@ def test_evaluate_host_pipeline_matches_reference_shaped_calls(dev, tmp_path):
         ds = GraphTokenBlockDataset(tokens, 64, pad=1, eos=2, neighbor_offsets=nbr, n_datastore=cfg["n_d"], neighbor_context=1,
                                     precompute_feats=feats, context_window=cw, knn_dists=kd, knn_ids=kid)
         res = {}
-        for threads in (True, False):
+        for threads in (True, False, "workers", "mmap"):
             knn = KNNModel(dstore.vals, vocab_size=cfg["V"], k=cfg["k_nn"])
-            res[threads] = evaluate(m, ds, dstore, scorer, knn_dstore=knn, max_sentences=2, device=dev, host_threads=threads)
-        assert res[True]["count"] == res[False]["count"] == n_tok
-        assert abs(res[True]["score_sum"] - res[False]["score_sum"]) <= 1e-12 * abs(res[False]["score_sum"])
+            d_ = ds
+            if threads == "mmap":            # read-only file mappings (what a data directory gives)
+                def mm(name, a):
+                    a.tofile(str(tmp_path / f"{name}{cw}"))
+                    return np.memmap(str(tmp_path / f"{name}{cw}"), dtype=a.dtype, mode="r", shape=a.shape)
+                d_ = GraphTokenBlockDataset(mm("t", tokens), 64, pad=1, eos=2, neighbor_offsets=mm("n", nbr), n_datastore=cfg["n_d"],
+                                            neighbor_context=1, precompute_feats=mm("f", feats), context_window=cw,
+                                            knn_dists=mm("kd", kd), knn_ids=mm("ki", kid))
+            res[threads] = evaluate(m, d_, dstore, scorer, knn_dstore=knn, max_sentences=2, device=dev, host_threads=bool(threads),
+                                    host_workers=2 if threads == "workers" else 0)
+        for k_ in (True, "workers", "mmap"):
+            assert res[k_]["count"] == res[False]["count"] == n_tok
+            assert abs(res[k_]["score_sum"] - res[False]["score_sum"]) <= 1e-12 * abs(res[False]["score_sum"])
         # the producer's tensors are the collater's
         ids = [2, 3]
         spec = ds.batch_spec(ids)

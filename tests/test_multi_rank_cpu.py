@@ -462,8 +462,10 @@ def test_host_batcher_fills_the_collaters_tensors():
         ds = GraphTokenBlockDataset(tokens, 64, pad=1, eos=2, neighbor_offsets=nbr, n_datastore=5000, neighbor_context=1,
                                     precompute_feats=feats, context_window=cw, knn_dists=kd, knn_ids=kid)
         want = list(batches(ds, 0, len(ds), 2))
+        got = [item["ids"] for item in HostBatcher(ds, want, depth=len(want), workers=0)]     # inline: calling thread, native copies
+        assert got == want
         got = []
-        for item in HostBatcher(ds, want, depth=2):                  # 3 buffer sets for 5-6 batches: recycling is exercised
+        for item in HostBatcher(ds, want, depth=2, workers=2):       # 3 buffer sets for 5-6 batches: recycling is exercised
             slow = host_inputs(ds.collater([ds[i] for i in item["ids"]]))
             assert set(item["host"]) == set(slow)
             for k_ in slow:
