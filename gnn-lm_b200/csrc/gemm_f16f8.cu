@@ -351,6 +351,7 @@ extern "C" int32_t gnnlm_linear_f16f8(const void* A1, const void* A1q, int64_t l
   const unsigned grid = 2u * (unsigned)(pairs < max_pairs ? pairs : max_pairs);
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("GNNLM_F8_DEBUG"); dbg = e ? atoi(e) : 0; }          // timing experiments only
+  es.dbg = (dbg >> 3) & 3;
   tc::gemm_f16f8_kernel<<<grid, 256, smem, stream>>>(maps, M, m_dev, N, K, (int)(K1 / tc::F8_BLOCK_K), es, 1.f / w_scale, dbg);
   GNNLM_LAUNCH_CHECK("gnnlm_linear_f16f8");
   return 0;
