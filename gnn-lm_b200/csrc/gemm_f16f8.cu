@@ -54,7 +54,7 @@ struct F8Maps {
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
     gemm_f16f8_kernel(const __grid_constant__ F8Maps maps, int64_t M_cap, const int32_t* __restrict__ m_dev, int64_t N, int64_t K,
-                      int kb_split, EpiStore es, float acc_scale, int dbg) {
+                      int kb_split, EpiStore es, float acc_scale, int dbg, long long* __restrict__ dbg_out) {
   constexpr int STAGES = F8_STAGES;
   constexpr uint32_t TX = 2u * F8_STAGE;                                  // both CTAs' six operand tiles -> leader
   const int n_mma = N <= BLOCK_N / 2 ? BLOCK_N / 2 : BLOCK_N;
@@ -118,11 +118,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
       int stage = 0;
       uint32_t phase = 0;
       const int half = (int)crank * (n_mma / 2);
+      long long t_wait = 0;
       for (int64_t tile = pair0; tile < total; tile += pair_stride) {
         const int64_t r = tile / n_n, c = tile % n_n;
         const int m0 = (int)((r * 2 + crank) * BLOCK_M), n0 = (int)(c * BLOCK_N) + half;
         for (int kb = 0; kb < n_kb; ++kb) {
+          const long long t0 = dbg_out ? clock64() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (dbg_out) t_wait += clock64() - t0;
           if (leader) mbar_expect_tx(&full_bar[stage], TX);
           const bool first = kb < kb_split;
           const int ka = (first ? kb : kb - kb_split) * F8_BLOCK_K, kw = kb * F8_BLOCK_K;
@@ -135,20 +138,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (dbg_out) dbg_out[blockIdx.x * 8 + 0] = t_wait;
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {                         // ---- MMA issuer (leader only)
       int stage = 0;
       uint32_t phase = 0;
       int64_t it = 0;
+      long long t_empty = 0, t_full = 0;
+      const long long t_begin = dbg_out ? clock64() : 0;
       for (int64_t tile = pair0; tile < total; tile += pair_stride, ++it) {
         const int acc = (int)(it & 1);
         const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+        const long long te0 = dbg_out ? clock64() : 0;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        if (dbg_out) t_empty += clock64() - te0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * BLOCK_N;
         for (int kb = 0; kb < n_kb; ++kb) {
+          const long long tf0 = dbg_out ? clock64() : 0;
           mbar_wait(&full_bar[stage], phase);
+          if (dbg_out) t_full += clock64() - tf0;
           tc_fence_after();
           const uint64_t dah = make_desc(smem_u32(sAh(stage))), dbh = make_desc(smem_u32(sBh(stage)));
           const uint64_t da8h = make_desc_sw64(smem_u32(sA8h(stage))), da8l = make_desc_sw64(smem_u32(sA8l(stage)));
@@ -170,24 +180,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
         }
         tc_commit_2sm(&tmem_full[acc]);
       }
+      if (dbg_out) {
+        dbg_out[blockIdx.x * 8 + 1] = t_empty;
+        dbg_out[blockIdx.x * 8 + 2] = t_full;
+        dbg_out[blockIdx.x * 8 + 3] = clock64() - t_begin;
+      }
     }
   } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) {
     const int q = warp & 3;                            // ---- epilogue (both CTAs)
     int64_t it = 0;
     EpiLse el{};
+    long long t_epi_wait = 0, t_epi_work = 0;
     for (int64_t tile = pair0; tile < total; tile += pair_stride, ++it) {
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
       const int64_t r = tile / n_n, n_blk = tile % n_n;
       const int64_t m_blk = r * 2 + crank;
       const int64_t m = m_blk * BLOCK_M + q * 32 + lane;
+      const long long tw0 = dbg_out ? clock64() : 0;
       mbar_wait(&tmem_full[acc], acc_phase);
+      const long long tw1 = dbg_out ? clock64() : 0;
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * BLOCK_N + ((uint32_t)(q * 32) << 16);
       if (!(dbg & 4)) epilogue_tile<false>(taddr, m, M, n_blk * BLOCK_N, n_blk, N, es, el, epi_smem + q * 32 * EPI_LD, acc_scale);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&tmem_empty[acc]);
+      if (dbg_out) { t_epi_wait += tw1 - tw0; t_epi_work += clock64() - tw1; }
+    }
+    if (dbg_out && lane == 0) {
+      dbg_out[blockIdx.x * 8 + 4 + (q & 1) * 2] = t_epi_wait;       // warps 0 / 1 of the four (2 / 3 overwrite: same order of magnitude)
+      dbg_out[blockIdx.x * 8 + 5 + (q & 1) * 2] = t_epi_work;
     }
   }
 
@@ -347,12 +370,36 @@ extern "C" int32_t gnnlm_linear_f16f8(const void* A1, const void* A1q, int64_t l
     GNNLM_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   const int64_t pairs = ceil_div(ceil_div(M, tc::BLOCK_M), 2) * ceil_div(N, tc::BLOCK_N);
-  const int64_t max_pairs = n_sm / 2;
+  static int pair_cap = -1;
+  if (pair_cap < 0) { const char* e = getenv("GNNLM_F8_MAXPAIRS"); pair_cap = e ? atoi(e) : 0; }   // timing experiments only
+  const int64_t max_pairs = pair_cap > 0 && pair_cap < n_sm / 2 ? pair_cap : n_sm / 2;
   const unsigned grid = 2u * (unsigned)(pairs < max_pairs ? pairs : max_pairs);
   static int dbg = -1;
   if (dbg < 0) { const char* e = getenv("GNNLM_F8_DEBUG"); dbg = e ? atoi(e) : 0; }          // timing experiments only
   es.dbg = (dbg >> 3) & 3;
-  tc::gemm_f16f8_kernel<<<grid, 256, smem, stream>>>(maps, M, m_dev, N, K, (int)(K1 / tc::F8_BLOCK_K), es, 1.f / w_scale, dbg);
+  long long* dbg_out = nullptr;
+  if (dbg & 32) {                                    // per-role wait cycles (timing experiments only; synchronises)
+    static long long* buf = nullptr;
+    if (!buf) GNNLM_CUDA(cudaMalloc(&buf, 148 * 8 * sizeof(long long)));
+    GNNLM_CUDA(cudaMemsetAsync(buf, 0, 148 * 8 * sizeof(long long), stream));
+    dbg_out = buf;
+  }
+  tc::gemm_f16f8_kernel<<<grid, 256, smem, stream>>>(maps, M, m_dev, N, K, (int)(K1 / tc::F8_BLOCK_K), es, 1.f / w_scale, dbg, dbg_out);
   GNNLM_LAUNCH_CHECK("gnnlm_linear_f16f8");
+  if (dbg_out) {
+    static long long host[148 * 8];
+    GNNLM_CUDA(cudaStreamSynchronize(stream));
+    GNNLM_CUDA(cudaMemcpy(host, dbg_out, sizeof(host), cudaMemcpyDeviceToHost));
+    double acc[8] = {0};
+    int n_lead = 0;
+    for (unsigned b = 0; b < grid; ++b) {
+      acc[0] += (double)host[b * 8];
+      for (int i = 4; i < 8; ++i) acc[i] += (double)host[b * 8 + i];
+      if (b % 2 == 0) { for (int i = 1; i < 4; ++i) acc[i] += (double)host[b * 8 + i]; ++n_lead; }
+    }
+    fprintf(stderr, "f16f8 M=%lld N=%lld K=%lld cycles: issuer total %.0f, wait tmem_empty %.0f, wait full %.0f | producer wait empty %.0f | "
+            "epi warp0 wait %.0f work %.0f, warp1 wait %.0f work %.0f\n", (long long)M, (long long)N, (long long)K, acc[3] / n_lead,
+            acc[1] / n_lead, acc[2] / n_lead, acc[0] / grid, acc[4] / grid, acc[5] / grid, acc[6] / grid, acc[7] / grid);
+  }
   return 0;
 }

@@ -180,6 +180,7 @@ class HGTLayer(nn.Module):
         self.use_cluster_kernel = True     # False: always go through the generic CSR kernel (tests compare both)
         self.use_fused_inter = True        # False: project every centre node to K' / V' and use the CSR kernel
         self.use_gemm_attention = True     # MATH_F16X3, long blocks: tgt-intra-tgt attention as tensor-core GEMMs
+        self.use_flash_attention = True    # tensor-core modes, d_k in {64, 128}: one flash kernel instead (gnnlm_hgt_causal_flash)
 
     # ------------------------------------------------------------------ weight preparation
     def prepare(self, math_mode: int, rot: Optional[torch.Tensor] = None):
@@ -292,7 +293,14 @@ class HGTLayer(nn.Module):
         (small) side are kept in fp32 in every mode.  `chunks`: [(t0, t1, chunk_graph, hc_chunk)] when the ntgt side
         was run in token chunks -- the inter attention is then applied chunk by chunk (hc / c_dev unused)."""
         d, H = P["d"], self.n_heads
-        qkv = _lin(h_t, P["tgt_qkv"], P["math"])
+        gemm_modes = (L.MATH_F16X3, L.MATH_F16F8, L.MATH_BF16, L.MATH_TF32)
+        flash = (P["math"] in gemm_modes and self.use_flash_attention and ops.causal_flash_supported(d, H)
+                 and L.load().gnnlm_has_tcgen05())
+        if flash:        # Q fp32 (the inter path and the flash kernel split it themselves), K' | V' as split fp16 from the epilogue
+            qkv = _lin(h_t, P["tgt_qkv"].rows(0, d), P["math"])
+            kv = _lin(h_t, P["tgt_qkv"].rows(d, 3 * d), P["math"], out_dtype=ops.SPLIT)
+        else:
+            qkv = _lin(h_t, P["tgt_qkv"], P["math"])
         t_agg = torch.empty((h_t.shape[0], d), device=qkv.device, dtype=torch.float32)
         # inter edges in compact centre numbering are the contiguous ranges of inter_indptr
         if P["inter_fused"] is not None and self.use_fused_inter:
@@ -310,8 +318,14 @@ class HGTLayer(nn.Module):
                               tag="inter")
         # tensor-core form (3xFP16 GEMMs on the fp32 Q / K' / V', fp32-level accuracy) in every mode that already puts fp16-range
         # operands on the tensor cores; tf32x3 / fp32 keep the CUDA-core kernel (no fp16 range limit on Q / K' / V')
-        gemm_modes = (L.MATH_F16X3, L.MATH_F16F8, L.MATH_BF16, L.MATH_TF32)
-        if P["math"] in gemm_modes and self.use_gemm_attention and ops.causal_attn_gemm_supported(d, H, G.L) and G.L >= 1024:
+        if flash:
+            act = act_dtype(P["math"])
+            if act == ops.SPLIT:       # the sum of the two edge types leaves as the output projection's operand
+                t_split = ops.Split.empty(h_t.shape[0], d, qkv.device)
+                ops.causal_attn_flash(qkv[:, :d], kv, G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5, accumulate=True, out_split=t_split)
+                return self._out(P, P["t"], t_split, h_t, None)
+            ops.causal_attn_flash(qkv[:, :d], kv, G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5, accumulate=True)
+        elif P["math"] in gemm_modes and self.use_gemm_attention and ops.causal_attn_gemm_supported(d, H, G.L) and G.L >= 1024:
             ops.causal_attn_gemm(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5,
                                  accumulate=True)
         else:

@@ -303,6 +303,23 @@ def causal_attn(q, k, v, B, Lb, intra_ctx, H, out, *, out_scale=1.0, accumulate=
     return out
 
 
+def causal_flash_supported(d: int, H: int) -> bool:
+    return d % H == 0 and d // H in (64, 128)
+
+
+def causal_attn_flash(q, kv: Split, B, Lb, intra_ctx, H, out, *, out_scale=1.0, accumulate=False, out_split: Optional[Split] = None):
+    """tgt-intra-tgt attention as one flash kernel (gnnlm_hgt_causal_flash): q fp32 [B*Lb, d] (column slice ok), kv = K' | V' as
+    one split-fp16 matrix [B*Lb, 2d]; out fp32 [B*Lb, d] (+)= out_scale * attention, or -- with out_split -- the final value as
+    split fp16 (out is then only read when accumulating)."""
+    d = q.shape[1]
+    assert kv.has_lo and kv.d == 2 * d and q.dtype == torch.float32 and q.stride(1) == 1
+    os_ptr, ldos, os_lo = (None, 0, 0) if out_split is None else (L.ptr(out_split.data), out_split.data.stride(0), out_split.d)
+    kd = kv.data
+    L.call("gnnlm_hgt_causal_flash", L.ptr(q), q.stride(0), L.ptr(kd), L.ptr(kd[:, d:]), kd.stride(0), 2 * d, B, Lb, intra_ctx, H, d // H,
+           L.ptr(out), out.stride(0), os_ptr, ldos, os_lo, float(out_scale), int(accumulate), L.stream_ptr(), tag="causal_flash")
+    return out if out_split is None else out_split
+
+
 CAUSAL_K_TILE = 256      # rows per tile pair of the batched GEMM (2 * BLOCK_M): the contraction limit of `causal = 2`
 
 

@@ -324,6 +324,21 @@ int32_t gnnlm_hgt_causal_attn(const void* q, int64_t ldq, const void* k, int64_t
                               int32_t d_k, float* out, int64_t ldo, float out_scale, int32_t accumulate,
                               gnnlm_stream_t stream);
 
+/* The same attention as ONE flash kernel on the tensor cores at fp32 parity (three-pass fp16 split on mma.sync, fp32
+ * accumulation, online softmax; S and P never leave the SM): replaces the heads_split / batched-GEMM / causal_softmax_split
+ * sequence below for d_k in {64, 128}.  Reference: fairseq/models/hgt.py:350-358 over the edges of
+ * fairseq/data/token_block_dataset.py:586-594.
+ *  q        fp32 [B*L, >= H*d_k] (row stride ldq)
+ *  k_split, v_split  K' / V' as split fp16 (GNNLM_F16X2): hi at [t, h*d_k + j], lo at [t, lo_off + h*d_k + j], row stride ldkv
+ *           (elements) -- e.g. column slices of a projection written with c_dtype = GNNLM_F16X2
+ *  out      fp32 [B*L, >= H*d_k]: out (+)= out_scale * attention (accumulate != 0 adds to what is there)
+ *  out_split  optional: the final value is written as split fp16 (hi at column c, lo at os_lo + c, row stride ldos) INSTEAD of
+ *           to `out`, which is then only read (accumulate != 0) -- the operand format of the output projection. */
+int32_t gnnlm_hgt_causal_flash(const float* q, int64_t ldq, const void* k_split, const void* v_split, int64_t ldkv,
+                               int64_t lo_off, int64_t B, int64_t L, int64_t intra_ctx, int32_t H, int32_t d_k, float* out,
+                               int64_t ldo, void* out_split, int64_t ldos, int64_t os_lo, float out_scale, int32_t accumulate,
+                               gnnlm_stream_t stream);
+
 /* ('ntgt','inter','tgt') attention with the K' / V' projections moved from the ~k*T centre nodes to the T target tokens
  * (every centre row is used by exactly one (token, neighbour) pair): with q~[t,h] = W_k'[h]^T q[t,h] in R^d (a per-head GEMM
  * of the caller) this kernel computes, per token and head, alpha = softmax_c <h_c, q~[t,h]> over the token's centre rows and

@@ -1069,6 +1069,41 @@ def test_causal_attn_gemm_form(B, L, H, d, ctx, dev):
     np.testing.assert_allclose(out.cpu().numpy(), out2.cpu().numpy(), rtol=1e-4, atol=5e-5)
 
 
+@pytest.mark.parametrize("B,L,H,d,ctx", [(1, 256, 8, 1024, 0), (2, 320, 8, 512, 0), (1, 512, 8, 1024, 100), (1, 1288, 8, 1024, 0),
+                                          (1, 3072, 8, 1024, 0), (1, 1024, 4, 512, 300), (3, 200, 8, 1024, 0), (2, 77, 8, 512, 5),
+                                          (1, 33, 8, 1024, 1)])
+@pytest.mark.parametrize("split_out", [False, True])
+def test_causal_flash_kernel(B, L, H, d, ctx, split_out, dev):
+    """gnnlm_hgt_causal_flash (one mma.sync flash kernel, K' / V' as split fp16) vs the fp64 definition of hgt.py:350-358 over the
+    edges of auto_regressive_edges, incl. ragged L, several blocks, a context window and the split-fp16 output."""
+    from gnnlm_b200 import ops
+    torch.manual_seed(11)
+    q, k, v = torch.randn(B * L, d) * 0.3, torch.randn(B * L, d) * 0.3, torch.randn(B * L, d)
+    base = torch.randn(B * L, d)
+    qkv = torch.cat([q, k, v], 1).to(dev)                      # q as a column slice (row stride 3d), as the layer passes it
+    kv = ops.to_split(qkv[:, d:].contiguous())
+    out = base.clone().to(dev)
+    if split_out:
+        res = ops.Split.empty(B * L, d, dev)
+        ops.causal_attn_flash(qkv[:, :d], kv, B, L, ctx, H, out, out_scale=0.5, accumulate=True, out_split=res)
+        assert torch.equal(out.cpu(), base)                    # only read
+        got = res.float().cpu().double()
+    else:
+        ops.causal_attn_flash(qkv[:, :d], kv, B, L, ctx, H, out, out_scale=0.5, accumulate=True)
+        got = out.cpu().double()
+        out0 = torch.full((B * L, d), float("nan"), device=dev)
+        ops.causal_attn_flash(qkv[:, :d], kv, B, L, ctx, H, out0, out_scale=1.0, accumulate=False)     # overwrite form
+    qh, kh, vh = (t.view(B, L, H, d // H).permute(0, 2, 1, 3).double() for t in (q, k, v))
+    s = qh @ kh.transpose(-1, -2)
+    i = torch.arange(L)
+    mask = (i[None, :] <= i[:, None]) & ((i[:, None] - i[None, :] < ctx) if ctx else True)
+    att = (torch.softmax(s.masked_fill(~mask, -float("inf")), -1) @ vh).permute(0, 2, 1, 3).reshape(B * L, d)
+    ref = base.double() + 0.5 * att
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), rtol=2e-5, atol=2e-5)
+    if not split_out:
+        np.testing.assert_allclose(out0.cpu().double().numpy(), att.numpy(), rtol=2e-5, atol=2e-5)
+
+
 @pytest.mark.parametrize("math", ["fp32", "f16x3"])
 def test_token_chunked_ntgt_side_matches(math, dev):
     """forward_tgt_chunked (ntgt side in token chunks, inter attention per chunk) == forward_tgt."""
