@@ -127,20 +127,22 @@ __global__ void __launch_bounds__(CF_THREADS, 2)
     float s[CF_BK / 8][4];
 #pragma unroll
     for (int nt = 0; nt < CF_BK / 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    static_assert(CF_BK == 32, "the score loop below issues the four n-tiles of a 32-key tile pass by pass");
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
+      // pass-major order: four independent accumulators between two MMAs on the same one (mma.sync latency ~22 clk, issue 8 clk)
+      uint32_t bh[2][4], bl[2][4];
 #pragma unroll
-      for (int np = 0; np < CF_BK / 16; ++np) {
-        uint32_t bh[4], bl[4];
-        ldsm_x4(bh, tile + np * 16 * RS + ks * 32 + k_off);
-        ldsm_x4(bl, tile + ARR + np * 16 * RS + ks * 32 + k_off);
-        mma16816(s[2 * np], ql[ks], bh[0], bh[1]);
-        mma16816(s[2 * np + 1], ql[ks], bh[2], bh[3]);
-        mma16816(s[2 * np], qh[ks], bl[0], bl[1]);
-        mma16816(s[2 * np + 1], qh[ks], bl[2], bl[3]);
-        mma16816(s[2 * np], qh[ks], bh[0], bh[1]);
-        mma16816(s[2 * np + 1], qh[ks], bh[2], bh[3]);
+      for (int np = 0; np < 2; ++np) {
+        ldsm_x4(bh[np], tile + np * 16 * RS + ks * 32 + k_off);
+        ldsm_x4(bl[np], tile + ARR + np * 16 * RS + ks * 32 + k_off);
       }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma16816(s[nt], ql[ks], bh[nt >> 1][(nt & 1) * 2], bh[nt >> 1][(nt & 1) * 2 + 1]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma16816(s[nt], qh[ks], bl[nt >> 1][(nt & 1) * 2], bl[nt >> 1][(nt & 1) * 2 + 1]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma16816(s[nt], qh[ks], bh[nt >> 1][(nt & 1) * 2], bh[nt >> 1][(nt & 1) * 2 + 1]);
     }
     // ---- mask (diagonal / context-window tiles only)
     if (kv0 + CF_BK - 1 > qw || (ctx > 0 && kv0 <= qw + 15 - ctx)) {
@@ -192,16 +194,19 @@ __global__ void __launch_bounds__(CF_THREADS, 2)
 #pragma unroll
     for (int j = 0; j < CF_BK / 16; ++j) {
 #pragma unroll
-      for (int np = 0; np < NT / 2; ++np) {
-        uint32_t bh[4], bl[4];
-        ldsm_x4_t(bh, vt + j * 16 * RS + np * 32 + v_off);
-        ldsm_x4_t(bl, vt + ARR + j * 16 * RS + np * 32 + v_off);
-        mma16816(o[2 * np], pl[j], bh[0], bh[1]);
-        mma16816(o[2 * np + 1], pl[j], bh[2], bh[3]);
-        mma16816(o[2 * np], ph[j], bl[0], bl[1]);
-        mma16816(o[2 * np + 1], ph[j], bl[2], bl[3]);
-        mma16816(o[2 * np], ph[j], bh[0], bh[1]);
-        mma16816(o[2 * np + 1], ph[j], bh[2], bh[3]);
+      for (int nq = 0; nq < NT / 4; ++nq) {              // four n-tiles at a time, pass-major
+        uint32_t bh[2][4], bl[2][4];
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          ldsm_x4_t(bh[np], vt + j * 16 * RS + (nq * 2 + np) * 32 + v_off);
+          ldsm_x4_t(bl[np], vt + ARR + j * 16 * RS + (nq * 2 + np) * 32 + v_off);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma16816(o[nq * 4 + nt], pl[j], bh[nt >> 1][(nt & 1) * 2], bh[nt >> 1][(nt & 1) * 2 + 1]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma16816(o[nq * 4 + nt], ph[j], bl[nt >> 1][(nt & 1) * 2], bl[nt >> 1][(nt & 1) * 2 + 1]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma16816(o[nq * 4 + nt], ph[j], bh[nt >> 1][(nt & 1) * 2], bh[nt >> 1][(nt & 1) * 2 + 1]);
       }
     }
   }

@@ -17,6 +17,8 @@ B200-first restructuring (results identical up to fp rounding, see tests/test_gp
 import math
 from typing import Dict, List, Optional
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -180,7 +182,8 @@ class HGTLayer(nn.Module):
         self.use_cluster_kernel = True     # False: always go through the generic CSR kernel (tests compare both)
         self.use_fused_inter = True        # False: project every centre node to K' / V' and use the CSR kernel
         self.use_gemm_attention = True     # MATH_F16X3, long blocks: tgt-intra-tgt attention as tensor-core GEMMs
-        self.use_flash_attention = True    # tensor-core modes, d_k in {64, 128}: one flash kernel instead (gnnlm_hgt_causal_flash)
+        # tensor-core modes, d_k in {64, 128}: one flash kernel instead (gnnlm_hgt_causal_flash); GNNLM_FLASH=0 for A/B timing
+        self.use_flash_attention = os.environ.get("GNNLM_FLASH", "1") != "0"
 
     # ------------------------------------------------------------------ weight preparation
     def prepare(self, math_mode: int, rot: Optional[torch.Tensor] = None):
@@ -296,11 +299,9 @@ class HGTLayer(nn.Module):
         gemm_modes = (L.MATH_F16X3, L.MATH_F16F8, L.MATH_BF16, L.MATH_TF32)
         flash = (P["math"] in gemm_modes and self.use_flash_attention and ops.causal_flash_supported(d, H)
                  and L.load().gnnlm_has_tcgen05())
-        if flash:        # Q fp32 (the inter path and the flash kernel split it themselves), K' | V' as split fp16 from the epilogue
-            qkv = _lin(h_t, P["tgt_qkv"].rows(0, d), P["math"])
-            kv = _lin(h_t, P["tgt_qkv"].rows(d, 3 * d), P["math"], out_dtype=ops.SPLIT)
-        else:
-            qkv = _lin(h_t, P["tgt_qkv"], P["math"])
+        qkv = _lin(h_t, P["tgt_qkv"], P["math"])
+        if flash:        # Q stays fp32 (the inter path and the flash kernel split it themselves); K' | V' as one split-fp16 matrix
+            kv = ops.to_split(qkv[:, d:])
         t_agg = torch.empty((h_t.shape[0], d), device=qkv.device, dtype=torch.float32)
         # inter edges in compact centre numbering are the contiguous ranges of inter_indptr
         if P["inter_fused"] is not None and self.use_fused_inter:
