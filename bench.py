@@ -52,6 +52,8 @@ def parse():
                         "one NCCL all-reduce of {sum log p, n_tokens}")
     p.add_argument("--strong-blocks", type=int, default=128)
     p.add_argument("--eval-blocks", type=int, default=16, help="blocks of the e2e_evaluate leg (0: skip it)")
+    p.add_argument("--locality", default="0.5,1048576",
+                   help="p_continue,n_hot of the realistic-duplication leg (synth.local_neighbours); empty: skip the leg")
     p.add_argument("--ncu-range", action="store_true",
                    help="after warm-up run ONE resident step inside cudaProfilerStart/Stop and exit "
                         "(use with `ncu --profile-from-start off`); prints no bench line")
@@ -531,6 +533,34 @@ def main():
             del ds, dstore_e, knn_e
         finally:
             shutil.rmtree(root, ignore_errors=True)
+    # ---- realistic duplication: neighbour ids with the locality of real kNN graphs (repeated centres, overlapping clusters)
+    # through (a) the default path, (b) the ntgt side once per distinct centre row (share_centres), (c) the --deprecated builder
+    if world == 1 and args.locality and not args.deprecated:
+        import copy
+        p_c, n_hot = args.locality.split(",")
+        loc = (float(p_c), int(n_hot))
+        lb = [synth.make_batch(cfg, tables, seed=5000 + i, device=dev, locality=loc) for i in range(2)]
+        flat = lb[0]["nbr"].reshape(-1)
+        ok = flat >= 0
+        n_pairs, n_cent = int(ok.sum()), int(torch.unique(flat[ok]).numel())
+        leg = {"p_continue": loc[0], "n_hot_rows": loc[1], "valid_pairs": n_pairs, "distinct_centres": n_cent,
+               "duplicate_rate": 1.0 - n_cent / max(n_pairs, 1),
+               "note": "synth.local_neighbours: neighbour j of token t continues neighbour j of token t-1 (row + 1) with probability "
+                       "p_continue, else a fresh retrieval from n_hot popular rows with 1/rank popularity; same model / datastore "
+                       "as the headline; results of (a) and (b) are identical (tested against the oracle)"}
+        for name, kw in (("new_builder", {}), ("new_builder_share_centres", {"share": True}), ("deprecated_builder", {"dep": True})):
+            c2 = dict(cfg, deprecated=True) if kw.get("dep") else cfg
+            m2 = copy.deepcopy(model)
+            m2.decoder.share_centres = bool(kw.get("share"))
+            r3 = synth.Runner(c2, m2, tables, dev, math)
+            f3 = lambda i: r3.step_resident(lb[i % 2], cuda_graph=args.cuda_graph)
+            for i in range(3):
+                f3(i)
+            ms3 = timed(f3, args.steps)
+            leg[name] = {"value": args.steps * T / (ms3 * 1e-3), "unit": "tokens/s", "ms_per_step": ms3 / args.steps,
+                         "score_sum": float(r3.acc[0].item())}
+            del r3, m2
+        line["locality"] = leg
     # secondary arithmetic modes (same workload, resident inputs, short timed loop) -- information only; the
     # headline stays the fp32-parity mode
     other = {}

@@ -36,6 +36,8 @@ SIGNATURES = {
     "gnnlm_graph_tt_csr": (_i32, [_i64, _i64, _i64, _p, _p, _p]),
     "gnnlm_graph_dedup_workspace_bytes": (_i64, [_i64, _i64, _i32]),
     "gnnlm_graph_dedup": (_i32, [_p, _p, _i64, _i64, _i64, _i64, _i32, _i32, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p]),
+    "gnnlm_unique_workspace_bytes": (_i64, [_i64]),
+    "gnnlm_unique_centres": (_i32, [_p, _p, _i64, _p, _p, _p, _p, _i64, _p]),
     "gnnlm_pq_gather_decode": (_i32, [_p, _i64, _i32, _p, _i32, _p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _i32, _p, _p, _p]),
     "gnnlm_pq_gather_decode_presplit": (_i32, [_p, _i64, _i32, _p, _p, _i32, _p, _p, _i64, _p, _p, _i64, _p]),
     "gnnlm_pq_gather_decode_presplit_q8": (_i32, [_p, _i64, _i32, _p, _p, _i32, _p, _p, _i64, _p, _p, _i64, _p, _i64, _p]),
@@ -80,7 +82,7 @@ SIGNATURES = {
 
 _lib = None
 launches = 0          # number of CUDA kernels launched through the C ABI (bench.py's gpu_launches)
-KERNELS_PER_CALL = {"gnnlm_graph_count": 3, "gnnlm_knn_full_prob": 2, "gnnlm_graph_dedup": 12,   # everything else launches exactly one
+KERNELS_PER_CALL = {"gnnlm_graph_count": 3, "gnnlm_unique_centres": 2, "gnnlm_knn_full_prob": 2, "gnnlm_graph_dedup": 12,   # everything else launches exactly one
                     "gnnlm_host_copy": 0}
 TIMING = None         # when a list: (name, tag, start_event, end_event, work) per call (bench.py per-kernel pass)
 

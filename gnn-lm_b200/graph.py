@@ -163,3 +163,22 @@ def token_chunk_graph(G: TokenGraph, t0: int, t1: int) -> TokenGraph:
     pos = None if G.tgt_pos is None else G.tgt_pos.reshape(-1)[t0:t1]
     return build_token_graph(nbr.contiguous(), G.n_datastore, G.left_ctx, G.right_ctx, tgt_pos=pos,
                              invalid_ctx=G.invalid_ctx, intra_ctx=G.intra_ctx)
+
+
+def unique_centre_graph(G: TokenGraph):
+    """(G_u, inv, n_unique): the graph of the DISTINCT centre rows of G's valid (token, neighbour) pairs -- one "token" per
+    distinct row with that row as its only neighbour -- and, per compact valid pair of G, the compact centre index in G_u.
+    Clusters with the same centre row are identical in every layer (they only exchange messages inside themselves), so the ntgt
+    side can run on G_u and be gathered back (HGT.forward_tgt_shared).  No host synchronisation: capacity-sized arrays."""
+    assert not G.dedup
+    n = G.T * G.k
+    dev = G.nbr.device
+    uniq = torch.empty(n, dtype=torch.int64, device=dev)
+    inv = torch.empty(n, dtype=torch.int32, device=dev)
+    n_unique = torch.empty(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(L.load().gnnlm_unique_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    L.call("gnnlm_unique_centres", L.ptr(G.nbr), L.ptr(G.valid_base), n, L.ptr(uniq), L.ptr(inv), L.ptr(n_unique), L.ptr(ws),
+           ws.numel(), L.stream_ptr())
+    # validity (missing ids, invalid_ctx) was decided pair by pair in G: every id in uniq is a real row
+    G_u = build_token_graph(uniq.view(1, n, 1), G.n_datastore, G.left_ctx, G.right_ctx)
+    return G_u, inv, n_unique

@@ -426,6 +426,25 @@ class HGT(nn.Module):
             h_t = self.gcs[l].tgt(prep[l], G, h_t, hc[l], G.n_valid_dev)
         return self.project_out(h_t)
 
+    @torch.no_grad()
+    def forward_tgt_shared(self, G: TokenGraph, h_tgt, decode, rot=None):
+        """Same result as forward_tgt with the ntgt side run once per DISTINCT centre row (graph.unique_centre_graph): clusters
+        that share a centre are identical in every layer, so their compact centre features are computed on the graph of the
+        distinct rows and gathered back per (token, neighbour) pair.  `decode(graph, centre_only)` as in forward_tgt_chunked."""
+        from .graph import unique_centre_graph
+        mode = self.math_mode
+        prep = self._prepare_layers(rot)
+        G_u, inv, _ = unique_centre_graph(G)
+        if self.n_layers == 1:
+            hc_u = self._ntgt_side(prep, G_u, None, hc0=decode(G_u, True))
+        else:
+            hc_u = self._ntgt_side(prep, G_u, decode(G_u, False), hc0=decode(G_u, True) if rot is not None else None)
+        hc = [ops.gather_rows(x, inv, n_dev=G.n_valid_dev) for x in hc_u]
+        h_t = as_act(self.adapt(h_tgt, "tgt"), mode)
+        for l in range(self.n_layers):
+            h_t = self.gcs[l].tgt(prep[l], G, h_t, hc[l], G.n_valid_dev)
+        return self.project_out(h_t)
+
     def can_fold_rotation(self, d_dec: int) -> bool:
         """MATH_F16F8 with no input adapters: the OPQ rotation of the ntgt features can be folded into layer 0
         (HGTLayer.prepare `rot`); needs the two-source f16f8 product (k-blocks of 64) and the fused inter kernel."""

@@ -245,6 +245,9 @@ class TokenGraphTransformerDecoder(nn.Module):
             nn.init.normal_(self.embed_out, mean=0, std=d ** -0.5)
         self.math_mode = L.MATH_FP32_SIMT
         self.fold_rotation = True          # MATH_F16F8: fold the OPQ rotation into HGT layer 0 (False: explicit rotation GEMM)
+        # cluster-level reuse: run the ntgt side once per DISTINCT centre row of a batch (same results; pays off on real kNN graphs,
+        # where centres repeat inside a block -- uniform synthetic ids have no duplicates)
+        self.share_centres = bool(_get(args, "share_centres", False))
         self._out_prep, self._out_key = None, None
 
     def set_math(self, mode):
@@ -332,6 +335,10 @@ class TokenGraphTransformerDecoder(nn.Module):
             per_token = graph.k * graph.w * self.embed_dim * 4 * 11
             budget = float(_get(self.args, "ntgt_memory_budget_gb", 48.0)) * 1e9
             chunk = max(64, int(budget // per_token) // 64 * 64)
+            if self.share_centres and not graph.dedup and graph.T <= chunk:
+                # cluster-level reuse: the ntgt side once per distinct centre row (identical results, HGT.forward_tgt_shared)
+                out = self.hgt_decoder.forward_tgt_shared(graph, h_tgt, decode, rot=rot)
+                return as_float(out).view(bsz, seq_len, -1)
             if NL > 1 and graph.T > chunk and graph.dedup:
                 raise NotImplementedError("--deprecated graphs share ntgt nodes between tokens, so the ntgt side cannot run "
                                           "in token chunks: raise ntgt_memory_budget_gb or evaluate shorter blocks")

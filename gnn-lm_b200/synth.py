@@ -83,13 +83,31 @@ def make_tables(cfg: dict, seed: int = 0, n_d: int = None, device="cpu") -> dict
     return dict(codes=codes, vals=vals, n_d=n_d)
 
 
-def make_batch(cfg: dict, tables: dict, seed: int = 0, device="cpu", stress: bool = True) -> dict:
-    """One batch of per-token inputs: neighbour ids, fp16 features, targets, kNN-LM search results."""
+def local_neighbours(B: int, L_: int, k: int, n_d: int, c: int, p_continue: float, n_hot: int, generator, device):
+    """Neighbour ids with the locality of real kNN graphs instead of uniform draws: with probability `p_continue` neighbour j of
+    token t continues neighbour j of token t-1 (row o + 1: adjacent tokens retrieve adjacent datastore rows, so their clusters
+    overlap), otherwise it is a fresh retrieval from `n_hot` popular rows with Zipfian (1 / rank) popularity, scattered over
+    the datastore -- recurring contexts retrieve the SAME row, which is what makes centres repeat inside a block."""
+    u = torch.rand((B, L_, k), generator=generator, device=device, dtype=torch.float64)
+    rank = torch.exp(u * float(np.log(n_hot))).long().clamp_(1, n_hot)                  # P(rank = r) ~ 1 / r
+    fresh = (rank * 2654435761 + 12345) % (n_d - 2 * c - L_) + c
+    cont = torch.rand((B, L_, k), generator=generator, device=device) < p_continue
+    cont[:, 0] = False
+    t = torch.arange(L_, device=device).view(1, L_, 1).expand(B, L_, k)
+    start = torch.cummax(torch.where(cont, torch.zeros_like(t), t), dim=1).values       # first token of the run each entry is in
+    return torch.gather(fresh, 1, start) + (t - start)
+
+
+def make_batch(cfg: dict, tables: dict, seed: int = 0, device="cpu", stress: bool = True, locality=None) -> dict:
+    """One batch of per-token inputs: neighbour ids, fp16 features, targets, kNN-LM search results.
+    `locality` = (p_continue, n_hot): neighbour ids from local_neighbours instead of uniform draws."""
     c = SimpleNamespace(**cfg)
     n_d, vals = tables["n_d"], tables["vals"]
     g = torch.Generator(device=device).manual_seed(seed + 12345)
     T = c.B * c.L
     nbr = torch.randint(c.c, n_d - c.c, (c.B, c.L, c.k), generator=g, device=device, dtype=torch.int64)
+    if locality is not None:
+        nbr = local_neighbours(c.B, c.L, c.k, n_d, c.c, float(locality[0]), int(locality[1]), g, device)
     if stress:   # 1% missing, 0.1% within c of either boundary (SURVEY.md 8d)
         r = torch.rand((c.B, c.L, c.k), generator=g, device=device)
         nbr[r < 0.01] = -1
@@ -112,10 +130,10 @@ def make_batch(cfg: dict, tables: dict, seed: int = 0, device="cpu", stress: boo
                 positions=torch.arange(T, device=device).view(c.B, c.L))
 
 
-def make_data(cfg: dict, seed: int = 0, n_d: int = None, device="cpu", stress: bool = True) -> dict:
+def make_data(cfg: dict, seed: int = 0, n_d: int = None, device="cpu", stress: bool = True, locality=None) -> dict:
     tables = make_tables(cfg, seed, n_d, device)
     out = dict(tables)
-    out.update(make_batch(cfg, tables, seed, device, stress))
+    out.update(make_batch(cfg, tables, seed, device, stress, locality))
     return out
 
 

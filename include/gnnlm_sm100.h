@@ -103,6 +103,19 @@ int64_t gnnlm_graph_tt_num_edges(int64_t B, int64_t L, int64_t intra_ctx);
 int32_t gnnlm_graph_tt_csr(int64_t B, int64_t L, int64_t intra_ctx, int32_t* indptr, int32_t* indices,
                            gnnlm_stream_t stream);
 
+/* Distinct centre rows of a batch (cluster-level reuse).  new_build_graph creates a fresh cluster for every (token, neighbour)
+ * pair (token_block_dataset.py:355,363-374), and an ntgt node only ever receives messages from inside its cluster, so clusters
+ * with the same centre row carry identical features in every layer: the ntgt side can run once per DISTINCT centre.
+ *  nbr [n] neighbour ids (n = T*k), valid_base [n + 1] from gnnlm_graph_count
+ *  uniq [n]      out: the distinct ids of the valid pairs, -1 padded (a k = 1 neighbour array for gnnlm_graph_count / _fill);
+ *                order unspecified (first inserter into a hash table)
+ *  inv  [n]      out: inv[valid_base[i]] = index into uniq of pair i's id, for every valid pair
+ *  n_unique [1]  out (device): number of distinct ids
+ *  workspace: gnnlm_unique_workspace_bytes(n) bytes, 8 B aligned. */
+int64_t gnnlm_unique_workspace_bytes(int64_t n);
+int32_t gnnlm_unique_centres(const int64_t* nbr, const int32_t* valid_base, int64_t n, int64_t* uniq, int32_t* inv,
+                             int32_t* n_unique, void* workspace, int64_t workspace_bytes, gnnlm_stream_t stream);
+
 /* `--deprecated` graph assembly (GraphTokenBlockDataset.deprecated_build_graph, token_block_dataset.py:414-479): ONE ntgt
  * node per distinct datastore row of a block, numbered by first appearance (centre, left context ascending, right context
  * ascending, neighbour by neighbour, token by token); ntgt-ntgt edges between rows at distance <= 1 wherever they came

@@ -1130,6 +1130,54 @@ def test_token_chunked_ntgt_side_matches(math, dev):
         np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), rtol=1e-5, atol=1e-5)
 
 
+def test_unique_centres_kernel(dev):
+    """gnnlm_unique_centres: distinct valid ids (-1 padded), inverse map per compact valid pair, device-side count."""
+    from gnnlm_b200.graph import build_token_graph, unique_centre_graph
+    torch.manual_seed(3)
+    nbr = torch.randint(5, 60, (2, 40, 6), dtype=torch.int64)
+    nbr[torch.rand(nbr.shape) < 0.1] = -1
+    G = build_token_graph(nbr.to(dev), 1000, 1, 1)
+    G_u, inv, n_u = unique_centre_graph(G)
+    flat = nbr.reshape(-1)
+    valid = flat[flat >= 0]
+    want = torch.unique(valid)
+    uniq = G_u.nbr.reshape(-1).cpu()
+    n = int(n_u.item())
+    assert n == want.numel() and (uniq[n:] == -1).all()
+    assert torch.equal(torch.sort(uniq[:n]).values, want)
+    assert torch.equal(uniq[inv.cpu()[:valid.numel()].long()], valid)
+    assert G_u.counts()[1] == n
+
+
+@pytest.mark.parametrize("math,NL", [("fp32", 3), ("f16x3", 3), ("f16f8", 3), ("f16f8", 2), ("f16x3", 1), ("bf16", 3)])
+def test_shared_centres_on_duplicated_ids(math, NL, dev):
+    """Neighbour ids with real-graph locality (repeated centres, overlapping clusters): the ntgt side run once per distinct centre
+    (share_centres) scores like the oracle's duplicated clusters of new_build_graph, and like the plain CUDA path."""
+    if math != "fp32":
+        _need_tc()
+    import copy
+    from gnnlm_b200 import synth
+    from tests.synth import run_oracle
+    cfg = dict(synth.CONFIGS["c3mini"], L=128, NL=NL)
+    model = synth.make_model(cfg)
+    data = synth.make_data(cfg, device="cpu", locality=(0.5, 64))
+    flat = data["nbr"].reshape(-1)
+    n_valid, n_uni = int((flat >= 0).sum()), int(torch.unique(flat[flat >= 0]).numel())
+    assert n_uni < 0.8 * n_valid                                   # the workload does repeat centres
+    ref = run_oracle((cfg, model, data))
+    outs = {}
+    for share in (False, True):
+        m = copy.deepcopy(model)
+        m.decoder.share_centres = share
+        outs[share] = synth.run_gpu(cfg, m, data, dev, math)
+    tol = 1e-2 if math == "bf16" else 1e-4
+    lp = ref["logprob"].numpy()
+    for share in (False, True):
+        rel = np.abs(outs[share]["logprob"] - lp) / np.abs(lp)
+        assert rel.max() < tol, (share, rel.max())
+    np.testing.assert_allclose(outs[True]["logprob"], outs[False]["logprob"], rtol=1e-6 if math != "bf16" else 1e-2, atol=1e-6)
+
+
 @pytest.mark.parametrize("c,NL", [(3, 2), (3, 3), (2, 1), (2, 4)])
 def test_unreachable_context_pruning(c, NL, dev):
     """Context nodes further than NL-1 chain hops from their centre cannot reach a tgt node: the pruned graph
