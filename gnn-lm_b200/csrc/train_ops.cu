@@ -1,0 +1,352 @@
+// Backward kernels of the HGT fine-tuning step (`--freeze`: only decoder.hgt_decoder.* is trained,
+// fairseq/models/transformer_lm.py:183-186; loss = fairseq/criterions/adaptive_loss.py:31-83).
+//
+// The reference gets these from autograd over DGL's SDDMM / edge_softmax / SpMM (fairseq/models/hgt.py:350-358,383-386),
+// F.layer_norm (:405) and F.cross_entropy.  Here: one warp per destination for the segmented softmax + aggregation backward
+// (softmax statistics recomputed from Q / K' instead of stored per edge), one block per row for LayerNorm and the
+// softmax-cross-entropy of one adaptive-softmax cluster, plus the small data-movement kernels the GEMM backward needs
+// (transpose for dW = dY^T X through gnnlm_linear, column sums for the bias, scatter-add for gathered rows).
+// First training path: fp32, correctness before speed (three passes over the in-edges, fp32 atomics on dK' / dV').
+#include "common.cuh"
+
+namespace gnnlm {
+
+// ---------------------------------------------------------------------------------------------- edge attention backward
+// forward (edge_attn.cu):  out[v] = scale * sum_e alpha_e V'[u_e],  alpha = softmax_e <Q[v,h], K'[u_e,h]>   per head h
+// backward, per destination v and head h, with g_e = <dout[v,h], V'[u_e,h]> and D = sum_e alpha_e g_e:
+//   dV'[u_e] += scale * alpha_e dout[v]     ds_e = scale * alpha_e (g_e - D)     dQ[v] = sum_e ds_e K'[u_e]     dK'[u_e] += ds_e Q[v]
+// Edge sources: CSR (indptr / indices; indices == NULL: source = edge id) or, causal_L > 0, the implicit causal range of
+// token_block_dataset.py:586-594 inside blocks of causal_L destinations.
+template <int C>
+__global__ void __launch_bounds__(256) edge_attn_bwd_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k,
+                                                            int64_t ldk, const float* __restrict__ v, int64_t ldv,
+                                                            const float* __restrict__ dout, int64_t ldo,
+                                                            const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                                                            const int32_t* __restrict__ dst_ids, int64_t n_dst_cap,
+                                                            const int32_t* __restrict__ n_dst_dev, int64_t causal_L, int64_t intra_ctx,
+                                                            int group, float scale, float* __restrict__ dq, int64_t lddq,
+                                                            float* __restrict__ dk, int64_t lddk, float* __restrict__ dv, int64_t lddv) {
+  const int64_t n_dst = live_rows(n_dst_cap, n_dst_dev);
+  const int lane = threadIdx.x & 31;
+  const int col = lane * C;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n_dst; i += warps) {
+    int64_t e0, e1;
+    if (causal_L > 0) {
+      const int64_t b0 = (i / causal_L) * causal_L;
+      e0 = intra_ctx > 0 && i - intra_ctx + 1 > b0 ? i - intra_ctx + 1 : b0;
+      e1 = i + 1;
+    } else {
+      const int64_t row = dst_ids ? (int64_t)__ldg(dst_ids + i) : i;
+      e0 = __ldg(indptr + row);
+      e1 = __ldg(indptr + row + 1);
+    }
+    float qr[C], gr[C], dqr[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      qr[c] = q[i * ldq + col + c];
+      gr[c] = dout[i * ldo + col + c];
+      dqr[c] = 0.f;
+    }
+    auto src_of = [&](int64_t e) { return causal_L > 0 ? e : (indices ? (int64_t)__ldg(indices + e) : e); };
+    auto head_dot = [&](const float (&a)[C], const float* __restrict__ row) {
+      float p = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) p = fmaf(a[c], row[col + c], p);
+      for (int o = group >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      return p;
+    };
+    // pass A: softmax statistics
+    float m = -INFINITY, l = 0.f;
+    for (int64_t e = e0; e < e1; ++e) {
+      const float s = head_dot(qr, k + src_of(e) * ldk);
+      const float mx = fmaxf(m, s);
+      l = l * __expf(m - mx) + __expf(s - mx);
+      m = mx;
+    }
+    const float inv_l = l > 0.f ? 1.f / l : 0.f;
+    // pass B: D = sum_e alpha_e g_e
+    float D = 0.f;
+    for (int64_t e = e0; e < e1; ++e) {
+      const int64_t u = src_of(e);
+      const float a = __expf(head_dot(qr, k + u * ldk) - m) * inv_l;
+      D = fmaf(a, head_dot(gr, v + u * ldv), D);
+    }
+    // pass C: gradients
+    for (int64_t e = e0; e < e1; ++e) {
+      const int64_t u = src_of(e);
+      const float* kr = k + u * ldk;
+      const float a = __expf(head_dot(qr, kr) - m) * inv_l;
+      const float ds = scale * a * (head_dot(gr, v + u * ldv) - D);
+      const float av = scale * a;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        dqr[c] = fmaf(ds, kr[col + c], dqr[c]);
+        atomicAdd(dk + u * lddk + col + c, ds * qr[c]);
+        atomicAdd(dv + u * lddv + col + c, av * gr[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) dq[i * lddq + col + c] = dqr[c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- LayerNorm backward
+// y = LayerNorm(o + res) * gamma + beta (hgt.py:403-405).  dx = d(o) = d(res); dgamma / dbeta accumulated with atomics.
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) t += red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ o, int64_t ldo_, const float* __restrict__ res,
+                                                            int64_t ldr, const float* __restrict__ gamma, float eps,
+                                                            const float* __restrict__ dy, int64_t ldy, int64_t rows_cap,
+                                                            const int32_t* __restrict__ rows_dev, int d, float* __restrict__ dx,
+                                                            int64_t ldx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  constexpr int MAXC = 8;                                    // d <= 2048
+  __shared__ float red[8];
+  const int64_t rows = live_rows(rows_cap, rows_dev);
+  float ag[MAXC], ab[MAXC];
+#pragma unroll
+  for (int j = 0; j < MAXC; ++j) ag[j] = ab[j] = 0.f;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    float x[MAXC], g[MAXC];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+      const int c = threadIdx.x + j * 256;
+      x[j] = c < d ? o[r * ldo_ + c] + (res ? res[r * ldr + c] : 0.f) : 0.f;
+      s += x[j];
+    }
+    const float mean = block_sum_256(s, red) / d;
+    float vs = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+      const int c = threadIdx.x + j * 256;
+      x[j] = c < d ? x[j] - mean : 0.f;
+      vs += x[j] * x[j];
+    }
+    const float rstd = rsqrtf(block_sum_256(vs, red) / d + eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+      const int c = threadIdx.x + j * 256;
+      x[j] *= rstd;                                          // x hat
+      const float dyc = c < d ? dy[r * ldy + c] : 0.f;
+      g[j] = c < d ? dyc * gamma[c] : 0.f;
+      ag[j] += dyc * x[j];
+      ab[j] += dyc;
+      s1 += g[j];
+      s2 += g[j] * x[j];
+    }
+    const float m1 = block_sum_256(s1, red) / d, m2 = block_sum_256(s2, red) / d;
+#pragma unroll
+    for (int j = 0; j < MAXC; ++j) {
+      const int c = threadIdx.x + j * 256;
+      if (c < d) dx[r * ldx + c] = rstd * (g[j] - m1 - x[j] * m2);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < MAXC; ++j) {
+    const int c = threadIdx.x + j * 256;
+    if (c < d) {
+      atomicAdd(dgamma + c, ag[j]);
+      atomicAdd(dbeta + c, ab[j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- softmax cross-entropy
+// One cluster of the adaptive softmax (adaptive_softmax.py:147-168 + F.cross_entropy(reduction='sum'), adaptive_loss.py:62-70):
+// loss += -log softmax(logits[r])[target[r]];  logits[r] <- grad_scale * (softmax(logits[r]) - onehot(target[r])).
+// target < 0: the row is ignored (zero gradient).
+__global__ void __launch_bounds__(256) xent_fwd_bwd_kernel(float* __restrict__ logits, int64_t ld, const int64_t* __restrict__ target,
+                                                           int64_t rows, int64_t C, float grad_scale, double* __restrict__ loss) {
+  __shared__ float red[8];
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    float* x = logits + r * ld;
+    const int64_t t = target[r];
+    if (t < 0 || t >= C) {
+      for (int64_t c = threadIdx.x; c < C; c += 256) x[c] = 0.f;
+      continue;
+    }
+    float mx = -INFINITY;
+    for (int64_t c = threadIdx.x; c < C; c += 256) mx = fmaxf(mx, x[c]);
+    mx = warp_max(mx);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) mx = fmaxf(mx, red[w]);
+    float s = 0.f;
+    for (int64_t c = threadIdx.x; c < C; c += 256) s += __expf(x[c] - mx);
+    const float l = block_sum_256(s, red);
+    const float xt = x[t];
+    __syncthreads();
+    const float inv = grad_scale / l;
+    for (int64_t c = threadIdx.x; c < C; c += 256) x[c] = __expf(x[c] - mx) * inv - (c == t ? grad_scale : 0.f);
+    if (threadIdx.x == 0) atomicAdd(loss, (double)(mx + logf(l) - xt));
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- data movement
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows_cap,
+                                                        const int32_t* __restrict__ rows_dev, int64_t cols, float* __restrict__ dst,
+                                                        int64_t ld_dst, int64_t rows_pad) {
+  __shared__ float tile[32][33];
+  const int64_t rows = live_rows(rows_cap, rows_dev);
+  const int64_t r0 = (int64_t)blockIdx.x * 32, c0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t r = r0 + j, c = c0 + tx;
+    tile[j][tx] = (r < rows && c < cols) ? src[r * ld_src + c] : 0.f;     // rows past the live count: zeros (k-padding of dW)
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t c = c0 + j, r = r0 + tx;
+    if (c < cols && r < rows_pad) dst[c * ld_dst + r] = tile[tx][j];
+  }
+}
+
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int64_t ld, int64_t rows_cap,
+                                                     const int32_t* __restrict__ rows_dev, int64_t cols, float* __restrict__ out) {
+  const int64_t rows = live_rows(rows_cap, rows_dev);
+  const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int64_t r = blockIdx.y; r < rows; r += gridDim.y) s += x[r * ld + c];
+  atomicAdd(out + c, s);
+}
+
+__global__ void __launch_bounds__(256) axpy_kernel(float* __restrict__ y, int64_t ldy, const float* __restrict__ x, int64_t ldx,
+                                                   int64_t rows_cap, const int32_t* __restrict__ rows_dev, int64_t cols, float a) {
+  const int64_t n = live_rows(rows_cap, rows_dev) * cols;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int64_t r = i / cols, c = i % cols;
+    y[r * ldy + c] += a * x[r * ldx + c];
+  }
+}
+
+__global__ void __launch_bounds__(256) scatter_add_rows_kernel(float* __restrict__ dst, int64_t ld_dst, const float* __restrict__ src,
+                                                               int64_t ld_src, const int32_t* __restrict__ ids, int64_t rows_cap,
+                                                               const int32_t* __restrict__ rows_dev, int64_t cols) {
+  const int64_t n = live_rows(rows_cap, rows_dev) * cols;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int64_t r = i / cols, c = i % cols;
+    atomicAdd(dst + (int64_t)__ldg(ids + r) * ld_dst + c, src[r * ld_src + c]);
+  }
+}
+
+}  // namespace gnnlm
+
+using namespace gnnlm;
+
+#define BWD_DISPATCH_C(Cv, ...)                                                                   \
+  switch (Cv) {                                                                                   \
+    case 1: edge_attn_bwd_kernel<1><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;                 \
+    case 2: edge_attn_bwd_kernel<2><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;                 \
+    case 4: edge_attn_bwd_kernel<4><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;                 \
+    case 8: edge_attn_bwd_kernel<8><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;                 \
+    case 16: edge_attn_bwd_kernel<16><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;               \
+    default: edge_attn_bwd_kernel<32><<<grid, 256, 0, stream>>>(__VA_ARGS__); break;               \
+  }
+
+extern "C" int32_t gnnlm_hgt_edge_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                           const float* dout, int64_t ldo, const int32_t* indptr, const int32_t* indices,
+                                           const int32_t* dst_ids, int64_t n_dst_cap, const int32_t* n_dst_dev, int64_t causal_L,
+                                           int64_t intra_ctx, int32_t H, int32_t d_k, float scale, float* dq, int64_t lddq, float* dk,
+                                           int64_t lddk, float* dv, int64_t lddv, cudaStream_t stream) {
+  GNNLM_CHECK_ARG(q && k && v && dout && dq && dk && dv && (causal_L > 0 || indptr), GNNLM_E_ARG, "gnnlm_hgt_edge_attn_bwd: null pointer");
+  const int64_t d = (int64_t)H * d_k;
+  GNNLM_CHECK_ARG(H > 0 && d_k > 0 && d % 32 == 0 && 32 % H == 0 && d <= 1024, GNNLM_E_UNSUPPORTED,
+                  "gnnlm_hgt_edge_attn_bwd: needs d %% 32 == 0, d <= 1024 and H dividing 32 (H=%d d_k=%d)", H, d_k);
+  const int C = (int)(d / 32);
+  GNNLM_CHECK_ARG(C == 1 || C == 2 || C == 4 || C == 8 || C == 16 || C == 32, GNNLM_E_UNSUPPORTED,
+                  "gnnlm_hgt_edge_attn_bwd: d / 32 must be a power of two");
+  if (n_dst_cap == 0) return 0;
+  const int group = 32 / H;
+  const unsigned grid = (unsigned)(ceil_div(n_dst_cap, 8) < 148 * 32 ? ceil_div(n_dst_cap, 8) : 148 * 32);
+  BWD_DISPATCH_C(C, q, ldq, k, ldk, v, ldv, dout, ldo, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, causal_L, intra_ctx, group, scale,
+                 dq, lddq, dk, lddk, dv, lddv)
+  GNNLM_LAUNCH_CHECK("gnnlm_hgt_edge_attn_bwd");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_layernorm_bwd(const float* o, int64_t ldo, const float* residual, int64_t ldr, const float* gamma, float eps,
+                                       const float* dy, int64_t ldy, int64_t rows, const int32_t* rows_dev, int64_t d, float* dx,
+                                       int64_t ldx, float* dgamma, float* dbeta, cudaStream_t stream) {
+  GNNLM_CHECK_ARG(o && gamma && dy && dx && dgamma && dbeta, GNNLM_E_ARG, "gnnlm_layernorm_bwd: null pointer");
+  GNNLM_CHECK_ARG(d > 0 && d <= 2048 && rows >= 0, GNNLM_E_SHAPE, "gnnlm_layernorm_bwd: d must be in (0, 2048]");
+  if (rows == 0) return 0;
+  const unsigned grid = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
+  layernorm_bwd_kernel<<<grid, 256, 0, stream>>>(o, ldo, residual, ldr, gamma, eps, dy, ldy, rows, rows_dev, (int)d, dx, ldx, dgamma, dbeta);
+  GNNLM_LAUNCH_CHECK("gnnlm_layernorm_bwd");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_xent_fwd_bwd(float* logits, int64_t ld, const int64_t* target, int64_t rows, int64_t C, float grad_scale,
+                                      double* loss, cudaStream_t stream) {
+  GNNLM_CHECK_ARG(logits && target && loss, GNNLM_E_ARG, "gnnlm_xent_fwd_bwd: null pointer");
+  GNNLM_CHECK_ARG(rows >= 0 && C > 0 && ld >= C, GNNLM_E_SHAPE, "gnnlm_xent_fwd_bwd: bad shape");
+  if (rows == 0) return 0;
+  const unsigned grid = (unsigned)(rows < 148 * 8 ? rows : 148 * 8);
+  xent_fwd_bwd_kernel<<<grid, 256, 0, stream>>>(logits, ld, target, rows, C, grad_scale, loss);
+  GNNLM_LAUNCH_CHECK("gnnlm_xent_fwd_bwd");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_transpose_f32(const float* src, int64_t ld_src, int64_t rows, const int32_t* rows_dev, int64_t cols, float* dst,
+                                       int64_t ld_dst, int64_t rows_pad, cudaStream_t stream) {
+  GNNLM_CHECK_ARG(src && dst, GNNLM_E_ARG, "gnnlm_transpose_f32: null pointer");
+  GNNLM_CHECK_ARG(rows >= 0 && cols > 0 && ld_src >= cols && rows_pad >= rows && ld_dst >= rows_pad, GNNLM_E_SHAPE,
+                  "gnnlm_transpose_f32: bad shape");
+  if (rows_pad == 0) return 0;
+  dim3 grid((unsigned)ceil_div(rows_pad, 32), (unsigned)ceil_div(cols, 32));
+  GNNLM_CHECK_ARG(grid.y < 65536, GNNLM_E_SHAPE, "gnnlm_transpose_f32: too many columns");
+  transpose_kernel<<<grid, 256, 0, stream>>>(src, ld_src, rows, rows_dev, cols, dst, ld_dst, rows_pad);
+  GNNLM_LAUNCH_CHECK("gnnlm_transpose_f32");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_colsum_f32(const float* x, int64_t ld, int64_t rows, const int32_t* rows_dev, int64_t cols, float* out,
+                                    cudaStream_t stream) {
+  GNNLM_CHECK_ARG(x && out, GNNLM_E_ARG, "gnnlm_colsum_f32: null pointer");
+  GNNLM_CHECK_ARG(rows >= 0 && cols > 0 && ld >= cols, GNNLM_E_SHAPE, "gnnlm_colsum_f32: bad shape");
+  if (rows == 0) return 0;
+  dim3 grid((unsigned)ceil_div(cols, 256), (unsigned)(rows < 512 ? rows : 512));
+  colsum_kernel<<<grid, 256, 0, stream>>>(x, ld, rows, rows_dev, cols, out);
+  GNNLM_LAUNCH_CHECK("gnnlm_colsum_f32");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_axpy_f32(float* y, int64_t ldy, const float* x, int64_t ldx, int64_t rows, const int32_t* rows_dev, int64_t cols,
+                                  float a, cudaStream_t stream) {
+  GNNLM_CHECK_ARG(y && x, GNNLM_E_ARG, "gnnlm_axpy_f32: null pointer");
+  GNNLM_CHECK_ARG(rows >= 0 && cols > 0 && ldy >= cols && ldx >= cols, GNNLM_E_SHAPE, "gnnlm_axpy_f32: bad shape");
+  if (rows == 0) return 0;
+  const int64_t n = rows * cols;
+  const unsigned grid = (unsigned)(ceil_div(n, 256) < 148 * 16 ? ceil_div(n, 256) : 148 * 16);
+  axpy_kernel<<<grid, 256, 0, stream>>>(y, ldy, x, ldx, rows, rows_dev, cols, a);
+  GNNLM_LAUNCH_CHECK("gnnlm_axpy_f32");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_scatter_add_rows(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, const int32_t* ids, int64_t rows,
+                                          const int32_t* rows_dev, int64_t cols, cudaStream_t stream) {
+  GNNLM_CHECK_ARG(dst && src && ids, GNNLM_E_ARG, "gnnlm_scatter_add_rows: null pointer");
+  GNNLM_CHECK_ARG(rows >= 0 && cols > 0 && ld_dst >= cols && ld_src >= cols, GNNLM_E_SHAPE, "gnnlm_scatter_add_rows: bad shape");
+  if (rows == 0) return 0;
+  const int64_t n = rows * cols;
+  const unsigned grid = (unsigned)(ceil_div(n, 256) < 148 * 16 ? ceil_div(n, 256) : 148 * 16);
+  scatter_add_rows_kernel<<<grid, 256, 0, stream>>>(dst, ld_dst, src, ld_src, ids, rows, rows_dev, cols);
+  GNNLM_LAUNCH_CHECK("gnnlm_scatter_add_rows");
+  return 0;
+}

@@ -454,6 +454,9 @@ def main(argv=None, device="cuda", log=print) -> dict:
     parser.add_argument("--knn-dists-file", default=None, help="raw fp32 [N_split, k] distances of neighbors.mmap.{k}")
     parser.add_argument("--math", default="f16x3", choices=["f16x3", "f16f8", "tf32x3", "fp32", "tf32", "bf16"])
     parser.add_argument("--cuda-graph", action="store_true")
+    parser.add_argument("--share-centres", action="store_true",
+                        help="run the ntgt side once per distinct centre row of a batch (identical scores; faster when "
+                             "retrieved rows repeat inside a block, as they do in real kNN graphs)")
     parsed = parser.parse_args(argv)
     if parsed.path is None:
         raise ValueError("--path required for evaluation!")
@@ -472,6 +475,7 @@ def main(argv=None, device="cuda", log=print) -> dict:
     if args.knnlm and args.save_knnlm_dstore:
         raise ValueError("Cannot use knnlm while trying to build the datastore!")
     model = models[0].eval().to(device).set_math(args.math)
+    model.decoder.share_centres = bool(args.share_centres)
     dstore = task.load_datastore(device)
     knn = None
     if args.knnlm:

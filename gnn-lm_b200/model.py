@@ -92,6 +92,20 @@ class AdaptiveSoftmax(nn.Module):
         self._prep, self._prep_key = P, key
         return P
 
+    def train_weights(self) -> dict:
+        """fp32 matrices of the (frozen) clusters for the training loss (train._AdaptiveLoss): head [c0 + n_tail, d],
+        proj[i] [dim_i, d], out[i] [size_i, dim_i]."""
+        if self.tied:
+            head = torch.cat([self.head.word_proj.weight.detach(), self.head.class_proj.weight.detach()], 0)
+        else:
+            head = self.head.weight.detach()
+        W = {"head": head.float().contiguous(), "proj": [], "out": [], "plain": None}
+        for seq in self.tail:
+            p = seq[0].weight.detach().float()
+            W["proj"].append((p.t() if self.tie_proj else p).contiguous())
+            W["out"].append(seq[2].weight.detach().float().contiguous())
+        return W
+
     @torch.no_grad()
     def target_log_prob(self, x: torch.Tensor, target: torch.Tensor, math_mode: int = L.MATH_FP32_SIMT) -> torch.Tensor:
         """log p(target) per row: the only entries of get_log_prob's [T, V] tensor that the scorer reads
@@ -425,6 +439,10 @@ class TransformerLanguageModel(nn.Module):
                 nn.init.normal_(embed_tokens.weight, mean=0, std=d_in ** -0.5)
                 nn.init.constant_(embed_tokens.weight[dictionary.pad()], 0)
         dec = TokenGraphTransformerDecoder(args, dictionary, embed_tokens, no_encoder_attn=True, quantizer=quantizer)
+        if _get(args, "freeze", False):                          # transformer_lm.py:183-186: only the HGT is trained
+            for name, param in dec.named_parameters():
+                if "hgt" not in name:
+                    param.requires_grad = False
         return cls(dec)
 
     def forward(self, src_tokens, **kwargs):

@@ -1,0 +1,350 @@
+"""Training forward / backward of the HGT fine-tuning step.
+
+The reference fine-tunes with `--freeze` (fairseq/models/transformer_lm.py:183-186: every parameter without "hgt" in its
+name is frozen) under `--criterion adaptive_loss` (fairseq/criterions/adaptive_loss.py:31-83): the loss is the summed
+cross-entropy of the adaptive-softmax head and tail clusters on the HGT's tgt outputs, and gradients reach
+decoder.hgt_decoder.* only.  Its backward is autograd over DGL ops (fairseq/models/hgt.py:299-420).
+
+Here every differentiable stage is a `torch.autograd.Function` whose forward AND backward are C-ABI kernels of the library:
+projections (gnnlm_linear; dX = dY W and dW = dY^T X through the same GEMM on transposed copies, gnnlm_transpose_f32;
+biases by gnnlm_colsum_f32), the three edge types' segmented softmax + aggregation (forward gnnlm_hgt_edge_attn /
+gnnlm_hgt_causal_attn, backward gnnlm_hgt_edge_attn_bwd), residual + LayerNorm (gnnlm_layernorm / gnnlm_layernorm_bwd), the
+centre-row gather (gnnlm_gather_rows / gnnlm_scatter_add_rows) and the adaptive loss (logits by gnnlm_linear, softmax
+cross-entropy and its gradient by gnnlm_xent_fwd_bwd).  torch.autograd only chains them and differentiates the fold of the
+relation transforms into the projection weights (relation_att / relation_msg / relation_pri -> K' / V' weights: d x d matrices).
+
+Scope of this first training path: fp32 activations (GEMMs in fp32 FMA or 3xTF32), graphs of either builder (general CSR
+kernels for the ntgt edges, so `--deprecated` graphs train too), dropout = 0
+(the deterministic part of the reference step; hgt.py's `drop` / `attn_drop` masks are not generated -- a non-zero dropout
+raises).  The last layer's ntgt side is skipped as in evaluation (nothing reads it; its parameters get zero gradients in
+the reference too).
+"""
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .graph import TokenGraph
+
+
+def _st():
+    return L.stream_ptr()
+
+
+def _zeros(*shape, like):
+    return torch.zeros(shape, device=like.device, dtype=torch.float32)
+
+
+def _transpose(x: torch.Tensor, rows_pad: Optional[int] = None) -> torch.Tensor:
+    """[rows, cols] fp32 -> [cols, rows_pad] (zero-padded columns): an operand of dW = dY^T X."""
+    rows, cols = x.shape
+    rows_pad = rows if rows_pad is None else rows_pad
+    out = torch.empty((cols, rows_pad), device=x.device, dtype=torch.float32)
+    L.call("gnnlm_transpose_f32", L.ptr(x), x.stride(0), rows, None, cols, L.ptr(out), out.stride(0), rows_pad, _st())
+    return out
+
+
+def _gemm(a: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], mode: int) -> torch.Tensor:
+    """a [M, K] @ w [N, K]^T (+ b), fp32 in / out, in fp32 FMA or 3xTF32 (tcgen05; the weight operand split on the fly).
+    Row strides may exceed K (padded buffers)."""
+    if w.stride(1) != 1:
+        w = w.contiguous()
+    if mode == L.MATH_TF32X3:
+        hi, lo = ops.split_tf32(w)
+        return ops.linear(a, hi, b, W_lo=lo, math=mode)
+    return ops.linear(a, w, b, math=mode)
+
+
+class _Linear(torch.autograd.Function):
+    """y = x W^T + b through gnnlm_linear, forward and backward."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, mode):
+        x = x.contiguous()
+        ctx.save_for_backward(x, W)
+        ctx.mode, ctx.has_b = mode, b is not None
+        return _gemm(x, W.detach(), None if b is None else b.detach().contiguous(), mode)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, W = ctx.saved_tensors
+        dy = dy.contiguous()
+        mode = ctx.mode
+        dx = dW = db = None
+        if ctx.needs_input_grad[0]:
+            dx = _gemm(dy, _transpose(W.detach().contiguous()), None, mode)                            # dX = dY W
+        if ctx.needs_input_grad[1]:
+            m_pad = (x.shape[0] + 31) // 32 * 32                                                       # k of the product, zero-padded
+            dW = _gemm(_transpose(dy, m_pad), _transpose(x, m_pad), None, mode)                        # dW = dY^T X
+        if ctx.has_b and ctx.needs_input_grad[2]:
+            db = _zeros(dy.shape[1], like=dy)
+            L.call("gnnlm_colsum_f32", L.ptr(dy), dy.stride(0), dy.shape[0], None, dy.shape[1], L.ptr(db), _st())
+        return dx, dW, db, None
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ids):
+        ctx.save_for_backward(ids)
+        ctx.n = x.shape[0]
+        return ops.gather_rows(x.contiguous(), ids)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (ids,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = _zeros(ctx.n, dy.shape[1], like=dy)
+        L.call("gnnlm_scatter_add_rows", L.ptr(dx), dx.stride(0), L.ptr(dy), dy.stride(0), L.ptr(ids), dy.shape[0], None, dy.shape[1], _st())
+        return dx, None
+
+
+def _attn_bwd(q, k, v, dout, H, scale, *, indptr=None, indices=None, causal=(0, 0)):
+    d = q.shape[1]
+    dq = torch.empty_like(q)
+    dk, dv = torch.zeros_like(k), torch.zeros_like(v)
+    L.call("gnnlm_hgt_edge_attn_bwd", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0), L.ptr(dout), dout.stride(0),
+           L.ptr(indptr), L.ptr(indices), None, q.shape[0], None, causal[0], causal[1], H, d // H, float(scale), L.ptr(dq), dq.stride(0),
+           L.ptr(dk), dk.stride(0), L.ptr(dv), dv.stride(0), _st())
+    return dq, dk, dv
+
+
+class _EdgeAttention(torch.autograd.Function):
+    """out = softmax-by-destination attention over one CSR edge type (hgt.py:350-358)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, indptr, indices, H):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        ctx.save_for_backward(q, k, v, indptr, indices)
+        ctx.H = H
+        out = torch.empty_like(q)
+        return ops.edge_attn(q, k, v, indptr, indices, H, out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, indptr, indices = ctx.saved_tensors
+        dq, dk, dv = _attn_bwd(q, k, v, dout.contiguous(), ctx.H, 1.0, indptr=indptr, indices=indices)
+        return dq, dk, dv, None, None, None
+
+
+class _TgtAttention(torch.autograd.Function):
+    """mean over the two edge types into tgt (hgt.py:383-386, cross_reducer='mean'): 0.5 * inter(q, k_i, v_i) + 0.5 * causal(q, k_t, v_t)."""
+
+    @staticmethod
+    def forward(ctx, q, k_i, v_i, k_t, v_t, inter_indptr, B, Lb, intra_ctx, H):
+        q, k_i, v_i, k_t, v_t = (t.contiguous() for t in (q, k_i, v_i, k_t, v_t))
+        ctx.save_for_backward(q, k_i, v_i, k_t, v_t, inter_indptr)
+        ctx.cfg = (B, Lb, intra_ctx, H)
+        out = torch.empty_like(q)
+        ops.edge_attn(q, k_i, v_i, inter_indptr, None, H, out, out_scale=0.5, tag="inter")
+        ops.causal_attn(q, k_t, v_t, B, Lb, intra_ctx, H, out, out_scale=0.5, accumulate=True)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k_i, v_i, k_t, v_t, inter_indptr = ctx.saved_tensors
+        B, Lb, intra_ctx, H = ctx.cfg
+        dout = dout.contiguous()
+        dq, dk_i, dv_i = _attn_bwd(q, k_i, v_i, dout, H, 0.5, indptr=inter_indptr)
+        dq2, dk_t, dv_t = _attn_bwd(q, k_t, v_t, dout, H, 0.5, causal=(Lb, intra_ctx))
+        L.call("gnnlm_axpy_f32", L.ptr(dq), dq.stride(0), L.ptr(dq2), dq2.stride(0), dq.shape[0], None, dq.shape[1], 1.0, _st())
+        return dq, dk_i, dv_i, dk_t, dv_t, None, None, None, None, None
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    """LayerNorm(o + h) * gamma + beta (hgt.py:403-405)."""
+
+    @staticmethod
+    def forward(ctx, o, h, gamma, beta, eps):
+        o, h = o.contiguous(), h.contiguous()
+        ctx.save_for_backward(o, h, gamma)
+        ctx.eps = eps
+        return ops.layernorm(o, gamma.detach().contiguous(), beta.detach().contiguous(), eps, residual=h)
+
+    @staticmethod
+    def backward(ctx, dy):
+        o, h, gamma = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(o)
+        dg, db = _zeros(o.shape[1], like=o), _zeros(o.shape[1], like=o)
+        L.call("gnnlm_layernorm_bwd", L.ptr(o), o.stride(0), L.ptr(h), h.stride(0), L.ptr(gamma.detach().contiguous()), float(ctx.eps),
+               L.ptr(dy), dy.stride(0), o.shape[0], None, o.shape[1], L.ptr(dx), dx.stride(0), L.ptr(dg), L.ptr(db), _st())
+        return dx, dx, dg, db, None
+
+
+class _AdaptiveLoss(torch.autograd.Function):
+    """sum_t -log p(target_t | x_t) under the (frozen) adaptive softmax: adaptive_softmax.py:147-168 + adaptive_loss.py:62-70.
+    The gradient w.r.t. x is produced together with the loss (the softmax - onehot of every cluster's logits, pushed back
+    through the cluster's frozen projections) and scaled in backward."""
+
+    @staticmethod
+    def forward(ctx, x, target, soft, mode):
+        x = x.contiguous()
+        T, d = x.shape
+        dev = x.device
+        W = soft.train_weights()
+        loss = torch.zeros(1, device=dev, dtype=torch.float64)
+        pad4 = lambda n_: (n_ + 3) // 4 * 4
+
+        def logits(a, w):          # a w^T into a buffer whose row stride is a multiple of 16 B (it is a GEMM operand on the way back)
+            buf = torch.empty((a.shape[0], pad4(w.shape[0])), device=dev, dtype=torch.float32)
+            lg = buf[:, :w.shape[0]]
+            if mode == L.MATH_TF32X3:
+                hi, lo = ops.split_tf32(w)
+                return ops.linear(a, hi, None, W_lo=lo, math=mode, out=lg)
+            return ops.linear(a, w, None, math=mode, out=lg)
+
+        def back(dlg, w):          # dlogits w: the cluster's frozen weight transposed, k-extent = the cluster size
+            wt = _transpose(w, pad4(w.shape[0]))                       # [k_in, N padded to a 16 B row stride]
+            if mode == L.MATH_TF32X3:
+                hi, lo = ops.split_tf32(wt)
+                return ops.linear(dlg, hi[:, :w.shape[0]], None, W_lo=lo[:, :w.shape[0]], math=mode)
+            return ops.linear(dlg, wt[:, :w.shape[0]], None, math=mode)
+        xent = lambda lg, tg: L.call("gnnlm_xent_fwd_bwd", L.ptr(lg), lg.stride(0), L.ptr(tg), lg.shape[0], lg.shape[1], 1.0,
+                                     L.ptr(loss), _st())
+        if W.get("plain") is not None:                                 # plain softmax (C2): one cluster
+            lg = logits(x, W["plain"])
+            xent(lg, target.reshape(-1).long().contiguous())
+            dx = back(lg, W["plain"])
+        else:
+            head_pick, tail_rows, tail_pick, tail_count = ops.adapt_target(target.reshape(-1).contiguous(), soft.cutoff)
+            lg = logits(x, W["head"])
+            xent(lg, head_pick.long())
+            dx = back(lg, W["head"])
+            counts = tail_count.tolist()                               # host sync: the training path sizes tail batches exactly
+            for i, n_i in enumerate(counts[:len(W["proj"])]):
+                if n_i == 0:
+                    continue
+                rows = tail_rows[i, :n_i].contiguous()
+                xi = ops.gather_rows(x, rows)
+                pi = _gemm(xi, W["proj"][i], None, mode)
+                lg = logits(pi, W["out"][i])
+                xent(lg, tail_pick[i, :n_i].long().contiguous())
+                dxi = _gemm(back(lg, W["out"][i]), _transpose(W["proj"][i]), None, mode)
+                L.call("gnnlm_scatter_add_rows", L.ptr(dx), dx.stride(0), L.ptr(dxi), dxi.stride(0), L.ptr(rows), n_i, None, d, _st())
+        ctx.save_for_backward(dx)
+        return loss.float().squeeze(0)
+
+    @staticmethod
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return dx * g, None, None, None
+
+
+def fold_layer(layer, t: int, n: int) -> Dict[str, torch.Tensor]:
+    """Differentiable fold of the relation transforms into the projections (hgt.py:339-348,354-355):
+    K' = (h W_k^T + b_k) blockdiag(R_att[r]) pri[r] / sqrt(d_k),  V' = (h W_v^T + b_v) blockdiag(R_msg[r]).
+    Returns fp32 weights per (node type, relation); autograd carries their gradients back to k/v_linears, relation_*."""
+    H, dk = layer.n_heads, layer.d_k
+    d = H * dk
+    out = {}
+
+    def fold(lin, R, scale):
+        W3, b2 = lin.weight.view(H, dk, d), lin.bias.view(H, dk)
+        Rs = R if scale is None else R * scale[:, None, None]
+        return torch.einsum("hjk,hjc->hkc", Rs, W3).reshape(d, d), torch.einsum("hj,hjk->hk", b2, Rs).reshape(d)
+    for tau, rels in ((t, (0,)), (n, (0, 1))):                       # tgt is a source of intra only; ntgt of intra and inter
+        for r in rels:
+            out[f"k{tau}{r}"] = fold(layer.k_linears[tau], layer.relation_att[r], layer.relation_pri[r] / math.sqrt(dk))
+            out[f"v{tau}{r}"] = fold(layer.v_linears[tau], layer.relation_msg[r], None)
+    return out
+
+
+def hgt_forward_train(hgt, G: TokenGraph, h_t: torch.Tensor, h_n: torch.Tensor, mode: int = L.MATH_FP32_SIMT) -> torch.Tensor:
+    """tgt outputs of HGT.forward (hgt.py:494-513) with autograd through the library's kernels.  h_t [T, d], h_n [n_ntgt, d] fp32
+    (exact row counts: the caller sized them from G.counts())."""
+    assert hgt.in_dim == hgt.hidden_dim == hgt.out_dim, "training path: plain HGT stack (no input adapters / output projection)"
+    t, n = hgt.ntype2idx["tgt"], hgt.ntype2idx["ntgt"]
+    n_ntgt, n_valid = G.counts()
+    inter_ids = G.inter_indices[:n_valid].contiguous()
+    nn_indptr, nn_indices = G.nn_indptr[:n_ntgt + 1].contiguous(), G.nn_indices
+    NL = hgt.n_layers
+    for l, layer in enumerate(hgt.gcs):
+        if layer.drop.p > 0 or layer.attn_drop.p > 0:
+            raise NotImplementedError("the training path covers dropout = 0 (hgt.py's drop / attn_drop masks are not generated)")
+        H = layer.n_heads
+        F_ = fold_layer(layer, t, n)
+        lin = lambda x, wb: _Linear.apply(x, wb[0], wb[1], mode)
+        plain = lambda mods, tau: (mods[tau].weight, mods[tau].bias)
+        # ---- tgt: mean of inter (centre ntgt -> tgt) and causal intra attention, output projection, residual + LayerNorm
+        hc = _GatherRows.apply(h_n, inter_ids)
+        q_t = lin(h_t, plain(layer.q_linears, t))
+        agg = _TgtAttention.apply(q_t, lin(hc, F_[f"k{n}1"]), lin(hc, F_[f"v{n}1"]), lin(h_t, F_[f"k{t}0"]), lin(h_t, F_[f"v{t}0"]),
+                                  G.inter_indptr, G.B, G.L, G.intra_ctx, H)
+        new_t = _AddLayerNorm.apply(lin(agg, plain(layer.a_linears, t)), h_t, layer.norms[t].weight, layer.norms[t].bias, layer.norms[t].eps)
+        # ---- ntgt (not needed after the last layer: the decoder reads tgt rows only, transformer.py:1053)
+        if l < NL - 1:
+            agg_n = _EdgeAttention.apply(lin(h_n, plain(layer.q_linears, n)), lin(h_n, F_[f"k{n}0"]), lin(h_n, F_[f"v{n}0"]),
+                                         nn_indptr, nn_indices, H)
+            h_n = _AddLayerNorm.apply(lin(agg_n, plain(layer.a_linears, n)), h_n, layer.norms[n].weight, layer.norms[n].bias,
+                                      layer.norms[n].eps)
+        h_t = new_t
+    return h_t
+
+
+def train_step_loss(model, sample: dict, mode: str = "fp32") -> torch.Tensor:
+    """AdaptiveLoss.forward (adaptive_loss.py:31-83, reduce=True) for a model built with --freeze: the summed cross-entropy of the
+    batch, differentiable w.r.t. decoder.hgt_decoder.* (call .backward() on it).  `sample` as eval: net_input.graph (TokenGraph
+    with codes_table and tgt features), target."""
+    dec = model.decoder
+    G: TokenGraph = sample["net_input"]["graph"]
+    m = L.MATH_NAMES[mode]
+    assert m in (L.MATH_FP32_SIMT, L.MATH_TF32X3), "training runs the projections in fp32 FMA or 3xTF32"
+    if dec.orig_prob_ratio > 0:
+        raise NotImplementedError("orig_prob_ratio > 0 in training (adaptive_loss.py:55-59) is not used by the shipped scripts")
+    feats = G.nodes["tgt"].data["h"]
+    h_t = feats.float().contiguous()
+    n_ntgt, _ = G.counts()
+    with torch.no_grad():                                             # PQ decode + OPQ rotation: inputs, no parameters (pq_wrapper.py:169-203)
+        h_n = dec.tgt_quantizer.gather_decode(G.codes_table, G.ntgt_row, n_cap=G.node_cap, n_dev=G.n_ntgt_dev, math_mode=L.MATH_FP32_SIMT)
+        h_n = h_n[:n_ntgt].contiguous()
+    x = hgt_forward_train(dec.hgt_decoder, G, h_t, h_n, m)
+    soft = dec.adaptive_softmax if dec.adaptive_softmax is not None else _PlainSoftmax(dec.embed_out)
+    return _AdaptiveLoss.apply(x, sample["target"], soft, m)
+
+
+class _PlainSoftmax:
+    def __init__(self, embed_out):
+        self.w = embed_out
+
+    def train_weights(self):
+        return {"plain": self.w.detach().float().contiguous()}
+
+
+class AdaptiveLoss:
+    """fairseq/criterions/adaptive_loss.py:14-83 (`--criterion adaptive_loss`): forward(model, sample) -> (loss, sample_size,
+    logging_output) with the reference's keys; the loss is differentiable w.r.t. the trainable (HGT) parameters."""
+
+    def __init__(self, args=None, task=None, math: str = "fp32"):
+        self.args, self.math = args, math
+        self.sentence_avg = bool(getattr(args, "sentence_avg", False))
+
+    def forward(self, model, sample, reduce=True):
+        if not reduce:
+            raise NotImplementedError("reduce=False (per-token losses) is not used by the trainer (adaptive_loss.py:64-69)")
+        loss = train_step_loss(model, sample, self.math)
+        ntokens = int(sample["target"].numel())                     # graph LM blocks carry no padding (transformer.py:975)
+        nsentences = int(sample["target"].shape[0])
+        sample_size = nsentences if self.sentence_avg else ntokens
+        return loss, sample_size, {"loss": loss.detach(), "ntokens": ntokens, "nsentences": nsentences, "sample_size": sample_size}
+
+    __call__ = forward
+
+
+def train_step(model, sample, optimizer, criterion: Optional[AdaptiveLoss] = None, clip_norm: float = 0.0) -> dict:
+    """One update as fairseq's trainer performs it for this model (fairseq/trainer.py train_step: forward + backward, gradients
+    divided by the sample size, --clip-norm, optimizer step); the optimizer is any torch.optim instance over the trainable
+    parameters (the scripts use Adam, hgt_lm_wiki103_reproduce.sh:27-30)."""
+    criterion = criterion or AdaptiveLoss()
+    model.train()
+    optimizer.zero_grad(set_to_none=True)
+    loss, sample_size, log = criterion(model, sample)
+    loss.backward()
+    params = [p for p in model.parameters() if p.requires_grad and p.grad is not None]
+    for p in params:
+        p.grad.div_(float(sample_size))
+    gnorm = torch.nn.utils.clip_grad_norm_(params, clip_norm if clip_norm > 0 else float("inf"))
+    optimizer.step()
+    log.update(gnorm=float(gnorm), loss_per_token_base2=float(loss.detach()) / log["ntokens"] / math.log(2))
+    return log

@@ -444,6 +444,40 @@ int32_t gnnlm_knn_sims_pq(const float* queries, int64_t ldq, int32_t d_q, const 
                           const float* bias, const int64_t* ids, int64_t k_nn, int32_t metric, float* sims, int64_t T,
                           gnnlm_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (9) Training backward of the HGT fine-tuning step (`--freeze` trains decoder.hgt_decoder.* only,
+ *     fairseq/models/transformer_lm.py:183-186, under fairseq/criterions/adaptive_loss.py:31-83).  The reference obtains these
+ *     from autograd over DGL's SDDMM / edge_softmax / SpMM (hgt.py:350-358,383-386), F.layer_norm (hgt.py:405) and
+ *     F.cross_entropy; here they are explicit kernels (fp32), driven by torch.autograd.Function wrappers in train.py.
+ *
+ * gnnlm_hgt_edge_attn_bwd: backward of gnnlm_hgt_edge_attn / gnnlm_hgt_causal_attn for fp32 q / k / v and out = scale * attention.
+ *   dq [n_dst, d] is written; dk, dv [n_src, d] are ACCUMULATED with atomics (zero them first).  Edges: the CSR of the forward
+ *   (indptr / indices / dst_ids), or -- causal_L > 0 -- the implicit causal edges inside blocks of causal_L tokens.
+ * gnnlm_layernorm_bwd: y = LayerNorm(o + residual) * gamma + beta; dx = d o = d residual is written, dgamma / dbeta accumulated.
+ * gnnlm_xent_fwd_bwd: one adaptive-softmax cluster: loss += sum_r -log softmax(logits[r])[target[r]] (fp64 accumulate) and
+ *   logits[r] <- grad_scale * (softmax(logits[r]) - onehot(target[r])) in place; target < 0 rows are ignored.
+ * gnnlm_transpose_f32 (rows past the live count / up to rows_pad are written as zeros: k-padding of dW = dY^T X),
+ * gnnlm_colsum_f32 (out += column sums: bias gradients), gnnlm_axpy_f32 (y += a x), gnnlm_scatter_add_rows
+ * (dst[ids[r]] += src[r]: backward of gnnlm_gather_rows). */
+int32_t gnnlm_hgt_edge_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                const float* dout, int64_t ldo, const int32_t* indptr, const int32_t* indices,
+                                const int32_t* dst_ids, int64_t n_dst_cap, const int32_t* n_dst_dev, int64_t causal_L,
+                                int64_t intra_ctx, int32_t H, int32_t d_k, float scale, float* dq, int64_t lddq, float* dk,
+                                int64_t lddk, float* dv, int64_t lddv, gnnlm_stream_t stream);
+int32_t gnnlm_layernorm_bwd(const float* o, int64_t ldo, const float* residual, int64_t ldr, const float* gamma, float eps,
+                            const float* dy, int64_t ldy, int64_t rows, const int32_t* rows_dev, int64_t d, float* dx,
+                            int64_t ldx, float* dgamma, float* dbeta, gnnlm_stream_t stream);
+int32_t gnnlm_xent_fwd_bwd(float* logits, int64_t ld, const int64_t* target, int64_t rows, int64_t C, float grad_scale,
+                           double* loss, gnnlm_stream_t stream);
+int32_t gnnlm_transpose_f32(const float* src, int64_t ld_src, int64_t rows, const int32_t* rows_dev, int64_t cols, float* dst,
+                            int64_t ld_dst, int64_t rows_pad, gnnlm_stream_t stream);
+int32_t gnnlm_colsum_f32(const float* x, int64_t ld, int64_t rows, const int32_t* rows_dev, int64_t cols, float* out,
+                         gnnlm_stream_t stream);
+int32_t gnnlm_axpy_f32(float* y, int64_t ldy, const float* x, int64_t ldx, int64_t rows, const int32_t* rows_dev, int64_t cols,
+                       float a, gnnlm_stream_t stream);
+int32_t gnnlm_scatter_add_rows(float* dst, int64_t ld_dst, const float* src, int64_t ld_src, const int32_t* ids, int64_t rows,
+                               const int32_t* rows_dev, int64_t cols, gnnlm_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

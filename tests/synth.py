@@ -61,3 +61,25 @@ def run_gpu(prob, dev, math="fp32") -> dict:
     cfg, model, data = prob
     import copy
     return synth.run_gpu(cfg, copy.deepcopy(model), data, dev, math)
+
+
+def oracle_train(prob, dtype=torch.float64, deprecated=False):
+    """Loss of fairseq/criterions/adaptive_loss.py:31-83 through the oracle's HGT statements and its gradients w.r.t. every
+    decoder.hgt_decoder.* tensor by torch.autograd -- which is how the reference itself obtains them (autograd over hgt.py)."""
+    from oracle import graph_oracle as go
+    cfg, model, data = prob
+    om = oracle_model(cfg, model)
+    B, L = cfg["B"], cfg["L"]
+    if deprecated:
+        g = go.build_batch(data["nbr"].numpy(), data["positions"].numpy(), data["n_d"], cfg["c"], cfg["c"], deprecated=True)
+    else:
+        g = go.build_batch_vectorised(data["nbr"].numpy(), data["positions"].numpy(), data["n_d"], cfg["c"], cfg["c"])
+    codes = data["codes"].numpy()[g["ntgt_offsets"]]
+    h_ntgt = torch.from_numpy(mo.pq_decode(codes, om["centroids"], om.get("A"), om.get("b"), np.float64)).to(dtype)
+    sd = {k: v.detach().to(dtype).requires_grad_(True) for k, v in om["sd"].items()}
+    h = mo.hgt_forward_csr(sd, data["feats"].to(dtype), h_ntgt, g, (B, L), om["n_heads"], om["n_layers"])
+    soft = {k: ([t.to(dtype) for t in v] if isinstance(v, list) else v.to(dtype)) for k, v in om["softmax"].items()}
+    loss = mo.adaptive_loss(soft, om["cutoff"], h["tgt"], data["target"])
+    names = list(sd)
+    grads = torch.autograd.grad(loss, [sd[n] for n in names], allow_unused=True)
+    return float(loss.detach()), {n: g_ for n, g_ in zip(names, grads)}

@@ -1740,3 +1740,143 @@ def test_c_abi_rejects_bad_arguments(dev):
     # the library is still usable afterwards
     g = build_token_graph(torch.full((1, 4, 2), -1, dtype=torch.int64, device=dev), 100, 1, 1)
     assert g.counts() == (0, 0)
+
+
+# ------------------------------------------------------------------------------------------------ training
+def _train_problem(NL, cutoff, V, L_=48, d=64, H=4, k=4, c=1):
+    from gnnlm_b200 import synth
+    cfg = dict(d=d, H=H, V=V, cutoff=cutoff, tied=False, B=2, L=L_, k=k, c=c, M=8, NL=NL, n_d=1 << 12, k_nn=8, lmbda=0.25, temp=1.0)
+    model = synth.make_model(cfg)
+    data = synth.make_data(cfg, device="cpu")
+    return cfg, model, data
+
+
+@pytest.mark.parametrize("NL,cutoff,V,mode,deprecated", [(2, [40, 120], 300, "fp32", False), (3, None, 97, "fp32", False),
+                                                         (1, [40, 120], 300, "fp32", False), (2, [40, 120], 300, "tf32x3", False),
+                                                         (2, [40, 120], 300, "fp32", True)])
+def test_training_step_gradients_vs_oracle_autograd(NL, cutoff, V, mode, deprecated, dev):
+    """train.train_step_loss: the adaptive loss (adaptive_loss.py:31-83) and its gradients w.r.t. every decoder.hgt_decoder.*
+    parameter (the --freeze set, transformer_lm.py:183-186), every backward stage a kernel of the library, against
+    torch.autograd over the oracle's fp64 statement of hgt.py:299-420 -- the way the reference computes them."""
+    if mode != "fp32":
+        _need_tc()
+    import copy
+    from gnnlm_b200 import synth, train
+    from tests.synth import oracle_train
+    cfg, model, data = _train_problem(NL, cutoff, V)
+    if deprecated:                                                 # --deprecated graphs: shared ntgt nodes, general CSR
+        cfg = dict(cfg, deprecated=True)
+        data = dict(data, nbr=torch.randint(1, 200, data["nbr"].shape, dtype=torch.int64))     # overlapping clusters
+    ref_loss, ref_g = oracle_train((cfg, model, data), deprecated=deprecated)
+    m = copy.deepcopy(model).to(dev).train()
+    for name, p in m.named_parameters():                           # --freeze
+        p.requires_grad_("hgt" in name)
+    r = synth.Runner(cfg, m, data, dev, "fp32")
+    d_ = synth.to_device({k_: data[k_] for k_ in r.KEYS}, dev)
+    sample = r.sample_from(d_["nbr"], d_["feats"], d_["target"], d_["knn_dists"], d_["knn_ids"])
+    loss = train.train_step_loss(m, sample, mode)
+    loss.backward()
+    assert abs(float(loss.detach()) - ref_loss) < 2e-5 * abs(ref_loss)
+    checked = 0
+    gmax = max(float(g_.abs().max()) for g_ in ref_g.values() if g_ is not None)
+    for name, p in m.decoder.hgt_decoder.named_parameters():
+        g_ref = ref_g.get(name)
+        if g_ref is None or name.endswith("skip"):                 # unused by the forward (hgt.py:74,399)
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0
+            continue
+        if p.grad is None:                                         # last layer's ntgt side / tgt-as-source-of-inter: zero in the reference too
+            assert float(g_ref.abs().max()) == 0.0, name
+            continue
+        got = p.grad.detach().cpu().double()
+        scale = float(g_ref.abs().max())                           # (K biases cancel inside the softmax: their gradients are ~0)
+        err = float((got - g_ref).abs().max())
+        assert err < 2e-4 * scale + 2e-6 * gmax, (name, err, scale)
+        checked += 1
+    assert checked >= 10 * NL
+
+
+def test_training_backward_kernels_direct(dev):
+    """gnnlm_hgt_edge_attn_bwd (CSR and implicit-causal edge sources), gnnlm_layernorm_bwd and gnnlm_xent_fwd_bwd against
+    torch.autograd on fp64 statements of the same forward."""
+    from gnnlm_b200 import train, ops
+    from gnnlm_b200 import _lib as L
+    torch.manual_seed(5)
+    H, d, n_dst, n_src = 4, 128, 37, 90
+    deg = torch.randint(0, 6, (n_dst,))
+    indptr = torch.cat([torch.zeros(1, dtype=torch.long), deg.cumsum(0)]).int()
+    indices = torch.randint(0, n_src, (int(indptr[-1]),)).int()
+    q, k, v = torch.randn(n_dst, d), torch.randn(n_src, d) * 0.5, torch.randn(n_src, d)
+    dout = torch.randn(n_dst, d)
+
+    def ref(q_, k_, v_, src, dst):
+        qh, kh, vh = q_.view(-1, H, d // H), k_.view(-1, H, d // H), v_.view(-1, H, d // H)
+        s = (qh[dst] * kh[src]).sum(-1)
+        mx = torch.full((n_dst, H), -float("inf"), dtype=s.dtype).scatter_reduce(0, dst[:, None].expand(-1, H), s, "amax")
+        e = torch.exp(s - mx[dst])
+        den = torch.zeros((n_dst, H), dtype=s.dtype).index_add_(0, dst, e)
+        return torch.zeros_like(qh).index_add_(0, dst, vh[src] * (e / den[dst]).unsqueeze(-1)).reshape(-1, d)
+    dst = torch.repeat_interleave(torch.arange(n_dst), deg)
+    qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
+    out = ref(qd, kd, vd, indices.long(), dst)
+    g = torch.autograd.grad(out, [qd, kd, vd], dout.double())
+    dq, dk, dv = train._attn_bwd(q.to(dev), k.to(dev), v.to(dev), dout.to(dev), H, 1.0, indptr=indptr.to(dev), indices=indices.to(dev))
+    for a, b in zip((dq, dk, dv), g):
+        np.testing.assert_allclose(a.cpu().double().numpy(), b.numpy(), rtol=1e-4, atol=1e-5)
+    # implicit causal edges inside blocks of Lb tokens with a context window
+    Lb, ctx, B = 19, 7, 2
+    q2, k2, v2, do2 = (torch.randn(B * Lb, d) * 0.5 for _ in range(4))
+    i = torch.arange(Lb)
+    u, w_ = torch.nonzero((i[:, None] <= i[None, :]) & (i[None, :] - i[:, None] < ctx), as_tuple=True)
+    src = torch.cat([u + b * Lb for b in range(B)])
+    dsts = torch.cat([w_ + b * Lb for b in range(B)])
+    n_dst = B * Lb
+    qd, kd, vd = (t.double().requires_grad_(True) for t in (q2, k2, v2))
+    g = torch.autograd.grad(ref(qd, kd, vd, src, dsts), [qd, kd, vd], do2.double())
+    dq, dk, dv = train._attn_bwd(q2.to(dev), k2.to(dev), v2.to(dev), do2.to(dev), H, 1.0, causal=(Lb, ctx))
+    for a, b in zip((dq, dk, dv), g):
+        np.testing.assert_allclose(a.cpu().double().numpy(), b.numpy(), rtol=1e-4, atol=1e-5)
+    # LayerNorm(o + h)
+    rows, dd = 23, 320
+    o, h, gam, bet, dy = torch.randn(rows, dd), torch.randn(rows, dd), torch.randn(dd), torch.randn(dd), torch.randn(rows, dd)
+    od, hd, gd, bd = (t.double().requires_grad_(True) for t in (o, h, gam, bet))
+    g = torch.autograd.grad(torch.nn.functional.layer_norm(od + hd, (dd,), gd, bd, 1e-5), [od, gd, bd], dy.double())
+    o_, h_, g_, b_ = (t.to(dev).requires_grad_(True) for t in (o, h, gam, bet))
+    y = train._AddLayerNorm.apply(o_, h_, g_, b_, 1e-5)
+    y.backward(dy.to(dev))
+    for a, b in zip((o_.grad, g_.grad, b_.grad), g):
+        np.testing.assert_allclose(a.cpu().double().numpy(), b.numpy(), rtol=1e-4, atol=1e-4)
+    assert torch.equal(o_.grad, h_.grad)
+    # softmax cross-entropy of one cluster, with an ignored row
+    R, C = 9, 1000
+    lg = torch.randn(R, C) * 3
+    tg = torch.randint(0, C, (R,))
+    tg[4] = -1
+    ld = lg.double().requires_grad_(True)
+    keep = tg >= 0
+    ref_loss = torch.nn.functional.cross_entropy(ld[keep], tg[keep], reduction="sum")
+    (gl,) = torch.autograd.grad(ref_loss, [ld])
+    lg_dev, loss = lg.to(dev).clone(), torch.zeros(1, dtype=torch.float64, device=dev)
+    L.call("gnnlm_xent_fwd_bwd", L.ptr(lg_dev), lg_dev.stride(0), L.ptr(tg.to(dev)), R, C, 1.0, L.ptr(loss), L.stream_ptr())
+    assert abs(float(loss) - float(ref_loss.detach())) < 1e-5 * abs(float(ref_loss.detach()))
+    np.testing.assert_allclose(lg_dev.cpu().double().numpy(), gl.numpy(), rtol=1e-4, atol=1e-6)
+
+
+def test_training_steps_reduce_the_loss(dev):
+    """train.train_step (criterion + backward + --clip-norm + Adam) on a --freeze model: only decoder.hgt_decoder.* moves and
+    the loss of a fixed batch goes down."""
+    import copy
+    from gnnlm_b200 import synth, train
+    cfg, model, data = _train_problem(2, [40, 120], 300)
+    m = copy.deepcopy(model).to(dev)
+    for name, p in m.named_parameters():
+        p.requires_grad_("hgt" in name)
+    frozen = {n_: p.detach().clone() for n_, p in m.named_parameters() if not p.requires_grad}
+    r = synth.Runner(cfg, m, data, dev, "fp32")
+    d_ = synth.to_device({k_: data[k_] for k_ in r.KEYS}, dev)
+    sample = r.sample_from(d_["nbr"], d_["feats"], d_["target"], d_["knn_dists"], d_["knn_ids"])
+    opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.98))
+    losses = [train.train_step(m, sample, opt, clip_norm=0.1)["loss_per_token_base2"] for _ in range(8)]
+    assert losses[-1] < losses[0] - 0.01, losses
+    for n_, p in m.named_parameters():
+        if n_ in frozen:
+            assert torch.equal(p.detach(), frozen[n_])

@@ -151,3 +151,19 @@ def test_dense_causal_form_equals_coo_form(name, intra_ctx):
     assert (via_torch["logprob"] - dense["logprob"]).abs().max().item() < 1e-11
     if intra_ctx:
         assert (coo["logprob"] - mo.eval_batch(om, dict(batch, intra_ctx=0), None, dtype=torch.float64)["logprob"]).abs().max() > 1e-6
+
+
+def test_oracle_adaptive_loss_equals_target_logprob_sum():
+    """adaptive_loss.py:31-83 restated: the summed cross-entropy of the head and tail clusters equals -sum log p(target) of
+    get_log_prob (adaptive_softmax.py:170-206), for the adaptive layouts of the fixtures and for a plain output layer."""
+    torch.manual_seed(0)
+    d, V, cutoff = 32, 60, [10, 30, 60]
+    w = {"head": torch.randn(cutoff[0] + 2, d, dtype=torch.float64), "tail_proj": [torch.randn(8, d, dtype=torch.float64), torch.randn(4, d, dtype=torch.float64)],
+         "tail_out": [torch.randn(20, 8, dtype=torch.float64), torch.randn(30, 4, dtype=torch.float64)]}
+    x = torch.randn(50, d, dtype=torch.float64)
+    target = torch.randint(0, V, (50,))
+    loss = mo.adaptive_loss(w, cutoff, x, target)
+    lp = mo.adaptive_target_logprob(w, cutoff, x, target)
+    assert abs(float(loss) + float(lp.sum())) < 1e-9 * abs(float(loss))
+    wp = {"plain": torch.randn(V, d, dtype=torch.float64)}
+    assert abs(float(mo.adaptive_loss(wp, None, x, target)) + float(mo.plain_target_logprob(wp["plain"], x, target).sum())) < 1e-9
