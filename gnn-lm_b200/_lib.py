@@ -68,6 +68,7 @@ SIGNATURES = {
                                          _p, _i64, _i32, _p]),
     "gnnlm_hgt_causal_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _i64, _i64, _i64, _i32, _i32, _p, _i64, _f32, _i32, _p]),
     "gnnlm_hgt_causal_flash": (_i32, [_p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p, _i64, _i64, _f32, _i32, _p]),
+    "gnnlm_hgt_causal_flash_tc": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p, _i64, _i64, _f32, _i32, _p]),
     "gnnlm_hgt_inter_fused": (_i32, [_p, _i64, _p, _i32, _i64, _p, _i64, _i64, _i32, _i64, _p, _i64, _i64, _p, _f32, _p, _i64, _p]),
     "gnnlm_heads_split_f16": (_i32, [_p, _i64, _i64, _i32, _i32, _i32, _p, _p, _p]),
     "gnnlm_heads_transpose_split_f16": (_i32, [_p, _i64, _i64, _i32, _i32, _p, _p, _p]),

@@ -1,0 +1,370 @@
+// ('tgt','intra','tgt') attention as a tcgen05 flash kernel: S = Q K'^T and P V' on the 5th-generation tensor cores with
+// accumulators in TMEM, operands staged by TMA, the online softmax in registers between them.  S and P never reach HBM.
+//
+// Same mathematics and the same three-pass fp16 split as causal_flash.cu (the mma.sync form: hgt.py:350-358 over the causal edges
+// of token_block_dataset.py:586-594), on the tensor path that is four times wider (measured: mma.sync peaks at 557 TFLOP/s,
+// profiles/r2_mma_sync_peak.log).  d_k = 128.
+//
+// One CTA per (block, head, 128-query tile), heaviest tiles first; key tiles of 64:
+//   warp 0     TMA producer: Q once (hi / lo, two 64-wide k-chunks each, SWIZZLE_128B), then per key tile K' hi / lo (64 x 128) and
+//              V'^T hi / lo (128 x 64: V' pre-transposed per head so that it is a K-major B operand), two stages
+//   warp 1     MMA issuer (one thread): S[j % 2] = Q K_j^T -- 8 k-steps x 3 passes of tcgen05.mma.kind::f16, M = 128, N = 64 -- issued
+//              one tile ahead of the softmax; O[j % 2] = P_j V_j -- 4 k-steps x 3 passes, N = 128 -- when P_j is in shared memory
+//   warps 2-5  softmax: thread = query row = TMEM lane.  tcgen05.ld S (64 columns), mask, running max / sum in the base-2 domain,
+//              P = 2^10 exp2(s - m) split into fp16 hi / lo and written to shared memory in the SWIZZLE_128B K-major layout the MMA
+//              reads (16 B chunk c of row r at r * 128 + ((c ^ (r & 7)) << 4)), fence.proxy.async, mbarrier; then the PREVIOUS tile's
+//              O partial is read back from TMEM and folded into the fp32 accumulator row in registers
+//              (acc = (acc + O_{j-1}) * 2^(m_{j-1} - m_j)), so the rescale never touches TMEM
+// TMEM: S 2 x 64 columns + O 2 x 128 columns.  Shared memory: Q 64 KB + 2 x (K 32 KB + V^T 32 KB) + P 32 KB = 224 KB.
+#include "gemm_tc_common.cuh"
+
+namespace gnnlm {
+
+namespace ft {
+
+using namespace tc;
+
+constexpr int BQ = 128, BKV = 64, DK = 128;
+constexpr int Q_CHUNK = BQ * 128;                      // 16 KB: 128 rows x 64 halves
+constexpr int K_CHUNK = BKV * 128;                     // 8 KB
+constexpr int VT_TILE = DK * 128;                      // 16 KB: 128 dv rows x 64 keys
+constexpr int P_TILE = BQ * 128;                       // 16 KB: 128 rows x 64 keys
+constexpr int STAGE = 4 * K_CHUNK + 2 * VT_TILE;       // 64 KB
+constexpr int SMEM = 4 * Q_CHUNK + 2 * STAGE + 2 * P_TILE;
+constexpr int THREADS = 192;
+constexpr uint32_t S_COL = 0, O_COL = 128, TMEM_ALLOC = 512;
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct Maps {
+  CUtensorMap q, k, vt;        // q: box 64 x 128 rows, k: box 64 x 64 rows over the split [T, 4d] matrix; vt: box 64 keys x 128 rows
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+    causal_flash_tc_kernel(const __grid_constant__ Maps maps, int L, int ctx, int H, int64_t d, int64_t vt_lo_rows,
+                           float* __restrict__ out, int64_t ldo, __half* __restrict__ out_split, int64_t ldos, int64_t os_lo,
+                           float out_scale, int accumulate) {
+  constexpr float L2E = 1.4426950408889634f;
+  constexpr uint32_t IDESC_QK = (1u << 4) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+  constexpr uint32_t IDESC_PV = (1u << 4) | ((uint32_t)(DK >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+  extern __shared__ uint8_t ft_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;                                  // hi c0 | hi c1 | lo c0 | lo c1
+  uint8_t* sKV = smem + 4 * Q_CHUNK;                   // per stage: K hi c0 | K hi c1 | K lo c0 | K lo c1 | Vt hi | Vt lo
+  uint8_t* sP = sKV + 2 * STAGE;                       // P hi | P lo
+  __shared__ __align__(8) uint64_t q_full, kv_full[2], kv_empty[2], s_full[2], o_full[2], p_full;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_qt = (L + BQ - 1) / BQ;
+  const int qt = n_qt - 1 - (int)(blockIdx.x / H);     // heaviest query tiles first
+  const int h = (int)(blockIdx.x % H);
+  const int b = blockIdx.y;
+  const int q0 = qt * BQ;
+  const int q_last = (q0 + BQ < L ? q0 + BQ : L) - 1;
+  const int k_first = ctx > 0 ? (q0 - ctx + 1 > 0 ? q0 - ctx + 1 : 0) : 0;
+  const int t_begin = k_first / BKV, t_end = q_last / BKV + 1;
+  const int n_t = t_end - t_begin;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.q) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.k) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.vt) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(&q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&o_full[s], 1);
+    }
+    mbar_init(&p_full, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(TMEM_ALLOC)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {                                   // ===================== TMA producer
+      const int row_q = b * L + q0;
+      const int cq = h * DK;
+      mbar_expect_tx(&q_full, 4 * Q_CHUNK);
+      tma_load_2d(sQ, &maps.q, cq, row_q, &q_full);
+      tma_load_2d(sQ + Q_CHUNK, &maps.q, cq + 64, row_q, &q_full);
+      tma_load_2d(sQ + 2 * Q_CHUNK, &maps.q, (int)(2 * d) + cq, row_q, &q_full);
+      tma_load_2d(sQ + 3 * Q_CHUNK, &maps.q, (int)(2 * d) + cq + 64, row_q, &q_full);
+      const int ck = (int)d + h * DK, ckl = (int)(3 * d) + h * DK;
+      const int vt_row = (b * H + h) * DK;
+      for (int j = 0; j < n_t; ++j) {
+        const int st = j & 1;
+        mbar_wait(&kv_empty[st], (uint32_t)(((j >> 1) & 1) ^ 1));
+        uint8_t* s = sKV + st * STAGE;
+        const int kv0 = (t_begin + j) * BKV, row_k = b * L + kv0;
+        mbar_expect_tx(&kv_full[st], STAGE);
+        tma_load_2d(s, &maps.k, ck, row_k, &kv_full[st]);
+        tma_load_2d(s + K_CHUNK, &maps.k, ck + 64, row_k, &kv_full[st]);
+        tma_load_2d(s + 2 * K_CHUNK, &maps.k, ckl, row_k, &kv_full[st]);
+        tma_load_2d(s + 3 * K_CHUNK, &maps.k, ckl + 64, row_k, &kv_full[st]);
+        tma_load_2d(s + 4 * K_CHUNK, &maps.vt, kv0, vt_row, &kv_full[st]);
+        tma_load_2d(s + 4 * K_CHUNK + VT_TILE, &maps.vt, kv0, (int)vt_lo_rows + vt_row, &kv_full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                   // ===================== MMA issuer
+      const uint64_t dqh0 = make_desc(smem_u32(sQ)), dqh1 = make_desc(smem_u32(sQ + Q_CHUNK));
+      const uint64_t dql0 = make_desc(smem_u32(sQ + 2 * Q_CHUNK)), dql1 = make_desc(smem_u32(sQ + 3 * Q_CHUNK));
+      const uint64_t dph = make_desc(smem_u32(sP)), dpl = make_desc(smem_u32(sP + P_TILE));
+      auto issue_qk = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&kv_full[st], (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+        const uint8_t* s = sKV + st * STAGE;
+        const uint64_t dkh0 = make_desc(smem_u32(s)), dkh1 = make_desc(smem_u32(s + K_CHUNK));
+        const uint64_t dkl0 = make_desc(smem_u32(s + 2 * K_CHUNK)), dkl1 = make_desc(smem_u32(s + 3 * K_CHUNK));
+        const uint32_t d_tmem = tmem_base + S_COL + (uint32_t)st * BKV;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {                // 16 halves = 32 B of k per instruction
+          const uint64_t off = (uint64_t)((ks & 3) * 2);
+          const uint64_t qh = (ks < 4 ? dqh0 : dqh1) + off, ql = (ks < 4 ? dql0 : dql1) + off;
+          const uint64_t kh = (ks < 4 ? dkh0 : dkh1) + off, kl = (ks < 4 ? dkl0 : dkl1) + off;
+          umma_f16(d_tmem, qh, kl, IDESC_QK, ks > 0 ? 1u : 0u);
+          umma_f16(d_tmem, ql, kh, IDESC_QK, 1u);
+          umma_f16(d_tmem, qh, kh, IDESC_QK, 1u);
+        }
+        tc_commit(&s_full[st]);
+      };
+      mbar_wait(&q_full, 0);
+      tc_fence_after();
+      issue_qk(0);
+      for (int j = 0; j < n_t; ++j) {
+        if (j + 1 < n_t) issue_qk(j + 1);              // one tile ahead of the softmax
+        const int st = j & 1;
+        mbar_wait(&p_full, (uint32_t)(j & 1));          // P_j in shared memory (and S_j, O_{j-2} consumed)
+        tc_fence_after();
+        const uint8_t* s = sKV + st * STAGE;
+        const uint64_t dvh = make_desc(smem_u32(s + 4 * K_CHUNK)), dvl = make_desc(smem_u32(s + 4 * K_CHUNK + VT_TILE));
+        const uint32_t d_tmem = tmem_base + O_COL + (uint32_t)st * DK;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t off = (uint64_t)(ks * 2);
+          umma_f16(d_tmem, dph + off, dvl + off, IDESC_PV, ks > 0 ? 1u : 0u);
+          umma_f16(d_tmem, dpl + off, dvh + off, IDESC_PV, 1u);
+          umma_f16(d_tmem, dph + off, dvh + off, IDESC_PV, 1u);
+        }
+        tc_commit(&kv_empty[st]);                       // K_j / V_j consumed
+        tc_commit(&o_full[st]);                         // O partial of tile j complete (P_j consumed)
+      }
+    }
+  } else {
+    // ===================== softmax + output accumulation: thread = query row
+    const int lq = warp & 3;                            // TMEM lane quarter of this warp
+    const int r = lq * 32 + lane;                       // row inside the tile
+    const int v = q0 + r;                               // query position inside the block
+    const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
+    const uint32_t sp_row = smem_u32(sP) + (uint32_t)r * 128;
+    const uint32_t sw = (uint32_t)(r & 7);
+    float acc[DK];
+#pragma unroll
+    for (int c = 0; c < DK; ++c) acc[c] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_t; ++j) {
+      const int st = j & 1;
+      const int kv0 = (t_begin + j) * BKV;
+      mbar_wait(&s_full[st], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      float s[BKV];
+      tmem_ld32_nowait(tmem_base + lane_addr + S_COL + (uint32_t)st * BKV, s);
+      tmem_ld32_nowait(tmem_base + lane_addr + S_COL + (uint32_t)st * BKV + 32, s + 32);
+      tmem_wait_ld();
+      const bool need_mask = kv0 + BKV - 1 > q0 || (ctx > 0 && kv0 <= q0 + BQ - 1 - ctx);      // CTA-uniform
+      float mx = -INFINITY;
+      if (need_mask) {
+#pragma unroll
+        for (int c = 0; c < BKV; ++c) {
+          const int u = kv0 + c;
+          if (u > v || (ctx > 0 && v - u >= ctx)) s[c] = -INFINITY;
+          mx = fmaxf(mx, s[c]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < BKV; ++c) mx = fmaxf(mx, s[c]);
+      }
+      const float m_new = fmaxf(m_run, mx * L2E);
+      const float corr = m_new > -INFINITY ? fast_exp2(m_run - m_new) : 1.f;      // m_run = -inf: nothing accumulated yet
+      const float mb = m_new > -INFINITY ? m_new : 0.f;
+      m_run = m_new;
+      // P_{j-1} is free once the PV product of tile j - 1 has completed (that also delivers its O partial)
+      if (j > 0) {
+        mbar_wait(&o_full[st ^ 1], (uint32_t)(((j - 1) >> 1) & 1));
+        tc_fence_after();
+      }
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {                      // 16 B chunk c of this row: keys 8c .. 8c + 7
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = fast_exp2(fmaf(s[8 * c + 2 * e], L2E, -mb)), p1 = fast_exp2(fmaf(s[8 * c + 2 * e + 1], L2E, -mb));   // exp2(-inf) = 0
+          sum += p0 + p1;
+          const __half2 hh = __floats2half2_rn(p0 * 1024.f, p1 * 1024.f);
+          const float2 hf = __half22float2(hh);
+          const __half2 ll = __floats2half2_rn(p0 * 1024.f - hf.x, p1 * 1024.f - hf.y);
+          ph[e] = *reinterpret_cast<const uint32_t*>(&hh);
+          pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        const uint32_t a = sp_row + ((((uint32_t)c) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + P_TILE), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+      }
+      l_run = l_run * corr + sum;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the MMA
+      tc_fence_before();
+      mbar_arrive(&p_full);
+      // fold the previous tile's partial: acc = (acc + O_{j-1}) * 2^(m_{j-1} - m_j)
+      if (j > 0) {
+        const uint32_t o_addr = tmem_base + lane_addr + O_COL + (uint32_t)(st ^ 1) * DK;
+#pragma unroll
+        for (int c0 = 0; c0 < DK; c0 += 32) {
+          float o[32];
+          tmem_ld32_nowait(o_addr + c0, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) acc[c0 + c] = (acc[c0 + c] + o[c]) * corr;
+        }
+      }
+    }
+    // last partial
+    {
+      const int jl = n_t - 1, st = jl & 1;
+      mbar_wait(&o_full[st], (uint32_t)((jl >> 1) & 1));
+      tc_fence_after();
+      const uint32_t o_addr = tmem_base + lane_addr + O_COL + (uint32_t)st * DK;
+#pragma unroll
+      for (int c0 = 0; c0 < DK; c0 += 32) {
+        float o[32];
+        tmem_ld32_nowait(o_addr + c0, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c0 + c] += o[c];
+      }
+    }
+    if (v < L) {
+      const float inv = l_run > 0.f ? out_scale / (1024.f * l_run) : 0.f;
+      const int64_t row = (int64_t)b * L + v;
+      float* op = out + row * ldo + h * DK;
+      if (out_split) {
+        __half* sp = out_split + row * ldos + h * DK;
+#pragma unroll
+        for (int c = 0; c < DK; c += 4) {
+          float4 y = make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv);
+          if (accumulate) {
+            const float4 p = *reinterpret_cast<const float4*>(op + c);
+            y.x += p.x; y.y += p.y; y.z += p.z; y.w += p.w;
+          }
+          uint2 hi, lo;
+          split4_f16(y.x, y.y, y.z, y.w, hi, lo);
+          *reinterpret_cast<uint2*>(sp + c) = hi;
+          *reinterpret_cast<uint2*>(sp + os_lo + c) = lo;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < DK; c += 4) {
+          float4 y = make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv);
+          if (accumulate) {
+            const float4 p = *reinterpret_cast<const float4*>(op + c);
+            y.x += p.x; y.y += p.y; y.z += p.z; y.w += p.w;
+          }
+          *reinterpret_cast<float4*>(op + c) = y;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_ALLOC) : "memory");
+  }
+}
+
+// fp16 [rows, cols] row-major (row stride ld elements), boxes of 64 columns x box_rows, SWIZZLE_128B
+static int make_map_sw128(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return (int)encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+}  // namespace ft
+
+int32_t gemm_tc_supported();
+
+}  // namespace gnnlm
+
+using namespace gnnlm;
+
+extern "C" int32_t gnnlm_hgt_causal_flash_tc(const void* qk_split, int64_t ldqk, int64_t d, const void* vt, int64_t ldvt, int64_t B,
+                                             int64_t L, int64_t intra_ctx, int32_t H, int32_t d_k, float* out, int64_t ldo,
+                                             void* out_split, int64_t ldos, int64_t os_lo, float out_scale, int32_t accumulate,
+                                             cudaStream_t stream) {
+  GNNLM_CHECK_ARG(qk_split && vt && (out || (out_split && !accumulate)), GNNLM_E_ARG, "gnnlm_hgt_causal_flash_tc: null pointer");
+  GNNLM_CHECK_ARG(gemm_tc_supported(), GNNLM_E_UNSUPPORTED, "gnnlm_hgt_causal_flash_tc: needs an sm_100 device and driver TMA support");
+  GNNLM_CHECK_ARG(d_k == 128 && H > 0 && d == (int64_t)H * d_k, GNNLM_E_UNSUPPORTED, "gnnlm_hgt_causal_flash_tc: d_k must be 128, d = H d_k");
+  GNNLM_CHECK_ARG(B >= 0 && B < 65536 && L > 0 && B * L < (1ll << 31), GNNLM_E_SHAPE, "gnnlm_hgt_causal_flash_tc: bad sizes");
+  GNNLM_CHECK_ARG(ldqk >= 4 * d && ldqk % 8 == 0 && ldvt >= L && ldvt % 8 == 0 && (uintptr_t)qk_split % 16 == 0 && (uintptr_t)vt % 16 == 0,
+                  GNNLM_E_SHAPE, "gnnlm_hgt_causal_flash_tc: TMA needs 16 B aligned bases and row strides (ldqk=%lld ldvt=%lld)",
+                  (long long)ldqk, (long long)ldvt);
+  GNNLM_CHECK_ARG(!out || (ldo % 4 == 0 && (uintptr_t)out % 16 == 0), GNNLM_E_SHAPE, "gnnlm_hgt_causal_flash_tc: out rows must be 16 B aligned");
+  GNNLM_CHECK_ARG(!out_split || (ldos % 4 == 0 && os_lo % 4 == 0 && (uintptr_t)out_split % 8 == 0), GNNLM_E_SHAPE,
+                  "gnnlm_hgt_causal_flash_tc: split output rows must be 8 B aligned");
+  if (B == 0) return 0;
+  ft::Maps maps;
+  const int64_t T = B * L, vt_rows = B * H * d_k;
+  int r = ft::make_map_sw128(&maps.q, qk_split, T, 4 * d, ldqk, ft::BQ);
+  if (!r) r = ft::make_map_sw128(&maps.k, qk_split, T, 4 * d, ldqk, ft::BKV);
+  if (!r) r = ft::make_map_sw128(&maps.vt, vt, 2 * vt_rows, L, ldvt, ft::DK);
+  GNNLM_CHECK_ARG(r == 0, GNNLM_E_ARG, "gnnlm_hgt_causal_flash_tc: cuTensorMapEncodeTiled failed (%d)", r);
+  const int smem = ft::SMEM + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GNNLM_CUDA(cudaFuncSetAttribute(ft::causal_flash_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(ceil_div(L, ft::BQ) * H), (unsigned)B);
+  ft::causal_flash_tc_kernel<<<grid, ft::THREADS, smem, stream>>>(maps, (int)L, (int)intra_ctx, H, d, vt_rows, out, ldo,
+                                                                 reinterpret_cast<__half*>(out_split), ldos, os_lo, out_scale, accumulate);
+  GNNLM_LAUNCH_CHECK("gnnlm_hgt_causal_flash_tc");
+  return 0;
+}

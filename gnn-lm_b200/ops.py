@@ -320,6 +320,27 @@ def causal_attn_flash(q, kv: Split, B, Lb, intra_ctx, H, out, *, out_scale=1.0, 
     return out if out_split is None else out_split
 
 
+def causal_flash_tc_supported(d: int, H: int, Lb: int) -> bool:
+    return d % H == 0 and d // H == 128 and Lb % 8 == 0
+
+
+def causal_attn_flash_tc(qkv, B, Lb, intra_ctx, H, out, *, out_scale=1.0, accumulate=False, out_split: Optional[Split] = None):
+    """tgt-intra-tgt attention on tcgen05 (gnnlm_hgt_causal_flash_tc): qkv fp32 [B*Lb, 3d] (Q | K' | V' of the projection)."""
+    d = qkv.shape[1] // 3
+    dk = d // H
+    dev = qkv.device
+    qk = to_split(qkv[:, :2 * d])                                                     # Q hi | K' hi | Q lo | K' lo
+    vt = torch.empty((2, B * H * dk, Lb), device=dev, dtype=torch.float16)
+    for b in range(B):
+        vb = qkv[b * Lb:(b + 1) * Lb, 2 * d:]
+        L.call("gnnlm_heads_transpose_split_f16", L.ptr(vb), vb.stride(0), Lb, H, dk, L.ptr(vt[0, b * H * dk:]), L.ptr(vt[1, b * H * dk:]),
+               L.stream_ptr())
+    os_ptr, ldos, os_lo = (None, 0, 0) if out_split is None else (L.ptr(out_split.data), out_split.data.stride(0), out_split.d)
+    L.call("gnnlm_hgt_causal_flash_tc", L.ptr(qk.data), qk.data.stride(0), d, L.ptr(vt), Lb, B, Lb, intra_ctx, H, dk, L.ptr(out),
+           out.stride(0), os_ptr, ldos, os_lo, float(out_scale), int(accumulate), L.stream_ptr(), tag="causal_flash_tc")
+    return out if out_split is None else out_split
+
+
 CAUSAL_K_TILE = 256      # rows per tile pair of the batched GEMM (2 * BLOCK_M): the contraction limit of `causal = 2`
 
 

@@ -352,6 +352,15 @@ int32_t gnnlm_hgt_causal_flash(const float* q, int64_t ldq, const void* k_split,
                                int64_t ldo, void* out_split, int64_t ldos, int64_t os_lo, float out_scale, int32_t accumulate,
                                gnnlm_stream_t stream);
 
+/* tcgen05 form of the same flash attention (d_k = 128): both products on tcgen05.mma with TMEM accumulators, operands by TMA.
+ *  qk_split  [B*L, ldqk] fp16: Q hi | K' hi | Q lo | K' lo, each d = H*d_k columns wide (gnnlm_to_split_f16 of the Q | K' columns)
+ *  vt        [2][B*H*d_k][ldvt] fp16: V'^T hi, then lo -- row (b*H + h)*d_k + j holds V'[b*L + 0 .. L, h*d_k + j]
+ *            (gnnlm_heads_transpose_split_f16 per block); ldvt >= L, a multiple of 8
+ *  out / out_split / out_scale / accumulate as gnnlm_hgt_causal_flash. */
+int32_t gnnlm_hgt_causal_flash_tc(const void* qk_split, int64_t ldqk, int64_t d, const void* vt, int64_t ldvt, int64_t B, int64_t L,
+                                  int64_t intra_ctx, int32_t H, int32_t d_k, float* out, int64_t ldo, void* out_split,
+                                  int64_t ldos, int64_t os_lo, float out_scale, int32_t accumulate, gnnlm_stream_t stream);
+
 /* ('ntgt','inter','tgt') attention with the K' / V' projections moved from the ~k*T centre nodes to the T target tokens
  * (every centre row is used by exactly one (token, neighbour) pair): with q~[t,h] = W_k'[h]^T q[t,h] in R^d (a per-head GEMM
  * of the caller) this kernel computes, per token and head, alpha = softmax_c <h_c, q~[t,h]> over the token's centre rows and

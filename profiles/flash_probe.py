@@ -9,7 +9,17 @@ qkv = torch.randn(B * L, 3 * d, device=dev) * 0.3
 kv = ops.to_split(qkv[:, d:])
 out = torch.zeros(B * L, d, device=dev)
 res = ops.Split.empty(B * L, d, dev)
-f = lambda: ops.causal_attn_flash(qkv[:, :d], kv, B, L, 0, H, out, out_scale=0.5, accumulate=True, out_split=res)
+import os
+if os.environ.get("FLASH_TC") == "1":
+    qk = ops.to_split(qkv[:, :2 * d])
+    vt = torch.empty((2, B * H * (d // H), L), device=dev, dtype=torch.float16)
+    from gnnlm_b200 import _lib as LL
+    vb = qkv[:, 2 * d:]
+    LL.call("gnnlm_heads_transpose_split_f16", LL.ptr(vb), vb.stride(0), L, H, d // H, LL.ptr(vt[0]), LL.ptr(vt[1]), LL.stream_ptr())
+    f = lambda: LL.call("gnnlm_hgt_causal_flash_tc", LL.ptr(qk.data), qk.data.stride(0), d, LL.ptr(vt), L, B, L, 0, H, d // H, LL.ptr(out),
+                        out.stride(0), LL.ptr(res.data), res.data.stride(0), res.d, 0.5, 1, LL.stream_ptr())
+else:
+    f = lambda: ops.causal_attn_flash(qkv[:, :d], kv, B, L, 0, H, out, out_scale=0.5, accumulate=True, out_split=res)
 for _ in range(3):
     f()
 torch.cuda.synchronize()

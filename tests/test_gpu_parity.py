@@ -1104,6 +1104,35 @@ def test_causal_flash_kernel(B, L, H, d, ctx, split_out, dev):
         np.testing.assert_allclose(out0.cpu().double().numpy(), att.numpy(), rtol=2e-5, atol=2e-5)
 
 
+@pytest.mark.parametrize("B,L,H,d,ctx", [(1, 256, 8, 1024, 0), (1, 64, 8, 1024, 0), (1, 512, 8, 1024, 100), (1, 1288, 8, 1024, 0),
+                                          (1, 3072, 8, 1024, 0), (3, 200, 8, 1024, 0), (2, 72, 4, 512, 5), (1, 40, 8, 1024, 1)])
+@pytest.mark.parametrize("split_out", [False, True])
+def test_causal_flash_tc_kernel(B, L, H, d, ctx, split_out, dev):
+    """gnnlm_hgt_causal_flash_tc (tcgen05 / TMEM / TMA flash kernel, d_k = 128) vs the fp64 definition of hgt.py:350-358 over the
+    edges of auto_regressive_edges: ragged L, several blocks, a context window, fp32 and split-fp16 outputs."""
+    _need_tc()
+    from gnnlm_b200 import ops
+    torch.manual_seed(13)
+    q, k, v = torch.randn(B * L, d) * 0.3, torch.randn(B * L, d) * 0.3, torch.randn(B * L, d)
+    base = torch.randn(B * L, d)
+    qkv = torch.cat([q, k, v], 1).to(dev)
+    out = base.clone().to(dev)
+    if split_out:
+        res = ops.Split.empty(B * L, d, dev)
+        ops.causal_attn_flash_tc(qkv, B, L, ctx, H, out, out_scale=0.5, accumulate=True, out_split=res)
+        assert torch.equal(out.cpu(), base)
+        got = res.float().cpu().double()
+    else:
+        ops.causal_attn_flash_tc(qkv, B, L, ctx, H, out, out_scale=0.5, accumulate=True)
+        got = out.cpu().double()
+    qh, kh, vh = (t.view(B, L, H, d // H).permute(0, 2, 1, 3).double() for t in (q, k, v))
+    s = qh @ kh.transpose(-1, -2)
+    i = torch.arange(L)
+    mask = (i[None, :] <= i[:, None]) & ((i[:, None] - i[None, :] < ctx) if ctx else True)
+    att = (torch.softmax(s.masked_fill(~mask, -float("inf")), -1) @ vh).permute(0, 2, 1, 3).reshape(B * L, d)
+    np.testing.assert_allclose(got.numpy(), (base.double() + 0.5 * att).numpy(), rtol=2e-5, atol=2e-5)
+
+
 @pytest.mark.parametrize("math", ["fp32", "f16x3"])
 def test_token_chunked_ntgt_side_matches(math, dev):
     """forward_tgt_chunked (ntgt side in token chunks, inter attention per chunk) == forward_tgt."""
