@@ -12,10 +12,13 @@
 //              one tile ahead of the softmax; O[j % 2] = P_j V_j -- 4 k-steps x 3 passes, N = 128 -- when P_j is in shared memory
 //   warps 2-5  softmax: thread = query row = TMEM lane.  tcgen05.ld S (64 columns), mask, running max / sum in the base-2 domain,
 //              P = 2^10 exp2(s - m) split into fp16 hi / lo and written to shared memory in the SWIZZLE_128B K-major layout the MMA
-//              reads (16 B chunk c of row r at r * 128 + ((c ^ (r & 7)) << 4)), fence.proxy.async, mbarrier; then the PREVIOUS tile's
-//              O partial is read back from TMEM and folded into the fp32 accumulator row in registers
-//              (acc = (acc + O_{j-1}) * 2^(m_{j-1} - m_j)), so the rescale never touches TMEM
-// TMEM: S 2 x 64 columns + O 2 x 128 columns.  Shared memory: Q 64 KB + 2 x (K 32 KB + V^T 32 KB) + P 32 KB = 224 KB.
+//              reads (16 B chunk c of row r at r * 128 + ((c ^ (r & 7)) << 4)), fence.proxy.async, mbarrier.  O accumulates in TMEM
+//              across the key tiles; it is rescaled (tcgen05.ld -> multiply -> tcgen05.st, per warp) only when a row's maximum
+//              has grown by more than 2^8 over the reference the row's P values are scaled by (lazy rescale: P <= 2^8, times the
+//              2^7 split scale it stays inside fp16) -- on the first tiles of a row, practically never afterwards
+// TMEM: S 3 x 64 columns + O 128 columns.  Shared memory: Q 64 KB + 2 x (K 32 KB + V^T 32 KB) + P 32 KB = 224 KB.
+// First build (O partial per tile folded into registers by the softmax threads): 0.119 ms at L = 3072; the softmax warps (one per
+// scheduler, ~1200 dependent instructions per tile, half of them fp16 <-> fp32 conversions and the fold) paced it.
 #include "gemm_tc_common.cuh"
 
 namespace gnnlm {
@@ -31,8 +34,9 @@ constexpr int VT_TILE = DK * 128;                      // 16 KB: 128 dv rows x 6
 constexpr int P_TILE = BQ * 128;                       // 16 KB: 128 rows x 64 keys
 constexpr int STAGE = 4 * K_CHUNK + 2 * VT_TILE;       // 64 KB
 constexpr int SMEM = 4 * Q_CHUNK + 2 * STAGE + 2 * P_TILE;
-constexpr int THREADS = 192;
-constexpr uint32_t S_COL = 0, O_COL = 128, TMEM_ALLOC = 512;
+constexpr int THREADS = 224;                          // warp 0: Q + K' producer, 1: MMA issuer, 2-5: softmax, 6: V'^T producer
+constexpr uint32_t S_COL = 0, O_COL = 256, TMEM_ALLOC = 512;      // S: three 64-column buffers (scores run two tiles ahead), O: 128
+constexpr float P_SCALE = 128.f, RESCALE_AT = 8.f;   // P = 2^7 exp2(s - m_ref) <= 2^15 as long as the maximum stays within 2^8 of m_ref
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -47,6 +51,19 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
       : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -63,7 +80,7 @@ struct Maps {
 __global__ void __launch_bounds__(THREADS, 1)
     causal_flash_tc_kernel(const __grid_constant__ Maps maps, int L, int ctx, int H, int64_t d, int64_t vt_lo_rows,
                            float* __restrict__ out, int64_t ldo, __half* __restrict__ out_split, int64_t ldos, int64_t os_lo,
-                           float out_scale, int accumulate) {
+                           float out_scale, int accumulate, long long* __restrict__ dbg) {
   constexpr float L2E = 1.4426950408889634f;
   constexpr uint32_t IDESC_QK = (1u << 4) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
   constexpr uint32_t IDESC_PV = (1u << 4) | ((uint32_t)(DK >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
@@ -72,7 +89,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   uint8_t* sQ = smem;                                  // hi c0 | hi c1 | lo c0 | lo c1
   uint8_t* sKV = smem + 4 * Q_CHUNK;                   // per stage: K hi c0 | K hi c1 | K lo c0 | K lo c1 | Vt hi | Vt lo
   uint8_t* sP = sKV + 2 * STAGE;                       // P hi | P lo
-  __shared__ __align__(8) uint64_t q_full, kv_full[2], kv_empty[2], s_full[2], o_full[2], p_full;
+  __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[3], o_full, p_full;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,11 +111,13 @@ __global__ void __launch_bounds__(THREADS, 1)
   if (warp == 1 && lane == 0) {
     mbar_init(&q_full, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-      mbar_init(&s_full[s], 1);
-      mbar_init(&o_full[s], 1);
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
     }
+    for (int s = 0; s < 3; ++s) mbar_init(&s_full[s], 1);
+    mbar_init(&o_full, 1);
     mbar_init(&p_full, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -122,19 +141,31 @@ __global__ void __launch_bounds__(THREADS, 1)
       tma_load_2d(sQ + 2 * Q_CHUNK, &maps.q, (int)(2 * d) + cq, row_q, &q_full);
       tma_load_2d(sQ + 3 * Q_CHUNK, &maps.q, (int)(2 * d) + cq + 64, row_q, &q_full);
       const int ck = (int)d + h * DK, ckl = (int)(3 * d) + h * DK;
+      // K' and V'^T travel through separate rings: a K' stage is free as soon as its score product has retired (one tile before
+      // the PV product that frees the V'^T stage), so the load of K'_{j+2} starts two tile periods before it is needed
+      for (int j = 0; j < n_t; ++j) {
+        const int st = j & 1;
+        mbar_wait(&k_empty[st], (uint32_t)(((j >> 1) & 1) ^ 1));
+        uint8_t* s = sKV + st * STAGE;
+        const int row_k = b * L + (t_begin + j) * BKV;
+        mbar_expect_tx(&k_full[st], 4 * K_CHUNK);
+        tma_load_2d(s, &maps.k, ck, row_k, &k_full[st]);
+        tma_load_2d(s + K_CHUNK, &maps.k, ck + 64, row_k, &k_full[st]);
+        tma_load_2d(s + 2 * K_CHUNK, &maps.k, ckl, row_k, &k_full[st]);
+        tma_load_2d(s + 3 * K_CHUNK, &maps.k, ckl + 64, row_k, &k_full[st]);
+      }
+    }
+  } else if (warp == 6) {
+    if (lane == 0) {                                   // ===================== V'^T producer
       const int vt_row = (b * H + h) * DK;
       for (int j = 0; j < n_t; ++j) {
         const int st = j & 1;
-        mbar_wait(&kv_empty[st], (uint32_t)(((j >> 1) & 1) ^ 1));
-        uint8_t* s = sKV + st * STAGE;
-        const int kv0 = (t_begin + j) * BKV, row_k = b * L + kv0;
-        mbar_expect_tx(&kv_full[st], STAGE);
-        tma_load_2d(s, &maps.k, ck, row_k, &kv_full[st]);
-        tma_load_2d(s + K_CHUNK, &maps.k, ck + 64, row_k, &kv_full[st]);
-        tma_load_2d(s + 2 * K_CHUNK, &maps.k, ckl, row_k, &kv_full[st]);
-        tma_load_2d(s + 3 * K_CHUNK, &maps.k, ckl + 64, row_k, &kv_full[st]);
-        tma_load_2d(s + 4 * K_CHUNK, &maps.vt, kv0, vt_row, &kv_full[st]);
-        tma_load_2d(s + 4 * K_CHUNK + VT_TILE, &maps.vt, kv0, (int)vt_lo_rows + vt_row, &kv_full[st]);
+        mbar_wait(&v_empty[st], (uint32_t)(((j >> 1) & 1) ^ 1));
+        uint8_t* s = sKV + st * STAGE + 4 * K_CHUNK;
+        const int kv0 = (t_begin + j) * BKV;
+        mbar_expect_tx(&v_full[st], 2 * VT_TILE);
+        tma_load_2d(s, &maps.vt, kv0, vt_row, &v_full[st]);
+        tma_load_2d(s + VT_TILE, &maps.vt, kv0, (int)vt_lo_rows + vt_row, &v_full[st]);
       }
     }
   } else if (warp == 1) {
@@ -142,14 +173,18 @@ __global__ void __launch_bounds__(THREADS, 1)
       const uint64_t dqh0 = make_desc(smem_u32(sQ)), dqh1 = make_desc(smem_u32(sQ + Q_CHUNK));
       const uint64_t dql0 = make_desc(smem_u32(sQ + 2 * Q_CHUNK)), dql1 = make_desc(smem_u32(sQ + 3 * Q_CHUNK));
       const uint64_t dph = make_desc(smem_u32(sP)), dpl = make_desc(smem_u32(sP + P_TILE));
+      long long t_k = 0, t_p = 0, t_v = 0;
+      const long long t_begin_clk = dbg ? clock64() : 0;
       auto issue_qk = [&](int j) {
         const int st = j & 1;
-        mbar_wait(&kv_full[st], (uint32_t)((j >> 1) & 1));
+        const long long c0 = dbg ? clock64() : 0;
+        mbar_wait(&k_full[st], (uint32_t)((j >> 1) & 1));
+        if (dbg) t_k += clock64() - c0;
         tc_fence_after();
         const uint8_t* s = sKV + st * STAGE;
         const uint64_t dkh0 = make_desc(smem_u32(s)), dkh1 = make_desc(smem_u32(s + K_CHUNK));
         const uint64_t dkl0 = make_desc(smem_u32(s + 2 * K_CHUNK)), dkl1 = make_desc(smem_u32(s + 3 * K_CHUNK));
-        const uint32_t d_tmem = tmem_base + S_COL + (uint32_t)st * BKV;
+        const uint32_t d_tmem = tmem_base + S_COL + (uint32_t)(j % 3) * BKV;
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {                // 16 halves = 32 B of k per instruction
           const uint64_t off = (uint64_t)((ks & 3) * 2);
@@ -159,50 +194,67 @@ __global__ void __launch_bounds__(THREADS, 1)
           umma_f16(d_tmem, ql, kh, IDESC_QK, 1u);
           umma_f16(d_tmem, qh, kh, IDESC_QK, 1u);
         }
-        tc_commit(&s_full[st]);
+        tc_commit(&k_empty[st]);                        // K'_j consumed
+        tc_commit(&s_full[j % 3]);
       };
       mbar_wait(&q_full, 0);
       tc_fence_after();
+      // tensor-pipe order ... PV_{j-1}, QK_{j+1}, PV_j, QK_{j+2} ...: the score product of tile j + 2 is issued right AFTER the PV
+      // product of tile j, so that it runs under the softmax of tile j + 1 and PV_{j+1} never queues behind it
       issue_qk(0);
+      if (n_t > 1) issue_qk(1);
       for (int j = 0; j < n_t; ++j) {
-        if (j + 1 < n_t) issue_qk(j + 1);              // one tile ahead of the softmax
         const int st = j & 1;
-        mbar_wait(&p_full, (uint32_t)(j & 1));          // P_j in shared memory (and S_j, O_{j-2} consumed)
+        const long long c1 = dbg ? clock64() : 0;
+        mbar_wait(&p_full, (uint32_t)(j & 1));          // P_j in shared memory (S_j consumed, O rescaled if it had to be)
+        const long long c2 = dbg ? clock64() : 0;
+        mbar_wait(&v_full[st], (uint32_t)((j >> 1) & 1));
+        if (dbg) { t_p += c2 - c1; t_v += clock64() - c2; }
         tc_fence_after();
         const uint8_t* s = sKV + st * STAGE;
         const uint64_t dvh = make_desc(smem_u32(s + 4 * K_CHUNK)), dvl = make_desc(smem_u32(s + 4 * K_CHUNK + VT_TILE));
-        const uint32_t d_tmem = tmem_base + O_COL + (uint32_t)st * DK;
+        const uint32_t d_tmem = tmem_base + O_COL;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t off = (uint64_t)(ks * 2);
-          umma_f16(d_tmem, dph + off, dvl + off, IDESC_PV, ks > 0 ? 1u : 0u);
+          umma_f16(d_tmem, dph + off, dvl + off, IDESC_PV, (j | ks) > 0 ? 1u : 0u);      // O accumulates across the key tiles
           umma_f16(d_tmem, dpl + off, dvh + off, IDESC_PV, 1u);
           umma_f16(d_tmem, dph + off, dvh + off, IDESC_PV, 1u);
         }
-        tc_commit(&kv_empty[st]);                       // K_j / V_j consumed
-        tc_commit(&o_full[st]);                         // O partial of tile j complete (P_j consumed)
+        tc_commit(&v_empty[st]);                        // V_j consumed
+        tc_commit(&o_full);                             // P_j consumed, O includes tile j
+        if (j + 2 < n_t) issue_qk(j + 2);
+      }
+      if (dbg && blockIdx.x < 8 && blockIdx.y == 0) {   // the eight heaviest CTAs (timing experiments: GNNLM_FLASH_DEBUG=1)
+        dbg[blockIdx.x * 8 + 0] = clock64() - t_begin_clk;
+        dbg[blockIdx.x * 8 + 1] = t_k;
+        dbg[blockIdx.x * 8 + 2] = t_p;
+        dbg[blockIdx.x * 8 + 3] = t_v;
+        dbg[blockIdx.x * 8 + 4] = n_t;
       }
     }
-  } else {
-    // ===================== softmax + output accumulation: thread = query row
+  } else if (warp >= 2 && warp < 6) {
+    // ===================== softmax: thread = query row
     const int lq = warp & 3;                            // TMEM lane quarter of this warp
     const int r = lq * 32 + lane;                       // row inside the tile
     const int v = q0 + r;                               // query position inside the block
     const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
     const uint32_t sp_row = smem_u32(sP) + (uint32_t)r * 128;
     const uint32_t sw = (uint32_t)(r & 7);
-    float acc[DK];
-#pragma unroll
-    for (int c = 0; c < DK; ++c) acc[c] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    const uint32_t o_addr = tmem_base + lane_addr + O_COL;
+    float m_ref = -INFINITY, l_run = 0.f;               // reference maximum (base 2) the row's P and O are scaled by; denominator
+    long long t_s = 0, t_o = 0;
+    int n_resc = 0;
     for (int j = 0; j < n_t; ++j) {
       const int st = j & 1;
       const int kv0 = (t_begin + j) * BKV;
-      mbar_wait(&s_full[st], (uint32_t)((j >> 1) & 1));
+      const long long c0 = dbg ? clock64() : 0;
+      mbar_wait(&s_full[j % 3], (uint32_t)((j / 3) & 1));
+      if (dbg) t_s += clock64() - c0;
       tc_fence_after();
       float s[BKV];
-      tmem_ld32_nowait(tmem_base + lane_addr + S_COL + (uint32_t)st * BKV, s);
-      tmem_ld32_nowait(tmem_base + lane_addr + S_COL + (uint32_t)st * BKV + 32, s + 32);
+      tmem_ld32_nowait(tmem_base + lane_addr + S_COL + (uint32_t)(j % 3) * BKV, s);
+      tmem_ld32_nowait(tmem_base + lane_addr + S_COL + (uint32_t)(j % 3) * BKV + 32, s + 32);
       tmem_wait_ld();
       const bool need_mask = kv0 + BKV - 1 > q0 || (ctx > 0 && kv0 <= q0 + BQ - 1 - ctx);      // CTA-uniform
       float mx = -INFINITY;
@@ -217,15 +269,36 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
         for (int c = 0; c < BKV; ++c) mx = fmaxf(mx, s[c]);
       }
-      const float m_new = fmaxf(m_run, mx * L2E);
-      const float corr = m_new > -INFINITY ? fast_exp2(m_run - m_new) : 1.f;      // m_run = -inf: nothing accumulated yet
-      const float mb = m_new > -INFINITY ? m_new : 0.f;
-      m_run = m_new;
-      // P_{j-1} is free once the PV product of tile j - 1 has completed (that also delivers its O partial)
+      mx *= L2E;
+      // P_{j-1} is free, and O complete up to tile j - 1, once the PV product of tile j - 1 has retired
       if (j > 0) {
-        mbar_wait(&o_full[st ^ 1], (uint32_t)(((j - 1) >> 1) & 1));
+        const long long c1 = dbg ? clock64() : 0;
+        mbar_wait(&o_full, (uint32_t)((j - 1) & 1));
+        if (dbg) t_o += clock64() - c1;
         tc_fence_after();
       }
+      // lazy rescale: move the reference only when the maximum has outgrown it by 2^8 (always on a row's first finite tile)
+      const bool grow = mx > m_ref + RESCALE_AT;         // m_ref = -inf: true for any finite mx
+      if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = fmaxf(m_ref, mx);
+        const float corr = m_new > -INFINITY ? fast_exp2(m_ref - m_new) : 1.f;       // 0 when nothing was accumulated under -inf
+        m_ref = m_new;
+        l_run *= corr;
+        ++n_resc;
+        if (j > 0) {
+#pragma unroll
+          for (int c0 = 0; c0 < DK; c0 += 32) {
+            float o[32];
+            tmem_ld32_nowait(o_addr + c0, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] *= corr;
+            tmem_st32(o_addr + c0, o);
+          }
+          tmem_wait_st();
+        }
+      }
+      const float mb = m_ref > -INFINITY ? m_ref : 0.f;
       float sum = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {                      // 16 B chunk c of this row: keys 8c .. 8c + 7
@@ -234,9 +307,10 @@ __global__ void __launch_bounds__(THREADS, 1)
         for (int e = 0; e < 4; ++e) {
           const float p0 = fast_exp2(fmaf(s[8 * c + 2 * e], L2E, -mb)), p1 = fast_exp2(fmaf(s[8 * c + 2 * e + 1], L2E, -mb));   // exp2(-inf) = 0
           sum += p0 + p1;
-          const __half2 hh = __floats2half2_rn(p0 * 1024.f, p1 * 1024.f);
-          const float2 hf = __half22float2(hh);
-          const __half2 ll = __floats2half2_rn(p0 * 1024.f - hf.x, p1 * 1024.f - hf.y);
+          // hi = the top 11 significant bits (exact in fp16, no conversion back needed), lo = the exact fp32 remainder
+          const float x0 = p0 * P_SCALE, x1 = p1 * P_SCALE;
+          const float h0 = __uint_as_float(__float_as_uint(x0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(x1) & 0xffffe000u);
+          const __half2 hh = __floats2half2_rn(h0, h1), ll = __floats2half2_rn(x0 - h0, x1 - h1);
           ph[e] = *reinterpret_cast<const uint32_t*>(&hh);
           pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
         }
@@ -244,40 +318,25 @@ __global__ void __launch_bounds__(THREADS, 1)
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + P_TILE), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
       }
-      l_run = l_run * corr + sum;
+      l_run += sum;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the MMA
       tc_fence_before();
       mbar_arrive(&p_full);
-      // fold the previous tile's partial: acc = (acc + O_{j-1}) * 2^(m_{j-1} - m_j)
-      if (j > 0) {
-        const uint32_t o_addr = tmem_base + lane_addr + O_COL + (uint32_t)(st ^ 1) * DK;
-#pragma unroll
-        for (int c0 = 0; c0 < DK; c0 += 32) {
-          float o[32];
-          tmem_ld32_nowait(o_addr + c0, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int c = 0; c < 32; ++c) acc[c0 + c] = (acc[c0 + c] + o[c]) * corr;
-        }
-      }
     }
-    // last partial
-    {
-      const int jl = n_t - 1, st = jl & 1;
-      mbar_wait(&o_full[st], (uint32_t)((jl >> 1) & 1));
-      tc_fence_after();
-      const uint32_t o_addr = tmem_base + lane_addr + O_COL + (uint32_t)st * DK;
-#pragma unroll
-      for (int c0 = 0; c0 < DK; c0 += 32) {
-        float o[32];
-        tmem_ld32_nowait(o_addr + c0, o);
-        tmem_wait_ld();
-#pragma unroll
-        for (int c = 0; c < 32; ++c) acc[c0 + c] += o[c];
-      }
+    if (dbg && blockIdx.x < 8 && blockIdx.y == 0 && warp == 2 && lane == 0) {
+      dbg[blockIdx.x * 8 + 5] = t_s;
+      dbg[blockIdx.x * 8 + 6] = t_o;
+      dbg[blockIdx.x * 8 + 7] = n_resc;
     }
+    // the row's output: O / l
+    mbar_wait(&o_full, (uint32_t)((n_t - 1) & 1));
+    tc_fence_after();
+    float acc[DK];
+#pragma unroll
+    for (int c0 = 0; c0 < DK; c0 += 32) tmem_ld32_nowait(o_addr + c0, acc + c0);
+    tmem_wait_ld();
     if (v < L) {
-      const float inv = l_run > 0.f ? out_scale / (1024.f * l_run) : 0.f;
+      const float inv = l_run > 0.f ? out_scale / (P_SCALE * l_run) : 0.f;
       const int64_t row = (int64_t)b * L + v;
       float* op = out + row * ldo + h * DK;
       if (out_split) {
@@ -363,8 +422,26 @@ extern "C" int32_t gnnlm_hgt_causal_flash_tc(const void* qk_split, int64_t ldqk,
     attr_set = true;
   }
   dim3 grid((unsigned)(ceil_div(L, ft::BQ) * H), (unsigned)B);
+  static int dbg_on = -1;
+  if (dbg_on < 0) { const char* e = getenv("GNNLM_FLASH_DEBUG"); dbg_on = e ? atoi(e) : 0; }       // timing experiments only
+  long long* dbg = nullptr;
+  if (dbg_on) {
+    static long long* buf = nullptr;
+    if (!buf) GNNLM_CUDA(cudaMalloc(&buf, 64 * sizeof(long long)));
+    GNNLM_CUDA(cudaMemsetAsync(buf, 0, 64 * sizeof(long long), stream));
+    dbg = buf;
+  }
   ft::causal_flash_tc_kernel<<<grid, ft::THREADS, smem, stream>>>(maps, (int)L, (int)intra_ctx, H, d, vt_rows, out, ldo,
-                                                                 reinterpret_cast<__half*>(out_split), ldos, os_lo, out_scale, accumulate);
+                                                                 reinterpret_cast<__half*>(out_split), ldos, os_lo, out_scale, accumulate,
+                                                                 dbg);
   GNNLM_LAUNCH_CHECK("gnnlm_hgt_causal_flash_tc");
+  if (dbg) {
+    long long host[64];
+    GNNLM_CUDA(cudaStreamSynchronize(stream));
+    GNNLM_CUDA(cudaMemcpy(host, dbg, sizeof(host), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "flash_tc CTA 0: %lld key tiles, issuer total %lld cycles (%.0f per tile): wait K' %lld, wait P %lld, wait V' %lld | "
+            "softmax warp: wait S %lld, wait O %lld, rescales %lld\n", host[4], host[0], (double)host[0] / (double)(host[4] ? host[4] : 1),
+            host[1], host[2], host[3], host[5], host[6], host[7]);
+  }
   return 0;
 }

@@ -184,6 +184,7 @@ class HGTLayer(nn.Module):
         self.use_gemm_attention = True     # MATH_F16X3, long blocks: tgt-intra-tgt attention as tensor-core GEMMs
         # tensor-core modes, d_k in {64, 128}: one flash kernel instead (gnnlm_hgt_causal_flash); GNNLM_FLASH=0 for A/B timing
         self.use_flash_attention = os.environ.get("GNNLM_FLASH", "1") != "0"
+        self.use_flash_tc = os.environ.get("GNNLM_FLASH", "1") != "mma"      # d_k = 128: the tcgen05 form (GNNLM_FLASH=mma: mma.sync form)
 
     # ------------------------------------------------------------------ weight preparation
     def prepare(self, math_mode: int, rot: Optional[torch.Tensor] = None):
@@ -300,7 +301,8 @@ class HGTLayer(nn.Module):
         flash = (P["math"] in gemm_modes and self.use_flash_attention and ops.causal_flash_supported(d, H)
                  and L.load().gnnlm_has_tcgen05())
         qkv = _lin(h_t, P["tgt_qkv"], P["math"])
-        if flash:        # Q stays fp32 (the inter path and the flash kernel split it themselves); K' | V' as one split-fp16 matrix
+        flash_tc = flash and self.use_flash_tc and ops.causal_flash_tc_supported(d, H, G.L)      # tcgen05 form (d_k = 128)
+        if flash and not flash_tc:   # Q stays fp32 (the inter path and the mma.sync kernel split it themselves); K' | V' as split fp16
             kv = ops.to_split(qkv[:, d:])
         t_agg = torch.empty((h_t.shape[0], d), device=qkv.device, dtype=torch.float32)
         # inter edges in compact centre numbering are the contiguous ranges of inter_indptr
@@ -321,11 +323,13 @@ class HGTLayer(nn.Module):
         # operands on the tensor cores; tf32x3 / fp32 keep the CUDA-core kernel (no fp16 range limit on Q / K' / V')
         if flash:
             act = act_dtype(P["math"])
-            if act == ops.SPLIT:       # the sum of the two edge types leaves as the output projection's operand
-                t_split = ops.Split.empty(h_t.shape[0], d, qkv.device)
+            t_split = ops.Split.empty(h_t.shape[0], d, qkv.device) if act == ops.SPLIT else None    # the output projection's operand
+            if flash_tc:
+                ops.causal_attn_flash_tc(qkv, G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5, accumulate=True, out_split=t_split)
+            else:
                 ops.causal_attn_flash(qkv[:, :d], kv, G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5, accumulate=True, out_split=t_split)
+            if t_split is not None:
                 return self._out(P, P["t"], t_split, h_t, None)
-            ops.causal_attn_flash(qkv[:, :d], kv, G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5, accumulate=True)
         elif P["math"] in gemm_modes and self.use_gemm_attention and ops.causal_attn_gemm_supported(d, H, G.L) and G.L >= 1024:
             ops.causal_attn_gemm(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], G.B, G.L, G.intra_ctx, H, t_agg, out_scale=0.5,
                                  accumulate=True)
