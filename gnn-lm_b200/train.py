@@ -100,9 +100,16 @@ class _GatherRows(torch.autograd.Function):
         return dx, None
 
 
-def _attn_bwd(q, k, v, dout, H, scale, *, indptr=None, indices=None, causal=(0, 0)):
+def _attn_bwd(q, k, v, dout, H, scale, *, indptr=None, indices=None, causal=(0, 0), atomics: bool = False):
     d = q.shape[1]
     dq = torch.empty_like(q)
+    if causal[0] > 0 and not atomics:       # by-destination + by-source passes, no atomics (gnnlm_hgt_causal_attn_bwd)
+        dk, dv = torch.empty_like(k), torch.empty_like(v)
+        stats = torch.empty((q.shape[0], H, 3), device=q.device, dtype=torch.float32)
+        L.call("gnnlm_hgt_causal_attn_bwd", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0), L.ptr(dout), dout.stride(0),
+               q.shape[0] // causal[0], causal[0], causal[1], H, d // H, float(scale), L.ptr(dq), dq.stride(0), L.ptr(dk), dk.stride(0),
+               L.ptr(dv), dv.stride(0), L.ptr(stats), _st())
+        return dq, dk, dv
     dk, dv = torch.zeros_like(k), torch.zeros_like(v)
     L.call("gnnlm_hgt_edge_attn_bwd", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0), L.ptr(dout), dout.stride(0),
            L.ptr(indptr), L.ptr(indices), None, q.shape[0], None, causal[0], causal[1], H, d // H, float(scale), L.ptr(dq), dq.stride(0),

@@ -473,6 +473,12 @@ int32_t gnnlm_hgt_edge_attn_bwd(const float* q, int64_t ldq, const float* k, int
                                 const int32_t* dst_ids, int64_t n_dst_cap, const int32_t* n_dst_dev, int64_t causal_L,
                                 int64_t intra_ctx, int32_t H, int32_t d_k, float scale, float* dq, int64_t lddq, float* dk,
                                 int64_t lddk, float* dv, int64_t lddv, gnnlm_stream_t stream);
+/* The implicit causal edges without atomics: a by-destination pass writes dq and the softmax statistics {max, 1 / sum, D} per
+ * (destination, head) into `stats` [B*L*H*3] floats; a by-source pass writes dk, dv (NOT accumulated). */
+int32_t gnnlm_hgt_causal_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                  const float* dout, int64_t ldo, int64_t B, int64_t L, int64_t intra_ctx, int32_t H, int32_t d_k,
+                                  float scale, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv, int64_t lddv,
+                                  float* stats, gnnlm_stream_t stream);
 int32_t gnnlm_layernorm_bwd(const float* o, int64_t ldo, const float* residual, int64_t ldr, const float* gamma, float eps,
                             const float* dy, int64_t ldy, int64_t rows, const int32_t* rows_dev, int64_t d, float* dx,
                             int64_t ldx, float* dgamma, float* dbeta, gnnlm_stream_t stream);

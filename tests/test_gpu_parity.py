@@ -1861,9 +1861,10 @@ def test_training_backward_kernels_direct(dev):
     n_dst = B * Lb
     qd, kd, vd = (t.double().requires_grad_(True) for t in (q2, k2, v2))
     g = torch.autograd.grad(ref(qd, kd, vd, src, dsts), [qd, kd, vd], do2.double())
-    dq, dk, dv = train._attn_bwd(q2.to(dev), k2.to(dev), v2.to(dev), do2.to(dev), H, 1.0, causal=(Lb, ctx))
-    for a, b in zip((dq, dk, dv), g):
-        np.testing.assert_allclose(a.cpu().double().numpy(), b.numpy(), rtol=1e-4, atol=1e-5)
+    for atomics in (False, True):          # the two-pass form without atomics, and the CSR kernel's causal mode
+        dq, dk, dv = train._attn_bwd(q2.to(dev), k2.to(dev), v2.to(dev), do2.to(dev), H, 1.0, causal=(Lb, ctx), atomics=atomics)
+        for a, b in zip((dq, dk, dv), g):
+            np.testing.assert_allclose(a.cpu().double().numpy(), b.numpy(), rtol=1e-4, atol=1e-5)
     # LayerNorm(o + h)
     rows, dd = 23, 320
     o, h, gam, bet, dy = torch.randn(rows, dd), torch.randn(rows, dd), torch.randn(dd), torch.randn(dd), torch.randn(rows, dd)
