@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(NW * 32, 1) inter_mma_kernel(const float* __re
                                                                const int32_t* __restrict__ indptr, int64_t t0, int64_t n_tokens,
                                                                __half* __restrict__ a_out, int64_t a_hs, int64_t lda,
                                                                const float* __restrict__ bias_v, float out_scale,
-                                                               float* __restrict__ t_agg, int64_t ldt) {
+                                                               float* __restrict__ t_agg, int64_t ldt, int bulk) {
   constexpr int H = 8, D = 128 * KS, NT = NW * 32;
   constexpr int KW = KS * 8 / NW;                          // 16-column k-steps of a warp
   static_assert(KW * NW == KS * 8, "d / 16 must divide by the number of warps");
@@ -502,6 +502,13 @@ __global__ void __launch_bounds__(NW * 32, 1) inter_mma_kernel(const float* __re
     const int e0 = __ldg(indptr + tok);
     tab[j] = make_int2(e0, __ldg(indptr + tok + 1) - e0);
   }
+  // `bulk`: the rows of a tile arrive by one cp.async.bulk each (TMA engine, mbarrier complete_tx) instead of 256 x 16 B cp.async per
+  // row -- no LSU instruction per 16 B (ncu on the cp.async form: MIO-throttle / short-scoreboard stalls on the load issue)
+  __shared__ __align__(8) uint64_t full_bar[IM_STAGES];
+  if (bulk && tid == 0) {
+    for (int s_ = 0; s_ < IM_STAGES; ++s_) ms_mbar_init(&full_bar[s_], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
 
   struct Tile { int j, e0, deg, r0; };                     // token j of this CTA, first row of the tile
@@ -520,6 +527,21 @@ __global__ void __launch_bounds__(NW * 32, 1) inter_mma_kernel(const float* __re
     return it;
   };
   auto issue = [&](const Tile& it, int st) {               // cp.async of one tile; always exactly one commit
+    if (bulk) {
+      if (it.j < n_mine) {
+        const int nr = (it.deg - it.r0) < IM_ROWS ? (it.deg - it.r0) : IM_ROWS;
+        char* dst = rows + st * IM_ROWS * RS;
+        if (warp == 0) {
+          if (lane == 0) ms_mbar_expect_tx(&full_bar[st], (uint32_t)(nr > 0 ? nr : 0) * ROWB);
+          __syncwarp();
+          if (lane < nr) ms_bulk_g2s(dst + lane * RS, hc + (int64_t)(it.e0 + it.r0 + lane) * ldh * 2, ROWB, &full_bar[st]);
+        } else {                                           // rows past the token's last centre: finite (zero)
+          for (int r = (nr > 0 ? nr : 0) + (warp - 1); r < IM_ROWS; r += NW - 1)
+            for (int c = lane * 16; c < ROWB; c += 512) *reinterpret_cast<uint4*>(dst + r * RS + c) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      return;
+    }
     if (it.j < n_mine && copier) {
       const int nr = (it.deg - it.r0) < IM_ROWS ? (it.deg - it.r0) : IM_ROWS;
       char* dst = rows + st * IM_ROWS * RS + chunk * 16;
@@ -557,11 +579,14 @@ __global__ void __launch_bounds__(NW * 32, 1) inter_mma_kernel(const float* __re
   float m_run = -INFINITY, l_run = 0.f;                    // head g (replicated over tq and over the warps)
   float isc[NW > 8 ? 1 : NW];                              // 1 / scale of head g's q~ slice in every warp (NW > 8: read from shared memory)
   int stage = 0;
+  uint32_t tile_no = 0;
   while (cur.j < n_mine) {
     const bool first = cur.r0 == 0;
     const int nr = (cur.deg - cur.r0) < IM_ROWS ? (cur.deg - cur.r0) : IM_ROWS;        // 0 for a token without centres
     const bool last = cur.r0 + IM_ROWS >= cur.deg;
-    asm volatile("cp.async.wait_group %0;" ::"n"(IM_STAGES - 2) : "memory");
+    if (bulk) ms_mbar_wait(&full_bar[stage], (tile_no / IM_STAGES) & 1);
+    else asm volatile("cp.async.wait_group %0;" ::"n"(IM_STAGES - 2) : "memory");
+    ++tile_no;
     __syncthreads();                                       // tile visible; everyone is past the previous tile
     issue(n2, stage == 0 ? IM_STAGES - 1 : stage - 1);     // into the buffer of the previous tile
     const Tile n3 = advance(n2);
@@ -744,8 +769,10 @@ static int32_t launch_inter_mma(const float* qt, int64_t q_hs, const void* hc, i
   for (int64_t b0 = 0; b0 < n_tokens; b0 += per_launch) {
     const int64_t n = n_tokens - b0 < per_launch ? n_tokens - b0 : per_launch;
     const int64_t grid = n < n_sm ? n : n_sm;
+    // GNNLM_INTER_BULK=0: cp.async tile loads (the round-1 form) instead of one bulk copy per row (A/B timing switch)
+    static const int bulk = [] { const char* e = getenv("GNNLM_INTER_BULK"); return e ? atoi(e) : 1; }();
     inter_mma_kernel<KS, BF16, NW><<<(unsigned)grid, NW * 32, smem, st>>>(qt, q_hs, hc, ldh, indptr + b0, t0 + b0, n, (__half*)a_out,
-                                                                         a_hs, lda, bias_v, out_scale, t_agg, ldt);
+                                                                         a_hs, lda, bias_v, out_scale, t_agg, ldt, bulk);
     GNNLM_LAUNCH_CHECK("gnnlm_hgt_inter_fused");
   }
   return 0;
