@@ -11,12 +11,14 @@
 //   warp 1     MMA issuer (one thread): S[j % 2] = Q K_j^T -- 8 k-steps x 3 passes of tcgen05.mma.kind::f16, M = 128, N = 64 -- issued
 //              one tile ahead of the softmax; O[j % 2] = P_j V_j -- 4 k-steps x 3 passes, N = 128 -- when P_j is in shared memory
 //   warps 2-5  softmax: thread = query row = TMEM lane.  tcgen05.ld S (64 columns), mask, running max / sum in the base-2 domain,
-//              P = 2^10 exp2(s - m) split into fp16 hi / lo and written to shared memory in the SWIZZLE_128B K-major layout the MMA
-//              reads (16 B chunk c of row r at r * 128 + ((c ^ (r & 7)) << 4)), fence.proxy.async, mbarrier.  O accumulates in TMEM
+//              P = 2^7 exp2(s - m_ref) split into fp16 hi / lo and written with tcgen05.st into one of two P buffers IN TMEM (two keys
+//              per 32-bit column): the PV product takes P as its TMEM A-operand, so P costs no shared memory, is double-buffered
+//              (the softmax of tile j + 1 runs under the PV product of tile j), and the MMA reads only V'^T from shared memory.
+//              (The first builds passed P through shared memory in the SWIZZLE_128B layout: one buffer, 224 KB.)  O accumulates in TMEM
 //              across the key tiles; it is rescaled (tcgen05.ld -> multiply -> tcgen05.st, per warp) only when a row's maximum
 //              has grown by more than 2^8 over the reference the row's P values are scaled by (lazy rescale: P <= 2^8, times the
 //              2^7 split scale it stays inside fp16) -- on the first tiles of a row, practically never afterwards
-// TMEM: S 3 x 64 columns + O 128 columns.  Shared memory: Q 64 KB + 2 x (K 32 KB + V^T 32 KB) + P 32 KB = 224 KB.
+// TMEM: S 3 x 64 columns + O 128 + P 2 x 64 = 448.  Shared memory: Q 64 KB + 2 x (K 32 KB + V^T 32 KB) = 192 KB.
 // First build (O partial per tile folded into registers by the softmax threads): 0.119 ms at L = 3072; the softmax warps (one per
 // scheduler, ~1200 dependent instructions per tile, half of them fp16 <-> fp32 conversions and the fold) paced it.
 #include "gemm_tc_common.cuh"
@@ -33,9 +35,9 @@ constexpr int K_CHUNK = BKV * 128;                     // 8 KB
 constexpr int VT_TILE = DK * 128;                      // 16 KB: 128 dv rows x 64 keys
 constexpr int P_TILE = BQ * 128;                       // 16 KB: 128 rows x 64 keys
 constexpr int STAGE = 4 * K_CHUNK + 2 * VT_TILE;       // 64 KB
-constexpr int SMEM = 4 * Q_CHUNK + 2 * STAGE + 2 * P_TILE;
+constexpr int SMEM = 4 * Q_CHUNK + 2 * STAGE;          // P lives in TMEM
 constexpr int THREADS = 224;                          // warp 0: Q + K' producer, 1: MMA issuer, 2-5: softmax, 6: V'^T producer
-constexpr uint32_t S_COL = 0, O_COL = 256, TMEM_ALLOC = 512;      // S: three 64-column buffers (scores run two tiles ahead), O: 128
+constexpr uint32_t S_COL = 0, O_COL = 256, P_COL = 384, TMEM_ALLOC = 512;   // S: 3 x 64 columns, O: 128, P: 2 x (32 hi + 32 lo)
 constexpr float P_SCALE = 128.f, RESCALE_AT = 8.f;   // P = 2^7 exp2(s - m_ref) <= 2^15 as long as the maximum stays within 2^8 of m_ref
 
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
@@ -63,7 +65,24 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
       "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// A operand from TMEM (lane = row, one 32-bit column = two consecutive k elements), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -88,8 +107,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                                  // hi c0 | hi c1 | lo c0 | lo c1
   uint8_t* sKV = smem + 4 * Q_CHUNK;                   // per stage: K hi c0 | K hi c1 | K lo c0 | K lo c1 | Vt hi | Vt lo
-  uint8_t* sP = sKV + 2 * STAGE;                       // P hi | P lo
-  __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[3], o_full, p_full;
+  __shared__ __align__(8) uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[3], o_done[2], p_full;
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -117,7 +135,8 @@ __global__ void __launch_bounds__(THREADS, 1)
       mbar_init(&v_empty[s], 1);
     }
     for (int s = 0; s < 3; ++s) mbar_init(&s_full[s], 1);
-    mbar_init(&o_full, 1);
+    mbar_init(&o_done[0], 1);
+    mbar_init(&o_done[1], 1);
     mbar_init(&p_full, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -172,7 +191,6 @@ __global__ void __launch_bounds__(THREADS, 1)
     if (lane == 0) {                                   // ===================== MMA issuer
       const uint64_t dqh0 = make_desc(smem_u32(sQ)), dqh1 = make_desc(smem_u32(sQ + Q_CHUNK));
       const uint64_t dql0 = make_desc(smem_u32(sQ + 2 * Q_CHUNK)), dql1 = make_desc(smem_u32(sQ + 3 * Q_CHUNK));
-      const uint64_t dph = make_desc(smem_u32(sP)), dpl = make_desc(smem_u32(sP + P_TILE));
       long long t_k = 0, t_p = 0, t_v = 0;
       const long long t_begin_clk = dbg ? clock64() : 0;
       auto issue_qk = [&](int j) {
@@ -217,12 +235,13 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint64_t off = (uint64_t)(ks * 2);
-          umma_f16(d_tmem, dph + off, dvl + off, IDESC_PV, (j | ks) > 0 ? 1u : 0u);      // O accumulates across the key tiles
-          umma_f16(d_tmem, dpl + off, dvh + off, IDESC_PV, 1u);
-          umma_f16(d_tmem, dph + off, dvh + off, IDESC_PV, 1u);
+          const uint32_t pa = tmem_base + P_COL + (uint32_t)st * 64 + (uint32_t)ks * 8;      // 16 keys = 8 packed columns
+          umma_f16_ts(d_tmem, pa, dvl + off, IDESC_PV, (j | ks) > 0 ? 1u : 0u);          // O accumulates across the key tiles
+          umma_f16_ts(d_tmem, pa + 32, dvh + off, IDESC_PV, 1u);
+          umma_f16_ts(d_tmem, pa, dvh + off, IDESC_PV, 1u);
         }
         tc_commit(&v_empty[st]);                        // V_j consumed
-        tc_commit(&o_full);                             // P_j consumed, O includes tile j
+        tc_commit(&o_done[st]);                         // P_j consumed (its buffer is free), O includes tile j
         if (j + 2 < n_t) issue_qk(j + 2);
       }
       if (dbg && blockIdx.x < 8 && blockIdx.y == 0) {   // the eight heaviest CTAs (timing experiments: GNNLM_FLASH_DEBUG=1)
@@ -239,8 +258,6 @@ __global__ void __launch_bounds__(THREADS, 1)
     const int r = lq * 32 + lane;                       // row inside the tile
     const int v = q0 + r;                               // query position inside the block
     const uint32_t lane_addr = (uint32_t)(lq * 32) << 16;
-    const uint32_t sp_row = smem_u32(sP) + (uint32_t)r * 128;
-    const uint32_t sw = (uint32_t)(r & 7);
     const uint32_t o_addr = tmem_base + lane_addr + O_COL;
     float m_ref = -INFINITY, l_run = 0.f;               // reference maximum (base 2) the row's P and O are scaled by; denominator
     long long t_s = 0, t_o = 0;
@@ -270,12 +287,11 @@ __global__ void __launch_bounds__(THREADS, 1)
         for (int c = 0; c < BKV; ++c) mx = fmaxf(mx, s[c]);
       }
       mx *= L2E;
-      // P_{j-1} is free, and O complete up to tile j - 1, once the PV product of tile j - 1 has retired
-      if (j > 0) {
+      // P buffer j & 1 is free once the PV product of tile j - 2 has retired
+      if (j > 1) {
         const long long c1 = dbg ? clock64() : 0;
-        mbar_wait(&o_full, (uint32_t)((j - 1) & 1));
+        mbar_wait(&o_done[st], (uint32_t)(((j - 2) >> 1) & 1));
         if (dbg) t_o += clock64() - c1;
-        tc_fence_after();
       }
       // lazy rescale: move the reference only when the maximum has outgrown it by 2^8 (always on a row's first finite tile)
       const bool grow = mx > m_ref + RESCALE_AT;         // m_ref = -inf: true for any finite mx
@@ -285,7 +301,9 @@ __global__ void __launch_bounds__(THREADS, 1)
         m_ref = m_new;
         l_run *= corr;
         ++n_resc;
-        if (j > 0) {
+        if (j > 0) {                                     // O must be complete up to tile j - 1 before it is rescaled
+          mbar_wait(&o_done[st ^ 1], (uint32_t)(((j - 1) >> 1) & 1));
+          tc_fence_after();
 #pragma unroll
           for (int c0 = 0; c0 < DK; c0 += 32) {
             float o[32];
@@ -300,26 +318,28 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
       const float mb = m_ref > -INFINITY ? m_ref : 0.f;
       float sum = 0.f;
+      const uint32_t p_addr = tmem_base + lane_addr + P_COL + (uint32_t)st * 64;
+      tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {                      // 16 B chunk c of this row: keys 8c .. 8c + 7
-        uint32_t ph[4], pl[4];
+      for (int half_ = 0; half_ < 2; ++half_) {           // 32 keys at a time: 16 packed hi + 16 packed lo columns
+        float ph[16], pl[16];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float p0 = fast_exp2(fmaf(s[8 * c + 2 * e], L2E, -mb)), p1 = fast_exp2(fmaf(s[8 * c + 2 * e + 1], L2E, -mb));   // exp2(-inf) = 0
+        for (int e = 0; e < 16; ++e) {
+          const int c = half_ * 32 + 2 * e;
+          const float p0 = fast_exp2(fmaf(s[c], L2E, -mb)), p1 = fast_exp2(fmaf(s[c + 1], L2E, -mb));      // exp2(-inf) = 0
           sum += p0 + p1;
           // hi = the top 11 significant bits (exact in fp16, no conversion back needed), lo = the exact fp32 remainder
           const float x0 = p0 * P_SCALE, x1 = p1 * P_SCALE;
           const float h0 = __uint_as_float(__float_as_uint(x0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(x1) & 0xffffe000u);
           const __half2 hh = __floats2half2_rn(h0, h1), ll = __floats2half2_rn(x0 - h0, x1 - h1);
-          ph[e] = *reinterpret_cast<const uint32_t*>(&hh);
-          pl[e] = *reinterpret_cast<const uint32_t*>(&ll);
+          ph[e] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&hh));
+          pl[e] = __uint_as_float(*reinterpret_cast<const uint32_t*>(&ll));
         }
-        const uint32_t a = sp_row + ((((uint32_t)c) ^ sw) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(ph[0]), "r"(ph[1]), "r"(ph[2]), "r"(ph[3]) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a + P_TILE), "r"(pl[0]), "r"(pl[1]), "r"(pl[2]), "r"(pl[3]) : "memory");
+        tmem_st16(p_addr + half_ * 16, ph);
+        tmem_st16(p_addr + 32 + half_ * 16, pl);
       }
+      tmem_wait_st();
       l_run += sum;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the MMA
       tc_fence_before();
       mbar_arrive(&p_full);
     }
@@ -329,7 +349,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       dbg[blockIdx.x * 8 + 7] = n_resc;
     }
     // the row's output: O / l
-    mbar_wait(&o_full, (uint32_t)((n_t - 1) & 1));
+    mbar_wait(&o_done[(n_t - 1) & 1], (uint32_t)(((n_t - 1) >> 1) & 1));
     tc_fence_after();
     float acc[DK];
 #pragma unroll
