@@ -51,7 +51,7 @@ def parse():
                         "(+ a ragged tail) through eval_lm.evaluate(rank, world_size): contiguous block shards, replicated datastore, "
                         "one NCCL all-reduce of {sum log p, n_tokens}")
     p.add_argument("--strong-blocks", type=int, default=128)
-    p.add_argument("--eval-blocks", type=int, default=16, help="blocks of the e2e_evaluate leg (0: skip it)")
+    p.add_argument("--eval-blocks", type=int, default=32, help="blocks of the e2e_evaluate leg (0: skip it)")
     p.add_argument("--locality", default="0.5,1048576",
                    help="p_continue,n_hot of the realistic-duplication leg (synth.local_neighbours); empty: skip the leg")
     p.add_argument("--ncu-range", action="store_true",

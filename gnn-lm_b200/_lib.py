@@ -79,9 +79,12 @@ SIGNATURES = {
     "gnnlm_knn_full_prob": (_i32, [_p, _p, _i64, _p, _i32, _i64, _f32, _f32, _p, _i64, _i64, _p]),
     "gnnlm_knn_sims_keys": (_i32, [_p, _i64, _p, _i32, _i64, _i32, _p, _i64, _i32, _i32, _p, _i64, _p]),
     "gnnlm_hgt_edge_attn_bwd": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _i32, _f32, _p, _i64,
-                                       _p, _i64, _p, _i64, _p]),
+                                       _p, _i64, _p, _i64, _f32, C.c_uint64, _p]),
+    "gnnlm_hgt_edge_attn_train_fwd": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i64, _i64, _i32, _i32, _f32, _i32, _p, _i64, _f32,
+                                             C.c_uint64, _p]),
+    "gnnlm_dropout_f32": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _f32, C.c_uint64, _p]),
     "gnnlm_hgt_causal_attn_bwd": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i32, _i32, _f32, _p, _i64, _p, _i64, _p, _i64,
-                                         _p, _p]),
+                                         _p, _f32, C.c_uint64, _p]),
     "gnnlm_layernorm_bwd": (_i32, [_p, _i64, _p, _i64, _p, _f32, _p, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _p]),
     "gnnlm_xent_fwd_bwd": (_i32, [_p, _i64, _p, _i64, _i64, _f32, _p, _p]),
     "gnnlm_transpose_f32": (_i32, [_p, _i64, _i64, _p, _i64, _p, _i64, _i64, _p]),

@@ -11,6 +11,30 @@
 
 namespace gnnlm {
 
+// ---------------------------------------------------------------------------------------------- dropout masks
+// hgt.py's `drop` (on the output projection, :401) and `attn_drop` (on the edge-softmax weights, one draw per edge and head, :356)
+// and the adaptive softmax's input / tail dropouts draw from torch's generator in the reference; here a mask is a pure function
+// of (seed, element) -- splitmix64 of seed + index * golden ratio, top 24 bits against p -- so that forward and backward
+// regenerate it instead of storing it, and the tests can replay the same mask through the oracle.
+__host__ __device__ __forceinline__ uint64_t dm_mix(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// multiplier of a kept element: 1 / (1 - p); dropped: 0.  p_thresh = floor(p * 2^24)
+__device__ __forceinline__ float dm_scale(uint64_t seed, uint64_t idx, uint32_t p_thresh, float keep_scale) {
+  return (uint32_t)(dm_mix(seed, idx) >> 40) >= p_thresh ? keep_scale : 0.f;
+}
+__device__ __forceinline__ uint64_t dm_edge(int64_t dst, int64_t src, int head) {
+  return ((uint64_t)dst << 38) ^ ((uint64_t)src << 6) ^ (uint64_t)head;
+}
+struct AttnDrop {
+  uint64_t seed;
+  uint32_t p_thresh;      // 0: no dropout
+  float keep_scale;
+};
+
 // ---------------------------------------------------------------------------------------------- edge attention backward
 // forward (edge_attn.cu):  out[v] = scale * sum_e alpha_e V'[u_e],  alpha = softmax_e <Q[v,h], K'[u_e,h]>   per head h
 // backward, per destination v and head h, with g_e = <dout[v,h], V'[u_e,h]> and D = sum_e alpha_e g_e:
@@ -25,7 +49,8 @@ __global__ void __launch_bounds__(256) edge_attn_bwd_kernel(const float* __restr
                                                             const int32_t* __restrict__ dst_ids, int64_t n_dst_cap,
                                                             const int32_t* __restrict__ n_dst_dev, int64_t causal_L, int64_t intra_ctx,
                                                             int group, float scale, float* __restrict__ dq, int64_t lddq,
-                                                            float* __restrict__ dk, int64_t lddk, float* __restrict__ dv, int64_t lddv) {
+                                                            float* __restrict__ dk, int64_t lddk, float* __restrict__ dv, int64_t lddv,
+                                                            AttnDrop ad) {
   const int64_t n_dst = live_rows(n_dst_cap, n_dst_dev);
   const int lane = threadIdx.x & 31;
   const int col = lane * C;
@@ -65,20 +90,24 @@ __global__ void __launch_bounds__(256) edge_attn_bwd_kernel(const float* __restr
       m = mx;
     }
     const float inv_l = l > 0.f ? 1.f / l : 0.f;
-    // pass B: D = sum_e alpha_e g_e
+    // attention dropout (hgt.py:356): out = sum_e alpha_e beta_e V'_e with beta_e in {0, 1 / (1 - p)}; then g_e -> beta_e g_e
+    const int head = lane / group;
+    auto beta = [&](int64_t u) { return ad.p_thresh ? dm_scale(ad.seed, dm_edge(i, u, head), ad.p_thresh, ad.keep_scale) : 1.f; };
+    // pass B: D = sum_e alpha_e beta_e g_e
     float D = 0.f;
     for (int64_t e = e0; e < e1; ++e) {
       const int64_t u = src_of(e);
       const float a = __expf(head_dot(qr, k + u * ldk) - m) * inv_l;
-      D = fmaf(a, head_dot(gr, v + u * ldv), D);
+      D = fmaf(a * beta(u), head_dot(gr, v + u * ldv), D);
     }
     // pass C: gradients
     for (int64_t e = e0; e < e1; ++e) {
       const int64_t u = src_of(e);
       const float* kr = k + u * ldk;
       const float a = __expf(head_dot(qr, kr) - m) * inv_l;
-      const float ds = scale * a * (head_dot(gr, v + u * ldv) - D);
-      const float av = scale * a;
+      const float be = beta(u);
+      const float ds = scale * a * (be * head_dot(gr, v + u * ldv) - D);
+      const float av = scale * a * be;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         dqr[c] = fmaf(ds, kr[col + c], dqr[c]);
@@ -99,7 +128,7 @@ __global__ void __launch_bounds__(256) causal_bwd_dq_kernel(const float* __restr
                                                             int64_t ldk, const float* __restrict__ v, int64_t ldv,
                                                             const float* __restrict__ dout, int64_t ldo, int64_t T, int64_t Lb,
                                                             int64_t intra_ctx, int group, int H, float scale, float* __restrict__ dq,
-                                                            int64_t lddq, float* __restrict__ stats) {
+                                                            int64_t lddq, float* __restrict__ stats, AttnDrop ad) {
   const int lane = threadIdx.x & 31;
   const int col = lane * C;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -122,9 +151,11 @@ __global__ void __launch_bounds__(256) causal_bwd_dq_kernel(const float* __restr
       for (int o = group >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
       return p;
     };
+    const int head = lane / group;
+    auto beta = [&](int64_t u) { return ad.p_thresh ? dm_scale(ad.seed, dm_edge(i, u, head), ad.p_thresh, ad.keep_scale) : 1.f; };
     float m = -INFINITY, l = 0.f, dn = 0.f;
     for (int64_t u = e0; u <= i; ++u) {
-      const float s = head_dot(qr, k + u * ldk), g = head_dot(gr, v + u * ldv);
+      const float s = head_dot(qr, k + u * ldk), g = beta(u) * head_dot(gr, v + u * ldv);
       const float mx = fmaxf(m, s), corr = __expf(m - mx), w = __expf(s - mx);
       l = l * corr + w;
       dn = dn * corr + w * g;
@@ -138,7 +169,7 @@ __global__ void __launch_bounds__(256) causal_bwd_dq_kernel(const float* __restr
     for (int64_t u = e0; u <= i; ++u) {
       const float* kr = k + u * ldk;
       const float a = __expf(head_dot(qr, kr) - m) * inv_l;
-      const float ds = scale * a * (head_dot(gr, v + u * ldv) - D);
+      const float ds = scale * a * (beta(u) * head_dot(gr, v + u * ldv) - D);
 #pragma unroll
       for (int c = 0; c < C; ++c) dqr[c] = fmaf(ds, kr[col + c], dqr[c]);
     }
@@ -153,7 +184,7 @@ __global__ void __launch_bounds__(256) causal_bwd_dkv_kernel(const float* __rest
                                                              const float* __restrict__ dout, int64_t ldo, int64_t T, int64_t Lb,
                                                              int64_t intra_ctx, int group, int H, float scale,
                                                              const float* __restrict__ stats, float* __restrict__ dk, int64_t lddk,
-                                                             float* __restrict__ dv, int64_t lddv) {
+                                                             float* __restrict__ dv, int64_t lddv, AttnDrop ad) {
   const int lane = threadIdx.x & 31;
   const int col = lane * C;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -186,11 +217,13 @@ __global__ void __launch_bounds__(256) causal_bwd_dkv_kernel(const float* __rest
       }
       const float* st = stats + (i * H + head) * 3;
       const float a = scale * __expf(s - st[0]) * st[1];
-      const float ds = a * (g - st[2]);
+      const float be = ad.p_thresh ? dm_scale(ad.seed, dm_edge(i, u, head), ad.p_thresh, ad.keep_scale) : 1.f;
+      const float ds = a * (be * g - st[2]);
+      const float ab = a * be;
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         dkr[c] = fmaf(ds, qr[col + c], dkr[c]);
-        dvr[c] = fmaf(a, gr[col + c], dvr[c]);
+        dvr[c] = fmaf(ab, gr[col + c], dvr[c]);
       }
     }
 #pragma unroll
@@ -198,6 +231,75 @@ __global__ void __launch_bounds__(256) causal_bwd_dkv_kernel(const float* __rest
       dk[u * lddk + col + c] = dkr[c];
       dv[u * lddv + col + c] = dvr[c];
     }
+  }
+}
+
+// Training forward with attention dropout: out[v] (+)= scale * sum_e alpha_e beta_e V'[u_e] (two passes over the in-edges; the
+// evaluation kernels of edge_attn.cu have no dropout).  Same edge sources as edge_attn_bwd_kernel.
+template <int C>
+__global__ void __launch_bounds__(256) edge_attn_train_fwd_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k,
+                                                                  int64_t ldk, const float* __restrict__ v, int64_t ldv,
+                                                                  const int32_t* __restrict__ indptr,
+                                                                  const int32_t* __restrict__ indices, int64_t n_dst, int64_t causal_L,
+                                                                  int64_t intra_ctx, int group, float scale, int accumulate,
+                                                                  float* __restrict__ out, int64_t ldo, AttnDrop ad) {
+  const int lane = threadIdx.x & 31;
+  const int col = lane * C;
+  const int head = lane / group;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n_dst; it += warps) {
+    const int64_t i = causal_L > 0 ? n_dst - 1 - it : it;
+    int64_t e0, e1;
+    if (causal_L > 0) {
+      const int64_t b0 = (i / causal_L) * causal_L;
+      e0 = intra_ctx > 0 && i - intra_ctx + 1 > b0 ? i - intra_ctx + 1 : b0;
+      e1 = i + 1;
+    } else {
+      e0 = __ldg(indptr + i);
+      e1 = __ldg(indptr + i + 1);
+    }
+    float qr[C], acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      qr[c] = q[i * ldq + col + c];
+      acc[c] = 0.f;
+    }
+    auto src_of = [&](int64_t e) { return causal_L > 0 ? e : (indices ? (int64_t)__ldg(indices + e) : e); };
+    auto score = [&](int64_t u) {
+      const float* row = k + u * ldk;
+      float p = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) p = fmaf(qr[c], row[col + c], p);
+      for (int o = group >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      return p;
+    };
+    float m = -INFINITY, l = 0.f;
+    for (int64_t e = e0; e < e1; ++e) {
+      const float s = score(src_of(e));
+      const float mx = fmaxf(m, s);
+      l = l * __expf(m - mx) + __expf(s - mx);
+      m = mx;
+    }
+    const float inv_l = l > 0.f ? scale / l : 0.f;
+    for (int64_t e = e0; e < e1; ++e) {
+      const int64_t u = src_of(e);
+      const float w = __expf(score(u) - m) * inv_l * (ad.p_thresh ? dm_scale(ad.seed, dm_edge(i, u, head), ad.p_thresh, ad.keep_scale) : 1.f);
+      const float* vr = v + u * ldv;
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = fmaf(w, vr[col + c], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) out[i * ldo + col + c] = (accumulate ? out[i * ldo + col + c] : 0.f) + acc[c];
+  }
+}
+
+// y = x * mask / (1 - p), mask = f(seed, row * cols + col): the forward of nn.Dropout in training mode and, applied to dy, its backward
+__global__ void __launch_bounds__(256) dropout_kernel(const float* __restrict__ x, int64_t ldx, float* __restrict__ y, int64_t ldy,
+                                                      int64_t rows, int64_t cols, uint64_t seed, uint32_t p_thresh, float keep_scale) {
+  const int64_t n = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int64_t r = i / cols, c = i % cols;
+    y[r * ldy + c] = x[r * ldx + c] * dm_scale(seed, (uint64_t)i, p_thresh, keep_scale);
   }
 }
 
@@ -373,8 +475,10 @@ extern "C" int32_t gnnlm_hgt_edge_attn_bwd(const float* q, int64_t ldq, const fl
                                            const float* dout, int64_t ldo, const int32_t* indptr, const int32_t* indices,
                                            const int32_t* dst_ids, int64_t n_dst_cap, const int32_t* n_dst_dev, int64_t causal_L,
                                            int64_t intra_ctx, int32_t H, int32_t d_k, float scale, float* dq, int64_t lddq, float* dk,
-                                           int64_t lddk, float* dv, int64_t lddv, cudaStream_t stream) {
+                                           int64_t lddk, float* dv, int64_t lddv, float p_drop, uint64_t seed, cudaStream_t stream) {
   GNNLM_CHECK_ARG(q && k && v && dout && dq && dk && dv && (causal_L > 0 || indptr), GNNLM_E_ARG, "gnnlm_hgt_edge_attn_bwd: null pointer");
+  GNNLM_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, GNNLM_E_ARG, "gnnlm_hgt_edge_attn_bwd: dropout rate must be in [0, 1)");
+  const AttnDrop ad{seed, (uint32_t)(p_drop * 16777216.f), 1.f / (1.f - p_drop)};
   const int64_t d = (int64_t)H * d_k;
   GNNLM_CHECK_ARG(H > 0 && d_k > 0 && d % 32 == 0 && 32 % H == 0 && d <= 1024, GNNLM_E_UNSUPPORTED,
                   "gnnlm_hgt_edge_attn_bwd: needs d %% 32 == 0, d <= 1024 and H dividing 32 (H=%d d_k=%d)", H, d_k);
@@ -385,7 +489,7 @@ extern "C" int32_t gnnlm_hgt_edge_attn_bwd(const float* q, int64_t ldq, const fl
   const int group = 32 / H;
   const unsigned grid = (unsigned)(ceil_div(n_dst_cap, 8) < 148 * 32 ? ceil_div(n_dst_cap, 8) : 148 * 32);
   BWD_DISPATCH_C(C, q, ldq, k, ldk, v, ldv, dout, ldo, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, causal_L, intra_ctx, group, scale,
-                 dq, lddq, dk, lddk, dv, lddv)
+                 dq, lddq, dk, lddk, dv, lddv, ad)
   GNNLM_LAUNCH_CHECK("gnnlm_hgt_edge_attn_bwd");
   return 0;
 }
@@ -403,8 +507,10 @@ extern "C" int32_t gnnlm_hgt_edge_attn_bwd(const float* q, int64_t ldq, const fl
 extern "C" int32_t gnnlm_hgt_causal_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                                              const float* dout, int64_t ldo, int64_t B, int64_t L, int64_t intra_ctx, int32_t H,
                                              int32_t d_k, float scale, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
-                                             int64_t lddv, float* stats, cudaStream_t stream) {
+                                             int64_t lddv, float* stats, float p_drop, uint64_t seed, cudaStream_t stream) {
   GNNLM_CHECK_ARG(q && k && v && dout && dq && dk && dv && stats, GNNLM_E_ARG, "gnnlm_hgt_causal_attn_bwd: null pointer");
+  GNNLM_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, GNNLM_E_ARG, "gnnlm_hgt_causal_attn_bwd: dropout rate must be in [0, 1)");
+  const AttnDrop ad{seed, (uint32_t)(p_drop * 16777216.f), 1.f / (1.f - p_drop)};
   const int64_t d = (int64_t)H * d_k;
   GNNLM_CHECK_ARG(H > 0 && d_k > 0 && d % 32 == 0 && 32 % H == 0 && d <= 1024, GNNLM_E_UNSUPPORTED,
                   "gnnlm_hgt_causal_attn_bwd: needs d %% 32 == 0, d <= 1024 and H dividing 32 (H=%d d_k=%d)", H, d_k);
@@ -416,11 +522,46 @@ extern "C" int32_t gnnlm_hgt_causal_attn_bwd(const float* q, int64_t ldq, const 
   if (T == 0) return 0;
   const int group = 32 / H;
   const unsigned grid = (unsigned)(ceil_div(T, 8) < 148 * 32 ? ceil_div(T, 8) : 148 * 32);
-  CAUSAL_BWD_DISPATCH(causal_bwd_dq_kernel, C, q, ldq, k, ldk, v, ldv, dout, ldo, T, L, intra_ctx, group, H, scale, dq, lddq, stats)
+  CAUSAL_BWD_DISPATCH(causal_bwd_dq_kernel, C, q, ldq, k, ldk, v, ldv, dout, ldo, T, L, intra_ctx, group, H, scale, dq, lddq, stats, ad)
   GNNLM_LAUNCH_CHECK("gnnlm_hgt_causal_attn_bwd(dq)");
   CAUSAL_BWD_DISPATCH(causal_bwd_dkv_kernel, C, q, ldq, k, ldk, v, ldv, dout, ldo, T, L, intra_ctx, group, H, scale, stats, dk, lddk, dv,
-                      lddv)
+                      lddv, ad)
   GNNLM_LAUNCH_CHECK("gnnlm_hgt_causal_attn_bwd(dkv)");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_hgt_edge_attn_train_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                                 const int32_t* indptr, const int32_t* indices, int64_t n_dst, int64_t causal_L,
+                                                 int64_t intra_ctx, int32_t H, int32_t d_k, float scale, int32_t accumulate, float* out,
+                                                 int64_t ldo, float p_drop, uint64_t seed, cudaStream_t stream) {
+  GNNLM_CHECK_ARG(q && k && v && out && (causal_L > 0 || indptr), GNNLM_E_ARG, "gnnlm_hgt_edge_attn_train_fwd: null pointer");
+  GNNLM_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, GNNLM_E_ARG, "gnnlm_hgt_edge_attn_train_fwd: dropout rate must be in [0, 1)");
+  const int64_t d = (int64_t)H * d_k;
+  GNNLM_CHECK_ARG(H > 0 && d_k > 0 && d % 32 == 0 && 32 % H == 0 && d <= 1024, GNNLM_E_UNSUPPORTED,
+                  "gnnlm_hgt_edge_attn_train_fwd: needs d %% 32 == 0, d <= 1024 and H dividing 32 (H=%d d_k=%d)", H, d_k);
+  const int C = (int)(d / 32);
+  GNNLM_CHECK_ARG(C == 1 || C == 2 || C == 4 || C == 8 || C == 16 || C == 32, GNNLM_E_UNSUPPORTED,
+                  "gnnlm_hgt_edge_attn_train_fwd: d / 32 must be a power of two");
+  if (n_dst == 0) return 0;
+  const AttnDrop ad{seed, (uint32_t)(p_drop * 16777216.f), 1.f / (1.f - p_drop)};
+  const int group = 32 / H;
+  const unsigned grid = (unsigned)(ceil_div(n_dst, 8) < 148 * 32 ? ceil_div(n_dst, 8) : 148 * 32);
+  CAUSAL_BWD_DISPATCH(edge_attn_train_fwd_kernel, C, q, ldq, k, ldk, v, ldv, indptr, indices, n_dst, causal_L, intra_ctx, group, scale,
+                      accumulate, out, ldo, ad)
+  GNNLM_LAUNCH_CHECK("gnnlm_hgt_edge_attn_train_fwd");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_dropout_f32(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int64_t cols, float p_drop,
+                                     uint64_t seed, cudaStream_t stream) {
+  GNNLM_CHECK_ARG(x && y, GNNLM_E_ARG, "gnnlm_dropout_f32: null pointer");
+  GNNLM_CHECK_ARG(rows >= 0 && cols > 0 && ldx >= cols && ldy >= cols && p_drop >= 0.f && p_drop < 1.f, GNNLM_E_SHAPE,
+                  "gnnlm_dropout_f32: bad shape / rate");
+  if (rows == 0) return 0;
+  const int64_t n = rows * cols;
+  const unsigned grid = (unsigned)(ceil_div(n, 256) < 148 * 16 ? ceil_div(n, 256) : 148 * 16);
+  dropout_kernel<<<grid, 256, 0, stream>>>(x, ldx, y, ldy, rows, cols, seed, (uint32_t)(p_drop * 16777216.f), 1.f / (1.f - p_drop));
+  GNNLM_LAUNCH_CHECK("gnnlm_dropout_f32");
   return 0;
 }
 

@@ -63,6 +63,7 @@ class AdaptiveSoftmax(nn.Module):
         else:
             assert vocab_size == cutoff[-1], "cannot specify cutoff larger than vocab size"
         self.vocab_size, self.cutoff, self.input_dim, self.factor, self.tied = vocab_size, cutoff, input_dim, factor, tied
+        self.dropout = dropout                    # training only (adaptive_softmax.py:156 on the input, :101 inside the tails)
         n_tail = len(cutoff) - 1
         if tied:
             self.head = _TiedHead(cutoff[0], input_dim, n_tail)
@@ -249,7 +250,7 @@ class TokenGraphTransformerDecoder(nn.Module):
                 # TiedHeadModule then wraps word_proj in nn.Sequential(Linear, TiedLinear) (adaptive_softmax.py:32-36)
                 raise NotImplementedError("--tie-adaptive-weights with decoder_input_dim != decoder_output_dim "
                                           "(Sequential head word_proj) is not used by any graph LM config")
-            self.adaptive_softmax = AdaptiveSoftmax(self.num_classes, d, cut, dropout=0.0,
+            self.adaptive_softmax = AdaptiveSoftmax(self.num_classes, d, cut, dropout=float(_get(args, "adaptive_softmax_dropout", 0.0) or 0.0),
                                                     factor=_get(args, "adaptive_softmax_factor", 4), tied=tied,
                                                     tie_proj=_get(args, "tie_adaptive_proj", None))
             self.embed_out = None

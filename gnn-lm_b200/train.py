@@ -14,10 +14,13 @@ cross-entropy and its gradient by gnnlm_xent_fwd_bwd).  torch.autograd only chai
 relation transforms into the projection weights (relation_att / relation_msg / relation_pri -> K' / V' weights: d x d matrices).
 
 Scope of this first training path: fp32 activations (GEMMs in fp32 FMA or 3xTF32), graphs of either builder (general CSR
-kernels for the ntgt edges, so `--deprecated` graphs train too), dropout = 0
-(the deterministic part of the reference step; hgt.py's `drop` / `attn_drop` masks are not generated -- a non-zero dropout
-raises).  The last layer's ntgt side is skipped as in evaluation (nothing reads it; its parameters get zero gradients in
-the reference too).
+kernels for the ntgt edges, so `--deprecated` graphs train too).  Dropout (model.train()): hgt.py's `drop` on the output
+projections (:401), `attn_drop` on the edge-softmax weights (:356, one draw per edge and head) and the adaptive softmax's input /
+tail dropouts (adaptive_softmax.py:156,101) are applied with masks that are pure functions of (seed, element)
+(gnnlm_dropout_f32, the p_drop / seed arguments of the attention kernels): forward and backward regenerate them, and the tests replay
+them through the oracle.  The draws are not torch's generator's, so a run is not sample-for-sample the reference's (neither are
+two reference runs on different GPUs); the distribution and the gradient of the masked network are.  The last layer's ntgt
+side is skipped as in evaluation (nothing reads it; its parameters get zero gradients in the reference too).
 """
 import math
 from typing import Dict, List, Optional
@@ -100,7 +103,47 @@ class _GatherRows(torch.autograd.Function):
         return dx, None
 
 
-def _attn_bwd(q, k, v, dout, H, scale, *, indptr=None, indices=None, causal=(0, 0), atomics: bool = False):
+SITE_STRIDE = 0x632BE59BD9B4E019
+
+
+def site_seed(seed: int, site: int) -> int:
+    """Seed of one dropout site of a step: layer l -> 16 l + {0: tgt-intra-tgt attention, 1: inter, 2: ntgt-intra-ntgt, 3: `drop`
+    on the tgt output projection, 4: on the ntgt one}; 1000: adaptive-softmax input, 1001 + i: tail i."""
+    return (int(seed) + site * SITE_STRIDE) & 0xFFFFFFFFFFFFFFFF
+
+
+class _Dropout(torch.autograd.Function):
+    """nn.Dropout in training mode with a (seed, element)-addressed mask: y = x m / (1 - p); backward applies the same mask."""
+
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        x = x.contiguous()
+        ctx.p, ctx.seed = p, seed
+        y = torch.empty_like(x)
+        L.call("gnnlm_dropout_f32", L.ptr(x), x.stride(0), L.ptr(y), y.stride(0), x.shape[0], x.shape[1], float(p), seed, _st())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        L.call("gnnlm_dropout_f32", L.ptr(dy), dy.stride(0), L.ptr(dx), dx.stride(0), dy.shape[0], dy.shape[1], float(ctx.p), ctx.seed, _st())
+        return dx, None, None
+
+
+def _dropout(x, p, seed):
+    return x if p <= 0 else _Dropout.apply(x, p, seed)
+
+
+def _attn_fwd_train(q, k, v, H, scale, out, accumulate, p, seed, *, indptr=None, indices=None, causal=(0, 0)):
+    """Attention forward with dropout on the softmax weights (gnnlm_hgt_edge_attn_train_fwd)."""
+    d = q.shape[1]
+    L.call("gnnlm_hgt_edge_attn_train_fwd", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0), L.ptr(indptr), L.ptr(indices),
+           q.shape[0], causal[0], causal[1], H, d // H, float(scale), int(accumulate), L.ptr(out), out.stride(0), float(p), seed, _st())
+    return out
+
+
+def _attn_bwd(q, k, v, dout, H, scale, *, indptr=None, indices=None, causal=(0, 0), atomics: bool = False, p: float = 0.0, seed: int = 0):
     d = q.shape[1]
     dq = torch.empty_like(q)
     if causal[0] > 0 and not atomics:       # by-destination + by-source passes, no atomics (gnnlm_hgt_causal_attn_bwd)
@@ -108,12 +151,12 @@ def _attn_bwd(q, k, v, dout, H, scale, *, indptr=None, indices=None, causal=(0, 
         stats = torch.empty((q.shape[0], H, 3), device=q.device, dtype=torch.float32)
         L.call("gnnlm_hgt_causal_attn_bwd", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0), L.ptr(dout), dout.stride(0),
                q.shape[0] // causal[0], causal[0], causal[1], H, d // H, float(scale), L.ptr(dq), dq.stride(0), L.ptr(dk), dk.stride(0),
-               L.ptr(dv), dv.stride(0), L.ptr(stats), _st())
+               L.ptr(dv), dv.stride(0), L.ptr(stats), float(p), seed, _st())
         return dq, dk, dv
     dk, dv = torch.zeros_like(k), torch.zeros_like(v)
     L.call("gnnlm_hgt_edge_attn_bwd", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0), L.ptr(dout), dout.stride(0),
            L.ptr(indptr), L.ptr(indices), None, q.shape[0], None, causal[0], causal[1], H, d // H, float(scale), L.ptr(dq), dq.stride(0),
-           L.ptr(dk), dk.stride(0), L.ptr(dv), dv.stride(0), _st())
+           L.ptr(dk), dk.stride(0), L.ptr(dv), dv.stride(0), float(p), seed, _st())
     return dq, dk, dv
 
 
@@ -121,29 +164,35 @@ class _EdgeAttention(torch.autograd.Function):
     """out = softmax-by-destination attention over one CSR edge type (hgt.py:350-358)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, indptr, indices, H):
+    def forward(ctx, q, k, v, indptr, indices, H, p, seed):
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         ctx.save_for_backward(q, k, v, indptr, indices)
-        ctx.H = H
+        ctx.H, ctx.p, ctx.seed = H, p, seed
         out = torch.empty_like(q)
+        if p > 0:
+            return _attn_fwd_train(q, k, v, H, 1.0, out, False, p, seed, indptr=indptr, indices=indices)
         return ops.edge_attn(q, k, v, indptr, indices, H, out)
 
     @staticmethod
     def backward(ctx, dout):
         q, k, v, indptr, indices = ctx.saved_tensors
-        dq, dk, dv = _attn_bwd(q, k, v, dout.contiguous(), ctx.H, 1.0, indptr=indptr, indices=indices)
-        return dq, dk, dv, None, None, None
+        dq, dk, dv = _attn_bwd(q, k, v, dout.contiguous(), ctx.H, 1.0, indptr=indptr, indices=indices, p=ctx.p, seed=ctx.seed)
+        return dq, dk, dv, None, None, None, None, None
 
 
 class _TgtAttention(torch.autograd.Function):
     """mean over the two edge types into tgt (hgt.py:383-386, cross_reducer='mean'): 0.5 * inter(q, k_i, v_i) + 0.5 * causal(q, k_t, v_t)."""
 
     @staticmethod
-    def forward(ctx, q, k_i, v_i, k_t, v_t, inter_indptr, B, Lb, intra_ctx, H):
+    def forward(ctx, q, k_i, v_i, k_t, v_t, inter_indptr, B, Lb, intra_ctx, H, p, seed_inter, seed_tt):
         q, k_i, v_i, k_t, v_t = (t.contiguous() for t in (q, k_i, v_i, k_t, v_t))
         ctx.save_for_backward(q, k_i, v_i, k_t, v_t, inter_indptr)
-        ctx.cfg = (B, Lb, intra_ctx, H)
+        ctx.cfg = (B, Lb, intra_ctx, H, p, seed_inter, seed_tt)
         out = torch.empty_like(q)
+        if p > 0:
+            _attn_fwd_train(q, k_i, v_i, H, 0.5, out, False, p, seed_inter, indptr=inter_indptr)
+            _attn_fwd_train(q, k_t, v_t, H, 0.5, out, True, p, seed_tt, causal=(Lb, intra_ctx))
+            return out
         ops.edge_attn(q, k_i, v_i, inter_indptr, None, H, out, out_scale=0.5, tag="inter")
         ops.causal_attn(q, k_t, v_t, B, Lb, intra_ctx, H, out, out_scale=0.5, accumulate=True)
         return out
@@ -151,12 +200,12 @@ class _TgtAttention(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         q, k_i, v_i, k_t, v_t, inter_indptr = ctx.saved_tensors
-        B, Lb, intra_ctx, H = ctx.cfg
+        B, Lb, intra_ctx, H, p, seed_inter, seed_tt = ctx.cfg
         dout = dout.contiguous()
-        dq, dk_i, dv_i = _attn_bwd(q, k_i, v_i, dout, H, 0.5, indptr=inter_indptr)
-        dq2, dk_t, dv_t = _attn_bwd(q, k_t, v_t, dout, H, 0.5, causal=(Lb, intra_ctx))
+        dq, dk_i, dv_i = _attn_bwd(q, k_i, v_i, dout, H, 0.5, indptr=inter_indptr, p=p, seed=seed_inter)
+        dq2, dk_t, dv_t = _attn_bwd(q, k_t, v_t, dout, H, 0.5, causal=(Lb, intra_ctx), p=p, seed=seed_tt)
         L.call("gnnlm_axpy_f32", L.ptr(dq), dq.stride(0), L.ptr(dq2), dq2.stride(0), dq.shape[0], None, dq.shape[1], 1.0, _st())
-        return dq, dk_i, dv_i, dk_t, dv_t, None, None, None, None, None
+        return dq, dk_i, dv_i, dk_t, dv_t, None, None, None, None, None, None, None, None
 
 
 class _AddLayerNorm(torch.autograd.Function):
@@ -180,15 +229,22 @@ class _AddLayerNorm(torch.autograd.Function):
         return dx, dx, dg, db, None
 
 
+class _Ctx:
+    """Stand-in ctx for calling an autograd Function's forward outside the graph (frozen stages)."""
+
+
 class _AdaptiveLoss(torch.autograd.Function):
     """sum_t -log p(target_t | x_t) under the (frozen) adaptive softmax: adaptive_softmax.py:147-168 + adaptive_loss.py:62-70.
     The gradient w.r.t. x is produced together with the loss (the softmax - onehot of every cluster's logits, pushed back
     through the cluster's frozen projections) and scaled in backward."""
 
     @staticmethod
-    def forward(ctx, x, target, soft, mode):
+    def forward(ctx, x, target, soft, mode, p_drop, seed):
         x = x.contiguous()
         T, d = x.shape
+        drop = lambda a, site: a if p_drop <= 0 else _Dropout.forward(_Ctx(), a, p_drop, site_seed(seed, site))    # frozen part: no graph
+        x_in = x
+        x = drop(x, 1000)                                              # F.dropout(input) (adaptive_softmax.py:156)
         dev = x.device
         W = soft.train_weights()
         loss = torch.zeros(1, device=dev, dtype=torch.float64)
@@ -225,18 +281,20 @@ class _AdaptiveLoss(torch.autograd.Function):
                     continue
                 rows = tail_rows[i, :n_i].contiguous()
                 xi = ops.gather_rows(x, rows)
-                pi = _gemm(xi, W["proj"][i], None, mode)
+                pi = drop(_gemm(xi, W["proj"][i], None, mode), 1001 + i)    # the tail's nn.Dropout (:101)
                 lg = logits(pi, W["out"][i])
                 xent(lg, tail_pick[i, :n_i].long().contiguous())
-                dxi = _gemm(back(lg, W["out"][i]), _transpose(W["proj"][i]), None, mode)
+                dxi = _gemm(drop(back(lg, W["out"][i]), 1001 + i), _transpose(W["proj"][i]), None, mode)
                 L.call("gnnlm_scatter_add_rows", L.ptr(dx), dx.stride(0), L.ptr(dxi), dxi.stride(0), L.ptr(rows), n_i, None, d, _st())
+        dx = drop(dx, 1000)                                            # back through the input dropout
+        del x_in
         ctx.save_for_backward(dx)
         return loss.float().squeeze(0)
 
     @staticmethod
     def backward(ctx, g):
         (dx,) = ctx.saved_tensors
-        return dx * g, None, None, None
+        return dx * g, None, None, None, None, None
 
 
 def fold_layer(layer, t: int, n: int) -> Dict[str, torch.Tensor]:
@@ -258,7 +316,8 @@ def fold_layer(layer, t: int, n: int) -> Dict[str, torch.Tensor]:
     return out
 
 
-def hgt_forward_train(hgt, G: TokenGraph, h_t: torch.Tensor, h_n: torch.Tensor, mode: int = L.MATH_FP32_SIMT) -> torch.Tensor:
+def hgt_forward_train(hgt, G: TokenGraph, h_t: torch.Tensor, h_n: torch.Tensor, mode: int = L.MATH_FP32_SIMT, training: bool = False,
+                      seed: int = 0) -> torch.Tensor:
     """tgt outputs of HGT.forward (hgt.py:494-513) with autograd through the library's kernels.  h_t [T, d], h_n [n_ntgt, d] fp32
     (exact row counts: the caller sized them from G.counts())."""
     assert hgt.in_dim == hgt.hidden_dim == hgt.out_dim, "training path: plain HGT stack (no input adapters / output projection)"
@@ -268,8 +327,8 @@ def hgt_forward_train(hgt, G: TokenGraph, h_t: torch.Tensor, h_n: torch.Tensor, 
     nn_indptr, nn_indices = G.nn_indptr[:n_ntgt + 1].contiguous(), G.nn_indices
     NL = hgt.n_layers
     for l, layer in enumerate(hgt.gcs):
-        if layer.drop.p > 0 or layer.attn_drop.p > 0:
-            raise NotImplementedError("the training path covers dropout = 0 (hgt.py's drop / attn_drop masks are not generated)")
+        p_feat, p_att = (float(layer.drop.p), float(layer.attn_drop.p)) if training else (0.0, 0.0)
+        sd = lambda site: site_seed(seed, 16 * l + site)
         H = layer.n_heads
         F_ = fold_layer(layer, t, n)
         lin = lambda x, wb: _Linear.apply(x, wb[0], wb[1], mode)
@@ -278,19 +337,20 @@ def hgt_forward_train(hgt, G: TokenGraph, h_t: torch.Tensor, h_n: torch.Tensor, 
         hc = _GatherRows.apply(h_n, inter_ids)
         q_t = lin(h_t, plain(layer.q_linears, t))
         agg = _TgtAttention.apply(q_t, lin(hc, F_[f"k{n}1"]), lin(hc, F_[f"v{n}1"]), lin(h_t, F_[f"k{t}0"]), lin(h_t, F_[f"v{t}0"]),
-                                  G.inter_indptr, G.B, G.L, G.intra_ctx, H)
-        new_t = _AddLayerNorm.apply(lin(agg, plain(layer.a_linears, t)), h_t, layer.norms[t].weight, layer.norms[t].bias, layer.norms[t].eps)
+                                  G.inter_indptr, G.B, G.L, G.intra_ctx, H, p_att, sd(1), sd(0))
+        new_t = _AddLayerNorm.apply(_dropout(lin(agg, plain(layer.a_linears, t)), p_feat, sd(3)), h_t, layer.norms[t].weight,
+                                    layer.norms[t].bias, layer.norms[t].eps)
         # ---- ntgt (not needed after the last layer: the decoder reads tgt rows only, transformer.py:1053)
         if l < NL - 1:
             agg_n = _EdgeAttention.apply(lin(h_n, plain(layer.q_linears, n)), lin(h_n, F_[f"k{n}0"]), lin(h_n, F_[f"v{n}0"]),
-                                         nn_indptr, nn_indices, H)
-            h_n = _AddLayerNorm.apply(lin(agg_n, plain(layer.a_linears, n)), h_n, layer.norms[n].weight, layer.norms[n].bias,
-                                      layer.norms[n].eps)
+                                         nn_indptr, nn_indices, H, p_att, sd(2))
+            h_n = _AddLayerNorm.apply(_dropout(lin(agg_n, plain(layer.a_linears, n)), p_feat, sd(4)), h_n, layer.norms[n].weight,
+                                      layer.norms[n].bias, layer.norms[n].eps)
         h_t = new_t
     return h_t
 
 
-def train_step_loss(model, sample: dict, mode: str = "fp32") -> torch.Tensor:
+def train_step_loss(model, sample: dict, mode: str = "fp32", seed: int = 0) -> torch.Tensor:
     """AdaptiveLoss.forward (adaptive_loss.py:31-83, reduce=True) for a model built with --freeze: the summed cross-entropy of the
     batch, differentiable w.r.t. decoder.hgt_decoder.* (call .backward() on it).  `sample` as eval: net_input.graph (TokenGraph
     with codes_table and tgt features), target."""
@@ -306,12 +366,16 @@ def train_step_loss(model, sample: dict, mode: str = "fp32") -> torch.Tensor:
     with torch.no_grad():                                             # PQ decode + OPQ rotation: inputs, no parameters (pq_wrapper.py:169-203)
         h_n = dec.tgt_quantizer.gather_decode(G.codes_table, G.ntgt_row, n_cap=G.node_cap, n_dev=G.n_ntgt_dev, math_mode=L.MATH_FP32_SIMT)
         h_n = h_n[:n_ntgt].contiguous()
-    x = hgt_forward_train(dec.hgt_decoder, G, h_t, h_n, m)
+    training = bool(model.training)                                    # dropout masks only in train mode; `seed`: one per update
+    x = hgt_forward_train(dec.hgt_decoder, G, h_t, h_n, m, training, seed)
     soft = dec.adaptive_softmax if dec.adaptive_softmax is not None else _PlainSoftmax(dec.embed_out)
-    return _AdaptiveLoss.apply(x, sample["target"], soft, m)
+    p_soft = float(getattr(soft, "dropout", 0.0)) if training else 0.0
+    return _AdaptiveLoss.apply(x, sample["target"], soft, m, p_soft, seed)
 
 
 class _PlainSoftmax:
+    dropout = 0.0
+
     def __init__(self, embed_out):
         self.w = embed_out
 
@@ -323,14 +387,16 @@ class AdaptiveLoss:
     """fairseq/criterions/adaptive_loss.py:14-83 (`--criterion adaptive_loss`): forward(model, sample) -> (loss, sample_size,
     logging_output) with the reference's keys; the loss is differentiable w.r.t. the trainable (HGT) parameters."""
 
-    def __init__(self, args=None, task=None, math: str = "fp32"):
+    def __init__(self, args=None, task=None, math: str = "fp32", seed: int = 1):
         self.args, self.math = args, math
         self.sentence_avg = bool(getattr(args, "sentence_avg", False))
+        self.seed, self.calls = int(getattr(args, "seed", seed) or seed), 0       # dropout masks: a fresh seed per forward
 
     def forward(self, model, sample, reduce=True):
         if not reduce:
             raise NotImplementedError("reduce=False (per-token losses) is not used by the trainer (adaptive_loss.py:64-69)")
-        loss = train_step_loss(model, sample, self.math)
+        self.calls += 1
+        loss = train_step_loss(model, sample, self.math, seed=(self.seed * 0x9E3779B97F4A7C15 + self.calls) & 0xFFFFFFFFFFFFFFFF)
         ntokens = int(sample["target"].numel())                     # graph LM blocks carry no padding (transformer.py:975)
         nsentences = int(sample["target"].shape[0])
         sample_size = nsentences if self.sentence_avg else ntokens

@@ -472,13 +472,26 @@ int32_t gnnlm_hgt_edge_attn_bwd(const float* q, int64_t ldq, const float* k, int
                                 const float* dout, int64_t ldo, const int32_t* indptr, const int32_t* indices,
                                 const int32_t* dst_ids, int64_t n_dst_cap, const int32_t* n_dst_dev, int64_t causal_L,
                                 int64_t intra_ctx, int32_t H, int32_t d_k, float scale, float* dq, int64_t lddq, float* dk,
-                                int64_t lddk, float* dv, int64_t lddv, gnnlm_stream_t stream);
+                                int64_t lddk, float* dv, int64_t lddv, float p_drop, uint64_t seed, gnnlm_stream_t stream);
 /* The implicit causal edges without atomics: a by-destination pass writes dq and the softmax statistics {max, 1 / sum, D} per
  * (destination, head) into `stats` [B*L*H*3] floats; a by-source pass writes dk, dv (NOT accumulated). */
 int32_t gnnlm_hgt_causal_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                                   const float* dout, int64_t ldo, int64_t B, int64_t L, int64_t intra_ctx, int32_t H, int32_t d_k,
                                   float scale, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv, int64_t lddv,
-                                  float* stats, gnnlm_stream_t stream);
+                                  float* stats, float p_drop, uint64_t seed, gnnlm_stream_t stream);
+/* Dropout in training (hgt.py:74-75: `drop` on the output projection :401, `attn_drop` on the edge-softmax weights :356; the
+ * adaptive softmax's input / tail dropouts, adaptive_softmax.py:156,101).  A mask is a pure function of (seed, element): splitmix64
+ * of seed + index * 0x9E3779B97F4A7C15, keep iff its top 24 bits >= floor(p * 2^24), kept values scaled by 1 / (1 - p); element
+ * index = row * cols + col (gnnlm_dropout_f32) or (dst << 38) ^ (src << 6) ^ head (attention; `p_drop` / `seed` of the two
+ * backward entries above and of the training forward below).  Forward and backward regenerate the mask; nothing is stored.
+ * gnnlm_hgt_edge_attn_train_fwd: out (+)= scale * sum_e dropout(alpha)_e V'[src_e] for fp32 q / k / v, CSR or implicit causal
+ * edges (the evaluation kernels have no dropout). */
+int32_t gnnlm_hgt_edge_attn_train_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                      const int32_t* indptr, const int32_t* indices, int64_t n_dst, int64_t causal_L,
+                                      int64_t intra_ctx, int32_t H, int32_t d_k, float scale, int32_t accumulate, float* out,
+                                      int64_t ldo, float p_drop, uint64_t seed, gnnlm_stream_t stream);
+int32_t gnnlm_dropout_f32(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int64_t cols, float p_drop,
+                          uint64_t seed, gnnlm_stream_t stream);
 int32_t gnnlm_layernorm_bwd(const float* o, int64_t ldo, const float* residual, int64_t ldr, const float* gamma, float eps,
                             const float* dy, int64_t ldy, int64_t rows, const int32_t* rows_dev, int64_t d, float* dx,
                             int64_t ldx, float* dgamma, float* dbeta, gnnlm_stream_t stream);

@@ -1910,3 +1910,46 @@ def test_training_steps_reduce_the_loss(dev):
     for n_, p in m.named_parameters():
         if n_ in frozen:
             assert torch.equal(p.detach(), frozen[n_])
+
+
+@pytest.mark.parametrize("NL,cutoff,V,mode", [(2, [40, 120], 300, "fp32"), (3, None, 97, "fp32"), (2, [40, 120], 300, "tf32x3")])
+def test_training_step_with_dropout_vs_oracle_autograd(NL, cutoff, V, mode, dev):
+    """model.train(): hgt.py's `drop` (0.3) / `attn_drop` (0.1) and the adaptive softmax's input / tail dropout (0.2) -- the rates of
+    transformer_lm_wiki103 -- with the library's (seed, element)-addressed masks replayed through the oracle: loss and every
+    decoder.hgt_decoder.* gradient against torch.autograd over the masked fp64 statement."""
+    if mode != "fp32":
+        _need_tc()
+    import copy
+    from gnnlm_b200 import synth, train
+    from tests.synth import oracle_train
+    cfg, model, data = _train_problem(NL, cutoff, V)
+    p_feat, p_att, p_soft, seed = 0.3, 0.1, 0.2, 20240917
+    ref_loss, ref_g = oracle_train((cfg, model, data), dropout=(seed, p_feat, p_att, p_soft if cutoff is not None else 0.0))
+    ref0, _ = oracle_train((cfg, model, data))
+    assert abs(ref_loss - ref0) > 1e-6 * abs(ref0)                 # the masks do something
+    m = copy.deepcopy(model).to(dev).train()
+    for layer in m.decoder.hgt_decoder.gcs:
+        layer.drop.p, layer.attn_drop.p = p_feat, p_att
+    if m.decoder.adaptive_softmax is not None:
+        m.decoder.adaptive_softmax.dropout = p_soft
+    for name, p in m.named_parameters():
+        p.requires_grad_("hgt" in name)
+    r = synth.Runner(cfg, m, data, dev, "fp32")
+    m.train()
+    d_ = synth.to_device({k_: data[k_] for k_ in r.KEYS}, dev)
+    sample = r.sample_from(d_["nbr"], d_["feats"], d_["target"], d_["knn_dists"], d_["knn_ids"])
+    loss = train.train_step_loss(m, sample, mode, seed=seed)
+    loss.backward()
+    assert abs(float(loss.detach()) - ref_loss) < 2e-5 * abs(ref_loss), (float(loss.detach()), ref_loss)
+    gmax = max(float(g_.abs().max()) for g_ in ref_g.values() if g_ is not None)
+    checked = 0
+    for name, p in m.decoder.hgt_decoder.named_parameters():
+        g_ref = ref_g.get(name)
+        if g_ref is None or p.grad is None or name.endswith("skip"):
+            continue
+        err = float((p.grad.detach().cpu().double() - g_ref).abs().max())
+        assert err < 2e-4 * float(g_ref.abs().max()) + 2e-6 * gmax, (name, err)
+        checked += 1
+    assert checked >= 10 * NL
+    m.eval()                                                       # eval mode: no masks, the deterministic loss
+    assert abs(float(train.train_step_loss(m, sample, mode, seed=seed).detach()) - ref0) < 2e-5 * abs(ref0)
