@@ -399,7 +399,7 @@ def main():
     live = {g.node_cap: n_ntgt, T * cfg["k"]: n_valid}              # capacity-sized launches -> live rows of batch 0
     per, gemm = {}, {}
     for name, tag, a, b, work in L.TIMING:
-        base = name.replace("gnnlm_", "").replace("_q8", "").replace("_hiq8", "").replace("_presplit", "")
+        base = name.replace("gnnlm_", "").replace("_q8", "").replace("_hiq8", "").replace("_presplit", "").replace("cluster_attn_hq", "cluster_attn")
         key = base + (f":{tag}" if tag else "")
         dt = a.elapsed_time(b)
         d_ = per.setdefault(key, [0.0, 0])
@@ -449,12 +449,15 @@ def main():
     # ---- edge-aggregation kernels (the metric's second half): algorithmic bytes / device time, vs the HBM peak
     d, s = cfg["d"], (2 if math == "bf16" else 4)          # bytes per activation element (bf16 mode: Q | K' | V' and outputs in bf16)
     out_b = {"f16f8": 3}.get(math, s)                       # f16f8: cluster attention writes fp16 hi + 2 companion bytes per element
+    hq_env = os.environ.get("GNNLM_HQ", "1")
+    in_c = 3 if (math == "f16f8" and hq_env != "0") else s        # f16f8: Q | K' | V' of the centre-only layer rounded to three bytes (GNNLM_F24)
+    in_b = 3 if (math == "f16f8" and hq_env == "all") else s      # (the all-nodes layers keep fp32 rows unless GNNLM_HQ=all)
 
     def _edge_bytes(key):
         if key.endswith("nn_full"):
-            return n_ntgt * 2 * d * s + n_ntgt * d * s + n_ntgt * d * out_b + (3 * n_ntgt - 2 * n_valid) * 4 + (n_ntgt + 1) * 4
+            return n_ntgt * 2 * d * in_b + n_ntgt * d * in_b + n_ntgt * d * out_b + (3 * n_ntgt - 2 * n_valid) * 4 + (n_ntgt + 1) * 4
         if key.endswith("nn_centre"):
-            return min(n_ntgt, 3 * n_valid) * 2 * d * s + n_valid * d * s + n_valid * d * out_b + 3 * n_valid * 4 + 2 * n_valid * 4
+            return min(n_ntgt, 3 * n_valid) * 2 * d * in_c + n_valid * d * in_c + n_valid * d * out_b + 3 * n_valid * 4 + 2 * n_valid * 4
         return n_valid * 2 * d * s + T * d * s + T * d * 4 + (T + 1) * 4
     edge_all = {key: {"GB/s": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9,
                       "frac": _edge_bytes(key) / (kv["ms_per_launch"] * 1e-3) / 1e9 / hbm_peak,

@@ -8,7 +8,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libgnnlm_sm100.so")
 
-F32, BF16, F16, F16X2 = 0, 1, 2, 3
+F32, BF16, F16, F16X2, F24 = 0, 1, 2, 3, 4
 MATH_FP32_SIMT, MATH_TF32X3, MATH_TF32, MATH_BF16, MATH_F16X3 = 0, 1, 2, 3, 4
 # host-level mode: MATH_F16X3 everywhere, except that products whose activation operand carries an e4m3 companion (ops.Split.q8)
 # run gnnlm_linear_f16f8 (fp16 main product + FP8 correction MMAs: two tensor-pass equivalents instead of three)
@@ -51,7 +51,7 @@ SIGNATURES = {
     "gnnlm_split_to_q8": (_i32, [_p, _i64, _p, _i64, _i64, _p, _i64, _p]),
     "gnnlm_quant_w8": (_i32, [_p, _p, _i64, _p, _i64, _i64, _i64, _p]),
     "gnnlm_linear_f16f8": (_i32, [_p, _p, _i64, _i64, _i64, _p, _p, _i64, _i64, _i64, _p, _p, _f32, _i64, _i64, _p, _p, _i32, _i64,
-                                  _i64, _p, _i64, _p]),
+                                  _i64, _p, _i64, _p, _p]),
     "gnnlm_lse_num_tiles": (_i64, [_i64, _i32]),
     "gnnlm_linear_lse": (_i32, [_p, _i32, _i64, _p, _p, _f32, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i64, _i32, _p]),
     "gnnlm_lse_finish": (_i32, [_p, _p, _p, _i64, _p, _p, _i32, _i64, _p, _p]),
@@ -66,6 +66,8 @@ SIGNATURES = {
     "gnnlm_hgt_cluster_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i64, _p]),
     "gnnlm_hgt_cluster_attn_q8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i64,
                                          _p, _i64, _i32, _p]),
+    "gnnlm_hgt_cluster_attn_hq": (_i32, [_p, _p, _i64, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i64, _p, _i64,
+                                         _i32, _p]),
     "gnnlm_hgt_causal_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _i64, _i64, _i64, _i32, _i32, _p, _i64, _f32, _i32, _p]),
     "gnnlm_hgt_causal_flash": (_i32, [_p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p, _i64, _i64, _f32, _i32, _p]),
     "gnnlm_hgt_causal_flash_tc": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p, _i64, _i64, _f32, _i32, _p]),

@@ -102,7 +102,11 @@ __device__ __forceinline__ void store_out(OutT* __restrict__ p, const float (&r)
 // One warp per (cluster, 32*C-feature slice).  WMAX > 0: all nodes of clusters of at most WMAX (1, 3, 5, 7) nodes, every row
 // loaded up front.  WMAX == 0: centre-only variant (its own instantiation: 3 rows of K'/V' per cluster and a third of the
 // registers of the all-nodes form).  GROUP: lanes per head (0 = run time).
-template <typename T, typename OutT, int C, int WMAX, int GROUP>
+// HQ: q / k / v are GNNLM_F24 (T = a 2-byte element: the 16-bit plane; the byte of the element at 16-bit address a is at a / 2 + bias)
+// (Measured on the Wiki103 shape: the centre-only form gains from the 3-byte rows, 0.47 -> 0.43 ms; the all-nodes form does not --
+// 0.78 -> 0.93 ms even at four CTAs per SM: two narrower loads per row segment plus two byte-permute instructions per element make
+// it issue-bound -- so the host only feeds GNNLM_F24 to the centre-only layer.)
+template <typename T, typename OutT, int C, int WMAX, int GROUP, bool HQ = false>
 __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __restrict__ q, int64_t ldq, const T* __restrict__ k,
                                                                   int64_t ldk, const T* __restrict__ v, int64_t ldv,
                                                                   const int32_t* __restrict__ node_base,
@@ -110,8 +114,13 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
                                                                   const int32_t* __restrict__ cluster_nl, int64_t n_clusters,
                                                                   int group, int n_slices,
                                                                   OutT* __restrict__ out, int64_t ldo, int lo_off,
-                                                                  uint8_t* __restrict__ q8, int64_t ldq8, bool write_lo) {
+                                                                  uint8_t* __restrict__ q8, int64_t ldq8, bool write_lo,
+                                                                  int64_t q_bias = 0, int64_t k_bias = 0, int64_t v_bias = 0) {
   constexpr bool centre_only = WMAX == 0;
+  auto ld_row = [](const T* __restrict__ p, int64_t bias, float (&r)[C]) {
+    if constexpr (HQ) load_row_f24(p, bias, r);
+    else load_row<T, C>(p, r);
+  };
   constexpr int WM = WMAX > 0 ? WMAX : 1;
   const int lane = threadIdx.x & 31;
   const int64_t n_items = n_clusters * n_slices;
@@ -133,9 +142,9 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
       for (int p = 0; p < WM; ++p) {
         if (p < w) {
           const int64_t id = ca_pos_to_id(p, nl);
-          load_row<T, C>(qb + id * ldq, qq[p]);
-          load_row<T, C>(kb + id * ldk, kk[p]);
-          load_row<T, C>(vb + id * ldv, vv[p]);
+          ld_row(qb + id * ldq, q_bias, qq[p]);
+          ld_row(kb + id * ldk, k_bias, kk[p]);
+          ld_row(vb + id * ldv, v_bias, vv[p]);
         }
       }
 #pragma unroll
@@ -157,15 +166,15 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
       // centre node (sorted position nl) attends to positions nl-1, nl, nl+1
       const int64_t ci = __ldg(valid_base + c);             // compact row of q / out
       float qq[C], kk[3][C], vv[3][C];
-      load_row<T, C>(q + ci * ldq + col, qq);
+      ld_row(q + ci * ldq + col, q_bias, qq);
       const bool has_l = nl > 0, has_r = nl + 1 < w;
       const int64_t idl = base + (has_l ? ca_pos_to_id(nl - 1, nl) : 0), idr = base + (has_r ? ca_pos_to_id(nl + 1, nl) : 0);
-      load_row<T, C>(k + (int64_t)base * ldk + col, kk[1]);
-      load_row<T, C>(v + (int64_t)base * ldv + col, vv[1]);
-      load_row<T, C>(k + idl * ldk + col, kk[0]);            // an absent side re-reads the centre row (L1 hit), masked below
-      load_row<T, C>(v + idl * ldv + col, vv[0]);
-      load_row<T, C>(k + idr * ldk + col, kk[2]);
-      load_row<T, C>(v + idr * ldv + col, vv[2]);
+      ld_row(k + (int64_t)base * ldk + col, k_bias, kk[1]);
+      ld_row(v + (int64_t)base * ldv + col, v_bias, vv[1]);
+      ld_row(k + idl * ldk + col, k_bias, kk[0]);            // an absent side re-reads the centre row (L1 hit), masked below
+      ld_row(v + idl * ldv + col, v_bias, vv[0]);
+      ld_row(k + idr * ldk + col, k_bias, kk[2]);
+      ld_row(v + idr * ldv + col, v_bias, vv[2]);
       const float s1 = group_dot<C, GROUP>(qq, kk[1], group);
       const float s0 = group_dot<C, GROUP>(qq, kk[0], group);
       const float s2 = group_dot<C, GROUP>(qq, kk[2], group);
@@ -283,9 +292,64 @@ static int32_t dispatch_group(int wmax, const void* q, int64_t ldq, const void* 
 #undef GNNLM_DG
 }
 
+template <int GROUP>
+static int32_t launch_hq(int wmax, const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, int64_t qb,
+                         int64_t kb, int64_t vb, const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl,
+                         int64_t n_clusters, int centre_only, int group, int n_slices, __half* out, int64_t ldo, int lo_off,
+                         uint8_t* q8, int64_t ldq8, bool write_lo, cudaStream_t st) {
+  int64_t blocks = ceil_div(n_clusters * n_slices, CA_THREADS / 32);
+  if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
+#define GNNLM_CLH(W)                                                                                                               \
+  cluster_attn_kernel<__half, __half, 4, W, GROUP, true><<<(unsigned)blocks, CA_THREADS, 0, st>>>(                                 \
+      q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, group, n_slices, out, ldo, lo_off, q8, ldq8, write_lo, \
+      qb, kb, vb)
+  if (centre_only) GNNLM_CLH(0);
+  else if (wmax <= 1) GNNLM_CLH(1);
+  else if (wmax <= 3) GNNLM_CLH(3);
+  else if (wmax <= 5) GNNLM_CLH(5);
+  else GNNLM_CLH(7);
+#undef GNNLM_CLH
+  GNNLM_LAUNCH_CHECK("gnnlm_hgt_cluster_attn_hq");
+  return 0;
+}
+
 }  // namespace gnnlm
 
 using namespace gnnlm;
+
+extern "C" int32_t gnnlm_hgt_cluster_attn_hq(const void* q, const void* q_lo8, int64_t ldq, const void* k, const void* k_lo8, int64_t ldk,
+                                             const void* v, const void* v_lo8, int64_t ldv, const int32_t* node_base,
+                                             const int32_t* valid_base, const int32_t* cluster_nl, int64_t n_clusters,
+                                             int32_t max_cluster, int32_t centre_only, int32_t H, int32_t d_k, void* out, int64_t ldo,
+                                             void* q8v, int64_t ldq8, int32_t write_lo, gnnlm_stream_t stream) {
+  uint8_t* q8 = reinterpret_cast<uint8_t*>(q8v);
+  GNNLM_CHECK_ARG(q && k && v && q_lo8 && k_lo8 && v_lo8 && node_base && cluster_nl && out, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn_hq: null pointer");
+  GNNLM_CHECK_ARG(!centre_only || valid_base, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn_hq: centre_only needs valid_base");
+  GNNLM_CHECK_ARG(write_lo || q8, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn_hq: write_lo = 0 (hi + companion only) needs q8");
+  GNNLM_CHECK_ARG(H > 0 && d_k > 0 && max_cluster >= 1 && max_cluster <= 7, GNNLM_E_UNSUPPORTED,
+                  "gnnlm_hgt_cluster_attn_hq: clusters of at most 7 nodes");
+  const int64_t d = (int64_t)H * d_k;
+  GNNLM_CHECK_ARG(d % 128 == 0 && d_k % 4 == 0 && d_k / 4 <= 32 && 32 % (d_k / 4) == 0, GNNLM_E_UNSUPPORTED,
+                  "gnnlm_hgt_cluster_attn_hq: unsupported (H=%d, d_k=%d)", H, d_k);
+  GNNLM_CHECK_ARG(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 8 == 0 && (uintptr_t)q % 8 == 0 && (uintptr_t)k % 8 == 0 &&
+                      (uintptr_t)v % 8 == 0 && (uintptr_t)q_lo8 % 4 == 0 && (uintptr_t)k_lo8 % 4 == 0 && (uintptr_t)v_lo8 % 4 == 0,
+                  GNNLM_E_SHAPE, "gnnlm_hgt_cluster_attn_hq: rows must keep 8 B (16-bit plane) / 4 B (byte plane) alignment");
+  GNNLM_CHECK_ARG(ldo >= (write_lo ? 2 : 1) * d && (!q8 || ((uintptr_t)q8 % 4 == 0 && ldq8 % 4 == 0 && ldq8 >= 2 * d)), GNNLM_E_SHAPE,
+                  "gnnlm_hgt_cluster_attn_hq: split output needs ldo >= 2d (d when only the hi half is written), ldq8 >= 2d");
+  if (n_clusters == 0) return 0;
+  const int group = d_k / 4, n_slices = (int)(d / 128);
+  auto bias = [](const void* hi, const void* lo8) { return (int64_t)((uintptr_t)lo8) - (int64_t)((uintptr_t)hi >> 1); };
+  const int64_t qb = bias(q, q_lo8), kb = bias(k, k_lo8), vb = bias(v, v_lo8);
+  cudaStream_t st = (cudaStream_t)stream;
+#define GNNLM_HQ(G)                                                                                                                \
+  return launch_hq<G>(max_cluster, (const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv, qb, kb, vb, node_base,     \
+                      valid_base, cluster_nl, n_clusters, centre_only, group, n_slices, (__half*)out, ldo, (int)d, q8, ldq8,       \
+                      write_lo != 0, st)
+  if (group == 32) GNNLM_HQ(32);
+  if (group == 16) GNNLM_HQ(16);
+  GNNLM_HQ(0);
+#undef GNNLM_HQ
+}
 
 extern "C" int32_t gnnlm_hgt_cluster_attn(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                           int32_t dtype, const int32_t* node_base, const int32_t* valid_base,

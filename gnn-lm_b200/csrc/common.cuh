@@ -151,4 +151,26 @@ __device__ __forceinline__ void q8_from_split4(uint2 hi, uint2 lo, uint32_t& hi8
   lo8 = e4m3x4(ls);
 }
 
+// ---- GNNLM_F24: an fp32 value rounded to its top three bytes (sign, 8 exponent bits, 15 mantissa bits: 2^-16 relative), stored
+// as a 16-bit plane (bytes 3, 2 -- the value's bf16 truncation) and a byte plane (byte 1) with the SAME row stride in elements, so the
+// byte of the element at 16-bit address a sits at a / 2 + bias.  No float conversions either way: byte permutes only.
+// The attention inputs Q | K' | V' of the ntgt side in MATH_F16F8 (written by the projection's epilogue, read by cluster_attn.cu):
+// 3 bytes per element instead of 4 through HBM, twice.
+__device__ __forceinline__ void f24_pack4(float y0, float y1, float y2, float y3, uint2& hi, uint32_t& lo) {
+  const uint32_t u0 = __float_as_uint(y0) + 0x80u, u1 = __float_as_uint(y1) + 0x80u, u2 = __float_as_uint(y2) + 0x80u,
+                 u3 = __float_as_uint(y3) + 0x80u;                              // round to nearest at bit 8 (sign-magnitude: ties away)
+  hi.x = __byte_perm(u0, u1, 0x7632);
+  hi.y = __byte_perm(u2, u3, 0x7632);
+  lo = __byte_perm(__byte_perm(u0, u1, 0x0051), __byte_perm(u2, u3, 0x0051), 0x5410);
+}
+// C = 4 features: 8 B of the 16-bit plane + 4 B of the byte plane (byte address = 16-bit address / 2 + bias)
+__device__ __forceinline__ void load_row_f24(const __half* __restrict__ p, int64_t bias, float (&r)[4]) {
+  const uint2 h = __ldg(reinterpret_cast<const uint2*>(p));
+  const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>((int64_t)(reinterpret_cast<uintptr_t>(p) >> 1) + bias));
+  r[0] = __uint_as_float(__byte_perm(h.x, l, 0x1040) & 0xffffff00u);
+  r[1] = __uint_as_float(__byte_perm(h.x, l, 0x3250) & 0xffffff00u);
+  r[2] = __uint_as_float(__byte_perm(h.y, l, 0x1060) & 0xffffff00u);
+  r[3] = __uint_as_float(__byte_perm(h.y, l, 0x3270) & 0xffffff00u);
+}
+
 }  // namespace gnnlm

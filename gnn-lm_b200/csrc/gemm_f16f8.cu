@@ -317,12 +317,14 @@ extern "C" int32_t gnnlm_quant_w8(const void* w_hi, const void* w_lo, int64_t ld
 extern "C" int32_t gnnlm_linear_f16f8(const void* A1, const void* A1q, int64_t lda1, int64_t ldq1, int64_t K1, const void* A2,
                                       const void* A2q, int64_t lda2, int64_t ldq2, int64_t K2, const void* W_hi, const void* W8,
                                       float w_scale, int64_t ldw, int64_t ldw8, const float* bias, void* C, int32_t c_dtype,
-                                      int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, cudaStream_t stream) {
+                                      int64_t ldc, int64_t M, const int32_t* m_dev, int64_t N, void* C8, cudaStream_t stream) {
   GNNLM_CHECK_ARG(A1 && A1q && W_hi && W8 && C && M >= 0 && N > 0 && K1 > 0 && K2 >= 0 && w_scale > 0.f, GNNLM_E_ARG,
                   "gnnlm_linear_f16f8: null pointer / bad sizes");
   GNNLM_CHECK_ARG(K2 == 0 || (A2 && A2q), GNNLM_E_ARG, "gnnlm_linear_f16f8: K2 > 0 needs the second source");
-  GNNLM_CHECK_ARG(c_dtype == GNNLM_F32 || c_dtype == GNNLM_BF16 || c_dtype == GNNLM_F16X2, GNNLM_E_ARG,
-                  "gnnlm_linear_f16f8: output dtype must be f32 / bf16 / split fp16");
+  GNNLM_CHECK_ARG(c_dtype == GNNLM_F32 || c_dtype == GNNLM_BF16 || c_dtype == GNNLM_F16X2 || c_dtype == GNNLM_F24, GNNLM_E_ARG,
+                  "gnnlm_linear_f16f8: output dtype must be f32 / bf16 / split fp16 / f24");
+  GNNLM_CHECK_ARG(c_dtype != GNNLM_F24 || (C8 && N % 4 == 0 && ldc % 4 == 0 && (uintptr_t)C % 16 == 0 && (uintptr_t)C8 % 4 == 0),
+                  GNNLM_E_SHAPE, "gnnlm_linear_f16f8: GNNLM_F24 output needs the byte plane, N and ldc multiples of 4, aligned bases");
   GNNLM_CHECK_ARG(gemm_tc_supported(), GNNLM_E_UNSUPPORTED, "gnnlm_linear_f16f8: needs an sm_100 device and driver TMA support");
   const int64_t K = K1 + K2;
   // k-blocks of 64 must not straddle the two sources; e4m3 halves sit K1 (resp. K2, K) bytes apart inside their rows
@@ -356,7 +358,8 @@ extern "C" int32_t gnnlm_linear_f16f8(const void* A1, const void* A1q, int64_t l
   if (!r) r = tc::make_map_k64(&maps.w8_hi, w8 + K, 1, N, K, ldw8, tc::BLOCK_N / 2);
   GNNLM_CHECK_ARG(r == 0, GNNLM_E_ARG, "gnnlm_linear_f16f8: cuTensorMapEncodeTiled failed (%d)", r);
 
-  tc::EpiStore es{bias, nullptr, 0, C, ldc, c_dtype == GNNLM_BF16 ? 1 : (c_dtype == GNNLM_F16X2 ? 2 : 0), 0, N, N};
+  tc::EpiStore es{bias, nullptr, 0, C, ldc, c_dtype == GNNLM_BF16 ? 1 : (c_dtype == GNNLM_F16X2 ? 2 : (c_dtype == GNNLM_F24 ? 3 : 0)), 0, N, N};
+  es.C8 = reinterpret_cast<uint8_t*>(C8);
   const size_t smem = (size_t)tc::F8_STAGES * tc::F8_STAGE + tc::EPI_SMEM + 1024;
   static bool attr_set = false;
   if (!attr_set) {

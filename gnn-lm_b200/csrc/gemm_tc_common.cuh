@@ -170,10 +170,11 @@ struct EpiStore {
   int64_t ldr;
   void* C;
   int64_t ldc;
-  int c_bf16;      // C element type: 0 = f32, 1 = bf16, 2 = split-fp16 (hi | lo, lo at column offset c_lo)
+  int c_bf16;      // C element type: 0 = f32, 1 = bf16, 2 = split-fp16 (hi | lo, lo at column offset c_lo), 3 = GNNLM_F24: 16-bit plane at C + byte plane at C8
   int r_bf16;      // residual type, same encoding (lo at column offset r_lo)
   int64_t c_lo, r_lo;
   int dbg;         // timing experiments only (GNNLM_F8_DEBUG bits 3 / 4): 1 = no global stores, 2 = no TMEM loads / staging
+  uint8_t* C8;     // c_bf16 == 3 (GNNLM_F24): the byte plane, same row stride (ldc elements = ldc bytes)
 };
 struct EpiLse {
   const int32_t* pick;
@@ -193,7 +194,7 @@ constexpr int EPI_SMEM = 4 * 32 * EPI_LD * 4;               // 4 epilogue warps
 // through 32-bit shared addresses, and the TMEM load of chunk c+1 issued before chunk c is written out.  The profile of
 // the generic form showed ~400 dependent instructions per 32-column chunk at 0.11 IPC per epilogue warp -- 14 us per tile,
 // three times the single-pass (bf16) main loop.
-template <int CMODE>      // 0 = f32, 1 = bf16, 2 = split fp16
+template <int CMODE>      // 0 = f32, 1 = bf16, 2 = split fp16, 3 = GNNLM_F24 (16-bit plane + byte plane)
 __device__ __forceinline__ void epilogue_store_fast(uint32_t taddr, int64_t m, int64_t M, int64_t n_base, int64_t N,
                                                     const EpiStore& es, float* stage_smem, float acc_scale, int tile_cols) {
   constexpr int ES = CMODE == 0 ? 4 : 2;
@@ -249,6 +250,12 @@ __device__ __forceinline__ void epilogue_store_fast(uint32_t taddr, int64_t m, i
           split4_f16(y0, y1, y2, y3, hi, lo);
           *reinterpret_cast<uint2*>(p) = hi;
           *reinterpret_cast<uint2*>(p + lo_bytes) = lo;
+        } else if constexpr (CMODE == 3) {
+          uint2 hi;
+          uint32_t lo;
+          f24_pack4(y0, y1, y2, y3, hi, lo);
+          *reinterpret_cast<uint2*>(p) = hi;
+          *reinterpret_cast<uint32_t*>(es.C8 + ((p - reinterpret_cast<char*>(es.C)) >> 1)) = lo;
         } else {
           const __nv_bfloat162 p0 = __floats2bfloat162_rn(y0, y1), p1 = __floats2bfloat162_rn(y2, y3);
           uint2 u;
@@ -274,6 +281,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t taddr, int64_t m, int64_t
               (reinterpret_cast<uintptr_t>(es.C) & 15) == 0 && (!es.bias || (reinterpret_cast<uintptr_t>(es.bias) & 15) == 0)) {
             if (es.c_bf16 == 0) epilogue_store_fast<0>(taddr, m, M, n_base, N, es, stage_smem, acc_scale, tile_cols);
             else if (es.c_bf16 == 2) epilogue_store_fast<2>(taddr, m, M, n_base, N, es, stage_smem, acc_scale, tile_cols);
+            else if (es.c_bf16 == 3) epilogue_store_fast<3>(taddr, m, M, n_base, N, es, stage_smem, acc_scale, tile_cols);
             else epilogue_store_fast<1>(taddr, m, M, n_base, N, es, stage_smem, acc_scale, tile_cols);
             return;
           }

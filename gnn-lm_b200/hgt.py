@@ -133,8 +133,11 @@ def as_act(x, math_mode: int):
     return ops.convert(x, dt)
 
 
-def _attn_in_dtype(math_mode: int):
-    """Q | K' | V' storage: bf16 in MATH_BF16, fp32 otherwise (the attention kernels read fp32 / bf16)."""
+def _attn_in_dtype(math_mode: int, hq: bool = False):
+    """Q | K' | V' storage: bf16 in MATH_BF16, fp32 otherwise (the attention kernels read fp32 / bf16); `hq`: the 3-byte
+    GNNLM_F24 form (the value's top three bytes) when the MATH_F16F8 projection feeds the cluster kernel."""
+    if hq and math_mode == L.MATH_F16F8:
+        return ops.HILO8
     return torch.bfloat16 if math_mode == L.MATH_BF16 else torch.float32
 
 
@@ -185,6 +188,8 @@ class HGTLayer(nn.Module):
         # tensor-core modes, d_k in {64, 128}: one flash kernel instead (gnnlm_hgt_causal_flash); GNNLM_FLASH=0 for A/B timing
         self.use_flash_attention = os.environ.get("GNNLM_FLASH", "1") != "0"
         self.use_flash_tc = os.environ.get("GNNLM_FLASH", "1") != "mma"      # d_k = 128: the tcgen05 form (GNNLM_FLASH=mma: mma.sync form)
+        # MATH_F16F8: Q | K' | V' of the ntgt side rounded to three bytes (GNNLM_F24) instead of fp32 (GNNLM_HQ=0: fp32, for A/B)
+        self.use_hq_attention = {"0": False, "all": "all"}.get(os.environ.get("GNNLM_HQ", "1"), True)
 
     # ------------------------------------------------------------------ weight preparation
     def prepare(self, math_mode: int, rot: Optional[torch.Tensor] = None):
@@ -259,12 +264,20 @@ class HGTLayer(nn.Module):
             return ops.layernorm(o, g, b, eps, out=o, n_dev=n_dev, residual=h_in)
         return ops.layernorm(o, g, b, eps, out_dtype=act, n_dev=n_dev, residual=h_in)       # bf16 or split fp16 (+ e4m3 companion)
 
+    def _hq(self, G, h_n, centre: bool) -> bool:
+        """Q | K' | V' of the ntgt side as GNNLM_F24 (3 bytes per element instead of 4): when the f16f8 product writes them (the
+        operand carries its e4m3 companion) and the centre-only cluster kernel reads them.  The all-nodes cluster kernel is faster on
+        fp32 rows (cluster_attn.cu), so only the centre-only layer uses the format unless GNNLM_HQ=all."""
+        d, H = self.in_dim, self.n_heads
+        return ((centre or self.use_hq_attention == "all") and bool(self.use_hq_attention) and isinstance(h_n, ops.Split)
+                and self.use_cluster_kernel and not G.dedup and ops.cluster_attn_hq_supported(d, H, G.w) and ops.f16f8_supported(d))
+
     def _nn_attn(self, P, G, q, k, v, rows, *, centre: bool, n_dev, c_dev):
         """ntgt-intra-ntgt attention -> [rows, d] in the activation dtype."""
         d, H = P["d"], self.n_heads
         act = act_dtype(P["math"])
         tag = "nn_centre" if centre else "nn_full"
-        if self.use_cluster_kernel and not G.dedup and ops.cluster_attn_supported(d, H, q.dtype, G.w):
+        if isinstance(q, ops.HiLo8) or (self.use_cluster_kernel and not G.dedup and ops.cluster_attn_supported(d, H, q.dtype, G.w)):
             t_agg = ops.empty_act(rows, d, gemm_act(P["math"], rows, d, lo=False), q.device)   # feeds the A-linear and nothing else
             ops.cluster_attn(q, k, v, G, H, t_agg, centre_only=centre, tag=tag)
             return t_agg
@@ -278,7 +291,7 @@ class HGTLayer(nn.Module):
     def ntgt_full(self, P, G: TokenGraph, h_n, n_dev):
         """All ntgt nodes: Q|K'|V' -> chain attention -> A-linear + residual + LN."""
         d = P["d"]
-        qkv = _lin(with_q8(h_n, P["math"], n_dev), P["ntgt_qkv"], P["math"], m_dev=n_dev, out_dtype=_attn_in_dtype(P["math"]))
+        qkv = _lin(with_q8(h_n, P["math"], n_dev), P["ntgt_qkv"], P["math"], m_dev=n_dev, out_dtype=_attn_in_dtype(P["math"], self._hq(G, h_n, centre=False)))
         t_agg = self._nn_attn(P, G, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], h_n.shape[0], centre=False, n_dev=n_dev,
                               c_dev=None)
         return self._out(P, P["n"], t_agg, h_n, n_dev, feeds_gemm=True)        # h of the next layer: a GEMM operand
@@ -286,7 +299,7 @@ class HGTLayer(nn.Module):
     def ntgt_centre(self, P, G: TokenGraph, h_n, n_dev, hc, c_dev):
         """Centre nodes only (compact rows): K'|V' for every node, Q / A-linear / LN for centres."""
         d = P["d"]
-        act = _attn_in_dtype(P["math"])
+        act = _attn_in_dtype(P["math"], self._hq(G, h_n, centre=True))
         kv = _lin(with_q8(h_n, P["math"], n_dev), P["ntgt_qkv"].rows(d, 3 * d), P["math"], m_dev=n_dev, out_dtype=act)
         qc = _lin(with_q8(hc, P["math"], c_dev), P["ntgt_qkv"].rows(0, d), P["math"], m_dev=c_dev, out_dtype=act)
         t_agg = self._nn_attn(P, G, qc, kv[:, :d], kv[:, d:], hc.shape[0], centre=True, n_dev=n_dev, c_dev=c_dev)

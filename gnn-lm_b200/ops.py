@@ -13,6 +13,37 @@ _I32 = torch.int32
 SPLIT = "split"          # out_dtype selector for the split-fp16 activation format (GNNLM_F16X2)
 SPLIT_Q8 = "split+q8"    # the same with the e4m3 companion (Split.q8) written by the producing kernel (MATH_F16F8 GEMM operands)
 HI_Q8 = "hi+q8"          # fp16 hi half + companion only (no lo half): for matrices that only feed gnnlm_linear_f16f8
+HILO8 = "f24"            # GNNLM_F24: 16-bit plane + byte plane (3 bytes per element): Q | K' | V' of the ntgt side in MATH_F16F8
+
+
+class HiLo8:
+    """An fp32 matrix [rows, d] rounded to its top three bytes (GNNLM_F24): `hi` [rows, d] bfloat16 (bytes 3, 2 of every value: its
+    bf16 truncation) + `lo8` [rows, d] uint8 (byte 1).  Written by gnnlm_linear_f16f8, read by gnnlm_hgt_cluster_attn_hq.  Column
+    slices keep the two planes aligned."""
+
+    def __init__(self, hi: torch.Tensor, lo8: torch.Tensor):
+        assert hi.dtype == torch.bfloat16 and lo8.dtype == torch.uint8 and hi.shape == lo8.shape and hi.stride(0) == lo8.stride(0)
+        self.hi, self.lo8 = hi, lo8
+
+    @staticmethod
+    def empty(rows: int, d: int, device) -> "HiLo8":
+        return HiLo8(torch.empty((rows, d), device=device, dtype=torch.bfloat16), torch.empty((rows, d), device=device, dtype=torch.uint8))
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    @property
+    def device(self):
+        return self.hi.device
+
+    def __getitem__(self, idx):
+        return HiLo8(self.hi[idx], self.lo8[idx])
+
+    def float(self) -> torch.Tensor:
+        """fp32 reconstruction (tests / API boundary; torch ops)."""
+        bits = ((self.hi.contiguous().view(torch.int16).to(torch.int32) & 0xFFFF) << 16) | (self.lo8.to(torch.int32) << 8)
+        return bits.view(torch.float32)
 
 
 class Split:
@@ -51,6 +82,8 @@ class Split:
 
 
 def empty_act(rows: int, d: int, act, device):
+    if act == HILO8:
+        return HiLo8.empty(rows, d, device)
     if act in (SPLIT, SPLIT_Q8, HI_Q8):
         return Split.empty(rows, d, device, q8=act != SPLIT, lo=act != HI_Q8)
     return torch.empty((rows, d), device=device, dtype=act)
@@ -134,12 +167,15 @@ def linear_f16f8(A1: Split, W_hi, W8, bias=None, *, A2: Optional[Split] = None, 
     assert W_hi.shape[1] == K1 + K2 and W8.shape == (N, 2 * (K1 + K2)) and W_hi.dtype == torch.float16
     if out is None:
         out = empty_act(M, N, out_dtype or torch.float32, W_hi.device)
-    c_ptr, c_code, ldc, n_out = _mat(out)
+    if isinstance(out, HiLo8):
+        c_ptr, c_code, ldc, n_out, c8 = L.ptr(out.hi), L.F24, out.hi.stride(0), out.hi.shape[1], L.ptr(out.lo8)
+    else:
+        (c_ptr, c_code, ldc, n_out), c8 = _mat(out), None
     assert n_out == N and out.shape[0] == M
     a2 = (None, None, 0, 0) if A2 is None else (L.ptr(A2.data), L.ptr(A2.q8), A2.data.stride(0), A2.q8.stride(0))
     L.call("gnnlm_linear_f16f8", L.ptr(A1.data), L.ptr(A1.q8), A1.data.stride(0), A1.q8.stride(0), K1, a2[0], a2[1], a2[2], a2[3],
            K2, L.ptr(W_hi), L.ptr(W8), float(w_scale), W_hi.stride(0), W8.stride(0), L.ptr(bias), c_ptr, c_code, ldc, M,
-           _dev_count(m_dev), N, L.stream_ptr(), tag=tag or f"linear_f16f8[{N}x{K1 + K2}]", work=(M, N, K1 + K2))
+           _dev_count(m_dev), N, c8, L.stream_ptr(), tag=tag or f"linear_f16f8[{N}x{K1 + K2}]", work=(M, N, K1 + K2))
     return out
 
 
@@ -244,6 +280,12 @@ def edge_attn(q, k, v, indptr, indices, H, out, *, dst_ids=None, n_dst=None, n_d
     return out
 
 
+def cluster_attn_hq_supported(d: int, H: int, w: int) -> bool:
+    """Shape envelope of gnnlm_hgt_cluster_attn_hq (GNNLM_F24 inputs)."""
+    dk = d // H
+    return d % 128 == 0 and dk % 4 == 0 and dk // 4 <= 32 and 32 % (dk // 4) == 0 and w <= 7
+
+
 def cluster_attn_supported(d: int, H: int, dtype, w: int) -> bool:
     """Shape envelope of gnnlm_hgt_cluster_attn (else use edge_attn over the CSR)."""
     cs = 4 if dtype == torch.float32 else 8
@@ -254,6 +296,13 @@ def cluster_attn_supported(d: int, H: int, dtype, w: int) -> bool:
 def cluster_attn(q, k, v, G, H, out, *, centre_only=False, tag=None):
     """ntgt-intra-ntgt chain attention per (token, neighbour) cluster; G is a TokenGraph."""
     d = k.shape[1]
+    if isinstance(q, HiLo8):       # the 3-byte Q | K' | V' of MATH_F16F8
+        assert isinstance(k, HiLo8) and isinstance(v, HiLo8) and isinstance(out, Split) and G.w <= 7
+        q8p, ldq8 = (None, 0) if out.q8 is None else (L.ptr(out.q8), out.q8.stride(0))
+        L.call("gnnlm_hgt_cluster_attn_hq", L.ptr(q.hi), L.ptr(q.lo8), q.hi.stride(0), L.ptr(k.hi), L.ptr(k.lo8), k.hi.stride(0),
+               L.ptr(v.hi), L.ptr(v.lo8), v.hi.stride(0), L.ptr(G.node_base), L.ptr(G.valid_base), L.ptr(G.cluster_nl), G.T * G.k, G.w,
+               int(centre_only), H, d // H, L.ptr(out.data), out.data.stride(0), q8p, ldq8, int(out.has_lo), L.stream_ptr(), tag=tag)
+        return out
     if isinstance(out, Split) and out.q8 is not None:
         L.call("gnnlm_hgt_cluster_attn_q8", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0),
                L.dtype_code(q.dtype), L.ptr(G.node_base), L.ptr(G.valid_base), L.ptr(G.cluster_nl), G.T * G.k, G.w,

@@ -39,6 +39,10 @@ typedef struct CUstream_st* gnnlm_stream_t; /* == cudaStream_t */
  * operand split) and the producing kernels (PQ decode, GEMM epilogue, LayerNorm, cluster attention) emit it.
  * Leading dimensions of F16X2 buffers are in fp16 elements (>= 2d). */
 #define GNNLM_F16X2 3
+/* An fp32 value rounded to its top three bytes (15 mantissa bits, 2^-16 relative): a 16-bit plane [rows, ld] (bytes 3, 2 of the
+ * value: its bf16 truncation) + a byte plane (byte 1) with the same row stride in elements.  Output of gnnlm_linear_f16f8 / input of
+ * gnnlm_hgt_cluster_attn_hq: the ntgt-side Q | K' | V' of MATH_F16F8 in 3 bytes per element instead of 4, decoded by byte permutes. */
+#define GNNLM_F24 4
 
 /* argument errors */
 #define GNNLM_E_ARG (-1)
@@ -234,7 +238,7 @@ int32_t gnnlm_quant_w8(const void* w_hi, const void* w_lo, int64_t ldw, void* q,
 int32_t gnnlm_linear_f16f8(const void* A1, const void* A1q, int64_t lda1, int64_t ldq1, int64_t K1, const void* A2,
                            const void* A2q, int64_t lda2, int64_t ldq2, int64_t K2, const void* W_hi, const void* W8,
                            float w_scale, int64_t ldw, int64_t ldw8, const float* bias, void* C, int32_t c_dtype, int64_t ldc,
-                           int64_t M, const int32_t* m_dev, int64_t N, gnnlm_stream_t stream);
+                           int64_t M, const int32_t* m_dev, int64_t N, void* C8, gnnlm_stream_t stream);
 
 /* Same contraction, but instead of storing C the epilogue keeps, per row and per column tile,
  * (max, sum exp(x - max)) and the single column `pick[m]` -- the [rows, vocab] tensor of
@@ -328,6 +332,16 @@ int32_t gnnlm_hgt_cluster_attn_q8(const void* q, int64_t ldq, const void* k, int
                                   int32_t dtype, const int32_t* node_base, const int32_t* valid_base,
                                   const int32_t* cluster_nl, int64_t n_clusters, int32_t max_cluster, int32_t centre_only,
                                   int32_t H, int32_t d_k, void* out, int32_t out_dtype, int64_t ldo, void* q8, int64_t ldq8,
+                                  int32_t write_lo, gnnlm_stream_t stream);
+
+/* The same with GNNLM_F24 inputs (the 3-byte form the MATH_F16F8 projection writes: 25 % fewer bytes in and out of HBM than
+ * fp32 Q | K' | V'): q / k / v point at the 16-bit planes (row strides ldq / ldk / ldv in elements), q_lo8 / k_lo8 / v_lo8 at the
+ * byte of the byte planes that belongs to the same element (the planes share the row stride in elements).  Split-fp16 output
+ * (+ e4m3 companion, write_lo) as gnnlm_hgt_cluster_attn_q8.  Clusters of at most 7 nodes; d % 128 == 0. */
+int32_t gnnlm_hgt_cluster_attn_hq(const void* q, const void* q_lo8, int64_t ldq, const void* k, const void* k_lo8, int64_t ldk,
+                                  const void* v, const void* v_lo8, int64_t ldv, const int32_t* node_base,
+                                  const int32_t* valid_base, const int32_t* cluster_nl, int64_t n_clusters, int32_t max_cluster,
+                                  int32_t centre_only, int32_t H, int32_t d_k, void* out, int64_t ldo, void* q8, int64_t ldq8,
                                   int32_t write_lo, gnnlm_stream_t stream);
 
 /* ('tgt','intra','tgt') as implicit causal attention inside each of B blocks of L tokens

@@ -1953,3 +1953,44 @@ def test_training_step_with_dropout_vs_oracle_autograd(NL, cutoff, V, mode, dev)
     assert checked >= 10 * NL
     m.eval()                                                       # eval mode: no masks, the deterministic loss
     assert abs(float(train.train_step_loss(m, sample, mode, seed=seed).detach()) - ref0) < 2e-5 * abs(ref0)
+
+
+def test_f24_projection_output_and_cluster_attention(dev):
+    """GNNLM_F24 (an fp32 value rounded to its top three bytes: 16-bit plane + byte plane): gnnlm_linear_f16f8 writes exactly the
+    rounding of its fp32 output, and gnnlm_hgt_cluster_attn_hq on it equals gnnlm_hgt_cluster_attn on the same values as fp32
+    (all-nodes and centre-only forms, chains of 3 and 5 nodes)."""
+    _need_tc()
+    from gnnlm_b200 import ops
+    from gnnlm_b200.graph import build_token_graph
+    torch.manual_seed(21)
+    d, H, k = 1024, 8, 4
+    for c in (1, 2):
+        nbr = torch.randint(c, 5000 - c, (1, 24, k), dtype=torch.int64)
+        nbr[0, 3, 1] = -1
+        nbr[0, 5, 0] = 0                                    # clipped at the left boundary
+        G = build_token_graph(nbr.to(dev), 5000, c, c)
+        n_ntgt, n_valid = G.counts()
+        x = ops.to_q8(ops.to_split(torch.randn(G.node_cap, d, device=dev)))
+        W = torch.randn(3 * d, d, device=dev) / 32
+        b = torch.randn(3 * d, device=dev)
+        Wh, Wl, sc = ops.split_f16(W)
+        W8 = ops.quant_w8(Wh, Wl)
+        ref = ops.linear_f16f8(x, Wh, W8, b, w_scale=sc, m_dev=G.n_ntgt_dev)
+        hq = ops.linear_f16f8(x, Wh, W8, b, w_scale=sc, m_dev=G.n_ntgt_dev, out_dtype=ops.HILO8)
+        deq = hq.float()
+        want = ((ref[:n_ntgt].view(torch.int32) + 0x80) & ~0xFF).view(torch.float32)       # round at bit 8, keep the top 24 bits
+        assert torch.equal(deq[:n_ntgt], want)
+        assert float(((deq[:n_ntgt] - ref[:n_ntgt]).abs() / ref[:n_ntgt].abs().clamp_min(1e-30)).max()) <= 2 ** -16
+        for centre in (False, True):
+            rows = n_valid if centre else G.node_cap
+            qf = deq[:, :d] if not centre else ops.gather_rows(deq[:, :d].contiguous(), G.inter_indices, n_cap=n_valid)
+            qh = hq[:, :d] if not centre else ops.HiLo8(ops.gather_rows(hq.hi[:, :d].contiguous(), G.inter_indices, n_cap=n_valid),
+                                                        ops.gather_rows(hq.lo8[:, :d].contiguous().view(torch.float16), G.inter_indices,
+                                                                        n_cap=n_valid).view(torch.uint8))
+            o_ref = ops.Split.empty(rows, d, dev, q8=True)
+            o_hq = ops.Split.empty(rows, d, dev, q8=True)
+            ops.cluster_attn(qf, deq[:, d:2 * d], deq[:, 2 * d:], G, H, o_ref, centre_only=centre)
+            ops.cluster_attn(qh, hq[:, d:2 * d], hq[:, 2 * d:], G, H, o_hq, centre_only=centre)
+            n = n_valid if centre else n_ntgt
+            np.testing.assert_allclose(o_hq.float()[:n].cpu().numpy(), o_ref.float()[:n].cpu().numpy(), rtol=2e-6, atol=2e-6)
+            assert torch.equal(o_hq.q8[:n].cpu(), o_ref.q8[:n].cpu()) or (o_hq.q8[:n].cpu() != o_ref.q8[:n].cpu()).float().mean() < 1e-3
