@@ -67,7 +67,8 @@ SIGNATURES = {
     "gnnlm_hgt_cluster_attn_q8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _i64,
                                          _p, _i64, _i32, _p]),
     "gnnlm_hgt_cluster_attn_hq": (_i32, [_p, _p, _i64, _p, _p, _i64, _p, _p, _i64, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _i64, _p, _i64,
-                                         _i32, _p]),
+                                         _i32, _p, _p, _p, _p, _p, _p]),
+    "gnnlm_rowstats_q8": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _f32, _p, _i64, _p, _i64, _p, _i64, _p, _i64, _p]),
     "gnnlm_hgt_causal_attn": (_i32, [_p, _i64, _p, _i64, _p, _i64, _i32, _i64, _i64, _i64, _i32, _i32, _p, _i64, _f32, _i32, _p]),
     "gnnlm_hgt_causal_flash": (_i32, [_p, _i64, _p, _p, _i64, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p, _i64, _i64, _f32, _i32, _p]),
     "gnnlm_hgt_causal_flash_tc": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i64, _p, _i64, _i64, _f32, _i32, _p]),

@@ -115,7 +115,12 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
                                                                   int group, int n_slices,
                                                                   OutT* __restrict__ out, int64_t ldo, int lo_off,
                                                                   uint8_t* __restrict__ q8, int64_t ldq8, bool write_lo,
-                                                                  int64_t q_bias = 0, int64_t k_bias = 0, int64_t v_bias = 0) {
+                                                                  int64_t q_bias = 0, int64_t k_bias = 0, int64_t v_bias = 0,
+                                                                  const float2* __restrict__ kv_stats = nullptr,
+                                                                  const float* __restrict__ k_c = nullptr,
+                                                                  const float* __restrict__ k_b = nullptr,
+                                                                  const float* __restrict__ v_c = nullptr,
+                                                                  const float* __restrict__ v_b = nullptr) {
   constexpr bool centre_only = WMAX == 0;
   auto ld_row = [](const T* __restrict__ p, int64_t bias, float (&r)[C]) {
     if constexpr (HQ) load_row_f24(p, bias, r);
@@ -175,11 +180,52 @@ __global__ void __launch_bounds__(CA_THREADS) cluster_attn_kernel(const T* __res
       ld_row(v + idl * ldv + col, v_bias, vv[0]);
       ld_row(k + idr * ldk + col, k_bias, kk[2]);
       ld_row(v + idr * ldv + col, v_bias, vv[2]);
-      const float s1 = group_dot<C, GROUP>(qq, kk[1], group);
-      const float s0 = group_dot<C, GROUP>(qq, kk[0], group);
-      const float s2 = group_dot<C, GROUP>(qq, kk[2], group);
       float r[C];
-      chain_mix<C>(s0, s1, s2, has_l, has_r, vv[0], vv[1], vv[2], r);
+      bool done = false;
+      if constexpr (HQ) {
+        // deferred LayerNorm of the previous layer (rowops.cu rowstats_q8_kernel): the rows are RAW products z' W~^T and the K' / V'
+        // of node m are rs_m (raw_m - mean_m c) + b with per-column vectors (c, b) and per-node statistics (mean_m, rs_m).  Applied
+        // without touching the rows: <q, K'_m> = rs_m <q, k_raw_m> + <q, k_b> - mean_m rs_m <q, k_c>, and
+        // sum_m w_m V'_m = sum_m (w_m rs_m) v_raw_m + v_b - v_c sum_m w_m mean_m rs_m   (the weights sum to one).
+        if (kv_stats) {
+          float2 st[3];
+          st[0] = __ldg(kv_stats + idl);
+          st[1] = __ldg(kv_stats + base);
+          st[2] = __ldg(kv_stats + idr);
+          float tmp[C];
+          load_f32<C>(k_b + col, tmp);
+          const float qb = group_dot<C, GROUP>(qq, tmp, group);
+          load_f32<C>(k_c + col, tmp);
+          const float qc = group_dot<C, GROUP>(qq, tmp, group);
+          float sc[3], wm[3];
+#pragma unroll
+          for (int p = 0; p < 3; ++p) sc[p] = fmaf(st[p].y, group_dot<C, GROUP>(qq, kk[p], group), qb - st[p].x * st[p].y * qc);
+          if (!has_l) sc[0] = -INFINITY;
+          if (!has_r) sc[2] = -INFINITY;
+          const float mx = fmaxf(sc[1], fmaxf(sc[0], sc[2]));
+          const float e0 = __expf(sc[0] - mx), e1 = __expf(sc[1] - mx), e2 = __expf(sc[2] - mx);
+          const float inv = __fdividef(1.f, e0 + e1 + e2);
+          wm[0] = e0 * inv * st[0].y; wm[1] = e1 * inv * st[1].y; wm[2] = e2 * inv * st[2].y;      // w_m rs_m (0 for a missing side)
+          const float shift = wm[0] * st[0].x + wm[1] * st[1].x + wm[2] * st[2].x;               // sum_m w_m rs_m mean_m
+          float vb[C];
+          load_f32<C>(v_c + col, tmp);
+          load_f32<C>(v_b + col, vb);
+#pragma unroll
+          for (int cc = 0; cc < C; ++cc) {
+            float a = fmaf(wm[1], vv[1][cc], fmaf(-shift, tmp[cc], vb[cc]));
+            if (has_l) a = fmaf(wm[0], vv[0][cc], a);
+            if (has_r) a = fmaf(wm[2], vv[2][cc], a);
+            r[cc] = a;
+          }
+          done = true;
+        }
+      }
+      if (!done) {
+        const float s1 = group_dot<C, GROUP>(qq, kk[1], group);
+        const float s0 = group_dot<C, GROUP>(qq, kk[0], group);
+        const float s2 = group_dot<C, GROUP>(qq, kk[2], group);
+        chain_mix<C>(s0, s1, s2, has_l, has_r, vv[0], vv[1], vv[2], r);
+      }
       store_out<OutT, C>(out + ci * ldo + col, r, lo_off, q8 ? q8 + ci * ldq8 + col : nullptr, write_lo);
     }
   }
@@ -296,13 +342,14 @@ template <int GROUP>
 static int32_t launch_hq(int wmax, const __half* q, int64_t ldq, const __half* k, int64_t ldk, const __half* v, int64_t ldv, int64_t qb,
                          int64_t kb, int64_t vb, const int32_t* node_base, const int32_t* valid_base, const int32_t* cluster_nl,
                          int64_t n_clusters, int centre_only, int group, int n_slices, __half* out, int64_t ldo, int lo_off,
-                         uint8_t* q8, int64_t ldq8, bool write_lo, cudaStream_t st) {
+                         uint8_t* q8, int64_t ldq8, bool write_lo, const float2* kv_stats, const float* k_c, const float* k_b,
+                         const float* v_c, const float* v_b, cudaStream_t st) {
   int64_t blocks = ceil_div(n_clusters * n_slices, CA_THREADS / 32);
   if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
 #define GNNLM_CLH(W)                                                                                                               \
   cluster_attn_kernel<__half, __half, 4, W, GROUP, true><<<(unsigned)blocks, CA_THREADS, 0, st>>>(                                 \
       q, ldq, k, ldk, v, ldv, node_base, valid_base, cluster_nl, n_clusters, group, n_slices, out, ldo, lo_off, q8, ldq8, write_lo, \
-      qb, kb, vb)
+      qb, kb, vb, kv_stats, k_c, k_b, v_c, v_b)
   if (centre_only) GNNLM_CLH(0);
   else if (wmax <= 1) GNNLM_CLH(1);
   else if (wmax <= 3) GNNLM_CLH(3);
@@ -321,13 +368,17 @@ extern "C" int32_t gnnlm_hgt_cluster_attn_hq(const void* q, const void* q_lo8, i
                                              const void* v, const void* v_lo8, int64_t ldv, const int32_t* node_base,
                                              const int32_t* valid_base, const int32_t* cluster_nl, int64_t n_clusters,
                                              int32_t max_cluster, int32_t centre_only, int32_t H, int32_t d_k, void* out, int64_t ldo,
-                                             void* q8v, int64_t ldq8, int32_t write_lo, gnnlm_stream_t stream) {
+                                             void* q8v, int64_t ldq8, int32_t write_lo, const float* kv_stats, const float* k_c,
+                                             const float* k_b, const float* v_c, const float* v_b, gnnlm_stream_t stream) {
   uint8_t* q8 = reinterpret_cast<uint8_t*>(q8v);
   GNNLM_CHECK_ARG(q && k && v && q_lo8 && k_lo8 && v_lo8 && node_base && cluster_nl && out, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn_hq: null pointer");
   GNNLM_CHECK_ARG(!centre_only || valid_base, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn_hq: centre_only needs valid_base");
   GNNLM_CHECK_ARG(write_lo || q8, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn_hq: write_lo = 0 (hi + companion only) needs q8");
   GNNLM_CHECK_ARG(H > 0 && d_k > 0 && max_cluster >= 1 && max_cluster <= 7, GNNLM_E_UNSUPPORTED,
                   "gnnlm_hgt_cluster_attn_hq: clusters of at most 7 nodes");
+  GNNLM_CHECK_ARG(!kv_stats || (centre_only && k_c && k_b && v_c && v_b && (uintptr_t)kv_stats % 8 == 0 && (uintptr_t)k_c % 16 == 0 &&
+                                (uintptr_t)k_b % 16 == 0 && (uintptr_t)v_c % 16 == 0 && (uintptr_t)v_b % 16 == 0),
+                  GNNLM_E_ARG, "gnnlm_hgt_cluster_attn_hq: the deferred-LayerNorm affine needs the centre-only form and its four vectors");
   const int64_t d = (int64_t)H * d_k;
   GNNLM_CHECK_ARG(d % 128 == 0 && d_k % 4 == 0 && d_k / 4 <= 32 && 32 % (d_k / 4) == 0, GNNLM_E_UNSUPPORTED,
                   "gnnlm_hgt_cluster_attn_hq: unsupported (H=%d, d_k=%d)", H, d_k);
@@ -344,7 +395,7 @@ extern "C" int32_t gnnlm_hgt_cluster_attn_hq(const void* q, const void* q_lo8, i
 #define GNNLM_HQ(G)                                                                                                                \
   return launch_hq<G>(max_cluster, (const __half*)q, ldq, (const __half*)k, ldk, (const __half*)v, ldv, qb, kb, vb, node_base,     \
                       valid_base, cluster_nl, n_clusters, centre_only, group, n_slices, (__half*)out, ldo, (int)d, q8, ldq8,       \
-                      write_lo != 0, st)
+                      write_lo != 0, reinterpret_cast<const float2*>(kv_stats), k_c, k_b, v_c, v_b, st)
   if (group == 32) GNNLM_HQ(32);
   if (group == 16) GNNLM_HQ(16);
   GNNLM_HQ(0);

@@ -4,6 +4,8 @@
 // All are HBM-bound streaming kernels: vectorised 16 B accesses, one warp per row.
 #include <type_traits>
 
+#include <cuda_fp8.h>
+
 #include "common.cuh"
 
 namespace gnnlm {
@@ -167,6 +169,64 @@ __global__ void __launch_bounds__(256, 4) layernorm_vec_kernel(const float* __re
         u.y = *reinterpret_cast<uint32_t*>(&c);
         reinterpret_cast<uint2*>(y + i * ldy)[lane + 32 * j] = u;
       }
+    }
+  }
+}
+
+// Deferred LayerNorm (HGT layer 0 with the OPQ rotation folded, hgt.py:401-405): z' = o + x is the pre-norm sum in the UN-rotated
+// basis (z = z' rot^T is what the reference normalises; rot orthonormal).  The statistics of z follow from z':
+// mean(z) = <z', u> with u = rot^T 1 / d, var(z) = |z' - mean d u|^2 / d.  This kernel writes z' as a gnnlm_linear_f16f8 operand
+// (fp16 hi + e4m3 companion) and (mean, 1 / sqrt(var + eps)) per row; the consumers apply the normalisation as a per-row affine
+// (the next layer's K' / V': inside gnnlm_hgt_cluster_attn_hq), so neither the rotation of the residual nor the normalised rows of
+// the non-centre nodes are ever materialised.  x: fp16 hi [rows, d] + e4m3 companion [rows, hi8 | lo8] (value = hi + lo8 / 2^10).
+template <int NV>
+__global__ void __launch_bounds__(256, 3) rowstats_q8_kernel(const float* __restrict__ o, int64_t ldo, const __half* __restrict__ x_hi,
+                                                             int64_t ldxh, const uint8_t* __restrict__ x_q8, int64_t ldxq,
+                                                             const float* __restrict__ u, float eps, __half* __restrict__ y, int64_t ldy,
+                                                             uint8_t* __restrict__ q8, int64_t ldq, float2* __restrict__ stats,
+                                                             int64_t n_cap, const int32_t* __restrict__ n_dev) {
+  const int64_t n = live_rows(n_cap, n_dev);
+  const int lane = threadIdx.x & 31;
+  constexpr int d = NV * 128;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float4* u4 = reinterpret_cast<const float4*>(u) + lane;          // re-read per pass (L1 hits): keeping u in registers spilled
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+    float4 r[NV];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      r[j] = reinterpret_cast<const float4*>(o + i * ldo)[lane + 32 * j];
+      const uint2 h = __ldg(reinterpret_cast<const uint2*>(x_hi + i * ldxh) + lane + 32 * j);
+      const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(x_q8 + i * ldxq + d) + lane + 32 * j);
+      const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&h.x)), h1 = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
+      const __half2_raw l0r = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(l & 0xffff), __NV_E4M3);
+      const __half2_raw l1r = __nv_cvt_fp8x2_to_halfraw2((__nv_fp8x2_storage_t)(l >> 16), __NV_E4M3);
+      const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&l0r)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&l1r));
+      r[j].x += fmaf(l0.x, 1.f / 1024.f, h0.x); r[j].y += fmaf(l0.y, 1.f / 1024.f, h0.y);
+      r[j].z += fmaf(l1.x, 1.f / 1024.f, h1.x); r[j].w += fmaf(l1.y, 1.f / 1024.f, h1.y);
+      const float4 uj = __ldg(u4 + 32 * j);
+      dot += r[j].x * uj.x + r[j].y * uj.y + r[j].z * uj.z + r[j].w * uj.w;
+    }
+    const float mean = warp_sum(dot);
+    const float md = mean * d;
+    float vs = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float4 uj = __ldg(u4 + 32 * j);
+      const float a = r[j].x - md * uj.x, b = r[j].y - md * uj.y, c = r[j].z - md * uj.z, e = r[j].w - md * uj.w;
+      vs += a * a + b * b + c * c + e * e;
+    }
+    const float rstd = rsqrtf(warp_sum(vs) * (1.f / d) + eps);
+    if (lane == 0) stats[i] = make_float2(mean, rstd);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      uint2 hi, lo;
+      split4_f16(r[j].x, r[j].y, r[j].z, r[j].w, hi, lo);
+      reinterpret_cast<uint2*>(y + i * ldy)[lane + 32 * j] = hi;
+      uint32_t h8, l8;
+      q8_from_split4(hi, lo, h8, l8);
+      reinterpret_cast<uint32_t*>(q8 + i * ldq)[lane + 32 * j] = h8;
+      reinterpret_cast<uint32_t*>(q8 + i * ldq + d)[lane + 32 * j] = l8;
     }
   }
 }
@@ -368,6 +428,30 @@ extern "C" int32_t gnnlm_layernorm_q8(const float* x, int64_t ldx, const void* r
     layernorm_kernel<__nv_bfloat16><<<g, 256, 0, st>>>(x, ldx, res, res_mode, ldres, gamma, beta, eps, (__nv_bfloat16*)y, ldy, n_cap, n_dev, d);
 #undef LN_VEC
   GNNLM_LAUNCH_CHECK("gnnlm_layernorm");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_rowstats_q8(const float* o, int64_t ldo, const void* x_hi, int64_t ldxh, const void* x_q8, int64_t ldxq,
+                                     const float* u, float eps, void* y_hi, int64_t ldy, void* y_q8, int64_t ldq, float* stats,
+                                     int64_t n_cap, const int32_t* n_dev, int64_t d, gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(o && x_hi && x_q8 && u && y_hi && y_q8 && stats, GNNLM_E_ARG, "gnnlm_rowstats_q8: null pointer");
+  GNNLM_CHECK_ARG(d == 128 || d == 256 || d == 512 || d == 1024, GNNLM_E_UNSUPPORTED, "gnnlm_rowstats_q8: d in {128, 256, 512, 1024}");
+  GNNLM_CHECK_ARG(ldo % 4 == 0 && ldo >= d && ldxh % 4 == 0 && ldxh >= d && ldxq % 4 == 0 && ldxq >= 2 * d && ldy % 4 == 0 && ldy >= d &&
+                      ldq % 4 == 0 && ldq >= 2 * d && (uintptr_t)o % 16 == 0 && (uintptr_t)x_hi % 8 == 0 && (uintptr_t)x_q8 % 4 == 0 &&
+                      (uintptr_t)u % 16 == 0 && (uintptr_t)y_hi % 8 == 0 && (uintptr_t)y_q8 % 4 == 0 && (uintptr_t)stats % 8 == 0,
+                  GNNLM_E_SHAPE, "gnnlm_rowstats_q8: alignment / leading dimensions");
+  if (n_cap == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned g = grid_for(n_cap, 8);
+#define RS_VEC(NV)                                                                                                                \
+  rowstats_q8_kernel<NV><<<g, 256, 0, st>>>(o, ldo, (const __half*)x_hi, ldxh, (const uint8_t*)x_q8, ldxq, u, eps, (__half*)y_hi, ldy, \
+                                           (uint8_t*)y_q8, ldq, reinterpret_cast<float2*>(stats), n_cap, n_dev)
+  if (d == 1024) RS_VEC(8);
+  else if (d == 512) RS_VEC(4);
+  else if (d == 256) RS_VEC(2);
+  else RS_VEC(1);
+#undef RS_VEC
+  GNNLM_LAUNCH_CHECK("gnnlm_rowstats_q8");
   return 0;
 }
 

@@ -190,15 +190,20 @@ class HGTLayer(nn.Module):
         self.use_flash_tc = os.environ.get("GNNLM_FLASH", "1") != "mma"      # d_k = 128: the tcgen05 form (GNNLM_FLASH=mma: mma.sync form)
         # MATH_F16F8: Q | K' | V' of the ntgt side rounded to three bytes (GNNLM_F24) instead of fp32 (GNNLM_HQ=0: fp32, for A/B)
         self.use_hq_attention = {"0": False, "all": "all"}.get(os.environ.get("GNNLM_HQ", "1"), True)
+        # layer 0 with the rotation folded, followed by the centre-only layer: LayerNorm deferred into its consumers (HGT._ntgt_side)
+        self.use_deferred_ln = os.environ.get("GNNLM_DEFER_LN", "1") != "0"
 
     # ------------------------------------------------------------------ weight preparation
-    def prepare(self, math_mode: int, rot: Optional[torch.Tensor] = None):
+    def prepare(self, math_mode: int, rot: Optional[torch.Tensor] = None, prev_ln=None):
         """`rot` [d, d_dec] (layer 0, MATH_F16F8): the ntgt input features are given UN-rotated, h = x @ rot^T (the OPQ inverse
         rotation `x @ A` of pq_wrapper.py:202, rot = A^T), and the rotation is folded into this layer's ntgt-side weights in
         fp64 -- Q|K'|V' = x (W rot)^T, the inter K' / V' likewise, and the residual of hgt.py:403 inside the output projection:
         A-linear(t) + h = [t | x] [W_a | rot]^T -- so the rotated features are never materialised."""
+        # `prev_ln` = (gamma, beta, rot) of the PREVIOUS layer when that layer defers its ntgt LayerNorm (HGT._prepare_layers): this
+        # layer's ntgt K' | V' projection is then prepared for the un-normalised, un-rotated input z' as well ("kv_deferred")
         key = (math_mode, self.relation_pri.device, tuple(int(p._version) for p in self.parameters()),
-               None if rot is None else (rot.data_ptr(), int(rot._version)))
+               None if rot is None else (rot.data_ptr(), int(rot._version)),
+               None if prev_ln is None else tuple((t.data_ptr(), int(t._version)) for t in prev_ln))
         if self._prep is not None and self._prep_key == key:
             return self._prep
         if not self.use_norm:
@@ -244,6 +249,25 @@ class HGTLayer(nn.Module):
             "a_rot": None if rot is None else _Weight(torch.cat([self.a_linears[n].weight.detach().float(), rot.detach().float()], 1),
                                                       self.a_linears[n].bias.detach(), math_mode),
         }
+        if rot is not None and self.use_deferred_ln and math_mode == L.MATH_F16F8 and rot.shape[0] == rot.shape[1]:
+            r64 = rot.detach().double()
+            eye = torch.eye(r64.shape[0], dtype=r64.dtype, device=r64.device)
+            if torch.allclose(r64.T @ r64, eye, atol=1e-5) and torch.allclose(r64 @ r64.T, eye, atol=1e-5):     # orthonormal rotation
+                Wa, ba = self.a_linears[n].weight.detach().double(), self.a_linears[n].bias.detach().double()
+                P["defer"] = {
+                    "a": _Weight((r64.T @ Wa).float(), (ba @ r64).float(), math_mode),        # z' = t (rot^T W_a)^T + b_a rot (+ x)
+                    "u": (r64.sum(0) / r64.shape[0]).float().contiguous(),                      # mean(z) = <z', rot^T 1 / d>
+                    "rot": _Weight(rot.detach().float(), None, math_mode),                      # z = z' rot^T
+                }
+        if prev_ln is not None and math_mode == L.MATH_F16F8:
+            g64, b64, r64 = (t.detach().double() for t in prev_ln)
+            Wk, bk, Wv, bv = kv(n, intra)
+            W = torch.cat([Wk, Wv], 0).double()
+            bias = torch.cat([bk, bv], 0).double()
+            c = (W @ g64).float()
+            bt = (W @ b64 + bias).float()
+            P["kv_deferred"] = {"w": _Weight(((W * g64[None, :]) @ r64).float(), None, math_mode),   # raw = z' (W diag(gamma) rot)^T
+                                "k_c": c[:d].contiguous(), "k_b": bt[:d].contiguous(), "v_c": c[d:].contiguous(), "v_b": bt[d:].contiguous()}
         self._prep, self._prep_key = P, key
         return P
 
@@ -272,15 +296,16 @@ class HGTLayer(nn.Module):
         return ((centre or self.use_hq_attention == "all") and bool(self.use_hq_attention) and isinstance(h_n, ops.Split)
                 and self.use_cluster_kernel and not G.dedup and ops.cluster_attn_hq_supported(d, H, G.w) and ops.f16f8_supported(d))
 
-    def _nn_attn(self, P, G, q, k, v, rows, *, centre: bool, n_dev, c_dev):
+    def _nn_attn(self, P, G, q, k, v, rows, *, centre: bool, n_dev, c_dev, kv_affine=None):
         """ntgt-intra-ntgt attention -> [rows, d] in the activation dtype."""
         d, H = P["d"], self.n_heads
         act = act_dtype(P["math"])
         tag = "nn_centre" if centre else "nn_full"
         if isinstance(q, ops.HiLo8) or (self.use_cluster_kernel and not G.dedup and ops.cluster_attn_supported(d, H, q.dtype, G.w)):
             t_agg = ops.empty_act(rows, d, gemm_act(P["math"], rows, d, lo=False), q.device)   # feeds the A-linear and nothing else
-            ops.cluster_attn(q, k, v, G, H, t_agg, centre_only=centre, tag=tag)
+            ops.cluster_attn(q, k, v, G, H, t_agg, centre_only=centre, tag=tag, kv_affine=kv_affine)
             return t_agg
+        assert kv_affine is None
         t_agg = torch.empty((rows, d), device=q.device, dtype=torch.float32)
         if centre:
             ops.edge_attn(q, k, v, G.nn_indptr, G.nn_indices, H, t_agg, dst_ids=G.inter_indices, n_dst_dev=c_dev, tag=tag)
@@ -296,13 +321,40 @@ class HGTLayer(nn.Module):
                               c_dev=None)
         return self._out(P, P["n"], t_agg, h_n, n_dev, feeds_gemm=True)        # h of the next layer: a GEMM operand
 
-    def ntgt_centre(self, P, G: TokenGraph, h_n, n_dev, hc, c_dev):
-        """Centre nodes only (compact rows): K'|V' for every node, Q / A-linear / LN for centres."""
+    def ntgt_full_deferred(self, P, G: TokenGraph, x_n, n_dev):
+        """ntgt_full of layer 0 with the rotation folded and the LayerNorm DEFERRED: returns (z', stats) -- the pre-norm sum in the
+        un-rotated basis as a GEMM operand and (mean, 1 / std) of its rotation per node (ops.rowstats_q8) -- instead of h1.  The
+        residual x is added un-rotated (z' = A-linear(t) rot + x), which halves the output projection (K = d instead of 2 d)."""
+        d, D = P["d"], P["defer"]
+        qkv = _lin(with_q8(x_n, P["math"], n_dev), P["ntgt_qkv"], P["math"], m_dev=n_dev, out_dtype=_attn_in_dtype(P["math"], self._hq(G, x_n, centre=False)))
+        t_agg = self._nn_attn(P, G, qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], x_n.shape[0], centre=False, n_dev=n_dev, c_dev=None)
+        o = _lin(with_q8(t_agg, P["math"], n_dev), D["a"], P["math"], m_dev=n_dev)
+        return ops.rowstats_q8(o, x_n, D["u"], P["ln"][P["n"]][2], n_dev)
+
+    def deferred_centres(self, P, G: TokenGraph, z, n_dev, c_dev):
+        """h1 of the centre nodes from the deferred sum: LayerNorm(z'_c rot^T) -- what the inter edges and the next layer's Q /
+        residual read (compact rows)."""
+        zc = ops.gather_rows(z, G.inter_indices, n_dev=c_dev)
+        o = _lin(zc, P["defer"]["rot"], P["math"], m_dev=c_dev)
+        g, b, eps = P["ln"][P["n"]]
+        return ops.layernorm(o, g, b, eps, out_dtype=gemm_act(P["math"], o.shape[0], o.shape[1]), n_dev=c_dev)
+
+    def ntgt_centre(self, P, G: TokenGraph, h_n, n_dev, hc, c_dev, deferred=None):
+        """Centre nodes only (compact rows): K'|V' for every node, Q / A-linear / LN for centres.  `deferred` = stats of
+        ntgt_full_deferred: h_n is then the un-normalised z' and K' | V' are its raw products, normalised inside the attention
+        kernel (P["kv_deferred"])."""
         d = P["d"]
         act = _attn_in_dtype(P["math"], self._hq(G, h_n, centre=True))
-        kv = _lin(with_q8(h_n, P["math"], n_dev), P["ntgt_qkv"].rows(d, 3 * d), P["math"], m_dev=n_dev, out_dtype=act)
+        kv_affine = None
+        if deferred is not None:
+            KD = P["kv_deferred"]
+            assert act == ops.HILO8
+            kv = _lin(h_n, KD["w"], P["math"], m_dev=n_dev, out_dtype=act)
+            kv_affine = (deferred, KD["k_c"], KD["k_b"], KD["v_c"], KD["v_b"])
+        else:
+            kv = _lin(with_q8(h_n, P["math"], n_dev), P["ntgt_qkv"].rows(d, 3 * d), P["math"], m_dev=n_dev, out_dtype=act)
         qc = _lin(with_q8(hc, P["math"], c_dev), P["ntgt_qkv"].rows(0, d), P["math"], m_dev=c_dev, out_dtype=act)
-        t_agg = self._nn_attn(P, G, qc, kv[:, :d], kv[:, d:], hc.shape[0], centre=True, n_dev=n_dev, c_dev=c_dev)
+        t_agg = self._nn_attn(P, G, qc, kv[:, :d], kv[:, d:], hc.shape[0], centre=True, n_dev=n_dev, c_dev=c_dev, kv_affine=kv_affine)
         return self._out(P, P["n"], t_agg, hc, c_dev)
 
     def tgt(self, P, G: TokenGraph, h_t, hc, c_dev, chunks=None):
@@ -472,7 +524,14 @@ class HGT(nn.Module):
     def _prepare_layers(self, rot=None):
         """`rot`: ntgt input features (h_ntgt / hc0 and whatever `decode` returns) are un-rotated; folded into layer 0."""
         assert rot is None or self.can_fold_rotation(rot.shape[1])
-        return [layer.prepare(self.math_mode, rot if l == 0 else None) for l, layer in enumerate(self.gcs)]
+        prep = []
+        for l, layer in enumerate(self.gcs):
+            prev_ln = None
+            if l == 1 and rot is not None and self.n_layers == 3 and "defer" in prep[0]:      # layer 0 may defer its ntgt LayerNorm
+                n = self.gcs[0].ntype2idx["ntgt"]
+                prev_ln = (self.gcs[0].norms[n].weight, self.gcs[0].norms[n].bias, rot)
+            prep.append(layer.prepare(self.math_mode, rot if l == 0 else None, prev_ln))
+        return prep
 
     def _ntgt_side(self, prep, G: TokenGraph, h_ntgt, hc0=None) -> List:
         """All layers of the ntgt side of one (chunk) graph -> compact centre features entering each layer."""
@@ -489,6 +548,13 @@ class HGT(nn.Module):
             hc0 = ops.gather_rows(h_ntgt, G.inter_indices, n_dev=c_dev)
         hc.append(hc0)
         h_n = h_ntgt
+        if (NL == 3 and "defer" in prep[0] and "kv_deferred" in prep[1] and isinstance(h_n, ops.Split) and h_n.q8 is not None
+                and self.gcs[1]._hq(G, h_n, centre=True)):
+            # layer 0's LayerNorm deferred into its consumers: no rotation of the residual, no normalised non-centre rows
+            z, stats = self.gcs[0].ntgt_full_deferred(prep[0], G, h_n, n_dev)
+            hc.append(self.gcs[0].deferred_centres(prep[0], G, z, n_dev, c_dev))
+            hc.append(self.gcs[1].ntgt_centre(prep[1], G, z, n_dev, hc[1], c_dev, deferred=stats))
+            return hc
         for l in range(NL - 1):
             if l < NL - 2:
                 h_n = self.gcs[l].ntgt_full(prep[l], G, h_n, n_dev)

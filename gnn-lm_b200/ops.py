@@ -293,16 +293,32 @@ def cluster_attn_supported(d: int, H: int, dtype, w: int) -> bool:
     return d % (32 * cs) == 0 and dk % cs == 0 and dk // cs <= 32 and 32 % (dk // cs) == 0       # any H
 
 
-def cluster_attn(q, k, v, G, H, out, *, centre_only=False, tag=None):
-    """ntgt-intra-ntgt chain attention per (token, neighbour) cluster; G is a TokenGraph."""
+def rowstats_q8(o: torch.Tensor, x: "Split", u: torch.Tensor, eps: float, n_dev=None):
+    """Deferred LayerNorm (gnnlm_rowstats_q8): z' = o + x as fp16 hi + e4m3 companion and (mean, 1 / std) per row of the ROTATED sum.
+    o fp32 [rows, d]; x: hi + companion (Split without a lo half or with one); u fp32 [d] = rot^T 1 / d."""
+    rows, d = o.shape
+    assert x.q8 is not None and x.shape == (rows, d) and u.shape == (d,)
+    z = Split.empty(rows, d, o.device, q8=True, lo=False)
+    stats = torch.empty((rows, 2), device=o.device, dtype=torch.float32)
+    L.call("gnnlm_rowstats_q8", L.ptr(o), o.stride(0), L.ptr(x.data), x.data.stride(0), L.ptr(x.q8), x.q8.stride(0), L.ptr(u), float(eps),
+           L.ptr(z.data), z.data.stride(0), L.ptr(z.q8), z.q8.stride(0), L.ptr(stats), rows, _dev_count(n_dev), d, L.stream_ptr(),
+           tag="rowstats")
+    return z, stats
+
+
+def cluster_attn(q, k, v, G, H, out, *, centre_only=False, tag=None, kv_affine=None):
+    """ntgt-intra-ntgt chain attention per (token, neighbour) cluster; G is a TokenGraph.  kv_affine = (stats, k_c, k_b, v_c, v_b):
+    k / v are raw products under a deferred LayerNorm (rowstats_q8) -- GNNLM_F24 inputs, centre-only form."""
     d = k.shape[1]
     if isinstance(q, HiLo8):       # the 3-byte Q | K' | V' of MATH_F16F8
         assert isinstance(k, HiLo8) and isinstance(v, HiLo8) and isinstance(out, Split) and G.w <= 7
         q8p, ldq8 = (None, 0) if out.q8 is None else (L.ptr(out.q8), out.q8.stride(0))
         L.call("gnnlm_hgt_cluster_attn_hq", L.ptr(q.hi), L.ptr(q.lo8), q.hi.stride(0), L.ptr(k.hi), L.ptr(k.lo8), k.hi.stride(0),
                L.ptr(v.hi), L.ptr(v.lo8), v.hi.stride(0), L.ptr(G.node_base), L.ptr(G.valid_base), L.ptr(G.cluster_nl), G.T * G.k, G.w,
-               int(centre_only), H, d // H, L.ptr(out.data), out.data.stride(0), q8p, ldq8, int(out.has_lo), L.stream_ptr(), tag=tag)
+               int(centre_only), H, d // H, L.ptr(out.data), out.data.stride(0), q8p, ldq8, int(out.has_lo),
+               *([None] * 5 if kv_affine is None else [L.ptr(t) for t in kv_affine]), L.stream_ptr(), tag=tag)
         return out
+    assert kv_affine is None
     if isinstance(out, Split) and out.q8 is not None:
         L.call("gnnlm_hgt_cluster_attn_q8", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0),
                L.dtype_code(q.dtype), L.ptr(G.node_base), L.ptr(G.valid_base), L.ptr(G.cluster_nl), G.T * G.k, G.w,

@@ -337,12 +337,26 @@ int32_t gnnlm_hgt_cluster_attn_q8(const void* q, int64_t ldq, const void* k, int
 /* The same with GNNLM_F24 inputs (the 3-byte form the MATH_F16F8 projection writes: 25 % fewer bytes in and out of HBM than
  * fp32 Q | K' | V'): q / k / v point at the 16-bit planes (row strides ldq / ldk / ldv in elements), q_lo8 / k_lo8 / v_lo8 at the
  * byte of the byte planes that belongs to the same element (the planes share the row stride in elements).  Split-fp16 output
- * (+ e4m3 companion, write_lo) as gnnlm_hgt_cluster_attn_q8.  Clusters of at most 7 nodes; d % 128 == 0. */
+ * (+ e4m3 companion, write_lo) as gnnlm_hgt_cluster_attn_q8.  Clusters of at most 7 nodes; d % 128 == 0.
+ *  kv_stats (nullable, centre-only form): the k / v rows are RAW products of a deferred LayerNorm (gnnlm_rowstats_q8): K'[m] =
+ *  rs_m (k_raw[m] - mean_m k_c) + k_b, V' likewise, with kv_stats [n_ntgt] = (mean, rs) per node and per-column vectors [H*d_k]. */
 int32_t gnnlm_hgt_cluster_attn_hq(const void* q, const void* q_lo8, int64_t ldq, const void* k, const void* k_lo8, int64_t ldk,
                                   const void* v, const void* v_lo8, int64_t ldv, const int32_t* node_base,
                                   const int32_t* valid_base, const int32_t* cluster_nl, int64_t n_clusters, int32_t max_cluster,
                                   int32_t centre_only, int32_t H, int32_t d_k, void* out, int64_t ldo, void* q8, int64_t ldq8,
-                                  int32_t write_lo, gnnlm_stream_t stream);
+                                  int32_t write_lo, const float* kv_stats, const float* k_c, const float* k_b, const float* v_c,
+                                  const float* v_b, gnnlm_stream_t stream);
+
+/* Deferred LayerNorm of HGT layer 0 when the OPQ rotation is folded (hgt.py:401-405 with h = x rot^T, rot orthonormal): the
+ * pre-norm sum is kept in the UN-rotated basis, z' = o + x (o = A-linear(t) rot, a K = d product; x the decoded features as fp16 hi
+ * [rows, d] + e4m3 companion [rows, hi8 | lo8]), and the statistics of the rotated sum z = z' rot^T follow from z' alone:
+ * mean = <z', u> with u = rot^T 1 / d, var = |z' - mean d u|^2 / d.  Writes z' as a gnnlm_linear_f16f8 operand (y_hi fp16 [rows, d],
+ * y_q8 [rows, hi8 | lo8]) and stats [rows] = (mean, 1 / sqrt(var + eps)).  The consumers apply the normalisation as a per-row
+ * affine, so the residual is never rotated (half of the output projection's flops) and the normalised rows of the non-centre nodes
+ * are never materialised. */
+int32_t gnnlm_rowstats_q8(const float* o, int64_t ldo, const void* x_hi, int64_t ldxh, const void* x_q8, int64_t ldxq, const float* u,
+                          float eps, void* y_hi, int64_t ldy, void* y_q8, int64_t ldq, float* stats, int64_t n_cap,
+                          const int32_t* n_dev, int64_t d, gnnlm_stream_t stream);
 
 /* ('tgt','intra','tgt') as implicit causal attention inside each of B blocks of L tokens
  * (edges u -> v for u <= v, v - u < intra_ctx when intra_ctx > 0; token_block_dataset.py:586-594). */

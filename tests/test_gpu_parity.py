@@ -1994,3 +1994,43 @@ def test_f24_projection_output_and_cluster_attention(dev):
             n = n_valid if centre else n_ntgt
             np.testing.assert_allclose(o_hq.float()[:n].cpu().numpy(), o_ref.float()[:n].cpu().numpy(), rtol=2e-6, atol=2e-6)
             assert torch.equal(o_hq.q8[:n].cpu(), o_ref.q8[:n].cpu()) or (o_hq.q8[:n].cpu() != o_ref.q8[:n].cpu()).float().mean() < 1e-3
+
+
+def test_deferred_layernorm_path(dev):
+    """Layer 0's ntgt LayerNorm deferred into its consumers (HGT._ntgt_side: un-rotated pre-norm sum + per-node statistics, the
+    normalisation applied inside the centre-only cluster kernel): same scores as the explicit rotation + LayerNorm path and within
+    the parity bar of the oracle; the statistics kernel against torch."""
+    _need_tc()
+    import copy
+    from gnnlm_b200 import ops, synth
+    from tests.synth import run_oracle
+    cfg = dict(synth.CONFIGS["c3mini"])
+    model = synth.make_model(cfg)
+    data = synth.make_data(cfg, device="cpu")
+    ref = run_oracle((cfg, model, data))
+    outs = {}
+    for defer in (True, False):
+        m = copy.deepcopy(model)
+        for layer in m.decoder.hgt_decoder.gcs:
+            layer.use_deferred_ln = defer
+        outs[defer] = synth.run_gpu(cfg, m, data, dev, "f16f8")
+        hgt_ = m.decoder.hgt_decoder
+        assert ("defer" in hgt_.gcs[0]._prep) == defer            # the path under test was the one that ran
+    lp = ref["logprob"].numpy()
+    for defer in (True, False):
+        assert (np.abs(outs[defer]["logprob"] - lp) / np.abs(lp)).max() < 1e-4
+    np.testing.assert_allclose(outs[True]["logprob"], outs[False]["logprob"], rtol=2e-5, atol=2e-5)
+    # gnnlm_rowstats_q8 vs torch: z' = o + x, statistics of z' rot^T
+    torch.manual_seed(9)
+    rows, d = 300, 1024
+    rot = torch.linalg.qr(torch.randn(d, d, dtype=torch.float64))[0]
+    o = torch.randn(rows, d, device=dev)
+    x = ops.to_q8(ops.to_split(torch.randn(rows, d, device=dev)))
+    xq = x.data[:, :d].float() + x.q8[:, d:].view(torch.float8_e4m3fn).float() / 1024.0         # hi + lo8 / 2^10: what the kernel reads
+    u = (rot.sum(0) / d).float().to(dev)
+    z, stats = ops.rowstats_q8(o, x, u, 1e-5)
+    zp = (o + xq).double().cpu()
+    zr = zp @ rot.T
+    np.testing.assert_allclose(stats[:, 0].cpu().double().numpy(), zr.mean(1).numpy(), rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(stats[:, 1].cpu().double().numpy(), (1.0 / torch.sqrt(zr.var(1, unbiased=False) + 1e-5)).numpy(), rtol=1e-5)
+    np.testing.assert_allclose(z.data.float().cpu().numpy(), zp.float().numpy(), rtol=2 ** -10, atol=1e-6)
