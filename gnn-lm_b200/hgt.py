@@ -25,6 +25,8 @@ import torch.nn as nn
 from . import _lib as L
 from . import ops
 from .graph import TokenGraph
+from . import hetero
+from .hetero import HeteroGraph
 
 
 def _fold(W: torch.Tensor, b: torch.Tensor, R: torch.Tensor, scale: Optional[torch.Tensor]):
@@ -145,14 +147,13 @@ def as_float(x) -> torch.Tensor:
     return x.float() if isinstance(x, ops.Split) or x.dtype != torch.float32 else x
 
 
-class HGTLayer(nn.Module):
-    """Same parameters as the reference layer (hgt.py:27-79)."""
+class HGTLayer(hetero.IncrementalState, nn.Module):
+    """Same parameters as the reference layer (hgt.py:27-79; @with_incremental_state, :21)."""
 
     def __init__(self, in_dim: int, out_dim: int, ntype2idx: Dict[str, int], etype2idx: Dict[str, int], n_heads: int,
                  dropout=0.2, use_norm=True, two_stream=False, attn_drop=0.2):
         super().__init__()
-        if two_stream:
-            raise NotImplementedError("two_stream is hard-wired False in the reference decoder (transformer.py:931)")
+        self.init_incremental_state()
         self.in_dim, self.out_dim = in_dim, out_dim
         self.ntype2idx, self.etype2idx = ntype2idx, etype2idx
         self.num_types, self.num_relations = len(ntype2idx), len(etype2idx)
@@ -405,8 +406,14 @@ class HGTLayer(nn.Module):
 
     def forward(self, G: TokenGraph, h: Dict[str, torch.Tensor], etypes=None, incremental_state=None,
                 math_mode: int = L.MATH_FP32_SIMT) -> Dict[str, torch.Tensor]:
-        """Full layer, every node of both types (hgt.py:299-420)."""
-        assert incremental_state is None, "only support lm (transformer.py:1028)"
+        """Full layer, every node of both types (hgt.py:299-420).  A general heterograph (hetero.HeteroGraph: any node / edge
+        types, `two_stream`) and incremental decoding (`incremental_state`, hgt.py:308-310 -> infer) run in hetero.py."""
+        if incremental_state is not None:
+            return hetero.layer_infer(self, G, h, etypes, incremental_state, math_mode)
+        if isinstance(G, HeteroGraph):
+            return hetero.layer_forward(self, G, h, etypes, math_mode)
+        if self.two_stream:
+            raise KeyError(("src", "intra", "tgt"))      # the token graph has no 'src' node type (hgt.py:390-393 would raise)
         P = self.prepare(math_mode)
         n_valid = G.counts()[1]
         h_t, h_n = as_act(h["tgt"], math_mode), as_act(h["ntgt"], math_mode)
@@ -414,6 +421,11 @@ class HGTLayer(nn.Module):
         new_t = self.tgt(P, G, h_t, hc, None)
         new_n = self.ntgt_full(P, G, h_n, None)
         return {"tgt": new_t, "ntgt": new_n}       # activation format of the math mode (HGT.forward converts back)
+
+
+    def reorder_incremental_state(self, incremental_state, new_order):
+        """hgt.py:422-438."""
+        return hetero.reorder_incremental_state(self, incremental_state, new_order)
 
 
 class HGT(nn.Module):
@@ -467,9 +479,11 @@ class HGT(nn.Module):
         return _lin(as_act(h, self.math_mode), self._io()["out"], self.math_mode, m_dev=n_dev)
 
     def forward(self, G: TokenGraph, features: Dict[str, torch.Tensor] = None, etypes=None, incremental_state=None):
-        """Reference-shaped call (hgt.py:494-513): returns features of every node of both types."""
+        """Reference-shaped call (hgt.py:494-513): returns features of every node of every type."""
         h = {}
-        for ntype in ("tgt", "ntgt"):
+        if incremental_state is not None and not isinstance(G, HeteroGraph):
+            raise TypeError("incremental decoding runs over a hetero.HeteroGraph with max_len tgt nodes per block (hgt.py:93)")
+        for ntype in (G.ntypes if isinstance(G, HeteroGraph) else ("tgt", "ntgt")):
             x = None if not features else features.get(ntype)
             if x is None:
                 x = G.nodes[ntype].data["h"]

@@ -456,11 +456,21 @@ class _SubGraph:
         self.edata = g.edata_of[cet]
         self.n_dst = g.num_nodes(cet[2])
 
-    def apply_edges(self, f):
+    def apply_edges(self, f, edges=None):
         kind, a, b, out = f
         assert kind == "v_dot_u"   # out[e] = <dst[a][v_e], src[b][u_e]> over the last dim, keepdim
-        self.edata[out] = (self.dstdata[a][self.dst] * self.srcdata[b][self.src]).sum(-1, keepdim=True)
+        val = (self.dstdata[a][self.dst] * self.srcdata[b][self.src]).sum(-1, keepdim=True)
+        if edges is None:
+            self.edata[out] = val
+        else:                      # a subset of the edges: a new edge field starts as zeros (DGL's default initialiser)
+            if out not in self.edata:
+                self.edata[out] = torch.zeros_like(val)
+            self.edata[out][edges] = val[edges]
         self.g.srcdata_of[self.cet] = self.srcdata
+
+    def edges(self, form="uv", order="eid", etype=None):
+        assert form == "uv" and order == "eid" and (etype is None or tuple(etype) == tuple(self.cet))
+        return self.src, self.dst
 
 
 def _stub_edge_softmax(sub, score, norm_by="dst"):
@@ -489,7 +499,18 @@ class _StubGraph:
 
     def local_scope(self):
         import contextlib
-        return contextlib.nullcontext()
+
+        @contextlib.contextmanager
+        def scope():               # feature writes inside the scope do not outlive it (DGLGraph.local_scope)
+            saved = {nt: dict(ns.data) for nt, ns in self.nodes.items()}
+            try:
+                yield
+            finally:
+                for nt, ns in self.nodes.items():
+                    ns.data = saved[nt]
+                self.edata_of = {k: {} for k in self.edges_of}
+                self.srcdata_of, self._subs = {}, {}
+        return scope()
 
     def __getitem__(self, cet):
         if cet not in self._subs:
@@ -509,8 +530,15 @@ class _StubGraph:
         for (nt, oname), lst in per_dst.items():
             self.nodes[nt].data[oname] = torch.stack(lst, 0).mean(0)
 
+    def update_all(self, mf, rf, etype):
+        sub = self[tuple(etype)]
+        _, uname, ename, _ = mf
+        _, _, oname = rf
+        m = sub.srcdata[uname][sub.src] * sub.edata[ename]
+        self.nodes[etype[2]].data[oname] = torch.zeros((sub.n_dst,) + m.shape[1:], dtype=m.dtype).index_add_(0, sub.dst, m)
 
-def _ref_hgt():
+
+def _ref_hgt(patch=None):
     dgl = types.ModuleType("dgl")
     dgl.DGLHeteroGraph = _StubGraph
     dgl.DGLGraph = _StubGraph
@@ -520,8 +548,7 @@ def _ref_hgt():
     dgl_ops = types.ModuleType("dgl.ops")
     dgl_ops.edge_softmax = _stub_edge_softmax
     dgl.function, dgl.ops = dgl_fn, dgl_ops
-    inc = types.ModuleType("fairseq.incremental_decoding_utils")
-    inc.with_incremental_state = lambda cls: cls
+    inc = _load_by_path("ref_incremental_decoding_utils", "fairseq/incremental_decoding_utils.py")   # pure torch: the real mixin
     fs = types.ModuleType("fairseq")
     saved = {k: sys.modules.get(k) for k in ("dgl", "dgl.function", "dgl.ops", "fairseq",
                                               "fairseq.incremental_decoding_utils")}
@@ -530,6 +557,8 @@ def _ref_hgt():
     try:
         src = _src("fairseq/models/hgt.py")
         src = src[:src.index("if __name__ == '__main__':")]
+        if patch is not None:
+            src = patch(src)
         mod = types.ModuleType("ref_hgt")
         exec(compile(src, "ref_hgt.py", "exec"), mod.__dict__)
     finally:
@@ -595,6 +624,176 @@ def make_hgt_case(name, B, L, k, cl, cr, d, H, n_layers, seed, stress=True, hidd
         res["sd." + k_] = v_.numpy()
     np.savez_compressed(os.path.join(OUT, f"hgt_{name}.npz"), **res)
     print(f"hgt_{name}: n_tgt={bg['n_tgt']} n_ntgt={bg['n_ntgt']} |out|={float(out['tgt'].abs().mean()):.3f}")
+
+
+
+# ------------------------------------------------------------------------------------------
+# HGT on a general heterograph, two_stream, incremental infer() (hgt.py:81-297,324-330,360-394)
+# ------------------------------------------------------------------------------------------
+def _perturb(model, d):
+    with torch.no_grad():
+        for p in model.parameters():          # make every parameter non-trivial (biases, pri, LN affine)
+            if p.dim() <= 2 and p.shape[-1] != d or p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+
+
+def _save_hgt(name, model, res):
+    for k_, v_ in model.state_dict().items():
+        res["sd." + k_] = v_.numpy()
+    np.savez_compressed(os.path.join(OUT, f"hgt_{name}.npz"), **res)
+
+
+def _rand_edges(rng, n_src, n_dst, n_edges, skip_dst=()):
+    """Random COO list (duplicates allowed, as DGL multigraphs allow them); destinations in `skip_dst` get no in-edge."""
+    dst = rng.randint(0, n_dst, size=n_edges)
+    dst = dst[~np.isin(dst, list(skip_dst))]
+    return rng.randint(0, n_src, size=dst.shape[0]).astype(np.int64), dst.astype(np.int64)
+
+
+def make_hetero_case(name, d, H, n_layers, seed):
+    """The reference module's own self-test topology (hgt.py:516-552: four node types, ten canonical edge types), random sizes."""
+    rng = np.random.RandomState(seed)
+    n = {"src": 9, "nsrc": 14, "tgt": 7, "ntgt": 11}
+    cets = [("src", "intra", "src"), ("src", "intra", "tgt"), ("tgt", "intra", "tgt"), ("nsrc", "inter", "src"),
+            ("src", "inter", "nsrc"), ("ntgt", "inter", "tgt"), ("ntgt", "intra", "ntgt"), ("ntgt", "intra", "nsrc"),
+            ("nsrc", "intra", "ntgt"), ("nsrc", "intra", "nsrc")]
+    edges = {}
+    for i, (s_, r_, t_) in enumerate(cets):
+        if (s_, r_, t_) == ("tgt", "intra", "tgt"):
+            u, v = np.triu_indices(n["tgt"])
+            edges[(s_, r_, t_)] = (u.astype(np.int64), v.astype(np.int64))
+        else:
+            edges[(s_, r_, t_)] = _rand_edges(rng, n[s_], n[t_], 3 * n[t_], skip_dst=(1,) if i % 2 else ())
+    hgt = _ref_hgt()
+    torch.manual_seed(seed)
+    ntype2idx = {"src": 0, "nsrc": 1, "tgt": 2, "ntgt": 3}
+    model = hgt.HGT(ntype2idx=ntype2idx, etype2idx={"intra": 0, "inter": 1}, in_dim=d, hidden_dim=d, out_dim=d,
+                    n_layers=n_layers, n_heads=H, dropout=0.0, attn_drop=0.0).eval()
+    _perturb(model, d)
+    sg = _StubGraph(edges, n)
+    feats = {nt: torch.randn(n[nt], d) for nt in n}
+    for nt in n:
+        sg.nodes[nt].data["h"] = feats[nt]
+    with torch.no_grad():
+        out = model(sg, features={"tgt": feats["tgt"]})          # the other types come from G.nodes[.].data["h"] (hgt.py:501-503)
+    res = {"H": H, "n_layers": n_layers, "ntypes": np.array(list(n.keys())), "num_nodes": np.array(list(n.values())),
+           "cets": np.array(["|".join(c) for c in cets])}
+    for c in cets:
+        res["src." + "|".join(c)], res["dst." + "|".join(c)] = edges[c]
+    for nt in n:
+        res["h." + nt], res["out." + nt] = feats[nt].numpy(), out[nt].numpy()
+    _save_hgt(name, model, res)
+    print(f"hgt_{name}: |out tgt|={float(out['tgt'].abs().mean()):.3f}")
+
+
+TWO_STREAM_ANCHOR = "                sub_graph.srcdata['k'] = k\n                sub_graph.dstdata['q'] = q\n                sub_graph.srcdata[f'v_{srctype}_{etype}_{dsttype}'] = v\n\n                sub_graph.apply_edges(fn.v_dot_u('q', 'k', 't'))\n                attn_score = sub_graph.edata.pop('t').sum(-1) * relation_pri / self.sqrt_dk\n                attn_score = self.attn_drop(edge_softmax(sub_graph, attn_score, norm_by='dst'))\n\n                sub_graph.edata['t'] = attn_score.unsqueeze(-1)\n\n                if self.two_stream and"
+
+
+def _patch_two_stream(src):
+    """SURVEY.md-style quirk: the query stream's self-loop score reads srcdata['k_tilde'] (hgt.py:376), which the
+    reference never assigns -- as written, two_stream raises on any tgt-intra-tgt edge set.  The fixture applies the evident intent
+    as a one-statement fix: k_tilde = the relation-transformed keys of the query stream (tgt_tilde_k, hgt.py:330)."""
+    assert src.count(TWO_STREAM_ANCHOR) == 1
+    fix = ("                if self.two_stream and (srctype, etype, dsttype) == ('tgt', 'intra', 'tgt'):\n"
+           "                    sub_graph.srcdata['k_tilde'] = torch.einsum('bij,ijk->bik', G.nodes['tgt'].data['tgt_tilde_k'], relation_att)\n")
+    return src.replace(TWO_STREAM_ANCHOR, fix + TWO_STREAM_ANCHOR)
+
+
+def make_two_stream_case(name, d, H, n_layers, seed):
+    rng = np.random.RandomState(seed)
+    n = {"src": 10, "tgt": 8, "ntgt": 12}
+    u, v = np.triu_indices(n["tgt"])
+    su, sv = np.meshgrid(np.arange(n["src"]), np.arange(n["tgt"]), indexing="ij")
+    edges = {("src", "intra", "src"): _rand_edges(rng, n["src"], n["src"], 30),
+             ("src", "intra", "tgt"): (su.reshape(-1).astype(np.int64), sv.reshape(-1).astype(np.int64)),
+             ("tgt", "intra", "tgt"): (u.astype(np.int64), v.astype(np.int64)),
+             ("ntgt", "inter", "tgt"): _rand_edges(rng, n["ntgt"], n["tgt"], 20, skip_dst=(2,)),
+             ("ntgt", "intra", "ntgt"): _rand_edges(rng, n["ntgt"], n["ntgt"], 30)}
+    ntype2idx = {"src": 0, "tgt": 1, "ntgt": 2}
+    feats = {nt: torch.randn(n[nt], d, generator=torch.Generator().manual_seed(seed + 7 + i)) for i, nt in enumerate(n)}
+
+    def run(patch):
+        hgt = _ref_hgt(patch)
+        torch.manual_seed(seed)
+        model = hgt.HGT(ntype2idx=ntype2idx, etype2idx={"intra": 0, "inter": 1}, in_dim=d, hidden_dim=d, out_dim=d,
+                        n_layers=n_layers, n_heads=H, dropout=0.0, attn_drop=0.0, two_stream=True).eval()
+        _perturb(model, d)
+        sg = _StubGraph(edges, n)
+        for nt in n:
+            sg.nodes[nt].data["h"] = feats[nt]
+        with torch.no_grad():
+            return model, model(sg, features=dict(feats))
+
+    try:
+        run(None)
+        raise SystemExit("the unmodified two_stream path was expected to raise (k_tilde never assigned)")
+    except KeyError as e:
+        print(f"hgt_{name}: unmodified reference raises KeyError({e}) as documented")
+    model, out = run(_patch_two_stream)
+    res = {"H": H, "n_layers": n_layers, "ntypes": np.array(list(n.keys())), "num_nodes": np.array(list(n.values())),
+           "cets": np.array(["|".join(c) for c in edges])}
+    for c in edges:
+        res["src." + "|".join(c)], res["dst." + "|".join(c)] = edges[c]
+    for nt in n:
+        res["h." + nt] = feats[nt].numpy()
+    for nt in out:
+        res["out." + nt] = out[nt].numpy()
+    _save_hgt(name, model, res)
+    print(f"hgt_{name}: keys {sorted(out)} |out tgt_tilde|={float(out['tgt_tilde'].abs().mean()):.3f}")
+
+
+def make_infer_case(name, bsz, steps, n_per, d, H, n_layers, seed, reorder_at=None):
+    """HGTLayer.infer (hgt.py:81-297) driven through HGT.forward(incremental_state=...): `steps` decoding steps over a batched
+    graph of bsz blocks with max_len = 512 tgt nodes each (the constant at :93), causal tgt-intra-tgt edges, ntgt -> tgt inter edges
+    towards the first `steps` positions and random ntgt-intra-ntgt edges.  h['tgt'] is the current step's [bsz, d] feature."""
+    max_len = 512
+    rng = np.random.RandomState(seed)
+    n = {"tgt": bsz * max_len, "ntgt": bsz * n_per}
+    u, v = np.triu_indices(max_len)
+    tt = (np.concatenate([u + b * max_len for b in range(bsz)]).astype(np.int64),
+          np.concatenate([v + b * max_len for b in range(bsz)]).astype(np.int64))
+    i_src = np.arange(n["ntgt"], dtype=np.int64)
+    i_dst = (i_src // n_per) * max_len + rng.randint(0, steps, size=n["ntgt"])
+    i_dst[i_dst % max_len == 1] += 1                                      # position 1 of every block: no inter in-edge
+    nn_s, nn_d = [], []
+    for b in range(bsz):
+        s_, d_ = _rand_edges(rng, n_per, n_per, 3 * n_per)
+        nn_s += [s_ + b * n_per, np.arange(n_per) + b * n_per]
+        nn_d += [d_ + b * n_per, np.arange(n_per) + b * n_per]
+    edges = {("tgt", "intra", "tgt"): tt, ("ntgt", "inter", "tgt"): (i_src, i_dst.astype(np.int64)),
+             ("ntgt", "intra", "ntgt"): (np.concatenate(nn_s).astype(np.int64), np.concatenate(nn_d).astype(np.int64))}
+    hgt = _ref_hgt()
+    torch.manual_seed(seed)
+    model = hgt.HGT(ntype2idx={"tgt": 0, "ntgt": 1}, etype2idx={"intra": 0, "inter": 1}, in_dim=d, hidden_dim=d, out_dim=d,
+                    n_layers=n_layers, n_heads=H, dropout=0.0, attn_drop=0.0).eval()
+    _perturb(model, d)
+    etypes = list(edges.keys())
+    h_ntgt = torch.randn(n["ntgt"], d)
+    h_steps = torch.randn(steps, bsz, d)
+    sg = _StubGraph(edges, n)
+    sg.nodes["ntgt"].data["h"] = h_ntgt
+    inc: dict = {}
+    outs, outs_n = [], []
+    order = torch.arange(bsz)
+    with torch.no_grad():
+        for s_ in range(steps):
+            if reorder_at is not None and s_ == reorder_at:
+                order = torch.arange(bsz).flip(0)
+                for layer in model.gcs:
+                    layer.reorder_incremental_state(inc, order)
+            x = h_steps[s_][order] if reorder_at is not None and s_ >= reorder_at else h_steps[s_]
+            out = model(sg, features={"tgt": x}, etypes=etypes, incremental_state=inc)
+            outs.append(out["tgt"].clone())
+            outs_n.append(out["ntgt"].clone())
+    res = {"H": H, "n_layers": n_layers, "bsz": bsz, "steps": steps, "max_len": max_len, "reorder_at": -1 if reorder_at is None else reorder_at,
+           "ntypes": np.array(list(n.keys())), "num_nodes": np.array(list(n.values())), "cets": np.array(["|".join(c) for c in edges]),
+           "h.ntgt": h_ntgt.numpy(), "h_steps": h_steps.numpy(), "out_steps": torch.stack(outs).numpy(),
+           "out_ntgt_first": outs_n[0].numpy(), "out_ntgt_last": outs_n[-1].numpy()}
+    for c in edges:
+        if c != ("tgt", "intra", "tgt"):          # the causal list is regenerated by the test (triu per block)
+            res["src." + "|".join(c)], res["dst." + "|".join(c)] = edges[c]
+    _save_hgt(name, model, res)
+    print(f"hgt_{name}: steps={steps} |out|={float(outs[-1].abs().mean()):.3f}")
 
 
 def make_adaptive_input_case(name, V, d, cutoff, T, seed):
@@ -747,6 +946,12 @@ if __name__ == "__main__":
         # --tie-adaptive-weights WITHOUT --tie-adaptive-proj: tail projections are nn.Linear(d, dim_i) (adaptive_softmax.py:96-101)
         make_adaptive_case("tied_noproj", V=300, d=64, cutoff=[40, 120], tied=True, T=40, seed=2, tie_proj=False)
         sys.exit(0)
+    if "--hetero-only" in sys.argv:
+        make_hetero_case("hetero4", d=32, H=4, n_layers=2, seed=3)
+        make_two_stream_case("two_stream", d=32, H=2, n_layers=2, seed=4)
+        make_infer_case("infer_b2", bsz=2, steps=5, n_per=9, d=32, H=4, n_layers=2, seed=5)
+        make_infer_case("infer_b3_reorder", bsz=3, steps=4, n_per=6, d=32, H=2, n_layers=1, seed=6, reorder_at=2)
+        sys.exit(0)
     if "--adaptive-input-only" in sys.argv:
         make_adaptive_input_case("v300", V=300, d=64, cutoff=[40, 120], T=64, seed=0)
         sys.exit(0)
@@ -779,6 +984,10 @@ if __name__ == "__main__":
     make_hgt_case("l2_c1", B=2, L=6, k=3, cl=1, cr=1, d=32, H=4, n_layers=2, seed=0)
     make_hgt_case("l3_c2", B=1, L=8, k=2, cl=2, cr=2, d=32, H=2, n_layers=3, seed=1)
     make_hgt_case("l2_adapt", B=1, L=7, k=3, cl=1, cr=1, d=24, H=4, n_layers=2, seed=2, hidden=32, out_dim=24)
+    make_hetero_case("hetero4", d=32, H=4, n_layers=2, seed=3)
+    make_two_stream_case("two_stream", d=32, H=2, n_layers=2, seed=4)
+    make_infer_case("infer_b2", bsz=2, steps=5, n_per=9, d=32, H=4, n_layers=2, seed=5)
+    make_infer_case("infer_b3_reorder", bsz=3, steps=4, n_per=6, d=32, H=2, n_layers=1, seed=6, reorder_at=2)
     make_format_fixtures()
     make_adaptive_input_case("v300", V=300, d=64, cutoff=[40, 120], T=64, seed=0)
     make_registry_fixture()

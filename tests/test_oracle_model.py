@@ -167,3 +167,88 @@ def test_oracle_adaptive_loss_equals_target_logprob_sum():
     assert abs(float(loss) + float(lp.sum())) < 1e-9 * abs(float(loss))
     wp = {"plain": torch.randn(V, d, dtype=torch.float64)}
     assert abs(float(mo.adaptive_loss(wp, None, x, target)) + float(mo.plain_target_logprob(wp["plain"], x, target).sum())) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# General heterograph / two_stream / incremental infer (hgt.py:81-297,324-330,360-394): oracle/hetero_oracle.py
+# ---------------------------------------------------------------------------------------------------------------------
+def load_hetero_case(golden_dir, name):
+    """(z, sd, num_nodes, edges as int64 tensors, feats) of a tests/golden/hgt_{hetero4,two_stream,infer_*}.npz fixture."""
+    z = np.load(os.path.join(golden_dir, f"hgt_{name}.npz"))
+    num_nodes = {str(t): int(n) for t, n in zip(z["ntypes"], z["num_nodes"])}
+    edges = {}
+    for c in z["cets"]:
+        cet = tuple(str(c).split("|"))
+        if "src." + str(c) in z.files:
+            edges[cet] = (torch.from_numpy(z["src." + str(c)]), torch.from_numpy(z["dst." + str(c)]))
+        else:                                           # causal tgt-intra-tgt inside blocks of max_len (not stored)
+            L_, B = int(z["max_len"]), int(z["bsz"])
+            u, v = np.triu_indices(L_)
+            edges[cet] = (torch.from_numpy(np.concatenate([u + b * L_ for b in range(B)])),
+                          torch.from_numpy(np.concatenate([v + b * L_ for b in range(B)])))
+    feats = {t: torch.from_numpy(z["h." + t]) for t in num_nodes if "h." + t in z.files}
+    return z, _sd(z, "sd."), num_nodes, edges, feats
+
+
+def test_hetero_layer_matches_reference(golden_dir):
+    from oracle import hetero_oracle as ho
+    z, sd, nn_, edges, feats = load_hetero_case(golden_dir, "hetero4")
+    out = ho.hgt_forward_hetero(sd, feats, edges, nn_, {"src": 0, "nsrc": 1, "tgt": 2, "ntgt": 3}, {"intra": 0, "inter": 1},
+                                int(z["H"]), int(z["n_layers"]))
+    for t in nn_:
+        np.testing.assert_allclose(out[t].numpy(), z["out." + t], rtol=1e-5, atol=2e-6)
+
+
+def test_two_stream_matches_fixed_reference(golden_dir):
+    from oracle import hetero_oracle as ho
+    z, sd, nn_, edges, feats = load_hetero_case(golden_dir, "two_stream")
+    out = ho.hgt_forward_hetero(sd, feats, edges, nn_, {"src": 0, "tgt": 1, "ntgt": 2}, {"intra": 0, "inter": 1},
+                                int(z["H"]), int(z["n_layers"]), two_stream=True)
+    assert sorted(out) == ["ntgt", "src", "tgt", "tgt_tilde"]
+    for t in out:
+        np.testing.assert_allclose(out[t].numpy(), z["out." + t], rtol=1e-5, atol=2e-6)
+    assert np.abs(z["out.tgt_tilde"] - z["out.tgt"]).max() > 1e-2          # the query stream is a different function
+
+
+@pytest.mark.parametrize("case", ["infer_b2", "infer_b3_reorder"])
+def test_incremental_infer_matches_reference(case, golden_dir):
+    from oracle import hetero_oracle as ho
+    z, sd, nn_, edges, feats = load_hetero_case(golden_dir, case)
+    H, NL, steps, bsz = int(z["H"]), int(z["n_layers"]), int(z["steps"]), int(z["bsz"])
+    etypes = list(edges)
+    states = [dict() for _ in range(NL)]
+    h_steps = torch.from_numpy(z["h_steps"])
+    order = torch.arange(bsz)
+    for s in range(steps):
+        if int(z["reorder_at"]) == s:
+            order = torch.arange(bsz).flip(0)
+            states = [ho.reorder_state(st, order) for st in states]
+        h = {"tgt": h_steps[s][order] if 0 <= int(z["reorder_at"]) <= s else h_steps[s], "ntgt": feats["ntgt"]}
+        for l in range(NL):
+            h = ho.hgt_layer_infer(sd, f"gcs.{l}.", h, edges, nn_, {"tgt": 0, "ntgt": 1}, {"intra": 0, "inter": 1}, H, etypes,
+                                   states[l])
+        np.testing.assert_allclose(h["tgt"].numpy(), z["out_steps"][s], rtol=1e-5, atol=2e-6)
+        if s == 0:
+            np.testing.assert_allclose(h["ntgt"].numpy(), z["out_ntgt_first"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(h["ntgt"].numpy(), z["out_ntgt_last"], rtol=1e-5, atol=2e-6)
+    if int(z["reorder_at"]) < 0:
+        # incremental decoding with teacher forcing == the full layer on the same prefix: position s of every block
+        full = ho.hgt_forward_hetero(sd, {"tgt": _prefix_feats(h_steps, int(z["max_len"])), "ntgt": feats["ntgt"]}, edges, nn_,
+                                     {"tgt": 0, "ntgt": 1}, {"intra": 0, "inter": 1}, H, 1)
+        idx = torch.arange(bsz) * int(z["max_len"])
+        np.testing.assert_allclose(full["tgt"][idx].numpy(), _first_layer_step0(z, sd, nn_, edges, feats), rtol=1e-4, atol=1e-5)
+
+
+def _prefix_feats(h_steps, max_len):
+    steps, bsz, d = h_steps.shape
+    x = torch.zeros(bsz * max_len, d)
+    for s in range(steps):
+        x[torch.arange(bsz) * max_len + s] = h_steps[s]
+    return x
+
+
+def _first_layer_step0(z, sd, nn_, edges, feats):
+    from oracle import hetero_oracle as ho
+    h = {"tgt": torch.from_numpy(z["h_steps"])[0], "ntgt": feats["ntgt"]}
+    return ho.hgt_layer_infer(sd, "gcs.0.", h, edges, nn_, {"tgt": 0, "ntgt": 1}, {"intra": 0, "inter": 1}, int(z["H"]),
+                              list(edges), {})["tgt"].numpy()
