@@ -94,7 +94,7 @@ SIGNATURES = {
     "gnnlm_colsum_f32": (_i32, [_p, _i64, _i64, _p, _i64, _p, _p]),
     "gnnlm_axpy_f32": (_i32, [_p, _i64, _p, _i64, _i64, _p, _i64, _f32, _p]),
     "gnnlm_scatter_add_rows": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p]),
-    "gnnlm_knn_sims_pq": (_i32, [_p, _i64, _i32, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _i64, _i32, _p, _i64, _p]),
+    "gnnlm_knn_sims_pq": (_i32, [_p, _i64, _i32, _p, _i64, _p, _i64, _i32, _i32, _p, _p, _p, _i64, _i32, _p, _i32, _p, _i64, _p]),
 }
 
 _lib = None

@@ -104,37 +104,54 @@ __global__ void __launch_bounds__(KS_THREADS) knn_sims_keys_kernel(const float* 
 }
 
 // qr = q A^T (the caller's GEMM) [T, M*dsub]; table[m][c] per token in shared memory.
+// normalise (cosine index, knn_model.py:171-172,181-184): bit 1 = score with q / ||q|| (the rotation is linear, so qr is scaled
+// by the same factor); bit 0 (ip only) = divide by ||x^|| = sqrt(sum_m key_norm2[m][c_m]), key_norm2[m][c] = ||cen[m,c] - b_m||^2
+// (A A^T = I).
 __global__ void __launch_bounds__(1024) knn_sims_pq_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ qr,
                                                            int64_t ldqr, int d_q, const uint8_t* __restrict__ codes,
                                                            int64_t n_datastore, int M, int dsub,
                                                            const float* __restrict__ cen, const float* __restrict__ bias,
                                                            const int64_t* __restrict__ ids, int k_nn, int metric,
+                                                           const float* __restrict__ key_norm2, int normalise,
                                                            float* __restrict__ sims) {
   extern __shared__ float smem[];
   float* table = smem;                                           // [M, 256]
   float* sqr = smem + (size_t)M * 256;                           // [M*dsub] rotated query (+ b for l2)
   __shared__ float s_red[32];
-  __shared__ float s_const;
+  __shared__ float s_const, s_qn2;
   const int64_t t = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
   const int dr = M * dsub;
-  // constant term: ip: -<q', b>;  l2: ||q||^2 - ||q'||^2
   float part = 0.f;
-  for (int i = threadIdx.x; i < dr; i += blockDim.x) {
-    const float x = __ldg(qr + t * ldqr + i), b = bias ? __ldg(bias + i) : 0.f;
-    sqr[i] = metric == 0 ? x + b : x;
-    part += metric == 0 ? -x * x : -x * b;
-  }
-  if (metric == 0)
+  if (metric == 0 || (normalise & 2)) {                          // ||q||^2
     for (int i = threadIdx.x; i < d_q; i += blockDim.x) {
       const float x = __ldg(q + t * ldq + i);
       part = fmaf(x, x, part);
     }
+    part = warp_sum(part);
+    if (lane == 0) s_red[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < n_warps; ++w) s += s_red[w];
+      s_qn2 = s;
+    }
+    __syncthreads();
+  }
+  const float q_inv = (normalise & 2) ? rsqrtf(s_qn2) : 1.f;
+  // constant term: ip: -<q', b>;  l2: ||q||^2 - ||q'||^2
+  part = 0.f;
+  for (int i = threadIdx.x; i < dr; i += blockDim.x) {
+    const float x = __ldg(qr + t * ldqr + i) * q_inv, b = bias ? __ldg(bias + i) : 0.f;
+    sqr[i] = metric == 0 ? x + b : x;
+    part += metric == 0 ? -x * x : -x * b;
+  }
   part = warp_sum(part);
+  __syncthreads();                                               // s_red is reused
   if (lane == 0) s_red[warp] = part;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float s = 0.f;
+    float s = metric == 0 ? s_qn2 * q_inv * q_inv : 0.f;
     for (int w = 0; w < n_warps; ++w) s += s_red[w];
     s_const = s;
   }
@@ -157,6 +174,7 @@ __global__ void __launch_bounds__(1024) knn_sims_pq_kernel(const float* __restri
   }
   __syncthreads();
   const float cst = s_const;
+  const bool key_n = metric == 1 && (normalise & 1);             // the reference's l2 branch never normalises the keys (:159-165)
   for (int j0 = warp * KS_ROWS; j0 < k_nn; j0 += n_warps * KS_ROWS) {
     const uint8_t* row[KS_ROWS];
 #pragma unroll
@@ -166,9 +184,9 @@ __global__ void __launch_bounds__(1024) knn_sims_pq_kernel(const float* __restri
       if (id < 0 || id >= n_datastore) id = 0;
       row[r] = codes + id * (int64_t)M;
     }
-    float acc[KS_ROWS];
+    float acc[KS_ROWS], nrm[KS_ROWS];
 #pragma unroll
-    for (int r = 0; r < KS_ROWS; ++r) acc[r] = 0.f;
+    for (int r = 0; r < KS_ROWS; ++r) acc[r] = nrm[r] = 0.f;
     for (int m0 = lane * 4; m0 < M; m0 += 128) {                 // M % 4 == 0: 4 code bytes per lane per pass
       uint32_t cw[KS_ROWS];
 #pragma unroll
@@ -176,13 +194,18 @@ __global__ void __launch_bounds__(1024) knn_sims_pq_kernel(const float* __restri
 #pragma unroll
       for (int r = 0; r < KS_ROWS; ++r) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[r] += table[((m0 + i) << 8) + ((cw[r] >> (8 * i)) & 0xff)];
+        for (int i = 0; i < 4; ++i) {
+          const int e = ((m0 + i) << 8) + ((cw[r] >> (8 * i)) & 0xff);
+          acc[r] += table[e];
+          if (key_n) nrm[r] += __ldg(key_norm2 + e);
+        }
       }
     }
 #pragma unroll
     for (int r = 0; r < KS_ROWS; ++r) {
       const float a = warp_sum(acc[r]);
-      if (lane == 0 && j0 + r < k_nn) sims[t * k_nn + j0 + r] = metric == 0 ? -(a + cst) : a + cst;
+      const float n2 = key_n ? warp_sum(nrm[r]) : 1.f;
+      if (lane == 0 && j0 + r < k_nn) sims[t * k_nn + j0 + r] = metric == 0 ? -(a + cst) : (a + cst) * (key_n ? rsqrtf(n2) : 1.f);
     }
   }
 }
@@ -216,9 +239,12 @@ extern "C" int32_t gnnlm_knn_sims_keys(const float* queries, int64_t ldq, const 
 extern "C" int32_t gnnlm_knn_sims_pq(const float* queries, int64_t ldq, int32_t d_q, const float* rotated, int64_t ldr,
                                      const uint8_t* codes, int64_t n_datastore, int32_t M, int32_t dsub,
                                      const float* centroids, const float* bias, const int64_t* ids, int64_t k_nn,
-                                     int32_t metric, float* sims, int64_t T, gnnlm_stream_t stream) {
+                                     int32_t metric, const float* key_norm2, int32_t normalise, float* sims, int64_t T,
+                                     gnnlm_stream_t stream) {
   GNNLM_CHECK_ARG(queries && rotated && codes && centroids && ids && sims, GNNLM_E_ARG, "gnnlm_knn_sims_pq: null pointer");
   GNNLM_CHECK_ARG(metric == 0 || metric == 1, GNNLM_E_ARG, "gnnlm_knn_sims_pq: metric must be 0 (l2) or 1 (ip)");
+  GNNLM_CHECK_ARG(normalise >= 0 && normalise <= 3 && (!(normalise & 1) || metric == 0 || key_norm2), GNNLM_E_ARG,
+                  "gnnlm_knn_sims_pq: normalise bit 0 (cosine keys) needs key_norm2 [M, 256]");
   GNNLM_CHECK_ARG(M > 0 && M % 4 == 0 && dsub > 0 && n_datastore > 0 && k_nn > 0 && T >= 0, GNNLM_E_SHAPE,
                   "gnnlm_knn_sims_pq: M must be a multiple of 4");
   const size_t smem = ((size_t)M * 256 + (size_t)M * dsub) * sizeof(float);
@@ -230,7 +256,8 @@ extern "C" int32_t gnnlm_knn_sims_pq(const float* queries, int64_t ldq, int32_t 
     configured = smem;
   }
   knn_sims_pq_kernel<<<(unsigned)T, 1024, smem, (cudaStream_t)stream>>>(queries, ldq, rotated, ldr, d_q, codes, n_datastore, M,
-                                                                       dsub, centroids, bias, ids, (int)k_nn, metric, sims);
+                                                                       dsub, centroids, bias, ids, (int)k_nn, metric, key_norm2, normalise,
+                                                                       sims);
   GNNLM_LAUNCH_CHECK("gnnlm_knn_sims_pq");
   return 0;
 }

@@ -418,9 +418,18 @@ def load_model_ensemble(filenames, arg_overrides=None, task=None):
             setattr(args, k, v)
         if getattr(args, "reinit_nfeat", None) is None and getattr(getattr(task, "args", None), "reinit_nfeat", False):
             args.reinit_nfeat = True
-        if getattr(args, "quantizer_path", ""):
-            args.quantizer_path = ""        # the codec is in the checkpoint (decoder.tgt_quantizer.*, convert_ckpt.py:40-45)
         quantizer = None
+        qpath = getattr(args, "quantizer_path", "") or ""
+        if qpath:
+            args.quantizer_path = ""        # the codec is in the checkpoint (decoder.tgt_quantizer.*, convert_ckpt.py:40-45) ...
+        if qpath and os.path.exists(qpath) and not any(k.startswith("decoder.tgt_quantizer.") for k in state["model"]):
+            # ... or, for a checkpoint convert_ckpt.py was never run on, in the faiss `quantizer` file: the conversion's buffer
+            # injection (convert_ckpt.py:40-45) done on the fly from the parsed file (formats.read_faiss_quantizer)
+            from .formats import read_faiss_quantizer
+            from .pq_codec import TorchPQCodec
+            cen, A, b = read_faiss_quantizer(qpath)
+            for k, v in TorchPQCodec(centroids=cen, A=A, b=b).state_dict().items():
+                state["model"]["decoder.tgt_quantizer." + k] = v
         if any(k.startswith("decoder.tgt_quantizer.") for k in state["model"]):
             from .pq_codec import TorchPQCodec
             sd = state["model"]

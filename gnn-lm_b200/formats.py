@@ -8,6 +8,8 @@
   {split}_dstore/vals.npy        RAW memmap int16/int32 [N, 1]
   {split}_dstore/neighbors.mmap.{k}   RAW memmap int64 [N_split, k], -1 = missing (knn/find_knn.py:45-66)
   train_dstore/quantized-keys.npy     real NPY uint8 [N_d, M] (knn/quantize_features.py:151-152; read by DeviceDatastore)
+  quantizer                      faiss index file `IndexPreTransform(OPQMatrix -> IndexPQ)` or a bare `IndexPQ`
+                                 (knn/quantize_features.py:92,108-109; read at transformer.py:936-937 through faiss.read_index)
 
 Nothing here touches the GPU; arrays stay memory-mapped and `GraphTokenBlockDataset` slices them per block."""
 import json
@@ -187,3 +189,121 @@ def load_graph_lm_dataset(data_path: str, split: str, *, tokens_per_sample: int,
         context_window=gcn_context_window, intra_context=intra_context, knn_dists=knn_dists, knn_ids=knn_ids,
         break_mode=sample_break_mode, deprecated=deprecated, sizes=np.asarray(sentences.sizes))
     return ds, dictionary
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# faiss `quantizer` file (transformer.py:936-937 + knn/pq_wrapper.py:20-37 need exactly three arrays out of it)
+# ----------------------------------------------------------------------------------------------------------------------
+# faiss (>= 1.5.3, README.md:46) is a third-party dependency that is NOT under /root/reference and is not installed here: the layout
+# below restates faiss/impl/index_write.cpp (write_index_header, write_VectorTransform's generic-LinearTransform branch that an
+# OPQMatrix takes, write_ProductQuantizer, the IndexPQ branch of write_index) as published for 1.5.3 - 1.7.x.  No faiss-written
+# file is available offline, so this reader is "parity unpinned": it checks every fourcc and every redundant size the format
+# carries and raises ValueError on the first mismatch instead of guessing.
+def _fourcc(tag: str) -> int:
+    return struct.unpack("<I", tag.encode("ascii"))[0]
+
+
+class _Reader:
+    def __init__(self, f, path):
+        self.f, self.path = f, path
+
+    def take(self, fmt: str):
+        size = struct.calcsize(fmt)
+        raw = self.f.read(size)
+        if len(raw) != size:
+            raise ValueError(f"{self.path}: truncated faiss index file")
+        return struct.unpack(fmt, raw)[0]
+
+    def vector(self, dtype) -> np.ndarray:
+        n = self.take("<Q")
+        raw = self.f.read(n * np.dtype(dtype).itemsize)
+        if len(raw) != n * np.dtype(dtype).itemsize:
+            raise ValueError(f"{self.path}: truncated faiss index file (vector of {n} x {np.dtype(dtype).name})")
+        return np.frombuffer(raw, dtype=dtype).copy()
+
+    def header(self) -> dict:
+        """write_index_header: d (int32), ntotal (int64), two dummies (int64 = 1 << 20), is_trained (bool), metric_type (int32)
+        [, metric_arg (float32) when metric_type > 1]."""
+        h = {"d": self.take("<i"), "ntotal": self.take("<q")}
+        self.take("<q"), self.take("<q")
+        h["is_trained"] = bool(self.take("<B"))
+        h["metric_type"] = self.take("<i")
+        if h["metric_type"] > 1:
+            h["metric_arg"] = self.take("<f")
+        return h
+
+
+def read_faiss_quantizer(path: str) -> Tuple[np.ndarray, Optional[np.ndarray], Optional[np.ndarray]]:
+    """(centroids [M, 256, dsub] fp32, A [d_out, d_in] or None, b [d_out] / empty or None) -- what NumpyPQCodec / TorchPQCodec
+    extract from `faiss.read_index(path)` (knn/pq_wrapper.py:20-37), without faiss."""
+    with open(path, "rb") as f:
+        r = _Reader(f, path)
+        tag = r.take("<I")
+        A = b = None
+        if tag == _fourcc("IxPT"):
+            outer = r.header()
+            if not outer["is_trained"]:
+                raise ValueError(f"{path}: index is not trained (pq_wrapper.py:15)")
+            nt = r.take("<i")
+            if nt < 1:
+                raise ValueError(f"{path}: IndexPreTransform without a transform")
+            for i in range(nt):
+                vt = r.take("<I")
+                if vt != _fourcc("LTra"):
+                    raise ValueError(f"{path}: transform {i} is not a plain LinearTransform / OPQMatrix (pq_wrapper.py:21-22)")
+                have_bias = bool(r.take("<B"))
+                A_i, b_i = r.vector(np.float32), r.vector(np.float32)
+                d_in, d_out, trained = r.take("<i"), r.take("<i"), bool(r.take("<B"))
+                if A_i.size != d_in * d_out or (have_bias and b_i.size != d_out) or not trained:
+                    raise ValueError(f"{path}: inconsistent LinearTransform ({A_i.size} coefficients for {d_out} x {d_in})")
+                if i == 0:                                        # index.chain.at(0) is the only transform the codec reads (:21)
+                    A, b = A_i.reshape(d_out, d_in), b_i
+            if nt != 1:
+                raise ValueError(f"{path}: {nt} chained transforms; the reference codec applies only the first (pq_wrapper.py:21)")
+            tag = r.take("<I")
+        if tag != _fourcc("IxPq"):
+            raise ValueError(f"{path}: expected an IndexPQ (pq_wrapper.py:32), found {struct.pack('<I', tag)!r}")
+        inner = r.header()
+        d, M, nbits = r.take("<Q"), r.take("<Q"), r.take("<Q")
+        cen = r.vector(np.float32)
+        if nbits != 8:
+            raise ValueError(f"{path}: {nbits}-bit PQ; 8-bit expected (pq_wrapper.py:36)")
+        if M == 0 or d % M or cen.size != d * 256 or d != inner["d"] or (A is not None and A.shape[0] != d):
+            raise ValueError(f"{path}: inconsistent ProductQuantizer (d={d}, M={M}, {cen.size} centroid values)")
+        return cen.reshape(M, 256, d // M), A, b
+
+
+def write_faiss_quantizer(path: str, centroids: np.ndarray, A: Optional[np.ndarray] = None, b: Optional[np.ndarray] = None,
+                          metric_type: int = 1) -> None:
+    """The same layout written back (empty code store): synthetic data directories and the reader's round-trip test."""
+    cen = np.ascontiguousarray(centroids, dtype=np.float32)
+    M, ksub, dsub = cen.shape
+    assert ksub == 256
+    d = M * dsub
+
+    def header(f, dim):
+        f.write(struct.pack("<iqqqBi", dim, 0, 1 << 20, 1 << 20, 1, metric_type))
+
+    def vector(f, a, dtype):
+        a = np.ascontiguousarray(a, dtype=dtype).reshape(-1)
+        f.write(struct.pack("<Q", a.size))
+        f.write(a.tobytes())
+
+    with open(path, "wb") as f:
+        if A is not None:
+            A = np.ascontiguousarray(A, dtype=np.float32)
+            assert A.shape[0] == d
+            bias = np.zeros(0, np.float32) if b is None else np.asarray(b, np.float32)
+            f.write(struct.pack("<I", _fourcc("IxPT")))
+            header(f, A.shape[1])
+            f.write(struct.pack("<i", 1))
+            f.write(struct.pack("<IB", _fourcc("LTra"), int(bias.size > 0)))
+            vector(f, A, np.float32)
+            vector(f, bias, np.float32)
+            f.write(struct.pack("<iiB", A.shape[1], A.shape[0], 1))
+        f.write(struct.pack("<I", _fourcc("IxPq")))
+        header(f, d)
+        f.write(struct.pack("<QQQ", d, M, 8))
+        vector(f, cen, np.float32)
+        vector(f, np.zeros(0, np.uint8), np.uint8)
+        f.write(struct.pack("<iBi", 0, 0, 0))                     # search_type, encode_signs, polysemous_ht

@@ -21,7 +21,7 @@ class KNNModel(object):
         metric_type `l2` / `ip` recompute the similarities (knn_model.py:159-177) from `keys` ([N_d, d] fp16/fp32 in
         HBM, the reference's keys.npy) or, when the keys only exist PQ-compressed, from `pq_codes` [N_d, M] uint8 +
         `quantizer` (TorchPQCodec) -- then against the decoded keys.  `index_file`: as in the reference, a name
-        containing "cosine" switches on the query / key normalisation (:171-172,181-184)."""
+        containing "cosine" switches on the query / key normalisation (:171-172,181-184), for raw and PQ-decoded keys alike."""
         assert metric_type in ["do_not_recomp_l2", "do_not_recomp_ip", "l2", "ip"]
         self.recompute = metric_type in ("l2", "ip")
         if self.recompute and keys is None and pq_codes is None:
@@ -29,13 +29,12 @@ class KNNModel(object):
                              "(pq_codes=..., quantizer=...)")
         self.keys, self.pq_codes, self.quantizer, self.index_file = keys, pq_codes, quantizer, index_file
         self.cosine = "cosine" in index_file
+        self._key_norm2 = None
         if self.recompute and keys is None:
-            if self.cosine:
-                raise NotImplementedError("cosine similarity against PQ-decoded keys")
-            if metric_type == "l2" and quantizer.pre_torch:
+            if (metric_type == "l2" or self.cosine) and quantizer.pre_torch:
                 A = quantizer.A.double()
                 if not torch.allclose(A @ A.T, torch.eye(A.shape[0], dtype=A.dtype, device=A.device), atol=1e-4):
-                    raise NotImplementedError("l2 against PQ-decoded keys needs an orthonormal OPQ transform")
+                    raise NotImplementedError("l2 / cosine against PQ-decoded keys needs an orthonormal OPQ transform")
         self.vals = vals.reshape(-1)
         assert self.vals.dtype in (torch.int16, torch.int32)
         self.dstore_size = self.vals.numel()
@@ -62,7 +61,14 @@ class KNNModel(object):
         qz = self.quantizer
         rot = ops.linear(q, qz.A.contiguous(), None, math=0) if qz.pre_torch else q        # q @ A.T, fp32
         b = qz.b if qz.pre_torch and qz.b.numel() > 0 else None
-        return ops.knn_sims_pq(q, rot, self.pq_codes, qz.centroids_torch, b, knns, self.metric_type)
+        if self.cosine and self.metric_type == "ip" and self._key_norm2 is None:
+            # ||x^||^2 = ||y - b||^2 = sum_m ||centroid[m, c_m] - b_m||^2 for an orthonormal transform: one [M, 256] table per datastore
+            cen = qz.centroids_torch.double()
+            if b is not None:
+                cen = cen - b.double().view(cen.shape[0], 1, cen.shape[2])
+            self._key_norm2 = (cen ** 2).sum(-1).float().contiguous()
+        return ops.knn_sims_pq(q, rot, self.pq_codes, qz.centroids_torch, b, knns, self.metric_type, key_norm2=self._key_norm2,
+                               cosine=self.cosine)
 
     def set_search_results(self, dists: Optional[torch.Tensor], knns: torch.Tensor):
         """Provide the (out-of-scope) search output for the next get_knn_prob call: [num, k] each; dists may be None

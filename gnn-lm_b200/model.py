@@ -235,8 +235,9 @@ class TokenGraphTransformerDecoder(nn.Module):
         if quantizer is not None:
             self.tgt_quantizer = quantizer
         elif _get(args, "quantizer_path"):
-            import faiss  # reference behaviour (transformer.py:936-937); absent here -> pass `quantizer`
-            self.tgt_quantizer = TorchPQCodec(index=faiss.read_index(args.quantizer_path))
+            from .formats import read_faiss_quantizer      # transformer.py:936-937 (faiss.read_index) without faiss
+            cen, A, b = read_faiss_quantizer(args.quantizer_path)
+            self.tgt_quantizer = TorchPQCodec(centroids=cen, A=A, b=b)
         else:
             self.tgt_quantizer = None
         self.short_cut = _get(args, "short_cut", False)

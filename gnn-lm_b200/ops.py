@@ -562,8 +562,9 @@ def knn_sims_keys(queries, keys, ids, metric: str, cosine: bool = False):
     return sims
 
 
-def knn_sims_pq(queries, rotated, codes, centroids, bias, ids, metric: str):
-    """sims [T, k] against the PQ-decoded keys by asymmetric distance computation; rotated = queries @ A.T."""
+def knn_sims_pq(queries, rotated, codes, centroids, bias, ids, metric: str, *, key_norm2=None, cosine: bool = False):
+    """sims [T, k] against the PQ-decoded keys by asymmetric distance computation; rotated = queries @ A.T.
+    cosine: normalised queries (and, for `ip`, normalised decoded keys: key_norm2 [M, 256] = ||centroid - b_m||^2)."""
     T = queries.shape[0]
     M, ksub, dsub = centroids.shape
     assert ksub == 256 and codes.dtype == torch.uint8 and codes.is_contiguous() and codes.shape[1] == M
@@ -571,5 +572,5 @@ def knn_sims_pq(queries, rotated, codes, centroids, bias, ids, metric: str):
     sims = torch.empty(ids.shape, device=queries.device, dtype=torch.float32)
     L.call("gnnlm_knn_sims_pq", L.ptr(queries), queries.stride(0), queries.shape[1], L.ptr(rotated), rotated.stride(0),
            L.ptr(codes), codes.shape[0], M, dsub, L.ptr(centroids), L.ptr(bias), L.ptr(ids), ids.shape[1], METRICS[metric],
-           L.ptr(sims), T, L.stream_ptr())
+           L.ptr(key_norm2), (3 if metric == "ip" else 2) if cosine else 0, L.ptr(sims), T, L.stream_ptr())
     return sims

@@ -472,14 +472,16 @@ int32_t gnnlm_knn_full_prob(const float* dists, const int64_t* ids, int64_t k_nn
  *  _pq:   keys only as PQ codes [n_datastore, M] uint8 + centroids [M, 256, dsub] (+ OPQ bias [M*dsub], nullable):
  *         similarity to the DECODED key x^ = (y - b) A (knn/pq_wrapper.py:169-203) by asymmetric distance computation.
  *         rotated [T, M*dsub] = queries A^T (a gnnlm_linear call; pass the queries themselves when there is no OPQ
- *         transform).  l2 assumes A A^T = I (OPQ rotations are orthonormal).  M % 4 == 0, M*(256+dsub)*4 B <= 220 KB. */
+ *         transform).  l2 assumes A A^T = I (OPQ rotations are orthonormal).  M % 4 == 0, M*(256+dsub)*4 B <= 220 KB.
+ *         normalise as above (an extension: the reference needs the raw keys for a cosine index); bit 0 reads
+ *         key_norm2 [M, 256] = ||centroid[m, c] - b_m||^2, the squared norm of a decoded key being the sum over m (A A^T = I). */
 int32_t gnnlm_knn_sims_keys(const float* queries, int64_t ldq, const void* keys, int32_t key_dtype, int64_t n_datastore,
                             int32_t d, const int64_t* ids, int64_t k_nn, int32_t metric, int32_t normalise, float* sims,
                             int64_t T, gnnlm_stream_t stream);
 int32_t gnnlm_knn_sims_pq(const float* queries, int64_t ldq, int32_t d_q, const float* rotated, int64_t ldr,
                           const uint8_t* codes, int64_t n_datastore, int32_t M, int32_t dsub, const float* centroids,
-                          const float* bias, const int64_t* ids, int64_t k_nn, int32_t metric, float* sims, int64_t T,
-                          gnnlm_stream_t stream);
+                          const float* bias, const int64_t* ids, int64_t k_nn, int32_t metric, const float* key_norm2,
+                          int32_t normalise, float* sims, int64_t T, gnnlm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (9) Training backward of the HGT fine-tuning step (`--freeze` trains decoder.hgt_decoder.* only,

@@ -8,6 +8,7 @@ import shutil
 
 import numpy as np
 import pytest
+import torch
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -118,3 +119,79 @@ def test_load_graph_lm_dataset_errors(tmp_path):
         f.truncate(64)
     with pytest.raises(ValueError):                             # truncated neighbour file
         load_graph_lm_dataset(root, "valid", tokens_per_sample=8, gcn_k=4)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# faiss `quantizer` file (transformer.py:936-937, pq_wrapper.py:20-37) -- layout restated from faiss's index_write.cpp;
+# faiss is absent here, so this pins the reader to the writer of the same restatement and to hand-assembled bytes.
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("opq,with_b", [(True, False), (True, True), (False, False)])
+def test_faiss_quantizer_round_trip(tmp_path, opq, with_b):
+    from gnnlm_b200.formats import read_faiss_quantizer, write_faiss_quantizer
+    rng = np.random.RandomState(0)
+    M, dsub, d_in = 8, 4, 40
+    cen = rng.randn(M, 256, dsub).astype(np.float32)
+    A = rng.randn(M * dsub, d_in).astype(np.float32) if opq else None
+    b = rng.randn(M * dsub).astype(np.float32) if with_b else None
+    path = str(tmp_path / "quantizer")
+    write_faiss_quantizer(path, cen, A, b)
+    cen2, A2, b2 = read_faiss_quantizer(path)
+    assert (cen2 == cen).all()
+    if opq:
+        assert A2.shape == (M * dsub, d_in) and (A2 == A).all() and b2.size == (M * dsub if with_b else 0)
+        assert not with_b or (b2 == b).all()
+    else:
+        assert A2 is None and b2 is None
+
+
+def test_faiss_quantizer_hand_assembled_bytes(tmp_path):
+    """The byte layout spelled out field by field (index_write.cpp: write_index_header, generic LinearTransform 'LTra',
+    write_ProductQuantizer, IndexPQ 'IxPq'), independent of write_faiss_quantizer."""
+    import struct
+    from gnnlm_b200.formats import read_faiss_quantizer
+    M, dsub = 4, 2
+    d = M * dsub
+    cen = np.arange(M * 256 * dsub, dtype=np.float32)
+    A = np.arange(d * d, dtype=np.float32)
+    hdr = lambda dim: struct.pack("<i", dim) + struct.pack("<q", 0) + struct.pack("<qq", 1 << 20, 1 << 20) + b"\x01" + struct.pack("<i", 0)
+    raw = b"IxPT" + hdr(d) + struct.pack("<i", 1)
+    raw += b"LTra" + b"\x00" + struct.pack("<Q", d * d) + A.tobytes() + struct.pack("<Q", 0) + struct.pack("<ii", d, d) + b"\x01"
+    raw += b"IxPq" + hdr(d) + struct.pack("<QQQ", d, M, 8) + struct.pack("<Q", cen.size) + cen.tobytes()
+    raw += struct.pack("<Q", 0) + struct.pack("<i", 0) + b"\x00" + struct.pack("<i", 0)
+    path = tmp_path / "quantizer"
+    path.write_bytes(raw)
+    cen2, A2, b2 = read_faiss_quantizer(str(path))
+    assert cen2.shape == (M, 256, dsub) and (cen2.reshape(-1) == cen).all() and (A2.reshape(-1) == A).all() and b2.size == 0
+    for bad in (raw[:100], b"IxFl" + raw[4:], raw.replace(b"LTra", b"PcAm")):
+        path.write_bytes(bad)
+        with pytest.raises(ValueError):
+            read_faiss_quantizer(str(path))
+    nine_bit = raw.replace(struct.pack("<QQQ", d, M, 8), struct.pack("<QQQ", d, M, 9))
+    path.write_bytes(nine_bit)
+    with pytest.raises(ValueError):
+        read_faiss_quantizer(str(path))
+
+
+def test_decoder_builds_codec_from_quantizer_path(tmp_path):
+    """--quantizer_path (transformer_lm.py:122-139; transformer.py:936-937) without faiss: same buffers as the arrays give."""
+    from gnnlm_b200.formats import write_faiss_quantizer
+    from gnnlm_b200.model import TransformerLanguageModel, default_args
+    from gnnlm_b200.pq_codec import TorchPQCodec
+    rng = np.random.RandomState(1)
+    d, M = 64, 16
+    cen = rng.randn(M, 256, d // M).astype(np.float32)
+    A = np.linalg.qr(rng.randn(d, d))[0].astype(np.float32)
+    path = str(tmp_path / "quantizer")
+    write_faiss_quantizer(path, cen, A)
+    args = default_args(decoder_embed_dim=d, decoder_attention_heads=4, graph_layer=1, quantizer_path=path)
+
+    class _Dict:
+        def __len__(self):
+            return 50
+
+        def pad(self):
+            return 1
+    m = TransformerLanguageModel.build_model(args, None, dictionary=_Dict())
+    want = TorchPQCodec(centroids=cen, A=A, b=np.zeros(0, np.float32)).state_dict()
+    got = m.decoder.tgt_quantizer.state_dict()
+    assert sorted(got) == sorted(want) and all(torch.equal(got[k], want[k]) for k in want)

@@ -745,6 +745,18 @@ def test_eval_lm_main_from_checkpoint_and_data_dir(dev, tmp_path):
     m_pq.decoder.tgt_quantizer = TorchPQCodec(centroids=model.decoder.tgt_quantizer.centroids_torch.numpy())
     want_pq = evaluate(m_pq.to(dev).set_math("fp32"), ds_mem, dstore, plain, max_sentences=2, device=dev)
     assert got_pq["count"] == n_tok and got_pq["score_sum"] == want_pq["score_sum"] != want["score_sum"]
+    # a checkpoint convert_ckpt.py was never run on (no decoder.tgt_quantizer.* at all) + the faiss `quantizer` file its
+    # --quantizer_path names (transformer.py:936-937): the codec is parsed from the file (formats.read_faiss_quantizer)
+    from gnnlm_b200.formats import write_faiss_quantizer
+    q_ = model.decoder.tgt_quantizer
+    qfile = str(tmp_path / "quantizer")
+    write_faiss_quantizer(qfile, q_.centroids_torch.numpy(), q_.A.numpy(), q_.b.numpy())
+    sd_raw = {k: v for k, v in sd.items() if not k.startswith("decoder.tgt_quantizer.")}
+    ckpt_raw = str(tmp_path / "checkpoint_raw.pt")
+    raw_args = Namespace(**dict(vars(ckpt_args), quantizer_path=qfile))
+    torch.save({"args": raw_args, "model": sd_raw}, ckpt_raw)
+    got_raw = main([root, "--path", ckpt_raw] + argv[3:], device=dev, log=lines.append)
+    assert got_raw["count"] == n_tok and got_raw["score_sum"] == want["score_sum"]
 
 
 def test_knn_model_precomputed_arrays(dev):
@@ -1279,10 +1291,11 @@ def test_knn_sims_keys_golden(case, dev, golden_dir):
 
 
 @pytest.mark.parametrize("M,dsub,opq,with_b", [(128, 8, True, True), (64, 8, True, False), (16, 4, False, False), (32, 16, True, True)])
-@pytest.mark.parametrize("metric", ["l2", "ip"])
-def test_knn_sims_pq_vs_oracle(M, dsub, opq, with_b, metric, dev):
+@pytest.mark.parametrize("metric,cosine", [("l2", False), ("ip", False), ("ip", True), ("l2", True)])
+def test_knn_sims_pq_vs_oracle(M, dsub, opq, with_b, metric, cosine, dev):
     """Similarities against the PQ-decoded keys (asymmetric distance computation on the codes) == the oracle's
-    recompute on pq_decode(codes)."""
+    recompute on pq_decode(codes); with a cosine index the queries are normalised first (knn_model.py:181-184) and `ip`
+    normalises the (decoded) keys (:171-172)."""
     from gnnlm_b200.knn_model import KNNModel
     from gnnlm_b200.pq_codec import TorchPQCodec
     from oracle import model_oracle as mo
@@ -1296,10 +1309,11 @@ def test_knn_sims_pq_vs_oracle(M, dsub, opq, with_b, metric, dev):
     ids = rng.randint(0, n_d, size=(T, k)).astype(np.int64)
     ids[rng.rand(T, k) < 0.05] = -1
     keys_hat = mo.pq_decode(codes, cen, A, b if (b is not None and b.size) else None)
-    ref = mo.knn_sims(None, metric, torch.from_numpy(q), keys_hat, torch.from_numpy(ids)).numpy()
+    ref = mo.knn_sims(None, metric, mo.knn_queries(torch.from_numpy(q), cosine), keys_hat, torch.from_numpy(ids), cosine).numpy()
     codec = TorchPQCodec(centroids=cen, A=A, b=b).to(dev)
     vals = torch.zeros(n_d, dtype=torch.int32, device=dev)
-    m = KNNModel(vals, vocab_size=10, metric_type=metric, pq_codes=torch.from_numpy(codes).to(dev), quantizer=codec)
+    m = KNNModel(vals, vocab_size=10, metric_type=metric, pq_codes=torch.from_numpy(codes).to(dev), quantizer=codec,
+                 index_file="faiss_store.cosine" if cosine else "faiss_store")
     sims = m.similarities(torch.from_numpy(q).to(dev), None, torch.from_numpy(ids).to(dev)).cpu().numpy()
     scale = np.abs(ref).max()
     np.testing.assert_allclose(sims, ref, rtol=1e-4, atol=1e-5 * scale)
