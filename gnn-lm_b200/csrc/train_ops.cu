@@ -457,6 +457,123 @@ __global__ void __launch_bounds__(256) scatter_add_rows_kernel(float* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------- causal edges, GEMM form
+// The backward of the tgt-intra-tgt attention on the tensor cores at fp32 parity (MATH_F16X3 products through
+// gnnlm_linear_batched_f16x3, like the forward of attn_gemm.cu): per block and head
+//     S = Q K'^T            g = dOut V'^T                               (two products, causal tile schedule)
+//     P = softmax_causal(S)   D_i = sum_j P_ij beta_ij g_ij   w_ij = scale beta_ij P_ij   ds_ij = scale P_ij (beta_ij g_ij - D_i)
+//     dQ = ds K'            dV' = w^T dOut            dK' = ds^T Q      (three products)
+// and the two kernels below are everything in between: a row pass for the statistics {max, 1 / sum, D} and a 64 x 64 tile pass
+// that writes ds row-major and w, ds TRANSPOSED, all as split-fp16 A operands [H, L, 2L].  Only tiles on or below the diagonal are
+// touched: the buffers are zero above it once and stay so (the caller keeps them).  beta = the attention dropout multiplier of the
+// edge (dm_scale; 1 without dropout), regenerated from (seed, destination, source, head) as in the forward.
+__global__ void __launch_bounds__(256) causal_bwd_stats_kernel(const float* __restrict__ S, const float* __restrict__ G, int64_t L,
+                                                               int64_t ctx, int H, int64_t row0, float* __restrict__ stats, AttnDrop ad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)H * L;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const int64_t i = r % L;
+    const int head = (int)(r / L);
+    const float* s = S + r * L;
+    const float* g = G + r * L;
+    const int64_t lo_j = (ctx > 0 && i + 1 > ctx) ? i + 1 - ctx : 0;
+    float m = -INFINITY, l = 0.f;
+    for (int64_t j = (lo_j & ~(int64_t)3) + lane * 4; j <= i; j += 128) {
+      const float4 x4 = *reinterpret_cast<const float4*>(s + j);
+      float x[4] = {x4.x, x4.y, x4.z, x4.w};
+      float mx = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (j + e < lo_j || j + e > i) x[e] = -INFINITY;
+        mx = fmaxf(mx, x[e]);
+      }
+      if (mx > m) {
+        l *= __expf(m - mx);
+        m = mx;
+      }
+      if (m > -INFINITY) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) l += __expf(x[e] - m);
+      }
+    }
+    const float M = warp_max(m);                                  // the diagonal is always valid: M is finite
+    l = warp_sum(m > -INFINITY ? l * __expf(m - M) : 0.f);
+    const float inv = 1.f / l;
+    float D = 0.f;
+    for (int64_t j = (lo_j & ~(int64_t)3) + lane * 4; j <= i; j += 128) {
+      const float4 x4 = *reinterpret_cast<const float4*>(s + j), g4 = *reinterpret_cast<const float4*>(g + j);
+      const float x[4] = {x4.x, x4.y, x4.z, x4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (j + e >= lo_j && j + e <= i) {
+          const float be = ad.p_thresh ? dm_scale(ad.seed, dm_edge(row0 + i, row0 + j + e, head), ad.p_thresh, ad.keep_scale) : 1.f;
+          D = fmaf(__expf(x[e] - M) * inv, be * gg[e], D);
+        }
+    }
+    D = warp_sum(D);
+    if (lane == 0) {
+      stats[r * 3 + 0] = M;
+      stats[r * 3 + 1] = inv;
+      stats[r * 3 + 2] = D;
+    }
+  }
+}
+
+constexpr int CBT = 64;                                           // tile edge of the transposing pass
+__global__ void __launch_bounds__(256) causal_bwd_tile_kernel(const float* __restrict__ S, const float* __restrict__ G,
+                                                              const float* __restrict__ stats, int64_t L, int64_t ctx, int64_t row0,
+                                                              float scale, __half* __restrict__ dS, __half* __restrict__ WT,
+                                                              __half* __restrict__ dST, AttnDrop ad) {
+  const int jt = blockIdx.x, it = blockIdx.y, head = blockIdx.z;
+  if (jt > it) return;                                            // above the diagonal: zero, and never written
+  __shared__ float sw[CBT][CBT + 1], sd[CBT][CBT + 1];
+  const int64_t i0 = (int64_t)it * CBT, j0 = (int64_t)jt * CBT;
+  const int c4 = (threadIdx.x & 15) * 4, r0 = threadIdx.x >> 4;
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int il = r0 + 16 * rr;
+    const int64_t i = i0 + il, row = (int64_t)head * L + i;
+    const float M = stats[row * 3], inv = stats[row * 3 + 1], D = stats[row * 3 + 2];
+    const int64_t lo_j = (ctx > 0 && i + 1 > ctx) ? i + 1 - ctx : 0;
+    const float4 x4 = *reinterpret_cast<const float4*>(S + row * L + j0 + c4), g4 = *reinterpret_cast<const float4*>(G + row * L + j0 + c4);
+    const float x[4] = {x4.x, x4.y, x4.z, x4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    float w[4], ds[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t j = j0 + c4 + e;
+      w[e] = ds[e] = 0.f;
+      if (j >= lo_j && j <= i) {                                  // entries of S / G beyond the diagonal may be unwritten: never used
+        const float be = ad.p_thresh ? dm_scale(ad.seed, dm_edge(row0 + i, row0 + j, head), ad.p_thresh, ad.keep_scale) : 1.f;
+        const float P = __expf(x[e] - M) * inv;
+        w[e] = scale * be * P;
+        ds[e] = scale * P * (be * gg[e] - D);
+      }
+      sw[il][c4 + e] = w[e];
+      sd[il][c4 + e] = ds[e];
+    }
+    uint2 hi, lo;
+    split4_f16(ds[0], ds[1], ds[2], ds[3], hi, lo);
+    __half* p = dS + row * 2 * L + j0 + c4;
+    *reinterpret_cast<uint2*>(p) = hi;
+    *reinterpret_cast<uint2*>(p + L) = lo;
+  }
+  __syncthreads();
+  const int iq = (threadIdx.x & 15) * 4;                          // four consecutive destinations of one source row
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int jl = r0 + 16 * rr;
+    const int64_t trow = ((int64_t)head * L + j0 + jl) * 2 * L + i0 + iq;
+    uint2 hi, lo;
+    split4_f16(sw[iq][jl], sw[iq + 1][jl], sw[iq + 2][jl], sw[iq + 3][jl], hi, lo);
+    *reinterpret_cast<uint2*>(WT + trow) = hi;
+    *reinterpret_cast<uint2*>(WT + trow + L) = lo;
+    split4_f16(sd[iq][jl], sd[iq + 1][jl], sd[iq + 2][jl], sd[iq + 3][jl], hi, lo);
+    *reinterpret_cast<uint2*>(dST + trow) = hi;
+    *reinterpret_cast<uint2*>(dST + trow + L) = lo;
+  }
+}
+
 }  // namespace gnnlm
 
 using namespace gnnlm;
@@ -633,5 +750,25 @@ extern "C" int32_t gnnlm_scatter_add_rows(float* dst, int64_t ld_dst, const floa
   const unsigned grid = (unsigned)(ceil_div(n, 256) < 148 * 16 ? ceil_div(n, 256) : 148 * 16);
   scatter_add_rows_kernel<<<grid, 256, 0, stream>>>(dst, ld_dst, src, ld_src, ids, rows, rows_dev, cols);
   GNNLM_LAUNCH_CHECK("gnnlm_scatter_add_rows");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_causal_softmax_bwd_split(const float* S, const float* G, int64_t L, int64_t intra_ctx, int32_t H, int64_t row0,
+                                                  float scale, float p_drop, uint64_t seed, float* stats, void* dS, void* WT, void* dST,
+                                                  cudaStream_t stream) {
+  GNNLM_CHECK_ARG(S && G && stats && dS && WT && dST, GNNLM_E_ARG, "gnnlm_causal_softmax_bwd_split: null pointer");
+  GNNLM_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, GNNLM_E_ARG, "gnnlm_causal_softmax_bwd_split: dropout rate must be in [0, 1)");
+  GNNLM_CHECK_ARG(L > 0 && L % CBT == 0 && L / CBT <= 65535 && H > 0 && H <= 65535 && row0 >= 0, GNNLM_E_SHAPE,
+                  "gnnlm_causal_softmax_bwd_split: L must be a multiple of %d", CBT);
+  GNNLM_CHECK_ARG((uintptr_t)S % 16 == 0 && (uintptr_t)G % 16 == 0 && (uintptr_t)dS % 8 == 0 && (uintptr_t)WT % 8 == 0 && (uintptr_t)dST % 8 == 0,
+                  GNNLM_E_SHAPE, "gnnlm_causal_softmax_bwd_split: S / G must be 16 B, the split outputs 8 B aligned");
+  const AttnDrop ad{seed, (uint32_t)(p_drop * 16777216.f), 1.f / (1.f - p_drop)};
+  int64_t blocks = ceil_div((int64_t)H * L, 8);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  causal_bwd_stats_kernel<<<(unsigned)blocks, 256, 0, stream>>>(S, G, L, intra_ctx, H, row0, stats, ad);
+  GNNLM_LAUNCH_CHECK("gnnlm_causal_softmax_bwd_split (stats)");
+  const dim3 grid((unsigned)(L / CBT), (unsigned)(L / CBT), (unsigned)H);
+  causal_bwd_tile_kernel<<<grid, 256, 0, stream>>>(S, G, stats, L, intra_ctx, row0, scale, (__half*)dS, (__half*)WT, (__half*)dST, ad);
+  GNNLM_LAUNCH_CHECK("gnnlm_causal_softmax_bwd_split (tiles)");
   return 0;
 }

@@ -23,6 +23,7 @@ two reference runs on different GPUs); the distribution and the gradient of the 
 side is skipped as in evaluation (nothing reads it; its parameters get zero gradients in the reference too).
 """
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -143,8 +144,79 @@ def _attn_fwd_train(q, k, v, H, scale, out, accumulate, p, seed, *, indptr=None,
     return out
 
 
+_GEMM_BWD_BUFFERS = {}
+
+
+def causal_bwd_gemm_supported(d: int, H: int, Lb: int) -> bool:
+    """Shape envelope of the GEMM form of the causal-edge backward (GNNLM_TRAIN_GEMM_BWD=0 switches it off for A/B timing)."""
+    return os.environ.get("GNNLM_TRAIN_GEMM_BWD", "1") != "0" and Lb % 64 == 0 and Lb >= 256 and (d // H) % 8 == 0
+
+
+def _causal_bwd_gemm(q, k, v, dout, Lb: int, intra_ctx: int, H: int, scale: float, p: float, seed: int):
+    """Backward of out = scale * softmax_causal(Q K'^T) V' on the tensor cores at fp32 parity: five batched 3xFP16 products per
+    block (all heads in one launch each) around gnnlm_causal_softmax_bwd_split -- instead of streaming every K' / V' / Q / dOut row
+    of the L (L + 1) / 2 edges through L2 three times (gnnlm_hgt_causal_attn_bwd: 115 ms per layer at L = 3072)."""
+    T, d = q.shape
+    dk_ = d // H
+    dev = q.device
+    st = L.stream_ptr
+    f16 = dict(device=dev, dtype=torch.float16)
+    # gradients can be tiny: scale dOut into the fp16 range by a power of two (undone by the closing products' 1 / w_scale)
+    amax = float(dout.abs().max())
+    if not math.isfinite(amax):
+        raise FloatingPointError("non-finite gradient reached the attention backward")
+    s = 2.0 ** math.floor(math.log2(4.0 / amax)) if amax > 0 else 1.0
+    g = _zeros(T, d, like=dout)
+    L.call("gnnlm_axpy_f32", L.ptr(g), g.stride(0), L.ptr(dout), dout.stride(0), T, None, d, float(s), st())
+    key = (H, Lb, dev)
+    if key not in _GEMM_BWD_BUFFERS:        # split operands: zero above the diagonal once, only lower tiles are ever rewritten
+        _GEMM_BWD_BUFFERS.clear()
+        _GEMM_BWD_BUFFERS[key] = tuple(torch.zeros((H, Lb, 2 * Lb), **f16) for _ in range(3)) + \
+            tuple(torch.empty((H, Lb, Lb), device=dev, dtype=torch.float32) for _ in range(2)) + \
+            (torch.empty((H, Lb, 3), device=dev, dtype=torch.float32),)
+    dS, WT, dST, S, G, stats = _GEMM_BWD_BUFFERS[key]
+    dq, dkk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+
+    def a_style(x):                          # [H, Lb, 2 d_k] split rows: A operand of a product contracting over d_k
+        o = torch.empty((H, Lb, 2 * dk_), **f16)
+        L.call("gnnlm_heads_split_f16", L.ptr(x), x.stride(0), Lb, H, dk_, 1, L.ptr(o), None, st())
+        return o
+
+    def w_style(x):                          # hi, lo [H, Lb, d_k]: W operand contracting over d_k
+        hi, lo = torch.empty((H, Lb, dk_), **f16), torch.empty((H, Lb, dk_), **f16)
+        L.call("gnnlm_heads_split_f16", L.ptr(x), x.stride(0), Lb, H, dk_, 0, L.ptr(hi), L.ptr(lo), st())
+        return hi, lo
+
+    def w_transposed(x):                     # hi, lo [H, d_k, Lb]: W operand contracting over the block's tokens
+        hi, lo = torch.empty((H, dk_, Lb), **f16), torch.empty((H, dk_, Lb), **f16)
+        L.call("gnnlm_heads_transpose_split_f16", L.ptr(x), x.stride(0), Lb, H, dk_, L.ptr(hi), L.ptr(lo), st())
+        return hi, lo
+
+    def scores(a, w, out, tag):              # out[h] = a_h w_h^T, tiles above the diagonal skipped
+        L.call("gnnlm_linear_batched_f16x3", L.ptr(a), 2 * dk_, Lb * 2 * dk_, L.ptr(w[0]), L.ptr(w[1]), dk_, Lb * dk_, 1.0, None, 0, 0,
+               L.ptr(out), Lb, Lb * Lb, H, Lb, Lb, dk_, 1, st(), tag=tag)
+
+    def close(a, w, out, causal, tag):       # out[:, h] = (1 / s) a_h w_h^T, contraction over the block's tokens
+        L.call("gnnlm_linear_batched_f16x3", L.ptr(a), 2 * Lb, Lb * 2 * Lb, L.ptr(w[0]), L.ptr(w[1]), Lb, dk_ * Lb, float(s), None, 0, 0,
+               L.ptr(out), out.stride(0), dk_, H, Lb, dk_, Lb, causal, st(), tag=tag)
+
+    for b in range(T // Lb):
+        rows = slice(b * Lb, (b + 1) * Lb)
+        qb, kb, vb, gb = q[rows], k[rows], v[rows], g[rows]
+        scores(a_style(qb), w_style(kb), S, "attn_bwd_qk")
+        scores(a_style(gb), w_style(vb), G, "attn_bwd_gv")
+        L.call("gnnlm_causal_softmax_bwd_split", L.ptr(S), L.ptr(G), Lb, intra_ctx, H, b * Lb, float(scale), float(p), seed, L.ptr(stats),
+               L.ptr(dS), L.ptr(WT), L.ptr(dST), st())
+        close(dS, w_transposed(kb), dq[rows], 2, "attn_bwd_dq")       # row pair r contracts over k < 256 (r + 1): dS is causal
+        close(WT, w_transposed(gb), dv[rows], 0, "attn_bwd_dv")
+        close(dST, w_transposed(qb), dkk[rows], 0, "attn_bwd_dk")
+    return dq, dkk, dv
+
+
 def _attn_bwd(q, k, v, dout, H, scale, *, indptr=None, indices=None, causal=(0, 0), atomics: bool = False, p: float = 0.0, seed: int = 0):
     d = q.shape[1]
+    if causal[0] > 0 and not atomics and causal_bwd_gemm_supported(d, H, causal[0]):
+        return _causal_bwd_gemm(q, k, v, dout, causal[0], causal[1], H, scale, p, seed)
     dq = torch.empty_like(q)
     if causal[0] > 0 and not atomics:       # by-destination + by-source passes, no atomics (gnnlm_hgt_causal_attn_bwd)
         dk, dv = torch.empty_like(k), torch.empty_like(v)

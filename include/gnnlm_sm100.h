@@ -509,6 +509,16 @@ int32_t gnnlm_hgt_causal_attn_bwd(const float* q, int64_t ldq, const float* k, i
                                   const float* dout, int64_t ldo, int64_t B, int64_t L, int64_t intra_ctx, int32_t H, int32_t d_k,
                                   float scale, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv, int64_t lddv,
                                   float* stats, float p_drop, uint64_t seed, gnnlm_stream_t stream);
+/* The same backward in GEMM form (tensor cores at fp32 parity): S = Q K'^T and G = dOut V'^T come from gnnlm_linear_batched_f16x3
+ * (causal = 1), this entry turns them into the split-fp16 A operands [H, L, 2L] of the three closing products -- dS row-major
+ * (dQ = dS K', causal = 2), W^T (dV' = W^T dOut) and dS^T (dK' = dS^T Q) -- with P = softmax_causal(S), D_i = sum_j P_ij beta_ij G_ij,
+ * W_ij = scale beta_ij P_ij, dS_ij = scale P_ij (beta_ij G_ij - D_i), beta the attention-dropout multiplier of edge
+ * (row0 + i, row0 + j, head).  S, G fp32 [H, L, L] (entries above the diagonal are never read); stats [H, L, 3] scratch.
+ * Only the 64 x 64 tiles on or below the diagonal are written: dS / WT / dST must be zero above it (allocate them zeroed once
+ * and reuse them).  L % 64 == 0. */
+int32_t gnnlm_causal_softmax_bwd_split(const float* S, const float* G, int64_t L, int64_t intra_ctx, int32_t H, int64_t row0,
+                                       float scale, float p_drop, uint64_t seed, float* stats, void* dS, void* WT, void* dST,
+                                       gnnlm_stream_t stream);
 /* Dropout in training (hgt.py:74-75: `drop` on the output projection :401, `attn_drop` on the edge-softmax weights :356; the
  * adaptive softmax's input / tail dropouts, adaptive_softmax.py:156,101).  A mask is a pure function of (seed, element): splitmix64
  * of seed + index * 0x9E3779B97F4A7C15, keep iff its top 24 bits >= floor(p * 2^24), kept values scaled by 1 / (1 - p); element

@@ -1905,6 +1905,41 @@ def test_training_backward_kernels_direct(dev):
     np.testing.assert_allclose(lg_dev.cpu().double().numpy(), gl.numpy(), rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("Lb,ctx,H,d,p", [(256, 0, 4, 256, 0.0), (320, 100, 8, 512, 0.0), (512, 0, 8, 1024, 0.1), (384, 37, 2, 128, 0.25)])
+def test_causal_backward_gemm_form(Lb, ctx, H, d, p, dev, monkeypatch):
+    """The tensor-core (GEMM) form of the causal-edge backward (train._causal_bwd_gemm: five 3xFP16 batched products around
+    gnnlm_causal_softmax_bwd_split) == torch.autograd over the fp64 dense statement (no dropout), and == the streaming form
+    (gnnlm_hgt_causal_attn_bwd, same (seed, edge)-addressed masks) with attention dropout; tiny gradients keep their precision."""
+    _need_tc()
+    from gnnlm_b200 import train
+    torch.manual_seed(Lb + H)
+    B, scale, seed = 2, 0.5, 991
+    q, k, v = (torch.randn(B * Lb, d) * 0.4 for _ in range(3))
+    for gscale in (1.0, 1e-6):
+        dout = torch.randn(B * Lb, d) * gscale
+        assert train.causal_bwd_gemm_supported(d, H, Lb)
+        got = train._attn_bwd(q.to(dev), k.to(dev), v.to(dev), dout.to(dev), H, scale, causal=(Lb, ctx), p=p, seed=seed)
+        monkeypatch.setenv("GNNLM_TRAIN_GEMM_BWD", "0")
+        stream = train._attn_bwd(q.to(dev), k.to(dev), v.to(dev), dout.to(dev), H, scale, causal=(Lb, ctx), p=p, seed=seed)
+        monkeypatch.delenv("GNNLM_TRAIN_GEMM_BWD")
+        for a, b in zip(got, stream):
+            ref = b.cpu().double()
+            assert float((a.cpu().double() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+        if p == 0.0:
+            qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
+            i = torch.arange(Lb)
+            allowed = (i[None, :] <= i[:, None]) & ((i[:, None] - i[None, :] < ctx) if ctx > 0 else torch.ones(Lb, Lb, dtype=torch.bool))
+            dk_ = d // H
+            outs = []
+            for b in range(B):
+                qh, kh, vh = (t[b * Lb:(b + 1) * Lb].view(Lb, H, dk_).transpose(0, 1) for t in (qd, kd, vd))
+                sc = (qh @ kh.transpose(1, 2)).masked_fill(~allowed, -float("inf"))
+                outs.append((torch.softmax(sc, -1) @ vh).transpose(0, 1).reshape(Lb, d))
+            g = torch.autograd.grad(scale * torch.cat(outs), [qd, kd, vd], dout.double())
+            for a, b in zip(got, g):
+                assert float((a.cpu().double() - b).abs().max()) < 2e-5 * float(b.abs().max())
+
+
 def test_training_steps_reduce_the_loss(dev):
     """train.train_step (criterion + backward + --clip-norm + Adam) on a --freeze model: only decoder.hgt_decoder.* moves and
     the loss of a fixed batch goes down."""
