@@ -88,6 +88,8 @@ SIGNATURES = {
     "gnnlm_dropout_f32": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _f32, C.c_uint64, _p]),
     "gnnlm_hgt_causal_attn_bwd": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _i64, _i64, _i64, _i32, _i32, _f32, _p, _i64, _p, _i64, _p, _i64,
                                          _p, _f32, C.c_uint64, _p]),
+    "gnnlm_hgt_edge_attn_bwd_sym": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _i32, _f32, _p, _i64, _p, _i64, _p, _i64, _p,
+                                           _f32, C.c_uint64, _p]),
     "gnnlm_causal_softmax_bwd_split": (_i32, [_p, _p, _i64, _i64, _i32, _i64, _f32, _f32, C.c_uint64, _p, _p, _p, _p, _p]),
     "gnnlm_layernorm_bwd": (_i32, [_p, _i64, _p, _i64, _p, _f32, _p, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _p]),
     "gnnlm_xent_fwd_bwd": (_i32, [_p, _i64, _p, _i64, _i64, _f32, _p, _p]),
@@ -100,7 +102,7 @@ SIGNATURES = {
 
 _lib = None
 launches = 0          # number of CUDA kernels launched through the C ABI (bench.py's gpu_launches)
-KERNELS_PER_CALL = {"gnnlm_graph_count": 3, "gnnlm_unique_centres": 2, "gnnlm_hgt_causal_attn_bwd": 2, "gnnlm_causal_softmax_bwd_split": 2, "gnnlm_knn_full_prob": 2, "gnnlm_graph_dedup": 12,   # everything else launches exactly one
+KERNELS_PER_CALL = {"gnnlm_graph_count": 3, "gnnlm_unique_centres": 2, "gnnlm_hgt_causal_attn_bwd": 2, "gnnlm_causal_softmax_bwd_split": 2, "gnnlm_hgt_edge_attn_bwd_sym": 2, "gnnlm_knn_full_prob": 2, "gnnlm_graph_dedup": 12,   # everything else launches exactly one
                     "gnnlm_host_copy": 0}
 TIMING = None         # when a list: (name, tag, start_event, end_event, work) per call (bench.py per-kernel pass)
 

@@ -50,7 +50,9 @@ __global__ void __launch_bounds__(256) edge_attn_bwd_kernel(const float* __restr
                                                             const int32_t* __restrict__ n_dst_dev, int64_t causal_L, int64_t intra_ctx,
                                                             int group, float scale, float* __restrict__ dq, int64_t lddq,
                                                             float* __restrict__ dk, int64_t lddk, float* __restrict__ dv, int64_t lddv,
-                                                            AttnDrop ad) {
+                                                            AttnDrop ad, float* __restrict__ stats, int H, int exclusive) {
+  // stats != NULL: first pass of the atomic-free form -- dQ and {max, 1 / sum, D} per (destination, head) only; dK' / dV' come
+  // from csr_bwd_dkv_kernel.  exclusive: every source feeds exactly one edge (source id = edge id): plain stores.
   const int64_t n_dst = live_rows(n_dst_cap, n_dst_dev);
   const int lane = threadIdx.x & 31;
   const int col = lane * C;
@@ -111,12 +113,79 @@ __global__ void __launch_bounds__(256) edge_attn_bwd_kernel(const float* __restr
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         dqr[c] = fmaf(ds, kr[col + c], dqr[c]);
-        atomicAdd(dk + u * lddk + col + c, ds * qr[c]);
-        atomicAdd(dv + u * lddv + col + c, av * gr[c]);
+        if (stats) continue;
+        if (exclusive) {
+          dk[u * lddk + col + c] = ds * qr[c];
+          dv[u * lddv + col + c] = av * gr[c];
+        } else {
+          atomicAdd(dk + u * lddk + col + c, ds * qr[c]);
+          atomicAdd(dv + u * lddv + col + c, av * gr[c]);
+        }
       }
     }
 #pragma unroll
     for (int c = 0; c < C; ++c) dq[i * lddq + col + c] = dqr[c];
+    if (stats && (lane % group) == 0) {
+      float* st = stats + (i * H + head) * 3;
+      st[0] = m; st[1] = inv_l; st[2] = D;
+    }
+  }
+}
+
+// Second pass of the atomic-free CSR form for SYMMETRIC edge sets (u -> v exists iff v -> u does, with the same multiplicity --
+// build_ntgt_edges(bidirect=True) + self loops, token_block_dataset.py:395-400): the in-edge list of a node is then its out-edge
+// list as well, so one warp per SOURCE u walks row u of the same CSR, reads the statistics of each destination it feeds and
+// accumulates dK'[u] / dV'[u] in registers.
+template <int C>
+__global__ void __launch_bounds__(256) csr_bwd_dkv_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k, int64_t ldk,
+                                                          const float* __restrict__ v, int64_t ldv, const float* __restrict__ dout,
+                                                          int64_t ldo, const int32_t* __restrict__ indptr,
+                                                          const int32_t* __restrict__ indices, int64_t n, int group, int H, float scale,
+                                                          const float* __restrict__ stats, float* __restrict__ dk, int64_t lddk,
+                                                          float* __restrict__ dv, int64_t lddv, AttnDrop ad) {
+  const int lane = threadIdx.x & 31;
+  const int col = lane * C;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < n; u += warps) {
+    float kr[C], vr[C], dkr[C], dvr[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      kr[c] = k[u * ldk + col + c];
+      vr[c] = v[u * ldv + col + c];
+      dkr[c] = dvr[c] = 0.f;
+    }
+    const int head = lane / group;
+    const int64_t e1 = __ldg(indptr + u + 1);
+    for (int64_t e = __ldg(indptr + u); e < e1; ++e) {
+      const int64_t i = __ldg(indices + e);                       // a destination u feeds
+      const float* qr = q + i * ldq;
+      const float* gr = dout + i * ldo;
+      float sc = 0.f, g = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        sc = fmaf(kr[c], qr[col + c], sc);
+        g = fmaf(vr[c], gr[col + c], g);
+      }
+      for (int o = group >> 1; o > 0; o >>= 1) {
+        sc += __shfl_xor_sync(0xffffffffu, sc, o);
+        g += __shfl_xor_sync(0xffffffffu, g, o);
+      }
+      const float* st = stats + (i * H + head) * 3;
+      const float a = scale * __expf(sc - st[0]) * st[1];
+      const float be = ad.p_thresh ? dm_scale(ad.seed, dm_edge(i, u, head), ad.p_thresh, ad.keep_scale) : 1.f;
+      const float ds = a * (be * g - st[2]);
+      const float ab = a * be;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        dkr[c] = fmaf(ds, qr[col + c], dkr[c]);
+        dvr[c] = fmaf(ab, gr[col + c], dvr[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      dk[u * lddk + col + c] = dkr[c];
+      dv[u * lddv + col + c] = dvr[c];
+    }
   }
 }
 
@@ -605,9 +674,43 @@ extern "C" int32_t gnnlm_hgt_edge_attn_bwd(const float* q, int64_t ldq, const fl
   if (n_dst_cap == 0) return 0;
   const int group = 32 / H;
   const unsigned grid = (unsigned)(ceil_div(n_dst_cap, 8) < 148 * 32 ? ceil_div(n_dst_cap, 8) : 148 * 32);
+  const int exclusive = causal_L == 0 && indices == nullptr;      // source id = edge id: no two edges share a source
   BWD_DISPATCH_C(C, q, ldq, k, ldk, v, ldv, dout, ldo, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, causal_L, intra_ctx, group, scale,
-                 dq, lddq, dk, lddk, dv, lddv, ad)
+                 dq, lddq, dk, lddk, dv, lddv, ad, (float*)nullptr, H, exclusive)
   GNNLM_LAUNCH_CHECK("gnnlm_hgt_edge_attn_bwd");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_hgt_edge_attn_bwd_sym(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                               const float* dout, int64_t ldo, const int32_t* indptr, const int32_t* indices, int64_t n,
+                                               int32_t H, int32_t d_k, float scale, float* dq, int64_t lddq, float* dk, int64_t lddk,
+                                               float* dv, int64_t lddv, float* stats, float p_drop, uint64_t seed, cudaStream_t stream) {
+  GNNLM_CHECK_ARG(q && k && v && dout && dq && dk && dv && stats && indptr && indices, GNNLM_E_ARG, "gnnlm_hgt_edge_attn_bwd_sym: null pointer");
+  GNNLM_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, GNNLM_E_ARG, "gnnlm_hgt_edge_attn_bwd_sym: dropout rate must be in [0, 1)");
+  const AttnDrop ad{seed, (uint32_t)(p_drop * 16777216.f), 1.f / (1.f - p_drop)};
+  const int64_t d = (int64_t)H * d_k;
+  GNNLM_CHECK_ARG(H > 0 && d_k > 0 && d % 32 == 0 && 32 % H == 0 && d <= 1024, GNNLM_E_UNSUPPORTED,
+                  "gnnlm_hgt_edge_attn_bwd_sym: needs d %% 32 == 0, d <= 1024 and H dividing 32 (H=%d d_k=%d)", H, d_k);
+  const int C = (int)(d / 32);
+  GNNLM_CHECK_ARG(C == 1 || C == 2 || C == 4 || C == 8 || C == 16 || C == 32, GNNLM_E_UNSUPPORTED,
+                  "gnnlm_hgt_edge_attn_bwd_sym: d / 32 must be a power of two");
+  GNNLM_CHECK_ARG(n >= 0, GNNLM_E_SHAPE, "gnnlm_hgt_edge_attn_bwd_sym: bad sizes");
+  if (n == 0) return 0;
+  const int group = 32 / H;
+  const unsigned grid = (unsigned)(ceil_div(n, 8) < 148 * 32 ? ceil_div(n, 8) : 148 * 32);
+  const int32_t* no_ids = nullptr;
+  BWD_DISPATCH_C(C, q, ldq, k, ldk, v, ldv, dout, ldo, indptr, indices, no_ids, n, no_ids, (int64_t)0, (int64_t)0, group, scale, dq, lddq,
+                 dk, lddk, dv, lddv, ad, stats, H, 0)
+  GNNLM_LAUNCH_CHECK("gnnlm_hgt_edge_attn_bwd_sym (dq)");
+  switch (C) {
+    case 1: csr_bwd_dkv_kernel<1><<<grid, 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, dout, ldo, indptr, indices, n, group, H, scale, stats, dk, lddk, dv, lddv, ad); break;
+    case 2: csr_bwd_dkv_kernel<2><<<grid, 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, dout, ldo, indptr, indices, n, group, H, scale, stats, dk, lddk, dv, lddv, ad); break;
+    case 4: csr_bwd_dkv_kernel<4><<<grid, 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, dout, ldo, indptr, indices, n, group, H, scale, stats, dk, lddk, dv, lddv, ad); break;
+    case 8: csr_bwd_dkv_kernel<8><<<grid, 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, dout, ldo, indptr, indices, n, group, H, scale, stats, dk, lddk, dv, lddv, ad); break;
+    case 16: csr_bwd_dkv_kernel<16><<<grid, 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, dout, ldo, indptr, indices, n, group, H, scale, stats, dk, lddk, dv, lddv, ad); break;
+    default: csr_bwd_dkv_kernel<32><<<grid, 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, dout, ldo, indptr, indices, n, group, H, scale, stats, dk, lddk, dv, lddv, ad); break;
+  }
+  GNNLM_LAUNCH_CHECK("gnnlm_hgt_edge_attn_bwd_sym (dk, dv)");
   return 0;
 }
 

@@ -145,6 +145,10 @@ def _attn_fwd_train(q, k, v, H, scale, out, accumulate, p, seed, *, indptr=None,
 
 
 _GEMM_BWD_BUFFERS = {}
+# ntgt-intra-ntgt backward without atomics (gnnlm_hgt_edge_attn_bwd_sym: chains + self loops are a symmetric edge set): bit-reproducible
+# gradients, but measured SLOWER than the atomic form on the Wiki103 shape (28 vs 21 ms per layer: two passes of uncoalesced
+# 128 B-per-lane row reads; profiles/r2_train_probe.log), so it is opt-in (GNNLM_TRAIN_SYM_BWD=1).
+SYMMETRIC_NN_BWD = os.environ.get("GNNLM_TRAIN_SYM_BWD", "0") == "1"
 
 
 def causal_bwd_gemm_supported(d: int, H: int, Lb: int) -> bool:
@@ -213,8 +217,18 @@ def _causal_bwd_gemm(q, k, v, dout, Lb: int, intra_ctx: int, H: int, scale: floa
     return dq, dkk, dv
 
 
-def _attn_bwd(q, k, v, dout, H, scale, *, indptr=None, indices=None, causal=(0, 0), atomics: bool = False, p: float = 0.0, seed: int = 0):
+def _attn_bwd(q, k, v, dout, H, scale, *, indptr=None, indices=None, causal=(0, 0), atomics: bool = False, p: float = 0.0, seed: int = 0,
+              symmetric: bool = False):
+    """symmetric: the CSR's edge set is symmetric with n_dst == n_src (ntgt-intra-ntgt of the non-deduplicating builder): the
+    atomic-free two-pass form (gnnlm_hgt_edge_attn_bwd_sym)."""
     d = q.shape[1]
+    if symmetric and not atomics and causal[0] == 0 and indices is not None and q.shape[0] == k.shape[0]:
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        stats = torch.empty((q.shape[0], H, 3), device=q.device, dtype=torch.float32)
+        L.call("gnnlm_hgt_edge_attn_bwd_sym", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0), L.ptr(dout), dout.stride(0),
+               L.ptr(indptr), L.ptr(indices), q.shape[0], H, d // H, float(scale), L.ptr(dq), dq.stride(0), L.ptr(dk), dk.stride(0),
+               L.ptr(dv), dv.stride(0), L.ptr(stats), float(p), seed, _st())
+        return dq, dk, dv
     if causal[0] > 0 and not atomics and causal_bwd_gemm_supported(d, H, causal[0]):
         return _causal_bwd_gemm(q, k, v, dout, causal[0], causal[1], H, scale, p, seed)
     dq = torch.empty_like(q)
@@ -236,10 +250,10 @@ class _EdgeAttention(torch.autograd.Function):
     """out = softmax-by-destination attention over one CSR edge type (hgt.py:350-358)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, indptr, indices, H, p, seed):
+    def forward(ctx, q, k, v, indptr, indices, H, p, seed, symmetric=False):
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         ctx.save_for_backward(q, k, v, indptr, indices)
-        ctx.H, ctx.p, ctx.seed = H, p, seed
+        ctx.H, ctx.p, ctx.seed, ctx.symmetric = H, p, seed, symmetric
         out = torch.empty_like(q)
         if p > 0:
             return _attn_fwd_train(q, k, v, H, 1.0, out, False, p, seed, indptr=indptr, indices=indices)
@@ -248,8 +262,9 @@ class _EdgeAttention(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         q, k, v, indptr, indices = ctx.saved_tensors
-        dq, dk, dv = _attn_bwd(q, k, v, dout.contiguous(), ctx.H, 1.0, indptr=indptr, indices=indices, p=ctx.p, seed=ctx.seed)
-        return dq, dk, dv, None, None, None, None, None
+        dq, dk, dv = _attn_bwd(q, k, v, dout.contiguous(), ctx.H, 1.0, indptr=indptr, indices=indices, p=ctx.p, seed=ctx.seed,
+                               symmetric=ctx.symmetric)
+        return dq, dk, dv, None, None, None, None, None, None
 
 
 class _TgtAttention(torch.autograd.Function):
@@ -415,7 +430,7 @@ def hgt_forward_train(hgt, G: TokenGraph, h_t: torch.Tensor, h_n: torch.Tensor, 
         # ---- ntgt (not needed after the last layer: the decoder reads tgt rows only, transformer.py:1053)
         if l < NL - 1:
             agg_n = _EdgeAttention.apply(lin(h_n, plain(layer.q_linears, n)), lin(h_n, F_[f"k{n}0"]), lin(h_n, F_[f"v{n}0"]),
-                                         nn_indptr, nn_indices, H, p_att, sd(2))
+                                         nn_indptr, nn_indices, H, p_att, sd(2), SYMMETRIC_NN_BWD and not G.dedup)
             h_n = _AddLayerNorm.apply(_dropout(lin(agg_n, plain(layer.a_linears, n)), p_feat, sd(4)), h_n, layer.norms[n].weight,
                                       layer.norms[n].bias, layer.norms[n].eps)
         h_t = new_t

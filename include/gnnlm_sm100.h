@@ -503,6 +503,14 @@ int32_t gnnlm_hgt_edge_attn_bwd(const float* q, int64_t ldq, const float* k, int
                                 const int32_t* dst_ids, int64_t n_dst_cap, const int32_t* n_dst_dev, int64_t causal_L,
                                 int64_t intra_ctx, int32_t H, int32_t d_k, float scale, float* dq, int64_t lddq, float* dk,
                                 int64_t lddk, float* dv, int64_t lddv, float p_drop, uint64_t seed, gnnlm_stream_t stream);
+/* A CSR edge type whose edge set is SYMMETRIC (u -> v iff v -> u, equal multiplicities; n_dst == n_src == n -- the ntgt-intra-ntgt
+ * chains of build_ntgt_edges(bidirect=True), token_block_dataset.py:395-400) without atomics: the by-destination pass writes dq and
+ * `stats` [n*H*3], a by-source pass over the SAME CSR rows writes dk, dv (NOT accumulated).  (gnnlm_hgt_edge_attn_bwd itself uses
+ * plain stores instead of atomics when indices == NULL: source id = edge id, no two edges share a source.) */
+int32_t gnnlm_hgt_edge_attn_bwd_sym(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                    const float* dout, int64_t ldo, const int32_t* indptr, const int32_t* indices, int64_t n,
+                                    int32_t H, int32_t d_k, float scale, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
+                                    int64_t lddv, float* stats, float p_drop, uint64_t seed, gnnlm_stream_t stream);
 /* The implicit causal edges without atomics: a by-destination pass writes dq and the softmax statistics {max, 1 / sum, D} per
  * (destination, head) into `stats` [B*L*H*3] floats; a by-source pass writes dk, dv (NOT accumulated). */
 int32_t gnnlm_hgt_causal_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,

@@ -1865,6 +1865,41 @@ def test_training_backward_kernels_direct(dev):
     dq, dk, dv = train._attn_bwd(q.to(dev), k.to(dev), v.to(dev), dout.to(dev), H, 1.0, indptr=indptr.to(dev), indices=indices.to(dev))
     for a, b in zip((dq, dk, dv), g):
         np.testing.assert_allclose(a.cpu().double().numpy(), b.numpy(), rtol=1e-4, atol=1e-5)
+    # a symmetric edge set (chains with self loops, some isolated nodes): the atomic-free two-pass form, with and without dropout
+    n = 61
+    a = torch.arange(n - 1)
+    keep = torch.rand(n - 1) < 0.7
+    und = torch.stack([a[keep], a[keep] + 1])
+    loops = torch.arange(0, n, 2)
+    src_s = torch.cat([und[0], und[1], loops])
+    dst_s = torch.cat([und[1], und[0], loops])
+    order = torch.sort(dst_s, stable=True).indices
+    ip_s = torch.cat([torch.zeros(1, dtype=torch.long), torch.bincount(dst_s, minlength=n).cumsum(0)]).int()
+    ix_s = src_s[order].int()
+    qs_, ks_, vs_, ds_ = (torch.randn(n, d) * 0.7 for _ in range(4))
+    n_dst = n
+    qd, kd, vd = (t.double().requires_grad_(True) for t in (qs_, ks_, vs_))
+    g = torch.autograd.grad(ref(qd, kd, vd, ix_s.long(), dst_s[order]), [qd, kd, vd], ds_.double())
+    args = (qs_.to(dev), ks_.to(dev), vs_.to(dev), ds_.to(dev), H, 1.0)
+    sym = train._attn_bwd(*args, indptr=ip_s.to(dev), indices=ix_s.to(dev), symmetric=True)
+    for a_, b in zip(sym, g):
+        np.testing.assert_allclose(a_.cpu().double().numpy(), b.numpy(), rtol=1e-4, atol=1e-5)
+    sym_p = train._attn_bwd(*args, indptr=ip_s.to(dev), indices=ix_s.to(dev), symmetric=True, p=0.3, seed=77)
+    atom_p = train._attn_bwd(*args, indptr=ip_s.to(dev), indices=ix_s.to(dev), p=0.3, seed=77)
+    for a_, b in zip(sym_p, atom_p):
+        np.testing.assert_allclose(a_.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    assert float((sym_p[0] - sym[0]).abs().max()) > 1e-3               # the masks do something
+    # indices == None (source id = edge id, the inter edges): plain stores, rows past the last edge stay zero
+    deg2 = torch.randint(0, 5, (n_dst,))
+    ip2 = torch.cat([torch.zeros(1, dtype=torch.long), deg2.cumsum(0)]).int()
+    n_e = int(ip2[-1])
+    k3, v3 = torch.randn(n_e + 3, d) * 0.5, torch.randn(n_e + 3, d)
+    dst2 = torch.repeat_interleave(torch.arange(n_dst), deg2)
+    qd, kd, vd = (t.double().requires_grad_(True) for t in (qs_, k3, v3))
+    g = torch.autograd.grad(ref(qd, kd, vd, torch.arange(n_e), dst2), [qd, kd, vd], ds_.double())
+    ex = train._attn_bwd(qs_.to(dev), k3.to(dev), v3.to(dev), ds_.to(dev), H, 1.0, indptr=ip2.to(dev))
+    for a_, b in zip(ex, g):
+        np.testing.assert_allclose(a_.cpu().double().numpy(), b.numpy(), rtol=1e-4, atol=1e-5)
     # implicit causal edges inside blocks of Lb tokens with a context window
     Lb, ctx, B = 19, 7, 2
     q2, k2, v2, do2 = (torch.randn(B * Lb, d) * 0.5 for _ in range(4))
