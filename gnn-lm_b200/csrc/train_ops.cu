@@ -643,6 +643,108 @@ __global__ void __launch_bounds__(256) causal_bwd_tile_kernel(const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------- ntgt-intra-ntgt chains
+// Backward of gnnlm_hgt_cluster_attn (all-nodes form): every valid (token, neighbour) pair owns a chain of w <= 7 contiguous
+// node ids whose node at sorted position p attends to positions p-1, p, p+1 (cluster_attn.cu).  One warp per (cluster, head)
+// walks the chain once with a three-row window of K' / V' and their gradient accumulators in registers: every row of Q, K', V',
+// dOut is read once and every row of dQ, dK', dV' written once (512 B contiguous per warp and row at d_k = 128), no atomics.
+// (The CSR kernel on the same edges: 23 ms per Wiki103 layer, 1.4 G fp32 atomics.)
+template <int C>
+__global__ void __launch_bounds__(256) cluster_attn_bwd_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k,
+                                                               int64_t ldk, const float* __restrict__ v, int64_t ldv,
+                                                               const float* __restrict__ dout, int64_t ldo,
+                                                               const int32_t* __restrict__ node_base, const int32_t* __restrict__ cluster_nl,
+                                                               int64_t n_clusters, int H, float scale, float* __restrict__ dq, int64_t lddq,
+                                                               float* __restrict__ dk, int64_t lddk, float* __restrict__ dv, int64_t lddv,
+                                                               AttnDrop ad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_items = n_clusters * H;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  auto load = [&](const float* __restrict__ p, float (&r)[C]) {
+    if constexpr (C == 4) {
+      const float4 x = *reinterpret_cast<const float4*>(p);
+      r[0] = x.x; r[1] = x.y; r[2] = x.z; r[3] = x.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) r[c] = p[c];
+    }
+  };
+  auto store = [&](float* __restrict__ p, const float (&r)[C]) {
+    if constexpr (C == 4) {
+      *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) p[c] = r[c];
+    }
+  };
+  auto dot = [&](const float (&a)[C], const float (&b)[C]) {
+    float p = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) p = fmaf(a[c], b[c], p);
+    return warp_sum(p);
+  };
+  for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n_items; it += warps) {
+    const int64_t cl = it / H;
+    const int head = (int)(it - cl * H);
+    const int base = __ldg(node_base + cl);
+    const int w = __ldg(node_base + cl + 1) - base;
+    if (w <= 0) continue;
+    const int nl = __ldg(cluster_nl + cl);
+    const int col = head * 32 * C + lane * C;
+    auto id_of = [&](int p) { return (int64_t)base + (p == nl ? 0 : (p < nl ? p + 1 : p)); };
+    float Kp[C], Vp[C], Kc[C], Vc[C], Kn[C], Vn[C], dKp[C], dVp[C], dKc[C], dVc[C], dKn[C], dVn[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) Kp[c] = Vp[c] = Kn[c] = Vn[c] = dKp[c] = dVp[c] = dKc[c] = dVc[c] = dKn[c] = dVn[c] = 0.f;
+    int64_t id_p = 0, id_c = id_of(0), id_n = 0;
+    load(k + id_c * ldk + col, Kc);
+    load(v + id_c * ldv + col, Vc);
+    for (int p = 0; p < w; ++p) {
+      const bool has_l = p > 0, has_r = p + 1 < w;
+      if (has_r) {
+        id_n = id_of(p + 1);
+        load(k + id_n * ldk + col, Kn);
+        load(v + id_n * ldv + col, Vn);
+      }
+      float qr[C], gr[C];
+      load(q + id_c * ldq + col, qr);
+      load(dout + id_c * ldo + col, gr);
+      const float s1 = dot(qr, Kc), s0 = has_l ? dot(qr, Kp) : -INFINITY, s2 = has_r ? dot(qr, Kn) : -INFINITY;
+      const float m = fmaxf(s1, fmaxf(s0, s2));
+      const float e0 = has_l ? __expf(s0 - m) : 0.f, e1 = __expf(s1 - m), e2 = has_r ? __expf(s2 - m) : 0.f;
+      const float inv = 1.f / (e0 + e1 + e2);
+      auto beta = [&](int64_t u) { return ad.p_thresh ? dm_scale(ad.seed, dm_edge(id_c, u, head), ad.p_thresh, ad.keep_scale) : 1.f; };
+      const float b0 = has_l ? beta(id_p) : 0.f, b1 = beta(id_c), b2 = has_r ? beta(id_n) : 0.f;
+      const float g1 = dot(gr, Vc), g0 = has_l ? dot(gr, Vp) : 0.f, g2 = has_r ? dot(gr, Vn) : 0.f;
+      const float a0 = e0 * inv, a1 = e1 * inv, a2 = e2 * inv;
+      const float D = a0 * b0 * g0 + a1 * b1 * g1 + a2 * b2 * g2;
+      const float ds0 = scale * a0 * (b0 * g0 - D), ds1 = scale * a1 * (b1 * g1 - D), ds2 = scale * a2 * (b2 * g2 - D);
+      const float av0 = scale * a0 * b0, av1 = scale * a1 * b1, av2 = scale * a2 * b2;
+      float dqr[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        dqr[c] = ds0 * Kp[c] + ds1 * Kc[c] + ds2 * Kn[c];
+        dKp[c] = fmaf(ds0, qr[c], dKp[c]); dVp[c] = fmaf(av0, gr[c], dVp[c]);
+        dKc[c] = fmaf(ds1, qr[c], dKc[c]); dVc[c] = fmaf(av1, gr[c], dVc[c]);
+        dKn[c] = fmaf(ds2, qr[c], dKn[c]); dVn[c] = fmaf(av2, gr[c], dVn[c]);
+      }
+      store(dq + id_c * lddq + col, dqr);
+      if (has_l) {                                                 // position p-1 has received from p-2, p-1, p: complete
+        store(dk + id_p * lddk + col, dKp);
+        store(dv + id_p * lddv + col, dVp);
+      }
+      id_p = id_c; id_c = id_n;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        Kp[c] = Kc[c]; Vp[c] = Vc[c]; dKp[c] = dKc[c]; dVp[c] = dVc[c];
+        Kc[c] = Kn[c]; Vc[c] = Vn[c]; dKc[c] = dKn[c]; dVc[c] = dVn[c];
+        Kn[c] = Vn[c] = dKn[c] = dVn[c] = 0.f;
+      }
+    }
+    store(dk + id_p * lddk + col, dKp);                            // the last position
+    store(dv + id_p * lddv + col, dVp);
+  }
+}
+
 }  // namespace gnnlm
 
 using namespace gnnlm;
@@ -873,5 +975,31 @@ extern "C" int32_t gnnlm_causal_softmax_bwd_split(const float* S, const float* G
   const dim3 grid((unsigned)(L / CBT), (unsigned)(L / CBT), (unsigned)H);
   causal_bwd_tile_kernel<<<grid, 256, 0, stream>>>(S, G, stats, L, intra_ctx, row0, scale, (__half*)dS, (__half*)WT, (__half*)dST, ad);
   GNNLM_LAUNCH_CHECK("gnnlm_causal_softmax_bwd_split (tiles)");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_hgt_cluster_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                              const float* dout, int64_t ldo, const int32_t* node_base, const int32_t* cluster_nl,
+                                              int64_t n_clusters, int32_t H, int32_t d_k, float scale, float* dq, int64_t lddq, float* dk,
+                                              int64_t lddk, float* dv, int64_t lddv, float p_drop, uint64_t seed, cudaStream_t stream) {
+  GNNLM_CHECK_ARG(q && k && v && dout && dq && dk && dv && node_base && cluster_nl, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn_bwd: null pointer");
+  GNNLM_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn_bwd: dropout rate must be in [0, 1)");
+  GNNLM_CHECK_ARG(H > 0 && (d_k == 32 || d_k == 64 || d_k == 128), GNNLM_E_UNSUPPORTED,
+                  "gnnlm_hgt_cluster_attn_bwd: d_k must be 32, 64 or 128 (one warp per cluster and head)");
+  GNNLM_CHECK_ARG(d_k != 128 || (ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && lddq % 4 == 0 && lddk % 4 == 0 && lddv % 4 == 0 &&
+                                 ((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)dout | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) % 16 == 0),
+                  GNNLM_E_SHAPE, "gnnlm_hgt_cluster_attn_bwd: rows must be 16 B aligned");
+  GNNLM_CHECK_ARG(n_clusters >= 0, GNNLM_E_SHAPE, "gnnlm_hgt_cluster_attn_bwd: bad sizes");
+  if (n_clusters == 0) return 0;
+  const AttnDrop ad{seed, (uint32_t)(p_drop * 16777216.f), 1.f / (1.f - p_drop)};
+  int64_t blocks = ceil_div(n_clusters * H, 8);
+  if (blocks > 148 * 64) blocks = 148 * 64;
+#define GNNLM_CAB(Cv) cluster_attn_bwd_kernel<Cv><<<(unsigned)blocks, 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, dout, ldo, node_base, cluster_nl, \
+                                                                                 n_clusters, H, scale, dq, lddq, dk, lddk, dv, lddv, ad)
+  if (d_k == 128) GNNLM_CAB(4);
+  else if (d_k == 64) GNNLM_CAB(2);
+  else GNNLM_CAB(1);
+#undef GNNLM_CAB
+  GNNLM_LAUNCH_CHECK("gnnlm_hgt_cluster_attn_bwd");
   return 0;
 }

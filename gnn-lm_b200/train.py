@@ -41,24 +41,76 @@ def _zeros(*shape, like):
     return torch.zeros(shape, device=like.device, dtype=torch.float32)
 
 
-def _transpose(x: torch.Tensor, rows_pad: Optional[int] = None) -> torch.Tensor:
+def _transpose(x: torch.Tensor, rows_pad: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """[rows, cols] fp32 -> [cols, rows_pad] (zero-padded columns): an operand of dW = dY^T X."""
     rows, cols = x.shape
     rows_pad = rows if rows_pad is None else rows_pad
-    out = torch.empty((cols, rows_pad), device=x.device, dtype=torch.float32)
+    if out is None:
+        out = torch.empty((cols, rows_pad), device=x.device, dtype=torch.float32)
+    assert out.shape == (cols, rows_pad) and out.stride(1) == 1
     L.call("gnnlm_transpose_f32", L.ptr(x), x.stride(0), rows, None, cols, L.ptr(out), out.stride(0), rows_pad, _st())
     return out
 
 
-def _gemm(a: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], mode: int) -> torch.Tensor:
-    """a [M, K] @ w [N, K]^T (+ b), fp32 in / out, in fp32 FMA or 3xTF32 (tcgen05; the weight operand split on the fly).
-    Row strides may exceed K (padded buffers)."""
+def _gemm(a: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], mode: int, a_scale: float = 1.0) -> torch.Tensor:
+    """a [M, K] @ w [N, K]^T (+ b), fp32 in / out, in fp32 FMA, 3xTF32 or 3xFP16 (tcgen05; the weight operand split on the fly).
+    Row strides may exceed K (padded buffers).  a_scale: `a` has been multiplied by it (the power of two that brings a gradient
+    operand into the fp16 range, _pow2_scaled); the product divides it out."""
     if w.stride(1) != 1:
         w = w.contiguous()
+    if mode == L.MATH_F16X3:
+        hi, lo, sc = ops.split_f16(w.contiguous())
+        if a.shape[1] % 8 == 0 and a.stride(1) == 1:      # pre-split activation operand: the kernel without the in-loop operand split
+            a = ops.to_split(a)
+        return ops.linear(a, hi, b, W_lo=lo, w_scale=sc * a_scale, math=mode)
+    assert a_scale == 1.0
     if mode == L.MATH_TF32X3:
         hi, lo = ops.split_tf32(w)
         return ops.linear(a, hi, b, W_lo=lo, math=mode)
     return ops.linear(a, w, b, math=mode)
+
+
+def _pow2_scaled(x: torch.Tensor, target: float = 1024.0):
+    """(s x, s) with s the power of two that brings max |x| just below `target`: gradients can be far below the fp16 range the
+    3xFP16 products split their operands into (one host read of the maximum per call)."""
+    amax = float(x.abs().max())
+    if not math.isfinite(amax):
+        raise FloatingPointError("non-finite gradient")
+    if amax == 0.0:
+        return x, 1.0
+    s = 2.0 ** math.floor(math.log2(target / amax))
+    y = _zeros(*x.shape, like=x)
+    L.call("gnnlm_axpy_f32", L.ptr(y), y.stride(0), L.ptr(x), x.stride(0), x.shape[0], None, x.shape[1], float(s), _st())
+    return y, s
+
+
+SPLIT_K_MIN_ROWS = 32768
+
+
+def _dw_split_k(g: torch.Tensor, x: torch.Tensor, a_scale: float, n_split: int = 8) -> torch.Tensor:
+    """dW = g^T x / a_scale for a tall pair (g [R, N], x [R, K], R >> N, K) by split-K in the 3xFP16 arithmetic: the R rows are cut
+    into `n_split` chunks, ONE batched launch (gnnlm_linear_batched_f16x3) computes the partial products and they are summed.  A
+    [N, K] output alone is 32 tiles for N = K = 1024 -- a fifth of the SMs -- which is what bounded dW before (139 TFLOP/s)."""
+    R, N = g.shape
+    K = x.shape[1]
+    Kc = ((R + n_split - 1) // n_split + 31) // 32 * 32
+    S = (R + Kc - 1) // Kc
+    dev = g.device
+    gt = torch.empty((S, N, Kc), device=dev, dtype=torch.float32)
+    xt = torch.empty((S, K, Kc), device=dev, dtype=torch.float32)
+    for b in range(S):
+        r0, r1 = b * Kc, min(R, (b + 1) * Kc)
+        _transpose(g[r0:r1], Kc, out=gt[b])
+        _transpose(x[r0:r1], Kc, out=xt[b])
+    a = ops.to_split(gt.view(S * N, Kc))
+    hi, lo, sc = ops.split_f16(xt)
+    part = torch.empty((S, N, K), device=dev, dtype=torch.float32)
+    L.call("gnnlm_linear_batched_f16x3", L.ptr(a.data), a.data.stride(0), N * a.data.stride(0), L.ptr(hi), L.ptr(lo), Kc, K * Kc,
+           float(sc * a_scale), None, 0, 0, L.ptr(part), K, N * K, S, N, K, Kc, 0, _st(), tag="dw_split_k", work=(N, K, S * Kc))
+    dW = part[0]
+    for b in range(1, S):
+        L.call("gnnlm_axpy_f32", L.ptr(dW), dW.stride(0), L.ptr(part[b]), K, N, None, K, 1.0, _st())
+    return dW
 
 
 class _Linear(torch.autograd.Function):
@@ -77,11 +129,15 @@ class _Linear(torch.autograd.Function):
         dy = dy.contiguous()
         mode = ctx.mode
         dx = dW = db = None
+        g, s = _pow2_scaled(dy) if mode == L.MATH_F16X3 else (dy, 1.0)
         if ctx.needs_input_grad[0]:
-            dx = _gemm(dy, _transpose(W.detach().contiguous()), None, mode)                            # dX = dY W
+            dx = _gemm(g, _transpose(W.detach().contiguous()), None, mode, s)                          # dX = dY W
         if ctx.needs_input_grad[1]:
             m_pad = (x.shape[0] + 31) // 32 * 32                                                       # k of the product, zero-padded
-            dW = _gemm(_transpose(dy, m_pad), _transpose(x, m_pad), None, mode)                        # dW = dY^T X
+            if mode == L.MATH_F16X3 and x.shape[0] >= SPLIT_K_MIN_ROWS and x.shape[1] % 8 == 0:
+                dW = _dw_split_k(g, x, s)
+            else:
+                dW = _gemm(_transpose(g, m_pad), _transpose(x, m_pad), None, mode, s)                  # dW = dY^T X
         if ctx.has_b and ctx.needs_input_grad[2]:
             db = _zeros(dy.shape[1], like=dy)
             L.call("gnnlm_colsum_f32", L.ptr(dy), dy.stride(0), dy.shape[0], None, dy.shape[1], L.ptr(db), _st())
@@ -250,10 +306,12 @@ class _EdgeAttention(torch.autograd.Function):
     """out = softmax-by-destination attention over one CSR edge type (hgt.py:350-358)."""
 
     @staticmethod
-    def forward(ctx, q, k, v, indptr, indices, H, p, seed, symmetric=False):
+    def forward(ctx, q, k, v, indptr, indices, H, p, seed, symmetric=False, chains=None):
+        """chains = (node_base, cluster_nl, n_clusters) of a non-deduplicated TokenGraph: the edge type is ntgt-intra-ntgt and its
+        backward runs per chain (gnnlm_hgt_cluster_attn_bwd) instead of over the CSR."""
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         ctx.save_for_backward(q, k, v, indptr, indices)
-        ctx.H, ctx.p, ctx.seed, ctx.symmetric = H, p, seed, symmetric
+        ctx.H, ctx.p, ctx.seed, ctx.symmetric, ctx.chains = H, p, seed, symmetric, chains
         out = torch.empty_like(q)
         if p > 0:
             return _attn_fwd_train(q, k, v, H, 1.0, out, False, p, seed, indptr=indptr, indices=indices)
@@ -262,9 +320,17 @@ class _EdgeAttention(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         q, k, v, indptr, indices = ctx.saved_tensors
-        dq, dk, dv = _attn_bwd(q, k, v, dout.contiguous(), ctx.H, 1.0, indptr=indptr, indices=indices, p=ctx.p, seed=ctx.seed,
+        dout = dout.contiguous()
+        if ctx.chains is not None and (q.shape[1] // ctx.H) in (32, 64, 128) and os.environ.get("GNNLM_TRAIN_CHAIN_BWD", "1") != "0":
+            node_base, cluster_nl, n_clusters = ctx.chains
+            dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+            L.call("gnnlm_hgt_cluster_attn_bwd", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0), L.ptr(dout),
+                   dout.stride(0), L.ptr(node_base), L.ptr(cluster_nl), n_clusters, ctx.H, q.shape[1] // ctx.H, 1.0, L.ptr(dq), dq.stride(0),
+                   L.ptr(dk), dk.stride(0), L.ptr(dv), dv.stride(0), float(ctx.p), ctx.seed, _st())
+            return dq, dk, dv, None, None, None, None, None, None, None
+        dq, dk, dv = _attn_bwd(q, k, v, dout, ctx.H, 1.0, indptr=indptr, indices=indices, p=ctx.p, seed=ctx.seed,
                                symmetric=ctx.symmetric)
-        return dq, dk, dv, None, None, None, None, None, None
+        return dq, dk, dv, None, None, None, None, None, None, None
 
 
 class _TgtAttention(torch.autograd.Function):
@@ -430,7 +496,8 @@ def hgt_forward_train(hgt, G: TokenGraph, h_t: torch.Tensor, h_n: torch.Tensor, 
         # ---- ntgt (not needed after the last layer: the decoder reads tgt rows only, transformer.py:1053)
         if l < NL - 1:
             agg_n = _EdgeAttention.apply(lin(h_n, plain(layer.q_linears, n)), lin(h_n, F_[f"k{n}0"]), lin(h_n, F_[f"v{n}0"]),
-                                         nn_indptr, nn_indices, H, p_att, sd(2), SYMMETRIC_NN_BWD and not G.dedup)
+                                         nn_indptr, nn_indices, H, p_att, sd(2), SYMMETRIC_NN_BWD and not G.dedup,
+                                         None if G.dedup else (G.node_base, G.cluster_nl, G.T * G.k))
             h_n = _AddLayerNorm.apply(_dropout(lin(agg_n, plain(layer.a_linears, n)), p_feat, sd(4)), h_n, layer.norms[n].weight,
                                       layer.norms[n].bias, layer.norms[n].eps)
         h_t = new_t
@@ -444,20 +511,23 @@ def train_step_loss(model, sample: dict, mode: str = "fp32", seed: int = 0) -> t
     dec = model.decoder
     G: TokenGraph = sample["net_input"]["graph"]
     m = L.MATH_NAMES[mode]
-    assert m in (L.MATH_FP32_SIMT, L.MATH_TF32X3), "training runs the projections in fp32 FMA or 3xTF32"
+    assert m in (L.MATH_FP32_SIMT, L.MATH_TF32X3, L.MATH_F16X3), "training runs the projections in fp32 FMA, 3xTF32 or 3xFP16"
     if dec.orig_prob_ratio > 0:
         raise NotImplementedError("orig_prob_ratio > 0 in training (adaptive_loss.py:55-59) is not used by the shipped scripts")
     feats = G.nodes["tgt"].data["h"]
     h_t = feats.float().contiguous()
     n_ntgt, _ = G.counts()
     with torch.no_grad():                                             # PQ decode + OPQ rotation: inputs, no parameters (pq_wrapper.py:169-203)
-        h_n = dec.tgt_quantizer.gather_decode(G.codes_table, G.ntgt_row, n_cap=G.node_cap, n_dev=G.n_ntgt_dev, math_mode=L.MATH_FP32_SIMT)
+        # the OPQ rotation in 3xTF32 whenever the projections run on the tensor cores (fp32 rows out either way)
+        h_n = dec.tgt_quantizer.gather_decode(G.codes_table, G.ntgt_row, n_cap=G.node_cap, n_dev=G.n_ntgt_dev,
+                                              math_mode=L.MATH_FP32_SIMT if m == L.MATH_FP32_SIMT else L.MATH_TF32X3)
         h_n = h_n[:n_ntgt].contiguous()
     training = bool(model.training)                                    # dropout masks only in train mode; `seed`: one per update
     x = hgt_forward_train(dec.hgt_decoder, G, h_t, h_n, m, training, seed)
     soft = dec.adaptive_softmax if dec.adaptive_softmax is not None else _PlainSoftmax(dec.embed_out)
     p_soft = float(getattr(soft, "dropout", 0.0)) if training else 0.0
-    return _AdaptiveLoss.apply(x, sample["target"], soft, m, p_soft, seed)
+    # the (frozen) output layer's logits keep 3xTF32 in the 3xFP16 mode: its gradient operand is produced inside one Function
+    return _AdaptiveLoss.apply(x, sample["target"], soft, L.MATH_TF32X3 if m == L.MATH_F16X3 else m, p_soft, seed)
 
 
 class _PlainSoftmax:

@@ -511,6 +511,13 @@ int32_t gnnlm_hgt_edge_attn_bwd_sym(const float* q, int64_t ldq, const float* k,
                                     const float* dout, int64_t ldo, const int32_t* indptr, const int32_t* indices, int64_t n,
                                     int32_t H, int32_t d_k, float scale, float* dq, int64_t lddq, float* dk, int64_t lddk, float* dv,
                                     int64_t lddv, float* stats, float p_drop, uint64_t seed, gnnlm_stream_t stream);
+/* Backward of gnnlm_hgt_cluster_attn (all-nodes form, fp32): the ntgt-intra-ntgt chains of the non-deduplicating builder, one warp per
+ * (cluster, head) walking the chain with a three-row window in registers -- every row read / written once, no atomics.  dq, dk, dv
+ * [n_ntgt, H*d_k] are written for every node of a valid cluster (NOT accumulated).  d_k in {32, 64, 128}. */
+int32_t gnnlm_hgt_cluster_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                   const float* dout, int64_t ldo, const int32_t* node_base, const int32_t* cluster_nl,
+                                   int64_t n_clusters, int32_t H, int32_t d_k, float scale, float* dq, int64_t lddq, float* dk,
+                                   int64_t lddk, float* dv, int64_t lddv, float p_drop, uint64_t seed, gnnlm_stream_t stream);
 /* The implicit causal edges without atomics: a by-destination pass writes dq and the softmax statistics {max, 1 / sum, D} per
  * (destination, head) into `stats` [B*L*H*3] floats; a by-source pass writes dk, dv (NOT accumulated). */
 int32_t gnnlm_hgt_causal_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,

@@ -42,6 +42,17 @@ for i, (nm, tag, a, b, work) in enumerate(L.TIMING):
     key = ("fwd " if i < n_fwd else "bwd ") + nm.replace("gnnlm_", "") + (f":{tag}" if tag and not tag.startswith("linear[") else "")
     v = agg.setdefault(key, [0.0, 0])
     v[0] += a.elapsed_time(b); v[1] += 1
-L.TIMING = None
+timing, L.TIMING = L.TIMING, None
 for k_, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]:
     print(f"{k_:45s} {v[0]:9.2f} ms  x{v[1]}")
+# the projections by shape: useful TFLOP/s of each (M, N, K)
+shapes = {}
+for i, (nm, tag, a, b, work) in enumerate(L.TIMING_LAST if hasattr(L, "TIMING_LAST") else []):
+    pass
+for i, (nm, tag, a, b, work) in enumerate(timing):
+    if nm == "gnnlm_linear" and work:
+        v = shapes.setdefault(("fwd" if i < n_fwd else "bwd",) + tuple(work), [0.0, 0])
+        v[0] += a.elapsed_time(b); v[1] += 1
+for k_, v in sorted(shapes.items(), key=lambda kv: -kv[1][0])[:12]:
+    M_, N_, K_ = k_[1:]
+    print(f"linear {k_[0]} M={M_} N={N_} K={K_}: {v[0]:8.2f} ms x{v[1]}  {2 * M_ * N_ * K_ * v[1] / v[0] / 1e9:7.1f} TFLOP/s useful")

@@ -1796,7 +1796,8 @@ def _train_problem(NL, cutoff, V, L_=48, d=64, H=4, k=4, c=1):
 
 @pytest.mark.parametrize("NL,cutoff,V,mode,deprecated", [(2, [40, 120], 300, "fp32", False), (3, None, 97, "fp32", False),
                                                          (1, [40, 120], 300, "fp32", False), (2, [40, 120], 300, "tf32x3", False),
-                                                         (2, [40, 120], 300, "fp32", True)])
+                                                         (2, [40, 120], 300, "fp32", True), (2, [40, 120], 300, "f16x3", False),
+                                                         (3, None, 97, "f16x3", False)])
 def test_training_step_gradients_vs_oracle_autograd(NL, cutoff, V, mode, deprecated, dev):
     """train.train_step_loss: the adaptive loss (adaptive_loss.py:31-83) and its gradients w.r.t. every decoder.hgt_decoder.*
     parameter (the --freeze set, transformer_lm.py:183-186), every backward stage a kernel of the library, against
@@ -1975,6 +1976,82 @@ def test_causal_backward_gemm_form(Lb, ctx, H, d, p, dev, monkeypatch):
                 assert float((a.cpu().double() - b).abs().max()) < 2e-5 * float(b.abs().max())
 
 
+@pytest.mark.parametrize("d,H,c,p", [(128, 4, 1, 0.0), (256, 2, 2, 0.2), (512, 8, 3, 0.0), (64, 2, 0, 0.1), (1024, 8, 1, 0.1)])
+def test_cluster_chain_backward(d, H, c, p, dev):
+    """gnnlm_hgt_cluster_attn_bwd (one warp per chain and head, no atomics) == the CSR backward over nn_indptr / nn_indices
+    (itself pinned to fp64 autograd above), with invalid neighbours, datastore-boundary chains and attention dropout."""
+    from gnnlm_b200 import train
+    from gnnlm_b200.graph import build_token_graph
+    rng = np.random.RandomState(d + c)
+    torch.manual_seed(d)
+    B, Lb, k, n_d = 2, 24, 5, 400
+    nbr = rng.randint(0, n_d, size=(B, Lb, k)).astype(np.int64)
+    nbr[rng.rand(B, Lb, k) < 0.1] = -1
+    nbr[0, 0, 0], nbr[0, 0, 1], nbr[1, 2] = 0, n_d - 1, -1
+    G = build_token_graph(torch.from_numpy(nbr).to(dev), n_d, c, c)
+    n = G.counts()[0]
+    q, k_, v, do = (torch.randn(n, d, device=dev) * 0.6 for _ in range(4))
+    ip, ix = G.nn_indptr[:n + 1].contiguous(), G.nn_indices
+    ref = train._attn_bwd(q, k_, v, do, H, 1.0, indptr=ip, indices=ix, p=p, seed=5)
+    qa, ka, va = (t.clone().requires_grad_(True) for t in (q, k_, v))
+    out = train._EdgeAttention.apply(qa, ka, va, ip, ix, H, p, 5, False, (G.node_base, G.cluster_nl, G.T * G.k))
+    out.backward(do)
+    for a, b in zip((qa.grad, ka.grad, va.grad), ref):       # (c = 0: one-node chains, dQ = dK' = 0 up to rounding noise)
+        assert float((a - b).abs().max()) < 2e-5 * float(b.abs().max()) + 1e-6
+
+
+def test_training_step_gradients_wide_heads(dev):
+    """The same end-to-end gradient check at d_k = 32 -- the width from which the ntgt-intra-ntgt backward runs per chain."""
+    import copy
+    from gnnlm_b200 import synth, train
+    from tests.synth import oracle_train
+    cfg, model, data = _train_problem(2, [40, 120], 300, d=128, H=4)
+    ref_loss, ref_g = oracle_train((cfg, model, data))
+    m = copy.deepcopy(model).to(dev).train()
+    for name, p_ in m.named_parameters():
+        p_.requires_grad_("hgt" in name)
+    r = synth.Runner(cfg, m, data, dev, "fp32")
+    d_ = synth.to_device({k_: data[k_] for k_ in r.KEYS}, dev)
+    sample = r.sample_from(d_["nbr"], d_["feats"], d_["target"], d_["knn_dists"], d_["knn_ids"])
+    loss = train.train_step_loss(m, sample, "fp32")
+    loss.backward()
+    assert abs(float(loss.detach()) - ref_loss) < 2e-5 * abs(ref_loss)
+    gmax = max(float(g_.abs().max()) for g_ in ref_g.values() if g_ is not None)
+    checked = 0
+    for name, p_ in m.decoder.hgt_decoder.named_parameters():
+        g_ref = ref_g.get(name)
+        if g_ref is None or name.endswith("skip") or p_.grad is None:
+            continue
+        err = float((p_.grad.detach().cpu().double() - g_ref).abs().max())
+        assert err < 2e-4 * float(g_ref.abs().max()) + 2e-6 * gmax, (name, err)
+        checked += 1
+    assert checked >= 20
+
+
+def test_training_dw_split_k(dev):
+    """train._dw_split_k: dW = dY^T X of a tall pair by split-K in 3xFP16 (one batched launch + partial sums) against fp64, with
+    1e-5-sized gradients pre-scaled by a power of two (train._pow2_scaled) and a ragged last chunk."""
+    _need_tc()
+    from gnnlm_b200 import train
+    torch.manual_seed(9)
+    R, N, K = 40000 + 13, 256, 128
+    g, x = torch.randn(R, N) * 1e-5, torch.randn(R, K)
+    ref = g.double().T @ x.double()
+    gs, s = train._pow2_scaled(g.to(dev))
+    assert 512.0 <= float(gs.abs().max()) <= 1024.0
+    dW = train._dw_split_k(gs, x.to(dev), s)
+    assert dW.shape == (N, K)
+    assert float((dW.cpu().double() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+    # through the autograd Function (rows above the split-K threshold)
+    W = (torch.randn(N, K) * 0.1).to(dev).requires_grad_(True)
+    xd = x.to(dev).requires_grad_(True)
+    y = train._Linear.apply(xd, W, None, train.L.MATH_F16X3)
+    y.backward(g.to(dev))
+    assert float((W.grad.cpu().double() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+    ref_dx = g.double() @ W.detach().cpu().double()
+    assert float((xd.grad.cpu().double() - ref_dx).abs().max()) < 2e-5 * float(ref_dx.abs().max())
+
+
 def test_training_steps_reduce_the_loss(dev):
     """train.train_step (criterion + backward + --clip-norm + Adam) on a --freeze model: only decoder.hgt_decoder.* moves and
     the loss of a fixed batch goes down."""
@@ -1996,7 +2073,8 @@ def test_training_steps_reduce_the_loss(dev):
             assert torch.equal(p.detach(), frozen[n_])
 
 
-@pytest.mark.parametrize("NL,cutoff,V,mode", [(2, [40, 120], 300, "fp32"), (3, None, 97, "fp32"), (2, [40, 120], 300, "tf32x3")])
+@pytest.mark.parametrize("NL,cutoff,V,mode", [(2, [40, 120], 300, "fp32"), (3, None, 97, "fp32"), (2, [40, 120], 300, "tf32x3"),
+                                              (2, [40, 120], 300, "f16x3")])
 def test_training_step_with_dropout_vs_oracle_autograd(NL, cutoff, V, mode, dev):
     """model.train(): hgt.py's `drop` (0.3) / `attn_drop` (0.1) and the adaptive softmax's input / tail dropout (0.2) -- the rates of
     transformer_lm_wiki103 -- with the library's (seed, element)-addressed masks replayed through the oracle: loss and every
