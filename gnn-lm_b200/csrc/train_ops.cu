@@ -7,6 +7,8 @@
 // softmax-cross-entropy of one adaptive-softmax cluster, plus the small data-movement kernels the GEMM backward needs
 // (transpose for dW = dY^T X through gnnlm_linear, column sums for the bias, scatter-add for gathered rows).
 // First training path: fp32, correctness before speed (three passes over the in-edges, fp32 atomics on dK' / dV').
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace gnnlm {
@@ -745,6 +747,113 @@ __global__ void __launch_bounds__(256) cluster_attn_bwd_kernel(const float* __re
   }
 }
 
+// Backward of an edge type whose sources are CONTIGUOUS and EXCLUSIVE per destination (indices == NULL: source id = edge id -- the
+// ('ntgt','inter','tgt') edges over the compact centre rows): one warp per (destination, head), 32 * C = d_k features per row-head
+// (512 B contiguous at d_k = 128), two passes over the destination's rows (the second from L1 / L2), plain stores for dK' / dV'.
+template <int C>
+__global__ void __launch_bounds__(256) ranged_attn_bwd_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k,
+                                                              int64_t ldk, const float* __restrict__ v, int64_t ldv,
+                                                              const float* __restrict__ dout, int64_t ldo,
+                                                              const int32_t* __restrict__ indptr, int64_t n_dst, int H, float scale,
+                                                              float* __restrict__ dq, int64_t lddq, float* __restrict__ dk, int64_t lddk,
+                                                              float* __restrict__ dv, int64_t lddv, AttnDrop ad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_items = n_dst * H;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  auto load = [&](const float* __restrict__ p, float (&r)[C]) {
+    if constexpr (C == 4) {
+      const float4 x = *reinterpret_cast<const float4*>(p);
+      r[0] = x.x; r[1] = x.y; r[2] = x.z; r[3] = x.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) r[c] = p[c];
+    }
+  };
+  auto store = [&](float* __restrict__ p, const float (&r)[C]) {
+    if constexpr (C == 4) {
+      *reinterpret_cast<float4*>(p) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) p[c] = r[c];
+    }
+  };
+  auto dot = [&](const float (&a)[C], const float (&b)[C]) {
+    float p = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) p = fmaf(a[c], b[c], p);
+    return warp_sum(p);
+  };
+  for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n_items; it += warps) {
+    const int64_t i = it / H;
+    const int head = (int)(it - i * H);
+    const int col = head * 32 * C + lane * C;
+    const int64_t e0 = __ldg(indptr + i), e1 = __ldg(indptr + i + 1);
+    float qr[C], gr[C], dqr[C];
+    load(q + i * ldq + col, qr);
+    load(dout + i * ldo + col, gr);
+#pragma unroll
+    for (int c = 0; c < C; ++c) dqr[c] = 0.f;
+    auto beta = [&](int64_t u) { return ad.p_thresh ? dm_scale(ad.seed, dm_edge(i, u, head), ad.p_thresh, ad.keep_scale) : 1.f; };
+    float m = -INFINITY, l = 0.f, dn = 0.f;
+    for (int64_t u = e0; u < e1; ++u) {
+      float kr[C], vr[C];
+      load(k + u * ldk + col, kr);
+      load(v + u * ldv + col, vr);
+      const float sc = dot(qr, kr), g = beta(u) * dot(gr, vr);
+      const float mx = fmaxf(m, sc), corr = __expf(m - mx), w = __expf(sc - mx);
+      l = l * corr + w;
+      dn = dn * corr + w * g;
+      m = mx;
+    }
+    const float inv_l = l > 0.f ? 1.f / l : 0.f, D = dn * inv_l;
+    for (int64_t u = e0; u < e1; ++u) {
+      float kr[C], vr[C], o1[C], o2[C];
+      load(k + u * ldk + col, kr);
+      load(v + u * ldv + col, vr);
+      const float be = beta(u);
+      const float a = __expf(dot(qr, kr) - m) * inv_l;
+      const float ds = scale * a * (be * dot(gr, vr) - D), av = scale * a * be;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        dqr[c] = fmaf(ds, kr[c], dqr[c]);
+        o1[c] = ds * qr[c];
+        o2[c] = av * gr[c];
+      }
+      store(dk + u * lddk + col, o1);
+      store(dv + u * lddv + col, o2);
+    }
+    store(dq + i * lddq + col, dqr);
+  }
+}
+
+// dst = split-fp16 of (scale * src)^T in one pass: the operands of dW = dY^T X straight from the row-major fp32 tensors (instead of
+// a scaled copy, an fp32 transpose and a split pass each).  src [rows, cols] -> a_style: dst_hi [cols, 2 * rows_pad] with hi | lo in
+// one row (A operand); else dst_hi, dst_lo [cols, rows_pad] (W operand).  Columns rows .. rows_pad are written as zeros.
+__global__ void __launch_bounds__(256) transpose_split_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows, int64_t cols,
+                                                              float scale, int64_t rows_pad, int a_style, __half* __restrict__ hi,
+                                                              __half* __restrict__ lo) {
+  __shared__ float tile[64][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 64, c0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 64; j += 8) {
+    const int64_t r = r0 + j, c = c0 + tx;
+    tile[j][tx] = (r < rows && c < cols) ? scale * src[r * ld_src + c] : 0.f;
+  }
+  __syncthreads();
+  const int64_t ld = a_style ? 2 * rows_pad : rows_pad;
+  __half* lo_base = a_style ? hi + rows_pad : lo;
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t c = c0 + j, r = r0 + 2 * tx;
+    if (c < cols && r < rows_pad) {                                // rows_pad is even: r and r + 1 are written together
+      const float x0 = fminf(fmaxf(tile[2 * tx][j], -65504.f), 65504.f), x1 = fminf(fmaxf(tile[2 * tx + 1][j], -65504.f), 65504.f);
+      const __half2 h = __floats2half2_rn(x0, x1);
+      const float2 f = __half22float2(h);
+      *reinterpret_cast<__half2*>(hi + c * ld + r) = h;
+      *reinterpret_cast<__half2*>(lo_base + c * ld + r) = __floats2half2_rn(x0 - f.x, x1 - f.y);
+    }
+  }
+}
+
 }  // namespace gnnlm
 
 using namespace gnnlm;
@@ -777,6 +886,23 @@ extern "C" int32_t gnnlm_hgt_edge_attn_bwd(const float* q, int64_t ldq, const fl
   const int group = 32 / H;
   const unsigned grid = (unsigned)(ceil_div(n_dst_cap, 8) < 148 * 32 ? ceil_div(n_dst_cap, 8) : 148 * 32);
   const int exclusive = causal_L == 0 && indices == nullptr;      // source id = edge id: no two edges share a source
+  {
+    const bool aligned = ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 && lddq % 4 == 0 && lddk % 4 == 0 && lddv % 4 == 0 &&
+                         ((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)dout | (uintptr_t)dq | (uintptr_t)dk | (uintptr_t)dv) % 16 == 0;
+    static const bool off = [] { const char* e = getenv("GNNLM_TRAIN_RANGED_BWD"); return e && e[0] == '0'; }();   // A/B switch
+    if (exclusive && !off && !dst_ids && !n_dst_dev && n_dst_cap > 0 && (d_k == 32 || d_k == 64 || (d_k == 128 && aligned))) {
+      int64_t blocks = ceil_div(n_dst_cap * H, 8);
+      if (blocks > 148 * 64) blocks = 148 * 64;
+#define GNNLM_RAB(Cv) ranged_attn_bwd_kernel<Cv><<<(unsigned)blocks, 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, dout, ldo, indptr, n_dst_cap, H, scale, \
+                                                                                dq, lddq, dk, lddk, dv, lddv, ad)
+      if (d_k == 128) GNNLM_RAB(4);
+      else if (d_k == 64) GNNLM_RAB(2);
+      else GNNLM_RAB(1);
+#undef GNNLM_RAB
+      GNNLM_LAUNCH_CHECK("gnnlm_hgt_edge_attn_bwd (ranged)");
+      return 0;
+    }
+  }
   BWD_DISPATCH_C(C, q, ldq, k, ldk, v, ldv, dout, ldo, indptr, indices, dst_ids, n_dst_cap, n_dst_dev, causal_L, intra_ctx, group, scale,
                  dq, lddq, dk, lddk, dv, lddv, ad, (float*)nullptr, H, exclusive)
   GNNLM_LAUNCH_CHECK("gnnlm_hgt_edge_attn_bwd");
@@ -1001,5 +1127,18 @@ extern "C" int32_t gnnlm_hgt_cluster_attn_bwd(const float* q, int64_t ldq, const
   else GNNLM_CAB(1);
 #undef GNNLM_CAB
   GNNLM_LAUNCH_CHECK("gnnlm_hgt_cluster_attn_bwd");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_transpose_split_f16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, float scale, int64_t rows_pad,
+                                             int32_t a_style, void* hi, void* lo, cudaStream_t stream) {
+  GNNLM_CHECK_ARG(src && hi && (a_style || lo), GNNLM_E_ARG, "gnnlm_transpose_split_f16: null pointer");
+  GNNLM_CHECK_ARG(rows >= 0 && cols > 0 && ld_src >= cols && rows_pad >= rows && rows_pad % 2 == 0 && (uintptr_t)hi % 4 == 0 &&
+                      (a_style || (uintptr_t)lo % 4 == 0),
+                  GNNLM_E_SHAPE, "gnnlm_transpose_split_f16: rows_pad must be even and >= rows");
+  if (rows_pad == 0) return 0;
+  const dim3 grid((unsigned)ceil_div(rows_pad, 64), (unsigned)ceil_div(cols, 32));
+  transpose_split_kernel<<<grid, 256, 0, stream>>>(src, ld_src, rows, cols, scale, rows_pad, a_style, (__half*)hi, (__half*)lo);
+  GNNLM_LAUNCH_CHECK("gnnlm_transpose_split_f16");
   return 0;
 }

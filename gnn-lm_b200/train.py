@@ -87,30 +87,39 @@ def _pow2_scaled(x: torch.Tensor, target: float = 1024.0):
 SPLIT_K_MIN_ROWS = 32768
 
 
-def _dw_split_k(g: torch.Tensor, x: torch.Tensor, a_scale: float, n_split: int = 8) -> torch.Tensor:
-    """dW = g^T x / a_scale for a tall pair (g [R, N], x [R, K], R >> N, K) by split-K in the 3xFP16 arithmetic: the R rows are cut
-    into `n_split` chunks, ONE batched launch (gnnlm_linear_batched_f16x3) computes the partial products and they are summed.  A
-    [N, K] output alone is 32 tiles for N = K = 1024 -- a fifth of the SMs -- which is what bounded dW before (139 TFLOP/s)."""
+def _dw_split_k(g: torch.Tensor, x: torch.Tensor, g_scale: float, n_split: int = 8) -> torch.Tensor:
+    """dW = g^T x for a tall pair (g [R, N], x [R, K], R >> N, K) by split-K in the 3xFP16 arithmetic: the R rows are cut into
+    `n_split` chunks, ONE batched launch (gnnlm_linear_batched_f16x3) computes the partial products and they are summed.  A
+    [N, K] output alone is 32 tiles for N = K = 1024 -- a fifth of the SMs -- which is what bounded dW before (139 TFLOP/s).
+    The operands come straight from the row-major tensors (gnnlm_transpose_split_f16: transpose + split, g scaled by the power
+    of two g_scale on the way, divided out by the product)."""
     R, N = g.shape
     K = x.shape[1]
     Kc = ((R + n_split - 1) // n_split + 31) // 32 * 32
     S = (R + Kc - 1) // Kc
     dev = g.device
-    gt = torch.empty((S, N, Kc), device=dev, dtype=torch.float32)
-    xt = torch.empty((S, K, Kc), device=dev, dtype=torch.float32)
+    f16 = dict(device=dev, dtype=torch.float16)
+    a = torch.empty((S, N, 2 * Kc), **f16)
+    hi, lo = torch.empty((S, K, Kc), **f16), torch.empty((S, K, Kc), **f16)
     for b in range(S):
         r0, r1 = b * Kc, min(R, (b + 1) * Kc)
-        _transpose(g[r0:r1], Kc, out=gt[b])
-        _transpose(x[r0:r1], Kc, out=xt[b])
-    a = ops.to_split(gt.view(S * N, Kc))
-    hi, lo, sc = ops.split_f16(xt)
+        L.call("gnnlm_transpose_split_f16", L.ptr(g[r0:r1]), g.stride(0), r1 - r0, N, float(g_scale), Kc, 1, L.ptr(a[b]), None, _st())
+        L.call("gnnlm_transpose_split_f16", L.ptr(x[r0:r1]), x.stride(0), r1 - r0, K, 1.0, Kc, 0, L.ptr(hi[b]), L.ptr(lo[b]), _st())
     part = torch.empty((S, N, K), device=dev, dtype=torch.float32)
-    L.call("gnnlm_linear_batched_f16x3", L.ptr(a.data), a.data.stride(0), N * a.data.stride(0), L.ptr(hi), L.ptr(lo), Kc, K * Kc,
-           float(sc * a_scale), None, 0, 0, L.ptr(part), K, N * K, S, N, K, Kc, 0, _st(), tag="dw_split_k", work=(N, K, S * Kc))
+    L.call("gnnlm_linear_batched_f16x3", L.ptr(a), 2 * Kc, N * 2 * Kc, L.ptr(hi), L.ptr(lo), Kc, K * Kc, float(g_scale), None, 0, 0,
+           L.ptr(part), K, N * K, S, N, K, Kc, 0, _st(), tag="dw_split_k", work=(N, K, S * Kc))
     dW = part[0]
     for b in range(1, S):
         L.call("gnnlm_axpy_f32", L.ptr(dW), dW.stride(0), L.ptr(part[b]), K, N, None, K, 1.0, _st())
     return dW
+
+
+def _pow2_scale_of(x: torch.Tensor, target: float = 1024.0) -> float:
+    """The power of two that brings max |x| just below `target` (one host read of the maximum)."""
+    amax = float(x.abs().max())
+    if not math.isfinite(amax):
+        raise FloatingPointError("non-finite gradient")
+    return 1.0 if amax == 0.0 else 2.0 ** math.floor(math.log2(target / amax))
 
 
 class _Linear(torch.autograd.Function):
@@ -129,13 +138,19 @@ class _Linear(torch.autograd.Function):
         dy = dy.contiguous()
         mode = ctx.mode
         dx = dW = db = None
-        g, s = _pow2_scaled(dy) if mode == L.MATH_F16X3 else (dy, 1.0)
+        split_k = mode == L.MATH_F16X3 and ctx.needs_input_grad[1] and x.shape[0] >= SPLIT_K_MIN_ROWS and x.shape[1] % 8 == 0
+        g, s = dy, 1.0
+        if mode == L.MATH_F16X3:
+            if split_k and not ctx.needs_input_grad[0]:      # only the split-K product reads dY: it scales on the way, no scaled copy
+                s = _pow2_scale_of(dy)
+            else:
+                g, s = _pow2_scaled(dy)
         if ctx.needs_input_grad[0]:
             dx = _gemm(g, _transpose(W.detach().contiguous()), None, mode, s)                          # dX = dY W
         if ctx.needs_input_grad[1]:
             m_pad = (x.shape[0] + 31) // 32 * 32                                                       # k of the product, zero-padded
-            if mode == L.MATH_F16X3 and x.shape[0] >= SPLIT_K_MIN_ROWS and x.shape[1] % 8 == 0:
-                dW = _dw_split_k(g, x, s)
+            if split_k:
+                dW = _dw_split_k(dy, x, s)
             else:
                 dW = _gemm(_transpose(g, m_pad), _transpose(x, m_pad), None, mode, s)                  # dW = dY^T X
         if ctx.has_b and ctx.needs_input_grad[2]:

@@ -498,6 +498,11 @@ int32_t gnnlm_knn_sims_pq(const float* queries, int64_t ldq, int32_t d_q, const 
  * gnnlm_transpose_f32 (rows past the live count / up to rows_pad are written as zeros: k-padding of dW = dY^T X),
  * gnnlm_colsum_f32 (out += column sums: bias gradients), gnnlm_axpy_f32 (y += a x), gnnlm_scatter_add_rows
  * (dst[ids[r]] += src[r]: backward of gnnlm_gather_rows). */
+/* gnnlm_transpose_split_f16: (scale * src)^T as split fp16 in one pass -- the operands of dW = dY^T X for the 3xFP16 products straight
+ * from the row-major fp32 tensors: src [rows, cols] -> a_style != 0: hi [cols, 2 * rows_pad], hi | lo in one row (A operand);
+ * a_style == 0: hi, lo [cols, rows_pad] (W operand).  Columns rows .. rows_pad are zeros; rows_pad even. */
+int32_t gnnlm_transpose_split_f16(const float* src, int64_t ld_src, int64_t rows, int64_t cols, float scale, int64_t rows_pad,
+                                  int32_t a_style, void* hi, void* lo, gnnlm_stream_t stream);
 int32_t gnnlm_hgt_edge_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                                 const float* dout, int64_t ldo, const int32_t* indptr, const int32_t* indices,
                                 const int32_t* dst_ids, int64_t n_dst_cap, const int32_t* n_dst_dev, int64_t causal_L,

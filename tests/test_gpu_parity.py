@@ -1901,6 +1901,12 @@ def test_training_backward_kernels_direct(dev):
     ex = train._attn_bwd(qs_.to(dev), k3.to(dev), v3.to(dev), ds_.to(dev), H, 1.0, indptr=ip2.to(dev))
     for a_, b in zip(ex, g):
         np.testing.assert_allclose(a_.cpu().double().numpy(), b.numpy(), rtol=1e-4, atol=1e-5)
+    # ... and with attention dropout == the generic (atomic) kernel given the same edges explicitly
+    ex_p = train._attn_bwd(qs_.to(dev), k3.to(dev), v3.to(dev), ds_.to(dev), H, 0.5, indptr=ip2.to(dev), p=0.2, seed=3)
+    at_p = train._attn_bwd(qs_.to(dev), k3.to(dev), v3.to(dev), ds_.to(dev), H, 0.5, indptr=ip2.to(dev),
+                           indices=torch.arange(n_e, dtype=torch.int32, device=dev), p=0.2, seed=3)
+    for a_, b in zip(ex_p, at_p):
+        np.testing.assert_allclose(a_.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-5)
     # implicit causal edges inside blocks of Lb tokens with a context window
     Lb, ctx, B = 19, 7, 2
     q2, k2, v2, do2 = (torch.randn(B * Lb, d) * 0.5 for _ in range(4))
@@ -2038,8 +2044,8 @@ def test_training_dw_split_k(dev):
     g, x = torch.randn(R, N) * 1e-5, torch.randn(R, K)
     ref = g.double().T @ x.double()
     gs, s = train._pow2_scaled(g.to(dev))
-    assert 512.0 <= float(gs.abs().max()) <= 1024.0
-    dW = train._dw_split_k(gs, x.to(dev), s)
+    assert 512.0 <= float(gs.abs().max()) <= 1024.0 and s == train._pow2_scale_of(g.to(dev))
+    dW = train._dw_split_k(g.to(dev), x.to(dev), s)          # scaled on the way into the split operand
     assert dW.shape == (N, K)
     assert float((dW.cpu().double() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
     # through the autograd Function (rows above the split-K threshold)
