@@ -47,8 +47,6 @@ for k_, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:14]:
     print(f"{k_:45s} {v[0]:9.2f} ms  x{v[1]}")
 # the projections by shape: useful TFLOP/s of each (M, N, K)
 shapes = {}
-for i, (nm, tag, a, b, work) in enumerate(L.TIMING_LAST if hasattr(L, "TIMING_LAST") else []):
-    pass
 for i, (nm, tag, a, b, work) in enumerate(timing):
     if nm == "gnnlm_linear" and work:
         v = shapes.setdefault(("fwd" if i < n_fwd else "bwd",) + tuple(work), [0.0, 0])
