@@ -831,25 +831,59 @@ __global__ void __launch_bounds__(256) ranged_attn_bwd_kernel(const float* __res
 // one row (A operand); else dst_hi, dst_lo [cols, rows_pad] (W operand).  Columns rows .. rows_pad are written as zeros.
 __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows, int64_t cols,
                                                               float scale, int64_t rows_pad, int a_style, __half* __restrict__ hi,
-                                                              __half* __restrict__ lo) {
-  __shared__ float tile[64][33];
-  const int64_t r0 = (int64_t)blockIdx.x * 64, c0 = (int64_t)blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (int j = ty; j < 64; j += 8) {
-    const int64_t r = r0 + j, c = c0 + tx;
-    tile[j][tx] = (r < rows && c < cols) ? scale * src[r * ld_src + c] : 0.f;
+                                                              __half* __restrict__ lo, int vec) {
+  // 64 x 64 tile: 256 B row segments in (float4 per lane when `vec`), 128 B column segments out (16 halves per lane)
+  __shared__ float tile[64][65];
+  const int64_t r0 = (int64_t)blockIdx.x * 64, c0 = (int64_t)blockIdx.y * 64;
+  {
+    const int c4 = (threadIdx.x & 15) * 4, rr = threadIdx.x >> 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rl = rr + 16 * j;
+      const int64_t r = r0 + rl, c = c0 + c4;
+      float x[4] = {0.f, 0.f, 0.f, 0.f};
+      if (r < rows) {
+        if (vec && c + 3 < cols) {
+          const float4 v4 = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+          x[0] = v4.x; x[1] = v4.y; x[2] = v4.z; x[3] = v4.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (c + e < cols) x[e] = src[r * ld_src + c + e];
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) tile[rl][c4 + e] = scale * x[e];
+    }
   }
   __syncthreads();
   const int64_t ld = a_style ? 2 * rows_pad : rows_pad;
   __half* lo_base = a_style ? hi + rows_pad : lo;
-  for (int j = ty; j < 32; j += 8) {
-    const int64_t c = c0 + j, r = r0 + 2 * tx;
-    if (c < cols && r < rows_pad) {                                // rows_pad is even: r and r + 1 are written together
-      const float x0 = fminf(fmaxf(tile[2 * tx][j], -65504.f), 65504.f), x1 = fminf(fmaxf(tile[2 * tx + 1][j], -65504.f), 65504.f);
-      const __half2 h = __floats2half2_rn(x0, x1);
-      const float2 f = __half22float2(h);
-      *reinterpret_cast<__half2*>(hi + c * ld + r) = h;
-      *reinterpret_cast<__half2*>(lo_base + c * ld + r) = __floats2half2_rn(x0 - f.x, x1 - f.y);
+  const int cl = threadIdx.x >> 2, rq = (threadIdx.x & 3) * 16;
+  const int64_t c = c0 + cl, r = r0 + rq;
+  if (c < cols && r < rows_pad) {
+    __align__(16) __half2 h[8], l[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float x0 = fminf(fmaxf(tile[rq + 2 * e][cl], -65504.f), 65504.f), x1 = fminf(fmaxf(tile[rq + 2 * e + 1][cl], -65504.f), 65504.f);
+      h[e] = __floats2half2_rn(x0, x1);
+      const float2 f = __half22float2(h[e]);
+      l[e] = __floats2half2_rn(x0 - f.x, x1 - f.y);
+    }
+    __half* ph = hi + c * ld + r;
+    __half* pl = lo_base + c * ld + r;
+    if (vec && r + 15 < rows_pad) {                                // rows_pad % 8 == 0 and 16 B aligned bases (checked by the host)
+      reinterpret_cast<uint4*>(ph)[0] = reinterpret_cast<const uint4*>(h)[0];
+      reinterpret_cast<uint4*>(ph)[1] = reinterpret_cast<const uint4*>(h)[1];
+      reinterpret_cast<uint4*>(pl)[0] = reinterpret_cast<const uint4*>(l)[0];
+      reinterpret_cast<uint4*>(pl)[1] = reinterpret_cast<const uint4*>(l)[1];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (r + 2 * e < rows_pad) {                                // rows_pad is even: pairs are written together
+          reinterpret_cast<__half2*>(ph)[e] = h[e];
+          reinterpret_cast<__half2*>(pl)[e] = l[e];
+        }
     }
   }
 }
@@ -1137,8 +1171,9 @@ extern "C" int32_t gnnlm_transpose_split_f16(const float* src, int64_t ld_src, i
                       (a_style || (uintptr_t)lo % 4 == 0),
                   GNNLM_E_SHAPE, "gnnlm_transpose_split_f16: rows_pad must be even and >= rows");
   if (rows_pad == 0) return 0;
-  const dim3 grid((unsigned)ceil_div(rows_pad, 64), (unsigned)ceil_div(cols, 32));
-  transpose_split_kernel<<<grid, 256, 0, stream>>>(src, ld_src, rows, cols, scale, rows_pad, a_style, (__half*)hi, (__half*)lo);
+  const dim3 grid((unsigned)ceil_div(rows_pad, 64), (unsigned)ceil_div(cols, 64));
+  const int vec = ld_src % 4 == 0 && (uintptr_t)src % 16 == 0 && rows_pad % 8 == 0 && (uintptr_t)hi % 16 == 0 && (a_style || (uintptr_t)lo % 16 == 0);
+  transpose_split_kernel<<<grid, 256, 0, stream>>>(src, ld_src, rows, cols, scale, rows_pad, a_style, (__half*)hi, (__half*)lo, vec);
   GNNLM_LAUNCH_CHECK("gnnlm_transpose_split_f16");
   return 0;
 }

@@ -2034,6 +2034,26 @@ def test_training_step_gradients_wide_heads(dev):
     assert checked >= 20
 
 
+@pytest.mark.parametrize("rows,cols,rows_pad,ld", [(77, 50, 80, 50), (130, 64, 136, 72), (64, 128, 64, 128), (5, 3, 6, 3)])
+def test_transpose_split_f16(rows, cols, rows_pad, ld, dev):
+    """gnnlm_transpose_split_f16: (scale * src)^T as split fp16, A style (hi | lo in one row) and W style (two arrays), zero padding,
+    vector and scalar paths."""
+    from gnnlm_b200 import _lib as L
+    torch.manual_seed(rows)
+    buf = torch.randn(rows, ld, device=dev)
+    src = buf[:, :cols]
+    want = (8.0 * src).T.contiguous()
+    a = torch.full((cols, 2 * rows_pad), 7.0, device=dev, dtype=torch.float16)
+    L.call("gnnlm_transpose_split_f16", L.ptr(src), src.stride(0), rows, cols, 8.0, rows_pad, 1, L.ptr(a), None, L.stream_ptr())
+    hi, lo = torch.full((cols, rows_pad), 7.0, device=dev, dtype=torch.float16), torch.full((cols, rows_pad), 7.0, device=dev, dtype=torch.float16)
+    L.call("gnnlm_transpose_split_f16", L.ptr(src), src.stride(0), rows, cols, 8.0, rows_pad, 0, L.ptr(hi), L.ptr(lo), L.stream_ptr())
+    assert torch.equal(a[:, :rows_pad], hi) and torch.equal(a[:, rows_pad:], lo)
+    got = hi.float() + lo.float()
+    assert float((got[:, :rows] - want).abs().max()) <= 2.0 ** -20 * float(want.abs().max())
+    assert float(got[:, rows:].abs().max()) == 0.0 if rows_pad > rows else True
+    assert torch.equal(hi[:, :rows], want.half())
+
+
 def test_training_dw_split_k(dev):
     """train._dw_split_k: dW = dY^T X of a tall pair by split-K in 3xFP16 (one batched launch + partial sums) against fp64, with
     1e-5-sized gradients pre-scaled by a power of two (train._pow2_scaled) and a ragged last chunk."""
