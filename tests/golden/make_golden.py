@@ -28,6 +28,11 @@ faiss and pyarrow.plasma are not installed), so each function is lifted out of i
                    five calls the layer makes.  This pins the layer code (projection order,
                    einsum, scaling, residual, LayerNorm); the DGL semantics themselves are
                    restated, not executed (DGL is absent) -> "parity unpinned" at that boundary.
+  hgt_hetero4 / hgt_two_stream / hgt_infer_*   the same module on a GENERAL heterograph (its own self-test topology, hgt.py:516-552),
+                   with two_stream=True (after the one-statement fix of quirk Q11: the unmodified source raises KeyError('k_tilde'),
+                   asserted here) and through HGTLayer.infer / reorder_incremental_state step by step (hgt.py:81-297,422-438); the
+                   stub gains apply_edges(edges=subset), edges(), update_all(etype=), a scoping local_scope, and the reference's own
+                   fairseq/incremental_decoding_utils.py mixin loaded by file path.  (`--hetero-only` regenerates just these.)
   adaptive_input_* fairseq/modules/adaptive_input.py AdaptiveInput.forward (the `--reinit-nfeat` ntgt features).
   registry.json    flag defaults of the model / task / eval-lm parsers and the `transformer_lm*` architecture presets, from the
                    reference's own add_args and architecture functions.
