@@ -888,6 +888,191 @@ __global__ void __launch_bounds__(256) transpose_split_kernel(const float* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------- training forward, fast forms
+// (the dropout rates of transformer_lm_wiki103 make these the forward of every real training step; the generic one-warp-per-
+// destination kernel above streams the 4.7 M causal edges of a Wiki103 block at 60 ms per layer)
+//
+// causal edges: the GEMM form of attn_gemm.cu with the dropout multiplier applied to the softmax weights -- S [H, L, L] from
+// gnnlm_linear_batched_f16x3 (causal = 1) -> P~ = beta softmax_causal(S) as split fp16 [H, L, 2L] for the P~ V' product (causal = 2).
+__global__ void __launch_bounds__(256) causal_softmax_drop_kernel(const float* __restrict__ S, int64_t L, int64_t ctx, int H, int64_t k_tile,
+                                                                  int64_t row0, __half* __restrict__ P, AttnDrop ad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t rows = (int64_t)H * L;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps) {
+    const int64_t i = r % L;
+    const int head = (int)(r / L);
+    const float* s = S + r * L;
+    __half* p = P + r * 2 * L;
+    const int64_t lo_j = (ctx > 0 && i + 1 > ctx) ? i + 1 - ctx : 0;
+    float m = -INFINITY, l = 0.f;
+    for (int64_t j = (lo_j & ~(int64_t)3) + lane * 4; j <= i; j += 128) {
+      const float4 x4 = *reinterpret_cast<const float4*>(s + j);
+      float x[4] = {x4.x, x4.y, x4.z, x4.w};
+      float mx = -INFINITY;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (j + e < lo_j || j + e > i) x[e] = -INFINITY;
+        mx = fmaxf(mx, x[e]);
+      }
+      if (mx > m) {
+        l *= __expf(m - mx);
+        m = mx;
+      }
+      if (m > -INFINITY) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) l += __expf(x[e] - m);
+      }
+    }
+    const float M = warp_max(m);
+    l = warp_sum(m > -INFINITY ? l * __expf(m - M) : 0.f);
+    const float inv = 1.f / l;
+    const int64_t j_end = k_tile > 0 ? min(L, (i / k_tile + 1) * k_tile) : L;
+    for (int64_t j = lane * 4; j < j_end; j += 128) {
+      float w[4] = {0.f, 0.f, 0.f, 0.f};
+      if (j <= i && j + 3 >= lo_j) {
+        const float4 x4 = *reinterpret_cast<const float4*>(s + j);
+        const float x[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (j + e >= lo_j && j + e <= i)
+            w[e] = __expf(x[e] - M) * inv *
+                   (ad.p_thresh ? dm_scale(ad.seed, dm_edge(row0 + i, row0 + j + e, head), ad.p_thresh, ad.keep_scale) : 1.f);
+      }
+      uint2 hi, lo;
+      split4_f16(w[0], w[1], w[2], w[3], hi, lo);
+      *reinterpret_cast<uint2*>(p + j) = hi;
+      *reinterpret_cast<uint2*>(p + L + j) = lo;
+    }
+  }
+}
+
+// ntgt-intra-ntgt chains (forward of cluster_attn_bwd_kernel): one warp per (cluster, head), three-row window.
+template <int C>
+__global__ void __launch_bounds__(256) cluster_attn_train_fwd_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k,
+                                                                     int64_t ldk, const float* __restrict__ v, int64_t ldv,
+                                                                     const int32_t* __restrict__ node_base,
+                                                                     const int32_t* __restrict__ cluster_nl, int64_t n_clusters, int H,
+                                                                     float scale, float* __restrict__ out, int64_t ldo, AttnDrop ad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_items = n_clusters * H;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  auto load = [&](const float* __restrict__ p, float (&r)[C]) {
+    if constexpr (C == 4) {
+      const float4 x = *reinterpret_cast<const float4*>(p);
+      r[0] = x.x; r[1] = x.y; r[2] = x.z; r[3] = x.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) r[c] = p[c];
+    }
+  };
+  auto dot = [&](const float (&a)[C], const float (&b)[C]) {
+    float p = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) p = fmaf(a[c], b[c], p);
+    return warp_sum(p);
+  };
+  for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n_items; it += warps) {
+    const int64_t cl = it / H;
+    const int head = (int)(it - cl * H);
+    const int base = __ldg(node_base + cl);
+    const int w = __ldg(node_base + cl + 1) - base;
+    if (w <= 0) continue;
+    const int nl = __ldg(cluster_nl + cl);
+    const int col = head * 32 * C + lane * C;
+    auto id_of = [&](int p) { return (int64_t)base + (p == nl ? 0 : (p < nl ? p + 1 : p)); };
+    float Kp[C], Vp[C], Kc[C], Vc[C], Kn[C], Vn[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) Kp[c] = Vp[c] = Kn[c] = Vn[c] = 0.f;
+    int64_t id_p = 0, id_c = id_of(0), id_n = 0;
+    load(k + id_c * ldk + col, Kc);
+    load(v + id_c * ldv + col, Vc);
+    for (int p = 0; p < w; ++p) {
+      const bool has_l = p > 0, has_r = p + 1 < w;
+      if (has_r) {
+        id_n = id_of(p + 1);
+        load(k + id_n * ldk + col, Kn);
+        load(v + id_n * ldv + col, Vn);
+      }
+      float qr[C];
+      load(q + id_c * ldq + col, qr);
+      const float s1 = dot(qr, Kc), s0 = has_l ? dot(qr, Kp) : -INFINITY, s2 = has_r ? dot(qr, Kn) : -INFINITY;
+      const float m = fmaxf(s1, fmaxf(s0, s2));
+      const float e0 = has_l ? __expf(s0 - m) : 0.f, e1 = __expf(s1 - m), e2 = has_r ? __expf(s2 - m) : 0.f;
+      const float inv = scale / (e0 + e1 + e2);
+      auto beta = [&](int64_t u) { return ad.p_thresh ? dm_scale(ad.seed, dm_edge(id_c, u, head), ad.p_thresh, ad.keep_scale) : 1.f; };
+      const float a0 = has_l ? e0 * inv * beta(id_p) : 0.f, a1 = e1 * inv * beta(id_c), a2 = has_r ? e2 * inv * beta(id_n) : 0.f;
+      float o[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) o[c] = a0 * Vp[c] + a1 * Vc[c] + a2 * Vn[c];
+      float* op = out + id_c * ldo + col;
+      if constexpr (C == 4) {
+        *reinterpret_cast<float4*>(op) = make_float4(o[0], o[1], o[2], o[3]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) op[c] = o[c];
+      }
+      id_p = id_c; id_c = id_n;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        Kp[c] = Kc[c]; Vp[c] = Vc[c];
+        Kc[c] = Kn[c]; Vc[c] = Vn[c];
+      }
+    }
+  }
+}
+
+// contiguous sources per destination (indices == NULL: the inter edges): one warp per (destination, head), ONE pass with an
+// online softmax -- out = scale * (sum_e w_e beta_e V'_e) / (sum_e w_e): dropout multiplies the normalised weights.
+template <int C>
+__global__ void __launch_bounds__(256) ranged_attn_train_fwd_kernel(const float* __restrict__ q, int64_t ldq, const float* __restrict__ k,
+                                                                    int64_t ldk, const float* __restrict__ v, int64_t ldv,
+                                                                    const int32_t* __restrict__ indptr, int64_t n_dst, int H, float scale,
+                                                                    int accumulate, float* __restrict__ out, int64_t ldo, AttnDrop ad) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n_items = n_dst * H;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  auto load = [&](const float* __restrict__ p, float (&r)[C]) {
+    if constexpr (C == 4) {
+      const float4 x = *reinterpret_cast<const float4*>(p);
+      r[0] = x.x; r[1] = x.y; r[2] = x.z; r[3] = x.w;
+    } else {
+#pragma unroll
+      for (int c = 0; c < C; ++c) r[c] = p[c];
+    }
+  };
+  for (int64_t it = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; it < n_items; it += warps) {
+    const int64_t i = it / H;
+    const int head = (int)(it - i * H);
+    const int col = head * 32 * C + lane * C;
+    const int64_t e0 = __ldg(indptr + i), e1 = __ldg(indptr + i + 1);
+    float qr[C], acc[C];
+    load(q + i * ldq + col, qr);
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    float m = -INFINITY, l = 0.f;
+    for (int64_t u = e0; u < e1; ++u) {
+      float kr[C], vr[C];
+      load(k + u * ldk + col, kr);
+      load(v + u * ldv + col, vr);
+      float sc = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) sc = fmaf(qr[c], kr[c], sc);
+      sc = warp_sum(sc);
+      const float mx = fmaxf(m, sc), corr = __expf(m - mx), wgt = __expf(sc - mx);
+      const float wb = wgt * (ad.p_thresh ? dm_scale(ad.seed, dm_edge(i, u, head), ad.p_thresh, ad.keep_scale) : 1.f);
+      l = l * corr + wgt;
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = fmaf(wb, vr[c], acc[c] * corr);
+      m = mx;
+    }
+    const float f = l > 0.f ? scale / l : 0.f;
+    float* op = out + i * ldo + col;
+#pragma unroll
+    for (int c = 0; c < C; ++c) op[c] = (accumulate ? op[c] : 0.f) + f * acc[c];
+  }
+}
+
 }  // namespace gnnlm
 
 using namespace gnnlm;
@@ -1026,6 +1211,21 @@ extern "C" int32_t gnnlm_hgt_edge_attn_train_fwd(const float* q, int64_t ldq, co
                   "gnnlm_hgt_edge_attn_train_fwd: d / 32 must be a power of two");
   if (n_dst == 0) return 0;
   const AttnDrop ad{seed, (uint32_t)(p_drop * 16777216.f), 1.f / (1.f - p_drop)};
+  if (causal_L == 0 && indices == nullptr && (d_k == 32 || d_k == 64 || d_k == 128)) {         // contiguous sources: one pass per (dst, head)
+    const bool aligned = ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ((uintptr_t)q | (uintptr_t)k | (uintptr_t)v) % 16 == 0;
+    if (d_k != 128 || aligned) {
+      int64_t blocks = ceil_div(n_dst * H, 8);
+      if (blocks > 148 * 64) blocks = 148 * 64;
+#define GNNLM_RAF(Cv) ranged_attn_train_fwd_kernel<Cv><<<(unsigned)blocks, 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, indptr, n_dst, H, scale, \
+                                                                                      accumulate, out, ldo, ad)
+      if (d_k == 128) GNNLM_RAF(4);
+      else if (d_k == 64) GNNLM_RAF(2);
+      else GNNLM_RAF(1);
+#undef GNNLM_RAF
+      GNNLM_LAUNCH_CHECK("gnnlm_hgt_edge_attn_train_fwd (ranged)");
+      return 0;
+    }
+  }
   const int group = 32 / H;
   const unsigned grid = (unsigned)(ceil_div(n_dst, 8) < 148 * 32 ? ceil_div(n_dst, 8) : 148 * 32);
   CAUSAL_BWD_DISPATCH(edge_attn_train_fwd_kernel, C, q, ldq, k, ldk, v, ldv, indptr, indices, n_dst, causal_L, intra_ctx, group, scale,
@@ -1175,5 +1375,44 @@ extern "C" int32_t gnnlm_transpose_split_f16(const float* src, int64_t ld_src, i
   const int vec = ld_src % 4 == 0 && (uintptr_t)src % 16 == 0 && rows_pad % 8 == 0 && (uintptr_t)hi % 16 == 0 && (a_style || (uintptr_t)lo % 16 == 0);
   transpose_split_kernel<<<grid, 256, 0, stream>>>(src, ld_src, rows, cols, scale, rows_pad, a_style, (__half*)hi, (__half*)lo, vec);
   GNNLM_LAUNCH_CHECK("gnnlm_transpose_split_f16");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_causal_softmax_drop_split(const float* S, int64_t L, int64_t intra_ctx, int32_t H, int64_t k_tile, int64_t row0,
+                                                   float p_drop, uint64_t seed, void* P, cudaStream_t stream) {
+  GNNLM_CHECK_ARG(S && P, GNNLM_E_ARG, "gnnlm_causal_softmax_drop_split: null pointer");
+  GNNLM_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, GNNLM_E_ARG, "gnnlm_causal_softmax_drop_split: dropout rate must be in [0, 1)");
+  GNNLM_CHECK_ARG(L > 0 && L % 4 == 0 && H > 0 && k_tile >= 0 && row0 >= 0 && (uintptr_t)S % 16 == 0 && (uintptr_t)P % 8 == 0, GNNLM_E_SHAPE,
+                  "gnnlm_causal_softmax_drop_split: L must be a multiple of 4 and S / P 16 B / 8 B aligned");
+  const AttnDrop ad{seed, (uint32_t)(p_drop * 16777216.f), 1.f / (1.f - p_drop)};
+  int64_t blocks = ceil_div((int64_t)H * L, 8);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  causal_softmax_drop_kernel<<<(unsigned)blocks, 256, 0, stream>>>(S, L, intra_ctx, H, k_tile, row0, (__half*)P, ad);
+  GNNLM_LAUNCH_CHECK("gnnlm_causal_softmax_drop_split");
+  return 0;
+}
+
+extern "C" int32_t gnnlm_hgt_cluster_attn_train_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                                    const int32_t* node_base, const int32_t* cluster_nl, int64_t n_clusters, int32_t H,
+                                                    int32_t d_k, float scale, float* out, int64_t ldo, float p_drop, uint64_t seed,
+                                                    cudaStream_t stream) {
+  GNNLM_CHECK_ARG(q && k && v && out && node_base && cluster_nl, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn_train_fwd: null pointer");
+  GNNLM_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, GNNLM_E_ARG, "gnnlm_hgt_cluster_attn_train_fwd: dropout rate must be in [0, 1)");
+  GNNLM_CHECK_ARG(H > 0 && (d_k == 32 || d_k == 64 || d_k == 128), GNNLM_E_UNSUPPORTED,
+                  "gnnlm_hgt_cluster_attn_train_fwd: d_k must be 32, 64 or 128 (one warp per cluster and head)");
+  GNNLM_CHECK_ARG(d_k != 128 || (ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0 &&
+                                 ((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) % 16 == 0),
+                  GNNLM_E_SHAPE, "gnnlm_hgt_cluster_attn_train_fwd: rows must be 16 B aligned");
+  if (n_clusters <= 0) return 0;
+  const AttnDrop ad{seed, (uint32_t)(p_drop * 16777216.f), 1.f / (1.f - p_drop)};
+  int64_t blocks = ceil_div(n_clusters * H, 8);
+  if (blocks > 148 * 64) blocks = 148 * 64;
+#define GNNLM_CAF(Cv) cluster_attn_train_fwd_kernel<Cv><<<(unsigned)blocks, 256, 0, stream>>>(q, ldq, k, ldk, v, ldv, node_base, cluster_nl, \
+                                                                                       n_clusters, H, scale, out, ldo, ad)
+  if (d_k == 128) GNNLM_CAF(4);
+  else if (d_k == 64) GNNLM_CAF(2);
+  else GNNLM_CAF(1);
+#undef GNNLM_CAF
+  GNNLM_LAUNCH_CHECK("gnnlm_hgt_cluster_attn_train_fwd");
   return 0;
 }

@@ -414,7 +414,7 @@ def causal_attn_gemm_supported(d: int, H: int, Lb: int) -> bool:
     return Lb % 8 == 0 and dk % 8 == 0 and Lb >= 256
 
 
-def causal_attn_gemm(q, k, v, B, Lb, intra_ctx, H, out, *, out_scale=1.0, accumulate=False):
+def causal_attn_gemm(q, k, v, B, Lb, intra_ctx, H, out, *, out_scale=1.0, accumulate=False, drop=None):
     """tgt-intra-tgt attention on the tensor cores at fp32 parity (MATH_F16X3): per block and head two 3xFP16 GEMMs
     (S = Q K'^T, O = softmax_causal(S) V') with split-fp16 operands; q / k / v fp32 [B*Lb, d] (column slices ok)."""
     d = q.shape[1]
@@ -436,7 +436,10 @@ def causal_attn_gemm(q, k, v, B, Lb, intra_ctx, H, out, *, out_scale=1.0, accumu
         L.call("gnnlm_linear_batched_f16x3", L.ptr(qs), 2 * dk, Lb * 2 * dk, L.ptr(kh), L.ptr(kl), dk, Lb * dk, 1.0, None, 0, 0,
                L.ptr(S), Lb, Lb * Lb, H, Lb, Lb, dk, 1, st(), tag="attn_qk")      # causal = 1: tiles above the diagonal skipped
         P = torch.empty((H, Lb, 2 * Lb), **f16)
-        L.call("gnnlm_causal_softmax_split", L.ptr(S), Lb, intra_ctx, H, CAUSAL_K_TILE, L.ptr(P), st())
+        if drop is not None and drop[0] > 0:      # training: (p, seed) -- the attention dropout on the softmax weights (hgt.py:356)
+            L.call("gnnlm_causal_softmax_drop_split", L.ptr(S), Lb, intra_ctx, H, CAUSAL_K_TILE, b * Lb, float(drop[0]), drop[1], L.ptr(P), st())
+        else:
+            L.call("gnnlm_causal_softmax_split", L.ptr(S), Lb, intra_ctx, H, CAUSAL_K_TILE, L.ptr(P), st())
         ob = out[rows]
         L.call("gnnlm_linear_batched_f16x3", L.ptr(P), 2 * Lb, Lb * 2 * Lb, L.ptr(vh), L.ptr(vl), Lb, dk * Lb, 1.0 / out_scale,
                L.ptr(ob) if accumulate else None, ob.stride(0), dk, L.ptr(ob), ob.stride(0), dk, H, Lb, dk, Lb, 2, st(),

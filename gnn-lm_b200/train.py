@@ -329,6 +329,11 @@ class _EdgeAttention(torch.autograd.Function):
         ctx.H, ctx.p, ctx.seed, ctx.symmetric, ctx.chains = H, p, seed, symmetric, chains
         out = torch.empty_like(q)
         if p > 0:
+            if chains is not None and (q.shape[1] // H) in (32, 64, 128) and os.environ.get("GNNLM_TRAIN_CHAIN_BWD", "1") != "0":
+                node_base, cluster_nl, n_clusters = chains
+                L.call("gnnlm_hgt_cluster_attn_train_fwd", L.ptr(q), q.stride(0), L.ptr(k), k.stride(0), L.ptr(v), v.stride(0),
+                       L.ptr(node_base), L.ptr(cluster_nl), n_clusters, H, q.shape[1] // H, 1.0, L.ptr(out), out.stride(0), float(p), seed, _st())
+                return out
             return _attn_fwd_train(q, k, v, H, 1.0, out, False, p, seed, indptr=indptr, indices=indices)
         return ops.edge_attn(q, k, v, indptr, indices, H, out)
 
@@ -357,12 +362,20 @@ class _TgtAttention(torch.autograd.Function):
         ctx.save_for_backward(q, k_i, v_i, k_t, v_t, inter_indptr)
         ctx.cfg = (B, Lb, intra_ctx, H, p, seed_inter, seed_tt)
         out = torch.empty_like(q)
+        d = q.shape[1]
+        gemm = ops.causal_attn_gemm_supported(d, H, Lb) and os.environ.get("GNNLM_TRAIN_GEMM_FWD", "1") != "0"     # tensor cores, fp32 parity
         if p > 0:
             _attn_fwd_train(q, k_i, v_i, H, 0.5, out, False, p, seed_inter, indptr=inter_indptr)
-            _attn_fwd_train(q, k_t, v_t, H, 0.5, out, True, p, seed_tt, causal=(Lb, intra_ctx))
+            if gemm:
+                ops.causal_attn_gemm(q, k_t, v_t, B, Lb, intra_ctx, H, out, out_scale=0.5, accumulate=True, drop=(p, seed_tt))
+            else:
+                _attn_fwd_train(q, k_t, v_t, H, 0.5, out, True, p, seed_tt, causal=(Lb, intra_ctx))
             return out
         ops.edge_attn(q, k_i, v_i, inter_indptr, None, H, out, out_scale=0.5, tag="inter")
-        ops.causal_attn(q, k_t, v_t, B, Lb, intra_ctx, H, out, out_scale=0.5, accumulate=True)
+        if gemm:
+            ops.causal_attn_gemm(q, k_t, v_t, B, Lb, intra_ctx, H, out, out_scale=0.5, accumulate=True)
+        else:
+            ops.causal_attn(q, k_t, v_t, B, Lb, intra_ctx, H, out, out_scale=0.5, accumulate=True)
         return out
 
     @staticmethod

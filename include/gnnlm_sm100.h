@@ -550,6 +550,19 @@ int32_t gnnlm_hgt_edge_attn_train_fwd(const float* q, int64_t ldq, const float* 
                                       const int32_t* indptr, const int32_t* indices, int64_t n_dst, int64_t causal_L,
                                       int64_t intra_ctx, int32_t H, int32_t d_k, float scale, int32_t accumulate, float* out,
                                       int64_t ldo, float p_drop, uint64_t seed, gnnlm_stream_t stream);
+/* Fast forms of the training forward (the generic kernel above handles any CSR; it also takes the contiguous-source case
+ * indices == NULL in one pass per (destination, head) when d_k is 32 / 64 / 128):
+ *   gnnlm_causal_softmax_drop_split: gnnlm_causal_softmax_split with the dropout multiplier of edge (row0 + i, row0 + j, head) on
+ *     the softmax weights -- the middle of the GEMM form of the causal edges (S from gnnlm_linear_batched_f16x3 causal = 1, P~ V'
+ *     with causal = 2);
+ *   gnnlm_hgt_cluster_attn_train_fwd: the ntgt-intra-ntgt chains, one warp per (cluster, head); out [n_ntgt, H*d_k] fp32 written
+ *     for every node of a valid cluster. */
+int32_t gnnlm_causal_softmax_drop_split(const float* S, int64_t L, int64_t intra_ctx, int32_t H, int64_t k_tile, int64_t row0,
+                                        float p_drop, uint64_t seed, void* P, gnnlm_stream_t stream);
+int32_t gnnlm_hgt_cluster_attn_train_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                                         const int32_t* node_base, const int32_t* cluster_nl, int64_t n_clusters, int32_t H,
+                                         int32_t d_k, float scale, float* out, int64_t ldo, float p_drop, uint64_t seed,
+                                         gnnlm_stream_t stream);
 int32_t gnnlm_dropout_f32(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t rows, int64_t cols, float p_drop,
                           uint64_t seed, gnnlm_stream_t stream);
 int32_t gnnlm_layernorm_bwd(const float* o, int64_t ldo, const float* residual, int64_t ldr, const float* gamma, float eps,

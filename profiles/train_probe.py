@@ -10,6 +10,13 @@ cfg = dict(synth.CONFIGS[name], n_d=1 << 24)
 model = synth.make_model(cfg).to(dev)
 for n_, p in model.named_parameters():
     p.requires_grad_("hgt" in n_)
+dropout = len(sys.argv) > 3 and sys.argv[3] == "dropout"          # model.train() with the rates of transformer_lm_wiki103
+if dropout:
+    model.train()
+    for layer in model.decoder.hgt_decoder.gcs:
+        layer.drop.p, layer.attn_drop.p = 0.3, 0.1
+    if model.decoder.adaptive_softmax is not None:
+        model.decoder.adaptive_softmax.dropout = 0.2
 tables = synth.make_tables(cfg, device=dev)
 batch = synth.make_batch(cfg, tables, device=dev)
 r = synth.Runner(cfg, model, tables, dev, "fp32", prune_unreachable=False)
@@ -25,7 +32,7 @@ for it in range(3):
     loss.backward()
     torch.cuda.synchronize()
     t2 = time.perf_counter()
-    out = {"config": name, "math": mode, "tokens": cfg["B"] * cfg["L"], "forward_ms": (t1 - t0) * 1e3, "backward_ms": (t2 - t1) * 1e3,
+    out = {"config": name, "math": mode, "dropout": dropout, "tokens": cfg["B"] * cfg["L"], "forward_ms": (t1 - t0) * 1e3, "backward_ms": (t2 - t1) * 1e3,
            "tokens_per_s": cfg["B"] * cfg["L"] / (t2 - t0), "loss_per_token": float(loss.detach()) / (cfg["B"] * cfg["L"]),
            "peak_mem_gb": torch.cuda.max_memory_allocated() / 1e9}
 print(json.dumps(out))

@@ -1907,6 +1907,13 @@ def test_training_backward_kernels_direct(dev):
                            indices=torch.arange(n_e, dtype=torch.int32, device=dev), p=0.2, seed=3)
     for a_, b in zip(ex_p, at_p):
         np.testing.assert_allclose(a_.cpu().numpy(), b.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    # the training forward over contiguous sources (one online-softmax pass per destination and head) == the generic kernel
+    base = torch.randn(n_dst, d, device=dev)
+    f_ranged, f_generic = base.clone(), base.clone()
+    train._attn_fwd_train(qs_.to(dev), k3.to(dev), v3.to(dev), H, 0.5, f_ranged, True, 0.2, 3, indptr=ip2.to(dev))
+    train._attn_fwd_train(qs_.to(dev), k3.to(dev), v3.to(dev), H, 0.5, f_generic, True, 0.2, 3, indptr=ip2.to(dev),
+                          indices=torch.arange(n_e, dtype=torch.int32, device=dev))
+    np.testing.assert_allclose(f_ranged.cpu().numpy(), f_generic.cpu().numpy(), rtol=1e-5, atol=1e-5)
     # implicit causal edges inside blocks of Lb tokens with a context window
     Lb, ctx, B = 19, 7, 2
     q2, k2, v2, do2 = (torch.randn(B * Lb, d) * 0.5 for _ in range(4))
@@ -1967,6 +1974,12 @@ def test_causal_backward_gemm_form(Lb, ctx, H, d, p, dev, monkeypatch):
         for a, b in zip(got, stream):
             ref = b.cpu().double()
             assert float((a.cpu().double() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+        if gscale == 1.0:                     # the forward in GEMM form (with the dropout multiplier) == the streaming training forward
+            from gnnlm_b200 import ops
+            o_gemm, o_stream = (torch.zeros(B * Lb, d, device=dev) for _ in range(2))
+            ops.causal_attn_gemm(q.to(dev), k.to(dev), v.to(dev), B, Lb, ctx, H, o_gemm, out_scale=scale, drop=(p, seed))
+            train._attn_fwd_train(q.to(dev), k.to(dev), v.to(dev), H, scale, o_stream, False, p, seed, causal=(Lb, ctx))
+            assert float((o_gemm - o_stream).abs().max()) < 2e-5 * float(o_stream.abs().max())
         if p == 0.0:
             qd, kd, vd = (t.double().requires_grad_(True) for t in (q, k, v))
             i = torch.arange(Lb)
@@ -2001,6 +2014,13 @@ def test_cluster_chain_backward(d, H, c, p, dev):
     ref = train._attn_bwd(q, k_, v, do, H, 1.0, indptr=ip, indices=ix, p=p, seed=5)
     qa, ka, va = (t.clone().requires_grad_(True) for t in (q, k_, v))
     out = train._EdgeAttention.apply(qa, ka, va, ip, ix, H, p, 5, False, (G.node_base, G.cluster_nl, G.T * G.k))
+    fwd_ref = torch.empty_like(q)                                 # the forward per chain (dropout on) == the generic CSR forward
+    if p > 0:
+        train._attn_fwd_train(q, k_, v, H, 1.0, fwd_ref, False, p, 5, indptr=ip, indices=ix)
+    else:
+        from gnnlm_b200 import ops
+        ops.edge_attn(q, k_, v, ip, ix, H, fwd_ref)
+    assert float((out.detach() - fwd_ref).abs().max()) < 2e-5 * float(fwd_ref.abs().max())
     out.backward(do)
     for a, b in zip((qa.grad, ka.grad, va.grad), ref):       # (c = 0: one-node chains, dQ = dK' = 0 up to rounding noise)
         assert float((a - b).abs().max()) < 2e-5 * float(b.abs().max()) + 1e-6
