@@ -2026,20 +2026,35 @@ def test_cluster_chain_backward(d, H, c, p, dev):
         assert float((a - b).abs().max()) < 2e-5 * float(b.abs().max()) + 1e-6
 
 
-def test_training_step_gradients_wide_heads(dev):
-    """The same end-to-end gradient check at d_k = 32 -- the width from which the ntgt-intra-ntgt backward runs per chain."""
+@pytest.mark.parametrize("L_,mode,drop", [(48, "fp32", False), (48, "fp32", True), (256, "f16x3", True), (256, "tf32x3", False)])
+def test_training_step_gradients_wide_heads(L_, mode, drop, dev):
+    """The end-to-end loss / gradient check at d_k = 32 -- the width from which the ntgt-intra-ntgt and inter edges run their
+    per-chain / per-token kernels (forward under dropout and backward) -- and at 256-token blocks, from which the causal edges run
+    in GEMM form (forward with the dropout multiplier, backward); masks replayed through the oracle."""
+    if mode != "fp32":
+        _need_tc()
     import copy
     from gnnlm_b200 import synth, train
     from tests.synth import oracle_train
-    cfg, model, data = _train_problem(2, [40, 120], 300, d=128, H=4)
-    ref_loss, ref_g = oracle_train((cfg, model, data))
+    cfg, model, data = _train_problem(2, [40, 120], 300, L_=L_, d=128, H=4)
+    p_feat, p_att, p_soft, seed = 0.3, 0.1, 0.2, 4711
+    ref_loss, ref_g = oracle_train((cfg, model, data), dropout=(seed, p_feat, p_att, p_soft) if drop else None)
     m = copy.deepcopy(model).to(dev).train()
+    if drop:
+        for layer in m.decoder.hgt_decoder.gcs:
+            layer.drop.p, layer.attn_drop.p = p_feat, p_att
+        m.decoder.adaptive_softmax.dropout = p_soft
+    else:
+        m.eval()
     for name, p_ in m.named_parameters():
         p_.requires_grad_("hgt" in name)
     r = synth.Runner(cfg, m, data, dev, "fp32")
+    if drop:
+        m.train()
+    assert train.causal_bwd_gemm_supported(128, 4, L_) == (L_ >= 256)
     d_ = synth.to_device({k_: data[k_] for k_ in r.KEYS}, dev)
     sample = r.sample_from(d_["nbr"], d_["feats"], d_["target"], d_["knn_dists"], d_["knn_ids"])
-    loss = train.train_step_loss(m, sample, "fp32")
+    loss = train.train_step_loss(m, sample, mode, seed=seed)
     loss.backward()
     assert abs(float(loss.detach()) - ref_loss) < 2e-5 * abs(ref_loss)
     gmax = max(float(g_.abs().max()) for g_ in ref_g.values() if g_ is not None)
@@ -2052,26 +2067,6 @@ def test_training_step_gradients_wide_heads(dev):
         assert err < 2e-4 * float(g_ref.abs().max()) + 2e-6 * gmax, (name, err)
         checked += 1
     assert checked >= 20
-
-
-@pytest.mark.parametrize("rows,cols,rows_pad,ld", [(77, 50, 80, 50), (130, 64, 136, 72), (64, 128, 64, 128), (5, 3, 6, 3)])
-def test_transpose_split_f16(rows, cols, rows_pad, ld, dev):
-    """gnnlm_transpose_split_f16: (scale * src)^T as split fp16, A style (hi | lo in one row) and W style (two arrays), zero padding,
-    vector and scalar paths."""
-    from gnnlm_b200 import _lib as L
-    torch.manual_seed(rows)
-    buf = torch.randn(rows, ld, device=dev)
-    src = buf[:, :cols]
-    want = (8.0 * src).T.contiguous()
-    a = torch.full((cols, 2 * rows_pad), 7.0, device=dev, dtype=torch.float16)
-    L.call("gnnlm_transpose_split_f16", L.ptr(src), src.stride(0), rows, cols, 8.0, rows_pad, 1, L.ptr(a), None, L.stream_ptr())
-    hi, lo = torch.full((cols, rows_pad), 7.0, device=dev, dtype=torch.float16), torch.full((cols, rows_pad), 7.0, device=dev, dtype=torch.float16)
-    L.call("gnnlm_transpose_split_f16", L.ptr(src), src.stride(0), rows, cols, 8.0, rows_pad, 0, L.ptr(hi), L.ptr(lo), L.stream_ptr())
-    assert torch.equal(a[:, :rows_pad], hi) and torch.equal(a[:, rows_pad:], lo)
-    got = hi.float() + lo.float()
-    assert float((got[:, :rows] - want).abs().max()) <= 2.0 ** -20 * float(want.abs().max())
-    assert float(got[:, rows:].abs().max()) == 0.0 if rows_pad > rows else True
-    assert torch.equal(hi[:, :rows], want.half())
 
 
 def test_training_dw_split_k(dev):
