@@ -54,6 +54,8 @@ def parse():
     p.add_argument("--eval-blocks", type=int, default=32, help="blocks of the e2e_evaluate leg (0: skip it)")
     p.add_argument("--locality", default="0.5,1048576",
                    help="p_continue,n_hot of the realistic-duplication leg (synth.local_neighbours); empty: skip the leg")
+    p.add_argument("--no-train-leg", dest="train_leg", action="store_false",
+                   help="skip the fine-tuning-step leg (`train_step` in the line; information only, after the timed regions)")
     p.add_argument("--ncu-range", action="store_true",
                    help="after warm-up run ONE resident step inside cudaProfilerStart/Stop and exit "
                         "(use with `ncu --profile-from-start off`); prints no bench line")
@@ -584,6 +586,43 @@ def main():
                                "f16f8": "log-probs within 1e-4 of fp32 (tested)"}.get(m, "")}
         del r2
     line["other_modes"] = other
+    # the fine-tuning step of the same shape -- information only, outside every timed region above: forward +
+    # backward of train.train_step_loss on one block with the dropout rates of transformer_lm_wiki103, 3xFP16 projections
+    if world == 1 and args.train_leg and lib.gnnlm_has_tcgen05() and not args.deprecated:
+        try:
+            import copy
+            from gnnlm_b200 import train
+            tm = copy.deepcopy(model).train()
+            for n_, p_ in tm.named_parameters():
+                p_.requires_grad_("hgt" in n_)
+            for layer in tm.decoder.hgt_decoder.gcs:
+                layer.drop.p, layer.attn_drop.p = 0.3, 0.1
+            if tm.decoder.adaptive_softmax is not None:
+                tm.decoder.adaptive_softmax.dropout = 0.2
+            tr = synth.Runner(cfg, tm, tables, dev, "fp32", prune_unreachable=False)
+            tm.train()
+            b0 = dev_batches[0]
+            ts = tr.sample_from(b0["nbr"], b0["feats"], b0["target"], b0["knn_dists"], b0["knn_ids"])
+            best = None
+            for it in range(3):
+                tm.zero_grad(set_to_none=True)
+                e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                e0.record()
+                loss = train.train_step_loss(tm, ts, "f16x3", seed=it)
+                e1.record()
+                loss.backward()
+                e2.record()
+                torch.cuda.synchronize()
+                fw, bw = e0.elapsed_time(e1), e1.elapsed_time(e2)
+                if it and (best is None or fw + bw < best[0] + best[1]):
+                    best = (fw, bw)
+            line["train_step"] = {"value": T / ((best[0] + best[1]) * 1e-3), "unit": "tokens/s", "forward_ms": best[0], "backward_ms": best[1],
+                                  "math": "f16x3", "dropout": [0.3, 0.1, 0.2],
+                                  "api": "train.train_step_loss(model, sample).backward() on one block, --freeze parameter set; best of 2 after 1 warm-up"}
+            del tm, tr, ts, loss
+            torch.cuda.empty_cache()
+        except Exception as e:                                    # never let the extra leg take the bench line down
+            line["train_step"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if world == 1 and not args.no_cpu_baseline:
         ccfg, cmodel, cdata = cpu_sample(args.config, args.cpu_tokens)
         sec, _ = time_oracle((ccfg, cmodel, cdata), 2, 1)       # ~10 s of CPU work: one warm-up + two timed passes
