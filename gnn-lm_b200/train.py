@@ -52,6 +52,32 @@ def _transpose(x: torch.Tensor, rows_pad: Optional[int] = None, out: Optional[to
     return out
 
 
+class _Last:
+    """One-entry cache keyed by tensor identity + version: q / k / v (and the inter K' / V') project the SAME activation in
+    consecutive calls, forward and backward, so its split-fp16 copies are made once.  The entry keeps the source tensor alive,
+    which is what makes the identity check sound."""
+
+    def __init__(self):
+        self.src, self.version, self.value = None, -1, None
+
+    def get(self, x: torch.Tensor, make):
+        if self.src is not x or self.version != x._version:
+            self.src, self.version, self.value = x, x._version, make(x)
+        return self.value
+
+    def clear(self):
+        self.src, self.version, self.value = None, -1, None
+
+
+_SPLIT_A, _SPLIT_XT = _Last(), _Last()
+
+
+def release_caches():
+    """Drop the cached operand copies (a step's activations stay referenced until the next step otherwise)."""
+    _SPLIT_A.clear()
+    _SPLIT_XT.clear()
+
+
 def _gemm(a: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], mode: int, a_scale: float = 1.0) -> torch.Tensor:
     """a [M, K] @ w [N, K]^T (+ b), fp32 in / out, in fp32 FMA, 3xTF32 or 3xFP16 (tcgen05; the weight operand split on the fly).
     Row strides may exceed K (padded buffers).  a_scale: `a` has been multiplied by it (the power of two that brings a gradient
@@ -61,7 +87,7 @@ def _gemm(a: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], mode: int
     if mode == L.MATH_F16X3:
         hi, lo, sc = ops.split_f16(w.contiguous())
         if a.shape[1] % 8 == 0 and a.stride(1) == 1:      # pre-split activation operand: the kernel without the in-loop operand split
-            a = ops.to_split(a)
+            a = _SPLIT_A.get(a, ops.to_split) if a.shape[0] >= SPLIT_K_MIN_ROWS else ops.to_split(a)
         return ops.linear(a, hi, b, W_lo=lo, w_scale=sc * a_scale, math=mode)
     assert a_scale == 1.0
     if mode == L.MATH_TF32X3:
@@ -100,11 +126,18 @@ def _dw_split_k(g: torch.Tensor, x: torch.Tensor, g_scale: float, n_split: int =
     dev = g.device
     f16 = dict(device=dev, dtype=torch.float16)
     a = torch.empty((S, N, 2 * Kc), **f16)
-    hi, lo = torch.empty((S, K, Kc), **f16), torch.empty((S, K, Kc), **f16)
+
+    def x_operand(x_):
+        hi_, lo_ = torch.empty((S, K, Kc), **f16), torch.empty((S, K, Kc), **f16)
+        for b in range(S):
+            r0, r1 = b * Kc, min(R, (b + 1) * Kc)
+            L.call("gnnlm_transpose_split_f16", L.ptr(x_[r0:r1]), x_.stride(0), r1 - r0, K, 1.0, Kc, 0, L.ptr(hi_[b]), L.ptr(lo_[b]), _st())
+        return hi_, lo_, S, Kc
+    hi, lo, s_c, kc_c = _SPLIT_XT.get(x, x_operand)
+    assert (s_c, kc_c) == (S, Kc)
     for b in range(S):
         r0, r1 = b * Kc, min(R, (b + 1) * Kc)
         L.call("gnnlm_transpose_split_f16", L.ptr(g[r0:r1]), g.stride(0), r1 - r0, N, float(g_scale), Kc, 1, L.ptr(a[b]), None, _st())
-        L.call("gnnlm_transpose_split_f16", L.ptr(x[r0:r1]), x.stride(0), r1 - r0, K, 1.0, Kc, 0, L.ptr(hi[b]), L.ptr(lo[b]), _st())
     part = torch.empty((S, N, K), device=dev, dtype=torch.float32)
     L.call("gnnlm_linear_batched_f16x3", L.ptr(a), 2 * Kc, N * 2 * Kc, L.ptr(hi), L.ptr(lo), Kc, K * Kc, float(g_scale), None, 0, 0,
            L.ptr(part), K, N * K, S, N, K, Kc, 0, _st(), tag="dw_split_k", work=(N, K, S * Kc))
@@ -420,7 +453,7 @@ class _AdaptiveLoss(torch.autograd.Function):
     through the cluster's frozen projections) and scaled in backward."""
 
     @staticmethod
-    def forward(ctx, x, target, soft, mode, p_drop, seed):
+    def forward(ctx, x, target, soft, mode, p_drop, seed, split_k=False):
         x = x.contiguous()
         T, d = x.shape
         drop = lambda a, site: a if p_drop <= 0 else _Dropout.forward(_Ctx(), a, p_drop, site_seed(seed, site))    # frozen part: no graph
@@ -440,6 +473,8 @@ class _AdaptiveLoss(torch.autograd.Function):
             return ops.linear(a, w, None, math=mode, out=lg)
 
         def back(dlg, w):          # dlogits w: the cluster's frozen weight transposed, k-extent = the cluster size
+            if split_k and w.shape[0] >= SPLIT_K_MIN_ROWS and dlg.shape[0] > 0:
+                return _back_split_k(dlg, w)
             wt = _transpose(w, pad4(w.shape[0]))                       # [k_in, N padded to a 16 B row stride]
             if mode == L.MATH_TF32X3:
                 hi, lo = ops.split_tf32(wt)
@@ -475,7 +510,39 @@ class _AdaptiveLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (dx,) = ctx.saved_tensors
-        return dx * g, None, None, None, None, None
+        return dx * g, None, None, None, None, None, None
+
+
+def _back_split_k(dlg: torch.Tensor, w: torch.Tensor, n_split: int = 8) -> torch.Tensor:
+    """dlogits [M, V_c] @ w [V_c, k_in] for a wide cluster (V_c = 207,744 and k_in = 64 on the Wiki103 tail: ONE tile column, 19 CTAs
+    as a plain product) by split-K over V_c in the 3xFP16 arithmetic: dlogits column chunks as split-fp16 rows, the weight's row
+    chunks transposed + split in one pass, one batched launch, partial sums.  dlogits = softmax - onehot lies in [-1, 1]."""
+    M, V = dlg.shape
+    k_in = w.shape[1]
+    Kc = ((V + n_split - 1) // n_split + 31) // 32 * 32
+    S = (V + Kc - 1) // Kc
+    dev = dlg.device
+    f16 = dict(device=dev, dtype=torch.float16)
+    a = torch.empty((S, M, 2 * Kc), **f16)
+    hi, lo = torch.empty((S, k_in, Kc), **f16), torch.empty((S, k_in, Kc), **f16)
+    for b in range(S):
+        c0, c1 = b * Kc, min(V, (b + 1) * Kc)
+        blk = dlg[:, c0:c1]
+        L.call("gnnlm_transpose_split_f16", L.ptr(w[c0:c1]), w.stride(0), c1 - c0, k_in, 1.0, Kc, 0, L.ptr(hi[b]), L.ptr(lo[b]), _st())
+        if c1 - c0 == Kc:                    # hi | lo halves of the chunk written in place, each Kc wide
+            L.call("gnnlm_to_split_f16", L.ptr(blk), L.dtype_code(blk.dtype), blk.stride(0), L.ptr(a[b]), 2 * Kc, M, None, Kc, _st())
+        else:                                # the ragged last chunk: zero padding up to Kc in both halves
+            t = ops.to_split(blk)
+            a[b].zero_()
+            a[b, :, :c1 - c0].copy_(t.data[:, :c1 - c0])
+            a[b, :, Kc:Kc + c1 - c0].copy_(t.data[:, c1 - c0:])
+    part = torch.empty((S, M, k_in), device=dev, dtype=torch.float32)
+    L.call("gnnlm_linear_batched_f16x3", L.ptr(a), 2 * Kc, M * 2 * Kc, L.ptr(hi), L.ptr(lo), Kc, k_in * Kc, 1.0, None, 0, 0,
+           L.ptr(part), k_in, M * k_in, S, M, k_in, Kc, 0, _st(), tag="softmax_back_split_k", work=(M, k_in, S * Kc))
+    out = part[0]
+    for b in range(1, S):
+        L.call("gnnlm_axpy_f32", L.ptr(out), out.stride(0), L.ptr(part[b]), k_in, M, None, k_in, 1.0, _st())
+    return out
 
 
 def fold_layer(layer, t: int, n: int) -> Dict[str, torch.Tensor]:
@@ -555,7 +622,8 @@ def train_step_loss(model, sample: dict, mode: str = "fp32", seed: int = 0) -> t
     soft = dec.adaptive_softmax if dec.adaptive_softmax is not None else _PlainSoftmax(dec.embed_out)
     p_soft = float(getattr(soft, "dropout", 0.0)) if training else 0.0
     # the (frozen) output layer's logits keep 3xTF32 in the 3xFP16 mode: its gradient operand is produced inside one Function
-    return _AdaptiveLoss.apply(x, sample["target"], soft, L.MATH_TF32X3 if m == L.MATH_F16X3 else m, p_soft, seed)
+    out = _AdaptiveLoss.apply(x, sample["target"], soft, L.MATH_TF32X3 if m == L.MATH_F16X3 else m, p_soft, seed, m == L.MATH_F16X3)
+    return out
 
 
 class _PlainSoftmax:
@@ -599,6 +667,7 @@ def train_step(model, sample, optimizer, criterion: Optional[AdaptiveLoss] = Non
     optimizer.zero_grad(set_to_none=True)
     loss, sample_size, log = criterion(model, sample)
     loss.backward()
+    release_caches()
     params = [p for p in model.parameters() if p.requires_grad and p.grad is not None]
     for p in params:
         p.grad.div_(float(sample_size))

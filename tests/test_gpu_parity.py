@@ -2091,6 +2091,27 @@ def test_training_dw_split_k(dev):
     assert float((W.grad.cpu().double() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
     ref_dx = g.double() @ W.detach().cpu().double()
     assert float((xd.grad.cpu().double() - ref_dx).abs().max()) < 2e-5 * float(ref_dx.abs().max())
+    # two more projections of the SAME activation: the cached split operands (train._Last) give the same gradients
+    W2 = (torch.randn(N // 2, K) * 0.1).to(dev).requires_grad_(True)
+    for Wi in (W2, W2):
+        Wi.grad = None
+        yi = train._Linear.apply(xd, Wi, None, train.L.MATH_F16X3)
+        yi.backward(g.to(dev)[:, :N // 2].contiguous())
+        ref2 = g[:, :N // 2].double().T @ x.double()
+        assert float((Wi.grad.cpu().double() - ref2).abs().max()) < 2e-5 * float(ref2.abs().max())
+    assert train._SPLIT_XT.src is xd
+    train.release_caches()
+    assert train._SPLIT_XT.src is None
+    # the adaptive softmax's wide back-product dlogits @ W (split-K over the cluster, ragged last chunk)
+    M_, V_, k_in = 300, 40000 + 77, 64
+    dlg = torch.softmax(torch.randn(M_, V_) * 3, -1)
+    dlg[torch.arange(M_), torch.randint(0, V_, (M_,))] -= 1.0
+    buf = torch.zeros(M_, (V_ + 3) // 4 * 4)
+    buf[:, :V_] = dlg
+    wv = torch.randn(V_, k_in) * 0.05
+    got = train._back_split_k(buf.to(dev)[:, :V_], wv.to(dev))
+    want = dlg.double() @ wv.double()
+    assert got.shape == (M_, k_in) and float((got.cpu().double() - want).abs().max()) < 2e-5 * float(want.abs().max())
 
 
 def test_training_steps_reduce_the_loss(dev):
