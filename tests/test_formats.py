@@ -195,3 +195,12 @@ def test_decoder_builds_codec_from_quantizer_path(tmp_path):
     want = TorchPQCodec(centroids=cen, A=A, b=np.zeros(0, np.float32)).state_dict()
     got = m.decoder.tgt_quantizer.state_dict()
     assert sorted(got) == sorted(want) and all(torch.equal(got[k], want[k]) for k in want)
+
+
+def test_quantize_features_command_line_matches_the_reference_script():
+    """Flag names / defaults of knn/quantize_features.py:31-46 (+ our --batch-size)."""
+    from gnnlm_b200.quantize_features import build_parser, quantizer_path
+    a = build_parser().parse_args(["--data-dir", "X"])
+    assert (a.prefix, a.index, a.subset, a.code_size, a.chunk_size) == ("de-en", "OPQ64_512,PQ64", "train", 64, 10000000)
+    assert not (a.compute_error or a.use_gpu or a.norm or a.pretrained_quantizer)
+    assert quantizer_path("D") == os.path.join("D", "quantizer") and quantizer_path("D", norm=True) == os.path.join("D", "quantizer-norm")

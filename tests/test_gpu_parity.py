@@ -1290,6 +1290,50 @@ def test_knn_sims_keys_golden(case, dev, golden_dir):
     assert (rec.cpu().numpy() == z["recall"]).all()
 
 
+@pytest.mark.parametrize("fp16,norm,opq", [(True, False, True), (False, True, False)])
+def test_quantize_features_script(fp16, norm, opq, dev, tmp_path):
+    """gnnlm_b200.quantize_features (knn/quantize_features.py:46-72,115-152, --pretrained_quantizer): keys.npy -> quantized-keys.npy
+    through the parsed faiss quantizer file, several GPU batches with a ragged tail; codes == the oracle's encode of the same keys
+    (up to numerical ties), reconstruction error as the reference computes it."""
+    import json as _json
+    from gnnlm_b200 import quantize_features as qf
+    from gnnlm_b200.formats import write_faiss_quantizer
+    from oracle import model_oracle as mo
+    rng = np.random.RandomState(3)
+    M, dsub, n = 16, 8, 2500
+    d = M * dsub
+    cen = rng.randn(M, 256, dsub).astype(np.float32) * (0.1 if norm else 1.0)
+    A = np.linalg.qr(rng.randn(d, d))[0].astype(np.float32) if opq else None
+    keys = rng.randn(n, d).astype(np.float16 if fp16 else np.float32)
+    root = str(tmp_path)
+    os.makedirs(os.path.join(root, "train_dstore"))
+    keys.tofile(os.path.join(root, "train_dstore", "keys.npy"))
+    _json.dump({"dstore_size": n, "hidden_size": d, "vocab_size": 10, "dstore_fp16": fp16, "val_size": 1},
+               open(os.path.join(root, "train_dstore", "info.json"), "w"))
+    write_faiss_quantizer(qf.quantizer_path(root, norm=norm), cen, A)
+    with pytest.raises(NotImplementedError):                     # training a quantizer is faiss's job
+        qf.main(["--data-dir", root], device=dev, log=lambda *_: None)
+    argv = ["--data-dir", root, "--subset", "train", "--code-size", str(M), "--pretrained_quantizer", "--compute-error", "--batch-size", "1024"]
+    res = qf.main(argv + (["--norm"] if norm else []), device=dev, log=lambda *_: None)
+    codes = np.load(os.path.join(root, "train_dstore", "quantized-keys.npy"))
+    assert codes.shape == (n, M) and codes.dtype == np.uint8 and res["n"] == n and res["M"] == M
+    x = keys.astype(np.float32)
+    if norm:
+        x = x / np.sqrt((x ** 2).sum(-1, keepdims=True))
+    ref_codes, dist = mo.pq_encode(x, cen, A, None)
+    diff = codes != ref_codes
+    assert diff.mean() < 2e-3
+    if diff.any():
+        nn_, mm = np.nonzero(diff)
+        gap = np.abs(dist[nn_, mm, codes[nn_, mm]] - dist[nn_, mm, ref_codes[nn_, mm]])
+        assert (gap <= 1e-4 * np.maximum(1.0, np.abs(dist[nn_, mm, ref_codes[nn_, mm]]))).all()
+    rec = mo.pq_decode(ref_codes, cen, A, None)
+    want_err = float(((x - rec) ** 2).sum() / (x ** 2).sum())
+    assert abs(res["avg_error"] - want_err) < 2e-2 * want_err     # the reference averages per-batch ratios
+    with pytest.raises(ValueError):
+        qf.main(["--data-dir", root, "--code-size", "64", "--pretrained_quantizer"] + (["--norm"] if norm else []), device=dev, log=lambda *_: None)
+
+
 @pytest.mark.parametrize("M,dsub,opq,with_b", [(128, 8, True, True), (64, 8, True, False), (16, 4, False, False), (32, 16, True, True)])
 @pytest.mark.parametrize("metric,cosine", [("l2", False), ("ip", False), ("ip", True), ("l2", True)])
 def test_knn_sims_pq_vs_oracle(M, dsub, opq, with_b, metric, cosine, dev):
