@@ -204,3 +204,29 @@ def test_quantize_features_command_line_matches_the_reference_script():
     assert (a.prefix, a.index, a.subset, a.code_size, a.chunk_size) == ("de-en", "OPQ64_512,PQ64", "train", 64, 10000000)
     assert not (a.compute_error or a.use_gpu or a.norm or a.pretrained_quantizer)
     assert quantizer_path("D") == os.path.join("D", "quantizer") and quantizer_path("D", norm=True) == os.path.join("D", "quantizer-norm")
+
+
+@pytest.mark.parametrize("opq", [True, False])
+def test_convert_ckpt_injects_the_codec_buffers(tmp_path, opq):
+    """gnnlm_b200.convert_ckpt == fairseq_cli/convert_ckpt.py:36-51: decoder.tgt_quantizer.{centroids_torch, norm2_centroids_torch,
+    sdc_table_torch[, A, b]} from the quantizer file, args.graph = True, everything else untouched."""
+    from argparse import Namespace
+    from gnnlm_b200 import convert_ckpt
+    from gnnlm_b200.formats import write_faiss_quantizer
+    from gnnlm_b200.pq_codec import TorchPQCodec
+    rng = np.random.RandomState(5)
+    M, dsub = 8, 4
+    cen = rng.randn(M, 256, dsub).astype(np.float32)
+    A = rng.randn(M * dsub, M * dsub).astype(np.float32) if opq else None
+    qfile = str(tmp_path / "quantizer")
+    write_faiss_quantizer(qfile, cen, A)
+    src, out = str(tmp_path / "in.pt"), str(tmp_path / "sub" / "out.pt")
+    w = torch.randn(3, 3)
+    torch.save({"args": Namespace(arch="transformer_lm", graph=False), "model": {"decoder.layers.0.fc1.weight": w}, "extra_state": {"epoch": 7}}, src)
+    convert_ckpt.main(["--ckpt", src, "--out", out, "--quantizer", qfile], log=lambda *_: None)
+    st = torch.load(out, map_location="cpu", weights_only=False)
+    assert st["args"].graph is True and st["extra_state"] == {"epoch": 7} and torch.equal(st["model"]["decoder.layers.0.fc1.weight"], w)
+    want = TorchPQCodec(centroids=cen, A=A, b=None if A is None else np.zeros(0, np.float32)).state_dict()
+    got = {k[len("decoder.tgt_quantizer."):]: v for k, v in st["model"].items() if k.startswith("decoder.tgt_quantizer.")}
+    assert sorted(got) == sorted(want) == (["A", "b"] if opq else []) + ["centroids_torch", "norm2_centroids_torch", "sdc_table_torch"]
+    assert all(torch.equal(got[k], want[k]) for k in want)
