@@ -24,3 +24,13 @@ for name, f in (("fp32 codebook -> split", lambda: ops.pq_gather_decode(tables['
                 ("pre-split codebook", lambda: ops.pq_gather_decode_presplit(tables['codes'], hi, lo, rows))):
     ms = t(f)
     print(f"{name:26s} {ms:.3f} ms  {by / ms / 1e6:.0f} GB/s ({by / ms / 1e6 / peak * 100:.0f}%)", flush=True)
+q8cb = q._q8_codebook()
+ms = t(lambda: ops.pq_gather_decode_hiq8(tables['codes'], hi, q8cb, rows))
+print(f"{'hi + e4m3 companion (default)':26s} {ms:.3f} ms  {by / ms / 1e6:.0f} GB/s ({by / ms / 1e6 / peak * 100:.0f}%)", flush=True)
+# two-phase form: gather the code rows compactly first (one coalesced 128 B row per node), then decode from sequential codes
+ar = torch.arange(n, device=dev)
+gather = lambda: ops.pq_gather_decode(tables['codes'], q.centroids_torch, rows, want_codes=True, decode=False)[2]
+ms_g = t(gather)
+compact = gather()
+ms_d = t(lambda: ops.pq_gather_decode_hiq8(compact, hi, q8cb, ar))
+print(f"two-phase: gather codes {ms_g:.3f} ms + decode from compact codes {ms_d:.3f} ms = {ms_g + ms_d:.3f} ms", flush=True)
