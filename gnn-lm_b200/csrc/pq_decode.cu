@@ -194,6 +194,8 @@ __global__ void __launch_bounds__(PQ_THREADS, 1)
   const bool active = sub < mc_here;
   const int64_t node_end = min(n, node0 + nodes_per_cta);
   const int64_t lo_off = (int64_t)M * 8;                              // lo half of the row, in fp16 elements
+  // HIQ8: 16-byte companion stores need an even subspace count here and 16 B aligned companion rows
+  const bool pair16 = HIQ8 && (mc_here % 2 == 0) && ldq % 16 == 0 && lo_off % 16 == 0 && ((uintptr_t)q8 % 16 == 0);
   for (int64_t i = node0 + warp * (2 * PQS_INFLIGHT); i < node_end; i += (PQ_THREADS / 32) * (2 * PQS_INFLIGHT)) {
     int64_t r[PQS_INFLIGHT];
     uint32_t c[PQS_INFLIGHT];
@@ -209,6 +211,23 @@ __global__ void __launch_bounds__(PQ_THREADS, 1)
       c[u] = (r[u] >= 0 && active) ? (uint32_t)__ldg(codes + (size_t)r[u] * M + m0 + sub) : 0u;
 #pragma unroll
     for (int u = 0; u < PQS_INFLIGHT; ++u) {
+      if constexpr (HIQ8) {
+        if (pair16) {
+          // companion bytes as ONE 16-byte store per lane: neighbouring subspaces swap halves, the even lane writes hi8 of both,
+          // the odd lane lo8 of both (8-byte stores at two offsets made this form 20 % slower than the hi | lo one)
+          const bool ok = r[u] >= 0 && active;
+          const uint4 vl = s_lo[sub * 256 + c[u]];                // (x, y) = hi8, (z, w) = lo8 of this subspace's 8 elements
+          const bool odd = sub & 1;
+          const uint32_t rx = __shfl_xor_sync(0xffffffffu, odd ? vl.x : vl.z, 1), ry = __shfl_xor_sync(0xffffffffu, odd ? vl.y : vl.w, 1);
+          if (ok) {
+            __half* dst = out + (size_t)(i + 2 * u + half) * ld_out + (size_t)(m0 + sub) * 8;
+            *reinterpret_cast<uint4*>(dst) = s_hi[sub * 256 + c[u]];
+            uint8_t* qd = q8 + (size_t)(i + 2 * u + half) * ldq + (size_t)(m0 + (sub & ~1)) * 8 + (odd ? lo_off : 0);
+            *reinterpret_cast<uint4*>(qd) = odd ? make_uint4(rx, ry, vl.z, vl.w) : make_uint4(vl.x, vl.y, rx, ry);
+          }
+          continue;
+        }
+      }
       if (r[u] >= 0 && active) {
         __half* dst = out + (size_t)(i + 2 * u + half) * ld_out + (size_t)(m0 + sub) * 8;
         const uint4 vh = s_hi[sub * 256 + c[u]], vl = s_lo[sub * 256 + c[u]];
