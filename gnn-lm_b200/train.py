@@ -13,8 +13,12 @@ centre-row gather (gnnlm_gather_rows / gnnlm_scatter_add_rows) and the adaptive 
 cross-entropy and its gradient by gnnlm_xent_fwd_bwd).  torch.autograd only chains them and differentiates the fold of the
 relation transforms into the projection weights (relation_att / relation_msg / relation_pri -> K' / V' weights: d x d matrices).
 
-Scope of this first training path: fp32 activations (GEMMs in fp32 FMA or 3xTF32), graphs of either builder (general CSR
-kernels for the ntgt edges, so `--deprecated` graphs train too).  Dropout (model.train()): hgt.py's `drop` on the output
+Scope: fp32 activations, projections in fp32 FMA, 3xTF32 or 3xFP16 (`f16x3`: pre-split operands, gradients scaled into the fp16
+range by a power of two, dW by split-K through one batched launch), graphs of either builder (general CSR kernels for the ntgt
+edges, so `--deprecated` graphs train too).  Fast forms, chosen by shape (each checked against the generic kernel and fp64 autograd):
+causal edges in GEMM form on the tensor cores from 256-token blocks (forward with the dropout multiplier inside the softmax-split
+pass, backward through gnnlm_causal_softmax_bwd_split), the ntgt-intra-ntgt chains one warp per (cluster, head) (forward under
+dropout and backward, no atomics) and the inter edges one warp per (token, head) from d_k = 32.  Dropout (model.train()): hgt.py's `drop` on the output
 projections (:401), `attn_drop` on the edge-softmax weights (:356, one draw per edge and head) and the adaptive softmax's input /
 tail dropouts (adaptive_softmax.py:156,101) are applied with masks that are pure functions of (seed, element)
 (gnnlm_dropout_f32, the p_drop / seed arguments of the attention kernels): forward and backward regenerate them, and the tests replay
