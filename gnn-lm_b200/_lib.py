@@ -92,6 +92,7 @@ SIGNATURES = {
                                            _f32, C.c_uint64, _p]),
     "gnnlm_hgt_cluster_attn_bwd": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _i32, _f32, _p, _i64, _p, _i64, _p, _i64,
                                           _f32, C.c_uint64, _p]),
+    "gnnlm_scale_split_f16": (_i32, [_p, _i64, _f32, _p, _i64, _i64, _p, _i64, _p]),
     "gnnlm_transpose_split_f16": (_i32, [_p, _i64, _i64, _i64, _f32, _i64, _i32, _p, _p, _p]),
     "gnnlm_causal_softmax_drop_split": (_i32, [_p, _i64, _i64, _i32, _i64, _i64, _f32, C.c_uint64, _p, _p]),
     "gnnlm_hgt_cluster_attn_train_fwd": (_i32, [_p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _i32, _i32, _f32, _p, _i64, _f32, C.c_uint64, _p]),

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256) convert_kernel(const S* __restrict__ src,
 template <typename S>
 __global__ void __launch_bounds__(256) to_split_kernel(const S* __restrict__ src, int64_t ld_src, __half* __restrict__ dst,
                                                        int64_t ld_dst, int64_t rows_cap, const int32_t* __restrict__ rows_dev,
-                                                       int64_t d) {
+                                                       int64_t d, float scale) {
   const int64_t rows = live_rows(rows_cap, rows_dev);
   const int lane = threadIdx.x & 31;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) to_split_kernel(const S* __restrict__ src
     for (int64_t c = lane * 4; c < d; c += 128) {
       float x[4];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) x[e] = c + e < d ? (float)s[c + e] : 0.f;
+      for (int e = 0; e < 4; ++e) x[e] = c + e < d ? scale * (float)s[c + e] : 0.f;      // scale = 1 (exact) except gnnlm_scale_split_f16
       uint2 hi, lo;
       split4_f16(x[0], x[1], x[2], x[3], hi, lo);
       if (c + 3 < d && (d & 3) == 0 && (ld_dst & 3) == 0) {
@@ -500,9 +500,21 @@ extern "C" int32_t gnnlm_to_split_f16(const void* src, int32_t src_dtype, int64_
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned g = grid_for(rows, 8);
-  if (src_dtype == GNNLM_F32) to_split_kernel<float><<<g, 256, 0, st>>>((const float*)src, ld_src, (__half*)dst, ld_dst, rows, rows_dev, d);
-  else to_split_kernel<__half><<<g, 256, 0, st>>>((const __half*)src, ld_src, (__half*)dst, ld_dst, rows, rows_dev, d);
+  if (src_dtype == GNNLM_F32) to_split_kernel<float><<<g, 256, 0, st>>>((const float*)src, ld_src, (__half*)dst, ld_dst, rows, rows_dev, d, 1.f);
+  else to_split_kernel<__half><<<g, 256, 0, st>>>((const __half*)src, ld_src, (__half*)dst, ld_dst, rows, rows_dev, d, 1.f);
   GNNLM_LAUNCH_CHECK("gnnlm_to_split_f16");
+  return 0;
+}
+
+// split-fp16 of scale * src: a gradient operand brought into the fp16 range by a power of two on its way into the operand format
+// (train.py: the product divides the scale out) instead of a scaled fp32 copy first
+extern "C" int32_t gnnlm_scale_split_f16(const float* src, int64_t ld_src, float scale, void* dst, int64_t ld_dst, int64_t rows,
+                                         const int32_t* rows_dev, int64_t d, gnnlm_stream_t stream) {
+  GNNLM_CHECK_ARG(src && dst, GNNLM_E_ARG, "gnnlm_scale_split_f16: null pointer");
+  GNNLM_CHECK_ARG(d > 0 && ld_src >= d && ld_dst >= 2 * d, GNNLM_E_SHAPE, "gnnlm_scale_split_f16: bad shape");
+  if (rows == 0) return 0;
+  to_split_kernel<float><<<grid_for(rows, 8), 256, 0, (cudaStream_t)stream>>>(src, ld_src, (__half*)dst, ld_dst, rows, rows_dev, d, scale);
+  GNNLM_LAUNCH_CHECK("gnnlm_scale_split_f16");
   return 0;
 }
 

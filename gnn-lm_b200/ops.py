@@ -98,10 +98,15 @@ def _mat(x):
     return L.ptr(x), L.dtype_code(x.dtype), x.stride(0), x.shape[1]
 
 
-def to_split(x: torch.Tensor, rows_dev=None) -> Split:
-    """fp16 / fp32 [rows, d] -> split fp16."""
+def to_split(x: torch.Tensor, rows_dev=None, scale: float = 1.0) -> Split:
+    """fp16 / fp32 [rows, d] -> split fp16 (of scale * x when scale != 1: fp32 sources, gnnlm_scale_split_f16)."""
     assert x.dim() == 2 and x.stride(1) == 1 and x.dtype in (torch.float16, torch.float32)
     out = Split.empty(x.shape[0], x.shape[1], x.device)
+    if scale != 1.0:
+        assert x.dtype == torch.float32
+        L.call("gnnlm_scale_split_f16", L.ptr(x), x.stride(0), float(scale), L.ptr(out.data), out.data.stride(0), x.shape[0],
+               L.ptr(rows_dev), x.shape[1], L.stream_ptr())
+        return out
     L.call("gnnlm_to_split_f16", L.ptr(x), L.dtype_code(x.dtype), x.stride(0), L.ptr(out.data), out.data.stride(0), x.shape[0],
            L.ptr(rows_dev), x.shape[1], L.stream_ptr())
     return out

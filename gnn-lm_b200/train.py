@@ -82,7 +82,7 @@ def release_caches():
     _SPLIT_XT.clear()
 
 
-def _gemm(a: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], mode: int, a_scale: float = 1.0) -> torch.Tensor:
+def _gemm(a: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], mode: int, a_scale: float = 1.0, a_prescale: float = 1.0) -> torch.Tensor:
     """a [M, K] @ w [N, K]^T (+ b), fp32 in / out, in fp32 FMA, 3xTF32 or 3xFP16 (tcgen05; the weight operand split on the fly).
     Row strides may exceed K (padded buffers).  a_scale: `a` has been multiplied by it (the power of two that brings a gradient
     operand into the fp16 range, _pow2_scaled); the product divides it out."""
@@ -90,7 +90,10 @@ def _gemm(a: torch.Tensor, w: torch.Tensor, b: Optional[torch.Tensor], mode: int
         w = w.contiguous()
     if mode == L.MATH_F16X3:
         hi, lo, sc = ops.split_f16(w.contiguous())
-        if a.shape[1] % 8 == 0 and a.stride(1) == 1:      # pre-split activation operand: the kernel without the in-loop operand split
+        if a_prescale != 1.0:                             # `a` is still UN-scaled: a_prescale (== a_scale) is applied by the split pass
+            assert a_prescale == a_scale and a.shape[1] % 8 == 0 and a.stride(1) == 1
+            a = ops.to_split(a, scale=a_prescale)
+        elif a.shape[1] % 8 == 0 and a.stride(1) == 1:    # pre-split activation operand: the kernel without the in-loop operand split
             a = _SPLIT_A.get(a, ops.to_split) if a.shape[0] >= SPLIT_K_MIN_ROWS else ops.to_split(a)
         return ops.linear(a, hi, b, W_lo=lo, w_scale=sc * a_scale, math=mode)
     assert a_scale == 1.0
@@ -176,20 +179,24 @@ class _Linear(torch.autograd.Function):
         mode = ctx.mode
         dx = dW = db = None
         split_k = mode == L.MATH_F16X3 and ctx.needs_input_grad[1] and x.shape[0] >= SPLIT_K_MIN_ROWS and x.shape[1] % 8 == 0
-        g, s = dy, 1.0
+        # 3xFP16: dY is scaled into the fp16 range by a power of two INSIDE the pass that writes its operand format (split /
+        # transposing split); the products divide it out.  (Widths that are not a multiple of 8 take a scaled copy first.)
+        g, s, pre = dy, 1.0, 1.0
         if mode == L.MATH_F16X3:
-            if split_k and not ctx.needs_input_grad[0]:      # only the split-K product reads dY: it scales on the way, no scaled copy
-                s = _pow2_scale_of(dy)
+            s = _pow2_scale_of(dy)
+            m_pad8 = (x.shape[0] + 31) // 32 * 32
+            if dy.shape[1] % 8 == 0 and m_pad8 % 8 == 0:
+                pre = s
             else:
                 g, s = _pow2_scaled(dy)
         if ctx.needs_input_grad[0]:
-            dx = _gemm(g, _transpose(W.detach().contiguous()), None, mode, s)                          # dX = dY W
+            dx = _gemm(g, _transpose(W.detach().contiguous()), None, mode, s, pre)                     # dX = dY W
         if ctx.needs_input_grad[1]:
             m_pad = (x.shape[0] + 31) // 32 * 32                                                       # k of the product, zero-padded
             if split_k:
                 dW = _dw_split_k(dy, x, s)
             else:
-                dW = _gemm(_transpose(g, m_pad), _transpose(x, m_pad), None, mode, s)                  # dW = dY^T X
+                dW = _gemm(_transpose(g, m_pad), _transpose(x, m_pad), None, mode, s, pre)             # dW = dY^T X
         if ctx.has_b and ctx.needs_input_grad[2]:
             db = _zeros(dy.shape[1], like=dy)
             L.call("gnnlm_colsum_f32", L.ptr(dy), dy.stride(0), dy.shape[0], None, dy.shape[1], L.ptr(db), _st())

@@ -283,6 +283,10 @@ int32_t gnnlm_layernorm_q8(const float* x, int64_t ldx, const void* residual, in
 /* fp16 / fp32 rows [rows, d] (ld_src elements) -> split-fp16 [rows, 2d] (GNNLM_F16X2, ld_dst >= 2d fp16 elements). */
 int32_t gnnlm_to_split_f16(const void* src, int32_t src_dtype, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows,
                            const int32_t* rows_dev, int64_t d, gnnlm_stream_t stream);
+/* The same of scale * src (fp32 source): a gradient operand scaled into the fp16 range by a power of two on its way into the operand
+ * format (the training products divide it out) -- instead of a scaled fp32 copy first. */
+int32_t gnnlm_scale_split_f16(const float* src, int64_t ld_src, float scale, void* dst, int64_t ld_dst, int64_t rows,
+                              const int32_t* rows_dev, int64_t d, gnnlm_stream_t stream);
 /* y = gelu(x), exact erf form -- the activation of HGT's input adapters `gelu(adapt_ws[t](h))` (hgt.py:505-507), used when
  * --decoder_gcn_dim differs from the embedding width.  x fp32 [rows, d]; y F32 / BF16 / F16X2. */
 int32_t gnnlm_gelu(const float* src, int64_t ld_src, void* dst, int32_t dst_dtype, int64_t ld_dst, int64_t rows,
